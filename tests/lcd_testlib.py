@@ -1,0 +1,133 @@
+"""Shared helpers for the test-suite: ctypes bindings for the oracle port (oracle/liblcd_oracle.so),
+the reference shim (oracle/_ref/libref_shim.so, built from /root/reference where present) and the
+product C-ABI (longcalld_b200/csrc/liblcd_gpu.so), plus seeded workload generators.
+
+TEST INFRASTRUCTURE: nothing in the product imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "liblcd_oracle.so")
+REF_SHIM_SO = os.path.join(ORACLE_DIR, "_ref", "libref_shim.so")
+
+
+class WfaParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "mismatch", "gap_open1", "gap_ext1", "gap_open2", "gap_ext2", "affine2p", "heuristic",
+        "min_wavefront_length", "max_distance_threshold", "zdrop", "steps_between_cutoffs")]
+
+
+class WfaResult(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("status", "score", "n_ops", "end_v", "end_h")]
+
+
+class EdlibResult(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("status", "edit_distance", "start_loc", "end_loc", "aln_len")]
+
+
+HEUR_NONE, HEUR_ADAPTIVE, HEUR_ZDROP = 0, 1, 2
+
+
+def wfa_params(heuristic=HEUR_NONE, affine2p=1, plen=0, tlen=0, x=6, o1=6, e1=2, o2=24, e2=1):
+    """Parameter points longcallD uses (src/align.h:21-26, src/align.c:398-406)."""
+    p = WfaParams(x, o1, e1, o2, e2, affine2p, heuristic, 10, 50, 0, 1)
+    if heuristic == HEUR_ZDROP:
+        p.zdrop = min(500, int(min(plen, tlen) * 0.1))
+        p.steps_between_cutoffs = 100
+    return p
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "port"])
+    if os.path.isdir("/root/reference/src"):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref"])
+
+
+_libs = {}
+
+
+def _load(path):
+    if path not in _libs:
+        _libs[path] = C.CDLL(path)
+    return _libs[path]
+
+
+def oracle_lib():
+    if not os.path.exists(ORACLE_SO):
+        build_oracle()
+    return _load(ORACLE_SO)
+
+
+def ref_lib():
+    """The unmodified reference behind a flat-C shim; None when it was never built."""
+    if not os.path.exists(REF_SHIM_SO):
+        if os.path.isdir("/root/reference/src"):
+            build_oracle()
+        else:
+            return None
+    return _load(REF_SHIM_SO)
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a, a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def wfa_align(lib, fn, pattern, text, par):
+    p, pp = _u8(pattern)
+    t, tp = _u8(text)
+    ops = C.create_string_buffer(2 * (len(p) + len(t)) + 16)
+    res = WfaResult()
+    getattr(lib, fn)(pp, C.c_int(len(p)), tp, C.c_int(len(t)), C.byref(par), ops, C.byref(res))
+    return res.status, res.score, ops.raw[:res.n_ops], res.end_v, res.end_h
+
+
+def edlib_align(lib, fn, query, target, mode=0, want_path=1):
+    q, qp = _u8(query)
+    t, tp = _u8(target)
+    aln = np.zeros(len(q) + len(t) + 8, dtype=np.uint8)
+    res = EdlibResult()
+    getattr(lib, fn)(qp, C.c_int(len(q)), tp, C.c_int(len(t)), C.c_int(mode), C.c_int(want_path),
+                     aln.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(res))
+    return res.status, res.edit_distance, res.start_loc, res.end_loc, bytes(aln[:res.aln_len])
+
+
+# ----------------------------------------------------------------------------- workload generators
+def mutate(rng, seq, sub=0.01, ins=0.01, dele=0.01, max_indel=1, sv=None):
+    """Return a mutated copy of `seq` (uint8 codes 0..3).  `sv`=(pos, kind, length) plants one large
+    indel.  Homopolymer-style indels repeat the neighbouring base (what HiFi errors look like)."""
+    out = []
+    i = 0
+    n = len(seq)
+    while i < n:
+        if sv is not None and i == sv[0]:
+            if sv[1] == "ins":
+                out.extend(rng.integers(0, 4, sv[2]).tolist())
+            else:
+                i += sv[2]
+                if i >= n:
+                    break
+        r = rng.random()
+        if r < sub:
+            out.append((int(seq[i]) + int(rng.integers(1, 4))) % 4)
+            i += 1
+        elif r < sub + ins:
+            L = int(rng.integers(1, max_indel + 1))
+            out.extend([int(seq[i])] * L if rng.random() < 0.7 else rng.integers(0, 4, L).tolist())
+            out.append(int(seq[i]))
+            i += 1
+        elif r < sub + ins + dele:
+            i += int(rng.integers(1, max_indel + 1))
+        else:
+            out.append(int(seq[i]))
+            i += 1
+    return np.array(out, dtype=np.uint8)
+
+
+def random_pair(rng, n, **kw):
+    a = rng.integers(0, 4, n).astype(np.uint8)
+    return a, mutate(rng, a, **kw)
