@@ -1,0 +1,94 @@
+/* include/lcd_gpu.h -- C ABI of liblcd_gpu.so, the B200 (sm_100a) implementation of the
+ * re-alignment stack on the hot path of `longcallD call` (yangao07/longcallD @ 491f055).
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  Every entry point names the reference
+ * interface it replaces.  The reference calls its engines one problem at a time from inside
+ * collect_noisy_reg_aln_strs() (src/align.c:1760); a GPU needs many problems per launch, so each
+ * engine is exposed
+ *   (1) as a *batch* call over host buffers  -- lcd_<engine>_batch()      (drop-in, e2e)
+ *   (2) as a *plan* whose inputs stay resident in HBM -- lcd_<engine>_plan_*() (re-runnable;
+ *       what bench.py times for the device-resident number and what ncu profiles).
+ * Results are bit-identical to the reference's for the same inputs (tests/ -m gpu).
+ *
+ * Threading: one context per process (lcd_gpu_init).  Plans may be created and run from several
+ * host threads; runs on the same CUDA stream serialise.  There is NO CPU fallback: every call
+ * fails with a non-zero code (and lcd_gpu_last_error()) when the GPU or the kernels are missing.
+ */
+#ifndef LCD_GPU_H
+#define LCD_GPU_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCD_GPU_ABI_VERSION 1
+
+/* ---------------------------------------------------------------- context */
+/* Select the device, create the library stream and size the wavefront/DP workspace pool.
+ * pool_bytes == 0 picks a default (a fraction of free HBM).  Returns 0 on success. */
+int  lcd_gpu_init(int device, size_t pool_bytes);
+void lcd_gpu_shutdown(void);
+const char *lcd_gpu_last_error(void);
+int  lcd_gpu_abi_version(void);
+/* Number of kernel launches issued by this library since init (bench.py's gpu_launches). */
+uint64_t lcd_gpu_launch_count(void);
+/* The library's CUDA stream (a cudaStream_t cast to void*) -- callers record their timing events
+ * on it; NULL before lcd_gpu_init. */
+void *lcd_gpu_stream(void);
+
+/* ---------------------------------------------------------------- K6: WFA gap-affine(-2p)
+ * Replaces wavefront_aligner_new + wavefront_align + reading wf_aligner->cigar, as called by
+ * wfa_end2end_aln (src/align.c:374-460) and is_diff_between_ref_hap_aln (src/assign_hap.c:972).
+ * The left-alignment reversal and the aligned-string construction (src/align.c:410-452,277-329)
+ * are host glue: see longcalld_b200/host. */
+enum { LCD_WFA_HEUR_NONE = 0, LCD_WFA_HEUR_ADAPTIVE = 1, LCD_WFA_HEUR_ZDROP = 2 };
+enum { LCD_WFA_STATUS_COMPLETED = 0, LCD_WFA_STATUS_PARTIAL = 1, LCD_WFA_STATUS_ERROR = -1,
+       LCD_WFA_STATUS_OOM = -2 };
+
+typedef struct {
+    int32_t mismatch, gap_open1, gap_ext1, gap_open2, gap_ext2; /* match == 0 (src/align.c:383) */
+    int32_t affine2p;              /* 1: gap_affine_2p, 0: gap_affine (o1,e1) */
+    int32_t heuristic;             /* LCD_WFA_HEUR_* (src/align.c:398-406) */
+    int32_t min_wavefront_length, max_distance_threshold;       /* wf-adaptive (10,50) */
+    int32_t zdrop;                 /* z-drop */
+    int32_t steps_between_cutoffs; /* 1 (adaptive) / 100 (z-drop) */
+} lcd_wfa_params_t;
+
+typedef struct {
+    int32_t status;                /* LCD_WFA_STATUS_* */
+    int32_t score;                 /* cigar->score */
+    int32_t n_ops;                 /* edit operations in ops[] ('M','X','I','D') */
+    int32_t end_v, end_h;          /* cigar->end_v / end_h */
+} lcd_wfa_result_t;
+
+/* Problem i aligns pattern = seqs[pat_off[i] .. +plen[i]) against text = seqs[txt_off[i] .. +tlen[i])
+ * (base codes 0..4 as in the reference).  Its operations are written to ops[ops_off[i] ..], which
+ * must have room for 2*(plen+tlen)+8 bytes.  All pointers are HOST memory. */
+int lcd_wfa_batch(int n, const uint8_t *seqs, size_t seqs_len,
+                  const int64_t *pat_off, const int32_t *plen,
+                  const int64_t *txt_off, const int32_t *tlen,
+                  const lcd_wfa_params_t *params,       /* n entries */
+                  char *ops, const int64_t *ops_off, lcd_wfa_result_t *results);
+
+typedef struct lcd_plan lcd_plan_t;
+/* Upload once (H2D), run many times.  `stream` is a cudaStream_t cast to void* (NULL: library stream). */
+lcd_plan_t *lcd_wfa_plan_create(int n, const uint8_t *seqs, size_t seqs_len,
+                                const int64_t *pat_off, const int32_t *plen,
+                                const int64_t *txt_off, const int32_t *tlen,
+                                const lcd_wfa_params_t *params);
+int  lcd_plan_run(lcd_plan_t *plan, void *stream);           /* async launch(es) on stream */
+int  lcd_plan_sync(lcd_plan_t *plan, void *stream);          /* wait + check device status */
+/* Copy results back (D2H).  ops may be NULL.  Layout as in the matching *_batch call. */
+int  lcd_wfa_plan_fetch(lcd_plan_t *plan, void *stream, char *ops, const int64_t *ops_off,
+                        lcd_wfa_result_t *results);
+void lcd_plan_destroy(lcd_plan_t *plan);
+/* Algorithmic work of one run of the plan (units of SURVEY.md section 8d: WFA wavefront cells,
+ * edlib block-columns, POA banded cells) -- filled by the kernels themselves. */
+int  lcd_plan_work_units(lcd_plan_t *plan, void *stream, uint64_t *units);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

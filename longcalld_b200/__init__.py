@@ -1,0 +1,14 @@
+"""longcalld_b200 -- B200 (sm_100a) implementation of the re-alignment hot path of `longcallD call`.
+
+The product is the C-ABI shared library ``longcalld_b200/csrc/liblcd_gpu.so`` (declared in
+``include/lcd_gpu.h``); this package is the thin Python host binding used by the tests, bench.py
+and the multi-GPU driver.  There is no CPU fallback: importing works anywhere, but every compute
+call raises ``LcdGpuError`` when the library or a B200 is missing.
+"""
+from .capi import (LcdGpuError, lib, lib_path, build_library, init, shutdown, launch_count, stream,  # noqa: F401
+                   WfaParams, WfaResult, wfa_params, WfaPlan, wfa_batch,
+                   HEUR_NONE, HEUR_ADAPTIVE, HEUR_ZDROP)
+
+__all__ = ["LcdGpuError", "lib", "lib_path", "build_library", "init", "shutdown", "launch_count", "stream",
+           "WfaParams", "WfaResult", "wfa_params", "WfaPlan", "wfa_batch",
+           "HEUR_NONE", "HEUR_ADAPTIVE", "HEUR_ZDROP"]

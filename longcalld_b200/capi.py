@@ -1,0 +1,224 @@
+"""ctypes binding of include/lcd_gpu.h (liblcd_gpu.so).  Plain pointers and sizes only.
+
+Every wrapper raises LcdGpuError with lcd_gpu_last_error() on a non-zero return: the CUDA path is
+the only path (no CPU fallback, no oracle import).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_SO = os.path.join(_CSRC, "liblcd_gpu.so")
+
+HEUR_NONE, HEUR_ADAPTIVE, HEUR_ZDROP = 0, 1, 2
+GAP_RIGHT_ALN, GAP_LEFT_ALN = 0, 1           # reference src/call_var_main.h (LONGCALLD_GAP_*_ALN)
+
+
+class LcdGpuError(RuntimeError):
+    pass
+
+
+class WfaParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "mismatch", "gap_open1", "gap_ext1", "gap_open2", "gap_ext2", "affine2p", "heuristic",
+        "min_wavefront_length", "max_distance_threshold", "zdrop", "steps_between_cutoffs")]
+
+
+class WfaResult(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("status", "score", "n_ops", "end_v", "end_h")]
+
+
+WFA_PARAMS_DTYPE = np.dtype([(n, np.int32) for n, _ in WfaParams._fields_])
+WFA_RESULT_DTYPE = np.dtype([(n, np.int32) for n, _ in WfaResult._fields_])
+
+
+def wfa_params(heuristic=HEUR_NONE, affine2p=1, plen=0, tlen=0, x=6, o1=6, e1=2, o2=24, e2=1):
+    """The parameter points wfa_end2end_aln builds (reference src/align.c:379-408, src/align.h:21-26)."""
+    p = (x, o1, e1, o2, e2, affine2p, heuristic, 10, 50, 0, 1)
+    if heuristic == HEUR_ZDROP:
+        p = (x, o1, e1, o2, e2, affine2p, heuristic, 10, 50, min(500, int(min(plen, tlen) * 0.1)), 100)
+    return p
+
+
+def lib_path():
+    return _SO
+
+
+def build_library(verbose=False):
+    """Compile liblcd_gpu.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-s" if not verbose else "-j1", "-C", _CSRC])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise LcdGpuError(f"{_SO} is missing: run `make -C longcalld_b200/csrc` "
+                          "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(_SO)
+    L.lcd_gpu_last_error.restype = C.c_char_p
+    L.lcd_gpu_launch_count.restype = C.c_uint64
+    L.lcd_gpu_init.argtypes = [C.c_int, C.c_size_t]
+    L.lcd_gpu_stream.restype = C.c_void_p
+    for fn in ("lcd_wfa_plan_create", "lcd_edlib_plan_create", "lcd_poa_plan_create"):
+        if hasattr(L, fn):
+            getattr(L, fn).restype = C.c_void_p
+    L.lcd_plan_run.argtypes = [C.c_void_p, C.c_void_p]
+    L.lcd_plan_sync.argtypes = [C.c_void_p, C.c_void_p]
+    L.lcd_plan_destroy.argtypes = [C.c_void_p]
+    L.lcd_plan_work_units.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    _lib = L
+    return L
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise LcdGpuError(f"{what} failed ({rc}): {lib().lcd_gpu_last_error().decode()}")
+
+
+def init(device=0, pool_bytes=0):
+    _check(lib().lcd_gpu_init(device, pool_bytes), "lcd_gpu_init")
+
+
+def shutdown():
+    lib().lcd_gpu_shutdown()
+
+
+def stream():
+    """The library stream as an integer cudaStream_t (wrap with torch.cuda.ExternalStream)."""
+    return int(lib().lcd_gpu_stream() or 0)
+
+
+def launch_count():
+    return int(lib().lcd_gpu_launch_count())
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def pack_pairs(pairs):
+    """[(pattern, text), ...] of uint8 arrays -> (seqs, a_off, a_len, b_off, b_len)."""
+    n = len(pairs)
+    a_len = np.fromiter((len(p) for p, _ in pairs), dtype=np.int32, count=n)
+    b_len = np.fromiter((len(t) for _, t in pairs), dtype=np.int32, count=n)
+    tot = a_len.astype(np.int64) + b_len
+    start = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(tot, out=start[1:])
+    seqs = np.empty(max(int(start[-1]), 1), dtype=np.uint8)
+    for i, (p, t) in enumerate(pairs):
+        s = int(start[i])
+        seqs[s:s + a_len[i]] = p
+        seqs[s + a_len[i]:s + a_len[i] + b_len[i]] = t
+    a_off = start[:-1].copy()
+    b_off = a_off + a_len
+    return seqs, a_off, a_len, b_off, b_len
+
+
+class _Plan:
+    def __init__(self, handle, n):
+        if not handle:
+            raise LcdGpuError("plan creation failed: " + lib().lcd_gpu_last_error().decode())
+        self.h = C.c_void_p(handle)
+        self.n = n
+
+    def run(self, stream=None):
+        _check(lib().lcd_plan_run(self.h, C.c_void_p(stream or 0)), "lcd_plan_run")
+
+    def sync(self, stream=None):
+        _check(lib().lcd_plan_sync(self.h, C.c_void_p(stream or 0)), "lcd_plan_sync")
+
+    def work_units(self, stream=None):
+        u = C.c_uint64(0)
+        _check(lib().lcd_plan_work_units(self.h, C.c_void_p(stream or 0), C.byref(u)), "lcd_plan_work_units")
+        return int(u.value)
+
+    def destroy(self):
+        if self.h:
+            lib().lcd_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def _params_array(params, n):
+    arr = np.zeros(n, dtype=WFA_PARAMS_DTYPE)
+    if isinstance(params, np.ndarray) and params.dtype == WFA_PARAMS_DTYPE:
+        arr[:] = params
+    elif isinstance(params, (list,)) and len(params) == n and not isinstance(params[0], (int, np.integer)):
+        for i, p in enumerate(params):
+            arr[i] = tuple(getattr(p, f) for f, _ in WfaParams._fields_) if isinstance(p, WfaParams) else tuple(p)
+    else:
+        arr[:] = tuple(getattr(params, f) for f, _ in WfaParams._fields_) if isinstance(params, WfaParams) else tuple(params)
+    return arr
+
+
+class WfaPlan(_Plan):
+    """Inputs resident in HBM; run() re-executes the batch (what bench.py times)."""
+
+    def __init__(self, seqs, pat_off, plen, txt_off, tlen, params):
+        n = len(plen)
+        self.seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        self.pat_off = np.ascontiguousarray(pat_off, dtype=np.int64)
+        self.txt_off = np.ascontiguousarray(txt_off, dtype=np.int64)
+        self.plen = np.ascontiguousarray(plen, dtype=np.int32)
+        self.tlen = np.ascontiguousarray(tlen, dtype=np.int32)
+        self.params = _params_array(params, n)
+        h = lib().lcd_wfa_plan_create(C.c_int(n), _ptr(self.seqs, C.c_uint8), C.c_size_t(self.seqs.size),
+                                      _ptr(self.pat_off, C.c_int64), _ptr(self.plen, C.c_int32),
+                                      _ptr(self.txt_off, C.c_int64), _ptr(self.tlen, C.c_int32),
+                                      self.params.ctypes.data_as(C.c_void_p))
+        super().__init__(h, n)
+
+    def ops_layout(self):
+        cap = 2 * (self.plen.astype(np.int64) + self.tlen) + 8
+        off = np.zeros(self.n + 1, dtype=np.int64)
+        np.cumsum(cap, out=off[1:])
+        return off
+
+    def fetch(self, stream=None, want_ops=True):
+        res = np.zeros(self.n, dtype=WFA_RESULT_DTYPE)
+        off = self.ops_layout()
+        ops = np.zeros(max(int(off[-1]), 1), dtype=np.uint8) if want_ops else None
+        rc = lib().lcd_wfa_plan_fetch(self.h, C.c_void_p(stream or 0),
+                                      ops.ctypes.data_as(C.c_char_p) if want_ops else None,
+                                      _ptr(off, C.c_int64) if want_ops else None,
+                                      res.ctypes.data_as(C.c_void_p))
+        _check(rc, "lcd_wfa_plan_fetch")
+        return res, ops, off
+
+
+def wfa_batch(pairs, params):
+    """Drop-in batch call over HOST buffers (lcd_wfa_batch): H2D, kernels, D2H.
+    Returns [(status, score, ops_bytes, end_v, end_h)] per problem."""
+    n = len(pairs)
+    seqs, po, pl, to, tl = pack_pairs(pairs)
+    par = _params_array(params, n)
+    res = np.zeros(n, dtype=WFA_RESULT_DTYPE)
+    cap = 2 * (pl.astype(np.int64) + tl) + 8
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(cap, out=off[1:])
+    ops = np.zeros(max(int(off[-1]), 1), dtype=np.uint8)
+    rc = lib().lcd_wfa_batch(C.c_int(n), _ptr(seqs, C.c_uint8), C.c_size_t(seqs.size),
+                             _ptr(po, C.c_int64), _ptr(pl, C.c_int32), _ptr(to, C.c_int64), _ptr(tl, C.c_int32),
+                             par.ctypes.data_as(C.c_void_p), ops.ctypes.data_as(C.c_char_p),
+                             _ptr(off, C.c_int64), res.ctypes.data_as(C.c_void_p))
+    _check(rc, "lcd_wfa_batch")
+    out = []
+    for i in range(n):
+        r = res[i]
+        out.append((int(r["status"]), int(r["score"]), ops[off[i]:off[i] + r["n_ops"]].tobytes(),
+                    int(r["end_v"]), int(r["end_h"])))
+    return out

@@ -1,0 +1,78 @@
+// lcd_common.cuh -- shared host/device plumbing of liblcd_gpu.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <mutex>
+#include "../../include/lcd_gpu.h"
+
+namespace lcd {
+
+void set_error(const char *fmt, ...);
+#define LCD_CUDA_OK(call)                                                                      \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            lcd::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return -1;                                                                         \
+        }                                                                                      \
+    } while (0)
+#define LCD_CUDA_OK_PTR(call)                                                                  \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            lcd::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return nullptr;                                                                    \
+        }                                                                                      \
+    } while (0)
+
+// One context per process: device, library stream, SM count, and the workspace pool that the DP
+// kernels carve wavefronts / DP planes from.  The pool is one allocation: [private arenas | overflow].
+struct Context {
+    bool ready = false;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    int32_t *pool = nullptr;          // int32 words
+    size_t pool_words = 0;
+    unsigned long long *overflow_used = nullptr;  // device counter (in 16-byte units)
+    std::mutex mu;                    // serialises plan runs that share the pool
+    unsigned long long launches = 0;
+};
+Context &ctx();
+int ensure_ready();
+
+struct Plan {
+    virtual ~Plan() {}
+    virtual int run(cudaStream_t s) = 0;
+    virtual int work_units(cudaStream_t s, uint64_t *units) = 0;
+    int n = 0;
+};
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    int alloc(size_t count) {
+        free_(); n = count;
+        if (count == 0) return 0;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e != cudaSuccess) { set_error("cudaMalloc(%zu) -> %s", count * sizeof(T), cudaGetErrorString(e)); p = nullptr; return -1; }
+        return 0;
+    }
+    int upload(const T *h, size_t count, cudaStream_t s) {
+        if (alloc(count)) return -1;
+        if (count == 0) return 0;
+        cudaError_t e = cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) { set_error("H2D -> %s", cudaGetErrorString(e)); return -1; }
+        return 0;
+    }
+    void free_() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { free_(); }
+};
+
+inline cudaStream_t pick_stream(void *s) { return s ? (cudaStream_t)s : ctx().stream; }
+
+} // namespace lcd

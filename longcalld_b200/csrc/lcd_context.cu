@@ -1,0 +1,108 @@
+// lcd_context.cu -- context, error reporting and plan plumbing of liblcd_gpu.so.
+#include <stdarg.h>
+#include "lcd_common.cuh"
+
+namespace lcd {
+
+static thread_local char g_err[512] = "";
+static char g_err_global[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    strncpy(g_err_global, g_err, sizeof(g_err_global) - 1);
+}
+
+Context &ctx() { static Context c; return c; }
+
+int ensure_ready() {
+    if (ctx().ready) return 0;
+    return lcd_gpu_init(0, 0);
+}
+
+} // namespace lcd
+
+using namespace lcd;
+
+extern "C" {
+
+int lcd_gpu_abi_version(void) { return LCD_GPU_ABI_VERSION; }
+const char *lcd_gpu_last_error(void) { return g_err[0] ? g_err : g_err_global; }
+uint64_t lcd_gpu_launch_count(void) { return ctx().launches; }
+void *lcd_gpu_stream(void) { return ctx().ready ? (void*)ctx().stream : nullptr; }
+
+int lcd_gpu_init(int device, size_t pool_bytes) {
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.ready) return 0;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("lcd_gpu_init: no CUDA device (%s); liblcd_gpu has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return -1;
+    }
+    if (device < 0 || device >= ndev) { set_error("lcd_gpu_init: device %d out of range (0..%d)", device, ndev - 1); return -1; }
+    LCD_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LCD_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("lcd_gpu_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return -1;
+    }
+    c.device = device;
+    c.sm_count = prop.multiProcessorCount;
+    LCD_CUDA_OK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    if (pool_bytes == 0) {
+        size_t free_b = 0, total_b = 0;
+        LCD_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+        pool_bytes = free_b / 4;                       // a quarter of free HBM ...
+        const size_t cap = (size_t)32 << 30;           // ... at most 32 GiB
+        if (pool_bytes > cap) pool_bytes = cap;
+    }
+    pool_bytes &= ~(size_t)255;
+    LCD_CUDA_OK(cudaMalloc((void**)&c.pool, pool_bytes));
+    c.pool_words = pool_bytes / 4;
+    LCD_CUDA_OK(cudaMalloc((void**)&c.overflow_used, sizeof(unsigned long long)));
+    LCD_CUDA_OK(cudaMemset(c.overflow_used, 0, sizeof(unsigned long long)));
+    c.ready = true;
+    return 0;
+}
+
+void lcd_gpu_shutdown(void) {
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (!c.ready) return;
+    cudaDeviceSynchronize();
+    if (c.pool) cudaFree(c.pool);
+    if (c.overflow_used) cudaFree(c.overflow_used);
+    if (c.stream) cudaStreamDestroy(c.stream);
+    c.pool = nullptr; c.overflow_used = nullptr; c.stream = nullptr; c.ready = false;
+}
+
+int lcd_plan_run(lcd_plan_t *plan, void *stream) {
+    if (!plan) { set_error("lcd_plan_run: null plan"); return -1; }
+    if (ensure_ready()) return -1;
+    Context &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    return reinterpret_cast<Plan*>(plan)->run(pick_stream(stream));
+}
+
+int lcd_plan_sync(lcd_plan_t *plan, void *stream) {
+    (void)plan;
+    LCD_CUDA_OK(cudaStreamSynchronize(pick_stream(stream)));
+    LCD_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int lcd_plan_work_units(lcd_plan_t *plan, void *stream, uint64_t *units) {
+    if (!plan) { set_error("lcd_plan_work_units: null plan"); return -1; }
+    return reinterpret_cast<Plan*>(plan)->work_units(pick_stream(stream), units);
+}
+
+void lcd_plan_destroy(lcd_plan_t *plan) {
+    if (plan) delete reinterpret_cast<Plan*>(plan);
+}
+
+}

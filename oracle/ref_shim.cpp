@@ -9,6 +9,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include "lcd_oracle.h"
+#include <thread>
+#include <atomic>
+#include <vector>
 extern "C" {
 #include "wavefront/wavefront_align.h"
 }
@@ -74,6 +77,29 @@ int ref_edlib_align(const uint8_t *query, int qlen, const uint8_t *target, int t
     res->aln_len = 0;
     if (want_path && r.alignment) { res->aln_len = r.alignmentLength; if (aln) memcpy(aln, r.alignment, r.alignmentLength); }
     edlibFreeAlignResult(r);
+    return 0;
+}
+
+
+// Batch driver for the cpu_baseline / --impl reference legs of bench.py: the reference's own
+// parallelism is "one problem per kt_for worker" (src/kthread.c), restated here with std::thread
+// pulling problems from an atomic counter.  Same buffer layout as lcd_wfa_batch (include/lcd_gpu.h).
+int ref_wfa_batch(int n, const uint8_t *seqs, const int64_t *pat_off, const int32_t *plen,
+                  const int64_t *txt_off, const int32_t *tlen, const lcd_wfa_params_t *params,
+                  char *ops, const int64_t *ops_off, lcd_wfa_result_t *results, int n_threads) {
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (;;) {
+            int i = next.fetch_add(1);
+            if (i >= n) break;
+            ref_wfa_align(seqs + pat_off[i], plen[i], seqs + txt_off[i], tlen[i], &params[i],
+                          ops ? ops + ops_off[i] : NULL, &results[i]);
+        }
+    };
+    if (n_threads <= 1) { work(); return 0; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work);
+    for (auto &t : th) t.join();
     return 0;
 }
 

@@ -1,0 +1,108 @@
+#!/usr/bin/env python3
+"""Regenerates tests/golden/*.json.gz.  Needs /root/reference (this container only).
+
+  wfa_utest.json.gz   WFA2-lib's own regression vectors (WFA2-lib/tests/wfa.utest.seq + the
+                      match==0 goldens in tests/wfa.utest.check/: affine, affine2p, p0-p2,
+                      wfapt0/1) -- pins the recurrence, the backtrace tie-breaks and wf-adaptive.
+  wfa_lcd.json.gz     outputs of the UNMODIFIED reference WFA2-lib (oracle/_ref/libref_shim.so)
+                      at longcallD's own parameter points (src/align.h:21-26, src/align.c:398-406)
+                      on seeded inputs: end2end 2p/no-heuristic, 1p/wf-adaptive, 2p/z-drop.
+"""
+import gzip
+import json
+import os
+import re
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import lcd_testlib as T  # noqa: E402
+
+REF = "/root/reference"
+
+
+def rle(ops: bytes) -> str:
+    out, i = [], 0
+    while i < len(ops):
+        j = i
+        while j < len(ops) and ops[j] == ops[i]:
+            j += 1
+        out.append(f"{j - i}{chr(ops[i])}")
+        i = j
+    return "".join(out)
+
+
+def wfa_utest():
+    seqs = open(f"{REF}/WFA2-lib/tests/wfa.utest.seq").read().split("\n")
+    pairs = [(seqs[i][1:], seqs[i + 1][1:]) for i in range(0, len(seqs) - 1, 2) if seqs[i].startswith(">")]
+    sets = {  # name -> (x, o1, e1, o2, e2, affine2p, heuristic, min_wf, max_dist, zdrop, steps)
+        "affine": (4, 6, 2, 0, 0, 0, 0, 0, 0, 0, 1),
+        "affine2p": (4, 6, 2, 24, 1, 1, 0, 0, 0, 0, 1),
+        "affine.p0": (1, 2, 1, 0, 0, 0, 0, 0, 0, 0, 1),
+        "affine.p1": (3, 1, 4, 0, 0, 0, 0, 0, 0, 0, 1),
+        "affine.p2": (5, 3, 2, 0, 0, 0, 0, 0, 0, 0, 1),
+        "affine.wfapt0": (4, 6, 2, 0, 0, 0, 1, 10, 50, 0, 1),
+        "affine.wfapt1": (4, 6, 2, 0, 0, 0, 1, 10, 50, 0, 10),
+    }
+    golden = {}
+    for name in sets:
+        rows = open(f"{REF}/WFA2-lib/tests/wfa.utest.check/test.{name}.alg").read().strip().split("\n")
+        assert len(rows) == len(pairs), (name, len(rows), len(pairs))
+        golden[name] = [(int(r.split("\t")[0]), r.split("\t")[1]) for r in rows]
+    return {"pairs": pairs, "params": sets, "golden": golden}
+
+
+def wfa_lcd():
+    ref = T.ref_lib()
+    assert ref is not None, "reference shim not built: make -C oracle ref"
+    rng = np.random.default_rng(20261017)
+    cases = []
+
+    def add(p, t, par):
+        st, score, ops, ev, eh = T.wfa_align(ref, "ref_wfa_align", p, t, T.WfaParams(*par))
+        cases.append({"p": "".join(map(str, p.tolist())), "t": "".join(map(str, t.tolist())), "par": list(par),
+                      "status": st, "score": score, "ops": rle(ops), "end_v": ev, "end_h": eh})
+
+    for n in (0, 1, 2, 5, 17, 33, 64, 65, 127, 200, 333, 512, 800, 1500):
+        for rep in range(6):
+            a = rng.integers(0, 4, n).astype(np.uint8)
+            b = T.mutate(rng, a, sub=0.02, ins=0.01, dele=0.01, max_indel=3) if n else a.copy()
+            if rep == 4 and n > 64:   # one SV
+                b = T.mutate(rng, a, sub=0.005, ins=0.002, dele=0.002, sv=(n // 3, "ins" if n % 2 else "del", n // 4))
+            if rep == 5:
+                b = rng.integers(0, 4, max(0, n + int(rng.integers(-3, 4)))).astype(np.uint8)   # unrelated
+            add(a, b, T.wfa_params_tuple(T.HEUR_NONE, 1))
+            add(a, b, T.wfa_params_tuple(T.HEUR_ADAPTIVE, 0))
+            add(a, b, T.wfa_params_tuple(T.HEUR_ZDROP, 1, len(a), len(b)))
+    # partial-read shaped z-drop cases: text is a prefix of the pattern plus junk (src/align.c:667-707)
+    for n in (300, 900, 2500):
+        for rep in range(4):
+            a = rng.integers(0, 4, n).astype(np.uint8)
+            cut = int(n * (0.3 + 0.15 * rep))
+            b = np.concatenate([T.mutate(rng, a[:cut], sub=0.01, ins=0.01, dele=0.01), rng.integers(0, 4, n - cut).astype(np.uint8)])
+            add(a, b, T.wfa_params_tuple(T.HEUR_ZDROP, 1, len(a), len(b)))
+            add(b, a, T.wfa_params_tuple(T.HEUR_ZDROP, 1, len(b), len(a)))
+    # low-complexity (homopolymer / STR) pairs: tie-break heavy
+    for unit in ("0", "01", "012", "0011"):
+        for n in (40, 150, 600):
+            a = np.array([int(c) for c in (unit * n)[:n]], dtype=np.uint8)
+            for d in (-7, -1, 1, 2, 30):
+                m = max(0, n + d)
+                b = np.array([int(c) for c in (unit * (m + 1))[:m]], dtype=np.uint8)
+                add(a, b, T.wfa_params_tuple(T.HEUR_NONE, 1))
+                add(a, b, T.wfa_params_tuple(T.HEUR_ADAPTIVE, 0))
+    return {"cases": cases}
+
+
+def main():
+    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd)):
+        path = os.path.join(HERE, name + ".json.gz")
+        with gzip.GzipFile(path, "wb", mtime=0) as f:
+            f.write(json.dumps(fn(), separators=(",", ":")).encode())
+        print(path, os.path.getsize(path))
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,24 @@ def wfa_params(heuristic=HEUR_NONE, affine2p=1, plen=0, tlen=0, x=6, o1=6, e1=2,
     return p
 
 
+def wfa_params_tuple(heuristic=HEUR_NONE, affine2p=1, plen=0, tlen=0, x=6, o1=6, e1=2, o2=24, e2=1):
+    p = wfa_params(heuristic, affine2p, plen, tlen, x, o1, e1, o2, e2)
+    return tuple(getattr(p, f) for f, _ in WfaParams._fields_)
+
+
+def unrle(s):
+    """'14M1I86M' -> b'MMMM...'"""
+    import re
+    return b"".join(op.encode() * int(n) for n, op in re.findall(r"(\d+)([MXID])", s))
+
+
+def load_golden(name):
+    import gzip
+    import json
+    with gzip.open(os.path.join(ROOT, "tests", "golden", name + ".json.gz"), "rb") as f:
+        return json.loads(f.read().decode())
+
+
 def build_oracle():
     subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "port"])
     if os.path.isdir("/root/reference/src"):
