@@ -38,7 +38,8 @@ struct Context {
     cudaStream_t stream = nullptr;
     int32_t *pool = nullptr;          // int32 words
     size_t pool_words = 0;
-    unsigned long long *overflow_used = nullptr;  // device counter (in 16-byte units)
+    static constexpr int BITMAP_WORDS = 4096;     // overflow chunks in use (bit set), device memory
+    uint32_t *chunk_bitmap = nullptr;
     std::mutex mu;                    // serialises plan runs that share the pool
     unsigned long long launches = 0;
 };

@@ -64,8 +64,8 @@ int lcd_gpu_init(int device, size_t pool_bytes) {
     pool_bytes &= ~(size_t)255;
     LCD_CUDA_OK(cudaMalloc((void**)&c.pool, pool_bytes));
     c.pool_words = pool_bytes / 4;
-    LCD_CUDA_OK(cudaMalloc((void**)&c.overflow_used, sizeof(unsigned long long)));
-    LCD_CUDA_OK(cudaMemset(c.overflow_used, 0, sizeof(unsigned long long)));
+    LCD_CUDA_OK(cudaMalloc((void**)&c.chunk_bitmap, sizeof(uint32_t) * Context::BITMAP_WORDS));
+    LCD_CUDA_OK(cudaMemset(c.chunk_bitmap, 0, sizeof(uint32_t) * Context::BITMAP_WORDS));
     c.ready = true;
     return 0;
 }
@@ -76,9 +76,9 @@ void lcd_gpu_shutdown(void) {
     if (!c.ready) return;
     cudaDeviceSynchronize();
     if (c.pool) cudaFree(c.pool);
-    if (c.overflow_used) cudaFree(c.overflow_used);
+    if (c.chunk_bitmap) cudaFree(c.chunk_bitmap);
     if (c.stream) cudaStreamDestroy(c.stream);
-    c.pool = nullptr; c.overflow_used = nullptr; c.stream = nullptr; c.ready = false;
+    c.pool = nullptr; c.chunk_bitmap = nullptr; c.stream = nullptr; c.ready = false;
 }
 
 int lcd_plan_run(lcd_plan_t *plan, void *stream) {
