@@ -52,6 +52,21 @@ typedef struct {
 int lcd_oracle_edlib_align(const uint8_t *query, int qlen, const uint8_t *target, int tlen,
                            int mode, int want_path, uint8_t *aln, lcd_edlib_result_t *res);
 
+/* ---- abPOA (abPOA/src) --------------------------------------------------------------- */
+typedef struct {
+    int32_t match, mismatch, gap_open1, gap_ext1, gap_open2, gap_ext2;  /* 2,6,6,2,24,1 (src/align.h:21-26) */
+    int32_t wb; float wf;      /* adaptive band: 10, 0.01 (phased POA); wb = -1: unbanded (de-novo POA) */
+    int32_t sub_aln;           /* 1: abpoa_partial_aln_msa_cons (inc_both_ends = 0, span-read consensus rule);
+                                  0: abpoa_aln_msa_cons / abpoa_msa (inc_both_ends = 1) */
+    int32_t max_n_cons;        /* 1 (2 = de-novo clustering: not restated yet) */
+} lcd_poa_params_t;
+/* One progressive POA over n_seq full-cover sequences (base codes 0..4): consensus (most frequent) and
+ * the row-column MSA, (n_seq + 1) rows of msa_len columns (gap = 5), row n_seq = consensus.
+ * cons must hold sum(seq_len) bytes.  Returns 0, or <0 when the case is outside the restated path. */
+int lcd_oracle_poa(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len,
+                   const lcd_poa_params_t *p, uint8_t *cons, int32_t *cons_len,
+                   uint8_t *msa, int32_t *msa_len, int32_t msa_cap);
+
 #ifdef __cplusplus
 }
 #endif

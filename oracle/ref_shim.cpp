@@ -16,6 +16,9 @@ extern "C" {
 #include "wavefront/wavefront_align.h"
 }
 #include "edlib.h"
+extern "C" {
+#include "abpoa.h"
+}
 
 extern "C" {
 
@@ -101,6 +104,52 @@ int ref_wfa_batch(int n, const uint8_t *seqs, const int64_t *pat_off, const int3
     for (int t = 0; t < n_threads; ++t) th.emplace_back(work);
     for (auto &t : th) t.join();
     return 0;
+}
+
+
+// Mirrors abpoa_partial_aln_msa_cons (src/align.c:762-870) for full-cover reads when sub_aln == 1
+// and abpoa_aln_msa_cons (src/align.c:872-953) when sub_aln == 0, with max_n_cons == 1.
+int ref_poa(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len,
+            const lcd_poa_params_t *p, uint8_t *cons, int32_t *cons_len,
+            uint8_t *msa, int32_t *msa_len, int32_t msa_cap) {
+    abpoa_t *ab = abpoa_init();
+    abpoa_para_t *abpt = abpoa_init_para();
+    abpt->cons_algrm = ABPOA_MF;
+    abpt->inc_path_score = 1;
+    abpt->out_cons = 1; abpt->out_msa = 1;
+    abpt->max_n_cons = p->max_n_cons; abpt->min_freq = 0.20;
+    abpt->match = p->match; abpt->mismatch = p->mismatch;
+    abpt->gap_open1 = p->gap_open1; abpt->gap_ext1 = p->gap_ext1;
+    abpt->gap_open2 = p->gap_open2; abpt->gap_ext2 = p->gap_ext2;
+    abpt->wb = p->wb; abpt->wf = p->wf;
+    *cons_len = 0; *msa_len = 0;
+    if (p->sub_aln) {
+        abpt->sub_aln = 1;
+        abpoa_post_set_para(abpt);
+        ab->abs->n_seq = n_seq;
+        for (int i = 0; i < n_seq; ++i) {
+            abpoa_res_t res; res.graph_cigar = 0; res.n_cigar = 0;
+            uint8_t *q = (uint8_t*)seqs + seq_off[i];
+            abpoa_align_sequence_to_subgraph(ab, abpt, 0, 1, q, seq_len[i], &res);
+            abpoa_add_subgraph_alignment(ab, abpt, 0, 1, q, NULL, seq_len[i], NULL, res, i, n_seq, 0);
+            if (res.n_cigar) free(res.graph_cigar);
+        }
+        abpoa_output(ab, abpt, NULL);
+    } else {
+        abpoa_post_set_para(abpt);
+        std::vector<uint8_t*> ptr(n_seq); std::vector<int> len(n_seq);
+        for (int i = 0; i < n_seq; ++i) { ptr[i] = (uint8_t*)seqs + seq_off[i]; len[i] = seq_len[i]; }
+        abpoa_msa(ab, abpt, n_seq, NULL, len.data(), ptr.data(), NULL, NULL);
+    }
+    abpoa_cons_t *abc = ab->abc;
+    int rc = 0;
+    if (abc->n_cons > 0) { *cons_len = abc->cons_len[0]; memcpy(cons, abc->cons_base[0], abc->cons_len[0]); }
+    if (msa) {
+        if ((int64_t)(abc->n_seq + abc->n_cons) * abc->msa_len > msa_cap || abc->n_cons != 1) rc = -5;
+        else { *msa_len = abc->msa_len; for (int i = 0; i < abc->n_seq + 1; ++i) memcpy(msa + (size_t)i * abc->msa_len, abc->msa_base[i], abc->msa_len); }
+    }
+    abpoa_free_para(abpt); abpoa_free(ab);
+    return rc;
 }
 
 }

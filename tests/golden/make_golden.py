@@ -96,8 +96,36 @@ def wfa_lcd():
     return {"cases": cases}
 
 
+def poa_lcd():
+    """Outputs of the UNMODIFIED abPOA (AVX-512BW build of oracle/_ref) driven as longcallD drives it
+    (src/align.c:762-870 phased / :872-953 de-novo set-up, max_n_cons = 1) on seeded noisy regions."""
+    import hashlib
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from longcalld_b200 import synth
+    ref = T.ref_lib()
+    cases = []
+    for tech, mbp, seed in (("hifi", 0.25, 21), ("ont", 0.03, 22)):
+        for r in synth.make_regions(mbp, tech, seed=seed):
+            for hap in (1, 2):
+                seqs = [s for s, h in zip(r.reads, r.read_hap) if h == hap]
+                if not seqs or min(len(s) for s in seqs) == 0 or max(len(s) for s in seqs) > 1200:
+                    continue
+                for sub, wb in ((1, 10), (0, -1)):
+                    if wb < 0 and len(cases) % 3:
+                        continue
+                    rc, cons, msa = T.poa(ref, "ref_poa", seqs, T.poa_params(sub, wb))
+                    assert rc == 0
+                    cases.append({"seqs": ["".join(map(str, s.tolist())) for s in seqs], "sub_aln": sub, "wb": wb,
+                                  "cons": "".join(map(str, cons)), "msa_shape": list(msa.shape),
+                                  "msa_sha1": hashlib.sha1(msa.tobytes()).hexdigest()})
+    return {"cases": cases}
+
+
 def main():
-    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd)):
+    only = sys.argv[1:]
+    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd), ("poa_lcd", poa_lcd)):
+        if only and name not in only:
+            continue
         path = os.path.join(HERE, name + ".json.gz")
         with gzip.GzipFile(path, "wb", mtime=0) as f:
             f.write(json.dumps(fn(), separators=(",", ":")).encode())

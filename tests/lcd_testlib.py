@@ -149,3 +149,35 @@ def mutate(rng, seq, sub=0.01, ins=0.01, dele=0.01, max_indel=1, sv=None):
 def random_pair(rng, n, **kw):
     a = rng.integers(0, 4, n).astype(np.uint8)
     return a, mutate(rng, a, **kw)
+
+
+# ----------------------------------------------------------------------------- POA helpers
+class PoaParams(C.Structure):
+    _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open1", C.c_int32), ("gap_ext1", C.c_int32),
+                ("gap_open2", C.c_int32), ("gap_ext2", C.c_int32), ("wb", C.c_int32), ("wf", C.c_float),
+                ("sub_aln", C.c_int32), ("max_n_cons", C.c_int32)]
+
+
+def poa_params(sub_aln=1, wb=10, wf=0.01):
+    """longcallD's two abPOA set-ups (src/align.c:769-783 phased, :876-889 de-novo uses wb=-1)."""
+    return PoaParams(2, 6, 6, 2, 24, 1, wb, wf, sub_aln, 1)
+
+
+def poa(lib, fn, seqs, par):
+    """-> (rc, consensus bytes, msa as (n_seq+1, msa_len) uint8 array)"""
+    n = len(seqs)
+    lens = np.array([len(s) for s in seqs], dtype=np.int32)
+    off = np.zeros(n, dtype=np.int64)
+    if n > 1:
+        off[1:] = np.cumsum(lens[:-1])
+    flat = np.concatenate([np.asarray(s, dtype=np.uint8) for s in seqs]) if n else np.zeros(1, np.uint8)
+    flat = np.ascontiguousarray(flat)
+    tot = int(lens.sum())
+    cons = np.zeros(tot + 8, dtype=np.uint8)
+    cap = (n + 1) * (tot + 8)
+    msa = np.zeros(cap, dtype=np.uint8)
+    cl, ml = C.c_int32(0), C.c_int32(0)
+    rc = getattr(lib, fn)(C.c_int(n), flat.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
+                          lens.ctypes.data_as(C.c_void_p), C.byref(par), cons.ctypes.data_as(C.c_void_p), C.byref(cl),
+                          msa.ctypes.data_as(C.c_void_p), C.byref(ml), C.c_int32(min(cap, 2**31 - 1)))
+    return rc, cons[:cl.value].tobytes(), msa[:(n + 1) * ml.value].reshape(n + 1, ml.value).copy()
