@@ -88,6 +88,48 @@ void lcd_plan_destroy(lcd_plan_t *plan);
  * edlib block-columns, POA banded cells) -- filled by the kernels themselves. */
 int  lcd_plan_work_units(lcd_plan_t *plan, void *stream, uint64_t *units);
 
+/* ---------------------------------------------------------------- K5: abPOA consensus + MSA
+ * One *problem* is the progressive partial-order alignment of the reads of one (noisy region,
+ * haplotype): it replaces the abPOA call sequence of abpoa_partial_aln_msa_cons (src/align.c:762-870;
+ * sub_aln = 1) and abpoa_aln_msa_cons (src/align.c:872-953; sub_aln = 0, wb = -1) for full-cover reads:
+ * abpoa_init / abpoa_init_para / abpoa_post_set_para / abpoa_align_sequence_to_subgraph /
+ * abpoa_add_subgraph_alignment (or abpoa_msa) / abpoa_output, then reading ab->abc
+ * (cons_base[0], cons_len[0], msa_base, msa_len).  Results are those of abPOA's AVX-512BW build. */
+typedef struct {
+    int32_t match, mismatch, gap_open1, gap_ext1, gap_open2, gap_ext2;  /* 2,6,6,2,24,1: src/align.h:21-26 */
+    int32_t wb; float wf;          /* adaptive band (abpoa.h:17-18: 10, 0.01); wb = -1: unbanded */
+    int32_t sub_aln;               /* 1: phased set-up (inc_both_ends = 0, span-read consensus rule); 0: abpoa_msa */
+    int32_t max_n_cons;            /* 1 (the 2-consensus de-novo clustering is not on the GPU yet: rejected) */
+} lcd_poa_params_t;
+
+enum { LCD_POA_OK = 0, LCD_POA_NEEDS_INT32 = -1, LCD_POA_BAND = -2, LCD_POA_BACKTRACK = -3,
+       LCD_POA_NO_BASE = -4, LCD_POA_OOM = -5, LCD_POA_MSA_CAP = -6 };
+typedef struct {
+    int32_t status;                /* LCD_POA_* */
+    int32_t cons_len;              /* abc->cons_len[0] */
+    int32_t msa_len;               /* abc->msa_len */
+    int32_t n_nodes;               /* abg->node_n */
+} lcd_poa_result_t;
+
+/* Problem i owns reads first_read[i] .. first_read[i]+n_reads[i]-1; read r is seqs[read_off[r] .. +read_len[r])
+ * (base codes 0..4), aligned in that order.  cons[cons_off[i] ..] needs the sum of the problem's read
+ * lengths.  msa may be NULL; otherwise problem i's (n_reads+1) x msa_len row-major matrix (gap = 5, last
+ * row = consensus) goes to msa[msa_off[i] ..] if it fits in msa_cap[i] bytes (else LCD_POA_MSA_CAP). */
+int lcd_poa_batch(int n, const uint8_t *seqs, size_t seqs_len,
+                  const int32_t *first_read, const int32_t *n_reads,
+                  const int64_t *read_off, const int32_t *read_len, int n_total_reads,
+                  const lcd_poa_params_t *params,
+                  uint8_t *cons, const int64_t *cons_off,
+                  uint8_t *msa, const int64_t *msa_off, const int64_t *msa_cap,
+                  lcd_poa_result_t *results);
+lcd_plan_t *lcd_poa_plan_create(int n, const uint8_t *seqs, size_t seqs_len,
+                                const int32_t *first_read, const int32_t *n_reads,
+                                const int64_t *read_off, const int32_t *read_len, int n_total_reads,
+                                const lcd_poa_params_t *params);
+int  lcd_poa_plan_fetch(lcd_plan_t *plan, void *stream, uint8_t *cons, const int64_t *cons_off,
+                        uint8_t *msa, const int64_t *msa_off, const int64_t *msa_cap,
+                        lcd_poa_result_t *results);
+
 #ifdef __cplusplus
 }
 #endif

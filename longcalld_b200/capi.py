@@ -222,3 +222,120 @@ def wfa_batch(pairs, params):
         out.append((int(r["status"]), int(r["score"]), ops[off[i]:off[i] + r["n_ops"]].tobytes(),
                     int(r["end_v"]), int(r["end_h"])))
     return out
+
+
+# ----------------------------------------------------------------------------- K5: POA
+class PoaParams(C.Structure):
+    _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open1", C.c_int32), ("gap_ext1", C.c_int32),
+                ("gap_open2", C.c_int32), ("gap_ext2", C.c_int32), ("wb", C.c_int32), ("wf", C.c_float),
+                ("sub_aln", C.c_int32), ("max_n_cons", C.c_int32)]
+
+
+POA_PARAMS_DTYPE = np.dtype([("match", np.int32), ("mismatch", np.int32), ("gap_open1", np.int32), ("gap_ext1", np.int32),
+                             ("gap_open2", np.int32), ("gap_ext2", np.int32), ("wb", np.int32), ("wf", np.float32),
+                             ("sub_aln", np.int32), ("max_n_cons", np.int32)])
+POA_RESULT_DTYPE = np.dtype([(n, np.int32) for n in ("status", "cons_len", "msa_len", "n_nodes")])
+
+
+def poa_params(sub_aln=1, wb=10, wf=0.01):
+    """longcallD's abPOA set-ups (reference src/align.c:769-783 phased; :876-889 de-novo uses wb=-1)."""
+    return (2, 6, 6, 2, 24, 1, wb, wf, sub_aln, 1)
+
+
+def pack_poa(problems):
+    """[[read, read, ...], ...] -> (seqs, first_read, n_reads, read_off, read_len)"""
+    reads = [r for p in problems for r in p]
+    n_reads = np.fromiter((len(p) for p in problems), dtype=np.int32, count=len(problems))
+    first = np.zeros(len(problems), dtype=np.int32)
+    if len(problems) > 1:
+        first[1:] = np.cumsum(n_reads[:-1])
+    read_len = np.fromiter((len(r) for r in reads), dtype=np.int32, count=len(reads))
+    read_off = np.zeros(len(reads), dtype=np.int64)
+    if len(reads) > 1:
+        read_off[1:] = np.cumsum(read_len[:-1].astype(np.int64))
+    seqs = np.concatenate([np.asarray(r, dtype=np.uint8) for r in reads]) if reads else np.zeros(1, np.uint8)
+    return np.ascontiguousarray(seqs), first, n_reads, read_off, read_len
+
+
+def _poa_params_array(params, n):
+    arr = np.zeros(n, dtype=POA_PARAMS_DTYPE)
+    if isinstance(params, list) and len(params) == n and isinstance(params[0], (tuple, list)):
+        for i, p in enumerate(params):
+            arr[i] = tuple(p)
+    else:
+        arr[:] = tuple(params)
+    return arr
+
+
+class PoaPlan(_Plan):
+    def __init__(self, seqs, first_read, n_reads, read_off, read_len, params):
+        n = len(n_reads)
+        self.seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        self.first = np.ascontiguousarray(first_read, dtype=np.int32)
+        self.n_reads = np.ascontiguousarray(n_reads, dtype=np.int32)
+        self.read_off = np.ascontiguousarray(read_off, dtype=np.int64)
+        self.read_len = np.ascontiguousarray(read_len, dtype=np.int32)
+        self.params = _poa_params_array(params, n)
+        h = lib().lcd_poa_plan_create(C.c_int(n), _ptr(self.seqs, C.c_uint8), C.c_size_t(self.seqs.size),
+                                      _ptr(self.first, C.c_int32), _ptr(self.n_reads, C.c_int32),
+                                      _ptr(self.read_off, C.c_int64), _ptr(self.read_len, C.c_int32),
+                                      C.c_int(len(self.read_len)), self.params.ctypes.data_as(C.c_void_p))
+        super().__init__(h, n)
+
+    def layout(self):
+        """Host output layout: consensus capacity = sum of read lengths; MSA capacity (n_reads+1) x (2*max_len+64)."""
+        sum_len = np.add.reduceat(self.read_len.astype(np.int64), self.first) if self.n else np.zeros(0, np.int64)
+        max_len = np.maximum.reduceat(self.read_len, self.first).astype(np.int64) if self.n else np.zeros(0, np.int64)
+        cons_off = np.zeros(self.n + 1, dtype=np.int64)
+        np.cumsum(sum_len, out=cons_off[1:])
+        msa_cap = (self.n_reads.astype(np.int64) + 1) * (2 * max_len + 64)
+        msa_off = np.zeros(self.n + 1, dtype=np.int64)
+        np.cumsum(msa_cap, out=msa_off[1:])
+        return cons_off, msa_off, msa_cap
+
+    def fetch(self, stream=None, want_msa=True):
+        cons_off, msa_off, msa_cap = self.layout()
+        cons = np.zeros(max(int(cons_off[-1]), 1), dtype=np.uint8)
+        msa = np.zeros(max(int(msa_off[-1]), 1), dtype=np.uint8) if want_msa else None
+        res = np.zeros(self.n, dtype=POA_RESULT_DTYPE)
+        rc = lib().lcd_poa_plan_fetch(self.h, C.c_void_p(stream or 0), _ptr(cons, C.c_uint8), _ptr(cons_off, C.c_int64),
+                                      _ptr(msa, C.c_uint8) if want_msa else None, _ptr(msa_off, C.c_int64) if want_msa else None,
+                                      _ptr(msa_cap, C.c_int64) if want_msa else None, res.ctypes.data_as(C.c_void_p))
+        _check(rc, "lcd_poa_plan_fetch")
+        return res, cons, cons_off, msa, msa_off
+
+
+def poa_batch(problems, params, want_msa=True):
+    """Drop-in batch call over HOST buffers (lcd_poa_batch).  -> [(status, consensus bytes, msa (n+1, msa_len))]"""
+    n = len(problems)
+    if n == 0:
+        return []
+    seqs, first, n_reads, read_off, read_len = pack_poa(problems)
+    par = _poa_params_array(params, n)
+    sum_len = np.add.reduceat(read_len.astype(np.int64), first)
+    max_len = np.maximum.reduceat(read_len, first).astype(np.int64)
+    cons_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(sum_len, out=cons_off[1:])
+    msa_cap = (n_reads.astype(np.int64) + 1) * (2 * max_len + 64)
+    msa_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(msa_cap, out=msa_off[1:])
+    cons = np.zeros(max(int(cons_off[-1]), 1), dtype=np.uint8)
+    msa = np.zeros(max(int(msa_off[-1]), 1), dtype=np.uint8) if want_msa else None
+    res = np.zeros(n, dtype=POA_RESULT_DTYPE)
+    rc = lib().lcd_poa_batch(C.c_int(n), _ptr(seqs, C.c_uint8), C.c_size_t(seqs.size), _ptr(first, C.c_int32),
+                             _ptr(n_reads, C.c_int32), _ptr(read_off, C.c_int64), _ptr(read_len, C.c_int32),
+                             C.c_int(len(read_len)), par.ctypes.data_as(C.c_void_p),
+                             _ptr(cons, C.c_uint8), _ptr(cons_off, C.c_int64),
+                             _ptr(msa, C.c_uint8) if want_msa else None, _ptr(msa_off, C.c_int64) if want_msa else None,
+                             _ptr(msa_cap, C.c_int64) if want_msa else None, res.ctypes.data_as(C.c_void_p))
+    _check(rc, "lcd_poa_batch")
+    out = []
+    for i in range(n):
+        r = res[i]
+        c = cons[cons_off[i]:cons_off[i] + r["cons_len"]].tobytes()
+        m = None
+        if want_msa:
+            rows = int(n_reads[i]) + 1
+            m = msa[msa_off[i]:msa_off[i] + rows * int(r["msa_len"])].reshape(rows, int(r["msa_len"])).copy()
+        out.append((int(r["status"]), c, m))
+    return out

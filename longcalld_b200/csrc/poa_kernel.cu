@@ -1,0 +1,245 @@
+// poa_kernel.cu -- K5/K5b launcher and host plan: batched partial-order alignment (consensus + MSA).
+// Device logic and design notes: poa_device.cuh.
+#include "lcd_common.cuh"
+#include "poa_device.cuh"
+#include <algorithm>
+
+namespace lcd {
+namespace poa {
+
+constexpr int WARPS_PER_CTA = 4;
+
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA)
+poa_kernel(const KernelArgs a) {
+    const int gi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group_id = blockIdx.x * WARPS_PER_CTA + gi;
+    int32_t *arena = a.arena + (size_t)group_id * a.arena_words;
+    Poa<WarpLanes> poa;
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(a.queue, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= (uint32_t)a.n) break;
+        const int pi = a.order[item];
+        poa.run(a, a.problems[pi], a.results + pi, arena);
+    }
+}
+
+// arena words a problem needs (mirrors Poa::carve) for a given DP cell budget
+static uint64_t arena_need_words(int sum_len, int max_len, int n_reads, uint64_t dp_cells) {
+    const uint64_t N = (uint64_t)sum_len + 2 + 32;
+    uint64_t top = 23 * ((N + 3) & ~3ull);
+    const uint64_t E = 4ull * (sum_len + n_reads) + 64;
+    const uint64_t stride = 2 + 2 * (1 + ((n_reads - 1) >> 6));
+    top += E * 4 + ((E * stride + 3) & ~3ull) + E + 2 * ((uint64_t)max_len + N + 8);
+    top = (top + 31) & ~31ull;
+    return top + 1024 + (dp_cells + 1) / 2;
+}
+
+struct PoaPlan : Plan {
+    DevBuf<uint8_t> d_seqs, d_cons, d_msa;
+    DevBuf<Problem> d_problems;
+    DevBuf<int64_t> d_read_off;
+    DevBuf<int32_t> d_read_len, d_order;
+    DevBuf<DevResult> d_results;
+    DevBuf<uint32_t> d_queue;
+    DevBuf<unsigned long long> d_msa_used;
+    std::vector<Problem> problems;
+    std::vector<int64_t> cons_dev_off;
+    std::vector<uint64_t> need_small;      // arena words with the estimated DP budget
+    std::vector<uint64_t> need_full;       // arena words with the worst-case (full matrix) DP budget
+    std::vector<int32_t> order_all;
+    size_t cons_bytes = 0, msa_pool_bytes = 0;
+    std::vector<DevResult> h_results;
+    std::vector<uint8_t> h_cons, h_msa;
+    int n_rescued = 0;
+
+    int build(int n_, const uint8_t *seqs, size_t seqs_len, const int32_t *first_read, const int32_t *n_reads,
+              const int64_t *read_off, const int32_t *read_len, int n_total_reads, const lcd_poa_params_t *params) {
+        n = n_;
+        Context &c = ctx();
+        problems.resize(n); cons_dev_off.resize(n); need_small.resize(n); need_full.resize(n);
+        std::vector<double> work(n);
+        for (int r = 0; r < n_total_reads; ++r)
+            if (read_len[r] < 0 || read_off[r] < 0 || (size_t)read_off[r] + read_len[r] > seqs_len) { set_error("lcd_poa: read %d has an invalid range", r); return -1; }
+        size_t cons_total = 0; double msa_est = 0;
+        for (int i = 0; i < n; ++i) {
+            if (n_reads[i] < 1 || first_read[i] < 0 || first_read[i] + n_reads[i] > n_total_reads) { set_error("lcd_poa: problem %d has an invalid read range", i); return -1; }
+            if (params[i].max_n_cons != 1) { set_error("lcd_poa: problem %d asks for max_n_cons=%d; only the single-consensus path is implemented on the GPU", i, params[i].max_n_cons); return -1; }
+            Problem &p = problems[i];
+            memset(&p, 0, sizeof(p));
+            p.seq_base = 0; p.read_first = first_read[i]; p.n_reads = n_reads[i]; p.par = params[i];
+            int mn = INT32_MAX;
+            for (int r = 0; r < n_reads[i]; ++r) { const int l = read_len[first_read[i] + r]; p.sum_len += l; p.max_len = std::max(p.max_len, l); mn = std::min(mn, l); }
+            p.cons_off = (int32_t)cons_total; cons_dev_off[i] = (int64_t)cons_total;
+            cons_total += ((size_t)p.sum_len + 15) & ~(size_t)15;
+            if (cons_total > 0x7fffffffull) { set_error("lcd_poa: batch too large (consensus buffer > 2 GiB); split it"); return -1; }
+            // DP cell budgets: rows ~ graph nodes, vectors per row ~ band / 32
+            const double rows = 1.25 * p.max_len + 64;
+            const int dp_sn = (p.max_len + 32) / 32;
+            const int wband = params[i].wb < 0 ? p.max_len : params[i].wb + (int)(params[i].wf * p.max_len);
+            double nv = params[i].wb < 0 ? dp_sn + 1 : std::min<double>(dp_sn + 1, (2.0 * wband + 2.0 * (p.max_len - mn) + 64) / 32 + 3);
+            need_small[i] = arena_need_words(p.sum_len, p.max_len, p.n_reads, (uint64_t)(rows * nv * 160));
+            need_full[i] = arena_need_words(p.sum_len, p.max_len, p.n_reads, (uint64_t)((double)(p.sum_len + 34) * (dp_sn + 1) * 160));
+            work[i] = (double)p.n_reads * rows * nv;
+            msa_est += (double)(p.n_reads + 1) * (1.5 * p.max_len + 64);
+        }
+        cons_bytes = cons_total;
+        msa_pool_bytes = ((size_t)(msa_est * 1.5) + 4096 + 15) & ~(size_t)15;
+        order_all.resize(n);
+        for (int i = 0; i < n; ++i) order_all[i] = i;
+        std::sort(order_all.begin(), order_all.end(), [&](int32_t x, int32_t y) { return work[x] != work[y] ? work[x] > work[y] : x < y; });
+        cudaStream_t s = c.stream;
+        if (d_seqs.upload(seqs, std::max<size_t>(seqs_len, 1), s)) return -1;
+        if (d_problems.upload(problems.data(), n, s)) return -1;
+        if (d_read_off.upload(read_off, n_total_reads, s)) return -1;
+        if (d_read_len.upload(read_len, n_total_reads, s)) return -1;
+        if (d_order.alloc(std::max(n, 1))) return -1;
+        if (d_cons.alloc(cons_bytes + 16)) return -1;
+        if (d_msa.alloc(msa_pool_bytes)) return -1;
+        if (d_results.alloc(std::max(n, 1))) return -1;
+        if (d_queue.alloc(1)) return -1;
+        if (d_msa_used.alloc(1)) return -1;
+        LCD_CUDA_OK(cudaStreamSynchronize(s));
+        return 0;
+    }
+
+    // one launch over `idx` with per-group arenas of `words`
+    int launch(cudaStream_t s, const std::vector<int32_t> &idx, uint64_t words, int max_groups) {
+        Context &c = ctx();
+        if (idx.empty()) return 0;
+        const uint64_t fit = c.pool_words / words;
+        if (fit == 0) { set_error("lcd_poa: a problem needs %zu MiB of workspace but the pool has %zu MiB", (size_t)(words * 4 >> 20), (size_t)(c.pool_words * 4 >> 20)); return -1; }
+        int groups = (int)std::min<uint64_t>(std::min<uint64_t>(fit, (uint64_t)max_groups), idx.size());
+        int grid = (groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        if ((uint64_t)grid * WARPS_PER_CTA > fit) grid = (int)(fit / WARPS_PER_CTA);
+        if (grid == 0) { grid = 1; }
+        if ((uint64_t)grid * WARPS_PER_CTA * words > c.pool_words) {      // fewer than one CTA's worth of arenas: shrink to what fits
+            set_error("lcd_poa: workspace pool too small for one CTA of %d arenas of %zu MiB", WARPS_PER_CTA, (size_t)(words * 4 >> 20)); return -1;
+        }
+        LCD_CUDA_OK(cudaMemcpyAsync(d_order.p, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        LCD_CUDA_OK(cudaMemsetAsync(d_queue.p, 0, sizeof(uint32_t), s));
+        KernelArgs ka;
+        ka.problems = d_problems.p; ka.order = d_order.p; ka.n = (int)idx.size(); ka.queue = d_queue.p;
+        ka.seqs = d_seqs.p; ka.read_off = d_read_off.p; ka.read_len = d_read_len.p;
+        ka.cons = d_cons.p; ka.msa = d_msa.p; ka.msa_cap = msa_pool_bytes; ka.msa_used = d_msa_used.p;
+        ka.results = d_results.p; ka.arena = c.pool; ka.arena_words = words;
+        poa_kernel<<<grid, 32 * WARPS_PER_CTA, 0, s>>>(ka);
+        LCD_CUDA_OK(cudaGetLastError());
+        c.launches++;
+        return 0;
+    }
+
+    int run(cudaStream_t s) override {
+        Context &c = ctx();
+        if (n == 0) return 0;
+        LCD_CUDA_OK(cudaMemsetAsync(d_msa_used.p, 0, sizeof(unsigned long long), s));
+        // class 1: every problem whose estimated need fits a "small" arena; class 2: the rest, estimated need;
+        // rescue: problems that ran out of DP space, with the worst-case budget.
+        const uint64_t small_words = (uint64_t)(6u << 20) / 4;        // 6 MiB
+        std::vector<int32_t> small, large;
+        uint64_t large_words = 0;
+        for (int32_t i : order_all) { if (need_small[i] <= small_words) small.push_back(i); else { large.push_back(i); large_words = std::max(large_words, need_small[i]); } }
+        const int max_groups = c.sm_count * 12;
+        if (launch(s, small, small_words, max_groups)) return -1;
+        if (!large.empty() && launch(s, large, (large_words + 63) & ~63ull, max_groups)) return -1;
+        // statuses back: anything that ran out of workspace is re-run with the full-matrix budget
+        h_results.resize(n);
+        LCD_CUDA_OK(cudaMemcpyAsync(h_results.data(), d_results.p, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, s));
+        LCD_CUDA_OK(cudaStreamSynchronize(s));
+        std::vector<int32_t> rescue; uint64_t rescue_words = 0;
+        for (int32_t i : order_all) if (h_results[i].status == ST_OOM) { rescue.push_back(i); rescue_words = std::max(rescue_words, need_full[i]); }
+        n_rescued = (int)rescue.size();
+        if (!rescue.empty()) {
+            rescue_words = std::min<uint64_t>((rescue_words + 63) & ~63ull, (c.pool_words / WARPS_PER_CTA) & ~63ull);
+            if (launch(s, rescue, rescue_words, max_groups)) return -1;
+        }
+        return 0;
+    }
+
+    int download(cudaStream_t s) {
+        h_results.resize(n); h_cons.resize(cons_bytes + 16);
+        if (n == 0) return 0;
+        unsigned long long used = 0;
+        LCD_CUDA_OK(cudaMemcpyAsync(h_results.data(), d_results.p, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, s));
+        LCD_CUDA_OK(cudaMemcpyAsync(h_cons.data(), d_cons.p, cons_bytes, cudaMemcpyDeviceToHost, s));
+        LCD_CUDA_OK(cudaMemcpyAsync(&used, d_msa_used.p, sizeof(used), cudaMemcpyDeviceToHost, s));
+        LCD_CUDA_OK(cudaStreamSynchronize(s));
+        used = std::min<unsigned long long>(used, msa_pool_bytes);
+        h_msa.resize(used + 16);
+        if (used) LCD_CUDA_OK(cudaMemcpyAsync(h_msa.data(), d_msa.p, used, cudaMemcpyDeviceToHost, s));
+        LCD_CUDA_OK(cudaStreamSynchronize(s));
+        return 0;
+    }
+
+    int work_units(cudaStream_t s, uint64_t *units) override {
+        if (download(s)) return -1;
+        uint64_t t = 0;
+        for (int i = 0; i < n; ++i) t += ((uint64_t)h_results[i].cells_hi << 32) | h_results[i].cells_lo;
+        *units = t;
+        return 0;
+    }
+
+    int fetch(cudaStream_t s, uint8_t *cons, const int64_t *cons_off, uint8_t *msa, const int64_t *msa_off, const int64_t *msa_cap,
+              lcd_poa_result_t *results) {
+        if (download(s)) return -1;
+        int bad = 0, first_bad = 0;
+        for (int i = 0; i < n; ++i) {
+            const DevResult &r = h_results[i];
+            results[i].status = r.status; results[i].cons_len = r.cons_len; results[i].msa_len = r.msa_len; results[i].n_nodes = r.n_nodes;
+            if (r.status != ST_OK) { if (!bad) first_bad = r.status; ++bad; continue; }
+            if (cons && cons_off) memcpy(cons + cons_off[i], h_cons.data() + cons_dev_off[i], r.cons_len);
+            if (msa && msa_off && msa_cap) {
+                const int64_t bytes = (int64_t)(problems[i].n_reads + 1) * r.msa_len;
+                if (bytes > msa_cap[i]) { results[i].status = LCD_POA_MSA_CAP; if (!bad) first_bad = LCD_POA_MSA_CAP; ++bad; continue; }
+                memcpy(msa + msa_off[i], h_msa.data() + r.msa_off, bytes);
+            }
+        }
+        if (bad) { set_error("lcd_poa: %d of %d problems failed on the device (first status %d; see LCD_POA_* in lcd_gpu.h)", bad, n, first_bad); return -2; }
+        return 0;
+    }
+};
+
+} // namespace poa
+} // namespace lcd
+
+using namespace lcd;
+
+extern "C" {
+
+lcd_plan_t *lcd_poa_plan_create(int n, const uint8_t *seqs, size_t seqs_len,
+                                const int32_t *first_read, const int32_t *n_reads,
+                                const int64_t *read_off, const int32_t *read_len, int n_total_reads,
+                                const lcd_poa_params_t *params) {
+    if (ensure_ready()) return nullptr;
+    if (n < 0 || (n > 0 && (!seqs || !first_read || !n_reads || !read_off || !read_len || !params))) {
+        set_error("lcd_poa_plan_create: invalid arguments"); return nullptr;
+    }
+    poa::PoaPlan *p = new poa::PoaPlan();
+    if (p->build(n, seqs, seqs_len, first_read, n_reads, read_off, read_len, n_total_reads, params)) { delete p; return nullptr; }
+    return reinterpret_cast<lcd_plan_t *>(p);
+}
+
+int lcd_poa_plan_fetch(lcd_plan_t *plan, void *stream, uint8_t *cons, const int64_t *cons_off,
+                       uint8_t *msa, const int64_t *msa_off, const int64_t *msa_cap, lcd_poa_result_t *results) {
+    poa::PoaPlan *p = dynamic_cast<poa::PoaPlan *>(reinterpret_cast<Plan *>(plan));
+    if (!p || !results) { set_error("lcd_poa_plan_fetch: not a POA plan / null results"); return -1; }
+    return p->fetch(pick_stream(stream), cons, cons_off, msa, msa_off, msa_cap, results);
+}
+
+int lcd_poa_batch(int n, const uint8_t *seqs, size_t seqs_len,
+                  const int32_t *first_read, const int32_t *n_reads,
+                  const int64_t *read_off, const int32_t *read_len, int n_total_reads,
+                  const lcd_poa_params_t *params,
+                  uint8_t *cons, const int64_t *cons_off,
+                  uint8_t *msa, const int64_t *msa_off, const int64_t *msa_cap,
+                  lcd_poa_result_t *results) {
+    lcd_plan_t *plan = lcd_poa_plan_create(n, seqs, seqs_len, first_read, n_reads, read_off, read_len, n_total_reads, params);
+    if (!plan) return -1;
+    int rc = lcd_plan_run(plan, nullptr);
+    if (!rc) rc = lcd_poa_plan_fetch(plan, nullptr, cons, cons_off, msa, msa_off, msa_cap, results);
+    lcd_plan_destroy(plan);
+    return rc;
+}
+
+}

@@ -14,6 +14,8 @@
 struct int4 { int x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
 struct int2 { int x, y; };
+static inline int2 make_int2(int x, int y) { int2 r = {x, y}; return r; }
+static inline int4 make_int4(int x, int y, int z, int w) { int4 r = {x, y, z, w}; return r; }
 using std::max;
 using std::min;
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }

@@ -1,0 +1,58 @@
+// tests/emu/poa_emu.cpp -- TEST INFRASTRUCTURE: runs the product's K5 device logic
+// (longcalld_b200/csrc/poa_device.cuh) on the host.  A "warp" is a 32-element array (HostLanes), so
+// the lane-level vector semantics (shuffle scans, band masks) are exercised exactly as on the GPU.
+// Same signature as the oracle's lcd_oracle_poa so the tests can diff the two.
+#include "cuda_emu.h"
+#include "../../longcalld_b200/csrc/poa_device.cuh"
+#include <stdlib.h>
+#include <vector>
+
+namespace lcd { namespace poa {
+struct HostLanes {
+    struct vec { int v[32]; };
+    static constexpr int STRIDE = 1;
+    static int lane() { return 0; }
+    static void sync() {}
+    static vec load(const int16_t *p) { vec r; for (int l = 0; l < 32; ++l) r.v[l] = p[l]; return r; }
+    static vec load_m1(const int16_t *p, int first) { vec r; r.v[0] = first; for (int l = 1; l < 32; ++l) r.v[l] = p[l - 1]; return r; }
+    static void store(int16_t *p, vec x) { for (int l = 0; l < 32; ++l) p[l] = (int16_t)x.v[l]; }
+    static vec set1(int x) { vec r; for (int l = 0; l < 32; ++l) r.v[l] = x; return r; }
+    static vec add(vec a, vec b) { vec r; for (int l = 0; l < 32; ++l) r.v[l] = (int16_t)(a.v[l] + b.v[l]); return r; }
+    static vec sub(vec a, vec b) { vec r; for (int l = 0; l < 32; ++l) r.v[l] = (int16_t)(a.v[l] - b.v[l]); return r; }
+    static vec vmax(vec a, vec b) { vec r; for (int l = 0; l < 32; ++l) r.v[l] = a.v[l] > b.v[l] ? a.v[l] : b.v[l]; return r; }
+    static vec shift_up(vec x, int n, int fill) { vec r; for (int l = 0; l < 32; ++l) r.v[l] = l < n ? fill : x.v[l - n]; return r; }
+    static int lane_value(vec x, int l) { return x.v[l]; }
+    static vec keep(vec x, int lo, int hi, int fill) { vec r; for (int l = 0; l < 32; ++l) r.v[l] = (l >= lo && l <= hi) ? x.v[l] : fill; return r; }
+    template <class F> static vec map_cols(int col0, F f) { vec r; for (int l = 0; l < 32; ++l) r.v[l] = f(col0 + l); return r; }
+    static bool row_max(vec x, int lo, int hi, int &m, int &first, int &last) {
+        if (lo > hi) return false;
+        m = INT32_MIN; for (int l = lo; l <= hi; ++l) if (x.v[l] > m) m = x.v[l];
+        first = -1; for (int l = lo; l <= hi; ++l) if (x.v[l] == m) { if (first < 0) first = l; last = l; }
+        return true;
+    }
+};
+}}
+using namespace lcd::poa;
+
+extern "C" int emu_poa(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len,
+                       const lcd_poa_params_t *p, uint8_t *cons, int32_t *cons_len,
+                       uint8_t *msa, int32_t *msa_len, int32_t msa_cap) {
+    Problem pb; memset(&pb, 0, sizeof(pb));
+    pb.seq_base = 0; pb.read_first = 0; pb.n_reads = n_seq; pb.par = *p; pb.cons_off = 0;
+    for (int i = 0; i < n_seq; ++i) { pb.sum_len += seq_len[i]; if (seq_len[i] > pb.max_len) pb.max_len = seq_len[i]; }
+    const uint64_t words = (uint64_t)48 << 20;            // 192 MiB arena
+    static int32_t *arena = (int32_t *)malloc(words * 4);
+    { static uint32_t x = 12345; for (size_t i = 0; i < ((size_t)4 << 20); ++i) { x = x * 1664525u + 1013904223u; arena[i] = (int32_t)x; } }   // poison
+    std::vector<uint8_t> msa_pool((size_t)msa_cap + 64);
+    unsigned long long msa_used = 0; uint32_t queue = 0; int32_t order = 0;
+    DevResult dr; memset(&dr, 0, sizeof(dr));
+    KernelArgs a; memset(&a, 0, sizeof(a));
+    a.problems = &pb; a.order = &order; a.n = 1; a.queue = &queue; a.seqs = seqs; a.read_off = seq_off; a.read_len = seq_len;
+    a.cons = cons; a.msa = msa_pool.data(); a.msa_cap = (unsigned long long)msa_cap; a.msa_used = &msa_used;
+    a.results = &dr; a.arena = arena; a.arena_words = words;
+    Poa<HostLanes> poa;
+    poa.run(a, pb, &dr, arena);
+    *cons_len = dr.cons_len; *msa_len = 0;
+    if (dr.status == ST_OK && msa) { *msa_len = dr.msa_len; memcpy(msa, msa_pool.data() + dr.msa_off, (size_t)(n_seq + 1) * dr.msa_len); }
+    return dr.status;
+}

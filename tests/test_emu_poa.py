@@ -1,0 +1,48 @@
+"""CPU: the product's K5 device logic (longcalld_b200/csrc/poa_device.cuh) compiled for the host with
+32-element arrays standing in for warp lanes (tests/emu) against the oracle: consensus and full MSA."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import lcd_testlib as T
+
+EMU_DIR = os.path.join(T.ROOT, "tests", "emu")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR, "libpoa_emu.so"])
+    return C.CDLL(os.path.join(EMU_DIR, "libpoa_emu.so"))
+
+
+@pytest.mark.parametrize("tech,mbp,seed", [("hifi", 0.12, 41), ("ont", 0.03, 42)])
+def test_emu_poa_vs_oracle(emu, oracle, tech, mbp, seed):
+    from longcalld_b200 import synth
+    n = 0
+    for r in synth.make_regions(mbp, tech, seed=seed):
+        for hap in (1, 2):
+            seqs = [s for s, h in zip(r.reads, r.read_hap) if h == hap]
+            if not seqs or min(len(s) for s in seqs) == 0:
+                continue
+            for sub, wb in ((1, 10), (0, -1)):
+                if wb < 0 and max(len(s) for s in seqs) > 500:
+                    continue
+                par = T.poa_params(sub, wb)
+                a = T.poa(oracle, "lcd_oracle_poa", seqs, par)
+                b = T.poa(emu, "emu_poa", seqs, par)
+                assert a[0] == b[0] == 0 and a[1] == b[1] and a[2].shape == b[2].shape and (a[2] == b[2]).all(), (n, sub, wb)
+                n += 1
+    assert n > 60
+
+
+def test_emu_poa_vs_fixtures(emu):
+    import hashlib
+    g = T.load_golden("poa_lcd")
+    for i, c in enumerate(g["cases"][::3]):
+        seqs = [np.array([int(x) for x in s], dtype=np.uint8) for s in c["seqs"]]
+        rc, cons, msa = T.poa(emu, "emu_poa", seqs, T.poa_params(c["sub_aln"], c["wb"]))
+        assert rc == 0 and "".join(map(str, cons)) == c["cons"], i
+        assert list(msa.shape) == c["msa_shape"] and hashlib.sha1(msa.tobytes()).hexdigest() == c["msa_sha1"], i

@@ -1,0 +1,92 @@
+"""GPU: liblcd_gpu.so's POA kernel (through the C-ABI) against the oracle / golden fixtures, bit-exact on
+consensus and on every cell of the row-column MSA."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import lcd_testlib as T
+
+pytestmark = pytest.mark.gpu
+
+
+def _problems(tech, mbp, seed, max_len=None):
+    from longcalld_b200 import synth
+    out = []
+    for r in synth.make_regions(mbp, tech, seed=seed):
+        for hap in (1, 2):
+            seqs = [s for s, h in zip(r.reads, r.read_hap) if h == hap]
+            if not seqs or min(len(s) for s in seqs) == 0:
+                continue
+            if max_len and max(len(s) for s in seqs) > max_len:
+                continue
+            out.append(seqs)
+    return out
+
+
+def _check(gpu, oracle, problems, sub, wb):
+    got = gpu.poa_batch(problems, gpu.poa_params(sub, wb))
+    par = T.poa_params(sub, wb)
+    bad = []
+    for i, seqs in enumerate(problems):
+        rc, cons, msa = T.poa(oracle, "lcd_oracle_poa", seqs, par)
+        g = got[i]
+        if not (g[0] == rc == 0 and g[1] == cons and g[2].shape == msa.shape and (g[2] == msa).all()):
+            bad.append(i)
+    assert not bad, (len(bad), bad[:10])
+
+
+def test_gpu_poa_vs_reference_fixtures(gpu):
+    g = T.load_golden("poa_lcd")
+    for sub, wb in ((1, 10), (0, -1)):
+        cases = [c for c in g["cases"] if c["sub_aln"] == sub and c["wb"] == wb]
+        problems = [[np.array([int(x) for x in s], dtype=np.uint8) for s in c["seqs"]] for c in cases]
+        got = gpu.poa_batch(problems, gpu.poa_params(sub, wb))
+        for i, (c, (st, cons, msa)) in enumerate(zip(cases, got)):
+            assert st == 0 and "".join(map(str, cons)) == c["cons"], (sub, wb, i)
+            assert list(msa.shape) == c["msa_shape"] and hashlib.sha1(msa.tobytes()).hexdigest() == c["msa_sha1"], (sub, wb, i)
+
+
+def test_gpu_poa_vs_oracle_hifi(gpu, oracle):
+    _check(gpu, oracle, _problems("hifi", 0.6, 51), 1, 10)
+
+
+def test_gpu_poa_vs_oracle_ont(gpu, oracle):
+    _check(gpu, oracle, _problems("ont", 0.12, 52), 1, 10)
+
+
+def test_gpu_poa_vs_oracle_unbanded(gpu, oracle):
+    _check(gpu, oracle, _problems("hifi", 0.3, 53, max_len=700), 0, -1)
+
+
+def test_gpu_poa_edge_cases_and_rerun(gpu, oracle):
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 4, 50).astype(np.uint8)
+    problems = [[a], [a, a], [a, a[:25]], [a[:1], a[:1], a[:2]], [a, T.mutate(rng, a, sub=0.3), T.mutate(rng, a, ins=0.2)],
+                [np.zeros(40, np.uint8)] * 5 + [np.zeros(37, np.uint8)] * 4]
+    _check(gpu, oracle, problems, 1, 10)
+    _check(gpu, oracle, problems, 0, -1)
+    assert gpu.poa_batch([], gpu.poa_params()) == []
+    seqs, first, n_reads, read_off, read_len = gpu.pack_poa(problems)
+    plan = gpu.PoaPlan(seqs, first, n_reads, read_off, read_len, gpu.poa_params())
+    ref = None
+    for _ in range(3):
+        plan.run(); plan.sync()
+        res, cons, cons_off, msa, msa_off = plan.fetch()
+        cur = [(int(r["status"]), cons[cons_off[i]:cons_off[i] + r["cons_len"]].tobytes()) for i, r in enumerate(res)]
+        ref = ref or cur
+        assert cur == ref
+    assert plan.work_units() > 0
+
+
+def test_gpu_poa_full_size_properties(gpu):
+    """BASELINE-sized slice (5 Mb of regions; too slow for the scalar oracle): every MSA row, gaps removed,
+    must spell its read; the consensus row, gaps removed, must equal the consensus."""
+    problems = _problems("hifi", 5.0, 54)
+    got = gpu.poa_batch(problems, gpu.poa_params())
+    for seqs, (st, cons, msa) in zip(problems, got):
+        assert st == 0
+        for r, s in enumerate(seqs):
+            row = msa[r]
+            assert row[row != 5].tobytes() == np.asarray(s, np.uint8).tobytes()
+        assert msa[len(seqs)][msa[len(seqs)] != 5].tobytes() == cons
