@@ -152,4 +152,26 @@ int ref_poa(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_
     return rc;
 }
 
+
+// Batch driver for bench.py's cpu_baseline / --impl reference legs (one problem per worker thread, like kt_for).
+int ref_poa_batch(int n, const uint8_t *seqs, const int32_t *first_read, const int32_t *n_reads,
+                  const int64_t *read_off, const int32_t *read_len, const lcd_poa_params_t *params,
+                  uint8_t *cons, const int64_t *cons_off, int32_t *cons_len, int n_threads) {
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (;;) {
+            int i = next.fetch_add(1);
+            if (i >= n) break;
+            int32_t ml = 0;
+            ref_poa(n_reads[i], seqs, read_off + first_read[i], read_len + first_read[i], &params[i],
+                    cons + cons_off[i], &cons_len[i], NULL, &ml, 0);
+        }
+    };
+    if (n_threads <= 1) { work(); return 0; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work);
+    for (auto &t : th) t.join();
+    return 0;
+}
+
 }
