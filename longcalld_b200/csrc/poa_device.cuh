@@ -42,6 +42,8 @@ struct __align__(16) Problem {
     int32_t n_reads;
     int32_t sum_len, max_len;
     int32_t cons_off;         // byte offset in the consensus buffer (capacity sum_len)
+    int32_t node_cap;         // workspace budget of the first attempt (host estimate); a problem that outgrows
+    int32_t edge_cap;         // it ends with ST_OOM and is re-run with worst-case budgets (KernelArgs.worst_case)
     int32_t pad;
     lcd_poa_params_t par;
 };
@@ -53,7 +55,18 @@ struct __align__(16) DevResult {
     int32_t n_nodes;
     uint64_t msa_off;         // byte offset in the MSA output pool
     uint32_t cells_lo, cells_hi;
+#ifdef LCD_POA_TIMING
+    unsigned long long t_dp, t_bt, t_add, t_after, t_fin;   // SM clock cycles per phase (debug builds)
+#endif
 };
+
+#if defined(LCD_POA_TIMING) && !defined(LCD_EMU)
+#define LCD_T0() const long long t0_ = clock64()
+#define LCD_T1(x) (x) += (unsigned long long)(clock64() - t0_)
+#else
+#define LCD_T0()
+#define LCD_T1(x)
+#endif
 
 struct KernelArgs {
     const Problem *problems;
@@ -68,6 +81,7 @@ struct KernelArgs {
     DevResult *results;
     int32_t *arena;               // per-group arenas
     uint64_t arena_words;         // int32 words per group
+    int32_t worst_case;           // 1: ignore Problem.node_cap / edge_cap, size for the worst case
 };
 
 // per-group workspace carved from the arena for one problem
@@ -75,12 +89,13 @@ struct WS {
     int N;                        // node capacity
     int *base, *in_off, *in_n, *in_cap, *out_off, *out_n, *out_cap, *n_read, *n_span;
     int *aln_off, *aln_n, *aln_cap, *next, *remain, *maxl, *maxr, *msa_rank;
-    int *row_off, *dp_beg, *dp_end, *wsum, *order, *tmp;
+    int *wsum, *order, *tmp, *s1, *s2, *s3, *s4, *s5, *s6, *s7;
+    int4 *rinfo;                                     // per node: DP row descriptor of the current read (see Poa::pack)
     int4 *in_pool; int in_top, in_capacity;          // {from, w, ps, -}
     int *out_pool; int out_top, out_capacity, out_stride, rid_w;   // {to, w, rid[2*rid_w]}
     int *aln_pool; int aln_top, aln_capacity;
     int2 *cigar; int cigar_cap;                      // {op | len << 2, node_id}
-    int16_t *dp; uint32_t dp_top, dp_capacity;       // in cells
+    int16_t *dp; uint32_t dp_capacity;               // in cells
     int n_nodes;
     int oom;
 };
@@ -90,8 +105,11 @@ struct WS {
 #ifndef LCD_EMU
 struct WarpLanes {
     typedef int vec;                                  // this lane's cell (int16 value in an int)
-    static constexpr int STRIDE = 32;
+    static constexpr int NT = 32, NW = 1;             // threads / warps cooperating on one problem
+    static constexpr bool TWO_PHASE = false;
     __device__ static __forceinline__ int lane() { return threadIdx.x & 31; }
+    __device__ static __forceinline__ int tid() { return threadIdx.x & 31; }
+    __device__ static __forceinline__ int warp() { return 0; }
     __device__ static __forceinline__ void sync() { __syncwarp(); }
     __device__ static __forceinline__ vec load(const int16_t *p) { return p[lane()]; }
     __device__ static __forceinline__ vec load_m1(const int16_t *p, int first) {   // lane l <- p[l-1], lane 0 <- first
@@ -121,7 +139,97 @@ struct WarpLanes {
         return true;
     }
 };
+// one CTA of W warps per problem (kilobase regions): same lane semantics per warp; the vectors of a DP row are
+// dealt to the warps and the F carries are resolved through shared memory (Poa::align, two-phase rows)
+template <int W> struct CtaLanes : WarpLanes {
+    static constexpr int NT = 32 * W, NW = W;
+    static constexpr bool TWO_PHASE = true;
+    __device__ static __forceinline__ int tid() { return threadIdx.x; }
+    __device__ static __forceinline__ int warp() { return threadIdx.x >> 5; }
+    __device__ static __forceinline__ void sync() { __syncthreads(); }
+};
 #endif
+
+
+// ---------------------------------------------------------------------------------------------
+// lane policy for one THREAD per problem (thousands of ~100-node problems): the 32 int16 lanes of a
+// vector are packed two per 32-bit register and processed with the SIMD-in-word instructions
+// (__vadd2 / __vsub2 / __vmaxs2 wrap / compare per halfword exactly like the epi16 instructions).
+// Word i holds lane 2i (low half) and lane 2i+1 (high half).
+struct ThreadLanes {
+    struct vec { uint32_t w[16]; };
+    static constexpr int NT = 1, NW = 1;
+    static constexpr bool TWO_PHASE = false;
+    __device__ static __forceinline__ int lane() { return 0; }
+    __device__ static __forceinline__ int tid() { return 0; }
+    __device__ static __forceinline__ int warp() { return 0; }
+    __device__ static __forceinline__ void sync() {}
+    __device__ static __forceinline__ vec load(const int16_t *p) {
+        vec r; const uint4 *q = reinterpret_cast<const uint4 *>(p);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const uint4 t = q[i]; r.w[4 * i] = t.x; r.w[4 * i + 1] = t.y; r.w[4 * i + 2] = t.z; r.w[4 * i + 3] = t.w; }
+        return r;
+    }
+    __device__ static __forceinline__ vec shift1(const vec &x, int first) {     // lane l <- x[l-1], lane 0 <- first
+        vec r;
+#pragma unroll
+        for (int i = 15; i > 0; --i) r.w[i] = (x.w[i] << 16) | (x.w[i - 1] >> 16);
+        r.w[0] = (x.w[0] << 16) | ((uint32_t)first & 0xffffu);
+        return r;
+    }
+    __device__ static __forceinline__ vec load_m1(const int16_t *p, int first) { return shift1(load(p), first); }
+    __device__ static __forceinline__ void store(int16_t *p, const vec &v) {
+        uint4 *q = reinterpret_cast<uint4 *>(p);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { uint4 t; t.x = v.w[4 * i]; t.y = v.w[4 * i + 1]; t.z = v.w[4 * i + 2]; t.w = v.w[4 * i + 3]; q[i] = t; }
+    }
+    __device__ static __forceinline__ vec set1(int x) { vec r; const uint32_t v = ((uint32_t)x & 0xffffu) * 0x10001u;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r.w[i] = v; return r; }
+    __device__ static __forceinline__ vec add(const vec &a, const vec &b) { vec r;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r.w[i] = __vadd2(a.w[i], b.w[i]); return r; }
+    __device__ static __forceinline__ vec sub(const vec &a, const vec &b) { vec r;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r.w[i] = __vsub2(a.w[i], b.w[i]); return r; }
+    __device__ static __forceinline__ vec vmax(const vec &a, const vec &b) { vec r;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r.w[i] = __vmaxs2(a.w[i], b.w[i]); return r; }
+    __device__ static __forceinline__ vec shift_up(const vec &x, int n, int fill) {   // n in {1,2,4,8,16} (compile-time after unrolling)
+        if (n == 1) return shift1(x, fill);
+        vec r; const int k = n >> 1; const uint32_t f = ((uint32_t)fill & 0xffffu) * 0x10001u;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r.w[i] = i < k ? f : x.w[i - k < 0 ? 0 : i - k];
+        return r;
+    }
+    __device__ static __forceinline__ int lane_value(const vec &x, int l) { return (int)(int16_t)(x.w[l >> 1] >> ((l & 1) * 16)); }
+    __device__ static __forceinline__ vec keep(const vec &x, int lo, int hi, int fill) {
+        vec r; const uint32_t f = (uint32_t)fill & 0xffffu;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t m = ((2 * i >= lo && 2 * i <= hi) ? 0xffffu : 0u) | ((2 * i + 1 >= lo && 2 * i + 1 <= hi) ? 0xffff0000u : 0u);
+            r.w[i] = (x.w[i] & m) | ((f * 0x10001u) & ~m);
+        }
+        return r;
+    }
+    template <class F> __device__ static __forceinline__ vec map_cols(int col0, F f) {
+        vec r;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r.w[i] = ((uint32_t)f(col0 + 2 * i) & 0xffffu) | ((uint32_t)f(col0 + 2 * i + 1) << 16);
+        return r;
+    }
+    __device__ static __forceinline__ bool row_max(const vec &x, int lo, int hi, int &m, int &first, int &last) {
+        if (lo > hi) return false;
+        int mm = INT32_MIN;
+#pragma unroll
+        for (int l = 0; l < 32; ++l) { const int v = lane_value(x, l); if (l >= lo && l <= hi && v > mm) mm = v; }
+        int fi = -1, la = -1;
+#pragma unroll
+        for (int l = 0; l < 32; ++l) { const int v = lane_value(x, l); if (l >= lo && l <= hi && v == mm) { if (fi < 0) fi = l; la = l; } }
+        m = mm; first = fi; last = la;
+        return true;
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 template <class L> struct Poa {
@@ -131,22 +239,30 @@ template <class L> struct Poa {
     int n_reads;
     int inf_min, oe1, oe2;
     unsigned long long cells;
+    unsigned long long t_dp, t_bt, t_add, t_after, t_fin;
+    // optional per-group on-chip cache of the previous row's H/E1/E2 band (2 buffers x 3 planes x NVC vectors):
+    // in a chain graph the only predecessor of a row is the row computed just before it, and reading it
+    // back from HBM/L2 (~250 cycles) is the critical path of the whole DP.  nullptr = disabled.
+    int16_t *row_cache = nullptr;
+    static constexpr int NVC = 8;
+    // scratch of a multi-warp group (shared memory): F carries of the row's vectors + row-max partials
+    int *gs = nullptr;
+    static constexpr int MAXV = 512, GS_INTS = 2 * MAXV + 4 + 3 * 32;
 
     // ---- workspace ---------------------------------------------------------------------------
-    __device__ bool carve(int32_t *arena, uint64_t words, int sum_len, int max_len, int n_reads_) {
+    __device__ bool carve(int32_t *arena, uint64_t words, int N, int E, int max_len, int n_reads_) {
         uint64_t top = 0;
-        const int N = sum_len + 2 + 32;
         w.N = N;
         int **arr[] = { &w.base, &w.in_off, &w.in_n, &w.in_cap, &w.out_off, &w.out_n, &w.out_cap, &w.n_read, &w.n_span,
                         &w.aln_off, &w.aln_n, &w.aln_cap, &w.next, &w.remain, &w.maxl, &w.maxr, &w.msa_rank,
-                        &w.row_off, &w.dp_beg, &w.dp_end, &w.wsum, &w.order, &w.tmp };
+                        &w.wsum, &w.order, &w.tmp, &w.s1, &w.s2, &w.s3, &w.s4, &w.s5, &w.s6, &w.s7 };
         for (unsigned i = 0; i < sizeof(arr) / sizeof(arr[0]); ++i) { *arr[i] = arena + top; top += (uint64_t)((N + 3) & ~3); }
-        const int E = 4 * (sum_len + n_reads_) + 64;
+        w.rinfo = reinterpret_cast<int4 *>(arena + top); top += (uint64_t)N * 4;
         w.in_capacity = E; w.in_pool = reinterpret_cast<int4 *>(arena + top); top += (uint64_t)E * 4;
         w.rid_w = 1 + ((n_reads_ - 1) >> 6);
         w.out_stride = 2 + 2 * w.rid_w;
         w.out_capacity = E; w.out_pool = arena + top; top += ((uint64_t)E * w.out_stride + 3) & ~3ull;
-        w.aln_capacity = E; w.aln_pool = arena + top; top += (uint64_t)E;
+        w.aln_capacity = E; w.aln_pool = arena + top; top += (uint64_t)((E + 3) & ~3);
         w.cigar_cap = max_len + N + 8; w.cigar = reinterpret_cast<int2 *>(arena + top); top += (uint64_t)w.cigar_cap * 2;
         top = (top + 31) & ~31ull;
         if (top + 1024 > words) return false;
@@ -176,7 +292,7 @@ template <class L> struct Poa {
         }
         if (!exist) {
             if (w.in_n[to] == w.in_cap[to]) {
-                const int nc = w.in_cap[to] ? w.in_cap[to] * 2 : 4;
+                const int nc = w.in_cap[to] ? w.in_cap[to] * 2 : 2;
                 if (w.in_top + nc > w.in_capacity) { w.oom = 1; return; }
                 int4 *src = w.in_pool + w.in_off[to], *dst = w.in_pool + w.in_top;
                 for (int i = 0; i < w.in_n[to]; ++i) dst[i] = src[i];
@@ -185,7 +301,7 @@ template <class L> struct Poa {
             w.in_pool[w.in_off[to] + w.in_n[to]] = make_int4(from, 1, 0, 0);
             w.in_n[to]++;
             if (w.out_n[from] == w.out_cap[from]) {
-                const int nc = w.out_cap[from] ? w.out_cap[from] * 2 : 4;
+                const int nc = w.out_cap[from] ? w.out_cap[from] * 2 : 2;
                 if (w.out_top + nc > w.out_capacity) { w.oom = 1; return; }
                 int *src = w.out_pool + (size_t)w.out_off[from] * w.out_stride, *dst = w.out_pool + (size_t)w.out_top * w.out_stride;
                 const int nw = w.out_n[from] * w.out_stride;
@@ -203,7 +319,7 @@ template <class L> struct Poa {
     }
     __device__ void add_aligned1(int node, int id) {
         if (w.aln_n[node] == w.aln_cap[node]) {
-            const int nc = w.aln_cap[node] ? w.aln_cap[node] * 2 : 4;
+            const int nc = w.aln_cap[node] ? w.aln_cap[node] * 2 : 2;
             if (w.aln_top + nc > w.aln_capacity) { w.oom = 1; return; }
             for (int i = 0; i < w.aln_n[node]; ++i) w.aln_pool[w.aln_top + i] = w.aln_pool[w.aln_off[node] + i];
             w.aln_off[node] = w.aln_top; w.aln_top += nc; w.aln_cap[node] = nc;
@@ -305,11 +421,14 @@ template <class L> struct Poa {
 
     // after fusing a read (abpoa_topological_sort :322-357 + abpoa_update_node_n_span_reads :559-571):
     // per-node exchange sort of the edge lists, out-weight sums, edge path scores (abpoa_get_incre_path_score
-    // :429-437), n_span, band seeds, flattened topological order and heaviest-path remain values.
+    // :429-437), n_span; then the flattened topological order and the heaviest-path remain values
+    // (abpoa_BFS_set_node_remain :268-309) by pointer jumping over the list / heaviest-successor links.
     __device__ void after_add(int first_read) {
-        const int n = w.n_nodes, lane = L::lane();
+        const int n = w.n_nodes, lane = L::tid();
         const int inc = par.sub_aln ? 0 : 1;
-        for (int i = lane; i < n; i += L::STRIDE) {
+        int *jn_a = w.s1, *jn_b = w.s2, *dn_a = w.s3, *dn_b = w.s4;       // list links / distance to list end
+        int *jh_a = w.s5, *jh_b = w.s6, *dh_a = w.remain, *dh_b = w.s7;   // heaviest-successor links / hops to SINK
+        for (int i = lane; i < n; i += L::NT) {
             int4 *ie = w.in_pool + w.in_off[i];
             const int nin = w.in_n[i];
             for (int j = 0; j < nin - 1; ++j) for (int k = j + 1; k < nin; ++k) if (ie[j].y < ie[k].y) { const int4 t = ie[j]; ie[j] = ie[k]; ie[k] = t; }
@@ -321,11 +440,15 @@ template <class L> struct Poa {
             }
             for (int j = 0; j < nout; ++j) ws += out_entry(i, j)[1];
             w.wsum[i] = ws;
-            w.maxr[i] = 0; w.maxl[i] = n;
             if (first_read || inc || i >= 2) w.n_span[i] += 1;
+            const int nx = w.next[i];
+            jn_a[i] = nx < 0 ? i : nx; dn_a[i] = nx < 0 ? 0 : 1;
+            // heaviest out edge = first entry after the descending exchange sort
+            const int hv = (i == 1 || nout == 0) ? i : out_entry(i, 0)[0];
+            jh_a[i] = hv; dh_a[i] = hv == i ? 0 : 1;
         }
         L::sync();
-        for (int i = lane; i < n; i += L::STRIDE) {
+        for (int i = lane; i < n; i += L::NT) {
             int4 *ie = w.in_pool + w.in_off[i];
             for (int k = 0; k < w.in_n[i]; ++k) {
                 const int node_w = w.wsum[ie[k].x], edge_w = ie[k].y;
@@ -334,49 +457,94 @@ template <class L> struct Poa {
                 ie[k].z = ps;
             }
         }
-        if (lane == 0) {
+        if (L::NT == 1) {
+            // one thread: walk the list once and follow the heaviest-successor links backwards
             int cnt = 0;
             for (int id = 0; id != -1; id = w.next[id]) w.order[cnt++] = id;
-            if (par.wb >= 0) {                      // abpoa_BFS_set_node_remain :268-309
-                w.remain[1] = -1;
-                for (int i = cnt - 1; i >= 0; --i) {
-                    const int id = w.order[i];
-                    if (id == 1) continue;
-                    // heaviest out edge = first entry after the descending exchange sort
-                    w.remain[id] = (w.out_n[id] > 0 ? w.remain[out_entry(id, 0)[0]] : -1) + 1;
-                }
+            w.remain[1] = -1;
+            for (int i = cnt - 1; i >= 0; --i) { const int id = w.order[i]; if (id != 1) w.remain[id] = (jh_a[id] == id ? -1 : w.remain[jh_a[id]]) + 1; }
+            return;
+        }
+        for (int span = 1; span < n; span <<= 1) {
+            for (int i = lane; i < n; i += L::NT) {
+                const int a = jn_a[i]; dn_b[i] = dn_a[i] + dn_a[a]; jn_b[i] = jn_a[a];
+                const int h = jh_a[i]; dh_b[i] = dh_a[i] + dh_a[h]; jh_b[i] = jh_a[h];
             }
+            L::sync();
+            int *t;
+            t = jn_a; jn_a = jn_b; jn_b = t;  t = dn_a; dn_a = dn_b; dn_b = t;
+            t = jh_a; jh_a = jh_b; jh_b = t;  t = dh_a; dh_a = dh_b; dh_b = t;
+        }
+        for (int i = lane; i < n; i += L::NT) {
+            w.order[n - 1 - dn_a[i]] = i;
+            w.remain[i] = dh_a[i] - 1;             // remain[SINK] = -1, remain[x] = remain[heaviest successor] + 1
         }
         L::sync();
     }
 
     // ---- DP ---------------------------------------------------------------------------------
-    __device__ int nvec(int id) const { return (w.dp_end[id] >> 5) - (w.dp_beg[id] >> 5) + 2; }
-    // plane p (0 H, 1 E1, 2 E2, 3 F1, 4 F2) of row `id`, addressed by absolute column
-    __device__ const int16_t *plane(int id, int p) const { return w.dp + w.row_off[id] + (size_t)p * nvec(id) * PN - (size_t)(w.dp_beg[id] >> 5) * PN; }
-    __device__ int cell(int id, int p, int col) const {       // bounds-checked scalar read (backtrack)
-        const int lo = (w.dp_beg[id] >> 5) * PN, hi = lo + nvec(id) * PN;
-        if (col < lo || col >= hi) return GARBAGE;
-        return plane(id, p)[col];
+    // row descriptor: {offset of the row's planes in the DP arena (cells), dp_beg | dp_end << 16,
+    //                  (left_max_i + 1) | (right_max_i + 1) << 16, -}
+    struct Row { int off, beg, end, nv, left1, right1; };
+    __device__ static __forceinline__ Row unpack(const int4 r) {
+        Row x; x.off = r.x; x.beg = r.y & 0xffff; x.end = (r.y >> 16) & 0xffff; x.nv = (x.end >> 5) - (x.beg >> 5) + 2;
+        x.left1 = r.z & 0xffff; x.right1 = (r.z >> 16) & 0xffff; return x;
     }
-    __device__ bool alloc_row(int id) {
-        const uint32_t need = (uint32_t)nvec(id) * PN * 5;
-        if (w.dp_top + need > w.dp_capacity) { w.oom = 1; return false; }
-        w.row_off[id] = (int)w.dp_top; w.dp_top += need;
-        return true;
+    __device__ static __forceinline__ int4 pack(int off, int beg, int end, int left, int right) {
+        return make_int4(off, beg | (end << 16), (left + 1) | ((right + 1) << 16), 0);
+    }
+    // plane p (0 H, 1 E1, 2 E2, 3 F1, 4 F2) of a row, addressed by absolute column
+    __device__ const int16_t *plane(const Row &r, int p) const { return w.dp + r.off + (size_t)p * r.nv * PN - (size_t)(r.beg >> 5) * PN; }
+    __device__ int cell(const Row &r, int p, int col) const {       // bounds-checked scalar read (backtrack)
+        const int lo = (r.beg >> 5) * PN, hi = lo + r.nv * PN;
+        if (col < lo || col >= hi) return GARBAGE;
+        return plane(r, p)[col];
     }
     // SIMD_SET_F, abpoa_align_simd.c:691-725
-    __device__ vec set_f(vec F, int set_num, int e) const {
+    __device__ __forceinline__ vec set_f(vec F, int set_num, int e) const {
+        if (set_num == PN) {
+#pragma unroll
+            for (int s = 0; s < LOGN; ++s)
+                F = L::vmax(F, L::shift_up(L::sub(F, L::set1((int16_t)(e << s))), 1 << s, inf_min));
+            return F;
+        }
         int cov = set_num;
 #pragma unroll
         for (int s = 0; s < LOGN; ++s) {
             const int sh = 1 << s;
-            if (set_num != PN && s > 0) cov += sh;
+            if (s > 0) cov += sh;
             vec t = L::shift_up(L::sub(F, L::set1((int16_t)(e << s))), sh, inf_min);
-            if (set_num != PN) t = L::keep(t, 0, cov < PN - 1 ? cov : PN - 1, inf_min);
+            t = L::keep(t, 0, cov < PN - 1 ? cov : PN - 1, inf_min);
             F = L::vmax(F, t);
         }
         return F;
+    }
+
+    struct Pred { const int16_t *ph, *pe1, *pe2; int bsn, esn_m, esn_e, ps, from_mem; };
+    __device__ __forceinline__ Pred make_pred(const int4 e, const Row &r, int beg_sn, int end_sn, int dp_sn, const int16_t *cache = nullptr) const {
+        Pred p;
+        if (cache) { p.ph = cache - (size_t)(r.beg >> 5) * PN; p.pe1 = p.ph + NVC * PN; p.pe2 = p.pe1 + NVC * PN; }
+        else { p.ph = plane(r, 0); p.pe1 = plane(r, 1); p.pe2 = plane(r, 2); }
+        p.ps = e.z;
+        const int pre_beg_sn = r.beg >> 5, pre_end_sn = r.end >> 5;
+        p.from_mem = pre_beg_sn < beg_sn;
+        p.bsn = p.from_mem ? beg_sn : pre_beg_sn;
+        int esn = (r.end + 1) >> 5; if (esn > end_sn) esn = end_sn; if (esn > dp_sn - 1) esn = dp_sn - 1;
+        p.esn_m = esn;
+        p.esn_e = pre_end_sn < end_sn ? pre_end_sn : end_sn;
+        return p;
+    }
+    __device__ __forceinline__ void pred_accumulate(const Pred &p, int k, int sn, int col0, vec &h, vec &ve1, vec &ve2) const {
+        if (sn >= p.bsn && sn <= p.esn_m) {
+            const int first = (sn == p.bsn && !p.from_mem) ? inf_min : (int)p.ph[col0 - 1];
+            const vec v = L::add(L::load_m1(p.ph + col0, first), L::set1(p.ps));
+            h = k == 0 ? v : L::vmax(v, h);
+        }
+        if (sn >= p.bsn && sn <= p.esn_e) {
+            const vec v1 = L::add(L::load(p.pe1 + col0), L::set1(p.ps)), v2 = L::add(L::load(p.pe2 + col0), L::set1(p.ps));
+            ve1 = k == 0 ? v1 : L::vmax(v1, ve1);
+            ve2 = k == 0 ? v2 : L::vmax(v2, ve2);
+        }
     }
 
     // one sequence against the whole graph: simd_abpoa_cg_align_sequence_to_graph_core (:1200-1228)
@@ -387,26 +555,23 @@ template <class L> struct Poa {
         const int wband = par.wb < 0 ? qlen : par.wb + (int)(par.wf * qlen);
         const int o1 = par.gap_open1, e1 = par.gap_ext1, o2 = par.gap_open2, e2 = par.gap_ext2;
         const int match = par.match, mism = par.mismatch;
-        w.dp_top = 0;
-        const int rem_end = par.wb >= 0 ? w.remain[1] : 0;
-        // ---- first row (SRC) :627-688
+        const bool banded = par.wb >= 0;
+        uint32_t dp_top = 0;
+        int last_id = 0, cache_buf = 0; bool last_cached = false; Row last_row;
+        const int rem_end = banded ? w.remain[1] : 0;
+        // ---- first row (SRC) :627-688 ; max_pos_left/right of SRC are 0, i.e. left_max_i = right_max_i = -1 + ...
         {
-            if (par.wb >= 0) {
-                L::sync();
-                if (L::lane() == 0) {
-                    w.maxl[0] = w.maxr[0] = 0;
-                    for (int i = 0; i < w.out_n[0]; ++i) { const int o = out_entry(0, i)[0]; w.maxl[o] = w.maxr[o] = 1; }
-                }
-                L::sync();
+            int end0 = qlen;
+            if (banded) {
                 const int r = qlen - (w.remain[0] - rem_end - 1);
-                int e = (w.maxr[0] > r ? w.maxr[0] : r) + wband; if (e > qlen) e = qlen;
-                w.dp_beg[0] = 0; w.dp_end[0] = e;
-            } else { w.dp_beg[0] = 0; w.dp_end[0] = qlen; }
-            L::sync();
-            if (!alloc_row(0)) return ST_OOM;
-            const int end0 = w.dp_end[0], nv = nvec(0);
-            int16_t *h = const_cast<int16_t *>(plane(0, 0)), *pe1 = const_cast<int16_t *>(plane(0, 1)), *pe2 = const_cast<int16_t *>(plane(0, 2));
-            int16_t *pf1 = const_cast<int16_t *>(plane(0, 3)), *pf2 = const_cast<int16_t *>(plane(0, 4));
+                end0 = (0 > r ? 0 : r) + wband; if (end0 > qlen) end0 = qlen;
+            }
+            const int nv = (end0 >> 5) + 2;
+            if ((uint64_t)nv * PN * 5 > w.dp_capacity) return ST_OOM;
+            // successors of SRC start from max_pos_left = max_pos_right = 1: encode as left_max_i = right_max_i = 0
+            if (L::tid() == 0) w.rinfo[0] = pack(0, 0, end0, 0, 0);
+            dp_top = (uint32_t)nv * PN * 5;
+            int16_t *h = w.dp, *pe1 = h + (size_t)nv * PN, *pe2 = pe1 + (size_t)nv * PN, *pf1 = pe2 + (size_t)nv * PN, *pf2 = pf1 + (size_t)nv * PN;
             const int esn = ((end0 >> 5) + 1 < dp_sn - 1) ? (end0 >> 5) + 1 : dp_sn - 1;
             for (int sn = 0; sn < nv; ++sn) {
                 const int col0 = sn * PN;
@@ -422,63 +587,87 @@ template <class L> struct Poa {
                 L::store(h + col0, vh); L::store(pe1 + col0, ve1); L::store(pe2 + col0, ve2); L::store(pf1 + col0, vf1); L::store(pf2 + col0, vf2);
             }
             cells += (unsigned long long)(end0 + 1);
+            last_row = unpack(pack(0, 0, end0, 0, 0));
+            if (row_cache && nv <= NVC) {
+                for (int sn = 0; sn < nv; ++sn) {
+                    L::store(row_cache + sn * PN, L::load(h + sn * PN));
+                    L::store(row_cache + (NVC + sn) * PN, L::load(pe1 + sn * PN));
+                    L::store(row_cache + (2 * NVC + sn) * PN, L::load(pe2 + sn * PN));
+                }
+                last_cached = true;
+            }
         }
         L::sync();
-        // ---- rows in topological (list) order, SINK excluded
+        // ---- rows in topological (list) order, SINK excluded.  The node metadata of the NEXT row is fetched
+        //      while the current row is computed (it does not depend on the DP).
+        int nid = w.order[1], nnin = w.in_n[nid], nbase = w.base[nid], nrem = banded ? w.remain[nid] : 0;
+        const int4 *nie = w.in_pool + w.in_off[nid];
+        int4 nie0 = nnin > 0 ? nie[0] : make_int4(0, 0, 0, 0);
         for (int oi = 1; oi < n; ++oi) {
-            const int id = w.order[oi];
+            const int id = nid, nin = nnin, nb = nbase, rem = nrem;
+            const int4 *ie = nie; const int4 ie0 = nie0;
+            if (oi + 1 < n) {
+                nid = w.order[oi + 1]; nnin = w.in_n[nid]; nbase = w.base[nid]; nrem = banded ? w.remain[nid] : 0;
+                nie = w.in_pool + w.in_off[nid];
+                nie0 = nnin > 0 ? nie[0] : make_int4(0, 0, 0, 0);
+            }
             if (id == 1) continue;
-            const int nin = w.in_n[id];
-            const int4 *ie = w.in_pool + w.in_off[id];
-            int beg, end, beg_sn, end_sn, min_pre_beg_sn, max_pre_end_sn;
-            if (par.wb < 0) { beg = 0; end = qlen; beg_sn = 0; end_sn = end >> 5; min_pre_beg_sn = 0; max_pre_end_sn = end_sn; }
+            // predecessor descriptors: the first MAXP in registers, any further ones re-read per vector
+            constexpr int MAXP = 4;
+            int4 pe[MAXP]; Row pr[MAXP];
+#pragma unroll
+            for (int k = 0; k < MAXP; ++k) if (k < nin) pe[k] = k == 0 ? ie0 : ie[k];
+#pragma unroll
+            for (int k = 0; k < MAXP; ++k) if (k < nin) pr[k] = pe[k].x == last_id ? last_row : unpack(w.rinfo[pe[k].x]);
+            int beg, end, beg_sn, end_sn, max_pre_end_sn;
+            if (!banded) { beg = 0; end = qlen; beg_sn = 0; end_sn = end >> 5; max_pre_end_sn = end_sn; }
             else {
-                const int r = qlen - (w.remain[id] - rem_end - 1);
-                beg = (w.maxl[id] < r ? w.maxl[id] : r) - wband; if (beg < 0) beg = 0;
-                end = (w.maxr[id] > r ? w.maxr[id] : r) + wband; if (end > qlen) end = qlen;
-                beg_sn = beg >> 5;
-                int min_pre_beg = INT32_MAX; min_pre_beg_sn = INT32_MAX; max_pre_end_sn = -1;
+                // max_pos_left/right pulled from the predecessors' row maxima (simd_abpoa_ada_max_i :1121-1130
+                // pushes left_max_i+1 / right_max_i+1 to every successor; reset values are node_n and 0)
+                int maxl = n, maxr = 0, min_pre_beg = INT32_MAX, min_pre_beg_sn = INT32_MAX; max_pre_end_sn = -1;
                 for (int k = 0; k < nin; ++k) {
-                    const int p = ie[k].x;
-                    if (min_pre_beg > w.dp_beg[p]) { min_pre_beg = w.dp_beg[p]; min_pre_beg_sn = w.dp_beg[p] >> 5; }
-                    if (max_pre_end_sn < (w.dp_end[p] >> 5)) max_pre_end_sn = w.dp_end[p] >> 5;
+                    Row r;
+                    if (k < MAXP) {
+#pragma unroll
+                        for (int q = 0; q < MAXP; ++q) if (q == k) r = pr[q];
+                    } else r = unpack(w.rinfo[ie[k].x]);
+                    if (r.left1 < maxl) maxl = r.left1;
+                    if (r.right1 > maxr) maxr = r.right1;
+                    if (min_pre_beg > r.beg) { min_pre_beg = r.beg; min_pre_beg_sn = r.beg >> 5; }
+                    if (max_pre_end_sn < (r.end >> 5)) max_pre_end_sn = r.end >> 5;
                 }
+                const int rr = qlen - (rem - rem_end - 1);
+                beg = (maxl < rr ? maxl : rr) - wband; if (beg < 0) beg = 0;
+                end = (maxr > rr ? maxr : rr) + wband; if (end > qlen) end = qlen;
+                beg_sn = beg >> 5;
                 if (beg_sn < min_pre_beg_sn) { beg = min_pre_beg; beg_sn = min_pre_beg_sn; }
                 end_sn = end >> 5;
             }
-            L::sync();                       // everyone has read the predecessors' band before this row's is published
-            w.dp_beg[id] = beg; w.dp_end[id] = end;
-            L::sync();
-            if (!alloc_row(id)) return ST_OOM;
-            if (beg_sn < min_pre_beg_sn) return ST_BAND;
+            const int nv = end_sn - beg_sn + 2;
+            const uint32_t need = (uint32_t)nv * PN * 5;
+            if (dp_top + need > w.dp_capacity) return ST_OOM;
+            const uint32_t off = dp_top; dp_top += need;
             cells += (unsigned long long)(end - beg + 1);
-            int16_t *H = const_cast<int16_t *>(plane(id, 0)), *E1 = const_cast<int16_t *>(plane(id, 1)), *E2 = const_cast<int16_t *>(plane(id, 2));
-            int16_t *F1 = const_cast<int16_t *>(plane(id, 3)), *F2 = const_cast<int16_t *>(plane(id, 4));
-            const int nb = w.base[id];
+            int16_t *H = w.dp + off - (size_t)beg_sn * PN, *E1 = H + (size_t)nv * PN, *E2 = E1 + (size_t)nv * PN;
+            int16_t *F1 = E2 + (size_t)nv * PN, *F2 = F1 + (size_t)nv * PN;
+            const int16_t *cache_rd = (row_cache && last_cached) ? row_cache + cache_buf * 3 * NVC * PN : nullptr;
+            const bool cache_wr = row_cache && nv <= NVC;
+            int16_t *cwH = cache_wr ? row_cache + (cache_buf ^ 1) * 3 * NVC * PN - (size_t)beg_sn * PN : nullptr;
+            Pred pd[MAXP];
+#pragma unroll
+            for (int k = 0; k < MAXP; ++k) if (k < nin) pd[k] = make_pred(pe[k], pr[k], beg_sn, end_sn, dp_sn, pe[k].x == last_id ? cache_rd : nullptr);
             int first1 = 0, first2 = 0;
             int mx = inf_min, left = -1, right = -1;
+            if (!L::TWO_PHASE) {
             for (int sn = beg_sn; sn <= end_sn; ++sn) {
                 const int col0 = sn * PN;
                 vec h = L::set1(inf_min), ve1 = L::set1(inf_min), ve2 = L::set1(inf_min);
-                for (int k = 0; k < nin; ++k) {
-                    const int p = ie[k].x, ps = ie[k].z;
-                    const int pre_end = w.dp_end[p], pre_beg_sn = w.dp_beg[p] >> 5, pre_end_sn = pre_end >> 5;
-                    int bsn, esn;
-                    const bool from_mem = pre_beg_sn < beg_sn;
-                    bsn = from_mem ? beg_sn : pre_beg_sn;
-                    esn = (pre_end + 1) >> 5; if (esn > end_sn) esn = end_sn; if (esn > dp_sn - 1) esn = dp_sn - 1;
-                    if (sn >= bsn && sn <= esn) {
-                        const int16_t *ph = plane(p, 0);
-                        const int first = (sn == bsn && !from_mem) ? inf_min : (int)ph[col0 - 1];
-                        const vec v = L::add(L::load_m1(ph + col0, first), L::set1(ps));
-                        h = k == 0 ? v : L::vmax(v, h);
-                    }
-                    esn = pre_end_sn < end_sn ? pre_end_sn : end_sn;
-                    if (sn >= bsn && sn <= esn) {
-                        const vec v1 = L::add(L::load(plane(p, 1) + col0), L::set1(ps)), v2 = L::add(L::load(plane(p, 2) + col0), L::set1(ps));
-                        ve1 = k == 0 ? v1 : L::vmax(v1, ve1);
-                        ve2 = k == 0 ? v2 : L::vmax(v2, ve2);
-                    }
+#pragma unroll
+                for (int k = 0; k < MAXP; ++k) if (k < nin) pred_accumulate(pd[k], k, sn, col0, h, ve1, ve2);
+                for (int k = MAXP; k < nin; ++k) {
+                    const int4 e = ie[k];
+                    const Pred p = make_pred(e, unpack(w.rinfo[e.x]), beg_sn, end_sn, dp_sn);
+                    pred_accumulate(p, k, sn, col0, h, ve1, ve2);
                 }
                 // + query profile, band mask
                 const vec q = L::map_cols(col0, [&](int j) -> int {
@@ -487,7 +676,7 @@ template <class L> struct Poa {
                     return (nb > 3 || qb > 3) ? 0 : (nb == qb ? match : -mism); });
                 h = L::add(h, q);
                 const int klo = beg - col0, khi = end - col0;       // lanes inside the band
-                h = L::keep(h, klo, khi, inf_min); ve1 = L::keep(ve1, klo, khi, inf_min); ve2 = L::keep(ve2, klo, khi, inf_min);
+                if (klo > 0 || khi < PN - 1) { h = L::keep(h, klo, khi, inf_min); ve1 = L::keep(ve1, klo, khi, inf_min); ve2 = L::keep(ve2, klo, khi, inf_min); }
                 if (sn == beg_sn) first1 = first2 = L::lane_value(h, 0);
                 const int set_num = sn > max_pre_end_sn ? (sn == max_pre_end_sn + 1 ? 2 : 1) : PN;
                 h = L::vmax(L::vmax(h, ve1), ve2);
@@ -498,11 +687,12 @@ template <class L> struct Poa {
                 first1 = L::lane_value(L::vmax(h, L::add(f1, L::set1(o1))), PN - 1);
                 first2 = L::lane_value(L::vmax(h, L::add(f2, L::set1(o2))), PN - 1);
                 h = L::vmax(h, L::vmax(f1, f2));
-                if (sn == end_sn) { h = L::keep(h, -1, khi, inf_min); ve1 = L::keep(ve1, -1, khi, inf_min); ve2 = L::keep(ve2, -1, khi, inf_min); }
+                if (sn == end_sn && khi < PN - 1) { h = L::keep(h, -1, khi, inf_min); ve1 = L::keep(ve1, -1, khi, inf_min); ve2 = L::keep(ve2, -1, khi, inf_min); }
                 ve1 = L::vmax(L::sub(ve1, L::set1(e1)), L::sub(h, L::set1(oe1)));
                 ve2 = L::vmax(L::sub(ve2, L::set1(e2)), L::sub(h, L::set1(oe2)));
                 L::store(H + col0, h); L::store(E1 + col0, ve1); L::store(E2 + col0, ve2); L::store(F1 + col0, f1); L::store(F2 + col0, f2);
-                if (par.wb >= 0) {           // simd_abpoa_max_in_row :1107-1119
+                if (cache_wr) { L::store(cwH + col0, h); L::store(cwH + NVC * PN + col0, ve1); L::store(cwH + 2 * NVC * PN + col0, ve2); }
+                if (banded) {                // simd_abpoa_max_in_row :1107-1119
                     int m, fi, la;
                     if (L::row_max(h, klo < 0 ? 0 : klo, khi > PN - 1 ? PN - 1 : khi, m, fi, la)) {
                         if (m > mx) { mx = m; left = col0 + fi; right = col0 + la; }
@@ -510,26 +700,97 @@ template <class L> struct Poa {
                     }
                 }
             }
-            // the vector after the band: INF_MIN in H (read by successors' M), undefined elsewhere
-            if (end_sn + 1 <= dp_sn - 1) L::store(H + (end_sn + 1) * PN, L::set1(inf_min));
-            if (par.wb >= 0) {               // simd_abpoa_ada_max_i :1121-1130
+            } else {
+                // Two-phase row for a group of NW warps: the vectors of the row are dealt to the warps.  Phase A
+                // computes everything that does not depend on the F carry of the vectors to the left: hm = max(M+q,
+                // E1, E2) and G = SIMD_SET_F of the F start vector with a never-winning value in lane 0.  SIMD_SET_F
+                // is max-plus affine, so the true F is max(G, carry - oe - e*lane), and the carry obeys
+                // c' = max(max(hm[31], G[31] + o), c - 32 e)  -- a scalar recurrence resolved through shared memory.
+                int *B1 = gs, *B2 = gs + MAXV, *misc = gs + 2 * MAXV;
+                if (end_sn - beg_sn + 1 > MAXV) return ST_OOM;
+                const int lowf = inf_min - 900;
+                for (int sn = beg_sn + L::warp(); sn <= end_sn; sn += L::NW) {
+                    const int col0 = sn * PN;
+                    vec h = L::set1(inf_min), ve1 = L::set1(inf_min), ve2 = L::set1(inf_min);
+#pragma unroll
+                    for (int k = 0; k < MAXP; ++k) if (k < nin) pred_accumulate(pd[k], k, sn, col0, h, ve1, ve2);
+                    for (int k = MAXP; k < nin; ++k) {
+                        const int4 e = ie[k];
+                        const Pred p = make_pred(e, unpack(w.rinfo[e.x]), beg_sn, end_sn, dp_sn);
+                        pred_accumulate(p, k, sn, col0, h, ve1, ve2);
+                    }
+                    const vec q = L::map_cols(col0, [&](int j) -> int {
+                        if (j == 0 || j > qlen) return 0;
+                        const int qb = query[j - 1];
+                        return (nb > 3 || qb > 3) ? 0 : (nb == qb ? match : -mism); });
+                    h = L::add(h, q);
+                    const int klo = beg - col0, khi = end - col0;
+                    if (klo > 0 || khi < PN - 1) { h = L::keep(h, klo, khi, inf_min); ve1 = L::keep(ve1, klo, khi, inf_min); ve2 = L::keep(ve2, klo, khi, inf_min); }
+                    if (sn == beg_sn) { const int c0 = L::lane_value(h, 0); if (L::lane() == 0) misc[0] = c0; }
+                    const int set_num = sn > max_pre_end_sn ? (sn == max_pre_end_sn + 1 ? 2 : 1) : PN;
+                    h = L::vmax(L::vmax(h, ve1), ve2);
+                    vec g1 = L::keep(L::sub(L::shift_up(h, 1, 0), L::set1(oe1)), 1, PN - 1, lowf);
+                    vec g2 = L::keep(L::sub(L::shift_up(h, 1, 0), L::set1(oe2)), 1, PN - 1, lowf);
+                    g1 = set_f(g1, set_num, e1);
+                    g2 = set_f(g2, set_num, e2);
+                    const int b1 = L::lane_value(L::vmax(h, L::add(g1, L::set1(o1))), PN - 1);
+                    const int b2 = L::lane_value(L::vmax(h, L::add(g2, L::set1(o2))), PN - 1);
+                    if (L::lane() == 0) { B1[sn - beg_sn] = b1; B2[sn - beg_sn] = b2; }
+                    L::store(H + col0, h); L::store(E1 + col0, ve1); L::store(E2 + col0, ve2); L::store(F1 + col0, g1); L::store(F2 + col0, g2);
+                }
                 L::sync();
-                if (L::lane() == 0) {
-                    for (int i = 0; i < w.out_n[id]; ++i) {
-                        const int o = out_entry(id, i)[0];
-                        if (right + 1 > w.maxr[o]) w.maxr[o] = right + 1;
-                        if (left + 1 < w.maxl[o]) w.maxl[o] = left + 1;
+                for (int sn = beg_sn + L::warp(); sn <= end_sn; sn += L::NW) {
+                    const int col0 = sn * PN;
+                    int c1 = misc[0], c2 = c1;
+                    for (int u = 0; u < sn - beg_sn; ++u) {
+                        const int x1 = B1[u], x2 = B2[u];
+                        c1 = x1 > c1 - 32 * e1 ? x1 : c1 - 32 * e1;
+                        c2 = x2 > c2 - 32 * e2 ? x2 : c2 - 32 * e2;
+                    }
+                    vec h = L::load(H + col0), ve1 = L::load(E1 + col0), ve2 = L::load(E2 + col0);
+                    const int khi = end - col0, klo = beg - col0;
+                    const vec f1 = L::vmax(L::load(F1 + col0), L::map_cols(0, [&](int l) -> int { return c1 - oe1 - e1 * l; }));
+                    const vec f2 = L::vmax(L::load(F2 + col0), L::map_cols(0, [&](int l) -> int { return c2 - oe2 - e2 * l; }));
+                    h = L::vmax(h, L::vmax(f1, f2));
+                    if (sn == end_sn && khi < PN - 1) { h = L::keep(h, -1, khi, inf_min); ve1 = L::keep(ve1, -1, khi, inf_min); ve2 = L::keep(ve2, -1, khi, inf_min); }
+                    ve1 = L::vmax(L::sub(ve1, L::set1(e1)), L::sub(h, L::set1(oe1)));
+                    ve2 = L::vmax(L::sub(ve2, L::set1(e2)), L::sub(h, L::set1(oe2)));
+                    L::store(H + col0, h); L::store(E1 + col0, ve1); L::store(E2 + col0, ve2); L::store(F1 + col0, f1); L::store(F2 + col0, f2);
+                    if (banded) {
+                        int m, fi, la;
+                        if (L::row_max(h, klo < 0 ? 0 : klo, khi > PN - 1 ? PN - 1 : khi, m, fi, la)) {
+                            if (m > mx) { mx = m; left = col0 + fi; right = col0 + la; }
+                            else if (m == mx) right = col0 + la;
+                        }
                     }
                 }
+                if (banded && L::NW > 1) {        // combine the per-warp row maxima: first / last column attaining the maximum
+                    if (L::lane() == 0) { misc[4 + 3 * L::warp()] = mx; misc[5 + 3 * L::warp()] = left; misc[6 + 3 * L::warp()] = right; }
+                    L::sync();
+                    int M = inf_min;
+                    for (int x = 0; x < L::NW; ++x) if (misc[4 + 3 * x] > M) M = misc[4 + 3 * x];
+                    int lft = INT32_MAX, rgt = -1;
+                    for (int x = 0; x < L::NW; ++x) if (misc[4 + 3 * x] == M) {
+                        if (misc[5 + 3 * x] >= 0 && misc[5 + 3 * x] < lft) lft = misc[5 + 3 * x];
+                        if (misc[6 + 3 * x] > rgt) rgt = misc[6 + 3 * x];
+                    }
+                    mx = M; left = lft == INT32_MAX ? -1 : lft; right = rgt;
+                }
             }
+            // the vector after the band: INF_MIN in H (read by successors' M), undefined elsewhere
+            if (end_sn + 1 <= dp_sn - 1) {
+                L::store(H + (end_sn + 1) * PN, L::set1(inf_min));
+                if (cache_wr) L::store(cwH + (end_sn + 1) * PN, L::set1(inf_min));
+            }
+            if (L::tid() == 0) w.rinfo[id] = pack((int)off, beg, end, left, right);
+            last_id = id; last_row = unpack(pack((int)off, beg, end, left, right));
+            last_cached = cache_wr; if (cache_wr) cache_buf ^= 1;
             L::sync();
         }
         // ---- best cell :1092-1105 and backtrack :309-458 (lane 0; result broadcast through memory)
-        int n_cig = 0;
-        if (L::lane() == 0) n_cig = backtrack(query, qlen);
-        L::sync();
-        n_cig = w.tmp[0];
-        return n_cig;
+        { LCD_T0(); if (L::tid() == 0) backtrack(query, qlen);
+        L::sync(); LCD_T1(t_bt); }
+        return w.tmp[0];
     }
 
     __device__ void cig_push(int &n, int op, int len, int node) {
@@ -544,56 +805,60 @@ template <class L> struct Poa {
             const int4 *ie = w.in_pool + w.in_off[1];
             for (int k = 0; k < w.in_n[1]; ++k) {
                 const int r = ie[k].x;
-                const int e = qlen > w.dp_end[r] ? w.dp_end[r] : qlen;
-                const int s = cell(r, 0, e);
+                const Row rr = unpack(w.rinfo[r]);
+                const int e = qlen > rr.end ? rr.end : qlen;
+                const int s = cell(rr, 0, e);
                 if (s > best) { best = s; bi = r; bj = e; }
             }
         }
         enum { M_OP = 1, E1_OP = 2, E2_OP = 4, E_OP = 6, F1_OP = 8, F2_OP = 16, F_OP = 24, ALL_OP = 31 };
         int n = 0, id = bi, j = bj, cur_op = ALL_OP, rc = 0;
         if (bj < qlen) cig_push(n, 1, qlen - bj, -1);
+        Row cur = unpack(w.rinfo[id]);
         while (id != 0 && j > 0) {
             const int nb = w.base[id], qb = query[j - 1];
             const int s = (nb > 3 || qb > 3) ? 0 : (nb == qb ? par.match : -par.mismatch);
             const int4 *ie = w.in_pool + w.in_off[id];
             const int nin = w.in_n[id];
-            const int hj = cell(id, 0, j);
+            const int hj = cell(cur, 0, j);
             int hit = 0;
             for (int pass = 0; pass < 2 && !hit; ++pass) {
                 if (pass == 1) {
                     if (cur_op & E_OP) {
-                        const int e1j = cell(id, 1, j), e2j = cell(id, 2, j);
+                        const int e1j = cell(cur, 1, j), e2j = cell(cur, 2, j);
                         for (int k = 0; k < nin && !hit; ++k) {
-                            const int p = ie[k].x, ps = ie[k].z;
-                            if (j < w.dp_beg[p] || j > w.dp_end[p]) continue;
-                            const int phj = cell(p, 0, j);
+                            const int4 e = ie[k];
+                            const int p = e.x, ps = e.z;
+                            const Row pr = unpack(w.rinfo[p]);
+                            if (j < pr.beg || j > pr.end) continue;
+                            const int phj = cell(pr, 0, j);
                             if (cur_op & E1_OP) {
-                                const int pe = cell(p, 1, j);
+                                const int pe = cell(pr, 1, j);
                                 const int ok = (cur_op & M_OP) ? (hj == pe + ps) : (e1j == pe - e1 + ps);
                                 if (ok) { cur_op = (phj - oe1 == pe) ? (M_OP | F_OP) : E1_OP; hit = 1; }
                             }
                             if (!hit && (cur_op & E2_OP)) {
-                                const int pe = cell(p, 2, j);
+                                const int pe = cell(pr, 2, j);
                                 const int ok = (cur_op & M_OP) ? (hj == pe + ps) : (e2j == pe - e2 + ps);
                                 if (ok) { cur_op = (phj - oe2 == pe) ? (M_OP | F_OP) : E2_OP; hit = 1; }
                             }
-                            if (hit) { cig_push(n, 2, 1, id); id = p; }
+                            if (hit) { cig_push(n, 2, 1, id); id = p; cur = pr; }
                         }
                     }
                     if (!hit && (cur_op & F_OP)) {
-                        const int hj1 = cell(id, 0, j - 1);
+                        const int hj1 = cell(cur, 0, j - 1);
                         if (cur_op & F1_OP) {
-                            const int f = cell(id, 3, j);
+                            const int f = cell(cur, 3, j);
                             if (!(cur_op & M_OP) || hj == f) {
                                 if (hj1 - oe1 == f) { cur_op = M_OP | E_OP; hit = 1; }
-                                else if (cell(id, 3, j - 1) - e1 == f) { cur_op = F1_OP; hit = 1; }
+                                else if (cell(cur, 3, j - 1) - e1 == f) { cur_op = F1_OP; hit = 1; }
                             }
                         }
                         if (!hit && (cur_op & F2_OP)) {
-                            const int f = cell(id, 4, j);
+                            const int f = cell(cur, 4, j);
                             if (!(cur_op & M_OP) || hj == f) {
                                 if (hj1 - oe2 == f) { cur_op = M_OP | E_OP; hit = 1; }
-                                else if (cell(id, 4, j - 1) - e2 == f) { cur_op = F2_OP; hit = 1; }
+                                else if (cell(cur, 4, j - 1) - e2 == f) { cur_op = F2_OP; hit = 1; }
                             }
                         }
                         if (hit) { cig_push(n, 1, 1, id); --j; }
@@ -602,11 +867,13 @@ template <class L> struct Poa {
                 }
                 if (cur_op & M_OP) {
                     for (int k = 0; k < nin; ++k) {
-                        const int p = ie[k].x, ps = ie[k].z;
-                        if (j - 1 < w.dp_beg[p] || j - 1 > w.dp_end[p]) continue;
-                        if (cell(p, 0, j - 1) + s + ps == hj) {
+                        const int4 e = ie[k];
+                        const int p = e.x, ps = e.z;
+                        const Row pr = unpack(w.rinfo[p]);
+                        if (j - 1 < pr.beg || j - 1 > pr.end) continue;
+                        if (cell(pr, 0, j - 1) + s + ps == hj) {
                             cig_push(n, 0, 1, id);
-                            id = p; --j; hit = 1; cur_op = ALL_OP;
+                            id = p; cur = pr; --j; hit = 1; cur_op = ALL_OP;
                             break;
                         }
                     }
@@ -622,7 +889,7 @@ template <class L> struct Poa {
 
     // ---- output: MSA ranks (abpoa_DFS_set_msa_rank :359-410), most-frequent consensus, RC-MSA ----------
     __device__ int finish(int n_seq, uint8_t *cons, int *cons_len_out, const KernelArgs &a, unsigned long long *msa_off_out, int *msa_len_out) {
-        const int n = w.n_nodes, lane = L::lane();
+        const int n = w.n_nodes, lane = L::tid();
         int *deg = w.tmp, *st = w.order;          // order[] is free now; DFS stack needs <= n entries... see below
         if (lane == 0) {
             for (int i = 0; i < n; ++i) deg[i] = w.in_n[i];
@@ -655,19 +922,19 @@ template <class L> struct Poa {
         int *col = w.remain;
         int *cnt = reinterpret_cast<int *>(w.dp), *nid = cnt + (size_t)ml * 5;
         if ((uint64_t)ml * 10 * 2 + 64 > w.dp_capacity) return ST_OOM;
-        for (int i = lane; i < ml * 5; i += L::STRIDE) { cnt[i] = 0; nid[i] = 0; }
-        for (int i = lane; i < n; i += L::STRIDE) {
+        for (int i = lane; i < ml * 5; i += L::NT) { cnt[i] = 0; nid[i] = 0; }
+        for (int i = lane; i < n; i += L::NT) {
             int r = w.msa_rank[i];
             for (int j = 0; j < w.aln_n[i]; ++j) { const int rr = w.msa_rank[w.aln_pool[w.aln_off[i] + j]]; if (rr > r) r = rr; }
             col[i] = r - 1;
         }
         L::sync();
-        for (int i = 2 + lane; i < n; i += L::STRIDE) { cnt[col[i] * 5 + w.base[i]] = w.n_read[i]; nid[col[i] * 5 + w.base[i]] = i; }
+        for (int i = 2 + lane; i < n; i += L::NT) { cnt[col[i] * 5 + w.base[i]] = w.n_read[i]; nid[col[i] * 5 + w.base[i]] = i; }
         L::sync();
         // voting (abpoa_set_major_voting_cons :393-424); ordered compaction by lane 0 over per-column flags
         int *emit = w.maxl;        // per column: consensus node id or -1   (ml <= N)
         int bad = 0;
-        for (int i = lane; i < ml; i += L::STRIDE) {
+        for (int i = lane; i < ml; i += L::NT) {
             int max_c = 0, total = 0, max_base = 5;
             for (int j = 0; j < 4; ++j) { const int c = cnt[i * 5 + j]; if (c > max_c) { max_c = c; max_base = j; } total += c; }
             if (max_base == 5) { bad = 1; emit[i] = -1; continue; }
@@ -695,9 +962,9 @@ template <class L> struct Poa {
         if (!w.tmp[1]) return ST_OOM;
         uint8_t *msa = a.msa + off;
         const long long tot = (long long)(n_seq + 1) * ml;
-        for (long long i = lane; i < tot; i += L::STRIDE) msa[i] = 5;
+        for (long long i = lane; i < tot; i += L::NT) msa[i] = 5;
         L::sync();
-        for (int i = 2 + lane; i < n; i += L::STRIDE) {
+        for (int i = 2 + lane; i < n; i += L::NT) {
             const int c = col[i], b = w.base[i];
             for (int e = 0; e < w.out_n[i]; ++e) {
                 const int *ent = out_entry(i, e);
@@ -707,14 +974,14 @@ template <class L> struct Poa {
                 }
             }
         }
-        for (int i = lane; i < cl; i += L::STRIDE) msa[(size_t)n_seq * ml + col[cons_ids[i]]] = cons[i];
+        for (int i = lane; i < cl; i += L::NT) msa[(size_t)n_seq * ml + col[cons_ids[i]]] = cons[i];
         L::sync();
         return ST_OK;
     }
 
     // ---- whole problem ---------------------------------------------------------------------------
     __device__ void run(const KernelArgs &a, const Problem &pb, DevResult *res, int32_t *arena) {
-        par = pb.par; n_reads = pb.n_reads; cells = 0;
+        par = pb.par; n_reads = pb.n_reads; cells = 0; t_dp = t_bt = t_add = t_after = t_fin = 0;
         oe1 = par.gap_open1 + par.gap_ext1; oe2 = par.gap_open2 + par.gap_ext2;
         int status = ST_OK, cons_len = 0, msa_len = 0; unsigned long long msa_off = 0;
         {
@@ -723,10 +990,11 @@ template <class L> struct Poa {
             inf_min = (int16_t)(m + 512 * (par.gap_ext1 > par.gap_ext2 ? par.gap_ext1 : par.gap_ext2));
         }
         L::sync();
-        if (!carve(arena, a.arena_words, pb.sum_len, pb.max_len, pb.n_reads) || par.max_n_cons != 1) status = ST_OOM;
+        const int ncap = a.worst_case ? pb.sum_len + 34 : pb.node_cap, ecap = a.worst_case ? 3 * (pb.sum_len + pb.n_reads) + 64 : pb.edge_cap;
+        if (!carve(arena, a.arena_words, ncap, ecap, pb.max_len, pb.n_reads) || par.max_n_cons != 1) status = ST_OOM;
         else {
-            w.in_top = w.out_top = w.aln_top = 0; w.n_nodes = 0; w.oom = 0; w.dp_top = 0;
-            if (L::lane() == 0) { add_node(0); add_node(0); w.next[0] = 1; w.next[1] = -1; }
+            w.in_top = w.out_top = w.aln_top = 0; w.n_nodes = 0; w.oom = 0;
+            if (L::tid() == 0) { add_node(0); add_node(0); w.next[0] = 1; w.next[1] = -1; }
             else w.n_nodes = 2;
             L::sync();
             const uint8_t *seqs = a.seqs + pb.seq_base;
@@ -739,27 +1007,34 @@ template <class L> struct Poa {
                     const int gn = w.n_nodes, len = ql > gn ? ql : gn;
                     const int ms = (ql * par.match > len * par.gap_ext1 + par.gap_open1) ? ql * par.match : len * par.gap_ext1 + par.gap_open1;
                     if (!(ms <= INT16_MAX - par.mismatch - oe1 - oe2)) { status = ST_INT32; break; }
-                    n_cig = align(q, ql);
+                    { LCD_T0(); n_cig = align(q, ql); LCD_T1(t_dp); }
                     if (n_cig < 0) { status = n_cig; break; }
                 }
-                if (L::lane() == 0) {
+                { LCD_T0();
+                if (L::tid() == 0) {
                     add_alignment(q, ql, n_cig, r);
                     w.tmp[0] = w.n_nodes; w.tmp[1] = w.oom;
                 }
-                L::sync();
+                L::sync(); LCD_T1(t_add); }
                 w.n_nodes = w.tmp[0]; w.oom = w.tmp[1];
                 // pool cursors are only used by lane 0; n_nodes and oom are shared through tmp[]
                 L::sync();
                 if (w.oom) { status = ST_OOM; break; }
-                if (w.n_nodes > 2) after_add(first_read);
+                if (w.n_nodes > 2) { LCD_T0(); after_add(first_read); LCD_T1(t_after); }
             }
-            if (status == ST_OK && w.n_nodes > 2)
+            if (status == ST_OK && w.n_nodes > 2) {
+                LCD_T0();
                 status = finish(pb.n_reads, a.cons + pb.cons_off, &cons_len, a, &msa_off, &msa_len);
+                LCD_T1(t_fin);
+            }
         }
-        if (L::lane() == 0) {
+        if (L::tid() == 0) {
             DevResult r;
             r.status = status; r.cons_len = cons_len; r.msa_len = msa_len; r.n_nodes = w.n_nodes; r.msa_off = msa_off;
             r.cells_lo = (uint32_t)cells; r.cells_hi = (uint32_t)(cells >> 32);
+#ifdef LCD_POA_TIMING
+            r.t_dp = t_dp - t_bt; r.t_bt = t_bt; r.t_add = t_add; r.t_after = t_after; r.t_fin = t_fin;
+#endif
             *res = r;
         }
         L::sync();

@@ -14,7 +14,9 @@ poa_kernel(const KernelArgs a) {
     const int gi = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group_id = blockIdx.x * WARPS_PER_CTA + gi;
     int32_t *arena = a.arena + (size_t)group_id * a.arena_words;
+    __shared__ __align__(16) int16_t row_cache[WARPS_PER_CTA][2 * 3 * Poa<WarpLanes>::NVC * PN];
     Poa<WarpLanes> poa;
+    poa.row_cache = row_cache[gi];
     for (;;) {
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(a.queue, 1u);
@@ -25,13 +27,48 @@ poa_kernel(const KernelArgs a) {
     }
 }
 
-// arena words a problem needs (mirrors Poa::carve) for a given DP cell budget
-static uint64_t arena_need_words(int sum_len, int max_len, int n_reads, uint64_t dp_cells) {
-    const uint64_t N = (uint64_t)sum_len + 2 + 32;
-    uint64_t top = 23 * ((N + 3) & ~3ull);
-    const uint64_t E = 4ull * (sum_len + n_reads) + 64;
+// one THREAD per problem (ThreadLanes): for the thousands of ~100-node problems, where the serial graph
+// phases dominate and run 32 problems per warp instead of one
+constexpr int THREADS_PER_CTA = 64;
+__global__ void __launch_bounds__(THREADS_PER_CTA)
+poa_thread_kernel(const KernelArgs a) {
+    const int tid = blockIdx.x * THREADS_PER_CTA + threadIdx.x;
+    int32_t *arena = a.arena + (size_t)tid * a.arena_words;
+    Poa<ThreadLanes> poa;
+    for (;;) {
+        const uint32_t item = atomicAdd(a.queue, 1u);
+        if (item >= (uint32_t)a.n) break;
+        const int pi = a.order[item];
+        poa.run(a, a.problems[pi], a.results + pi, arena);
+    }
+}
+
+// one CTA of CTA_WARPS warps per problem (kilobase regions): the vectors of every DP row are dealt to the warps
+constexpr int CTA_WARPS = 4;
+__global__ void __launch_bounds__(32 * CTA_WARPS)
+poa_cta_kernel(const KernelArgs a) {
+    typedef Poa<CtaLanes<CTA_WARPS>> P;
+    __shared__ int gs[P::GS_INTS];
+    __shared__ uint32_t next_item;
+    int32_t *arena = a.arena + (size_t)blockIdx.x * a.arena_words;
+    P poa;
+    poa.gs = gs;
+    for (;;) {
+        if (threadIdx.x == 0) next_item = atomicAdd(a.queue, 1u);
+        __syncthreads();
+        const uint32_t item = next_item;
+        __syncthreads();
+        if (item >= (uint32_t)a.n) break;
+        const int pi = a.order[item];
+        poa.run(a, a.problems[pi], a.results + pi, arena);
+    }
+}
+
+// arena words a problem needs (mirrors Poa::carve) for given node / edge / DP cell budgets
+static uint64_t arena_need_words(uint64_t N, uint64_t E, int max_len, int n_reads, uint64_t dp_cells) {
+    uint64_t top = 27 * ((N + 3) & ~3ull) + N * 4;
     const uint64_t stride = 2 + 2 * (1 + ((n_reads - 1) >> 6));
-    top += E * 4 + ((E * stride + 3) & ~3ull) + E + 2 * ((uint64_t)max_len + N + 8);
+    top += E * 4 + ((E * stride + 3) & ~3ull) + ((E + 3) & ~3ull) + 2 * ((uint64_t)max_len + N + 8);
     top = (top + 31) & ~31ull;
     return top + 1024 + (dp_cells + 1) / 2;
 }
@@ -53,6 +90,12 @@ struct PoaPlan : Plan {
     std::vector<DevResult> h_results;
     std::vector<uint8_t> h_cons, h_msa;
     int n_rescued = 0;
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    ~PoaPlan() override {
+        for (int k = 0; k < 2; ++k) { if (side[k]) cudaStreamDestroy(side[k]); if (ev_join[k]) cudaEventDestroy(ev_join[k]); }
+        if (ev_fork) cudaEventDestroy(ev_fork);
+    }
 
     int build(int n_, const uint8_t *seqs, size_t seqs_len, const int32_t *first_read, const int32_t *n_reads,
               const int64_t *read_off, const int32_t *read_len, int n_total_reads, const lcd_poa_params_t *params) {
@@ -74,13 +117,17 @@ struct PoaPlan : Plan {
             p.cons_off = (int32_t)cons_total; cons_dev_off[i] = (int64_t)cons_total;
             cons_total += ((size_t)p.sum_len + 15) & ~(size_t)15;
             if (cons_total > 0x7fffffffull) { set_error("lcd_poa: batch too large (consensus buffer > 2 GiB); split it"); return -1; }
-            // DP cell budgets: rows ~ graph nodes, vectors per row ~ band / 32
-            const double rows = 1.25 * p.max_len + 64;
+            // first-attempt budgets: nodes ~ longest read + branches, 3 edge slots per node, DP rows ~ nodes,
+            // vectors per row ~ band / 32; the worst case (every base a new node, full matrix) is the rescue budget
+            p.node_cap = (int32_t)std::min<int64_t>((int64_t)p.sum_len + 34, 2ll * p.max_len + 64 + 2ll * p.n_reads);
+            p.edge_cap = 3 * p.node_cap;
+            const double rows = 1.15 * p.max_len + 24;
             const int dp_sn = (p.max_len + 32) / 32;
             const int wband = params[i].wb < 0 ? p.max_len : params[i].wb + (int)(params[i].wf * p.max_len);
             double nv = params[i].wb < 0 ? dp_sn + 1 : std::min<double>(dp_sn + 1, (2.0 * wband + 2.0 * (p.max_len - mn) + 64) / 32 + 3);
-            need_small[i] = arena_need_words(p.sum_len, p.max_len, p.n_reads, (uint64_t)(rows * nv * 160));
-            need_full[i] = arena_need_words(p.sum_len, p.max_len, p.n_reads, (uint64_t)((double)(p.sum_len + 34) * (dp_sn + 1) * 160));
+            need_small[i] = arena_need_words(p.node_cap, p.edge_cap, p.max_len, p.n_reads, (uint64_t)(rows * nv * 160));
+            need_full[i] = arena_need_words((uint64_t)p.sum_len + 34, 3ull * (p.sum_len + p.n_reads) + 64, p.max_len, p.n_reads,
+                                            (uint64_t)((double)(p.sum_len + 34) * (dp_sn + 1) * 160));
             work[i] = (double)p.n_reads * rows * nv;
             msa_est += (double)(p.n_reads + 1) * (1.5 * p.max_len + 64);
         }
@@ -98,33 +145,47 @@ struct PoaPlan : Plan {
         if (d_cons.alloc(cons_bytes + 16)) return -1;
         if (d_msa.alloc(msa_pool_bytes)) return -1;
         if (d_results.alloc(std::max(n, 1))) return -1;
-        if (d_queue.alloc(1)) return -1;
+        if (d_queue.alloc(4)) return -1;
+        for (int k = 0; k < 2; ++k) {
+            LCD_CUDA_OK(cudaStreamCreateWithFlags(&side[k], cudaStreamNonBlocking));
+            LCD_CUDA_OK(cudaEventCreateWithFlags(&ev_join[k], cudaEventDisableTiming));
+        }
+        LCD_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         if (d_msa_used.alloc(1)) return -1;
         LCD_CUDA_OK(cudaStreamSynchronize(s));
         return 0;
     }
 
     // one launch over `idx` with per-group arenas of `words`
-    int launch(cudaStream_t s, const std::vector<int32_t> &idx, uint64_t words, int max_groups) {
+    // kind: 0 = poa_thread_kernel (one problem per thread), 1 = poa_kernel (one per warp), 2 = poa_cta_kernel (one per CTA).
+    // The launch uses pool words [pool_lo, pool_hi) for its arenas and reports how many it took in *used.
+    int launch(cudaStream_t s, const std::vector<int32_t> &idx, int32_t *d_idx, uint32_t *d_q, uint64_t words, int max_groups,
+               int kind, bool worst_case, uint64_t pool_lo, uint64_t pool_hi, uint64_t *used) {
         Context &c = ctx();
+        if (used) *used = 0;
         if (idx.empty()) return 0;
-        const uint64_t fit = c.pool_words / words;
+        const int per_cta = kind == 0 ? THREADS_PER_CTA : kind == 1 ? WARPS_PER_CTA : 1;
+        const uint64_t avail = pool_hi > pool_lo ? pool_hi - pool_lo : 0;
+        const uint64_t fit = avail / words;
         if (fit == 0) { set_error("lcd_poa: a problem needs %zu MiB of workspace but the pool has %zu MiB", (size_t)(words * 4 >> 20), (size_t)(c.pool_words * 4 >> 20)); return -1; }
         int groups = (int)std::min<uint64_t>(std::min<uint64_t>(fit, (uint64_t)max_groups), idx.size());
-        int grid = (groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-        if ((uint64_t)grid * WARPS_PER_CTA > fit) grid = (int)(fit / WARPS_PER_CTA);
+        int grid = (groups + per_cta - 1) / per_cta;
+        if ((uint64_t)grid * per_cta > fit) grid = (int)(fit / per_cta);
         if (grid == 0) { grid = 1; }
-        if ((uint64_t)grid * WARPS_PER_CTA * words > c.pool_words) {      // fewer than one CTA's worth of arenas: shrink to what fits
-            set_error("lcd_poa: workspace pool too small for one CTA of %d arenas of %zu MiB", WARPS_PER_CTA, (size_t)(words * 4 >> 20)); return -1;
+        if ((uint64_t)grid * per_cta * words > avail) {
+            set_error("lcd_poa: workspace pool too small for one CTA of %d arenas of %zu MiB", per_cta, (size_t)(words * 4 >> 20)); return -1;
         }
-        LCD_CUDA_OK(cudaMemcpyAsync(d_order.p, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-        LCD_CUDA_OK(cudaMemsetAsync(d_queue.p, 0, sizeof(uint32_t), s));
+        if (used) *used = (uint64_t)grid * per_cta * words;
+        LCD_CUDA_OK(cudaMemcpyAsync(d_idx, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        LCD_CUDA_OK(cudaMemsetAsync(d_q, 0, sizeof(uint32_t), s));
         KernelArgs ka;
-        ka.problems = d_problems.p; ka.order = d_order.p; ka.n = (int)idx.size(); ka.queue = d_queue.p;
+        ka.problems = d_problems.p; ka.order = d_idx; ka.n = (int)idx.size(); ka.queue = d_q;
         ka.seqs = d_seqs.p; ka.read_off = d_read_off.p; ka.read_len = d_read_len.p;
         ka.cons = d_cons.p; ka.msa = d_msa.p; ka.msa_cap = msa_pool_bytes; ka.msa_used = d_msa_used.p;
-        ka.results = d_results.p; ka.arena = c.pool; ka.arena_words = words;
-        poa_kernel<<<grid, 32 * WARPS_PER_CTA, 0, s>>>(ka);
+        ka.results = d_results.p; ka.arena = c.pool + pool_lo; ka.arena_words = words; ka.worst_case = worst_case ? 1 : 0;
+        if (kind == 0) poa_thread_kernel<<<grid, THREADS_PER_CTA, 0, s>>>(ka);
+        else if (kind == 1) poa_kernel<<<grid, 32 * WARPS_PER_CTA, 0, s>>>(ka);
+        else poa_cta_kernel<<<grid, 32 * CTA_WARPS, 0, s>>>(ka);
         LCD_CUDA_OK(cudaGetLastError());
         c.launches++;
         return 0;
@@ -134,15 +195,43 @@ struct PoaPlan : Plan {
         Context &c = ctx();
         if (n == 0) return 0;
         LCD_CUDA_OK(cudaMemsetAsync(d_msa_used.p, 0, sizeof(unsigned long long), s));
-        // class 1: every problem whose estimated need fits a "small" arena; class 2: the rest, estimated need;
-        // rescue: problems that ran out of DP space, with the worst-case budget.
-        const uint64_t small_words = (uint64_t)(6u << 20) / 4;        // 6 MiB
-        std::vector<int32_t> small, large;
-        uint64_t large_words = 0;
-        for (int32_t i : order_all) { if (need_small[i] <= small_words) small.push_back(i); else { large.push_back(i); large_words = std::max(large_words, need_small[i]); } }
-        const int max_groups = c.sm_count * 12;
-        if (launch(s, small, small_words, max_groups)) return -1;
-        if (!large.empty() && launch(s, large, (large_words + 63) & ~63ull, max_groups)) return -1;
+        // class T: small problems, one per THREAD; class W: medium, one per warp; class C: kilobase regions, one per
+        // CTA; rescue: problems that outgrew their first-attempt budget, re-run with the worst-case budget.
+        // The three classes run concurrently (two side streams) in disjoint parts of the pool.
+        const uint64_t thread_words = (uint64_t)(512u << 10) / 4;     // <= 512 KiB per thread arena
+        std::vector<int32_t> cls[3];
+        uint64_t cw[3] = {0, 0, 0};
+        for (int32_t i : order_all) {
+            const int k = (need_small[i] <= thread_words && problems[i].max_len <= 640) ? 0 : (problems[i].max_len <= 1200 ? 1 : 2);
+            cls[k].push_back(i); cw[k] = std::max(cw[k], need_small[i]);
+        }
+        for (int k = 0; k < 3; ++k) cw[k] = (cw[k] + 63) & ~63ull;
+        const int max_groups[3] = { c.sm_count * 256, c.sm_count * 8, c.sm_count * 4 };
+        // pool split: threads get what they need (at most half), CTAs and warps share the rest in proportion to demand
+        uint64_t want[3];
+        const int per_cta[3] = { THREADS_PER_CTA, WARPS_PER_CTA, 1 };
+        for (int k = 0; k < 3; ++k) {
+            const uint64_t g = std::min<uint64_t>(cls[k].size(), (uint64_t)max_groups[k]);
+            want[k] = (g + per_cta[k] - 1) / per_cta[k] * per_cta[k] * cw[k];       // launches round up to whole CTAs
+        }
+        uint64_t lo[4]; lo[0] = 0;
+        lo[1] = std::min<uint64_t>(want[0], c.pool_words / 2);
+        const uint64_t rest_pool = c.pool_words - lo[1];
+        const uint64_t w12 = want[1] + want[2];
+        lo[2] = lo[1] + (w12 <= rest_pool ? want[1] : (uint64_t)((double)rest_pool * ((double)want[1] / (double)w12)));
+        lo[3] = c.pool_words;
+        for (int k = 1; k < 4; ++k) lo[k] &= ~63ull;
+        LCD_CUDA_OK(cudaEventRecord(ev_fork, s));
+        for (int k = 2; k >= 1; --k) {            // big problems first
+            if (cls[k].empty()) continue;
+            cudaStream_t ss = side[k - 1];
+            LCD_CUDA_OK(cudaStreamWaitEvent(ss, ev_fork, 0));
+            const size_t off = k == 1 ? cls[0].size() : cls[0].size() + cls[1].size();
+            if (launch(ss, cls[k], d_order.p + off, d_queue.p + k, cw[k], max_groups[k], k, false, lo[k], lo[k + 1], nullptr)) return -1;
+            LCD_CUDA_OK(cudaEventRecord(ev_join[k - 1], ss));
+        }
+        if (!cls[0].empty() && launch(s, cls[0], d_order.p, d_queue.p, cw[0], max_groups[0], 0, false, lo[0], lo[1], nullptr)) return -1;
+        for (int k = 1; k <= 2; ++k) if (!cls[k].empty()) LCD_CUDA_OK(cudaStreamWaitEvent(s, ev_join[k - 1], 0));
         // statuses back: anything that ran out of workspace is re-run with the full-matrix budget
         h_results.resize(n);
         LCD_CUDA_OK(cudaMemcpyAsync(h_results.data(), d_results.p, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, s));
@@ -152,7 +241,7 @@ struct PoaPlan : Plan {
         n_rescued = (int)rescue.size();
         if (!rescue.empty()) {
             rescue_words = std::min<uint64_t>((rescue_words + 63) & ~63ull, (c.pool_words / WARPS_PER_CTA) & ~63ull);
-            if (launch(s, rescue, rescue_words, max_groups)) return -1;
+            if (launch(s, rescue, d_order.p, d_queue.p, rescue_words, c.sm_count * 4, 2, true, 0, c.pool_words, nullptr)) return -1;
         }
         return 0;
     }
@@ -174,6 +263,19 @@ struct PoaPlan : Plan {
 
     int work_units(cudaStream_t s, uint64_t *units) override {
         if (download(s)) return -1;
+#ifdef LCD_POA_TIMING
+        {   // debug: phase cycles of the 12 slowest problems and the batch totals
+            std::vector<int> idx(n); for (int i = 0; i < n; ++i) idx[i] = i;
+            auto tot = [&](int i) { const DevResult &r = h_results[i]; return r.t_dp + r.t_bt + r.t_add + r.t_after + r.t_fin; };
+            std::sort(idx.begin(), idx.end(), [&](int x, int y) { return tot(x) > tot(y); });
+            unsigned long long T[5] = {0, 0, 0, 0, 0};
+            for (int i = 0; i < n; ++i) { const DevResult &r = h_results[i]; T[0] += r.t_dp; T[1] += r.t_bt; T[2] += r.t_add; T[3] += r.t_after; T[4] += r.t_fin; }
+            fprintf(stderr, "[poa timing] batch Mcycles: dp %.1f bt %.1f add %.1f after %.1f fin %.1f\n", T[0] / 1e6, T[1] / 1e6, T[2] / 1e6, T[3] / 1e6, T[4] / 1e6);
+            for (int k = 0; k < std::min(n, 12); ++k) { const int i = idx[k]; const DevResult &r = h_results[i];
+                fprintf(stderr, "[poa timing] #%d reads %d max_len %d nodes %d cells %u : dp %.1f bt %.1f add %.1f after %.1f fin %.1f Mcycles\n", i, problems[i].n_reads,
+                        problems[i].max_len, r.n_nodes, r.cells_lo, r.t_dp / 1e6, r.t_bt / 1e6, r.t_add / 1e6, r.t_after / 1e6, r.t_fin / 1e6); }
+        }
+#endif
         uint64_t t = 0;
         for (int i = 0; i < n; ++i) t += ((uint64_t)h_results[i].cells_hi << 32) | h_results[i].cells_lo;
         *units = t;

@@ -14,6 +14,7 @@ namespace wfa {
 constexpr int RING = 32;            // >= max_score_scope (26 for longcallD's penalties)
 constexpr int NCOMP = 5;            // M, I1, D1, I2, D2
 enum { C_M = 0, C_I1 = 1, C_D1 = 2, C_I2 = 3, C_D2 = 4 };
+constexpr int STATUS_ESCALATED = -100;   // internal: handed over to the CTA kernel
 constexpr int WARP_GROUPS_PER_CTA = 8;
 constexpr int CTA_GROUP_THREADS = 256;
 constexpr int WARP_SEQ_SMEM = 2560;   // bytes of staged pattern+text per warp group
@@ -64,6 +65,11 @@ struct KernelArgs {
     // (bit set = in use) and returned when the problem that took them finishes
     uint32_t overflow_base, n_chunks;
     uint32_t *chunk_bitmap;
+    // escalation: a warp group gives up a problem whose score reaches esc_score (quadratic work on 32
+    // lanes) and queues it for the CTA kernel; n_dev (if set) overrides n with a device-side count
+    int32_t esc_score;
+    int32_t *esc_list; uint32_t *esc_count;
+    const uint32_t *n_dev;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -531,7 +537,7 @@ template <int G> struct Aligner {
 
     // ---- whole alignment (wavefront_unialign.c:242-275 + terminate :146-236) ----
     __device__ void align(const Problem &pb, DevResult *res, uint8_t *seq_smem, int seq_smem_bytes,
-                          uint32_t arena_lo, uint32_t arena_hi) {
+                          uint32_t arena_lo, uint32_t arena_hi, int problem_index) {
         plen = pb.plen; tlen = pb.tlen; par = pb.par;
         cur = arena_lo; end = arena_hi; oom = false; cells = 0; chunk_head = 0xffffffffu;
         // stage sequences (+ sentinel padding) in shared memory when they fit
@@ -573,6 +579,7 @@ template <int G> struct Aligner {
             while (!done) {
                 ++score;
                 if (score >= pb.s_cap || oom) { status = oom ? LCD_WFA_STATUS_OOM : LCD_WFA_STATUS_ERROR; break; }
+                if (a.esc_score > 0 && score >= a.esc_score) { status = STATUS_ESCALATED; break; }
                 const int st = step(score, num_null_steps);
                 if (!(st & 1)) {
                     if (num_null_steps > max_score_scope) { unreachable = true; break; }
@@ -611,6 +618,7 @@ template <int G> struct Aligner {
                 r.cells_lo = (uint32_t)cells; r.cells_hi = (uint32_t)(cells >> 32);
                 *res = r;
                 chunks_release();
+                if (status == STATUS_ESCALATED) a.esc_list[atomicAdd(a.esc_count, 1u)] = problem_index;
             }
         }
         g.sync();

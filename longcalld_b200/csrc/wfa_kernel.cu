@@ -54,14 +54,15 @@ wfa_kernel(const KernelArgs a) {
     al.gmeta = a.meta + (size_t)group_id * a.meta_cap;
     const uint32_t arena_lo = a.arena_base + (uint32_t)group_id * a.arena_units;
     const uint32_t arena_hi = arena_lo + a.arena_units;
+    const uint32_t n_items = a.n_dev ? *a.n_dev : (uint32_t)a.n;
     for (;;) {
         if (al.g.lane == 0) next_item[gi] = atomicAdd(a.queue, 1u);
         al.g.sync();
         const uint32_t item = next_item[gi];
         al.g.sync();
-        if (item >= (uint32_t)a.n) break;
+        if (item >= n_items) break;
         const int pi = a.order[item];
-        al.align(a.problems[pi], a.results + pi, seqbuf + gi * SEQ_BYTES, SEQ_BYTES, arena_lo, arena_hi);
+        al.align(a.problems[pi], a.results + pi, seqbuf + gi * SEQ_BYTES, SEQ_BYTES, arena_lo, arena_hi, pi);
     }
 }
 
@@ -90,13 +91,16 @@ static int score_cap(const lcd_wfa_params_t &p, int plen, int tlen) {
     return (int)std::min<long>(cap, INT32_MAX / 2);
 }
 
+constexpr int ESC_SCORE = 160;      // warp groups hand problems over to the CTA kernel at this score
+
 struct WfaPlan : Plan {
     DevBuf<uint8_t> d_seqs;
     DevBuf<Problem> d_problems;
     DevBuf<int32_t> d_order_small, d_order_large;
     DevBuf<char> d_ops;
     DevBuf<DevResult> d_results;
-    DevBuf<uint32_t> d_queue;     // [0] small, [1] large
+    DevBuf<uint32_t> d_queue;     // [0] small, [1] large, [2] escalated, [3] number of escalated problems
+    DevBuf<int32_t> d_esc_list;
     std::vector<Problem> problems;
     std::vector<int64_t> ops_dev_off;
     int n_small = 0, n_large = 0;
@@ -150,7 +154,10 @@ struct WfaPlan : Plan {
         std::vector<int32_t> small, large;
         for (int i = 0; i < n; ++i) {
             const Problem &p = problems[i];
-            const bool is_small = ((p.plen + 27) & ~15) + ((p.tlen + 27) & ~15) <= WARP_SEQ_SMEM && p.s_cap <= 4096;
+            // a length difference alone already costs gap_cost(|d|): such problems never finish below the
+            // escalation score, so they go to the CTA kernel directly
+            const bool is_small = ((p.plen + 27) & ~15) + ((p.tlen + 27) & ~15) <= WARP_SEQ_SMEM && p.s_cap <= 4096 &&
+                                  gap_cost(params[i], std::abs(p.tlen - p.plen)) < ESC_SCORE;
             (is_small ? small : large).push_back(i);
         }
         auto by_size = [&](int32_t x, int32_t y) {
@@ -169,7 +176,8 @@ struct WfaPlan : Plan {
         if (d_order_large.upload(large.data(), large.size(), s)) return -1;
         if (d_ops.alloc(ops_bytes + 16)) return -1;
         if (d_results.alloc(n)) return -1;
-        if (d_queue.alloc(2)) return -1;
+        if (d_queue.alloc(4)) return -1;
+        if (d_esc_list.alloc(std::max(n_small, 1))) return -1;
         LCD_CUDA_OK(cudaStreamSynchronize(s));      // host staging vectors go out of scope
         LCD_CUDA_OK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
         LCD_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
@@ -183,7 +191,9 @@ struct WfaPlan : Plan {
         // pool layout (16-byte units): [meta small | meta large | arenas small | arenas large | overflow]
         const int occ_small = 4;                                   // CTAs per SM of the warp kernel
         int grid_small = n_small ? std::min((n_small + WARP_GROUPS_PER_CTA - 1) / WARP_GROUPS_PER_CTA, c.sm_count * occ_small) : 0;
-        int grid_large = n_large ? std::min(n_large, c.sm_count * 2) : 0;
+        // CTA groups serve the pre-classified large problems and, afterwards, whatever the warp kernel escalates
+        int grid_large = (n_large || n_small) ? c.sm_count * 2 : 0;
+        const int cap_large = std::max(this->cap_large, n_small ? cap_small : 0);
         const size_t groups_small = (size_t)grid_small * WARP_GROUPS_PER_CTA, groups_large = grid_large;
         const size_t pool_units = c.pool_words / 4;
         const size_t meta_small_units = groups_small * (size_t)cap_small * (sizeof(WfSet) / 16);
@@ -205,7 +215,8 @@ struct WfaPlan : Plan {
         ka.pool = c.pool; ka.chunk_bitmap = c.chunk_bitmap;
         ka.overflow_base = (uint32_t)(meta_small_units + meta_large_units + arenas);
         ka.n_chunks = (uint32_t)n_chunks;
-        LCD_CUDA_OK(cudaMemsetAsync(d_queue.p, 0, 2 * sizeof(uint32_t), s));
+        ka.esc_score = 0; ka.esc_list = d_esc_list.p; ka.esc_count = d_queue.p + 3; ka.n_dev = nullptr;
+        LCD_CUDA_OK(cudaMemsetAsync(d_queue.p, 0, 4 * sizeof(uint32_t), s));
         LCD_CUDA_OK(cudaMemsetAsync(c.chunk_bitmap, 0, sizeof(uint32_t) * Context::BITMAP_WORDS, s));
         static bool attr_set = false;
         if (!attr_set) {
@@ -213,15 +224,15 @@ struct WfaPlan : Plan {
             LCD_CUDA_OK(cudaFuncSetAttribute(wfa_kernel<CTA_GROUP_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(CTA_GROUP_THREADS)));
             attr_set = true;
         }
-        if (grid_large) {          // large problems on the side stream, concurrently with the small ones
+        KernelArgs kl = ka;
+        kl.meta = reinterpret_cast<WfSet *>(c.pool + meta_small_units * 4); kl.meta_cap = cap_large;
+        kl.arena_base = (uint32_t)(meta_small_units + meta_large_units + arena_small * groups_small);
+        kl.arena_units = (uint32_t)arena_large;
+        if (n_large) {             // large problems on the side stream, concurrently with the small ones
             LCD_CUDA_OK(cudaEventRecord(ev_fork, s));
             LCD_CUDA_OK(cudaStreamWaitEvent(side, ev_fork, 0));
-            KernelArgs kl = ka;
             kl.order = d_order_large.p; kl.n = n_large; kl.queue = d_queue.p + 1;
-            kl.meta = reinterpret_cast<WfSet *>(c.pool + meta_small_units * 4); kl.meta_cap = cap_large;
-            kl.arena_base = (uint32_t)(meta_small_units + meta_large_units + arena_small * groups_small);
-            kl.arena_units = (uint32_t)arena_large;
-            wfa_kernel<CTA_GROUP_THREADS><<<grid_large, CTA_GROUP_THREADS, smem_bytes(CTA_GROUP_THREADS), side>>>(kl);
+            wfa_kernel<CTA_GROUP_THREADS><<<std::min(n_large, grid_large), CTA_GROUP_THREADS, smem_bytes(CTA_GROUP_THREADS), side>>>(kl);
             LCD_CUDA_OK(cudaGetLastError());
             LCD_CUDA_OK(cudaEventRecord(ev_join, side));
             c.launches++;
@@ -232,11 +243,18 @@ struct WfaPlan : Plan {
             ks.meta = reinterpret_cast<WfSet *>(c.pool); ks.meta_cap = cap_small;
             ks.arena_base = (uint32_t)(meta_small_units + meta_large_units);
             ks.arena_units = (uint32_t)arena_small;
+            ks.esc_score = ESC_SCORE;
             wfa_kernel<32><<<grid_small, 32 * WARP_GROUPS_PER_CTA, smem_bytes(32), s>>>(ks);
             LCD_CUDA_OK(cudaGetLastError());
             c.launches++;
         }
-        if (grid_large) LCD_CUDA_OK(cudaStreamWaitEvent(s, ev_join, 0));
+        if (n_large) LCD_CUDA_OK(cudaStreamWaitEvent(s, ev_join, 0));
+        if (grid_small) {          // the escalated problems, one CTA each (count read on the device)
+            kl.order = d_esc_list.p; kl.n = 0; kl.n_dev = d_queue.p + 3; kl.queue = d_queue.p + 2;
+            wfa_kernel<CTA_GROUP_THREADS><<<grid_large, CTA_GROUP_THREADS, smem_bytes(CTA_GROUP_THREADS), s>>>(kl);
+            LCD_CUDA_OK(cudaGetLastError());
+            c.launches++;
+        }
         return 0;
     }
 

@@ -10,8 +10,11 @@
 namespace lcd { namespace poa {
 struct HostLanes {
     struct vec { int v[32]; };
-    static constexpr int STRIDE = 1;
+    static constexpr int NT = 1, NW = 1;
+    static constexpr bool TWO_PHASE = false;
     static int lane() { return 0; }
+    static int tid() { return 0; }
+    static int warp() { return 0; }
     static void sync() {}
     static vec load(const int16_t *p) { vec r; for (int l = 0; l < 32; ++l) r.v[l] = p[l]; return r; }
     static vec load_m1(const int16_t *p, int first) { vec r; r.v[0] = first; for (int l = 1; l < 32; ++l) r.v[l] = p[l - 1]; return r; }
@@ -31,9 +34,12 @@ struct HostLanes {
         return true;
     }
 };
+struct HostLanes2 : HostLanes { static constexpr bool TWO_PHASE = true; };   // exercises the two-phase (CTA) row code
 }}
 using namespace lcd::poa;
 
+static int mode = 0;     /* bit0: thread-per-problem lane policy (packed int16x2); bit1: tight workspace budgets; bit2: on-chip previous-row cache; bit3: two-phase rows (the CTA-per-problem code path) */
+extern "C" void emu_poa_mode(int m) { mode = m; }
 extern "C" int emu_poa(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len,
                        const lcd_poa_params_t *p, uint8_t *cons, int32_t *cons_len,
                        uint8_t *msa, int32_t *msa_len, int32_t msa_cap) {
@@ -50,8 +56,11 @@ extern "C" int emu_poa(int n_seq, const uint8_t *seqs, const int64_t *seq_off, c
     a.problems = &pb; a.order = &order; a.n = 1; a.queue = &queue; a.seqs = seqs; a.read_off = seq_off; a.read_len = seq_len;
     a.cons = cons; a.msa = msa_pool.data(); a.msa_cap = (unsigned long long)msa_cap; a.msa_used = &msa_used;
     a.results = &dr; a.arena = arena; a.arena_words = words;
-    Poa<HostLanes> poa;
-    poa.run(a, pb, &dr, arena);
+    pb.node_cap = pb.sum_len + 34; pb.edge_cap = 3 * (pb.sum_len + n_seq) + 64;
+    if (mode & 2) { pb.node_cap = 2 * pb.max_len + 64; pb.edge_cap = 3 * pb.node_cap; }   /* tight first-attempt budgets */
+    if (mode & 1) { Poa<ThreadLanes> poa; poa.run(a, pb, &dr, arena); }
+    else if (mode & 8) { Poa<HostLanes2> poa; static int gsbuf[Poa<HostLanes2>::GS_INTS]; poa.gs = gsbuf; poa.run(a, pb, &dr, arena); }
+    else { Poa<HostLanes> poa; static int16_t cache[2 * 3 * 8 * 32]; poa.row_cache = (mode & 4) ? cache : nullptr; poa.run(a, pb, &dr, arena); }
     *cons_len = dr.cons_len; *msa_len = 0;
     if (dr.status == ST_OK && msa) { *msa_len = dr.msa_len; memcpy(msa, msa_pool.data() + dr.msa_off, (size_t)(n_seq + 1) * dr.msa_len); }
     return dr.status;

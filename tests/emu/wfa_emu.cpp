@@ -43,7 +43,7 @@ extern "C" int emu_wfa_align(const uint8_t *pattern, int plen, const uint8_t *te
     Aligner<1> al(a);
     al.g.lane = 0; al.g.ring = ring; al.g.red = red; al.g.phase = 0;
     al.pool = pool; al.gmeta = meta.data();
-    al.align(p, &dr, seq_smem.data(), WARP_SEQ_SMEM, a.arena_base, a.arena_base + a.arena_units);
+    al.align(p, &dr, seq_smem.data(), WARP_SEQ_SMEM, a.arena_base, a.arena_base + a.arena_units, 0);
     res->status = dr.status; res->score = dr.score; res->n_ops = dr.n_ops; res->end_v = dr.end_v; res->end_h = dr.end_h;
     if (ops && dr.status >= 0) { memcpy(ops, opsbuf.data() + dr.ops_begin, dr.n_ops); ops[dr.n_ops] = 0; }
     return 0;

@@ -18,9 +18,13 @@ def emu():
     return C.CDLL(os.path.join(EMU_DIR, "libpoa_emu.so"))
 
 
+# mode bits: 1 = thread-per-problem lane policy (packed int16x2), 2 = tight first-attempt workspace budgets,
+#            4 = on-chip previous-row cache (warp policy), 8 = two-phase rows (CTA-per-problem policy)
+@pytest.mark.parametrize("mode", [0, 3, 4, 8])
 @pytest.mark.parametrize("tech,mbp,seed", [("hifi", 0.12, 41), ("ont", 0.03, 42)])
-def test_emu_poa_vs_oracle(emu, oracle, tech, mbp, seed):
+def test_emu_poa_vs_oracle(emu, oracle, tech, mbp, seed, mode):
     from longcalld_b200 import synth
+    emu.emu_poa_mode(mode)
     n = 0
     for r in synth.make_regions(mbp, tech, seed=seed):
         for hap in (1, 2):
@@ -40,6 +44,7 @@ def test_emu_poa_vs_oracle(emu, oracle, tech, mbp, seed):
 
 def test_emu_poa_vs_fixtures(emu):
     import hashlib
+    emu.emu_poa_mode(0)
     g = T.load_golden("poa_lcd")
     for i, c in enumerate(g["cases"][::3]):
         seqs = [np.array([int(x) for x in s], dtype=np.uint8) for s in c["seqs"]]

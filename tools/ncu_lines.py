@@ -1,10 +1,11 @@
 #!/usr/bin/env python3
 """Per-source-line hot spots of one kernel: joins `ncu --page source --csv` (SASS rows with stall samples and
 instruction counts) with `nvdisasm -g` line info of the same cubin.  Usage:
-  tools/ncu_lines.py <report.ncu-rep> <cubin> [top_n]"""
+  tools/ncu_lines.py <report.ncu-rep> <cubin> [top_n] [mangled-name substring of the kernel, when the cubin holds several]"""
 import csv, re, subprocess, sys
 rep, cubin = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+fun = sys.argv[4] if len(sys.argv) > 4 else None
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hi = next(i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r)
@@ -12,6 +13,15 @@ h = rows[hi]
 si, ie, te = h.index("# Samples"), h.index("Instructions Executed"), h.index("Thread Instructions Executed")
 sass = [(int(r[si]), int(r[ie]), int(r[te]), r[h.index("Source")].strip()) for r in rows[hi + 1:] if len(r) > te and r[si].isdigit()]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+if fun:      # keep only the .text section of the requested kernel
+    keep, out_l = False, []
+    for l in dis:
+        m = re.match(r"\s*\.section\s+(\S+)", l)
+        if m:
+            keep = m.group(1).startswith(".text.") and fun in m.group(1)
+        if keep:
+            out_l.append(l)
+    dis = out_l
 lines, cur = [], ("?", 0)
 for l in dis:
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
