@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-_SO = os.path.join(_CSRC, "liblcd_gpu.so")
+_SO = os.environ.get("LCD_GPU_SO") or os.path.join(_CSRC, "liblcd_gpu.so")   # LCD_GPU_SO: debug builds (e.g. -DLCD_POA_TIMING)
 
 HEUR_NONE, HEUR_ADAPTIVE, HEUR_ZDROP = 0, 1, 2
 GAP_RIGHT_ALN, GAP_LEFT_ALN = 0, 1           # reference src/call_var_main.h (LONGCALLD_GAP_*_ALN)

@@ -4,6 +4,7 @@
   wfa_utest.json.gz   WFA2-lib's own regression vectors (WFA2-lib/tests/wfa.utest.seq + the
                       match==0 goldens in tests/wfa.utest.check/: affine, affine2p, p0-p2,
                       wfapt0/1) -- pins the recurrence, the backtrace tie-breaks and wf-adaptive.
+  edlib_lcd.json.gz   outputs of the UNMODIFIED reference edlib (NW / HW, path) on seeded inputs.
   wfa_lcd.json.gz     outputs of the UNMODIFIED reference WFA2-lib (oracle/_ref/libref_shim.so)
                       at longcallD's own parameter points (src/align.h:21-26, src/align.c:398-406)
                       on seeded inputs: end2end 2p/no-heuristic, 1p/wf-adaptive, 2p/z-drop.
@@ -121,9 +122,25 @@ def poa_lcd():
     return {"cases": cases}
 
 
+def edlib_lcd():
+    """Outputs of the UNMODIFIED edlib (oracle/_ref/libref_shim.so) as longcallD calls it (src/align.c:210-275:
+    k = -1, NW or HW, TASK_PATH) on seeded read-vs-consensus / infix shaped inputs, incl. one Hirschberg case."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from test_oracle_edlib import edlib_cases
+    ref = T.ref_lib()
+    rng = np.random.default_rng(20261018)
+    cases = []
+    for q, t, mode in edlib_cases(rng, 330) + edlib_cases(rng, 2, big=True)[:1]:
+        st, ed, s, e, aln = T.edlib_align(ref, "ref_edlib_align", q, t, mode, 1)
+        assert st == 0
+        cases.append({"q": "".join(map(str, q.tolist())), "t": "".join(map(str, t.tolist())), "mode": mode,
+                      "ed": ed, "start": s, "end": e, "aln": "".join(map(str, aln))})
+    return {"cases": cases}
+
+
 def main():
     only = sys.argv[1:]
-    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd), ("poa_lcd", poa_lcd)):
+    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd), ("poa_lcd", poa_lcd), ("edlib_lcd", edlib_lcd)):
         if only and name not in only:
             continue
         path = os.path.join(HERE, name + ".json.gz")
