@@ -88,6 +88,35 @@ void lcd_plan_destroy(lcd_plan_t *plan);
  * edlib block-columns, POA banded cells) -- filled by the kernels themselves. */
 int  lcd_plan_work_units(lcd_plan_t *plan, void *stream, uint64_t *units);
 
+/* ---------------------------------------------------------------- K7: edlib NW / HW with path
+ * Replaces edlibAlign(query, qlen, target, tlen, edlibNewAlignConfig(-1, mode, task, NULL, 0)) as called by
+ * edlib_edit_distance / edlib_xgaps / edlib_end2end_aln / edlib_infix_aln (src/align.c:210-275) and reading
+ * result.editDistance, startLocations[0], endLocations[0], alignment, alignmentLength.  The reductions of the
+ * path that the reference applies next (edlibAlignmentToXGAPS / XID, src/align.c:164-208) are host glue. */
+enum { LCD_EDLIB_MODE_NW = 0, LCD_EDLIB_MODE_SHW = 1, LCD_EDLIB_MODE_HW = 2 };          /* EdlibAlignMode */
+enum { LCD_EDLIB_STATUS_OK = 0, LCD_EDLIB_STATUS_SYMBOL = -1 /* a base code > 5 */, LCD_EDLIB_STATUS_NO_SPLIT = -2,
+       LCD_EDLIB_STATUS_OOM = -3, LCD_EDLIB_STATUS_NO_SOLUTION = -4 };
+typedef struct {
+    int32_t status;                /* LCD_EDLIB_STATUS_* */
+    int32_t edit_distance;         /* result.editDistance */
+    int32_t start_loc, end_loc;    /* startLocations[0] (-1 when want_path == 0: EDLIB_TASK_DISTANCE) / endLocations[0] */
+    int32_t aln_len;               /* result.alignmentLength (0 when want_path == 0) */
+} lcd_edlib_result_t;
+
+/* Problem i aligns query = seqs[query_off[i] .. +qlen[i]) to target = seqs[target_off[i] .. +tlen[i]) (base codes 0..5).
+ * want_path[i] != 0 (EDLIB_TASK_PATH): the path (EDLIB_EDOP_* codes 0 '=', 1 insert, 2 delete, 3 'X') goes to
+ * aln[aln_off[i] ..], which needs qlen + tlen bytes.  All pointers are HOST memory. */
+int lcd_edlib_batch(int n, const uint8_t *seqs, size_t seqs_len,
+                    const int64_t *query_off, const int32_t *qlen,
+                    const int64_t *target_off, const int32_t *tlen,
+                    const int32_t *mode, const int32_t *want_path,
+                    uint8_t *aln, const int64_t *aln_off, lcd_edlib_result_t *results);
+lcd_plan_t *lcd_edlib_plan_create(int n, const uint8_t *seqs, size_t seqs_len,
+                                  const int64_t *query_off, const int32_t *qlen,
+                                  const int64_t *target_off, const int32_t *tlen,
+                                  const int32_t *mode, const int32_t *want_path);
+int  lcd_edlib_plan_fetch(lcd_plan_t *plan, void *stream, uint8_t *aln, const int64_t *aln_off, lcd_edlib_result_t *results);
+
 /* ---------------------------------------------------------------- K5: abPOA consensus + MSA
  * One *problem* is the progressive partial-order alignment of the reads of one (noisy region,
  * haplotype): it replaces the abPOA call sequence of abpoa_partial_aln_msa_cons (src/align.c:762-870;

@@ -8,9 +8,11 @@ call raises ``LcdGpuError`` when the library or a B200 is missing.
 from .capi import (LcdGpuError, lib, lib_path, build_library, init, shutdown, launch_count, stream,  # noqa: F401
                    WfaParams, WfaResult, wfa_params, WfaPlan, wfa_batch,
                    HEUR_NONE, HEUR_ADAPTIVE, HEUR_ZDROP,
-                   PoaParams, poa_params, PoaPlan, poa_batch, pack_poa)
+                   PoaParams, poa_params, PoaPlan, poa_batch, pack_poa,
+                   MODE_NW, MODE_SHW, MODE_HW, EdlibPlan, edlib_batch, xgaps)
 
 __all__ = ["LcdGpuError", "lib", "lib_path", "build_library", "init", "shutdown", "launch_count", "stream",
            "WfaParams", "WfaResult", "wfa_params", "WfaPlan", "wfa_batch",
            "HEUR_NONE", "HEUR_ADAPTIVE", "HEUR_ZDROP",
-           "PoaParams", "poa_params", "PoaPlan", "poa_batch", "pack_poa"]
+           "PoaParams", "poa_params", "PoaPlan", "poa_batch", "pack_poa",
+           "MODE_NW", "MODE_SHW", "MODE_HW", "EdlibPlan", "edlib_batch", "xgaps"]

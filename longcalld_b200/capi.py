@@ -224,6 +224,77 @@ def wfa_batch(pairs, params):
     return out
 
 
+# ----------------------------------------------------------------------------- K7: edlib
+MODE_NW, MODE_SHW, MODE_HW = 0, 1, 2          # EdlibAlignMode (reference edlib/include/edlib.h)
+EDLIB_RESULT_DTYPE = np.dtype([(n, np.int32) for n in ("status", "edit_distance", "start_loc", "end_loc", "aln_len")])
+
+
+def _edlib_modes(n, mode, want_path):
+    m = np.empty(n, dtype=np.int32); m[:] = mode
+    w = np.empty(n, dtype=np.int32); w[:] = want_path
+    return m, w
+
+
+class EdlibPlan(_Plan):
+    """(query, target) pairs resident in HBM; run() re-executes the batch."""
+
+    def __init__(self, seqs, q_off, qlen, t_off, tlen, mode=MODE_NW, want_path=1):
+        n = len(qlen)
+        self.seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        self.q_off = np.ascontiguousarray(q_off, dtype=np.int64)
+        self.t_off = np.ascontiguousarray(t_off, dtype=np.int64)
+        self.qlen = np.ascontiguousarray(qlen, dtype=np.int32)
+        self.tlen = np.ascontiguousarray(tlen, dtype=np.int32)
+        self.mode, self.want_path = _edlib_modes(n, mode, want_path)
+        h = lib().lcd_edlib_plan_create(C.c_int(n), _ptr(self.seqs, C.c_uint8), C.c_size_t(self.seqs.size),
+                                        _ptr(self.q_off, C.c_int64), _ptr(self.qlen, C.c_int32),
+                                        _ptr(self.t_off, C.c_int64), _ptr(self.tlen, C.c_int32),
+                                        _ptr(self.mode, C.c_int32), _ptr(self.want_path, C.c_int32))
+        super().__init__(h, n)
+
+    def fetch(self, stream=None, want_aln=True):
+        res = np.zeros(self.n, dtype=EDLIB_RESULT_DTYPE)
+        cap = self.qlen.astype(np.int64) + self.tlen + 2
+        off = np.zeros(self.n + 1, dtype=np.int64)
+        np.cumsum(cap, out=off[1:])
+        aln = np.zeros(max(int(off[-1]), 1), dtype=np.uint8) if want_aln else None
+        rc = lib().lcd_edlib_plan_fetch(self.h, C.c_void_p(stream or 0), _ptr(aln, C.c_uint8) if want_aln else None,
+                                        _ptr(off, C.c_int64) if want_aln else None, res.ctypes.data_as(C.c_void_p))
+        _check(rc, "lcd_edlib_plan_fetch")
+        return res, aln, off
+
+
+def edlib_batch(pairs, mode=MODE_NW, want_path=1):
+    """Drop-in batch call over HOST buffers (lcd_edlib_batch) for [(query, target), ...].
+    Returns [(status, edit_distance, start_loc, end_loc, path bytes)] per problem."""
+    n = len(pairs)
+    if n == 0:
+        return []
+    seqs, qo, ql, to, tl = pack_pairs(pairs)
+    m, w = _edlib_modes(n, mode, want_path)
+    res = np.zeros(n, dtype=EDLIB_RESULT_DTYPE)
+    cap = ql.astype(np.int64) + tl + 2
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(cap, out=off[1:])
+    aln = np.zeros(max(int(off[-1]), 1), dtype=np.uint8)
+    rc = lib().lcd_edlib_batch(C.c_int(n), _ptr(seqs, C.c_uint8), C.c_size_t(seqs.size), _ptr(qo, C.c_int64), _ptr(ql, C.c_int32),
+                               _ptr(to, C.c_int64), _ptr(tl, C.c_int32), _ptr(m, C.c_int32), _ptr(w, C.c_int32),
+                               _ptr(aln, C.c_uint8), _ptr(off, C.c_int64), res.ctypes.data_as(C.c_void_p))
+    _check(rc, "lcd_edlib_batch")
+    return [(int(r["status"]), int(r["edit_distance"]), int(r["start_loc"]), int(r["end_loc"]),
+             aln[off[i]:off[i] + r["aln_len"]].tobytes()) for i, r in enumerate(res)]
+
+
+def xgaps(path):
+    """edlibAlignmentToXGAPS (reference src/align.c:189-208): mismatches + gap openings of an edlib path."""
+    a = np.frombuffer(path, dtype=np.uint8)
+    if a.size == 0:
+        return 0
+    gap = (a == 1) | (a == 2)
+    opens = gap & np.concatenate(([True], a[1:] != a[:-1]))
+    return int((a == 3).sum() + opens.sum())
+
+
 # ----------------------------------------------------------------------------- K5: POA
 class PoaParams(C.Structure):
     _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open1", C.c_int32), ("gap_ext1", C.c_int32),
