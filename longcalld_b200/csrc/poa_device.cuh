@@ -90,6 +90,7 @@ struct WS {
     int *base, *in_off, *in_n, *in_cap, *out_off, *out_n, *out_cap, *n_read, *n_span;
     int *aln_off, *aln_n, *aln_cap, *next, *remain, *maxl, *maxr, *msa_rank;
     int *wsum, *order, *tmp, *s1, *s2, *s3, *s4, *s5, *s6, *s7;
+    int *pos, *fp_id, *fp_ps;                        // inverse of order[]; first (heaviest) in-edge of a node: source and path score
     int4 *rinfo;                                     // per node: DP row descriptor of the current read (see Poa::pack)
     int4 *in_pool; int in_top, in_capacity;          // {from, w, ps, -}
     int *out_pool; int out_top, out_capacity, out_stride, rid_w;   // {to, w, rid[2*rid_w]}
@@ -107,6 +108,7 @@ struct WarpLanes {
     typedef int vec;                                  // this lane's cell (int16 value in an int)
     static constexpr int NT = 32, NW = 1;             // threads / warps cooperating on one problem
     static constexpr bool TWO_PHASE = false;
+    static constexpr bool STRIP = true;               // rows are computed by Poa::strip_row (each lane owns C consecutive columns)
     __device__ static __forceinline__ int lane() { return threadIdx.x & 31; }
     __device__ static __forceinline__ int tid() { return threadIdx.x & 31; }
     __device__ static __forceinline__ int warp() { return 0; }
@@ -144,6 +146,7 @@ struct WarpLanes {
 template <int W> struct CtaLanes : WarpLanes {
     static constexpr int NT = 32 * W, NW = W;
     static constexpr bool TWO_PHASE = true;
+    static constexpr bool STRIP = false;
     __device__ static __forceinline__ int tid() { return threadIdx.x; }
     __device__ static __forceinline__ int warp() { return threadIdx.x >> 5; }
     __device__ static __forceinline__ void sync() { __syncthreads(); }
@@ -160,6 +163,7 @@ struct ThreadLanes {
     struct vec { uint32_t w[16]; };
     static constexpr int NT = 1, NW = 1;
     static constexpr bool TWO_PHASE = false;
+    static constexpr bool STRIP = false;
     __device__ static __forceinline__ int lane() { return 0; }
     __device__ static __forceinline__ int tid() { return 0; }
     __device__ static __forceinline__ int warp() { return 0; }
@@ -255,7 +259,8 @@ template <class L> struct Poa {
         w.N = N;
         int **arr[] = { &w.base, &w.in_off, &w.in_n, &w.in_cap, &w.out_off, &w.out_n, &w.out_cap, &w.n_read, &w.n_span,
                         &w.aln_off, &w.aln_n, &w.aln_cap, &w.next, &w.remain, &w.maxl, &w.maxr, &w.msa_rank,
-                        &w.wsum, &w.order, &w.tmp, &w.s1, &w.s2, &w.s3, &w.s4, &w.s5, &w.s6, &w.s7 };
+                        &w.wsum, &w.order, &w.tmp, &w.s1, &w.s2, &w.s3, &w.s4, &w.s5, &w.s6, &w.s7,
+                        &w.pos, &w.fp_id, &w.fp_ps };
         for (unsigned i = 0; i < sizeof(arr) / sizeof(arr[0]); ++i) { *arr[i] = arena + top; top += (uint64_t)((N + 3) & ~3); }
         w.rinfo = reinterpret_cast<int4 *>(arena + top); top += (uint64_t)N * 4;
         w.in_capacity = E; w.in_pool = reinterpret_cast<int4 *>(arena + top); top += (uint64_t)E * 4;
@@ -419,6 +424,271 @@ template <class L> struct Poa {
         add_edge(last_id, 1, 1 - last_new, 1, read_id);
     }
 
+
+#ifndef LCD_EMU
+    // ---- warp policy: backtrack and graph fusion with all 32 lanes ------------------------------------------
+    // The backtrack (simd_abpoa_cg_backtrack :309-458) yields, per query base, the graph node it is matched to
+    // (path[q] = node id) or -1 (inserted base); deletions leave no trace, which is all abpoa_add_subgraph_alignment
+    // needs.  Runs of plain diagonal matches through the heaviest in-edge -- almost every step for a read that
+    // agrees with the graph -- are verified 32 at a time: lane l checks step l of the run along the topological
+    // order (its node's first in-edge must come from the node before it in the order, and the MATCH test of the
+    // reference must hold for that edge, which is then the first edge the reference would accept).  Any other step
+    // is taken by the scalar rules, executed uniformly by the warp.
+    __device__ int backtrack_warp(const uint8_t *query, int qlen, int *path) {
+        const int lane = threadIdx.x & 31;
+        const int e1 = par.gap_ext1, e2 = par.gap_ext2;
+        for (int q = lane; q < qlen; q += 32) path[q] = -1;
+        int best = inf_min, bi = 0, bj = 0;
+        {
+            const int4 *ie = w.in_pool + w.in_off[1];
+            for (int k = 0; k < w.in_n[1]; ++k) {
+                const int r = ie[k].x;
+                const Row rr = unpack(w.rinfo[r]);
+                const int e = qlen > rr.end ? rr.end : qlen;
+                const int s = cell(rr, 0, e);
+                if (s > best) { best = s; bi = r; bj = e; }
+            }
+        }
+        __syncwarp();
+        enum { M_OP = 1, E1_OP = 2, E2_OP = 4, E_OP = 6, F1_OP = 8, F2_OP = 16, F_OP = 24, ALL_OP = 31 };
+        int id = bi, j = bj, cur_op = ALL_OP, rc = 0;
+        Row cur = unpack(w.rinfo[id]);
+        while (id != 0 && j > 0) {
+            if (cur_op == ALL_OP) {
+                const int pos = w.pos[id];
+                int ok = 0, nl = -1, pl = -1;
+                if (pos - lane >= 1 && j - lane >= 1) {
+                    nl = w.order[pos - lane]; pl = w.order[pos - lane - 1];
+                    if (w.fp_id[nl] == pl) {
+                        const Row rn = lane == 0 ? cur : unpack(w.rinfo[nl]), rp = unpack(w.rinfo[pl]);
+                        const int jl = j - lane;
+                        if (jl - 1 >= rp.beg && jl - 1 <= rp.end) {
+                            const int nb = w.base[nl], qb = query[jl - 1];
+                            const int s = (nb > 3 || qb > 3) ? 0 : (nb == qb ? par.match : -par.mismatch);
+                            ok = cell(rp, 0, jl - 1) + s + w.fp_ps[nl] == cell(rn, 0, jl);
+                        }
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                const int run = __ffs(~m) - 1 < 0 ? 32 : __ffs(~m) - 1;
+                if (run > 0) {
+                    if (lane < run) path[j - lane - 1] = nl;
+                    id = __shfl_sync(0xffffffffu, pl, run - 1);
+                    j -= run;
+                    cur = unpack(w.rinfo[id]);
+                    continue;
+                }
+            }
+            const int nb = w.base[id], qb = query[j - 1];
+            const int s = (nb > 3 || qb > 3) ? 0 : (nb == qb ? par.match : -par.mismatch);
+            const int4 *ie = w.in_pool + w.in_off[id];
+            const int nin = w.in_n[id];
+            const int hj = cell(cur, 0, j);
+            int hit = 0;
+            for (int pass = 0; pass < 2 && !hit; ++pass) {
+                if (pass == 1) {
+                    if (cur_op & E_OP) {
+                        const int e1j = cell(cur, 1, j), e2j = cell(cur, 2, j);
+                        for (int k = 0; k < nin && !hit; ++k) {
+                            const int4 e = ie[k];
+                            const int p = e.x, ps = e.z;
+                            const Row pr = unpack(w.rinfo[p]);
+                            if (j < pr.beg || j > pr.end) continue;
+                            const int phj = cell(pr, 0, j);
+                            if (cur_op & E1_OP) {
+                                const int pe = cell(pr, 1, j);
+                                const int okk = (cur_op & M_OP) ? (hj == pe + ps) : (e1j == pe - e1 + ps);
+                                if (okk) { cur_op = (phj - oe1 == pe) ? (M_OP | F_OP) : E1_OP; hit = 1; }
+                            }
+                            if (!hit && (cur_op & E2_OP)) {
+                                const int pe = cell(pr, 2, j);
+                                const int okk = (cur_op & M_OP) ? (hj == pe + ps) : (e2j == pe - e2 + ps);
+                                if (okk) { cur_op = (phj - oe2 == pe) ? (M_OP | F_OP) : E2_OP; hit = 1; }
+                            }
+                            if (hit) { id = p; cur = pr; }                 // DEL: the node is skipped by the read
+                        }
+                    }
+                    if (!hit && (cur_op & F_OP)) {
+                        const int hj1 = cell(cur, 0, j - 1);
+                        if (cur_op & F1_OP) {
+                            const int f = cell(cur, 3, j);
+                            if (!(cur_op & M_OP) || hj == f) {
+                                if (hj1 - oe1 == f) { cur_op = M_OP | E_OP; hit = 1; }
+                                else if (cell(cur, 3, j - 1) - e1 == f) { cur_op = F1_OP; hit = 1; }
+                            }
+                        }
+                        if (!hit && (cur_op & F2_OP)) {
+                            const int f = cell(cur, 4, j);
+                            if (!(cur_op & M_OP) || hj == f) {
+                                if (hj1 - oe2 == f) { cur_op = M_OP | E_OP; hit = 1; }
+                                else if (cell(cur, 4, j - 1) - e2 == f) { cur_op = F2_OP; hit = 1; }
+                            }
+                        }
+                        if (hit) --j;                                      // INS: path[j-1] stays -1
+                    }
+                    if (hit) break;
+                }
+                if (cur_op & M_OP) {
+                    for (int k = 0; k < nin; ++k) {
+                        const int4 e = ie[k];
+                        const int p = e.x, ps = e.z;
+                        const Row pr = unpack(w.rinfo[p]);
+                        if (j - 1 < pr.beg || j - 1 > pr.end) continue;
+                        if (cell(pr, 0, j - 1) + s + ps == hj) {
+                            if (lane == 0) path[j - 1] = id;
+                            id = p; cur = pr; --j; hit = 1; cur_op = ALL_OP;
+                            break;
+                        }
+                    }
+                }
+            }
+            if (!hit) { rc = ST_BACKTRACK; break; }
+        }
+        __syncwarp();
+        return rc;
+    }
+
+    // abpoa_add_graph_edge (:480-556) for the parallel fusion: every node is the source of at most one and the
+    // target of at most one edge of a read's path, so the 32 lanes update disjoint lists; only the bump cursors of
+    // the two edge pools (kept in the arena: tmp[8], tmp[9]) are shared and advanced atomically.
+    __device__ void add_edge_par(int from, int to, int check, int add_rid, int read_id) {
+        int exist = 0, oi = -1;
+        if (check) {
+            int4 *ie = w.in_pool + w.in_off[to];
+            for (int i = 0; i < w.in_n[to]; ++i) if (ie[i].x == from) { ie[i].y += 1; break; }
+            for (int i = 0; i < w.out_n[from]; ++i) { int *e = out_entry(from, i); if (e[0] == to) { e[1] += 1; exist = 1; oi = i; break; } }
+        }
+        if (!exist) {
+            if (w.in_n[to] == w.in_cap[to]) {
+                const int nc = w.in_cap[to] ? w.in_cap[to] * 2 : 2;
+                const int at = atomicAdd(&w.tmp[8], nc);
+                if (at + nc > w.in_capacity) { w.tmp[1] = 1; return; }
+                int4 *src = w.in_pool + w.in_off[to], *dst = w.in_pool + at;
+                for (int i = 0; i < w.in_n[to]; ++i) dst[i] = src[i];
+                w.in_off[to] = at; w.in_cap[to] = nc;
+            }
+            w.in_pool[w.in_off[to] + w.in_n[to]] = make_int4(from, 1, 0, 0);
+            w.in_n[to]++;
+            if (w.out_n[from] == w.out_cap[from]) {
+                const int nc = w.out_cap[from] ? w.out_cap[from] * 2 : 2;
+                const int at = atomicAdd(&w.tmp[9], nc);
+                if (at + nc > w.out_capacity) { w.tmp[1] = 1; return; }
+                int *src = w.out_pool + (size_t)w.out_off[from] * w.out_stride, *dst = w.out_pool + (size_t)at * w.out_stride;
+                const int nw = w.out_n[from] * w.out_stride;
+                for (int i = 0; i < nw; ++i) dst[i] = src[i];
+                w.out_off[from] = at; w.out_cap[from] = nc;
+            }
+            oi = w.out_n[from];
+            int *e = out_entry(from, oi);
+            e[0] = to; e[1] = 1;
+            for (int x = 0; x < 2 * w.rid_w; ++x) e[2 + x] = 0;
+            w.out_n[from]++;
+        }
+        if (add_rid) { out_entry(from, oi)[2 + (read_id >> 5)] |= 1 << (read_id & 31); w.n_read[from] += 1; }
+    }
+
+    // abpoa_add_subgraph_alignment (:689-774) / abpoa_add_graph_sequence (:573-593) with the 32 lanes dealt over the
+    // read's bases.  path[q] is the matched node of base q or -1 (inserted; every base of the first read).
+    //   1. target node of every base: the matched node, its aligned twin carrying the read's base, or a NEW node;
+    //      new ids are handed out in read order (ballot ranks), exactly the ids sequential creation would give.
+    //   2. new nodes form chains (consecutive ids); the chain heads are spliced into the topological list and the
+    //      aligned-node sets are updated by lane 0 (rare: read errors and the first read carrying an insertion).
+    //   3. the edges (previous target -> target) are applied in parallel (add_edge_par).
+    __device__ void add_alignment_warp(const uint8_t *seq, int seq_l, int *path, int read_id, bool first_read) {
+        const int lane = threadIdx.x & 31;
+        const int inc = par.sub_aln ? 0 : 1;
+        const int n0 = w.n_nodes;
+        if (seq_l <= 0) return;
+        int *tgt = path + ((seq_l + 3) & ~3), *heads = w.s1;
+        if (lane == 0) { w.tmp[8] = w.in_top; w.tmp[9] = w.out_top; w.tmp[1] = 0; }
+        int n_new = 0, n_heads = 0, last_exist = 0, prev_t = 0, prev_node = 0;   // carries across 32-base chunks
+        for (int base = 0; base < seq_l; base += 32) {
+            const int q = base + lane;
+            const bool in = q < seq_l;
+            int node = -1, t = -1, b = 0;
+            if (in) {
+                b = seq[q];
+                node = first_read ? -1 : path[q];
+                if (node >= 0) {
+                    if (w.base[node] == b) t = node;
+                    else for (int i = 0; i < w.aln_n[node]; ++i) { const int a = w.aln_pool[w.aln_off[node] + i]; if (w.base[a] == b) { t = a; break; } }
+                }
+            }
+            const bool isnew = in && t < 0;
+            const unsigned mnew = __ballot_sync(0xffffffffu, isnew);
+            if (isnew) t = n0 + n_new + __popc(mnew & ((1u << lane) - 1));
+            // last existing node at or before this base (n_span of a new node is inherited from it)
+            const unsigned mexist = __ballot_sync(0xffffffffu, in && !isnew) & ((2u << lane) - 1);
+            const int src_lane = mexist ? 31 - __clz(mexist) : -1;
+            const int le_t = __shfl_sync(0xffffffffu, t, src_lane < 0 ? 0 : src_lane);
+            const int le = src_lane < 0 ? last_exist : le_t;
+            // predecessor target in the path
+            int pt = __shfl_up_sync(0xffffffffu, t, 1), pnode = __shfl_up_sync(0xffffffffu, node, 1);
+            if (lane == 0) { pt = prev_t; pnode = prev_node; }
+            // a new node continues the chain of the previous one only if that one is an INSERTED new node (no aligned
+            // column to step over); anything else starts a chain that lane 0 splices in behind the right column
+            const bool interior = isnew && node < 0 && q > 0 && pt >= n0 && pnode < 0;
+            const bool head = isnew && !interior;
+            const unsigned mhead = __ballot_sync(0xffffffffu, head);
+            const bool fits = isnew && t < w.N;
+            if (fits) {
+                w.base[t] = b; w.in_n[t] = w.in_cap[t] = w.out_n[t] = w.out_cap[t] = 0; w.in_off[t] = w.out_off[t] = 0;
+                w.n_read[t] = 0; w.aln_n[t] = w.aln_cap[t] = 0; w.aln_off[t] = 0;
+                w.n_span[t] = w.n_span[le];
+                w.next[t] = -1;
+            }
+            __syncwarp();
+            if (fits) {
+                if (head) heads[n_heads + __popc(mhead & ((1u << lane) - 1))] = q;
+                else w.next[pt] = t;                                         // interior link of a chain
+            }
+            if (in) tgt[q] = t;
+            n_new += __popc(mnew); n_heads += __popc(mhead);
+            const unsigned mall = __ballot_sync(0xffffffffu, in && !isnew);
+            if (mall) last_exist = __shfl_sync(0xffffffffu, t, 31 - __clz(mall));
+            prev_t = __shfl_sync(0xffffffffu, t, 31); prev_node = __shfl_sync(0xffffffffu, node, 31);
+        }
+        if (n0 + n_new > w.N) { w.oom = 1; return; }
+        w.n_nodes = n0 + n_new;
+        __syncwarp();
+        // 2. splice the chains into the list; aligned-node sets (lane 0; aln pool cursor stays in its registers)
+        if (lane == 0) {
+            for (int i = 0; i < n_heads; ++i) {
+                const int q = heads[i], h = tgt[q];
+                const int tail = (i + 1 < n_heads ? tgt[heads[i + 1]] : n0 + n_new) - 1;
+                const int node = first_read ? -1 : path[q];
+                int at;
+                if (node >= 0) { at = node; add_aligned(node, h); }
+                else {
+                    const int last = q > 0 ? tgt[q - 1] : 0;
+                    at = last;
+                    for (;;) {                                               // end of the aligned column of `last`
+                        const int nx = w.next[at];
+                        if (nx < 0) break;
+                        bool member = false;
+                        for (int x = 0; x < w.aln_n[last]; ++x) if (w.aln_pool[w.aln_off[last] + x] == nx) { member = true; break; }
+                        if (!member) break;
+                        at = nx;
+                    }
+                }
+                w.next[tail] = w.next[at]; w.next[at] = h;
+            }
+            if (w.oom) w.tmp[1] = 1;
+        }
+        __syncwarp();
+        // 3. edges
+        for (int q = lane; q <= seq_l; q += 32) {
+            const int from = q == 0 ? 0 : tgt[q - 1], to = q == seq_l ? 1 : tgt[q];
+            const int check = (q > 0 && from >= n0) ? 0 : 1;
+            const int add = (first_read || q == seq_l) ? 1 : ((from != 0 || inc) ? 1 : 0);
+            add_edge_par(from, to, check, add, read_id);
+        }
+        __syncwarp();
+        w.in_top = w.tmp[8]; w.out_top = w.tmp[9]; w.oom = w.tmp[1];
+        __syncwarp();
+    }
+#endif
+
     // after fusing a read (abpoa_topological_sort :322-357 + abpoa_update_node_n_span_reads :559-571):
     // per-node exchange sort of the edge lists, out-weight sums, edge path scores (abpoa_get_incre_path_score
     // :429-437), n_span; then the flattened topological order and the heaviest-path remain values
@@ -456,11 +726,13 @@ template <class L> struct Poa {
                 if (node_w != 0 && edge_w != 0) { ps = (int)round(log((double)edge_w / (double)node_w)); if (ps < -20) ps = -20; }
                 ie[k].z = ps;
             }
+            w.fp_id[i] = w.in_n[i] > 0 ? ie[0].x : -1;
+            w.fp_ps[i] = w.in_n[i] > 0 ? ie[0].z : 0;
         }
         if (L::NT == 1) {
             // one thread: walk the list once and follow the heaviest-successor links backwards
             int cnt = 0;
-            for (int id = 0; id != -1; id = w.next[id]) w.order[cnt++] = id;
+            for (int id = 0; id != -1; id = w.next[id]) { w.pos[id] = cnt; w.order[cnt++] = id; }
             w.remain[1] = -1;
             for (int i = cnt - 1; i >= 0; --i) { const int id = w.order[i]; if (id != 1) w.remain[id] = (jh_a[id] == id ? -1 : w.remain[jh_a[id]]) + 1; }
             return;
@@ -476,7 +748,7 @@ template <class L> struct Poa {
             t = jh_a; jh_a = jh_b; jh_b = t;  t = dh_a; dh_a = dh_b; dh_b = t;
         }
         for (int i = lane; i < n; i += L::NT) {
-            w.order[n - 1 - dn_a[i]] = i;
+            w.order[n - 1 - dn_a[i]] = i; w.pos[i] = n - 1 - dn_a[i];
             w.remain[i] = dh_a[i] - 1;             // remain[SINK] = -1, remain[x] = remain[heaviest successor] + 1
         }
         L::sync();
@@ -546,6 +818,157 @@ template <class L> struct Poa {
             ve2 = k == 0 ? v2 : L::vmax(v2, ve2);
         }
     }
+
+#ifndef LCD_EMU
+    // ---- strip rows (warp policy) -------------------------------------------------------------------
+    // The vectors sn in [beg_sn, sn_hi] of a row whose F scan is the plain prefix maximum (set_num == PN: every
+    // vector up to the predecessors' last one) are computed in ONE pass: lane l owns the C consecutive columns
+    // c0 + l*C .. c0 + l*C + C-1 (c0 = beg_sn * 32), walks them sequentially in registers, and the F carries of
+    // the 32 strips are resolved by one max-plus warp scan per gap model instead of one 5-step scan per
+    // 32-column vector.  Cell values are exactly those of the per-vector code below (same formulas per cell; the
+    // F recurrence F[j] = max(Hm[j-1] - oe, F[j-1] - e) is associative, and no in-band value wraps in int16).
+    // Vectors beyond the predecessors' last one keep the reference's 2-then-1 lane propagation: they are left to
+    // the per-vector code, which continues from the carries (first1, first2) returned here.
+    template <int C> __device__ static __forceinline__ void load_strip(const int16_t *p, int (&v)[C]) {
+        if (C == 8) { const uint4 t = *reinterpret_cast<const uint4 *>(p);
+            v[0] = (int16_t)(t.x & 0xffff); v[1] = (int)t.x >> 16; v[2 % C] = (int16_t)(t.y & 0xffff); v[3 % C] = (int)t.y >> 16;
+            v[4 % C] = (int16_t)(t.z & 0xffff); v[5 % C] = (int)t.z >> 16; v[6 % C] = (int16_t)(t.w & 0xffff); v[7 % C] = (int)t.w >> 16; }
+        else if (C == 4) { const uint2 t = *reinterpret_cast<const uint2 *>(p);
+            v[0] = (int16_t)(t.x & 0xffff); v[1] = (int)t.x >> 16; v[2 % C] = (int16_t)(t.y & 0xffff); v[3 % C] = (int)t.y >> 16; }
+        else { const uint32_t t = *reinterpret_cast<const uint32_t *>(p); v[0] = (int16_t)(t & 0xffff); v[1] = (int)t >> 16; }
+    }
+    template <int C> __device__ static __forceinline__ void store_strip(int16_t *p, const int (&v)[C]) {
+        auto pk = [](int a, int b) -> uint32_t { return ((uint32_t)a & 0xffffu) | ((uint32_t)b << 16); };
+        if (C == 8) *reinterpret_cast<uint4 *>(p) = make_uint4(pk(v[0], v[1]), pk(v[2 % C], v[3 % C]), pk(v[4 % C], v[5 % C]), pk(v[6 % C], v[7 % C]));
+        else if (C == 4) *reinterpret_cast<uint2 *>(p) = make_uint2(pk(v[0], v[1]), pk(v[2 % C], v[3 % C]));
+        else *reinterpret_cast<uint32_t *>(p) = pk(v[0], v[1]);
+    }
+    struct StripArgs {
+        int nin, beg, end, beg_sn, end_sn, sn_hi, nb, qlen;
+        const uint8_t *query;
+        int16_t *H, *E1, *E2, *F1, *F2, *cwH;       // plane pointers addressed by absolute column; cwH: smem copy or nullptr
+        bool banded;
+    };
+    template <int C> __device__ __forceinline__ void strip_row(const StripArgs &a, const Pred (&pd)[4],
+                                                                 int &first1, int &first2, int &mx, int &left, int &right) {
+        const int lane = threadIdx.x & 31;
+        const int c0 = a.beg_sn * PN, width = (a.sn_hi - a.beg_sn + 1) * PN;
+        const int j0 = c0 + lane * C, sn = j0 >> 5;
+        const bool act = lane * C < width;
+        const bool vfirst = (j0 & 31) == 0;
+        const int e1 = par.gap_ext1, e2 = par.gap_ext2, o1 = par.gap_open1, o2 = par.gap_open2;
+        int h[C], ve1[C], ve2[C];
+#pragma unroll
+        for (int i = 0; i < C; ++i) { h[i] = inf_min; ve1[i] = inf_min; ve2[i] = inf_min; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (k < a.nin) {
+            const Pred &p = pd[k];
+            if (act && sn >= p.bsn && sn <= p.esn_m) {
+                int v[C];
+                load_strip<C>(p.ph + j0, v);
+                const int lft = (vfirst && sn == p.bsn && !p.from_mem) ? inf_min : (int)p.ph[j0 - 1];
+#pragma unroll
+                for (int i = C - 1; i > 0; --i) v[i] = v[i - 1];
+                v[0] = lft;
+#pragma unroll
+                for (int i = 0; i < C; ++i) { const int x = v[i] + p.ps; h[i] = k == 0 ? x : (x > h[i] ? x : h[i]); }
+            }
+            if (act && sn >= p.bsn && sn <= p.esn_e) {
+                int v1[C], v2[C];
+                load_strip<C>(p.pe1 + j0, v1); load_strip<C>(p.pe2 + j0, v2);
+#pragma unroll
+                for (int i = 0; i < C; ++i) {
+                    const int x1 = v1[i] + p.ps, x2 = v2[i] + p.ps;
+                    ve1[i] = k == 0 ? x1 : (x1 > ve1[i] ? x1 : ve1[i]);
+                    ve2[i] = k == 0 ? x2 : (x2 > ve2[i] ? x2 : ve2[i]);
+                }
+            }
+        }
+        // + query profile, band mask, Hm = max(M + q, E1, E2)
+        int hm[C];
+        {
+#pragma unroll
+            for (int i = 0; i < C; ++i) {
+                const int j = j0 + i;
+                int q = 0;
+                if (act && j >= 1 && j <= a.qlen) { const int qb = a.query[j - 1]; q = (a.nb > 3 || qb > 3) ? 0 : (a.nb == qb ? par.match : -par.mismatch); }
+                int x = h[i] + q;
+                if (j < a.beg || j > a.end) { x = inf_min; ve1[i] = inf_min; ve2[i] = inf_min; }
+                h[i] = x;
+            }
+        }
+        const int row_first = __shfl_sync(0xffffffffu, h[0], 0);          // (M + q) of the row's first stored column
+#pragma unroll
+        for (int i = 0; i < C; ++i) { int x = h[i]; x = x > ve1[i] ? x : ve1[i]; x = x > ve2[i] ? x : ve2[i]; hm[i] = x; }
+        // F: local pass without carry-in, then a max-plus scan of the strip aggregates
+        const int lowf = inf_min - 20000;
+        int hl = __shfl_up_sync(0xffffffffu, hm[C - 1], 1);
+        if (lane == 0) hl = row_first;
+        int f1[C], f2[C];
+        {
+            int g1 = lowf, g2 = lowf, prev = hl;
+#pragma unroll
+            for (int i = 0; i < C; ++i) {
+                const int a1 = prev - oe1, a2 = prev - oe2;
+                g1 = g1 - e1 > a1 ? g1 - e1 : a1;
+                g2 = g2 - e2 > a2 ? g2 - e2 : a2;
+                f1[i] = g1; f2[i] = g2;
+                prev = hm[i];
+            }
+            int s1 = g1, s2 = g2;                                            // F at the strip's last column without carry-in
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y1 = __shfl_up_sync(0xffffffffu, s1, d) - e1 * C * d, y2 = __shfl_up_sync(0xffffffffu, s2, d) - e2 * C * d;
+                if (lane >= d) { s1 = s1 > y1 ? s1 : y1; s2 = s2 > y2 ? s2 : y2; }
+            }
+            int c1 = __shfl_up_sync(0xffffffffu, s1, 1), c2 = __shfl_up_sync(0xffffffffu, s2, 1);   // F at the column left of the strip
+            if (lane == 0) { c1 = lowf; c2 = lowf; }
+#pragma unroll
+            for (int i = 0; i < C; ++i) {
+                c1 -= e1; c2 -= e2;
+                f1[i] = f1[i] > c1 ? f1[i] : c1;
+                f2[i] = f2[i] > c2 ? f2[i] : c2;
+            }
+        }
+        // carries for the vectors after sn_hi: lane 31 of max(Hm, F + o) in vector sn_hi
+        {
+            const int last_lane = width / C - 1;
+            const int x1 = hm[C - 1] > f1[C - 1] + o1 ? hm[C - 1] : f1[C - 1] + o1;
+            const int x2 = hm[C - 1] > f2[C - 1] + o2 ? hm[C - 1] : f2[C - 1] + o2;
+            first1 = __shfl_sync(0xffffffffu, x1, last_lane);
+            first2 = __shfl_sync(0xffffffffu, x2, last_lane);
+        }
+        // H, stored E, row maximum
+        int lm = INT32_MIN, lf = INT32_MAX, ll = -1;
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            const int j = j0 + i;
+            int x = hm[i]; x = x > f1[i] ? x : f1[i]; x = x > f2[i] ? x : f2[i];
+            if (j > a.end && (j >> 5) == a.end_sn) { x = inf_min; ve1[i] = inf_min; ve2[i] = inf_min; }
+            h[i] = x;
+            const int y1 = ve1[i] - e1, y2 = ve2[i] - e2;
+            ve1[i] = y1 > x - oe1 ? y1 : x - oe1;
+            ve2[i] = y2 > x - oe2 ? y2 : x - oe2;
+            if (act && j >= a.beg && j <= a.end) {
+                if (x > lm) { lm = x; lf = j; ll = j; } else if (x == lm) ll = j;
+            }
+        }
+        if (act) {
+            store_strip<C>(a.H + j0, h); store_strip<C>(a.E1 + j0, ve1); store_strip<C>(a.E2 + j0, ve2);
+            store_strip<C>(a.F1 + j0, f1); store_strip<C>(a.F2 + j0, f2);
+            if (a.cwH) { store_strip<C>(a.cwH + j0, h); store_strip<C>(a.cwH + NVC * PN + j0, ve1); store_strip<C>(a.cwH + 2 * NVC * PN + j0, ve2); }
+        }
+        if (a.banded) {
+            const int m = __reduce_max_sync(0xffffffffu, lm);
+            if (m != INT32_MIN) {
+                const int fi = __reduce_min_sync(0xffffffffu, lm == m ? lf : INT32_MAX);
+                const int la = __reduce_max_sync(0xffffffffu, lm == m ? ll : -1);
+                if (m > mx) { mx = m; left = fi; right = la; }
+                else if (m == mx) right = la;
+            }
+        }
+    }
+#endif
 
     // one sequence against the whole graph: simd_abpoa_cg_align_sequence_to_graph_core (:1200-1228)
     // returns number of cigar entries (reverse order) or <0
@@ -659,7 +1082,23 @@ template <class L> struct Poa {
             int first1 = 0, first2 = 0;
             int mx = inf_min, left = -1, right = -1;
             if (!L::TWO_PHASE) {
-            for (int sn = beg_sn; sn <= end_sn; ++sn) {
+            int sn0 = beg_sn;
+#ifndef LCD_EMU
+            if constexpr (L::STRIP) {
+                const int sn_hi = end_sn < max_pre_end_sn ? end_sn : max_pre_end_sn;
+                const int nvs = sn_hi - beg_sn + 1;
+                if (nin >= 1 && nin <= MAXP && nvs >= 1 && nvs <= 8) {
+                    StripArgs sa;
+                    sa.nin = nin; sa.beg = beg; sa.end = end; sa.beg_sn = beg_sn; sa.end_sn = end_sn; sa.sn_hi = sn_hi; sa.nb = nb; sa.qlen = qlen;
+                    sa.query = query; sa.H = H; sa.E1 = E1; sa.E2 = E2; sa.F1 = F1; sa.F2 = F2; sa.cwH = cwH; sa.banded = banded;
+                    if (nvs <= 2) strip_row<2>(sa, pd, first1, first2, mx, left, right);
+                    else if (nvs <= 4) strip_row<4>(sa, pd, first1, first2, mx, left, right);
+                    else strip_row<8>(sa, pd, first1, first2, mx, left, right);
+                    sn0 = sn_hi + 1;
+                }
+            }
+#endif
+            for (int sn = sn0; sn <= end_sn; ++sn) {
                 const int col0 = sn * PN;
                 vec h = L::set1(inf_min), ve1 = L::set1(inf_min), ve2 = L::set1(inf_min);
 #pragma unroll
@@ -788,6 +1227,12 @@ template <class L> struct Poa {
             L::sync();
         }
         // ---- best cell :1092-1105 and backtrack :309-458 (lane 0; result broadcast through memory)
+#ifndef LCD_EMU
+        if constexpr (L::STRIP) {
+            LCD_T0(); const int rc = backtrack_warp(query, qlen, reinterpret_cast<int *>(w.cigar)); LCD_T1(t_bt);
+            return rc;
+        }
+#endif
         { LCD_T0(); if (L::tid() == 0) backtrack(query, qlen);
         L::sync(); LCD_T1(t_bt); }
         return w.tmp[0];
@@ -1010,6 +1455,14 @@ template <class L> struct Poa {
                     { LCD_T0(); n_cig = align(q, ql); LCD_T1(t_dp); }
                     if (n_cig < 0) { status = n_cig; break; }
                 }
+                bool fused = false;
+#ifndef LCD_EMU
+                if constexpr (L::STRIP) {
+                    LCD_T0(); add_alignment_warp(q, ql, reinterpret_cast<int *>(w.cigar), r, first_read != 0); LCD_T1(t_add);
+                    fused = true;
+                }
+#endif
+                if (!fused) {
                 { LCD_T0();
                 if (L::tid() == 0) {
                     add_alignment(q, ql, n_cig, r);
@@ -1017,6 +1470,7 @@ template <class L> struct Poa {
                 }
                 L::sync(); LCD_T1(t_add); }
                 w.n_nodes = w.tmp[0]; w.oom = w.tmp[1];
+                }
                 // pool cursors are only used by lane 0; n_nodes and oom are shared through tmp[]
                 L::sync();
                 if (w.oom) { status = ST_OOM; break; }

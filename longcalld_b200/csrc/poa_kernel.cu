@@ -3,6 +3,7 @@
 #include "lcd_common.cuh"
 #include "poa_device.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace lcd {
 namespace poa {
@@ -66,7 +67,7 @@ poa_cta_kernel(const KernelArgs a) {
 
 // arena words a problem needs (mirrors Poa::carve) for given node / edge / DP cell budgets
 static uint64_t arena_need_words(uint64_t N, uint64_t E, int max_len, int n_reads, uint64_t dp_cells) {
-    uint64_t top = 27 * ((N + 3) & ~3ull) + N * 4;
+    uint64_t top = 30 * ((N + 3) & ~3ull) + N * 4;
     const uint64_t stride = 2 + 2 * (1 + ((n_reads - 1) >> 6));
     top += E * 4 + ((E * stride + 3) & ~3ull) + ((E + 3) & ~3ull) + 2 * ((uint64_t)max_len + N + 8);
     top = (top + 31) & ~31ull;
@@ -201,8 +202,10 @@ struct PoaPlan : Plan {
         const uint64_t thread_words = (uint64_t)(512u << 10) / 4;     // <= 512 KiB per thread arena
         std::vector<int32_t> cls[3];
         uint64_t cw[3] = {0, 0, 0};
+        const char *force = getenv("LCD_POA_FORCE_KIND");      // debug / profiling: 0 thread, 1 warp, 2 CTA for every problem
         for (int32_t i : order_all) {
-            const int k = (need_small[i] <= thread_words && problems[i].max_len <= 640) ? 0 : (problems[i].max_len <= 1200 ? 1 : 2);
+            int k = (need_small[i] <= thread_words && problems[i].max_len <= 640) ? 0 : (problems[i].max_len <= 1200 ? 1 : 2);
+            if (force && force[0] >= '0' && force[0] <= '2' && !(force[0] == '0' && need_small[i] > thread_words)) k = force[0] - '0';
             cls[k].push_back(i); cw[k] = std::max(cw[k], need_small[i]);
         }
         for (int k = 0; k < 3; ++k) cw[k] = (cw[k] + 63) & ~63ull;
