@@ -96,6 +96,7 @@ struct WS {
     int *out_pool; int out_top, out_capacity, out_stride, rid_w;   // {to, w, rid[2*rid_w]}
     int *aln_pool; int aln_top, aln_capacity;
     int2 *cigar; int cigar_cap;                      // {op | len << 2, node_id}
+    uint8_t *qs;                                     // the read shifted by one with sentinels: qs[j] = query[j-1] (strip rows)
     int16_t *dp; uint32_t dp_capacity;               // in cells
     int n_nodes;
     int oom;
@@ -269,6 +270,7 @@ template <class L> struct Poa {
         w.out_capacity = E; w.out_pool = arena + top; top += ((uint64_t)E * w.out_stride + 3) & ~3ull;
         w.aln_capacity = E; w.aln_pool = arena + top; top += (uint64_t)((E + 3) & ~3);
         w.cigar_cap = max_len + N + 8; w.cigar = reinterpret_cast<int2 *>(arena + top); top += (uint64_t)w.cigar_cap * 2;
+        w.qs = reinterpret_cast<uint8_t *>(arena + top); top += (uint64_t)(max_len + 192) / 4;
         top = (top + 31) & ~31ull;
         if (top + 1024 > words) return false;
         w.dp = reinterpret_cast<int16_t *>(arena + top);
@@ -723,7 +725,7 @@ template <class L> struct Poa {
             for (int k = 0; k < w.in_n[i]; ++k) {
                 const int node_w = w.wsum[ie[k].x], edge_w = ie[k].y;
                 int ps = 0;
-                if (node_w != 0 && edge_w != 0) { ps = (int)round(log((double)edge_w / (double)node_w)); if (ps < -20) ps = -20; }
+                if (node_w != 0 && edge_w != 0 && node_w != edge_w) { ps = (int)round(log((double)edge_w / (double)node_w)); if (ps < -20) ps = -20; }
                 ie[k].z = ps;
             }
             w.fp_id[i] = w.in_n[i] > 0 ? ie[0].x : -1;
@@ -738,9 +740,16 @@ template <class L> struct Poa {
             return;
         }
         for (int span = 1; span < n; span <<= 1) {
-            for (int i = lane; i < n; i += L::NT) {
-                const int a = jn_a[i]; dn_b[i] = dn_a[i] + dn_a[a]; jn_b[i] = jn_a[a];
-                const int h = jh_a[i]; dh_b[i] = dh_a[i] + dh_a[h]; jh_b[i] = jh_a[h];
+            // 4 nodes per lane and step: the two dependent gathers of a node overlap with those of the other three
+            for (int i0 = lane; i0 < n; i0 += 4 * L::NT) {
+                int a[4], h[4], da[4], dh[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int i = i0 + u * L::NT; if (i < n) { a[u] = jn_a[i]; h[u] = jh_a[i]; da[u] = dn_a[i]; dh[u] = dh_a[i]; } }
+                int a2[4], h2[4], da2[4], dh2[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int i = i0 + u * L::NT; if (i < n) { da2[u] = dn_a[a[u]]; a2[u] = jn_a[a[u]]; dh2[u] = dh_a[h[u]]; h2[u] = jh_a[h[u]]; } }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int i = i0 + u * L::NT; if (i < n) { dn_b[i] = da[u] + da2[u]; jn_b[i] = a2[u]; dh_b[i] = dh[u] + dh2[u]; jh_b[i] = h2[u]; } }
             }
             L::sync();
             int *t;
@@ -844,62 +853,40 @@ template <class L> struct Poa {
         else *reinterpret_cast<uint32_t *>(p) = pk(v[0], v[1]);
     }
     struct StripArgs {
-        int nin, beg, end, beg_sn, end_sn, sn_hi, nb, qlen;
-        const uint8_t *query;
+        int beg, end, beg_sn, end_sn, sn_hi, nb;
         int16_t *H, *E1, *E2, *F1, *F2, *cwH;       // plane pointers addressed by absolute column; cwH: smem copy or nullptr
         bool banded;
     };
-    template <int C> __device__ __forceinline__ void strip_row(const StripArgs &a, const Pred (&pd)[4],
+    // Everything of a strip row after the predecessor maxima: h = max_p(H_p[j-1] + ps), ve1/ve2 = max_p(E*_p[j] + ps).
+    template <int C> __device__ __forceinline__ void strip_core(const StripArgs &a, int (&h)[C], int (&ve1)[C], int (&ve2)[C],
                                                                  int &first1, int &first2, int &mx, int &left, int &right) {
         const int lane = threadIdx.x & 31;
         const int c0 = a.beg_sn * PN, width = (a.sn_hi - a.beg_sn + 1) * PN;
-        const int j0 = c0 + lane * C, sn = j0 >> 5;
+        const int j0 = c0 + lane * C;
         const bool act = lane * C < width;
-        const bool vfirst = (j0 & 31) == 0;
         const int e1 = par.gap_ext1, e2 = par.gap_ext2, o1 = par.gap_open1, o2 = par.gap_open2;
-        int h[C], ve1[C], ve2[C];
-#pragma unroll
-        for (int i = 0; i < C; ++i) { h[i] = inf_min; ve1[i] = inf_min; ve2[i] = inf_min; }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (k < a.nin) {
-            const Pred &p = pd[k];
-            if (act && sn >= p.bsn && sn <= p.esn_m) {
-                int v[C];
-                load_strip<C>(p.ph + j0, v);
-                const int lft = (vfirst && sn == p.bsn && !p.from_mem) ? inf_min : (int)p.ph[j0 - 1];
-#pragma unroll
-                for (int i = C - 1; i > 0; --i) v[i] = v[i - 1];
-                v[0] = lft;
-#pragma unroll
-                for (int i = 0; i < C; ++i) { const int x = v[i] + p.ps; h[i] = k == 0 ? x : (x > h[i] ? x : h[i]); }
-            }
-            if (act && sn >= p.bsn && sn <= p.esn_e) {
-                int v1[C], v2[C];
-                load_strip<C>(p.pe1 + j0, v1); load_strip<C>(p.pe2 + j0, v2);
-#pragma unroll
-                for (int i = 0; i < C; ++i) {
-                    const int x1 = v1[i] + p.ps, x2 = v2[i] + p.ps;
-                    ve1[i] = k == 0 ? x1 : (x1 > ve1[i] ? x1 : ve1[i]);
-                    ve2[i] = k == 0 ? x2 : (x2 > ve2[i] ? x2 : ve2[i]);
-                }
-            }
-        }
-        // + query profile, band mask, Hm = max(M + q, E1, E2)
+        // + query profile (qs[j] = query[j-1], sentinel 7 outside the read), band mask, Hm = max(M + q, E1, E2)
+        const int s_eq = a.nb > 3 ? 0 : par.match, s_ne = a.nb > 3 ? 0 : -par.mismatch;
+        const int lo = a.beg - j0, span = a.end - a.beg;                   // cell i is inside the band iff 0 <= i - lo <= span
         int hm[C];
         {
+            uint32_t qw[2];
+            if (C == 8) { const uint2 t = *reinterpret_cast<const uint2 *>(w.qs + j0); qw[0] = t.x; qw[1] = t.y; }
+            else if (C == 4) { qw[0] = *reinterpret_cast<const uint32_t *>(w.qs + j0); qw[1] = 0; }
+            else { qw[0] = *reinterpret_cast<const uint16_t *>(w.qs + j0); qw[1] = 0; }
 #pragma unroll
             for (int i = 0; i < C; ++i) {
-                const int j = j0 + i;
-                int q = 0;
-                if (act && j >= 1 && j <= a.qlen) { const int qb = a.query[j - 1]; q = (a.nb > 3 || qb > 3) ? 0 : (a.nb == qb ? par.match : -par.mismatch); }
-                int x = h[i] + q;
-                if (j < a.beg || j > a.end) { x = inf_min; ve1[i] = inf_min; ve2[i] = inf_min; }
+                const int qb = (int)((qw[i >> 2] >> (8 * (i & 3))) & 0xff);
+                const int sc = qb > 3 ? 0 : (qb == a.nb ? s_eq : s_ne);
+                const bool inb = (unsigned)(i - lo) <= (unsigned)span;
+                const int x = inb ? h[i] + sc : inf_min;
+                if (!inb) { ve1[i] = inf_min; ve2[i] = inf_min; }
                 h[i] = x;
+                int y = x > ve1[i] ? x : ve1[i]; y = y > ve2[i] ? y : ve2[i];
+                hm[i] = y;
             }
         }
         const int row_first = __shfl_sync(0xffffffffu, h[0], 0);          // (M + q) of the row's first stored column
-#pragma unroll
-        for (int i = 0; i < C; ++i) { int x = h[i]; x = x > ve1[i] ? x : ve1[i]; x = x > ve2[i] ? x : ve2[i]; hm[i] = x; }
         // F: local pass without carry-in, then a max-plus scan of the strip aggregates
         const int lowf = inf_min - 20000;
         int hl = __shfl_up_sync(0xffffffffu, hm[C - 1], 1);
@@ -931,26 +918,26 @@ template <class L> struct Poa {
             }
         }
         // carries for the vectors after sn_hi: lane 31 of max(Hm, F + o) in vector sn_hi
-        {
+        if (a.sn_hi < a.end_sn) {
             const int last_lane = width / C - 1;
             const int x1 = hm[C - 1] > f1[C - 1] + o1 ? hm[C - 1] : f1[C - 1] + o1;
             const int x2 = hm[C - 1] > f2[C - 1] + o2 ? hm[C - 1] : f2[C - 1] + o2;
             first1 = __shfl_sync(0xffffffffu, x1, last_lane);
             first2 = __shfl_sync(0xffffffffu, x2, last_lane);
         }
-        // H, stored E, row maximum
-        int lm = INT32_MIN, lf = INT32_MAX, ll = -1;
+        // H, stored E, row maximum.  Cells right of the band in the row's last vector are reset to INF_MIN.
+        const int hi_m = ((j0 >> 5) == a.end_sn) ? a.end - j0 : C;          // cells i > hi_m are reset
+        int lm = INT32_MIN, lf = 0, ll = 0;
 #pragma unroll
         for (int i = 0; i < C; ++i) {
-            const int j = j0 + i;
             int x = hm[i]; x = x > f1[i] ? x : f1[i]; x = x > f2[i] ? x : f2[i];
-            if (j > a.end && (j >> 5) == a.end_sn) { x = inf_min; ve1[i] = inf_min; ve2[i] = inf_min; }
+            if (i > hi_m) { x = inf_min; ve1[i] = inf_min; ve2[i] = inf_min; }
             h[i] = x;
             const int y1 = ve1[i] - e1, y2 = ve2[i] - e2;
             ve1[i] = y1 > x - oe1 ? y1 : x - oe1;
             ve2[i] = y2 > x - oe2 ? y2 : x - oe2;
-            if (act && j >= a.beg && j <= a.end) {
-                if (x > lm) { lm = x; lf = j; ll = j; } else if (x == lm) ll = j;
+            if ((unsigned)(i - lo) <= (unsigned)span) {
+                if (x > lm) { lm = x; lf = i; ll = i; } else if (x == lm) ll = i;
             }
         }
         if (act) {
@@ -959,14 +946,75 @@ template <class L> struct Poa {
             if (a.cwH) { store_strip<C>(a.cwH + j0, h); store_strip<C>(a.cwH + NVC * PN + j0, ve1); store_strip<C>(a.cwH + 2 * NVC * PN + j0, ve2); }
         }
         if (a.banded) {
+            if (!act) lm = INT32_MIN;
             const int m = __reduce_max_sync(0xffffffffu, lm);
             if (m != INT32_MIN) {
-                const int fi = __reduce_min_sync(0xffffffffu, lm == m ? lf : INT32_MAX);
-                const int la = __reduce_max_sync(0xffffffffu, lm == m ? ll : -1);
+                const int fi = __reduce_min_sync(0xffffffffu, lm == m ? j0 + lf : INT32_MAX);
+                const int la = __reduce_max_sync(0xffffffffu, lm == m ? j0 + ll : -1);
                 if (m > mx) { mx = m; left = fi; right = la; }
                 else if (m == mx) right = la;
             }
         }
+    }
+    // general strip row: up to 4 predecessors anywhere in the arena
+    template <int C> __device__ __forceinline__ void strip_row(const StripArgs &a, int nin, const Pred (&pd)[4],
+                                                                 int &first1, int &first2, int &mx, int &left, int &right) {
+        const int lane = threadIdx.x & 31;
+        const int c0 = a.beg_sn * PN, width = (a.sn_hi - a.beg_sn + 1) * PN;
+        const int j0 = c0 + lane * C, sn = j0 >> 5;
+        const bool act = lane * C < width;
+        const bool vfirst = (j0 & 31) == 0;
+        int h[C], ve1[C], ve2[C];
+#pragma unroll
+        for (int i = 0; i < C; ++i) { h[i] = inf_min; ve1[i] = inf_min; ve2[i] = inf_min; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (k < nin) {
+            const Pred &p = pd[k];
+            if (act && sn >= p.bsn && sn <= p.esn_m) {
+                int v[C];
+                load_strip<C>(p.ph + j0, v);
+                const int lft = (vfirst && sn == p.bsn && !p.from_mem) ? inf_min : (int)p.ph[j0 - 1];
+#pragma unroll
+                for (int i = C - 1; i > 0; --i) v[i] = v[i - 1];
+                v[0] = lft;
+#pragma unroll
+                for (int i = 0; i < C; ++i) { const int x = v[i] + p.ps; h[i] = k == 0 ? x : (x > h[i] ? x : h[i]); }
+            }
+            if (act && sn >= p.bsn && sn <= p.esn_e) {
+                int v1[C], v2[C];
+                load_strip<C>(p.pe1 + j0, v1); load_strip<C>(p.pe2 + j0, v2);
+#pragma unroll
+                for (int i = 0; i < C; ++i) {
+                    const int x1 = v1[i] + p.ps, x2 = v2[i] + p.ps;
+                    ve1[i] = k == 0 ? x1 : (x1 > ve1[i] ? x1 : ve1[i]);
+                    ve2[i] = k == 0 ? x2 : (x2 > ve2[i] ? x2 : ve2[i]);
+                }
+            }
+        }
+        strip_core<C>(a, h, ve1, ve2, first1, first2, mx, left, right);
+    }
+    // chain row: the only predecessor is the row computed just before, whose H / E1 / E2 band sits in shared memory
+    // (crd, first vector = pre_beg_sn) and covers every vector of this row
+    template <int C> __device__ __forceinline__ void chain_row(const StripArgs &a, const int16_t *crd, int pre_beg_sn, int ps,
+                                                                 int &first1, int &first2, int &mx, int &left, int &right) {
+        const int lane = threadIdx.x & 31;
+        const int j0 = a.beg_sn * PN + lane * C;
+        const bool act = lane * C < (a.sn_hi - a.beg_sn + 1) * PN;
+        const int16_t *ph = crd + (j0 - pre_beg_sn * PN);
+        int h[C], ve1[C], ve2[C];
+        if (act) { load_strip<C>(ph, h); load_strip<C>(ph + NVC * PN, ve1); load_strip<C>(ph + 2 * NVC * PN, ve2); }
+        else {
+#pragma unroll
+            for (int i = 0; i < C; ++i) { h[i] = inf_min; ve1[i] = inf_min; ve2[i] = inf_min; }
+        }
+        int lft = __shfl_up_sync(0xffffffffu, h[C - 1], 1);
+        if (lane == 0) lft = pre_beg_sn < a.beg_sn ? (int)ph[-1] : inf_min;
+#pragma unroll
+        for (int i = C - 1; i > 0; --i) h[i] = h[i - 1] + ps;
+        h[0] = lft + ps;
+#pragma unroll
+        for (int i = 0; i < C; ++i) { ve1[i] += ps; ve2[i] += ps; }
+        strip_core<C>(a, h, ve1, ve2, first1, first2, mx, left, right);
     }
 #endif
 
@@ -979,6 +1027,12 @@ template <class L> struct Poa {
         const int o1 = par.gap_open1, e1 = par.gap_ext1, o2 = par.gap_open2, e2 = par.gap_ext2;
         const int match = par.match, mism = par.mismatch;
         const bool banded = par.wb >= 0;
+#ifndef LCD_EMU
+        if constexpr (L::STRIP) {       // the read shifted by one, padded with a never-matching sentinel (strip_core)
+            const int qs_len = (dp_sn + 2) * PN + 16;
+            for (int j = L::tid(); j < qs_len; j += L::NT) w.qs[j] = (j >= 1 && j <= qlen) ? query[j - 1] : 7;
+        }
+#endif
         uint32_t dp_top = 0;
         int last_id = 0, cache_buf = 0; bool last_cached = false; Row last_row;
         const int rem_end = banded ? w.remain[1] : 0;
@@ -1035,6 +1089,51 @@ template <class L> struct Poa {
                 nie0 = nnin > 0 ? nie[0] : make_int4(0, 0, 0, 0);
             }
             if (id == 1) continue;
+#ifndef LCD_EMU
+            if constexpr (L::STRIP) {
+                // chain fast path: one in-edge, from the row computed just before, whose band is on chip and reaches at
+                // least as far right as this row's (no vector with the reference's partial F propagation)
+                if (nin == 1 && ie0.x == last_id && last_cached) {
+                    const int pre_beg_sn = last_row.beg >> 5, pre_end_sn = last_row.end >> 5;
+                    int beg = 0, end = qlen, beg_sn = 0;
+                    if (banded) {
+                        const int rr = qlen - (rem - rem_end - 1);
+                        const int maxl = last_row.left1 < n ? last_row.left1 : n, maxr = last_row.right1 > 0 ? last_row.right1 : 0;
+                        beg = (maxl < rr ? maxl : rr) - wband; if (beg < 0) beg = 0;
+                        end = (maxr > rr ? maxr : rr) + wband; if (end > qlen) end = qlen;
+                        beg_sn = beg >> 5;
+                        if (beg_sn < pre_beg_sn) { beg = last_row.beg; beg_sn = pre_beg_sn; }
+                    }
+                    const int end_sn = end >> 5, nv = end_sn - beg_sn + 2;
+                    if (end_sn <= pre_end_sn && nv <= NVC) {
+                        const uint32_t need = (uint32_t)nv * PN * 5;
+                        if (dp_top + need > w.dp_capacity) return ST_OOM;
+                        const uint32_t off = dp_top; dp_top += need;
+                        cells += (unsigned long long)(end - beg + 1);
+                        StripArgs sa;
+                        sa.beg = beg; sa.end = end; sa.beg_sn = beg_sn; sa.end_sn = end_sn; sa.sn_hi = end_sn; sa.nb = nb;
+                        sa.H = w.dp + off - (size_t)beg_sn * PN; sa.E1 = sa.H + (size_t)nv * PN; sa.E2 = sa.E1 + (size_t)nv * PN;
+                        sa.F1 = sa.E2 + (size_t)nv * PN; sa.F2 = sa.F1 + (size_t)nv * PN;
+                        sa.cwH = row_cache + (cache_buf ^ 1) * 3 * NVC * PN - (size_t)beg_sn * PN; sa.banded = banded;
+                        const int16_t *crd = row_cache + cache_buf * 3 * NVC * PN;
+                        int f1_ = 0, f2_ = 0, mx = inf_min, left = -1, right = -1;
+                        if (nv <= 3) chain_row<2>(sa, crd, pre_beg_sn, ie0.z, f1_, f2_, mx, left, right);
+                        else if (nv <= 5) chain_row<4>(sa, crd, pre_beg_sn, ie0.z, f1_, f2_, mx, left, right);
+                        else chain_row<8>(sa, crd, pre_beg_sn, ie0.z, f1_, f2_, mx, left, right);
+                        if (end_sn + 1 <= dp_sn - 1) {
+                            L::store(sa.H + (end_sn + 1) * PN, L::set1(inf_min));
+                            L::store(sa.cwH + (end_sn + 1) * PN, L::set1(inf_min));
+                        }
+                        const int4 packed = pack((int)off, beg, end, left, right);
+                        if (L::tid() == 0) w.rinfo[id] = packed;
+                        last_id = id; last_row = unpack(packed);
+                        cache_buf ^= 1;                      // last_cached stays true
+                        L::sync();
+                        continue;
+                    }
+                }
+            }
+#endif
             // predecessor descriptors: the first MAXP in registers, any further ones re-read per vector
             constexpr int MAXP = 4;
             int4 pe[MAXP]; Row pr[MAXP];
@@ -1089,11 +1188,17 @@ template <class L> struct Poa {
                 const int nvs = sn_hi - beg_sn + 1;
                 if (nin >= 1 && nin <= MAXP && nvs >= 1 && nvs <= 8) {
                     StripArgs sa;
-                    sa.nin = nin; sa.beg = beg; sa.end = end; sa.beg_sn = beg_sn; sa.end_sn = end_sn; sa.sn_hi = sn_hi; sa.nb = nb; sa.qlen = qlen;
-                    sa.query = query; sa.H = H; sa.E1 = E1; sa.E2 = E2; sa.F1 = F1; sa.F2 = F2; sa.cwH = cwH; sa.banded = banded;
-                    if (nvs <= 2) strip_row<2>(sa, pd, first1, first2, mx, left, right);
-                    else if (nvs <= 4) strip_row<4>(sa, pd, first1, first2, mx, left, right);
-                    else strip_row<8>(sa, pd, first1, first2, mx, left, right);
+                    sa.beg = beg; sa.end = end; sa.beg_sn = beg_sn; sa.end_sn = end_sn; sa.sn_hi = sn_hi; sa.nb = nb;
+                    sa.H = H; sa.E1 = E1; sa.E2 = E2; sa.F1 = F1; sa.F2 = F2; sa.cwH = cwH; sa.banded = banded;
+                    if (nin == 1 && cache_rd && pe[0].x == last_id && sn_hi == end_sn) {      // chain row, predecessor on chip
+                        const int pbs = pr[0].beg >> 5;
+                        if (nvs <= 2) chain_row<2>(sa, cache_rd, pbs, pe[0].z, first1, first2, mx, left, right);
+                        else if (nvs <= 4) chain_row<4>(sa, cache_rd, pbs, pe[0].z, first1, first2, mx, left, right);
+                        else chain_row<8>(sa, cache_rd, pbs, pe[0].z, first1, first2, mx, left, right);
+                    }
+                    else if (nvs <= 2) strip_row<2>(sa, nin, pd, first1, first2, mx, left, right);
+                    else if (nvs <= 4) strip_row<4>(sa, nin, pd, first1, first2, mx, left, right);
+                    else strip_row<8>(sa, nin, pd, first1, first2, mx, left, right);
                     sn0 = sn_hi + 1;
                 }
             }

@@ -69,7 +69,7 @@ poa_cta_kernel(const KernelArgs a) {
 static uint64_t arena_need_words(uint64_t N, uint64_t E, int max_len, int n_reads, uint64_t dp_cells) {
     uint64_t top = 30 * ((N + 3) & ~3ull) + N * 4;
     const uint64_t stride = 2 + 2 * (1 + ((n_reads - 1) >> 6));
-    top += E * 4 + ((E * stride + 3) & ~3ull) + ((E + 3) & ~3ull) + 2 * ((uint64_t)max_len + N + 8);
+    top += E * 4 + ((E * stride + 3) & ~3ull) + ((E + 3) & ~3ull) + 2 * ((uint64_t)max_len + N + 8) + ((uint64_t)max_len + 192) / 4;
     top = (top + 31) & ~31ull;
     return top + 1024 + (dp_cells + 1) / 2;
 }
