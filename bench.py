@@ -104,8 +104,23 @@ class Workload:
         self.cons_off = np.zeros(self.n_poa + 1, dtype=np.int64)
         np.cumsum(self.sum_len, out=self.cons_off[1:])
 
+    def wfa_layout(self):
+        """Zero-copy hand-over POA -> WFA: one host buffer [region references | consensus slots]; lcd_poa_batch writes the
+        consensus of problem i into its slot and lcd_wfa_batch reads (reference, consensus) pairs by offset."""
+        if not hasattr(self, "_layout"):
+            seen, parts, off, ref_off = {}, [], 0, np.zeros(self.n_poa, dtype=np.int64)
+            for i, r in enumerate(self.refs):
+                if id(r) not in seen:
+                    seen[id(r)] = off; parts.append(np.asarray(r, dtype=np.uint8)); off += len(r)
+                ref_off[i] = seen[id(r)]
+            ref_len = np.fromiter((len(r) for r in self.refs), dtype=np.int32, count=self.n_poa)
+            buf = np.zeros(off + int(self.cons_off[-1]) + 16, dtype=np.uint8)
+            buf[:off] = np.concatenate(parts)
+            self._layout = (buf, off, ref_off, ref_len, np.ascontiguousarray(off + self.cons_off[:-1]))
+        return self._layout
+
     def wfa_inputs(self, cons, cons_len, idx=None):
-        """(ref, consensus) pairs packed for lcd_wfa_batch; consensus i = cons[cons_off[i] : +cons_len[i]]."""
+        """(ref, consensus) pairs packed for the reference arm; consensus i = cons[cons_off[i] : +cons_len[i]]."""
         from longcalld_b200.capi import pack_pairs
         idx = range(self.n_poa) if idx is None else idx
         pairs = [(self.refs[i], cons[self.cons_off[i]:self.cons_off[i] + cons_len[i]]) for i in idx]
@@ -229,26 +244,27 @@ def run_b200(args, rank, world):
     n = wl.n_poa
     ppar = np.zeros(n, dtype=POA_PARAMS_DTYPE); ppar[:] = lcd.poa_params()
     wpar = np.zeros(n, dtype=WFA_PARAMS_DTYPE); wpar[:] = lcd.wfa_params()
-    cons = np.zeros(int(wl.cons_off[-1]) + 16, dtype=np.uint8)
+    buf, R, ref_off, ref_len, txt_off = wl.wfa_layout()
+    cons = buf[R:]
     pres = np.zeros(n, dtype=POA_RESULT_DTYPE)
     wres = np.zeros(n, dtype=WFA_RESULT_DTYPE)
 
     def e2e_step():
-        """host reads -> lcd_poa_batch -> host consensus -> lcd_wfa_batch -> host CIGAR ops (all copies inside)"""
+        """host reads -> lcd_poa_batch -> consensus in host memory -> lcd_wfa_batch -> host CIGAR ops (all copies inside)"""
         rc = L.lcd_poa_batch(C.c_int(n), _vp(wl.seqs), C.c_size_t(wl.seqs.size), _vp(wl.first), _vp(wl.n_reads),
                              _vp(wl.read_off), _vp(wl.read_len), C.c_int(len(wl.read_len)), _vp(ppar),
                              _vp(cons), _vp(wl.cons_off), None, None, None, _vp(pres))
         if rc:
             raise RuntimeError(L.lcd_gpu_last_error().decode())
-        seqs, po, pl, to, tl = wl.wfa_inputs(cons, pres["cons_len"])
-        cap = 2 * (pl.astype(np.int64) + tl) + 8
+        tl = np.ascontiguousarray(pres["cons_len"])
+        cap = 2 * (ref_len.astype(np.int64) + tl) + 8
         off = np.zeros(n + 1, dtype=np.int64); np.cumsum(cap, out=off[1:])
         ops = np.empty(int(off[-1]) + 1, dtype=np.uint8)
-        rc = L.lcd_wfa_batch(C.c_int(n), _vp(seqs), C.c_size_t(seqs.size), _vp(po), _vp(pl), _vp(to), _vp(tl),
+        rc = L.lcd_wfa_batch(C.c_int(n), _vp(buf), C.c_size_t(buf.size), _vp(ref_off), _vp(ref_len), _vp(txt_off), _vp(tl),
                              _vp(wpar), ops.ctypes.data_as(C.c_char_p), _vp(off), _vp(wres))
         if rc:
             raise RuntimeError(L.lcd_gpu_last_error().decode())
-        return seqs, po, pl, to, tl
+        return buf, ref_off, ref_len, txt_off, tl
 
     wseqs, po, pl, to, tl = e2e_step()                              # also yields the consensus sequences for the WFA plan
     poa_plan = lcd.PoaPlan(wl.seqs, wl.first, wl.n_reads, wl.read_off, wl.read_len, lcd.poa_params())
@@ -299,8 +315,8 @@ def run_b200(args, rank, world):
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
-    h2d = int(wl.seqs.size + 12 * len(wl.read_len) + 64 * n + wseqs.size + 96 * n)
-    d2h = int(wl.cons_off[-1] + pres.nbytes + wres.nbytes + 2 * (pl.astype(np.int64) + tl + 4).sum())
+    h2d = int(wl.seqs.size + 12 * len(wl.read_len) + 64 * n + (pl.astype(np.int64) + tl + 56).sum() + 96 * n)
+    d2h = int(pres["cons_len"].sum() + 32 * n + wres.nbytes + 2 * (pl.astype(np.int64) + tl + 4).sum())
 
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:

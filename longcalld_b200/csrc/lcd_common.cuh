@@ -53,24 +53,29 @@ struct Plan {
     int n = 0;
 };
 
+// Device buffer from the stream-ordered pool of the library stream (cudaMallocAsync; the pool keeps freed
+// memory, so the per-call plans of the *_batch entry points do not pay cudaMalloc / cudaFree every time).
+// Every plan synchronises the library stream after its uploads, which orders the allocation before any use on
+// another stream; buffers are released when the plan is destroyed, after its last fetch has synchronised.
 template <typename T>
 struct DevBuf {
     T *p = nullptr; size_t n = 0;
     int alloc(size_t count) {
         free_(); n = count;
         if (count == 0) return 0;
-        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
-        if (e != cudaSuccess) { set_error("cudaMalloc(%zu) -> %s", count * sizeof(T), cudaGetErrorString(e)); p = nullptr; return -1; }
+        cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), ctx().stream);
+        if (e != cudaSuccess) { set_error("cudaMallocAsync(%zu) -> %s", count * sizeof(T), cudaGetErrorString(e)); p = nullptr; return -1; }
         return 0;
     }
     int upload(const T *h, size_t count, cudaStream_t s) {
         if (alloc(count)) return -1;
         if (count == 0) return 0;
-        cudaError_t e = cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+        cudaError_t e = cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, ctx().stream);
+        (void)s;
         if (e != cudaSuccess) { set_error("H2D -> %s", cudaGetErrorString(e)); return -1; }
         return 0;
     }
-    void free_() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void free_() { if (p) cudaFreeAsync(p, ctx().stream); p = nullptr; n = 0; }
     ~DevBuf() { free_(); }
 };
 

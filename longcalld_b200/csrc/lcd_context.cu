@@ -54,6 +54,12 @@ int lcd_gpu_init(int device, size_t pool_bytes) {
     c.device = device;
     c.sm_count = prop.multiProcessorCount;
     LCD_CUDA_OK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    {   // plans allocate from the device's stream-ordered pool; keep what they free for the next plan
+        cudaMemPool_t mp;
+        LCD_CUDA_OK(cudaDeviceGetDefaultMemPool(&mp, device));
+        unsigned long long keep = ~0ull;
+        LCD_CUDA_OK(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     if (pool_bytes == 0) {
         size_t free_b = 0, total_b = 0;
         LCD_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));

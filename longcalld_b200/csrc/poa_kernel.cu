@@ -65,6 +65,20 @@ poa_cta_kernel(const KernelArgs a) {
     }
 }
 
+// D2H of the consensus sequences: the device layout reserves the worst case (sum of the read lengths) per problem;
+// the bytes actually produced are packed back to back first, so the copy moves ~7 % of the buffer.
+__global__ void __launch_bounds__(256)
+poa_gather_cons_kernel(const uint8_t *cons, const Problem *problems, const DevResult *results, const unsigned long long *dst_off,
+                       uint8_t *packed, int n) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int i = wid; i < n; i += nw) {
+        if (results[i].status != ST_OK) continue;
+        const uint8_t *src = cons + problems[i].cons_off;
+        uint8_t *dst = packed + dst_off[i];
+        for (int k = lane; k < results[i].cons_len; k += 32) dst[k] = src[k];
+    }
+}
+
 // arena words a problem needs (mirrors Poa::carve) for given node / edge / DP cell budgets
 static uint64_t arena_need_words(uint64_t N, uint64_t E, int max_len, int n_reads, uint64_t dp_cells) {
     uint64_t top = 30 * ((N + 3) & ~3ull) + N * 4;
@@ -81,7 +95,9 @@ struct PoaPlan : Plan {
     DevBuf<int32_t> d_read_len, d_order;
     DevBuf<DevResult> d_results;
     DevBuf<uint32_t> d_queue;
-    DevBuf<unsigned long long> d_msa_used;
+    DevBuf<unsigned long long> d_msa_used, d_pack_off;
+    DevBuf<uint8_t> d_pack;
+    std::vector<unsigned long long> pack_off;
     std::vector<Problem> problems;
     std::vector<int64_t> cons_dev_off;
     std::vector<uint64_t> need_small;      // arena words with the estimated DP budget
@@ -202,9 +218,13 @@ struct PoaPlan : Plan {
         const uint64_t thread_words = (uint64_t)(512u << 10) / 4;     // <= 512 KiB per thread arena
         std::vector<int32_t> cls[3];
         uint64_t cw[3] = {0, 0, 0};
+        const char *tml = getenv("LCD_POA_THREAD_MAXLEN");      // tuning knob: longest read of a thread-per-problem POA
+        const int thread_max_len = tml ? atoi(tml) : 0;          // default: every banded problem on the warp kernel (measured fastest)
         const char *force = getenv("LCD_POA_FORCE_KIND");      // debug / profiling: 0 thread, 1 warp, 2 CTA for every problem
         for (int32_t i : order_all) {
-            int k = (need_small[i] <= thread_words && problems[i].max_len <= 640) ? 0 : (problems[i].max_len <= 1200 ? 1 : 2);
+            // kilobase problems run on the warp kernel as well: its strip rows, 32-wide backtrack and parallel fusion beat
+            // the CTA kernel's two-phase rows (kept for rows wider than the warp kernel's on-chip row cache: unbanded POA)
+            int k = (need_small[i] <= thread_words && problems[i].max_len <= thread_max_len) ? 0 : ((problems[i].par.wb >= 0 || problems[i].max_len <= 224) ? 1 : 2);
             if (force && force[0] >= '0' && force[0] <= '2' && !(force[0] == '0' && need_small[i] > thread_words)) k = force[0] - '0';
             cls[k].push_back(i); cw[k] = std::max(cw[k], need_small[i]);
         }
@@ -249,23 +269,43 @@ struct PoaPlan : Plan {
         return 0;
     }
 
-    int download(cudaStream_t s) {
-        h_results.resize(n); h_cons.resize(cons_bytes + 16);
+    // results always; consensus bytes (packed on the device first) and the MSA pool only when asked for
+    int download(cudaStream_t s, bool want_cons, bool want_msa) {
+        Context &c = ctx();
+        h_results.resize(n);
         if (n == 0) return 0;
         unsigned long long used = 0;
         LCD_CUDA_OK(cudaMemcpyAsync(h_results.data(), d_results.p, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, s));
-        LCD_CUDA_OK(cudaMemcpyAsync(h_cons.data(), d_cons.p, cons_bytes, cudaMemcpyDeviceToHost, s));
         LCD_CUDA_OK(cudaMemcpyAsync(&used, d_msa_used.p, sizeof(used), cudaMemcpyDeviceToHost, s));
         LCD_CUDA_OK(cudaStreamSynchronize(s));
-        used = std::min<unsigned long long>(used, msa_pool_bytes);
-        h_msa.resize(used + 16);
-        if (used) LCD_CUDA_OK(cudaMemcpyAsync(h_msa.data(), d_msa.p, used, cudaMemcpyDeviceToHost, s));
+        if (want_cons) {
+            pack_off.resize(n + 1);
+            unsigned long long tot = 0;
+            for (int i = 0; i < n; ++i) { pack_off[i] = tot; if (h_results[i].status == ST_OK) tot += (unsigned long long)h_results[i].cons_len; }
+            pack_off[n] = tot;
+            h_cons.resize(tot + 16);
+            if (tot) {
+                if (d_pack.n < tot + 16 && d_pack.alloc(tot + 16 + tot / 8)) return -1;
+                if (d_pack_off.n < (size_t)n + 1 && d_pack_off.alloc(n + 1)) return -1;
+                LCD_CUDA_OK(cudaStreamSynchronize(c.stream));                 // allocation ordered before use on s
+                LCD_CUDA_OK(cudaMemcpyAsync(d_pack_off.p, pack_off.data(), sizeof(unsigned long long) * (n + 1), cudaMemcpyHostToDevice, s));
+                poa_gather_cons_kernel<<<c.sm_count * 4, 256, 0, s>>>(d_cons.p, d_problems.p, d_results.p, d_pack_off.p, d_pack.p, n);
+                LCD_CUDA_OK(cudaGetLastError());
+                c.launches++;
+                LCD_CUDA_OK(cudaMemcpyAsync(h_cons.data(), d_pack.p, tot, cudaMemcpyDeviceToHost, s));
+            }
+        }
+        if (want_msa) {
+            used = std::min<unsigned long long>(used, msa_pool_bytes);
+            h_msa.resize(used + 16);
+            if (used) LCD_CUDA_OK(cudaMemcpyAsync(h_msa.data(), d_msa.p, used, cudaMemcpyDeviceToHost, s));
+        }
         LCD_CUDA_OK(cudaStreamSynchronize(s));
         return 0;
     }
 
     int work_units(cudaStream_t s, uint64_t *units) override {
-        if (download(s)) return -1;
+        if (download(s, false, false)) return -1;
 #ifdef LCD_POA_TIMING
         {   // debug: phase cycles of the 12 slowest problems and the batch totals
             std::vector<int> idx(n); for (int i = 0; i < n; ++i) idx[i] = i;
@@ -287,13 +327,13 @@ struct PoaPlan : Plan {
 
     int fetch(cudaStream_t s, uint8_t *cons, const int64_t *cons_off, uint8_t *msa, const int64_t *msa_off, const int64_t *msa_cap,
               lcd_poa_result_t *results) {
-        if (download(s)) return -1;
+        if (download(s, cons && cons_off, msa && msa_off && msa_cap)) return -1;
         int bad = 0, first_bad = 0;
         for (int i = 0; i < n; ++i) {
             const DevResult &r = h_results[i];
             results[i].status = r.status; results[i].cons_len = r.cons_len; results[i].msa_len = r.msa_len; results[i].n_nodes = r.n_nodes;
             if (r.status != ST_OK) { if (!bad) first_bad = r.status; ++bad; continue; }
-            if (cons && cons_off) memcpy(cons + cons_off[i], h_cons.data() + cons_dev_off[i], r.cons_len);
+            if (cons && cons_off) memcpy(cons + cons_off[i], h_cons.data() + pack_off[i], r.cons_len);
             if (msa && msa_off && msa_cap) {
                 const int64_t bytes = (int64_t)(problems[i].n_reads + 1) * r.msa_len;
                 if (bytes > msa_cap[i]) { results[i].status = LCD_POA_MSA_CAP; if (!bad) first_bad = LCD_POA_MSA_CAP; ++bad; continue; }
