@@ -67,6 +67,36 @@ int lcd_oracle_poa(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const
                    const lcd_poa_params_t *p, uint8_t *cons, int32_t *cons_len,
                    uint8_t *msa, int32_t *msa_len, int32_t msa_cap);
 
+/* ---- read -> haplotype assignment and phasing (src/assign_hap.c:16-547) ----------------------------- */
+typedef struct {
+    int32_t n_reads, n_vars;
+    int32_t target_var_cate;           /* LONGCALLD_* category mask (src/collect_var.h:11-28) */
+    int32_t is_ont;                    /* opt->is_ont */
+    const int32_t *ordered_read_ids;   /* chunk->ordered_read_ids [n_reads] */
+    const uint8_t *is_skipped;         /* chunk->is_skipped [n_reads] */
+    const int32_t *prof_start, *prof_end;  /* read_var_profile_t.start_var_idx / end_var_idx; (-1, -2) = no variant */
+    const int64_t *allele_off;         /* read r's alleles: alleles[allele_off[r] + (var - prof_start[r])] */
+    const int8_t *alleles;             /* 0 ref, 1 alt, -1 other, -2 low-quality alt */
+    const int32_t *var_cate;           /* chunk->var_i_to_cate [n_vars] */
+    const int32_t *var_type;           /* cand_var_t.var_type: BAM_CDIFF 8 / BAM_CINS 1 / BAM_CDEL 2 */
+    const int32_t *is_hp_indel;        /* cand_var_t.is_homopolymer_indel */
+    const int32_t *n_uniq_alles;       /* <= 4 */
+    const int32_t *alle_covs;          /* [n_vars][4] */
+    const int32_t *total_cov;
+    const int64_t *pos;                /* cand_var_t.pos */
+} lcd_phase_input_t;
+typedef struct {
+    int32_t *haps;                     /* chunk->haps [n_reads] */
+    int64_t *phase_sets;               /* chunk->phase_sets [n_reads] */
+    int32_t *hap_to_cons_alle;         /* [n_vars][3] (only variants in the target mask are written) */
+    int32_t *hap_to_alle_profile;      /* [n_vars][3][4] */
+    int64_t *var_phase_set;            /* [n_vars] */
+    int32_t *n_clean_agree_snps, *n_clean_conflict_snps;   /* [n_reads] */
+} lcd_phase_output_t;
+int lcd_oracle_assign_hap(const lcd_phase_input_t *in, lcd_phase_output_t *out);
+/* The order cgranges returns intervals in after cr_index (in-place MSD radix sort by start, not stable). */
+void lcd_oracle_cr_order(int n, const int32_t *start, const int32_t *label, int32_t *order_out);
+
 #ifdef __cplusplus
 }
 #endif

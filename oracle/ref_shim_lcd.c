@@ -1,0 +1,99 @@
+/* oracle/ref_shim_lcd.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Flat-C entry points over the UNMODIFIED longcallD sources (oracle/_ref/liblcdref.so) for the parts of the
+ * per-region worker that operate on bam_chunk_t: a chunk is assembled around the caller's flat arrays (only the
+ * fields the called function reads), the reference function is called, and its results are copied back out.
+ * Compiled only where /root/reference exists (oracle/Makefile, target _ref/libref_shim.so). */
+#include <stdlib.h>
+#include <string.h>
+#include "lcd_oracle.h"
+#include "call_var_main.h"
+#include "bam_utils.h"
+#include "collect_var.h"
+#include "assign_hap.h"
+#include "cgranges.h"
+
+/* globals of the reference's main.c, which is not linked here */
+int LONGCALLD_VERBOSE = 0;
+const char PROG[20] = "longcallD";
+char *CMD = (char *)"";
+
+/* assign_hap_based_on_germline_het_vars_kmeans (src/assign_hap.c:473) on a synthetic chunk */
+int ref_assign_hap(const lcd_phase_input_t *in, lcd_phase_output_t *out) {
+    const int nr = in->n_reads, nv = in->n_vars;
+    call_var_opt_t opt; memset(&opt, 0, sizeof(opt));
+    opt.is_ont = in->is_ont;
+    bam_chunk_t chunk; memset(&chunk, 0, sizeof(chunk));
+    chunk.n_reads = chunk.m_reads = nr;
+    chunk.ordered_read_ids = (int*)malloc(sizeof(int) * (nr + 1));
+    chunk.is_skipped = (uint8_t*)malloc(nr + 1);
+    chunk.haps = (int*)calloc(nr + 1, sizeof(int)); chunk.phase_scores = (int*)calloc(nr + 1, sizeof(int));
+    chunk.phase_sets = (hts_pos_t*)calloc(nr + 1, sizeof(hts_pos_t));
+    chunk.n_clean_agree_snps = (int*)calloc(nr + 1, sizeof(int)); chunk.n_clean_conflict_snps = (int*)calloc(nr + 1, sizeof(int));
+    for (int i = 0; i < nr; ++i) { chunk.ordered_read_ids[i] = in->ordered_read_ids[i]; chunk.is_skipped[i] = in->is_skipped[i]; }
+    for (int r = 0; r < nr; ++r) {          /* the output arrays are in/out: what the reference does not touch keeps its value */
+        chunk.haps[r] = out->haps[r]; chunk.phase_sets[r] = out->phase_sets[r];
+        chunk.n_clean_agree_snps[r] = out->n_clean_agree_snps[r]; chunk.n_clean_conflict_snps[r] = out->n_clean_conflict_snps[r];
+    }
+    chunk.n_cand_vars = nv;
+    chunk.cand_vars = (cand_var_t*)calloc(nv + 1, sizeof(cand_var_t));
+    chunk.var_i_to_cate = (int*)malloc(sizeof(int) * (nv + 1));
+    for (int v = 0; v < nv; ++v) {
+        cand_var_t *c = chunk.cand_vars + v;
+        c->pos = in->pos[v]; c->phase_set = -1; c->var_type = in->var_type[v]; c->is_homopolymer_indel = in->is_hp_indel[v];
+        c->total_cov = in->total_cov[v]; c->n_uniq_alles = in->n_uniq_alles[v];
+        c->alle_covs = (int*)malloc(sizeof(int) * 4);
+        for (int i = 0; i < 4; ++i) c->alle_covs[i] = in->alle_covs[4 * v + i];
+        c->ref_len = 1; c->alt_len = 1;
+        chunk.var_i_to_cate[v] = in->var_cate[v];
+    }
+    /* read_var_profile + read_var_cr exactly as collect_read_var_profile leaves them (src/collect_var.c:1389-1431) */
+    read_var_profile_t *p = (read_var_profile_t*)calloc(nr + 1, sizeof(read_var_profile_t));
+    cgranges_t *cr = cr_init();
+    for (int r = 0; r < nr; ++r) {
+        p[r].read_id = r; p[r].start_var_idx = in->prof_start[r]; p[r].end_var_idx = in->prof_end[r];
+        const int n = in->prof_end[r] - in->prof_start[r] + 1;
+        p[r].alleles = (int*)malloc(sizeof(int) * (n > 0 ? n : 1)); p[r].alt_qi = (int*)malloc(sizeof(int) * (n > 0 ? n : 1));
+        for (int i = 0; i < n; ++i) { p[r].alleles[i] = in->alleles[in->allele_off[r] + i]; p[r].alt_qi[i] = -1; }
+    }
+    for (int i = 0; i < nr; ++i) {
+        const int r = in->ordered_read_ids[i];
+        if (chunk.is_skipped[r]) continue;
+        if (p[r].start_var_idx < 0 || p[r].end_var_idx < 0) continue;
+        cr_add(cr, "cr", p[r].start_var_idx, p[r].end_var_idx + 1, r);
+    }
+    cr_index(cr);
+    chunk.read_var_profile = p; chunk.read_var_cr = cr;
+    assign_hap_based_on_germline_het_vars_kmeans(&opt, &chunk, in->target_var_cate);
+    for (int r = 0; r < nr; ++r) {
+        out->haps[r] = chunk.haps[r]; out->phase_sets[r] = chunk.phase_sets[r];
+        out->n_clean_agree_snps[r] = chunk.n_clean_agree_snps[r]; out->n_clean_conflict_snps[r] = chunk.n_clean_conflict_snps[r];
+    }
+    for (int v = 0; v < nv; ++v) {
+        cand_var_t *c = chunk.cand_vars + v;
+        if (c->hap_to_cons_alle) {
+            for (int h = 0; h < 3; ++h) {
+                out->hap_to_cons_alle[3 * v + h] = c->hap_to_cons_alle[h];
+                for (int a = 0; a < 4; ++a) out->hap_to_alle_profile[12 * v + 4 * h + a] = a < c->n_uniq_alles ? c->hap_to_alle_profile[h][a] : 0;
+                free(c->hap_to_alle_profile[h]);
+            }
+            free(c->hap_to_alle_profile); free(c->hap_to_cons_alle);
+            out->var_phase_set[v] = c->phase_set;
+        }
+        free(c->alle_covs);
+    }
+    for (int r = 0; r < nr; ++r) { free(p[r].alleles); free(p[r].alt_qi); }
+    free(p); cr_destroy(cr);
+    free(chunk.cand_vars); free(chunk.var_i_to_cate); free(chunk.ordered_read_ids); free(chunk.is_skipped); free(chunk.haps);
+    free(chunk.phase_scores); free(chunk.phase_sets); free(chunk.n_clean_agree_snps); free(chunk.n_clean_conflict_snps);
+    return 0;
+}
+
+/* cr_index + in-order listing: the order reads come back from cr_overlap */
+void ref_cr_order(int n, const int32_t *start, const int32_t *label, int32_t *order_out) {
+    cgranges_t *cr = cr_init();
+    for (int i = 0; i < n; ++i) cr_add(cr, "cr", start[i], start[i] + 1, label[i]);
+    cr_index(cr);
+    for (int i = 0; i < n; ++i) order_out[i] = cr_label(cr, i);
+    cr_destroy(cr);
+}

@@ -4,6 +4,7 @@
   wfa_utest.json.gz   WFA2-lib's own regression vectors (WFA2-lib/tests/wfa.utest.seq + the
                       match==0 goldens in tests/wfa.utest.check/: affine, affine2p, p0-p2,
                       wfapt0/1) -- pins the recurrence, the backtrace tie-breaks and wf-adaptive.
+  phase_lcd.json.gz   outputs of the UNMODIFIED reference read->haplotype assignment / phasing on seeded chunks.
   edlib_lcd.json.gz   outputs of the UNMODIFIED reference edlib (NW / HW, path) on seeded inputs.
   wfa_lcd.json.gz     outputs of the UNMODIFIED reference WFA2-lib (oracle/_ref/libref_shim.so)
                       at longcallD's own parameter points (src/align.h:21-26, src/align.c:398-406)
@@ -138,9 +139,25 @@ def edlib_lcd():
     return {"cases": cases}
 
 
+def phase_lcd():
+    """Outputs of the UNMODIFIED assign_hap_based_on_germline_het_vars_kmeans (src/assign_hap.c:473, via
+    oracle/_ref/libref_shim.so: ref_assign_hap) on seeded synthetic chunks (read x variant allele profiles)."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from test_oracle_phase import phase_cases, CMP
+    ref = T.ref_lib()
+    cases = []
+    for d, target, is_ont in phase_cases(20261019, 120):
+        if d["n_reads"] > 200 or d["n_vars"] > 150:
+            continue
+        out = T.phase(ref, "ref_assign_hap", d, target, is_ont)
+        cases.append({"in": {k: (np.asarray(v).reshape(-1).tolist() if hasattr(v, "tolist") else v) for k, v in d.items()},
+                      "target": target, "is_ont": is_ont, "out": {k: out[k].tolist() for k in CMP}})
+    return {"cases": cases}
+
+
 def main():
     only = sys.argv[1:]
-    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd), ("poa_lcd", poa_lcd), ("edlib_lcd", edlib_lcd)):
+    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd), ("poa_lcd", poa_lcd), ("edlib_lcd", edlib_lcd), ("phase_lcd", phase_lcd)):
         if only and name not in only:
             continue
         path = os.path.join(HERE, name + ".json.gz")
