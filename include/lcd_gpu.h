@@ -117,6 +117,41 @@ lcd_plan_t *lcd_edlib_plan_create(int n, const uint8_t *seqs, size_t seqs_len,
                                   const int32_t *mode, const int32_t *want_path);
 int  lcd_edlib_plan_fetch(lcd_plan_t *plan, void *stream, uint8_t *aln, const int64_t *aln_off, lcd_edlib_result_t *results);
 
+/* ---------------------------------------------------------------- K4: read -> haplotype assignment and phasing
+ * Replaces int assign_hap_based_on_germline_het_vars_kmeans(const call_var_opt_t *opt, bam_chunk_t *chunk,
+ * int target_var_cate) (src/assign_hap.h:12, src/assign_hap.c:473-547), called from collect_var_main
+ * (src/collect_var.c:2942,2975).  One lcd_phase_input_t is the flattened view of what the reference reads from a
+ * bam_chunk_t; lcd_phase_output_t is what it writes (in/out: entries the reference leaves alone keep their values,
+ * e.g. variants outside target_var_cate).  Chunks of a batch are independent (one CTA each). */
+typedef struct {
+    int32_t n_reads, n_vars;
+    int32_t target_var_cate;           /* LONGCALLD_* category mask (src/collect_var.h:11-28) */
+    int32_t is_ont;                    /* opt->is_ont */
+    const int32_t *ordered_read_ids;   /* chunk->ordered_read_ids [n_reads] */
+    const uint8_t *is_skipped;         /* chunk->is_skipped [n_reads] */
+    const int32_t *prof_start, *prof_end;  /* read_var_profile_t.start_var_idx / end_var_idx; (-1, -2) = no variant */
+    const int64_t *allele_off;         /* read r's alleles: alleles[allele_off[r] + (var - prof_start[r])] */
+    const int8_t *alleles;             /* read_var_profile_t.alleles: 0 ref, 1 alt, -1 other, -2 low-quality alt */
+    const int32_t *var_cate;           /* chunk->var_i_to_cate [n_vars] */
+    const int32_t *var_type;           /* cand_var_t.var_type: BAM_CDIFF 8 / BAM_CINS 1 / BAM_CDEL 2 */
+    const int32_t *is_hp_indel;        /* cand_var_t.is_homopolymer_indel */
+    const int32_t *n_uniq_alles;       /* cand_var_t.n_uniq_alles (<= 4) */
+    const int32_t *alle_covs;          /* cand_var_t.alle_covs, [n_vars][4] */
+    const int32_t *total_cov;          /* cand_var_t.total_cov */
+    const int64_t *pos;                /* cand_var_t.pos */
+} lcd_phase_input_t;
+typedef struct {
+    int32_t *haps;                     /* chunk->haps [n_reads] */
+    int64_t *phase_sets;               /* chunk->phase_sets [n_reads] */
+    int32_t *hap_to_cons_alle;         /* cand_var_t.hap_to_cons_alle, [n_vars][3] */
+    int32_t *hap_to_alle_profile;      /* cand_var_t.hap_to_alle_profile, [n_vars][3][4] */
+    int64_t *var_phase_set;            /* cand_var_t.phase_set [n_vars] */
+    int32_t *n_clean_agree_snps, *n_clean_conflict_snps;   /* chunk->n_clean_*_snps [n_reads] */
+} lcd_phase_output_t;
+int lcd_phase_batch(int n_chunks, const lcd_phase_input_t *in, lcd_phase_output_t *out);
+lcd_plan_t *lcd_phase_plan_create(int n_chunks, const lcd_phase_input_t *in, const lcd_phase_output_t *state);
+int  lcd_phase_plan_fetch(lcd_plan_t *plan, void *stream, lcd_phase_output_t *out);
+
 /* ---------------------------------------------------------------- K5: abPOA consensus + MSA
  * One *problem* is the progressive partial-order alignment of the reads of one (noisy region,
  * haplotype): it replaces the abPOA call sequence of abpoa_partial_aln_msa_cons (src/align.c:762-870;

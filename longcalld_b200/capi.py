@@ -68,7 +68,7 @@ def lib():
     L.lcd_gpu_launch_count.restype = C.c_uint64
     L.lcd_gpu_init.argtypes = [C.c_int, C.c_size_t]
     L.lcd_gpu_stream.restype = C.c_void_p
-    for fn in ("lcd_wfa_plan_create", "lcd_edlib_plan_create", "lcd_poa_plan_create"):
+    for fn in ("lcd_wfa_plan_create", "lcd_edlib_plan_create", "lcd_poa_plan_create", "lcd_phase_plan_create"):
         if hasattr(L, fn):
             getattr(L, fn).restype = C.c_void_p
     L.lcd_plan_run.argtypes = [C.c_void_p, C.c_void_p]
@@ -293,6 +293,61 @@ def xgaps(path):
     gap = (a == 1) | (a == 2)
     opens = gap & np.concatenate(([True], a[1:] != a[:-1]))
     return int((a == 3).sum() + opens.sum())
+
+
+# ----------------------------------------------------------------------------- K4: read -> haplotype assignment / phasing
+class PhaseInput(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("n_vars", C.c_int32), ("target_var_cate", C.c_int32), ("is_ont", C.c_int32),
+                ("ordered_read_ids", C.c_void_p), ("is_skipped", C.c_void_p), ("prof_start", C.c_void_p), ("prof_end", C.c_void_p),
+                ("allele_off", C.c_void_p), ("alleles", C.c_void_p), ("var_cate", C.c_void_p), ("var_type", C.c_void_p),
+                ("is_hp_indel", C.c_void_p), ("n_uniq_alles", C.c_void_p), ("alle_covs", C.c_void_p), ("total_cov", C.c_void_p),
+                ("pos", C.c_void_p)]
+
+
+class PhaseOutput(C.Structure):
+    _fields_ = [("haps", C.c_void_p), ("phase_sets", C.c_void_p), ("hap_to_cons_alle", C.c_void_p), ("hap_to_alle_profile", C.c_void_p),
+                ("var_phase_set", C.c_void_p), ("n_clean_agree_snps", C.c_void_p), ("n_clean_conflict_snps", C.c_void_p)]
+
+
+_PHASE_IN = (("ordered_read_ids", np.int32), ("is_skipped", np.uint8), ("prof_start", np.int32), ("prof_end", np.int32),
+             ("allele_off", np.int64), ("alleles", np.int8), ("var_cate", np.int32), ("var_type", np.int32),
+             ("is_hp_indel", np.int32), ("n_uniq_alles", np.int32), ("alle_covs", np.int32), ("total_cov", np.int32), ("pos", np.int64))
+_PHASE_OUT = (("haps", np.int32, 1, "r"), ("phase_sets", np.int64, 1, "r"), ("hap_to_cons_alle", np.int32, 3, "v"),
+              ("hap_to_alle_profile", np.int32, 12, "v"), ("var_phase_set", np.int64, 1, "v"),
+              ("n_clean_agree_snps", np.int32, 1, "r"), ("n_clean_conflict_snps", np.int32, 1, "r"))
+
+
+def _phase_structs(chunks, prefill):
+    """chunks: [(dict of flat arrays (the fields of lcd_phase_input_t), target_var_cate, is_ont)] -> ctypes arrays + keep-alives."""
+    n = len(chunks)
+    ins, outs, keep, results = (PhaseInput * max(n, 1))(), (PhaseOutput * max(n, 1))(), [], []
+    for i, (d, target, is_ont) in enumerate(chunks):
+        arrs = {k: np.ascontiguousarray(d[k], dtype=t) for k, t in _PHASE_IN}
+        keep.append(arrs)
+        ins[i] = PhaseInput(d["n_reads"], d["n_vars"], target, is_ont, *[arrs[k].ctypes.data for k, _ in _PHASE_IN])
+        out = {k: np.full(m * (d["n_reads"] if w == "r" else d["n_vars"]) + m, prefill, dtype=t) for k, t, m, w in _PHASE_OUT}
+        results.append(out)
+        outs[i] = PhaseOutput(*[out[k].ctypes.data for k, _, _, _ in _PHASE_OUT])
+    return ins, outs, keep, results
+
+
+def phase_batch(chunks, prefill=-9):
+    """Drop-in batch call over HOST buffers (lcd_phase_batch): one entry per region chunk.  Returns the output arrays per
+    chunk (entries the reference leaves untouched keep `prefill`)."""
+    ins, outs, keep, results = _phase_structs(chunks, prefill)
+    _check(lib().lcd_phase_batch(C.c_int(len(chunks)), ins, outs), "lcd_phase_batch")
+    return results
+
+
+class PhasePlan(_Plan):
+    def __init__(self, chunks, prefill=-9):
+        self.ins, self.outs, self.keep, self.results = _phase_structs(chunks, prefill)
+        lib().lcd_phase_plan_create.restype = C.c_void_p
+        super().__init__(lib().lcd_phase_plan_create(C.c_int(len(chunks)), self.ins, self.outs), len(chunks))
+
+    def fetch(self, stream=None):
+        _check(lib().lcd_phase_plan_fetch(self.h, C.c_void_p(stream or 0), self.outs), "lcd_phase_plan_fetch")
+        return self.results
 
 
 # ----------------------------------------------------------------------------- K5: POA
