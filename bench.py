@@ -264,7 +264,32 @@ def run_b200(args, rank, world):
                              _vp(wpar), ops.ctypes.data_as(C.c_char_p), _vp(off), _vp(wres))
         if rc:
             raise RuntimeError(L.lcd_gpu_last_error().decode())
+        if world > 1:
+            gather_step(tl)
         return buf, ref_off, ref_len, txt_off, tl
+
+    # N > 1: the one exchange of the path -- per region chunk (500 kb) the result records
+    # go to rank 0, which would stitch and write the VCF; NCCL gather over NVLink, inside the e2e region
+    from longcalld_b200 import shard
+    reg_per_chunk = max(1, int(round(0.5 * wl.n_regions / max(args.mbp, 1e-9))))
+    k_local = -(-wl.n_regions // reg_per_chunk)
+    k_pad = -(-k_local // shard.CHUNK_BLOCK) * shard.CHUNK_BLOCK
+    my_chunks = shard.deal_chunks(k_pad * world, world)[rank] if world > 1 else None
+    chunk_of_problem = wl.region_of // reg_per_chunk
+    chunk_first = np.searchsorted(chunk_of_problem, np.arange(k_pad + 1))
+    gathered = {"bytes": 0}
+
+    def gather_step(tl):
+        blobs = []
+        for j in range(k_pad):
+            a, b = int(chunk_first[j]), int(chunk_first[j + 1])
+            if a == b:
+                blobs.append(b"")
+                continue
+            blobs.append(pres[a:b].tobytes() + wres[a:b].tobytes())
+        out = shard.gather_chunk_results(my_chunks, blobs, k_pad * world, dst=0, device=torch.device("cuda", local))
+        if rank == 0:
+            gathered["bytes"] = sum(len(x) for x in out)
 
     wseqs, po, pl, to, tl = e2e_step()                              # also yields the consensus sequences for the WFA plan
     poa_plan = lcd.PoaPlan(wl.seqs, wl.first, wl.n_reads, wl.read_off, wl.read_len, lcd.poa_params())
@@ -349,6 +374,8 @@ def run_b200(args, rank, world):
                 "dtype": "int16/int32", "data": "synthetic", "config": workload_config(args, wl),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "clocks": clocks,
+                "gather": (None if world == 1 else {"what": "per-chunk POA/WFA result records to rank 0 (NCCL gather, inside e2e)",
+                                                    "bytes_per_step": int(gathered["bytes"])}),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "kernel": "poa_kernel" if dominant_is_poa else "wfa_kernel<32>+wfa_kernel<256>",
                              "algorithmic": (f"{poa_cells} banded POA cells x {POA_BYTES_PER_CELL} B" if dominant_is_poa
