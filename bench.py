@@ -236,7 +236,16 @@ def run_b200(args, rank, world):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL may print its version banner on stdout when it initialises; stdout carries exactly one JSON line, so the
+        # process group is brought up (first collective included) with fd 1 pointed at stderr
+        sys.stdout.flush()
+        saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
     lcd.init(local, 0)
     stream = torch.cuda.ExternalStream(lcd.stream(), device=local)
     wl = Workload(args.mbp, args.tech, args.seed + rank)            # weak scaling: one shard per GPU
