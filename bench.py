@@ -32,6 +32,8 @@ METRIC = "ref_Mbp_per_s_called"
 UNIT = "Mbp/s"
 WFA_BYTES_PER_CELL = 48          # 5 components written + 7 read, int32
 POA_BYTES_PER_CELL = 16          # 5 int16 planes written + 3 predecessor planes read
+EDLIB_BYTES_PER_BLOCKCOL = 28    # Peq word in + (P, M, score) stored for the traceback
+PHASE_BYTES_PER_PAIR = 24        # allele + variant state in, counts out, per (read, variant) pair and pass
 
 
 def load_peaks():
@@ -97,6 +99,11 @@ class Workload:
                 if reads:
                     self.problems.append(reads); self.refs.append(r.ref); self.region_of.append(ri)
         self.region_of = np.asarray(self.region_of)
+        # K4: the 500 kb chunks of the batch, phased twice per step (clean mask, then germline mask: collect_var.c:2942,2975)
+        self.phase = [(d, mask, int(tech == "ont")) for d in synth.phase_chunks(mbp, tech, seed) for mask in (synth.CATE_CLEAN, synth.CATE_GERMLINE)]
+        # K7: the sampling filter's read-vs-first-read NW paths (align.c:722-733)
+        from longcalld_b200.capi import pack_pairs
+        self.edlib = pack_pairs(synth.edlib_pairs(regions, seed=seed, mbp=mbp))
         self.seqs, self.first, self.n_reads, self.read_off, self.read_len = pack_poa(self.problems)
         self.n_poa = len(self.problems)
         self.n_poa_reads = int(self.n_reads.sum())
@@ -170,7 +177,24 @@ def reference_step(lib, wl, idx, n_threads):
     t2 = time.perf_counter()
     lib.ref_wfa_batch(C.c_int(n), _vp(seqs), _vp(po), _vp(pl), _vp(to), _vp(tl), _vp(wpar), _vp(ops), _vp(off), _vp(res), C.c_int(n_threads))
     t3 = time.perf_counter()
-    return (t1 - t0) + (t3 - t2), (t1 - t0), (t3 - t2)
+    # K4 / K7 on the same fraction of the batch
+    from longcalld_b200.capi import _phase_structs, EDLIB_RESULT_DTYPE
+    frac = n / max(1, wl.n_poa)
+    ph = wl.phase[:max(2, 2 * int(round(frac * len(wl.phase) / 2)))]
+    ins, outs, keep, _ = _phase_structs(ph, -9)
+    t4 = time.perf_counter()
+    lib.ref_phase_batch(C.c_int(len(ph)), ins, outs, C.c_int(n_threads))
+    t5 = time.perf_counter()
+    eseqs, qo, ql, to_, tl_ = wl.edlib
+    ne = max(1, int(round(frac * len(ql))))
+    m = np.zeros(ne, np.int32); w = np.ones(ne, np.int32); eres = np.zeros(ne, dtype=EDLIB_RESULT_DTYPE)
+    ecap = ql[:ne].astype(np.int64) + tl_[:ne] + 2
+    eoff = np.zeros(ne + 1, dtype=np.int64); np.cumsum(ecap, out=eoff[1:])
+    ealn = np.zeros(int(eoff[-1]) + 1, dtype=np.uint8)
+    t6 = time.perf_counter()
+    lib.ref_edlib_batch(C.c_int(ne), _vp(eseqs), _vp(qo), _vp(ql), _vp(to_), _vp(tl_), _vp(m), _vp(w), _vp(ealn), _vp(eoff), _vp(eres), C.c_int(n_threads))
+    t7 = time.perf_counter()
+    return (t1 - t0) + (t3 - t2) + (t5 - t4) + (t7 - t6), (t1 - t0), (t3 - t2), (t5 - t4), (t7 - t6)
 
 
 def region_sample(wl, frac, seed=1):
@@ -212,7 +236,8 @@ def run_reference(args, rank):
             "config": workload_config(args, wl),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_threads, "kind": "reference",
                              "sample": f"{len(regs)} of {wl.n_regions} regions ({mbp_sample:.3f} Mb) per step",
-                             "poa_s": sum(x[1] for x in t) / args.steps, "wfa_s": sum(x[2] for x in t) / args.steps},
+                             "poa_s": sum(x[1] for x in t) / args.steps, "wfa_s": sum(x[2] for x in t) / args.steps,
+                             "phase_s": sum(x[3] for x in t) / args.steps, "edlib_s": sum(x[4] for x in t) / args.steps},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -220,9 +245,13 @@ def run_reference(args, rank):
 def workload_config(args, wl):
     return {"workload": f"synthetic {args.tech.upper()} 30x noisy-region re-alignment, {args.mbp:g} Mb ref per GPU "
                         f"(BASELINE configs[1] shape), {wl.n_regions} regions",
-            "stages": ["K5 abPOA consensus+MSA per (region, haplotype) (align.c:762)",
+            "stages": ["K4 read->haplotype assignment + phasing per 500 kb chunk, clean then germline mask (assign_hap.c:473)",
+                       "K7 edlib NW path read-vs-first-read sampling filter (align.c:722)",
+                       "K5 abPOA consensus+MSA per (region, haplotype) (align.c:762)",
                        "K6 WFA gap-affine-2p ref-vs-consensus (align.c:565)"],
-            "stages_not_yet_on_gpu": ["K7 edlib + partial-read sub-graph POA", "2-consensus de-novo clustering", "K1-K4 pileup/phasing"],
+            "stages_not_yet_on_gpu": ["partial-read sub-graph POA", "2-consensus de-novo clustering", "K1-K3 pileup scan / sites / profile",
+                                      "vars from MSA (a13), somatic chain (a14)"],
+            "n_phase_chunk_passes": len(wl.phase), "n_edlib": int(len(wl.edlib[1])),
             "n_poa": wl.n_poa, "n_poa_reads": wl.n_poa_reads, "n_wfa": wl.n_poa,
             "l2": "flushed between timed steps (256 MiB write)", "seed": args.seed}
 
@@ -258,6 +287,14 @@ def run_b200(args, rank, world):
     pres = np.zeros(n, dtype=POA_RESULT_DTYPE)
     wres = np.zeros(n, dtype=WFA_RESULT_DTYPE)
 
+    from longcalld_b200.capi import _phase_structs, EDLIB_RESULT_DTYPE
+    ph_ins, ph_outs, ph_keep, ph_res = _phase_structs(wl.phase, -9)
+    eseqs, eqo, eql, eto, etl = wl.edlib
+    ne = len(eql)
+    emode = np.zeros(ne, np.int32); ewant = np.ones(ne, np.int32); eres = np.zeros(ne, dtype=EDLIB_RESULT_DTYPE)
+    eoff = np.zeros(ne + 1, dtype=np.int64); np.cumsum(eql.astype(np.int64) + etl + 2, out=eoff[1:])
+    ealn = np.zeros(int(eoff[-1]) + 1, dtype=np.uint8)
+
     def e2e_step():
         """host reads -> lcd_poa_batch -> consensus in host memory -> lcd_wfa_batch -> host CIGAR ops (all copies inside)"""
         rc = L.lcd_poa_batch(C.c_int(n), _vp(wl.seqs), C.c_size_t(wl.seqs.size), _vp(wl.first), _vp(wl.n_reads),
@@ -272,6 +309,12 @@ def run_b200(args, rank, world):
         rc = L.lcd_wfa_batch(C.c_int(n), _vp(buf), C.c_size_t(buf.size), _vp(ref_off), _vp(ref_len), _vp(txt_off), _vp(tl),
                              _vp(wpar), ops.ctypes.data_as(C.c_char_p), _vp(off), _vp(wres))
         if rc:
+            raise RuntimeError(L.lcd_gpu_last_error().decode())
+        # K4 and K7 through their host-buffer batch calls
+        if L.lcd_phase_batch(C.c_int(len(wl.phase)), ph_ins, ph_outs):
+            raise RuntimeError(L.lcd_gpu_last_error().decode())
+        if L.lcd_edlib_batch(C.c_int(ne), _vp(eseqs), C.c_size_t(eseqs.size), _vp(eqo), _vp(eql), _vp(eto), _vp(etl), _vp(emode), _vp(ewant),
+                             _vp(ealn), _vp(eoff), _vp(eres)):
             raise RuntimeError(L.lcd_gpu_last_error().decode())
         if world > 1:
             gather_step(tl)
@@ -303,6 +346,8 @@ def run_b200(args, rank, world):
     wseqs, po, pl, to, tl = e2e_step()                              # also yields the consensus sequences for the WFA plan
     poa_plan = lcd.PoaPlan(wl.seqs, wl.first, wl.n_reads, wl.read_off, wl.read_len, lcd.poa_params())
     wfa_plan = lcd.WfaPlan(wseqs, po, pl, to, tl, lcd.wfa_params())
+    phase_plan = lcd.PhasePlan(wl.phase)
+    edlib_plan = lcd.EdlibPlan(eseqs, eqo, eql, eto, etl, lcd.MODE_NW, 1)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -314,12 +359,16 @@ def run_b200(args, rank, world):
     def device_step():
         with torch.cuda.stream(stream):
             flush.zero_()
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             ev[0].record(stream)
             poa_plan.run()
             ev[1].record(stream)
             wfa_plan.run()
             ev[2].record(stream)
+            phase_plan.run()
+            ev[3].record(stream)
+            edlib_plan.run()
+            ev[4].record(stream)
         return ev
 
     for _ in range(args.warmup):
@@ -334,7 +383,11 @@ def run_b200(args, rank, world):
     launches = lcd.launch_count() - launches0
     poa_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
     wfa_ms = sum(e[1].elapsed_time(e[2]) for e in evs)
-    dev_ms = poa_ms + wfa_ms
+    phase_ms = sum(e[2].elapsed_time(e[3]) for e in evs)
+    edlib_ms = sum(e[3].elapsed_time(e[4]) for e in evs)
+    dev_ms = poa_ms + wfa_ms + phase_ms + edlib_ms
+    phase_pairs = phase_plan.work_units()
+    edlib_units = edlib_plan.work_units()
     poa_cells = poa_plan.work_units()
     wfa_cells = wfa_plan.work_units()
     r1 = poa_plan.fetch(want_msa=False)[0]
@@ -349,8 +402,9 @@ def run_b200(args, rank, world):
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
-    h2d = int(wl.seqs.size + 12 * len(wl.read_len) + 64 * n + (pl.astype(np.int64) + tl + 56).sum() + 96 * n)
-    d2h = int(pres["cons_len"].sum() + 32 * n + wres.nbytes + 2 * (pl.astype(np.int64) + tl + 4).sum())
+    phase_bytes = sum(a.nbytes for k in ph_keep for a in k.values())
+    h2d = int(phase_bytes + eseqs.size + 24 * ne + wl.seqs.size + 12 * len(wl.read_len) + 64 * n + (pl.astype(np.int64) + tl + 56).sum() + 96 * n)
+    d2h = int(sum(a.nbytes for r in ph_res for a in r.values()) + eres.nbytes + int(eres["aln_len"].sum()) + pres["cons_len"].sum() + 32 * n + wres.nbytes + 2 * (pl.astype(np.int64) + tl + 4).sum())
 
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -367,11 +421,11 @@ def run_b200(args, rank, world):
             nt = os.cpu_count() or 1
             frac = calibrate_sample(lib, wl, nt, target_s=15.0)
             regs, idx = region_sample(wl, frac)
-            dt, dt_poa, dt_wfa = reference_step(lib, wl, idx, nt)
+            dt, dt_poa, dt_wfa, dt_phase, dt_edlib = reference_step(lib, wl, idx, nt)
             mbp_sample = args.mbp * len(regs) / wl.n_regions
             cpu_baseline = {"value": mbp_sample / dt, "unit": UNIT, "cores": nt, "kind": "reference",
                             "sample": f"{len(regs)} of {wl.n_regions} regions ({mbp_sample:.3f} Mb): abPOA + WFA2-lib via oracle/_ref",
-                            "poa_s": dt_poa, "wfa_s": dt_wfa}
+                            "poa_s": dt_poa, "wfa_s": dt_wfa, "phase_s": dt_phase, "edlib_s": dt_edlib}
     if rank == 0:
         peak, which = load_peaks()
         poa_gbs = poa_cells * POA_BYTES_PER_CELL / (poa_ms / args.steps / 1e3) / 1e9
@@ -391,7 +445,12 @@ def run_b200(args, rank, world):
                                              else f"{wfa_cells} wavefront cells x {WFA_BYTES_PER_CELL} B"),
                              "peak_source": which,
                              "per_kernel": {"poa_kernel": {"ms": poa_ms / args.steps, "cells": poa_cells, "GBps": poa_gbs, "frac": poa_gbs / peak},
-                                            "wfa_kernels": {"ms": wfa_ms / args.steps, "cells": wfa_cells, "GBps": wfa_gbs, "frac": wfa_gbs / peak}}},
+                                            "wfa_kernels": {"ms": wfa_ms / args.steps, "cells": wfa_cells, "GBps": wfa_gbs, "frac": wfa_gbs / peak},
+                                            "phase_kernel": {"ms": phase_ms / args.steps, "read_var_pairs": phase_pairs,
+                                                             "GBps": phase_pairs * PHASE_BYTES_PER_PAIR / (phase_ms / args.steps / 1e3) / 1e9,
+                                                             "note": "one pass of the pair list; the kernel makes 2-11 passes (seed + iterations), latency-bound"},
+                                            "edlib_kernel": {"ms": edlib_ms / args.steps, "block_columns": edlib_units,
+                                                             "GBps": edlib_units * EDLIB_BYTES_PER_BLOCKCOL / (edlib_ms / args.steps / 1e3) / 1e9}}},
                 "cpu_baseline": cpu_baseline}
         print(json.dumps(line))
     if world > 1:

@@ -129,3 +129,152 @@ def wfa_problems(regions):
     """The ref-vs-consensus gap-affine-2p / no-heuristic alignments of wfa_collect_aln_str
     (reference src/align.c:565): one per (region, haplotype)."""
     return [(r.ref, h) for r in regions for h in r.haps]
+
+
+# ----------------------------------------------------------------------------- K4 workload: read x variant profiles of region chunks
+CATE = {"CLEAN_HET_SNP": 0x004, "CLEAN_HET_INDEL": 0x008, "CLEAN_HOM_VAR": 0x080, "NOISY_CAND_HET_VAR": 0x100,
+        "NOISY_CAND_HOM_VAR": 0x200, "LOW_COV_VAR": 0x001, "CAND_SOMATIC_VAR": 0x040}
+CATE_CLEAN = 0x004 | 0x008 | 0x080
+CATE_GERMLINE = CATE_CLEAN | 0x100 | 0x200
+
+
+def make_phase_chunk(rng, n_vars=60, n_reads=200, err=0.02, tech="hifi", shuffle_order=False):
+    """A synthetic chunk for the read -> haplotype assignment: a diploid truth over sorted candidate variants of mixed
+    categories, reads sampled from the two haplotypes spanning contiguous variant ranges (some skipped, some empty,
+    some carrying noise / low-quality calls), with coverage counts derived from the reads."""
+    pos = np.sort(rng.choice(np.arange(1000, 1000 + 400 * max(n_vars, 1)), size=n_vars, replace=False)).astype(np.int64)
+    cats = np.array([CATE["CLEAN_HET_SNP"], CATE["CLEAN_HET_INDEL"], CATE["CLEAN_HOM_VAR"], CATE["NOISY_CAND_HET_VAR"],
+                     CATE["NOISY_CAND_HOM_VAR"], CATE["LOW_COV_VAR"], CATE["CAND_SOMATIC_VAR"]], dtype=np.int32)
+    var_cate = rng.choice(cats, size=n_vars, p=[0.45, 0.12, 0.12, 0.12, 0.05, 0.08, 0.06]).astype(np.int32)
+    var_type = np.where(var_cate == CATE["CLEAN_HET_SNP"], 8, rng.choice([8, 1, 2], size=n_vars)).astype(np.int32)
+    var_type[var_cate == CATE["CLEAN_HET_INDEL"]] = rng.choice([1, 2], size=int((var_cate == CATE["CLEAN_HET_INDEL"]).sum()))
+    is_hp = ((var_type != 8) & (rng.random(n_vars) < 0.3)).astype(np.int32)
+    is_hom = (var_cate == CATE["CLEAN_HOM_VAR"]) | (var_cate == CATE["NOISY_CAND_HOM_VAR"])
+    alt_hap = rng.integers(1, 3, n_vars)                                   # which haplotype carries the alt allele of a het variant
+    n_uniq = np.where(rng.random(n_vars) < 0.1, 3, 2).astype(np.int32)
+    starts, ends, haps_true = [], [], []
+    for _ in range(n_reads):
+        if n_vars == 0 or rng.random() < 0.05:
+            starts.append(-1); ends.append(-2)
+        else:
+            s = int(rng.integers(0, n_vars)); L = int(np.clip(rng.poisson(12 if tech == "hifi" else 25), 1, n_vars))
+            starts.append(s); ends.append(min(n_vars - 1, s + L - 1))
+        haps_true.append(int(rng.integers(1, 3)))
+    order = np.argsort(np.array(starts), kind="stable")                    # reads arrive position-sorted
+    starts = np.array(starts, dtype=np.int32)[order]; ends = np.array(ends, dtype=np.int32)[order]; haps_true = np.array(haps_true)[order]
+    allele_off = np.zeros(n_reads, dtype=np.int64); alle = []
+    alle_covs = np.zeros((n_vars, 4), dtype=np.int32)
+    is_skipped = (rng.random(n_reads) < 0.04).astype(np.uint8)
+    for r in range(n_reads):
+        allele_off[r] = len(alle)
+        for v in range(starts[r], ends[r] + 1) if starts[r] >= 0 else ():
+            a = 1 if (is_hom[v] or alt_hap[v] == haps_true[r]) else 0
+            u = rng.random()
+            if u < err: a = 1 - a
+            elif u < err + 0.02: a = -1
+            elif u < err + 0.03: a = -2
+            elif u < err + 0.035 and n_uniq[v] == 3: a = 2
+            alle.append(a)
+            if a >= 0 and not is_skipped[r]: alle_covs[v, a] += 1
+    ordered = np.arange(n_reads, dtype=np.int32)
+    if shuffle_order: rng.shuffle(ordered)
+    d = dict(n_reads=n_reads, n_vars=n_vars, ordered_read_ids=ordered, is_skipped=is_skipped, prof_start=starts, prof_end=ends,
+             allele_off=allele_off, alleles=np.array(alle + [0], dtype=np.int8), var_cate=var_cate, var_type=var_type, is_hp_indel=is_hp,
+             n_uniq_alles=n_uniq, alle_covs=np.ascontiguousarray(alle_covs), total_cov=alle_covs.sum(axis=1).astype(np.int32), pos=pos)
+    return d
+
+
+
+def phase_chunks(mbp, tech="hifi", seed=11):
+    """The 500 kb region chunks of `mbp` megabases (LONGCALLD_BAM_CHUNK_REG_SIZE, reference src/bam_utils.h:10) as inputs of
+    the read -> haplotype assignment: ~1 050 reads (30x of 15 kb reads incl. overlap reads) and ~6 candidate variants per kb."""
+    rng = np.random.default_rng(seed + 7)
+    n = max(1, int(round(mbp / 0.5)))
+    return [make_phase_chunk(rng, n_vars=int(rng.integers(2500, 3500)), n_reads=int(rng.integers(950, 1150)), err=0.01, tech=tech)
+            for _ in range(n)]
+
+
+def edlib_pairs(regions, per_mb=210, seed=11, mbp=1.0):
+    """(read window, first read) pairs of the sampling filter (edlib_xgaps in collect_partial_aln_beg_end, reference
+    src/align.c:722-733): ~42 calls per 0.2 Mb on the bundled HiFi data."""
+    rng = np.random.default_rng(seed + 13)
+    want = max(1, int(round(per_mb * mbp)))
+    # the calls observed on the bundled data are 42 per 0.2 Mb with a median of 202 x 202 and a maximum of 941 x 941
+    # (only deep regions are sampled), so pairs come from windows of 100-1000 bp
+    cand = [(ri, k) for ri, r in enumerate(regions) if 100 <= len(r.reads[0]) <= 1000
+            for k in range(1, len(r.reads)) if 100 <= len(r.reads[k]) <= 1000]
+    pick = rng.choice(len(cand), size=min(want, len(cand)), replace=False)
+    return [(regions[cand[i][0]].reads[cand[i][1]], regions[cand[i][0]].reads[0]) for i in np.sort(pick)]
+
+
+# ----------------------------------------------------------------------------- K2 workload: difference lists vs candidate sites
+def make_pileup_chunk(rng, ref_len=20000, n_reads=200, read_len=(3000, 8000), var_every=150, err_every=800, min_sv_len=50):
+    """A synthetic region chunk for the per-site coverage pass: sorted candidate sites (SNPs, small and large insertions,
+    deletions) and, per read, the difference list the pileup scan derives from an =/X CIGAR (digar1_t: '=' runs, X bases,
+    I / D events with read offset, low-quality flag) plus base qualities.  Reads carry the variants of their haplotype, random
+    errors (some promoted to sites), and length-perturbed copies of large insertions (the reference matches those fuzzily)."""
+    INS, DEL, EQ, DIFF = 1, 2, 7, 8
+    ref0 = 100000
+    truth = []
+    p = ref0 + int(rng.integers(20, var_every))
+    while p < ref0 + ref_len - 200:
+        u = rng.random()
+        if u < 0.7: v = (p, DIFF, 1, 1, rng.integers(0, 4, 1).astype(np.uint8))
+        elif u < 0.85:
+            n = int(rng.integers(min_sv_len, 130)) if rng.random() < 0.15 else int(rng.integers(1, 11))
+            v = (p, INS, 0, n, rng.integers(0, 4, n).astype(np.uint8))
+        else:
+            n = int(rng.integers(1, 11)); v = (p, DEL, n, 0, np.zeros(0, np.uint8))
+        truth.append((v, int(rng.integers(1, 4))))                     # carried by hap 1, hap 2 or both (3)
+        p += int(rng.integers(12, 2 * var_every)) + v[2]
+    reads, extra_sites = [], []
+    for _ in range(n_reads):
+        L = int(rng.integers(*read_len)); beg = ref0 + int(rng.integers(0, max(1, ref_len - L))); end = min(ref0 + ref_len - 1, beg + L - 1)
+        hap = int(rng.integers(1, 3)); ev = []
+        for v, h in truth:
+            if beg < v[0] and v[0] + v[2] + 2 < end and (h & hap) and rng.random() < 0.95:
+                alt = v[4]
+                if v[1] == INS and v[3] >= min_sv_len and rng.random() < 0.6:       # a noisy copy of a large insertion
+                    alt = rng.integers(0, 4, max(1, int(v[3] * rng.uniform(0.7, 1.3)))).astype(np.uint8)
+                ev.append((v[0], v[1], v[2], len(alt), alt, int(rng.random() < 0.05)))
+        q = beg + int(rng.integers(1, err_every))
+        while q + 12 < end:
+            t = [DIFF, INS, DEL][int(rng.integers(0, 3))]; n = 1 if t == DIFF else int(rng.integers(1, 4))
+            alt = rng.integers(0, 4, n).astype(np.uint8) if t != DEL else np.zeros(0, np.uint8)
+            ev.append((q, t, 0 if t == INS else (n if t == DEL else 1), len(alt), alt, int(rng.random() < 0.3)))
+            q += int(rng.integers(12, 2 * err_every))
+        ev.sort(key=lambda e: (e[0], e[1]))
+        keep, last = [], beg
+        for e in ev:                                                    # events at least 12 reference bases apart
+            if e[0] >= last + 12 and e[0] + e[2] + 12 < end: keep.append(e); last = e[0] + e[2]
+        for e in keep:
+            if rng.random() < 0.02: extra_sites.append((e[0], e[1], e[2], e[3], e[4]))
+        reads.append((beg, end, int(rng.random() < 0.5), keep))
+    key = lambda s: (s[0] if s[1] == DIFF else s[0] - 1, s[1], s[2], s[3], bytes(s[4]))
+    sites, seen = [], set()
+    for s_ in sorted([t[0] for t in truth] + extra_sites, key=key):
+        if key(s_) not in seen: seen.add(key(s_)); sites.append(s_)
+    d = dict(n_reads=n_reads, n_sites=len(sites), min_bq=10, min_sv_len=min_sv_len)
+    dpos, dtype, dlen, dqi, dlow, daoff, dalt, dfirst, ndig, qoff, quals = [], [], [], [], [], [], [], [], [], [], []
+    for beg, end, rev, ev in reads:
+        dfirst.append(len(dpos)); cur, qi = beg, 0
+        for pos, t, rl, al, alt, low in ev:
+            if pos > cur: dpos.append(cur); dtype.append(EQ); dlen.append(pos - cur); dqi.append(qi); dlow.append(0); daoff.append(len(dalt)); qi += pos - cur
+            dpos.append(pos); dtype.append(t); dlen.append(rl if t == DEL else al); dqi.append(qi); dlow.append(low); daoff.append(len(dalt)); dalt.extend(alt.tolist())
+            if t == DIFF: qi += 1; cur = pos + 1
+            elif t == INS: qi += al; cur = pos
+            else: cur = pos + rl
+        if end >= cur: dpos.append(cur); dtype.append(EQ); dlen.append(end - cur + 1); dqi.append(qi); dlow.append(0); daoff.append(len(dalt)); qi += end - cur + 1
+        ndig.append(len(dpos) - dfirst[-1]); qoff.append(len(quals)); quals.extend(rng.integers(3, 41, qi + 1).tolist())
+    d.update(ordered_read_ids=np.arange(n_reads, dtype=np.int32), is_skipped=(rng.random(n_reads) < 0.04).astype(np.uint8),
+             read_beg=np.array([r[0] for r in reads], np.int64), read_end=np.array([r[1] for r in reads], np.int64),
+             read_is_rev=np.array([r[2] for r in reads], np.uint8), digar_first=np.array(dfirst, np.int64), n_digar=np.array(ndig, np.int32),
+             qual_off=np.array(qoff, np.int64), qual=np.array(quals + [0], np.uint8), digar_pos=np.array(dpos + [0], np.int64),
+             digar_type=np.array(dtype + [0], np.int8), digar_len=np.array(dlen + [0], np.int32), digar_qi=np.array(dqi + [0], np.int32),
+             digar_low_qual=np.array(dlow + [0], np.uint8), digar_alt_off=np.array(daoff + [0], np.int64), digar_alt=np.array(dalt + [0], np.uint8),
+             site_pos=np.array([s_[0] for s_ in sites] + [0], np.int64), site_type=np.array([s_[1] for s_ in sites] + [0], np.int32),
+             site_ref_len=np.array([s_[2] for s_ in sites] + [0], np.int32), site_alt_len=np.array([s_[3] for s_ in sites] + [0], np.int32))
+    aoff, flat = [], []
+    for s_ in sites: aoff.append(len(flat)); flat.extend(s_[4].tolist())
+    d.update(site_alt_off=np.array(aoff + [0], np.int64), site_alt=np.array(flat + [0], np.uint8))
+    return d

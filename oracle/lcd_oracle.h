@@ -97,6 +97,34 @@ int lcd_oracle_assign_hap(const lcd_phase_input_t *in, lcd_phase_output_t *out);
 /* The order cgranges returns intervals in after cr_index (in-place MSD radix sort by start, not stable). */
 void lcd_oracle_cr_order(int n, const int32_t *start, const int32_t *label, int32_t *order_out);
 
+/* ---- pileup scan: per-site coverage (src/collect_var.c:238-249, src/bam_utils.c:287-329) ------------- */
+typedef struct {
+    int32_t n_reads, n_sites;
+    int32_t min_bq, min_sv_len;        /* opt->min_bq, opt->min_sv_len */
+    const int32_t *ordered_read_ids;   /* chunk->ordered_read_ids [n_reads] */
+    const uint8_t *is_skipped;         /* chunk->is_skipped [n_reads] */
+    const int64_t *read_beg, *read_end;/* digar_t.beg / end (1-based, inclusive) */
+    const uint8_t *read_is_rev;        /* digar_t.is_rev */
+    const int64_t *digar_first;        /* first digar1_t of read r in the digar_* arrays */
+    const int32_t *n_digar;            /* digar_t.n_digar */
+    const int64_t *qual_off;           /* read r's base qualities: qual[qual_off[r] + qi] */
+    const uint8_t *qual;
+    const int64_t *digar_pos;          /* digar1_t.pos */
+    const int8_t  *digar_type;         /* BAM_CEQUAL 7 / BAM_CDIFF 8 / BAM_CINS 1 / BAM_CDEL 2 / clips 4,5 */
+    const int32_t *digar_len, *digar_qi;
+    const uint8_t *digar_low_qual;
+    const int64_t *digar_alt_off;      /* X / I: alt bases digar_alt[digar_alt_off[d] .. +len) */
+    const uint8_t *digar_alt;
+    const int64_t *site_pos;           /* var_site_t.pos, sorted as collect_all_cand_var_sites leaves them */
+    const int32_t *site_type, *site_ref_len, *site_alt_len;
+    const int64_t *site_alt_off;
+    const uint8_t *site_alt;
+} lcd_pileup_input_t;
+typedef struct {
+    int32_t *site_counts;              /* [n_sites][8]: total_cov, low_qual_cov, alle_covs[0..1], strand_to_alle_covs[0..1][0..1] */
+} lcd_pileup_output_t;
+int lcd_oracle_collect_cand_vars(const lcd_pileup_input_t *in, lcd_pileup_output_t *out);
+
 #ifdef __cplusplus
 }
 #endif

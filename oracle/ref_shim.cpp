@@ -174,4 +174,40 @@ int ref_poa_batch(int n, const uint8_t *seqs, const int32_t *first_read, const i
     return 0;
 }
 
+
+// Batch drivers for the K7 / K4 legs of bench.py's reference arm (one problem / one chunk per worker thread, like kt_for).
+int ref_edlib_batch(int n, const uint8_t *seqs, const int64_t *q_off, const int32_t *qlen, const int64_t *t_off, const int32_t *tlen,
+                    const int32_t *mode, const int32_t *want_path, uint8_t *aln, const int64_t *aln_off, lcd_edlib_result_t *results, int n_threads) {
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (;;) {
+            int i = next.fetch_add(1);
+            if (i >= n) break;
+            ref_edlib_align(seqs + q_off[i], qlen[i], seqs + t_off[i], tlen[i], mode[i], want_path[i], aln ? aln + aln_off[i] : NULL, &results[i]);
+        }
+    };
+    if (n_threads <= 1) { work(); return 0; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work);
+    for (auto &t : th) t.join();
+    return 0;
+}
+
+int ref_assign_hap(const lcd_phase_input_t *in, lcd_phase_output_t *out);      // ref_shim_lcd.c
+int ref_phase_batch(int n, const lcd_phase_input_t *in, lcd_phase_output_t *out, int n_threads) {
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (;;) {
+            int i = next.fetch_add(1);
+            if (i >= n) break;
+            ref_assign_hap(&in[i], &out[i]);
+        }
+    };
+    if (n_threads <= 1) { work(); return 0; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work);
+    for (auto &t : th) t.join();
+    return 0;
+}
+
 }

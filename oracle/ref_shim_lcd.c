@@ -97,3 +97,49 @@ void ref_cr_order(int n, const int32_t *start, const int32_t *label, int32_t *or
     for (int i = 0; i < n; ++i) order_out[i] = cr_label(cr, i);
     cr_destroy(cr);
 }
+
+int collect_cand_vars(const call_var_opt_t *opt, bam_chunk_t *chunk, int n_var_sites, var_site_t *var_sites);   /* src/collect_var.c:238 (no prototype in the headers) */
+/* collect_cand_vars (src/collect_var.c:238) on a synthetic chunk: digar_t / var_site_t records around the flat arrays */
+int ref_collect_cand_vars(const lcd_pileup_input_t *in, lcd_pileup_output_t *out) {
+    const int nr = in->n_reads, ns = in->n_sites;
+    call_var_opt_t opt; memset(&opt, 0, sizeof(opt));
+    opt.min_bq = in->min_bq; opt.min_sv_len = in->min_sv_len;
+    bam_chunk_t chunk; memset(&chunk, 0, sizeof(chunk));
+    chunk.n_reads = chunk.m_reads = nr; chunk.tid = 0;
+    chunk.ordered_read_ids = (int*)malloc(sizeof(int) * (nr + 1));
+    chunk.is_skipped = (uint8_t*)malloc(nr + 1);
+    chunk.digars = (digar_t*)calloc(nr + 1, sizeof(digar_t));
+    for (int r = 0; r < nr; ++r) {
+        chunk.ordered_read_ids[r] = in->ordered_read_ids[r]; chunk.is_skipped[r] = in->is_skipped[r];
+        digar_t *g = chunk.digars + r;
+        g->beg = in->read_beg[r]; g->end = in->read_end[r]; g->is_rev = in->read_is_rev[r];
+        g->n_digar = g->m_digar = in->n_digar[r];
+        g->digars = (digar1_t*)calloc(g->n_digar + 1, sizeof(digar1_t));
+        g->qual = (uint8_t*)(in->qual + in->qual_off[r]);
+        for (int k = 0; k < g->n_digar; ++k) {
+            const int64_t d = in->digar_first[r] + k;
+            digar1_t *x = g->digars + k;
+            x->pos = in->digar_pos[d]; x->type = in->digar_type[d]; x->len = in->digar_len[d]; x->qi = in->digar_qi[d];
+            x->is_low_qual = in->digar_low_qual[d];
+            x->alt_seq = (x->type == BAM_CDIFF || x->type == BAM_CINS) ? (uint8_t*)(in->digar_alt + in->digar_alt_off[d]) : NULL;
+        }
+    }
+    var_site_t *sites = (var_site_t*)calloc(ns + 1, sizeof(var_site_t));
+    for (int i = 0; i < ns; ++i) {
+        sites[i].tid = 0; sites[i].pos = in->site_pos[i]; sites[i].var_type = in->site_type[i];
+        sites[i].ref_len = in->site_ref_len[i]; sites[i].alt_len = in->site_alt_len[i];
+        sites[i].alt_seq = (uint8_t*)(in->site_alt + in->site_alt_off[i]);
+    }
+    collect_cand_vars(&opt, &chunk, ns, sites);
+    for (int i = 0; i < ns; ++i) {
+        cand_var_t *c = chunk.cand_vars + i; int32_t *o = out->site_counts + 8 * i;
+        o[0] = c->total_cov; o[1] = c->low_qual_cov; o[2] = c->alle_covs[0]; o[3] = c->alle_covs[1];
+        for (int s = 0; s < 2; ++s) for (int a = 0; a < 2; ++a) o[4 + 2 * s + a] = c->strand_to_alle_covs[s][a];
+        free(c->alle_covs); free(c->strand_to_alle_covs[0]); free(c->strand_to_alle_covs[1]); free(c->strand_to_alle_covs);
+        if (c->alt_seq) free(c->alt_seq);
+    }
+    free(chunk.cand_vars); free(sites);
+    for (int r = 0; r < nr; ++r) free(chunk.digars[r].digars);
+    free(chunk.digars); free(chunk.ordered_read_ids); free(chunk.is_skipped);
+    return 0;
+}

@@ -4,6 +4,7 @@
   wfa_utest.json.gz   WFA2-lib's own regression vectors (WFA2-lib/tests/wfa.utest.seq + the
                       match==0 goldens in tests/wfa.utest.check/: affine, affine2p, p0-p2,
                       wfapt0/1) -- pins the recurrence, the backtrace tie-breaks and wf-adaptive.
+  pileup_lcd.json.gz  outputs of the UNMODIFIED reference per-site coverage pass (collect_cand_vars) on seeded chunks.
   phase_lcd.json.gz   outputs of the UNMODIFIED reference read->haplotype assignment / phasing on seeded chunks.
   edlib_lcd.json.gz   outputs of the UNMODIFIED reference edlib (NW / HW, path) on seeded inputs.
   wfa_lcd.json.gz     outputs of the UNMODIFIED reference WFA2-lib (oracle/_ref/libref_shim.so)
@@ -155,9 +156,24 @@ def phase_lcd():
     return {"cases": cases}
 
 
+def pileup_lcd():
+    """Outputs of the UNMODIFIED collect_cand_vars (src/collect_var.c:238, via oracle/_ref/libref_shim.so) on seeded chunks."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from longcalld_b200 import synth
+    ref = T.ref_lib()
+    rng = np.random.default_rng(20261020)
+    cases = []
+    for it in range(24):
+        d = synth.make_pileup_chunk(rng, ref_len=int(rng.choice([600, 3000])), n_reads=int(rng.choice([1, 8, 40])),
+                                    read_len=(200, 500) if it % 3 == 0 else (800, 2500), var_every=int(rng.choice([40, 150])), err_every=int(rng.choice([60, 800])))
+        counts = T.pileup(ref, "ref_collect_cand_vars", d)
+        cases.append({"in": {k: (np.asarray(v).reshape(-1).tolist() if hasattr(v, "tolist") else v) for k, v in d.items()}, "counts": counts.tolist()})
+    return {"cases": cases}
+
+
 def main():
     only = sys.argv[1:]
-    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd), ("poa_lcd", poa_lcd), ("edlib_lcd", edlib_lcd), ("phase_lcd", phase_lcd)):
+    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd), ("poa_lcd", poa_lcd), ("edlib_lcd", edlib_lcd), ("phase_lcd", phase_lcd), ("pileup_lcd", pileup_lcd)):
         if only and name not in only:
             continue
         path = os.path.join(HERE, name + ".json.gz")

@@ -197,59 +197,10 @@ class PhaseOutput(C.Structure):
                 ("var_phase_set", C.c_void_p), ("n_clean_agree_snps", C.c_void_p), ("n_clean_conflict_snps", C.c_void_p)]
 
 
-CATE = {"CLEAN_HET_SNP": 0x004, "CLEAN_HET_INDEL": 0x008, "CLEAN_HOM_VAR": 0x080, "NOISY_CAND_HET_VAR": 0x100,
-        "NOISY_CAND_HOM_VAR": 0x200, "LOW_COV_VAR": 0x001, "CAND_SOMATIC_VAR": 0x040}
-CATE_CLEAN = 0x004 | 0x008 | 0x080
-CATE_GERMLINE = CATE_CLEAN | 0x100 | 0x200
+from longcalld_b200.synth import CATE, CATE_CLEAN, CATE_GERMLINE, make_phase_chunk  # noqa: E402,F401  (the generator lives with the workloads)
 PHASE_IN_FIELDS = (("ordered_read_ids", np.int32), ("is_skipped", np.uint8), ("prof_start", np.int32), ("prof_end", np.int32),
                    ("allele_off", np.int64), ("alleles", np.int8), ("var_cate", np.int32), ("var_type", np.int32),
                    ("is_hp_indel", np.int32), ("n_uniq_alles", np.int32), ("alle_covs", np.int32), ("total_cov", np.int32), ("pos", np.int64))
-
-
-def make_phase_chunk(rng, n_vars=60, n_reads=200, err=0.02, tech="hifi", shuffle_order=False):
-    """A synthetic chunk for the read -> haplotype assignment: a diploid truth over sorted candidate variants of mixed
-    categories, reads sampled from the two haplotypes spanning contiguous variant ranges (some skipped, some empty,
-    some carrying noise / low-quality calls), with coverage counts derived from the reads."""
-    pos = np.sort(rng.choice(np.arange(1000, 1000 + 400 * max(n_vars, 1)), size=n_vars, replace=False)).astype(np.int64)
-    cats = np.array([CATE["CLEAN_HET_SNP"], CATE["CLEAN_HET_INDEL"], CATE["CLEAN_HOM_VAR"], CATE["NOISY_CAND_HET_VAR"],
-                     CATE["NOISY_CAND_HOM_VAR"], CATE["LOW_COV_VAR"], CATE["CAND_SOMATIC_VAR"]], dtype=np.int32)
-    var_cate = rng.choice(cats, size=n_vars, p=[0.45, 0.12, 0.12, 0.12, 0.05, 0.08, 0.06]).astype(np.int32)
-    var_type = np.where(var_cate == CATE["CLEAN_HET_SNP"], 8, rng.choice([8, 1, 2], size=n_vars)).astype(np.int32)
-    var_type[var_cate == CATE["CLEAN_HET_INDEL"]] = rng.choice([1, 2], size=int((var_cate == CATE["CLEAN_HET_INDEL"]).sum()))
-    is_hp = ((var_type != 8) & (rng.random(n_vars) < 0.3)).astype(np.int32)
-    is_hom = (var_cate == CATE["CLEAN_HOM_VAR"]) | (var_cate == CATE["NOISY_CAND_HOM_VAR"])
-    alt_hap = rng.integers(1, 3, n_vars)                                   # which haplotype carries the alt allele of a het variant
-    n_uniq = np.where(rng.random(n_vars) < 0.1, 3, 2).astype(np.int32)
-    starts, ends, haps_true = [], [], []
-    for _ in range(n_reads):
-        if n_vars == 0 or rng.random() < 0.05:
-            starts.append(-1); ends.append(-2)
-        else:
-            s = int(rng.integers(0, n_vars)); L = int(np.clip(rng.poisson(12 if tech == "hifi" else 25), 1, n_vars))
-            starts.append(s); ends.append(min(n_vars - 1, s + L - 1))
-        haps_true.append(int(rng.integers(1, 3)))
-    order = np.argsort(np.array(starts), kind="stable")                    # reads arrive position-sorted
-    starts = np.array(starts, dtype=np.int32)[order]; ends = np.array(ends, dtype=np.int32)[order]; haps_true = np.array(haps_true)[order]
-    allele_off = np.zeros(n_reads, dtype=np.int64); alle = []
-    alle_covs = np.zeros((n_vars, 4), dtype=np.int32)
-    is_skipped = (rng.random(n_reads) < 0.04).astype(np.uint8)
-    for r in range(n_reads):
-        allele_off[r] = len(alle)
-        for v in range(starts[r], ends[r] + 1) if starts[r] >= 0 else ():
-            a = 1 if (is_hom[v] or alt_hap[v] == haps_true[r]) else 0
-            u = rng.random()
-            if u < err: a = 1 - a
-            elif u < err + 0.02: a = -1
-            elif u < err + 0.03: a = -2
-            elif u < err + 0.035 and n_uniq[v] == 3: a = 2
-            alle.append(a)
-            if a >= 0 and not is_skipped[r]: alle_covs[v, a] += 1
-    ordered = np.arange(n_reads, dtype=np.int32)
-    if shuffle_order: rng.shuffle(ordered)
-    d = dict(n_reads=n_reads, n_vars=n_vars, ordered_read_ids=ordered, is_skipped=is_skipped, prof_start=starts, prof_end=ends,
-             allele_off=allele_off, alleles=np.array(alle + [0], dtype=np.int8), var_cate=var_cate, var_type=var_type, is_hp_indel=is_hp,
-             n_uniq_alles=n_uniq, alle_covs=np.ascontiguousarray(alle_covs), total_cov=alle_covs.sum(axis=1).astype(np.int32), pos=pos)
-    return d
 
 
 def phase(lib, fn, d, target, is_ont=0):
@@ -264,3 +215,32 @@ def phase(lib, fn, d, target, is_ont=0):
     rc = getattr(lib, fn)(C.byref(inp), C.byref(o))
     assert rc == 0
     return out
+
+
+# ----------------------------------------------------------------------------- pileup (K2) helpers
+PILEUP_IN_FIELDS = (("ordered_read_ids", np.int32), ("is_skipped", np.uint8), ("read_beg", np.int64), ("read_end", np.int64),
+                    ("read_is_rev", np.uint8), ("digar_first", np.int64), ("n_digar", np.int32), ("qual_off", np.int64), ("qual", np.uint8),
+                    ("digar_pos", np.int64), ("digar_type", np.int8), ("digar_len", np.int32), ("digar_qi", np.int32),
+                    ("digar_low_qual", np.uint8), ("digar_alt_off", np.int64), ("digar_alt", np.uint8),
+                    ("site_pos", np.int64), ("site_type", np.int32), ("site_ref_len", np.int32), ("site_alt_len", np.int32),
+                    ("site_alt_off", np.int64), ("site_alt", np.uint8))
+
+
+class PileupInput(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("n_sites", C.c_int32), ("min_bq", C.c_int32), ("min_sv_len", C.c_int32)] + \
+               [(k, C.c_void_p) for k, _ in PILEUP_IN_FIELDS]
+
+
+class PileupOutput(C.Structure):
+    _fields_ = [("site_counts", C.c_void_p)]
+
+
+def pileup(lib, fn, d):
+    """Run a per-site coverage implementation with the flat-array interface -> (n_sites, 8) counts."""
+    keep = {k: np.ascontiguousarray(d[k], dtype=t) for k, t in PILEUP_IN_FIELDS}
+    inp = PileupInput(d["n_reads"], d["n_sites"], d["min_bq"], d["min_sv_len"], *[keep[k].ctypes.data for k, _ in PILEUP_IN_FIELDS])
+    counts = np.full((d["n_sites"] + 1, 8), -9, np.int32)
+    out = PileupOutput(counts.ctypes.data)
+    rc = getattr(lib, fn)(C.byref(inp), C.byref(out))
+    assert rc == 0
+    return counts[:d["n_sites"]]
