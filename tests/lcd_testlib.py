@@ -7,9 +7,12 @@ TEST INFRASTRUCTURE: nothing in the product imports this module.
 import ctypes as C
 import os
 import subprocess
+import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "liblcd_oracle.so")
 REF_SHIM_SO = os.path.join(ORACLE_DIR, "_ref", "libref_shim.so")
