@@ -117,6 +117,41 @@ lcd_plan_t *lcd_edlib_plan_create(int n, const uint8_t *seqs, size_t seqs_len,
                                   const int32_t *mode, const int32_t *want_path);
 int  lcd_edlib_plan_fetch(lcd_plan_t *plan, void *stream, uint8_t *aln, const int64_t *aln_off, lcd_edlib_result_t *results);
 
+/* ---------------------------------------------------------------- K2: pileup scan, per-site coverage
+ * Replaces int collect_cand_vars(const call_var_opt_t *opt, bam_chunk_t *chunk, int n_var_sites, var_site_t *var_sites)
+ * (src/collect_var.c:238-249: update_cand_vars_from_digar, src/bam_utils.c:287-329, for every kept read), called from
+ * collect_var_main step 1.3 (src/collect_var.c:2913).  Inputs are the flattened digar_t / digar1_t records of the chunk's
+ * reads (src/bam_utils.h:27-43) and its sorted var_site_t list (src/collect_var.h:43-47); the output is, per site, what the
+ * reference leaves in cand_var_t: total_cov, low_qual_cov, alle_covs[0..1], strand_to_alle_covs[0..1][0..1]. */
+typedef struct {
+    int32_t n_reads, n_sites;
+    int32_t min_bq, min_sv_len;        /* opt->min_bq, opt->min_sv_len */
+    const int32_t *ordered_read_ids;   /* chunk->ordered_read_ids [n_reads] */
+    const uint8_t *is_skipped;         /* chunk->is_skipped [n_reads] */
+    const int64_t *read_beg, *read_end;/* digar_t.beg / end (1-based, inclusive) */
+    const uint8_t *read_is_rev;        /* digar_t.is_rev */
+    const int64_t *digar_first;        /* first digar1_t of read r in the digar_* arrays */
+    const int32_t *n_digar;            /* digar_t.n_digar */
+    const int64_t *qual_off;           /* read r's base qualities: qual[qual_off[r] + qi] */
+    const uint8_t *qual;
+    const int64_t *digar_pos;          /* digar1_t.pos */
+    const int8_t  *digar_type;         /* BAM_CEQUAL 7 / BAM_CDIFF 8 / BAM_CINS 1 / BAM_CDEL 2 / clips 4,5 */
+    const int32_t *digar_len, *digar_qi;
+    const uint8_t *digar_low_qual;
+    const int64_t *digar_alt_off;      /* X / I: alt bases digar_alt[digar_alt_off[d] .. +len) (digar1_t.alt_seq) */
+    const uint8_t *digar_alt;
+    const int64_t *site_pos;           /* var_site_t.pos, sorted as collect_all_cand_var_sites leaves them */
+    const int32_t *site_type, *site_ref_len, *site_alt_len;
+    const int64_t *site_alt_off;       /* var_site_t.alt_seq */
+    const uint8_t *site_alt;
+} lcd_pileup_input_t;
+typedef struct {
+    int32_t *site_counts;              /* [n_sites][8]: total_cov, low_qual_cov, alle_covs[0..1], strand_to_alle_covs[0..1][0..1] */
+} lcd_pileup_output_t;
+int lcd_pileup_batch(int n_chunks, const lcd_pileup_input_t *in, lcd_pileup_output_t *out);
+lcd_plan_t *lcd_pileup_plan_create(int n_chunks, const lcd_pileup_input_t *in);
+int  lcd_pileup_plan_fetch(lcd_plan_t *plan, void *stream, lcd_pileup_output_t *out);
+
 /* ---------------------------------------------------------------- K4: read -> haplotype assignment and phasing
  * Replaces int assign_hap_based_on_germline_het_vars_kmeans(const call_var_opt_t *opt, bam_chunk_t *chunk,
  * int target_var_cate) (src/assign_hap.h:12, src/assign_hap.c:473-547), called from collect_var_main

@@ -68,7 +68,7 @@ def lib():
     L.lcd_gpu_launch_count.restype = C.c_uint64
     L.lcd_gpu_init.argtypes = [C.c_int, C.c_size_t]
     L.lcd_gpu_stream.restype = C.c_void_p
-    for fn in ("lcd_wfa_plan_create", "lcd_edlib_plan_create", "lcd_poa_plan_create", "lcd_phase_plan_create"):
+    for fn in ("lcd_wfa_plan_create", "lcd_edlib_plan_create", "lcd_poa_plan_create", "lcd_phase_plan_create", "lcd_pileup_plan_create"):
         if hasattr(L, fn):
             getattr(L, fn).restype = C.c_void_p
     L.lcd_plan_run.argtypes = [C.c_void_p, C.c_void_p]
@@ -293,6 +293,56 @@ def xgaps(path):
     gap = (a == 1) | (a == 2)
     opens = gap & np.concatenate(([True], a[1:] != a[:-1]))
     return int((a == 3).sum() + opens.sum())
+
+
+# ----------------------------------------------------------------------------- K2: pileup scan, per-site coverage
+_PILEUP_IN = (("ordered_read_ids", np.int32), ("is_skipped", np.uint8), ("read_beg", np.int64), ("read_end", np.int64),
+              ("read_is_rev", np.uint8), ("digar_first", np.int64), ("n_digar", np.int32), ("qual_off", np.int64), ("qual", np.uint8),
+              ("digar_pos", np.int64), ("digar_type", np.int8), ("digar_len", np.int32), ("digar_qi", np.int32),
+              ("digar_low_qual", np.uint8), ("digar_alt_off", np.int64), ("digar_alt", np.uint8),
+              ("site_pos", np.int64), ("site_type", np.int32), ("site_ref_len", np.int32), ("site_alt_len", np.int32),
+              ("site_alt_off", np.int64), ("site_alt", np.uint8))
+
+
+class PileupInput(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("n_sites", C.c_int32), ("min_bq", C.c_int32), ("min_sv_len", C.c_int32)] + \
+               [(k, C.c_void_p) for k, _ in _PILEUP_IN]
+
+
+class PileupOutput(C.Structure):
+    _fields_ = [("site_counts", C.c_void_p)]
+
+
+def _pileup_structs(chunks):
+    n = len(chunks)
+    ins, outs, keep, results = (PileupInput * max(n, 1))(), (PileupOutput * max(n, 1))(), [], []
+    for i, d in enumerate(chunks):
+        arrs = {k: np.ascontiguousarray(d[k], dtype=t) for k, t in _PILEUP_IN}
+        keep.append(arrs)
+        ins[i] = PileupInput(d["n_reads"], d["n_sites"], d["min_bq"], d["min_sv_len"], *[arrs[k].ctypes.data for k, _ in _PILEUP_IN])
+        counts = np.zeros((d["n_sites"] + 1, 8), dtype=np.int32)
+        results.append(counts)
+        outs[i] = PileupOutput(counts.ctypes.data)
+    return ins, outs, keep, results
+
+
+def pileup_batch(chunks):
+    """Drop-in batch call over HOST buffers (lcd_pileup_batch): per chunk the (n_sites, 8) coverage counters
+    [total_cov, low_qual_cov, alle_covs[0..1], strand_to_alle_covs[0..1][0..1]]."""
+    ins, outs, keep, results = _pileup_structs(chunks)
+    _check(lib().lcd_pileup_batch(C.c_int(len(chunks)), ins, outs), "lcd_pileup_batch")
+    return [r[:d["n_sites"]] for r, d in zip(results, chunks)]
+
+
+class PileupPlan(_Plan):
+    def __init__(self, chunks):
+        self.chunks = chunks
+        self.ins, self.outs, self.keep, self.results = _pileup_structs(chunks)
+        super().__init__(lib().lcd_pileup_plan_create(C.c_int(len(chunks)), self.ins), len(chunks))
+
+    def fetch(self, stream=None):
+        _check(lib().lcd_pileup_plan_fetch(self.h, C.c_void_p(stream or 0), self.outs), "lcd_pileup_plan_fetch")
+        return [r[:d["n_sites"]] for r, d in zip(self.results, self.chunks)]
 
 
 # ----------------------------------------------------------------------------- K4: read -> haplotype assignment / phasing

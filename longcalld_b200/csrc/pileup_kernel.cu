@@ -1,0 +1,154 @@
+// pileup_kernel.cu -- K2 launcher and host plan: batched per-site coverage pass, one thread per read.
+// Device logic and design notes: pileup_device.cuh.
+#include "lcd_common.cuh"
+#include "pileup_device.cuh"
+#include <algorithm>
+
+namespace lcd {
+namespace pileup {
+
+constexpr int THREADS = 128;
+
+__global__ void __launch_bounds__(THREADS)
+pileup_kernel(const KernelArgs a) {
+    for (long long g = (long long)blockIdx.x * THREADS + threadIdx.x; g < a.n_reads_total; g += (long long)gridDim.x * THREADS)
+        process_read(a, g);
+}
+
+template <typename T, typename U> static void append(std::vector<T> &dst, const U *src, size_t n, long long add = 0) {
+    const size_t o = dst.size(); dst.resize(o + n);
+    for (size_t i = 0; i < n; ++i) dst[o + i] = (T)(src[i] + (U)add);
+}
+
+struct PileupPlan : Plan {
+    std::vector<Chunk> chunks; std::vector<long long> site_off;
+    long long tot_reads = 0, tot_sites = 0, tot_events = 0;
+    DevBuf<Chunk> d_chunks; DevBuf<int32_t> d_read_chunk, d_ndig, d_dlen, d_dqi, d_stype, d_sref, d_salt, d_counts;
+    DevBuf<uint8_t> d_active, d_rev, d_qual, d_dlow, d_dalt, d_site_alt; DevBuf<int8_t> d_dtype;
+    DevBuf<long long> d_beg, d_end, d_dfirst, d_qoff, d_dpos, d_daoff, d_spos, d_saoff;
+    std::vector<int32_t> h_counts;
+
+    int build(int n_, const lcd_pileup_input_t *in) {
+        n = n_;
+        Context &c = ctx();
+        if (n == 0) return 0;
+        std::vector<int32_t> read_chunk, ndig, dlen, dqi, stype, sref, salt;
+        std::vector<uint8_t> active, rev, qual, dlow, dalt, site_alt; std::vector<int8_t> dtype;
+        std::vector<long long> beg, end, dfirst, qoff, dpos, daoff, spos, saoff;
+        chunks.resize(n); site_off.resize(n);
+        for (int i = 0; i < n; ++i) {
+            const lcd_pileup_input_t &x = in[i];
+            if (x.n_reads < 0 || x.n_sites < 0) { set_error("lcd_pileup: chunk %d has negative sizes", i); return -1; }
+            Chunk &k = chunks[i];
+            k.n_sites = x.n_sites; k.min_bq = x.min_bq; k.min_sv_len = x.min_sv_len; k.pad = 0; k.site_off = tot_sites; site_off[i] = tot_sites;
+            long long n_ev = 0, n_q = 0, n_alt = 0, n_salt = 0;
+            for (int r = 0; r < x.n_reads; ++r) {
+                if (x.n_digar[r] < 0 || x.digar_first[r] < 0) { set_error("lcd_pileup: chunk %d read %d has an invalid event range", i, r); return -1; }
+                n_ev = std::max<long long>(n_ev, x.digar_first[r] + x.n_digar[r]);
+            }
+            for (long long d = 0; d < n_ev; ++d) {
+                const int t = x.digar_type[d];
+                if (t == CDIFF || t == CINS) n_alt = std::max<long long>(n_alt, x.digar_alt_off[d] + x.digar_len[d]);
+            }
+            for (int r = 0; r < x.n_reads; ++r) {                   // qualities: up to the last read base an event of the read points at
+                long long hi = 0;
+                for (long long d = x.digar_first[r]; d < x.digar_first[r] + x.n_digar[r]; ++d) {
+                    const int t = x.digar_type[d];
+                    const long long last = t == CDEL ? x.digar_qi[d] : (long long)x.digar_qi[d] + x.digar_len[d] - 1;
+                    if (t == CDIFF || t == CINS || t == CDEL) hi = std::max(hi, last + 1);
+                }
+                n_q = std::max(n_q, x.qual_off[r] + hi);
+            }
+            for (int s = 0; s < x.n_sites; ++s) if (x.site_type[s] == CDIFF || x.site_type[s] == CINS) n_salt = std::max<long long>(n_salt, x.site_alt_off[s] + x.site_alt_len[s]);
+            std::vector<uint8_t> listed(x.n_reads, 0);
+            for (int r = 0; r < x.n_reads; ++r) { const int id = x.ordered_read_ids[r]; if (id >= 0 && id < x.n_reads) listed[id] = 1; }
+            const long long ev0 = (long long)dpos.size(), q0 = (long long)qual.size(), a0 = (long long)dalt.size(), sa0 = (long long)site_alt.size();
+            for (int r = 0; r < x.n_reads; ++r) { read_chunk.push_back(i); active.push_back(listed[r] && !x.is_skipped[r]); }
+            append(beg, x.read_beg, x.n_reads); append(end, x.read_end, x.n_reads); append(rev, x.read_is_rev, x.n_reads);
+            append(dfirst, x.digar_first, x.n_reads, ev0); append(ndig, x.n_digar, x.n_reads); append(qoff, x.qual_off, x.n_reads, q0);
+            append(qual, x.qual, (size_t)n_q);
+            append(dpos, x.digar_pos, (size_t)n_ev); append(dtype, x.digar_type, (size_t)n_ev); append(dlen, x.digar_len, (size_t)n_ev);
+            append(dqi, x.digar_qi, (size_t)n_ev); append(dlow, x.digar_low_qual, (size_t)n_ev); append(daoff, x.digar_alt_off, (size_t)n_ev, a0);
+            append(dalt, x.digar_alt, (size_t)n_alt);
+            append(spos, x.site_pos, x.n_sites); append(stype, x.site_type, x.n_sites); append(sref, x.site_ref_len, x.n_sites);
+            append(salt, x.site_alt_len, x.n_sites); append(saoff, x.site_alt_off, x.n_sites, sa0); append(site_alt, x.site_alt, (size_t)n_salt);
+            tot_reads += x.n_reads; tot_sites += x.n_sites; tot_events += n_ev;
+        }
+        auto pad = [](auto &v) { v.push_back(0); };
+        pad(read_chunk); pad(active); pad(beg); pad(end); pad(rev); pad(dfirst); pad(ndig); pad(qoff); pad(qual); pad(dpos); pad(dtype); pad(dlen); pad(dqi);
+        pad(dlow); pad(daoff); pad(dalt); pad(spos); pad(stype); pad(sref); pad(salt); pad(saoff); pad(site_alt);
+        cudaStream_t s = c.stream;
+        if (d_chunks.upload(chunks.data(), n, s) || d_read_chunk.upload(read_chunk.data(), read_chunk.size(), s) || d_active.upload(active.data(), active.size(), s) ||
+            d_beg.upload(beg.data(), beg.size(), s) || d_end.upload(end.data(), end.size(), s) || d_rev.upload(rev.data(), rev.size(), s) ||
+            d_dfirst.upload(dfirst.data(), dfirst.size(), s) || d_ndig.upload(ndig.data(), ndig.size(), s) || d_qoff.upload(qoff.data(), qoff.size(), s) ||
+            d_qual.upload(qual.data(), qual.size(), s) || d_dpos.upload(dpos.data(), dpos.size(), s) || d_dtype.upload(dtype.data(), dtype.size(), s) ||
+            d_dlen.upload(dlen.data(), dlen.size(), s) || d_dqi.upload(dqi.data(), dqi.size(), s) || d_dlow.upload(dlow.data(), dlow.size(), s) ||
+            d_daoff.upload(daoff.data(), daoff.size(), s) || d_dalt.upload(dalt.data(), dalt.size(), s) || d_spos.upload(spos.data(), spos.size(), s) ||
+            d_stype.upload(stype.data(), stype.size(), s) || d_sref.upload(sref.data(), sref.size(), s) || d_salt.upload(salt.data(), salt.size(), s) ||
+            d_saoff.upload(saoff.data(), saoff.size(), s) || d_site_alt.upload(site_alt.data(), site_alt.size(), s)) return -1;
+        if (d_counts.alloc(8 * (size_t)tot_sites + 8)) return -1;
+        LCD_CUDA_OK(cudaStreamSynchronize(s));
+        return 0;
+    }
+
+    int run(cudaStream_t s) override {
+        Context &c = ctx();
+        if (n == 0 || tot_reads == 0) return 0;
+        LCD_CUDA_OK(cudaMemsetAsync(d_counts.p, 0, sizeof(int32_t) * 8 * (size_t)tot_sites, s));
+        KernelArgs a;
+        a.chunks = d_chunks.p; a.n_reads_total = tot_reads; a.read_chunk = d_read_chunk.p; a.read_active = d_active.p;
+        a.read_beg = d_beg.p; a.read_end = d_end.p; a.read_is_rev = d_rev.p; a.digar_first = d_dfirst.p; a.n_digar = d_ndig.p;
+        a.qual_off = d_qoff.p; a.qual = d_qual.p; a.digar_pos = d_dpos.p; a.digar_type = d_dtype.p; a.digar_len = d_dlen.p; a.digar_qi = d_dqi.p;
+        a.digar_low_qual = d_dlow.p; a.digar_alt_off = d_daoff.p; a.digar_alt = d_dalt.p;
+        a.site_pos = d_spos.p; a.site_type = d_stype.p; a.site_ref_len = d_sref.p; a.site_alt_len = d_salt.p; a.site_alt_off = d_saoff.p; a.site_alt = d_site_alt.p;
+        a.site_counts = d_counts.p;
+        const int grid = (int)std::min<long long>((tot_reads + THREADS - 1) / THREADS, (long long)c.sm_count * 16);
+        pileup_kernel<<<grid, THREADS, 0, s>>>(a);
+        LCD_CUDA_OK(cudaGetLastError());
+        c.launches++;
+        return 0;
+    }
+
+    int work_units(cudaStream_t, uint64_t *units) override { *units = (uint64_t)tot_events; return 0; }   // difference-list entries walked
+
+    int fetch(cudaStream_t s, lcd_pileup_output_t *out) {
+        if (n == 0) return 0;
+        h_counts.resize(8 * (size_t)tot_sites + 8);
+        if (tot_sites) LCD_CUDA_OK(cudaMemcpyAsync(h_counts.data(), d_counts.p, sizeof(int32_t) * 8 * (size_t)tot_sites, cudaMemcpyDeviceToHost, s));
+        LCD_CUDA_OK(cudaStreamSynchronize(s));
+        for (int i = 0; i < n; ++i) if (chunks[i].n_sites) memcpy(out[i].site_counts, h_counts.data() + 8 * site_off[i], sizeof(int32_t) * 8 * (size_t)chunks[i].n_sites);
+        return 0;
+    }
+};
+
+} // namespace pileup
+} // namespace lcd
+
+using namespace lcd;
+
+extern "C" {
+
+lcd_plan_t *lcd_pileup_plan_create(int n_chunks, const lcd_pileup_input_t *in) {
+    if (ensure_ready()) return nullptr;
+    if (n_chunks < 0 || (n_chunks > 0 && !in)) { set_error("lcd_pileup_plan_create: invalid arguments"); return nullptr; }
+    pileup::PileupPlan *p = new pileup::PileupPlan();
+    if (p->build(n_chunks, in)) { delete p; return nullptr; }
+    return reinterpret_cast<lcd_plan_t *>(p);
+}
+
+int lcd_pileup_plan_fetch(lcd_plan_t *plan, void *stream, lcd_pileup_output_t *out) {
+    pileup::PileupPlan *p = dynamic_cast<pileup::PileupPlan *>(reinterpret_cast<Plan *>(plan));
+    if (!p || !out) { set_error("lcd_pileup_plan_fetch: not a pileup plan / null outputs"); return -1; }
+    return p->fetch(pick_stream(stream), out);
+}
+
+int lcd_pileup_batch(int n_chunks, const lcd_pileup_input_t *in, lcd_pileup_output_t *out) {
+    lcd_plan_t *plan = lcd_pileup_plan_create(n_chunks, in);
+    if (!plan) return -1;
+    int rc = lcd_plan_run(plan, nullptr);
+    if (!rc) rc = lcd_pileup_plan_fetch(plan, nullptr, out);
+    lcd_plan_destroy(plan);
+    return rc;
+}
+
+}
