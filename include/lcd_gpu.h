@@ -152,6 +152,31 @@ int lcd_pileup_batch(int n_chunks, const lcd_pileup_input_t *in, lcd_pileup_outp
 lcd_plan_t *lcd_pileup_plan_create(int n_chunks, const lcd_pileup_input_t *in);
 int  lcd_pileup_plan_fetch(lcd_plan_t *plan, void *stream, lcd_pileup_output_t *out);
 
+/* ---------------------------------------------------------------- K3: pileup scan, read x variant profile
+ * Replaces read_var_profile_t *collect_read_var_profile(const call_var_opt_t *opt, bam_chunk_t *chunk)
+ * (src/collect_var.c:1389-1431: update_read_vs_all_var_profile_from_digar, src/bam_utils.c:446-552, for every kept read;
+ * germline categories -- a chunk with LONGCALLD_CAND_SOMATIC_VAR candidates (-s) is rejected), called from collect_var_main
+ * step 3.1 (src/collect_var.c:2933).  The sites of lcd_pileup_input_t are the chunk's cand_vars.  The output is exactly what
+ * K4 (lcd_phase_input_t) consumes: prof_start / prof_end / allele_off / alleles, plus alt_qi. */
+typedef struct {
+    const int32_t *var_cate;           /* chunk->var_i_to_cate [n_sites] */
+    const int64_t *nreg_first;         /* read r's noisy intervals (digar_t.noisy_regs): nreg_*[nreg_first[r] .. +n_nreg[r]) */
+    const int32_t *n_nreg;
+    const int64_t *nreg_beg, *nreg_end;/* cgranges coordinates: [beg, end) */
+} lcd_profile_extra_t;
+typedef struct {
+    int32_t *prof_start, *prof_end;    /* read_var_profile_t.start_var_idx / end_var_idx [n_reads]; (-1, -2): none */
+    int64_t *allele_off;               /* read r's row: alleles[allele_off[r] + (var - prof_start[r])] */
+    int8_t  *alleles;                  /* read_var_profile_t.alleles: 0 ref, 1 alt, -1 other / not set, -2 low-quality alt */
+    int32_t *alt_qi;                   /* read_var_profile_t.alt_qi */
+    int64_t alleles_cap;               /* capacity of alleles[] / alt_qi[] (>= lcd_profile_capacity(in)) */
+    int64_t n_alleles;                 /* out: entries used */
+} lcd_profile_output_t;
+int64_t lcd_profile_capacity(const lcd_pileup_input_t *in);
+int lcd_profile_batch(int n_chunks, const lcd_pileup_input_t *in, const lcd_profile_extra_t *extra, lcd_profile_output_t *out);
+lcd_plan_t *lcd_profile_plan_create(int n_chunks, const lcd_pileup_input_t *in, const lcd_profile_extra_t *extra);
+int  lcd_profile_plan_fetch(lcd_plan_t *plan, void *stream, lcd_profile_output_t *out);
+
 /* ---------------------------------------------------------------- K4: read -> haplotype assignment and phasing
  * Replaces int assign_hap_based_on_germline_het_vars_kmeans(const call_var_opt_t *opt, bam_chunk_t *chunk,
  * int target_var_cate) (src/assign_hap.h:12, src/assign_hap.c:473-547), called from collect_var_main

@@ -68,7 +68,7 @@ def lib():
     L.lcd_gpu_launch_count.restype = C.c_uint64
     L.lcd_gpu_init.argtypes = [C.c_int, C.c_size_t]
     L.lcd_gpu_stream.restype = C.c_void_p
-    for fn in ("lcd_wfa_plan_create", "lcd_edlib_plan_create", "lcd_poa_plan_create", "lcd_phase_plan_create", "lcd_pileup_plan_create"):
+    for fn in ("lcd_wfa_plan_create", "lcd_edlib_plan_create", "lcd_poa_plan_create", "lcd_phase_plan_create", "lcd_pileup_plan_create", "lcd_profile_plan_create"):
         if hasattr(L, fn):
             getattr(L, fn).restype = C.c_void_p
     L.lcd_plan_run.argtypes = [C.c_void_p, C.c_void_p]
@@ -343,6 +343,45 @@ class PileupPlan(_Plan):
     def fetch(self, stream=None):
         _check(lib().lcd_pileup_plan_fetch(self.h, C.c_void_p(stream or 0), self.outs), "lcd_pileup_plan_fetch")
         return [r[:d["n_sites"]] for r, d in zip(self.results, self.chunks)]
+
+
+# ----------------------------------------------------------------------------- K3: pileup scan, read x variant profile
+_PROFILE_EX = (("var_cate", np.int32), ("nreg_first", np.int64), ("n_nreg", np.int32), ("nreg_beg", np.int64), ("nreg_end", np.int64))
+
+
+class ProfileExtra(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k, _ in _PROFILE_EX]
+
+
+class ProfileOutput(C.Structure):
+    _fields_ = [("prof_start", C.c_void_p), ("prof_end", C.c_void_p), ("allele_off", C.c_void_p), ("alleles", C.c_void_p), ("alt_qi", C.c_void_p),
+                ("alleles_cap", C.c_int64), ("n_alleles", C.c_int64)]
+
+
+def profile_batch(chunks):
+    """Drop-in batch call over HOST buffers (lcd_profile_batch).  chunks: dicts with the fields of lcd_pileup_input_t and
+    lcd_profile_extra_t.  Returns per chunk a dict(prof_start, prof_end, allele_off, alleles, alt_qi) -- the arrays
+    lcd_phase_input_t takes."""
+    n = len(chunks)
+    if n == 0:
+        return []
+    L = lib()
+    L.lcd_profile_capacity.restype = C.c_int64
+    ins, _, keep, _ = _pileup_structs(chunks)
+    exs, outs, res = (ProfileExtra * n)(), (ProfileOutput * n)(), []
+    for i, d in enumerate(chunks):
+        arrs = {k: np.ascontiguousarray(d[k], dtype=t) for k, t in _PROFILE_EX}
+        keep.append(arrs)
+        exs[i] = ProfileExtra(*[arrs[k].ctypes.data for k, _ in _PROFILE_EX])
+        cap = int(L.lcd_profile_capacity(C.byref(ins[i])))
+        nr = d["n_reads"]
+        o = dict(prof_start=np.zeros(nr + 1, np.int32), prof_end=np.zeros(nr + 1, np.int32), allele_off=np.zeros(nr + 1, np.int64),
+                 alleles=np.zeros(cap + 1, np.int8), alt_qi=np.zeros(cap + 1, np.int32))
+        res.append(o)
+        outs[i] = ProfileOutput(o["prof_start"].ctypes.data, o["prof_end"].ctypes.data, o["allele_off"].ctypes.data, o["alleles"].ctypes.data,
+                                o["alt_qi"].ctypes.data, cap, 0)
+    _check(L.lcd_profile_batch(C.c_int(n), ins, exs, outs), "lcd_profile_batch")
+    return res
 
 
 # ----------------------------------------------------------------------------- K4: read -> haplotype assignment / phasing

@@ -15,6 +15,12 @@ pileup_kernel(const KernelArgs a) {
         process_read(a, g);
 }
 
+__global__ void __launch_bounds__(THREADS)
+profile_kernel(const KernelArgs a) {
+    for (long long g = (long long)blockIdx.x * THREADS + threadIdx.x; g < a.n_reads_total; g += (long long)gridDim.x * THREADS)
+        profile_read(a, g);
+}
+
 template <typename T, typename U> static void append(std::vector<T> &dst, const U *src, size_t n, long long add = 0) {
     const size_t o = dst.size(); dst.resize(o + n);
     for (size_t i = 0; i < n; ++i) dst[o + i] = (T)(src[i] + (U)add);
@@ -27,19 +33,26 @@ struct PileupPlan : Plan {
     DevBuf<uint8_t> d_active, d_rev, d_qual, d_dlow, d_dalt, d_site_alt; DevBuf<int8_t> d_dtype;
     DevBuf<long long> d_beg, d_end, d_dfirst, d_qoff, d_dpos, d_daoff, d_spos, d_saoff;
     std::vector<int32_t> h_counts;
+    // read x variant profile (K3)
+    bool profile = false;
+    std::vector<long long> read_off, row_off, chunk_row0; std::vector<int32_t> row_cap;
+    DevBuf<int32_t> d_cate, d_nnreg, d_row_cap, d_pstart, d_pend, d_altqi, d_status; DevBuf<long long> d_nfirst, d_nbeg, d_nend, d_row_off, d_aoff;
+    DevBuf<int8_t> d_alleles;
+    long long tot_rows = 0;
 
-    int build(int n_, const lcd_pileup_input_t *in) {
-        n = n_;
+    int build(int n_, const lcd_pileup_input_t *in, const lcd_profile_extra_t *ex = nullptr) {
+        n = n_; profile = ex != nullptr;
         Context &c = ctx();
         if (n == 0) return 0;
         std::vector<int32_t> read_chunk, ndig, dlen, dqi, stype, sref, salt;
         std::vector<uint8_t> active, rev, qual, dlow, dalt, site_alt; std::vector<int8_t> dtype;
-        std::vector<long long> beg, end, dfirst, qoff, dpos, daoff, spos, saoff;
-        chunks.resize(n); site_off.resize(n);
+        std::vector<long long> beg, end, dfirst, qoff, dpos, daoff, spos, saoff, nfirst, nbeg, nend;
+        std::vector<int32_t> cate, nnreg;
+        chunks.resize(n); site_off.resize(n); read_off.resize(n + 1);
         for (int i = 0; i < n; ++i) {
             const lcd_pileup_input_t &x = in[i];
             if (x.n_reads < 0 || x.n_sites < 0) { set_error("lcd_pileup: chunk %d has negative sizes", i); return -1; }
-            Chunk &k = chunks[i];
+            Chunk &k = chunks[i]; read_off[i] = tot_reads;
             k.n_sites = x.n_sites; k.min_bq = x.min_bq; k.min_sv_len = x.min_sv_len; k.pad = 0; k.site_off = tot_sites; site_off[i] = tot_sites;
             long long n_ev = 0, n_q = 0, n_alt = 0, n_salt = 0;
             for (int r = 0; r < x.n_reads; ++r) {
@@ -72,7 +85,29 @@ struct PileupPlan : Plan {
             append(dalt, x.digar_alt, (size_t)n_alt);
             append(spos, x.site_pos, x.n_sites); append(stype, x.site_type, x.n_sites); append(sref, x.site_ref_len, x.n_sites);
             append(salt, x.site_alt_len, x.n_sites); append(saoff, x.site_alt_off, x.n_sites, sa0); append(site_alt, x.site_alt, (size_t)n_salt);
+            if (profile) {
+                long long n_iv = 0;
+                for (int r = 0; r < x.n_reads; ++r) n_iv = std::max<long long>(n_iv, ex[i].nreg_first[r] + ex[i].n_nreg[r]);
+                for (int v = 0; v < x.n_sites; ++v) if (ex[i].var_cate[v] == CAND_SOMATIC_VAR) { set_error("lcd_profile: chunk %d holds candidate somatic variants (-s); only the germline path is implemented on the GPU", i); return -1; }
+                const long long iv0 = (long long)nbeg.size();
+                append(cate, ex[i].var_cate, x.n_sites); append(nfirst, ex[i].nreg_first, x.n_reads, iv0); append(nnreg, ex[i].n_nreg, x.n_reads);
+                append(nbeg, ex[i].nreg_beg, (size_t)n_iv); append(nend, ex[i].nreg_end, (size_t)n_iv);
+            }
             tot_reads += x.n_reads; tot_sites += x.n_sites; tot_events += n_ev;
+        }
+        read_off[n] = tot_reads;
+        if (profile) {       // profile rows: per read the candidate sites its merge-join can visit
+            row_off.assign(tot_reads + 1, 0); row_cap.assign(tot_reads + 1, 0); chunk_row0.assign(n + 1, 0);
+            for (int i = 0; i < n; ++i) {
+                chunk_row0[i] = tot_rows;
+                const long long s0 = site_off[i], s1 = s0 + chunks[i].n_sites;
+                for (long long g = read_off[i]; g < read_off[i + 1]; ++g) {
+                    const long long v0 = first_site(spos.data(), stype.data(), s0, s1, beg[g]);
+                    const long long v1 = row_end_site(spos.data(), stype.data(), v0, s1, end[g]);
+                    row_off[g] = tot_rows; row_cap[g] = (int32_t)(v1 - v0); tot_rows += v1 - v0;
+                }
+            }
+            chunk_row0[n] = tot_rows;
         }
         auto pad = [](auto &v) { v.push_back(0); };
         pad(read_chunk); pad(active); pad(beg); pad(end); pad(rev); pad(dfirst); pad(ndig); pad(qoff); pad(qual); pad(dpos); pad(dtype); pad(dlen); pad(dqi);
@@ -87,6 +122,14 @@ struct PileupPlan : Plan {
             d_stype.upload(stype.data(), stype.size(), s) || d_sref.upload(sref.data(), sref.size(), s) || d_salt.upload(salt.data(), salt.size(), s) ||
             d_saoff.upload(saoff.data(), saoff.size(), s) || d_site_alt.upload(site_alt.data(), site_alt.size(), s)) return -1;
         if (d_counts.alloc(8 * (size_t)tot_sites + 8)) return -1;
+        if (profile) {
+            pad(cate); pad(nfirst); pad(nnreg); pad(nbeg); pad(nend);
+            if (d_cate.upload(cate.data(), cate.size(), s) || d_nfirst.upload(nfirst.data(), nfirst.size(), s) || d_nnreg.upload(nnreg.data(), nnreg.size(), s) ||
+                d_nbeg.upload(nbeg.data(), nbeg.size(), s) || d_nend.upload(nend.data(), nend.size(), s) ||
+                d_row_off.upload(row_off.data(), row_off.size(), s) || d_row_cap.upload(row_cap.data(), row_cap.size(), s)) return -1;
+            if (d_pstart.alloc(tot_reads + 1) || d_pend.alloc(tot_reads + 1) || d_aoff.alloc(tot_reads + 1) || d_alleles.alloc(tot_rows + 16) ||
+                d_altqi.alloc(tot_rows + 16) || d_status.alloc(1)) return -1;
+        }
         LCD_CUDA_OK(cudaStreamSynchronize(s));
         return 0;
     }
@@ -103,6 +146,16 @@ struct PileupPlan : Plan {
         a.site_pos = d_spos.p; a.site_type = d_stype.p; a.site_ref_len = d_sref.p; a.site_alt_len = d_salt.p; a.site_alt_off = d_saoff.p; a.site_alt = d_site_alt.p;
         a.site_counts = d_counts.p;
         const int grid = (int)std::min<long long>((tot_reads + THREADS - 1) / THREADS, (long long)c.sm_count * 16);
+        if (profile) {
+            a.var_cate = d_cate.p; a.nreg_first = d_nfirst.p; a.n_nreg = d_nnreg.p; a.nreg_beg = d_nbeg.p; a.nreg_end = d_nend.p;
+            a.row_off = d_row_off.p; a.row_cap = d_row_cap.p; a.prof_start = d_pstart.p; a.prof_end = d_pend.p; a.allele_off = d_aoff.p;
+            a.alleles = d_alleles.p; a.alt_qi = d_altqi.p; a.status = d_status.p;
+            LCD_CUDA_OK(cudaMemsetAsync(d_status.p, 0, sizeof(int32_t), s));
+            profile_kernel<<<grid, THREADS, 0, s>>>(a);
+            LCD_CUDA_OK(cudaGetLastError());
+            c.launches++;
+            return 0;
+        }
         pileup_kernel<<<grid, THREADS, 0, s>>>(a);
         LCD_CUDA_OK(cudaGetLastError());
         c.launches++;
@@ -117,6 +170,32 @@ struct PileupPlan : Plan {
         if (tot_sites) LCD_CUDA_OK(cudaMemcpyAsync(h_counts.data(), d_counts.p, sizeof(int32_t) * 8 * (size_t)tot_sites, cudaMemcpyDeviceToHost, s));
         LCD_CUDA_OK(cudaStreamSynchronize(s));
         for (int i = 0; i < n; ++i) if (chunks[i].n_sites) memcpy(out[i].site_counts, h_counts.data() + 8 * site_off[i], sizeof(int32_t) * 8 * (size_t)chunks[i].n_sites);
+        return 0;
+    }
+
+    long long capacity(int i) const { return chunk_row0[i + 1] - chunk_row0[i]; }
+
+    int fetch_profile(cudaStream_t s, lcd_profile_output_t *out) {
+        if (n == 0) return 0;
+        std::vector<int32_t> ps(tot_reads + 1), pe(tot_reads + 1), qi(tot_rows + 16); std::vector<long long> ao(tot_reads + 1); std::vector<int8_t> al(tot_rows + 16);
+        int32_t status = 0;
+        LCD_CUDA_OK(cudaMemcpyAsync(ps.data(), d_pstart.p, sizeof(int32_t) * tot_reads, cudaMemcpyDeviceToHost, s));
+        LCD_CUDA_OK(cudaMemcpyAsync(pe.data(), d_pend.p, sizeof(int32_t) * tot_reads, cudaMemcpyDeviceToHost, s));
+        LCD_CUDA_OK(cudaMemcpyAsync(ao.data(), d_aoff.p, sizeof(long long) * tot_reads, cudaMemcpyDeviceToHost, s));
+        if (tot_rows) {
+            LCD_CUDA_OK(cudaMemcpyAsync(al.data(), d_alleles.p, (size_t)tot_rows, cudaMemcpyDeviceToHost, s));
+            LCD_CUDA_OK(cudaMemcpyAsync(qi.data(), d_altqi.p, sizeof(int32_t) * (size_t)tot_rows, cudaMemcpyDeviceToHost, s));
+        }
+        LCD_CUDA_OK(cudaMemcpyAsync(&status, d_status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        LCD_CUDA_OK(cudaStreamSynchronize(s));
+        if (status) { set_error("lcd_profile: a profile row overflowed its capacity on the device (status %d)", status); return -2; }
+        for (int i = 0; i < n; ++i) {
+            const long long r0 = read_off[i], nr = read_off[i + 1] - r0, row0 = chunk_row0[i], rows = capacity(i);
+            if (rows > out[i].alleles_cap) { set_error("lcd_profile: chunk %d needs %lld profile entries, the caller provided %lld (lcd_profile_capacity)", i, rows, (long long)out[i].alleles_cap); return -3; }
+            for (long long r = 0; r < nr; ++r) { out[i].prof_start[r] = ps[r0 + r]; out[i].prof_end[r] = pe[r0 + r]; out[i].allele_off[r] = ao[r0 + r] - row0; }
+            if (rows) { memcpy(out[i].alleles, al.data() + row0, (size_t)rows); memcpy(out[i].alt_qi, qi.data() + row0, sizeof(int32_t) * (size_t)rows); }
+            out[i].n_alleles = rows;
+        }
         return 0;
     }
 };
@@ -140,6 +219,39 @@ int lcd_pileup_plan_fetch(lcd_plan_t *plan, void *stream, lcd_pileup_output_t *o
     pileup::PileupPlan *p = dynamic_cast<pileup::PileupPlan *>(reinterpret_cast<Plan *>(plan));
     if (!p || !out) { set_error("lcd_pileup_plan_fetch: not a pileup plan / null outputs"); return -1; }
     return p->fetch(pick_stream(stream), out);
+}
+
+lcd_plan_t *lcd_profile_plan_create(int n_chunks, const lcd_pileup_input_t *in, const lcd_profile_extra_t *extra) {
+    if (ensure_ready()) return nullptr;
+    if (n_chunks < 0 || (n_chunks > 0 && (!in || !extra))) { set_error("lcd_profile_plan_create: invalid arguments"); return nullptr; }
+    pileup::PileupPlan *p = new pileup::PileupPlan();
+    if (p->build(n_chunks, in, extra)) { delete p; return nullptr; }
+    return reinterpret_cast<lcd_plan_t *>(p);
+}
+
+int lcd_profile_plan_fetch(lcd_plan_t *plan, void *stream, lcd_profile_output_t *out) {
+    pileup::PileupPlan *p = dynamic_cast<pileup::PileupPlan *>(reinterpret_cast<Plan *>(plan));
+    if (!p || !p->profile || !out) { set_error("lcd_profile_plan_fetch: not a profile plan / null outputs"); return -1; }
+    return p->fetch_profile(pick_stream(stream), out);
+}
+
+int lcd_profile_batch(int n_chunks, const lcd_pileup_input_t *in, const lcd_profile_extra_t *extra, lcd_profile_output_t *out) {
+    lcd_plan_t *plan = lcd_profile_plan_create(n_chunks, in, extra);
+    if (!plan) return -1;
+    int rc = lcd_plan_run(plan, nullptr);
+    if (!rc) rc = lcd_profile_plan_fetch(plan, nullptr, out);
+    lcd_plan_destroy(plan);
+    return rc;
+}
+
+int64_t lcd_profile_capacity(const lcd_pileup_input_t *in) {
+    if (!in) return -1;
+    int64_t tot = 0;
+    for (int r = 0; r < in->n_reads; ++r) {
+        const long long v0 = pileup::first_site((const long long *)in->site_pos, in->site_type, 0, in->n_sites, in->read_beg[r]);
+        tot += pileup::row_end_site((const long long *)in->site_pos, in->site_type, v0, in->n_sites, in->read_end[r]) - v0;
+    }
+    return tot;
 }
 
 int lcd_pileup_batch(int n_chunks, const lcd_pileup_input_t *in, lcd_pileup_output_t *out) {

@@ -278,3 +278,19 @@ def make_pileup_chunk(rng, ref_len=20000, n_reads=200, read_len=(3000, 8000), va
     for s_ in sites: aoff.append(len(flat)); flat.extend(s_[4].tolist())
     d.update(site_alt_off=np.array(aoff + [0], np.int64), site_alt=np.array(flat + [0], np.uint8))
     return d
+
+
+def add_profile_inputs(rng, d):
+    """Extend a pileup chunk with what the read x variant profile pass reads besides it: a category per candidate variant
+    (a few LONGCALLD_NON_VAR entries are skipped by the reference) and per-read noisy intervals (cgranges [beg, end))."""
+    cats = np.array([CATE["CLEAN_HET_SNP"], CATE["CLEAN_HET_INDEL"], CATE["CLEAN_HOM_VAR"], CATE["NOISY_CAND_HET_VAR"], CATE["LOW_COV_VAR"], 0x800], dtype=np.int32)
+    d = dict(d)
+    d["var_cate"] = rng.choice(cats, size=d["n_sites"] + 1, p=[0.5, 0.15, 0.1, 0.1, 0.05, 0.1]).astype(np.int32)
+    first, cnt, nb, ne = [], [], [], []
+    for r in range(d["n_reads"]):
+        first.append(len(nb)); k = int(rng.integers(0, 3)) if rng.random() < 0.4 else 0
+        for _ in range(k):
+            b = int(rng.integers(d["read_beg"][r], d["read_end"][r] + 1)); nb.append(b); ne.append(b + int(rng.integers(1, 400)))
+        cnt.append(k)
+    d.update(nreg_first=np.array(first + [0], np.int64), n_nreg=np.array(cnt + [0], np.int32), nreg_beg=np.array(nb + [0], np.int64), nreg_end=np.array(ne + [0], np.int64))
+    return d

@@ -125,6 +125,23 @@ typedef struct {
 } lcd_pileup_output_t;
 int lcd_oracle_collect_cand_vars(const lcd_pileup_input_t *in, lcd_pileup_output_t *out);
 
+/* ---- read x variant profile (src/collect_var.c:1389-1431, src/bam_utils.c:446-552), germline categories ---- */
+typedef struct {
+    const int32_t *var_cate;           /* chunk->var_i_to_cate [n_sites]; the sites of lcd_pileup_input_t are the cand_vars */
+    const int64_t *nreg_first;         /* read r's noisy intervals (digar_t.noisy_regs after cr_index): nreg_*[nreg_first[r] .. +n_nreg[r]) */
+    const int32_t *n_nreg;
+    const int64_t *nreg_beg, *nreg_end;/* cgranges coordinates: [beg, end) */
+} lcd_profile_extra_t;
+typedef struct {
+    int32_t *prof_start, *prof_end;    /* read_var_profile_t.start_var_idx / end_var_idx [n_reads]; (-1, -2): none */
+    int64_t *allele_off;               /* read r's row: alleles[allele_off[r] + (var - prof_start[r])] (what K4 consumes) */
+    int8_t  *alleles;                  /* 0 ref, 1 alt, -1 other / not set, -2 low-quality alt */
+    int32_t *alt_qi;                   /* read offset of the alt allele, -1 otherwise */
+    int64_t alleles_cap;               /* capacity of alleles[] / alt_qi[]: sum over reads of (variants with pos in the read's span + 2) suffices */
+    int64_t n_alleles;                 /* entries used */
+} lcd_profile_output_t;
+int lcd_oracle_read_var_profile(const lcd_pileup_input_t *in, const lcd_profile_extra_t *ex, lcd_profile_output_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -143,3 +143,60 @@ int ref_collect_cand_vars(const lcd_pileup_input_t *in, lcd_pileup_output_t *out
     free(chunk.digars); free(chunk.ordered_read_ids); free(chunk.is_skipped);
     return 0;
 }
+
+read_var_profile_t *collect_read_var_profile(const call_var_opt_t *opt, bam_chunk_t *chunk);   /* src/collect_var.c:1389 (no prototype in the headers) */
+/* collect_read_var_profile (src/collect_var.c:1389) on a synthetic chunk; the rows are returned in the CSR layout of
+ * lcd_profile_output_t (row r = the reference's alleles[0 .. end_var_idx - start_var_idx]). */
+int ref_read_var_profile(const lcd_pileup_input_t *in, const lcd_profile_extra_t *ex, lcd_profile_output_t *out) {
+    const int nr = in->n_reads, nv = in->n_sites;
+    call_var_opt_t opt; memset(&opt, 0, sizeof(opt));
+    opt.min_bq = in->min_bq; opt.min_sv_len = in->min_sv_len; opt.out_somatic = 0;
+    bam_chunk_t chunk; memset(&chunk, 0, sizeof(chunk));
+    chunk.n_reads = chunk.m_reads = nr; chunk.tid = 0;
+    chunk.ordered_read_ids = (int*)malloc(sizeof(int) * (nr + 1));
+    chunk.is_skipped = (uint8_t*)malloc(nr + 1);
+    chunk.digars = (digar_t*)calloc(nr + 1, sizeof(digar_t));
+    for (int r = 0; r < nr; ++r) {
+        chunk.ordered_read_ids[r] = in->ordered_read_ids[r]; chunk.is_skipped[r] = in->is_skipped[r];
+        digar_t *g = chunk.digars + r;
+        g->beg = in->read_beg[r]; g->end = in->read_end[r]; g->is_rev = in->read_is_rev[r];
+        g->n_digar = g->m_digar = in->n_digar[r];
+        g->digars = (digar1_t*)calloc(g->n_digar + 1, sizeof(digar1_t));
+        g->qual = (uint8_t*)(in->qual + in->qual_off[r]);
+        for (int k = 0; k < g->n_digar; ++k) {
+            const int64_t d = in->digar_first[r] + k;
+            digar1_t *x = g->digars + k;
+            x->pos = in->digar_pos[d]; x->type = in->digar_type[d]; x->len = in->digar_len[d]; x->qi = in->digar_qi[d];
+            x->is_low_qual = in->digar_low_qual[d];
+            x->alt_seq = (x->type == BAM_CDIFF || x->type == BAM_CINS) ? (uint8_t*)(in->digar_alt + in->digar_alt_off[d]) : NULL;
+        }
+        g->noisy_regs = cr_init();
+        for (int64_t k = ex->nreg_first[r]; k < ex->nreg_first[r] + ex->n_nreg[r]; ++k) cr_add(g->noisy_regs, "cr", (int32_t)ex->nreg_beg[k], (int32_t)ex->nreg_end[k], 0);
+        cr_index(g->noisy_regs);
+    }
+    chunk.n_cand_vars = nv;
+    chunk.cand_vars = (cand_var_t*)calloc(nv + 1, sizeof(cand_var_t));
+    chunk.var_i_to_cate = (int*)malloc(sizeof(int) * (nv + 1));
+    for (int v = 0; v < nv; ++v) {
+        cand_var_t *c = chunk.cand_vars + v;
+        c->tid = 0; c->pos = in->site_pos[v]; c->var_type = in->site_type[v]; c->ref_len = in->site_ref_len[v]; c->alt_len = in->site_alt_len[v];
+        c->alt_seq = (uint8_t*)(in->site_alt + in->site_alt_off[v]);
+        chunk.var_i_to_cate[v] = ex->var_cate[v];
+    }
+    read_var_profile_t *p = collect_read_var_profile(&opt, &chunk);
+    int64_t top = 0; int rc = 0;
+    for (int r = 0; r < nr; ++r) {
+        out->prof_start[r] = p[r].start_var_idx; out->prof_end[r] = p[r].end_var_idx; out->allele_off[r] = top;
+        const int n = p[r].end_var_idx - p[r].start_var_idx + 1;
+        if (p[r].start_var_idx < 0 || n <= 0) continue;
+        if (top + n > out->alleles_cap) { rc = -3; break; }
+        for (int k = 0; k < n; ++k) { out->alleles[top + k] = (int8_t)p[r].alleles[k]; out->alt_qi[top + k] = p[r].alt_qi[k]; }
+        top += n;
+    }
+    out->n_alleles = top;
+    free(p);                                      /* one allocation: init_read_var_profile_inner, src/bam_utils.c:13-36 */
+    cr_destroy(chunk.read_var_cr);
+    for (int r = 0; r < nr; ++r) { free(chunk.digars[r].digars); cr_destroy(chunk.digars[r].noisy_regs); }
+    free(chunk.digars); free(chunk.cand_vars); free(chunk.var_i_to_cate); free(chunk.ordered_read_ids); free(chunk.is_skipped);
+    return rc;
+}

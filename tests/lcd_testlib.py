@@ -247,3 +247,41 @@ def pileup(lib, fn, d):
     rc = getattr(lib, fn)(C.byref(inp), C.byref(out))
     assert rc == 0
     return counts[:d["n_sites"]]
+
+
+# ----------------------------------------------------------------------------- read x variant profile (K3) helpers
+PROFILE_EX_FIELDS = (("var_cate", np.int32), ("nreg_first", np.int64), ("n_nreg", np.int32), ("nreg_beg", np.int64), ("nreg_end", np.int64))
+
+
+class ProfileExtra(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k, _ in PROFILE_EX_FIELDS]
+
+
+class ProfileOutput(C.Structure):
+    _fields_ = [("prof_start", C.c_void_p), ("prof_end", C.c_void_p), ("allele_off", C.c_void_p), ("alleles", C.c_void_p), ("alt_qi", C.c_void_p),
+                ("alleles_cap", C.c_int64), ("n_alleles", C.c_int64)]
+
+
+def profile_capacity(d):
+    """Entries that always suffice: per read the variants positioned inside its span, plus 2."""
+    pos = np.asarray(d["site_pos"][:d["n_sites"]])
+    lo = np.searchsorted(pos, np.asarray(d["read_beg"]) - 1, side="left"); hi = np.searchsorted(pos, np.asarray(d["read_end"]), side="right")
+    return int((hi - lo + 2).sum()) + 8
+
+
+def read_var_profile(lib, fn, d):
+    """-> per read (start, end, alleles tuple, alt_qi tuple): the rows of read_var_profile_t."""
+    keep = {k: np.ascontiguousarray(d[k], dtype=t) for k, t in PILEUP_IN_FIELDS + PROFILE_EX_FIELDS}
+    inp = PileupInput(d["n_reads"], d["n_sites"], d["min_bq"], d["min_sv_len"], *[keep[k].ctypes.data for k, _ in PILEUP_IN_FIELDS])
+    ex = ProfileExtra(*[keep[k].ctypes.data for k, _ in PROFILE_EX_FIELDS])
+    nr, cap = d["n_reads"], profile_capacity(d)
+    ps, pe, ao = np.full(nr + 1, -7, np.int32), np.full(nr + 1, -7, np.int32), np.zeros(nr + 1, np.int64)
+    al, qi = np.full(cap, -7, np.int8), np.full(cap, -7, np.int32)
+    out = ProfileOutput(ps.ctypes.data, pe.ctypes.data, ao.ctypes.data, al.ctypes.data, qi.ctypes.data, cap, 0)
+    rc = getattr(lib, fn)(C.byref(inp), C.byref(ex), C.byref(out))
+    assert rc == 0, rc
+    rows = []
+    for r in range(nr):
+        n = max(0, int(pe[r]) - int(ps[r]) + 1) if ps[r] >= 0 else 0
+        rows.append((int(ps[r]), int(pe[r]), tuple(al[ao[r]:ao[r] + n].tolist()), tuple(qi[ao[r]:ao[r] + n].tolist())))
+    return rows

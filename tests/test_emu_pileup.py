@@ -28,3 +28,9 @@ def test_emu_vs_fixtures(emu):
     for c in T.load_golden("pileup_lcd")["cases"]:
         d = {k: (np.array(v, dtype=dict(T.PILEUP_IN_FIELDS)[k]) if k in dict(T.PILEUP_IN_FIELDS) else v) for k, v in c["in"].items()}
         assert T.pileup(emu, "emu_collect_cand_vars", d).tolist() == c["counts"]
+
+
+def test_emu_profile_vs_oracle(emu, oracle):
+    from test_oracle_pileup import profile_cases
+    for i, d in enumerate(profile_cases(19, 80)):
+        assert T.read_var_profile(emu, "emu_read_var_profile", d) == T.read_var_profile(oracle, "lcd_oracle_read_var_profile", d), i

@@ -32,3 +32,20 @@ def test_oracle_vs_reference_fixtures(oracle):
     for c in g["cases"]:
         d = {k: (np.array(v, dtype=dict(T.PILEUP_IN_FIELDS)[k]) if k in dict(T.PILEUP_IN_FIELDS) else v) for k, v in c["in"].items()}
         assert T.pileup(oracle, "lcd_oracle_collect_cand_vars", d).tolist() == c["counts"]
+
+
+def profile_cases(seed, n):
+    rng = np.random.default_rng(seed)
+    for d in pileup_cases(seed + 1, n):
+        yield synth.add_profile_inputs(rng, d)
+
+
+def test_profile_oracle_vs_live_reference(oracle, ref):
+    n = tot = 0
+    for d in profile_cases(9, 150):
+        a = T.read_var_profile(oracle, "lcd_oracle_read_var_profile", d)
+        b = T.read_var_profile(ref, "ref_read_var_profile", d)
+        bad = [r for r in range(len(a)) if a[r] != b[r]]
+        assert not bad, (n, d["n_reads"], d["n_sites"], bad[:3], a[bad[0]][:2], b[bad[0]][:2])
+        n += 1; tot += sum(sum(1 for x in row[2] if x == 1) for row in a)
+    assert tot > 10000
