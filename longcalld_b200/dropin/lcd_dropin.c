@@ -1,0 +1,259 @@
+/* lcd_dropin.c -- the reference-side binding of liblcd_gpu.so, as a link-time / LD_PRELOAD drop-in.
+ *
+ * Defines, with the reference's own signatures, the functions of `longcallD call`'s per-region worker that have a
+ * B200 implementation, marshals the reference's structures (bam_chunk_t, digar_t, cand_var_t, read_var_profile_t:
+ * reference src/bam_utils.h, src/collect_var.h) into the flat views of include/lcd_gpu.h, calls the library, and
+ * writes the results back exactly where the reference leaves them:
+ *     collect_cand_vars                              (src/collect_var.c:238)   -> lcd_pileup_batch   (K2)
+ *     collect_read_var_profile                       (src/collect_var.c:1389)  -> lcd_profile_batch  (K3)
+ *     assign_hap_based_on_germline_het_vars_kmeans   (src/assign_hap.c:473)    -> lcd_phase_batch    (K4)
+ *     edlib_edit_distance / edlib_xgaps / edlib_end2end_aln / edlib_infix_aln (src/align.c:210-275) -> lcd_edlib_batch (K7)
+ * Everything else of the reference runs unchanged.  The reference calls these once per chunk / per pair, so every
+ * call here is a batch of one (the batched two-phase worker of INTEGRATION.md section 1 is what a maintainer would
+ * adopt for speed); this file exists to prove the boundary: with it preloaded the reference writes the same VCF.
+ * There is no CPU fallback: a failing library call aborts the run.  (Only the -s somatic profile path, which the GPU
+ * library rejects, is forwarded to the reference's own implementation.)
+ *
+ * Built only where the reference headers exist (make -C longcalld_b200/dropin REF=/root/reference). */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "call_var_main.h"
+#include "bam_utils.h"
+#include "collect_var.h"
+#include "assign_hap.h"
+#include "cgranges.h"
+#include "utils.h"
+#include "lcd_gpu.h"
+
+static void die(const char *what) { fprintf(stderr, "[lcd_dropin] %s failed: %s\n", what, lcd_gpu_last_error()); exit(1); }
+static unsigned long n_calls[4];
+__attribute__((destructor)) static void report(void) {
+    if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: pileup %lu, profile %lu, phase %lu, edlib %lu; kernel launches %llu\n",
+                                              n_calls[0], n_calls[1], n_calls[2], n_calls[3], (unsigned long long)lcd_gpu_launch_count());
+}
+
+/* ------------------------------------------------------------------------------------------ digars -> flat */
+typedef struct {
+    lcd_pileup_input_t in;
+    int64_t *read_beg, *read_end, *digar_first, *qual_off, *digar_pos, *digar_alt_off, *site_pos, *site_alt_off;
+    uint8_t *read_is_rev, *qual, *digar_low_qual, *digar_alt, *site_alt;
+    int32_t *n_digar, *digar_len, *digar_qi, *site_type, *site_ref_len, *site_alt_len; int8_t *digar_type;
+} flat_t;
+
+static void flat_free(flat_t *f) {
+    free(f->read_beg); free(f->read_end); free(f->digar_first); free(f->qual_off); free(f->digar_pos); free(f->digar_alt_off); free(f->site_pos);
+    free(f->site_alt_off); free(f->read_is_rev); free(f->qual); free(f->digar_low_qual); free(f->digar_alt); free(f->site_alt); free(f->n_digar);
+    free(f->digar_len); free(f->digar_qi); free(f->site_type); free(f->site_ref_len); free(f->site_alt_len); free(f->digar_type);
+}
+
+/* sites: either var_site_t[] (collect_cand_vars) or cand_var_t[] (collect_read_var_profile) */
+static void flatten(const call_var_opt_t *opt, bam_chunk_t *chunk, int n_sites, const var_site_t *sites, const cand_var_t *vars, flat_t *f) {
+    const int nr = chunk->n_reads;
+    memset(f, 0, sizeof(*f));
+    size_t n_ev = 0, n_q = 0, n_alt = 0, n_salt = 0;
+    for (int r = 0; r < nr; ++r) {
+        const digar_t *g = chunk->digars + r;
+        if (chunk->is_skipped[r]) continue;
+        n_ev += g->n_digar; n_q += g->qlen;
+        for (int k = 0; k < g->n_digar; ++k) if (g->digars[k].type == BAM_CDIFF || g->digars[k].type == BAM_CINS) n_alt += g->digars[k].len;
+    }
+    for (int i = 0; i < n_sites; ++i) n_salt += sites ? sites[i].alt_len : vars[i].alt_len;
+#define A(field, type, n) f->field = (type*)calloc((n) + 1, sizeof(type))
+    A(read_beg, int64_t, nr); A(read_end, int64_t, nr); A(digar_first, int64_t, nr); A(qual_off, int64_t, nr); A(read_is_rev, uint8_t, nr); A(n_digar, int32_t, nr);
+    A(digar_pos, int64_t, n_ev); A(digar_alt_off, int64_t, n_ev); A(digar_low_qual, uint8_t, n_ev); A(digar_len, int32_t, n_ev); A(digar_qi, int32_t, n_ev);
+    A(digar_type, int8_t, n_ev); A(qual, uint8_t, n_q); A(digar_alt, uint8_t, n_alt);
+    A(site_pos, int64_t, n_sites); A(site_alt_off, int64_t, n_sites); A(site_type, int32_t, n_sites); A(site_ref_len, int32_t, n_sites);
+    A(site_alt_len, int32_t, n_sites); A(site_alt, uint8_t, n_salt);
+#undef A
+    size_t ev = 0, q = 0, alt = 0;
+    for (int r = 0; r < nr; ++r) {
+        const digar_t *g = chunk->digars + r;
+        f->digar_first[r] = (int64_t)ev; f->qual_off[r] = (int64_t)q;
+        if (chunk->is_skipped[r]) continue;                 /* skipped reads carry no usable digars; the kernels never look at them */
+        f->read_beg[r] = g->beg; f->read_end[r] = g->end; f->read_is_rev[r] = g->is_rev; f->n_digar[r] = g->n_digar;
+        memcpy(f->qual + q, g->qual, g->qlen); q += g->qlen;
+        for (int k = 0; k < g->n_digar; ++k, ++ev) {
+            const digar1_t *x = g->digars + k;
+            f->digar_pos[ev] = x->pos; f->digar_type[ev] = (int8_t)x->type; f->digar_len[ev] = x->len; f->digar_qi[ev] = x->qi;
+            f->digar_low_qual[ev] = x->is_low_qual; f->digar_alt_off[ev] = (int64_t)alt;
+            if (x->type == BAM_CDIFF || x->type == BAM_CINS) { memcpy(f->digar_alt + alt, x->alt_seq, x->len); alt += x->len; }
+        }
+    }
+    size_t sa = 0;
+    for (int i = 0; i < n_sites; ++i) {
+        const int type = sites ? sites[i].var_type : vars[i].var_type, alt_len = sites ? sites[i].alt_len : vars[i].alt_len;
+        const uint8_t *as = sites ? sites[i].alt_seq : vars[i].alt_seq;
+        f->site_pos[i] = sites ? sites[i].pos : vars[i].pos; f->site_type[i] = type; f->site_ref_len[i] = sites ? sites[i].ref_len : vars[i].ref_len;
+        f->site_alt_len[i] = alt_len; f->site_alt_off[i] = (int64_t)sa;
+        if ((type == BAM_CDIFF || type == BAM_CINS) && as) { memcpy(f->site_alt + sa, as, alt_len); sa += alt_len; }
+    }
+    lcd_pileup_input_t *in = &f->in;
+    in->n_reads = nr; in->n_sites = n_sites; in->min_bq = opt->min_bq; in->min_sv_len = opt->min_sv_len;
+    in->ordered_read_ids = chunk->ordered_read_ids; in->is_skipped = chunk->is_skipped;
+    in->read_beg = f->read_beg; in->read_end = f->read_end; in->read_is_rev = f->read_is_rev; in->digar_first = f->digar_first; in->n_digar = f->n_digar;
+    in->qual_off = f->qual_off; in->qual = f->qual; in->digar_pos = f->digar_pos; in->digar_type = f->digar_type; in->digar_len = f->digar_len;
+    in->digar_qi = f->digar_qi; in->digar_low_qual = f->digar_low_qual; in->digar_alt_off = f->digar_alt_off; in->digar_alt = f->digar_alt;
+    in->site_pos = f->site_pos; in->site_type = f->site_type; in->site_ref_len = f->site_ref_len; in->site_alt_len = f->site_alt_len;
+    in->site_alt_off = f->site_alt_off; in->site_alt = f->site_alt;
+}
+
+/* ------------------------------------------------------------------------------------------ K2 */
+cand_var_t *init_cand_vars_based_on_sites(int n_var_sites, var_site_t *var_sites);          /* src/collect_var.c:20 */
+
+int collect_cand_vars(const call_var_opt_t *opt, bam_chunk_t *chunk, int n_var_sites, var_site_t *var_sites) {
+    chunk->cand_vars = init_cand_vars_based_on_sites(n_var_sites, var_sites);
+    chunk->n_cand_vars = n_var_sites;
+    flat_t f; flatten(opt, chunk, n_var_sites, var_sites, NULL, &f);
+    int32_t *counts = (int32_t*)calloc(8 * (size_t)n_var_sites + 8, sizeof(int32_t));
+    lcd_pileup_output_t out = { counts };
+    if (lcd_pileup_batch(1, &f.in, &out)) die("lcd_pileup_batch");
+    for (int i = 0; i < n_var_sites; ++i) {
+        cand_var_t *c = chunk->cand_vars + i; const int32_t *o = counts + 8 * i;
+        c->total_cov = o[0]; c->low_qual_cov = o[1]; c->alle_covs[0] = o[2]; c->alle_covs[1] = o[3];
+        for (int s = 0; s < 2; ++s) for (int a = 0; a < 2; ++a) c->strand_to_alle_covs[s][a] = o[4 + 2 * s + a];
+    }
+    free(counts); flat_free(&f);
+    n_calls[0]++;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ K3 */
+read_var_profile_t *init_read_var_profile(int n_reads, int n_total_vars);                     /* src/bam_utils.c:38 */
+
+read_var_profile_t *collect_read_var_profile(const call_var_opt_t *opt, bam_chunk_t *chunk) {
+    if (opt->out_somatic) {      /* -s: candidate somatic variants take the reference's fuzzy path, which the GPU library rejects */
+        static read_var_profile_t *(*orig)(const call_var_opt_t *, bam_chunk_t *) = NULL;
+        if (!orig) orig = (read_var_profile_t *(*)(const call_var_opt_t *, bam_chunk_t *))dlsym(RTLD_NEXT, "collect_read_var_profile");
+        return orig(opt, chunk);
+    }
+    const int nr = chunk->n_reads, nv = chunk->n_cand_vars;
+    flat_t f; flatten(opt, chunk, nv, NULL, chunk->cand_vars, &f);
+    size_t n_iv = 0;
+    for (int r = 0; r < nr; ++r) if (!chunk->is_skipped[r] && chunk->digars[r].noisy_regs) n_iv += chunk->digars[r].noisy_regs->n_r;
+    int64_t *nfirst = (int64_t*)calloc(nr + 1, sizeof(int64_t)), *nbeg = (int64_t*)calloc(n_iv + 1, sizeof(int64_t)), *nend = (int64_t*)calloc(n_iv + 1, sizeof(int64_t));
+    int32_t *nn = (int32_t*)calloc(nr + 1, sizeof(int32_t));
+    size_t iv = 0;
+    for (int r = 0; r < nr; ++r) {
+        nfirst[r] = (int64_t)iv;
+        cgranges_t *cr = chunk->digars[r].noisy_regs;
+        if (chunk->is_skipped[r] || cr == NULL) continue;
+        nn[r] = (int32_t)cr->n_r;
+        for (int64_t k = 0; k < cr->n_r; ++k, ++iv) { nbeg[iv] = cr_start(cr, k); nend[iv] = cr_end(cr, k); }
+    }
+    lcd_profile_extra_t ex = { chunk->var_i_to_cate, nfirst, nn, nbeg, nend };
+    const int64_t cap = lcd_profile_capacity(&f.in);
+    lcd_profile_output_t out; memset(&out, 0, sizeof(out));
+    out.prof_start = (int32_t*)calloc(nr + 1, sizeof(int32_t)); out.prof_end = (int32_t*)calloc(nr + 1, sizeof(int32_t));
+    out.allele_off = (int64_t*)calloc(nr + 1, sizeof(int64_t)); out.alleles = (int8_t*)calloc(cap + 1, 1); out.alt_qi = (int32_t*)calloc(cap + 1, sizeof(int32_t));
+    out.alleles_cap = cap;
+    if (lcd_profile_batch(1, &f.in, &ex, &out)) die("lcd_profile_batch");
+    read_var_profile_t *p = init_read_var_profile(nr, nv);
+    cgranges_t *read_var_cr = cr_init();
+    for (int i = 0; i < nr; ++i) {                       /* same order of cr_add as the reference (src/collect_var.c:1407-1412) */
+        const int r = chunk->ordered_read_ids[i];
+        if (chunk->is_skipped[r]) continue;
+        p[r].start_var_idx = out.prof_start[r]; p[r].end_var_idx = out.prof_end[r];
+        for (int v = out.prof_start[r]; v <= out.prof_end[r] && out.prof_start[r] >= 0; ++v) {
+            p[r].alleles[v - out.prof_start[r]] = out.alleles[out.allele_off[r] + (v - out.prof_start[r])];
+            p[r].alt_qi[v - out.prof_start[r]] = out.alt_qi[out.allele_off[r] + (v - out.prof_start[r])];
+        }
+        if (p[r].start_var_idx < 0 || p[r].end_var_idx < 0) continue;
+        cr_add(read_var_cr, "cr", p[r].start_var_idx, p[r].end_var_idx + 1, r);
+    }
+    cr_index(read_var_cr); chunk->read_var_cr = read_var_cr;
+    free(out.prof_start); free(out.prof_end); free(out.allele_off); free(out.alleles); free(out.alt_qi);
+    free(nfirst); free(nbeg); free(nend); free(nn); flat_free(&f);
+    n_calls[1]++;
+    return p;
+}
+
+/* ------------------------------------------------------------------------------------------ K4 */
+int assign_hap_based_on_germline_het_vars_kmeans(const call_var_opt_t *opt, bam_chunk_t *chunk, int target_var_cate) {
+    const int nr = chunk->n_reads, nv = chunk->n_cand_vars;
+    read_var_profile_t *p = chunk->read_var_profile;
+    int n_valid = 0;
+    for (int v = 0; v < nv; ++v) if (chunk->var_i_to_cate[v] & target_var_cate) n_valid++;
+    if (n_valid == 0) return 0;                                            /* src/assign_hap.c:483-486 */
+    size_t n_al = 0;
+    for (int r = 0; r < nr; ++r) if (p[r].start_var_idx >= 0 && p[r].end_var_idx >= p[r].start_var_idx) n_al += p[r].end_var_idx - p[r].start_var_idx + 1;
+    int32_t *ps = (int32_t*)calloc(nr + 1, sizeof(int32_t)), *pe = (int32_t*)calloc(nr + 1, sizeof(int32_t));
+    int64_t *ao = (int64_t*)calloc(nr + 1, sizeof(int64_t)); int8_t *al = (int8_t*)calloc(n_al + 1, 1);
+    size_t top = 0;
+    for (int r = 0; r < nr; ++r) {
+        ps[r] = p[r].start_var_idx; pe[r] = p[r].end_var_idx; ao[r] = (int64_t)top;
+        if (ps[r] < 0 || pe[r] < ps[r]) continue;
+        for (int k = 0; k <= pe[r] - ps[r]; ++k) al[top++] = (int8_t)p[r].alleles[k];
+    }
+    int32_t *type = (int32_t*)calloc(nv + 1, 4), *hp = (int32_t*)calloc(nv + 1, 4), *nu = (int32_t*)calloc(nv + 1, 4), *covs = (int32_t*)calloc(4 * (size_t)nv + 4, 4),
+            *tc = (int32_t*)calloc(nv + 1, 4), *cons = (int32_t*)calloc(3 * (size_t)nv + 3, 4), *prof = (int32_t*)calloc(12 * (size_t)nv + 12, 4);
+    int64_t *pos = (int64_t*)calloc(nv + 1, 8), *vps = (int64_t*)calloc(nv + 1, 8);
+    for (int v = 0; v < nv; ++v) {
+        const cand_var_t *c = chunk->cand_vars + v;
+        type[v] = c->var_type; hp[v] = c->is_homopolymer_indel; nu[v] = c->n_uniq_alles; tc[v] = c->total_cov; pos[v] = c->pos; vps[v] = c->phase_set;
+        for (int a = 0; a < c->n_uniq_alles && a < 4; ++a) covs[4 * v + a] = c->alle_covs[a];
+    }
+    lcd_phase_input_t in = { nr, nv, target_var_cate, opt->is_ont, chunk->ordered_read_ids, chunk->is_skipped, ps, pe, ao, al,
+                             chunk->var_i_to_cate, type, hp, nu, covs, tc, pos };
+    lcd_phase_output_t out = { chunk->haps, (int64_t*)chunk->phase_sets, cons, prof, vps, chunk->n_clean_agree_snps, chunk->n_clean_conflict_snps };
+    if (lcd_phase_batch(1, &in, &out)) die("lcd_phase_batch");
+    for (int r = 0; r < nr; ++r) chunk->phase_scores[r] = 0;              /* read_init_hap_phase_set, src/assign_hap.c:16-20 */
+    for (int v = 0; v < nv; ++v) {
+        if ((chunk->var_i_to_cate[v] & target_var_cate) == 0) continue;
+        cand_var_t *c = chunk->cand_vars + v;
+        if (c->hap_to_alle_profile == NULL) {                             /* var_init_hap_profile_cons_allele, src/assign_hap.c:42-45 */
+            c->hap_to_alle_profile = (int**)malloc((LONGCALLD_DEF_PLOID + 1) * sizeof(int*));
+            for (int h = 0; h <= LONGCALLD_DEF_PLOID; ++h) c->hap_to_alle_profile[h] = (int*)calloc(c->n_uniq_alles, sizeof(int));
+            c->hap_to_cons_alle = (int*)malloc((LONGCALLD_DEF_PLOID + 1) * sizeof(int));
+        }
+        for (int h = 0; h <= LONGCALLD_DEF_PLOID; ++h) {
+            c->hap_to_cons_alle[h] = cons[3 * v + h];
+            for (int a = 0; a < c->n_uniq_alles && a < 4; ++a) c->hap_to_alle_profile[h][a] = prof[12 * v + 4 * h + a];
+        }
+        c->phase_set = vps[v];
+    }
+    free(ps); free(pe); free(ao); free(al); free(type); free(hp); free(nu); free(covs); free(tc); free(cons); free(prof); free(pos); free(vps);
+    n_calls[2]++;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ K7 */
+static int edlib1(uint8_t *target, int tlen, uint8_t *query, int qlen, int mode, int want_path, uint8_t **aln, lcd_edlib_result_t *res) {
+    uint8_t *seqs = (uint8_t*)malloc((size_t)qlen + tlen + 1);
+    memcpy(seqs, query, qlen); memcpy(seqs + qlen, target, tlen);
+    int64_t qo = 0, to = qlen, ao = 0; int32_t ql = qlen, tl = tlen, m = mode, w = want_path;
+    *aln = (uint8_t*)malloc((size_t)qlen + tlen + 2);
+    const int rc = lcd_edlib_batch(1, seqs, (size_t)qlen + tlen, &qo, &ql, &to, &tl, &m, &w, *aln, &ao, res);
+    free(seqs);
+    if (rc) die("lcd_edlib_batch");
+    n_calls[3]++;
+    return 0;
+}
+int edlib_edit_distance(uint8_t *target, int tlen, uint8_t *query, int qlen) {                 /* src/align.c:210 */
+    uint8_t *aln; lcd_edlib_result_t r; edlib1(target, tlen, query, qlen, LCD_EDLIB_MODE_NW, 0, &aln, &r); free(aln);
+    return r.edit_distance;
+}
+int edlib_xgaps(uint8_t *target, int tlen, uint8_t *query, int qlen) {                         /* src/align.c:222 + edlibAlignmentToXGAPS :189 */
+    uint8_t *aln; lcd_edlib_result_t r; edlib1(target, tlen, query, qlen, LCD_EDLIB_MODE_NW, 1, &aln, &r);
+    int n_gaps = 0, n_mis = 0;
+    for (int i = 0; i < r.aln_len; ++i) {
+        if (aln[i] == 3) n_mis++;
+        else if ((aln[i] == 1 || aln[i] == 2) && (i == 0 || aln[i - 1] != aln[i])) n_gaps++;
+    }
+    free(aln);
+    return n_mis + n_gaps;
+}
+static int edlib_path_counts(uint8_t *target, int tlen, uint8_t *query, int qlen, int mode, int *n_eq, int *n_xid) {
+    uint8_t *aln; lcd_edlib_result_t r; edlib1(target, tlen, query, qlen, mode, 1, &aln, &r);
+    if (n_eq != NULL && n_xid != NULL) {                                                        /* edlibAlignmentToXID, src/align.c:164-187 */
+        int eq = 0, x = 0;
+        for (int i = 0; i < r.aln_len; ++i) { if (aln[i] == 0) eq++; else x++; }
+        *n_eq = eq; *n_xid = x;
+    }
+    free(aln);
+    return r.edit_distance;
+}
+int edlib_end2end_aln(uint8_t *target, int tlen, uint8_t *query, int qlen, int *n_eq, int *n_xid) { return edlib_path_counts(target, tlen, query, qlen, LCD_EDLIB_MODE_NW, n_eq, n_xid); }   /* src/align.c:234 */
+int edlib_infix_aln(uint8_t *target, int tlen, uint8_t *query, int qlen, int *n_eq, int *n_xid) { return edlib_path_counts(target, tlen, query, qlen, LCD_EDLIB_MODE_HW, n_eq, n_xid); }     /* src/align.c:256 */

@@ -1,0 +1,42 @@
+"""GPU, end to end: `longcallD call` on the reference's bundled HiFi / ONT data with the UNMODIFIED reference linked as a shared
+library (oracle/_ref/longcallD_so) and longcalld_b200/dropin/liblcd_dropin.so preloaded, so that the per-site coverage pass
+(K2), the read x variant profile (K3), the read->haplotype assignment / phasing (K4) and every edlib call (K7) of the run execute on
+the B200 through the C-ABI.  The VCF body must be the reference's own (md5 of the non-header lines)."""
+import hashlib
+import os
+import subprocess
+
+import pytest
+
+import lcd_testlib as T
+
+pytestmark = pytest.mark.gpu
+REF_DIR = os.path.join(T.ROOT, "oracle", "_ref")
+DROPIN = os.path.join(T.ROOT, "longcalld_b200", "dropin", "liblcd_dropin.so")
+GOLDEN = {"hifi": "dcbd4523c01ab37cce5dd88d5e56b564", "ont": "71f0e1aa2ee7667ad2a1f31e2eace81d"}
+
+
+def _run(tech, preload, threads=4):
+    exe = os.path.join(REF_DIR, "longcallD_so")
+    data = os.path.join(REF_DIR, "test_data")
+    if not (os.path.exists(exe) and os.path.exists(DROPIN) and os.path.exists(os.path.join(data, "chr11_2M.fa"))):
+        pytest.skip("oracle/_ref/longcallD_so, the drop-in or the bundled test data were not built in this checkout")
+    env = dict(os.environ, LCD_DROPIN_VERBOSE="1")
+    if preload:
+        env["LD_PRELOAD"] = DROPIN
+    cmd = [exe, "call", "--hifi" if tech == "hifi" else "--ont", os.path.join(data, "chr11_2M.fa"),
+           os.path.join(data, f"HG002_chr11_{tech}_test.bam"), "-t", str(threads)]
+    r = subprocess.run(cmd, env=env, capture_output=True, timeout=1500)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    body = b"".join(l + b"\n" for l in r.stdout.split(b"\n") if l and not l.startswith(b"#"))
+    return hashlib.md5(body).hexdigest(), r.stderr.decode()
+
+
+@pytest.mark.parametrize("tech", ["hifi", "ont"])
+def test_vcf_identical_with_gpu_dropin(tech):
+    md5, err = _run(tech, preload=True)
+    calls = [l[l.index("[lcd_dropin] GPU calls"):] for l in err.splitlines() if "[lcd_dropin] GPU calls" in l]
+    assert calls, "the drop-in was not loaded"
+    counts = [int(x) for x in __import__("re").findall(r"(?:pileup|profile|phase|edlib) (\d+)", calls[-1])]
+    assert counts[0] > 0 and counts[1] > 0 and counts[2] > 0, calls[-1]       # K2, K3, K4 really ran on the GPU
+    assert md5 == GOLDEN[tech], (md5, calls[-1])
