@@ -8,6 +8,10 @@
  *     collect_read_var_profile                       (src/collect_var.c:1389)  -> lcd_profile_batch  (K3)
  *     assign_hap_based_on_germline_het_vars_kmeans   (src/assign_hap.c:473)    -> lcd_phase_batch    (K4)
  *     edlib_edit_distance / edlib_xgaps / edlib_end2end_aln / edlib_infix_aln (src/align.c:210-275) -> lcd_edlib_batch (K7)
+ *     wfa_end2end_aln                                (src/align.c:374)         -> lcd_wfa_batch      (K6)
+ *     abpoa_partial_aln_msa_cons                     (src/align.c:762)         -> lcd_poa_batch      (K5; regions whose reads all
+ *                                                     cover the region -- partial-cover / sampled regions, which need the sub-graph
+ *                                                     alignment the GPU library does not have yet, are forwarded to the reference)
  * Everything else of the reference runs unchanged.  The reference calls these once per chunk / per pair, so every
  * call here is a batch of one (the batched two-phase worker of INTEGRATION.md section 1 is what a maintainer would
  * adopt for speed); this file exists to prove the boundary: with it preloaded the reference writes the same VCF.
@@ -29,10 +33,10 @@
 #include "lcd_gpu.h"
 
 static void die(const char *what) { fprintf(stderr, "[lcd_dropin] %s failed: %s\n", what, lcd_gpu_last_error()); exit(1); }
-static unsigned long n_calls[4];
+static unsigned long n_calls[8];
 __attribute__((destructor)) static void report(void) {
-    if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: pileup %lu, profile %lu, phase %lu, edlib %lu; kernel launches %llu\n",
-                                              n_calls[0], n_calls[1], n_calls[2], n_calls[3], (unsigned long long)lcd_gpu_launch_count());
+    if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: pileup %lu, profile %lu, phase %lu, edlib %lu, wfa %lu, poa %lu (forwarded to abPOA: %lu); kernel launches %llu\n",
+                                              n_calls[0], n_calls[1], n_calls[2], n_calls[3], n_calls[4], n_calls[5], n_calls[6], (unsigned long long)lcd_gpu_launch_count());
 }
 
 /* ------------------------------------------------------------------------------------------ digars -> flat */
@@ -257,3 +261,109 @@ static int edlib_path_counts(uint8_t *target, int tlen, uint8_t *query, int qlen
 }
 int edlib_end2end_aln(uint8_t *target, int tlen, uint8_t *query, int qlen, int *n_eq, int *n_xid) { return edlib_path_counts(target, tlen, query, qlen, LCD_EDLIB_MODE_NW, n_eq, n_xid); }   /* src/align.c:234 */
 int edlib_infix_aln(uint8_t *target, int tlen, uint8_t *query, int qlen, int *n_eq, int *n_xid) { return edlib_path_counts(target, tlen, query, qlen, LCD_EDLIB_MODE_HW, n_eq, n_xid); }     /* src/align.c:256 */
+
+/* ------------------------------------------------------------------------------------------ K6 */
+#include "align.h"
+#include "abpoa.h"
+int wfa_end2end_aln(uint8_t *pattern, int plen, uint8_t *text, int tlen, int gap_aln, int b, int q, int e, int q2, int e2, int heuristic, int affine_gap,
+                    uint32_t **cigar_buf, int *cigar_length, uint8_t **pattern_alg, uint8_t **text_alg, int *alg_length) {      /* src/align.c:374-460 */
+    lcd_wfa_params_t par; memset(&par, 0, sizeof(par));
+    par.mismatch = b; par.gap_open1 = q; par.gap_ext1 = e; par.gap_open2 = q2; par.gap_ext2 = e2;
+    par.affine2p = affine_gap == LONGCALLD_WFA_AFFINE_2P;
+    par.min_wavefront_length = 10; par.max_distance_threshold = 50; par.steps_between_cutoffs = 1;     /* wavefront_aligner_attr_default */
+    if (heuristic == LONGCALLD_WFA_ADAPTIVE) par.heuristic = LCD_WFA_HEUR_ADAPTIVE;
+    else if (heuristic == LONGCALLD_WFA_ZDROP) {
+        par.heuristic = LCD_WFA_HEUR_ZDROP;
+        const int mn = plen < tlen ? plen : tlen; const int z = (int)(mn * 0.1);
+        par.zdrop = z < 500 ? z : 500; par.steps_between_cutoffs = 100;
+    } else par.heuristic = LCD_WFA_HEUR_NONE;
+    const int left = gap_aln == LONGCALLD_GAP_LEFT_ALN;
+    uint8_t *seqs = (uint8_t*)malloc((size_t)plen + tlen + 1), *p = seqs, *t = seqs + plen;
+    if (left) {                                              /* gaps at the left-most position: align the reversed sequences (:410-414) */
+        for (int i = 0; i < plen; ++i) p[i] = pattern[plen - i - 1];
+        for (int i = 0; i < tlen; ++i) t[i] = text[tlen - i - 1];
+    } else { memcpy(p, pattern, plen); memcpy(t, text, tlen); }
+    int64_t po = 0, to = plen, oo = 0; int32_t pl = plen, tl = tlen;
+    char *ops = (char*)malloc(2 * ((size_t)plen + tlen) + 16);
+    lcd_wfa_result_t res;
+    if (lcd_wfa_batch(1, seqs, (size_t)plen + tlen, &po, &pl, &to, &tl, &par, ops, &oo, &res)) die("lcd_wfa_batch");
+    n_calls[4]++;
+    const int n = res.n_ops;
+    if (cigar_buf != NULL && cigar_length != NULL) {         /* cigar_get_CIGAR(cigar, true, ...) (WFA2-lib/alignment/cigar.c:181-240), reversed for left alignment */
+        uint32_t *tmp = (uint32_t*)malloc(((size_t)n + 1) * sizeof(uint32_t)); int m = 0;
+        for (int i = 0; i < n;) {
+            int j = i; while (j < n && ops[j] == ops[i]) ++j;
+            const uint32_t op = ops[i] == 'M' ? BAM_CEQUAL : ops[i] == 'X' ? BAM_CDIFF : ops[i] == 'I' ? BAM_CINS : BAM_CDEL;
+            tmp[m++] = ((uint32_t)(j - i) << 4) | op;
+            i = j;
+        }
+        *cigar_length = m;
+        *cigar_buf = (uint32_t*)malloc(((size_t)m + 1) * sizeof(uint32_t));
+        for (int i = 0; i < m; ++i) (*cigar_buf)[i] = left ? tmp[m - i - 1] : tmp[i];
+        free(tmp);
+    }
+    if (pattern_alg != NULL && text_alg != NULL) {           /* wfa_collect_pretty_alignment (:277-329), reversed for left alignment (:440-452) */
+        const int max_len = tlen + plen + 1;
+        uint8_t *mem = (uint8_t*)calloc(2 * (size_t)max_len, 1), *pa = mem, *ta = mem + max_len;
+        int k = 0, pp = 0, tp = 0;
+        for (int i = 0; i < n; ++i) {
+            switch (ops[i]) {
+                case 'M': case 'X': pa[k] = p[pp++]; ta[k++] = t[tp++]; break;
+                case 'I': pa[k] = 5; ta[k++] = t[tp++]; break;
+                case 'D': pa[k] = p[pp++]; ta[k++] = 5; break;
+                default: break;
+            }
+        }
+        if (left) for (int i = 0; i < k / 2; ++i) { uint8_t x = pa[i]; pa[i] = pa[k - i - 1]; pa[k - i - 1] = x; x = ta[i]; ta[i] = ta[k - i - 1]; ta[k - i - 1] = x; }
+        *pattern_alg = pa; *text_alg = ta; *alg_length = k;
+    }
+    free(ops); free(seqs);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ K5 */
+int abpoa_partial_aln_msa_cons(const call_var_opt_t *opt, abpoa_t *ab, int sampling_reads, int n_reads, int *read_ids, uint8_t **read_seqs, uint8_t **read_quals,
+                               int *read_lens, int *read_full_cover, char **names, int max_n_cons, int *cons_lens, uint8_t **cons_seqs, int *clu_n_seqs,
+                               int **clu_read_ids, int *msa_seq_lens, uint8_t **msa_seqs) {                                        /* src/align.c:762-857 */
+    typedef int (*fn_t)(const call_var_opt_t *, abpoa_t *, int, int, int *, uint8_t **, uint8_t **, int *, int *, char **, int, int *, uint8_t **, int *, int **, int *, uint8_t **);
+    static fn_t orig = NULL;
+    if (!orig) orig = (fn_t)dlsym(RTLD_NEXT, "abpoa_partial_aln_msa_cons");
+    /* the GPU kernel covers the case every read is aligned end to end against the whole graph: collect_partial_aln_beg_end
+     * (:709-745) returns the full range for reads that cover the region (or reach a side with a gap) when reads are not sampled */
+    int ok = ab == NULL && !sampling_reads && max_n_cons == 1 && n_reads >= 1 && cons_lens && cons_seqs && LONGCALLD_NOISY_IS_BOTH_COVER(read_full_cover[0]);
+    size_t tot = 0;
+    for (int i = 0; ok && i < n_reads; ++i) {
+        const int c = read_full_cover[i];
+        if (!(LONGCALLD_NOISY_IS_BOTH_COVER(c) || (LONGCALLD_NOISY_IS_LEFT_COVER(c) && LONGCALLD_NOISY_IS_RIGHT_GAP(c)) ||
+              (LONGCALLD_NOISY_IS_RIGHT_COVER(c) && LONGCALLD_NOISY_IS_LEFT_GAP(c))) || read_lens[i] <= 0) ok = 0;
+        tot += read_lens[i] > 0 ? read_lens[i] : 0;
+    }
+    if (ok) {
+        uint8_t *seqs = (uint8_t*)malloc(tot + 1), *cons = (uint8_t*)malloc(tot + 1);
+        int64_t *off = (int64_t*)malloc(sizeof(int64_t) * n_reads); int32_t *len = (int32_t*)malloc(sizeof(int32_t) * n_reads);
+        size_t o = 0; int max_len = 0;
+        for (int i = 0; i < n_reads; ++i) { off[i] = (int64_t)o; len[i] = read_lens[i]; memcpy(seqs + o, read_seqs[i], read_lens[i]); o += read_lens[i]; if (len[i] > max_len) max_len = len[i]; }
+        lcd_poa_params_t par = { opt->match, opt->mismatch, opt->gap_open1, opt->gap_ext1, opt->gap_open2, opt->gap_ext2, 10, 0.01f, 1, 1 };   /* abpoa_init_para defaults wb / wf */
+        int32_t first = 0, nr = n_reads; int64_t cons_off = 0, msa_off = 0, msa_cap = (int64_t)(n_reads + 1) * (2 * (int64_t)max_len + 64);
+        uint8_t *msa = (msa_seq_lens && msa_seqs) ? (uint8_t*)malloc((size_t)msa_cap) : NULL;
+        lcd_poa_result_t res;
+        const int rc = lcd_poa_batch(1, seqs, tot, &first, &nr, off, len, n_reads, &par, cons, &cons_off, msa, msa ? &msa_off : NULL, msa ? &msa_cap : NULL, &res);
+        if (rc == -1) die("lcd_poa_batch");                    /* -2: the problem itself was refused on the device (status below) */
+        if (rc == 0 && res.status == LCD_POA_OK && res.cons_len > 0) {
+            cons_lens[0] = res.cons_len; cons_seqs[0] = (uint8_t*)malloc(res.cons_len); memcpy(cons_seqs[0], cons, res.cons_len);
+            if (clu_n_seqs != NULL && clu_read_ids != NULL) { *clu_n_seqs = n_reads; *clu_read_ids = (int*)malloc(n_reads * sizeof(int)); for (int i = 0; i < n_reads; ++i) (*clu_read_ids)[i] = read_ids[i]; }
+            if (msa) {
+                *msa_seq_lens = res.msa_len;
+                for (int i = 0; i < n_reads + 1; ++i) { msa_seqs[i] = (uint8_t*)malloc(res.msa_len); memcpy(msa_seqs[i], msa + (size_t)i * res.msa_len, res.msa_len); }
+            }
+            free(seqs); free(cons); free(off); free(len); free(msa);
+            n_calls[5]++;
+            return 1;
+        }
+        /* outside the kernel's envelope (e.g. LCD_POA_NEEDS_INT32, MSA wider than the estimate): let abPOA handle this region */
+        free(seqs); free(cons); free(off); free(len); free(msa);
+    }
+    n_calls[6]++;
+    return orig(opt, ab, sampling_reads, n_reads, read_ids, read_seqs, read_quals, read_lens, read_full_cover, names, max_n_cons, cons_lens, cons_seqs,
+                clu_n_seqs, clu_read_ids, msa_seq_lens, msa_seqs);
+}
