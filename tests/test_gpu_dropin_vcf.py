@@ -13,7 +13,8 @@ import lcd_testlib as T
 pytestmark = pytest.mark.gpu
 REF_DIR = os.path.join(T.ROOT, "oracle", "_ref")
 DROPIN = os.path.join(T.ROOT, "longcalld_b200", "dropin", "liblcd_dropin.so")
-GOLDEN = {"hifi": "dcbd4523c01ab37cce5dd88d5e56b564", "ont": "71f0e1aa2ee7667ad2a1f31e2eace81d"}
+GOLDEN = {"hifi": "dcbd4523c01ab37cce5dd88d5e56b564", "ont": "71f0e1aa2ee7667ad2a1f31e2eace81d",
+          "mosaic": "ea77d40096193eb9ad4497c297c21fd7"}          # mosaic: HiFi with -s -T <TE consensus> (BASELINE configs[4] on the bundled data)
 
 
 def _run(tech, preload, threads=4):
@@ -24,20 +25,23 @@ def _run(tech, preload, threads=4):
     env = dict(os.environ, LCD_DROPIN_VERBOSE="1")
     if preload:
         env["LD_PRELOAD"] = DROPIN
-    cmd = [exe, "call", "--hifi" if tech == "hifi" else "--ont", os.path.join(data, "chr11_2M.fa"),
-           os.path.join(data, f"HG002_chr11_{tech}_test.bam"), "-t", str(threads)]
+    bam = "ont" if tech == "ont" else "hifi"
+    extra = ["-s", "-T", os.path.join(data, "AluY_L1_SVA_cons_noPA.fa")] if tech == "mosaic" else []
+    cmd = [exe, "call", "--ont" if tech == "ont" else "--hifi"] + extra + [os.path.join(data, "chr11_2M.fa"),
+           os.path.join(data, f"HG002_chr11_{bam}_test.bam"), "-t", str(threads)]
     r = subprocess.run(cmd, env=env, capture_output=True, timeout=1500)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     body = b"".join(l + b"\n" for l in r.stdout.split(b"\n") if l and not l.startswith(b"#"))
     return hashlib.md5(body).hexdigest(), r.stderr.decode()
 
 
-@pytest.mark.parametrize("tech", ["hifi", "ont"])
+@pytest.mark.parametrize("tech", ["hifi", "ont", "mosaic"])
 def test_vcf_identical_with_gpu_dropin(tech):
     md5, err = _run(tech, preload=True)
     calls = [l[l.index("[lcd_dropin] GPU calls"):] for l in err.splitlines() if "[lcd_dropin] GPU calls" in l]
     assert calls, "the drop-in was not loaded"
     counts = dict((k, int(v)) for k, v in __import__("re").findall(r"(pileup|profile|phase|edlib|wfa|poa) (\d+)", calls[-1]))
-    assert all(counts[k] > 0 for k in ("pileup", "profile", "phase", "wfa", "poa")), calls[-1]     # K2-K6 really ran on the GPU
+    need = ("pileup", "phase", "wfa", "poa") if tech == "mosaic" else ("pileup", "profile", "phase", "wfa", "poa")   # -s: the profile takes the reference's somatic path
+    assert all(counts[k] > 0 for k in need), calls[-1]                                             # the kernels really ran on the GPU
     print(calls[-1])
     assert md5 == GOLDEN[tech], (md5, calls[-1])
