@@ -36,6 +36,23 @@ EDLIB_BYTES_PER_BLOCKCOL = 28    # Peq word in + (P, M, score) s
 PHASE_BYTES_PER_PAIR = 24        # allele + variant state in, counts out, per (read, variant) pair and pass
 
 
+def ncu_traffic(kernel="poa_kernel"):
+    """DRAM bytes (read + write) of one launch of the dominant kernel from the committed `ncu --set full` capture of this
+    same command (profiles/r1_poa_full_v3.raw.csv); None when the file is missing."""
+    try:
+        import csv
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1_poa_full_v3.raw.csv"))))
+        h, u, v = rows[0], rows[1], rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = h.index(name)
+            tot += float(v[i].replace(",", "")) * scale[u[i]]
+        return tot if kernel in v[h.index("Kernel Name")] else None
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -440,7 +457,9 @@ def run_b200(args, rank, world):
                 "gather": (None if world == 1 else {"what": "per-chunk POA/WFA result records to rank 0 (NCCL gather, inside e2e)",
                                                     "bytes_per_step": int(gathered["bytes"])}),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "poa_kernel" if dominant_is_poa else "wfa_kernel<32>+wfa_kernel<256>",
+                             "traffic": ncu_traffic() if dominant_is_poa else None,
+                             "traffic_source": "profiles/r1_poa_full_v3.raw.csv (ncu --set full of this command, one poa_kernel launch)",
+                             "kernel": "poa_kernel" if dominant_is_poa else "wfa_kernel<32>+wfa_kernel<256>",
                              "algorithmic": (f"{poa_cells} banded POA cells x {POA_BYTES_PER_CELL} B" if dominant_is_poa
                                              else f"{wfa_cells} wavefront cells x {WFA_BYTES_PER_CELL} B"),
                              "peak_source": which,
