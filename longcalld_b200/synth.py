@@ -294,3 +294,57 @@ def add_profile_inputs(rng, d):
         cnt.append(k)
     d.update(nreg_first=np.array(first + [0], np.int64), n_nreg=np.array(cnt + [0], np.int32), nreg_beg=np.array(nb + [0], np.int64), nreg_end=np.array(ne + [0], np.int64))
     return d
+
+
+# ----------------------------------------------------------------------------- K1 workload: =/X CIGAR reads of a chunk
+def make_digar_chunk(rng, n_reads=100, read_len=(800, 4000), err_every=300, tech="hifi", low_qual_frac=0.05, ref0=100000, ref_len=30000):
+    """A synthetic region chunk as the loader hands it to the pileup scan: per read the BAM fields the =/X path reads
+    (0-based pos, strand, CIGAR words, 4-bit packed SEQ, QUAL).  Reads alternate '=' runs with X runs, insertions, deletions and
+    the odd N skip; some carry dense clusters of differences (they become noisy intervals), long soft / hard clips (clip
+    intervals; a few flagged as ONT palindromes), sit at the very start / end of the contig, or are dense enough to be dropped."""
+    EQ, X, I, D, N, S, H = 7, 8, 1, 2, 3, 4, 5
+    ont = tech == "ont"
+    whole = ref0 + ref_len + (5 if rng.random() < 0.3 else 5000)
+    cig, cig_off, n_cig, pos0, rev, pal, lq, seq_off, qual_off, bseq, qual = [], [], [], [], [], [], [], [], [], [], []
+    for r in range(n_reads):
+        L = int(rng.integers(*read_len)); ops = []
+        start = 0 if rng.random() < 0.03 else ref0 + int(rng.integers(0, max(1, ref_len - L)))
+        if rng.random() < 0.25: ops.append((S if rng.random() < 0.8 else H, int(rng.choice([3, 25, 31, 120, 700]))))
+        dense_read = rng.random() < 0.04
+        every = max(2, err_every // 40) if dense_read else err_every
+        left = L
+        while left > 0:
+            cluster = rng.random() < 0.1
+            k = int(rng.integers(3, 12)) if cluster else 1
+            run = min(left, int(rng.integers(1, 2 * every)))
+            ops.append((EQ, run)); left -= run
+            for _ in range(k):
+                if left <= 0: break
+                u = rng.random()
+                if u < 0.5: n = int(rng.integers(1, 4)); ops.append((X, n)); left -= n
+                elif u < 0.72: ops.append((I, int(rng.integers(1, 8)) if rng.random() < 0.9 else int(rng.integers(20, 300))))
+                elif u < 0.97: n = int(rng.integers(1, 8)) if rng.random() < 0.9 else int(rng.integers(20, 300)); ops.append((D, n)); left -= n
+                else: n = int(rng.integers(50, 500)); ops.append((N, n)); left -= n
+                if cluster and left > 0: g = min(left, int(rng.integers(1, 30 if not ont else 12))); ops.append((EQ, g)); left -= g
+        if ops[-1][0] not in (EQ, X): ops.append((EQ, int(rng.integers(1, 50))))
+        if rng.random() < 0.25: ops.append((S if rng.random() < 0.8 else H, int(rng.choice([3, 25, 31, 120, 700]))))
+        merged = []
+        for o in ops:                                                  # no two equal neighbouring ops
+            if merged and merged[-1][0] == o[0]: merged[-1] = (o[0], merged[-1][1] + o[1])
+            else: merged.append(o)
+        ql = sum(n for t, n in merged if t in (EQ, X, I, S))
+        cig_off.append(len(cig)); n_cig.append(len(merged)); cig.extend((n << 4) | t for t, n in merged)
+        pos0.append(start); rev.append(int(rng.random() < 0.5)); pal.append(int(ont and rng.random() < 0.2)); lq.append(ql)
+        codes = rng.choice(np.array([1, 2, 4, 8, 15], np.uint8), size=ql + (ql & 1), p=[0.245, 0.245, 0.245, 0.245, 0.02])
+        seq_off.append(len(bseq)); bseq.extend(((codes[0::2] << 4) | codes[1::2]).tolist())
+        q = rng.integers(12, 45, ql); q[rng.random(ql) < low_qual_frac] = rng.integers(0, 10)
+        qual_off.append(len(qual)); qual.extend(q.tolist())
+    hifi_win, ont_win = 100, 25
+    return dict(n_reads=n_reads, min_bq=10, noisy_reg_max_xgaps=5, noisy_reg_slide_win=ont_win if ont else hifi_win, end_clip_reg=30,
+                end_clip_reg_flank_win=100, max_noisy_frac_per_read=0.5, max_var_ratio_per_read=0.05, whole_ref_len=whole,
+                reg_beg=ref0 + ref_len // 4, reg_end=ref0 + 3 * ref_len // 4,
+                ordered_read_ids=rng.permutation(n_reads).astype(np.int32), is_skipped=(rng.random(n_reads) < 0.05).astype(np.uint8),
+                read_pos0=np.array(pos0, np.int64), read_is_rev=np.array(rev, np.uint8), is_palindrome=np.array(pal, np.uint8),
+                n_cigar=np.array(n_cig, np.int32), cigar_off=np.array(cig_off, np.int64), cigar=np.array(cig + [0], np.uint32),
+                l_qseq=np.array(lq, np.int32), seq_off=np.array(seq_off, np.int64), bseq=np.array(bseq + [0], np.uint8),
+                qual_off=np.array(qual_off, np.int64), qual=np.array(qual + [0], np.uint8))

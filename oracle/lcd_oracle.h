@@ -142,6 +142,36 @@ typedef struct {
 } lcd_profile_output_t;
 int lcd_oracle_read_var_profile(const lcd_pileup_input_t *in, const lcd_profile_extra_t *ex, lcd_profile_output_t *out);
 
+/* ---- pileup scan, step 1: difference lists from =/X CIGARs (src/bam_utils.c:701-841, :161-205) ------------ */
+typedef struct {
+    int32_t n_reads;
+    int32_t min_bq, noisy_reg_max_xgaps, noisy_reg_slide_win, end_clip_reg, end_clip_reg_flank_win;   /* call_var_opt_t */
+    double max_noisy_frac_per_read, max_var_ratio_per_read;
+    int64_t whole_ref_len;             /* chunk->whole_ref_len */
+    int64_t reg_beg, reg_end;          /* chunk->reg_beg / reg_end: a kept read's intervals overlapping it go to chunk_noisy_regs */
+    const int32_t *ordered_read_ids;   /* chunk->ordered_read_ids [n_reads] */
+    const uint8_t *is_skipped;         /* chunk->is_skipped (reads already skipped by the loader) */
+    const int64_t *read_pos0;          /* bam1_t core.pos (0-based) */
+    const uint8_t *read_is_rev;        /* bam_is_rev */
+    const uint8_t *is_palindrome;      /* is_ont_palindrome_clip (SA-tag test, host side; 0 for HiFi) */
+    const int32_t *n_cigar; const int64_t *cigar_off; const uint32_t *cigar;      /* BAM CIGAR words */
+    const int32_t *l_qseq; const int64_t *seq_off; const uint8_t *bseq;           /* 4-bit packed SEQ, (l_qseq+1)/2 bytes per read */
+    const int64_t *qual_off; const uint8_t *qual;                                   /* QUAL, l_qseq bytes per read */
+} lcd_digar_input_t;
+typedef struct {
+    uint8_t *skip;                     /* 1: the reference returns -1 (read dropped as BAM_RECORD_WRONG_MAP) */
+    int64_t *read_beg, *read_end;      /* digar_t.beg / end */
+    int64_t *digar_first; int32_t *n_digar;                                        /* per read: its digar1_t records */
+    int64_t *digar_pos; int8_t *digar_type; int32_t *digar_len, *digar_qi; uint8_t *digar_low_qual; int64_t *digar_alt_off; uint8_t *digar_alt;
+    int64_t digar_cap, alt_cap;        /* capacities of the digar_* arrays / digar_alt */
+    int64_t *nreg_first; int32_t *n_nreg; int64_t *nreg_beg, *nreg_end; int32_t *nreg_label;   /* digar_t.noisy_regs in the order cr_index leaves them */
+    int64_t nreg_cap;
+    int64_t *cnreg_beg, *cnreg_end; int32_t *cnreg_label; int64_t cnreg_cap, n_cnreg;          /* chunk->chunk_noisy_regs in cr_add order (:819-832) */
+    int64_t *qual_counts;              /* chunk->qual_counts [256] */
+    int64_t n_digar_total, n_alt_total, n_nreg_total;
+} lcd_digar_output_t;
+int lcd_oracle_collect_digar_eqx(const lcd_digar_input_t *in, lcd_digar_output_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -200,3 +200,87 @@ int ref_read_var_profile(const lcd_pileup_input_t *in, const lcd_profile_extra_t
     free(chunk.digars); free(chunk.cand_vars); free(chunk.var_i_to_cate); free(chunk.ordered_read_ids); free(chunk.is_skipped);
     return rc;
 }
+
+/* collect_digar_from_eqx_cigar (src/bam_utils.c:701-841) for every listed, not yet skipped read of a synthetic chunk, as
+ * collect_digars_from_bam drives it (src/collect_var.c:1063-1082): bam1_t records are built with htslib's bam_set1 from
+ * the flat CIGAR / packed SEQ / QUAL arrays (reads flagged is_palindrome get an SA tag that passes the reference's
+ * 90 % overlap test when opt.is_ont is set), results are copied out in the layout of lcd_digar_output_t. */
+#include "htslib/sam.h"
+int ref_collect_digar_eqx(const lcd_digar_input_t *in, lcd_digar_output_t *out) {
+    const int nr = in->n_reads;
+    call_var_opt_t opt; memset(&opt, 0, sizeof(opt));
+    opt.min_bq = in->min_bq; opt.noisy_reg_max_xgaps = in->noisy_reg_max_xgaps; opt.noisy_reg_slide_win = in->noisy_reg_slide_win;
+    opt.end_clip_reg = in->end_clip_reg; opt.end_clip_reg_flank_win = in->end_clip_reg_flank_win;
+    opt.max_noisy_frac_per_read = in->max_noisy_frac_per_read; opt.max_var_ratio_per_read = in->max_var_ratio_per_read;
+    opt.is_ont = 0;
+    for (int r = 0; r < nr; ++r) if (in->is_palindrome[r]) opt.is_ont = 1;
+    bam_chunk_t chunk; memset(&chunk, 0, sizeof(chunk));
+    chunk.n_reads = chunk.m_reads = nr; chunk.tid = 0; chunk.tname = (char*)"chr";
+    chunk.reg_beg = in->reg_beg; chunk.reg_end = in->reg_end; chunk.whole_ref_len = in->whole_ref_len;
+    chunk.qual_counts = (int*)calloc(256, sizeof(int));
+    chunk.is_ont_palindrome = (uint8_t*)calloc(nr + 1, 1);
+    chunk.digars = (digar_t*)calloc(nr + 1, sizeof(digar_t));
+    chunk.reads = (bam1_t**)calloc(nr + 1, sizeof(bam1_t*));
+    chunk.chunk_noisy_regs = cr_init();
+    for (int r = 0; r < nr; ++r) {
+        const int L = in->l_qseq[r];
+        char *seq = (char*)malloc(L + 1), *ql = (char*)malloc(L + 1);
+        const uint8_t *bs = in->bseq + in->seq_off[r];
+        for (int k = 0; k < L; ++k) { seq[k] = seq_nt16_str[(bs[k >> 1] >> ((~k & 1) << 2)) & 15]; ql[k] = (char)in->qual[in->qual_off[r] + k]; }
+        seq[L] = 0;
+        char name[32]; snprintf(name, sizeof(name), "r%d", r);
+        bam1_t *b = bam_init1();
+        if (bam_set1(b, strlen(name), name, in->read_is_rev[r] ? BAM_FREVERSE : 0, 0, in->read_pos0[r], 60, in->n_cigar[r], in->cigar + in->cigar_off[r],
+                     -1, -1, 0, L, seq, ql, 64) < 0) return -9;
+        if (in->is_palindrome[r]) {
+            char sa[64]; snprintf(sa, sizeof(sa), "chr,%lld,%c,%lldM,60,0;", (long long)in->read_pos0[r] + 1, in->read_is_rev[r] ? '+' : '-',
+                                  (long long)(bam_endpos(b) - in->read_pos0[r]));
+            bam_aux_append(b, "SA", 'Z', (int)strlen(sa) + 1, (uint8_t*)sa);
+        }
+        chunk.reads[r] = b; free(seq); free(ql);
+    }
+    int64_t dtop = 0, atop = 0, rtop = 0; int rc = 0;
+    for (int i = 0; i < nr && !rc; ++i) {
+        const int r = in->ordered_read_ids[i];
+        out->skip[r] = 0;
+        if (in->is_skipped[r]) continue;
+        digar_t *g = chunk.digars + r;
+        out->skip[r] = collect_digar_from_eqx_cigar(&chunk, r, &opt, g) < 0;
+        out->read_beg[r] = g->beg; out->read_end[r] = g->end;
+        out->digar_first[r] = dtop; out->n_digar[r] = g->n_digar; out->nreg_first[r] = rtop; out->n_nreg[r] = (int32_t)g->noisy_regs->n_r;
+        if (chunk.is_ont_palindrome[r] != in->is_palindrome[r]) rc = -8;
+        for (int k = 0; k < g->n_digar && !rc; ++k) {
+            const digar1_t *x = g->digars + k;
+            if (dtop >= out->digar_cap) { rc = -3; break; }
+            out->digar_pos[dtop] = x->pos; out->digar_type[dtop] = (int8_t)x->type; out->digar_len[dtop] = x->len; out->digar_qi[dtop] = x->qi;
+            out->digar_low_qual[dtop] = x->is_low_qual; out->digar_alt_off[dtop] = atop; dtop++;
+            if (x->type == BAM_CDIFF || x->type == BAM_CINS) {
+                if (atop + x->len > out->alt_cap) { rc = -3; break; }
+                memcpy(out->digar_alt + atop, x->alt_seq, x->len); atop += x->len;
+            }
+        }
+        for (int64_t k = 0; k < g->noisy_regs->n_r && !rc; ++k) {
+            if (rtop >= out->nreg_cap) { rc = -4; break; }
+            out->nreg_beg[rtop] = cr_start(g->noisy_regs, k); out->nreg_end[rtop] = cr_end(g->noisy_regs, k); out->nreg_label[rtop] = cr_label(g->noisy_regs, k); rtop++;
+        }
+    }
+    out->n_digar_total = dtop; out->n_alt_total = atop; out->n_nreg_total = rtop;
+    for (int k = 0; k < 256; ++k) out->qual_counts[k] = chunk.qual_counts[k];
+    out->n_cnreg = 0;
+    for (int64_t k = 0; k < chunk.chunk_noisy_regs->n_r && !rc; ++k) {
+        if (out->n_cnreg >= out->cnreg_cap) { rc = -4; break; }
+        /* not indexed yet: x = ctg << 32 | start, y = end (src/cgranges.h:38-42) */
+        out->cnreg_beg[out->n_cnreg] = (int32_t)chunk.chunk_noisy_regs->r[k].x; out->cnreg_end[out->n_cnreg] = (int32_t)chunk.chunk_noisy_regs->r[k].y;
+        out->cnreg_label[out->n_cnreg] = cr_label(chunk.chunk_noisy_regs, k); out->n_cnreg++;
+    }
+    for (int r = 0; r < nr; ++r) {
+        digar_t *g = chunk.digars + r;
+        if (g->digars) { for (int k = 0; k < g->n_digar; ++k) if (g->digars[k].alt_seq) free(g->digars[k].alt_seq); free(g->digars); }
+        if (g->noisy_regs) cr_destroy(g->noisy_regs);
+        free(g->bseq); free(g->qual);
+        bam_destroy1(chunk.reads[r]);
+    }
+    cr_destroy(chunk.chunk_noisy_regs);
+    free(chunk.reads); free(chunk.digars); free(chunk.is_ont_palindrome); free(chunk.qual_counts);
+    return rc;
+}

@@ -4,6 +4,7 @@
   wfa_utest.json.gz   WFA2-lib's own regression vectors (WFA2-lib/tests/wfa.utest.seq + the
                       match==0 goldens in tests/wfa.utest.check/: affine, affine2p, p0-p2,
                       wfapt0/1) -- pins the recurrence, the backtrace tie-breaks and wf-adaptive.
+  digar_lcd.json.gz   digests of the UNMODIFIED reference =/X difference-list pass (collect_digar_from_eqx_cigar) on seeded chunks.
   pileup_lcd.json.gz  outputs of the UNMODIFIED reference per-site coverage pass (collect_cand_vars) on seeded chunks.
   phase_lcd.json.gz   outputs of the UNMODIFIED reference read->haplotype assignment / phasing on seeded chunks.
   edlib_lcd.json.gz   outputs of the UNMODIFIED reference edlib (NW / HW, path) on seeded inputs.
@@ -171,9 +172,26 @@ def pileup_lcd():
     return {"cases": cases}
 
 
+def digar_lcd():
+    """Per-read records (sha1 digest, T.digar_digest) + chunk noisy list of the UNMODIFIED collect_digar_from_eqx_cigar
+    (src/bam_utils.c:701, via oracle/_ref/libref_shim.so: ref_collect_digar_eqx) on seeded chunks."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from longcalld_b200 import synth
+    ref = T.ref_lib()
+    rng = np.random.default_rng(20261021)
+    cases = []
+    for it in range(16):
+        d = synth.make_digar_chunk(rng, n_reads=int(rng.choice([1, 5, 14])), read_len=(60, 300) if it % 4 == 0 else (400, 1500),
+                                   err_every=int(rng.choice([15, 80, 300])), tech="ont" if it % 3 == 0 else "hifi", low_qual_frac=float(rng.choice([0.0, 0.05, 0.4])))
+        res = T.collect_digar(ref, "ref_collect_digar_eqx", d)
+        cases.append({"in": T.digar_case_to_json(d), "digest": T.digar_digest(res), "chunk_noisy": res["chunk_noisy"],
+                      "n_skip": sum(v[0] for v in res["reads"].values()), "n_intervals": sum(len(v[4]) for v in res["reads"].values())})
+    return {"cases": cases}
+
+
 def main():
     only = sys.argv[1:]
-    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd), ("poa_lcd", poa_lcd), ("edlib_lcd", edlib_lcd), ("phase_lcd", phase_lcd), ("pileup_lcd", pileup_lcd)):
+    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd), ("poa_lcd", poa_lcd), ("edlib_lcd", edlib_lcd), ("phase_lcd", phase_lcd), ("pileup_lcd", pileup_lcd), ("digar_lcd", digar_lcd)):
         if only and name not in only:
             continue
         path = os.path.join(HERE, name + ".json.gz")

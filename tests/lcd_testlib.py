@@ -285,3 +285,93 @@ def read_var_profile(lib, fn, d):
         n = max(0, int(pe[r]) - int(ps[r]) + 1) if ps[r] >= 0 else 0
         rows.append((int(ps[r]), int(pe[r]), tuple(al[ao[r]:ao[r] + n].tolist()), tuple(qi[ao[r]:ao[r] + n].tolist())))
     return rows
+
+
+# ----------------------------------------------------------------------------- difference lists from =/X CIGARs (K1) helpers
+DIGAR_IN_FIELDS = (("ordered_read_ids", np.int32), ("is_skipped", np.uint8), ("read_pos0", np.int64), ("read_is_rev", np.uint8),
+                   ("is_palindrome", np.uint8), ("n_cigar", np.int32), ("cigar_off", np.int64), ("cigar", np.uint32),
+                   ("l_qseq", np.int32), ("seq_off", np.int64), ("bseq", np.uint8), ("qual_off", np.int64), ("qual", np.uint8))
+DIGAR_SCALARS = (("n_reads", C.c_int32), ("min_bq", C.c_int32), ("noisy_reg_max_xgaps", C.c_int32), ("noisy_reg_slide_win", C.c_int32),
+                 ("end_clip_reg", C.c_int32), ("end_clip_reg_flank_win", C.c_int32), ("max_noisy_frac_per_read", C.c_double),
+                 ("max_var_ratio_per_read", C.c_double), ("whole_ref_len", C.c_int64), ("reg_beg", C.c_int64), ("reg_end", C.c_int64))
+
+
+class DigarInput(C.Structure):
+    _fields_ = list(DIGAR_SCALARS) + [(k, C.c_void_p) for k, _ in DIGAR_IN_FIELDS]
+
+
+DIGAR_OUT_FIELDS = (("skip", np.uint8, "r"), ("read_beg", np.int64, "r"), ("read_end", np.int64, "r"), ("digar_first", np.int64, "r"), ("n_digar", np.int32, "r"),
+                    ("digar_pos", np.int64, "d"), ("digar_type", np.int8, "d"), ("digar_len", np.int32, "d"), ("digar_qi", np.int32, "d"),
+                    ("digar_low_qual", np.uint8, "d"), ("digar_alt_off", np.int64, "d"), ("digar_alt", np.uint8, "a"))
+
+
+class DigarOutput(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k, _, _ in DIGAR_OUT_FIELDS] + [("digar_cap", C.c_int64), ("alt_cap", C.c_int64)] + \
+               [(k, C.c_void_p) for k in ("nreg_first", "n_nreg", "nreg_beg", "nreg_end", "nreg_label")] + [("nreg_cap", C.c_int64)] + \
+               [(k, C.c_void_p) for k in ("cnreg_beg", "cnreg_end", "cnreg_label")] + [("cnreg_cap", C.c_int64), ("n_cnreg", C.c_int64)] + \
+               [("qual_counts", C.c_void_p), ("n_digar_total", C.c_int64), ("n_alt_total", C.c_int64), ("n_nreg_total", C.c_int64)]
+
+
+def digar_capacity(d):
+    """(digar1_t records, alt bases, intervals) that always suffice for a chunk: from the CIGAR words alone."""
+    cig = np.asarray(d["cigar"], np.uint32); op = cig & 15; ln = (cig >> 4).astype(np.int64)
+    n_dig = int(np.where(op == 8, ln, 1).sum()); n_alt = int(ln[(op == 8) | (op == 1)].sum())
+    return n_dig + 8, n_alt + 8, n_dig + 2 * d["n_reads"] + 8
+
+
+def digar_input(d):
+    keep = {k: np.ascontiguousarray(d[k], dtype=t) for k, t in DIGAR_IN_FIELDS}
+    inp = DigarInput(*[d[k] for k, _ in DIGAR_SCALARS], *[keep[k].ctypes.data for k, _ in DIGAR_IN_FIELDS])
+    return inp, keep
+
+
+def collect_digar(lib, fn, d):
+    """Run an implementation of the =/X difference-list pass -> dict with per-read records (in read-id order, layout independent)."""
+    inp, keep = digar_input(d)
+    nr = d["n_reads"]; dc, ac, rc_ = digar_capacity(d)
+    size = {"r": nr + 1, "d": dc, "a": ac}
+    buf = {k: np.full(size[w], 77, t) for k, t, w in DIGAR_OUT_FIELDS}
+    nf, nn = np.zeros(nr + 1, np.int64), np.zeros(nr + 1, np.int32)
+    nb, ne, nl = np.zeros(rc_, np.int64), np.zeros(rc_, np.int64), np.zeros(rc_, np.int32)
+    cb, ce, cl = np.zeros(rc_, np.int64), np.zeros(rc_, np.int64), np.zeros(rc_, np.int32)
+    qc = np.zeros(256, np.int64)
+    out = DigarOutput(*[buf[k].ctypes.data for k, _, _ in DIGAR_OUT_FIELDS], dc, ac, nf.ctypes.data, nn.ctypes.data, nb.ctypes.data, ne.ctypes.data,
+                      nl.ctypes.data, rc_, cb.ctypes.data, ce.ctypes.data, cl.ctypes.data, rc_, 0, qc.ctypes.data, 0, 0, 0)
+    rc = getattr(lib, fn)(C.byref(inp), C.byref(out))
+    assert rc == 0, rc
+    reads = {}
+    for i in range(nr):
+        r = int(d["ordered_read_ids"][i])
+        if d["is_skipped"][r]: continue
+        f, n = int(buf["digar_first"][r]), int(buf["n_digar"][r])
+        ev = []
+        for k in range(f, f + n):
+            t, ln = int(buf["digar_type"][k]), int(buf["digar_len"][k])
+            alt = bytes(buf["digar_alt"][buf["digar_alt_off"][k]:buf["digar_alt_off"][k] + ln]) if t in (1, 8) else b""
+            ev.append((int(buf["digar_pos"][k]), t, ln, int(buf["digar_qi"][k]), int(buf["digar_low_qual"][k]), alt))
+        iv = [(int(nb[k]), int(ne[k]), int(nl[k])) for k in range(int(nf[r]), int(nf[r]) + int(nn[r]))]
+        reads[r] = (int(buf["skip"][r]), int(buf["read_beg"][r]), int(buf["read_end"][r]), ev, iv)
+    chunk_iv = [(int(cb[k]), int(ce[k]), int(cl[k])) for k in range(out.n_cnreg)]
+    return dict(reads=reads, chunk_noisy=chunk_iv, qual_counts=qc.tolist(), totals=(out.n_digar_total, out.n_alt_total, out.n_nreg_total))
+
+
+def digar_digest(res):
+    """sha1 over the per-read records (read-id order) + histogram of a collect_digar() result: what the fixtures store."""
+    import hashlib
+    h = hashlib.sha1()
+    for r in sorted(res["reads"]):
+        h.update(repr((r, res["reads"][r])).encode())
+    h.update(repr(res["qual_counts"]).encode())
+    return h.hexdigest()
+
+
+def digar_case_from_json(j):
+    d = {k: j[k] for k, _ in DIGAR_SCALARS}
+    for k, t in DIGAR_IN_FIELDS: d[k] = np.array(j[k], dtype=t)
+    return d
+
+
+def digar_case_to_json(d):
+    j = {k: (float(d[k]) if isinstance(d[k], float) else int(d[k])) for k, _ in DIGAR_SCALARS}
+    for k, t in DIGAR_IN_FIELDS: j[k] = np.asarray(d[k]).tolist()
+    return j
