@@ -117,6 +117,51 @@ lcd_plan_t *lcd_edlib_plan_create(int n, const uint8_t *seqs, size_t seqs_len,
                                   const int32_t *mode, const int32_t *want_path);
 int  lcd_edlib_plan_fetch(lcd_plan_t *plan, void *stream, uint8_t *aln, const int64_t *aln_off, lcd_edlib_result_t *results);
 
+/* ---------------------------------------------------------------- K1: pileup scan, difference lists from =/X CIGARs
+ * Replaces void collect_digars_from_bam(bam_chunk_t *chunk, const struct call_var_pl_t *pl) (src/collect_var.c:1063-1110) for reads
+ * whose CIGAR uses =/X: per read int collect_digar_from_eqx_cigar(bam_chunk_t *chunk, int read_i, const call_var_opt_t *opt,
+ * digar_t *digar) (src/bam_utils.c:701-841) with push_xid_size_queue_win (src/bam_utils.c:161-205), plus the chunk's base-quality
+ * histogram (longcalld_copy_digar_read_buffers, src/bam_utils.c:90-103).  Inputs are the BAM record fields the reference reads
+ * (SURVEY 8b): core.pos, reverse flag, CIGAR words, 4-bit packed SEQ, QUAL; is_palindrome is is_ont_palindrome_clip's SA-tag
+ * test (src/bam_utils.c:659-698: host string parsing, 0 unless --ont).  Outputs are, per read, what the reference leaves in
+ * digar_t (beg, end, digars[] in the flat layout lcd_pileup_input_t consumes, noisy_regs after cr_index), its return value
+ * (skip: the caller sets chunk->is_skipped[r] = BAM_RECORD_WRONG_MAP), and per chunk qual_counts[256] and the intervals the kept
+ * reads add to chunk->chunk_noisy_regs, in cr_add order.  Reads with an 'M' op (cs / MD / reference-compare paths) are rejected. */
+typedef struct {
+    int32_t n_reads;
+    int32_t min_bq, noisy_reg_max_xgaps, noisy_reg_slide_win, end_clip_reg, end_clip_reg_flank_win;   /* call_var_opt_t */
+    double max_noisy_frac_per_read, max_var_ratio_per_read;
+    int64_t whole_ref_len;             /* chunk->whole_ref_len */
+    int64_t reg_beg, reg_end;          /* chunk->reg_beg / reg_end */
+    const int32_t *ordered_read_ids;   /* chunk->ordered_read_ids [n_reads] */
+    const uint8_t *is_skipped;         /* chunk->is_skipped (reads already skipped by the loader) */
+    const int64_t *read_pos0;          /* bam1_t core.pos (0-based) */
+    const uint8_t *read_is_rev;        /* bam_is_rev */
+    const uint8_t *is_palindrome;      /* is_ont_palindrome_clip */
+    const int32_t *n_cigar; const int64_t *cigar_off; const uint32_t *cigar;      /* BAM CIGAR words: cigar[cigar_off[r] .. +n_cigar[r]) */
+    const int32_t *l_qseq; const int64_t *seq_off; const uint8_t *bseq;           /* 4-bit packed SEQ, (l_qseq + 1) / 2 bytes per read */
+    const int64_t *qual_off; const uint8_t *qual;                                   /* QUAL, l_qseq bytes per read */
+} lcd_digar_input_t;
+typedef struct {
+    uint8_t *skip;                     /* [n_reads] 1: collect_digar_from_eqx_cigar returns -1 */
+    int64_t *read_beg, *read_end;      /* digar_t.beg / end */
+    int64_t *digar_first; int32_t *n_digar;                                        /* read r's records: digar_*[digar_first[r] .. +n_digar[r]) */
+    int64_t *digar_pos; int8_t *digar_type; int32_t *digar_len, *digar_qi; uint8_t *digar_low_qual; int64_t *digar_alt_off; uint8_t *digar_alt;
+    int64_t digar_cap, alt_cap;        /* capacities of digar_*[] / digar_alt[] (lcd_digar_capacity or lcd_digar_plan_sizes) */
+    int64_t *nreg_first; int32_t *n_nreg; int64_t *nreg_beg, *nreg_end; int32_t *nreg_label;   /* digar_t.noisy_regs, cr_index order */
+    int64_t nreg_cap;
+    int64_t *cnreg_beg, *cnreg_end; int32_t *cnreg_label; int64_t cnreg_cap, n_cnreg;          /* chunk->chunk_noisy_regs additions, cr_add order */
+    int64_t *qual_counts;              /* chunk->qual_counts [256] */
+    int64_t n_digar_total, n_alt_total, n_nreg_total;                                /* entries used */
+} lcd_digar_output_t;
+/* Capacities that always suffice for one chunk (one host pass over its CIGAR words). */
+int lcd_digar_capacity(const lcd_digar_input_t *in, int64_t *digar_cap, int64_t *alt_cap, int64_t *nreg_cap);
+int lcd_digar_batch(int n_chunks, const lcd_digar_input_t *in, lcd_digar_output_t *out);
+lcd_plan_t *lcd_digar_plan_create(int n_chunks, const lcd_digar_input_t *in);
+/* After lcd_plan_run: exact sizes of chunk i's outputs (records, alt bases, per-read intervals; the chunk list needs <= the last). */
+int  lcd_digar_plan_sizes(lcd_plan_t *plan, void *stream, int chunk, int64_t *n_digar, int64_t *n_alt, int64_t *n_nreg);
+int  lcd_digar_plan_fetch(lcd_plan_t *plan, void *stream, lcd_digar_output_t *out);
+
 /* ---------------------------------------------------------------- K2: pileup scan, per-site coverage
  * Replaces int collect_cand_vars(const call_var_opt_t *opt, bam_chunk_t *chunk, int n_var_sites, var_site_t *var_sites)
  * (src/collect_var.c:238-249: update_cand_vars_from_digar, src/bam_utils.c:287-329, for every kept read), called from

@@ -68,7 +68,7 @@ def lib():
     L.lcd_gpu_launch_count.restype = C.c_uint64
     L.lcd_gpu_init.argtypes = [C.c_int, C.c_size_t]
     L.lcd_gpu_stream.restype = C.c_void_p
-    for fn in ("lcd_wfa_plan_create", "lcd_edlib_plan_create", "lcd_poa_plan_create", "lcd_phase_plan_create", "lcd_pileup_plan_create", "lcd_profile_plan_create"):
+    for fn in ("lcd_wfa_plan_create", "lcd_edlib_plan_create", "lcd_poa_plan_create", "lcd_phase_plan_create", "lcd_pileup_plan_create", "lcd_profile_plan_create", "lcd_digar_plan_create"):
         if hasattr(L, fn):
             getattr(L, fn).restype = C.c_void_p
     L.lcd_plan_run.argtypes = [C.c_void_p, C.c_void_p]
@@ -293,6 +293,102 @@ def xgaps(path):
     gap = (a == 1) | (a == 2)
     opens = gap & np.concatenate(([True], a[1:] != a[:-1]))
     return int((a == 3).sum() + opens.sum())
+
+
+# ----------------------------------------------------------------------------- K1: pileup scan, difference lists from =/X CIGARs
+_DIGAR_SCALARS = (("n_reads", C.c_int32), ("min_bq", C.c_int32), ("noisy_reg_max_xgaps", C.c_int32), ("noisy_reg_slide_win", C.c_int32),
+                  ("end_clip_reg", C.c_int32), ("end_clip_reg_flank_win", C.c_int32), ("max_noisy_frac_per_read", C.c_double),
+                  ("max_var_ratio_per_read", C.c_double), ("whole_ref_len", C.c_int64), ("reg_beg", C.c_int64), ("reg_end", C.c_int64))
+_DIGAR_IN = (("ordered_read_ids", np.int32), ("is_skipped", np.uint8), ("read_pos0", np.int64), ("read_is_rev", np.uint8),
+             ("is_palindrome", np.uint8), ("n_cigar", np.int32), ("cigar_off", np.int64), ("cigar", np.uint32),
+             ("l_qseq", np.int32), ("seq_off", np.int64), ("bseq", np.uint8), ("qual_off", np.int64), ("qual", np.uint8))
+_DIGAR_OUT = (("skip", np.uint8, "r"), ("read_beg", np.int64, "r"), ("read_end", np.int64, "r"), ("digar_first", np.int64, "r"), ("n_digar", np.int32, "r"),
+              ("digar_pos", np.int64, "d"), ("digar_type", np.int8, "d"), ("digar_len", np.int32, "d"), ("digar_qi", np.int32, "d"),
+              ("digar_low_qual", np.uint8, "d"), ("digar_alt_off", np.int64, "d"), ("digar_alt", np.uint8, "a"))
+_DIGAR_NREG = (("nreg_first", np.int64, "r"), ("n_nreg", np.int32, "r"), ("nreg_beg", np.int64, "n"), ("nreg_end", np.int64, "n"), ("nreg_label", np.int32, "n"))
+_DIGAR_CNREG = (("cnreg_beg", np.int64), ("cnreg_end", np.int64), ("cnreg_label", np.int32))
+
+
+class DigarInput(C.Structure):
+    _fields_ = list(_DIGAR_SCALARS) + [(k, C.c_void_p) for k, _ in _DIGAR_IN]
+
+
+class DigarOutput(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k, _, _ in _DIGAR_OUT] + [("digar_cap", C.c_int64), ("alt_cap", C.c_int64)] + \
+               [(k, C.c_void_p) for k, _, _ in _DIGAR_NREG] + [("nreg_cap", C.c_int64)] + \
+               [(k, C.c_void_p) for k, _ in _DIGAR_CNREG] + [("cnreg_cap", C.c_int64), ("n_cnreg", C.c_int64)] + \
+               [("qual_counts", C.c_void_p), ("n_digar_total", C.c_int64), ("n_alt_total", C.c_int64), ("n_nreg_total", C.c_int64)]
+
+
+def _digar_inputs(chunks):
+    n = len(chunks)
+    ins, keep = (DigarInput * max(n, 1))(), []
+    for i, d in enumerate(chunks):
+        arrs = {k: np.ascontiguousarray(d[k], dtype=t) for k, t in _DIGAR_IN}
+        keep.append(arrs)
+        ins[i] = DigarInput(*[d[k] for k, _ in _DIGAR_SCALARS], *[arrs[k].ctypes.data for k, _ in _DIGAR_IN])
+    return ins, keep
+
+
+def _digar_outputs(chunks, sizes):
+    """sizes[i] = (records, alt bases, intervals) capacities of chunk i."""
+    n = len(chunks)
+    outs, results = (DigarOutput * max(n, 1))(), []
+    for i, d in enumerate(chunks):
+        cap = {"r": d["n_reads"] + 1, "d": sizes[i][0] + 1, "a": sizes[i][1] + 1, "n": sizes[i][2] + 1}
+        o = {k: np.zeros(cap[w], dtype=t) for k, t, w in _DIGAR_OUT + _DIGAR_NREG}
+        o.update({k: np.zeros(cap["n"], dtype=t) for k, t in _DIGAR_CNREG})
+        o["qual_counts"] = np.zeros(256, np.int64)
+        results.append(o)
+        outs[i] = DigarOutput(*[o[k].ctypes.data for k, _, _ in _DIGAR_OUT], cap["d"], cap["a"], *[o[k].ctypes.data for k, _, _ in _DIGAR_NREG], cap["n"],
+                              *[o[k].ctypes.data for k, _ in _DIGAR_CNREG], cap["n"], 0, o["qual_counts"].ctypes.data, 0, 0, 0)
+    return outs, results
+
+
+def _digar_finish(outs, results):
+    for i, o in enumerate(results):
+        o["n_cnreg"] = int(outs[i].n_cnreg); o["n_digar_total"] = int(outs[i].n_digar_total)
+        o["n_alt_total"] = int(outs[i].n_alt_total); o["n_nreg_total"] = int(outs[i].n_nreg_total)
+    return results
+
+
+def digar_capacity(ins, n):
+    sizes = []
+    for i in range(n):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _check(lib().lcd_digar_capacity(C.byref(ins[i]), C.byref(a), C.byref(b), C.byref(c)), "lcd_digar_capacity")
+        sizes.append((a.value, b.value, c.value))
+    return sizes
+
+
+def digar_batch(chunks):
+    """Drop-in batch call over HOST buffers (lcd_digar_batch).  chunks: dicts with the fields of lcd_digar_input_t.  Returns per
+    chunk a dict with the arrays of lcd_digar_output_t (+ the n_* totals)."""
+    ins, keep = _digar_inputs(chunks)
+    outs, results = _digar_outputs(chunks, digar_capacity(ins, len(chunks)))
+    _check(lib().lcd_digar_batch(C.c_int(len(chunks)), ins, outs), "lcd_digar_batch")
+    return _digar_finish(outs, results)
+
+
+class DigarPlan(_Plan):
+    """Inputs (CIGAR words, packed SEQ, QUAL of every chunk) resident in HBM; run() = count + scan + fill + histogram."""
+    def __init__(self, chunks):
+        self.chunks = chunks
+        self.ins, self.keep = _digar_inputs(chunks)
+        super().__init__(lib().lcd_digar_plan_create(C.c_int(len(chunks)), self.ins), len(chunks))
+
+    def sizes(self, stream=None):
+        out = []
+        for i in range(self.n):
+            a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+            _check(lib().lcd_digar_plan_sizes(self.h, C.c_void_p(stream or 0), C.c_int(i), C.byref(a), C.byref(b), C.byref(c)), "lcd_digar_plan_sizes")
+            out.append((a.value, b.value, c.value))
+        return out
+
+    def fetch(self, stream=None):
+        outs, results = _digar_outputs(self.chunks, self.sizes(stream))
+        _check(lib().lcd_digar_plan_fetch(self.h, C.c_void_p(stream or 0), outs), "lcd_digar_plan_fetch")
+        return _digar_finish(outs, results)
 
 
 # ----------------------------------------------------------------------------- K2: pileup scan, per-site coverage

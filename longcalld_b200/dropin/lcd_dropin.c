@@ -4,6 +4,8 @@
  * B200 implementation, marshals the reference's structures (bam_chunk_t, digar_t, cand_var_t, read_var_profile_t:
  * reference src/bam_utils.h, src/collect_var.h) into the flat views of include/lcd_gpu.h, calls the library, and
  * writes the results back exactly where the reference leaves them:
+ *     collect_digars_from_bam                        (src/collect_var.c:1063)  -> lcd_digar_batch    (K1; chunks whose reads all carry
+ *                                                     =/X CIGARs -- chunks with cs / MD / plain-M reads are forwarded to the reference)
  *     collect_cand_vars                              (src/collect_var.c:238)   -> lcd_pileup_batch   (K2)
  *     collect_read_var_profile                       (src/collect_var.c:1389)  -> lcd_profile_batch  (K3)
  *     assign_hap_based_on_germline_het_vars_kmeans   (src/assign_hap.c:473)    -> lcd_phase_batch    (K4)
@@ -33,10 +35,10 @@
 #include "lcd_gpu.h"
 
 static void die(const char *what) { fprintf(stderr, "[lcd_dropin] %s failed: %s\n", what, lcd_gpu_last_error()); exit(1); }
-static unsigned long n_calls[8];
+static unsigned long n_calls[10];
 __attribute__((destructor)) static void report(void) {
-    if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: pileup %lu, profile %lu, phase %lu, edlib %lu, wfa %lu, poa %lu (forwarded to abPOA: %lu); kernel launches %llu\n",
-                                              n_calls[0], n_calls[1], n_calls[2], n_calls[3], n_calls[4], n_calls[5], n_calls[6], (unsigned long long)lcd_gpu_launch_count());
+    if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: digar %lu (forwarded: %lu), pileup %lu, profile %lu, phase %lu, edlib %lu, wfa %lu, poa %lu (forwarded to abPOA: %lu); kernel launches %llu\n",
+                                              n_calls[8], n_calls[9], n_calls[0], n_calls[1], n_calls[2], n_calls[3], n_calls[4], n_calls[5], n_calls[6], (unsigned long long)lcd_gpu_launch_count());
 }
 
 /* ------------------------------------------------------------------------------------------ digars -> flat */
@@ -102,6 +104,101 @@ static void flatten(const call_var_opt_t *opt, bam_chunk_t *chunk, int n_sites, 
     in->digar_qi = f->digar_qi; in->digar_low_qual = f->digar_low_qual; in->digar_alt_off = f->digar_alt_off; in->digar_alt = f->digar_alt;
     in->site_pos = f->site_pos; in->site_type = f->site_type; in->site_ref_len = f->site_ref_len; in->site_alt_len = f->site_alt_len;
     in->site_alt_off = f->site_alt_off; in->site_alt = f->site_alt;
+}
+
+/* ------------------------------------------------------------------------------------------ K1 */
+int is_ont_palindrome_clip(const call_var_opt_t *opt, bam1_t *read);                            /* src/bam_utils.c:662 */
+extern int LONGCALLD_VERBOSE;                                                                    /* src/main.c */
+
+void collect_digars_from_bam(bam_chunk_t *chunk, const struct call_var_pl_t *pl) {               /* src/collect_var.c:1063-1110 */
+    const call_var_opt_t *opt = pl->opt;
+    const int nr = chunk->n_reads;
+    int all_eqx = 1;
+    for (int i = 0; i < nr && all_eqx; ++i) {
+        const int r = chunk->ordered_read_ids[i];
+        if (!chunk->is_skipped[r] && !has_equal_X_in_bam_cigar(chunk->reads[r])) all_eqx = 0;
+    }
+    if (!all_eqx) {              /* cs / MD / plain-M reads: the reference's string-parsing paths */
+        static void (*orig)(bam_chunk_t *, const struct call_var_pl_t *) = NULL;
+        if (!orig) orig = (void (*)(bam_chunk_t *, const struct call_var_pl_t *))dlsym(RTLD_NEXT, "collect_digars_from_bam");
+        n_calls[9]++;
+        orig(chunk, pl);
+        return;
+    }
+    chunk->chunk_noisy_regs = cr_init();
+    size_t n_cig = 0, n_seq = 0, n_q = 0;
+    for (int r = 0; r < nr; ++r) { const bam1_t *b = chunk->reads[r]; n_cig += b->core.n_cigar; n_seq += ((size_t)b->core.l_qseq + 1) / 2; n_q += b->core.l_qseq; }
+    lcd_digar_input_t in; memset(&in, 0, sizeof(in));
+    int64_t *pos0 = (int64_t*)calloc(nr + 1, sizeof(int64_t)), *coff = (int64_t*)calloc(nr + 1, sizeof(int64_t)), *soff = (int64_t*)calloc(nr + 1, sizeof(int64_t)), *qoff = (int64_t*)calloc(nr + 1, sizeof(int64_t));
+    uint8_t *rev = (uint8_t*)calloc(nr + 1, 1), *pal = (uint8_t*)calloc(nr + 1, 1), *bseq = (uint8_t*)calloc(n_seq + 1, 1), *qual = (uint8_t*)calloc(n_q + 1, 1);
+    int32_t *ncig = (int32_t*)calloc(nr + 1, sizeof(int32_t)), *lq = (int32_t*)calloc(nr + 1, sizeof(int32_t)); uint32_t *cig = (uint32_t*)calloc(n_cig + 1, sizeof(uint32_t));
+    size_t c = 0, s = 0, q = 0;
+    for (int r = 0; r < nr; ++r) {
+        bam1_t *b = chunk->reads[r];
+        pos0[r] = b->core.pos; rev[r] = bam_is_rev(b); ncig[r] = b->core.n_cigar; lq[r] = b->core.l_qseq; coff[r] = (int64_t)c; soff[r] = (int64_t)s; qoff[r] = (int64_t)q;
+        if (!chunk->is_skipped[r]) { pal[r] = (uint8_t)is_ont_palindrome_clip(opt, b); if (pal[r]) chunk->is_ont_palindrome[r] = 1; }
+        memcpy(cig + c, bam_get_cigar(b), sizeof(uint32_t) * b->core.n_cigar); c += b->core.n_cigar;
+        memcpy(bseq + s, bam_get_seq(b), ((size_t)b->core.l_qseq + 1) / 2); s += ((size_t)b->core.l_qseq + 1) / 2;
+        memcpy(qual + q, bam_get_qual(b), b->core.l_qseq); q += b->core.l_qseq;
+    }
+    in.n_reads = nr; in.min_bq = opt->min_bq; in.noisy_reg_max_xgaps = opt->noisy_reg_max_xgaps; in.noisy_reg_slide_win = opt->noisy_reg_slide_win;
+    in.end_clip_reg = opt->end_clip_reg; in.end_clip_reg_flank_win = opt->end_clip_reg_flank_win;
+    in.max_noisy_frac_per_read = opt->max_noisy_frac_per_read; in.max_var_ratio_per_read = opt->max_var_ratio_per_read;
+    in.whole_ref_len = chunk->whole_ref_len; in.reg_beg = chunk->reg_beg; in.reg_end = chunk->reg_end;
+    in.ordered_read_ids = chunk->ordered_read_ids; in.is_skipped = chunk->is_skipped; in.read_pos0 = pos0; in.read_is_rev = rev; in.is_palindrome = pal;
+    in.n_cigar = ncig; in.cigar_off = coff; in.cigar = cig; in.l_qseq = lq; in.seq_off = soff; in.bseq = bseq; in.qual_off = qoff; in.qual = qual;
+    int64_t dcap = 0, acap = 0, ncap = 0;
+    if (lcd_digar_capacity(&in, &dcap, &acap, &ncap)) die("lcd_digar_capacity");
+    lcd_digar_output_t o; memset(&o, 0, sizeof(o));
+#define A(field, type, n) o.field = (type*)calloc((size_t)(n) + 1, sizeof(type))
+    A(skip, uint8_t, nr); A(read_beg, int64_t, nr); A(read_end, int64_t, nr); A(digar_first, int64_t, nr); A(n_digar, int32_t, nr);
+    A(digar_pos, int64_t, dcap); A(digar_type, int8_t, dcap); A(digar_len, int32_t, dcap); A(digar_qi, int32_t, dcap); A(digar_low_qual, uint8_t, dcap);
+    A(digar_alt_off, int64_t, dcap); A(digar_alt, uint8_t, acap); A(nreg_first, int64_t, nr); A(n_nreg, int32_t, nr);
+    A(nreg_beg, int64_t, ncap); A(nreg_end, int64_t, ncap); A(nreg_label, int32_t, ncap); A(cnreg_beg, int64_t, ncap); A(cnreg_end, int64_t, ncap); A(cnreg_label, int32_t, ncap);
+    A(qual_counts, int64_t, 256);
+#undef A
+    o.digar_cap = dcap; o.alt_cap = acap; o.nreg_cap = ncap; o.cnreg_cap = ncap;
+    if (lcd_digar_batch(1, &in, &o)) die("lcd_digar_batch");
+    n_calls[8]++;
+    for (int i = 0; i < nr; ++i) {
+        const int r = chunk->ordered_read_ids[i];
+        if (chunk->is_skipped[r]) continue;
+        bam1_t *b = chunk->reads[r]; digar_t *g = chunk->digars + r;
+        g->beg = o.read_beg[r]; g->end = o.read_end[r]; g->is_rev = rev[r]; g->qlen = b->core.l_qseq;
+        const size_t nb = ((size_t)g->qlen + 1) / 2;
+        g->bseq = nb ? (uint8_t*)malloc(nb) : NULL; if (nb) memcpy(g->bseq, bam_get_seq(b), nb);
+        g->qual = g->qlen ? (uint8_t*)malloc(g->qlen) : NULL; if (g->qlen) memcpy(g->qual, bam_get_qual(b), g->qlen);
+        g->n_digar = o.n_digar[r]; g->m_digar = g->n_digar > 0 ? g->n_digar : 1;
+        g->digars = (digar1_t*)malloc(sizeof(digar1_t) * g->m_digar);
+        for (int k = 0; k < g->n_digar; ++k) {
+            const int64_t d = o.digar_first[r] + k; digar1_t *x = g->digars + k;
+            x->pos = o.digar_pos[d]; x->type = o.digar_type[d]; x->len = o.digar_len[d]; x->qi = o.digar_qi[d]; x->is_low_qual = o.digar_low_qual[d]; x->alt_seq = NULL;
+            if (x->type == BAM_CDIFF || x->type == BAM_CINS) { x->alt_seq = (uint8_t*)malloc(x->len > 0 ? x->len : 1); memcpy(x->alt_seq, o.digar_alt + o.digar_alt_off[d], x->len); }
+        }
+        g->noisy_regs = cr_init();      /* already in cr_index order: cr_index_prepare finds them sorted and leaves the order alone */
+        for (int64_t k = o.nreg_first[r]; k < o.nreg_first[r] + o.n_nreg[r]; ++k) cr_add(g->noisy_regs, "cr", (int32_t)o.nreg_beg[k], (int32_t)o.nreg_end[k], o.nreg_label[k]);
+        cr_index(g->noisy_regs);
+        if (o.skip[r]) chunk->is_skipped[r] = BAM_RECORD_WRONG_MAP;
+    }
+    for (int64_t k = 0; k < o.n_cnreg; ++k) cr_add(chunk->chunk_noisy_regs, "cr", (int32_t)o.cnreg_beg[k], (int32_t)o.cnreg_end[k], o.cnreg_label[k]);
+    for (int k = 0; k < 256; ++k) chunk->qual_counts[k] += (int)o.qual_counts[k];
+    free(pos0); free(coff); free(soff); free(qoff); free(rev); free(pal); free(bseq); free(qual); free(ncig); free(lq); free(cig);
+    free(o.skip); free(o.read_beg); free(o.read_end); free(o.digar_first); free(o.n_digar); free(o.digar_pos); free(o.digar_type); free(o.digar_len); free(o.digar_qi);
+    free(o.digar_low_qual); free(o.digar_alt_off); free(o.digar_alt); free(o.nreg_first); free(o.n_nreg); free(o.nreg_beg); free(o.nreg_end); free(o.nreg_label);
+    free(o.cnreg_beg); free(o.cnreg_end); free(o.cnreg_label); free(o.qual_counts);
+    /* the tail of collect_digars_from_bam, verbatim in behaviour: base-quality quartiles of the chunk, then the records are released (:1083-1109) */
+    int valid_quals[256], n_valid_quals = 0; int64_t n_total_counts = 0;
+    for (int i = 0; i < 256; ++i) n_total_counts += chunk->qual_counts[i];
+    for (int i = 0; i < 256; ++i) if (chunk->qual_counts[i] > 0 && chunk->qual_counts[i] >= 0.0001 * n_total_counts) valid_quals[n_valid_quals++] = i;
+    if (n_valid_quals == 0) chunk->min_qual = chunk->first_quar_qual = chunk->median_qual = chunk->third_quar_qual = chunk->max_qual = 0;
+    else {
+        chunk->min_qual = valid_quals[0]; chunk->first_quar_qual = valid_quals[n_valid_quals / 4]; chunk->median_qual = valid_quals[n_valid_quals / 2];
+        chunk->third_quar_qual = valid_quals[n_valid_quals * 3 / 4]; chunk->max_qual = valid_quals[n_valid_quals - 1];
+    }
+    if (LONGCALLD_VERBOSE < 2) {
+        for (int i = 0; i < chunk->m_reads; ++i) bam_destroy1(chunk->reads[i]);
+        free(chunk->reads);
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ K2 */

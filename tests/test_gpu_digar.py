@@ -1,0 +1,114 @@
+"""GPU: liblcd_gpu.so's K1 kernels (count / scan / fill one thread per read, warp-per-read quality histogram; through the
+C-ABI) against the oracle and the golden fixtures, bit-exact: every digar1_t record, read span, skip decision, per-read noisy
+interval, the chunk's noisy list and base-quality histogram; then K1's device layout handed to K2 unchanged."""
+import numpy as np
+import pytest
+
+import lcd_testlib as T
+from longcalld_b200 import synth
+from test_oracle_digar import digar_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def view(d, o):
+    """A lcd_digar_output_t dict in the layout-independent form T.collect_digar returns."""
+    reads = {}
+    for i in range(d["n_reads"]):
+        r = int(d["ordered_read_ids"][i])
+        if d["is_skipped"][r]: continue
+        f, n = int(o["digar_first"][r]), int(o["n_digar"][r])
+        ev = []
+        for k in range(f, f + n):
+            t, ln = int(o["digar_type"][k]), int(o["digar_len"][k])
+            a0 = int(o["digar_alt_off"][k])
+            ev.append((int(o["digar_pos"][k]), t, ln, int(o["digar_qi"][k]), int(o["digar_low_qual"][k]), bytes(o["digar_alt"][a0:a0 + ln]) if t in (1, 8) else b""))
+        nf, nn = int(o["nreg_first"][r]), int(o["n_nreg"][r])
+        iv = [(int(o["nreg_beg"][k]), int(o["nreg_end"][k]), int(o["nreg_label"][k])) for k in range(nf, nf + nn)]
+        reads[r] = (int(o["skip"][r]), int(o["read_beg"][r]), int(o["read_end"][r]), ev, iv)
+    civ = [(int(o["cnreg_beg"][k]), int(o["cnreg_end"][k]), int(o["cnreg_label"][k])) for k in range(o["n_cnreg"])]
+    return dict(reads=reads, chunk_noisy=civ, qual_counts=o["qual_counts"].tolist(), totals=(o["n_digar_total"], o["n_alt_total"], o["n_nreg_total"]))
+
+
+def same(a, b, tag):
+    for r in b["reads"]:
+        assert a["reads"][r] == b["reads"][r], (tag, r, [x for x, y in zip(a["reads"][r], b["reads"][r]) if x != y][:1])
+    assert a["qual_counts"] == b["qual_counts"], tag
+    assert a["chunk_noisy"] == b["chunk_noisy"] and a["totals"] == b["totals"], tag
+
+
+def test_gpu_vs_reference_fixtures(gpu):
+    g = T.load_golden("digar_lcd")
+    chunks = [T.digar_case_from_json(c["in"]) for c in g["cases"]]
+    for c, d, o in zip(g["cases"], chunks, gpu.digar_batch(chunks)):
+        a = view(d, o)
+        assert T.digar_digest(a) == c["digest"] and a["chunk_noisy"] == [tuple(x) for x in c["chunk_noisy"]]
+
+
+def test_gpu_vs_oracle_random(gpu, oracle):
+    cases = list(digar_cases(33, 160))
+    for i, (d, o) in enumerate(zip(cases, gpu.digar_batch(cases))):          # one batch of 160 chunks
+        same(view(d, o), T.collect_digar(oracle, "lcd_oracle_collect_digar_eqx", d), i)
+    assert gpu.digar_batch([]) == []
+
+
+def test_gpu_many_intervals_and_edges(gpu, oracle):
+    """Reads with more than 64 noisy intervals (cgranges' unstable radix order on the host side of the plan), empty chunks,
+    chunks whose reads are all skipped, a single one-base read."""
+    rng = np.random.default_rng(35)
+    big = synth.make_digar_chunk(rng, n_reads=6, read_len=(100000, 140000), err_every=300, tech="ont", low_qual_frac=0.0)
+    none = synth.make_digar_chunk(rng, n_reads=5); none["is_skipped"][:] = 1
+    one = synth.make_digar_chunk(rng, n_reads=1, read_len=(1, 2), err_every=5)
+    empty = synth.make_digar_chunk(rng, n_reads=3); empty["n_reads"] = 0
+    cases = [big, none, one, empty, big]
+    res = gpu.digar_batch(cases)
+    want = [T.collect_digar(oracle, "lcd_oracle_collect_digar_eqx", d) for d in cases]
+    assert max(len(v[4]) for v in want[0]["reads"].values()) > 64
+    for i, (d, o) in enumerate(zip(cases, res)):
+        same(view(d, o), want[i], i)
+
+
+def test_gpu_rejects_m_cigar(gpu):
+    rng = np.random.default_rng(36)
+    d = synth.make_digar_chunk(rng, n_reads=4)
+    d["cigar"] = d["cigar"].copy(); d["cigar"][int(d["cigar_off"][int(d["ordered_read_ids"][0])]) + 1] &= ~np.uint32(15)      # an 'M' op
+    d["is_skipped"][:] = 0
+    with pytest.raises(gpu.LcdGpuError, match="'M' op"):
+        gpu.digar_batch([d])
+
+
+def test_gpu_chunk_shaped_plan_and_chain_into_pileup(gpu, oracle):
+    """Chunks shaped like 500 kb at 30x (scaled: 120 kb windows, 15 kb reads), resident plan re-run; then the records feed K2
+    (lcd_pileup_batch) with candidate sites drawn from them: same per-site coverage as the oracle chain."""
+    rng = np.random.default_rng(37)
+    cases = [synth.make_digar_chunk(rng, n_reads=240, read_len=(10000, 20000), err_every=400, ref_len=120000) for _ in range(4)]
+    plan = gpu.DigarPlan(cases)
+    for _ in range(2):
+        plan.run(); plan.sync()
+    assert plan.work_units() > 4 * 240 * 10000
+    res = plan.fetch()
+    for i, (d, o) in enumerate(zip(cases, res)):
+        same(view(d, o), T.collect_digar(oracle, "lcd_oracle_collect_digar_eqx", d), i)
+    d, o = cases[0], res[0]
+    nd = o["n_digar_total"]
+    ev = [k for k in range(nd) if o["digar_type"][k] in (1, 2, 8) and not o["digar_low_qual"][k]]
+    pick = sorted(set(rng.choice(ev, size=400, replace=False).tolist()))
+    key = lambda k: (int(o["digar_pos"][k]) - (0 if o["digar_type"][k] == 8 else 1), int(o["digar_type"][k]), int(o["digar_len"][k]),
+                     bytes(o["digar_alt"][int(o["digar_alt_off"][k]):int(o["digar_alt_off"][k]) + int(o["digar_len"][k])]) if o["digar_type"][k] != 2 else b"")
+    sites = sorted({key(k): k for k in pick}.values(), key=key)
+    alt, aoff = [], []
+    for k in sites:
+        aoff.append(len(alt))
+        if o["digar_type"][k] != 2: alt.extend(o["digar_alt"][int(o["digar_alt_off"][k]):int(o["digar_alt_off"][k]) + int(o["digar_len"][k])].tolist())
+    t = o["digar_type"]
+    pile = dict(n_reads=d["n_reads"], n_sites=len(sites), min_bq=d["min_bq"], min_sv_len=50, ordered_read_ids=d["ordered_read_ids"],
+                is_skipped=np.maximum(d["is_skipped"], o["skip"][:d["n_reads"]]), read_beg=o["read_beg"], read_end=o["read_end"], read_is_rev=d["read_is_rev"],
+                digar_first=o["digar_first"], n_digar=o["n_digar"], qual_off=d["qual_off"], qual=d["qual"], digar_pos=o["digar_pos"], digar_type=t,
+                digar_len=o["digar_len"], digar_qi=o["digar_qi"], digar_low_qual=o["digar_low_qual"], digar_alt_off=o["digar_alt_off"], digar_alt=o["digar_alt"],
+                site_pos=np.array([o["digar_pos"][k] for k in sites] + [0], np.int64), site_type=np.array([t[k] for k in sites] + [0], np.int32),
+                site_ref_len=np.array([(0 if t[k] == 1 else (o["digar_len"][k] if t[k] == 2 else 1)) for k in sites] + [0], np.int32),
+                site_alt_len=np.array([(0 if t[k] == 2 else o["digar_len"][k]) for k in sites] + [0], np.int32),
+                site_alt_off=np.array(aoff + [0], np.int64), site_alt=np.array(alt + [0], np.uint8))
+    got = gpu.pileup_batch([pile])[0]
+    assert np.array_equal(got, T.pileup(oracle, "lcd_oracle_collect_cand_vars", pile))
+    assert int(got[:, 3].sum()) > len(sites) // 2          # (events of reads K1 dropped are not counted)
