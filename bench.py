@@ -155,6 +155,44 @@ class Workload:
         return np.nonzero(np.isin(self.region_of, regs))[0]
 
 
+class PileupStage:
+    """K1 -> K2 -> K3 of the same batch: mbp / 0.5 region chunks (500 kb, 30x, ~1 050 reads of ~15 kb with =/X CIGARs), tiled
+    from a template of <= 10 distinct chunks.  The candidate-site list (a3) and the classification (a5) are not on the GPU
+    yet: they are derived once at set-up from K1's / K2's results (synth.sites_from_digar_output / classify_sites) and are
+    not timed in either arm."""
+    N_TEMPLATE = 10
+
+    def __init__(self, mbp, tech, seed, digar_fn, pileup_fn, pin=False):
+        from longcalld_b200 import synth
+        self.n_chunks = max(1, int(round(mbp / 0.5)))
+        nt = min(self.N_TEMPLATE, self.n_chunks)
+        self.template = synth.digar_chunks_30x(nt, tech, seed)
+        if pin:                                     # the loader's buffers: page-locked, so the e2e H2D copies run at PCIe speed
+            import torch
+            for d in self.template:
+                for k in ("cigar", "bseq", "qual"):
+                    t = torch.from_numpy(d[k]).pin_memory(); d["_pin_" + k] = t; d[k] = t.numpy()
+        outs = digar_fn(self.template)
+        raw = [synth.sites_from_digar_output(d, o) for d, o in zip(self.template, outs)]
+        piles = [synth.pileup_input_from_digar(d, o, s) for d, o, s in zip(self.template, outs, raw)]
+        counts = pileup_fn(piles)
+        var = [synth.classify_sites(s, c) for s, c in zip(raw, counts)]
+        profs = [synth.pileup_input_from_digar(d, o, s) for d, o, s in zip(self.template, outs, var)]
+        tile = lambda xs: [xs[i % nt] for i in range(self.n_chunks)]
+        self.chunks, self.raw_sites, self.var_sites, self.piles, self.profs = tile(self.template), tile(raw), tile(var), tile(piles), tile(profs)
+        self.n_reads = [d["n_reads"] for d in self.chunks]
+        self.read_bases = int(sum(int(d["l_qseq"].sum()) for d in self.chunks))
+        self.cigar_ops = int(sum(int(d["n_cigar"].sum()) for d in self.chunks))
+        self.records = int(sum(int(outs[i % nt]["n_digar_total"]) for i in range(self.n_chunks)))
+        self.n_raw_sites = int(sum(s["n_sites"] for s in self.raw_sites)); self.n_vars = int(sum(s["n_sites"] for s in self.var_sites))
+        self.h2d = int(sum(d["cigar"].nbytes + d["bseq"].nbytes + d["qual"].nbytes + 46 * d["n_reads"] for d in self.chunks) +
+                       sum(sum(s[k].nbytes for k in ("site_pos", "site_type", "site_ref_len", "site_alt_len", "site_alt_off", "site_alt")) for s in self.raw_sites + self.var_sites))
+        # algorithmic bytes (SURVEY 8d): K1 1.5 B per read base + 4 B per CIGAR op in, 32 B per record out; K2 / K3 32 B per record + 24 B per site (+ 8 B per profile entry)
+        self.k1_bytes = int(1.5 * self.read_bases + 4 * self.cigar_ops + 32 * self.records)
+        self.k2_bytes = int(32 * self.records + 24 * self.n_raw_sites)
+        self.k3_bytes = int(32 * self.records + 24 * self.n_vars)
+
+
 # ------------------------------------------------------------------------------------------ reference arm
 def ref_shim():
     path = os.path.join(ROOT, "oracle", "_ref", "libref_shim.so")
@@ -214,6 +252,50 @@ def reference_step(lib, wl, idx, n_threads):
     return (t1 - t0) + (t3 - t2) + (t5 - t4) + (t7 - t6), (t1 - t0), (t3 - t2), (t5 - t4), (t7 - t6)
 
 
+def ref_pileup_fns(lib, n_threads):
+    """K1 / K2 / K3 of the unmodified reference (oracle/_ref/libref_shim.so) behind the same dict interface as longcalld_b200.capi."""
+    from longcalld_b200 import capi
+
+    def digar(chunks):
+        ins, keep = capi._digar_inputs(chunks)
+        outs, results = capi._digar_outputs(chunks, capi.digar_capacity(ins, len(chunks)))
+        if lib.ref_digar_batch(C.c_int(len(chunks)), ins, outs, C.c_int(n_threads), None): raise RuntimeError("ref_digar_batch failed")
+        return capi._digar_finish(outs, results)
+
+    def pileup(piles):
+        ins, outs, keep, results = capi._pileup_structs(piles)
+        if lib.ref_pileup_batch(C.c_int(len(piles)), ins, outs, C.c_int(n_threads)): raise RuntimeError("ref_pileup_batch failed")
+        return [r[:d["n_sites"]] for r, d in zip(results, piles)]
+    return digar, pileup
+
+
+def reference_pileup_step(lib, ps, k, n_threads):
+    """K1 + K2 + K3 of the reference on the first k chunks of the batch; returns seconds."""
+    from longcalld_b200 import capi
+    chunks, piles, profs = ps.chunks[:k], ps.piles[:k], ps.profs[:k]
+    ins, keep = capi._digar_inputs(chunks)
+    outs, results = capi._digar_outputs(chunks, capi.digar_capacity(ins, k))
+    pins, pouts, pkeep, pres = capi._pileup_structs(piles)
+    fins, _, fkeep, _ = capi._pileup_structs(profs)
+    exs, fouts, fres = (capi.ProfileExtra * k)(), (capi.ProfileOutput * k)(), []
+    capi.lib().lcd_profile_capacity.restype = C.c_int64
+    for i, d in enumerate(profs):
+        arrs = {kk: np.ascontiguousarray(d[kk], dtype=t) for kk, t in capi._PROFILE_EX}; fkeep.append(arrs)
+        exs[i] = capi.ProfileExtra(*[arrs[kk].ctypes.data for kk, _ in capi._PROFILE_EX])
+        cap = int(capi.lib().lcd_profile_capacity(C.byref(fins[i]))) + 8
+        o = [np.zeros(d["n_reads"] + 1, np.int32), np.zeros(d["n_reads"] + 1, np.int32), np.zeros(d["n_reads"] + 1, np.int64), np.zeros(cap, np.int8), np.zeros(cap, np.int32)]
+        fres.append(o); fouts[i] = capi.ProfileOutput(*[a.ctypes.data for a in o], cap, 0)
+    core = C.c_double(0.0)        # K1: the reference's own calls only (the shim's bam1_t construction and copy-out are not the reference's work)
+    rc = lib.ref_digar_batch(C.c_int(k), ins, outs, C.c_int(n_threads), C.byref(core))
+    t1 = time.perf_counter(); t0 = t1 - core.value
+    rc |= lib.ref_pileup_batch(C.c_int(k), pins, pouts, C.c_int(n_threads))
+    t2 = time.perf_counter()
+    rc |= lib.ref_profile_batch(C.c_int(k), fins, exs, fouts, C.c_int(n_threads))
+    t3 = time.perf_counter()
+    if rc: raise RuntimeError("reference K1-K3 failed")
+    return t3 - t0, t1 - t0, t2 - t1, t3 - t2
+
+
 def region_sample(wl, frac, seed=1):
     """Whole regions, uniformly sampled: a bounded slice of the batch."""
     rng = np.random.default_rng(seed)
@@ -239,35 +321,49 @@ def run_reference(args, rank):
         return
     n_threads = os.cpu_count() or 1
     wl = Workload(args.mbp, args.tech, args.seed)
+    ps = PileupStage(args.mbp, args.tech, args.seed, *ref_pileup_fns(lib, n_threads))
     frac = calibrate_sample(lib, wl, n_threads, target_s=max(2.0, 90.0 / max(1, args.steps + args.warmup)))
     regs, idx = region_sample(wl, frac)
     mbp_sample = args.mbp * len(regs) / wl.n_regions
+    k_chunks = min(ps.n_chunks, max(1, int(round(ps.n_chunks * len(regs) / wl.n_regions))))
+    pile_scale = (len(regs) / wl.n_regions) / (k_chunks / ps.n_chunks)          # K1-K3 run on whole chunks; their time is scaled to the region sample
     for _ in range(args.warmup):
-        reference_step(lib, wl, idx, n_threads)
-    t = [reference_step(lib, wl, idx, n_threads) for _ in range(args.steps)]
-    total = sum(x[0] for x in t)
+        reference_step(lib, wl, idx, n_threads); reference_pileup_step(lib, ps, k_chunks, n_threads)
+    t, tp = [], []
+    for _ in range(args.steps):
+        t.append(reference_step(lib, wl, idx, n_threads)); tp.append(reference_pileup_step(lib, ps, k_chunks, n_threads))
+    total = sum(x[0] for x in t) + pile_scale * sum(x[0] for x in tp)
     value = mbp_sample * args.steps / total
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int16/int32", "data": "synthetic",
-            "config": workload_config(args, wl),
+            "config": workload_config(args, wl, ps),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_threads, "kind": "reference",
-                             "sample": f"{len(regs)} of {wl.n_regions} regions ({mbp_sample:.3f} Mb) per step",
+                             "sample": f"{len(regs)} of {wl.n_regions} regions ({mbp_sample:.3f} Mb) per step; K1-K3 on {k_chunks} of {ps.n_chunks} chunks, time scaled by {pile_scale:.4f}",
                              "poa_s": sum(x[1] for x in t) / args.steps, "wfa_s": sum(x[2] for x in t) / args.steps,
-                             "phase_s": sum(x[3] for x in t) / args.steps, "edlib_s": sum(x[4] for x in t) / args.steps},
+                             "phase_s": sum(x[3] for x in t) / args.steps, "edlib_s": sum(x[4] for x in t) / args.steps,
+                             "digar_s": pile_scale * sum(x[1] for x in tp) / args.steps, "pileup_s": pile_scale * sum(x[2] for x in tp) / args.steps,
+                             "profile_s": pile_scale * sum(x[3] for x in tp) / args.steps},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_config(args, wl):
+def workload_config(args, wl, ps=None):
     return {"workload": f"synthetic {args.tech.upper()} 30x noisy-region re-alignment, {args.mbp:g} Mb ref per GPU "
                         f"(BASELINE configs[1] shape), {wl.n_regions} regions",
-            "stages": ["K4 read->haplotype assignment + phasing per 500 kb chunk, clean then germline mask (assign_hap.c:473)",
+            "stages": ["K1 difference lists + noisy intervals + quality histogram from =/X CIGARs per 500 kb chunk (bam_utils.c:701)",
+                       "K2 per-site coverage of the candidate sites, on K1's lists in HBM (collect_var.c:238)",
+                       "K3 read x variant profile of the classified variants, on K1's lists in HBM (collect_var.c:1389)",
+                       "K4 read->haplotype assignment + phasing per 500 kb chunk, clean then germline mask (assign_hap.c:473)",
                        "K7 edlib NW path read-vs-first-read sampling filter (align.c:722)",
                        "K5 abPOA consensus+MSA per (region, haplotype) (align.c:762)",
                        "K6 WFA gap-affine-2p ref-vs-consensus (align.c:565)"],
-            "stages_not_yet_on_gpu": ["partial-read sub-graph POA", "2-consensus de-novo clustering", "K1-K3 pileup scan / sites / profile",
-                                      "vars from MSA (a13), somatic chain (a14)"],
+            "stages_not_yet_on_gpu": ["partial-read sub-graph POA", "2-consensus de-novo clustering",
+                                      "candidate-site list (a3) and classification / noisy-region set (a5): prepared at set-up, untimed in both arms",
+                                      "noisy-region orchestration (a8), vars from MSA (a13), somatic chain (a14)"],
+            "pileup": (None if ps is None else {"chunks": ps.n_chunks, "distinct_chunks": min(ps.N_TEMPLATE, ps.n_chunks), "reads": int(sum(ps.n_reads)),
+                                                 "read_bases": ps.read_bases, "cigar_ops": ps.cigar_ops, "records": ps.records,
+                                                 "candidate_sites": ps.n_raw_sites, "classified_variants": ps.n_vars}),
             "n_phase_chunk_passes": len(wl.phase), "n_edlib": int(len(wl.edlib[1])),
             "n_poa": wl.n_poa, "n_poa_reads": wl.n_poa_reads, "n_wfa": wl.n_poa,
             "l2": "flushed between timed steps (256 MiB write)", "seed": args.seed}
@@ -333,6 +429,7 @@ def run_b200(args, rank, world):
         if L.lcd_edlib_batch(C.c_int(ne), _vp(eseqs), C.c_size_t(eseqs.size), _vp(eqo), _vp(eql), _vp(eto), _vp(etl), _vp(emode), _vp(ewant),
                              _vp(ealn), _vp(eoff), _vp(eres)):
             raise RuntimeError(L.lcd_gpu_last_error().decode())
+        pileup_e2e_step()
         if world > 1:
             gather_step(tl)
         return buf, ref_off, ref_len, txt_off, tl
@@ -360,7 +457,20 @@ def run_b200(args, rank, world):
         if rank == 0:
             gathered["bytes"] = sum(len(x) for x in out)
 
+    ps = PileupStage(args.mbp, args.tech, args.seed + rank, lcd.digar_batch, lcd.pileup_batch, pin=True)
+    pile_res = {}
+
+    def pileup_e2e_step():
+        """host BAM fields -> K1 plan (H2D inside) -> K2 / K3 on the lists in HBM -> coverage counters and profile rows back on the host"""
+        dp = lcd.DigarPlan(ps.chunks); dp.run()
+        k2 = lcd.PileupOnDigarPlan(dp, ps.raw_sites); k2.run(); pile_res["counts"] = k2.fetch()
+        k3 = lcd.ProfileOnDigarPlan(dp, ps.var_sites, ps.n_reads); k3.run(); pile_res["prof"] = k3.fetch()
+        for x in (k3, k2, dp): x.destroy()
+
     wseqs, po, pl, to, tl = e2e_step()                              # also yields the consensus sequences for the WFA plan
+    digar_plan = lcd.DigarPlan(ps.chunks); digar_plan.run(); digar_plan.sync()
+    k2_plan = lcd.PileupOnDigarPlan(digar_plan, ps.raw_sites)
+    k3_plan = lcd.ProfileOnDigarPlan(digar_plan, ps.var_sites, ps.n_reads)
     poa_plan = lcd.PoaPlan(wl.seqs, wl.first, wl.n_reads, wl.read_off, wl.read_len, lcd.poa_params())
     wfa_plan = lcd.WfaPlan(wseqs, po, pl, to, tl, lcd.wfa_params())
     phase_plan = lcd.PhasePlan(wl.phase)
@@ -376,7 +486,13 @@ def run_b200(args, rank, world):
     def device_step():
         with torch.cuda.stream(stream):
             flush.zero_()
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+            ev[5].record(stream)
+            digar_plan.run()
+            ev[6].record(stream)
+            k2_plan.run()
+            ev[7].record(stream)
+            k3_plan.run()
             ev[0].record(stream)
             poa_plan.run()
             ev[1].record(stream)
@@ -402,7 +518,8 @@ def run_b200(args, rank, world):
     wfa_ms = sum(e[1].elapsed_time(e[2]) for e in evs)
     phase_ms = sum(e[2].elapsed_time(e[3]) for e in evs)
     edlib_ms = sum(e[3].elapsed_time(e[4]) for e in evs)
-    dev_ms = poa_ms + wfa_ms + phase_ms + edlib_ms
+    k1_ms = sum(e[5].elapsed_time(e[6]) for e in evs); k2_ms = sum(e[6].elapsed_time(e[7]) for e in evs); k3_ms = sum(e[7].elapsed_time(e[0]) for e in evs)
+    dev_ms = poa_ms + wfa_ms + phase_ms + edlib_ms + k1_ms + k2_ms + k3_ms
     phase_pairs = phase_plan.work_units()
     edlib_units = edlib_plan.work_units()
     poa_cells = poa_plan.work_units()
@@ -420,8 +537,9 @@ def run_b200(args, rank, world):
     barrier()
     e2e_s = time.perf_counter() - t0
     phase_bytes = sum(a.nbytes for k in ph_keep for a in k.values())
-    h2d = int(phase_bytes + eseqs.size + 24 * ne + wl.seqs.size + 12 * len(wl.read_len) + 64 * n + (pl.astype(np.int64) + tl + 56).sum() + 96 * n)
-    d2h = int(sum(a.nbytes for r in ph_res for a in r.values()) + eres.nbytes + int(eres["aln_len"].sum()) + pres["cons_len"].sum() + 32 * n + wres.nbytes + 2 * (pl.astype(np.int64) + tl + 4).sum())
+    pile_d2h = int(sum(c.nbytes for c in pile_res["counts"]) + sum(sum(a.nbytes for a in o.values()) for o in pile_res["prof"]))
+    h2d = int(ps.h2d + phase_bytes + eseqs.size + 24 * ne + wl.seqs.size + 12 * len(wl.read_len) + 64 * n + (pl.astype(np.int64) + tl + 56).sum() + 96 * n)
+    d2h = int(pile_d2h + sum(a.nbytes for r in ph_res for a in r.values()) + eres.nbytes + int(eres["aln_len"].sum()) + pres["cons_len"].sum() + 32 * n + wres.nbytes + 2 * (pl.astype(np.int64) + tl + 4).sum())
 
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -440,9 +558,14 @@ def run_b200(args, rank, world):
             regs, idx = region_sample(wl, frac)
             dt, dt_poa, dt_wfa, dt_phase, dt_edlib = reference_step(lib, wl, idx, nt)
             mbp_sample = args.mbp * len(regs) / wl.n_regions
-            cpu_baseline = {"value": mbp_sample / dt, "unit": UNIT, "cores": nt, "kind": "reference",
-                            "sample": f"{len(regs)} of {wl.n_regions} regions ({mbp_sample:.3f} Mb): abPOA + WFA2-lib via oracle/_ref",
-                            "poa_s": dt_poa, "wfa_s": dt_wfa, "phase_s": dt_phase, "edlib_s": dt_edlib}
+            k_chunks = min(ps.n_chunks, max(1, int(round(ps.n_chunks * len(regs) / wl.n_regions))))
+            pile_scale = (len(regs) / wl.n_regions) / (k_chunks / ps.n_chunks)
+            dtp = reference_pileup_step(lib, ps, k_chunks, nt)
+            cpu_baseline = {"value": mbp_sample / (dt + pile_scale * dtp[0]), "unit": UNIT, "cores": nt, "kind": "reference",
+                            "sample": f"{len(regs)} of {wl.n_regions} regions ({mbp_sample:.3f} Mb): the unmodified reference's own functions via oracle/_ref; "
+                                      f"K1-K3 on {k_chunks} of {ps.n_chunks} chunks, time scaled by {pile_scale:.4f}",
+                            "poa_s": dt_poa, "wfa_s": dt_wfa, "phase_s": dt_phase, "edlib_s": dt_edlib,
+                            "digar_s": pile_scale * dtp[1], "pileup_s": pile_scale * dtp[2], "profile_s": pile_scale * dtp[3]}
     if rank == 0:
         peak, which = load_peaks()
         poa_gbs = poa_cells * POA_BYTES_PER_CELL / (poa_ms / args.steps / 1e3) / 1e9
@@ -451,7 +574,7 @@ def run_b200(args, rank, world):
         achieved = poa_gbs if dominant_is_poa else wfa_gbs
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int16/int32", "data": "synthetic", "config": workload_config(args, wl),
+                "dtype": "int16/int32", "data": "synthetic", "config": workload_config(args, wl, ps),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "gather": (None if world == 1 else {"what": "per-chunk POA/WFA result records to rank 0 (NCCL gather, inside e2e)",
@@ -468,6 +591,13 @@ def run_b200(args, rank, world):
                                             "phase_kernel": {"ms": phase_ms / args.steps, "read_var_pairs": phase_pairs,
                                                              "GBps": phase_pairs * PHASE_BYTES_PER_PAIR / (phase_ms / args.steps / 1e3) / 1e9,
                                                              "note": "one pass of the pair list; the kernel makes 2-11 passes (seed + iterations), latency-bound"},
+                                            "digar_kernels": {"ms": k1_ms / args.steps, "read_bases": ps.read_bases, "records": ps.records,
+                                                              "GBps": ps.k1_bytes / (k1_ms / args.steps / 1e3) / 1e9, "frac": ps.k1_bytes / (k1_ms / args.steps / 1e3) / 1e9 / peak,
+                                                              "note": "count + scan + fill + histogram; 1.5 B per read base + 4 B per CIGAR op in, 32 B per record out"},
+                                            "pileup_kernel": {"ms": k2_ms / args.steps, "records": ps.records, "sites": ps.n_raw_sites,
+                                                              "GBps": ps.k2_bytes / (k2_ms / args.steps / 1e3) / 1e9},
+                                            "profile_kernel": {"ms": k3_ms / args.steps, "records": ps.records, "variants": ps.n_vars,
+                                                               "GBps": ps.k3_bytes / (k3_ms / args.steps / 1e3) / 1e9},
                                             "edlib_kernel": {"ms": edlib_ms / args.steps, "block_columns": edlib_units,
                                                              "GBps": edlib_units * EDLIB_BYTES_PER_BLOCKCOL / (edlib_ms / args.steps / 1e3) / 1e9}}},
                 "cpu_baseline": cpu_baseline}

@@ -222,6 +222,24 @@ int lcd_profile_batch(int n_chunks, const lcd_pileup_input_t *in, const lcd_prof
 lcd_plan_t *lcd_profile_plan_create(int n_chunks, const lcd_pileup_input_t *in, const lcd_profile_extra_t *extra);
 int  lcd_profile_plan_fetch(lcd_plan_t *plan, void *stream, lcd_profile_output_t *out);
 
+/* ---------------------------------------------------------------- K1 -> K2 / K3 in place
+ * The difference lists a digar plan (lcd_digar_plan_create + lcd_plan_run) left in HBM are consumed where they lie: only the
+ * chunk's candidate sites (collect_all_cand_var_sites, src/collect_var.c:1209) -- for K3 the classified candidate variants with
+ * their categories (chunk->var_i_to_cate) -- are uploaded.  Reads K1 dropped (skip) are left out, as the reference leaves out
+ * reads with chunk->is_skipped set.  The digar plan must outlive the plans created on it.  Results come back through
+ * lcd_pileup_plan_fetch / lcd_profile_plan_fetch (row capacity of chunk i: lcd_profile_plan_capacity). */
+typedef struct {
+    int32_t n_sites, min_sv_len;       /* opt->min_sv_len */
+    const int64_t *site_pos;           /* as in lcd_pileup_input_t */
+    const int32_t *site_type, *site_ref_len, *site_alt_len;
+    const int64_t *site_alt_off;
+    const uint8_t *site_alt;
+    const int32_t *var_cate;           /* K3 only: chunk->var_i_to_cate [n_sites] */
+} lcd_site_list_t;
+lcd_plan_t *lcd_pileup_plan_create_on_digar(lcd_plan_t *digar_plan, int n_chunks, const lcd_site_list_t *sites);
+lcd_plan_t *lcd_profile_plan_create_on_digar(lcd_plan_t *digar_plan, int n_chunks, const lcd_site_list_t *sites);
+int64_t lcd_profile_plan_capacity(lcd_plan_t *plan, int chunk);
+
 /* ---------------------------------------------------------------- K4: read -> haplotype assignment and phasing
  * Replaces int assign_hap_based_on_germline_het_vars_kmeans(const call_var_opt_t *opt, bam_chunk_t *chunk,
  * int target_var_cate) (src/assign_hap.h:12, src/assign_hap.c:473-547), called from collect_var_main

@@ -441,6 +441,65 @@ class PileupPlan(_Plan):
         return [r[:d["n_sites"]] for r, d in zip(self.results, self.chunks)]
 
 
+# ----------------------------------------------------------------------------- K1 -> K2 / K3 in place (difference lists stay in HBM)
+_SITE_LIST = (("site_pos", np.int64), ("site_type", np.int32), ("site_ref_len", np.int32), ("site_alt_len", np.int32),
+              ("site_alt_off", np.int64), ("site_alt", np.uint8))
+
+
+class SiteList(C.Structure):
+    _fields_ = [("n_sites", C.c_int32), ("min_sv_len", C.c_int32)] + [(k, C.c_void_p) for k, _ in _SITE_LIST] + [("var_cate", C.c_void_p)]
+
+
+def _site_lists(sites, want_cate):
+    n = len(sites)
+    arr, keep = (SiteList * max(n, 1))(), []
+    for i, d in enumerate(sites):
+        a = {k: np.ascontiguousarray(d[k], dtype=t) for k, t in _SITE_LIST}
+        a["var_cate"] = np.ascontiguousarray(d["var_cate"], dtype=np.int32) if want_cate else None
+        keep.append(a)
+        arr[i] = SiteList(d["n_sites"], d["min_sv_len"], *[a[k].ctypes.data for k, _ in _SITE_LIST], a["var_cate"].ctypes.data if want_cate else None)
+    return arr, keep
+
+
+class PileupOnDigarPlan(_Plan):
+    """K2 on the difference lists a DigarPlan left in HBM; sites: per chunk a dict(n_sites, min_sv_len, site_*)."""
+    def __init__(self, digar_plan, sites):
+        self.sites, self.digar_plan = sites, digar_plan
+        self.arr, self.keep = _site_lists(sites, False)
+        lib().lcd_pileup_plan_create_on_digar.restype = C.c_void_p
+        super().__init__(lib().lcd_pileup_plan_create_on_digar(digar_plan.h, C.c_int(len(sites)), self.arr), len(sites))
+        self.results = [np.zeros((d["n_sites"] + 1, 8), dtype=np.int32) for d in sites]
+        self.outs = (PileupOutput * max(self.n, 1))(*[PileupOutput(r.ctypes.data) for r in self.results])
+
+    def fetch(self, stream=None):
+        _check(lib().lcd_pileup_plan_fetch(self.h, C.c_void_p(stream or 0), self.outs), "lcd_pileup_plan_fetch")
+        return [r[:d["n_sites"]] for r, d in zip(self.results, self.sites)]
+
+
+class ProfileOnDigarPlan(_Plan):
+    """K3 on the difference lists (and per-read noisy intervals) a DigarPlan left in HBM; sites carry var_cate."""
+    def __init__(self, digar_plan, sites, n_reads):
+        self.sites, self.digar_plan, self.n_reads = sites, digar_plan, n_reads
+        self.arr, self.keep = _site_lists(sites, True)
+        L = lib()
+        L.lcd_profile_plan_create_on_digar.restype = C.c_void_p
+        L.lcd_profile_plan_capacity.restype = C.c_int64
+        L.lcd_profile_plan_capacity.argtypes = [C.c_void_p, C.c_int]
+        super().__init__(L.lcd_profile_plan_create_on_digar(digar_plan.h, C.c_int(len(sites)), self.arr), len(sites))
+        self.res, self.outs = [], (ProfileOutput * max(self.n, 1))()
+        for i in range(self.n):
+            cap = int(L.lcd_profile_plan_capacity(self.h, i)); nr = n_reads[i]
+            o = dict(prof_start=np.zeros(nr + 1, np.int32), prof_end=np.zeros(nr + 1, np.int32), allele_off=np.zeros(nr + 1, np.int64),
+                     alleles=np.zeros(cap + 1, np.int8), alt_qi=np.zeros(cap + 1, np.int32))
+            self.res.append(o)
+            self.outs[i] = ProfileOutput(o["prof_start"].ctypes.data, o["prof_end"].ctypes.data, o["allele_off"].ctypes.data, o["alleles"].ctypes.data,
+                                         o["alt_qi"].ctypes.data, cap, 0)
+
+    def fetch(self, stream=None):
+        _check(lib().lcd_profile_plan_fetch(self.h, C.c_void_p(stream or 0), self.outs), "lcd_profile_plan_fetch")
+        return self.res
+
+
 # ----------------------------------------------------------------------------- K3: pileup scan, read x variant profile
 _PROFILE_EX = (("var_cate", np.int32), ("nreg_first", np.int64), ("n_nreg", np.int32), ("nreg_beg", np.int64), ("nreg_end", np.int64))
 

@@ -47,7 +47,7 @@ struct KernelArgs {
     const long long *first;                                      // [3][n_reads_total + 1]: exclusive scans of cnt
     long long stride;                                            // n_reads_total + 1
     // outputs
-    uint8_t *skip; long long *read_beg, *read_end;
+    uint8_t *skip; long long *read_beg, *read_end; int32_t *n_digar;
     long long *digar_pos; int8_t *digar_type; int32_t *digar_len, *digar_qi; uint8_t *digar_low_qual; long long *digar_alt_off; uint8_t *digar_alt;
     int32_t *n_nreg; long long *nreg_beg, *nreg_end; int32_t *nreg_label;
     unsigned long long *qual_counts;                             // [n_chunks][256]
@@ -76,7 +76,7 @@ __device__ void count_read(const KernelArgs &a, long long g) {
         // a dense window holds an indel or more than max_s X bases of its own; plus the two clip intervals
         ncap = n_gap + n_x / (max_s > 0 ? max_s + 1 : 1) + 2;
     }
-    a.cnt[g] = nd; a.cnt[a.stride + g] = na; a.cnt[2 * a.stride + g] = ncap;
+    a.cnt[g] = nd; a.cnt[a.stride + g] = na; a.cnt[2 * a.stride + g] = ncap; a.n_digar[g] = (int32_t)nd;
 }
 
 struct Win {                      // the reference's xid_queue_t + the pending interval (cr_cur_start / cr_cur_end / cr_q_start / cr_q_end)

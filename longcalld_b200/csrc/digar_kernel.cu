@@ -131,7 +131,7 @@ struct DigarPlan : Plan {
     DevBuf<Chunk> d_chunks; DevBuf<int32_t> d_read_chunk, d_ncig, d_lq; DevBuf<uint8_t> d_active, d_rev, d_pal, d_bseq, d_qual; DevBuf<uint32_t> d_cigar;
     DevBuf<long long> d_pos0, d_coff, d_soff, d_qoff, d_cnt, d_first;
     DevBuf<uint8_t> d_skip, d_dlow, d_dalt; DevBuf<long long> d_beg, d_end, d_dpos, d_daoff, d_nbeg, d_nend; DevBuf<int8_t> d_dtype;
-    DevBuf<int32_t> d_dlen, d_dqi, d_nnreg, d_nlabel, d_status; DevBuf<unsigned long long> d_qc;
+    DevBuf<int32_t> d_dlen, d_dqi, d_nnreg, d_nlabel, d_status, d_ndig; DevBuf<unsigned long long> d_qc;
     std::vector<long long> h_first; std::vector<int32_t> h_nnreg; bool have_index = false;
 
     int build(int n_, const lcd_digar_input_t *in) {
@@ -183,7 +183,7 @@ struct DigarPlan : Plan {
             if (seq_n[i]) LCD_CUDA_OK(cudaMemcpyAsync(d_bseq.p + seq_base[i], in[i].bseq, seq_n[i], cudaMemcpyHostToDevice, s));
             if (qual_n[i]) LCD_CUDA_OK(cudaMemcpyAsync(d_qual.p + qual_base[i], in[i].qual, qual_n[i], cudaMemcpyHostToDevice, s));
         }
-        if (d_cnt.alloc(3 * stride) || d_first.alloc(3 * stride) || d_skip.alloc(stride) || d_beg.alloc(stride) || d_end.alloc(stride) || d_nnreg.alloc(stride) ||
+        if (d_cnt.alloc(3 * stride) || d_first.alloc(3 * stride) || d_skip.alloc(stride) || d_beg.alloc(stride) || d_end.alloc(stride) || d_nnreg.alloc(stride) || d_ndig.alloc(stride) ||
             d_qc.alloc(256 * (size_t)n) || d_status.alloc(1)) return -1;
         LCD_CUDA_OK(cudaStreamSynchronize(s));
         return 0;
@@ -195,7 +195,7 @@ struct DigarPlan : Plan {
         a.read_pos0 = d_pos0.p; a.read_is_rev = d_rev.p; a.is_palindrome = d_pal.p; a.n_cigar = d_ncig.p; a.cigar_off = d_coff.p; a.cigar = d_cigar.p;
         a.l_qseq = d_lq.p; a.seq_off = d_soff.p; a.bseq = d_bseq.p; a.qual_off = d_qoff.p; a.qual = d_qual.p;
         a.cnt = d_cnt.p; a.first = d_first.p; a.stride = stride;
-        a.skip = d_skip.p; a.read_beg = d_beg.p; a.read_end = d_end.p;
+        a.skip = d_skip.p; a.read_beg = d_beg.p; a.read_end = d_end.p; a.n_digar = d_ndig.p;
         a.digar_pos = d_dpos.p; a.digar_type = d_dtype.p; a.digar_len = d_dlen.p; a.digar_qi = d_dqi.p; a.digar_low_qual = d_dlow.p; a.digar_alt_off = d_daoff.p; a.digar_alt = d_dalt.p;
         a.n_nreg = d_nnreg.p; a.nreg_beg = d_nbeg.p; a.nreg_end = d_nend.p; a.nreg_label = d_nlabel.p; a.qual_counts = d_qc.p; a.status = d_status.p;
     }
@@ -248,6 +248,24 @@ struct DigarPlan : Plan {
         if (status == ST_BAD_OP) { set_error("lcd_digar: a read's CIGAR holds an 'M' op; only =/X CIGARs are implemented on the GPU (the reference stops as well: src/bam_utils.c:766)"); return -2; }
         if (status) { set_error("lcd_digar: an output slice overflowed on the device (status %d)", status); return -3; }
         have_index = true;
+        return 0;
+    }
+
+    int view(cudaStream_t s, DigarView *v) {
+        if (tot_reads && index(s)) return -1;
+        v->n_chunks = n; v->n_reads_total = tot_reads; v->tot_events = tot_digar < 0 ? 0 : tot_digar;
+        v->read_off = read_off; v->alt_base.assign(n, 0); v->min_bq.assign(n, 0); v->h_active = h_active;
+        for (int i = 0; i < n; ++i) { v->alt_base[i] = tot_reads ? h_first[stride + read_off[i]] : 0; v->min_bq[i] = chunks[i].min_bq; }
+        v->h_beg.assign(stride, 0); v->h_end.assign(stride, 0);
+        if (tot_reads) {
+            LCD_CUDA_OK(cudaMemcpyAsync(v->h_beg.data(), d_beg.p, sizeof(long long) * tot_reads, cudaMemcpyDeviceToHost, s));
+            LCD_CUDA_OK(cudaMemcpyAsync(v->h_end.data(), d_end.p, sizeof(long long) * tot_reads, cudaMemcpyDeviceToHost, s));
+            LCD_CUDA_OK(cudaStreamSynchronize(s));
+        }
+        v->active = d_active.p; v->dropped = d_skip.p; v->rev = d_rev.p; v->qual = d_qual.p; v->dlow = d_dlow.p; v->dalt = d_dalt.p;
+        v->beg = d_beg.p; v->end = d_end.p; v->dfirst = d_first.p; v->qoff = d_qoff.p; v->dpos = d_dpos.p; v->daoff = d_daoff.p;
+        v->nfirst = d_first.p + 2 * stride; v->nbeg = d_nbeg.p; v->nend = d_nend.p;
+        v->ndig = d_ndig.p; v->dlen = d_dlen.p; v->dqi = d_dqi.p; v->nnreg = d_nnreg.p; v->dtype = d_dtype.p;
         return 0;
     }
 
@@ -342,6 +360,13 @@ struct DigarPlan : Plan {
 };
 
 } // namespace digar
+
+int digar_plan_view(Plan *plan, cudaStream_t s, DigarView *v) {
+    digar::DigarPlan *p = dynamic_cast<digar::DigarPlan *>(plan);
+    if (!p) { set_error("not a digar plan"); return -1; }
+    if (p->n && p->tot_reads && p->tot_digar < 0) { set_error("the digar plan has not been run"); return -1; }
+    return p->view(s, v);
+}
 } // namespace lcd
 
 using namespace lcd;

@@ -79,6 +79,16 @@ struct DevBuf {
     ~DevBuf() { free_(); }
 };
 
+// K1's results as K2 / K3 consume them in place (device pointers into a digar plan that has been run; valid while it lives).
+struct DigarView {
+    int n_chunks = 0; long long n_reads_total = 0, tot_events = 0;
+    std::vector<long long> read_off, alt_base, h_beg, h_end; std::vector<int32_t> min_bq; std::vector<uint8_t> h_active;
+    const uint8_t *active = nullptr, *dropped = nullptr, *rev = nullptr, *qual = nullptr, *dlow = nullptr, *dalt = nullptr;
+    const long long *beg = nullptr, *end = nullptr, *dfirst = nullptr, *qoff = nullptr, *dpos = nullptr, *daoff = nullptr, *nfirst = nullptr, *nbeg = nullptr, *nend = nullptr;
+    const int32_t *ndig = nullptr, *dlen = nullptr, *dqi = nullptr, *nnreg = nullptr; const int8_t *dtype = nullptr;
+};
+int digar_plan_view(Plan *plan, cudaStream_t s, DigarView *v);      // digar_kernel.cu
+
 inline cudaStream_t pick_stream(void *s) { return s ? (cudaStream_t)s : ctx().stream; }
 
 } // namespace lcd

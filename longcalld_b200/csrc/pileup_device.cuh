@@ -17,12 +17,13 @@ namespace pileup {
 
 enum { CINS = 1, CDEL = 2, CEQUAL = 7, CDIFF = 8 };
 
-struct __align__(16) Chunk { int32_t n_sites, min_bq, min_sv_len, pad; int64_t site_off; };
+struct __align__(16) Chunk { int32_t n_sites, min_bq, min_sv_len, pad; int64_t site_off; int64_t alt_base; };   // alt_base: first digar_alt byte of the chunk (digar_alt_off is relative to it)
 
 struct KernelArgs {
     const Chunk *chunks; int64_t n_reads_total;
     // per read (concatenated)
     const int32_t *read_chunk; const uint8_t *read_active;      // active = listed in ordered_read_ids and not skipped
+    const uint8_t *read_dropped;                                 // optional (K1 -> K2 on the device): reads K1's skip test dropped
     const long long *read_beg, *read_end; const uint8_t *read_is_rev;
     const long long *digar_first; const int32_t *n_digar; const long long *qual_off; const uint8_t *qual;
     // per event
@@ -41,7 +42,7 @@ struct KernelArgs {
 
 // exact_comp_var_site_ins (src/collect_var.c:1901-1935) of site s against the site made from event d
 // (make_var_site_from_digar, src/collect_var.c:1113-1121)
-__device__ __forceinline__ int comp_site_event(const KernelArgs &a, long long s, long long d, int min_sv_len) {
+__device__ __forceinline__ int comp_site_event(const KernelArgs &a, long long s, long long d, int min_sv_len, long long alt_base) {
     const int st = a.site_type[s], dt = a.digar_type[d];
     const long long ps = st == CDIFF ? a.site_pos[s] : a.site_pos[s] - 1, pd = dt == CDIFF ? a.digar_pos[d] : a.digar_pos[d] - 1;
     if (ps < pd) return -1;
@@ -56,7 +57,7 @@ __device__ __forceinline__ int comp_site_event(const KernelArgs &a, long long s,
     if (st == CDIFF || (st == CINS && s_alt < min_sv_len)) {
         if (s_alt < d_alt) return -1;
         if (s_alt > d_alt) return 1;
-        const uint8_t *x = a.site_alt + a.site_alt_off[s], *y = a.digar_alt + a.digar_alt_off[d];
+        const uint8_t *x = a.site_alt + a.site_alt_off[s], *y = a.digar_alt + alt_base + a.digar_alt_off[d];
         for (int i = 0; i < s_alt; ++i) if (x[i] != y[i]) return x[i] < y[i] ? -1 : 1;
         return 0;
     } else if (st == CINS) {
@@ -76,7 +77,7 @@ __device__ __forceinline__ void count(const KernelArgs &a, long long s, bool low
 
 // update_cand_vars_from_digar, src/bam_utils.c:287-329, for read g
 __device__ void process_read(const KernelArgs &a, long long g) {
-    if (!a.read_active[g]) return;
+    if (!a.read_active[g] || (a.read_dropped && a.read_dropped[g])) return;
     const Chunk ch = a.chunks[a.read_chunk[g]];
     const long long s0 = ch.site_off, s_end = ch.site_off + ch.n_sites;
     const long long beg = a.read_beg[g], end = a.read_end[g];
@@ -99,7 +100,7 @@ __device__ void process_read(const KernelArgs &a, long long g) {
     while (s < s_end && d < d_end) {
         const int dt = a.digar_type[d];
         if (dt == CEQUAL) { d++; continue; }
-        const int ret = comp_site_event(a, s, d, ch.min_sv_len);
+        const int ret = comp_site_event(a, s, d, ch.min_sv_len, ch.alt_base);
         if (ret < 0) { count(a, s, false, strand, 0); s++; }
         else if (ret == 0) {
             bool low = a.digar_low_qual[d] != 0;
@@ -156,7 +157,7 @@ enum { NON_VAR = 0x800, CAND_SOMATIC_VAR = 0x040 };
 // (src/collect_var.c:1389-1431) would leave it in read_var_profile_t relative to start_var_idx
 __device__ void profile_read(const KernelArgs &a, long long g) {
     a.prof_start[g] = -1; a.prof_end[g] = -2; a.allele_off[g] = a.row_off[g];
-    if (!a.read_active[g]) return;
+    if (!a.read_active[g] || (a.read_dropped && a.read_dropped[g])) return;
     const Chunk ch = a.chunks[a.read_chunk[g]];
     const long long s0 = ch.site_off, s_end = ch.site_off + ch.n_sites;
     const long long beg = a.read_beg[g], end = a.read_end[g];
@@ -197,7 +198,7 @@ __device__ void profile_read(const KernelArgs &a, long long g) {
             else {
                 ret = 0;
                 if (st == CDIFF || st == CINS) {
-                    const uint8_t *x = a.site_alt + a.site_alt_off[v], *y = a.digar_alt + a.digar_alt_off[d];
+                    const uint8_t *x = a.site_alt + a.site_alt_off[v], *y = a.digar_alt + ch.alt_base + a.digar_alt_off[d];
                     for (int i = 0; i < s_alt; ++i) if (x[i] != y[i]) { ret = x[i] < y[i] ? -1 : 1; break; }
                 }
             }

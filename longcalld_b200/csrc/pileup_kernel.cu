@@ -39,6 +39,81 @@ struct PileupPlan : Plan {
     DevBuf<int32_t> d_cate, d_nnreg, d_row_cap, d_pstart, d_pend, d_altqi, d_status; DevBuf<long long> d_nfirst, d_nbeg, d_nend, d_row_off, d_aoff;
     DevBuf<int8_t> d_alleles;
     long long tot_rows = 0;
+    KernelArgs base;                 // device pointers of the read / event arrays: this plan's own buffers, or a digar plan's (K1 -> K2 / K3 in place)
+    std::vector<long long> h_beg, h_end;
+
+    void own_pointers() {
+        memset(&base, 0, sizeof(base));
+        base.read_chunk = d_read_chunk.p; base.read_active = d_active.p; base.read_beg = d_beg.p; base.read_end = d_end.p; base.read_is_rev = d_rev.p;
+        base.digar_first = d_dfirst.p; base.n_digar = d_ndig.p; base.qual_off = d_qoff.p; base.qual = d_qual.p; base.digar_pos = d_dpos.p; base.digar_type = d_dtype.p;
+        base.digar_len = d_dlen.p; base.digar_qi = d_dqi.p; base.digar_low_qual = d_dlow.p; base.digar_alt_off = d_daoff.p; base.digar_alt = d_dalt.p;
+        base.nreg_first = d_nfirst.p; base.n_nreg = d_nnreg.p; base.nreg_beg = d_nbeg.p; base.nreg_end = d_nend.p;
+    }
+
+    // K2 / K3 on the difference lists a digar plan left in HBM: only the site lists (and categories) are uploaded
+    int build_on_digar(Plan *digar, int n_, const lcd_site_list_t *sl, bool want_profile) {
+        n = n_; profile = want_profile;
+        Context &c = ctx();
+        DigarView v;
+        if (digar_plan_view(digar, c.stream, &v)) return -1;
+        if (v.n_chunks != n) { set_error("lcd_pileup: %d site lists for a digar plan of %d chunks", n, v.n_chunks); return -1; }
+        if (n == 0) return 0;
+        std::vector<int32_t> read_chunk, stype, sref, salt, cate; std::vector<long long> spos, saoff; std::vector<uint8_t> site_alt;
+        chunks.resize(n); site_off.resize(n); read_off = v.read_off;
+        tot_reads = v.n_reads_total; tot_events = v.tot_events;
+        for (int i = 0; i < n; ++i) {
+            const lcd_site_list_t &x = sl[i];
+            if (x.n_sites < 0 || (want_profile && !x.var_cate)) { set_error("lcd_pileup: chunk %d has an invalid site list", i); return -1; }
+            Chunk &k = chunks[i];
+            k.n_sites = x.n_sites; k.min_bq = v.min_bq[i]; k.min_sv_len = x.min_sv_len; k.pad = 0; k.site_off = tot_sites; k.alt_base = v.alt_base[i]; site_off[i] = tot_sites;
+            long long n_salt = 0;
+            for (int s = 0; s < x.n_sites; ++s) if (x.site_type[s] == CDIFF || x.site_type[s] == CINS) n_salt = std::max<long long>(n_salt, x.site_alt_off[s] + x.site_alt_len[s]);
+            const long long sa0 = (long long)site_alt.size();
+            append(spos, x.site_pos, x.n_sites); append(stype, x.site_type, x.n_sites); append(sref, x.site_ref_len, x.n_sites);
+            append(salt, x.site_alt_len, x.n_sites); append(saoff, x.site_alt_off, x.n_sites, sa0); append(site_alt, x.site_alt, (size_t)n_salt);
+            if (want_profile) {
+                for (int s = 0; s < x.n_sites; ++s) if (x.var_cate[s] == CAND_SOMATIC_VAR) { set_error("lcd_profile: chunk %d holds candidate somatic variants (-s); only the germline path is implemented on the GPU", i); return -1; }
+                append(cate, x.var_cate, x.n_sites);
+            }
+            for (long long g = read_off[i]; g < read_off[i + 1]; ++g) read_chunk.push_back(i);
+            tot_sites += x.n_sites;
+        }
+        if (want_profile) {
+            row_off.assign(tot_reads + 1, 0); row_cap.assign(tot_reads + 1, 0); chunk_row0.assign(n + 1, 0);
+            for (int i = 0; i < n; ++i) {
+                chunk_row0[i] = tot_rows;
+                const long long s0 = site_off[i], s1 = s0 + chunks[i].n_sites;
+                for (long long g = read_off[i]; g < read_off[i + 1]; ++g) {
+                    row_off[g] = tot_rows;
+                    if (!v.h_active[g]) continue;
+                    const long long v0 = first_site(spos.data(), stype.data(), s0, s1, v.h_beg[g]);
+                    const long long v1 = row_end_site(spos.data(), stype.data(), v0, s1, v.h_end[g]);
+                    row_cap[g] = (int32_t)(v1 - v0); tot_rows += v1 - v0;
+                }
+            }
+            chunk_row0[n] = tot_rows;
+        }
+        auto pad = [](auto &x) { x.push_back(0); };
+        pad(read_chunk); pad(spos); pad(stype); pad(sref); pad(salt); pad(saoff); pad(site_alt);
+        cudaStream_t s = c.stream;
+        if (d_chunks.upload(chunks.data(), n, s) || d_read_chunk.upload(read_chunk.data(), read_chunk.size(), s) || d_spos.upload(spos.data(), spos.size(), s) ||
+            d_stype.upload(stype.data(), stype.size(), s) || d_sref.upload(sref.data(), sref.size(), s) || d_salt.upload(salt.data(), salt.size(), s) ||
+            d_saoff.upload(saoff.data(), saoff.size(), s) || d_site_alt.upload(site_alt.data(), site_alt.size(), s)) return -1;
+        if (d_counts.alloc(8 * (size_t)tot_sites + 8)) return -1;
+        if (want_profile) {
+            pad(cate);
+            if (d_cate.upload(cate.data(), cate.size(), s) || d_row_off.upload(row_off.data(), row_off.size(), s) || d_row_cap.upload(row_cap.data(), row_cap.size(), s)) return -1;
+            if (d_pstart.alloc(tot_reads + 1) || d_pend.alloc(tot_reads + 1) || d_aoff.alloc(tot_reads + 1) || d_alleles.alloc(tot_rows + 16) ||
+                d_altqi.alloc(tot_rows + 16) || d_status.alloc(1)) return -1;
+        }
+        memset(&base, 0, sizeof(base));
+        base.read_chunk = d_read_chunk.p; base.read_active = v.active; base.read_dropped = v.dropped; base.read_beg = v.beg; base.read_end = v.end; base.read_is_rev = v.rev;
+        base.digar_first = v.dfirst; base.n_digar = v.ndig; base.qual_off = v.qoff; base.qual = v.qual; base.digar_pos = v.dpos; base.digar_type = v.dtype;
+        base.digar_len = v.dlen; base.digar_qi = v.dqi; base.digar_low_qual = v.dlow; base.digar_alt_off = v.daoff; base.digar_alt = v.dalt;
+        base.nreg_first = v.nfirst; base.n_nreg = v.nnreg; base.nreg_beg = v.nbeg; base.nreg_end = v.nend;
+        LCD_CUDA_OK(cudaStreamSynchronize(s));
+        return 0;
+    }
 
     int build(int n_, const lcd_pileup_input_t *in, const lcd_profile_extra_t *ex = nullptr) {
         n = n_; profile = ex != nullptr;
@@ -53,7 +128,7 @@ struct PileupPlan : Plan {
             const lcd_pileup_input_t &x = in[i];
             if (x.n_reads < 0 || x.n_sites < 0) { set_error("lcd_pileup: chunk %d has negative sizes", i); return -1; }
             Chunk &k = chunks[i]; read_off[i] = tot_reads;
-            k.n_sites = x.n_sites; k.min_bq = x.min_bq; k.min_sv_len = x.min_sv_len; k.pad = 0; k.site_off = tot_sites; site_off[i] = tot_sites;
+            k.n_sites = x.n_sites; k.min_bq = x.min_bq; k.min_sv_len = x.min_sv_len; k.pad = 0; k.site_off = tot_sites; k.alt_base = 0; site_off[i] = tot_sites;
             long long n_ev = 0, n_q = 0, n_alt = 0, n_salt = 0;
             for (int r = 0; r < x.n_reads; ++r) {
                 if (x.n_digar[r] < 0 || x.digar_first[r] < 0) { set_error("lcd_pileup: chunk %d read %d has an invalid event range", i, r); return -1; }
@@ -130,6 +205,7 @@ struct PileupPlan : Plan {
             if (d_pstart.alloc(tot_reads + 1) || d_pend.alloc(tot_reads + 1) || d_aoff.alloc(tot_reads + 1) || d_alleles.alloc(tot_rows + 16) ||
                 d_altqi.alloc(tot_rows + 16) || d_status.alloc(1)) return -1;
         }
+        own_pointers();
         LCD_CUDA_OK(cudaStreamSynchronize(s));
         return 0;
     }
@@ -138,16 +214,13 @@ struct PileupPlan : Plan {
         Context &c = ctx();
         if (n == 0 || tot_reads == 0) return 0;
         LCD_CUDA_OK(cudaMemsetAsync(d_counts.p, 0, sizeof(int32_t) * 8 * (size_t)tot_sites, s));
-        KernelArgs a;
-        a.chunks = d_chunks.p; a.n_reads_total = tot_reads; a.read_chunk = d_read_chunk.p; a.read_active = d_active.p;
-        a.read_beg = d_beg.p; a.read_end = d_end.p; a.read_is_rev = d_rev.p; a.digar_first = d_dfirst.p; a.n_digar = d_ndig.p;
-        a.qual_off = d_qoff.p; a.qual = d_qual.p; a.digar_pos = d_dpos.p; a.digar_type = d_dtype.p; a.digar_len = d_dlen.p; a.digar_qi = d_dqi.p;
-        a.digar_low_qual = d_dlow.p; a.digar_alt_off = d_daoff.p; a.digar_alt = d_dalt.p;
+        KernelArgs a = base;
+        a.chunks = d_chunks.p; a.n_reads_total = tot_reads;
         a.site_pos = d_spos.p; a.site_type = d_stype.p; a.site_ref_len = d_sref.p; a.site_alt_len = d_salt.p; a.site_alt_off = d_saoff.p; a.site_alt = d_site_alt.p;
         a.site_counts = d_counts.p;
         const int grid = (int)std::min<long long>((tot_reads + THREADS - 1) / THREADS, (long long)c.sm_count * 16);
         if (profile) {
-            a.var_cate = d_cate.p; a.nreg_first = d_nfirst.p; a.n_nreg = d_nnreg.p; a.nreg_beg = d_nbeg.p; a.nreg_end = d_nend.p;
+            a.var_cate = d_cate.p;
             a.row_off = d_row_off.p; a.row_cap = d_row_cap.p; a.prof_start = d_pstart.p; a.prof_end = d_pend.p; a.allele_off = d_aoff.p;
             a.alleles = d_alleles.p; a.alt_qi = d_altqi.p; a.status = d_status.p;
             LCD_CUDA_OK(cudaMemsetAsync(d_status.p, 0, sizeof(int32_t), s));
@@ -233,6 +306,28 @@ int lcd_profile_plan_fetch(lcd_plan_t *plan, void *stream, lcd_profile_output_t 
     pileup::PileupPlan *p = dynamic_cast<pileup::PileupPlan *>(reinterpret_cast<Plan *>(plan));
     if (!p || !p->profile || !out) { set_error("lcd_profile_plan_fetch: not a profile plan / null outputs"); return -1; }
     return p->fetch_profile(pick_stream(stream), out);
+}
+
+lcd_plan_t *lcd_pileup_plan_create_on_digar(lcd_plan_t *digar_plan, int n_chunks, const lcd_site_list_t *sites) {
+    if (ensure_ready()) return nullptr;
+    if (!digar_plan || n_chunks < 0 || (n_chunks > 0 && !sites)) { set_error("lcd_pileup_plan_create_on_digar: invalid arguments"); return nullptr; }
+    pileup::PileupPlan *p = new pileup::PileupPlan();
+    if (p->build_on_digar(reinterpret_cast<Plan *>(digar_plan), n_chunks, sites, false)) { delete p; return nullptr; }
+    return reinterpret_cast<lcd_plan_t *>(p);
+}
+
+lcd_plan_t *lcd_profile_plan_create_on_digar(lcd_plan_t *digar_plan, int n_chunks, const lcd_site_list_t *sites) {
+    if (ensure_ready()) return nullptr;
+    if (!digar_plan || n_chunks < 0 || (n_chunks > 0 && !sites)) { set_error("lcd_profile_plan_create_on_digar: invalid arguments"); return nullptr; }
+    pileup::PileupPlan *p = new pileup::PileupPlan();
+    if (p->build_on_digar(reinterpret_cast<Plan *>(digar_plan), n_chunks, sites, true)) { delete p; return nullptr; }
+    return reinterpret_cast<lcd_plan_t *>(p);
+}
+
+int64_t lcd_profile_plan_capacity(lcd_plan_t *plan, int chunk) {
+    pileup::PileupPlan *p = dynamic_cast<pileup::PileupPlan *>(reinterpret_cast<Plan *>(plan));
+    if (!p || !p->profile || chunk < 0 || chunk >= p->n) { set_error("lcd_profile_plan_capacity: not a profile plan / chunk out of range"); return -1; }
+    return p->capacity(chunk);
 }
 
 int lcd_profile_batch(int n_chunks, const lcd_pileup_input_t *in, const lcd_profile_extra_t *extra, lcd_profile_output_t *out) {

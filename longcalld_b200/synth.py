@@ -348,3 +348,135 @@ def make_digar_chunk(rng, n_reads=100, read_len=(800, 4000), err_every=300, tech
                 n_cigar=np.array(n_cig, np.int32), cigar_off=np.array(cig_off, np.int64), cigar=np.array(cig + [0], np.uint32),
                 l_qseq=np.array(lq, np.int32), seq_off=np.array(seq_off, np.int64), bseq=np.array(bseq + [0], np.uint8),
                 qual_off=np.array(qual_off, np.int64), qual=np.array(qual + [0], np.uint8))
+
+
+def digar_chunks_30x(n_chunks, tech="hifi", seed=11, chunk_len=500000, read_mean=15000, coverage=30):
+    """K1 workload at BASELINE shape: `n_chunks` 500 kb region chunks at 30x, ~1 050 reads of ~15 kb each with =/X CIGARs.
+    Two haplotypes carry het / hom SNPs (1 per kb) and small indels (1 per 8 kb); reads add sequencing errors (HiFi 0.2 %,
+    mostly 1-bp indels; ONT 1.5 %) and 3 % of them a >= 100 bp soft clip.  Built with numpy per read (no simulator in the image)."""
+    EQ, X, I, D, S = 7, 8, 1, 2, 4
+    rng = np.random.default_rng(seed)
+    ont = tech == "ont"
+    err = 0.015 if ont else 0.002
+    out = []
+    for c in range(n_chunks):
+        reg_beg = 1000000 + c * chunk_len; reg_end = reg_beg + chunk_len - 1
+        n_var = chunk_len // 1000 + chunk_len // 8000
+        vpos = np.sort(rng.choice(np.arange(reg_beg - read_mean, reg_end + read_mean, 3), size=n_var * 2, replace=False))[: n_var * 2]
+        vtype = rng.choice(np.array([X, I, D]), size=len(vpos), p=[0.89, 0.055, 0.055])
+        vlen = np.where(vtype == X, 1, rng.integers(1, 9, len(vpos)))
+        vhap = rng.integers(1, 4, len(vpos))                         # carried by hap 1, hap 2, or both
+        valt = rng.integers(0, 4, (len(vpos), 8)).astype(np.uint8)
+        n_reads = int(coverage * (chunk_len + read_mean) / read_mean)
+        starts = np.sort(rng.integers(reg_beg - read_mean, reg_end, n_reads))
+        lens = np.clip(rng.normal(read_mean, read_mean / 5, n_reads).astype(np.int64), 2000, 3 * read_mean) if not ont else \
+            np.clip(rng.lognormal(np.log(read_mean), 0.6, n_reads).astype(np.int64), 2000, 6 * read_mean)
+        cig, cig_off, n_cig, lq, seq_off, qual_off, seqs, quals = [], [], [], [], [], [], [], []
+        c_top = s_top = q_top = 0
+        code = np.array([1, 2, 4, 8], np.uint8)
+        for r in range(n_reads):
+            beg, L = int(starts[r]), int(lens[r]); hap = int(rng.integers(1, 3))
+            lo, hi = np.searchsorted(vpos, [beg + 20, beg + L - 20])
+            m = (vhap[lo:hi] & hap) != 0
+            p1, t1, l1 = vpos[lo:hi][m], vtype[lo:hi][m], vlen[lo:hi][m]; a1 = valt[lo:hi][m]
+            ne = rng.poisson(err * L)
+            p2 = rng.integers(beg + 20, beg + L - 20, ne); u = rng.random(ne)
+            t2 = np.where(u < (0.4 if ont else 0.2), X, np.where(u < (0.65 if ont else 0.6), I, D)); l2 = np.where(t2 == X, 1, rng.integers(1, 3, ne))
+            a2 = rng.integers(0, 4, (ne, 8)).astype(np.uint8)
+            p, t, l, a = np.concatenate([p1, p2]), np.concatenate([t1, t2]), np.concatenate([l1, l2]), np.concatenate([a1, a2])
+            o = np.argsort(p, kind="stable"); p, t, l, a = p[o], t[o], l[o], a[o]
+            ref_span = np.where(t == I, 0, l)
+            keep = np.ones(len(p), bool)
+            if len(p) > 1:
+                keep[1:] = p[1:] >= (p[:-1] + ref_span[:-1] + 2)          # an '=' run of >= 2 between neighbouring events
+            p, t, l, a, ref_span = p[keep], t[keep], l[keep], a[keep], ref_span[keep]
+            if len(p) > 1:                                                # second pass: dropping can only widen gaps, but re-check chained overlaps
+                ok = np.ones(len(p), bool); ok[1:] = p[1:] >= p[:-1] + ref_span[:-1] + 2
+                p, t, l, a, ref_span = p[ok], t[ok], l[ok], a[ok], ref_span[ok]
+            k = len(p)
+            eq = np.empty(k + 1, np.int64)
+            eq[0] = (p[0] - beg) if k else L
+            if k: eq[1:k] = p[1:] - (p[:-1] + ref_span[:-1]); eq[k] = beg + L - (p[-1] + ref_span[-1])
+            ops = np.empty(2 * k + 1, np.uint32); ops[0::2] = (eq.astype(np.uint32) << 4) | EQ
+            if k: ops[1::2] = (l.astype(np.uint32) << 4) | t.astype(np.uint32)
+            clip = int(rng.integers(100, 2000)) if rng.random() < 0.03 else 0
+            if clip: ops = np.concatenate([np.array([(clip << 4) | S], np.uint32), ops])
+            q_adv = np.where(t == D, 0, l)                                 # read bases an event consumes
+            qlen = clip + int(eq.sum()) + int(q_adv.sum())
+            bases = rng.integers(0, 4, qlen + (qlen & 1)).astype(np.uint8)
+            if k:                                                          # planted alt bases at the events' read offsets
+                qi = clip + np.cumsum(eq[:k]) + np.concatenate([[0], np.cumsum(q_adv[:-1])])
+                for j in np.nonzero(t != D)[0]: bases[qi[j]:qi[j] + l[j]] = a[j, :l[j]]
+            packed = (code[bases[0::2]] << 4) | code[bases[1::2]]
+            qv = rng.choice(np.array([93, 60, 40, 30, 20, 8], np.uint8), size=qlen, p=[0.6, 0.12, 0.1, 0.08, 0.06, 0.04]) if not ont else \
+                rng.integers(5, 40, qlen).astype(np.uint8)
+            cig_off.append(c_top); n_cig.append(len(ops)); cig.append(ops); c_top += len(ops)
+            lq.append(qlen); seq_off.append(s_top); seqs.append(packed); s_top += len(packed)
+            qual_off.append(q_top); quals.append(qv); q_top += qlen
+        out.append(dict(n_reads=n_reads, min_bq=10, noisy_reg_max_xgaps=5, noisy_reg_slide_win=25 if ont else 100, end_clip_reg=30,
+                        end_clip_reg_flank_win=100, max_noisy_frac_per_read=0.5, max_var_ratio_per_read=0.05, whole_ref_len=250000000,
+                        reg_beg=reg_beg, reg_end=reg_end, ordered_read_ids=np.arange(n_reads, dtype=np.int32), is_skipped=np.zeros(n_reads, np.uint8),
+                        read_pos0=(starts - 1).astype(np.int64), read_is_rev=rng.integers(0, 2, n_reads).astype(np.uint8), is_palindrome=np.zeros(n_reads, np.uint8),
+                        n_cigar=np.array(n_cig, np.int32), cigar_off=np.array(cig_off, np.int64), cigar=np.concatenate(cig + [np.zeros(1, np.uint32)]),
+                        l_qseq=np.array(lq, np.int32), seq_off=np.array(seq_off, np.int64), bseq=np.concatenate(seqs + [np.zeros(1, np.uint8)]),
+                        qual_off=np.array(qual_off, np.int64), qual=np.concatenate(quals + [np.zeros(1, np.uint8)])))
+    return out
+
+
+def sites_from_digar_output(d, o, min_sv_len=50):
+    """Workload preparation (the reference's step 1.2, collect_all_cand_var_sites src/collect_var.c:1209, restated with numpy for
+    the bench set-up; large insertions are matched exactly here): the sorted unique candidate sites of a chunk from K1's output
+    `o` -- every non-low-quality X / I / D record of a kept read that starts inside [reg_beg, reg_end]."""
+    nr = d["n_reads"]; nd = int(o["n_digar_total"])
+    t = o["digar_type"][:nd].astype(np.int32); pos = o["digar_pos"][:nd]; ln = o["digar_len"][:nd]; aoff = o["digar_alt_off"][:nd]
+    read_of = np.repeat(np.arange(nr), o["n_digar"][:nr])
+    dropped = (np.asarray(d["is_skipped"][:nr]) != 0) | (o["skip"][:nr] != 0)
+    ok = ((t == 8) | (t == 1) | (t == 2)) & (o["digar_low_qual"][:nd] == 0) & (pos >= d["reg_beg"]) & (pos <= d["reg_end"]) & ~dropped[read_of]
+    idx = np.nonzero(ok)[0]
+    alt = o["digar_alt"]
+    keys = {}
+    for k in idx.tolist():
+        tk, lk = int(t[k]), int(ln[k])
+        a = bytes(alt[aoff[k]:aoff[k] + lk]) if tk != 2 else b""
+        keys.setdefault((int(pos[k]) - (0 if tk == 8 else 1), tk, lk if tk == 2 else (0 if tk == 1 else 1), 0 if tk == 2 else lk, a), int(pos[k]))
+    order = sorted(keys)
+    site_alt, site_alt_off = [], []
+    for key in order:
+        site_alt_off.append(len(site_alt)); site_alt.extend(key[4])
+    return dict(n_sites=len(order), min_sv_len=min_sv_len,
+                site_pos=np.array([keys[k] for k in order] + [0], np.int64), site_type=np.array([k[1] for k in order] + [0], np.int32),
+                site_ref_len=np.array([k[2] for k in order] + [0], np.int32), site_alt_len=np.array([k[3] for k in order] + [0], np.int32),
+                site_alt_off=np.array(site_alt_off + [0], np.int64), site_alt=np.array(site_alt + [0], np.uint8))
+
+
+def classify_sites(sites, counts, min_alt=2, min_af=0.20, max_af=0.80):
+    """Workload preparation (stand-in for the reference's step 2, classify_cand_vars src/collect_var.c:902, allele-fraction rule
+    only): keeps sites with >= min_alt alternative observations and labels them clean het SNP / het indel / hom by allele
+    fraction (src/call_var_main.h:22-23); everything else is dropped, as the reference compacts cand_vars."""
+    n = sites["n_sites"]; c = counts[:n]
+    tot, alt = c[:, 0].astype(np.float64), c[:, 3]
+    af = np.where(tot > 0, alt / np.maximum(tot, 1), 0.0)
+    keep = np.nonzero((alt >= min_alt) & (af >= min_af))[0]
+    t = sites["site_type"][keep]
+    cate = np.where(af[keep] > max_af, CATE["CLEAN_HOM_VAR"], np.where(t == 8, CATE["CLEAN_HET_SNP"], CATE["CLEAN_HET_INDEL"])).astype(np.int32)
+    alt_len = sites["site_alt_len"][keep]; off = sites["site_alt_off"][keep]
+    new_alt, new_off = [], []
+    for o_, l_ in zip(off.tolist(), alt_len.tolist()):
+        new_off.append(len(new_alt)); new_alt.extend(sites["site_alt"][o_:o_ + l_].tolist())
+    pad = lambda a, dt: np.concatenate([a, np.zeros(1, dt)]).astype(dt)
+    return dict(n_sites=len(keep), min_sv_len=sites["min_sv_len"], site_pos=pad(sites["site_pos"][keep], np.int64), site_type=pad(t, np.int32),
+                site_ref_len=pad(sites["site_ref_len"][keep], np.int32), site_alt_len=pad(alt_len, np.int32),
+                site_alt_off=np.array(new_off + [0], np.int64), site_alt=np.array(new_alt + [0], np.uint8), var_cate=pad(cate, np.int32))
+
+
+def pileup_input_from_digar(d, o, sites):
+    """lcd_pileup_input_t (+ lcd_profile_extra_t when `sites` carries var_cate) for a chunk from K1's host-side output."""
+    nr = d["n_reads"]
+    p = dict(n_reads=nr, n_sites=sites["n_sites"], min_bq=d["min_bq"], min_sv_len=sites["min_sv_len"], ordered_read_ids=d["ordered_read_ids"],
+             is_skipped=np.maximum(np.asarray(d["is_skipped"][:nr]), o["skip"][:nr]), read_beg=o["read_beg"], read_end=o["read_end"], read_is_rev=d["read_is_rev"],
+             digar_first=o["digar_first"], n_digar=o["n_digar"], qual_off=d["qual_off"], qual=d["qual"], digar_pos=o["digar_pos"], digar_type=o["digar_type"],
+             digar_len=o["digar_len"], digar_qi=o["digar_qi"], digar_low_qual=o["digar_low_qual"], digar_alt_off=o["digar_alt_off"], digar_alt=o["digar_alt"],
+             **{k: sites[k] for k in ("site_pos", "site_type", "site_ref_len", "site_alt_len", "site_alt_off", "site_alt")})
+    if "var_cate" in sites:
+        p.update(var_cate=sites["var_cate"], nreg_first=o["nreg_first"], n_nreg=o["n_nreg"], nreg_beg=o["nreg_beg"], nreg_end=o["nreg_end"])
+    return p

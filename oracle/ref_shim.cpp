@@ -10,6 +10,7 @@
 #include <string.h>
 #include "lcd_oracle.h"
 #include <thread>
+#include <chrono>
 #include <atomic>
 #include <vector>
 extern "C" {
@@ -208,6 +209,39 @@ int ref_phase_batch(int n, const lcd_phase_input_t *in, lcd_phase_output_t *out,
     for (int t = 0; t < n_threads; ++t) th.emplace_back(work);
     for (auto &t : th) t.join();
     return 0;
+}
+
+// K1 / K2 / K3 over many chunks on n_threads host threads (the reference's kt_for runs one chunk per thread as well)
+int ref_collect_cand_vars(const lcd_pileup_input_t *in, lcd_pileup_output_t *out);
+int ref_read_var_profile(const lcd_pileup_input_t *in, const lcd_profile_extra_t *ex, lcd_profile_output_t *out);
+}
+template <typename F> static int run_chunks(int n, int n_threads, F f) {
+    std::atomic<int> next(0), bad(0);
+    auto work = [&]() { for (;;) { int i = next.fetch_add(1); if (i >= n) break; if (f(i)) bad = 1; } };
+    if (n_threads <= 1) { work(); return bad; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work);
+    for (auto &t : th) t.join();
+    return bad;
+}
+extern "C" {
+// bam1_t records are built first and results copied out last; *core_wall_s is the wall time of the reference's own calls
+void *ref_digar_prepare(const lcd_digar_input_t *in);
+void ref_digar_core(void *job, const lcd_digar_input_t *in);
+int ref_digar_finish(void *job, const lcd_digar_input_t *in, lcd_digar_output_t *out);
+int ref_digar_batch(int n, const lcd_digar_input_t *in, lcd_digar_output_t *out, int n_threads, double *core_wall_s) {
+    std::vector<void *> jobs(n, nullptr);
+    if (run_chunks(n, n_threads, [&](int i) { jobs[i] = ref_digar_prepare(&in[i]); return jobs[i] ? 0 : 1; })) return -9;
+    const auto t0 = std::chrono::steady_clock::now();
+    run_chunks(n, n_threads, [&](int i) { ref_digar_core(jobs[i], &in[i]); return 0; });
+    if (core_wall_s) *core_wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return run_chunks(n, n_threads, [&](int i) { return ref_digar_finish(jobs[i], &in[i], &out[i]); });
+}
+int ref_pileup_batch(int n, const lcd_pileup_input_t *in, lcd_pileup_output_t *out, int n_threads) {
+    return run_chunks(n, n_threads, [&](int i) { return ref_collect_cand_vars(&in[i], &out[i]); });
+}
+int ref_profile_batch(int n, const lcd_pileup_input_t *in, const lcd_profile_extra_t *ex, lcd_profile_output_t *out, int n_threads) {
+    return run_chunks(n, n_threads, [&](int i) { return ref_read_var_profile(&in[i], &ex[i], &out[i]); });
 }
 
 }

@@ -202,26 +202,30 @@ int ref_read_var_profile(const lcd_pileup_input_t *in, const lcd_profile_extra_t
 }
 
 /* collect_digar_from_eqx_cigar (src/bam_utils.c:701-841) for every listed, not yet skipped read of a synthetic chunk, as
- * collect_digars_from_bam drives it (src/collect_var.c:1063-1082): bam1_t records are built with htslib's bam_set1 from
- * the flat CIGAR / packed SEQ / QUAL arrays (reads flagged is_palindrome get an SA tag that passes the reference's
- * 90 % overlap test when opt.is_ont is set), results are copied out in the layout of lcd_digar_output_t. */
+ * collect_digars_from_bam drives it (src/collect_var.c:1063-1082).  Three steps so that a benchmark can time the reference's own
+ * work alone: prepare (bam1_t records built with htslib's bam_set1 from the flat CIGAR / packed SEQ / QUAL arrays; reads flagged
+ * is_palindrome get an SA tag that passes the reference's 90 % overlap test when opt.is_ont is set), core (the reference calls),
+ * finish (results copied out in the layout of lcd_digar_output_t, everything freed). */
 #include "htslib/sam.h"
-int ref_collect_digar_eqx(const lcd_digar_input_t *in, lcd_digar_output_t *out) {
+typedef struct { bam_chunk_t chunk; call_var_opt_t opt; uint8_t *ret; } ref_digar_job_t;
+
+void *ref_digar_prepare(const lcd_digar_input_t *in) {
     const int nr = in->n_reads;
-    call_var_opt_t opt; memset(&opt, 0, sizeof(opt));
-    opt.min_bq = in->min_bq; opt.noisy_reg_max_xgaps = in->noisy_reg_max_xgaps; opt.noisy_reg_slide_win = in->noisy_reg_slide_win;
-    opt.end_clip_reg = in->end_clip_reg; opt.end_clip_reg_flank_win = in->end_clip_reg_flank_win;
-    opt.max_noisy_frac_per_read = in->max_noisy_frac_per_read; opt.max_var_ratio_per_read = in->max_var_ratio_per_read;
-    opt.is_ont = 0;
-    for (int r = 0; r < nr; ++r) if (in->is_palindrome[r]) opt.is_ont = 1;
-    bam_chunk_t chunk; memset(&chunk, 0, sizeof(chunk));
-    chunk.n_reads = chunk.m_reads = nr; chunk.tid = 0; chunk.tname = (char*)"chr";
-    chunk.reg_beg = in->reg_beg; chunk.reg_end = in->reg_end; chunk.whole_ref_len = in->whole_ref_len;
-    chunk.qual_counts = (int*)calloc(256, sizeof(int));
-    chunk.is_ont_palindrome = (uint8_t*)calloc(nr + 1, 1);
-    chunk.digars = (digar_t*)calloc(nr + 1, sizeof(digar_t));
-    chunk.reads = (bam1_t**)calloc(nr + 1, sizeof(bam1_t*));
-    chunk.chunk_noisy_regs = cr_init();
+    ref_digar_job_t *job = (ref_digar_job_t*)calloc(1, sizeof(ref_digar_job_t));
+    call_var_opt_t *opt = &job->opt; bam_chunk_t *chunk = &job->chunk;
+    opt->min_bq = in->min_bq; opt->noisy_reg_max_xgaps = in->noisy_reg_max_xgaps; opt->noisy_reg_slide_win = in->noisy_reg_slide_win;
+    opt->end_clip_reg = in->end_clip_reg; opt->end_clip_reg_flank_win = in->end_clip_reg_flank_win;
+    opt->max_noisy_frac_per_read = in->max_noisy_frac_per_read; opt->max_var_ratio_per_read = in->max_var_ratio_per_read;
+    opt->is_ont = 0;
+    for (int r = 0; r < nr; ++r) if (in->is_palindrome[r]) opt->is_ont = 1;
+    chunk->n_reads = chunk->m_reads = nr; chunk->tid = 0; chunk->tname = (char*)"chr";
+    chunk->reg_beg = in->reg_beg; chunk->reg_end = in->reg_end; chunk->whole_ref_len = in->whole_ref_len;
+    chunk->qual_counts = (int*)calloc(256, sizeof(int));
+    chunk->is_ont_palindrome = (uint8_t*)calloc(nr + 1, 1);
+    chunk->digars = (digar_t*)calloc(nr + 1, sizeof(digar_t));
+    chunk->reads = (bam1_t**)calloc(nr + 1, sizeof(bam1_t*));
+    chunk->chunk_noisy_regs = cr_init();
+    job->ret = (uint8_t*)calloc(nr + 1, 1);
     for (int r = 0; r < nr; ++r) {
         const int L = in->l_qseq[r];
         char *seq = (char*)malloc(L + 1), *ql = (char*)malloc(L + 1);
@@ -231,21 +235,36 @@ int ref_collect_digar_eqx(const lcd_digar_input_t *in, lcd_digar_output_t *out) 
         char name[32]; snprintf(name, sizeof(name), "r%d", r);
         bam1_t *b = bam_init1();
         if (bam_set1(b, strlen(name), name, in->read_is_rev[r] ? BAM_FREVERSE : 0, 0, in->read_pos0[r], 60, in->n_cigar[r], in->cigar + in->cigar_off[r],
-                     -1, -1, 0, L, seq, ql, 64) < 0) return -9;
+                     -1, -1, 0, L, seq, ql, 64) < 0) return NULL;
         if (in->is_palindrome[r]) {
             char sa[64]; snprintf(sa, sizeof(sa), "chr,%lld,%c,%lldM,60,0;", (long long)in->read_pos0[r] + 1, in->read_is_rev[r] ? '+' : '-',
                                   (long long)(bam_endpos(b) - in->read_pos0[r]));
             bam_aux_append(b, "SA", 'Z', (int)strlen(sa) + 1, (uint8_t*)sa);
         }
-        chunk.reads[r] = b; free(seq); free(ql);
+        chunk->reads[r] = b; free(seq); free(ql);
     }
+    return job;
+}
+
+void ref_digar_core(void *h, const lcd_digar_input_t *in) {          /* the reference's own work: the loop of collect_digars_from_bam */
+    ref_digar_job_t *job = (ref_digar_job_t*)h;
+    for (int i = 0; i < in->n_reads; ++i) {
+        const int r = in->ordered_read_ids[i];
+        if (in->is_skipped[r]) continue;
+        job->ret[r] = collect_digar_from_eqx_cigar(&job->chunk, r, &job->opt, job->chunk.digars + r) < 0;
+    }
+}
+
+int ref_digar_finish(void *h, const lcd_digar_input_t *in, lcd_digar_output_t *out) {
+    ref_digar_job_t *job = (ref_digar_job_t*)h; bam_chunk_t chunk = job->chunk;
+    const int nr = in->n_reads;
     int64_t dtop = 0, atop = 0, rtop = 0; int rc = 0;
     for (int i = 0; i < nr && !rc; ++i) {
         const int r = in->ordered_read_ids[i];
         out->skip[r] = 0;
         if (in->is_skipped[r]) continue;
         digar_t *g = chunk.digars + r;
-        out->skip[r] = collect_digar_from_eqx_cigar(&chunk, r, &opt, g) < 0;
+        out->skip[r] = job->ret[r];
         out->read_beg[r] = g->beg; out->read_end[r] = g->end;
         out->digar_first[r] = dtop; out->n_digar[r] = g->n_digar; out->nreg_first[r] = rtop; out->n_nreg[r] = (int32_t)g->noisy_regs->n_r;
         if (chunk.is_ont_palindrome[r] != in->is_palindrome[r]) rc = -8;
@@ -281,6 +300,13 @@ int ref_collect_digar_eqx(const lcd_digar_input_t *in, lcd_digar_output_t *out) 
         bam_destroy1(chunk.reads[r]);
     }
     cr_destroy(chunk.chunk_noisy_regs);
-    free(chunk.reads); free(chunk.digars); free(chunk.is_ont_palindrome); free(chunk.qual_counts);
+    free(chunk.reads); free(chunk.digars); free(chunk.is_ont_palindrome); free(chunk.qual_counts); free(job->ret); free(job);
     return rc;
+}
+
+int ref_collect_digar_eqx(const lcd_digar_input_t *in, lcd_digar_output_t *out) {
+    void *job = ref_digar_prepare(in);
+    if (!job) return -9;
+    ref_digar_core(job, in);
+    return ref_digar_finish(job, in, out);
 }

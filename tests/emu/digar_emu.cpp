@@ -25,6 +25,7 @@ extern "C" int emu_collect_digar_eqx(const lcd_digar_input_t *in, lcd_digar_outp
     a.read_pos0 = (const long long *)in->read_pos0; a.read_is_rev = in->read_is_rev; a.is_palindrome = in->is_palindrome;
     a.n_cigar = in->n_cigar; a.cigar_off = (const long long *)in->cigar_off; a.cigar = in->cigar;
     a.l_qseq = in->l_qseq; a.seq_off = (const long long *)in->seq_off; a.bseq = in->bseq; a.qual_off = (const long long *)in->qual_off; a.qual = qual;
+    std::vector<int32_t> ndig(nr + 1, 0); a.n_digar = ndig.data();
     a.cnt = cnt.data(); a.first = first.data(); a.stride = stride; a.qual_counts = qc.data(); a.status = &status;
     for (long long g = 0; g < nr; ++g) count_read(a, g);
     for (int j = 0; j < 3; ++j) { long long run = 0; for (long long g = 0; g <= nr; ++g) { first[j * stride + g] = run; run += g < nr ? cnt[j * stride + g] : 0; } }

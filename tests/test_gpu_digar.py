@@ -110,5 +110,24 @@ def test_gpu_chunk_shaped_plan_and_chain_into_pileup(gpu, oracle):
                 site_alt_len=np.array([(0 if t[k] == 2 else o["digar_len"][k]) for k in sites] + [0], np.int32),
                 site_alt_off=np.array(aoff + [0], np.int64), site_alt=np.array(alt + [0], np.uint8))
     got = gpu.pileup_batch([pile])[0]
-    assert np.array_equal(got, T.pileup(oracle, "lcd_oracle_collect_cand_vars", pile))
+    want = T.pileup(oracle, "lcd_oracle_collect_cand_vars", pile)
+    assert np.array_equal(got, want)
+    # the same, in place: K2 / K3 on the difference lists the digar plan left in HBM (only site lists are uploaded)
+    site_keys = ("site_pos", "site_type", "site_ref_len", "site_alt_len", "site_alt_off", "site_alt")
+    empty = dict(n_sites=0, min_sv_len=50, var_cate=np.zeros(1, np.int32), **{k: np.zeros(1, pile[k].dtype) for k in site_keys})
+    sl = dict(n_sites=len(sites), min_sv_len=50, **{k: pile[k] for k in site_keys})
+    sl["var_cate"] = rng.choice(np.array([0x004, 0x008, 0x080, 0x100, 0x800], np.int32), size=len(sites) + 1, p=[0.5, 0.15, 0.15, 0.1, 0.1])
+    k2 = gpu.PileupOnDigarPlan(plan, [sl, empty, empty, empty])
+    k2.run(); k2.sync()
+    assert np.array_equal(k2.fetch()[0], want)
+    k3 = gpu.ProfileOnDigarPlan(plan, [sl, empty, empty, empty], [c["n_reads"] for c in cases])
+    k3.run(); k3.sync()
+    po = k3.fetch()[0]
+    prof_in = dict(pile, var_cate=sl["var_cate"], nreg_first=o["nreg_first"], n_nreg=o["n_nreg"], nreg_beg=o["nreg_beg"], nreg_end=o["nreg_end"])
+    rows = []
+    for r in range(d["n_reads"]):
+        ps, pe = int(po["prof_start"][r]), int(po["prof_end"][r]); n = max(0, pe - ps + 1) if ps >= 0 else 0; a0 = int(po["allele_off"][r])
+        rows.append((ps, pe, tuple(po["alleles"][a0:a0 + n].tolist()), tuple(po["alt_qi"][a0:a0 + n].tolist())))
+    assert rows == T.read_var_profile(oracle, "lcd_oracle_read_var_profile", prof_in)
+    assert sum(1 for row in rows for x in row[2] if x == 1) > len(sites) // 2
     assert int(got[:, 3].sum()) > len(sites) // 2          # (events of reads K1 dropped are not counted)
