@@ -409,7 +409,10 @@ def run_b200(args, rank, world):
     ealn = np.zeros(int(eoff[-1]) + 1, dtype=np.uint8)
 
     def e2e_step():
-        """host reads -> lcd_poa_batch -> consensus in host memory -> lcd_wfa_batch -> host CIGAR ops (all copies inside)"""
+        """host reads -> lcd_poa_batch -> consensus in host memory -> lcd_wfa_batch -> host CIGAR ops (all copies inside); the pileup
+        stages' inputs (host BAM fields of every chunk, 2.4 GB) are staged by a second host thread on the library's auxiliary stream
+        while the POA launch runs; K1 -> K2 -> K3 then run on them and return counters and profile rows to the host"""
+        pile_thread = threading.Thread(target=pileup_stage_thread); pile_thread.start()
         rc = L.lcd_poa_batch(C.c_int(n), _vp(wl.seqs), C.c_size_t(wl.seqs.size), _vp(wl.first), _vp(wl.n_reads),
                              _vp(wl.read_off), _vp(wl.read_len), C.c_int(len(wl.read_len)), _vp(ppar),
                              _vp(cons), _vp(wl.cons_off), None, None, None, _vp(pres))
@@ -429,7 +432,9 @@ def run_b200(args, rank, world):
         if L.lcd_edlib_batch(C.c_int(ne), _vp(eseqs), C.c_size_t(eseqs.size), _vp(eqo), _vp(eql), _vp(eto), _vp(etl), _vp(emode), _vp(ewant),
                              _vp(ealn), _vp(eoff), _vp(eres)):
             raise RuntimeError(L.lcd_gpu_last_error().decode())
-        pileup_e2e_step()
+        pile_thread.join()
+        if "error" in pile_res: raise pile_res.pop("error")
+        pileup_e2e_step(*pile_res.pop("plan"))
         if world > 1:
             gather_step(tl)
         return buf, ref_off, ref_len, txt_off, tl
@@ -460,12 +465,25 @@ def run_b200(args, rank, world):
     ps = PileupStage(args.mbp, args.tech, args.seed + rank, lcd.digar_batch, lcd.pileup_batch, pin=True)
     pile_res = {}
 
-    def pileup_e2e_step():
-        """host BAM fields -> K1 plan (H2D inside) -> K2 / K3 on the lists in HBM -> coverage counters and profile rows back on the host"""
-        dp = lcd.DigarPlan(ps.chunks); dp.run()
-        k2 = lcd.PileupOnDigarPlan(dp, ps.raw_sites); k2.run(); pile_res["counts"] = k2.fetch()
-        k3 = lcd.ProfileOnDigarPlan(dp, ps.var_sites, ps.n_reads); k3.run(); pile_res["prof"] = k3.fetch()
+    def pileup_e2e_step(dp, t_plan):
+        """K1 plan (its H2D copies were issued by the staging thread) -> K1 -> K2 / K3 on the lists in HBM -> coverage counters and profile rows on the host"""
+        t = [time.perf_counter()]
+        dp.run(); dp.sync(); t.append(time.perf_counter())
+        k2 = lcd.PileupOnDigarPlan(dp, ps.raw_sites); t.append(time.perf_counter()); k2.run(); pile_res["counts"] = k2.fetch(); t.append(time.perf_counter())
+        k3 = lcd.ProfileOnDigarPlan(dp, ps.var_sites, ps.n_reads); t.append(time.perf_counter()); k3.run(); pile_res["prof"] = k3.fetch(); t.append(time.perf_counter())
         for x in (k3, k2, dp): x.destroy()
+        t.append(time.perf_counter())
+        # ms: K1 plan incl. H2D (staging thread, overlapped with the POA launch), K1 run, K2 plan, K2 run+fetch, K3 plan, K3 run+fetch, destroy
+        pile_res["t"] = [round(1e3 * t_plan, 2)] + [round(1e3 * (b - a), 2) for a, b in zip(t, t[1:])]
+
+    def pileup_stage_thread():
+        try:
+            lcd.set_thread_stream(lcd.aux_stream())                  # H2D of the K1 inputs on the auxiliary stream, while the POA launch runs
+            t0 = time.perf_counter()
+            dp = lcd.DigarPlan(ps.chunks)
+            pile_res["plan"] = (dp, time.perf_counter() - t0)
+        except Exception as e:                                       # re-raised by the main thread
+            pile_res["error"] = e
 
     wseqs, po, pl, to, tl = e2e_step()                              # also yields the consensus sequences for the WFA plan
     digar_plan = lcd.DigarPlan(ps.chunks); digar_plan.run(); digar_plan.sync()
@@ -576,6 +594,7 @@ def run_b200(args, rank, world):
                 "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int16/int32", "data": "synthetic", "config": workload_config(args, wl, ps),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e_pileup_ms": pile_res.get("t"),
                 "gpu_launches": int(launches), "clocks": clocks,
                 "gather": (None if world == 1 else {"what": "per-chunk POA/WFA result records to rank 0 (NCCL gather, inside e2e)",
                                                     "bytes_per_step": int(gathered["bytes"])}),

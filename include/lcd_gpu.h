@@ -37,6 +37,12 @@ uint64_t lcd_gpu_launch_count(void);
 /* The library's CUDA stream (a cudaStream_t cast to void*) -- callers record their timing events
  * on it; NULL before lcd_gpu_init. */
 void *lcd_gpu_stream(void);
+/* A second stream of the library, and the per-host-thread default: plans created / run / fetched by a thread that passes no stream use
+ * the stream it set here (NULL: back to the library stream).  One host thread can so stage one stage's buffers (K1's H2D copies) while
+ * another thread's kernels (the POA launch) occupy the library stream.  The POA and WFA plans share the workspace pool and must all
+ * run on one stream. */
+void *lcd_gpu_aux_stream(void);
+void lcd_gpu_set_thread_stream(void *stream);
 
 /* ---------------------------------------------------------------- K6: WFA gap-affine(-2p)
  * Replaces wavefront_aligner_new + wavefront_align + reading wf_aligner->cigar, as called by

@@ -5,14 +5,14 @@ The product is the C-ABI shared library ``longcalld_b200/csrc/liblcd_gpu.so`` (d
 and the multi-GPU driver.  There is no CPU fallback: importing works anywhere, but every compute
 call raises ``LcdGpuError`` when the library or a B200 is missing.
 """
-from .capi import (LcdGpuError, lib, lib_path, build_library, init, shutdown, launch_count, stream,  # noqa: F401
+from .capi import (LcdGpuError, lib, lib_path, build_library, init, shutdown, launch_count, stream, aux_stream, set_thread_stream,  # noqa: F401
                    WfaParams, WfaResult, wfa_params, WfaPlan, wfa_batch,
                    HEUR_NONE, HEUR_ADAPTIVE, HEUR_ZDROP,
                    PoaParams, poa_params, PoaPlan, poa_batch, pack_poa,
                    MODE_NW, MODE_SHW, MODE_HW, EdlibPlan, edlib_batch, xgaps,
                    PhasePlan, phase_batch, PileupPlan, pileup_batch, profile_batch, DigarPlan, digar_batch, PileupOnDigarPlan, ProfileOnDigarPlan)
 
-__all__ = ["LcdGpuError", "lib", "lib_path", "build_library", "init", "shutdown", "launch_count", "stream",
+__all__ = ["LcdGpuError", "lib", "lib_path", "build_library", "init", "shutdown", "launch_count", "stream", "aux_stream", "set_thread_stream",
            "WfaParams", "WfaResult", "wfa_params", "WfaPlan", "wfa_batch",
            "HEUR_NONE", "HEUR_ADAPTIVE", "HEUR_ZDROP",
            "PoaParams", "poa_params", "PoaPlan", "poa_batch", "pack_poa",

@@ -97,6 +97,16 @@ def stream():
     return int(lib().lcd_gpu_stream() or 0)
 
 
+def aux_stream():
+    lib().lcd_gpu_aux_stream.restype = C.c_void_p
+    return int(lib().lcd_gpu_aux_stream() or 0)
+
+
+def set_thread_stream(s):
+    """Default stream of the calling host thread's plans (0 / None: the library stream)."""
+    lib().lcd_gpu_set_thread_stream(C.c_void_p(s or 0))
+
+
 def launch_count():
     return int(lib().lcd_gpu_launch_count())
 

@@ -214,25 +214,40 @@ __device__ void fill_read(const KernelArgs &a, long long g) {
 }
 
 // Base-quality histogram of read g (longcalld_copy_digar_read_buffers, src/bam_utils.c:90-103), for lane `lane` of `lanes`:
-// 16-byte aligned loads over the read's QUAL bytes, equal neighbours aggregated in registers before the shared-memory add.
+// 16-byte aligned loads over the read's QUAL bytes; equal neighbours are aggregated in registers (a whole word equal to the
+// running value costs one compare) before the shared-memory add.  Only the first and last 16-byte chunk need byte masks.
+__device__ __forceinline__ void hist_word(unsigned wd, int &cur, unsigned &run, unsigned *hist) {
+    if (wd == (unsigned)cur * 0x01010101u) { run += 4; return; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int b = (wd >> (8 * i)) & 255;
+        if (b != cur) { if (run) atomicAdd(hist + cur, run); cur = b; run = 0; }
+        ++run;
+    }
+}
 __device__ __forceinline__ void hist_read(const KernelArgs &a, long long g, int lane, int lanes, unsigned *hist) {
     const uint8_t *q = a.qual + a.qual_off[g]; const long long n = a.l_qseq[g];
+    if (n <= 0) return;
     const uintptr_t p0 = (uintptr_t)q, p1 = p0 + (uintptr_t)n;
-    const uintptr_t base = p0 & ~(uintptr_t)15;
-    for (uintptr_t p = base + 16 * (uintptr_t)lane; p < p1; p += 16 * (uintptr_t)lanes) {
+    const uintptr_t base = p0 & ~(uintptr_t)15, last = (p1 - 1) & ~(uintptr_t)15;
+    int cur = 0; unsigned run = 0;
+    for (uintptr_t p = base + 16 * (uintptr_t)lane; p <= last; p += 16 * (uintptr_t)lanes) {
         const uint4 v = *reinterpret_cast<const uint4 *>(p);
-        const unsigned w[4] = { v.x, v.y, v.z, v.w };
-        int cur = -1; unsigned run = 0;
+        if (p != base && p != last) {
+            hist_word(v.x, cur, run, hist); hist_word(v.y, cur, run, hist); hist_word(v.z, cur, run, hist); hist_word(v.w, cur, run, hist);
+        } else {
+            const unsigned w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const uintptr_t addr = p + i;
-            if (addr < p0 || addr >= p1) continue;
-            const int b = (w[i >> 2] >> ((i & 3) * 8)) & 255;
-            if (b == cur) ++run;
-            else { if (run) atomicAdd(hist + cur, run); cur = b; run = 1; }
+            for (int i = 0; i < 16; ++i) {
+                const uintptr_t addr = p + i;
+                if (addr < p0 || addr >= p1) continue;
+                const int b = (w[i >> 2] >> ((i & 3) * 8)) & 255;
+                if (b != cur) { if (run) atomicAdd(hist + cur, run); cur = b; run = 0; }
+                ++run;
+            }
         }
-        if (run) atomicAdd(hist + cur, run);
     }
+    if (run) atomicAdd(hist + cur, run);
 }
 
 } // namespace digar

@@ -170,7 +170,7 @@ struct DigarPlan : Plan {
         read_off[n] = tot_reads; stride = tot_reads + 1;
         auto pad = [](auto &v) { v.push_back(0); };
         pad(read_chunk); pad(h_active); pad(pos0); pad(rev); pad(pal); pad(ncig); pad(lq); pad(coff); pad(soff); pad(qoff);
-        cudaStream_t s = c.stream;
+        cudaStream_t s = cur_stream();
         if (d_chunks.upload(chunks.data(), n, s) || d_read_chunk.upload(read_chunk.data(), read_chunk.size(), s) || d_active.upload(h_active.data(), h_active.size(), s) ||
             d_pos0.upload(pos0.data(), pos0.size(), s) || d_rev.upload(rev.data(), rev.size(), s) || d_pal.upload(pal.data(), pal.size(), s) ||
             d_ncig.upload(ncig.data(), ncig.size(), s) || d_lq.upload(lq.data(), lq.size(), s) || d_coff.upload(coff.data(), coff.size(), s) ||

@@ -73,7 +73,7 @@ struct EdlibPlan : Plan {
             p.ws_off = top; top += p.ws_words;
         }
         if (n > begin) launches.push_back({begin, n});
-        cudaStream_t s = c.stream;
+        cudaStream_t s = cur_stream();
         if (d_seqs.upload(seqs, std::max<size_t>(seqs_len, 1), s)) return -1;
         if (d_problems.upload(problems.data(), n, s)) return -1;
         if (d_order.upload(order.data(), n, s)) return -1;

@@ -36,6 +36,7 @@ struct Context {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream = nullptr;  // created on first lcd_gpu_aux_stream()
     int32_t *pool = nullptr;          // int32 words
     size_t pool_words = 0;
     static constexpr int BITMAP_WORDS = 4096;     // overflow chunks in use (bit set), device memory
@@ -45,6 +46,10 @@ struct Context {
 };
 Context &ctx();
 int ensure_ready();
+// The stream a host thread's plans upload, run and fetch on when it passes no stream: the library stream, unless the thread chose
+// another one with lcd_gpu_set_thread_stream (e.g. the auxiliary stream, to overlap one stage's copies with another's kernels).
+cudaStream_t &thread_stream();
+inline cudaStream_t cur_stream() { cudaStream_t t = thread_stream(); return t ? t : ctx().stream; }
 
 struct Plan {
     virtual ~Plan() {}
@@ -59,23 +64,24 @@ struct Plan {
 // another stream; buffers are released when the plan is destroyed, after its last fetch has synchronised.
 template <typename T>
 struct DevBuf {
-    T *p = nullptr; size_t n = 0;
+    T *p = nullptr; size_t n = 0; cudaStream_t st = nullptr;     // st: the stream the buffer was allocated on (and is freed on)
     int alloc(size_t count) {
         free_(); n = count;
         if (count == 0) return 0;
-        cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), ctx().stream);
+        st = cur_stream();
+        cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), st);
         if (e != cudaSuccess) { set_error("cudaMallocAsync(%zu) -> %s", count * sizeof(T), cudaGetErrorString(e)); p = nullptr; return -1; }
         return 0;
     }
     int upload(const T *h, size_t count, cudaStream_t s) {
         if (alloc(count)) return -1;
         if (count == 0) return 0;
-        cudaError_t e = cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, ctx().stream);
+        cudaError_t e = cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, st);
         (void)s;
         if (e != cudaSuccess) { set_error("H2D -> %s", cudaGetErrorString(e)); return -1; }
         return 0;
     }
-    void free_() { if (p) cudaFreeAsync(p, ctx().stream); p = nullptr; n = 0; }
+    void free_() { if (p) cudaFreeAsync(p, st); p = nullptr; n = 0; }
     ~DevBuf() { free_(); }
 };
 
@@ -89,6 +95,6 @@ struct DigarView {
 };
 int digar_plan_view(Plan *plan, cudaStream_t s, DigarView *v);      // digar_kernel.cu
 
-inline cudaStream_t pick_stream(void *s) { return s ? (cudaStream_t)s : ctx().stream; }
+inline cudaStream_t pick_stream(void *s) { return s ? (cudaStream_t)s : cur_stream(); }
 
 } // namespace lcd

@@ -15,6 +15,7 @@ void set_error(const char *fmt, ...) {
 }
 
 Context &ctx() { static Context c; return c; }
+cudaStream_t &thread_stream() { static thread_local cudaStream_t s = nullptr; return s; }
 
 int ensure_ready() {
     if (ctx().ready) return 0;
@@ -31,6 +32,14 @@ int lcd_gpu_abi_version(void) { return LCD_GPU_ABI_VERSION; }
 const char *lcd_gpu_last_error(void) { return g_err[0] ? g_err : g_err_global; }
 uint64_t lcd_gpu_launch_count(void) { return ctx().launches; }
 void *lcd_gpu_stream(void) { return ctx().ready ? (void*)ctx().stream : nullptr; }
+void *lcd_gpu_aux_stream(void) {
+    Context &c = ctx();
+    if (!c.ready) return nullptr;
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (!c.aux_stream && cudaStreamCreateWithFlags(&c.aux_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("lcd_gpu_aux_stream: cudaStreamCreate failed"); return nullptr; }
+    return (void*)c.aux_stream;
+}
+void lcd_gpu_set_thread_stream(void *stream) { thread_stream() = (cudaStream_t)stream; }
 
 int lcd_gpu_init(int device, size_t pool_bytes) {
     Context &c = ctx();
@@ -84,6 +93,8 @@ void lcd_gpu_shutdown(void) {
     if (c.pool) cudaFree(c.pool);
     if (c.chunk_bitmap) cudaFree(c.chunk_bitmap);
     if (c.stream) cudaStreamDestroy(c.stream);
+    if (c.aux_stream) cudaStreamDestroy(c.aux_stream);
+    c.aux_stream = nullptr;
     c.pool = nullptr; c.chunk_bitmap = nullptr; c.stream = nullptr; c.ready = false;
 }
 

@@ -125,7 +125,7 @@ struct PhasePlan : Plan {
         }
         tot_alleles = (int64_t)alleles.size();
         alleles.push_back(0);
-        cudaStream_t s = c.stream;
+        cudaStream_t s = cur_stream();
         if (d_chunks.upload(chunks.data(), std::max(n, 1), s)) return -1;
         if (d_ordered.upload(ordered.data(), ordered.size(), s) || d_skipped.upload(skipped.data(), skipped.size(), s) ||
             d_pstart.upload(pstart.data(), pstart.size(), s) || d_pend.upload(pend.data(), pend.size(), s) ||

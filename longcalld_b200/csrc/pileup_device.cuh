@@ -17,7 +17,7 @@ namespace pileup {
 
 enum { CINS = 1, CDEL = 2, CEQUAL = 7, CDIFF = 8 };
 
-struct __align__(16) Chunk { int32_t n_sites, min_bq, min_sv_len, pad; int64_t site_off; int64_t alt_base; };   // alt_base: first digar_alt byte of the chunk (digar_alt_off is relative to it)
+struct __align__(16) Chunk { int32_t n_sites, min_bq, min_sv_len, pad; int64_t site_off; int64_t alt_base; int64_t salt_base; int64_t pad2; };   // alt_base / salt_base: first digar_alt / site_alt byte of the chunk (digar_alt_off / site_alt_off are relative to them)
 
 struct KernelArgs {
     const Chunk *chunks; int64_t n_reads_total;
@@ -42,7 +42,7 @@ struct KernelArgs {
 
 // exact_comp_var_site_ins (src/collect_var.c:1901-1935) of site s against the site made from event d
 // (make_var_site_from_digar, src/collect_var.c:1113-1121)
-__device__ __forceinline__ int comp_site_event(const KernelArgs &a, long long s, long long d, int min_sv_len, long long alt_base) {
+__device__ __forceinline__ int comp_site_event(const KernelArgs &a, long long s, long long d, int min_sv_len, long long alt_base, long long salt_base) {
     const int st = a.site_type[s], dt = a.digar_type[d];
     const long long ps = st == CDIFF ? a.site_pos[s] : a.site_pos[s] - 1, pd = dt == CDIFF ? a.digar_pos[d] : a.digar_pos[d] - 1;
     if (ps < pd) return -1;
@@ -57,7 +57,7 @@ __device__ __forceinline__ int comp_site_event(const KernelArgs &a, long long s,
     if (st == CDIFF || (st == CINS && s_alt < min_sv_len)) {
         if (s_alt < d_alt) return -1;
         if (s_alt > d_alt) return 1;
-        const uint8_t *x = a.site_alt + a.site_alt_off[s], *y = a.digar_alt + alt_base + a.digar_alt_off[d];
+        const uint8_t *x = a.site_alt + salt_base + a.site_alt_off[s], *y = a.digar_alt + alt_base + a.digar_alt_off[d];
         for (int i = 0; i < s_alt; ++i) if (x[i] != y[i]) return x[i] < y[i] ? -1 : 1;
         return 0;
     } else if (st == CINS) {
@@ -100,7 +100,7 @@ __device__ void process_read(const KernelArgs &a, long long g) {
     while (s < s_end && d < d_end) {
         const int dt = a.digar_type[d];
         if (dt == CEQUAL) { d++; continue; }
-        const int ret = comp_site_event(a, s, d, ch.min_sv_len, ch.alt_base);
+        const int ret = comp_site_event(a, s, d, ch.min_sv_len, ch.alt_base, ch.salt_base);
         if (ret < 0) { count(a, s, false, strand, 0); s++; }
         else if (ret == 0) {
             bool low = a.digar_low_qual[d] != 0;
@@ -198,7 +198,7 @@ __device__ void profile_read(const KernelArgs &a, long long g) {
             else {
                 ret = 0;
                 if (st == CDIFF || st == CINS) {
-                    const uint8_t *x = a.site_alt + a.site_alt_off[v], *y = a.digar_alt + ch.alt_base + a.digar_alt_off[d];
+                    const uint8_t *x = a.site_alt + ch.salt_base + a.site_alt_off[v], *y = a.digar_alt + ch.alt_base + a.digar_alt_off[d];
                     for (int i = 0; i < s_alt; ++i) if (x[i] != y[i]) { ret = x[i] < y[i] ? -1 : 1; break; }
                 }
             }

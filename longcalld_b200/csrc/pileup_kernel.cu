@@ -55,26 +55,24 @@ struct PileupPlan : Plan {
         n = n_; profile = want_profile;
         Context &c = ctx();
         DigarView v;
-        if (digar_plan_view(digar, c.stream, &v)) return -1;
+        if (digar_plan_view(digar, cur_stream(), &v)) return -1;
         if (v.n_chunks != n) { set_error("lcd_pileup: %d site lists for a digar plan of %d chunks", n, v.n_chunks); return -1; }
         if (n == 0) return 0;
-        std::vector<int32_t> read_chunk, stype, sref, salt, cate; std::vector<long long> spos, saoff; std::vector<uint8_t> site_alt;
+        std::vector<int32_t> read_chunk; std::vector<long long> salt_n(n, 0);
         chunks.resize(n); site_off.resize(n); read_off = v.read_off;
         tot_reads = v.n_reads_total; tot_events = v.tot_events;
+        long long tot_salt = 0;
         for (int i = 0; i < n; ++i) {
             const lcd_site_list_t &x = sl[i];
             if (x.n_sites < 0 || (want_profile && !x.var_cate)) { set_error("lcd_pileup: chunk %d has an invalid site list", i); return -1; }
             Chunk &k = chunks[i];
-            k.n_sites = x.n_sites; k.min_bq = v.min_bq[i]; k.min_sv_len = x.min_sv_len; k.pad = 0; k.site_off = tot_sites; k.alt_base = v.alt_base[i]; site_off[i] = tot_sites;
+            k.n_sites = x.n_sites; k.min_bq = v.min_bq[i]; k.min_sv_len = x.min_sv_len; k.pad = 0; k.site_off = tot_sites; k.alt_base = v.alt_base[i];
+            k.salt_base = tot_salt; k.pad2 = 0; site_off[i] = tot_sites;
             long long n_salt = 0;
             for (int s = 0; s < x.n_sites; ++s) if (x.site_type[s] == CDIFF || x.site_type[s] == CINS) n_salt = std::max<long long>(n_salt, x.site_alt_off[s] + x.site_alt_len[s]);
-            const long long sa0 = (long long)site_alt.size();
-            append(spos, x.site_pos, x.n_sites); append(stype, x.site_type, x.n_sites); append(sref, x.site_ref_len, x.n_sites);
-            append(salt, x.site_alt_len, x.n_sites); append(saoff, x.site_alt_off, x.n_sites, sa0); append(site_alt, x.site_alt, (size_t)n_salt);
-            if (want_profile) {
+            salt_n[i] = n_salt; tot_salt += n_salt;
+            if (want_profile)
                 for (int s = 0; s < x.n_sites; ++s) if (x.var_cate[s] == CAND_SOMATIC_VAR) { set_error("lcd_profile: chunk %d holds candidate somatic variants (-s); only the germline path is implemented on the GPU", i); return -1; }
-                append(cate, x.var_cate, x.n_sites);
-            }
             for (long long g = read_off[i]; g < read_off[i + 1]; ++g) read_chunk.push_back(i);
             tot_sites += x.n_sites;
         }
@@ -82,27 +80,37 @@ struct PileupPlan : Plan {
             row_off.assign(tot_reads + 1, 0); row_cap.assign(tot_reads + 1, 0); chunk_row0.assign(n + 1, 0);
             for (int i = 0; i < n; ++i) {
                 chunk_row0[i] = tot_rows;
-                const long long s0 = site_off[i], s1 = s0 + chunks[i].n_sites;
+                const long long *sp = (const long long *)sl[i].site_pos; const int32_t *st = sl[i].site_type; const long long ns = sl[i].n_sites;
                 for (long long g = read_off[i]; g < read_off[i + 1]; ++g) {
                     row_off[g] = tot_rows;
                     if (!v.h_active[g]) continue;
-                    const long long v0 = first_site(spos.data(), stype.data(), s0, s1, v.h_beg[g]);
-                    const long long v1 = row_end_site(spos.data(), stype.data(), v0, s1, v.h_end[g]);
+                    const long long v0 = first_site(sp, st, 0, ns, v.h_beg[g]);
+                    const long long v1 = row_end_site(sp, st, v0, ns, v.h_end[g]);
                     row_cap[g] = (int32_t)(v1 - v0); tot_rows += v1 - v0;
                 }
             }
             chunk_row0[n] = tot_rows;
         }
-        auto pad = [](auto &x) { x.push_back(0); };
-        pad(read_chunk); pad(spos); pad(stype); pad(sref); pad(salt); pad(saoff); pad(site_alt);
-        cudaStream_t s = c.stream;
-        if (d_chunks.upload(chunks.data(), n, s) || d_read_chunk.upload(read_chunk.data(), read_chunk.size(), s) || d_spos.upload(spos.data(), spos.size(), s) ||
-            d_stype.upload(stype.data(), stype.size(), s) || d_sref.upload(sref.data(), sref.size(), s) || d_salt.upload(salt.data(), salt.size(), s) ||
-            d_saoff.upload(saoff.data(), saoff.size(), s) || d_site_alt.upload(site_alt.data(), site_alt.size(), s)) return -1;
+        read_chunk.push_back(0);
+        cudaStream_t s = cur_stream();
+        if (d_chunks.upload(chunks.data(), n, s) || d_read_chunk.upload(read_chunk.data(), read_chunk.size(), s)) return -1;
+        // the site lists go straight from the caller's arrays into their slice of the device arrays (offsets stay chunk-relative)
+        if (d_spos.alloc(tot_sites + 1) || d_stype.alloc(tot_sites + 1) || d_sref.alloc(tot_sites + 1) || d_salt.alloc(tot_sites + 1) || d_saoff.alloc(tot_sites + 1) ||
+            d_site_alt.alloc(tot_salt + 1) || (want_profile && d_cate.alloc(tot_sites + 1))) return -1;
+        for (int i = 0; i < n; ++i) {
+            const lcd_site_list_t &x = sl[i]; const long long o = site_off[i]; const size_t ns = (size_t)x.n_sites;
+            if (!ns) continue;
+            LCD_CUDA_OK(cudaMemcpyAsync(d_spos.p + o, x.site_pos, sizeof(long long) * ns, cudaMemcpyHostToDevice, s));
+            LCD_CUDA_OK(cudaMemcpyAsync(d_stype.p + o, x.site_type, sizeof(int32_t) * ns, cudaMemcpyHostToDevice, s));
+            LCD_CUDA_OK(cudaMemcpyAsync(d_sref.p + o, x.site_ref_len, sizeof(int32_t) * ns, cudaMemcpyHostToDevice, s));
+            LCD_CUDA_OK(cudaMemcpyAsync(d_salt.p + o, x.site_alt_len, sizeof(int32_t) * ns, cudaMemcpyHostToDevice, s));
+            LCD_CUDA_OK(cudaMemcpyAsync(d_saoff.p + o, x.site_alt_off, sizeof(long long) * ns, cudaMemcpyHostToDevice, s));
+            if (salt_n[i]) LCD_CUDA_OK(cudaMemcpyAsync(d_site_alt.p + chunks[i].salt_base, x.site_alt, (size_t)salt_n[i], cudaMemcpyHostToDevice, s));
+            if (want_profile) LCD_CUDA_OK(cudaMemcpyAsync(d_cate.p + o, x.var_cate, sizeof(int32_t) * ns, cudaMemcpyHostToDevice, s));
+        }
         if (d_counts.alloc(8 * (size_t)tot_sites + 8)) return -1;
         if (want_profile) {
-            pad(cate);
-            if (d_cate.upload(cate.data(), cate.size(), s) || d_row_off.upload(row_off.data(), row_off.size(), s) || d_row_cap.upload(row_cap.data(), row_cap.size(), s)) return -1;
+            if (d_row_off.upload(row_off.data(), row_off.size(), s) || d_row_cap.upload(row_cap.data(), row_cap.size(), s)) return -1;
             if (d_pstart.alloc(tot_reads + 1) || d_pend.alloc(tot_reads + 1) || d_aoff.alloc(tot_reads + 1) || d_alleles.alloc(tot_rows + 16) ||
                 d_altqi.alloc(tot_rows + 16) || d_status.alloc(1)) return -1;
         }
@@ -128,7 +136,7 @@ struct PileupPlan : Plan {
             const lcd_pileup_input_t &x = in[i];
             if (x.n_reads < 0 || x.n_sites < 0) { set_error("lcd_pileup: chunk %d has negative sizes", i); return -1; }
             Chunk &k = chunks[i]; read_off[i] = tot_reads;
-            k.n_sites = x.n_sites; k.min_bq = x.min_bq; k.min_sv_len = x.min_sv_len; k.pad = 0; k.site_off = tot_sites; k.alt_base = 0; site_off[i] = tot_sites;
+            k.n_sites = x.n_sites; k.min_bq = x.min_bq; k.min_sv_len = x.min_sv_len; k.pad = 0; k.site_off = tot_sites; k.alt_base = 0; k.salt_base = 0; k.pad2 = 0; site_off[i] = tot_sites;
             long long n_ev = 0, n_q = 0, n_alt = 0, n_salt = 0;
             for (int r = 0; r < x.n_reads; ++r) {
                 if (x.n_digar[r] < 0 || x.digar_first[r] < 0) { set_error("lcd_pileup: chunk %d read %d has an invalid event range", i, r); return -1; }
@@ -187,7 +195,7 @@ struct PileupPlan : Plan {
         auto pad = [](auto &v) { v.push_back(0); };
         pad(read_chunk); pad(active); pad(beg); pad(end); pad(rev); pad(dfirst); pad(ndig); pad(qoff); pad(qual); pad(dpos); pad(dtype); pad(dlen); pad(dqi);
         pad(dlow); pad(daoff); pad(dalt); pad(spos); pad(stype); pad(sref); pad(salt); pad(saoff); pad(site_alt);
-        cudaStream_t s = c.stream;
+        cudaStream_t s = cur_stream();
         if (d_chunks.upload(chunks.data(), n, s) || d_read_chunk.upload(read_chunk.data(), read_chunk.size(), s) || d_active.upload(active.data(), active.size(), s) ||
             d_beg.upload(beg.data(), beg.size(), s) || d_end.upload(end.data(), end.size(), s) || d_rev.upload(rev.data(), rev.size(), s) ||
             d_dfirst.upload(dfirst.data(), dfirst.size(), s) || d_ndig.upload(ndig.data(), ndig.size(), s) || d_qoff.upload(qoff.data(), qoff.size(), s) ||
@@ -239,10 +247,9 @@ struct PileupPlan : Plan {
 
     int fetch(cudaStream_t s, lcd_pileup_output_t *out) {
         if (n == 0) return 0;
-        h_counts.resize(8 * (size_t)tot_sites + 8);
-        if (tot_sites) LCD_CUDA_OK(cudaMemcpyAsync(h_counts.data(), d_counts.p, sizeof(int32_t) * 8 * (size_t)tot_sites, cudaMemcpyDeviceToHost, s));
+        for (int i = 0; i < n; ++i)       // straight into the caller's arrays
+            if (chunks[i].n_sites) LCD_CUDA_OK(cudaMemcpyAsync(out[i].site_counts, d_counts.p + 8 * site_off[i], sizeof(int32_t) * 8 * (size_t)chunks[i].n_sites, cudaMemcpyDeviceToHost, s));
         LCD_CUDA_OK(cudaStreamSynchronize(s));
-        for (int i = 0; i < n; ++i) if (chunks[i].n_sites) memcpy(out[i].site_counts, h_counts.data() + 8 * site_off[i], sizeof(int32_t) * 8 * (size_t)chunks[i].n_sites);
         return 0;
     }
 

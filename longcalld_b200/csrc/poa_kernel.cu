@@ -153,7 +153,7 @@ struct PoaPlan : Plan {
         order_all.resize(n);
         for (int i = 0; i < n; ++i) order_all[i] = i;
         std::sort(order_all.begin(), order_all.end(), [&](int32_t x, int32_t y) { return work[x] != work[y] ? work[x] > work[y] : x < y; });
-        cudaStream_t s = c.stream;
+        cudaStream_t s = cur_stream();
         if (d_seqs.upload(seqs, std::max<size_t>(seqs_len, 1), s)) return -1;
         if (d_problems.upload(problems.data(), n, s)) return -1;
         if (d_read_off.upload(read_off, n_total_reads, s)) return -1;
@@ -287,7 +287,7 @@ struct PoaPlan : Plan {
             if (tot) {
                 if (d_pack.n < tot + 16 && d_pack.alloc(tot + 16 + tot / 8)) return -1;
                 if (d_pack_off.n < (size_t)n + 1 && d_pack_off.alloc(n + 1)) return -1;
-                LCD_CUDA_OK(cudaStreamSynchronize(c.stream));                 // allocation ordered before use on s
+                LCD_CUDA_OK(cudaStreamSynchronize(cur_stream()));                 // allocation ordered before use on s
                 LCD_CUDA_OK(cudaMemcpyAsync(d_pack_off.p, pack_off.data(), sizeof(unsigned long long) * (n + 1), cudaMemcpyHostToDevice, s));
                 poa_gather_cons_kernel<<<c.sm_count * 4, 256, 0, s>>>(d_cons.p, d_problems.p, d_results.p, d_pack_off.p, d_pack.p, n);
                 LCD_CUDA_OK(cudaGetLastError());

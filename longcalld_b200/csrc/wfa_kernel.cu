@@ -169,7 +169,7 @@ struct WfaPlan : Plan {
         n_small = (int)small.size(); n_large = (int)large.size();
         for (int32_t i : small) cap_small = std::max(cap_small, problems[i].s_cap);
         for (int32_t i : large) cap_large = std::max(cap_large, problems[i].s_cap);
-        cudaStream_t s = c.stream;
+        cudaStream_t s = cur_stream();
         if (d_seqs.upload(packed.data(), packed.size(), s)) return -1;
         if (d_problems.upload(problems.data(), problems.size(), s)) return -1;
         if (d_order_small.upload(small.data(), small.size(), s)) return -1;

@@ -367,6 +367,10 @@ def digar_chunks_30x(n_chunks, tech="hifi", seed=11, chunk_len=500000, read_mean
         vlen = np.where(vtype == X, 1, rng.integers(1, 9, len(vpos)))
         vhap = rng.integers(1, 4, len(vpos))                         # carried by hap 1, hap 2, or both
         valt = rng.integers(0, 4, (len(vpos), 8)).astype(np.uint8)
+        # sequencing errors: 80 % recur at homopolymer-like hot spots (a fixed 1-bp insertion or deletion per spot, one per 250 bp),
+        # 20 % fall anywhere -- so a chunk has a few thousand distinct candidate sites, as real data does
+        hpos = np.sort(rng.choice(np.arange(reg_beg - read_mean, reg_end + read_mean, 5), size=(chunk_len + 2 * read_mean) // 250, replace=False))
+        htype = rng.choice(np.array([I, D]), size=len(hpos)); halt = rng.integers(0, 4, (len(hpos), 8)).astype(np.uint8)
         n_reads = int(coverage * (chunk_len + read_mean) / read_mean)
         starts = np.sort(rng.integers(reg_beg - read_mean, reg_end, n_reads))
         lens = np.clip(rng.normal(read_mean, read_mean / 5, n_reads).astype(np.int64), 2000, 3 * read_mean) if not ont else \
@@ -379,11 +383,14 @@ def digar_chunks_30x(n_chunks, tech="hifi", seed=11, chunk_len=500000, read_mean
             lo, hi = np.searchsorted(vpos, [beg + 20, beg + L - 20])
             m = (vhap[lo:hi] & hap) != 0
             p1, t1, l1 = vpos[lo:hi][m], vtype[lo:hi][m], vlen[lo:hi][m]; a1 = valt[lo:hi][m]
-            ne = rng.poisson(err * L)
+            ne_all = rng.poisson(err * L); nh = int(rng.binomial(ne_all, 0.8)); ne = ne_all - nh
             p2 = rng.integers(beg + 20, beg + L - 20, ne); u = rng.random(ne)
-            t2 = np.where(u < (0.4 if ont else 0.2), X, np.where(u < (0.65 if ont else 0.6), I, D)); l2 = np.where(t2 == X, 1, rng.integers(1, 3, ne))
+            t2 = np.where(u < (0.6 if ont else 0.5), X, np.where(u < (0.8 if ont else 0.75), I, D)); l2 = np.where(t2 == X, 1, rng.integers(1, 3, ne))
             a2 = rng.integers(0, 4, (ne, 8)).astype(np.uint8)
-            p, t, l, a = np.concatenate([p1, p2]), np.concatenate([t1, t2]), np.concatenate([l1, l2]), np.concatenate([a1, a2])
+            hl, hh = np.searchsorted(hpos, [beg + 20, beg + L - 20])
+            hi_ = np.unique(rng.integers(hl, max(hl + 1, hh), nh)) if hh > hl else np.zeros(0, np.int64)
+            p, t, l, a = (np.concatenate([p1, p2, hpos[hi_]]), np.concatenate([t1, t2, htype[hi_]]), np.concatenate([l1, l2, np.ones(len(hi_), np.int64)]),
+                          np.concatenate([a1, a2, halt[hi_]]))
             o = np.argsort(p, kind="stable"); p, t, l, a = p[o], t[o], l[o], a[o]
             ref_span = np.where(t == I, 0, l)
             keep = np.ones(len(p), bool)

@@ -7,7 +7,7 @@
 using namespace lcd::pileup;
 
 extern "C" int emu_collect_cand_vars(const lcd_pileup_input_t *in, lcd_pileup_output_t *out) {
-    Chunk c; c.n_sites = in->n_sites; c.min_bq = in->min_bq; c.min_sv_len = in->min_sv_len; c.pad = 0; c.site_off = 0; c.alt_base = 0;
+    Chunk c; c.n_sites = in->n_sites; c.min_bq = in->min_bq; c.min_sv_len = in->min_sv_len; c.pad = 0; c.site_off = 0; c.alt_base = 0; c.salt_base = 0; c.pad2 = 0;
     std::vector<int32_t> read_chunk(in->n_reads + 1, 0);
     std::vector<uint8_t> active(in->n_reads + 1, 0);
     for (int i = 0; i < in->n_reads; ++i) { const int r = in->ordered_read_ids[i]; if (!in->is_skipped[r]) active[r] = 1; }
@@ -26,7 +26,7 @@ extern "C" int emu_collect_cand_vars(const lcd_pileup_input_t *in, lcd_pileup_ou
 
 // K3: profile_read over one chunk, rows laid out as the host plan does (first_site / row_end_site)
 extern "C" int emu_read_var_profile(const lcd_pileup_input_t *in, const lcd_profile_extra_t *ex, lcd_profile_output_t *out) {
-    Chunk c; c.n_sites = in->n_sites; c.min_bq = in->min_bq; c.min_sv_len = in->min_sv_len; c.pad = 0; c.site_off = 0; c.alt_base = 0;
+    Chunk c; c.n_sites = in->n_sites; c.min_bq = in->min_bq; c.min_sv_len = in->min_sv_len; c.pad = 0; c.site_off = 0; c.alt_base = 0; c.salt_base = 0; c.pad2 = 0;
     const int nr = in->n_reads;
     std::vector<int32_t> read_chunk(nr + 1, 0), row_cap(nr + 1, 0);
     std::vector<uint8_t> active(nr + 1, 0);
