@@ -172,6 +172,14 @@ typedef struct {
 } lcd_digar_output_t;
 int lcd_oracle_collect_digar_eqx(const lcd_digar_input_t *in, lcd_digar_output_t *out);
 
+/* ---- pileup scan, step 1.2: sorted unique candidate sites (src/collect_var.c:1209-1254) ---------------------------- */
+typedef struct {
+    int64_t *site_pos; int32_t *site_type, *site_ref_len, *site_alt_len;   /* var_site_t, in collect_all_cand_var_sites' order */
+    int64_t *site_src;                 /* a record (index into the digar_* arrays) whose alt bases are the site's alt_seq */
+    int64_t cap, n_sites;
+} lcd_sites_output_t;
+int lcd_oracle_collect_sites(const lcd_pileup_input_t *in, int64_t reg_beg, int64_t reg_end, lcd_sites_output_t *out);
+
 #ifdef __cplusplus
 }
 #endif

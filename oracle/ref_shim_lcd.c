@@ -310,3 +310,41 @@ int ref_collect_digar_eqx(const lcd_digar_input_t *in, lcd_digar_output_t *out) 
     ref_digar_core(job, in);
     return ref_digar_finish(job, in, out);
 }
+
+
+int collect_all_cand_var_sites(const call_var_opt_t *opt, bam_chunk_t *chunk, var_site_t **var_sites);   /* src/collect_var.c:1209 (no prototype in the headers) */
+/* collect_all_cand_var_sites (src/collect_var.c:1209) on a synthetic chunk: digar_t records around the flat arrays */
+int ref_collect_sites(const lcd_pileup_input_t *in, int64_t reg_beg, int64_t reg_end, lcd_sites_output_t *out) {
+    const int nr = in->n_reads;
+    call_var_opt_t opt; memset(&opt, 0, sizeof(opt));
+    opt.min_bq = in->min_bq; opt.min_sv_len = in->min_sv_len;
+    bam_chunk_t chunk; memset(&chunk, 0, sizeof(chunk));
+    chunk.n_reads = chunk.m_reads = nr; chunk.tid = 0; chunk.tname = (char*)"chr"; chunk.reg_beg = reg_beg; chunk.reg_end = reg_end;
+    chunk.ordered_read_ids = (int*)malloc(sizeof(int) * (nr + 1));
+    chunk.is_skipped = (uint8_t*)malloc(nr + 1);
+    chunk.digars = (digar_t*)calloc(nr + 1, sizeof(digar_t));
+    for (int r = 0; r < nr; ++r) {
+        chunk.ordered_read_ids[r] = in->ordered_read_ids[r]; chunk.is_skipped[r] = in->is_skipped[r];
+        digar_t *g = chunk.digars + r;
+        g->n_digar = g->m_digar = in->n_digar[r];
+        g->digars = (digar1_t*)calloc(g->n_digar + 1, sizeof(digar1_t));
+        for (int k = 0; k < g->n_digar; ++k) {
+            const int64_t d = in->digar_first[r] + k; digar1_t *x = g->digars + k;
+            x->pos = in->digar_pos[d]; x->type = in->digar_type[d]; x->len = in->digar_len[d]; x->qi = in->digar_qi[d]; x->is_low_qual = in->digar_low_qual[d];
+            x->alt_seq = (x->type == BAM_CDIFF || x->type == BAM_CINS) ? (uint8_t*)(in->digar_alt + in->digar_alt_off[d]) : NULL;
+        }
+    }
+    var_site_t *sites = NULL;
+    const int n = collect_all_cand_var_sites(&opt, &chunk, &sites);
+    int rc = 0;
+    out->n_sites = n;
+    if (n > out->cap) rc = -3;
+    for (int i = 0; i < n && !rc; ++i) {
+        out->site_pos[i] = sites[i].pos; out->site_type[i] = sites[i].var_type; out->site_ref_len[i] = sites[i].ref_len; out->site_alt_len[i] = sites[i].alt_len;
+        out->site_src[i] = sites[i].alt_seq ? (int64_t)(sites[i].alt_seq - in->digar_alt) : -1;     /* offset of the alt bases in digar_alt (not a record index) */
+    }
+    if (sites) free(sites);
+    for (int r = 0; r < nr; ++r) free(chunk.digars[r].digars);
+    free(chunk.digars); free(chunk.ordered_read_ids); free(chunk.is_skipped);
+    return rc;
+}

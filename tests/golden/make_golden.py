@@ -5,6 +5,7 @@
                       match==0 goldens in tests/wfa.utest.check/: affine, affine2p, p0-p2,
                       wfapt0/1) -- pins the recurrence, the backtrace tie-breaks and wf-adaptive.
   digar_lcd.json.gz   digests of the UNMODIFIED reference =/X difference-list pass (collect_digar_from_eqx_cigar) on seeded chunks.
+  sites_lcd.json.gz   candidate-site lists of the UNMODIFIED reference (collect_all_cand_var_sites) on seeded chunks.
   pileup_lcd.json.gz  outputs of the UNMODIFIED reference per-site coverage pass (collect_cand_vars) on seeded chunks.
   phase_lcd.json.gz   outputs of the UNMODIFIED reference read->haplotype assignment / phasing on seeded chunks.
   edlib_lcd.json.gz   outputs of the UNMODIFIED reference edlib (NW / HW, path) on seeded inputs.
@@ -189,9 +190,30 @@ def digar_lcd():
     return {"cases": cases}
 
 
+def sites_lcd():
+    """Sorted unique candidate sites of the UNMODIFIED collect_all_cand_var_sites (src/collect_var.c:1209, via oracle/_ref/libref_shim.so)
+    on seeded chunks: [pos, type, ref_len, alt_len, alt bytes (hex)] per site."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from longcalld_b200 import synth
+    ref = T.ref_lib()
+    rng = np.random.default_rng(20261022)
+    cases = []
+    for it in range(20):
+        d = synth.make_pileup_chunk(rng, ref_len=int(rng.choice([600, 3000])), n_reads=int(rng.choice([1, 8, 40])),
+                                    read_len=(200, 500) if it % 3 == 0 else (800, 2500), var_every=int(rng.choice([40, 150])), err_every=int(rng.choice([60, 800])),
+                                    min_sv_len=int(rng.choice([30, 50])))
+        lo, hi = int(d["read_beg"].min()), int(d["read_end"].max())
+        reg = [-1, -1] if it % 4 == 0 else [lo + (hi - lo) // 6, hi - (hi - lo) // 6]
+        sites = T.collect_sites(ref, "ref_collect_sites", d, reg[0], reg[1], src_is_offset=True)
+        keys = [k for k, _ in T.PILEUP_IN_FIELDS if not k.startswith("site_")]
+        cases.append({"in": {**{k: np.asarray(d[k]).reshape(-1).tolist() for k in keys}, "n_reads": d["n_reads"], "min_bq": d["min_bq"], "min_sv_len": d["min_sv_len"]},
+                      "reg": reg, "sites": [[p_, t_, r_, a_, alt.hex()] for p_, t_, r_, a_, alt in sites]})
+    return {"cases": cases}
+
+
 def main():
     only = sys.argv[1:]
-    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd), ("poa_lcd", poa_lcd), ("edlib_lcd", edlib_lcd), ("phase_lcd", phase_lcd), ("pileup_lcd", pileup_lcd), ("digar_lcd", digar_lcd)):
+    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd), ("poa_lcd", poa_lcd), ("edlib_lcd", edlib_lcd), ("phase_lcd", phase_lcd), ("pileup_lcd", pileup_lcd), ("digar_lcd", digar_lcd), ("sites_lcd", sites_lcd)):
         if only and name not in only:
             continue
         path = os.path.join(HERE, name + ".json.gz")

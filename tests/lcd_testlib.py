@@ -375,3 +375,39 @@ def digar_case_to_json(d):
     j = {k: (float(d[k]) if isinstance(d[k], float) else int(d[k])) for k, _ in DIGAR_SCALARS}
     for k, t in DIGAR_IN_FIELDS: j[k] = np.asarray(d[k]).tolist()
     return j
+
+
+# ----------------------------------------------------------------------------- candidate-site list (a3) helpers
+class SitesOutput(C.Structure):
+    _fields_ = [("site_pos", C.c_void_p), ("site_type", C.c_void_p), ("site_ref_len", C.c_void_p), ("site_alt_len", C.c_void_p), ("site_src", C.c_void_p),
+                ("cap", C.c_int64), ("n_sites", C.c_int64)]
+
+
+def collect_sites(lib, fn, d, reg_beg, reg_end, src_is_offset=False):
+    """Run an implementation of collect_all_cand_var_sites over a chunk in lcd_pileup_input_t layout (sites unused)
+    -> [(pos, type, ref_len, alt_len, alt bytes)] in output order."""
+    keep = {k: np.ascontiguousarray(d[k], dtype=t) for k, t in PILEUP_IN_FIELDS}
+    inp = PileupInput(d["n_reads"], 0, d["min_bq"], d["min_sv_len"], *[keep[k].ctypes.data for k, _ in PILEUP_IN_FIELDS])
+    cap = int(np.asarray(d["n_digar"][:d["n_reads"]]).sum()) + 8
+    pos, typ, rl, al, src = np.zeros(cap, np.int64), np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int64)
+    out = SitesOutput(pos.ctypes.data, typ.ctypes.data, rl.ctypes.data, al.ctypes.data, src.ctypes.data, cap, 0)
+    getattr(lib, fn).argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    rc = getattr(lib, fn)(C.byref(inp), reg_beg, reg_end, C.byref(out))
+    assert rc == 0, rc
+    return sites_view(d, pos, typ, rl, al, src, out.n_sites, src_is_offset)
+
+
+def sites_view(d, pos, typ, rl, al, src, n, src_is_offset=False):
+    res = []
+    for i in range(int(n)):
+        a0 = int(src[i]) if src_is_offset else int(d["digar_alt_off"][int(src[i])])
+        alt = bytes(np.asarray(d["digar_alt"][a0:a0 + int(al[i])], np.uint8)) if typ[i] != 2 else b""
+        res.append((int(pos[i]), int(typ[i]), int(rl[i]), int(al[i]), alt))
+    return res
+
+
+def sites_case_from_json(c):
+    d = {k: (np.array(v, dtype=dict(PILEUP_IN_FIELDS)[k]) if k in dict(PILEUP_IN_FIELDS) else v) for k, v in c["in"].items()}
+    for k, t in PILEUP_IN_FIELDS:
+        if k.startswith("site_"): d[k] = np.zeros(1, t)
+    return d, c["reg"], [(p_, t_, r_, a_, bytes.fromhex(h)) for p_, t_, r_, a_, h in c["sites"]]
