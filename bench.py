@@ -156,13 +156,12 @@ class Workload:
 
 
 class PileupStage:
-    """K1 -> K2 -> K3 of the same batch: mbp / 0.5 region chunks (500 kb, 30x, ~1 050 reads of ~15 kb with =/X CIGARs), tiled
-    from a template of <= 10 distinct chunks.  The candidate-site list (a3) and the classification (a5) are not on the GPU
-    yet: they are derived once at set-up from K1's / K2's results (synth.sites_from_digar_output / classify_sites) and are
-    not timed in either arm."""
+    """K1 -> K1b -> K2 -> K3 of the same batch: mbp / 0.5 region chunks (500 kb, 30x, ~1 050 reads of ~15 kb with =/X CIGARs), tiled
+    from a template of <= 10 distinct chunks.  The classification (a5) is not on the GPU yet: the classified variants K3 runs on are
+    derived once at set-up from K2's counters (synth.classify_sites) and that step is not timed in either arm."""
     N_TEMPLATE = 10
 
-    def __init__(self, mbp, tech, seed, digar_fn, pileup_fn, pin=False):
+    def __init__(self, mbp, tech, seed, digar_fn, sites_fn, pileup_fn, pin=False):
         from longcalld_b200 import synth
         self.n_chunks = max(1, int(round(mbp / 0.5)))
         nt = min(self.N_TEMPLATE, self.n_chunks)
@@ -173,22 +172,26 @@ class PileupStage:
                 for k in ("cigar", "bseq", "qual"):
                     t = torch.from_numpy(d[k]).pin_memory(); d["_pin_" + k] = t; d[k] = t.numpy()
         outs = digar_fn(self.template)
-        raw = [synth.sites_from_digar_output(d, o) for d, o in zip(self.template, outs)]
+        self.regs = [(int(d["reg_beg"]), int(d["reg_end"])) for d in self.template]
+        bare = [synth.pileup_input_from_digar(d, o, synth.empty_site_list()) for d, o in zip(self.template, outs)]      # K1b's input: the lists without sites
+        raw = sites_fn(bare, outs, self.regs)
         piles = [synth.pileup_input_from_digar(d, o, s) for d, o, s in zip(self.template, outs, raw)]
         counts = pileup_fn(piles)
         var = [synth.classify_sites(s, c) for s, c in zip(raw, counts)]
         profs = [synth.pileup_input_from_digar(d, o, s) for d, o, s in zip(self.template, outs, var)]
         tile = lambda xs: [xs[i % nt] for i in range(self.n_chunks)]
         self.chunks, self.raw_sites, self.var_sites, self.piles, self.profs = tile(self.template), tile(raw), tile(var), tile(piles), tile(profs)
+        self.bare, self.regs = tile(bare), tile(self.regs)
         self.n_reads = [d["n_reads"] for d in self.chunks]
         self.read_bases = int(sum(int(d["l_qseq"].sum()) for d in self.chunks))
         self.cigar_ops = int(sum(int(d["n_cigar"].sum()) for d in self.chunks))
         self.records = int(sum(int(outs[i % nt]["n_digar_total"]) for i in range(self.n_chunks)))
         self.n_raw_sites = int(sum(s["n_sites"] for s in self.raw_sites)); self.n_vars = int(sum(s["n_sites"] for s in self.var_sites))
         self.h2d = int(sum(d["cigar"].nbytes + d["bseq"].nbytes + d["qual"].nbytes + 46 * d["n_reads"] for d in self.chunks) +
-                       sum(sum(s[k].nbytes for k in ("site_pos", "site_type", "site_ref_len", "site_alt_len", "site_alt_off", "site_alt")) for s in self.raw_sites + self.var_sites))
+                       sum(sum(s[k].nbytes for k in ("site_pos", "site_type", "site_ref_len", "site_alt_len", "site_alt_off", "site_alt")) for s in self.var_sites))
         # algorithmic bytes: K1 1.5 B per read base + 4 B per CIGAR op in, 32 B per record out; K2 / K3 32 B per record + 24 B per site (+ 8 B per profile entry)
         self.k1_bytes = int(1.5 * self.read_bases + 4 * self.cigar_ops + 32 * self.records)
+        self.k1b_bytes = int(14 * self.records + 36 * self.n_raw_sites)      # K1b: position, type, length and quality flag of every record in, a 36-byte site record out
         self.k2_bytes = int(32 * self.records + 24 * self.n_raw_sites)
         self.k3_bytes = int(32 * self.records + 24 * self.n_vars)
 
@@ -262,21 +265,32 @@ def ref_pileup_fns(lib, n_threads):
         if lib.ref_digar_batch(C.c_int(len(chunks)), ins, outs, C.c_int(n_threads), None): raise RuntimeError("ref_digar_batch failed")
         return capi._digar_finish(outs, results)
 
+    def sites(bare, digar_outs, regs):
+        from longcalld_b200 import synth
+        ins, _, keep, _ = capi._pileup_structs(bare)
+        souts, res = capi._sites_outputs([int(np.isin(np.asarray(d["digar_type"]), (1, 2, 8)).sum()) for d in bare])
+        reg = np.array(regs, np.int64).reshape(-1)
+        if lib.ref_sites_batch(C.c_int(len(bare)), ins, _vp(reg), souts, C.c_int(n_threads), None): raise RuntimeError("ref_sites_batch failed")
+        return [synth.site_list_from_sites(o, st, src_is_offset=True) for o, st in zip(digar_outs, capi._sites_finish(souts, res))]
+
     def pileup(piles):
         ins, outs, keep, results = capi._pileup_structs(piles)
         if lib.ref_pileup_batch(C.c_int(len(piles)), ins, outs, C.c_int(n_threads)): raise RuntimeError("ref_pileup_batch failed")
         return [r[:d["n_sites"]] for r, d in zip(results, piles)]
-    return digar, pileup
+    return digar, sites, pileup
 
 
 def reference_pileup_step(lib, ps, k, n_threads):
-    """K1 + K2 + K3 of the reference on the first k chunks of the batch; returns seconds."""
+    """K1 + K1b + K2 + K3 of the reference on the first k chunks of the batch; returns seconds (total, K1, K2, K3, K1b)."""
     from longcalld_b200 import capi
     chunks, piles, profs = ps.chunks[:k], ps.piles[:k], ps.profs[:k]
     ins, keep = capi._digar_inputs(chunks)
     outs, results = capi._digar_outputs(chunks, capi.digar_capacity(ins, k))
     pins, pouts, pkeep, pres = capi._pileup_structs(piles)
     fins, _, fkeep, _ = capi._pileup_structs(profs)
+    bins, _, bkeep, _ = capi._pileup_structs(ps.bare[:k])
+    souts, sres = capi._sites_outputs([int(s["n_sites"]) + 8 for s in ps.raw_sites[:k]])
+    reg = np.array(ps.regs[:k], np.int64).reshape(-1)
     exs, fouts, fres = (capi.ProfileExtra * k)(), (capi.ProfileOutput * k)(), []
     capi.lib().lcd_profile_capacity.restype = C.c_int64
     for i, d in enumerate(profs):
@@ -287,13 +301,15 @@ def reference_pileup_step(lib, ps, k, n_threads):
         fres.append(o); fouts[i] = capi.ProfileOutput(*[a.ctypes.data for a in o], cap, 0)
     core = C.c_double(0.0)        # K1: the reference's own calls only (the shim's bam1_t construction and copy-out are not the reference's work)
     rc = lib.ref_digar_batch(C.c_int(k), ins, outs, C.c_int(n_threads), C.byref(core))
-    t1 = time.perf_counter(); t0 = t1 - core.value
+    score = C.c_double(0.0)       # K1b: collect_all_cand_var_sites alone (the shim's digar_t construction is not the reference's work)
+    rc |= lib.ref_sites_batch(C.c_int(k), bins, _vp(reg), souts, C.c_int(n_threads), C.byref(score))
+    t1 = time.perf_counter()
     rc |= lib.ref_pileup_batch(C.c_int(k), pins, pouts, C.c_int(n_threads))
     t2 = time.perf_counter()
     rc |= lib.ref_profile_batch(C.c_int(k), fins, exs, fouts, C.c_int(n_threads))
     t3 = time.perf_counter()
     if rc: raise RuntimeError("reference K1-K3 failed")
-    return t3 - t0, t1 - t0, t2 - t1, t3 - t2
+    return core.value + score.value + (t3 - t1), core.value, t2 - t1, t3 - t2, score.value
 
 
 def region_sample(wl, frac, seed=1):
@@ -343,7 +359,7 @@ def run_reference(args, rank):
                              "poa_s": sum(x[1] for x in t) / args.steps, "wfa_s": sum(x[2] for x in t) / args.steps,
                              "phase_s": sum(x[3] for x in t) / args.steps, "edlib_s": sum(x[4] for x in t) / args.steps,
                              "digar_s": pile_scale * sum(x[1] for x in tp) / args.steps, "pileup_s": pile_scale * sum(x[2] for x in tp) / args.steps,
-                             "profile_s": pile_scale * sum(x[3] for x in tp) / args.steps},
+                             "profile_s": pile_scale * sum(x[3] for x in tp) / args.steps, "sites_s": pile_scale * sum(x[4] for x in tp) / args.steps},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -352,14 +368,15 @@ def workload_config(args, wl, ps=None):
     return {"workload": f"synthetic {args.tech.upper()} 30x noisy-region re-alignment, {args.mbp:g} Mb ref per GPU "
                         f"(BASELINE configs[1] shape), {wl.n_regions} regions",
             "stages": ["K1 difference lists + noisy intervals + quality histogram from =/X CIGARs per 500 kb chunk (bam_utils.c:701)",
-                       "K2 per-site coverage of the candidate sites, on K1's lists in HBM (collect_var.c:238)",
+                       "K1b candidate-site list: sorted distinct X/I/D records incl. the large-insertion merge, on K1's lists in HBM (collect_var.c:1209)",
+                       "K2 per-site coverage of the candidate sites, on K1's lists and K1b's sites in HBM (collect_var.c:238)",
                        "K3 read x variant profile of the classified variants, on K1's lists in HBM (collect_var.c:1389)",
                        "K4 read->haplotype assignment + phasing per 500 kb chunk, clean then germline mask (assign_hap.c:473)",
                        "K7 edlib NW path read-vs-first-read sampling filter (align.c:722)",
                        "K5 abPOA consensus+MSA per (region, haplotype) (align.c:762)",
                        "K6 WFA gap-affine-2p ref-vs-consensus (align.c:565)"],
             "stages_not_yet_on_gpu": ["partial-read sub-graph POA", "2-consensus de-novo clustering",
-                                      "candidate-site list (a3) and classification / noisy-region set (a5): prepared at set-up, untimed in both arms",
+                                      "classification / noisy-region set (a5): prepared at set-up, untimed in both arms",
                                       "noisy-region orchestration (a8), vars from MSA (a13), somatic chain (a14)"],
             "pileup": (None if ps is None else {"chunks": ps.n_chunks, "distinct_chunks": min(ps.N_TEMPLATE, ps.n_chunks), "reads": int(sum(ps.n_reads)),
                                                  "read_bases": ps.read_bases, "cigar_ops": ps.cigar_ops, "records": ps.records,
@@ -462,18 +479,22 @@ def run_b200(args, rank, world):
         if rank == 0:
             gathered["bytes"] = sum(len(x) for x in out)
 
-    ps = PileupStage(args.mbp, args.tech, args.seed + rank, lcd.digar_batch, lcd.pileup_batch, pin=True)
+    from longcalld_b200 import synth as _synth
+    gpu_sites = lambda bare, outs, regs: [_synth.site_list_from_sites(o, st) for o, st in zip(outs, lcd.sites_batch(bare, regs))]
+    ps = PileupStage(args.mbp, args.tech, args.seed + rank, lcd.digar_batch, gpu_sites, lcd.pileup_batch, pin=True)
+    min_sv = [50] * ps.n_chunks
     pile_res = {}
 
     def pileup_e2e_step(dp, t_plan):
-        """K1 plan (its H2D copies were issued by the staging thread) -> K1 -> K2 / K3 on the lists in HBM -> coverage counters and profile rows on the host"""
+        """K1 plan (its H2D copies were issued by the staging thread) -> K1 -> K1b -> K2 / K3 on the lists in HBM -> site lists, coverage counters and profile rows on the host"""
         t = [time.perf_counter()]
         dp.run(); dp.sync(); t.append(time.perf_counter())
-        k2 = lcd.PileupOnDigarPlan(dp, ps.raw_sites); t.append(time.perf_counter()); k2.run(); pile_res["counts"] = k2.fetch(); t.append(time.perf_counter())
+        k1b = lcd.SitesPlan(None, ps.regs, min_sv_len=min_sv, digar_plan=dp); k1b.run(); pile_res["sites"] = k1b.fetch()
+        k2 = lcd.PileupOnSitesPlan(dp, k1b); t.append(time.perf_counter()); k2.run(); pile_res["counts"] = k2.fetch(); t.append(time.perf_counter())
         k3 = lcd.ProfileOnDigarPlan(dp, ps.var_sites, ps.n_reads); t.append(time.perf_counter()); k3.run(); pile_res["prof"] = k3.fetch(); t.append(time.perf_counter())
-        for x in (k3, k2, dp): x.destroy()
+        for x in (k3, k2, k1b, dp): x.destroy()
         t.append(time.perf_counter())
-        # ms: K1 plan incl. H2D (staging thread, overlapped with the POA launch), K1 run, K2 plan, K2 run+fetch, K3 plan, K3 run+fetch, destroy
+        # ms: K1 plan incl. H2D (staging thread, overlapped with the POA launch), K1 run, K1b plan+run+fetch and K2 plan, K2 run+fetch, K3 plan, K3 run+fetch, destroy
         pile_res["t"] = [round(1e3 * t_plan, 2)] + [round(1e3 * (b - a), 2) for a, b in zip(t, t[1:])]
 
     def pileup_stage_thread():
@@ -487,7 +508,9 @@ def run_b200(args, rank, world):
 
     wseqs, po, pl, to, tl = e2e_step()                              # also yields the consensus sequences for the WFA plan
     digar_plan = lcd.DigarPlan(ps.chunks); digar_plan.run(); digar_plan.sync()
-    k2_plan = lcd.PileupOnDigarPlan(digar_plan, ps.raw_sites)
+    sites_plan = lcd.SitesPlan(None, ps.regs, min_sv_len=min_sv, digar_plan=digar_plan); sites_plan.run(); sites_plan.sync()
+    assert sum(sites_plan.sizes()) == ps.n_raw_sites
+    k2_plan = lcd.PileupOnSitesPlan(digar_plan, sites_plan)
     k3_plan = lcd.ProfileOnDigarPlan(digar_plan, ps.var_sites, ps.n_reads)
     poa_plan = lcd.PoaPlan(wl.seqs, wl.first, wl.n_reads, wl.read_off, wl.read_len, lcd.poa_params())
     wfa_plan = lcd.WfaPlan(wseqs, po, pl, to, tl, lcd.wfa_params())
@@ -504,9 +527,11 @@ def run_b200(args, rank, world):
     def device_step():
         with torch.cuda.stream(stream):
             flush.zero_()
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(9)]
             ev[5].record(stream)
             digar_plan.run()
+            ev[8].record(stream)
+            sites_plan.run()
             ev[6].record(stream)
             k2_plan.run()
             ev[7].record(stream)
@@ -536,8 +561,8 @@ def run_b200(args, rank, world):
     wfa_ms = sum(e[1].elapsed_time(e[2]) for e in evs)
     phase_ms = sum(e[2].elapsed_time(e[3]) for e in evs)
     edlib_ms = sum(e[3].elapsed_time(e[4]) for e in evs)
-    k1_ms = sum(e[5].elapsed_time(e[6]) for e in evs); k2_ms = sum(e[6].elapsed_time(e[7]) for e in evs); k3_ms = sum(e[7].elapsed_time(e[0]) for e in evs)
-    dev_ms = poa_ms + wfa_ms + phase_ms + edlib_ms + k1_ms + k2_ms + k3_ms
+    k1_ms = sum(e[5].elapsed_time(e[8]) for e in evs); k1b_ms = sum(e[8].elapsed_time(e[6]) for e in evs); k2_ms = sum(e[6].elapsed_time(e[7]) for e in evs); k3_ms = sum(e[7].elapsed_time(e[0]) for e in evs)
+    dev_ms = poa_ms + wfa_ms + phase_ms + edlib_ms + k1_ms + k1b_ms + k2_ms + k3_ms
     phase_pairs = phase_plan.work_units()
     edlib_units = edlib_plan.work_units()
     poa_cells = poa_plan.work_units()
@@ -555,7 +580,7 @@ def run_b200(args, rank, world):
     barrier()
     e2e_s = time.perf_counter() - t0
     phase_bytes = sum(a.nbytes for k in ph_keep for a in k.values())
-    pile_d2h = int(sum(c.nbytes for c in pile_res["counts"]) + sum(sum(a.nbytes for a in o.values()) for o in pile_res["prof"]))
+    pile_d2h = int(sum(sum(a.nbytes for a in st.values() if hasattr(a, "nbytes")) for st in pile_res["sites"]) + sum(c.nbytes for c in pile_res["counts"]) + sum(sum(a.nbytes for a in o.values()) for o in pile_res["prof"]))
     h2d = int(ps.h2d + phase_bytes + eseqs.size + 24 * ne + wl.seqs.size + 12 * len(wl.read_len) + 64 * n + (pl.astype(np.int64) + tl + 56).sum() + 96 * n)
     d2h = int(pile_d2h + sum(a.nbytes for r in ph_res for a in r.values()) + eres.nbytes + int(eres["aln_len"].sum()) + pres["cons_len"].sum() + 32 * n + wres.nbytes + 2 * (pl.astype(np.int64) + tl + 4).sum())
 
@@ -583,7 +608,7 @@ def run_b200(args, rank, world):
                             "sample": f"{len(regs)} of {wl.n_regions} regions ({mbp_sample:.3f} Mb): the unmodified reference's own functions via oracle/_ref; "
                                       f"K1-K3 on {k_chunks} of {ps.n_chunks} chunks, time scaled by {pile_scale:.4f}",
                             "poa_s": dt_poa, "wfa_s": dt_wfa, "phase_s": dt_phase, "edlib_s": dt_edlib,
-                            "digar_s": pile_scale * dtp[1], "pileup_s": pile_scale * dtp[2], "profile_s": pile_scale * dtp[3]}
+                            "digar_s": pile_scale * dtp[1], "pileup_s": pile_scale * dtp[2], "profile_s": pile_scale * dtp[3], "sites_s": pile_scale * dtp[4]}
     if rank == 0:
         peak, which = load_peaks()
         poa_gbs = poa_cells * POA_BYTES_PER_CELL / (poa_ms / args.steps / 1e3) / 1e9
@@ -613,6 +638,9 @@ def run_b200(args, rank, world):
                                             "digar_kernels": {"ms": k1_ms / args.steps, "read_bases": ps.read_bases, "records": ps.records,
                                                               "GBps": ps.k1_bytes / (k1_ms / args.steps / 1e3) / 1e9, "frac": ps.k1_bytes / (k1_ms / args.steps / 1e3) / 1e9 / peak,
                                                               "note": "count + scan + fill + histogram; 1.5 B per read base + 4 B per CIGAR op in, 32 B per record out"},
+                                            "sites_kernels": {"ms": k1b_ms / args.steps, "records": ps.records, "sites": ps.n_raw_sites,
+                                                              "GBps": ps.k1b_bytes / (k1b_ms / args.steps / 1e3) / 1e9,
+                                                              "note": "count + scan + scatter + group + scan + emit; 14 B per record in, 36 B per site out"},
                                             "pileup_kernel": {"ms": k2_ms / args.steps, "records": ps.records, "sites": ps.n_raw_sites,
                                                               "GBps": ps.k2_bytes / (k2_ms / args.steps / 1e3) / 1e9},
                                             "profile_kernel": {"ms": k3_ms / args.steps, "records": ps.records, "variants": ps.n_vars,

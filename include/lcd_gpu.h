@@ -246,6 +246,33 @@ lcd_plan_t *lcd_pileup_plan_create_on_digar(lcd_plan_t *digar_plan, int n_chunks
 lcd_plan_t *lcd_profile_plan_create_on_digar(lcd_plan_t *digar_plan, int n_chunks, const lcd_site_list_t *sites);
 int64_t lcd_profile_plan_capacity(lcd_plan_t *plan, int chunk);
 
+/* ---------------------------------------------------------------- K1b: pileup scan, candidate-site list
+ * Replaces int collect_all_cand_var_sites(const call_var_opt_t *opt, bam_chunk_t *chunk, var_site_t **var_sites)
+ * (src/collect_var.c:1209-1254; comparators exact_comp_var_site / exact_comp_var_site_ins :1878-1935; filter
+ * is_collectible_var_digar :1153-1160), called from collect_var_main step 1.2 (src/collect_var.c:2905): the sorted list of the
+ * distinct X / I / D records (not low quality, starting inside [reg_beg, reg_end]; -1 = open) of the kept reads, large insertions
+ * (>= min_sv_len) of similar length (shorter >= 0.8 x longer) at one anchor merged into the first of them.  The reads and difference
+ * lists are those of lcd_pileup_input_t (its site fields are not read; n_sites may be 0).
+ * Site k of a chunk stands for the record site_src[k] (index into the chunk's digar_* arrays; the lowest index among identical
+ * records): its alt bases are digar_alt[digar_alt_off[site_src[k]] .. + site_alt_len[k]). */
+typedef struct { int64_t reg_beg, reg_end; int32_t min_sv_len, pad; } lcd_sites_params_t;
+typedef struct {
+    int64_t *site_pos;                 /* var_site_t.pos / var_type / ref_len / alt_len, in collect_all_cand_var_sites' order */
+    int32_t *site_type, *site_ref_len, *site_alt_len;
+    int64_t *site_src;
+    int64_t cap;                       /* capacity of the arrays (lcd_sites_plan_sizes, or the chunk's X / I / D record count) */
+    int64_t n_sites;                   /* out */
+} lcd_sites_output_t;
+int lcd_sites_batch(int n_chunks, const lcd_pileup_input_t *in, const lcd_sites_params_t *params, lcd_sites_output_t *out);
+lcd_plan_t *lcd_sites_plan_create(int n_chunks, const lcd_pileup_input_t *in, const lcd_sites_params_t *params);
+/* on the difference lists a digar plan left in HBM (reads K1 dropped are left out); the digar plan must outlive the plan */
+lcd_plan_t *lcd_sites_plan_create_on_digar(lcd_plan_t *digar_plan, int n_chunks, const lcd_sites_params_t *params);
+int  lcd_sites_plan_sizes(lcd_plan_t *plan, void *stream, int chunk, int64_t *n_sites);   /* after lcd_plan_run */
+int  lcd_sites_plan_fetch(lcd_plan_t *plan, void *stream, lcd_sites_output_t *out);
+/* K1 -> K1b -> K2 in place: the coverage pass on the site lists a sites plan (created on the same digar plan, and run) left in HBM;
+ * nothing is uploaded.  Results through lcd_pileup_plan_fetch, chunk i's counters in the order of lcd_sites_plan_fetch. */
+lcd_plan_t *lcd_pileup_plan_create_on_sites(lcd_plan_t *digar_plan, lcd_plan_t *sites_plan);
+
 /* ---------------------------------------------------------------- K4: read -> haplotype assignment and phasing
  * Replaces int assign_hap_based_on_germline_het_vars_kmeans(const call_var_opt_t *opt, bam_chunk_t *chunk,
  * int target_var_cate) (src/assign_hap.h:12, src/assign_hap.c:473-547), called from collect_var_main

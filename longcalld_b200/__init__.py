@@ -10,11 +10,13 @@ from .capi import (LcdGpuError, lib, lib_path, build_library, init, shutdown, la
                    HEUR_NONE, HEUR_ADAPTIVE, HEUR_ZDROP,
                    PoaParams, poa_params, PoaPlan, poa_batch, pack_poa,
                    MODE_NW, MODE_SHW, MODE_HW, EdlibPlan, edlib_batch, xgaps,
-                   PhasePlan, phase_batch, PileupPlan, pileup_batch, profile_batch, DigarPlan, digar_batch, PileupOnDigarPlan, ProfileOnDigarPlan)
+                   PhasePlan, phase_batch, PileupPlan, pileup_batch, profile_batch, DigarPlan, digar_batch, PileupOnDigarPlan, ProfileOnDigarPlan,
+                   SitesPlan, sites_batch, PileupOnSitesPlan)
 
 __all__ = ["LcdGpuError", "lib", "lib_path", "build_library", "init", "shutdown", "launch_count", "stream", "aux_stream", "set_thread_stream",
            "WfaParams", "WfaResult", "wfa_params", "WfaPlan", "wfa_batch",
            "HEUR_NONE", "HEUR_ADAPTIVE", "HEUR_ZDROP",
            "PoaParams", "poa_params", "PoaPlan", "poa_batch", "pack_poa",
            "MODE_NW", "MODE_SHW", "MODE_HW", "EdlibPlan", "edlib_batch", "xgaps",
-           "PhasePlan", "phase_batch", "PileupPlan", "pileup_batch", "profile_batch", "DigarPlan", "digar_batch", "PileupOnDigarPlan", "ProfileOnDigarPlan"]
+           "PhasePlan", "phase_batch", "PileupPlan", "pileup_batch", "profile_batch", "DigarPlan", "digar_batch", "PileupOnDigarPlan", "ProfileOnDigarPlan",
+           "SitesPlan", "sites_batch", "PileupOnSitesPlan"]

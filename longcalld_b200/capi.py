@@ -510,6 +510,96 @@ class ProfileOnDigarPlan(_Plan):
         return self.res
 
 
+# ----------------------------------------------------------------------------- K1b: candidate-site list
+class SitesParams(C.Structure):
+    _fields_ = [("reg_beg", C.c_int64), ("reg_end", C.c_int64), ("min_sv_len", C.c_int32), ("pad", C.c_int32)]
+
+
+class SitesOutput(C.Structure):
+    _fields_ = [("site_pos", C.c_void_p), ("site_type", C.c_void_p), ("site_ref_len", C.c_void_p), ("site_alt_len", C.c_void_p), ("site_src", C.c_void_p),
+                ("cap", C.c_int64), ("n_sites", C.c_int64)]
+
+
+def _sites_params(regs, min_sv_len):
+    n = len(regs)
+    return (SitesParams * max(n, 1))(*[SitesParams(int(b), int(e), int(m), 0) for (b, e), m in zip(regs, min_sv_len)])
+
+
+def _sites_outputs(caps):
+    outs, res = (SitesOutput * max(len(caps), 1))(), []
+    for i, cap in enumerate(caps):
+        o = dict(site_pos=np.zeros(cap + 1, np.int64), site_type=np.zeros(cap + 1, np.int32), site_ref_len=np.zeros(cap + 1, np.int32),
+                 site_alt_len=np.zeros(cap + 1, np.int32), site_src=np.zeros(cap + 1, np.int64))
+        res.append(o)
+        outs[i] = SitesOutput(o["site_pos"].ctypes.data, o["site_type"].ctypes.data, o["site_ref_len"].ctypes.data, o["site_alt_len"].ctypes.data,
+                              o["site_src"].ctypes.data, cap, 0)
+    return outs, res
+
+
+def _sites_finish(outs, res):
+    return [{k: v[:outs[i].n_sites] for k, v in o.items()} | {"n_sites": int(outs[i].n_sites)} for i, o in enumerate(res)]
+
+
+def _sites_inputs(chunks):
+    z = {k: np.zeros(1, t) for k, t in _PILEUP_IN if k.startswith("site_")}
+    return _pileup_structs([{**d, **z, "n_sites": 0} for d in chunks])
+
+
+def sites_batch(chunks, regs):
+    """Drop-in batch call over HOST buffers (lcd_sites_batch): chunks in lcd_pileup_input_t layout (site fields unused),
+    regs[i] = (reg_beg, reg_end) -> per chunk dict(site_pos, site_type, site_ref_len, site_alt_len, site_src, n_sites)."""
+    ins, _, keep, _ = _sites_inputs(chunks)
+    par = _sites_params(regs, [d["min_sv_len"] for d in chunks])
+    outs, res = _sites_outputs([int(np.isin(np.asarray(d["digar_type"]), (1, 2, 8)).sum()) for d in chunks])
+    _check(lib().lcd_sites_batch(C.c_int(len(chunks)), ins, par, outs), "lcd_sites_batch")
+    return _sites_finish(outs, res)
+
+
+class SitesPlan(_Plan):
+    """Resident plan: on host difference lists (chunks) or, with digar_plan, on the lists K1 left in HBM (chunks ignored)."""
+    def __init__(self, chunks, regs, min_sv_len=None, digar_plan=None):
+        L = lib()
+        L.lcd_sites_plan_create.restype = C.c_void_p
+        L.lcd_sites_plan_create_on_digar.restype = C.c_void_p
+        self.digar_plan = digar_plan
+        n = len(regs)
+        self.par = _sites_params(regs, min_sv_len if min_sv_len is not None else [d["min_sv_len"] for d in chunks])
+        if digar_plan is not None:
+            h = L.lcd_sites_plan_create_on_digar(digar_plan.h, C.c_int(n), self.par)
+        else:
+            self.ins, _, self.keep, _ = _sites_inputs(chunks)
+            h = L.lcd_sites_plan_create(C.c_int(n), self.ins, self.par)
+        super().__init__(h, n)
+
+    def sizes(self, stream=None):
+        out = []
+        for i in range(self.n):
+            v = C.c_int64(0)
+            _check(lib().lcd_sites_plan_sizes(self.h, C.c_void_p(stream or 0), C.c_int(i), C.byref(v)), "lcd_sites_plan_sizes")
+            out.append(int(v.value))
+        return out
+
+    def fetch(self, stream=None):
+        outs, res = _sites_outputs(self.sizes(stream))
+        _check(lib().lcd_sites_plan_fetch(self.h, C.c_void_p(stream or 0), outs), "lcd_sites_plan_fetch")
+        return _sites_finish(outs, res)
+
+
+class PileupOnSitesPlan(_Plan):
+    """K2 on the site lists a SitesPlan (created on the same DigarPlan, and run) left in HBM."""
+    def __init__(self, digar_plan, sites_plan):
+        self.digar_plan, self.sites_plan = digar_plan, sites_plan
+        lib().lcd_pileup_plan_create_on_sites.restype = C.c_void_p
+        super().__init__(lib().lcd_pileup_plan_create_on_sites(digar_plan.h, sites_plan.h), sites_plan.n)
+        self.n_sites = sites_plan.sizes()
+        self.results = [np.zeros((k + 1, 8), dtype=np.int32) for k in self.n_sites]
+        self.outs = (PileupOutput * max(self.n, 1))(*[PileupOutput(r.ctypes.data) for r in self.results])
+
+    def fetch(self, stream=None):
+        _check(lib().lcd_pileup_plan_fetch(self.h, C.c_void_p(stream or 0), self.outs), "lcd_pileup_plan_fetch")
+        return [r[:k] for r, k in zip(self.results, self.n_sites)]
+
+
 # ----------------------------------------------------------------------------- K3: pileup scan, read x variant profile
 _PROFILE_EX = (("var_cate", np.int32), ("nreg_first", np.int64), ("n_nreg", np.int32), ("nreg_beg", np.int64), ("nreg_end", np.int64))
 

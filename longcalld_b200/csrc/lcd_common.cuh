@@ -95,6 +95,14 @@ struct DigarView {
 };
 int digar_plan_view(Plan *plan, cudaStream_t s, DigarView *v);      // digar_kernel.cu
 
+// K1b's site lists as K2 consumes them in place (device pointers into a sites plan that has been run; valid while it lives).
+struct SitesView {
+    int n_chunks = 0; std::vector<long long> site_off;      // n_chunks + 1 entries: chunk i's sites are [site_off[i], site_off[i + 1])
+    std::vector<int32_t> min_sv_len;
+    const long long *spos = nullptr, *saoff = nullptr; const int32_t *stype = nullptr, *sref = nullptr, *salt = nullptr;
+};
+int sites_plan_view(Plan *plan, Plan *digar, cudaStream_t s, SitesView *v);   // sites_kernel.cu
+
 inline cudaStream_t pick_stream(void *s) { return s ? (cudaStream_t)s : cur_stream(); }
 
 } // namespace lcd

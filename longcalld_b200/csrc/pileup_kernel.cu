@@ -41,6 +41,9 @@ struct PileupPlan : Plan {
     long long tot_rows = 0;
     KernelArgs base;                 // device pointers of the read / event arrays: this plan's own buffers, or a digar plan's (K1 -> K2 / K3 in place)
     std::vector<long long> h_beg, h_end;
+    // the site arrays: this plan's own buffers, or a sites plan's (K1b -> K2 in place)
+    const long long *p_spos = nullptr, *p_saoff = nullptr; const int32_t *p_stype = nullptr, *p_sref = nullptr, *p_salt = nullptr; const uint8_t *p_site_alt = nullptr;
+    void own_sites() { p_spos = d_spos.p; p_saoff = d_saoff.p; p_stype = d_stype.p; p_sref = d_sref.p; p_salt = d_salt.p; p_site_alt = d_site_alt.p; }
 
     void own_pointers() {
         memset(&base, 0, sizeof(base));
@@ -119,6 +122,35 @@ struct PileupPlan : Plan {
         base.digar_first = v.dfirst; base.n_digar = v.ndig; base.qual_off = v.qoff; base.qual = v.qual; base.digar_pos = v.dpos; base.digar_type = v.dtype;
         base.digar_len = v.dlen; base.digar_qi = v.dqi; base.digar_low_qual = v.dlow; base.digar_alt_off = v.daoff; base.digar_alt = v.dalt;
         base.nreg_first = v.nfirst; base.n_nreg = v.nnreg; base.nreg_beg = v.nbeg; base.nreg_end = v.nend;
+        own_sites();
+        LCD_CUDA_OK(cudaStreamSynchronize(s));
+        return 0;
+    }
+
+    // K2 on the site lists a sites plan left in HBM (created on the same digar plan): nothing is uploaded but the chunk table
+    int build_on_sites(Plan *digar, Plan *sites) {
+        DigarView v; SitesView sv;
+        if (digar_plan_view(digar, cur_stream(), &v) || sites_plan_view(sites, digar, cur_stream(), &sv)) return -1;
+        n = v.n_chunks; profile = false;
+        if (sv.n_chunks != n) { set_error("lcd_pileup: a sites plan of %d chunks for a digar plan of %d chunks", sv.n_chunks, n); return -1; }
+        if (n == 0) return 0;
+        std::vector<int32_t> read_chunk;
+        chunks.resize(n); site_off.resize(n); read_off = v.read_off;
+        tot_reads = v.n_reads_total; tot_events = v.tot_events; tot_sites = sv.site_off[n];
+        for (int i = 0; i < n; ++i) {
+            Chunk &k = chunks[i];
+            k.n_sites = (int32_t)(sv.site_off[i + 1] - sv.site_off[i]); k.min_bq = v.min_bq[i]; k.min_sv_len = sv.min_sv_len[i]; k.pad = 0; k.site_off = sv.site_off[i];
+            k.alt_base = v.alt_base[i]; k.salt_base = v.alt_base[i]; k.pad2 = 0; site_off[i] = sv.site_off[i];      // a site's alt bases are those of one of its records
+            for (long long g = read_off[i]; g < read_off[i + 1]; ++g) read_chunk.push_back(i);
+        }
+        read_chunk.push_back(0);
+        cudaStream_t s = cur_stream();
+        if (d_chunks.upload(chunks.data(), n, s) || d_read_chunk.upload(read_chunk.data(), read_chunk.size(), s) || d_counts.alloc(8 * (size_t)tot_sites + 8)) return -1;
+        memset(&base, 0, sizeof(base));
+        base.read_chunk = d_read_chunk.p; base.read_active = v.active; base.read_dropped = v.dropped; base.read_beg = v.beg; base.read_end = v.end; base.read_is_rev = v.rev;
+        base.digar_first = v.dfirst; base.n_digar = v.ndig; base.qual_off = v.qoff; base.qual = v.qual; base.digar_pos = v.dpos; base.digar_type = v.dtype;
+        base.digar_len = v.dlen; base.digar_qi = v.dqi; base.digar_low_qual = v.dlow; base.digar_alt_off = v.daoff; base.digar_alt = v.dalt;
+        p_spos = sv.spos; p_saoff = sv.saoff; p_stype = sv.stype; p_sref = sv.sref; p_salt = sv.salt; p_site_alt = v.dalt;
         LCD_CUDA_OK(cudaStreamSynchronize(s));
         return 0;
     }
@@ -213,7 +245,7 @@ struct PileupPlan : Plan {
             if (d_pstart.alloc(tot_reads + 1) || d_pend.alloc(tot_reads + 1) || d_aoff.alloc(tot_reads + 1) || d_alleles.alloc(tot_rows + 16) ||
                 d_altqi.alloc(tot_rows + 16) || d_status.alloc(1)) return -1;
         }
-        own_pointers();
+        own_pointers(); own_sites();
         LCD_CUDA_OK(cudaStreamSynchronize(s));
         return 0;
     }
@@ -224,7 +256,7 @@ struct PileupPlan : Plan {
         LCD_CUDA_OK(cudaMemsetAsync(d_counts.p, 0, sizeof(int32_t) * 8 * (size_t)tot_sites, s));
         KernelArgs a = base;
         a.chunks = d_chunks.p; a.n_reads_total = tot_reads;
-        a.site_pos = d_spos.p; a.site_type = d_stype.p; a.site_ref_len = d_sref.p; a.site_alt_len = d_salt.p; a.site_alt_off = d_saoff.p; a.site_alt = d_site_alt.p;
+        a.site_pos = p_spos; a.site_type = p_stype; a.site_ref_len = p_sref; a.site_alt_len = p_salt; a.site_alt_off = p_saoff; a.site_alt = p_site_alt;
         a.site_counts = d_counts.p;
         const int grid = (int)std::min<long long>((tot_reads + THREADS - 1) / THREADS, (long long)c.sm_count * 16);
         if (profile) {
@@ -320,6 +352,14 @@ lcd_plan_t *lcd_pileup_plan_create_on_digar(lcd_plan_t *digar_plan, int n_chunks
     if (!digar_plan || n_chunks < 0 || (n_chunks > 0 && !sites)) { set_error("lcd_pileup_plan_create_on_digar: invalid arguments"); return nullptr; }
     pileup::PileupPlan *p = new pileup::PileupPlan();
     if (p->build_on_digar(reinterpret_cast<Plan *>(digar_plan), n_chunks, sites, false)) { delete p; return nullptr; }
+    return reinterpret_cast<lcd_plan_t *>(p);
+}
+
+lcd_plan_t *lcd_pileup_plan_create_on_sites(lcd_plan_t *digar_plan, lcd_plan_t *sites_plan) {
+    if (ensure_ready()) return nullptr;
+    if (!digar_plan || !sites_plan) { set_error("lcd_pileup_plan_create_on_sites: invalid arguments"); return nullptr; }
+    pileup::PileupPlan *p = new pileup::PileupPlan();
+    if (p->build_on_sites(reinterpret_cast<Plan *>(digar_plan), reinterpret_cast<Plan *>(sites_plan))) { delete p; return nullptr; }
     return reinterpret_cast<lcd_plan_t *>(p);
 }
 

@@ -456,6 +456,26 @@ def sites_from_digar_output(d, o, min_sv_len=50):
                 site_alt_off=np.array(site_alt_off + [0], np.int64), site_alt=np.array(site_alt + [0], np.uint8))
 
 
+def site_list_from_sites(o, st, min_sv_len=50, src_is_offset=False):
+    """lcd_site_list_t arrays of a chunk from the candidate-site list `st` (K1b's output: site_pos / type / ref_len / alt_len / site_src) and
+    K1's output `o`: a site's alt bases are those of the record it stands for (site_src = record index, or the offset of the bases in
+    digar_alt when src_is_offset)."""
+    n = int(st["n_sites"])
+    src = np.asarray(st["site_src"][:n], np.int64); typ = np.asarray(st["site_type"][:n], np.int32)
+    al = np.where(typ == 2, 0, np.asarray(st["site_alt_len"][:n], np.int64))
+    a0 = src if src_is_offset else np.asarray(o["digar_alt_off"], np.int64)[src] if n else src
+    off = np.zeros(n + 1, np.int64); np.cumsum(al, out=off[1:])
+    idx = np.repeat(a0 - off[:-1], al) + np.arange(int(off[-1]), dtype=np.int64)
+    return dict(n_sites=n, min_sv_len=min_sv_len, site_pos=np.append(np.asarray(st["site_pos"][:n], np.int64), 0), site_type=np.append(typ, 0).astype(np.int32),
+                site_ref_len=np.append(np.asarray(st["site_ref_len"][:n], np.int32), 0).astype(np.int32), site_alt_len=np.append(np.asarray(st["site_alt_len"][:n], np.int32), 0).astype(np.int32),
+                site_alt_off=off.copy(), site_alt=np.append(np.asarray(o["digar_alt"], np.uint8)[idx], 0).astype(np.uint8))
+
+
+def empty_site_list(min_sv_len=50):
+    return dict(n_sites=0, min_sv_len=min_sv_len, site_pos=np.zeros(1, np.int64), site_type=np.zeros(1, np.int32), site_ref_len=np.zeros(1, np.int32),
+                site_alt_len=np.zeros(1, np.int32), site_alt_off=np.zeros(1, np.int64), site_alt=np.zeros(1, np.uint8))
+
+
 def classify_sites(sites, counts, min_alt=2, min_af=0.20, max_af=0.80):
     """Workload preparation (stand-in for the reference's step 2, classify_cand_vars src/collect_var.c:902, allele-fraction rule
     only): keeps sites with >= min_alt alternative observations and labels them clean het SNP / het indel / hom by allele

@@ -240,6 +240,18 @@ int ref_digar_batch(int n, const lcd_digar_input_t *in, lcd_digar_output_t *out,
 int ref_pileup_batch(int n, const lcd_pileup_input_t *in, lcd_pileup_output_t *out, int n_threads) {
     return run_chunks(n, n_threads, [&](int i) { return ref_collect_cand_vars(&in[i], &out[i]); });
 }
+// candidate-site list: records built first, results copied out last; *core_wall_s is the wall time of collect_all_cand_var_sites alone
+void *ref_sites_prepare(const lcd_pileup_input_t *in, int64_t reg_beg, int64_t reg_end);
+void ref_sites_core(void *job);
+int ref_sites_finish(void *job, const lcd_pileup_input_t *in, lcd_sites_output_t *out);
+int ref_sites_batch(int n, const lcd_pileup_input_t *in, const int64_t *reg, lcd_sites_output_t *out, int n_threads, double *core_wall_s) {
+    std::vector<void *> jobs(n, nullptr);
+    run_chunks(n, n_threads, [&](int i) { jobs[i] = ref_sites_prepare(&in[i], reg[2 * i], reg[2 * i + 1]); return 0; });
+    const auto t0 = std::chrono::steady_clock::now();
+    run_chunks(n, n_threads, [&](int i) { ref_sites_core(jobs[i]); return 0; });
+    if (core_wall_s) *core_wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return run_chunks(n, n_threads, [&](int i) { return ref_sites_finish(jobs[i], &in[i], &out[i]); });
+}
 int ref_profile_batch(int n, const lcd_pileup_input_t *in, const lcd_profile_extra_t *ex, lcd_profile_output_t *out, int n_threads) {
     return run_chunks(n, n_threads, [&](int i) { return ref_read_var_profile(&in[i], &ex[i], &out[i]); });
 }

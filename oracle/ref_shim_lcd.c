@@ -313,19 +313,21 @@ int ref_collect_digar_eqx(const lcd_digar_input_t *in, lcd_digar_output_t *out) 
 
 
 int collect_all_cand_var_sites(const call_var_opt_t *opt, bam_chunk_t *chunk, var_site_t **var_sites);   /* src/collect_var.c:1209 (no prototype in the headers) */
-/* collect_all_cand_var_sites (src/collect_var.c:1209) on a synthetic chunk: digar_t records around the flat arrays */
-int ref_collect_sites(const lcd_pileup_input_t *in, int64_t reg_beg, int64_t reg_end, lcd_sites_output_t *out) {
+/* collect_all_cand_var_sites (src/collect_var.c:1209) on a synthetic chunk: digar_t records around the flat arrays.
+ * Three steps so that a batch can time the reference's own call alone: prepare (build the records), core, finish (copy out). */
+typedef struct { call_var_opt_t opt; bam_chunk_t chunk; var_site_t *sites; int n; } ref_sites_job_t;
+void *ref_sites_prepare(const lcd_pileup_input_t *in, int64_t reg_beg, int64_t reg_end) {
     const int nr = in->n_reads;
-    call_var_opt_t opt; memset(&opt, 0, sizeof(opt));
-    opt.min_bq = in->min_bq; opt.min_sv_len = in->min_sv_len;
-    bam_chunk_t chunk; memset(&chunk, 0, sizeof(chunk));
-    chunk.n_reads = chunk.m_reads = nr; chunk.tid = 0; chunk.tname = (char*)"chr"; chunk.reg_beg = reg_beg; chunk.reg_end = reg_end;
-    chunk.ordered_read_ids = (int*)malloc(sizeof(int) * (nr + 1));
-    chunk.is_skipped = (uint8_t*)malloc(nr + 1);
-    chunk.digars = (digar_t*)calloc(nr + 1, sizeof(digar_t));
+    ref_sites_job_t *job = (ref_sites_job_t*)calloc(1, sizeof(ref_sites_job_t));
+    job->opt.min_bq = in->min_bq; job->opt.min_sv_len = in->min_sv_len;
+    bam_chunk_t *chunk = &job->chunk;
+    chunk->n_reads = chunk->m_reads = nr; chunk->tid = 0; chunk->tname = (char*)"chr"; chunk->reg_beg = reg_beg; chunk->reg_end = reg_end;
+    chunk->ordered_read_ids = (int*)malloc(sizeof(int) * (nr + 1));
+    chunk->is_skipped = (uint8_t*)malloc(nr + 1);
+    chunk->digars = (digar_t*)calloc(nr + 1, sizeof(digar_t));
     for (int r = 0; r < nr; ++r) {
-        chunk.ordered_read_ids[r] = in->ordered_read_ids[r]; chunk.is_skipped[r] = in->is_skipped[r];
-        digar_t *g = chunk.digars + r;
+        chunk->ordered_read_ids[r] = in->ordered_read_ids[r]; chunk->is_skipped[r] = in->is_skipped[r];
+        digar_t *g = chunk->digars + r;
         g->n_digar = g->m_digar = in->n_digar[r];
         g->digars = (digar1_t*)calloc(g->n_digar + 1, sizeof(digar1_t));
         for (int k = 0; k < g->n_digar; ++k) {
@@ -334,8 +336,14 @@ int ref_collect_sites(const lcd_pileup_input_t *in, int64_t reg_beg, int64_t reg
             x->alt_seq = (x->type == BAM_CDIFF || x->type == BAM_CINS) ? (uint8_t*)(in->digar_alt + in->digar_alt_off[d]) : NULL;
         }
     }
-    var_site_t *sites = NULL;
-    const int n = collect_all_cand_var_sites(&opt, &chunk, &sites);
+    return job;
+}
+void ref_sites_core(void *h) {                    /* the reference's own work */
+    ref_sites_job_t *job = (ref_sites_job_t*)h;
+    job->n = collect_all_cand_var_sites(&job->opt, &job->chunk, &job->sites);
+}
+int ref_sites_finish(void *h, const lcd_pileup_input_t *in, lcd_sites_output_t *out) {
+    ref_sites_job_t *job = (ref_sites_job_t*)h; var_site_t *sites = job->sites; const int n = job->n;
     int rc = 0;
     out->n_sites = n;
     if (n > out->cap) rc = -3;
@@ -344,7 +352,12 @@ int ref_collect_sites(const lcd_pileup_input_t *in, int64_t reg_beg, int64_t reg
         out->site_src[i] = sites[i].alt_seq ? (int64_t)(sites[i].alt_seq - in->digar_alt) : -1;     /* offset of the alt bases in digar_alt (not a record index) */
     }
     if (sites) free(sites);
-    for (int r = 0; r < nr; ++r) free(chunk.digars[r].digars);
-    free(chunk.digars); free(chunk.ordered_read_ids); free(chunk.is_skipped);
+    for (int r = 0; r < in->n_reads; ++r) free(job->chunk.digars[r].digars);
+    free(job->chunk.digars); free(job->chunk.ordered_read_ids); free(job->chunk.is_skipped); free(job);
     return rc;
+}
+int ref_collect_sites(const lcd_pileup_input_t *in, int64_t reg_beg, int64_t reg_end, lcd_sites_output_t *out) {
+    void *job = ref_sites_prepare(in, reg_beg, reg_end);
+    ref_sites_core(job);
+    return ref_sites_finish(job, in, out);
 }
