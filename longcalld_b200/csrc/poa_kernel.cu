@@ -221,11 +221,14 @@ struct PoaPlan : Plan {
         const char *tml = getenv("LCD_POA_THREAD_MAXLEN");      // tuning knob: longest read of a thread-per-problem POA
         const int thread_max_len = tml ? atoi(tml) : 0;          // default: every banded problem on the warp kernel (measured fastest)
         const char *force = getenv("LCD_POA_FORCE_KIND");      // debug / profiling: 0 thread, 1 warp, 2 CTA for every problem
+        const char *ctop = getenv("LCD_POA_CTA_TOP");          // tuning knob: the K largest problems (the tail of the launch) go to the CTA kernel
+        int cta_top = ctop ? atoi(ctop) : 0;
         for (int32_t i : order_all) {
             // kilobase problems run on the warp kernel as well: its strip rows, 32-wide backtrack and parallel fusion beat
             // the CTA kernel's two-phase rows (kept for rows wider than the warp kernel's on-chip row cache: unbanded POA)
             int k = (need_small[i] <= thread_words && problems[i].max_len <= thread_max_len) ? 0 : ((problems[i].par.wb >= 0 || problems[i].max_len <= 224) ? 1 : 2);
             if (force && force[0] >= '0' && force[0] <= '2' && !(force[0] == '0' && need_small[i] > thread_words)) k = force[0] - '0';
+            if (cta_top > 0) { k = 2; --cta_top; }
             cls[k].push_back(i); cw[k] = std::max(cw[k], need_small[i]);
         }
         for (int k = 0; k < 3; ++k) cw[k] = (cw[k] + 63) & ~63ull;

@@ -6,6 +6,7 @@
  * writes the results back exactly where the reference leaves them:
  *     collect_digars_from_bam                        (src/collect_var.c:1063)  -> lcd_digar_batch    (K1; chunks whose reads all carry
  *                                                     =/X CIGARs -- chunks with cs / MD / plain-M reads are forwarded to the reference)
+ *     collect_all_cand_var_sites                     (src/collect_var.c:1209)  -> lcd_sites_batch    (K1b)
  *     collect_cand_vars                              (src/collect_var.c:238)   -> lcd_pileup_batch   (K2)
  *     collect_read_var_profile                       (src/collect_var.c:1389)  -> lcd_profile_batch  (K3)
  *     assign_hap_based_on_germline_het_vars_kmeans   (src/assign_hap.c:473)    -> lcd_phase_batch    (K4)
@@ -35,10 +36,10 @@
 #include "lcd_gpu.h"
 
 static void die(const char *what) { fprintf(stderr, "[lcd_dropin] %s failed: %s\n", what, lcd_gpu_last_error()); exit(1); }
-static unsigned long n_calls[10];
+static unsigned long n_calls[11];
 __attribute__((destructor)) static void report(void) {
-    if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: digar %lu (forwarded: %lu), pileup %lu, profile %lu, phase %lu, edlib %lu, wfa %lu, poa %lu (forwarded to abPOA: %lu); kernel launches %llu\n",
-                                              n_calls[8], n_calls[9], n_calls[0], n_calls[1], n_calls[2], n_calls[3], n_calls[4], n_calls[5], n_calls[6], (unsigned long long)lcd_gpu_launch_count());
+    if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: digar %lu (forwarded: %lu), sites %lu, pileup %lu, profile %lu, phase %lu, edlib %lu, wfa %lu, poa %lu (forwarded to abPOA: %lu); kernel launches %llu\n",
+                                              n_calls[8], n_calls[9], n_calls[10], n_calls[0], n_calls[1], n_calls[2], n_calls[3], n_calls[4], n_calls[5], n_calls[6], (unsigned long long)lcd_gpu_launch_count());
 }
 
 /* ------------------------------------------------------------------------------------------ digars -> flat */
@@ -199,6 +200,40 @@ void collect_digars_from_bam(bam_chunk_t *chunk, const struct call_var_pl_t *pl)
         for (int i = 0; i < chunk->m_reads; ++i) bam_destroy1(chunk->reads[i]);
         free(chunk->reads);
     }
+}
+
+/* ------------------------------------------------------------------------------------------ K1b */
+int collect_all_cand_var_sites(const call_var_opt_t *opt, bam_chunk_t *chunk, var_site_t **var_sites) {      /* src/collect_var.c:1209-1254 */
+    *var_sites = NULL;
+    flat_t f; flatten(opt, chunk, 0, NULL, NULL, &f);
+    size_t n_ev = 0, cap = 0;
+    for (int r = 0; r < chunk->n_reads; ++r) if (!chunk->is_skipped[r]) n_ev += chunk->digars[r].n_digar;
+    digar1_t **rec = (digar1_t**)malloc((n_ev + 1) * sizeof(digar1_t*));           /* flattened record index -> the reference's record */
+    n_ev = 0;
+    for (int r = 0; r < chunk->n_reads; ++r) {
+        if (chunk->is_skipped[r]) continue;
+        for (int k = 0; k < chunk->digars[r].n_digar; ++k) {
+            digar1_t *x = chunk->digars[r].digars + k; rec[n_ev++] = x;
+            if (x->type == BAM_CDIFF || x->type == BAM_CINS || x->type == BAM_CDEL) cap++;
+        }
+    }
+    lcd_sites_params_t par = { chunk->reg_beg, chunk->reg_end, opt->min_sv_len, 0 };
+    lcd_sites_output_t out; memset(&out, 0, sizeof(out));
+    out.site_pos = (int64_t*)malloc((cap + 1) * sizeof(int64_t)); out.site_src = (int64_t*)malloc((cap + 1) * sizeof(int64_t));
+    out.site_type = (int32_t*)malloc((cap + 1) * sizeof(int32_t)); out.site_ref_len = (int32_t*)malloc((cap + 1) * sizeof(int32_t));
+    out.site_alt_len = (int32_t*)malloc((cap + 1) * sizeof(int32_t)); out.cap = (int64_t)cap;
+    if (lcd_sites_batch(1, &f.in, &par, &out)) die("lcd_sites_batch");
+    const int n = (int)out.n_sites;
+    if (n > 0) {
+        *var_sites = (var_site_t*)malloc((size_t)n * sizeof(var_site_t));
+        for (int i = 0; i < n; ++i) {
+            var_site_t v = { chunk->tid, out.site_pos[i], out.site_type[i], out.site_ref_len[i], out.site_alt_len[i], rec[out.site_src[i]]->alt_seq };
+            (*var_sites)[i] = v;
+        }
+    }
+    free(out.site_pos); free(out.site_src); free(out.site_type); free(out.site_ref_len); free(out.site_alt_len); free(rec); flat_free(&f);
+    n_calls[10]++;
+    return n;
 }
 
 /* ------------------------------------------------------------------------------------------ K2 */

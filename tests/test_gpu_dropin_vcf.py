@@ -1,5 +1,5 @@
 """GPU, end to end: `longcallD call` on the reference's bundled HiFi / ONT data with the UNMODIFIED reference linked as a shared
-library (oracle/_ref/longcallD_so) and longcalld_b200/dropin/liblcd_dropin.so preloaded, so that the =/X difference lists (K1), the per-site coverage pass
+library (oracle/_ref/longcallD_so) and longcalld_b200/dropin/liblcd_dropin.so preloaded, so that the =/X difference lists (K1), the candidate-site list (K1b), the per-site coverage pass
 (K2), the read x variant profile (K3), the read->haplotype assignment / phasing (K4), the POA consensus of full-cover regions (K5), every WFA alignment (K6) and every edlib call (K7) execute on
 the B200 through the C-ABI.  The VCF body must be the reference's own (md5 of the non-header lines)."""
 import hashlib
@@ -40,8 +40,8 @@ def test_vcf_identical_with_gpu_dropin(tech):
     md5, err = _run(tech, preload=True)
     calls = [l[l.index("[lcd_dropin] GPU calls"):] for l in err.splitlines() if "[lcd_dropin] GPU calls" in l]
     assert calls, "the drop-in was not loaded"
-    counts = dict((k, int(v)) for k, v in __import__("re").findall(r"(digar|pileup|profile|phase|edlib|wfa|poa) (\d+)", calls[-1]))
-    need = ("pileup", "phase", "wfa", "poa") if tech == "mosaic" else ("pileup", "profile", "phase", "wfa", "poa")   # -s: the profile takes the reference's somatic path
+    counts = dict((k, int(v)) for k, v in __import__("re").findall(r"(digar|sites|pileup|profile|phase|edlib|wfa|poa) (\d+)", calls[-1]))
+    need = ("sites", "pileup", "phase", "wfa", "poa") if tech == "mosaic" else ("sites", "pileup", "profile", "phase", "wfa", "poa")   # -s: the profile takes the reference's somatic path
     if tech != "ont": need += ("digar",)            # the bundled ONT BAM carries plain-M CIGARs + MD tags: the reference's string-parsing path
     assert all(counts[k] > 0 for k in need), calls[-1]                                             # the kernels really ran on the GPU
     print(calls[-1])
