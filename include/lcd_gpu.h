@@ -43,6 +43,15 @@ void *lcd_gpu_stream(void);
  * run on one stream. */
 void *lcd_gpu_aux_stream(void);
 void lcd_gpu_set_thread_stream(void *stream);
+/* The DP engines (K5, K6) run persistent grids that fill every SM until their queues drain; kernels of other plans launched meanwhile
+ * (K1 - K4 from a second host thread / stream: their plans own their buffers and are not serialised with the DP engines) would wait
+ * for the DP launch to end.  Reserving n SMs' worth of CTA slots shrinks the persistent grids by that much so that such kernels run
+ * alongside.  The DP launches are bounded by their longest problem, not by the SM count, so a small reservation costs them nothing. */
+int lcd_gpu_reserve_sms(int n_sms);
+/* Splits the workspace pool in two windows: the lower `lower_bytes` for the POA plans (K5), the rest for the WFA / edlib plans (K6, K7),
+ * serialised independently, so that the WFA launch of one region batch and the POA launch of the next may be in flight together (run
+ * them on different streams).  Call it right after lcd_gpu_init, before any plan exists; 0 restores the single window. */
+int lcd_gpu_split_pool(size_t lower_bytes);
 
 /* ---------------------------------------------------------------- K6: WFA gap-affine(-2p)
  * Replaces wavefront_aligner_new + wavefront_align + reading wf_aligner->cigar, as called by
@@ -85,7 +94,8 @@ lcd_plan_t *lcd_wfa_plan_create(int n, const uint8_t *seqs, size_t seqs_len,
                                 const int64_t *txt_off, const int32_t *tlen,
                                 const lcd_wfa_params_t *params);
 int  lcd_plan_run(lcd_plan_t *plan, void *stream);           /* async launch(es) on stream */
-int  lcd_plan_sync(lcd_plan_t *plan, void *stream);          /* wait + check device status */
+int  lcd_plan_sync(lcd_plan_t *plan, void *stream);          /* wait + check device status; a POA plan looks at its statuses here (or in its
+                                                                * fetch) and re-runs, with the worst-case workspace, any problem that outgrew its budget */
 /* Copy results back (D2H).  ops may be NULL.  Layout as in the matching *_batch call. */
 int  lcd_wfa_plan_fetch(lcd_plan_t *plan, void *stream, char *ops, const int64_t *ops_off,
                         lcd_wfa_result_t *results);

@@ -107,6 +107,17 @@ def set_thread_stream(s):
     lib().lcd_gpu_set_thread_stream(C.c_void_p(s or 0))
 
 
+def split_pool(lower_bytes):
+    """POA plans carve from the lower `lower_bytes` of the workspace pool, WFA / edlib plans from the rest (lcd_gpu_split_pool)."""
+    lib().lcd_gpu_split_pool.argtypes = [C.c_size_t]
+    _check(lib().lcd_gpu_split_pool(lower_bytes), "lcd_gpu_split_pool")
+
+
+def reserve_sms(n):
+    """CTA slots of n SMs are left free by the persistent DP grids (lcd_gpu_reserve_sms)."""
+    _check(lib().lcd_gpu_reserve_sms(C.c_int(n)), "lcd_gpu_reserve_sms")
+
+
 def launch_count():
     return int(lib().lcd_gpu_launch_count())
 

@@ -124,6 +124,7 @@ template <typename T, typename U> static void append(std::vector<T> &dst, const 
 }
 
 struct DigarPlan : Plan {
+    bool uses_pool() const override { return false; }
     std::vector<Chunk> chunks; std::vector<long long> read_off, reg_beg, reg_end; std::vector<int32_t> ordered;
     std::vector<uint8_t> h_active;
     long long tot_reads = 0, tot_cigar = 0, tot_seq = 0, tot_qual = 0, stride = 1;
@@ -215,6 +216,7 @@ struct DigarPlan : Plan {
         c.launches += 2;
         if (tot_digar < 0) {        // first run: the output arrays are sized from the scan totals (the sizes do not change between runs)
             long long t[3];
+            LCD_DRAIN(s);
             for (int j = 0; j < 3; ++j) LCD_CUDA_OK(cudaMemcpyAsync(t + j, d_first.p + j * stride + tot_reads, sizeof(long long), cudaMemcpyDeviceToHost, s));
             LCD_CUDA_OK(cudaStreamSynchronize(s));
             tot_digar = t[0]; tot_alt = t[1]; tot_ncap = t[2];
@@ -238,6 +240,7 @@ struct DigarPlan : Plan {
         if (have_index) return 0;
         if (tot_digar < 0) { set_error("lcd_digar: the plan has not been run"); return -1; }
         h_first.assign(3 * stride, 0); h_nnreg.assign(stride, 0);
+        LCD_DRAIN(s);
         int32_t status = 0;
         if (tot_reads) {
             LCD_CUDA_OK(cudaMemcpyAsync(h_first.data(), d_first.p, sizeof(long long) * 3 * stride, cudaMemcpyDeviceToHost, s));
@@ -288,6 +291,7 @@ struct DigarPlan : Plan {
             return 0;
         }
         if (index(s)) return -1;
+        LCD_DRAIN(s);
         std::vector<uint8_t> skip(stride); std::vector<long long> beg(stride), end(stride), nb(tot_ncap + 1), ne(tot_ncap + 1); std::vector<int32_t> nl(tot_ncap + 1);
         std::vector<unsigned long long> qc(256 * (size_t)n);
         LCD_CUDA_OK(cudaMemcpyAsync(skip.data(), d_skip.p, tot_reads, cudaMemcpyDeviceToHost, s));

@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <mutex>
+#include <atomic>
 #include "../../include/lcd_gpu.h"
 
 namespace lcd {
@@ -35,14 +36,21 @@ struct Context {
     bool ready = false;
     int device = 0;
     int sm_count = 148;
+    int reserved_sms = 0;             // CTA slots of this many SMs are left free by the persistent DP grids (lcd_gpu_reserve_sms)
+    int dp_sms() const { return sm_count - reserved_sms > 8 ? sm_count - reserved_sms : 8; }
     cudaStream_t stream = nullptr;
     cudaStream_t aux_stream = nullptr;  // created on first lcd_gpu_aux_stream()
     int32_t *pool = nullptr;          // int32 words
     size_t pool_words = 0;
+    // lcd_gpu_split_pool: window 0 = [0, split_words) for the POA plans, window 1 = the rest for the WFA / edlib plans (0: one window)
+    size_t split_words = 0;
+    int32_t *win_pool(int w) const { return pool + ((w && split_words) ? split_words : 0); }
+    size_t win_words(int w) const { return split_words ? (w ? pool_words - split_words : split_words) : pool_words; }
+    std::mutex mu1;                   // serialises the plans of window 1 when the pool is split
     static constexpr int BITMAP_WORDS = 4096;     // overflow chunks in use (bit set), device memory
     uint32_t *chunk_bitmap = nullptr;
     std::mutex mu;                    // serialises plan runs that share the pool
-    unsigned long long launches = 0;
+    std::atomic<unsigned long long> launches{0};
 };
 Context &ctx();
 int ensure_ready();
@@ -55,6 +63,12 @@ struct Plan {
     virtual ~Plan() {}
     virtual int run(cudaStream_t s) = 0;
     virtual int work_units(cudaStream_t s, uint64_t *units) = 0;
+    // plans whose kernels carve workspace from the context's pool are serialised by lcd_plan_run; the others (K1, K1b, K2, K3, K4:
+    // their buffers are their own) may run from another host thread / stream while a pool plan is in flight
+    virtual bool uses_pool() const { return true; }
+    virtual int pool_window() const { return 0; }
+    // completes what run() left pending on the stream (default: nothing beyond draining it); called by lcd_plan_sync and the fetches
+    virtual int finish(cudaStream_t s) { (void)s; return 0; }       // which window of a split pool the plan's kernels carve from
     int n = 0;
 };
 
@@ -102,6 +116,11 @@ struct SitesView {
     const long long *spos = nullptr, *saoff = nullptr; const int32_t *stype = nullptr, *sref = nullptr, *salt = nullptr;
 };
 int sites_plan_view(Plan *plan, Plan *digar, cudaStream_t s, SitesView *v);   // sites_kernel.cu
+
+// Host <-> device copies of pageable memory go through one staging path of the driver: a copy queued BEHIND a long kernel holds that path
+// until the kernel ends, and every other thread's copies wait with it (measured on B200: a second host thread's 2 MB D2H took 250 ms
+// while a POA launch with its status copy queued behind it was in flight).  So results are read back only after the stream has drained.
+#define LCD_DRAIN(s) LCD_CUDA_OK(cudaStreamSynchronize(s))
 
 inline cudaStream_t pick_stream(void *s) { return s ? (cudaStream_t)s : cur_stream(); }
 

@@ -39,6 +39,21 @@ void *lcd_gpu_aux_stream(void) {
     if (!c.aux_stream && cudaStreamCreateWithFlags(&c.aux_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("lcd_gpu_aux_stream: cudaStreamCreate failed"); return nullptr; }
     return (void*)c.aux_stream;
 }
+int lcd_gpu_split_pool(size_t lower_bytes) {
+    Context &c = ctx();
+    if (!c.ready) { set_error("lcd_gpu_split_pool: call lcd_gpu_init first"); return -1; }
+    std::lock_guard<std::mutex> lk(c.mu), lk1(c.mu1);
+    const size_t w = (lower_bytes / 4) & ~(size_t)63;
+    if (lower_bytes && (w < (1u << 20) || w + (1u << 20) > c.pool_words)) { set_error("lcd_gpu_split_pool: %zu bytes do not split a pool of %zu bytes", lower_bytes, c.pool_words * 4); return -1; }
+    c.split_words = w;
+    return 0;
+}
+int lcd_gpu_reserve_sms(int n_sms) {
+    Context &c = ctx();
+    if (n_sms < 0 || n_sms >= c.sm_count) { set_error("lcd_gpu_reserve_sms: %d out of range", n_sms); return -1; }
+    c.reserved_sms = n_sms;
+    return 0;
+}
 void lcd_gpu_set_thread_stream(void *stream) { thread_stream() = (cudaStream_t)stream; }
 
 int lcd_gpu_init(int device, size_t pool_bytes) {
@@ -102,13 +117,15 @@ int lcd_plan_run(lcd_plan_t *plan, void *stream) {
     if (!plan) { set_error("lcd_plan_run: null plan"); return -1; }
     if (ensure_ready()) return -1;
     Context &c = ctx();
-    std::lock_guard<std::mutex> lk(c.mu);
-    return reinterpret_cast<Plan*>(plan)->run(pick_stream(stream));
+    Plan *p = reinterpret_cast<Plan*>(plan);
+    if (!p->uses_pool()) return p->run(pick_stream(stream));
+    std::lock_guard<std::mutex> lk((c.split_words && p->pool_window() == 1) ? c.mu1 : c.mu);
+    return p->run(pick_stream(stream));
 }
 
 int lcd_plan_sync(lcd_plan_t *plan, void *stream) {
-    (void)plan;
     LCD_CUDA_OK(cudaStreamSynchronize(pick_stream(stream)));
+    if (plan && reinterpret_cast<Plan*>(plan)->finish(pick_stream(stream))) return -1;
     LCD_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -56,6 +56,7 @@ static void flag_sort(Intv *beg, Intv *end, int shift) {
 }
 
 struct PhasePlan : Plan {
+    bool uses_pool() const override { return false; }
     std::vector<Chunk> chunks;
     int64_t tot_reads = 0, tot_vars = 0, tot_alleles = 0;
     DevBuf<Chunk> d_chunks;
@@ -163,6 +164,7 @@ struct PhasePlan : Plan {
     int work_units(cudaStream_t, uint64_t *units) override { *units = (uint64_t)tot_alleles; return 0; }   // (read, variant) pairs
 
     int fetch(cudaStream_t s, lcd_phase_output_t *out) {
+        LCD_DRAIN(s);
         if (n == 0) return 0;
         LCD_CUDA_OK(cudaMemcpyAsync(h_haps.data(), d_haps.p, sizeof(int32_t) * tot_reads, cudaMemcpyDeviceToHost, s));
         LCD_CUDA_OK(cudaMemcpyAsync(h_psets.data(), d_psets.p, sizeof(long long) * tot_reads, cudaMemcpyDeviceToHost, s));

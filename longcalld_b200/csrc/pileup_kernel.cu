@@ -27,6 +27,7 @@ template <typename T, typename U> static void append(std::vector<T> &dst, const 
 }
 
 struct PileupPlan : Plan {
+    bool uses_pool() const override { return false; }
     std::vector<Chunk> chunks; std::vector<long long> site_off;
     long long tot_reads = 0, tot_sites = 0, tot_events = 0;
     DevBuf<Chunk> d_chunks; DevBuf<int32_t> d_read_chunk, d_ndig, d_dlen, d_dqi, d_stype, d_sref, d_salt, d_counts;
@@ -279,6 +280,7 @@ struct PileupPlan : Plan {
 
     int fetch(cudaStream_t s, lcd_pileup_output_t *out) {
         if (n == 0) return 0;
+        LCD_DRAIN(s);
         for (int i = 0; i < n; ++i)       // straight into the caller's arrays
             if (chunks[i].n_sites) LCD_CUDA_OK(cudaMemcpyAsync(out[i].site_counts, d_counts.p + 8 * site_off[i], sizeof(int32_t) * 8 * (size_t)chunks[i].n_sites, cudaMemcpyDeviceToHost, s));
         LCD_CUDA_OK(cudaStreamSynchronize(s));
@@ -289,6 +291,7 @@ struct PileupPlan : Plan {
 
     int fetch_profile(cudaStream_t s, lcd_profile_output_t *out) {
         if (n == 0) return 0;
+        LCD_DRAIN(s);
         std::vector<int32_t> ps(tot_reads + 1), pe(tot_reads + 1), qi(tot_rows + 16); std::vector<long long> ao(tot_reads + 1); std::vector<int8_t> al(tot_rows + 16);
         int32_t status = 0;
         LCD_CUDA_OK(cudaMemcpyAsync(ps.data(), d_pstart.p, sizeof(int32_t) * tot_reads, cudaMemcpyDeviceToHost, s));

@@ -107,6 +107,8 @@ struct PoaPlan : Plan {
     std::vector<DevResult> h_results;
     std::vector<uint8_t> h_cons, h_msa;
     int n_rescued = 0;
+    std::vector<int32_t> cls[3];
+    bool pending = false;                  // run() has launched; the statuses (and a rescue launch, if any) are still to be looked at
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     ~PoaPlan() override {
@@ -184,7 +186,7 @@ struct PoaPlan : Plan {
         const int per_cta = kind == 0 ? THREADS_PER_CTA : kind == 1 ? WARPS_PER_CTA : 1;
         const uint64_t avail = pool_hi > pool_lo ? pool_hi - pool_lo : 0;
         const uint64_t fit = avail / words;
-        if (fit == 0) { set_error("lcd_poa: a problem needs %zu MiB of workspace but the pool has %zu MiB", (size_t)(words * 4 >> 20), (size_t)(c.pool_words * 4 >> 20)); return -1; }
+        if (fit == 0) { set_error("lcd_poa: a problem needs %zu MiB of workspace but the pool has %zu MiB", (size_t)(words * 4 >> 20), (size_t)(c.win_words(0) * 4 >> 20)); return -1; }
         int groups = (int)std::min<uint64_t>(std::min<uint64_t>(fit, (uint64_t)max_groups), idx.size());
         int grid = (groups + per_cta - 1) / per_cta;
         if ((uint64_t)grid * per_cta > fit) grid = (int)(fit / per_cta);
@@ -199,7 +201,7 @@ struct PoaPlan : Plan {
         ka.problems = d_problems.p; ka.order = d_idx; ka.n = (int)idx.size(); ka.queue = d_q;
         ka.seqs = d_seqs.p; ka.read_off = d_read_off.p; ka.read_len = d_read_len.p;
         ka.cons = d_cons.p; ka.msa = d_msa.p; ka.msa_cap = msa_pool_bytes; ka.msa_used = d_msa_used.p;
-        ka.results = d_results.p; ka.arena = c.pool + pool_lo; ka.arena_words = words; ka.worst_case = worst_case ? 1 : 0;
+        ka.results = d_results.p; ka.arena = c.win_pool(0) + pool_lo; ka.arena_words = words; ka.worst_case = worst_case ? 1 : 0;
         if (kind == 0) poa_thread_kernel<<<grid, THREADS_PER_CTA, 0, s>>>(ka);
         else if (kind == 1) poa_kernel<<<grid, 32 * WARPS_PER_CTA, 0, s>>>(ka);
         else poa_cta_kernel<<<grid, 32 * CTA_WARPS, 0, s>>>(ka);
@@ -208,15 +210,18 @@ struct PoaPlan : Plan {
         return 0;
     }
 
+    // run() only enqueues the launch and returns: the host is free to start other engines' plans while the persistent grid works.
+    // Problems that outgrew their first-attempt workspace are found and re-run by finish() (lcd_plan_sync / fetch / work_units).
     int run(cudaStream_t s) override {
         Context &c = ctx();
         if (n == 0) return 0;
+        if (pending && finish_locked(s)) return -1;
         LCD_CUDA_OK(cudaMemsetAsync(d_msa_used.p, 0, sizeof(unsigned long long), s));
         // class T: small problems, one per THREAD; class W: medium, one per warp; class C: kilobase regions, one per
         // CTA; rescue: problems that outgrew their first-attempt budget, re-run with the worst-case budget.
         // The three classes run concurrently (two side streams) in disjoint parts of the pool.
         const uint64_t thread_words = (uint64_t)(512u << 10) / 4;     // <= 512 KiB per thread arena
-        std::vector<int32_t> cls[3];
+        for (int k = 0; k < 3; ++k) cls[k].clear();         // (member: the launch's index upload reads them after run() has returned)
         uint64_t cw[3] = {0, 0, 0};
         const char *tml = getenv("LCD_POA_THREAD_MAXLEN");      // tuning knob: longest read of a thread-per-problem POA
         const int thread_max_len = tml ? atoi(tml) : 0;          // default: every banded problem on the warp kernel (measured fastest)
@@ -232,7 +237,7 @@ struct PoaPlan : Plan {
             cls[k].push_back(i); cw[k] = std::max(cw[k], need_small[i]);
         }
         for (int k = 0; k < 3; ++k) cw[k] = (cw[k] + 63) & ~63ull;
-        const int max_groups[3] = { c.sm_count * 256, c.sm_count * 8, c.sm_count * 4 };
+        const int max_groups[3] = { c.sm_count * 256, c.dp_sms() * 8, c.sm_count * 4 };
         // pool split: threads get what they need (at most half), CTAs and warps share the rest in proportion to demand
         uint64_t want[3];
         const int per_cta[3] = { THREADS_PER_CTA, WARPS_PER_CTA, 1 };
@@ -241,11 +246,11 @@ struct PoaPlan : Plan {
             want[k] = (g + per_cta[k] - 1) / per_cta[k] * per_cta[k] * cw[k];       // launches round up to whole CTAs
         }
         uint64_t lo[4]; lo[0] = 0;
-        lo[1] = std::min<uint64_t>(want[0], c.pool_words / 2);
-        const uint64_t rest_pool = c.pool_words - lo[1];
+        lo[1] = std::min<uint64_t>(want[0], c.win_words(0) / 2);
+        const uint64_t rest_pool = c.win_words(0) - lo[1];
         const uint64_t w12 = want[1] + want[2];
         lo[2] = lo[1] + (w12 <= rest_pool ? want[1] : (uint64_t)((double)rest_pool * ((double)want[1] / (double)w12)));
-        lo[3] = c.pool_words;
+        lo[3] = c.win_words(0);
         for (int k = 1; k < 4; ++k) lo[k] &= ~63ull;
         LCD_CUDA_OK(cudaEventRecord(ev_fork, s));
         for (int k = 2; k >= 1; --k) {            // big problems first
@@ -258,16 +263,33 @@ struct PoaPlan : Plan {
         }
         if (!cls[0].empty() && launch(s, cls[0], d_order.p, d_queue.p, cw[0], max_groups[0], 0, false, lo[0], lo[1], nullptr)) return -1;
         for (int k = 1; k <= 2; ++k) if (!cls[k].empty()) LCD_CUDA_OK(cudaStreamWaitEvent(s, ev_join[k - 1], 0));
-        // statuses back: anything that ran out of workspace is re-run with the full-matrix budget
+        pending = true;
+        return 0;
+    }
+
+    int finish(cudaStream_t s) override {
+        if (!pending) return 0;
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);       // a rescue launch carves from the pool window of the POA plans
+        return finish_locked(s);
+    }
+
+    // statuses back: anything that ran out of workspace is re-run with the full-matrix budget
+    int finish_locked(cudaStream_t s) {
+        Context &c = ctx();
+        if (!pending) return 0;
+        pending = false;
         h_results.resize(n);
+        LCD_DRAIN(s);
         LCD_CUDA_OK(cudaMemcpyAsync(h_results.data(), d_results.p, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, s));
         LCD_CUDA_OK(cudaStreamSynchronize(s));
         std::vector<int32_t> rescue; uint64_t rescue_words = 0;
         for (int32_t i : order_all) if (h_results[i].status == ST_OOM) { rescue.push_back(i); rescue_words = std::max(rescue_words, need_full[i]); }
         n_rescued = (int)rescue.size();
         if (!rescue.empty()) {
-            rescue_words = std::min<uint64_t>((rescue_words + 63) & ~63ull, (c.pool_words / WARPS_PER_CTA) & ~63ull);
-            if (launch(s, rescue, d_order.p, d_queue.p, rescue_words, c.sm_count * 4, 2, true, 0, c.pool_words, nullptr)) return -1;
+            rescue_words = std::min<uint64_t>((rescue_words + 63) & ~63ull, (c.win_words(0) / WARPS_PER_CTA) & ~63ull);
+            if (launch(s, rescue, d_order.p, d_queue.p, rescue_words, c.sm_count * 4, 2, true, 0, c.win_words(0), nullptr)) return -1;
+            LCD_CUDA_OK(cudaStreamSynchronize(s));
         }
         return 0;
     }
@@ -277,6 +299,8 @@ struct PoaPlan : Plan {
         Context &c = ctx();
         h_results.resize(n);
         if (n == 0) return 0;
+        if (finish(s)) return -1;
+        LCD_DRAIN(s);
         unsigned long long used = 0;
         LCD_CUDA_OK(cudaMemcpyAsync(h_results.data(), d_results.p, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, s));
         LCD_CUDA_OK(cudaMemcpyAsync(&used, d_msa_used.p, sizeof(used), cudaMemcpyDeviceToHost, s));

@@ -47,6 +47,7 @@ template <typename T, typename U> static void append(std::vector<T> &dst, const 
 }
 
 struct SitesPlan : Plan {
+    bool uses_pool() const override { return false; }
     std::vector<Chunk> chunks; std::vector<long long> ev0;      // ev0[i]: first record of chunk i in the concatenated record arrays
     long long tot_reads = 0, tot_bins = 0, tot_events = 0, max_bins = 0;
     long long tot_cand = -1, tot_sites = -1;
@@ -173,6 +174,7 @@ struct SitesPlan : Plan {
         c.launches++;
         if (scan::exclusive_scan(d_bin_count.p, tot_bins, d_bin_first.p, d_tmp, s)) return -1;
         if (tot_cand < 0) {         // first run: the candidate array is sized from the scan total (the sizes do not change between runs)
+            LCD_DRAIN(s);
             LCD_CUDA_OK(cudaMemcpyAsync(&tot_cand, d_bin_first.p + tot_bins, sizeof(long long), cudaMemcpyDeviceToHost, s));
             LCD_CUDA_OK(cudaStreamSynchronize(s));
             if (d_cand.alloc(tot_cand + 1)) return -1;
@@ -185,6 +187,7 @@ struct SitesPlan : Plan {
         c.launches += 2;
         if (scan::exclusive_scan(d_bin_keep.p, tot_bins, d_keep_first.p, d_tmp, s)) return -1;
         if (tot_sites < 0) {
+            LCD_DRAIN(s);
             LCD_CUDA_OK(cudaMemcpyAsync(&tot_sites, d_keep_first.p + tot_bins, sizeof(long long), cudaMemcpyDeviceToHost, s));
             LCD_CUDA_OK(cudaStreamSynchronize(s));
             if (d_spos.alloc(tot_sites + 1) || d_stype.alloc(tot_sites + 1) || d_sref.alloc(tot_sites + 1) || d_salt.alloc(tot_sites + 1) || d_ssrc.alloc(tot_sites + 1) || d_saoff.alloc(tot_sites + 1)) return -1;
@@ -203,6 +206,7 @@ struct SitesPlan : Plan {
         h_site_off.assign(n + 1, 0);
         if (n) {
             if (tot_sites < 0) { set_error("lcd_sites: the plan has not been run"); return -1; }
+            LCD_DRAIN(s);
             LCD_CUDA_OK(cudaMemcpyAsync(h_site_off.data(), d_chunk_site_off.p, sizeof(long long) * (n + 1), cudaMemcpyDeviceToHost, s));
             LCD_CUDA_OK(cudaStreamSynchronize(s));
         }
@@ -213,6 +217,7 @@ struct SitesPlan : Plan {
     int fetch(cudaStream_t s, lcd_sites_output_t *out) {
         if (n == 0) return 0;
         if (index(s)) return -1;
+        LCD_DRAIN(s);
         for (int i = 0; i < n; ++i) {
             const long long o = h_site_off[i], ns = h_site_off[i + 1] - o;
             out[i].n_sites = ns;

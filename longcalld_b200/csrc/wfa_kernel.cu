@@ -94,6 +94,7 @@ static int score_cap(const lcd_wfa_params_t &p, int plen, int tlen) {
 constexpr int ESC_SCORE = 160;      // warp groups hand problems over to the CTA kernel at this score
 
 struct WfaPlan : Plan {
+    int pool_window() const override { return 1; }
     DevBuf<uint8_t> d_seqs;
     DevBuf<Problem> d_problems;
     DevBuf<int32_t> d_order_small, d_order_large;
@@ -190,12 +191,12 @@ struct WfaPlan : Plan {
         if (n == 0) return 0;
         // pool layout (16-byte units): [meta small | meta large | arenas small | arenas large | overflow]
         const int occ_small = 4;                                   // CTAs per SM of the warp kernel
-        int grid_small = n_small ? std::min((n_small + WARP_GROUPS_PER_CTA - 1) / WARP_GROUPS_PER_CTA, c.sm_count * occ_small) : 0;
+        int grid_small = n_small ? std::min((n_small + WARP_GROUPS_PER_CTA - 1) / WARP_GROUPS_PER_CTA, c.dp_sms() * occ_small) : 0;
         // CTA groups serve the pre-classified large problems and, afterwards, whatever the warp kernel escalates
-        int grid_large = (n_large || n_small) ? c.sm_count * 2 : 0;
+        int grid_large = (n_large || n_small) ? c.dp_sms() * 2 : 0;
         const int cap_large = std::max(this->cap_large, n_small ? cap_small : 0);
         const size_t groups_small = (size_t)grid_small * WARP_GROUPS_PER_CTA, groups_large = grid_large;
-        const size_t pool_units = c.pool_words / 4;
+        const size_t pool_units = c.win_words(1) / 4;
         const size_t meta_small_units = groups_small * (size_t)cap_small * (sizeof(WfSet) / 16);
         const size_t meta_large_units = groups_large * (size_t)cap_large * (sizeof(WfSet) / 16);
         if (meta_small_units + meta_large_units > pool_units / 2) {
@@ -212,7 +213,7 @@ struct WfaPlan : Plan {
         const size_t n_chunks = std::min<size_t>((rest - arenas) / wfa::OVERFLOW_CHUNK_UNITS, (size_t)Context::BITMAP_WORDS * 32);
         KernelArgs ka;
         ka.problems = d_problems.p; ka.seqs = d_seqs.p; ka.ops = d_ops.p; ka.results = d_results.p;
-        ka.pool = c.pool; ka.chunk_bitmap = c.chunk_bitmap;
+        ka.pool = c.win_pool(1); ka.chunk_bitmap = c.chunk_bitmap;
         ka.overflow_base = (uint32_t)(meta_small_units + meta_large_units + arenas);
         ka.n_chunks = (uint32_t)n_chunks;
         ka.esc_score = 0; ka.esc_list = d_esc_list.p; ka.esc_count = d_queue.p + 3; ka.n_dev = nullptr;
@@ -225,7 +226,7 @@ struct WfaPlan : Plan {
             attr_set = true;
         }
         KernelArgs kl = ka;
-        kl.meta = reinterpret_cast<WfSet *>(c.pool + meta_small_units * 4); kl.meta_cap = cap_large;
+        kl.meta = reinterpret_cast<WfSet *>(c.win_pool(1) + meta_small_units * 4); kl.meta_cap = cap_large;
         kl.arena_base = (uint32_t)(meta_small_units + meta_large_units + arena_small * groups_small);
         kl.arena_units = (uint32_t)arena_large;
         if (n_large) {             // large problems on the side stream, concurrently with the small ones
@@ -240,7 +241,7 @@ struct WfaPlan : Plan {
         if (grid_small) {
             KernelArgs ks = ka;
             ks.order = d_order_small.p; ks.n = n_small; ks.queue = d_queue.p;
-            ks.meta = reinterpret_cast<WfSet *>(c.pool); ks.meta_cap = cap_small;
+            ks.meta = reinterpret_cast<WfSet *>(c.win_pool(1)); ks.meta_cap = cap_small;
             ks.arena_base = (uint32_t)(meta_small_units + meta_large_units);
             ks.arena_units = (uint32_t)arena_small;
             ks.esc_score = ESC_SCORE;
@@ -262,6 +263,7 @@ struct WfaPlan : Plan {
         h_results.resize(n);
         h_ops.resize(ops_bytes + 16);
         if (n == 0) return 0;
+        LCD_DRAIN(s);
         LCD_CUDA_OK(cudaMemcpyAsync(h_results.data(), d_results.p, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, s));
         LCD_CUDA_OK(cudaMemcpyAsync(h_ops.data(), d_ops.p, ops_bytes, cudaMemcpyDeviceToHost, s));
         LCD_CUDA_OK(cudaStreamSynchronize(s));
