@@ -414,6 +414,7 @@ def run_b200(args, rank, world):
     lcd.reserve_sms(args.reserve_sms)              # room for the pileup / phasing kernels next to the persistent DP grids
     aux = torch.cuda.ExternalStream(aux_h, device=local)
     wl = Workload(args.mbp, args.tech, args.seed + rank)            # weak scaling: one shard per GPU
+    _pin = torch.from_numpy(wl.seqs).pin_memory(); wl.seqs = _pin.numpy()      # the loader's read buffer: page-locked, as the K1 inputs are
     L = lcd.lib()
     n = wl.n_poa
     ppar = np.zeros(n, dtype=POA_PARAMS_DTYPE); ppar[:] = lcd.poa_params()
@@ -440,18 +441,32 @@ def run_b200(args, rank, world):
 
     L.lcd_poa_plan_create.restype = C.c_void_p
 
-    def poa_stage(b, after_launch=None):
-        """host reads -> POA plan (H2D) -> launch -> consensus of every (region, haplotype) in host memory (slot b).  lcd_poa_batch
-        spelled out in its three C-ABI calls, so that the other engines' host threads can be released once the persistent grid is
-        in flight (lcd_plan_run only enqueues)."""
+    stage_stream = torch.cuda.Stream(device=local)
+
+    def poa_create():
+        """host reads -> POA plan (packing + H2D), on a stream of its own: the library stream is busy with the batch before, and
+        uploads queued behind its grid would wait for it (and hold up every other thread's copies of pageable memory meanwhile)"""
+        lcd.set_thread_stream(stage_stream.cuda_stream)
+        try:
+            return _poa_create()
+        finally:
+            lcd.set_thread_stream(0)
+
+    def _poa_create():
         h = L.lcd_poa_plan_create(C.c_int(n), _vp(wl.seqs), C.c_size_t(wl.seqs.size), _vp(wl.first), _vp(wl.n_reads),
                                   _vp(wl.read_off), _vp(wl.read_len), C.c_int(len(wl.read_len)), _vp(ppar))
         if not h:
             raise RuntimeError(L.lcd_gpu_last_error().decode())
-        h = C.c_void_p(h)
+        return C.c_void_p(h)
+
+    def poa_stage(b, h, after_launch=None, during_launch=None):
+        """POA plan -> launch -> consensus of every (region, haplotype) in host memory (slot b).  lcd_poa_batch spelled out in its
+        C-ABI calls, so that the other engines' host threads can be released once the persistent grid is in flight (lcd_plan_run
+        only enqueues) and the next batch's plan can be staged while this one's grid works."""
         tm = [time.perf_counter()]
         rc = L.lcd_plan_run(h, None)
         if after_launch: after_launch()
+        nxt = during_launch() if during_launch else None
         tm.append(time.perf_counter())
         rc = rc or L.lcd_poa_plan_fetch(h, None, _vp(bufs[b][R:]), _vp(wl.cons_off), None, None, None, _vp(press[b]))
         tm.append(time.perf_counter())
@@ -459,6 +474,7 @@ def run_b200(args, rank, world):
         stage_err["t_poa"] = [round(1e3 * (y - x), 1) for x, y in zip(tm, tm[1:])]
         if rc:
             raise RuntimeError(L.lcd_gpu_last_error().decode())
+        return nxt
 
     def wfa_stage(b, own_stream=False):
         """consensus in host memory (slot b) -> lcd_wfa_batch -> host CIGAR ops; then K7 through its host-buffer batch call"""
@@ -492,6 +508,7 @@ def run_b200(args, rank, world):
         the batch run from a third host thread on their own stream and pool window WHILE the next batch's K5 runs (two-stage software
         pipeline over the batches, --no-pipeline: in sequence); the last batch's K6 + K7 drain at the end, inside the timed region."""
         prev = None
+        h_next = poa_create()
         for k in range(steps):
             b = k & 1
             pile_gpu_done.clear()
@@ -499,13 +516,14 @@ def run_b200(args, rank, world):
             ph_thread = threading.Thread(target=phase_stage_thread); ph_thread.start()
             wt = threading.Thread(target=wfa_stage, args=(prev, True)) if (prev is not None and args.pipeline) else None
             t_it = time.perf_counter()
-            poa_stage(b, wt.start if wt is not None else None)          # K6 / K7 of the batch before are released once K5 is in flight
+            # K6 / K7 of the batch before are released once K5 is in flight; the next batch's POA plan is staged meanwhile
+            h_next = poa_stage(b, h_next, wt.start if wt is not None else None, poa_create if k + 1 < steps else None)
             t_poa_done = time.perf_counter()
             if not args.pipeline: wfa_stage(b)
             if wt is not None: wt.join()
             pile_thread.join(); ph_thread.join()
             if os.environ.get("LCD_BENCH_VERBOSE"):
-                print(f"[e2e step {k}] {1e3 * (time.perf_counter() - t_it):.1f} ms; main: POA create+launch {1e3 * (t_poa_done - t_it) - sum(stage_err.get('t_poa', [0])):.1f}, [after launch, fetch] {stage_err.get('t_poa')}; "
+                print(f"[e2e step {k}] {1e3 * (time.perf_counter() - t_it):.1f} ms; main: [launch + next plan, fetch] {stage_err.get('t_poa')}; "
                       f"K6/K7 thread [wait, wfa batch, edlib batch] {stage_err.get('t_wfa')}; pileup thread {pile_res.get('t')}; K4 batch {pile_res.get('t_phase')}", file=sys.stderr)
             for d in (pile_res, stage_err):
                 if "error" in d: raise d.pop("error")

@@ -9,7 +9,7 @@ namespace digar {
 
 constexpr int THREADS = 128;
 constexpr int HIST_WARPS = 8;
-constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_THREADS = 256;      // small CTAs: the scan has to fit next to a resident persistent DP grid (lcd_gpu_reserve_sms)
 
 __global__ void __launch_bounds__(THREADS)
 digar_count_kernel(const KernelArgs a) {
@@ -18,7 +18,7 @@ digar_count_kernel(const KernelArgs a) {
 }
 
 // Exclusive scan of cnt[j][0 .. n] (the entry at n counts as 0, so first[j][n] is the total); one CTA per array j:
-// every thread sums a contiguous segment, the 1024 partial sums are scanned through shared memory, the segment is rewritten.
+// every thread sums a contiguous segment, the partial sums are scanned through shared memory, the segment is rewritten.
 __global__ void __launch_bounds__(SCAN_THREADS)
 digar_scan_kernel(const long long *cnt, long long *first, long long n, long long stride) {
     __shared__ long long warp_sum[SCAN_THREADS / 32];
@@ -34,10 +34,10 @@ digar_scan_kernel(const long long *cnt, long long *first, long long n, long long
     if (lane == 31) warp_sum[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        long long w = warp_sum[lane], wi = w;
+        long long w = lane < SCAN_THREADS / 32 ? warp_sum[lane] : 0, wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const long long v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
-        warp_sum[lane] = wi - w;
+        if (lane < SCAN_THREADS / 32) warp_sum[lane] = wi - w;
     }
     __syncthreads();
     long long run = warp_sum[warp] + incl - s;

@@ -9,6 +9,7 @@ namespace lcd {
 namespace poa {
 
 constexpr int WARPS_PER_CTA = 4;
+constexpr int POA_CARVEOUT_PCT = 50;      // % of the SM's L1 / shared memory kept as shared memory where the persistent grid sits: with the driver's choice (just what the grid needs) a kernel with its own shared memory (K1's histogram: 8 KB) cannot join a half-free SM and waits for the grid to retire (measured: 196 ms instead of 23 ms)
 
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA)
 poa_kernel(const KernelArgs a) {
@@ -202,6 +203,12 @@ struct PoaPlan : Plan {
         ka.seqs = d_seqs.p; ka.read_off = d_read_off.p; ka.read_len = d_read_len.p;
         ka.cons = d_cons.p; ka.msa = d_msa.p; ka.msa_cap = msa_pool_bytes; ka.msa_used = d_msa_used.p;
         ka.results = d_results.p; ka.arena = c.win_pool(0) + pool_lo; ka.arena_words = words; ka.worst_case = worst_case ? 1 : 0;
+        static int carve_set = -2;          // shared-memory carve-out of the SMs the persistent grid sits on (see lcd_gpu_reserve_sms)
+        if (carve_set == -2) {
+            const char *cv = getenv("LCD_POA_CARVEOUT");
+            carve_set = cv ? atoi(cv) : POA_CARVEOUT_PCT;
+            if (carve_set >= 0) LCD_CUDA_OK(cudaFuncSetAttribute(poa_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve_set));
+        }
         if (kind == 0) poa_thread_kernel<<<grid, THREADS_PER_CTA, 0, s>>>(ka);
         else if (kind == 1) poa_kernel<<<grid, 32 * WARPS_PER_CTA, 0, s>>>(ka);
         else poa_cta_kernel<<<grid, 32 * CTA_WARPS, 0, s>>>(ka);

@@ -8,6 +8,7 @@ namespace lcd {
 namespace scan {
 
 constexpr int THREADS = 256, PER_THREAD = 8, TILE = THREADS * PER_THREAD;
+constexpr int TS = 256;          // threads of the one CTA that scans the tile sums (small: it has to fit next to a resident persistent DP grid)
 
 __device__ __forceinline__ long long block_exclusive(long long v, long long *smem, long long *total) {     // smem: THREADS / 32 + 1 entries
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -42,10 +43,10 @@ tile_sum_kernel(const int32_t *in, long long n, long long *tile_sum) {
     if (threadIdx.x == 0) tile_sum[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(TS)
 tile_scan_kernel(long long *tile_sum, long long n_tiles) {      // in place: tile_sum[t] <- sum of the tiles before t; tile_sum[n_tiles] <- total
-    __shared__ long long warp_sum[32];
-    const long long seg = (n_tiles + 1023) / 1024;
+    __shared__ long long warp_sum[TS / 32];
+    const long long seg = (n_tiles + TS - 1) / TS;
     const long long i0 = min(n_tiles, seg * (long long)threadIdx.x), i1 = min(n_tiles, i0 + seg);
     long long s = 0;
     for (long long i = i0; i < i1; ++i) s += tile_sum[i];
@@ -56,15 +57,15 @@ tile_scan_kernel(long long *tile_sum, long long n_tiles) {      // in place: til
     if (lane == 31) warp_sum[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        long long w = warp_sum[lane], wi = w;
+        long long w = lane < TS / 32 ? warp_sum[lane] : 0, wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += y; }
-        warp_sum[lane] = wi - w;
+        if (lane < TS / 32) warp_sum[lane] = wi - w;
     }
     __syncthreads();
     long long run = warp_sum[warp] + incl - s;
     for (long long i = i0; i < i1; ++i) { const long long v = tile_sum[i]; tile_sum[i] = run; run += v; }
-    if (threadIdx.x == 1023) tile_sum[n_tiles] = run;
+    if (threadIdx.x == TS - 1) tile_sum[n_tiles] = run;
 }
 
 __global__ void __launch_bounds__(THREADS)
@@ -86,7 +87,7 @@ inline int exclusive_scan(const int32_t *in, long long n, long long *out, DevBuf
     if (n_tiles == 0) { LCD_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(long long), s)); return 0; }
     if (tmp.n < (size_t)n_tiles + 2 && tmp.alloc((size_t)n_tiles + 2)) return -1;
     tile_sum_kernel<<<(unsigned)n_tiles, THREADS, 0, s>>>(in, n, tmp.p);
-    tile_scan_kernel<<<1, 1024, 0, s>>>(tmp.p, n_tiles);
+    tile_scan_kernel<<<1, TS, 0, s>>>(tmp.p, n_tiles);
     tile_rescan_kernel<<<(unsigned)n_tiles, THREADS, 0, s>>>(in, n, tmp.p, out);
     LCD_CUDA_OK(cudaGetLastError());
     ctx().launches += 3;
