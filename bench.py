@@ -36,12 +36,22 @@ EDLIB_BYTES_PER_BLOCKCOL = 28    # Peq word in + (P, M, score) s
 PHASE_BYTES_PER_PAIR = 24        # allele + variant state in, counts out, per (read, variant) pair and pass
 
 
+NCU_CAPTURES = ("r1_poa_full_v5.raw.csv", "r1_poa_full_v3.raw.csv")       # newest first
+
+
+def ncu_capture():
+    for f in NCU_CAPTURES:
+        if os.path.exists(os.path.join(ROOT, "profiles", f)):
+            return f
+    return None
+
+
 def ncu_traffic(kernel="poa_kernel"):
     """DRAM bytes (read + write) of one launch of the dominant kernel from the committed `ncu --set full` capture of this
-    same command (profiles/r1_poa_full_v3.raw.csv); None when the file is missing."""
+    same command (profiles/r1_poa_full_v*.raw.csv); None when the file is missing."""
     try:
         import csv
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1_poa_full_v3.raw.csv"))))
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", ncu_capture()))))
         h, u, v = rows[0], rows[1], rows[2]
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
         tot = 0.0
@@ -741,7 +751,7 @@ def run_b200(args, rank, world):
                                                     "bytes_per_step": int(gathered["bytes"])}),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": ncu_traffic() if dominant_is_poa else None,
-                             "traffic_source": "profiles/r1_poa_full_v3.raw.csv (ncu --set full of this command, one poa_kernel launch)",
+                             "traffic_source": f"profiles/{ncu_capture()} (ncu --set full of this command, one poa_kernel launch)",
                              "kernel": "poa_kernel" if dominant_is_poa else "wfa_kernel<32>+wfa_kernel<256>",
                              "algorithmic": (f"{poa_cells} banded POA cells x {POA_BYTES_PER_CELL} B" if dominant_is_poa
                                              else f"{wfa_cells} wavefront cells x {WFA_BYTES_PER_CELL} B"),
