@@ -213,6 +213,35 @@ int lcd_pileup_batch(int n_chunks, const lcd_pileup_input_t *in, lcd_pileup_outp
 lcd_plan_t *lcd_pileup_plan_create(int n_chunks, const lcd_pileup_input_t *in);
 int  lcd_pileup_plan_fetch(lcd_plan_t *plan, void *stream, lcd_pileup_output_t *out);
 
+/* ---------------------------------------------------------------- K2b: pileup scan, category of every candidate site
+ * Replaces the first loop of int classify_cand_vars(bam_chunk_t *chunk, int n_var_sites, const call_var_opt_t *opt)
+ * (src/collect_var.c:902-925): int classify_var_cate(opt, ref_seq, ref_beg, ref_end, var, min_dp, min_alt_dp, min_af, max_af, ...)
+ * (:413-432) for every site, with var_is_homopolymer (:306-358) and var_is_repeat_region (:361-400): depth and allele-fraction
+ * thresholds, then for small indels the reference context (1-6 bp unit repeated 3x on either side; the indel itself repeated 3x).
+ * The sites and counters are K2's (lcd_pileup_input_t / lcd_pileup_output_t); the result is chunk->var_i_to_cate before the
+ * noisy-region pass.  The reference window must reach 24 bases beyond every site on both sides (the reference reads it unchecked;
+ * chunks carry +-50 kb).  ONT's strand-bias Fisher test (var_is_strand_bias, :270) is floating point and stays on the host:
+ * chunks with is_ont set are rejected. */
+typedef struct {
+    int32_t n_sites;
+    int32_t min_dp, min_alt_dp;        /* opt->min_dp, opt->min_alt_dp */
+    int32_t max_xgaps;                 /* opt->noisy_reg_max_xgaps: longer indels skip the homopolymer / repeat tests */
+    int32_t is_ont;                    /* opt->is_ont (the strand-bias Fisher test of ONT data is not restated: must be 0) */
+    int32_t pad;
+    double min_af, max_af;             /* opt->min_af, opt->max_af */
+    int64_t ref_beg, ref_end;          /* chunk->ref_beg / ref_end: ref_seq[0] is base ref_beg */
+    const char *ref_seq;               /* chunk->ref_seq (ASCII) */
+    const int64_t *site_pos;           /* cand_var_t.pos / var_type / ref_len / alt_len / alt_seq, as in lcd_pileup_input_t */
+    const int32_t *site_type, *site_ref_len, *site_alt_len;
+    const int64_t *site_alt_off;
+    const uint8_t *site_alt;
+    const int32_t *site_counts;        /* [n_sites][8]: lcd_pileup_output_t (total_cov, low_qual_cov, alle_covs[0..1], strand x allele) */
+} lcd_classify_input_t;
+typedef struct { int32_t *var_cate; } lcd_classify_output_t;      /* [n_sites]: LONGCALLD_* category (src/collect_var.h:11-24) */
+int lcd_classify_batch(int n_chunks, const lcd_classify_input_t *in, lcd_classify_output_t *out);
+lcd_plan_t *lcd_classify_plan_create(int n_chunks, const lcd_classify_input_t *in);
+int  lcd_classify_plan_fetch(lcd_plan_t *plan, void *stream, lcd_classify_output_t *out);
+
 /* ---------------------------------------------------------------- K3: pileup scan, read x variant profile
  * Replaces read_var_profile_t *collect_read_var_profile(const call_var_opt_t *opt, bam_chunk_t *chunk)
  * (src/collect_var.c:1389-1431: update_read_vs_all_var_profile_from_digar, src/bam_utils.c:446-552, for every kept read;

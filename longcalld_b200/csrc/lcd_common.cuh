@@ -57,7 +57,10 @@ int ensure_ready();
 // The stream a host thread's plans upload, run and fetch on when it passes no stream: the library stream, unless the thread chose
 // another one with lcd_gpu_set_thread_stream (e.g. the auxiliary stream, to overlap one stage's copies with another's kernels).
 cudaStream_t &thread_stream();
-inline cudaStream_t cur_stream() { cudaStream_t t = thread_stream(); return t ? t : ctx().stream; }
+// A host thread other than the one that called lcd_gpu_init starts on device 0: every entry point binds the calling thread to the
+// library's device first (once per thread).
+void bind_thread();
+inline cudaStream_t cur_stream() { bind_thread(); cudaStream_t t = thread_stream(); return t ? t : ctx().stream; }
 
 struct Plan {
     virtual ~Plan() {}
@@ -122,6 +125,6 @@ int sites_plan_view(Plan *plan, Plan *digar, cudaStream_t s, SitesView *v);   //
 // while a POA launch with its status copy queued behind it was in flight).  So results are read back only after the stream has drained.
 #define LCD_DRAIN(s) LCD_CUDA_OK(cudaStreamSynchronize(s))
 
-inline cudaStream_t pick_stream(void *s) { return s ? (cudaStream_t)s : cur_stream(); }
+inline cudaStream_t pick_stream(void *s) { bind_thread(); return s ? (cudaStream_t)s : cur_stream(); }
 
 } // namespace lcd

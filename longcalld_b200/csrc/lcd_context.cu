@@ -17,8 +17,15 @@ void set_error(const char *fmt, ...) {
 Context &ctx() { static Context c; return c; }
 cudaStream_t &thread_stream() { static thread_local cudaStream_t s = nullptr; return s; }
 
+void bind_thread() {
+    static thread_local int bound = -1;
+    Context &c = ctx();
+    if (!c.ready || bound == c.device) return;
+    if (cudaSetDevice(c.device) == cudaSuccess) bound = c.device;
+}
+
 int ensure_ready() {
-    if (ctx().ready) return 0;
+    if (ctx().ready) { bind_thread(); return 0; }
     return lcd_gpu_init(0, 0);
 }
 
@@ -35,6 +42,7 @@ void *lcd_gpu_stream(void) { return ctx().ready ? (void*)ctx().stream : nullptr;
 void *lcd_gpu_aux_stream(void) {
     Context &c = ctx();
     if (!c.ready) return nullptr;
+    bind_thread();
     std::lock_guard<std::mutex> lk(c.mu);
     if (!c.aux_stream && cudaStreamCreateWithFlags(&c.aux_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("lcd_gpu_aux_stream: cudaStreamCreate failed"); return nullptr; }
     return (void*)c.aux_stream;
@@ -136,6 +144,7 @@ int lcd_plan_work_units(lcd_plan_t *plan, void *stream, uint64_t *units) {
 }
 
 void lcd_plan_destroy(lcd_plan_t *plan) {
+    bind_thread();
     if (plan) delete reinterpret_cast<Plan*>(plan);
 }
 

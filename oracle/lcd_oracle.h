@@ -180,6 +180,24 @@ typedef struct {
 } lcd_sites_output_t;
 int lcd_oracle_collect_sites(const lcd_pileup_input_t *in, int64_t reg_beg, int64_t reg_end, lcd_sites_output_t *out);
 
+/* ---- pileup scan, step 2 (first loop): category of every candidate site (src/collect_var.c:413-432 with :306-400) ---------- */
+typedef struct {
+    int32_t n_sites;
+    int32_t min_dp, min_alt_dp;        /* opt->min_dp, opt->min_alt_dp */
+    int32_t max_xgaps;                 /* opt->noisy_reg_max_xgaps: longer indels skip the homopolymer / repeat tests */
+    int32_t is_ont;                    /* opt->is_ont (the strand-bias Fisher test of ONT data is not restated: must be 0) */
+    int32_t pad;
+    double min_af, max_af;             /* opt->min_af, opt->max_af */
+    int64_t ref_beg, ref_end;          /* chunk->ref_beg / ref_end: ref_seq[0] is base ref_beg */
+    const char *ref_seq;               /* chunk->ref_seq (ASCII) */
+    const int64_t *site_pos;           /* cand_var_t.pos / var_type / ref_len / alt_len / alt_seq, as in lcd_pileup_input_t */
+    const int32_t *site_type, *site_ref_len, *site_alt_len;
+    const int64_t *site_alt_off;
+    const uint8_t *site_alt;
+    const int32_t *site_counts;        /* [n_sites][8]: lcd_pileup_output_t (total_cov, low_qual_cov, alle_covs[0..1], strand x allele) */
+} lcd_classify_input_t;
+int lcd_oracle_classify_sites(const lcd_classify_input_t *in, int32_t *var_cate);
+
 #ifdef __cplusplus
 }
 #endif

@@ -361,3 +361,21 @@ int ref_collect_sites(const lcd_pileup_input_t *in, int64_t reg_beg, int64_t reg
     ref_sites_core(job);
     return ref_sites_finish(job, in, out);
 }
+
+int classify_var_cate(const call_var_opt_t *opt, char *ref_seq, hts_pos_t ref_beg, hts_pos_t ref_end, cand_var_t *var, int min_dp_thres, int min_alt_dp_thres,
+                      double min_af_thres, double max_af_thres, double min_noisy_reg_ratio);          /* src/collect_var.c:413 (no prototype in the headers) */
+/* classify_var_cate (src/collect_var.c:413) for every site, as the first loop of classify_cand_vars (:915-918) calls it: cand_var_t records around the flat arrays */
+int ref_classify_sites(const lcd_classify_input_t *in, int32_t *var_cate) {
+    call_var_opt_t opt; memset(&opt, 0, sizeof(opt));
+    opt.noisy_reg_max_xgaps = in->max_xgaps; opt.is_ont = in->is_ont; opt.min_dp = in->min_dp; opt.min_alt_dp = in->min_alt_dp; opt.min_af = in->min_af; opt.max_af = in->max_af;
+    for (int i = 0; i < in->n_sites; ++i) {
+        const int32_t *c = in->site_counts + 8 * (int64_t)i;
+        cand_var_t var; memset(&var, 0, sizeof(var));
+        int alle_covs[2] = { c[2], c[3] }, s0[2] = { c[4], c[5] }, s1[2] = { c[6], c[7] }; int *strand[2] = { s0, s1 };
+        var.pos = in->site_pos[i]; var.var_type = in->site_type[i]; var.total_cov = c[0]; var.low_qual_cov = c[1]; var.n_uniq_alles = 2;
+        var.alle_covs = alle_covs; var.strand_to_alle_covs = strand; var.ref_len = in->site_ref_len[i]; var.alt_len = in->site_alt_len[i];
+        var.alt_seq = (var.var_type == BAM_CDIFF || var.var_type == BAM_CINS) ? (uint8_t*)(in->site_alt + in->site_alt_off[i]) : NULL;
+        var_cate[i] = classify_var_cate(&opt, (char*)in->ref_seq, in->ref_beg, in->ref_end, &var, opt.min_dp, opt.min_alt_dp, opt.min_af, opt.max_af, opt.min_af);
+    }
+    return 0;
+}

@@ -63,3 +63,28 @@ def test_concurrent_engines_split_pool(gpu):
         assert all(np.array_equal(g[k], w[k]) for k in w)
     # and back to one window
     assert gpu.wfa_batch(pairs[:50], gpu.wfa_params()) == want_wfa[:50]
+
+
+def test_worker_threads_follow_the_library_device():
+    """A host thread other than the one that called lcd_gpu_init starts on CUDA device 0; the entry points bind it to the library's
+    device.  Run in a child process that initialises the library on the LAST device of the box (device 0 on a one-GPU box)."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, threading
+        sys.path.insert(0, %r); sys.path.insert(0, %r + "/tests")
+        import numpy as np, torch
+        import longcalld_b200 as lcd
+        from longcalld_b200 import synth
+        dev = torch.cuda.device_count() - 1
+        torch.cuda.set_device(dev); lcd.init(dev, 1 << 30)
+        rng = np.random.default_rng(7)
+        chunks = [(synth.make_phase_chunk(rng, 300, 200), synth.CATE_CLEAN, 0)]
+        want = lcd.phase_batch(chunks); got = {}
+        def work():
+            lcd.set_thread_stream(lcd.aux_stream()); got["r"] = lcd.phase_batch(chunks)
+        t = threading.Thread(target=work); t.start(); t.join()
+        assert all(np.array_equal(got["r"][0][k], want[0][k]) for k in want[0])
+        print("ok", dev)
+    """ % (T.ROOT, T.ROOT))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

@@ -35,3 +35,22 @@ def test_oracle_vs_reference_fixtures(oracle):
     for c in g["cases"]:
         d, reg, want = T.sites_case_from_json(c)
         assert T.collect_sites(oracle, "lcd_oracle_collect_sites", d, reg[0], reg[1]) == want
+
+
+def test_site_list_from_sites_matches_the_records(oracle):
+    """bench / drop-in helper: the lcd_site_list_t arrays built from a site list carry the alt bases of the records the sites stand for."""
+    for n, (d, (b, e)) in enumerate(sites_cases(53, 12)):
+        keep = {k: np.ascontiguousarray(d[k], dtype=t) for k, t in T.PILEUP_IN_FIELDS}
+        inp = T.PileupInput(d["n_reads"], 0, d["min_bq"], d["min_sv_len"], *[keep[k].ctypes.data for k, _ in T.PILEUP_IN_FIELDS])
+        cap = int(np.asarray(d["n_digar"][:d["n_reads"]]).sum()) + 8
+        pos, typ, rl, al, src = np.zeros(cap, np.int64), np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int64)
+        out = T.SitesOutput(pos.ctypes.data, typ.ctypes.data, rl.ctypes.data, al.ctypes.data, src.ctypes.data, cap, 0)
+        assert oracle.lcd_oracle_collect_sites(T.C.byref(inp), T.C.c_int64(b), T.C.c_int64(e), T.C.byref(out)) == 0
+        ns = int(out.n_sites)
+        st = dict(n_sites=ns, site_pos=pos[:ns], site_type=typ[:ns], site_ref_len=rl[:ns], site_alt_len=al[:ns], site_src=src[:ns])
+        sl = synth.site_list_from_sites(d, st, min_sv_len=d["min_sv_len"])
+        want = T.sites_view(d, pos, typ, rl, al, src, ns)
+        got = [(int(sl["site_pos"][i]), int(sl["site_type"][i]), int(sl["site_ref_len"][i]), int(sl["site_alt_len"][i]),
+                bytes(sl["site_alt"][int(sl["site_alt_off"][i]):int(sl["site_alt_off"][i]) + (0 if sl["site_type"][i] == 2 else int(sl["site_alt_len"][i]))])) for i in range(ns)]
+        assert got == want, n
+        assert sl["n_sites"] == ns and len(sl["site_pos"]) == ns + 1
