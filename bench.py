@@ -187,11 +187,12 @@ class PileupStage:
         raw = sites_fn(bare, outs, self.regs)
         piles = [synth.pileup_input_from_digar(d, o, s) for d, o, s in zip(self.template, outs, raw)]
         counts = pileup_fn(piles)
+        self.cls = [synth.classify_input_from_sites(d, s, c, seed + 977 * i) for i, (d, s, c) in enumerate(zip(self.template, raw, counts))]      # K2b's input
         var = [synth.classify_sites(s, c) for s, c in zip(raw, counts)]
         profs = [synth.pileup_input_from_digar(d, o, s) for d, o, s in zip(self.template, outs, var)]
         tile = lambda xs: [xs[i % nt] for i in range(self.n_chunks)]
         self.chunks, self.raw_sites, self.var_sites, self.piles, self.profs = tile(self.template), tile(raw), tile(var), tile(piles), tile(profs)
-        self.bare, self.regs = tile(bare), tile(self.regs)
+        self.bare, self.regs, self.cls = tile(bare), tile(self.regs), tile(self.cls)
         self.n_reads = [d["n_reads"] for d in self.chunks]
         self.read_bases = int(sum(int(d["l_qseq"].sum()) for d in self.chunks))
         self.cigar_ops = int(sum(int(d["n_cigar"].sum()) for d in self.chunks))
@@ -203,6 +204,7 @@ class PileupStage:
         self.k1_bytes = int(1.5 * self.read_bases + 4 * self.cigar_ops + 32 * self.records)
         self.k1b_bytes = int(14 * self.records + 36 * self.n_raw_sites)      # K1b: position, type, length and quality flag of every record in, a 36-byte site record out
         self.k2_bytes = int(32 * self.records + 24 * self.n_raw_sites)
+        self.k2b_bytes = int((32 + 24 + 4) * self.n_raw_sites)              # K2b: the site's counters and record in, its category out (+ ~36 reference bases for small indels)
         self.k3_bytes = int(32 * self.records + 24 * self.n_vars)
 
 
@@ -291,7 +293,7 @@ def ref_pileup_fns(lib, n_threads):
 
 
 def reference_pileup_step(lib, ps, k, n_threads):
-    """K1 + K1b + K2 + K3 of the reference on the first k chunks of the batch; returns seconds (total, K1, K2, K3, K1b)."""
+    """K1 + K1b + K2 + K2b + K3 of the reference on the first k chunks of the batch; returns seconds (total, K1, K2, K3, K1b, K2b)."""
     from longcalld_b200 import capi
     chunks, piles, profs = ps.chunks[:k], ps.piles[:k], ps.profs[:k]
     ins, keep = capi._digar_inputs(chunks)
@@ -301,6 +303,8 @@ def reference_pileup_step(lib, ps, k, n_threads):
     bins, _, bkeep, _ = capi._pileup_structs(ps.bare[:k])
     souts, sres = capi._sites_outputs([int(s["n_sites"]) + 8 for s in ps.raw_sites[:k]])
     reg = np.array(ps.regs[:k], np.int64).reshape(-1)
+    cins, _, ckeep, cres = capi._classify_structs(ps.cls[:k])
+    cptr = (C.c_void_p * k)(*[r.ctypes.data for r in cres])
     exs, fouts, fres = (capi.ProfileExtra * k)(), (capi.ProfileOutput * k)(), []
     capi.lib().lcd_profile_capacity.restype = C.c_int64
     for i, d in enumerate(profs):
@@ -316,10 +320,12 @@ def reference_pileup_step(lib, ps, k, n_threads):
     t1 = time.perf_counter()
     rc |= lib.ref_pileup_batch(C.c_int(k), pins, pouts, C.c_int(n_threads))
     t2 = time.perf_counter()
+    rc |= lib.ref_classify_batch(C.c_int(k), cins, cptr, C.c_int(n_threads))
+    t2b = time.perf_counter()
     rc |= lib.ref_profile_batch(C.c_int(k), fins, exs, fouts, C.c_int(n_threads))
     t3 = time.perf_counter()
     if rc: raise RuntimeError("reference K1-K3 failed")
-    return core.value + score.value + (t3 - t1), core.value, t2 - t1, t3 - t2, score.value
+    return core.value + score.value + (t3 - t1), core.value, t2 - t1, t3 - t2b, score.value, t2b - t2
 
 
 def region_sample(wl, frac, seed=1):
@@ -369,7 +375,7 @@ def run_reference(args, rank):
                              "poa_s": sum(x[1] for x in t) / args.steps, "wfa_s": sum(x[2] for x in t) / args.steps,
                              "phase_s": sum(x[3] for x in t) / args.steps, "edlib_s": sum(x[4] for x in t) / args.steps,
                              "digar_s": pile_scale * sum(x[1] for x in tp) / args.steps, "pileup_s": pile_scale * sum(x[2] for x in tp) / args.steps,
-                             "profile_s": pile_scale * sum(x[3] for x in tp) / args.steps, "sites_s": pile_scale * sum(x[4] for x in tp) / args.steps},
+                             "profile_s": pile_scale * sum(x[3] for x in tp) / args.steps, "sites_s": pile_scale * sum(x[4] for x in tp) / args.steps, "classify_s": pile_scale * sum(x[5] for x in tp) / args.steps},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -380,13 +386,14 @@ def workload_config(args, wl, ps=None):
             "stages": ["K1 difference lists + noisy intervals + quality histogram from =/X CIGARs per 500 kb chunk (bam_utils.c:701)",
                        "K1b candidate-site list: sorted distinct X/I/D records incl. the large-insertion merge, on K1's lists in HBM (collect_var.c:1209)",
                        "K2 per-site coverage of the candidate sites, on K1's lists and K1b's sites in HBM (collect_var.c:238)",
+                       "K2b category of every candidate site: depth / allele-fraction thresholds, homopolymer and repeat context of small indels (collect_var.c:413)",
                        "K3 read x variant profile of the classified variants, on K1's lists in HBM (collect_var.c:1389)",
                        "K4 read->haplotype assignment + phasing per 500 kb chunk, clean then germline mask (assign_hap.c:473)",
                        "K7 edlib NW path read-vs-first-read sampling filter (align.c:722)",
                        "K5 abPOA consensus+MSA per (region, haplotype) (align.c:762)",
                        "K6 WFA gap-affine-2p ref-vs-consensus (align.c:565)"],
             "stages_not_yet_on_gpu": ["partial-read sub-graph POA", "2-consensus de-novo clustering",
-                                      "classification / noisy-region set (a5): prepared at set-up, untimed in both arms",
+                                      "noisy-region set of the classification (a5, second half): the variants K3 runs on are prepared at set-up, untimed in both arms",
                                       "noisy-region orchestration (a8), vars from MSA (a13), somatic chain (a14)"],
             "pileup": (None if ps is None else {"chunks": ps.n_chunks, "distinct_chunks": min(ps.N_TEMPLATE, ps.n_chunks), "reads": int(sum(ps.n_reads)),
                                                  "read_bases": ps.read_bases, "cigar_ops": ps.cigar_ops, "records": ps.records,
@@ -582,10 +589,11 @@ def run_b200(args, rank, world):
         dp.run(); dp.sync(); t.append(time.perf_counter())
         k1b = lcd.SitesPlan(None, ps.regs, min_sv_len=min_sv, digar_plan=dp); k1b.run(); pile_res["sites"] = k1b.fetch()
         k2 = lcd.PileupOnSitesPlan(dp, k1b); t.append(time.perf_counter()); k2.run(); pile_res["counts"] = k2.fetch(); t.append(time.perf_counter())
+        pile_res["cate"] = lcd.classify_batch(ps.cls)            # K2b on the host-resident site lists and counters (the reference window comes from the host)
         k3 = lcd.ProfileOnDigarPlan(dp, ps.var_sites, ps.n_reads); t.append(time.perf_counter()); k3.run(); pile_res["prof"] = k3.fetch(); t.append(time.perf_counter())
         for x in (k3, k2, k1b, dp): x.destroy()
         t.append(time.perf_counter())
-        # ms (second host thread, overlapped with the POA launch): K1 plan incl. H2D, K1 run, K1b plan+run+fetch and K2 plan, K2 run+fetch, K3 plan, K3 run+fetch, destroy
+        # ms (second host thread, overlapped with the POA launch): K1 plan incl. H2D, K1 run, K1b plan+run+fetch and K2 plan, K2 run+fetch, K2b batch and K3 plan, K3 run+fetch, destroy
         pile_res["t"] = [round(1e3 * t_plan, 2)] + [round(1e3 * (b - a), 2) for a, b in zip(t, t[1:])]
 
     def pileup_stage_thread():
@@ -617,6 +625,7 @@ def run_b200(args, rank, world):
     assert sum(sites_plan.sizes()) == ps.n_raw_sites
     k2_plan = lcd.PileupOnSitesPlan(digar_plan, sites_plan)
     k3_plan = lcd.ProfileOnDigarPlan(digar_plan, ps.var_sites, ps.n_reads)
+    k2b_plan = lcd.ClassifyPlan(ps.cls)
     poa_plan = lcd.PoaPlan(wl.seqs, wl.first, wl.n_reads, wl.read_off, wl.read_len, lcd.poa_params())
     wfa_plan = lcd.WfaPlan(wseqs, po, pl, to, tl, lcd.wfa_params())
     phase_plan = lcd.PhasePlan(wl.phase)
@@ -635,7 +644,7 @@ def run_b200(args, rank, world):
         overlap=True (what `value` is): the pool-free stages (K1 -> K1b -> K2 -> K3, K4) on the auxiliary stream, K5 on the library
         stream and, under the pipeline, K6 -> K7 -- which then stand for the batch before, whose consensus is resident -- on a third
         stream with their own window of the workspace pool; the library stream waits for the other two before ev[10]."""
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(13)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(14)]
         with torch.cuda.stream(stream):
             flush.zero_()
             ev[9].record(stream)
@@ -649,6 +658,7 @@ def run_b200(args, rank, world):
             ev[5].record(sa); digar_plan.run(sa_h)
             ev[8].record(sa); sites_plan.run(sa_h)
             ev[6].record(sa); k2_plan.run(sa_h)
+            ev[13].record(sa); k2b_plan.run(sa_h)
             ev[7].record(sa); k3_plan.run(sa_h)
             ev[2].record(sa); phase_plan.run(sa_h)
             ev[3].record(sa)
@@ -687,7 +697,7 @@ def run_b200(args, rank, world):
     wfa_ms = sum(e[1].elapsed_time(e[4]) for e in seq)
     phase_ms = sum(e[2].elapsed_time(e[3]) for e in seq)
     edlib_ms = sum(e[4].elapsed_time(e[11]) for e in seq)
-    k1_ms = sum(e[5].elapsed_time(e[8]) for e in seq); k1b_ms = sum(e[8].elapsed_time(e[6]) for e in seq); k2_ms = sum(e[6].elapsed_time(e[7]) for e in seq); k3_ms = sum(e[7].elapsed_time(e[2]) for e in seq)
+    k1_ms = sum(e[5].elapsed_time(e[8]) for e in seq); k1b_ms = sum(e[8].elapsed_time(e[6]) for e in seq); k2_ms = sum(e[6].elapsed_time(e[13]) for e in seq); k2b_ms = sum(e[13].elapsed_time(e[7]) for e in seq); k3_ms = sum(e[7].elapsed_time(e[2]) for e in seq)
     seq_ms = sum(e[9].elapsed_time(e[10]) for e in seq)
     dev_ms = sum(e[9].elapsed_time(e[10]) for e in evs)            # whole step: all streams, fork at ev[9], join at ev[10]
     poa_ovl_ms = sum(e[0].elapsed_time(e[12]) for e in evs)
@@ -707,7 +717,8 @@ def run_b200(args, rank, world):
     e2e_s = time.perf_counter() - t0
     phase_bytes = sum(a.nbytes for k in ph_keep for a in k.values())
     pile_d2h = int(sum(sum(a.nbytes for a in st.values() if hasattr(a, "nbytes")) for st in pile_res["sites"]) + sum(c.nbytes for c in pile_res["counts"]) + sum(sum(a.nbytes for a in o.values()) for o in pile_res["prof"]))
-    h2d = int(ps.h2d + phase_bytes + eseqs.size + 24 * ne + wl.seqs.size + 12 * len(wl.read_len) + 64 * n + (pl.astype(np.int64) + tl + 56).sum() + 96 * n)
+    cls_h2d = int(sum(sum(a.nbytes for a in d.values() if hasattr(a, "nbytes")) for d in ps.cls)); pile_d2h += int(sum(c.nbytes for c in pile_res["cate"]))
+    h2d = int(ps.h2d + cls_h2d + phase_bytes + eseqs.size + 24 * ne + wl.seqs.size + 12 * len(wl.read_len) + 64 * n + (pl.astype(np.int64) + tl + 56).sum() + 96 * n)
     d2h = int(pile_d2h + sum(a.nbytes for r in ph_res for a in r.values()) + eres.nbytes + int(eres["aln_len"].sum()) + pres["cons_len"].sum() + 32 * n + wres.nbytes + 2 * (pl.astype(np.int64) + tl + 4).sum())
 
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -734,7 +745,7 @@ def run_b200(args, rank, world):
                             "sample": f"{len(regs)} of {wl.n_regions} regions ({mbp_sample:.3f} Mb): the unmodified reference's own functions via oracle/_ref; "
                                       f"K1-K3 on {k_chunks} of {ps.n_chunks} chunks, time scaled by {pile_scale:.4f}",
                             "poa_s": dt_poa, "wfa_s": dt_wfa, "phase_s": dt_phase, "edlib_s": dt_edlib,
-                            "digar_s": pile_scale * dtp[1], "pileup_s": pile_scale * dtp[2], "profile_s": pile_scale * dtp[3], "sites_s": pile_scale * dtp[4]}
+                            "digar_s": pile_scale * dtp[1], "pileup_s": pile_scale * dtp[2], "profile_s": pile_scale * dtp[3], "sites_s": pile_scale * dtp[4], "classify_s": pile_scale * dtp[5]}
     if rank == 0:
         peak, which = load_peaks()
         poa_gbs = poa_cells * POA_BYTES_PER_CELL / (poa_ms / args.steps / 1e3) / 1e9
@@ -769,6 +780,7 @@ def run_b200(args, rank, world):
                                                               "note": "count + scan + scatter + group + scan + emit; 14 B per record in, 36 B per site out"},
                                             "pileup_kernel": {"ms": k2_ms / args.steps, "records": ps.records, "sites": ps.n_raw_sites,
                                                               "GBps": ps.k2_bytes / (k2_ms / args.steps / 1e3) / 1e9},
+                                            "classify_kernel": {"ms": k2b_ms / args.steps, "sites": ps.n_raw_sites, "GBps": ps.k2b_bytes / (k2b_ms / args.steps / 1e3) / 1e9},
                                             "profile_kernel": {"ms": k3_ms / args.steps, "records": ps.records, "variants": ps.n_vars,
                                                                "GBps": ps.k3_bytes / (k3_ms / args.steps / 1e3) / 1e9},
                                             "edlib_kernel": {"ms": edlib_ms / args.steps, "block_columns": edlib_units,

@@ -611,6 +611,55 @@ class PileupOnSitesPlan(_Plan):
         return [r[:k] for r, k in zip(self.results, self.n_sites)]
 
 
+# ----------------------------------------------------------------------------- K2b: category of every candidate site
+_CLASSIFY = (("site_pos", np.int64), ("site_type", np.int32), ("site_ref_len", np.int32), ("site_alt_len", np.int32),
+             ("site_alt_off", np.int64), ("site_alt", np.uint8), ("site_counts", np.int32))
+
+
+class ClassifyInput(C.Structure):
+    _fields_ = [("n_sites", C.c_int32), ("min_dp", C.c_int32), ("min_alt_dp", C.c_int32), ("max_xgaps", C.c_int32), ("is_ont", C.c_int32), ("pad", C.c_int32),
+                ("min_af", C.c_double), ("max_af", C.c_double), ("ref_beg", C.c_int64), ("ref_end", C.c_int64), ("ref_seq", C.c_void_p)] + \
+               [(k, C.c_void_p) for k, _ in _CLASSIFY]
+
+
+class ClassifyOutput(C.Structure):
+    _fields_ = [("var_cate", C.c_void_p)]
+
+
+def _classify_structs(chunks):
+    n = len(chunks)
+    ins, outs, keep, res = (ClassifyInput * max(n, 1))(), (ClassifyOutput * max(n, 1))(), [], []
+    for i, d in enumerate(chunks):
+        a = {k: np.ascontiguousarray(d[k], dtype=t) for k, t in _CLASSIFY}
+        a["ref_seq"] = np.ascontiguousarray(d["ref_seq"], dtype=np.uint8)
+        keep.append(a)
+        ins[i] = ClassifyInput(d["n_sites"], d["min_dp"], d["min_alt_dp"], d["max_xgaps"], d.get("is_ont", 0), 0, d["min_af"], d["max_af"], d["ref_beg"], d["ref_end"],
+                               a["ref_seq"].ctypes.data, *[a[k].ctypes.data for k, _ in _CLASSIFY])
+        r = np.full(d["n_sites"] + 1, -7, np.int32); res.append(r)
+        outs[i] = ClassifyOutput(r.ctypes.data)
+    return ins, outs, keep, res
+
+
+def classify_batch(chunks):
+    """Drop-in batch call over HOST buffers (lcd_classify_batch): per chunk the LONGCALLD_* category of every candidate site
+    (dict keys: n_sites, min_dp, min_alt_dp, max_xgaps, min_af, max_af, ref_beg, ref_end, ref_seq (ASCII bytes), site_*, site_counts)."""
+    ins, outs, keep, res = _classify_structs(chunks)
+    _check(lib().lcd_classify_batch(C.c_int(len(chunks)), ins, outs), "lcd_classify_batch")
+    return [r[:d["n_sites"]] for r, d in zip(res, chunks)]
+
+
+class ClassifyPlan(_Plan):
+    def __init__(self, chunks):
+        self.chunks = chunks
+        self.ins, self.outs, self.keep, self.res = _classify_structs(chunks)
+        lib().lcd_classify_plan_create.restype = C.c_void_p
+        super().__init__(lib().lcd_classify_plan_create(C.c_int(len(chunks)), self.ins), len(chunks))
+
+    def fetch(self, stream=None):
+        _check(lib().lcd_classify_plan_fetch(self.h, C.c_void_p(stream or 0), self.outs), "lcd_classify_plan_fetch")
+        return [r[:d["n_sites"]] for r, d in zip(self.res, self.chunks)]
+
+
 # ----------------------------------------------------------------------------- K3: pileup scan, read x variant profile
 _PROFILE_EX = (("var_cate", np.int32), ("nreg_first", np.int64), ("n_nreg", np.int32), ("nreg_beg", np.int64), ("nreg_end", np.int64))
 

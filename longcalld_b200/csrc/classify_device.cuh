@@ -1,0 +1,107 @@
+// classify_device.cuh -- device-side logic of K2b: the category of every candidate site, replacing classify_var_cate (reference
+// src/collect_var.c:413-432) as the first loop of classify_cand_vars (:915-918) calls it, with var_is_homopolymer (:306-358) and
+// var_is_repeat_region (:361-400).
+//
+// B200 design: ONE THREAD PER SITE over all chunks of a batch (~870 k sites per 50 Mb).  A site reads its 8 counters (one 32-byte
+// record, K2's output where it lies), its type / lengths and -- for the ~10 % of sites that are small indels between the allele-fraction
+// thresholds -- up to 36 reference bases around it (L2 resident: neighbouring sites share them) and its inserted bases.  The double
+// division of the allele fraction is IEEE on both sides, so the thresholds cut exactly where the reference's do.
+// The file compiles for the host as well (tests/emu).
+#pragma once
+#include <stdint.h>
+#include "../../include/lcd_gpu.h"
+
+namespace lcd {
+namespace classify {
+
+enum { CINS = 1, CDEL = 2, CDIFF = 8 };
+enum { NON_VAR = 0x800, LOW_COV_VAR = 0x001, LOW_AF_VAR = 0x400, CLEAN_HET_SNP = 0x004, CLEAN_HET_INDEL = 0x008, REP_HET_VAR = 0x010, CLEAN_HOM_VAR = 0x080 };
+
+struct __align__(16) Chunk {
+    int32_t min_dp, min_alt_dp, max_xgaps, pad;
+    double min_af, max_af;
+    long long ref_beg, ref_end;       // chunk->ref_beg / ref_end
+    long long ref_off;                // first byte of the chunk's reference window in the concatenated ref array
+    long long alt_base;               // first site_alt byte of the chunk (site_alt_off is relative to it)
+};
+
+struct KernelArgs {
+    const Chunk *chunks; long long n_sites_total;
+    const int32_t *site_chunk;
+    const long long *site_pos; const int32_t *site_type, *site_ref_len, *site_alt_len; const long long *site_alt_off; const uint8_t *site_alt;
+    const int32_t *site_counts;       // [n_sites_total][8]
+    const char *ref;
+    int32_t *var_cate;
+};
+
+__device__ __forceinline__ int nt4(char c) {                              // nst_nt4_table (src/seq.c): upper / lower case ACGT -> 0..3, anything else 4
+    const int u = c & 0xdf;
+    return u == 'A' ? 0 : u == 'C' ? 1 : u == 'G' ? 2 : u == 'T' ? 3 : 4;
+}
+
+// a unit of 1..6 bases starting at `at` and running in direction dir (+1 / -1) is followed by two more copies of itself
+__device__ __forceinline__ bool unit_repeats(const char *ref, long long at, int dir) {
+    int unit[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) unit[k] = nt4(ref[at + dir * k]);
+    for (int len = 1; len <= 6; ++len) {
+        bool hp = true;
+        for (int c = 1; c < 3 && hp; ++c)
+            for (int j = 0; j < len; ++j) if (nt4(ref[at + dir * (c * len + j)]) != unit[j]) { hp = false; break; }
+        if (hp) return true;
+    }
+    return false;
+}
+
+// var_is_homopolymer, src/collect_var.c:306-358 (called for insertions and deletions only)
+__device__ __forceinline__ bool is_homopolymer(const Chunk &ch, const char *ref, long long pos, int type, int ref_len, int alt_len) {
+    long long start_pos, end_pos;
+    if (type == CINS) { if (alt_len > ch.max_xgaps) return false; start_pos = pos - 1; end_pos = pos; }
+    else { if (ref_len > ch.max_xgaps) return false; start_pos = pos + ref_len - 1; end_pos = pos; }
+    return unit_repeats(ref, end_pos - ch.ref_beg, 1) || unit_repeats(ref, start_pos - ch.ref_beg, -1);
+}
+
+// var_is_repeat_region, src/collect_var.c:361-400
+__device__ __forceinline__ bool is_repeat_region(const Chunk &ch, const char *ref, long long pos, int type, int ref_len, int alt_len, const uint8_t *alt) {
+    const char *r = ref + (pos - ch.ref_beg);
+    if (type == CDEL) {
+        if (ref_len > ch.max_xgaps) return false;
+        const int len = ref_len * 3;
+        if (pos < ch.ref_beg || pos + ref_len + len >= ch.ref_end) return false;
+        for (int k = 0; k < len; ++k) if (nt4(r[k]) != nt4(r[ref_len + k])) return false;
+        return true;
+    }
+    if (alt_len > ch.max_xgaps) return false;
+    const int len = alt_len * 3;
+    if (pos < ch.ref_beg || pos + len >= ch.ref_end) return false;
+    // the reference compares the window with: the inserted bases, then twice the window's own first unit
+    for (int k = 0; k < len; ++k) {
+        const int a = k < alt_len ? (int)alt[k] : nt4(r[(k - alt_len) % alt_len]);
+        if (nt4(r[k]) != a) return false;
+    }
+    return true;
+}
+
+__device__ void classify_site(const KernelArgs &a, long long s) {
+    const Chunk ch = a.chunks[a.site_chunk[s]];
+    const int4 c = *reinterpret_cast<const int4 *>(a.site_counts + 8 * s);        // total_cov, low_qual_cov, alle_covs[0], alle_covs[1]
+    const int total_cov = c.x, low_qual_cov = c.y, alt_dp = c.w, type = a.site_type[s];
+    int cate;
+    if (total_cov + low_qual_cov < ch.min_dp) cate = LOW_COV_VAR;
+    else {
+        const double alt_af = (double)alt_dp / total_cov;
+        if (alt_dp < ch.min_alt_dp) cate = LOW_COV_VAR;
+        else if (alt_af < ch.min_af) cate = LOW_AF_VAR;
+        else if (alt_af > ch.max_af) cate = CLEAN_HOM_VAR;
+        else if (type == CDIFF) cate = CLEAN_HET_SNP;
+        else {
+            const char *ref = a.ref + ch.ref_off; const long long pos = a.site_pos[s]; const int rl = a.site_ref_len[s], al = a.site_alt_len[s];
+            const bool rep = is_homopolymer(ch, ref, pos, type, rl, al) || is_repeat_region(ch, ref, pos, type, rl, al, a.site_alt + ch.alt_base + a.site_alt_off[s]);
+            cate = rep ? REP_HET_VAR : CLEAN_HET_INDEL;
+        }
+    }
+    a.var_cate[s] = cate;
+}
+
+} // namespace classify
+} // namespace lcd

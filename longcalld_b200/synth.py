@@ -507,3 +507,60 @@ def pileup_input_from_digar(d, o, sites):
     if "var_cate" in sites:
         p.update(var_cate=sites["var_cate"], nreg_first=o["nreg_first"], n_nreg=o["n_nreg"], nreg_beg=o["nreg_beg"], nreg_end=o["nreg_end"])
     return p
+
+
+def make_classify_chunk(rng, ref_len=4000, n_sites=400, max_xgaps=5, ref0=100000):
+    """Candidate sites with K2-style counters on a reference window with planted homopolymers / short tandem repeats (and a few N /
+    lower-case bases): the input of the per-site category (classify_var_cate, src/collect_var.c:413).  Small indels often repeat the
+    reference's own bases, so that both context tests (var_is_homopolymer, var_is_repeat_region) fire."""
+    ref = rng.integers(0, 4, ref_len).astype(np.uint8)
+    p = 40
+    while p < ref_len - 80:
+        kind = rng.integers(0, 3)
+        if kind == 0:
+            n = int(rng.integers(3, 13)); ref[p:p + n] = rng.integers(0, 4)
+        elif kind == 1:
+            u = int(rng.integers(2, 7)); c = int(rng.integers(3, 9)); unit = rng.integers(0, 4, u).astype(np.uint8)
+            ref[p:p + u * c] = np.tile(unit, c)[:max(0, min(u * c, ref_len - p))]
+        p += int(rng.integers(15, 120))
+    letters = np.frombuffer(b"ACGT", np.uint8)[ref].copy()
+    for q in rng.integers(0, ref_len, 6): letters[q] = ord("N")
+    for q in rng.integers(0, ref_len, 12): letters[q] = letters[q] | 0x20                     # lower case
+    pos = np.sort(rng.choice(np.arange(ref0 + 40, ref0 + ref_len - 60), size=n_sites, replace=False)).astype(np.int64)
+    typ = rng.choice(np.array([8, 1, 2], np.int32), size=n_sites, p=[0.5, 0.25, 0.25])
+    ln = np.where(rng.random(n_sites) < 0.85, rng.integers(1, max_xgaps + 1, n_sites), rng.integers(max_xgaps + 1, 12, n_sites)).astype(np.int32)
+    ref_l = np.where(typ == 1, 0, np.where(typ == 2, ln, 1)).astype(np.int32); alt_l = np.where(typ == 2, 0, np.where(typ == 1, ln, 1)).astype(np.int32)
+    alt, off = [], []
+    for i in range(n_sites):
+        off.append(len(alt))
+        if typ[i] == 2: continue
+        k = int(alt_l[i]); q = int(pos[i] - ref0)
+        alt.extend((ref[q:q + k] if (typ[i] == 1 and rng.random() < 0.6) else rng.integers(0, 4, k)).tolist())
+    total = rng.integers(0, 60, n_sites).astype(np.int32); low = rng.integers(0, 12, n_sites).astype(np.int32)
+    frac = rng.choice(np.array([0.0, 0.1, 0.19, 0.2, 0.5, 0.8, 0.81, 1.0]), size=n_sites)
+    altc = np.minimum(total, np.round(total * frac)).astype(np.int32)
+    counts = np.zeros((n_sites + 1, 8), np.int32)
+    counts[:n_sites, 0] = total; counts[:n_sites, 1] = low; counts[:n_sites, 2] = total - altc; counts[:n_sites, 3] = altc
+    counts[:n_sites, 5] = altc // 2; counts[:n_sites, 7] = altc - altc // 2
+    return dict(n_sites=n_sites, min_dp=5, min_alt_dp=2, max_xgaps=max_xgaps, is_ont=0, min_af=0.20, max_af=0.80, ref_beg=ref0, ref_end=ref0 + ref_len - 1,
+                ref_seq=letters, site_pos=np.append(pos, 0), site_type=np.append(typ, 0).astype(np.int32), site_ref_len=np.append(ref_l, 0).astype(np.int32),
+                site_alt_len=np.append(alt_l, 0).astype(np.int32), site_alt_off=np.array(off + [0], np.int64), site_alt=np.array(alt + [0], np.uint8), site_counts=counts)
+
+
+def classify_input_from_sites(d, sites, counts, seed, flank=64, max_xgaps=5):
+    """lcd_classify_input_t of a bench chunk: its candidate sites and K2's counters on a synthetic reference window (uniform ACGT with a
+    homopolymer or short tandem repeat every ~200 bases; the bench's reads are CIGARs without a reference of their own)."""
+    n = int(sites["n_sites"]); pos = np.asarray(sites["site_pos"][:n], np.int64)
+    lo = int(min(int(d["reg_beg"]), int(pos.min()) if n else int(d["reg_beg"]))) - flank
+    hi = int(max(int(d["reg_end"]), int((pos + np.asarray(sites["site_ref_len"][:n])).max()) if n else int(d["reg_end"]))) + flank
+    rng = np.random.default_rng(seed)
+    L = hi - lo + 1
+    ref = rng.integers(0, 4, L).astype(np.uint8)
+    starts = np.arange(100, L - 100, 200) + rng.integers(0, 60, len(np.arange(100, L - 100, 200)))
+    unit_len = rng.integers(1, 7, len(starts)); copies = rng.integers(3, 9, len(starts))
+    for s0, u, c in zip(starts.tolist(), unit_len.tolist(), copies.tolist()):
+        ref[s0:s0 + u * c] = np.tile(ref[s0:s0 + u], c)
+    return dict(n_sites=n, min_dp=5, min_alt_dp=2, max_xgaps=max_xgaps, is_ont=0, min_af=0.20, max_af=0.80, ref_beg=lo, ref_end=hi,
+                ref_seq=np.frombuffer(b"ACGT", np.uint8)[ref].copy(), site_pos=sites["site_pos"], site_type=sites["site_type"], site_ref_len=sites["site_ref_len"],
+                site_alt_len=sites["site_alt_len"], site_alt_off=sites["site_alt_off"], site_alt=sites["site_alt"],
+                site_counts=np.ascontiguousarray(np.vstack([counts[:n], np.zeros((1, 8), np.int32)]), dtype=np.int32))

@@ -252,6 +252,11 @@ int ref_sites_batch(int n, const lcd_pileup_input_t *in, const int64_t *reg, lcd
     if (core_wall_s) *core_wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return run_chunks(n, n_threads, [&](int i) { return ref_sites_finish(jobs[i], &in[i], &out[i]); });
 }
+// per-site categories of many chunks (classify_var_cate per site, as the first loop of classify_cand_vars)
+int ref_classify_sites(const lcd_classify_input_t *in, int32_t *var_cate);
+int ref_classify_batch(int n, const lcd_classify_input_t *in, int32_t **var_cate, int n_threads) {
+    return run_chunks(n, n_threads, [&](int i) { return ref_classify_sites(&in[i], var_cate[i]); });
+}
 int ref_profile_batch(int n, const lcd_pileup_input_t *in, const lcd_profile_extra_t *ex, lcd_profile_output_t *out, int n_threads) {
     return run_chunks(n, n_threads, [&](int i) { return ref_read_var_profile(&in[i], &ex[i], &out[i]); });
 }

@@ -6,6 +6,7 @@
                       wfapt0/1) -- pins the recurrence, the backtrace tie-breaks and wf-adaptive.
   digar_lcd.json.gz   digests of the UNMODIFIED reference =/X difference-list pass (collect_digar_from_eqx_cigar) on seeded chunks.
   sites_lcd.json.gz   candidate-site lists of the UNMODIFIED reference (collect_all_cand_var_sites) on seeded chunks.
+  classify_lcd.json.gz per-site categories of the UNMODIFIED reference (classify_var_cate) on seeded sites / reference windows.
   pileup_lcd.json.gz  outputs of the UNMODIFIED reference per-site coverage pass (collect_cand_vars) on seeded chunks.
   phase_lcd.json.gz   outputs of the UNMODIFIED reference read->haplotype assignment / phasing on seeded chunks.
   edlib_lcd.json.gz   outputs of the UNMODIFIED reference edlib (NW / HW, path) on seeded inputs.
@@ -211,9 +212,24 @@ def sites_lcd():
     return {"cases": cases}
 
 
+def classify_lcd():
+    """Per-site categories of the UNMODIFIED classify_var_cate (src/collect_var.c:413, via oracle/_ref/libref_shim.so) on seeded sites,
+    counters and reference windows with planted homopolymers / tandem repeats."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from longcalld_b200 import synth
+    ref = T.ref_lib()
+    rng = np.random.default_rng(20261023)
+    cases = []
+    for it in range(16):
+        d = synth.make_classify_chunk(rng, ref_len=int(rng.choice([600, 2000])), n_sites=int(rng.choice([1, 30, 120])), max_xgaps=int(rng.choice([5, 3])),
+                                      ref0=int(rng.choice([1, 100000])))
+        cases.append({"in": T.classify_case_to_json(d), "cate": T.classify(ref, "ref_classify_sites", d).tolist()})
+    return {"cases": cases}
+
+
 def main():
     only = sys.argv[1:]
-    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd), ("poa_lcd", poa_lcd), ("edlib_lcd", edlib_lcd), ("phase_lcd", phase_lcd), ("pileup_lcd", pileup_lcd), ("digar_lcd", digar_lcd), ("sites_lcd", sites_lcd)):
+    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd), ("poa_lcd", poa_lcd), ("edlib_lcd", edlib_lcd), ("phase_lcd", phase_lcd), ("pileup_lcd", pileup_lcd), ("digar_lcd", digar_lcd), ("sites_lcd", sites_lcd), ("classify_lcd", classify_lcd)):
         if only and name not in only:
             continue
         path = os.path.join(HERE, name + ".json.gz")

@@ -411,3 +411,49 @@ def sites_case_from_json(c):
     for k, t in PILEUP_IN_FIELDS:
         if k.startswith("site_"): d[k] = np.zeros(1, t)
     return d, c["reg"], [(p_, t_, r_, a_, bytes.fromhex(h)) for p_, t_, r_, a_, h in c["sites"]]
+
+
+# ----------------------------------------------------------------------------- per-site category (K2b) helpers
+CLASSIFY_FIELDS = (("site_pos", np.int64), ("site_type", np.int32), ("site_ref_len", np.int32), ("site_alt_len", np.int32),
+                   ("site_alt_off", np.int64), ("site_alt", np.uint8), ("site_counts", np.int32))
+
+
+class ClassifyInput(C.Structure):
+    _fields_ = [("n_sites", C.c_int32), ("min_dp", C.c_int32), ("min_alt_dp", C.c_int32), ("max_xgaps", C.c_int32), ("is_ont", C.c_int32), ("pad", C.c_int32),
+                ("min_af", C.c_double), ("max_af", C.c_double), ("ref_beg", C.c_int64), ("ref_end", C.c_int64), ("ref_seq", C.c_void_p)] + \
+               [(k, C.c_void_p) for k, _ in CLASSIFY_FIELDS]
+
+
+def classify_input(d):
+    keep = {k: np.ascontiguousarray(d[k], dtype=t) for k, t in CLASSIFY_FIELDS}
+    keep["ref_seq"] = np.ascontiguousarray(d["ref_seq"], dtype=np.uint8)
+    inp = ClassifyInput(d["n_sites"], d["min_dp"], d["min_alt_dp"], d["max_xgaps"], d["is_ont"], 0, d["min_af"], d["max_af"], d["ref_beg"], d["ref_end"],
+                        keep["ref_seq"].ctypes.data, *[keep[k].ctypes.data for k, _ in CLASSIFY_FIELDS])
+    return inp, keep
+
+
+def classify(lib, fn, d):
+    """Run an implementation of the per-site category over one chunk -> int32 array [n_sites]."""
+    inp, keep = classify_input(d)
+    out = np.full(d["n_sites"] + 1, -7, np.int32)
+    rc = getattr(lib, fn)(C.byref(inp), out.ctypes.data_as(C.c_void_p))
+    assert rc == 0, rc
+    return out[:d["n_sites"]]
+
+
+CLASSIFY_SCALARS = ("n_sites", "min_dp", "min_alt_dp", "max_xgaps", "is_ont", "min_af", "max_af", "ref_beg", "ref_end")
+
+
+def classify_case_to_json(d):
+    j = {k: (float(d[k]) if isinstance(d[k], float) else int(d[k])) for k in CLASSIFY_SCALARS}
+    j["ref_seq"] = bytes(np.asarray(d["ref_seq"], np.uint8)).decode()
+    for k, _ in CLASSIFY_FIELDS: j[k] = np.asarray(d[k]).reshape(-1).tolist()
+    return j
+
+
+def classify_case_from_json(j):
+    d = {k: j[k] for k in CLASSIFY_SCALARS}
+    d["ref_seq"] = np.frombuffer(j["ref_seq"].encode(), np.uint8)
+    for k, t in CLASSIFY_FIELDS: d[k] = np.array(j[k], dtype=t)
+    d["site_counts"] = d["site_counts"].reshape(-1, 8)
+    return d
