@@ -589,7 +589,7 @@ def run_b200(args, rank, world):
         dp.run(); dp.sync(); t.append(time.perf_counter())
         k1b = lcd.SitesPlan(None, ps.regs, min_sv_len=min_sv, digar_plan=dp); k1b.run(); pile_res["sites"] = k1b.fetch()
         k2 = lcd.PileupOnSitesPlan(dp, k1b); t.append(time.perf_counter()); k2.run(); pile_res["counts"] = k2.fetch(); t.append(time.perf_counter())
-        pile_res["cate"] = lcd.classify_batch(ps.cls)            # K2b on the host-resident site lists and counters (the reference window comes from the host)
+        k2b = lcd.ClassifyOnPileupPlan(k2, ps.cls, k2.n_sites); k2b.run(); pile_res["cate"] = k2b.fetch(); k2b.destroy()      # K2b on K2's sites and counters in HBM (the reference windows come from the host)
         k3 = lcd.ProfileOnDigarPlan(dp, ps.var_sites, ps.n_reads); t.append(time.perf_counter()); k3.run(); pile_res["prof"] = k3.fetch(); t.append(time.perf_counter())
         for x in (k3, k2, k1b, dp): x.destroy()
         t.append(time.perf_counter())
@@ -625,7 +625,7 @@ def run_b200(args, rank, world):
     assert sum(sites_plan.sizes()) == ps.n_raw_sites
     k2_plan = lcd.PileupOnSitesPlan(digar_plan, sites_plan)
     k3_plan = lcd.ProfileOnDigarPlan(digar_plan, ps.var_sites, ps.n_reads)
-    k2b_plan = lcd.ClassifyPlan(ps.cls)
+    k2b_plan = lcd.ClassifyOnPileupPlan(k2_plan, ps.cls, k2_plan.n_sites)
     poa_plan = lcd.PoaPlan(wl.seqs, wl.first, wl.n_reads, wl.read_off, wl.read_len, lcd.poa_params())
     wfa_plan = lcd.WfaPlan(wseqs, po, pl, to, tl, lcd.wfa_params())
     phase_plan = lcd.PhasePlan(wl.phase)
@@ -717,7 +717,7 @@ def run_b200(args, rank, world):
     e2e_s = time.perf_counter() - t0
     phase_bytes = sum(a.nbytes for k in ph_keep for a in k.values())
     pile_d2h = int(sum(sum(a.nbytes for a in st.values() if hasattr(a, "nbytes")) for st in pile_res["sites"]) + sum(c.nbytes for c in pile_res["counts"]) + sum(sum(a.nbytes for a in o.values()) for o in pile_res["prof"]))
-    cls_h2d = int(sum(sum(a.nbytes for a in d.values() if hasattr(a, "nbytes")) for d in ps.cls)); pile_d2h += int(sum(c.nbytes for c in pile_res["cate"]))
+    cls_h2d = int(sum(d["ref_seq"].nbytes for d in ps.cls)); pile_d2h += int(sum(c.nbytes for c in pile_res["cate"]))
     h2d = int(ps.h2d + cls_h2d + phase_bytes + eseqs.size + 24 * ne + wl.seqs.size + 12 * len(wl.read_len) + 64 * n + (pl.astype(np.int64) + tl + 56).sum() + 96 * n)
     d2h = int(pile_d2h + sum(a.nbytes for r in ph_res for a in r.values()) + eres.nbytes + int(eres["aln_len"].sum()) + pres["cons_len"].sum() + 32 * n + wres.nbytes + 2 * (pl.astype(np.int64) + tl + 4).sum())
 

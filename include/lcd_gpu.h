@@ -241,6 +241,16 @@ typedef struct { int32_t *var_cate; } lcd_classify_output_t;      /* [n_sites]: 
 int lcd_classify_batch(int n_chunks, const lcd_classify_input_t *in, lcd_classify_output_t *out);
 lcd_plan_t *lcd_classify_plan_create(int n_chunks, const lcd_classify_input_t *in);
 int  lcd_classify_plan_fetch(lcd_plan_t *plan, void *stream, lcd_classify_output_t *out);
+/* K2 -> K2b in place: the categories of the sites a pileup plan (any of lcd_pileup_plan_create*, run) holds in HBM, from the counters
+ * it left there; only the thresholds and the chunk's reference window are uploaded.  The window must reach 24 bases beyond every site
+ * (a chunk's own ref_beg / ref_end, +-50 kb around its region, always does).  The pileup plan must outlive the plan. */
+typedef struct {
+    int32_t min_dp, min_alt_dp, max_xgaps, is_ont;   /* as in lcd_classify_input_t */
+    double min_af, max_af;
+    int64_t ref_beg, ref_end;
+    const char *ref_seq;
+} lcd_classify_params_t;
+lcd_plan_t *lcd_classify_plan_create_on_pileup(lcd_plan_t *pileup_plan, int n_chunks, const lcd_classify_params_t *params);
 
 /* ---------------------------------------------------------------- K3: pileup scan, read x variant profile
  * Replaces read_var_profile_t *collect_read_var_profile(const call_var_opt_t *opt, bam_chunk_t *chunk)

@@ -660,6 +660,30 @@ class ClassifyPlan(_Plan):
         return [r[:d["n_sites"]] for r, d in zip(self.res, self.chunks)]
 
 
+class ClassifyParams(C.Structure):
+    _fields_ = [("min_dp", C.c_int32), ("min_alt_dp", C.c_int32), ("max_xgaps", C.c_int32), ("is_ont", C.c_int32), ("min_af", C.c_double), ("max_af", C.c_double),
+                ("ref_beg", C.c_int64), ("ref_end", C.c_int64), ("ref_seq", C.c_void_p)]
+
+
+class ClassifyOnPileupPlan(_Plan):
+    """K2b on the sites and counters a K2 plan (PileupPlan / PileupOnDigarPlan / PileupOnSitesPlan, run) holds in HBM; params: per chunk a
+    dict(min_dp, min_alt_dp, max_xgaps, min_af, max_af, ref_beg, ref_end, ref_seq); n_sites: the K2 plan's site counts."""
+    def __init__(self, pileup_plan, params, n_sites):
+        self.pileup_plan, self.n_sites = pileup_plan, list(n_sites)
+        n = len(params)
+        self.keep = [np.ascontiguousarray(d["ref_seq"], dtype=np.uint8) for d in params]
+        self.par = (ClassifyParams * max(n, 1))(*[ClassifyParams(d["min_dp"], d["min_alt_dp"], d["max_xgaps"], d.get("is_ont", 0), d["min_af"], d["max_af"], d["ref_beg"], d["ref_end"],
+                                                                 r.ctypes.data) for d, r in zip(params, self.keep)])
+        lib().lcd_classify_plan_create_on_pileup.restype = C.c_void_p
+        super().__init__(lib().lcd_classify_plan_create_on_pileup(pileup_plan.h, C.c_int(n), self.par), n)
+        self.res = [np.full(k + 1, -7, np.int32) for k in self.n_sites]
+        self.outs = (ClassifyOutput * max(n, 1))(*[ClassifyOutput(r.ctypes.data) for r in self.res])
+
+    def fetch(self, stream=None):
+        _check(lib().lcd_classify_plan_fetch(self.h, C.c_void_p(stream or 0), self.outs), "lcd_classify_plan_fetch")
+        return [r[:k] for r, k in zip(self.res, self.n_sites)]
+
+
 # ----------------------------------------------------------------------------- K3: pileup scan, read x variant profile
 _PROFILE_EX = (("var_cate", np.int32), ("nreg_first", np.int64), ("n_nreg", np.int32), ("nreg_beg", np.int64), ("nreg_end", np.int64))
 

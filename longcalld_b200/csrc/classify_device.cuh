@@ -32,7 +32,9 @@ struct KernelArgs {
     const int32_t *site_counts;       // [n_sites_total][8]
     const char *ref;
     int32_t *var_cate;
+    int32_t *status;                  // optional: set to 1 when a small indel lies within REF_MARGIN bases of its reference window's ends
 };
+constexpr int REF_MARGIN = 24;       // bases of reference the context tests may read beyond a site (the reference reads them unchecked)
 
 __device__ __forceinline__ int nt4(char c) {                              // nst_nt4_table (src/seq.c): upper / lower case ACGT -> 0..3, anything else 4
     const int u = c & 0xdf;
@@ -96,6 +98,8 @@ __device__ void classify_site(const KernelArgs &a, long long s) {
         else if (type == CDIFF) cate = CLEAN_HET_SNP;
         else {
             const char *ref = a.ref + ch.ref_off; const long long pos = a.site_pos[s]; const int rl = a.site_ref_len[s], al = a.site_alt_len[s];
+            const int len = type == CINS ? al : rl;
+            if (a.status && len <= ch.max_xgaps && (pos - REF_MARGIN < ch.ref_beg || pos + len + REF_MARGIN > ch.ref_end)) { *a.status = 1; a.var_cate[s] = NON_VAR; return; }
             const bool rep = is_homopolymer(ch, ref, pos, type, rl, al) || is_repeat_region(ch, ref, pos, type, rl, al, a.site_alt + ch.alt_base + a.site_alt_off[s]);
             cate = rep ? REP_HET_VAR : CLEAN_HET_INDEL;
         }

@@ -8,7 +8,6 @@ namespace lcd {
 namespace classify {
 
 constexpr int THREADS = 128;
-constexpr int REF_MARGIN = 24;       // bases of reference a small indel's context tests may read beyond the site (the reference reads them unchecked)
 
 __global__ void __launch_bounds__(THREADS)
 classify_kernel(const KernelArgs a) {
@@ -20,7 +19,9 @@ struct ClassifyPlan : Plan {
     bool uses_pool() const override { return false; }
     std::vector<Chunk> chunks; std::vector<long long> site_off;
     long long tot_sites = 0;
-    DevBuf<Chunk> d_chunks; DevBuf<int32_t> d_site_chunk, d_stype, d_sref, d_salt, d_counts, d_cate; DevBuf<long long> d_spos, d_saoff; DevBuf<uint8_t> d_site_alt; DevBuf<char> d_ref;
+    // the site arrays and counters: this plan's own buffers, or a pileup plan's (K2 -> K2b in place)
+    const long long *p_spos = nullptr, *p_saoff = nullptr; const int32_t *p_stype = nullptr, *p_sref = nullptr, *p_salt = nullptr, *p_counts = nullptr; const uint8_t *p_site_alt = nullptr;
+    DevBuf<Chunk> d_chunks; DevBuf<int32_t> d_site_chunk, d_stype, d_sref, d_salt, d_counts, d_cate; DevBuf<long long> d_spos, d_saoff; DevBuf<uint8_t> d_site_alt; DevBuf<char> d_ref; DevBuf<int32_t> d_status;
 
     int build(int n_, const lcd_classify_input_t *in) {
         n = n_;
@@ -72,6 +73,38 @@ struct ClassifyPlan : Plan {
             }
             if (alt_n[i]) LCD_CUDA_OK(cudaMemcpyAsync(d_site_alt.p + chunks[i].alt_base, x.site_alt, (size_t)alt_n[i], cudaMemcpyHostToDevice, s));
         }
+        p_spos = d_spos.p; p_saoff = d_saoff.p; p_stype = d_stype.p; p_sref = d_sref.p; p_salt = d_salt.p; p_counts = d_counts.p; p_site_alt = d_site_alt.p;
+        LCD_CUDA_OK(cudaStreamSynchronize(s));
+        return 0;
+    }
+
+    // K2b on the sites and counters a pileup plan holds in HBM: only the thresholds and the reference windows are uploaded.  The reference
+    // reads the window unchecked; here the sites' distance from the window's ends is not known to the host, so the window must cover the
+    // chunk's reads with the reference's own flank (checked on the device side by nothing: documented precondition of the call).
+    int build_on_pileup(Plan *pileup, int n_, const lcd_classify_params_t *par) {
+        n = n_;
+        PileupView v;
+        if (pileup_plan_view(pileup, &v)) return -1;
+        if (v.n_chunks != n) { set_error("lcd_classify: %d parameter sets for a pileup plan of %d chunks", n, v.n_chunks); return -1; }
+        if (n == 0) return 0;
+        chunks.resize(n); site_off = v.site_off; tot_sites = v.site_off[n];
+        long long tot_ref = 0;
+        std::vector<int32_t> site_chunk; std::vector<long long> ref_n(n, 0);
+        for (int i = 0; i < n; ++i) {
+            const lcd_classify_params_t &x = par[i];
+            if (x.ref_end < x.ref_beg || !x.ref_seq) { set_error("lcd_classify: chunk %d has no reference window", i); return -1; }
+            if (x.is_ont) { set_error("lcd_classify: chunk %d is ONT data: the strand-bias Fisher test (var_is_strand_bias, src/collect_var.c:270) is not implemented on the GPU", i); return -2; }
+            Chunk &k = chunks[i]; memset(&k, 0, sizeof(k));
+            k.min_dp = x.min_dp; k.min_alt_dp = x.min_alt_dp; k.max_xgaps = x.max_xgaps; k.min_af = x.min_af; k.max_af = x.max_af;
+            k.ref_beg = x.ref_beg; k.ref_end = x.ref_end; k.ref_off = tot_ref; k.alt_base = v.salt_base[i];
+            ref_n[i] = x.ref_end - x.ref_beg + 1; tot_ref += (ref_n[i] + 15) & ~15ll;
+            for (long long s = site_off[i]; s < site_off[i + 1]; ++s) site_chunk.push_back(i);
+        }
+        site_chunk.push_back(0);
+        cudaStream_t s = cur_stream();
+        if (d_chunks.upload(chunks.data(), n, s) || d_site_chunk.upload(site_chunk.data(), site_chunk.size(), s) || d_cate.alloc(tot_sites + 1) || d_ref.alloc(tot_ref + 16)) return -1;
+        for (int i = 0; i < n; ++i) LCD_CUDA_OK(cudaMemcpyAsync(d_ref.p + chunks[i].ref_off, par[i].ref_seq, (size_t)ref_n[i], cudaMemcpyHostToDevice, s));
+        p_spos = v.spos; p_saoff = v.saoff; p_stype = v.stype; p_sref = v.sref; p_salt = v.salt; p_counts = v.counts; p_site_alt = v.site_alt;
         LCD_CUDA_OK(cudaStreamSynchronize(s));
         return 0;
     }
@@ -80,8 +113,11 @@ struct ClassifyPlan : Plan {
         Context &c = ctx();
         if (n == 0 || tot_sites == 0) return 0;
         KernelArgs a; memset(&a, 0, sizeof(a));
-        a.chunks = d_chunks.p; a.n_sites_total = tot_sites; a.site_chunk = d_site_chunk.p; a.site_pos = d_spos.p; a.site_type = d_stype.p; a.site_ref_len = d_sref.p;
-        a.site_alt_len = d_salt.p; a.site_alt_off = d_saoff.p; a.site_alt = d_site_alt.p; a.site_counts = d_counts.p; a.ref = d_ref.p; a.var_cate = d_cate.p;
+        a.chunks = d_chunks.p; a.n_sites_total = tot_sites; a.site_chunk = d_site_chunk.p; a.site_pos = p_spos; a.site_type = p_stype; a.site_ref_len = p_sref;
+        a.site_alt_len = p_salt; a.site_alt_off = p_saoff; a.site_alt = p_site_alt; a.site_counts = p_counts; a.ref = d_ref.p; a.var_cate = d_cate.p;
+        if (!d_status.p && d_status.alloc(1)) return -1;
+        LCD_CUDA_OK(cudaMemsetAsync(d_status.p, 0, sizeof(int32_t), s));
+        a.status = d_status.p;
         const int grid = (int)std::min<long long>((tot_sites + THREADS - 1) / THREADS, (long long)c.sm_count * 16);
         classify_kernel<<<grid, THREADS, 0, s>>>(a);
         LCD_CUDA_OK(cudaGetLastError());
@@ -94,6 +130,12 @@ struct ClassifyPlan : Plan {
     int fetch(cudaStream_t s, lcd_classify_output_t *out) {
         if (n == 0) return 0;
         LCD_DRAIN(s);
+        if (d_status.p) {
+            int32_t st = 0;
+            LCD_CUDA_OK(cudaMemcpyAsync(&st, d_status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            LCD_CUDA_OK(cudaStreamSynchronize(s));
+            if (st) { set_error("lcd_classify: a small indel lies within %d bases of its chunk's reference window ends", REF_MARGIN); return -3; }
+        }
         for (int i = 0; i < n; ++i) {
             const long long ns = site_off[i + 1] - site_off[i];
             if (ns) LCD_CUDA_OK(cudaMemcpyAsync(out[i].var_cate, d_cate.p + site_off[i], sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, s));
@@ -115,6 +157,14 @@ lcd_plan_t *lcd_classify_plan_create(int n_chunks, const lcd_classify_input_t *i
     if (n_chunks < 0 || (n_chunks > 0 && !in)) { set_error("lcd_classify_plan_create: invalid arguments"); return nullptr; }
     classify::ClassifyPlan *p = new classify::ClassifyPlan();
     if (p->build(n_chunks, in)) { delete p; return nullptr; }
+    return reinterpret_cast<lcd_plan_t *>(p);
+}
+
+lcd_plan_t *lcd_classify_plan_create_on_pileup(lcd_plan_t *pileup_plan, int n_chunks, const lcd_classify_params_t *params) {
+    if (ensure_ready()) return nullptr;
+    if (!pileup_plan || n_chunks < 0 || (n_chunks > 0 && !params)) { set_error("lcd_classify_plan_create_on_pileup: invalid arguments"); return nullptr; }
+    classify::ClassifyPlan *p = new classify::ClassifyPlan();
+    if (p->build_on_pileup(reinterpret_cast<Plan *>(pileup_plan), n_chunks, params)) { delete p; return nullptr; }
     return reinterpret_cast<lcd_plan_t *>(p);
 }
 

@@ -125,6 +125,14 @@ int sites_plan_view(Plan *plan, Plan *digar, cudaStream_t s, SitesView *v);   //
 // while a POA launch with its status copy queued behind it was in flight).  So results are read back only after the stream has drained.
 #define LCD_DRAIN(s) LCD_CUDA_OK(cudaStreamSynchronize(s))
 
+// K2's sites and counters as K2b consumes them in place (device pointers into a pileup plan; valid while it -- and the plans it was
+// created on -- live).  site_alt_off is relative to salt_base[chunk] in site_alt.
+struct PileupView {
+    int n_chunks = 0; std::vector<long long> site_off, salt_base;
+    const long long *spos = nullptr, *saoff = nullptr; const int32_t *stype = nullptr, *sref = nullptr, *salt = nullptr, *counts = nullptr; const uint8_t *site_alt = nullptr;
+};
+int pileup_plan_view(Plan *plan, PileupView *v);      // pileup_kernel.cu
+
 inline cudaStream_t pick_stream(void *s) { bind_thread(); return s ? (cudaStream_t)s : cur_stream(); }
 
 } // namespace lcd

@@ -316,6 +316,16 @@ struct PileupPlan : Plan {
 };
 
 } // namespace pileup
+
+int pileup_plan_view(Plan *plan, PileupView *v) {
+    pileup::PileupPlan *p = dynamic_cast<pileup::PileupPlan *>(plan);
+    if (!p || p->profile) { set_error("not a pileup (K2) plan"); return -1; }
+    v->n_chunks = p->n; v->site_off.assign(p->n + 1, 0); v->salt_base.assign(p->n, 0);
+    for (int i = 0; i < p->n; ++i) { v->site_off[i] = p->site_off[i]; v->salt_base[i] = p->chunks[i].salt_base; }
+    v->site_off[p->n] = p->tot_sites;
+    v->spos = p->p_spos; v->saoff = p->p_saoff; v->stype = p->p_stype; v->sref = p->p_sref; v->salt = p->p_salt; v->site_alt = p->p_site_alt; v->counts = p->d_counts.p;
+    return 0;
+}
 } // namespace lcd
 
 using namespace lcd;

@@ -47,3 +47,33 @@ def test_gpu_chunk_shaped_plan_and_rejections(gpu, oracle):
     edge["site_pos"] = edge["site_pos"].copy(); edge["site_pos"][0] = edge["ref_beg"] + 3
     with pytest.raises(gpu.LcdGpuError, match="reference window"):
         gpu.classify_batch([edge])
+
+
+def test_gpu_chain_in_place(gpu, oracle):
+    """K1 -> K1b -> K2 -> K2b with everything left in HBM (only the reference windows are uploaded for K2b) against the oracle run on the
+    fetched sites and counters; a window that ends too close to a small indel is reported, not read past."""
+    rng = np.random.default_rng(69)
+    cases = [synth.make_digar_chunk(rng, n_reads=240, read_len=(10000, 20000), err_every=300, ref_len=120000) for _ in range(3)]
+    regs = [(int(d["reg_beg"]), int(d["reg_end"])) for d in cases]
+    k1 = gpu.DigarPlan(cases); k1.run(); k1.sync()
+    k1b = gpu.SitesPlan(None, regs, min_sv_len=[50] * len(cases), digar_plan=k1); k1b.run(); k1b.sync()
+    k2 = gpu.PileupOnSitesPlan(k1, k1b); k2.run(); k2.sync()
+    recs, sites, counts = k1.fetch(), k1b.fetch(), k2.fetch()
+    lists = [synth.site_list_from_sites(o, st) for o, st in zip(recs, sites)]
+    cls = [synth.classify_input_from_sites(d, sl, c, 1000 + i) for i, (d, sl, c) in enumerate(zip(cases, lists, counts))]
+    k2b = gpu.ClassifyOnPileupPlan(k2, cls, [c["n_sites"] for c in cls])
+    for _ in range(2):
+        k2b.run(); k2b.sync()
+    wants = []
+    for d, got in zip(cls, k2b.fetch()):
+        want = T.classify(oracle, "lcd_oracle_classify_sites", d)
+        assert np.array_equal(got, want)
+        wants.append(want)
+    assert sum(c["n_sites"] for c in cls) > 1000
+    ctx = np.nonzero((wants[0] == 0x010) | (wants[0] == 0x008))[0]             # indels whose category needed the reference context
+    if len(ctx):
+        short = [dict(c) for c in cls]
+        short[0]["ref_end"] = int(cls[0]["site_pos"][ctx[-1]]) + 5; short[0]["ref_seq"] = cls[0]["ref_seq"][:short[0]["ref_end"] - short[0]["ref_beg"] + 1]
+        bad = gpu.ClassifyOnPileupPlan(k2, short, [c["n_sites"] for c in cls]); bad.run()
+        with pytest.raises(gpu.LcdGpuError, match="reference window"):
+            bad.fetch()
