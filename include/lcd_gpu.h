@@ -173,6 +173,14 @@ typedef struct {
 /* Capacities that always suffice for one chunk (one host pass over its CIGAR words). */
 int lcd_digar_capacity(const lcd_digar_input_t *in, int64_t *digar_cap, int64_t *alt_cap, int64_t *nreg_cap);
 int lcd_digar_batch(int n_chunks, const lcd_digar_input_t *in, lcd_digar_output_t *out);
+/* Reads with plain-M CIGARs and an MD tag (collect_digar_from_MD_tag, src/bam_utils.c:1003-1174; the reference takes this path for reads
+ * without =/X ops and without a cs tag, src/collect_var.c:1072-1080): the MD strings go to the device, where the reference's walk over
+ * (CIGAR, MD) (:1037-1094) turns them into the =/X CIGARs the kernels consume.  md_off[r] < 0: read r's CIGAR is =/X already.
+ * Capacities: lcd_digar_capacity counts an M op as one record; size the outputs for l_qseq more records / alt bases per read instead
+ * (or ask lcd_digar_plan_sizes after lcd_plan_run).  cs-tagged and untagged plain-M reads are not implemented on the GPU. */
+typedef struct { const int64_t *md_off; const char *md; } lcd_md_tags_t;      /* per chunk: NUL-terminated tag of read r at md + md_off[r] */
+int lcd_digar_md_batch(int n_chunks, const lcd_digar_input_t *in, const lcd_md_tags_t *tags, lcd_digar_output_t *out);
+lcd_plan_t *lcd_digar_md_plan_create(int n_chunks, const lcd_digar_input_t *in, const lcd_md_tags_t *tags);
 lcd_plan_t *lcd_digar_plan_create(int n_chunks, const lcd_digar_input_t *in);
 /* After lcd_plan_run: exact sizes of chunk i's outputs (records, alt bases, per-read intervals; the chunk list needs <= the last). */
 int  lcd_digar_plan_sizes(lcd_plan_t *plan, void *stream, int chunk, int64_t *n_digar, int64_t *n_alt, int64_t *n_nreg);

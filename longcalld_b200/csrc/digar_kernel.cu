@@ -2,6 +2,7 @@
 // Device logic and design notes: digar_device.cuh.
 #include "lcd_common.cuh"
 #include "digar_device.cuh"
+#include "md_device.cuh"
 #include <algorithm>
 
 namespace lcd {
@@ -42,6 +43,18 @@ digar_scan_kernel(const long long *cnt, long long *first, long long n, long long
     __syncthreads();
     long long run = warp_sum[warp] + incl - s;
     for (long long i = i0; i < i1; ++i) { out[i] = run; run += i < n ? in[i] : 0; }
+}
+
+// MD-tag front end (md_device.cuh): (CIGAR with M, MD) -> the =/X CIGAR the kernels above and below consume, thread per read
+__global__ void __launch_bounds__(THREADS)
+md_count_kernel(const md::KernelArgs a) {
+    for (long long g = (long long)blockIdx.x * THREADS + threadIdx.x; g < a.n_reads_total; g += (long long)gridDim.x * THREADS)
+        md::count_read(a, g);
+}
+__global__ void __launch_bounds__(THREADS)
+md_fill_kernel(const md::KernelArgs a) {
+    for (long long g = (long long)blockIdx.x * THREADS + threadIdx.x; g < a.n_reads_total; g += (long long)gridDim.x * THREADS)
+        md::fill_read(a, g);
 }
 
 __global__ void __launch_bounds__(THREADS)
@@ -135,12 +148,12 @@ struct DigarPlan : Plan {
     DevBuf<int32_t> d_dlen, d_dqi, d_nnreg, d_nlabel, d_status, d_ndig; DevBuf<unsigned long long> d_qc;
     std::vector<long long> h_first; std::vector<int32_t> h_nnreg; bool have_index = false;
 
-    int build(int n_, const lcd_digar_input_t *in) {
+    int build(int n_, const lcd_digar_input_t *in, const lcd_md_tags_t *tags = nullptr) {
         n = n_;
         Context &c = ctx();
         if (n == 0) return 0;
         std::vector<int32_t> read_chunk, ncig, lq; std::vector<uint8_t> rev, pal; std::vector<long long> pos0, coff, soff, qoff;
-        std::vector<long long> cig_base(n), seq_base(n), qual_base(n), cig_n(n), seq_n(n), qual_n(n);
+        std::vector<long long> cig_base(n), seq_base(n), qual_base(n), cig_n(n), seq_n(n), qual_n(n), md_base(n, 0), md_n(n, 0), md_off; long long tot_md = 0;
         chunks.resize(n); read_off.resize(n + 1); reg_beg.resize(n); reg_end.resize(n);
         for (int i = 0; i < n; ++i) {
             const lcd_digar_input_t &x = in[i];
@@ -162,6 +175,15 @@ struct DigarPlan : Plan {
                 nq = std::max<long long>(nq, x.qual_off[r] + x.l_qseq[r]);
             }
             cig_base[i] = tot_cigar; seq_base[i] = tot_seq; qual_base[i] = tot_qual; cig_n[i] = nc; seq_n[i] = ns; qual_n[i] = nq;
+            if (tags) {               // MD tags: NUL-terminated strings in tags[i].md at md_off[r] (< 0: the read's CIGAR is =/X already)
+                long long top = 0;
+                for (int r = 0; r < x.n_reads; ++r) {
+                    const bool act = listed[r] && !x.is_skipped[r]; const long long o = act ? tags[i].md_off[r] : -1;
+                    md_off.push_back(o < 0 ? -1 : tot_md + o);
+                    if (o >= 0) top = std::max<long long>(top, o + (long long)strlen(tags[i].md + o) + 1);
+                }
+                md_base[i] = tot_md; md_n[i] = top; tot_md += top;
+            }
             append(ordered, x.ordered_read_ids, x.n_reads);
             append(pos0, x.read_pos0, x.n_reads); append(rev, x.read_is_rev, x.n_reads); append(pal, x.is_palindrome, x.n_reads);
             append(ncig, x.n_cigar, x.n_reads); append(lq, x.l_qseq, x.n_reads);
@@ -171,6 +193,7 @@ struct DigarPlan : Plan {
         read_off[n] = tot_reads; stride = tot_reads + 1;
         auto pad = [](auto &v) { v.push_back(0); };
         pad(read_chunk); pad(h_active); pad(pos0); pad(rev); pad(pal); pad(ncig); pad(lq); pad(coff); pad(soff); pad(qoff);
+        if (tags) md_off.push_back(-1);
         cudaStream_t s = cur_stream();
         if (d_chunks.upload(chunks.data(), n, s) || d_read_chunk.upload(read_chunk.data(), read_chunk.size(), s) || d_active.upload(h_active.data(), h_active.size(), s) ||
             d_pos0.upload(pos0.data(), pos0.size(), s) || d_rev.upload(rev.data(), rev.size(), s) || d_pal.upload(pal.data(), pal.size(), s) ||
@@ -187,6 +210,44 @@ struct DigarPlan : Plan {
         if (d_cnt.alloc(3 * stride) || d_first.alloc(3 * stride) || d_skip.alloc(stride) || d_beg.alloc(stride) || d_end.alloc(stride) || d_nnreg.alloc(stride) || d_ndig.alloc(stride) ||
             d_qc.alloc(256 * (size_t)n) || d_status.alloc(1)) return -1;
         LCD_CUDA_OK(cudaStreamSynchronize(s));
+        if (tags && tot_reads && convert_md(s, md_off, tags, md_base, md_n, tot_md)) return -1;
+        return 0;
+    }
+
+    // MD-tagged reads: d_cigar / d_coff / d_ncig so far hold the reads' own CIGARs; replace them by the =/X CIGARs of the reference's MD walk
+    int convert_md(cudaStream_t s, const std::vector<long long> &md_off, const lcd_md_tags_t *tags, const std::vector<long long> &md_base,
+                   const std::vector<long long> &md_n, long long tot_md) {
+        Context &c = ctx();
+        DevBuf<long long> d_mdoff, d_cnt1, d_first1; DevBuf<char> d_md; DevBuf<uint32_t> d_cig2; DevBuf<long long> d_coff2; DevBuf<int32_t> d_ncig2, d_st;
+        if (d_mdoff.upload(md_off.data(), md_off.size(), s) || d_md.alloc(tot_md + 16) || d_cnt1.alloc(stride) || d_first1.alloc(stride) || d_coff2.alloc(stride) ||
+            d_ncig2.alloc(stride) || d_st.alloc(1)) return -1;
+        for (int i = 0; i < n; ++i) if (md_n[i]) LCD_CUDA_OK(cudaMemcpyAsync(d_md.p + md_base[i], tags[i].md, (size_t)md_n[i], cudaMemcpyHostToDevice, s));
+        LCD_CUDA_OK(cudaMemsetAsync(d_st.p, 0, sizeof(int32_t), s));
+        md::KernelArgs a; memset(&a, 0, sizeof(a));
+        a.n_reads_total = tot_reads; a.read_active = d_active.p; a.n_cigar0 = d_ncig.p; a.cigar_off0 = d_coff.p; a.cigar0 = d_cigar.p; a.md_off = d_mdoff.p; a.md = d_md.p;
+        a.cnt = d_cnt1.p; a.first = d_first1.p; a.n_cigar = d_ncig2.p; a.cigar_off = d_coff2.p; a.status = d_st.p;
+        const int grid = (int)std::min<long long>((tot_reads + THREADS - 1) / THREADS, (long long)c.sm_count * 16);
+        md_count_kernel<<<grid, THREADS, 0, s>>>(a);
+        digar_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(d_cnt1.p, d_first1.p, tot_reads, stride);
+        LCD_CUDA_OK(cudaGetLastError());
+        c.launches += 2;
+        long long total = 0; int32_t st = 0;
+        LCD_DRAIN(s);
+        LCD_CUDA_OK(cudaMemcpyAsync(&total, d_first1.p + tot_reads, sizeof(long long), cudaMemcpyDeviceToHost, s));
+        LCD_CUDA_OK(cudaMemcpyAsync(&st, d_st.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        LCD_CUDA_OK(cudaStreamSynchronize(s));
+        if (st == md::MD_MISMATCH) { set_error("lcd_digar: a read's MD tag and CIGAR do not match (the reference stops as well: src/bam_utils.c:1083)"); return -2; }
+        if (st == md::MD_EQX_OP) { set_error("lcd_digar: a read with an MD tag has =/X CIGAR ops (the reference stops as well: src/bam_utils.c:1139); pass md_off < 0 for such reads"); return -2; }
+        if (d_cig2.alloc(total + 4)) return -1;
+        a.cigar = d_cig2.p;
+        md_fill_kernel<<<grid, THREADS, 0, s>>>(a);
+        LCD_CUDA_OK(cudaGetLastError());
+        c.launches++;
+        LCD_CUDA_OK(cudaStreamSynchronize(s));
+        std::swap(d_cigar.p, d_cig2.p); std::swap(d_cigar.n, d_cig2.n); std::swap(d_cigar.st, d_cig2.st);
+        std::swap(d_coff.p, d_coff2.p); std::swap(d_coff.n, d_coff2.n); std::swap(d_coff.st, d_coff2.st);
+        std::swap(d_ncig.p, d_ncig2.p); std::swap(d_ncig.n, d_ncig2.n); std::swap(d_ncig.st, d_ncig2.st);
+        tot_cigar = total;
         return 0;
     }
 
@@ -393,6 +454,23 @@ int lcd_digar_capacity(const lcd_digar_input_t *in, int64_t *digar_cap, int64_t 
     }
     *digar_cap = nd + 1; *alt_cap = na + 1; *nreg_cap = ni + 1;
     return 0;
+}
+
+lcd_plan_t *lcd_digar_md_plan_create(int n_chunks, const lcd_digar_input_t *in, const lcd_md_tags_t *tags) {
+    if (ensure_ready()) return nullptr;
+    if (n_chunks < 0 || (n_chunks > 0 && (!in || !tags))) { set_error("lcd_digar_md_plan_create: invalid arguments"); return nullptr; }
+    digar::DigarPlan *p = new digar::DigarPlan();
+    if (p->build(n_chunks, in, tags)) { delete p; return nullptr; }
+    return reinterpret_cast<lcd_plan_t *>(p);
+}
+
+int lcd_digar_md_batch(int n_chunks, const lcd_digar_input_t *in, const lcd_md_tags_t *tags, lcd_digar_output_t *out) {
+    lcd_plan_t *plan = lcd_digar_md_plan_create(n_chunks, in, tags);
+    if (!plan) return -1;
+    int rc = lcd_plan_run(plan, nullptr);
+    if (!rc) rc = lcd_digar_plan_fetch(plan, nullptr, out);
+    lcd_plan_destroy(plan);
+    return rc;
 }
 
 lcd_plan_t *lcd_digar_plan_create(int n_chunks, const lcd_digar_input_t *in) {

@@ -379,3 +379,20 @@ int ref_classify_sites(const lcd_classify_input_t *in, int32_t *var_cate) {
     }
     return 0;
 }
+
+/* collect_digar_from_MD_tag (src/bam_utils.c:1003-1174) on the same synthetic chunk: the reads carry plain-M CIGARs and get an MD tag
+ * (md + md_off[r], NUL terminated). */
+int ref_collect_digar_md(const lcd_digar_input_t *in, const int64_t *md_off, const char *md, lcd_digar_output_t *out) {
+    ref_digar_job_t *job = (ref_digar_job_t*)ref_digar_prepare(in);
+    if (!job) return -9;
+    for (int r = 0; r < in->n_reads; ++r) {
+        const char *m = md + md_off[r];
+        if (bam_aux_append(job->chunk.reads[r], "MD", 'Z', (int)strlen(m) + 1, (const uint8_t*)m) < 0) return -9;
+    }
+    for (int i = 0; i < in->n_reads; ++i) {
+        const int r = in->ordered_read_ids[i];
+        if (in->is_skipped[r]) continue;
+        job->ret[r] = collect_digar_from_MD_tag(&job->chunk, r, &job->opt, job->chunk.digars + r) < 0;
+    }
+    return ref_digar_finish(job, in, out);
+}

@@ -325,10 +325,11 @@ def digar_input(d):
     return inp, keep
 
 
-def collect_digar(lib, fn, d):
-    """Run an implementation of the =/X difference-list pass -> dict with per-read records (in read-id order, layout independent)."""
+def collect_digar(lib, fn, d, mid_args=(), cap_like=None):
+    """Run an implementation of the =/X difference-list pass -> dict with per-read records (in read-id order, layout independent).
+    mid_args: extra ctypes arguments between the input and the output struct (the MD-tag shim takes the tags there)."""
     inp, keep = digar_input(d)
-    nr = d["n_reads"]; dc, ac, rc_ = digar_capacity(d)
+    nr = d["n_reads"]; dc, ac, rc_ = digar_capacity(cap_like if cap_like is not None else d)        # (cap_like: a chunk whose CIGARs size the outputs)
     size = {"r": nr + 1, "d": dc, "a": ac}
     buf = {k: np.full(size[w], 77, t) for k, t, w in DIGAR_OUT_FIELDS}
     nf, nn = np.zeros(nr + 1, np.int64), np.zeros(nr + 1, np.int32)
@@ -337,7 +338,7 @@ def collect_digar(lib, fn, d):
     qc = np.zeros(256, np.int64)
     out = DigarOutput(*[buf[k].ctypes.data for k, _, _ in DIGAR_OUT_FIELDS], dc, ac, nf.ctypes.data, nn.ctypes.data, nb.ctypes.data, ne.ctypes.data,
                       nl.ctypes.data, rc_, cb.ctypes.data, ce.ctypes.data, cl.ctypes.data, rc_, 0, qc.ctypes.data, 0, 0, 0)
-    rc = getattr(lib, fn)(C.byref(inp), C.byref(out))
+    rc = getattr(lib, fn)(C.byref(inp), *mid_args, C.byref(out))
     assert rc == 0, rc
     reads = {}
     for i in range(nr):
