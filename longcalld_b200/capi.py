@@ -391,6 +391,24 @@ def digar_batch(chunks):
     return _digar_finish(outs, results)
 
 
+class MdTags(C.Structure):
+    _fields_ = [("md_off", C.c_void_p), ("md", C.c_void_p)]
+
+
+def digar_md_batch(chunks, tags):
+    """lcd_digar_md_batch: chunks whose reads carry plain-M CIGARs + MD tags.  tags[i] = (md_off int64 [n_reads] (< 0: the read's CIGAR is =/X
+    already), md uint8 bytes: NUL-terminated strings)."""
+    ins, keep = _digar_inputs(chunks)
+    sizes = digar_capacity(ins, len(chunks))
+    sizes = [(d + int(np.asarray(c["l_qseq"][:c["n_reads"]]).sum()), a + int(np.asarray(c["l_qseq"][:c["n_reads"]]).sum()), r + int(np.asarray(c["l_qseq"][:c["n_reads"]]).sum()))
+             for (d, a, r), c in zip(sizes, chunks)]                      # an M op expands into up to its length in records
+    outs, results = _digar_outputs(chunks, sizes)
+    tkeep = [(np.ascontiguousarray(o, np.int64), np.ascontiguousarray(m, np.uint8)) for o, m in tags]
+    tarr = (MdTags * max(len(chunks), 1))(*[MdTags(o.ctypes.data, m.ctypes.data) for o, m in tkeep])
+    _check(lib().lcd_digar_md_batch(C.c_int(len(chunks)), ins, tarr, outs), "lcd_digar_md_batch")
+    return _digar_finish(outs, results)
+
+
 class DigarPlan(_Plan):
     """Inputs (CIGAR words, packed SEQ, QUAL of every chunk) resident in HBM; run() = count + scan + fill + histogram."""
     def __init__(self, chunks):

@@ -4,8 +4,8 @@
  * B200 implementation, marshals the reference's structures (bam_chunk_t, digar_t, cand_var_t, read_var_profile_t:
  * reference src/bam_utils.h, src/collect_var.h) into the flat views of include/lcd_gpu.h, calls the library, and
  * writes the results back exactly where the reference leaves them:
- *     collect_digars_from_bam                        (src/collect_var.c:1063)  -> lcd_digar_batch    (K1; chunks whose reads all carry
- *                                                     =/X CIGARs -- chunks with cs / MD / plain-M reads are forwarded to the reference)
+ *     collect_digars_from_bam                        (src/collect_var.c:1063)  -> lcd_digar_batch / lcd_digar_md_batch (K1; reads with =/X CIGARs or
+ *                                                     MD tags -- chunks with cs-tagged or untagged plain-M reads are forwarded to the reference)
  *     collect_all_cand_var_sites                     (src/collect_var.c:1209)  -> lcd_sites_batch    (K1b)
  *     collect_cand_vars                              (src/collect_var.c:238)   -> lcd_pileup_batch   (K2)
  *     collect_read_var_profile                       (src/collect_var.c:1389)  -> lcd_profile_batch  (K3)
@@ -114,12 +114,16 @@ extern int LONGCALLD_VERBOSE;                                                   
 void collect_digars_from_bam(bam_chunk_t *chunk, const struct call_var_pl_t *pl) {               /* src/collect_var.c:1063-1110 */
     const call_var_opt_t *opt = pl->opt;
     const int nr = chunk->n_reads;
-    int all_eqx = 1;
-    for (int i = 0; i < nr && all_eqx; ++i) {
+    /* the reference picks per read: =/X CIGAR, else cs tag, else MD tag, else the reference sequence (src/collect_var.c:1072-1080); on the
+       GPU: =/X CIGARs and MD tags.  A chunk with a read that would take the cs / reference-sequence path is forwarded whole. */
+    int all_eqx = 1, n_md = 0;
+    for (int i = 0; i < nr && all_eqx >= 0; ++i) {
         const int r = chunk->ordered_read_ids[i];
-        if (!chunk->is_skipped[r] && !has_equal_X_in_bam_cigar(chunk->reads[r])) all_eqx = 0;
+        if (chunk->is_skipped[r] || has_equal_X_in_bam_cigar(chunk->reads[r])) continue;
+        if (!has_cs_in_bam(chunk->reads[r]) && has_MD_in_bam(chunk->reads[r])) { all_eqx = 0; n_md++; }
+        else all_eqx = -1;
     }
-    if (!all_eqx) {              /* cs / MD / plain-M reads: the reference's string-parsing paths */
+    if (all_eqx < 0) {           /* cs-tagged / untagged plain-M reads: the reference's own paths */
         static void (*orig)(bam_chunk_t *, const struct call_var_pl_t *) = NULL;
         if (!orig) orig = (void (*)(bam_chunk_t *, const struct call_var_pl_t *))dlsym(RTLD_NEXT, "collect_digars_from_bam");
         n_calls[9]++;
@@ -150,6 +154,7 @@ void collect_digars_from_bam(bam_chunk_t *chunk, const struct call_var_pl_t *pl)
     in.n_cigar = ncig; in.cigar_off = coff; in.cigar = cig; in.l_qseq = lq; in.seq_off = soff; in.bseq = bseq; in.qual_off = qoff; in.qual = qual;
     int64_t dcap = 0, acap = 0, ncap = 0;
     if (lcd_digar_capacity(&in, &dcap, &acap, &ncap)) die("lcd_digar_capacity");
+    if (n_md) { dcap += (int64_t)n_q; acap += (int64_t)n_q; ncap += (int64_t)n_q; }          /* an M op expands into up to its length in records */
     lcd_digar_output_t o; memset(&o, 0, sizeof(o));
 #define A(field, type, n) o.field = (type*)calloc((size_t)(n) + 1, sizeof(type))
     A(skip, uint8_t, nr); A(read_beg, int64_t, nr); A(read_end, int64_t, nr); A(digar_first, int64_t, nr); A(n_digar, int32_t, nr);
@@ -159,7 +164,20 @@ void collect_digars_from_bam(bam_chunk_t *chunk, const struct call_var_pl_t *pl)
     A(qual_counts, int64_t, 256);
 #undef A
     o.digar_cap = dcap; o.alt_cap = acap; o.nreg_cap = ncap; o.cnreg_cap = ncap;
-    if (lcd_digar_batch(1, &in, &o)) die("lcd_digar_batch");
+    if (n_md == 0) { if (lcd_digar_batch(1, &in, &o)) die("lcd_digar_batch"); }
+    else {                       /* MD-tagged reads: the tags go along, the library walks them on the device */
+        int64_t *md_off = (int64_t*)calloc(nr + 1, sizeof(int64_t)); size_t md_len = 1;
+        for (int r = 0; r < nr; ++r) {
+            md_off[r] = -1;
+            if (chunk->is_skipped[r] || has_equal_X_in_bam_cigar(chunk->reads[r])) continue;
+            md_off[r] = (int64_t)md_len; md_len += strlen(bam_aux2Z(bam_aux_get(chunk->reads[r], "MD"))) + 1;
+        }
+        char *md = (char*)calloc(md_len + 1, 1);
+        for (int r = 0; r < nr; ++r) if (md_off[r] >= 0) strcpy(md + md_off[r], bam_aux2Z(bam_aux_get(chunk->reads[r], "MD")));
+        lcd_md_tags_t tags = { md_off, md };
+        if (lcd_digar_md_batch(1, &in, &tags, &o)) die("lcd_digar_md_batch");
+        free(md_off); free(md);
+    }
     n_calls[8]++;
     for (int i = 0; i < nr; ++i) {
         const int r = chunk->ordered_read_ids[i];

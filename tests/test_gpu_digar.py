@@ -131,3 +131,32 @@ def test_gpu_chunk_shaped_plan_and_chain_into_pileup(gpu, oracle):
     assert rows == T.read_var_profile(oracle, "lcd_oracle_read_var_profile", prof_in)
     assert sum(1 for row in rows for x in row[2] if x == 1) > len(sites) // 2
     assert int(got[:, 3].sum()) > len(sites) // 2          # (events of reads K1 dropped are not counted)
+
+
+def test_gpu_md_tagged_reads(gpu, oracle):
+    """Reads with plain-M CIGARs + MD tags (collect_digar_from_MD_tag): the device-side MD walk feeds the same kernels; results identical to the
+    =/X oracle on the chunk's own =/X CIGARs (which tests/test_oracle_md.py pins to the unmodified reference's MD path).  Mixed chunks (some reads
+    =/X already), a tag that does not match its CIGAR."""
+    from test_oracle_md import to_md
+    rng = np.random.default_rng(79)
+    cases = list(digar_cases(81, 60))
+    conv = [to_md(d, rng) for d in cases]
+    mixed = []
+    for d, (e, md_off, md) in zip(cases[:10], conv[:10]):            # every other read keeps its =/X CIGAR: md_off < 0
+        cig, off, cnt, mo = [], [], [], md_off.copy()
+        for r in range(d["n_reads"]):
+            src = d if r % 2 else e
+            ops = src["cigar"][int(src["cigar_off"][r]):int(src["cigar_off"][r]) + int(src["n_cigar"][r])]
+            off.append(len(cig)); cnt.append(len(ops)); cig.extend(ops.tolist())
+            if r % 2: mo[r] = -1
+        mixed.append((dict(d, cigar=np.array(cig + [0], np.uint32), cigar_off=np.array(off + [0], np.int64), n_cigar=np.array(cnt + [0], np.int32)), mo, md))
+    chunks = [e for e, _, _ in conv] + [m for m, _, _ in mixed]
+    tags = [(o, m) for _, o, m in conv] + [(o, m) for _, o, m in mixed]
+    res = gpu.digar_md_batch(chunks, tags)
+    for i, (d, o) in enumerate(zip(cases + cases[:10], res)):
+        same(view(d, o), T.collect_digar(oracle, "lcd_oracle_collect_digar_eqx", d), i)
+    e, md_off, md = conv[0]
+    bad = md.copy(); first = int(md_off[int(e["ordered_read_ids"][0])]); bad[first] = ord("#")
+    e2 = dict(e, is_skipped=np.zeros_like(e["is_skipped"]))
+    with pytest.raises(gpu.LcdGpuError, match="MD tag and CIGAR do not match"):
+        gpu.digar_md_batch([e2], [(md_off, bad)])

@@ -42,7 +42,9 @@ def test_vcf_identical_with_gpu_dropin(tech):
     assert calls, "the drop-in was not loaded"
     counts = dict((k, int(v)) for k, v in __import__("re").findall(r"(digar|sites|pileup|profile|phase|edlib|wfa|poa) (\d+)", calls[-1]))
     need = ("sites", "pileup", "phase", "wfa", "poa") if tech == "mosaic" else ("sites", "pileup", "profile", "phase", "wfa", "poa")   # -s: the profile takes the reference's somatic path
-    if tech != "ont": need += ("digar",)            # the bundled ONT BAM carries plain-M CIGARs + MD tags: the reference's string-parsing path
+    need += ("digar",)
+    fwd = int(__import__("re").search(r"digar \d+ \(forwarded: (\d+)\)", calls[-1]).group(1))
+    assert fwd == 0, calls[-1]                      # (the bundled ONT BAM carries plain-M CIGARs + MD tags: K1's MD front end)
     assert all(counts[k] > 0 for k in need), calls[-1]                                             # the kernels really ran on the GPU
     print(calls[-1])
     assert md5 == GOLDEN[tech], (md5, calls[-1])
