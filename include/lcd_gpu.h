@@ -11,7 +11,9 @@
  * Results are bit-identical to the reference's for the same inputs (tests/ -m gpu).
  *
  * Threading: one context per process (lcd_gpu_init).  Plans may be created and run from several
- * host threads; runs on the same CUDA stream serialise.  There is NO CPU fallback: every call
+ * host threads (each is bound to the library's device on entry); runs on the same CUDA stream
+ * serialise, plans that own their buffers (K1, K1b, K2, K2b, K3, K4) run unserialised next to the
+ * DP engines (lcd_gpu_reserve_sms, lcd_gpu_split_pool).  There is NO CPU fallback: every call
  * fails with a non-zero code (and lcd_gpu_last_error()) when the GPU or the kernels are missing.
  */
 #ifndef LCD_GPU_H
