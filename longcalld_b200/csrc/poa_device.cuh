@@ -27,11 +27,15 @@
 #include <math.h>
 #include "../../include/lcd_gpu.h"
 
+#ifdef LCD_SIMT_EMU
+static long simt_stat[8];       // test instrumentation: rows taken by chain segments / by the general path / ...
+#endif
 namespace lcd {
 namespace poa {
 
 constexpr int PN = 32;
 constexpr int LOGN = 5;
+constexpr int POA_SMEM_HALFS = 2 * 3 * 8 * 32;   // per-warp shared memory (int16): two row buffers x 3 planes x NVC vectors
 constexpr int GARBAGE = 0x5555;        // what a read of a never-written DP cell returns (never decisive)
 
 enum { ST_OK = 0, ST_INT32 = -1, ST_BAND = -2, ST_BACKTRACK = -3, ST_NOBASE = -4, ST_OOM = -5 };
@@ -56,7 +60,7 @@ struct __align__(16) DevResult {
     uint64_t msa_off;         // byte offset in the MSA output pool
     uint32_t cells_lo, cells_hi;
 #ifdef LCD_POA_TIMING
-    unsigned long long t_dp, t_bt, t_add, t_after, t_fin;   // SM clock cycles per phase (debug builds)
+    unsigned long long t_dp, t_bt, t_add, t_after, t_fin, t_seg, t_gen, n_seg, n_gen, t_pro;   // SM clock cycles per phase (debug builds); rows by chain segments / the general path
 #endif
 };
 
@@ -97,6 +101,8 @@ struct WS {
     int *aln_pool; int aln_top, aln_capacity;
     int2 *cigar; int cigar_cap;                      // {op | len << 2, node_id}
     uint8_t *qs;                                     // the read shifted by one with sentinels: qs[j] = query[j-1] (strip rows)
+    int4 *meta;                                      // per position of the topological order: {node, first in-edge source, base | min(n_in,255) << 8 | (path score & 0xff) << 16, remain}
+    int16_t *qp; int qp_stride;                      // query profile of the current read: qp[b * qp_stride + j] = score of column j against node base b (b = 4: N)
     int16_t *dp; uint32_t dp_capacity;               // in cells
     int n_nodes;
     int oom;
@@ -244,7 +250,7 @@ template <class L> struct Poa {
     int n_reads;
     int inf_min, oe1, oe2;
     unsigned long long cells;
-    unsigned long long t_dp, t_bt, t_add, t_after, t_fin;
+    unsigned long long t_dp, t_bt, t_add, t_after, t_fin, t_seg, t_gen, n_seg, n_gen, t_pro;
     // optional per-group on-chip cache of the previous row's H/E1/E2 band (2 buffers x 3 planes x NVC vectors):
     // in a chain graph the only predecessor of a row is the row computed just before it, and reading it
     // back from HBM/L2 (~250 cycles) is the critical path of the whole DP.  nullptr = disabled.
@@ -255,6 +261,8 @@ template <class L> struct Poa {
     static constexpr int MAXV = 512, GS_INTS = 2 * MAXV + 4 + 3 * 32;
 
     // ---- workspace ---------------------------------------------------------------------------
+    // columns of one base's row of the query profile: every vector a packed chain row can touch (dp_sn + 8) and 16-byte alignment
+    __host__ __device__ static int qp_stride_of(int max_len) { return ((max_len + 32) / 32 + 9) * 32; }
     __device__ bool carve(int32_t *arena, uint64_t words, int N, int E, int max_len, int n_reads_) {
         uint64_t top = 0;
         w.N = N;
@@ -271,6 +279,10 @@ template <class L> struct Poa {
         w.aln_capacity = E; w.aln_pool = arena + top; top += (uint64_t)((E + 3) & ~3);
         w.cigar_cap = max_len + N + 8; w.cigar = reinterpret_cast<int2 *>(arena + top); top += (uint64_t)w.cigar_cap * 2;
         w.qs = reinterpret_cast<uint8_t *>(arena + top); top += (uint64_t)(max_len + 192) / 4;
+        top = (top + 3) & ~3ull;
+        w.meta = reinterpret_cast<int4 *>(arena + top); top += (uint64_t)N * 4;
+        w.qp_stride = qp_stride_of(max_len);
+        w.qp = reinterpret_cast<int16_t *>(arena + top); top += (uint64_t)5 * w.qp_stride / 2;
         top = (top + 31) & ~31ull;
         if (top + 1024 > words) return false;
         w.dp = reinterpret_cast<int16_t *>(arena + top);
@@ -757,8 +769,12 @@ template <class L> struct Poa {
             t = jh_a; jh_a = jh_b; jh_b = t;  t = dh_a; dh_a = dh_b; dh_b = t;
         }
         for (int i = lane; i < n; i += L::NT) {
-            w.order[n - 1 - dn_a[i]] = i; w.pos[i] = n - 1 - dn_a[i];
-            w.remain[i] = dh_a[i] - 1;             // remain[SINK] = -1, remain[x] = remain[heaviest successor] + 1
+            const int at = n - 1 - dn_a[i], rem = dh_a[i] - 1;
+            w.order[at] = i; w.pos[i] = at;
+            w.remain[i] = rem;                     // remain[SINK] = -1, remain[x] = remain[heaviest successor] + 1
+            // everything the DP needs to know about the row at this position of the order, in one 16-byte record
+            const int nin = w.in_n[i];
+            w.meta[at] = make_int4(i, w.fp_id[i], w.base[i] | ((nin < 255 ? nin : 255) << 8) | ((w.fp_ps[i] & 0xff) << 16), rem);
         }
         L::sync();
     }
@@ -1016,6 +1032,263 @@ template <class L> struct Poa {
         for (int i = 0; i < C; ++i) { ve1[i] += ps; ve2[i] += ps; }
         strip_core<C>(a, h, ve1, ve2, first1, first2, mx, left, right);
     }
+
+    // ---- packed chain segments (warp policy) ---------------------------------------------------------
+    // A run of chain rows -- one in-edge, from the row computed just before, band not reaching past the last vector of
+    // that row (~95 % of all rows of a region's graph) -- is computed without touching memory on its critical path:
+    //   * the previous row's H / E1 / E2 stay in REGISTERS, two int16 cells per 32-bit register, lane l owning the C
+    //     consecutive columns c0 + l*C .. (c0 = 32 * the row's first vector); when the band's first vector moves right
+    //     the registers are shifted across lanes;
+    //   * cell arithmetic is the wrapping int16x2 SIMD-in-word set of sm_100a (VIADD.16x2, VIMNMX.S16x2, VIMNMX3.S16x2,
+    //     VIADDMNMX.S16x2 -- what _mm512_add_epi16 / _mm512_max_epi16 do per lane in the reference);
+    //   * the two gap models' F values of one column share a register (F1 low half, F2 high half), so the strip-local
+    //     recurrence and the max-plus warp scan of the strip aggregates cost one instruction stream for both;
+    //   * the node's row of the query profile (qp) is one 2C-byte load; the row's meta data (node, in-edge, base, path
+    //     score, remain) one 16-byte load fetched a row ahead.
+    // Results (all five planes of every row, the row descriptor) go to the same HBM layout the general path and the
+    // backtrack read.  Cell values are those of chain_row / strip_core (same formulas; see the notes there).
+    struct ChainState { int last_id; Row last_row; bool last_cached; int cache_buf; uint32_t dp_top; };
+    __device__ static __forceinline__ uint32_t pk2(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+    __device__ static __forceinline__ uint32_t dup2(int x) { return ((uint32_t)x & 0xffffu) * 0x10001u; }
+    template <int C> __device__ static __forceinline__ void ldp(const int16_t *p, uint32_t (&v)[C / 2]) {
+        if constexpr (C == 8) { const uint4 t = *reinterpret_cast<const uint4 *>(p); v[0] = t.x; v[1] = t.y; v[2 % (C / 2)] = t.z; v[3 % (C / 2)] = t.w; }
+        else if constexpr (C == 4) { const uint2 t = *reinterpret_cast<const uint2 *>(p); v[0] = t.x; v[1 % (C / 2)] = t.y; }
+        else v[0] = *reinterpret_cast<const uint32_t *>(p);
+    }
+    template <int C> __device__ static __forceinline__ void stp(int16_t *p, const uint32_t (&v)[C / 2]) {
+        if constexpr (C == 8) *reinterpret_cast<uint4 *>(p) = make_uint4(v[0], v[1], v[2 % (C / 2)], v[3 % (C / 2)]);
+        else if constexpr (C == 4) *reinterpret_cast<uint2 *>(p) = make_uint2(v[0], v[1 % (C / 2)]);
+        else *reinterpret_cast<uint32_t *>(p) = v[0];
+    }
+    // band of a chain row below the row `pr` (GET_AD_DP_BEGIN / END, abpoa_align.h:34-35, abpoa_align_simd.c:946-960)
+    __device__ __forceinline__ void chain_band(const Row &pr, int rem, int rem_end, int qlen, int n, int wband, bool banded,
+                                               int &beg, int &end, int &beg_sn) const {
+        beg = 0; end = qlen; beg_sn = 0;
+        if (banded) {
+            const int rr = qlen - (rem - rem_end - 1);
+            const int maxl = pr.left1 < n ? pr.left1 : n, maxr = pr.right1 > 0 ? pr.right1 : 0;
+            beg = (maxl < rr ? maxl : rr) - wband; if (beg < 0) beg = 0;
+            end = (maxr > rr ? maxr : rr) + wband; if (end > qlen) end = qlen;
+            beg_sn = beg >> 5;
+            if (beg_sn < (pr.beg >> 5)) { beg = pr.beg; beg_sn = pr.beg >> 5; }
+        }
+    }
+    // Computes rows oi, oi + 1, ... while they are chain rows that fit C columns per lane; returns the first position not taken.
+    // first_sn: first vector of row oi's band (the register window starts there).
+    template <int C> __device__ int chain_segment(int oi, const int first_sn, const int n, const int qlen, const int dp_sn, const int wband, const bool banded,
+                                                  const int rem_end, ChainState &st, int &err) {
+        constexpr int P = C / 2;
+        const int lane = threadIdx.x & 31;
+        const uint32_t INF2 = dup2(inf_min), MIN2 = 0x80008000u, LOW2 = dup2(-32600);
+        const int e1 = par.gap_ext1, e2 = par.gap_ext2;
+        const uint32_t NE12 = pk2(-e1, -e2), NOE12 = pk2(-oe1, -oe2);
+        const uint32_t NE1 = dup2(-e1), NE2 = dup2(-e2), NOE1 = dup2(-oe1), NOE2 = dup2(-oe2);
+        const int rel = lane * C;                        // this lane's first column, relative to the row's first vector
+        int c0sn = first_sn, pend_sn = st.last_row.end >> 5;
+        // the previous row, in a window of C vectors starting at the first vector of row oi: from the on-chip cache a
+        // general row left, else from its planes in the arena
+        uint32_t hp[P], e1p[P], e2p[P], lh_next = INF2;
+        {
+            const int16_t *src; int stride;
+            if (st.last_cached) { src = row_cache + st.cache_buf * 3 * NVC * PN; stride = NVC * PN; }
+            else { src = w.dp + st.last_row.off; stride = st.last_row.nv * PN; }
+            const int shift = (c0sn - (st.last_row.beg >> 5)) * PN;            // >= 0: a row's band never starts left of its predecessor's first vector
+            src += shift;
+            if (c0sn + (rel >> 5) <= pend_sn) { ldp<C>(src + rel, hp); ldp<C>(src + stride + rel, e1p); ldp<C>(src + 2 * stride + rel, e2p); }
+            else {
+#pragma unroll
+                for (int k = 0; k < P; ++k) { hp[k] = INF2; e1p[k] = INF2; e2p[k] = INF2; }
+            }
+            if (shift > 0) lh_next = (uint32_t)(uint16_t)src[-1] << 16;
+        }
+        Row lr = st.last_row; int last_id = st.last_id;
+        uint32_t dp_top = st.dp_top;
+        int4 mt = w.meta[oi];
+        int n_done = 0, narrow = 0;
+        for (;;) {
+            const int id = mt.x, nb = mt.z & 0xff, ps = (int)(int8_t)((mt.z >> 16) & 0xff);
+            if (id == 1 || ((mt.z >> 8) & 0xff) != 1 || mt.y != last_id) break;
+            int beg, end, beg_sn;
+            chain_band(lr, mt.w, rem_end, qlen, n, wband, banded, beg, end, beg_sn);
+            const int end_sn = end >> 5, nvd = end_sn - beg_sn + 1, nv = nvd + 1;
+            const int dl = (beg_sn - c0sn) * (32 / C);
+            // a band reaching ONE vector past the predecessor's last one (every ~32nd row of a diagonal) is taken too: that
+            // vector has the reference's truncated F propagation and is computed lane-per-column below
+            const bool extra = end_sn == pend_sn + 1;
+            if (end_sn > pend_sn + 1 || beg_sn > pend_sn || nvd > C || dl >= 32) break;
+            if (C > 2) { narrow = 2 * nvd <= C ? narrow + 1 : 0; if (narrow >= 48) break; }       // a band that got narrower: re-enter with fewer columns per lane
+            const uint32_t need = (uint32_t)nv * PN * 5;
+            if (dp_top + need > w.dp_capacity) { err = ST_OOM; return oi; }
+            const uint32_t off = dp_top; dp_top += need;
+            cells += (unsigned long long)(end - beg + 1);
+            if (oi + 1 < n) mt = w.meta[oi + 1];
+            // the band's first vector moved right: shift the previous row across the lanes
+            uint32_t lh = lh_next;                       // H of the previous row at column c0 - 1 (high half)
+            lh_next = INF2;
+            if (dl > 0) {
+                lh = __shfl_sync(0xffffffffu, hp[P - 1], dl - 1);
+#pragma unroll
+                for (int k = 0; k < P; ++k) {
+                    const uint32_t a = __shfl_down_sync(0xffffffffu, hp[k], dl), b = __shfl_down_sync(0xffffffffu, e1p[k], dl), c = __shfl_down_sync(0xffffffffu, e2p[k], dl);
+                    const bool in = lane + dl < 32;
+                    hp[k] = in ? a : INF2; e1p[k] = in ? b : INF2; e2p[k] = in ? c : INF2;
+                }
+                c0sn = beg_sn;
+            }
+            const int j0 = c0sn * PN + rel;
+            // M candidates: H of the previous row one column to the left, + path score + query profile
+            uint32_t q[P];
+            ldp<C>(w.qp + (size_t)(nb > 3 ? 4 : nb) * w.qp_stride + j0, q);
+            uint32_t up = __shfl_up_sync(0xffffffffu, hp[P - 1], 1);
+            if (lane == 0) up = lh;
+            uint32_t t[P], x1[P], x2[P];
+#pragma unroll
+            for (int k = 0; k < P; ++k) { t[k] = __vadd2(__byte_perm(k == 0 ? up : hp[k > 0 ? k - 1 : 0], hp[k], 0x5432), q[k]); x1[k] = e1p[k]; x2[k] = e2p[k]; }
+            if (ps != 0) {
+                const uint32_t ps2 = dup2(ps);
+#pragma unroll
+                for (int k = 0; k < P; ++k) { t[k] = __vadd2(t[k], ps2); x1[k] = __vadd2(x1[k], ps2); x2[k] = __vadd2(x2[k], ps2); }
+            }
+            // band mask, Hm = max(M + q, E1, E2)
+            const int lo = beg - j0, span = end - beg;
+            uint32_t m[P], hm[P];
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                const bool a = (unsigned)(2 * k - lo) <= (unsigned)span, b = (unsigned)(2 * k + 1 - lo) <= (unsigned)span;
+                m[k] = (a ? 0xffffu : 0u) | (b ? 0xffff0000u : 0u);
+                t[k] = (t[k] & m[k]) | (INF2 & ~m[k]); x1[k] = (x1[k] & m[k]) | (INF2 & ~m[k]); x2[k] = (x2[k] & m[k]) | (INF2 & ~m[k]);
+                hm[k] = __vimax3_s16x2(t[k], x1[k], x2[k]);
+            }
+            // F: strip-local recurrence (F1 | F2 packed per column), max-plus scan of the strip aggregates, carry-in
+            const uint32_t rf = __shfl_sync(0xffffffffu, t[0], 0);             // (M + q) of the row's first stored column
+            uint32_t hl = __shfl_up_sync(0xffffffffu, hm[P - 1], 1);
+            uint32_t prev2 = lane == 0 ? __byte_perm(rf, 0, 0x1010) : __byte_perm(hl, 0, 0x3232);
+            uint32_t f[C], g = 0;
+#pragma unroll
+            for (int i = 0; i < C; ++i) {
+                const uint32_t a2 = __vadd2(prev2, NOE12);
+                g = i == 0 ? a2 : __viaddmax_s16x2(g, NE12, a2);
+                f[i] = g;
+                prev2 = __byte_perm(hm[i >> 1], 0, (i & 1) ? 0x3232 : 0x1010);
+            }
+            {
+                uint32_t sg = g, dec = pk2(-e1 * C, -e2 * C);
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __vadd2(__shfl_up_sync(0xffffffffu, sg, d), dec);
+                    if (lane >= d) sg = __vmaxs2(sg, y);
+                    dec = __vadd2(dec, dec);
+                }
+                uint32_t c = __shfl_up_sync(0xffffffffu, sg, 1);
+                if (lane == 0) c = LOW2;
+#pragma unroll
+                for (int i = 0; i < C; ++i) { c = __vadd2(c, NE12); f[i] = __vmaxs2(f[i], c); }
+            }
+            // H, stored E, in-band row maximum
+            uint32_t hn[P], f1[P], f2[P], hb[P], lm2 = MIN2;
+            const bool in_strip = c0sn + (rel >> 5) <= pend_sn;          // false only for the lanes of an extra vector
+            if (!in_strip) {
+#pragma unroll
+                for (int k = 0; k < P; ++k) m[k] = 0;
+            }
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                f1[k] = __byte_perm(f[2 * k], f[2 * k + 1], 0x5410); f2[k] = __byte_perm(f[2 * k], f[2 * k + 1], 0x7632);
+                uint32_t h = __vimax3_s16x2(hm[k], f1[k], f2[k]);
+                h = (h & m[k]) | (INF2 & ~m[k]);
+                hn[k] = h;
+                x1[k] = __viaddmax_s16x2(x1[k], NE1, __vadd2(h, NOE1));
+                x2[k] = __viaddmax_s16x2(x2[k], NE2, __vadd2(h, NOE2));
+                hb[k] = (h & m[k]) | (MIN2 & ~m[k]);
+                lm2 = __vmaxs2(lm2, hb[k]);
+            }
+            int left = -1, right = -1, mxrow = inf_min;
+            if (banded) {
+                const int lo16 = (int)(int16_t)(lm2 & 0xffffu), hi16 = (int)lm2 >> 16;
+                const int mx = __reduce_max_sync(0xffffffffu, lo16 > hi16 ? lo16 : hi16);
+                const uint32_t mx2 = dup2(mx);
+                uint32_t bits = 0;
+#pragma unroll
+                for (int k = 0; k < P; ++k) { bool ph, pl; __vibmax_s16x2(hb[k], mx2, &ph, &pl); bits |= (pl ? 1u : 0u) << (2 * k) | (ph ? 1u : 0u) << (2 * k + 1); }
+                const int fi = __reduce_min_sync(0xffffffffu, bits ? j0 + __ffs(bits) - 1 : INT32_MAX);
+                const int la = __reduce_max_sync(0xffffffffu, bits ? j0 + 31 - __clz(bits) : -1);
+                if (mx > inf_min) { mxrow = mx; left = fi; right = la; }
+                else if (mx == inf_min) right = la;
+            }
+            // the five planes of the row (vectors beg_sn .. end_sn) and INF_MIN in H of the vector after the band
+            {
+                int16_t *H = w.dp + off;
+                if (extra) {
+                    // vector end_sn = pend_sn + 1, one column per lane (the per-vector code of the general path, set_num = 2):
+                    // M only from the predecessor's last column (when that is the last lane of its vector), no E, F seeded by
+                    // the strip pass' carries and propagated by the reference's truncated log-step scan
+                    const int o1 = par.gap_open1, o2 = par.gap_open2;
+                    const int last_lane = (pend_sn - c0sn + 1) * (32 / C) - 1;
+                    const int f1l = (int)f1[P - 1] >> 16, f2l = (int)f2[P - 1] >> 16, hml = (int)hm[P - 1] >> 16;
+                    const int first1 = __shfl_sync(0xffffffffu, hml > f1l + o1 ? hml : f1l + o1, last_lane);
+                    const int first2 = __shfl_sync(0xffffffffu, hml > f2l + o2 ? hml : f2l + o2, last_lane);
+                    const int hpl = __shfl_sync(0xffffffffu, (int)hp[P - 1] >> 16, last_lane);      // H of the previous row at column 32 * end_sn - 1
+                    const int col0 = end_sn * PN, khi = end - col0;
+                    int hv = inf_min;
+                    if (((lr.end + 1) >> 5) >= end_sn) hv = (int16_t)((lane == 0 ? hpl : inf_min) + ps);
+                    hv = (int16_t)(hv + w.qp[(size_t)(nb > 3 ? 4 : nb) * w.qp_stride + col0 + lane]);
+                    if (lane > khi || hv < inf_min) hv = inf_min;                                   // band mask; max(h, E1, E2) with E = INF_MIN
+                    int g1 = WarpLanes::sub(WarpLanes::shift_up(hv, 1, first1), oe1), g2 = WarpLanes::sub(WarpLanes::shift_up(hv, 1, first2), oe2);
+                    g1 = set_f(g1, 2, e1); g2 = set_f(g2, 2, e2);
+                    hv = hv > g1 ? hv : g1; hv = hv > g2 ? hv : g2;
+                    if (lane > khi) hv = inf_min;
+                    const int v1 = WarpLanes::vmax(WarpLanes::sub(inf_min, e1), WarpLanes::sub(hv, oe1)), v2 = WarpLanes::vmax(WarpLanes::sub(inf_min, e2), WarpLanes::sub(hv, oe2));
+                    int16_t *X = H + (size_t)(nvd - 1) * PN + lane;
+                    X[0] = (int16_t)hv; X[(size_t)nv * PN] = (int16_t)v1; X[(size_t)2 * nv * PN] = (int16_t)v2; X[(size_t)3 * nv * PN] = (int16_t)g1; X[(size_t)4 * nv * PN] = (int16_t)g2;
+                    if (banded) {
+                        int mv, fi, la;
+                        if (WarpLanes::row_max(hv, 0, khi > PN - 1 ? PN - 1 : khi, mv, fi, la)) {
+                            if (mv > mxrow) { left = col0 + fi; right = col0 + la; }
+                            else if (mv == mxrow) right = col0 + la;
+                        }
+                    }
+                    // into the register window: lanes L0 .. hold this vector, C columns each
+                    const int L0 = (end_sn - c0sn) * (32 / C);
+                    const bool mine = lane >= L0 && lane < L0 + 32 / C;
+#pragma unroll
+                    for (int k = 0; k < P; ++k) {
+                        const int s0 = ((lane - L0) * C + 2 * k) & 31;
+                        const uint32_t a = pk2(__shfl_sync(0xffffffffu, hv, s0), __shfl_sync(0xffffffffu, hv, s0 + 1));
+                        const uint32_t b = pk2(__shfl_sync(0xffffffffu, v1, s0), __shfl_sync(0xffffffffu, v1, s0 + 1));
+                        const uint32_t c = pk2(__shfl_sync(0xffffffffu, v2, s0), __shfl_sync(0xffffffffu, v2, s0 + 1));
+                        if (mine) { hn[k] = a; x1[k] = b; x2[k] = c; }
+                    }
+                }
+                if ((rel >> 5) < (extra ? nvd - 1 : nvd)) {
+                    stp<C>(H + rel, hn); stp<C>(H + (size_t)nv * PN + rel, x1); stp<C>(H + (size_t)2 * nv * PN + rel, x2);
+                    stp<C>(H + (size_t)3 * nv * PN + rel, f1); stp<C>(H + (size_t)4 * nv * PN + rel, f2);
+                }
+                if (end_sn + 1 <= dp_sn - 1) H[nvd * PN + lane] = (int16_t)inf_min;
+                const int4 packed = pack((int)off, beg, end, left, right);
+                if (lane == 0) w.rinfo[id] = packed;
+                lr = unpack(packed);
+            }
+#pragma unroll
+            for (int k = 0; k < P; ++k) { hp[k] = hn[k]; e1p[k] = x1[k]; e2p[k] = x2[k]; }
+            last_id = id; pend_sn = end_sn; ++n_done;
+#ifdef LCD_SIMT_EMU
+            if (lane == 0) { simt_stat[0]++; simt_stat[2 + P]++; }
+#endif
+            if (++oi >= n) break;
+        }
+        if (n_done == 0) return oi;
+        // leave the last row where a general row expects it
+        st.last_id = last_id; st.last_row = lr; st.dp_top = dp_top;
+        const int nvd = (lr.end >> 5) - (lr.beg >> 5) + 1;
+        if (nvd + 1 <= NVC) {
+            int16_t *dst = row_cache + st.cache_buf * 3 * NVC * PN;
+            if ((rel >> 5) < nvd) { stp<C>(dst + rel, hp); stp<C>(dst + NVC * PN + rel, e1p); stp<C>(dst + 2 * NVC * PN + rel, e2p); }
+            dst[nvd * PN + lane] = (int16_t)inf_min;
+            st.last_cached = true;
+        } else st.last_cached = false;
+        __syncwarp();
+        return oi;
+    }
 #endif
 
     // one sequence against the whole graph: simd_abpoa_cg_align_sequence_to_graph_core (:1200-1228)
@@ -1031,6 +1304,14 @@ template <class L> struct Poa {
         if constexpr (L::STRIP) {       // the read shifted by one, padded with a never-matching sentinel (strip_core)
             const int qs_len = (dp_sn + 2) * PN + 16;
             for (int j = L::tid(); j < qs_len; j += L::NT) w.qs[j] = (j >= 1 && j <= qlen) ? query[j - 1] : 7;
+            // query profile (simd_abpoa_cg_var :531-560): column 0 and the columns past the read score 0
+            const int qst = w.qp_stride;
+            for (int j = L::tid(); j < qst; j += L::NT) {
+                const int qb = (j >= 1 && j <= qlen) ? query[j - 1] : 7;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) w.qp[b * qst + j] = (int16_t)(qb > 3 ? 0 : (qb == b ? match : -mism));
+                w.qp[4 * qst + j] = 0;
+            }
         }
 #endif
         uint32_t dp_top = 0;
@@ -1075,65 +1356,54 @@ template <class L> struct Poa {
             }
         }
         L::sync();
-        // ---- rows in topological (list) order, SINK excluded.  The node metadata of the NEXT row is fetched
-        //      while the current row is computed (it does not depend on the DP).
-        int nid = w.order[1], nnin = w.in_n[nid], nbase = w.base[nid], nrem = banded ? w.remain[nid] : 0;
-        const int4 *nie = w.in_pool + w.in_off[nid];
-        int4 nie0 = nnin > 0 ? nie[0] : make_int4(0, 0, 0, 0);
-        for (int oi = 1; oi < n; ++oi) {
-            const int id = nid, nin = nnin, nb = nbase, rem = nrem;
-            const int4 *ie = nie; const int4 ie0 = nie0;
-            if (oi + 1 < n) {
-                nid = w.order[oi + 1]; nnin = w.in_n[nid]; nbase = w.base[nid]; nrem = banded ? w.remain[nid] : 0;
-                nie = w.in_pool + w.in_off[nid];
-                nie0 = nnin > 0 ? nie[0] : make_int4(0, 0, 0, 0);
-            }
-            if (id == 1) continue;
+        // ---- rows in topological (list) order, SINK excluded
+        int oi = 1;
+        while (oi < n) {
 #ifndef LCD_EMU
             if constexpr (L::STRIP) {
-                // chain fast path: one in-edge, from the row computed just before, whose band is on chip and reaches at
-                // least as far right as this row's (no vector with the reference's partial F propagation)
-                if (nin == 1 && ie0.x == last_id && last_cached) {
-                    const int pre_beg_sn = last_row.beg >> 5, pre_end_sn = last_row.end >> 5;
-                    int beg = 0, end = qlen, beg_sn = 0;
-                    if (banded) {
-                        const int rr = qlen - (rem - rem_end - 1);
-                        const int maxl = last_row.left1 < n ? last_row.left1 : n, maxr = last_row.right1 > 0 ? last_row.right1 : 0;
-                        beg = (maxl < rr ? maxl : rr) - wband; if (beg < 0) beg = 0;
-                        end = (maxr > rr ? maxr : rr) + wband; if (end > qlen) end = qlen;
-                        beg_sn = beg >> 5;
-                        if (beg_sn < pre_beg_sn) { beg = last_row.beg; beg_sn = pre_beg_sn; }
-                    }
-                    const int end_sn = end >> 5, nv = end_sn - beg_sn + 2;
-                    if (end_sn <= pre_end_sn && nv <= NVC) {
-                        const uint32_t need = (uint32_t)nv * PN * 5;
-                        if (dp_top + need > w.dp_capacity) return ST_OOM;
-                        const uint32_t off = dp_top; dp_top += need;
-                        cells += (unsigned long long)(end - beg + 1);
-                        StripArgs sa;
-                        sa.beg = beg; sa.end = end; sa.beg_sn = beg_sn; sa.end_sn = end_sn; sa.sn_hi = end_sn; sa.nb = nb;
-                        sa.H = w.dp + off - (size_t)beg_sn * PN; sa.E1 = sa.H + (size_t)nv * PN; sa.E2 = sa.E1 + (size_t)nv * PN;
-                        sa.F1 = sa.E2 + (size_t)nv * PN; sa.F2 = sa.F1 + (size_t)nv * PN;
-                        sa.cwH = row_cache + (cache_buf ^ 1) * 3 * NVC * PN - (size_t)beg_sn * PN; sa.banded = banded;
-                        const int16_t *crd = row_cache + cache_buf * 3 * NVC * PN;
-                        int f1_ = 0, f2_ = 0, mx = inf_min, left = -1, right = -1;
-                        if (nv <= 3) chain_row<2>(sa, crd, pre_beg_sn, ie0.z, f1_, f2_, mx, left, right);
-                        else if (nv <= 5) chain_row<4>(sa, crd, pre_beg_sn, ie0.z, f1_, f2_, mx, left, right);
-                        else chain_row<8>(sa, crd, pre_beg_sn, ie0.z, f1_, f2_, mx, left, right);
-                        if (end_sn + 1 <= dp_sn - 1) {
-                            L::store(sa.H + (end_sn + 1) * PN, L::set1(inf_min));
-                            L::store(sa.cwH + (end_sn + 1) * PN, L::set1(inf_min));
+                // Runs of chain rows (one in-edge, from the row computed just before, band not reaching past the predecessor's
+                // last vector) are computed by chain_segment: previous row in registers, int16x2 cells, no memory on the
+                // critical path.  It returns the position of the first row it did not take.
+                const int4 mt = w.meta[oi];
+                if (mt.x != 1 && ((mt.z >> 8) & 0xff) == 1 && mt.y == last_id) {
+                    int beg, end, beg_sn;
+                    chain_band(last_row, mt.w, rem_end, qlen, n, wband, banded, beg, end, beg_sn);
+                    const int end_sn = end >> 5, nvd = end_sn - beg_sn + 1;
+#ifdef LCD_SIMT_EMU
+                    if (L::tid() == 0 && getenv("SIMT_WHY")) { if (!(end_sn <= (last_row.end >> 5) + 1)) fprintf(stderr, "why: end_sn %d pend_sn %d beg_sn %d pbeg_sn %d qlen %d nin-prev? left1 %d right1 %d prev beg %d end %d\n", end_sn, last_row.end >> 5, beg_sn, last_row.beg >> 5, qlen, last_row.left1, last_row.right1, last_row.beg, last_row.end); else if (!(beg_sn <= (last_row.end >> 5))) fprintf(stderr, "why: beg_sn\n"); else if (nvd > 8) fprintf(stderr, "why: nvd %d\n", nvd); }
+#endif
+                    if (end_sn <= (last_row.end >> 5) + 1 && beg_sn <= (last_row.end >> 5) && nvd <= 8) {
+                        ChainState st; st.last_id = last_id; st.last_row = last_row; st.last_cached = last_cached; st.cache_buf = cache_buf; st.dp_top = dp_top;
+                        int err = 0, noi;
+                        LCD_T0();
+                        if (nvd <= 2) noi = chain_segment<2>(oi, beg_sn, n, qlen, dp_sn, wband, banded, rem_end, st, err);
+                        else if (nvd <= 4) noi = chain_segment<4>(oi, beg_sn, n, qlen, dp_sn, wband, banded, rem_end, st, err);
+                        else noi = chain_segment<8>(oi, beg_sn, n, qlen, dp_sn, wband, banded, rem_end, st, err);
+                        LCD_T1(t_seg);
+                        if (err) return err;
+                        if (noi > oi) {
+#ifdef LCD_POA_TIMING
+                            n_seg += noi - oi;
+#endif
+                            last_id = st.last_id; last_row = st.last_row; last_cached = st.last_cached; cache_buf = st.cache_buf; dp_top = st.dp_top;
+                            oi = noi;
+                            continue;
                         }
-                        const int4 packed = pack((int)off, beg, end, left, right);
-                        if (L::tid() == 0) w.rinfo[id] = packed;
-                        last_id = id; last_row = unpack(packed);
-                        cache_buf ^= 1;                      // last_cached stays true
-                        L::sync();
-                        continue;
                     }
                 }
             }
 #endif
+            const int id = w.order[oi++];
+            if (id == 1) continue;
+#ifdef LCD_POA_TIMING
+            const long long tg0_ = clock64(); n_gen++;
+#endif
+#ifdef LCD_SIMT_EMU
+            if (L::tid() == 0) { simt_stat[1]++; if (w.in_n[id] == 1 && w.in_pool[w.in_off[id]].x == last_id) simt_stat[2]++; }
+#endif
+            const int nin = w.in_n[id], nb = w.base[id], rem = banded ? w.remain[id] : 0;
+            const int4 *ie = w.in_pool + w.in_off[id];
+            const int4 ie0 = nin > 0 ? ie[0] : make_int4(0, 0, 0, 0);
             // predecessor descriptors: the first MAXP in registers, any further ones re-read per vector
             constexpr int MAXP = 4;
             int4 pe[MAXP]; Row pr[MAXP];
@@ -1330,6 +1600,9 @@ template <class L> struct Poa {
             last_id = id; last_row = unpack(pack((int)off, beg, end, left, right));
             last_cached = cache_wr; if (cache_wr) cache_buf ^= 1;
             L::sync();
+#ifdef LCD_POA_TIMING
+            t_gen += (unsigned long long)(clock64() - tg0_);
+#endif
         }
         // ---- best cell :1092-1105 and backtrack :309-458 (lane 0; result broadcast through memory)
 #ifndef LCD_EMU
@@ -1531,7 +1804,7 @@ template <class L> struct Poa {
 
     // ---- whole problem ---------------------------------------------------------------------------
     __device__ void run(const KernelArgs &a, const Problem &pb, DevResult *res, int32_t *arena) {
-        par = pb.par; n_reads = pb.n_reads; cells = 0; t_dp = t_bt = t_add = t_after = t_fin = 0;
+        par = pb.par; n_reads = pb.n_reads; cells = 0; t_dp = t_bt = t_add = t_after = t_fin = t_seg = t_gen = n_seg = n_gen = t_pro = 0;
         oe1 = par.gap_open1 + par.gap_ext1; oe2 = par.gap_open2 + par.gap_ext2;
         int status = ST_OK, cons_len = 0, msa_len = 0; unsigned long long msa_off = 0;
         {
@@ -1592,7 +1865,7 @@ template <class L> struct Poa {
             r.status = status; r.cons_len = cons_len; r.msa_len = msa_len; r.n_nodes = w.n_nodes; r.msa_off = msa_off;
             r.cells_lo = (uint32_t)cells; r.cells_hi = (uint32_t)(cells >> 32);
 #ifdef LCD_POA_TIMING
-            r.t_dp = t_dp - t_bt; r.t_bt = t_bt; r.t_add = t_add; r.t_after = t_after; r.t_fin = t_fin;
+            r.t_dp = t_dp - t_bt; r.t_bt = t_bt; r.t_add = t_add; r.t_after = t_after; r.t_fin = t_fin; r.t_seg = t_seg; r.t_gen = t_gen; r.n_seg = n_seg; r.n_gen = n_gen; r.t_pro = t_pro;
 #endif
             *res = r;
         }

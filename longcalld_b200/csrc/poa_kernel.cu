@@ -11,7 +11,10 @@ namespace poa {
 constexpr int WARPS_PER_CTA = 4;
 constexpr int POA_CARVEOUT_PCT = 50;      // % of the SM's L1 / shared memory kept as shared memory where the persistent grid sits: with the driver's choice (just what the grid needs) a kernel with its own shared memory (K1's histogram: 8 KB) cannot join a half-free SM and waits for the grid to retire (measured: 196 ms instead of 23 ms)
 
-__global__ void __launch_bounds__(32 * WARPS_PER_CTA)
+#ifndef POA_MIN_CTAS
+#define POA_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA, POA_MIN_CTAS)
 poa_kernel(const KernelArgs a) {
     const int gi = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group_id = blockIdx.x * WARPS_PER_CTA + gi;
@@ -85,6 +88,8 @@ static uint64_t arena_need_words(uint64_t N, uint64_t E, int max_len, int n_read
     uint64_t top = 30 * ((N + 3) & ~3ull) + N * 4;
     const uint64_t stride = 2 + 2 * (1 + ((n_reads - 1) >> 6));
     top += E * 4 + ((E * stride + 3) & ~3ull) + ((E + 3) & ~3ull) + 2 * ((uint64_t)max_len + N + 8) + ((uint64_t)max_len + 192) / 4;
+    top = (top + 3) & ~3ull;
+    top += N * 4 + (uint64_t)5 * Poa<WarpLanes>::qp_stride_of(max_len) / 2;          // row meta + query profile
     top = (top + 31) & ~31ull;
     return top + 1024 + (dp_cells + 1) / 2;
 }
@@ -244,7 +249,7 @@ struct PoaPlan : Plan {
             cls[k].push_back(i); cw[k] = std::max(cw[k], need_small[i]);
         }
         for (int k = 0; k < 3; ++k) cw[k] = (cw[k] + 63) & ~63ull;
-        const int max_groups[3] = { c.sm_count * 256, c.dp_sms() * 8, c.sm_count * 4 };
+        const int max_groups[3] = { c.sm_count * 256, c.dp_sms() * WARPS_PER_CTA * POA_MIN_CTAS, c.sm_count * 4 };
         // pool split: threads get what they need (at most half), CTAs and warps share the rest in proportion to demand
         uint64_t want[3];
         const int per_cta[3] = { THREADS_PER_CTA, WARPS_PER_CTA, 1 };
@@ -345,12 +350,12 @@ struct PoaPlan : Plan {
             std::vector<int> idx(n); for (int i = 0; i < n; ++i) idx[i] = i;
             auto tot = [&](int i) { const DevResult &r = h_results[i]; return r.t_dp + r.t_bt + r.t_add + r.t_after + r.t_fin; };
             std::sort(idx.begin(), idx.end(), [&](int x, int y) { return tot(x) > tot(y); });
-            unsigned long long T[5] = {0, 0, 0, 0, 0};
-            for (int i = 0; i < n; ++i) { const DevResult &r = h_results[i]; T[0] += r.t_dp; T[1] += r.t_bt; T[2] += r.t_add; T[3] += r.t_after; T[4] += r.t_fin; }
-            fprintf(stderr, "[poa timing] batch Mcycles: dp %.1f bt %.1f add %.1f after %.1f fin %.1f\n", T[0] / 1e6, T[1] / 1e6, T[2] / 1e6, T[3] / 1e6, T[4] / 1e6);
+            unsigned long long T[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int i = 0; i < n; ++i) { const DevResult &r = h_results[i]; T[0] += r.t_dp; T[1] += r.t_bt; T[2] += r.t_add; T[3] += r.t_after; T[4] += r.t_fin; T[5] += r.t_seg; T[6] += r.t_gen; T[7] += r.n_seg; T[8] += r.n_gen; }
+            fprintf(stderr, "[poa timing] batch Mcycles: dp %.1f (segments %.1f for %.2f Mrows, general %.1f for %.2f Mrows) bt %.1f add %.1f after %.1f fin %.1f\n", T[0] / 1e6, T[5] / 1e6, T[7] / 1e6, T[6] / 1e6, T[8] / 1e6, T[1] / 1e6, T[2] / 1e6, T[3] / 1e6, T[4] / 1e6);
             for (int k = 0; k < std::min(n, 12); ++k) { const int i = idx[k]; const DevResult &r = h_results[i];
-                fprintf(stderr, "[poa timing] #%d reads %d max_len %d nodes %d cells %u : dp %.1f bt %.1f add %.1f after %.1f fin %.1f Mcycles\n", i, problems[i].n_reads,
-                        problems[i].max_len, r.n_nodes, r.cells_lo, r.t_dp / 1e6, r.t_bt / 1e6, r.t_add / 1e6, r.t_after / 1e6, r.t_fin / 1e6); }
+                fprintf(stderr, "[poa timing] #%d reads %d max_len %d nodes %d cells %u : dp %.1f (seg %.1f / %llu rows, gen %.1f / %llu rows) bt %.1f add %.1f after %.1f fin %.1f Mcycles\n", i, problems[i].n_reads,
+                        problems[i].max_len, r.n_nodes, r.cells_lo, r.t_dp / 1e6, r.t_seg / 1e6, r.n_seg, r.t_gen / 1e6, r.n_gen, r.t_bt / 1e6, r.t_add / 1e6, r.t_after / 1e6, r.t_fin / 1e6); }
         }
 #endif
         uint64_t t = 0;
