@@ -187,7 +187,7 @@ class PileupStage:
         raw = sites_fn(bare, outs, self.regs)
         piles = [synth.pileup_input_from_digar(d, o, s) for d, o, s in zip(self.template, outs, raw)]
         counts = pileup_fn(piles)
-        self.cls = [synth.classify_input_from_sites(d, s, c, seed + 977 * i) for i, (d, s, c) in enumerate(zip(self.template, raw, counts))]      # K2b's input
+        self.cls = [synth.classify_input_from_sites(d, s, c, seed + 977 * i, is_ont=int(tech == "ont")) for i, (d, s, c) in enumerate(zip(self.template, raw, counts))]      # K2b's input
         var = [synth.classify_sites(s, c) for s, c in zip(raw, counts)]
         profs = [synth.pileup_input_from_digar(d, o, s) for d, o, s in zip(self.template, outs, var)]
         tile = lambda xs: [xs[i % nt] for i in range(self.n_chunks)]
@@ -223,8 +223,9 @@ def _vp(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def reference_step(lib, wl, idx, n_threads):
-    """The reference's CPU implementation (abPOA then WFA2-lib) of the same stages on problems `idx`."""
+def reference_step(lib, wl, idx, n_threads, keep=None):
+    """The reference's CPU implementation (abPOA then WFA2-lib) of the same stages on problems `idx`.
+    keep: dict that receives the reference's outputs (consensus, CIGAR ops, phasing, edlib paths) for the parity check of the bench line."""
     from longcalld_b200.capi import WFA_PARAMS_DTYPE, WFA_RESULT_DTYPE, POA_PARAMS_DTYPE, wfa_params, poa_params
     idx = np.asarray(idx, dtype=np.int64)
     n = len(idx)
@@ -251,7 +252,7 @@ def reference_step(lib, wl, idx, n_threads):
     from longcalld_b200.capi import _phase_structs, EDLIB_RESULT_DTYPE
     frac = n / max(1, wl.n_poa)
     ph = wl.phase[:max(2, 2 * int(round(frac * len(wl.phase) / 2)))]
-    ins, outs, keep, _ = _phase_structs(ph, -9)
+    ins, outs, ph_keep_, ph_results = _phase_structs(ph, -9)
     t4 = time.perf_counter()
     lib.ref_phase_batch(C.c_int(len(ph)), ins, outs, C.c_int(n_threads))
     t5 = time.perf_counter()
@@ -264,7 +265,63 @@ def reference_step(lib, wl, idx, n_threads):
     t6 = time.perf_counter()
     lib.ref_edlib_batch(C.c_int(ne), _vp(eseqs), _vp(qo), _vp(ql), _vp(to_), _vp(tl_), _vp(m), _vp(w), _vp(ealn), _vp(eoff), _vp(eres), C.c_int(n_threads))
     t7 = time.perf_counter()
+    if keep is not None:
+        keep.update(idx=idx, cons=cons, cons_len=cons_len, wfa_ops=ops, wfa_off=off, wfa_res=res, phase=ph_results,
+                    n_edlib=ne, edlib_res=eres, edlib_aln=ealn, edlib_off=eoff)
     return (t1 - t0) + (t3 - t2) + (t5 - t4) + (t7 - t6), (t1 - t0), (t3 - t2), (t5 - t4), (t7 - t6)
+
+
+def parity_check(ref, pile_ref, wl, ps, gpu):
+    """The reference arm's outputs of the bounded sample against the GPU outputs of the same batch (the last e2e batch): every byte
+    of every consensus, every CIGAR op, haplotype / phase set / per-variant consensus allele, edlib path, difference-list record, site,
+    counter, category and profile row.  Raises on the first difference; returns what was compared."""
+    idx = ref["idx"]
+    n_cons = n_ops = 0
+    for j, i in enumerate(idx.tolist()):
+        o, l = int(wl.cons_off[i]), int(ref["cons_len"][j])
+        if l != int(gpu["cons_len"][i]) or not np.array_equal(ref["cons"][o:o + l], gpu["cons"][o:o + l]):
+            raise AssertionError(f"parity: consensus of POA problem {i} differs from the reference's")
+        rr, gr = ref["wfa_res"][j], gpu["wfa_res"][i]
+        if tuple(rr) != tuple(gr):
+            raise AssertionError(f"parity: WFA result record of problem {i} differs: {tuple(rr)} vs {tuple(gr)}")
+        k = int(rr["n_ops"]); a, b = int(ref["wfa_off"][j]), int(gpu["wfa_off"][i])
+        if not np.array_equal(ref["wfa_ops"][a:a + k], gpu["wfa_ops"][b:b + k]):
+            raise AssertionError(f"parity: CIGAR of WFA problem {i} differs from the reference's")
+        n_cons += l; n_ops += k
+    for c, (r, g) in enumerate(zip(ref["phase"], gpu["phase"])):
+        for key in r:
+            if not np.array_equal(r[key], g[key]):
+                raise AssertionError(f"parity: phasing output {key} of chunk pass {c} differs from the reference's")
+    ne = ref["n_edlib"]
+    if not np.array_equal(ref["edlib_res"], gpu["edlib_res"][:ne]):
+        raise AssertionError("parity: edlib result records differ from the reference's")
+    for e in range(ne):
+        k = int(ref["edlib_res"]["aln_len"][e]); a, b = int(ref["edlib_off"][e]), int(gpu["edlib_off"][e])
+        if not np.array_equal(ref["edlib_aln"][a:a + k], gpu["edlib_aln"][b:b + k]):
+            raise AssertionError(f"parity: edlib path {e} differs from the reference's")
+    k = pile_ref["k"]
+    for c in range(k):
+        rs, gs = pile_ref["sites"][c], gpu["sites"][c]
+        if rs["n_sites"] != gs["n_sites"] or any(not np.array_equal(rs[key], gs[key]) for key in ("site_pos", "site_type", "site_ref_len", "site_alt_len")):
+            raise AssertionError(f"parity: candidate sites of chunk {c} differ from the reference's")
+        if not np.array_equal(pile_ref["counts"][c][:rs["n_sites"]], gpu["counts"][c][:rs["n_sites"]]):
+            raise AssertionError(f"parity: coverage counters of chunk {c} differ from the reference's")
+        if not np.array_equal(pile_ref["cate"][c][:rs["n_sites"]], gpu["cate"][c][:rs["n_sites"]]):
+            raise AssertionError(f"parity: site categories of chunk {c} differ from the reference's")
+        rp, gp = pile_ref["prof"][c], gpu["prof"][c]
+        nr = ps.n_reads[c]
+        if not (np.array_equal(rp[0][:nr], gp["prof_start"][:nr]) and np.array_equal(rp[1][:nr], gp["prof_end"][:nr])):
+            raise AssertionError(f"parity: profile row ranges of chunk {c} differ from the reference's")
+        for r in range(nr):
+            m = int(rp[1][r]) - int(rp[0][r]) + 1
+            if m <= 0: continue
+            a, b = int(rp[2][r]), int(gp["allele_off"][r])
+            if not (np.array_equal(rp[3][a:a + m], gp["alleles"][b:b + m]) and np.array_equal(rp[4][a:a + m], gp["alt_qi"][b:b + m])):
+                raise AssertionError(f"parity: profile row of read {r} of chunk {c} differs from the reference's")
+        from longcalld_b200.check import digar_view, digar_same
+        digar_same(digar_view(ps.chunks[c], gpu["digar"][c]), digar_view(ps.chunks[c], pile_ref["digar"][c]), f"parity: difference lists of chunk {c}")
+    return {"poa_consensus": len(idx), "consensus_bases": int(n_cons), "wfa_alignments": len(idx), "cigar_ops": int(n_ops), "phase_chunk_passes": len(ref["phase"]),
+            "edlib_paths": int(ne), "pileup_chunks": int(k), "sites": int(sum(s["n_sites"] for s in pile_ref["sites"])), "what": "reference arm (unmodified reference functions) == GPU e2e outputs of the same batch, bit for bit"}
 
 
 def ref_pileup_fns(lib, n_threads):
@@ -273,7 +330,7 @@ def ref_pileup_fns(lib, n_threads):
 
     def digar(chunks):
         ins, keep = capi._digar_inputs(chunks)
-        outs, results = capi._digar_outputs(chunks, capi.digar_capacity(ins, len(chunks)))
+        outs, results = capi._digar_outputs(chunks, capi.digar_capacity_host(chunks))
         if lib.ref_digar_batch(C.c_int(len(chunks)), ins, outs, C.c_int(n_threads), None): raise RuntimeError("ref_digar_batch failed")
         return capi._digar_finish(outs, results)
 
@@ -292,12 +349,12 @@ def ref_pileup_fns(lib, n_threads):
     return digar, sites, pileup
 
 
-def reference_pileup_step(lib, ps, k, n_threads):
+def reference_pileup_step(lib, ps, k, n_threads, out=None):
     """K1 + K1b + K2 + K2b + K3 of the reference on the first k chunks of the batch; returns seconds (total, K1, K2, K3, K1b, K2b)."""
     from longcalld_b200 import capi
     chunks, piles, profs = ps.chunks[:k], ps.piles[:k], ps.profs[:k]
     ins, keep = capi._digar_inputs(chunks)
-    outs, results = capi._digar_outputs(chunks, capi.digar_capacity(ins, k))
+    outs, results = capi._digar_outputs(chunks, capi.digar_capacity_host(chunks))
     pins, pouts, pkeep, pres = capi._pileup_structs(piles)
     fins, _, fkeep, _ = capi._pileup_structs(profs)
     bins, _, bkeep, _ = capi._pileup_structs(ps.bare[:k])
@@ -306,11 +363,13 @@ def reference_pileup_step(lib, ps, k, n_threads):
     cins, _, ckeep, cres = capi._classify_structs(ps.cls[:k])
     cptr = (C.c_void_p * k)(*[r.ctypes.data for r in cres])
     exs, fouts, fres = (capi.ProfileExtra * k)(), (capi.ProfileOutput * k)(), []
-    capi.lib().lcd_profile_capacity.restype = C.c_int64
     for i, d in enumerate(profs):
         arrs = {kk: np.ascontiguousarray(d[kk], dtype=t) for kk, t in capi._PROFILE_EX}; fkeep.append(arrs)
         exs[i] = capi.ProfileExtra(*[arrs[kk].ctypes.data for kk, _ in capi._PROFILE_EX])
-        cap = int(capi.lib().lcd_profile_capacity(C.byref(fins[i]))) + 8
+        # rows the profile can need: per read the sites whose span can touch it (numpy upper bound; the reference arm never loads the product library)
+        nsv = int(d["n_sites"]); sp = np.asarray(d["site_pos"][:nsv], np.int64); mrl = int(np.asarray(d["site_ref_len"][:nsv]).max()) + 2 if nsv else 2
+        nrd = int(d["n_reads"])
+        cap = int((np.searchsorted(sp, np.asarray(d["read_end"][:nrd], np.int64) + 2, "right") - np.searchsorted(sp, np.asarray(d["read_beg"][:nrd], np.int64) - mrl, "left") + 2).sum()) + 8
         o = [np.zeros(d["n_reads"] + 1, np.int32), np.zeros(d["n_reads"] + 1, np.int32), np.zeros(d["n_reads"] + 1, np.int64), np.zeros(cap, np.int8), np.zeros(cap, np.int32)]
         fres.append(o); fouts[i] = capi.ProfileOutput(*[a.ctypes.data for a in o], cap, 0)
     core = C.c_double(0.0)        # K1: the reference's own calls only (the shim's bam1_t construction and copy-out are not the reference's work)
@@ -325,6 +384,8 @@ def reference_pileup_step(lib, ps, k, n_threads):
     rc |= lib.ref_profile_batch(C.c_int(k), fins, exs, fouts, C.c_int(n_threads))
     t3 = time.perf_counter()
     if rc: raise RuntimeError("reference K1-K3 failed")
+    if out is not None:
+        out.update(k=k, digar=capi._digar_finish(outs, results), sites=capi._sites_finish(souts, sres), counts=[r for r in pres], cate=cres, prof=fres)
     return core.value + score.value + (t3 - t1), core.value, t2 - t1, t3 - t2b, score.value, t2b - t2
 
 
@@ -515,6 +576,7 @@ def run_b200(args, rank, world):
                 raise RuntimeError(L.lcd_gpu_last_error().decode())
             tw.append(time.perf_counter())
             stage_err["tl"] = tl; stage_err["t_wfa"] = [round(1e3 * (y - x), 1) for x, y in zip(tw, tw[1:])]
+            stage_err["ops"] = (ops, off, b)
         except Exception as e:                                       # re-raised by the main thread
             stage_err["error"] = e
 
@@ -587,6 +649,7 @@ def run_b200(args, rank, world):
         """K1 plan (its H2D copies were issued by the staging thread) -> K1 -> K1b -> K2 / K3 on the lists in HBM -> site lists, coverage counters and profile rows on the host"""
         t = [time.perf_counter()]
         dp.run(); dp.sync(); t.append(time.perf_counter())
+        if pile_res.get("want_digar"): pile_res["digar"] = dp.fetch()
         k1b = lcd.SitesPlan(None, ps.regs, min_sv_len=min_sv, digar_plan=dp); k1b.run(); pile_res["sites"] = k1b.fetch()
         k2 = lcd.PileupOnSitesPlan(dp, k1b); t.append(time.perf_counter()); k2.run(); pile_res["counts"] = k2.fetch(); t.append(time.perf_counter())
         k2b = lcd.ClassifyOnPileupPlan(k2, ps.cls, k2.n_sites); k2b.run(); pile_res["cate"] = k2b.fetch(); k2b.destroy()      # K2b on K2's sites and counters in HBM (the reference windows come from the host)
@@ -729,18 +792,26 @@ def run_b200(args, rank, world):
     value = total_mbp * args.steps / (dev_ms_max / 1e3)
     e2e_value = total_mbp * args.steps / (e2e_ms_max / 1e3)
 
-    cpu_baseline = None
+    cpu_baseline = None; parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         lib = ref_shim()
         if lib is not None:
             nt = os.cpu_count() or 1
             frac = calibrate_sample(lib, wl, nt, target_s=15.0)
             regs, idx = region_sample(wl, frac)
-            dt, dt_poa, dt_wfa, dt_phase, dt_edlib = reference_step(lib, wl, idx, nt)
+            ref_out, pile_out = {}, {}
+            dt, dt_poa, dt_wfa, dt_phase, dt_edlib = reference_step(lib, wl, idx, nt, keep=ref_out)
             mbp_sample = args.mbp * len(regs) / wl.n_regions
             k_chunks = min(ps.n_chunks, max(1, int(round(ps.n_chunks * len(regs) / wl.n_regions))))
             pile_scale = (len(regs) / wl.n_regions) / (k_chunks / ps.n_chunks)
-            dtp = reference_pileup_step(lib, ps, k_chunks, nt)
+            dtp = reference_pileup_step(lib, ps, k_chunks, nt, out=pile_out)
+            # parity at bench scale: one more e2e batch whose difference lists are fetched too, compared with the reference arm's outputs
+            pile_res["want_digar"] = True
+            e2e_run(2 if args.pipeline else 1)
+            ops_g, off_g, b_g = stage_err["ops"]
+            parity = parity_check(ref_out, pile_out, wl, ps, dict(cons=bufs[b_g][R:], cons_len=press[b_g]["cons_len"], wfa_res=wress[b_g], wfa_ops=ops_g, wfa_off=off_g,
+                                                                  phase=ph_res, edlib_res=eres, edlib_aln=ealn, edlib_off=eoff,
+                                                                  sites=pile_res["sites"], counts=pile_res["counts"], cate=pile_res["cate"], prof=pile_res["prof"], digar=pile_res["digar"]))
             cpu_baseline = {"value": mbp_sample / (dt + pile_scale * dtp[0]), "unit": UNIT, "cores": nt, "kind": "reference",
                             "sample": f"{len(regs)} of {wl.n_regions} regions ({mbp_sample:.3f} Mb): the unmodified reference's own functions via oracle/_ref; "
                                       f"K1-K3 on {k_chunks} of {ps.n_chunks} chunks, time scaled by {pile_scale:.4f}",
@@ -785,7 +856,7 @@ def run_b200(args, rank, world):
                                                                "GBps": ps.k3_bytes / (k3_ms / args.steps / 1e3) / 1e9},
                                             "edlib_kernel": {"ms": edlib_ms / args.steps, "block_columns": edlib_units,
                                                              "GBps": edlib_units * EDLIB_BYTES_PER_BLOCKCOL / (edlib_ms / args.steps / 1e3) / 1e9}}},
-                "cpu_baseline": cpu_baseline}
+                "cpu_baseline": cpu_baseline, "parity_checked": parity}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

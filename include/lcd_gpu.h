@@ -44,6 +44,7 @@ void *lcd_gpu_stream(void);
  * another thread's kernels (the POA launch) occupy the library stream.  The POA and WFA plans share the workspace pool and must all
  * run on one stream. */
 void *lcd_gpu_aux_stream(void);
+void *lcd_gpu_new_stream(void);        /* a new non-blocking stream on the library's device (owned by the library, released by lcd_gpu_shutdown); NULL on error */
 void lcd_gpu_set_thread_stream(void *stream);
 /* The DP engines (K5, K6) run persistent grids that fill every SM until their queues drain; kernels of other plans launched meanwhile
  * (K1 - K4 from a second host thread / stream: their plans own their buffers and are not serialised with the DP engines) would wait
@@ -231,12 +232,12 @@ int  lcd_pileup_plan_fetch(lcd_plan_t *plan, void *stream, lcd_pileup_output_t *
  * The sites and counters are K2's (lcd_pileup_input_t / lcd_pileup_output_t); the result is chunk->var_i_to_cate before the
  * noisy-region pass.  The reference window must reach 24 bases beyond every site on both sides (the reference reads it unchecked;
  * chunks carry +-50 kb).  ONT's strand-bias Fisher test (var_is_strand_bias, :270) is floating point and stays on the host:
- * chunks with is_ont set are rejected. */
+ * chunks with is_ont set add var_is_strand_bias (src/collect_var.c:270: two-tailed Fisher exact test, p < 0.01 -> LONGCALLD_STRAND_BIAS_VAR). */
 typedef struct {
     int32_t n_sites;
     int32_t min_dp, min_alt_dp;        /* opt->min_dp, opt->min_alt_dp */
     int32_t max_xgaps;                 /* opt->noisy_reg_max_xgaps: longer indels skip the homopolymer / repeat tests */
-    int32_t is_ont;                    /* opt->is_ont (the strand-bias Fisher test of ONT data is not restated: must be 0) */
+    int32_t is_ont;                    /* opt->is_ont: adds the strand-bias test of ONT data */
     int32_t pad;
     double min_af, max_af;             /* opt->min_af, opt->max_af */
     int64_t ref_beg, ref_end;          /* chunk->ref_beg / ref_end: ref_seq[0] is base ref_beg */

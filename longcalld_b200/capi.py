@@ -382,6 +382,21 @@ def digar_capacity(ins, n):
     return sizes
 
 
+def digar_capacity_host(chunks):
+    """lcd_digar_capacity in numpy (same formula, no library call): what callers that must not load liblcd_gpu.so -- the reference
+    arm of bench.py -- size their output arrays with."""
+    sizes = []
+    for d in chunks:
+        nr = int(d["n_reads"])
+        off, n = np.asarray(d["cigar_off"][:nr], np.int64), np.asarray(d["n_cigar"][:nr], np.int64)
+        tot = int(n.sum())
+        idx = np.repeat(off - (np.cumsum(n) - n), n) + np.arange(tot)
+        cg = np.asarray(d["cigar"], np.uint32)[idx]; op = cg & 15; ln = (cg >> 4).astype(np.int64)
+        x, i_, d_ = int(ln[op == 8].sum()), int((op == 1).sum()), int((op == 2).sum())
+        sizes.append((x + i_ + d_ + int(np.isin(op, (7, 4, 5)).sum()) + 1, x + int(ln[op == 1].sum()) + 1, x + i_ + d_ + 2 * nr + 1))
+    return sizes
+
+
 def digar_batch(chunks):
     """Drop-in batch call over HOST buffers (lcd_digar_batch).  chunks: dicts with the fields of lcd_digar_input_t.  Returns per
     chunk a dict with the arrays of lcd_digar_output_t (+ the n_* totals)."""

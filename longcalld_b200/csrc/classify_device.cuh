@@ -6,19 +6,21 @@
 // record, K2's output where it lies), its type / lengths and -- for the ~10 % of sites that are small indels between the allele-fraction
 // thresholds -- up to 36 reference bases around it (L2 resident: neighbouring sites share them) and its inserted bases.  The double
 // division of the allele fraction is IEEE on both sides, so the thresholds cut exactly where the reference's do.
+// ONT chunks add the strand-bias test (a two-tailed Fisher exact test on the strand counts of the alternative allele).
 // The file compiles for the host as well (tests/emu).
 #pragma once
 #include <stdint.h>
+#include <math.h>
 #include "../../include/lcd_gpu.h"
 
 namespace lcd {
 namespace classify {
 
 enum { CINS = 1, CDEL = 2, CDIFF = 8 };
-enum { NON_VAR = 0x800, LOW_COV_VAR = 0x001, LOW_AF_VAR = 0x400, CLEAN_HET_SNP = 0x004, CLEAN_HET_INDEL = 0x008, REP_HET_VAR = 0x010, CLEAN_HOM_VAR = 0x080 };
+enum { NON_VAR = 0x800, LOW_COV_VAR = 0x001, STRAND_BIAS_VAR = 0x002, LOW_AF_VAR = 0x400, CLEAN_HET_SNP = 0x004, CLEAN_HET_INDEL = 0x008, REP_HET_VAR = 0x010, CLEAN_HOM_VAR = 0x080 };
 
 struct __align__(16) Chunk {
-    int32_t min_dp, min_alt_dp, max_xgaps, pad;
+    int32_t min_dp, min_alt_dp, max_xgaps, is_ont;
     double min_af, max_af;
     long long ref_beg, ref_end;       // chunk->ref_beg / ref_end
     long long ref_off;                // first byte of the chunk's reference window in the concatenated ref array
@@ -32,6 +34,7 @@ struct KernelArgs {
     const int32_t *site_counts;       // [n_sites_total][8]
     const char *ref;
     int32_t *var_cate;
+    const double *lgamma_cache;       // lgamma(0 .. LGAMMA_MAX_I) as the host's libm returns them (opt->lgamma_cache, src/math_utils.c:6-11)
     int32_t *status;                  // optional: set to 1 when a small indel lies within REF_MARGIN bases of its reference window's ends
 };
 constexpr int REF_MARGIN = 24;       // bases of reference the context tests may read beyond a site (the reference reads them unchecked)
@@ -84,6 +87,50 @@ __device__ __forceinline__ bool is_repeat_region(const Chunk &ch, const char *re
     return true;
 }
 
+// ---- ONT strand bias: var_is_strand_bias (src/collect_var.c:270-284) -> fisher_exact_test (src/math_utils.c:119-170), two-tailed, on
+// the table {forward alt, reverse alt, expected, expected}.  Double arithmetic in the reference's order of operations; lgamma comes from
+// the host-built cache (bit-identical to the reference's), so only exp() can differ from the host's libm -- by an ulp of a p-value that
+// is then summed, rounded to float and compared with 0.01f.
+constexpr int LGAMMA_MAX_I = 500;                                            // LONGCALLD_LGAMMA_MAX_I, src/call_var_main.h:86
+constexpr float STRAND_BIAS_PVAL_ONT = 0.01f;                                // LONGCALLD_STRAND_BIAS_PVAL_ONT, src/call_var_main.h:74
+__device__ __forceinline__ double fast_lgamma(const double *cache, int x) { return (x >= 0 && x <= LGAMMA_MAX_I) ? cache[x] : lgamma((double)x); }
+__device__ inline double log_hypergeometric(const double *lg, int a, int b, int c, int d) {       // src/math_utils.c:101-116 (the recursion unrolled)
+    for (;;) {
+        const int n1 = a + b, n2 = c + d, m1 = a + c, m2 = b + d;
+        if (n1 > n2) { int t = a; a = c; c = t; t = b; b = d; d = t; continue; }                  // -> (c, d, a, b)
+        if (m1 > m2) { int t = a; a = b; b = t; t = c; c = d; d = t; continue; }                  // -> (b, a, d, c)
+        const int N = n1 + n2;
+        return fast_lgamma(lg, n1 + 1) + fast_lgamma(lg, n2 + 1) + fast_lgamma(lg, m1 + 1) + fast_lgamma(lg, m2 + 1) -
+               (fast_lgamma(lg, a + 1) + fast_lgamma(lg, b + 1) + fast_lgamma(lg, c + 1) + fast_lgamma(lg, d + 1) + fast_lgamma(lg, N + 1));
+    }
+}
+__device__ inline double fisher_exact_test(const double *lg, int a, int b, int c, int d) {        // src/math_utils.c:119-170
+    const double p_observed = exp(log_hypergeometric(lg, a, b, c, d));
+    double total_p = 0.0;
+    const int min_a = (0 > (a + c) - (a + b + c + d)) ? 0 : (a + c) - (b + d);
+    const int max_a = (a + b) < (a + c) ? (a + b) : (a + c);
+    const int mode_a = (int)((a + b) * (a + c) / (double)(a + b + c + d));
+    for (int delta = 0; delta <= max_a - min_a; delta++) {
+        for (int side = 0; side < 2; ++side) {
+            if (side == 1 && delta == 0) continue;
+            const int ca = side == 0 ? mode_a + delta : mode_a - delta;
+            if (side == 0 ? ca > max_a : ca < min_a) continue;
+            const int cb = (a + b) - ca, cc = (a + c) - ca, cd = (b + d) - cb;
+            if (cb >= 0 && cc >= 0 && cd >= 0) {
+                const double p = exp(log_hypergeometric(lg, ca, cb, cc, cd));
+                if (p <= p_observed + 2.2204460492503131e-16) total_p += p;
+            }
+        }
+    }
+    return total_p;
+}
+__device__ inline bool is_strand_bias(const double *lg, int for_alt_cov, int rev_alt_cov) {
+    const int expected = (for_alt_cov + rev_alt_cov) / 2;
+    if (expected == 0) return false;
+    const float fisher_p = (float)fisher_exact_test(lg, for_alt_cov, rev_alt_cov, expected, expected);
+    return fisher_p < STRAND_BIAS_PVAL_ONT;
+}
+
 __device__ void classify_site(const KernelArgs &a, long long s) {
     const Chunk ch = a.chunks[a.site_chunk[s]];
     const int4 c = *reinterpret_cast<const int4 *>(a.site_counts + 8 * s);        // total_cov, low_qual_cov, alle_covs[0], alle_covs[1]
@@ -93,6 +140,7 @@ __device__ void classify_site(const KernelArgs &a, long long s) {
     else {
         const double alt_af = (double)alt_dp / total_cov;
         if (alt_dp < ch.min_alt_dp) cate = LOW_COV_VAR;
+        else if (ch.is_ont && is_strand_bias(a.lgamma_cache, a.site_counts[8 * s + 5], a.site_counts[8 * s + 7])) cate = STRAND_BIAS_VAR;   // strand_to_alle_covs[0][1], [1][1]
         else if (alt_af < ch.min_af) cate = LOW_AF_VAR;
         else if (alt_af > ch.max_af) cate = CLEAN_HOM_VAR;
         else if (type == CDIFF) cate = CLEAN_HET_SNP;

@@ -3,6 +3,7 @@
 #include "lcd_common.cuh"
 #include "classify_device.cuh"
 #include <algorithm>
+#include <math.h>
 
 namespace lcd {
 namespace classify {
@@ -21,7 +22,7 @@ struct ClassifyPlan : Plan {
     long long tot_sites = 0;
     // the site arrays and counters: this plan's own buffers, or a pileup plan's (K2 -> K2b in place)
     const long long *p_spos = nullptr, *p_saoff = nullptr; const int32_t *p_stype = nullptr, *p_sref = nullptr, *p_salt = nullptr, *p_counts = nullptr; const uint8_t *p_site_alt = nullptr;
-    DevBuf<Chunk> d_chunks; DevBuf<int32_t> d_site_chunk, d_stype, d_sref, d_salt, d_counts, d_cate; DevBuf<long long> d_spos, d_saoff; DevBuf<uint8_t> d_site_alt; DevBuf<char> d_ref; DevBuf<int32_t> d_status;
+    DevBuf<Chunk> d_chunks; DevBuf<int32_t> d_site_chunk, d_stype, d_sref, d_salt, d_counts, d_cate; DevBuf<long long> d_spos, d_saoff; DevBuf<uint8_t> d_site_alt; DevBuf<char> d_ref; DevBuf<int32_t> d_status; DevBuf<double> d_lgamma;
 
     int build(int n_, const lcd_classify_input_t *in) {
         n = n_;
@@ -33,9 +34,8 @@ struct ClassifyPlan : Plan {
         for (int i = 0; i < n; ++i) {
             const lcd_classify_input_t &x = in[i];
             if (x.n_sites < 0 || x.ref_end < x.ref_beg || (x.n_sites > 0 && !x.ref_seq)) { set_error("lcd_classify: chunk %d has invalid sizes", i); return -1; }
-            if (x.is_ont) { set_error("lcd_classify: chunk %d is ONT data: the strand-bias Fisher test (var_is_strand_bias, src/collect_var.c:270) is not implemented on the GPU", i); return -2; }
             Chunk &k = chunks[i]; memset(&k, 0, sizeof(k));
-            k.min_dp = x.min_dp; k.min_alt_dp = x.min_alt_dp; k.max_xgaps = x.max_xgaps; k.min_af = x.min_af; k.max_af = x.max_af;
+            k.min_dp = x.min_dp; k.min_alt_dp = x.min_alt_dp; k.max_xgaps = x.max_xgaps; k.is_ont = x.is_ont ? 1 : 0; k.min_af = x.min_af; k.max_af = x.max_af;
             k.ref_beg = x.ref_beg; k.ref_end = x.ref_end; k.ref_off = tot_ref; k.alt_base = tot_alt;
             site_off[i] = tot_sites;
             for (int s = 0; s < x.n_sites; ++s) {
@@ -93,9 +93,8 @@ struct ClassifyPlan : Plan {
         for (int i = 0; i < n; ++i) {
             const lcd_classify_params_t &x = par[i];
             if (x.ref_end < x.ref_beg || !x.ref_seq) { set_error("lcd_classify: chunk %d has no reference window", i); return -1; }
-            if (x.is_ont) { set_error("lcd_classify: chunk %d is ONT data: the strand-bias Fisher test (var_is_strand_bias, src/collect_var.c:270) is not implemented on the GPU", i); return -2; }
             Chunk &k = chunks[i]; memset(&k, 0, sizeof(k));
-            k.min_dp = x.min_dp; k.min_alt_dp = x.min_alt_dp; k.max_xgaps = x.max_xgaps; k.min_af = x.min_af; k.max_af = x.max_af;
+            k.min_dp = x.min_dp; k.min_alt_dp = x.min_alt_dp; k.max_xgaps = x.max_xgaps; k.is_ont = x.is_ont ? 1 : 0; k.min_af = x.min_af; k.max_af = x.max_af;
             k.ref_beg = x.ref_beg; k.ref_end = x.ref_end; k.ref_off = tot_ref; k.alt_base = v.salt_base[i];
             ref_n[i] = x.ref_end - x.ref_beg + 1; tot_ref += (ref_n[i] + 15) & ~15ll;
             for (long long s = site_off[i]; s < site_off[i + 1]; ++s) site_chunk.push_back(i);
@@ -109,12 +108,23 @@ struct ClassifyPlan : Plan {
         return 0;
     }
 
+    // opt->lgamma_cache (initialize_lgamma_cache, src/math_utils.c:6-11): the host's libm, as the reference fills it
+    int upload_lgamma(cudaStream_t s) {
+        if (d_lgamma.p) return 0;
+        std::vector<double> h(LGAMMA_MAX_I + 1);
+        for (int i = 0; i <= LGAMMA_MAX_I; ++i) h[i] = lgamma((double)i);
+        if (d_lgamma.upload(h.data(), h.size(), s)) return -1;
+        LCD_CUDA_OK(cudaStreamSynchronize(d_lgamma.st));
+        return 0;
+    }
+
     int run(cudaStream_t s) override {
         Context &c = ctx();
         if (n == 0 || tot_sites == 0) return 0;
+        if (upload_lgamma(s)) return -1;
         KernelArgs a; memset(&a, 0, sizeof(a));
         a.chunks = d_chunks.p; a.n_sites_total = tot_sites; a.site_chunk = d_site_chunk.p; a.site_pos = p_spos; a.site_type = p_stype; a.site_ref_len = p_sref;
-        a.site_alt_len = p_salt; a.site_alt_off = p_saoff; a.site_alt = p_site_alt; a.site_counts = p_counts; a.ref = d_ref.p; a.var_cate = d_cate.p;
+        a.site_alt_len = p_salt; a.site_alt_off = p_saoff; a.site_alt = p_site_alt; a.site_counts = p_counts; a.ref = d_ref.p; a.var_cate = d_cate.p; a.lgamma_cache = d_lgamma.p;
         if (!d_status.p && d_status.alloc(1)) return -1;
         LCD_CUDA_OK(cudaMemsetAsync(d_status.p, 0, sizeof(int32_t), s));
         a.status = d_status.p;

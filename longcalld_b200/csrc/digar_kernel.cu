@@ -221,6 +221,7 @@ struct DigarPlan : Plan {
         DevBuf<long long> d_mdoff, d_cnt1, d_first1; DevBuf<char> d_md; DevBuf<uint32_t> d_cig2; DevBuf<long long> d_coff2; DevBuf<int32_t> d_ncig2, d_st;
         if (d_mdoff.upload(md_off.data(), md_off.size(), s) || d_md.alloc(tot_md + 16) || d_cnt1.alloc(stride) || d_first1.alloc(stride) || d_coff2.alloc(stride) ||
             d_ncig2.alloc(stride) || d_st.alloc(1)) return -1;
+        LCD_CUDA_OK(cudaMemsetAsync(d_md.p + tot_md, 0, 16, d_md.st));          // NUL slack behind the last tag: a truncated tag ends the walk, it is never read past
         for (int i = 0; i < n; ++i) if (md_n[i]) LCD_CUDA_OK(cudaMemcpyAsync(d_md.p + md_base[i], tags[i].md, (size_t)md_n[i], cudaMemcpyHostToDevice, s));
         LCD_CUDA_OK(cudaMemsetAsync(d_st.p, 0, sizeof(int32_t), s));
         md::KernelArgs a; memset(&a, 0, sizeof(a));

@@ -33,13 +33,14 @@ void set_error(const char *fmt, ...);
 // One context per process: device, library stream, SM count, and the workspace pool that the DP
 // kernels carve wavefronts / DP planes from.  The pool is one allocation: [private arenas | overflow].
 struct Context {
-    bool ready = false;
+    std::atomic<bool> ready{false};
     int device = 0;
     int sm_count = 148;
     int reserved_sms = 0;             // CTA slots of this many SMs are left free by the persistent DP grids (lcd_gpu_reserve_sms)
     int dp_sms() const { return sm_count - reserved_sms > 8 ? sm_count - reserved_sms : 8; }
     cudaStream_t stream = nullptr;
     cudaStream_t aux_stream = nullptr;  // created on first lcd_gpu_aux_stream()
+    std::vector<cudaStream_t> extra_streams;   // lcd_gpu_new_stream: one per host thread of a multi-threaded caller
     int32_t *pool = nullptr;          // int32 words
     size_t pool_words = 0;
     // lcd_gpu_split_pool: window 0 = [0, split_words) for the POA plans, window 1 = the rest for the WFA / edlib plans (0: one window)
@@ -50,6 +51,11 @@ struct Context {
     static constexpr int BITMAP_WORDS = 4096;     // overflow chunks in use (bit set), device memory
     uint32_t *chunk_bitmap = nullptr;
     std::mutex mu;                    // serialises plan runs that share the pool
+    // Every pool window orders its own users: the event is recorded behind the last launch that carves from the window and the next
+    // run() on that window -- whatever stream it was given -- waits for it first.  (The mutexes only cover the enqueue; the persistent
+    // grids keep using the window after run() has returned.)
+    cudaEvent_t win_done[2] = {nullptr, nullptr};
+    size_t requested_pool_bytes = 0;  // what lcd_gpu_init was first called with (0: default)
     std::atomic<unsigned long long> launches{0};
 };
 Context &ctx();

@@ -6,11 +6,13 @@ namespace lcd {
 
 static thread_local char g_err[512] = "";
 static char g_err_global[512] = "";
+static std::mutex g_err_mu;
 
 void set_error(const char *fmt, ...) {
     va_list ap; va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+    std::lock_guard<std::mutex> lk(g_err_mu);
     strncpy(g_err_global, g_err, sizeof(g_err_global) - 1);
 }
 
@@ -36,7 +38,12 @@ using namespace lcd;
 extern "C" {
 
 int lcd_gpu_abi_version(void) { return LCD_GPU_ABI_VERSION; }
-const char *lcd_gpu_last_error(void) { return g_err[0] ? g_err : g_err_global; }
+const char *lcd_gpu_last_error(void) {
+    if (g_err[0]) return g_err;
+    std::lock_guard<std::mutex> lk(g_err_mu);                 // another thread's last message, copied into this thread's buffer
+    strncpy(g_err, g_err_global, sizeof(g_err) - 1);
+    return g_err;
+}
 uint64_t lcd_gpu_launch_count(void) { return ctx().launches; }
 void *lcd_gpu_stream(void) { return ctx().ready ? (void*)ctx().stream : nullptr; }
 void *lcd_gpu_aux_stream(void) {
@@ -63,11 +70,26 @@ int lcd_gpu_reserve_sms(int n_sms) {
     return 0;
 }
 void lcd_gpu_set_thread_stream(void *stream) { thread_stream() = (cudaStream_t)stream; }
+void *lcd_gpu_new_stream(void) {
+    if (ensure_ready()) return nullptr;
+    Context &c = ctx();
+    cudaStream_t s = nullptr;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { set_error("lcd_gpu_new_stream: cudaStreamCreate failed"); return nullptr; }
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.extra_streams.push_back(s);
+    return (void*)s;
+}
 
 int lcd_gpu_init(int device, size_t pool_bytes) {
     Context &c = ctx();
     std::lock_guard<std::mutex> lk(c.mu);
-    if (c.ready) return 0;
+    if (c.ready) {
+        // a second init must describe the context that is up: the library is one context per process
+        if (device != c.device && !(device == 0 && pool_bytes == 0)) { set_error("lcd_gpu_init: already initialised on device %d (asked for %d)", c.device, device); return -1; }
+        if (pool_bytes && pool_bytes != c.requested_pool_bytes) { set_error("lcd_gpu_init: already initialised with a pool of %zu bytes (asked for %zu)", c.pool_words * 4, pool_bytes); return -1; }
+        return 0;
+    }
+    c.requested_pool_bytes = pool_bytes;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -104,6 +126,7 @@ int lcd_gpu_init(int device, size_t pool_bytes) {
     c.pool_words = pool_bytes / 4;
     LCD_CUDA_OK(cudaMalloc((void**)&c.chunk_bitmap, sizeof(uint32_t) * Context::BITMAP_WORDS));
     LCD_CUDA_OK(cudaMemset(c.chunk_bitmap, 0, sizeof(uint32_t) * Context::BITMAP_WORDS));
+    for (int k = 0; k < 2; ++k) LCD_CUDA_OK(cudaEventCreateWithFlags(&c.win_done[k], cudaEventDisableTiming));
     c.ready = true;
     return 0;
 }
@@ -117,6 +140,9 @@ void lcd_gpu_shutdown(void) {
     if (c.chunk_bitmap) cudaFree(c.chunk_bitmap);
     if (c.stream) cudaStreamDestroy(c.stream);
     if (c.aux_stream) cudaStreamDestroy(c.aux_stream);
+    for (int k = 0; k < 2; ++k) { if (c.win_done[k]) cudaEventDestroy(c.win_done[k]); c.win_done[k] = nullptr; }
+    for (cudaStream_t s : c.extra_streams) cudaStreamDestroy(s);
+    c.extra_streams.clear();
     c.aux_stream = nullptr;
     c.pool = nullptr; c.chunk_bitmap = nullptr; c.stream = nullptr; c.ready = false;
 }
@@ -127,8 +153,13 @@ int lcd_plan_run(lcd_plan_t *plan, void *stream) {
     Context &c = ctx();
     Plan *p = reinterpret_cast<Plan*>(plan);
     if (!p->uses_pool()) return p->run(pick_stream(stream));
-    std::lock_guard<std::mutex> lk((c.split_words && p->pool_window() == 1) ? c.mu1 : c.mu);
-    return p->run(pick_stream(stream));
+    const int win = (c.split_words && p->pool_window() == 1) ? 1 : 0;
+    std::lock_guard<std::mutex> lk(win ? c.mu1 : c.mu);
+    cudaStream_t s = pick_stream(stream);
+    LCD_CUDA_OK(cudaStreamWaitEvent(s, c.win_done[win], 0));        // the window's previous user, on whatever stream it ran
+    const int rc = p->run(s);
+    LCD_CUDA_OK(cudaEventRecord(c.win_done[win], s));
+    return rc;
 }
 
 int lcd_plan_sync(lcd_plan_t *plan, void *stream) {

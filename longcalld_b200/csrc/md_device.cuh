@@ -43,7 +43,8 @@ __device__ __forceinline__ int walk(const uint32_t *cg, int nc, const char *md, 
             }
         } else if (op == CDEL) {
             emit(CDEL, m);
-            ++md_i;                                                   // '^'
+            if (md[md_i] != '^') return MD_MISMATCH;                  // truncated / malformed tag: never step past its NUL
+            ++md_i;
             while (md[md_i] && is_alpha(md[md_i])) ++md_i;
             if (md[md_i] == '0') ++md_i;                              // the 0 after a deletion
         } else if (op == CEQUAL || op == CDIFF) return MD_EQX_OP;

@@ -300,7 +300,9 @@ struct PoaPlan : Plan {
         n_rescued = (int)rescue.size();
         if (!rescue.empty()) {
             rescue_words = std::min<uint64_t>((rescue_words + 63) & ~63ull, (c.win_words(0) / WARPS_PER_CTA) & ~63ull);
+            LCD_CUDA_OK(cudaStreamWaitEvent(s, c.win_done[0], 0));
             if (launch(s, rescue, d_order.p, d_queue.p, rescue_words, c.sm_count * 4, 2, true, 0, c.win_words(0), nullptr)) return -1;
+            LCD_CUDA_OK(cudaEventRecord(c.win_done[0], s));
             LCD_CUDA_OK(cudaStreamSynchronize(s));
         }
         return 0;

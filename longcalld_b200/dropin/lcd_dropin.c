@@ -15,9 +15,11 @@
  *     abpoa_partial_aln_msa_cons                     (src/align.c:762)         -> lcd_poa_batch      (K5; regions whose reads all
  *                                                     cover the region -- partial-cover / sampled regions, which need the sub-graph
  *                                                     alignment the GPU library does not have yet, are forwarded to the reference)
- * Everything else of the reference runs unchanged.  The reference calls these once per chunk / per pair, so every
- * call here is a batch of one (the batched two-phase worker of INTEGRATION.md section 1 is what a maintainer would
- * adopt for speed); this file exists to prove the boundary: with it preloaded the reference writes the same VCF.
+ *     collect_var_main                               (src/collect_var.c:2897)  -> the batched region driver below: the pending noisy regions
+ *                                                     of a chunk run side by side (coroutines) and their POA / WFA / edlib problems go to the
+ *                                                     library as ONE batch per engine, merged across the reference's worker threads
+ * Everything else of the reference runs unchanged.  K1 - K4 are called once per chunk (a batch of one chunk each, on the worker thread's
+ * own stream); K5 - K7 are batched over regions and threads.  With this file preloaded the reference writes the same VCF.
  * There is no CPU fallback: a failing library call aborts the run.  (Only the -s somatic profile path, which the GPU
  * library rejects, is forwarded to the reference's own implementation.)
  *
@@ -37,9 +39,10 @@
 
 static void die(const char *what) { fprintf(stderr, "[lcd_dropin] %s failed: %s\n", what, lcd_gpu_last_error()); exit(1); }
 static unsigned long n_calls[11];
+#define COUNT(i) __atomic_fetch_add(&n_calls[i], 1, __ATOMIC_RELAXED)      /* the reference's worker threads call in concurrently */
 __attribute__((destructor)) static void report(void) {
-    if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: digar %lu (forwarded: %lu), sites %lu, pileup %lu, profile %lu, phase %lu, edlib %lu, wfa %lu, poa %lu (forwarded to abPOA: %lu); kernel launches %llu\n",
-                                              n_calls[8], n_calls[9], n_calls[10], n_calls[0], n_calls[1], n_calls[2], n_calls[3], n_calls[4], n_calls[5], n_calls[6], (unsigned long long)lcd_gpu_launch_count());
+    if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: digar %lu (forwarded: %lu), sites %lu, pileup %lu, profile %lu, phase %lu, edlib %lu, wfa %lu, poa %lu (forwarded to abPOA: %lu) in %lu engine batches; kernel launches %llu\n",
+                                              n_calls[8], n_calls[9], n_calls[10], n_calls[0], n_calls[1], n_calls[2], n_calls[3], n_calls[4], n_calls[5], n_calls[6], n_calls[7], (unsigned long long)lcd_gpu_launch_count());
 }
 
 /* ------------------------------------------------------------------------------------------ digars -> flat */
@@ -126,7 +129,7 @@ void collect_digars_from_bam(bam_chunk_t *chunk, const struct call_var_pl_t *pl)
     if (all_eqx < 0) {           /* cs-tagged / untagged plain-M reads: the reference's own paths */
         static void (*orig)(bam_chunk_t *, const struct call_var_pl_t *) = NULL;
         if (!orig) orig = (void (*)(bam_chunk_t *, const struct call_var_pl_t *))dlsym(RTLD_NEXT, "collect_digars_from_bam");
-        n_calls[9]++;
+        COUNT(9);
         orig(chunk, pl);
         return;
     }
@@ -178,7 +181,7 @@ void collect_digars_from_bam(bam_chunk_t *chunk, const struct call_var_pl_t *pl)
         if (lcd_digar_md_batch(1, &in, &tags, &o)) die("lcd_digar_md_batch");
         free(md_off); free(md);
     }
-    n_calls[8]++;
+    COUNT(8);
     for (int i = 0; i < nr; ++i) {
         const int r = chunk->ordered_read_ids[i];
         if (chunk->is_skipped[r]) continue;
@@ -250,7 +253,7 @@ int collect_all_cand_var_sites(const call_var_opt_t *opt, bam_chunk_t *chunk, va
         }
     }
     free(out.site_pos); free(out.site_src); free(out.site_type); free(out.site_ref_len); free(out.site_alt_len); free(rec); flat_free(&f);
-    n_calls[10]++;
+    COUNT(10);
     return n;
 }
 
@@ -270,7 +273,7 @@ int collect_cand_vars(const call_var_opt_t *opt, bam_chunk_t *chunk, int n_var_s
         for (int s = 0; s < 2; ++s) for (int a = 0; a < 2; ++a) c->strand_to_alle_covs[s][a] = o[4 + 2 * s + a];
     }
     free(counts); flat_free(&f);
-    n_calls[0]++;
+    COUNT(0);
     return 0;
 }
 
@@ -320,7 +323,7 @@ read_var_profile_t *collect_read_var_profile(const call_var_opt_t *opt, bam_chun
     cr_index(read_var_cr); chunk->read_var_cr = read_var_cr;
     free(out.prof_start); free(out.prof_end); free(out.allele_off); free(out.alleles); free(out.alt_qi);
     free(nfirst); free(nbeg); free(nend); free(nn); flat_free(&f);
-    n_calls[1]++;
+    COUNT(1);
     return p;
 }
 
@@ -369,20 +372,274 @@ int assign_hap_based_on_germline_het_vars_kmeans(const call_var_opt_t *opt, bam_
         c->phase_set = vps[v];
     }
     free(ps); free(pe); free(ao); free(al); free(type); free(hp); free(nu); free(covs); free(tc); free(cons); free(prof); free(pos); free(vps);
-    n_calls[2]++;
+    COUNT(2);
     return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ the batched region driver (a8)
+ *
+ * The reference aligns one (region, haplotype) at a time from inside collect_noisy_vars1 (src/collect_var.c:2648); a GPU needs thousands
+ * of problems per launch.  The reference's host code is kept as it is and run as COROUTINES: every pending noisy region of a chunk gets
+ * its own stack (ucontext) on which the unmodified collect_noisy_vars1 runs until it reaches an engine call (abpoa_partial_aln_msa_cons,
+ * wfa_end2end_aln, edlib_*: defined below with the reference's signatures).  There the request is parked and the next region runs; when
+ * every region of the chunk is parked, the requests of one kind go to the library as ONE lcd_poa_batch / lcd_wfa_batch / lcd_edlib_batch,
+ * merged with what the other worker threads (kt_for) have parked meanwhile (leader / follower combiner).  Results are handed back and the
+ * regions continue.  What must stay sequential does: make_vars_from_msa_cons_aln + merge_var_profile (they edit the chunk's variant list)
+ * run in the reference's region order -- a region waits at the entry of make_vars_from_msa_cons_aln until all regions before it are done.
+ * The alignment phase reads only what a pass leaves fixed (difference lists, haplotypes, phase sets: src/align.c:1377-1461), so running
+ * the regions of one pass side by side computes exactly what the reference's loop computes. */
+#include <pthread.h>
+#include <ucontext.h>
+#include <unistd.h>
+#include "align.h"
+#include "abpoa.h"
+
+enum { RQ_POA = 0, RQ_WFA = 1, RQ_EDLIB = 2, RQ_KINDS = 3 };
+typedef struct req_t {
+    int kind; volatile int done; int rc;
+    /* inputs (owned by the caller, alive until done) */
+    const uint8_t *seqs; size_t seqs_len;                 /* POA: the reads back to back; WFA: pattern then text; edlib: query then target */
+    int n_reads; const int64_t *read_off; const int32_t *read_len; lcd_poa_params_t ppar; int want_msa; int max_len;
+    int plen, tlen; lcd_wfa_params_t wpar;
+    int qlen, mode, want_path;
+    /* outputs (buffers owned by the caller) */
+    uint8_t *cons; uint8_t *msa; int64_t msa_cap; lcd_poa_result_t pres;
+    char *ops; lcd_wfa_result_t wres;
+    uint8_t *aln; lcd_edlib_result_t eres;
+} req_t;
+
+static void *new_thread_stream(void) {                    /* every host thread that calls the library gets a stream of its own */
+    static __thread void *st = NULL;
+    if (!st) { st = lcd_gpu_new_stream(); if (!st) die("lcd_gpu_new_stream"); lcd_gpu_set_thread_stream(st); }
+    return st;
+}
+
+/* one library call over n requests of one kind */
+static void run_batch(int kind, req_t **r, int n) {
+    new_thread_stream();
+    if (kind == RQ_POA) {
+        size_t tot = 0, n_rd = 0, cons_tot = 0, msa_tot = 0;
+        for (int i = 0; i < n; ++i) { tot += r[i]->seqs_len; n_rd += r[i]->n_reads; cons_tot += r[i]->seqs_len + 16; msa_tot += r[i]->want_msa ? (size_t)r[i]->msa_cap : 0; }
+        uint8_t *seqs = (uint8_t*)malloc(tot + 1), *cons = (uint8_t*)malloc(cons_tot + 1), *msa = (uint8_t*)malloc(msa_tot + 1);
+        int32_t *first = (int32_t*)malloc(sizeof(int32_t) * n), *nr = (int32_t*)malloc(sizeof(int32_t) * n), *len = (int32_t*)malloc(sizeof(int32_t) * (n_rd + 1));
+        int64_t *off = (int64_t*)malloc(sizeof(int64_t) * (n_rd + 1)), *coff = (int64_t*)malloc(sizeof(int64_t) * n), *moff = (int64_t*)malloc(sizeof(int64_t) * n), *mcap = (int64_t*)malloc(sizeof(int64_t) * n);
+        lcd_poa_params_t *par = (lcd_poa_params_t*)malloc(sizeof(lcd_poa_params_t) * n);
+        lcd_poa_result_t *res = (lcd_poa_result_t*)calloc(n, sizeof(lcd_poa_result_t));
+        size_t o = 0, rd = 0, co = 0, mo = 0;
+        for (int i = 0; i < n; ++i) {
+            memcpy(seqs + o, r[i]->seqs, r[i]->seqs_len);
+            first[i] = (int32_t)rd; nr[i] = r[i]->n_reads; par[i] = r[i]->ppar; coff[i] = (int64_t)co; moff[i] = (int64_t)mo; mcap[i] = r[i]->want_msa ? r[i]->msa_cap : 0;
+            for (int k = 0; k < r[i]->n_reads; ++k, ++rd) { off[rd] = (int64_t)o + r[i]->read_off[k]; len[rd] = r[i]->read_len[k]; }
+            o += r[i]->seqs_len; co += r[i]->seqs_len + 16; mo += (size_t)mcap[i];
+        }
+        const int rc = lcd_poa_batch(n, seqs, tot, first, nr, off, len, (int)n_rd, par, cons, coff, msa, moff, mcap, res);
+        if (rc == -1) die("lcd_poa_batch");                /* -2: some problems were refused on the device (their status says why) */
+        for (int i = 0; i < n; ++i) {
+            r[i]->pres = res[i]; r[i]->rc = rc;
+            if (res[i].status == LCD_POA_OK) {
+                memcpy(r[i]->cons, cons + coff[i], res[i].cons_len);
+                if (r[i]->want_msa) memcpy(r[i]->msa, msa + moff[i], (size_t)(r[i]->n_reads + 1) * res[i].msa_len);
+            }
+        }
+        free(seqs); free(cons); free(msa); free(first); free(nr); free(len); free(off); free(coff); free(moff); free(mcap); free(par); free(res);
+        __atomic_fetch_add(&n_calls[5], (unsigned long)n, __ATOMIC_RELAXED); COUNT(7);
+    } else if (kind == RQ_WFA) {
+        size_t tot = 0, ops_tot = 0;
+        for (int i = 0; i < n; ++i) { tot += r[i]->seqs_len; ops_tot += 2 * r[i]->seqs_len + 16; }
+        uint8_t *seqs = (uint8_t*)malloc(tot + 1); char *ops = (char*)malloc(ops_tot + 1);
+        int64_t *po = (int64_t*)malloc(sizeof(int64_t) * n), *to = (int64_t*)malloc(sizeof(int64_t) * n), *oo = (int64_t*)malloc(sizeof(int64_t) * n);
+        int32_t *pl = (int32_t*)malloc(sizeof(int32_t) * n), *tl = (int32_t*)malloc(sizeof(int32_t) * n);
+        lcd_wfa_params_t *par = (lcd_wfa_params_t*)malloc(sizeof(lcd_wfa_params_t) * n);
+        lcd_wfa_result_t *res = (lcd_wfa_result_t*)calloc(n, sizeof(lcd_wfa_result_t));
+        size_t o = 0, op = 0;
+        for (int i = 0; i < n; ++i) {
+            memcpy(seqs + o, r[i]->seqs, r[i]->seqs_len);
+            po[i] = (int64_t)o; pl[i] = r[i]->plen; to[i] = (int64_t)o + r[i]->plen; tl[i] = r[i]->tlen; oo[i] = (int64_t)op; par[i] = r[i]->wpar;
+            o += r[i]->seqs_len; op += 2 * r[i]->seqs_len + 16;
+        }
+        if (lcd_wfa_batch(n, seqs, tot, po, pl, to, tl, par, ops, oo, res)) die("lcd_wfa_batch");
+        for (int i = 0; i < n; ++i) { r[i]->wres = res[i]; memcpy(r[i]->ops, ops + oo[i], res[i].n_ops > 0 ? (size_t)res[i].n_ops : 0); }
+        free(seqs); free(ops); free(po); free(to); free(oo); free(pl); free(tl); free(par); free(res);
+        __atomic_fetch_add(&n_calls[4], (unsigned long)n, __ATOMIC_RELAXED); COUNT(7);
+    } else {
+        size_t tot = 0;
+        for (int i = 0; i < n; ++i) tot += r[i]->seqs_len + 2;
+        uint8_t *seqs = (uint8_t*)malloc(tot + 1), *aln = (uint8_t*)malloc(tot + 1);
+        int64_t *qo = (int64_t*)malloc(sizeof(int64_t) * n), *to = (int64_t*)malloc(sizeof(int64_t) * n), *ao = (int64_t*)malloc(sizeof(int64_t) * n);
+        int32_t *ql = (int32_t*)malloc(sizeof(int32_t) * n), *tl = (int32_t*)malloc(sizeof(int32_t) * n), *md = (int32_t*)malloc(sizeof(int32_t) * n), *wp = (int32_t*)malloc(sizeof(int32_t) * n);
+        lcd_edlib_result_t *res = (lcd_edlib_result_t*)calloc(n, sizeof(lcd_edlib_result_t));
+        size_t o = 0;
+        for (int i = 0; i < n; ++i) {
+            memcpy(seqs + o, r[i]->seqs, r[i]->seqs_len);
+            qo[i] = (int64_t)o; ql[i] = r[i]->qlen; to[i] = (int64_t)o + r[i]->qlen; tl[i] = r[i]->tlen; ao[i] = (int64_t)o; md[i] = r[i]->mode; wp[i] = r[i]->want_path;
+            o += r[i]->seqs_len + 2;
+        }
+        if (lcd_edlib_batch(n, seqs, tot, qo, ql, to, tl, md, wp, aln, ao, res)) die("lcd_edlib_batch");
+        for (int i = 0; i < n; ++i) { r[i]->eres = res[i]; if (r[i]->want_path && res[i].aln_len > 0) memcpy(r[i]->aln, aln + ao[i], (size_t)res[i].aln_len); }
+        free(seqs); free(aln); free(qo); free(to); free(ao); free(ql); free(tl); free(md); free(wp); free(res);
+        __atomic_fetch_add(&n_calls[3], (unsigned long)n, __ATOMIC_RELAXED); COUNT(7);
+    }
+    for (int i = 0; i < n; ++i) __atomic_store_n(&r[i]->done, 1, __ATOMIC_RELEASE);
+}
+
+/* Leader / follower combiner: the first thread to arrive with requests of a kind lingers a moment, takes whatever the other worker
+ * threads have added meanwhile and makes the one library call; the others sleep until their requests are done. */
+typedef struct { pthread_mutex_t mu; pthread_cond_t cv; req_t **pend; int n, cap, leader; } comb_t;
+static comb_t comb[RQ_KINDS] = { { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, 0, 0 }, { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, 0, 0 },
+                                 { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, 0, 0 } };
+static int linger_us(void) { static int v = -1; if (v < 0) { const char *e = getenv("LCD_DROPIN_LINGER_US"); v = e ? atoi(e) : 200; } return v; }
+
+static void combine(int kind, req_t **r, int n) {
+    if (n == 0) return;
+    comb_t *c = &comb[kind];
+    pthread_mutex_lock(&c->mu);
+    if (c->n + n > c->cap) { c->cap = 2 * (c->n + n); c->pend = (req_t**)realloc(c->pend, sizeof(req_t*) * c->cap); }
+    memcpy(c->pend + c->n, r, sizeof(req_t*) * n); c->n += n;
+    if (!c->leader) {
+        c->leader = 1;
+        pthread_mutex_unlock(&c->mu);
+        if (linger_us() > 0) usleep(linger_us());
+        pthread_mutex_lock(&c->mu);
+        req_t **take = c->pend; const int nt = c->n;
+        c->pend = NULL; c->n = c->cap = 0; c->leader = 0;          /* the next batch may start collecting while this one runs */
+        pthread_mutex_unlock(&c->mu);
+        run_batch(kind, take, nt);
+        free(take);
+        pthread_mutex_lock(&c->mu);
+        pthread_cond_broadcast(&c->cv);
+    }
+    for (;;) {
+        int all = 1;
+        for (int i = 0; i < n; ++i) if (!__atomic_load_n(&r[i]->done, __ATOMIC_ACQUIRE)) { all = 0; break; }
+        if (all) break;
+        pthread_cond_wait(&c->cv, &c->mu);
+    }
+    pthread_mutex_unlock(&c->mu);
+}
+
+/* ---- coroutines: one per pending noisy region of the chunk a worker thread is on */
+enum { CO_READY, CO_PARKED, CO_TURN, CO_DONE };
+typedef struct co_t { ucontext_t ctx; void *stack; int state, idx, reg_i, ret; req_t *req; bam_chunk_t *chunk; const call_var_opt_t *opt; } co_t;
+typedef struct { ucontext_t main; co_t *cos; int n, next_turn; } sched_t;
+static __thread sched_t *tl_sched = NULL;
+static __thread co_t *tl_co = NULL;
+#define CO_STACK ((size_t)1 << 20)
+
+int collect_noisy_vars1(bam_chunk_t *chunk, const call_var_opt_t *opt, int noisy_reg_i);                                   /* src/collect_var.c:2648 */
+static void co_entry(void) {
+    co_t *c = tl_co;
+    c->ret = collect_noisy_vars1(c->chunk, c->opt, c->reg_i);
+    c->state = CO_DONE;
+    swapcontext(&c->ctx, &tl_sched->main);
+}
+
+/* an engine call: parked when made from a region's coroutine, a batch of one (merged with other threads' requests) otherwise */
+static void gpu_call(req_t *r) {
+    r->done = 0;
+    if (tl_co) { tl_co->req = r; tl_co->state = CO_PARKED; swapcontext(&tl_co->ctx, &tl_sched->main); }
+    else { req_t *one = r; combine(r->kind, &one, 1); }
+}
+
+/* all pending regions of one pass side by side; ret[k] = collect_noisy_vars1's return value for regs[k] */
+static void run_regions(bam_chunk_t *chunk, const call_var_opt_t *opt, int n, const int *regs, int *ret) {
+    static __thread void **stack_pool = NULL; static __thread int n_stacks = 0;
+    if (n > n_stacks) { stack_pool = (void**)realloc(stack_pool, sizeof(void*) * n); for (int i = n_stacks; i < n; ++i) stack_pool[i] = malloc(CO_STACK); n_stacks = n; }
+    sched_t sc; memset(&sc, 0, sizeof(sc));
+    sc.cos = (co_t*)calloc(n, sizeof(co_t)); sc.n = n; sc.next_turn = 0;
+    for (int i = 0; i < n; ++i) {
+        co_t *c = sc.cos + i;
+        c->stack = stack_pool[i]; c->state = CO_READY; c->idx = i; c->reg_i = regs[i]; c->chunk = chunk; c->opt = opt;
+        getcontext(&c->ctx); c->ctx.uc_stack.ss_sp = c->stack; c->ctx.uc_stack.ss_size = CO_STACK; c->ctx.uc_link = NULL;
+        makecontext(&c->ctx, co_entry, 0);
+    }
+    req_t **parked = (req_t**)malloc(sizeof(req_t*) * n), **byk = (req_t**)malloc(sizeof(req_t*) * n);
+    tl_sched = &sc;
+    for (;;) {
+        int ran = 0;
+        for (int i = 0; i < n; ++i) {
+            co_t *c = sc.cos + i;
+            if (c->state == CO_READY || (c->state == CO_TURN && i == sc.next_turn)) {
+                tl_co = c; swapcontext(&sc.main, &c->ctx); tl_co = NULL; ran = 1;
+                while (sc.next_turn < n && sc.cos[sc.next_turn].state == CO_DONE) sc.next_turn++;
+            }
+        }
+        int np = 0;
+        for (int i = 0; i < n; ++i) if (sc.cos[i].state == CO_PARKED) parked[np++] = sc.cos[i].req;
+        if (np) {
+            for (int k = 0; k < RQ_KINDS; ++k) { int m = 0; for (int i = 0; i < np; ++i) if (parked[i]->kind == k) byk[m++] = parked[i]; combine(k, byk, m); }
+            for (int i = 0; i < n; ++i) if (sc.cos[i].state == CO_PARKED) sc.cos[i].state = CO_READY;
+            continue;
+        }
+        if (sc.next_turn >= n) break;
+        if (!ran) { fprintf(stderr, "[lcd_dropin] region scheduler stalled\n"); exit(1); }
+    }
+    tl_sched = NULL;
+    for (int i = 0; i < n; ++i) ret[i] = sc.cos[i].ret;
+    free(parked); free(byk); free(sc.cos);
+}
+
+/* make_vars_from_msa_cons_aln (src/collect_var.c:2279) starts the part of a region that edits the chunk's variant list: regions take it
+ * in the reference's order */
+int make_vars_from_msa_cons_aln(const call_var_opt_t *opt, bam_chunk_t *chunk, int n_reads, int *read_ids, hts_pos_t noisy_reg_beg, int n_cons, int *clu_n_seqs,
+                                int **clu_read_ids, aln_str_t **aln_strs, cand_var_t **noisy_vars, int **noisy_var_cate, read_var_profile_t **p) {
+    typedef int (*fn_t)(const call_var_opt_t *, bam_chunk_t *, int, int *, hts_pos_t, int, int *, int **, aln_str_t **, cand_var_t **, int **, read_var_profile_t **);
+    static fn_t orig = NULL;
+    if (!orig) orig = (fn_t)dlsym(RTLD_NEXT, "make_vars_from_msa_cons_aln");
+    if (tl_co) while (tl_sched->next_turn != tl_co->idx) { tl_co->state = CO_TURN; swapcontext(&tl_co->ctx, &tl_sched->main); }
+    return orig(opt, chunk, n_reads, read_ids, noisy_reg_beg, n_cons, clu_n_seqs, clu_read_ids, aln_strs, noisy_vars, noisy_var_cate, p);
+}
+
+/* collect_var_main (src/collect_var.c:2897-2981): the same sequence of steps; step 4's inner loop over the pending regions runs them side by side */
+void pre_process_noisy_regs(bam_chunk_t *chunk, call_var_opt_t *opt);                                                       /* src/collect_var.c:557 */
+int classify_cand_vars(bam_chunk_t *chunk, int n_var_sites, const call_var_opt_t *opt);                                     /* :902 */
+int *sort_noisy_regs(bam_chunk_t *chunk);                                                                                   /* :2745 */
+void collect_somatic_var(bam_chunk_t *chunk, const call_var_opt_t *opt);                                                    /* :2857 */
+
+void collect_var_main(const call_var_pl_t *pl, bam_chunk_t *chunk) {
+    call_var_opt_t *opt = pl->opt;
+    new_thread_stream();
+    collect_digars_from_bam(chunk, pl);                                                                                      /* 1.1 */
+    var_site_t *var_sites = NULL;
+    const int n_var_sites = collect_all_cand_var_sites(opt, chunk, &var_sites);                                              /* 1.2 */
+    if (n_var_sites > 0) collect_cand_vars(opt, chunk, n_var_sites, var_sites);                                              /* 1.3 */
+    free(var_sites);
+    pre_process_noisy_regs(chunk, opt);                                                                                      /* 2.1 */
+    if (n_var_sites > 0) classify_cand_vars(chunk, n_var_sites, opt);                                                        /* 2.2 - 2.4 */
+    if (chunk->n_cand_vars == 0 && (chunk->chunk_noisy_regs == NULL || chunk->chunk_noisy_regs->n_r == 0)) return;
+    if (chunk->n_cand_vars > 0) {
+        chunk->read_var_profile = collect_read_var_profile(opt, chunk);                                                      /* 3.1 */
+        assign_hap_based_on_germline_het_vars_kmeans(opt, chunk, LONGCALLD_CLEAN_HET_SNP | LONGCALLD_CLEAN_HET_INDEL | LONGCALLD_CLEAN_HOM_VAR);   /* 3.2 */
+    }
+    if (chunk->chunk_noisy_regs != NULL && chunk->chunk_noisy_regs->n_r > 0) {                                               /* 4 */
+        const int n_regs = (int)chunk->chunk_noisy_regs->n_r;
+        int *sorted = sort_noisy_regs(chunk), *is_done = (int*)calloc(n_regs, sizeof(int));
+        int *pend = (int*)malloc(sizeof(int) * n_regs), *ret = (int*)malloc(sizeof(int) * n_regs);
+        /* -s / --refine-aln rewrite the reads' difference lists region by region (update_digars_from_aln_str, src/align.c:1796): one at a time */
+        const int one_by_one = opt->out_somatic || (opt->refine_bam && opt->out_aln_fp != NULL) || getenv("LCD_DROPIN_SERIAL") != NULL;
+        for (;;) {
+            int new_region_is_done = 0, new_var = 0, np = 0;
+            for (int i = 0; i < n_regs; ++i) if (!is_done[sorted[i]]) pend[np++] = sorted[i];
+            if (one_by_one) for (int k = 0; k < np; ++k) ret[k] = collect_noisy_vars1(chunk, opt, pend[k]);
+            else if (np > 0) run_regions(chunk, opt, np, pend, ret);
+            for (int k = 0; k < np; ++k) if (ret[k] >= 0) { is_done[pend[k]] = 1; new_region_is_done = 1; if (ret[k] > 0) new_var = 1; }
+            if (new_var) assign_hap_based_on_germline_het_vars_kmeans(opt, chunk, LONGCALLD_CAND_GERMLINE_VAR_CATE);
+            if (new_region_is_done == 0) break;
+        }
+        free(sorted); free(is_done); free(pend); free(ret);
+    }
+    if (opt->out_somatic == 1) collect_somatic_var(chunk, opt);                                                              /* 5 */
 }
 
 /* ------------------------------------------------------------------------------------------ K7 */
 static int edlib1(uint8_t *target, int tlen, uint8_t *query, int qlen, int mode, int want_path, uint8_t **aln, lcd_edlib_result_t *res) {
     uint8_t *seqs = (uint8_t*)malloc((size_t)qlen + tlen + 1);
     memcpy(seqs, query, qlen); memcpy(seqs + qlen, target, tlen);
-    int64_t qo = 0, to = qlen, ao = 0; int32_t ql = qlen, tl = tlen, m = mode, w = want_path;
     *aln = (uint8_t*)malloc((size_t)qlen + tlen + 2);
-    const int rc = lcd_edlib_batch(1, seqs, (size_t)qlen + tlen, &qo, &ql, &to, &tl, &m, &w, *aln, &ao, res);
+    req_t r; memset(&r, 0, sizeof(r));
+    r.kind = RQ_EDLIB; r.seqs = seqs; r.seqs_len = (size_t)qlen + tlen; r.qlen = qlen; r.tlen = tlen; r.mode = mode; r.want_path = want_path; r.aln = *aln;
+    gpu_call(&r);
+    *res = r.eres;
     free(seqs);
-    if (rc) die("lcd_edlib_batch");
-    n_calls[3]++;
     return 0;
 }
 int edlib_edit_distance(uint8_t *target, int tlen, uint8_t *query, int qlen) {                 /* src/align.c:210 */
@@ -413,8 +670,6 @@ int edlib_end2end_aln(uint8_t *target, int tlen, uint8_t *query, int qlen, int *
 int edlib_infix_aln(uint8_t *target, int tlen, uint8_t *query, int qlen, int *n_eq, int *n_xid) { return edlib_path_counts(target, tlen, query, qlen, LCD_EDLIB_MODE_HW, n_eq, n_xid); }     /* src/align.c:256 */
 
 /* ------------------------------------------------------------------------------------------ K6 */
-#include "align.h"
-#include "abpoa.h"
 int wfa_end2end_aln(uint8_t *pattern, int plen, uint8_t *text, int tlen, int gap_aln, int b, int q, int e, int q2, int e2, int heuristic, int affine_gap,
                     uint32_t **cigar_buf, int *cigar_length, uint8_t **pattern_alg, uint8_t **text_alg, int *alg_length) {      /* src/align.c:374-460 */
     lcd_wfa_params_t par; memset(&par, 0, sizeof(par));
@@ -433,11 +688,11 @@ int wfa_end2end_aln(uint8_t *pattern, int plen, uint8_t *text, int tlen, int gap
         for (int i = 0; i < plen; ++i) p[i] = pattern[plen - i - 1];
         for (int i = 0; i < tlen; ++i) t[i] = text[tlen - i - 1];
     } else { memcpy(p, pattern, plen); memcpy(t, text, tlen); }
-    int64_t po = 0, to = plen, oo = 0; int32_t pl = plen, tl = tlen;
     char *ops = (char*)malloc(2 * ((size_t)plen + tlen) + 16);
-    lcd_wfa_result_t res;
-    if (lcd_wfa_batch(1, seqs, (size_t)plen + tlen, &po, &pl, &to, &tl, &par, ops, &oo, &res)) die("lcd_wfa_batch");
-    n_calls[4]++;
+    req_t r; memset(&r, 0, sizeof(r));
+    r.kind = RQ_WFA; r.seqs = seqs; r.seqs_len = (size_t)plen + tlen; r.plen = plen; r.tlen = tlen; r.wpar = par; r.ops = ops;
+    gpu_call(&r);
+    const lcd_wfa_result_t res = r.wres;
     const int n = res.n_ops;
     if (cigar_buf != NULL && cigar_length != NULL) {         /* cigar_get_CIGAR(cigar, true, ...) (WFA2-lib/alignment/cigar.c:181-240), reversed for left alignment */
         uint32_t *tmp = (uint32_t*)malloc(((size_t)n + 1) * sizeof(uint32_t)); int m = 0;
@@ -489,17 +744,19 @@ int abpoa_partial_aln_msa_cons(const call_var_opt_t *opt, abpoa_t *ab, int sampl
         tot += read_lens[i] > 0 ? read_lens[i] : 0;
     }
     if (ok) {
-        uint8_t *seqs = (uint8_t*)malloc(tot + 1), *cons = (uint8_t*)malloc(tot + 1);
+        uint8_t *seqs = (uint8_t*)malloc(tot + 1), *cons = (uint8_t*)malloc(tot + 17);
         int64_t *off = (int64_t*)malloc(sizeof(int64_t) * n_reads); int32_t *len = (int32_t*)malloc(sizeof(int32_t) * n_reads);
         size_t o = 0; int max_len = 0;
         for (int i = 0; i < n_reads; ++i) { off[i] = (int64_t)o; len[i] = read_lens[i]; memcpy(seqs + o, read_seqs[i], read_lens[i]); o += read_lens[i]; if (len[i] > max_len) max_len = len[i]; }
-        lcd_poa_params_t par = { opt->match, opt->mismatch, opt->gap_open1, opt->gap_ext1, opt->gap_open2, opt->gap_ext2, 10, 0.01f, 1, 1 };   /* abpoa_init_para defaults wb / wf */
-        int32_t first = 0, nr = n_reads; int64_t cons_off = 0, msa_off = 0, msa_cap = (int64_t)(n_reads + 1) * (2 * (int64_t)max_len + 64);
+        const lcd_poa_params_t par = { opt->match, opt->mismatch, opt->gap_open1, opt->gap_ext1, opt->gap_open2, opt->gap_ext2, 10, 0.01f, 1, 1 };   /* abpoa_init_para defaults wb / wf */
+        const int64_t msa_cap = (int64_t)(n_reads + 1) * (2 * (int64_t)max_len + 64);
         uint8_t *msa = (msa_seq_lens && msa_seqs) ? (uint8_t*)malloc((size_t)msa_cap) : NULL;
-        lcd_poa_result_t res;
-        const int rc = lcd_poa_batch(1, seqs, tot, &first, &nr, off, len, n_reads, &par, cons, &cons_off, msa, msa ? &msa_off : NULL, msa ? &msa_cap : NULL, &res);
-        if (rc == -1) die("lcd_poa_batch");                    /* -2: the problem itself was refused on the device (status below) */
-        if (rc == 0 && res.status == LCD_POA_OK && res.cons_len > 0) {
+        req_t r; memset(&r, 0, sizeof(r));
+        r.kind = RQ_POA; r.seqs = seqs; r.seqs_len = tot; r.n_reads = n_reads; r.read_off = off; r.read_len = len; r.ppar = par; r.want_msa = msa != NULL; r.max_len = max_len;
+        r.cons = cons; r.msa = msa; r.msa_cap = msa_cap;
+        gpu_call(&r);
+        const lcd_poa_result_t res = r.pres;
+        if (res.status == LCD_POA_OK && res.cons_len > 0) {
             cons_lens[0] = res.cons_len; cons_seqs[0] = (uint8_t*)malloc(res.cons_len); memcpy(cons_seqs[0], cons, res.cons_len);
             if (clu_n_seqs != NULL && clu_read_ids != NULL) { *clu_n_seqs = n_reads; *clu_read_ids = (int*)malloc(n_reads * sizeof(int)); for (int i = 0; i < n_reads; ++i) (*clu_read_ids)[i] = read_ids[i]; }
             if (msa) {
@@ -507,13 +764,12 @@ int abpoa_partial_aln_msa_cons(const call_var_opt_t *opt, abpoa_t *ab, int sampl
                 for (int i = 0; i < n_reads + 1; ++i) { msa_seqs[i] = (uint8_t*)malloc(res.msa_len); memcpy(msa_seqs[i], msa + (size_t)i * res.msa_len, res.msa_len); }
             }
             free(seqs); free(cons); free(off); free(len); free(msa);
-            n_calls[5]++;
             return 1;
         }
         /* outside the kernel's envelope (e.g. LCD_POA_NEEDS_INT32, MSA wider than the estimate): let abPOA handle this region */
         free(seqs); free(cons); free(off); free(len); free(msa);
     }
-    n_calls[6]++;
+    COUNT(6);
     return orig(opt, ab, sampling_reads, n_reads, read_ids, read_seqs, read_quals, read_lens, read_full_cover, names, max_n_cons, cons_lens, cons_seqs,
                 clu_n_seqs, clu_read_ids, msa_seq_lens, msa_seqs);
 }

@@ -509,7 +509,7 @@ def pileup_input_from_digar(d, o, sites):
     return p
 
 
-def make_classify_chunk(rng, ref_len=4000, n_sites=400, max_xgaps=5, ref0=100000):
+def make_classify_chunk(rng, ref_len=4000, n_sites=400, max_xgaps=5, ref0=100000, is_ont=0):
     """Candidate sites with K2-style counters on a reference window with planted homopolymers / short tandem repeats (and a few N /
     lower-case bases): the input of the per-site category (classify_var_cate, src/collect_var.c:413).  Small indels often repeat the
     reference's own bases, so that both context tests (var_is_homopolymer, var_is_repeat_region) fire."""
@@ -542,12 +542,17 @@ def make_classify_chunk(rng, ref_len=4000, n_sites=400, max_xgaps=5, ref0=100000
     counts = np.zeros((n_sites + 1, 8), np.int32)
     counts[:n_sites, 0] = total; counts[:n_sites, 1] = low; counts[:n_sites, 2] = total - altc; counts[:n_sites, 3] = altc
     counts[:n_sites, 5] = altc // 2; counts[:n_sites, 7] = altc - altc // 2
-    return dict(n_sites=n_sites, min_dp=5, min_alt_dp=2, max_xgaps=max_xgaps, is_ont=0, min_af=0.20, max_af=0.80, ref_beg=ref0, ref_end=ref0 + ref_len - 1,
+    if is_ont:       # strand-skewed alternative-allele counts (ONT's strand-bias test, var_is_strand_bias src/collect_var.c:270): balanced, mildly and fully skewed
+        skew = rng.choice(np.array([0.5, 0.5, 0.35, 0.2, 0.1, 0.0, 1.0]), size=n_sites)
+        fwd = np.minimum(altc, np.round(altc * skew)).astype(np.int32)
+        counts[:n_sites, 5] = fwd; counts[:n_sites, 7] = altc - fwd
+        refc = total - altc; counts[:n_sites, 4] = refc // 2; counts[:n_sites, 6] = refc - refc // 2
+    return dict(n_sites=n_sites, min_dp=5, min_alt_dp=2, max_xgaps=max_xgaps, is_ont=int(is_ont), min_af=0.20, max_af=0.80, ref_beg=ref0, ref_end=ref0 + ref_len - 1,
                 ref_seq=letters, site_pos=np.append(pos, 0), site_type=np.append(typ, 0).astype(np.int32), site_ref_len=np.append(ref_l, 0).astype(np.int32),
                 site_alt_len=np.append(alt_l, 0).astype(np.int32), site_alt_off=np.array(off + [0], np.int64), site_alt=np.array(alt + [0], np.uint8), site_counts=counts)
 
 
-def classify_input_from_sites(d, sites, counts, seed, flank=64, max_xgaps=5):
+def classify_input_from_sites(d, sites, counts, seed, flank=64, max_xgaps=5, is_ont=0):
     """lcd_classify_input_t of a bench chunk: its candidate sites and K2's counters on a synthetic reference window (uniform ACGT with a
     homopolymer or short tandem repeat every ~200 bases; the bench's reads are CIGARs without a reference of their own)."""
     n = int(sites["n_sites"]); pos = np.asarray(sites["site_pos"][:n], np.int64)
@@ -560,7 +565,7 @@ def classify_input_from_sites(d, sites, counts, seed, flank=64, max_xgaps=5):
     unit_len = rng.integers(1, 7, len(starts)); copies = rng.integers(3, 9, len(starts))
     for s0, u, c in zip(starts.tolist(), unit_len.tolist(), copies.tolist()):
         ref[s0:s0 + u * c] = np.tile(ref[s0:s0 + u], c)
-    return dict(n_sites=n, min_dp=5, min_alt_dp=2, max_xgaps=max_xgaps, is_ont=0, min_af=0.20, max_af=0.80, ref_beg=lo, ref_end=hi,
+    return dict(n_sites=n, min_dp=5, min_alt_dp=2, max_xgaps=max_xgaps, is_ont=int(is_ont), min_af=0.20, max_af=0.80, ref_beg=lo, ref_end=hi,
                 ref_seq=np.frombuffer(b"ACGT", np.uint8)[ref].copy(), site_pos=sites["site_pos"], site_type=sites["site_type"], site_ref_len=sites["site_ref_len"],
                 site_alt_len=sites["site_alt_len"], site_alt_off=sites["site_alt_off"], site_alt=sites["site_alt"],
                 site_counts=np.ascontiguousarray(np.vstack([counts[:n], np.zeros((1, 8), np.int32)]), dtype=np.int32))

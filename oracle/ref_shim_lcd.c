@@ -12,6 +12,7 @@
 #include "collect_var.h"
 #include "assign_hap.h"
 #include "cgranges.h"
+#include "math_utils.h"
 
 /* globals of the reference's main.c, which is not linked here */
 int LONGCALLD_VERBOSE = 0;
@@ -368,6 +369,7 @@ int classify_var_cate(const call_var_opt_t *opt, char *ref_seq, hts_pos_t ref_be
 int ref_classify_sites(const lcd_classify_input_t *in, int32_t *var_cate) {
     call_var_opt_t opt; memset(&opt, 0, sizeof(opt));
     opt.noisy_reg_max_xgaps = in->max_xgaps; opt.is_ont = in->is_ont; opt.min_dp = in->min_dp; opt.min_alt_dp = in->min_alt_dp; opt.min_af = in->min_af; opt.max_af = in->max_af;
+    if (in->is_ont) { opt.strand_bias_pval = LONGCALLD_STRAND_BIAS_PVAL_ONT; initialize_lgamma_cache(&opt); }      /* set_ont_opt, call_var_init_para */
     for (int i = 0; i < in->n_sites; ++i) {
         const int32_t *c = in->site_counts + 8 * (int64_t)i;
         cand_var_t var; memset(&var, 0, sizeof(var));

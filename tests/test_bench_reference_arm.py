@@ -13,8 +13,9 @@ import lcd_testlib as T
 def test_reference_arm_line():
     if T.ref_lib() is None:
         pytest.skip("oracle/_ref/libref_shim.so not built (no /root/reference here)")
+    # the reference arm must never load the product library: point it at a file that does not exist
     r = subprocess.run([sys.executable, os.path.join(T.ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--mbp", "1"],
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, LCD_GPU_SO="/nonexistent/liblcd_gpu.so"))
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1                                         # stdout carries exactly one JSON line

@@ -24,6 +24,13 @@ def test_emu_vs_oracle(emu, oracle):
         assert np.array_equal(T.classify(emu, "emu_classify_sites", d), T.classify(oracle, "lcd_oracle_classify_sites", d)), n
 
 
+def test_emu_vs_oracle_ont(emu, oracle):
+    for n, d in enumerate(classify_cases(69, 60, is_ont=1)):
+        if n % 10 == 0:
+            d["site_counts"][:, :] *= 9          # beyond the lgamma cache
+        assert np.array_equal(T.classify(emu, "emu_classify_sites", d), T.classify(oracle, "lcd_oracle_classify_sites", d)), n
+
+
 def test_emu_vs_fixtures(emu):
     for c in T.load_golden("classify_lcd")["cases"]:
         assert T.classify(emu, "emu_classify_sites", T.classify_case_from_json(c["in"])).tolist() == c["cate"]

@@ -29,8 +29,23 @@ def test_gpu_vs_oracle_random(gpu, oracle):
     assert gpu.classify_batch([]) == []
 
 
+def test_gpu_vs_oracle_ont(gpu, oracle):
+    """ONT chunks (BASELINE configs[2]): the strand-bias Fisher test (var_is_strand_bias, src/collect_var.c:270) decides exactly where the oracle
+    -- pinned on the live reference -- does, deep sites beyond the lgamma cache included; HiFi and ONT chunks mixed in one batch."""
+    cases = list(classify_cases(71, 120, is_ont=1))
+    for n, d in enumerate(cases):
+        if n % 10 == 0:
+            d["site_counts"][:, :] *= 9
+    cases += list(classify_cases(73, 20))
+    seen = collections.Counter()
+    for i, (d, got) in enumerate(zip(cases, gpu.classify_batch(cases))):
+        assert np.array_equal(got, T.classify(oracle, "lcd_oracle_classify_sites", d)), (i, d["n_sites"], d["is_ont"])
+        seen.update(got.tolist())
+    assert seen[0x002] > 500, seen
+
+
 def test_gpu_chunk_shaped_plan_and_rejections(gpu, oracle):
-    """Chunks shaped like 500 kb (8 700 sites on a 600 kb window), resident plan re-run; ONT chunks and sites at the window's edge are rejected loudly."""
+    """Chunks shaped like 500 kb (8 700 sites on a 600 kb window), resident plan re-run; sites at the window's edge are rejected loudly."""
     rng = np.random.default_rng(67)
     cases = [synth.make_classify_chunk(rng, ref_len=600000, n_sites=8700) for _ in range(4)]
     plan = gpu.ClassifyPlan(cases)
@@ -39,9 +54,6 @@ def test_gpu_chunk_shaped_plan_and_rejections(gpu, oracle):
     assert plan.work_units() == 4 * 8700
     for d, got in zip(cases, plan.fetch()):
         assert np.array_equal(got, T.classify(oracle, "lcd_oracle_classify_sites", d))
-    ont = dict(cases[0], is_ont=1)
-    with pytest.raises(gpu.LcdGpuError, match="ONT"):
-        gpu.classify_batch([ont])
     edge = synth.make_classify_chunk(rng, ref_len=600, n_sites=20)
     edge["site_type"] = edge["site_type"].copy(); edge["site_type"][0] = 2; edge["site_ref_len"] = edge["site_ref_len"].copy(); edge["site_ref_len"][0] = 2
     edge["site_pos"] = edge["site_pos"].copy(); edge["site_pos"][0] = edge["ref_beg"] + 3

@@ -11,30 +11,7 @@ from test_oracle_digar import digar_cases
 pytestmark = pytest.mark.gpu
 
 
-def view(d, o):
-    """A lcd_digar_output_t dict in the layout-independent form T.collect_digar returns."""
-    reads = {}
-    for i in range(d["n_reads"]):
-        r = int(d["ordered_read_ids"][i])
-        if d["is_skipped"][r]: continue
-        f, n = int(o["digar_first"][r]), int(o["n_digar"][r])
-        ev = []
-        for k in range(f, f + n):
-            t, ln = int(o["digar_type"][k]), int(o["digar_len"][k])
-            a0 = int(o["digar_alt_off"][k])
-            ev.append((int(o["digar_pos"][k]), t, ln, int(o["digar_qi"][k]), int(o["digar_low_qual"][k]), bytes(o["digar_alt"][a0:a0 + ln]) if t in (1, 8) else b""))
-        nf, nn = int(o["nreg_first"][r]), int(o["n_nreg"][r])
-        iv = [(int(o["nreg_beg"][k]), int(o["nreg_end"][k]), int(o["nreg_label"][k])) for k in range(nf, nf + nn)]
-        reads[r] = (int(o["skip"][r]), int(o["read_beg"][r]), int(o["read_end"][r]), ev, iv)
-    civ = [(int(o["cnreg_beg"][k]), int(o["cnreg_end"][k]), int(o["cnreg_label"][k])) for k in range(o["n_cnreg"])]
-    return dict(reads=reads, chunk_noisy=civ, qual_counts=o["qual_counts"].tolist(), totals=(o["n_digar_total"], o["n_alt_total"], o["n_nreg_total"]))
-
-
-def same(a, b, tag):
-    for r in b["reads"]:
-        assert a["reads"][r] == b["reads"][r], (tag, r, [x for x, y in zip(a["reads"][r], b["reads"][r]) if x != y][:1])
-    assert a["qual_counts"] == b["qual_counts"], tag
-    assert a["chunk_noisy"] == b["chunk_noisy"] and a["totals"] == b["totals"], tag
+from longcalld_b200.check import digar_view as view, digar_same as same
 
 
 def test_gpu_vs_reference_fixtures(gpu):

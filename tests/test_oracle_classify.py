@@ -9,11 +9,11 @@ import lcd_testlib as T
 from longcalld_b200 import synth
 
 
-def classify_cases(seed, n):
+def classify_cases(seed, n, is_ont=0):
     rng = np.random.default_rng(seed)
     for it in range(n):
         yield synth.make_classify_chunk(rng, ref_len=int(rng.choice([600, 4000, 20000])), n_sites=int(rng.choice([1, 40, 400])),
-                                        max_xgaps=int(rng.choice([5, 5, 3, 8])), ref0=int(rng.choice([1, 100000])))
+                                        max_xgaps=int(rng.choice([5, 5, 3, 8])), ref0=int(rng.choice([1, 100000])), is_ont=is_ont)
 
 
 def test_oracle_vs_live_reference(oracle, ref):
@@ -25,6 +25,20 @@ def test_oracle_vs_live_reference(oracle, ref):
         seen.update(a.tolist())
     # every category the HiFi path can return, the context tests included
     assert all(seen[c] > 100 for c in (0x001, 0x400, 0x080, 0x010, 0x004, 0x008)), seen
+
+
+def test_oracle_vs_live_reference_ont(oracle, ref):
+    """ONT chunks: var_is_strand_bias (src/collect_var.c:270) -> fisher_exact_test with the lgamma cache (src/math_utils.c:6-170); the
+    `p < 0.01` decision of every site is compared (deep sites beyond the cache's 500 entries included)."""
+    seen = collections.Counter()
+    for n, d in enumerate(classify_cases(67, 120, is_ont=1)):
+        if n % 10 == 0:          # depth beyond the lgamma cache (LONGCALLD_LGAMMA_MAX_I = 500): lgamma() itself
+            d["site_counts"][:, :] *= 9
+        a = T.classify(oracle, "lcd_oracle_classify_sites", d)
+        r = T.classify(ref, "ref_classify_sites", d)
+        assert np.array_equal(a, r), (n, np.nonzero(a != r)[0][:5], a[a != r][:5], r[a != r][:5])
+        seen.update(a.tolist())
+    assert seen[0x002] > 500 and all(seen[c] > 100 for c in (0x001, 0x400, 0x080, 0x010, 0x004, 0x008)), seen
 
 
 def test_oracle_vs_reference_fixtures(oracle):

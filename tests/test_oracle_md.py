@@ -10,31 +10,7 @@ from longcalld_b200 import synth
 from test_oracle_digar import digar_cases
 
 
-def to_md(d, rng):
-    """A chunk with =/X CIGARs -> the same chunk with plain-M CIGARs + one standard MD tag per read ([0-9]+(([A-Z]|\\^[A-Z]+)[0-9]+)*)."""
-    cig = np.asarray(d["cigar"], np.uint32)
-    new_cig, new_off, new_n, mds, md_off = [], [], [], bytearray(), []
-    for r in range(d["n_reads"]):
-        ops = cig[int(d["cigar_off"][r]):int(d["cigar_off"][r]) + int(d["n_cigar"][r])]
-        out, md, run, m = [], "", 0, 0
-        for w in ops.tolist():
-            op, ln = w & 15, w >> 4
-            if op == 7: run += ln; m += ln
-            elif op == 8:
-                for _ in range(ln):
-                    md += str(run) + "ACGTN"[int(rng.integers(0, 5))]; run = 0
-                m += ln
-            else:
-                if m: out.append((m << 4) | 0); m = 0
-                if op == 2:
-                    md += str(run) + "^" + "".join("ACGT"[int(x)] for x in rng.integers(0, 4, ln)); run = 0
-                out.append(w)
-        if m: out.append((m << 4) | 0)
-        md += str(run)
-        new_off.append(len(new_cig)); new_n.append(len(out)); new_cig.extend(out)
-        md_off.append(len(mds)); mds += md.encode() + b"\0"
-    e = dict(d, cigar=np.array(new_cig + [0], np.uint32), cigar_off=np.array(new_off + [0], np.int64), n_cigar=np.array(new_n + [0], np.int32))
-    return e, np.array(md_off + [0], np.int64), np.frombuffer(bytes(mds), np.uint8).copy()
+from longcalld_b200.check import to_md      # noqa: E402  (shared with smoke())
 
 
 def convert(oracle, e, md_off, md):
