@@ -26,6 +26,7 @@
  * Built only where the reference headers exist (make -C longcalld_b200/dropin REF=/root/reference). */
 #define _GNU_SOURCE
 #include <dlfcn.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -38,12 +39,24 @@
 #include "lcd_gpu.h"
 
 static void die(const char *what) { fprintf(stderr, "[lcd_dropin] %s failed: %s\n", what, lcd_gpu_last_error()); exit(1); }
+#include <time.h>
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+static double t_batch[3], t_blocked, t_fwd_poa;       /* seconds inside the library per engine (leader threads), blocked in the combiner (all threads), in forwarded abPOA */
+static pthread_mutex_t t_mu = PTHREAD_MUTEX_INITIALIZER;
+static void t_add(double *acc, double dt) { pthread_mutex_lock(&t_mu); *acc += dt; pthread_mutex_unlock(&t_mu); }
 static unsigned long n_calls[11];
 #define COUNT(i) __atomic_fetch_add(&n_calls[i], 1, __ATOMIC_RELAXED)      /* the reference's worker threads call in concurrently */
 __attribute__((destructor)) static void report(void) {
-    if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: digar %lu (forwarded: %lu), sites %lu, pileup %lu, profile %lu, phase %lu, edlib %lu, wfa %lu, poa %lu (forwarded to abPOA: %lu) in %lu engine batches; kernel launches %llu\n",
-                                              n_calls[8], n_calls[9], n_calls[10], n_calls[0], n_calls[1], n_calls[2], n_calls[3], n_calls[4], n_calls[5], n_calls[6], n_calls[7], (unsigned long long)lcd_gpu_launch_count());
+    if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: digar %lu (forwarded: %lu), sites %lu, pileup %lu, profile %lu, phase %lu, edlib %lu, wfa %lu, poa %lu (forwarded to abPOA: %lu) in %lu engine batches (library time: poa %.2f s, wfa %.2f s, edlib %.2f s; threads blocked %.2f s in total; forwarded abPOA %.2f s); kernel launches %llu\n",
+                                              n_calls[8], n_calls[9], n_calls[10], n_calls[0], n_calls[1], n_calls[2], n_calls[3], n_calls[4], n_calls[5], n_calls[6], n_calls[7], t_batch[0], t_batch[1], t_batch[2], t_blocked, t_fwd_poa, (unsigned long long)lcd_gpu_launch_count());
 }
+
+/* LCD_DROPIN_STAGES=engines keeps the pileup scan and the phasing (K1 - K4) on the reference's own host code and sends only the DP engines
+ * (K5 - K7, batched) to the GPU: per chunk the reference's AoS structures have to be flattened for, and rebuilt from, every K1 - K4 call,
+ * which costs the host about what those stages cost it in the first place (measured: DESIGN.md, whole-program numbers).  Default: all. */
+static int pileup_on_gpu(void) { static int v = -1; if (v < 0) { const char *e = getenv("LCD_DROPIN_STAGES"); v = !(e && strcmp(e, "engines") == 0); } return v; }
+#define FORWARD_UNLESS_PILEUP_ON_GPU(ret_t, name, proto, args) \
+    if (!pileup_on_gpu()) { static ret_t (*orig_) proto = NULL; if (!orig_) orig_ = (ret_t (*) proto)dlsym(RTLD_NEXT, name); return orig_ args; }
 
 /* ------------------------------------------------------------------------------------------ digars -> flat */
 typedef struct {
@@ -115,6 +128,7 @@ int is_ont_palindrome_clip(const call_var_opt_t *opt, bam1_t *read);            
 extern int LONGCALLD_VERBOSE;                                                                    /* src/main.c */
 
 void collect_digars_from_bam(bam_chunk_t *chunk, const struct call_var_pl_t *pl) {               /* src/collect_var.c:1063-1110 */
+    FORWARD_UNLESS_PILEUP_ON_GPU(void, "collect_digars_from_bam", (bam_chunk_t *, const struct call_var_pl_t *), (chunk, pl))
     const call_var_opt_t *opt = pl->opt;
     const int nr = chunk->n_reads;
     /* the reference picks per read: =/X CIGAR, else cs tag, else MD tag, else the reference sequence (src/collect_var.c:1072-1080); on the
@@ -225,6 +239,7 @@ void collect_digars_from_bam(bam_chunk_t *chunk, const struct call_var_pl_t *pl)
 
 /* ------------------------------------------------------------------------------------------ K1b */
 int collect_all_cand_var_sites(const call_var_opt_t *opt, bam_chunk_t *chunk, var_site_t **var_sites) {      /* src/collect_var.c:1209-1254 */
+    FORWARD_UNLESS_PILEUP_ON_GPU(int, "collect_all_cand_var_sites", (const call_var_opt_t *, bam_chunk_t *, var_site_t **), (opt, chunk, var_sites))
     *var_sites = NULL;
     flat_t f; flatten(opt, chunk, 0, NULL, NULL, &f);
     size_t n_ev = 0, cap = 0;
@@ -261,6 +276,7 @@ int collect_all_cand_var_sites(const call_var_opt_t *opt, bam_chunk_t *chunk, va
 cand_var_t *init_cand_vars_based_on_sites(int n_var_sites, var_site_t *var_sites);          /* src/collect_var.c:20 */
 
 int collect_cand_vars(const call_var_opt_t *opt, bam_chunk_t *chunk, int n_var_sites, var_site_t *var_sites) {
+    FORWARD_UNLESS_PILEUP_ON_GPU(int, "collect_cand_vars", (const call_var_opt_t *, bam_chunk_t *, int, var_site_t *), (opt, chunk, n_var_sites, var_sites))
     chunk->cand_vars = init_cand_vars_based_on_sites(n_var_sites, var_sites);
     chunk->n_cand_vars = n_var_sites;
     flat_t f; flatten(opt, chunk, n_var_sites, var_sites, NULL, &f);
@@ -281,7 +297,7 @@ int collect_cand_vars(const call_var_opt_t *opt, bam_chunk_t *chunk, int n_var_s
 read_var_profile_t *init_read_var_profile(int n_reads, int n_total_vars);                     /* src/bam_utils.c:38 */
 
 read_var_profile_t *collect_read_var_profile(const call_var_opt_t *opt, bam_chunk_t *chunk) {
-    if (opt->out_somatic) {      /* -s: candidate somatic variants take the reference's fuzzy path, which the GPU library rejects */
+    if (opt->out_somatic || !pileup_on_gpu()) {      /* -s: candidate somatic variants take the reference's fuzzy path, which the GPU library rejects */
         static read_var_profile_t *(*orig)(const call_var_opt_t *, bam_chunk_t *) = NULL;
         if (!orig) orig = (read_var_profile_t *(*)(const call_var_opt_t *, bam_chunk_t *))dlsym(RTLD_NEXT, "collect_read_var_profile");
         return orig(opt, chunk);
@@ -329,6 +345,7 @@ read_var_profile_t *collect_read_var_profile(const call_var_opt_t *opt, bam_chun
 
 /* ------------------------------------------------------------------------------------------ K4 */
 int assign_hap_based_on_germline_het_vars_kmeans(const call_var_opt_t *opt, bam_chunk_t *chunk, int target_var_cate) {
+    FORWARD_UNLESS_PILEUP_ON_GPU(int, "assign_hap_based_on_germline_het_vars_kmeans", (const call_var_opt_t *, bam_chunk_t *, int), (opt, chunk, target_var_cate))
     const int nr = chunk->n_reads, nv = chunk->n_cand_vars;
     read_var_profile_t *p = chunk->read_var_profile;
     int n_valid = 0;
@@ -416,6 +433,7 @@ static void *new_thread_stream(void) {                    /* every host thread t
 
 /* one library call over n requests of one kind */
 static void run_batch(int kind, req_t **r, int n) {
+    const double t0_ = now_s();
     new_thread_stream();
     if (kind == RQ_POA) {
         size_t tot = 0, n_rd = 0, cons_tot = 0, msa_tot = 0;
@@ -480,41 +498,49 @@ static void run_batch(int kind, req_t **r, int n) {
         __atomic_fetch_add(&n_calls[3], (unsigned long)n, __ATOMIC_RELAXED); COUNT(7);
     }
     for (int i = 0; i < n; ++i) __atomic_store_n(&r[i]->done, 1, __ATOMIC_RELEASE);
+    t_add(&t_batch[kind], now_s() - t0_);
 }
 
-/* Leader / follower combiner: the first thread to arrive with requests of a kind lingers a moment, takes whatever the other worker
- * threads have added meanwhile and makes the one library call; the others sleep until their requests are done. */
-typedef struct { pthread_mutex_t mu; pthread_cond_t cv; req_t **pend; int n, cap, leader; } comb_t;
-static comb_t comb[RQ_KINDS] = { { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, 0, 0 }, { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, 0, 0 },
-                                 { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, 0, 0 } };
-static int linger_us(void) { static int v = -1; if (v < 0) { const char *e = getenv("LCD_DROPIN_LINGER_US"); v = e ? atoi(e) : 200; } return v; }
+/* Leader / follower combiner over ALL worker threads (kt_for) and all three engines: a thread that has parked requests adds them to
+ * the queue; the first one there becomes the leader and waits until every worker thread that is inside collect_var_main is blocked
+ * here too (nobody left who could add work) -- or a bounded linger has passed -- then takes the whole queue and makes one library call
+ * per engine; the others sleep until their requests are done.  With t threads on t chunks the batches are t chunks wide. */
+static struct { pthread_mutex_t mu; pthread_cond_t cv; req_t **pend; int n, cap, leader, n_active, n_blocked; } cq = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, 0, 0, 0, 0 };
+static int linger_us(void) { static int v = -1; if (v < 0) { const char *e = getenv("LCD_DROPIN_LINGER_US"); v = e ? atoi(e) : 3000; } return v; }
+static void worker_enter(void) { pthread_mutex_lock(&cq.mu); cq.n_active++; pthread_mutex_unlock(&cq.mu); }
+static void worker_leave(void) { pthread_mutex_lock(&cq.mu); cq.n_active--; pthread_cond_broadcast(&cq.cv); pthread_mutex_unlock(&cq.mu); }
 
-static void combine(int kind, req_t **r, int n) {
+static void combine(req_t **r, int n) {
     if (n == 0) return;
-    comb_t *c = &comb[kind];
-    pthread_mutex_lock(&c->mu);
-    if (c->n + n > c->cap) { c->cap = 2 * (c->n + n); c->pend = (req_t**)realloc(c->pend, sizeof(req_t*) * c->cap); }
-    memcpy(c->pend + c->n, r, sizeof(req_t*) * n); c->n += n;
-    if (!c->leader) {
-        c->leader = 1;
-        pthread_mutex_unlock(&c->mu);
-        if (linger_us() > 0) usleep(linger_us());
-        pthread_mutex_lock(&c->mu);
-        req_t **take = c->pend; const int nt = c->n;
-        c->pend = NULL; c->n = c->cap = 0; c->leader = 0;          /* the next batch may start collecting while this one runs */
-        pthread_mutex_unlock(&c->mu);
-        run_batch(kind, take, nt);
-        free(take);
-        pthread_mutex_lock(&c->mu);
-        pthread_cond_broadcast(&c->cv);
+    const double t0_ = now_s();
+    pthread_mutex_lock(&cq.mu);
+    if (cq.n + n > cq.cap) { cq.cap = 2 * (cq.n + n); cq.pend = (req_t**)realloc(cq.pend, sizeof(req_t*) * cq.cap); }
+    memcpy(cq.pend + cq.n, r, sizeof(req_t*) * n); cq.n += n;
+    cq.n_blocked++;
+    pthread_cond_broadcast(&cq.cv);                            /* a lingering leader re-checks whether everybody has arrived */
+    if (!cq.leader) {
+        cq.leader = 1;
+        struct timespec until; clock_gettime(CLOCK_REALTIME, &until);
+        until.tv_nsec += (long)linger_us() * 1000; until.tv_sec += until.tv_nsec / 1000000000; until.tv_nsec %= 1000000000;
+        while (cq.n_blocked < cq.n_active) if (pthread_cond_timedwait(&cq.cv, &cq.mu, &until) != 0) break;
+        req_t **take = cq.pend; const int nt = cq.n;
+        cq.pend = NULL; cq.n = cq.cap = 0; cq.leader = 0;      /* the next batch may start collecting while this one runs */
+        pthread_mutex_unlock(&cq.mu);
+        req_t **byk = (req_t**)malloc(sizeof(req_t*) * nt);
+        for (int k = 0; k < RQ_KINDS; ++k) { int m = 0; for (int i = 0; i < nt; ++i) if (take[i]->kind == k) byk[m++] = take[i]; if (m) run_batch(k, byk, m); }
+        free(byk); free(take);
+        pthread_mutex_lock(&cq.mu);
+        pthread_cond_broadcast(&cq.cv);
     }
     for (;;) {
         int all = 1;
         for (int i = 0; i < n; ++i) if (!__atomic_load_n(&r[i]->done, __ATOMIC_ACQUIRE)) { all = 0; break; }
         if (all) break;
-        pthread_cond_wait(&c->cv, &c->mu);
+        pthread_cond_wait(&cq.cv, &cq.mu);
     }
-    pthread_mutex_unlock(&c->mu);
+    cq.n_blocked--;
+    pthread_mutex_unlock(&cq.mu);
+    t_add(&t_blocked, now_s() - t0_);
 }
 
 /* ---- coroutines: one per pending noisy region of the chunk a worker thread is on */
@@ -537,7 +563,7 @@ static void co_entry(void) {
 static void gpu_call(req_t *r) {
     r->done = 0;
     if (tl_co) { tl_co->req = r; tl_co->state = CO_PARKED; swapcontext(&tl_co->ctx, &tl_sched->main); }
-    else { req_t *one = r; combine(r->kind, &one, 1); }
+    else { req_t *one = r; combine(&one, 1); }
 }
 
 /* all pending regions of one pass side by side; ret[k] = collect_noisy_vars1's return value for regs[k] */
@@ -552,7 +578,7 @@ static void run_regions(bam_chunk_t *chunk, const call_var_opt_t *opt, int n, co
         getcontext(&c->ctx); c->ctx.uc_stack.ss_sp = c->stack; c->ctx.uc_stack.ss_size = CO_STACK; c->ctx.uc_link = NULL;
         makecontext(&c->ctx, co_entry, 0);
     }
-    req_t **parked = (req_t**)malloc(sizeof(req_t*) * n), **byk = (req_t**)malloc(sizeof(req_t*) * n);
+    req_t **parked = (req_t**)malloc(sizeof(req_t*) * n);
     tl_sched = &sc;
     for (;;) {
         int ran = 0;
@@ -566,7 +592,7 @@ static void run_regions(bam_chunk_t *chunk, const call_var_opt_t *opt, int n, co
         int np = 0;
         for (int i = 0; i < n; ++i) if (sc.cos[i].state == CO_PARKED) parked[np++] = sc.cos[i].req;
         if (np) {
-            for (int k = 0; k < RQ_KINDS; ++k) { int m = 0; for (int i = 0; i < np; ++i) if (parked[i]->kind == k) byk[m++] = parked[i]; combine(k, byk, m); }
+            combine(parked, np);
             for (int i = 0; i < n; ++i) if (sc.cos[i].state == CO_PARKED) sc.cos[i].state = CO_READY;
             continue;
         }
@@ -575,7 +601,7 @@ static void run_regions(bam_chunk_t *chunk, const call_var_opt_t *opt, int n, co
     }
     tl_sched = NULL;
     for (int i = 0; i < n; ++i) ret[i] = sc.cos[i].ret;
-    free(parked); free(byk); free(sc.cos);
+    free(parked); free(sc.cos);
 }
 
 /* make_vars_from_msa_cons_aln (src/collect_var.c:2279) starts the part of a region that edits the chunk's variant list: regions take it
@@ -616,6 +642,7 @@ void collect_var_main(const call_var_pl_t *pl, bam_chunk_t *chunk) {
         int *pend = (int*)malloc(sizeof(int) * n_regs), *ret = (int*)malloc(sizeof(int) * n_regs);
         /* -s / --refine-aln rewrite the reads' difference lists region by region (update_digars_from_aln_str, src/align.c:1796): one at a time */
         const int one_by_one = opt->out_somatic || (opt->refine_bam && opt->out_aln_fp != NULL) || getenv("LCD_DROPIN_SERIAL") != NULL;
+        worker_enter();                                       /* from here on this thread's engine calls are batched with the other threads' */
         for (;;) {
             int new_region_is_done = 0, new_var = 0, np = 0;
             for (int i = 0; i < n_regs; ++i) if (!is_done[sorted[i]]) pend[np++] = sorted[i];
@@ -625,6 +652,7 @@ void collect_var_main(const call_var_pl_t *pl, bam_chunk_t *chunk) {
             if (new_var) assign_hap_based_on_germline_het_vars_kmeans(opt, chunk, LONGCALLD_CAND_GERMLINE_VAR_CATE);
             if (new_region_is_done == 0) break;
         }
+        worker_leave();
         free(sorted); free(is_done); free(pend); free(ret);
     }
     if (opt->out_somatic == 1) collect_somatic_var(chunk, opt);                                                              /* 5 */
@@ -770,6 +798,9 @@ int abpoa_partial_aln_msa_cons(const call_var_opt_t *opt, abpoa_t *ab, int sampl
         free(seqs); free(cons); free(off); free(len); free(msa);
     }
     COUNT(6);
-    return orig(opt, ab, sampling_reads, n_reads, read_ids, read_seqs, read_quals, read_lens, read_full_cover, names, max_n_cons, cons_lens, cons_seqs,
+    const double t0_ = now_s();
+    const int rc_ = orig(opt, ab, sampling_reads, n_reads, read_ids, read_seqs, read_quals, read_lens, read_full_cover, names, max_n_cons, cons_lens, cons_seqs,
                 clu_n_seqs, clu_read_ids, msa_seq_lens, msa_seqs);
+    t_add(&t_fwd_poa, now_s() - t0_);
+    return rc_;
 }

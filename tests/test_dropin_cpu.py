@@ -1,0 +1,55 @@
+"""CPU, end to end: the reference-side binding (longcalld_b200/dropin/lcd_dropin.c: marshalling of the reference's structures, the coroutine
+region driver that runs the pending noisy regions of a chunk side by side, the cross-thread combiner that turns their engine calls into
+one batch per engine) preloaded into the UNMODIFIED reference, with the C-ABI answered by an oracle-backed test double
+(tests/emu/fake_lcd_gpu.c) instead of liblcd_gpu.so -- so the host logic is checked where there is no GPU: the VCF body must be the
+reference's own (md5s of SURVEY.md section 6) at any thread count, and the engine calls must really have been batched."""
+import hashlib
+import os
+import re
+import subprocess
+
+import pytest
+
+import lcd_testlib as T
+
+REF_DIR = os.path.join(T.ROOT, "oracle", "_ref")
+EMU_DIR = os.path.join(T.ROOT, "tests", "emu")
+GOLDEN = {"hifi": "dcbd4523c01ab37cce5dd88d5e56b564", "ont": "71f0e1aa2ee7667ad2a1f31e2eace81d", "mosaic": "ea77d40096193eb9ad4497c297c21fd7"}
+
+
+@pytest.fixture(scope="module")
+def dropin_cpu():
+    if not (os.path.exists(os.path.join(REF_DIR, "longcallD_so")) and os.path.isdir("/root/reference/src")):
+        pytest.skip("needs the reference built by oracle/Makefile (oracle/_ref) and its headers")
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR, "liblcd_dropin_cpu.so"])
+    return os.path.join(EMU_DIR, "liblcd_dropin_cpu.so")
+
+
+def run(so, tech, threads, extra_env=None):
+    data = os.path.join(REF_DIR, "test_data")
+    bam = "ont" if tech == "ont" else "hifi"
+    extra = ["-s", "-T", os.path.join(data, "AluY_L1_SVA_cons_noPA.fa")] if tech == "mosaic" else []
+    cmd = [os.path.join(REF_DIR, "longcallD_so"), "call", "--ont" if tech == "ont" else "--hifi"] + extra + \
+          [os.path.join(data, "chr11_2M.fa"), os.path.join(data, f"HG002_chr11_{bam}_test.bam"), "-t", str(threads)]
+    r = subprocess.run(cmd, env=dict(os.environ, LD_PRELOAD=so, LCD_DROPIN_VERBOSE="1", **(extra_env or {})), capture_output=True, timeout=900)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    body = b"".join(l + b"\n" for l in r.stdout.split(b"\n") if l and not l.startswith(b"#"))
+    line = [l for l in r.stderr.decode().splitlines() if "[lcd_dropin] GPU calls" in l][-1]
+    return hashlib.md5(body).hexdigest(), line
+
+
+@pytest.mark.parametrize("tech,threads", [("hifi", 1), ("hifi", 8), ("ont", 4), ("mosaic", 4)])
+def test_vcf_identical_through_the_batched_driver(dropin_cpu, tech, threads):
+    md5, line = run(dropin_cpu, tech, threads)
+    assert md5 == GOLDEN[tech], line
+    c = {k: int(v) for k, v in re.findall(r"(edlib|wfa|poa) (\d+)", line.split("(library time")[0])}
+    batches = int(re.search(r"in (\d+) engine batches", line).group(1))
+    assert c["poa"] > 100 and c["wfa"] > 100
+    if tech != "mosaic":                 # -s rewrites the difference lists region by region: one region at a time there
+        assert batches * 4 < c["poa"] + c["wfa"] + c["edlib"], line
+
+
+def test_serial_regions_give_the_same_vcf(dropin_cpu):
+    """LCD_DROPIN_SERIAL=1 runs the regions one after the other (every engine call a batch of one): same records."""
+    md5, line = run(dropin_cpu, "hifi", 2, {"LCD_DROPIN_SERIAL": "1"})
+    assert md5 == GOLDEN["hifi"], line

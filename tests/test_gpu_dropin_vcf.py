@@ -41,7 +41,7 @@ def test_vcf_identical_with_gpu_dropin(tech):
     md5, err = _run(tech, preload=True)
     calls = [l[l.index("[lcd_dropin] GPU calls"):] for l in err.splitlines() if "[lcd_dropin] GPU calls" in l]
     assert calls, "the drop-in was not loaded"
-    counts = dict((k, int(v)) for k, v in __import__("re").findall(r"(digar|sites|pileup|profile|phase|edlib|wfa|poa) (\d+)", calls[-1]))
+    counts = dict((k, int(v)) for k, v in __import__("re").findall(r"(digar|sites|pileup|profile|phase|edlib|wfa|poa) (\d+)", calls[-1].split("(library time")[0]))
     need = ("sites", "pileup", "phase", "wfa", "poa") if tech == "mosaic" else ("sites", "pileup", "profile", "phase", "wfa", "poa")   # -s: the profile takes the reference's somatic path
     need += ("digar",)
     fwd = int(__import__("re").search(r"digar \d+ \(forwarded: (\d+)\)", calls[-1]).group(1))

@@ -4,8 +4,8 @@
  *   synth_bam <out_prefix> <ref_mb> <hifi|ont> [seed=11] [coverage=30] [n_contigs=1] [mosaic=0]
  *     -> <out_prefix>.fa (+ .fai), <out_prefix>.bam (+ .bai): coordinate-sorted, MAPQ 60, true alignments with =/X CIGARs + NM
  *
- * reference : uniform ACGT; a homopolymer (6-30 bp) every ~2 kb; an STR / VNTR (unit 2-60 bp x 3-40 copies) every ~20 kb
- * diploid   : SNPs 1 / 1 000 bp (2/3 het), small indels 1 / 8 000 bp (70 % as copy-number changes of the planted repeats), SV insertions /
+ * reference : uniform ACGT; a homopolymer (6-30 bp) every ~0.8 kb; an STR / VNTR (unit 2-60 bp x 3-40 copies) every ~6 kb
+ * diploid   : SNPs 1 / 1 000 bp (2/3 het), small indels 1 / 3 000 bp (70 % as copy-number changes of the planted repeats), SV insertions /
  *             deletions of 50 bp - 6 kb every ~300 kb; mosaic=1 adds TE-like inserts (300 bp - 6 kb random sequence + poly-A + 5-20 bp TSD)
  *             carried by 5 % of the reads, one per ~2 Mb
  * reads     : HiFi  length ~ N(15 kb, 3 kb), error 0.2 % (80 % homopolymer-length indels), Q20 - Q40
@@ -64,8 +64,8 @@ int main(int argc, char **argv) {
         for (int64_t i = 0; i < L; ++i) ref[i] = ACGT[rnd() & 3];
         ref[L] = 0;
         rep_t *reps = NULL; size_t n_rep = 0, m_rep = 0;
-        for (int64_t p = 1000; p < L - 4000; p += irand(1000, 3000)) {
-            if (rnd() % 10 == 0) {                       /* STR / VNTR: ~1 per 20 kb */
+        for (int64_t p = 1000; p < L - 4000; p += irand(250, 750)) {
+            if (rnd() % 8 == 0) {                        /* STR / VNTR: ~1 per 6 kb */
                 const int unit = (rnd() & 3) ? irand(2, 6) : irand(7, 60), copies = irand(3, unit > 20 ? 12 : 40);
                 for (int c = 1; c < copies; ++c) memcpy(ref + p + (int64_t)c * unit, ref + p, unit);
                 if (n_rep == m_rep) { m_rep = m_rep ? 2 * m_rep : 256; reps = (rep_t*)realloc(reps, m_rep * sizeof(rep_t)); }
@@ -82,7 +82,7 @@ int main(int argc, char **argv) {
             char *a = (char*)malloc(2); do { a[0] = ACGT[rnd() & 3]; } while (a[0] == ref[p]); a[1] = 0;
             const int h = rnd() % 3; add_var(p, 0, 1, a, h == 0 ? 3 : h, 0);
         }
-        for (int64_t p = 2000 + irand(0, 4000); p < L - 8000; p += irand(4000, 12000)) {              /* small indels */
+        for (int64_t p = 2000 + irand(0, 4000); p < L - 8000; p += irand(800, 2400)) {                /* small indels */
             const int hap = (rnd() % 3 == 0) ? 3 : 1 + (int)(rnd() & 1);
             if (rnd() % 10 < 7 && n_rep) {                /* a copy-number change of the nearest planted repeat */
                 size_t lo = 0, hi = n_rep; while (lo < hi) { size_t m = (lo + hi) / 2; if (reps[m].pos < p) lo = m + 1; else hi = m; }
