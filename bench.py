@@ -18,8 +18,10 @@ import argparse
 import ctypes as C
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -405,6 +407,32 @@ def calibrate_sample(lib, wl, n_threads, target_s):
     return float(min(1.0, max(frac, target_s / max(per_region, 1e-9) / wl.n_regions)))
 
 
+def whole_program(args, with_gpu):
+    """`longcallD call` itself, BAM + FASTA -> VCF, on a synthetic BAM of the same shape (tools/synth_bam.c, tools/whole_program.py): the
+    unmodified reference binary on all host threads and -- with_gpu -- the same program with the GPU drop-in preloaded; wall seconds from
+    the tool's own `Real time` line, VCF bodies compared by md5.  Bounded: one run each on args.mbp Mb."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import whole_program as wp
+        if not wp.available():
+            return {"unavailable": "oracle/_ref binaries, tools/_build/synth_bam or the drop-in were not built"}
+        if not with_gpu:
+            wd = tempfile.mkdtemp(prefix="lcd_wp_")
+            fa, bam = wp.make_bam(os.path.join(wd, "synth"), args.mbp, args.tech, args.seed)
+            nt = os.cpu_count() or 1
+            r = wp.call(os.path.join(wp.REF_DIR, "longcallD_ref"), fa, bam, args.tech, nt)
+            shutil.rmtree(wd, ignore_errors=True)
+            return {"what": "oracle/_ref/longcallD_ref call, BAM + FASTA -> VCF", "mb": args.mbp, "threads": nt, "real_s": r["real_s"], "cpu_s": r["cpu_s"],
+                    "mbp_per_s": args.mbp / r["real_s"], "vcf_md5": r["vcf_md5"], "vcf_records": r["vcf_records"]}
+        o = wp.run(args.mbp, args.tech, None, "engines", None, args.seed)
+        return {"what": "longcallD call, BAM + FASTA -> VCF: the unmodified reference binary vs the same program with liblcd_dropin.so preloaded (K5 - K7 batched over regions and threads on the GPU; LCD_DROPIN_STAGES=engines)",
+                "mb": o["mb"], "threads": o["threads"], "reference_real_s": o["reference"]["real_s"], "gpu_real_s": o["gpu"]["real_s"],
+                "reference_mbp_per_s": o["reference_mbp_s"], "gpu_mbp_per_s": o["gpu_mbp_s"], "speedup": o["speedup"], "vcf_md5_equal": o["vcf_md5_equal"],
+                "vcf_records": o["gpu"]["vcf_records"], "reference_cpu_s": o["reference"]["cpu_s"], "gpu_cpu_s": o["gpu"]["cpu_s"], "dropin": o["gpu"]["dropin"]}
+    except Exception as e:                      # a measurement that could not be made is reported, not hidden
+        return {"error": repr(e)[:300]}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -437,7 +465,8 @@ def run_reference(args, rank):
                              "phase_s": sum(x[3] for x in t) / args.steps, "edlib_s": sum(x[4] for x in t) / args.steps,
                              "digar_s": pile_scale * sum(x[1] for x in tp) / args.steps, "pileup_s": pile_scale * sum(x[2] for x in tp) / args.steps,
                              "profile_s": pile_scale * sum(x[3] for x in tp) / args.steps, "sites_s": pile_scale * sum(x[4] for x in tp) / args.steps, "classify_s": pile_scale * sum(x[5] for x in tp) / args.steps},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "whole_program": None if args.no_whole_program else whole_program(args, with_gpu=False)}
     print(json.dumps(line))
 
 
@@ -817,6 +846,10 @@ def run_b200(args, rank, world):
                                       f"K1-K3 on {k_chunks} of {ps.n_chunks} chunks, time scaled by {pile_scale:.4f}",
                             "poa_s": dt_poa, "wfa_s": dt_wfa, "phase_s": dt_phase, "edlib_s": dt_edlib,
                             "digar_s": pile_scale * dtp[1], "pileup_s": pile_scale * dtp[2], "profile_s": pile_scale * dtp[3], "sites_s": pile_scale * dtp[4], "classify_s": pile_scale * dtp[5]}
+    wp_line = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_whole_program:
+        torch.cuda.synchronize()
+        wp_line = whole_program(args, with_gpu=True)
     if rank == 0:
         peak, which = load_peaks()
         poa_gbs = poa_cells * POA_BYTES_PER_CELL / (poa_ms / args.steps / 1e3) / 1e9
@@ -856,7 +889,7 @@ def run_b200(args, rank, world):
                                                                "GBps": ps.k3_bytes / (k3_ms / args.steps / 1e3) / 1e9},
                                             "edlib_kernel": {"ms": edlib_ms / args.steps, "block_columns": edlib_units,
                                                              "GBps": edlib_units * EDLIB_BYTES_PER_BLOCKCOL / (edlib_ms / args.steps / 1e3) / 1e9}}},
-                "cpu_baseline": cpu_baseline, "parity_checked": parity}
+                "cpu_baseline": cpu_baseline, "parity_checked": parity, "whole_program": wp_line}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -872,6 +905,7 @@ def main():
     ap.add_argument("--tech", default="hifi", choices=["hifi", "ont"])
     ap.add_argument("--seed", type=int, default=11)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-whole-program", action="store_true", help="skip the BAM -> VCF run of `longcallD call` (reference binary vs GPU drop-in)")
     ap.add_argument("--no-pipeline", dest="pipeline", action="store_false", help="K6 / K7 after K5 on one stream instead of overlapping the next batch's K5")
     ap.add_argument("--reserve-sms", type=int, default=12, help="SMs whose CTA slots the persistent DP grids leave to the concurrently running pileup / phasing kernels")
     args = ap.parse_args()

@@ -55,6 +55,11 @@ int lcd_gpu_reserve_sms(int n_sms);
  * serialised independently, so that the WFA launch of one region batch and the POA launch of the next may be in flight together (run
  * them on different streams).  Call it right after lcd_gpu_init, before any plan exists; 0 restores the single window. */
 int lcd_gpu_split_pool(size_t lower_bytes);
+/* The general form: n_poa equal windows below `lower_bytes` for the POA plans and n_aln equal windows above it for the WFA / edlib plans.
+ * A plan takes an idle window of its class for the time of a run (else the next one in turn, ordered behind that window's last user),
+ * so up to n batches of one engine -- created and run by different host threads on different streams -- are on the GPU together: a
+ * batch whose launch has shrunk to its last long problems no longer keeps the next one waiting.  lcd_gpu_split_pool(b) is (1, 1, b). */
+int lcd_gpu_pool_windows(int n_poa, int n_aln, size_t lower_bytes);
 
 /* ---------------------------------------------------------------- K6: WFA gap-affine(-2p)
  * Replaces wavefront_aligner_new + wavefront_align + reading wf_aligner->cigar, as called by

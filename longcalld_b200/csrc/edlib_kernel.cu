@@ -65,7 +65,7 @@ struct EdlibPlan : Plan {
             const uint64_t wx = (uint64_t)(problems[x].qlen / 64 + 1) * (problems[x].tlen + 1), wy = (uint64_t)(problems[y].qlen / 64 + 1) * (problems[y].tlen + 1);
             return wx != wy ? wx > wy : x < y; });
         // workspace slices; a batch that does not fit the pool at once is split into several launches
-        const uint64_t pool_w = c.win_words(1) / 2;           // pool is counted in int32 words
+        const uint64_t pool_w = c.class_words(1) / 2;           // pool is counted in int32 words
         uint64_t top = 0; int begin = 0;
         for (int k = 0; k < n; ++k) {
             Problem &p = problems[order[k]];
@@ -93,7 +93,7 @@ struct EdlibPlan : Plan {
             const int cnt = launches[l].second - launches[l].first;
             KernelArgs ka;
             ka.problems = d_problems.p; ka.order = d_order.p + launches[l].first; ka.n = cnt; ka.queue = d_queue.p + l;
-            ka.seqs = d_seqs.p; ka.aln = d_aln.p; ka.results = d_results.p; ka.pool = reinterpret_cast<Word *>(c.win_pool(1));
+            ka.seqs = d_seqs.p; ka.aln = d_aln.p; ka.results = d_results.p; ka.pool = reinterpret_cast<Word *>(c.pool + win->off);
             const int grid = std::min((cnt + THREADS_PER_CTA - 1) / THREADS_PER_CTA, c.sm_count * 16);
             edlib_kernel<<<grid, THREADS_PER_CTA, 0, s>>>(ka);
             LCD_CUDA_OK(cudaGetLastError());

@@ -43,18 +43,21 @@ struct Context {
     std::vector<cudaStream_t> extra_streams;   // lcd_gpu_new_stream: one per host thread of a multi-threaded caller
     int32_t *pool = nullptr;          // int32 words
     size_t pool_words = 0;
-    // lcd_gpu_split_pool: window 0 = [0, split_words) for the POA plans, window 1 = the rest for the WFA / edlib plans (0: one window)
-    size_t split_words = 0;
-    int32_t *win_pool(int w) const { return pool + ((w && split_words) ? split_words : 0); }
-    size_t win_words(int w) const { return split_words ? (w ? pool_words - split_words : split_words) : pool_words; }
-    std::mutex mu1;                   // serialises the plans of window 1 when the pool is split
-    static constexpr int BITMAP_WORDS = 4096;     // overflow chunks in use (bit set), device memory
-    uint32_t *chunk_bitmap = nullptr;
-    std::mutex mu;                    // serialises plan runs that share the pool
-    // Every pool window orders its own users: the event is recorded behind the last launch that carves from the window and the next
-    // run() on that window -- whatever stream it was given -- waits for it first.  (The mutexes only cover the enqueue; the persistent
-    // grids keep using the window after run() has returned.)
-    cudaEvent_t win_done[2] = {nullptr, nullptr};
+    // The pool is cut into windows; a plan of the DP engines carves its workspace from ONE window for the time of a run.  Plans come in
+    // two classes -- 0: POA (K5), 1: WFA / edlib (K6, K7) -- and every class has its list of windows (lcd_gpu_init: one window for both;
+    // lcd_gpu_split_pool: one each; lcd_gpu_pool_windows: several each, so that several batches of one engine are in flight together).
+    // Every window orders its own users: the event is recorded behind the last launch that carves from the window and the next run() on
+    // that window -- whatever stream it was given -- waits for it first.  (The mutex only covers the enqueue; the persistent grids keep
+    // using the window after run() has returned.)
+    static constexpr int BITMAP_WORDS = 4096;     // overflow chunks in use (bit set), device memory, one bitmap per window
+    struct Window { size_t off = 0, words = 0; std::mutex mu; cudaEvent_t done = nullptr; uint32_t *bitmap = nullptr; };
+    std::vector<Window*> windows;
+    std::vector<int> cls_win[2];
+    std::atomic<unsigned> rr[2];
+    size_t class_words(int cls) const { return windows[cls_win[cls][0]]->words; }       // windows of a class have one size
+    Window *pick_window(int cls);     // an idle window of the class (its last user's event has fired), else the next one in turn
+    int set_windows(int n0, int n1, size_t lower_words);
+    std::mutex mu;                    // guards the context's own lists (streams, windows)
     size_t requested_pool_bytes = 0;  // what lcd_gpu_init was first called with (0: default)
     std::atomic<unsigned long long> launches{0};
 };
@@ -75,7 +78,8 @@ struct Plan {
     // plans whose kernels carve workspace from the context's pool are serialised by lcd_plan_run; the others (K1, K1b, K2, K3, K4:
     // their buffers are their own) may run from another host thread / stream while a pool plan is in flight
     virtual bool uses_pool() const { return true; }
-    virtual int pool_window() const { return 0; }
+    virtual int pool_window() const { return 0; }       // the plan's class: 0 POA, 1 WFA / edlib
+    Context::Window *win = nullptr;                     // the window lcd_plan_run chose for the current run
     // completes what run() left pending on the stream (default: nothing beyond draining it); called by lcd_plan_sync and the fetches
     virtual int finish(cudaStream_t s) { (void)s; return 0; }       // which window of a split pool the plan's kernels carve from
     int n = 0;

@@ -17,6 +17,33 @@ void set_error(const char *fmt, ...) {
 }
 
 Context &ctx() { static Context c; return c; }
+
+// n0 windows for class 0 in [0, lower_words), n1 for class 1 in the rest; n1 == 0: ONE window over the whole pool for both classes.
+// Called with c.mu held, before any plan runs (the windows of plans in flight would be pulled from under them).
+int Context::set_windows(int n0, int n1, size_t lower_words) {
+    for (Window *w : windows) { if (w->done) cudaEventDestroy(w->done); if (w->bitmap) cudaFree(w->bitmap); delete w; }
+    windows.clear(); cls_win[0].clear(); cls_win[1].clear(); rr[0] = 0; rr[1] = 0;
+    auto add = [&](size_t off, size_t words) -> int {
+        Window *w = new Window(); w->off = off; w->words = words;
+        if (cudaEventCreateWithFlags(&w->done, cudaEventDisableTiming) != cudaSuccess || cudaMalloc((void**)&w->bitmap, sizeof(uint32_t) * BITMAP_WORDS) != cudaSuccess ||
+            cudaMemset(w->bitmap, 0, sizeof(uint32_t) * BITMAP_WORDS) != cudaSuccess) { set_error("pool window: CUDA allocation failed"); delete w; return -1; }
+        windows.push_back(w); return (int)windows.size() - 1;
+    };
+    if (n1 == 0) { const int i = add(0, pool_words); if (i < 0) return -1; cls_win[0].push_back(i); cls_win[1].push_back(i); return 0; }
+    const size_t w0 = (lower_words / n0) & ~(size_t)63, w1 = ((pool_words - lower_words) / n1) & ~(size_t)63;
+    for (int k = 0; k < n0; ++k) { const int i = add((size_t)k * w0, w0); if (i < 0) return -1; cls_win[0].push_back(i); }
+    for (int k = 0; k < n1; ++k) { const int i = add(lower_words + (size_t)k * w1, w1); if (i < 0) return -1; cls_win[1].push_back(i); }
+    return 0;
+}
+Context::Window *Context::pick_window(int cls) {
+    const std::vector<int> &v = cls_win[cls];
+    const unsigned start = rr[cls]++;
+    for (size_t k = 0; k < v.size(); ++k) {
+        Window *w = windows[v[(start + k) % v.size()]];
+        if (cudaEventQuery(w->done) == cudaSuccess) return w;
+    }
+    return windows[v[start % v.size()]];
+}
 cudaStream_t &thread_stream() { static thread_local cudaStream_t s = nullptr; return s; }
 
 void bind_thread() {
@@ -54,15 +81,18 @@ void *lcd_gpu_aux_stream(void) {
     if (!c.aux_stream && cudaStreamCreateWithFlags(&c.aux_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("lcd_gpu_aux_stream: cudaStreamCreate failed"); return nullptr; }
     return (void*)c.aux_stream;
 }
-int lcd_gpu_split_pool(size_t lower_bytes) {
+int lcd_gpu_pool_windows(int n_poa, int n_aln, size_t lower_bytes) {
     Context &c = ctx();
-    if (!c.ready) { set_error("lcd_gpu_split_pool: call lcd_gpu_init first"); return -1; }
-    std::lock_guard<std::mutex> lk(c.mu), lk1(c.mu1);
+    if (!c.ready) { set_error("lcd_gpu_pool_windows: call lcd_gpu_init first"); return -1; }
+    std::lock_guard<std::mutex> lk(c.mu);
     const size_t w = (lower_bytes / 4) & ~(size_t)63;
-    if (lower_bytes && (w < (1u << 20) || w + (1u << 20) > c.pool_words)) { set_error("lcd_gpu_split_pool: %zu bytes do not split a pool of %zu bytes", lower_bytes, c.pool_words * 4); return -1; }
-    c.split_words = w;
-    return 0;
+    if (lower_bytes == 0) return c.set_windows(1, 0, 0);
+    if (n_poa < 1 || n_aln < 1 || n_poa > 64 || n_aln > 64 || w / n_poa < (1u << 20) || w + (size_t)n_aln * (1u << 20) > c.pool_words) {
+        set_error("lcd_gpu_pool_windows: %d + %d windows with %zu bytes below do not fit a pool of %zu bytes", n_poa, n_aln, lower_bytes, c.pool_words * 4); return -1;
+    }
+    return c.set_windows(n_poa, n_aln, w);
 }
+int lcd_gpu_split_pool(size_t lower_bytes) { return lcd_gpu_pool_windows(1, 1, lower_bytes); }
 int lcd_gpu_reserve_sms(int n_sms) {
     Context &c = ctx();
     if (n_sms < 0 || n_sms >= c.sm_count) { set_error("lcd_gpu_reserve_sms: %d out of range", n_sms); return -1; }
@@ -124,9 +154,7 @@ int lcd_gpu_init(int device, size_t pool_bytes) {
     pool_bytes &= ~(size_t)255;
     LCD_CUDA_OK(cudaMalloc((void**)&c.pool, pool_bytes));
     c.pool_words = pool_bytes / 4;
-    LCD_CUDA_OK(cudaMalloc((void**)&c.chunk_bitmap, sizeof(uint32_t) * Context::BITMAP_WORDS));
-    LCD_CUDA_OK(cudaMemset(c.chunk_bitmap, 0, sizeof(uint32_t) * Context::BITMAP_WORDS));
-    for (int k = 0; k < 2; ++k) LCD_CUDA_OK(cudaEventCreateWithFlags(&c.win_done[k], cudaEventDisableTiming));
+    if (c.set_windows(1, 0, 0)) return -1;
     c.ready = true;
     return 0;
 }
@@ -137,14 +165,14 @@ void lcd_gpu_shutdown(void) {
     if (!c.ready) return;
     cudaDeviceSynchronize();
     if (c.pool) cudaFree(c.pool);
-    if (c.chunk_bitmap) cudaFree(c.chunk_bitmap);
+    for (Context::Window *w : c.windows) { if (w->done) cudaEventDestroy(w->done); if (w->bitmap) cudaFree(w->bitmap); delete w; }
+    c.windows.clear(); c.cls_win[0].clear(); c.cls_win[1].clear();
     if (c.stream) cudaStreamDestroy(c.stream);
     if (c.aux_stream) cudaStreamDestroy(c.aux_stream);
-    for (int k = 0; k < 2; ++k) { if (c.win_done[k]) cudaEventDestroy(c.win_done[k]); c.win_done[k] = nullptr; }
     for (cudaStream_t s : c.extra_streams) cudaStreamDestroy(s);
     c.extra_streams.clear();
     c.aux_stream = nullptr;
-    c.pool = nullptr; c.chunk_bitmap = nullptr; c.stream = nullptr; c.ready = false;
+    c.pool = nullptr; c.stream = nullptr; c.ready = false;
 }
 
 int lcd_plan_run(lcd_plan_t *plan, void *stream) {
@@ -153,12 +181,13 @@ int lcd_plan_run(lcd_plan_t *plan, void *stream) {
     Context &c = ctx();
     Plan *p = reinterpret_cast<Plan*>(plan);
     if (!p->uses_pool()) return p->run(pick_stream(stream));
-    const int win = (c.split_words && p->pool_window() == 1) ? 1 : 0;
-    std::lock_guard<std::mutex> lk(win ? c.mu1 : c.mu);
     cudaStream_t s = pick_stream(stream);
-    LCD_CUDA_OK(cudaStreamWaitEvent(s, c.win_done[win], 0));        // the window's previous user, on whatever stream it ran
+    Context::Window *w = c.pick_window(p->pool_window() == 1 ? 1 : 0);
+    std::lock_guard<std::mutex> lk(w->mu);
+    p->win = w;
+    LCD_CUDA_OK(cudaStreamWaitEvent(s, w->done, 0));        // the window's previous user, on whatever stream it ran
     const int rc = p->run(s);
-    LCD_CUDA_OK(cudaEventRecord(c.win_done[win], s));
+    LCD_CUDA_OK(cudaEventRecord(w->done, s));
     return rc;
 }
 

@@ -192,7 +192,7 @@ struct PoaPlan : Plan {
         const int per_cta = kind == 0 ? THREADS_PER_CTA : kind == 1 ? WARPS_PER_CTA : 1;
         const uint64_t avail = pool_hi > pool_lo ? pool_hi - pool_lo : 0;
         const uint64_t fit = avail / words;
-        if (fit == 0) { set_error("lcd_poa: a problem needs %zu MiB of workspace but the pool has %zu MiB", (size_t)(words * 4 >> 20), (size_t)(c.win_words(0) * 4 >> 20)); return -1; }
+        if (fit == 0) { set_error("lcd_poa: a problem needs %zu MiB of workspace but the pool has %zu MiB", (size_t)(words * 4 >> 20), (size_t)(win->words * 4 >> 20)); return -1; }
         int groups = (int)std::min<uint64_t>(std::min<uint64_t>(fit, (uint64_t)max_groups), idx.size());
         int grid = (groups + per_cta - 1) / per_cta;
         if ((uint64_t)grid * per_cta > fit) grid = (int)(fit / per_cta);
@@ -207,7 +207,7 @@ struct PoaPlan : Plan {
         ka.problems = d_problems.p; ka.order = d_idx; ka.n = (int)idx.size(); ka.queue = d_q;
         ka.seqs = d_seqs.p; ka.read_off = d_read_off.p; ka.read_len = d_read_len.p;
         ka.cons = d_cons.p; ka.msa = d_msa.p; ka.msa_cap = msa_pool_bytes; ka.msa_used = d_msa_used.p;
-        ka.results = d_results.p; ka.arena = c.win_pool(0) + pool_lo; ka.arena_words = words; ka.worst_case = worst_case ? 1 : 0;
+        ka.results = d_results.p; ka.arena = c.pool + win->off + pool_lo; ka.arena_words = words; ka.worst_case = worst_case ? 1 : 0;
         static int carve_set = -2;          // shared-memory carve-out of the SMs the persistent grid sits on (see lcd_gpu_reserve_sms)
         if (carve_set == -2) {
             const char *cv = getenv("LCD_POA_CARVEOUT");
@@ -258,11 +258,11 @@ struct PoaPlan : Plan {
             want[k] = (g + per_cta[k] - 1) / per_cta[k] * per_cta[k] * cw[k];       // launches round up to whole CTAs
         }
         uint64_t lo[4]; lo[0] = 0;
-        lo[1] = std::min<uint64_t>(want[0], c.win_words(0) / 2);
-        const uint64_t rest_pool = c.win_words(0) - lo[1];
+        lo[1] = std::min<uint64_t>(want[0], win->words / 2);
+        const uint64_t rest_pool = win->words - lo[1];
         const uint64_t w12 = want[1] + want[2];
         lo[2] = lo[1] + (w12 <= rest_pool ? want[1] : (uint64_t)((double)rest_pool * ((double)want[1] / (double)w12)));
-        lo[3] = c.win_words(0);
+        lo[3] = win->words;
         for (int k = 1; k < 4; ++k) lo[k] &= ~63ull;
         LCD_CUDA_OK(cudaEventRecord(ev_fork, s));
         for (int k = 2; k >= 1; --k) {            // big problems first
@@ -282,7 +282,7 @@ struct PoaPlan : Plan {
     int finish(cudaStream_t s) override {
         if (!pending) return 0;
         Context &c = ctx();
-        std::lock_guard<std::mutex> lk(c.mu);       // a rescue launch carves from the pool window of the POA plans
+        std::lock_guard<std::mutex> lk(win->mu);     // a rescue launch carves from the plan's pool window again
         return finish_locked(s);
     }
 
@@ -299,10 +299,10 @@ struct PoaPlan : Plan {
         for (int32_t i : order_all) if (h_results[i].status == ST_OOM) { rescue.push_back(i); rescue_words = std::max(rescue_words, need_full[i]); }
         n_rescued = (int)rescue.size();
         if (!rescue.empty()) {
-            rescue_words = std::min<uint64_t>((rescue_words + 63) & ~63ull, (c.win_words(0) / WARPS_PER_CTA) & ~63ull);
-            LCD_CUDA_OK(cudaStreamWaitEvent(s, c.win_done[0], 0));
-            if (launch(s, rescue, d_order.p, d_queue.p, rescue_words, c.sm_count * 4, 2, true, 0, c.win_words(0), nullptr)) return -1;
-            LCD_CUDA_OK(cudaEventRecord(c.win_done[0], s));
+            rescue_words = std::min<uint64_t>((rescue_words + 63) & ~63ull, (win->words / WARPS_PER_CTA) & ~63ull);
+            LCD_CUDA_OK(cudaStreamWaitEvent(s, win->done, 0));
+            if (launch(s, rescue, d_order.p, d_queue.p, rescue_words, c.sm_count * 4, 2, true, 0, win->words, nullptr)) return -1;
+            LCD_CUDA_OK(cudaEventRecord(win->done, s));
             LCD_CUDA_OK(cudaStreamSynchronize(s));
         }
         return 0;

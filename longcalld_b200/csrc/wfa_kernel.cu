@@ -196,7 +196,7 @@ struct WfaPlan : Plan {
         int grid_large = (n_large || n_small) ? c.dp_sms() * 2 : 0;
         const int cap_large = std::max(this->cap_large, n_small ? cap_small : 0);
         const size_t groups_small = (size_t)grid_small * WARP_GROUPS_PER_CTA, groups_large = grid_large;
-        const size_t pool_units = c.win_words(1) / 4;
+        const size_t pool_units = win->words / 4;
         const size_t meta_small_units = groups_small * (size_t)cap_small * (sizeof(WfSet) / 16);
         const size_t meta_large_units = groups_large * (size_t)cap_large * (sizeof(WfSet) / 16);
         if (meta_small_units + meta_large_units > pool_units / 2) {
@@ -213,12 +213,12 @@ struct WfaPlan : Plan {
         const size_t n_chunks = std::min<size_t>((rest - arenas) / wfa::OVERFLOW_CHUNK_UNITS, (size_t)Context::BITMAP_WORDS * 32);
         KernelArgs ka;
         ka.problems = d_problems.p; ka.seqs = d_seqs.p; ka.ops = d_ops.p; ka.results = d_results.p;
-        ka.pool = c.win_pool(1); ka.chunk_bitmap = c.chunk_bitmap;
+        ka.pool = c.pool + win->off; ka.chunk_bitmap = win->bitmap;
         ka.overflow_base = (uint32_t)(meta_small_units + meta_large_units + arenas);
         ka.n_chunks = (uint32_t)n_chunks;
         ka.esc_score = 0; ka.esc_list = d_esc_list.p; ka.esc_count = d_queue.p + 3; ka.n_dev = nullptr;
         LCD_CUDA_OK(cudaMemsetAsync(d_queue.p, 0, 4 * sizeof(uint32_t), s));
-        LCD_CUDA_OK(cudaMemsetAsync(c.chunk_bitmap, 0, sizeof(uint32_t) * Context::BITMAP_WORDS, s));
+        LCD_CUDA_OK(cudaMemsetAsync(win->bitmap, 0, sizeof(uint32_t) * Context::BITMAP_WORDS, s));
         static bool attr_set = false;
         if (!attr_set) {
             LCD_CUDA_OK(cudaFuncSetAttribute(wfa_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(32)));
@@ -226,7 +226,7 @@ struct WfaPlan : Plan {
             attr_set = true;
         }
         KernelArgs kl = ka;
-        kl.meta = reinterpret_cast<WfSet *>(c.win_pool(1) + meta_small_units * 4); kl.meta_cap = cap_large;
+        kl.meta = reinterpret_cast<WfSet *>(c.pool + win->off + meta_small_units * 4); kl.meta_cap = cap_large;
         kl.arena_base = (uint32_t)(meta_small_units + meta_large_units + arena_small * groups_small);
         kl.arena_units = (uint32_t)arena_large;
         if (n_large) {             // large problems on the side stream, concurrently with the small ones
@@ -241,7 +241,7 @@ struct WfaPlan : Plan {
         if (grid_small) {
             KernelArgs ks = ka;
             ks.order = d_order_small.p; ks.n = n_small; ks.queue = d_queue.p;
-            ks.meta = reinterpret_cast<WfSet *>(c.win_pool(1)); ks.meta_cap = cap_small;
+            ks.meta = reinterpret_cast<WfSet *>(c.pool + win->off); ks.meta_cap = cap_small;
             ks.arena_base = (uint32_t)(meta_small_units + meta_large_units);
             ks.arena_units = (uint32_t)arena_small;
             ks.esc_score = ESC_SCORE;

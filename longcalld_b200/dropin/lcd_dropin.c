@@ -44,9 +44,22 @@ static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t
 static double t_batch[3], t_blocked, t_fwd_poa;       /* seconds inside the library per engine (leader threads), blocked in the combiner (all threads), in forwarded abPOA */
 static pthread_mutex_t t_mu = PTHREAD_MUTEX_INITIALIZER;
 static void t_add(double *acc, double dt) { pthread_mutex_lock(&t_mu); *acc += dt; pthread_mutex_unlock(&t_mu); }
+/* LCD_DROPIN_TRACE=<file>: a timeline of the worker threads (chunk begin / end, waits in the combiner, engine batches) as TSV */
+typedef struct { double t; unsigned long tid; const char *what; long a, b; } trace_t;
+static trace_t *trace_buf; static size_t trace_n, trace_cap; static int trace_on = -1;
+static void trace(const char *what, long a, long b) {
+    if (trace_on < 0) trace_on = getenv("LCD_DROPIN_TRACE") != NULL;
+    if (!trace_on) return;
+    const double t = now_s();
+    pthread_mutex_lock(&t_mu);
+    if (trace_n == trace_cap) { trace_cap = trace_cap ? 2 * trace_cap : 1 << 16; trace_buf = (trace_t*)realloc(trace_buf, trace_cap * sizeof(trace_t)); }
+    trace_t e = { t, (unsigned long)pthread_self(), what, a, b }; trace_buf[trace_n++] = e;
+    pthread_mutex_unlock(&t_mu);
+}
 static unsigned long n_calls[11];
 #define COUNT(i) __atomic_fetch_add(&n_calls[i], 1, __ATOMIC_RELAXED)      /* the reference's worker threads call in concurrently */
 __attribute__((destructor)) static void report(void) {
+    if (trace_on > 0 && trace_n) { FILE *f = fopen(getenv("LCD_DROPIN_TRACE"), "w"); if (f) { for (size_t i = 0; i < trace_n; ++i) fprintf(f, "%.6f\t%lx\t%s\t%ld\t%ld\n", trace_buf[i].t - trace_buf[0].t, trace_buf[i].tid, trace_buf[i].what, trace_buf[i].a, trace_buf[i].b); fclose(f); } }
     if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: digar %lu (forwarded: %lu), sites %lu, pileup %lu, profile %lu, phase %lu, edlib %lu, wfa %lu, poa %lu (forwarded to abPOA: %lu) in %lu engine batches (library time: poa %.2f s, wfa %.2f s, edlib %.2f s; threads blocked %.2f s in total; forwarded abPOA %.2f s); kernel launches %llu\n",
                                               n_calls[8], n_calls[9], n_calls[10], n_calls[0], n_calls[1], n_calls[2], n_calls[3], n_calls[4], n_calls[5], n_calls[6], n_calls[7], t_batch[0], t_batch[1], t_batch[2], t_blocked, t_fwd_poa, (unsigned long long)lcd_gpu_launch_count());
 }
@@ -425,15 +438,38 @@ typedef struct req_t {
     uint8_t *aln; lcd_edlib_result_t eres;
 } req_t;
 
+static pthread_once_t init_once = PTHREAD_ONCE_INIT;
+#define MAX_INFLIGHT 8
+static int max_inflight = 3;                               /* engine batches on the GPU at the same time, each in its own windows of the workspace pool */
+static void dropin_init(void) {                            /* LCD_DROPIN_DEVICE / _POOL_GB / _INFLIGHT / _RESERVE_SMS: the rank's GPU, the workspace pool, CTA slots left to K1 - K4 */
+    const char *d = getenv("LCD_DROPIN_DEVICE"), *g = getenv("LCD_DROPIN_POOL_GB"), *r = getenv("LCD_DROPIN_RESERVE_SMS"), *f = getenv("LCD_DROPIN_INFLIGHT");
+    const size_t pool = (size_t)(g ? atof(g) : 48.0) << 30;
+    trace("init_begin", 0, 0);
+    if (f) max_inflight = atoi(f) < 1 ? 1 : atoi(f) > MAX_INFLIGHT ? MAX_INFLIGHT : atoi(f);
+    if (lcd_gpu_init(d ? atoi(d) : 0, pool)) die("lcd_gpu_init");
+    /* K5 below, K6 / K7 above: the engines of one batch run side by side, and so do max_inflight batches */
+    if (lcd_gpu_pool_windows(max_inflight, max_inflight, pool / 8 * 5)) die("lcd_gpu_pool_windows");
+    if (lcd_gpu_reserve_sms(r ? atoi(r) : 8)) die("lcd_gpu_reserve_sms");
+    trace("init_end", 0, 0);
+}
+/* CUDA context creation and the pool allocation take 0.8 - 1.9 s (measured on B200: tools/init_probe.py): started when the library is
+ * loaded, on a thread of its own, they overlap the reference's start-up and the first chunks' BAM decoding */
+static void *init_thread(void *a) { (void)a; pthread_once(&init_once, dropin_init); return NULL; }
+__attribute__((constructor)) static void start_init(void) {
+    if (getenv("LCD_DROPIN_LAZY_INIT")) return;
+    pthread_t t; if (pthread_create(&t, NULL, init_thread, NULL) == 0) pthread_detach(t);
+}
+static __thread void *tl_stream = NULL;
 static void *new_thread_stream(void) {                    /* every host thread that calls the library gets a stream of its own */
-    static __thread void *st = NULL;
-    if (!st) { st = lcd_gpu_new_stream(); if (!st) die("lcd_gpu_new_stream"); lcd_gpu_set_thread_stream(st); }
-    return st;
+    pthread_once(&init_once, dropin_init);
+    if (!tl_stream) { tl_stream = lcd_gpu_new_stream(); if (!tl_stream) die("lcd_gpu_new_stream"); lcd_gpu_set_thread_stream(tl_stream); }
+    return tl_stream;
 }
 
 /* one library call over n requests of one kind */
 static void run_batch(int kind, req_t **r, int n) {
     const double t0_ = now_s();
+    trace("batch_begin", kind, n);
     new_thread_stream();
     if (kind == RQ_POA) {
         size_t tot = 0, n_rd = 0, cons_tot = 0, msa_tot = 0;
@@ -450,7 +486,9 @@ static void run_batch(int kind, req_t **r, int n) {
             for (int k = 0; k < r[i]->n_reads; ++k, ++rd) { off[rd] = (int64_t)o + r[i]->read_off[k]; len[rd] = r[i]->read_len[k]; }
             o += r[i]->seqs_len; co += r[i]->seqs_len + 16; mo += (size_t)mcap[i];
         }
+        trace("lib_begin", kind, n);
         const int rc = lcd_poa_batch(n, seqs, tot, first, nr, off, len, (int)n_rd, par, cons, coff, msa, moff, mcap, res);
+        trace("lib_end", kind, n);
         if (rc == -1) die("lcd_poa_batch");                /* -2: some problems were refused on the device (their status says why) */
         for (int i = 0; i < n; ++i) {
             r[i]->pres = res[i]; r[i]->rc = rc;
@@ -475,7 +513,9 @@ static void run_batch(int kind, req_t **r, int n) {
             po[i] = (int64_t)o; pl[i] = r[i]->plen; to[i] = (int64_t)o + r[i]->plen; tl[i] = r[i]->tlen; oo[i] = (int64_t)op; par[i] = r[i]->wpar;
             o += r[i]->seqs_len; op += 2 * r[i]->seqs_len + 16;
         }
+        trace("lib_begin", kind, n);
         if (lcd_wfa_batch(n, seqs, tot, po, pl, to, tl, par, ops, oo, res)) die("lcd_wfa_batch");
+        trace("lib_end", kind, n);
         for (int i = 0; i < n; ++i) { r[i]->wres = res[i]; memcpy(r[i]->ops, ops + oo[i], res[i].n_ops > 0 ? (size_t)res[i].n_ops : 0); }
         free(seqs); free(ops); free(po); free(to); free(oo); free(pl); free(tl); free(par); free(res);
         __atomic_fetch_add(&n_calls[4], (unsigned long)n, __ATOMIC_RELAXED); COUNT(7);
@@ -498,21 +538,37 @@ static void run_batch(int kind, req_t **r, int n) {
         __atomic_fetch_add(&n_calls[3], (unsigned long)n, __ATOMIC_RELAXED); COUNT(7);
     }
     for (int i = 0; i < n; ++i) __atomic_store_n(&r[i]->done, 1, __ATOMIC_RELEASE);
+    trace("batch_end", kind, n);
     t_add(&t_batch[kind], now_s() - t0_);
 }
 
-/* Leader / follower combiner over ALL worker threads (kt_for) and all three engines: a thread that has parked requests adds them to
- * the queue; the first one there becomes the leader and waits until every worker thread that is inside collect_var_main is blocked
- * here too (nobody left who could add work) -- or a bounded linger has passed -- then takes the whole queue and makes one library call
- * per engine; the others sleep until their requests are done.  With t threads on t chunks the batches are t chunks wide. */
-static struct { pthread_mutex_t mu; pthread_cond_t cv; req_t **pend; int n, cap, leader, n_active, n_blocked; } cq = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, 0, 0, 0, 0 };
-static int linger_us(void) { static int v = -1; if (v < 0) { const char *e = getenv("LCD_DROPIN_LINGER_US"); v = e ? atoi(e) : 3000; } return v; }
+/* Group-commit combiner over ALL worker threads (kt_for) and all three engines.  A thread that has parked requests adds them to the
+ * queue; the first one there becomes the leader.  Only ONE batch is in flight at a time: while the batch before is on the GPU the leader
+ * waits and the queue keeps growing (every thread that reaches an engine call meanwhile joins), so the batch size follows the GPU's
+ * round-trip time -- the slower a round, the wider the next one.  Before it goes the leader also gives the worker threads that are inside
+ * collect_var_main but not blocked here yet a bounded moment to arrive.  The three engines of one batch run side by side (K5 in the lower
+ * window of the workspace pool, K6 / K7 in the upper one: lcd_gpu_split_pool).  With more worker threads than cores (-t 64 on 16 cores:
+ * the threads mostly wait for the GPU) the batches are tens of chunks wide. */
+static struct { pthread_mutex_t mu; pthread_cond_t cv; req_t **pend; int n, cap, leader, busy, n_active, n_blocked; } cq = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, 0, 0, 0, 0, 0 };
+static int linger_us(void) { static int v = -1; if (v < 0) { const char *e = getenv("LCD_DROPIN_LINGER_US"); v = e ? atoi(e) : 2000; } return v; }
 static void worker_enter(void) { pthread_mutex_lock(&cq.mu); cq.n_active++; pthread_mutex_unlock(&cq.mu); }
 static void worker_leave(void) { pthread_mutex_lock(&cq.mu); cq.n_active--; pthread_cond_broadcast(&cq.cv); pthread_mutex_unlock(&cq.mu); }
+
+typedef struct { int kind, n, slot; req_t **r; } kind_job_t;
+static struct { int used; void *st[RQ_KINDS]; } slots[MAX_INFLIGHT];          /* a batch in flight: one stream per engine */
+static void run_kind(kind_job_t *j) {
+    void *mine = tl_stream;
+    if (!slots[j->slot].st[j->kind]) { slots[j->slot].st[j->kind] = lcd_gpu_new_stream(); if (!slots[j->slot].st[j->kind]) die("lcd_gpu_new_stream"); }
+    tl_stream = slots[j->slot].st[j->kind]; lcd_gpu_set_thread_stream(tl_stream);
+    run_batch(j->kind, j->r, j->n);
+    tl_stream = mine; lcd_gpu_set_thread_stream(mine);
+}
+static void *kind_thread(void *a) { pthread_once(&init_once, dropin_init); run_kind((kind_job_t*)a); return NULL; }
 
 static void combine(req_t **r, int n) {
     if (n == 0) return;
     const double t0_ = now_s();
+    trace("wait_begin", n, 0);
     pthread_mutex_lock(&cq.mu);
     if (cq.n + n > cq.cap) { cq.cap = 2 * (cq.n + n); cq.pend = (req_t**)realloc(cq.pend, sizeof(req_t*) * cq.cap); }
     memcpy(cq.pend + cq.n, r, sizeof(req_t*) * n); cq.n += n;
@@ -520,16 +576,24 @@ static void combine(req_t **r, int n) {
     pthread_cond_broadcast(&cq.cv);                            /* a lingering leader re-checks whether everybody has arrived */
     if (!cq.leader) {
         cq.leader = 1;
+        while (cq.busy >= max_inflight) pthread_cond_wait(&cq.cv, &cq.mu);     /* group commit: every batch slot is on the GPU */
         struct timespec until; clock_gettime(CLOCK_REALTIME, &until);
         until.tv_nsec += (long)linger_us() * 1000; until.tv_sec += until.tv_nsec / 1000000000; until.tv_nsec %= 1000000000;
         while (cq.n_blocked < cq.n_active) if (pthread_cond_timedwait(&cq.cv, &cq.mu, &until) != 0) break;
         req_t **take = cq.pend; const int nt = cq.n;
-        cq.pend = NULL; cq.n = cq.cap = 0; cq.leader = 0;      /* the next batch may start collecting while this one runs */
+        int slot = 0; while (slots[slot].used) ++slot;
+        slots[slot].used = 1;
+        cq.pend = NULL; cq.n = cq.cap = 0; cq.leader = 0; cq.busy++;        /* the next batch collects while this one runs */
         pthread_mutex_unlock(&cq.mu);
         req_t **byk = (req_t**)malloc(sizeof(req_t*) * nt);
-        for (int k = 0; k < RQ_KINDS; ++k) { int m = 0; for (int i = 0; i < nt; ++i) if (take[i]->kind == k) byk[m++] = take[i]; if (m) run_batch(k, byk, m); }
+        kind_job_t job[RQ_KINDS]; pthread_t th[RQ_KINDS]; int started[RQ_KINDS], m = 0, n_kinds = 0;
+        for (int k = 0; k < RQ_KINDS; ++k) { job[k].kind = k; job[k].slot = slot; job[k].r = byk + m; job[k].n = 0; for (int i = 0; i < nt; ++i) if (take[i]->kind == k) { byk[m++] = take[i]; job[k].n++; } if (job[k].n) n_kinds++; }
+        for (int k = RQ_KINDS - 1; k >= 1; --k) started[k] = job[k].n > 0 && n_kinds > 1 && pthread_create(&th[k], NULL, kind_thread, &job[k]) == 0;
+        if (job[0].n) run_kind(&job[0]);
+        for (int k = 1; k < RQ_KINDS; ++k) { if (started[k]) pthread_join(th[k], NULL); else if (job[k].n) run_kind(&job[k]); }
         free(byk); free(take);
         pthread_mutex_lock(&cq.mu);
+        cq.busy--; slots[slot].used = 0;
         pthread_cond_broadcast(&cq.cv);
     }
     for (;;) {
@@ -540,6 +604,7 @@ static void combine(req_t **r, int n) {
     }
     cq.n_blocked--;
     pthread_mutex_unlock(&cq.mu);
+    trace("wait_end", n, 0);
     t_add(&t_blocked, now_s() - t0_);
 }
 
@@ -615,6 +680,101 @@ int make_vars_from_msa_cons_aln(const call_var_opt_t *opt, bam_chunk_t *chunk, i
     return orig(opt, chunk, n_reads, read_ids, noisy_reg_beg, n_cons, clu_n_seqs, clu_read_ids, aln_strs, noisy_vars, noisy_var_cate, p);
 }
 
+/* ------------------------------------------------------------------------------------------ a13: merge_var_profile, once per pass
+ * The reference folds every region's new variants into the chunk's list as soon as the region is done (merge_var_profile,
+ * src/collect_var.c:1298-1385) and rebuilds the chunk's whole dense read x variant matrix each time (init_read_var_profile: n_reads x
+ * n_vars x 8 bytes allocated and filled per REGION -- a quarter of the reference's CPU time on a 30x HiFi BAM).  Nothing between two merges
+ * of a pass reads the merged state (make_vars_from_msa_cons_aln and the alignment phase work on the region's own arrays), so the regions'
+ * results are queued here and folded in once, after the last region of the pass: the variant lists by the same sequence of two-way merges
+ * (same comparator, same "the earlier one wins" rule for equal variants), the profile by one pass per read over its sources.  The chunk
+ * ends the pass with the same variants, categories, profile values and spans, and read_var_cr as after the reference's region-by-region merges. */
+int exact_comp_cand_var(const call_var_opt_t *opt, cand_var_t *var1, cand_var_t *var2);     /* src/collect_var.c:1255 */
+void free_cand_vars1(cand_var_t *cand_vars);                                                /* :54 */
+void free_read_var_profile(read_var_profile_t *p, int n_reads);                             /* src/bam_utils.c:46 */
+typedef struct { int n; cand_var_t *vars; int *cate; read_var_profile_t *p; int *map; } pend_merge_t;
+static __thread struct { pend_merge_t *v; int n, cap, on; } tl_merge;
+
+int merge_var_profile(const call_var_opt_t *opt, bam_chunk_t *chunk, int n_new_vars, cand_var_t *new_vars, int *new_var_cate, read_var_profile_t *new_p) {
+    if (!tl_merge.on) {
+        static int (*orig)(const call_var_opt_t *, bam_chunk_t *, int, cand_var_t *, int *, read_var_profile_t *) = NULL;
+        if (!orig) orig = (int (*)(const call_var_opt_t *, bam_chunk_t *, int, cand_var_t *, int *, read_var_profile_t *))dlsym(RTLD_NEXT, "merge_var_profile");
+        return orig(opt, chunk, n_new_vars, new_vars, new_var_cate, new_p);
+    }
+    if (n_new_vars <= 0) return 0;
+    if (tl_merge.n == tl_merge.cap) { tl_merge.cap = tl_merge.cap ? 2 * tl_merge.cap : 64; tl_merge.v = (pend_merge_t*)realloc(tl_merge.v, sizeof(pend_merge_t) * tl_merge.cap); }
+    pend_merge_t m = { n_new_vars, new_vars, new_var_cate, new_p, NULL };
+    tl_merge.v[tl_merge.n++] = m;
+    return n_new_vars;
+}
+
+static void flush_merges(const call_var_opt_t *opt, bam_chunk_t *chunk) {
+    const int np = tl_merge.n;
+    if (np == 0) return;
+    const int n_old = chunk->n_cand_vars;
+    int total = n_old;
+    for (int j = 0; j < np; ++j) total += tl_merge.v[j].n;
+    /* the variant list: np two-way merges; (src, idx) of every entry is kept so that the final position of every source variant is known */
+    cand_var_t *cur = (cand_var_t*)malloc(sizeof(cand_var_t) * (total ? total : 1)), *nxt = (cand_var_t*)malloc(sizeof(cand_var_t) * (total ? total : 1));
+    int *ccate = (int*)malloc(sizeof(int) * (total ? total : 1)), *ncate = (int*)malloc(sizeof(int) * (total ? total : 1));
+    int *csrc = (int*)malloc(sizeof(int) * 2 * (total ? total : 1)), *nsrc = (int*)malloc(sizeof(int) * 2 * (total ? total : 1));
+    int nc = n_old;
+    for (int i = 0; i < n_old; ++i) { cur[i] = chunk->cand_vars[i]; ccate[i] = chunk->var_i_to_cate[i]; csrc[2 * i] = -1; csrc[2 * i + 1] = i; }
+    for (int j = 0; j < np; ++j) {
+        pend_merge_t *pm = tl_merge.v + j;
+        int a = 0, b = 0, o = 0;
+#define TAKE_CUR() do { nxt[o] = cur[a]; ncate[o] = ccate[a]; nsrc[2 * o] = csrc[2 * a]; nsrc[2 * o + 1] = csrc[2 * a + 1]; ++o; ++a; } while (0)
+#define TAKE_NEW() do { nxt[o] = pm->vars[b]; ncate[o] = pm->cate[b]; nsrc[2 * o] = j; nsrc[2 * o + 1] = b; ++o; ++b; } while (0)
+        while (a < nc && b < pm->n) {
+            const int ret = exact_comp_cand_var(opt, cur + a, pm->vars + b);
+            if (ret < 0) TAKE_CUR();
+            else if (ret > 0) TAKE_NEW();
+            else { TAKE_CUR(); free_cand_vars1(pm->vars + b); ++b; }          /* equal: the one already in the list stays */
+        }
+        while (a < nc) TAKE_CUR();
+        while (b < pm->n) TAKE_NEW();
+#undef TAKE_CUR
+#undef TAKE_NEW
+        { cand_var_t *t = cur; cur = nxt; nxt = t; int *u = ccate; ccate = ncate; ncate = u; u = csrc; csrc = nsrc; nsrc = u; }
+        nc = o;
+    }
+    int *map_old = (int*)malloc(sizeof(int) * (n_old ? n_old : 1));
+    for (int j = 0; j < np; ++j) { tl_merge.v[j].map = (int*)malloc(sizeof(int) * tl_merge.v[j].n); for (int i = 0; i < tl_merge.v[j].n; ++i) tl_merge.v[j].map[i] = -1; }
+    for (int f = 0; f < nc; ++f) { if (csrc[2 * f] < 0) map_old[csrc[2 * f + 1]] = f; else tl_merge.v[csrc[2 * f]].map[csrc[2 * f + 1]] = f; }
+    /* the profile: per read the hull of its sources' spans in final positions, then every source entry at its final position */
+    read_var_profile_t *old_p = chunk->read_var_profile;
+    read_var_profile_t *mp = init_read_var_profile(chunk->n_reads, total);
+    cgranges_t *cr = cr_init();
+    for (int i = 0; i < chunk->n_reads; ++i) {
+        const int rd = chunk->ordered_read_ids[i];
+        if (chunk->is_skipped[rd]) continue;
+        int lo = INT32_MAX, hi = -1;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int j = -1; j < np; ++j) {
+                const read_var_profile_t *sp = j < 0 ? (old_p ? old_p + rd : NULL) : tl_merge.v[j].p + rd;
+                const int *map = j < 0 ? map_old : tl_merge.v[j].map;
+                if (sp == NULL || sp->start_var_idx < 0 || sp->end_var_idx < sp->start_var_idx) continue;
+                for (int v = sp->start_var_idx; v <= sp->end_var_idx; ++v) {
+                    const int f = map[v];
+                    if (f < 0) continue;
+                    if (pass == 0) { if (f < lo) lo = f; if (f > hi) hi = f; }
+                    else { mp[rd].alleles[f - lo] = sp->alleles[v - sp->start_var_idx]; mp[rd].alt_qi[f - lo] = sp->alt_qi[v - sp->start_var_idx]; }
+                }
+            }
+            if (hi < 0) break;
+            if (pass == 0) { mp[rd].start_var_idx = lo; mp[rd].end_var_idx = hi; }
+        }
+        if (mp[rd].start_var_idx < 0 || mp[rd].end_var_idx < 0) continue;
+        cr_add(cr, "cr", mp[rd].start_var_idx, mp[rd].end_var_idx + 1, rd);
+    }
+    cr_index(cr);
+    if (n_old > 0) free_read_var_profile(old_p, chunk->n_reads);
+    for (int j = 0; j < np; ++j) { free_read_var_profile(tl_merge.v[j].p, chunk->n_reads); free(tl_merge.v[j].vars); free(tl_merge.v[j].cate); free(tl_merge.v[j].map); }
+    free(chunk->var_i_to_cate); free(chunk->cand_vars); cr_destroy(chunk->read_var_cr);
+    chunk->read_var_profile = mp; chunk->cand_vars = cur; chunk->n_cand_vars = nc; chunk->var_i_to_cate = ccate; chunk->read_var_cr = cr;
+    free(nxt); free(ncate); free(csrc); free(nsrc); free(map_old);
+    tl_merge.n = 0;
+}
+
 /* collect_var_main (src/collect_var.c:2897-2981): the same sequence of steps; step 4's inner loop over the pending regions runs them side by side */
 void pre_process_noisy_regs(bam_chunk_t *chunk, call_var_opt_t *opt);                                                       /* src/collect_var.c:557 */
 int classify_cand_vars(bam_chunk_t *chunk, int n_var_sites, const call_var_opt_t *opt);                                     /* :902 */
@@ -624,6 +784,7 @@ void collect_somatic_var(bam_chunk_t *chunk, const call_var_opt_t *opt);        
 void collect_var_main(const call_var_pl_t *pl, bam_chunk_t *chunk) {
     call_var_opt_t *opt = pl->opt;
     new_thread_stream();
+    trace("chunk_begin", (long)chunk->reg_beg, chunk->n_reads);
     collect_digars_from_bam(chunk, pl);                                                                                      /* 1.1 */
     var_site_t *var_sites = NULL;
     const int n_var_sites = collect_all_cand_var_sites(opt, chunk, &var_sites);                                              /* 1.2 */
@@ -642,19 +803,22 @@ void collect_var_main(const call_var_pl_t *pl, bam_chunk_t *chunk) {
         int *pend = (int*)malloc(sizeof(int) * n_regs), *ret = (int*)malloc(sizeof(int) * n_regs);
         /* -s / --refine-aln rewrite the reads' difference lists region by region (update_digars_from_aln_str, src/align.c:1796): one at a time */
         const int one_by_one = opt->out_somatic || (opt->refine_bam && opt->out_aln_fp != NULL) || getenv("LCD_DROPIN_SERIAL") != NULL;
+        trace("regions_begin", (long)chunk->reg_beg, n_regs);
         worker_enter();                                       /* from here on this thread's engine calls are batched with the other threads' */
         for (;;) {
             int new_region_is_done = 0, new_var = 0, np = 0;
             for (int i = 0; i < n_regs; ++i) if (!is_done[sorted[i]]) pend[np++] = sorted[i];
             if (one_by_one) for (int k = 0; k < np; ++k) ret[k] = collect_noisy_vars1(chunk, opt, pend[k]);
-            else if (np > 0) run_regions(chunk, opt, np, pend, ret);
+            else if (np > 0) { tl_merge.on = 1; run_regions(chunk, opt, np, pend, ret); tl_merge.on = 0; flush_merges(opt, chunk); }
             for (int k = 0; k < np; ++k) if (ret[k] >= 0) { is_done[pend[k]] = 1; new_region_is_done = 1; if (ret[k] > 0) new_var = 1; }
             if (new_var) assign_hap_based_on_germline_het_vars_kmeans(opt, chunk, LONGCALLD_CAND_GERMLINE_VAR_CATE);
             if (new_region_is_done == 0) break;
         }
         worker_leave();
+        trace("regions_end", (long)chunk->reg_beg, n_regs);
         free(sorted); free(is_done); free(pend); free(ret);
     }
+    trace("chunk_end", (long)chunk->reg_beg, chunk->n_cand_vars);
     if (opt->out_somatic == 1) collect_somatic_var(chunk, opt);                                                              /* 5 */
 }
 

@@ -25,6 +25,10 @@ const char *lcd_gpu_last_error(void) { return "fake_lcd_gpu (oracle-backed test 
 uint64_t lcd_gpu_launch_count(void) { return n_batches; }
 void *lcd_gpu_new_stream(void) { return (void*)1; }
 void lcd_gpu_set_thread_stream(void *s) { (void)s; }
+int lcd_gpu_init(int device, size_t pool_bytes) { (void)device; (void)pool_bytes; return 0; }
+int lcd_gpu_split_pool(size_t lower_bytes) { (void)lower_bytes; return 0; }
+int lcd_gpu_pool_windows(int a, int b, size_t lower_bytes) { (void)a; (void)b; (void)lower_bytes; return 0; }
+int lcd_gpu_reserve_sms(int n) { (void)n; return 0; }
 
 int lcd_digar_capacity(const lcd_digar_input_t *in, int64_t *digar_cap, int64_t *alt_cap, int64_t *nreg_cap) {
     long long nd = 0, na = 0, ni = 0;
