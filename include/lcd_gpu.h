@@ -185,10 +185,28 @@ int lcd_digar_batch(int n_chunks, const lcd_digar_input_t *in, lcd_digar_output_
  * without =/X ops and without a cs tag, src/collect_var.c:1072-1080): the MD strings go to the device, where the reference's walk over
  * (CIGAR, MD) (:1037-1094) turns them into the =/X CIGARs the kernels consume.  md_off[r] < 0: read r's CIGAR is =/X already.
  * Capacities: lcd_digar_capacity counts an M op as one record; size the outputs for l_qseq more records / alt bases per read instead
- * (or ask lcd_digar_plan_sizes after lcd_plan_run).  cs-tagged and untagged plain-M reads are not implemented on the GPU. */
+ * (or ask lcd_digar_plan_sizes after lcd_plan_run). */
 typedef struct { const int64_t *md_off; const char *md; } lcd_md_tags_t;      /* per chunk: NUL-terminated tag of read r at md + md_off[r] */
 int lcd_digar_md_batch(int n_chunks, const lcd_digar_input_t *in, const lcd_md_tags_t *tags, lcd_digar_output_t *out);
 lcd_plan_t *lcd_digar_md_plan_create(int n_chunks, const lcd_digar_input_t *in, const lcd_md_tags_t *tags);
+/* The general form: every read names the variant the reference's driver would pick for it (src/collect_var.c:1072-1080) --
+ *   LCD_TAG_EQX     its CIGAR has =/X ops                       (collect_digar_from_eqx_cigar, src/bam_utils.c:701)
+ *   LCD_TAG_CS      plain-M CIGAR + cs tag at text + off[r]     (collect_digar_from_cs_tag,   :844; clips from the first / last CIGAR op only,
+ *                   introns not advanced over; the tag's letters must spell the read's own SEQ bases -- else the call fails loudly)
+ *   LCD_TAG_MD      plain-M CIGAR + MD tag at text + off[r]     (collect_digar_from_MD_tag,   :1003)
+ *   LCD_TAG_REFSEQ  plain-M CIGAR, no tag: bases are compared with the chunk's reference window ref_seq = positions ref_beg .. ref_end,
+ *                   1-based inclusive (collect_digar_from_ref_seq, :1176; bases outside the window are passed over as the reference does)
+ * -- and a front end on the device rewrites (CIGAR, tag / reference) into the op stream the difference-list kernels consume. */
+enum { LCD_TAG_EQX = -1, LCD_TAG_MD = 0, LCD_TAG_CS = 1, LCD_TAG_REFSEQ = 2 };
+typedef struct {
+    const int8_t *kind;            /* [n_reads] LCD_TAG_* */
+    const int64_t *off;            /* [n_reads] offset of the read's NUL-terminated tag value in text (LCD_TAG_MD / LCD_TAG_CS), else ignored */
+    const char *text;
+    const char *ref_seq;           /* the chunk's reference window (ASCII), needed when a read is LCD_TAG_REFSEQ */
+    int64_t ref_beg, ref_end;
+} lcd_read_tags_t;
+int lcd_digar_tags_batch(int n_chunks, const lcd_digar_input_t *in, const lcd_read_tags_t *tags, lcd_digar_output_t *out);
+lcd_plan_t *lcd_digar_tags_plan_create(int n_chunks, const lcd_digar_input_t *in, const lcd_read_tags_t *tags);
 lcd_plan_t *lcd_digar_plan_create(int n_chunks, const lcd_digar_input_t *in);
 /* After lcd_plan_run: exact sizes of chunk i's outputs (records, alt bases, per-read intervals; the chunk list needs <= the last). */
 int  lcd_digar_plan_sizes(lcd_plan_t *plan, void *stream, int chunk, int64_t *n_digar, int64_t *n_alt, int64_t *n_nreg);

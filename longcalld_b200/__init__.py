@@ -10,7 +10,7 @@ from .capi import (LcdGpuError, lib, lib_path, build_library, init, shutdown, la
                    HEUR_NONE, HEUR_ADAPTIVE, HEUR_ZDROP,
                    PoaParams, poa_params, PoaPlan, poa_batch, pack_poa,
                    MODE_NW, MODE_SHW, MODE_HW, EdlibPlan, edlib_batch, xgaps,
-                   PhasePlan, phase_batch, PileupPlan, pileup_batch, profile_batch, DigarPlan, digar_batch, digar_md_batch, PileupOnDigarPlan, ProfileOnDigarPlan,
+                   PhasePlan, phase_batch, PileupPlan, pileup_batch, profile_batch, DigarPlan, digar_batch, digar_md_batch, digar_tags_batch, PileupOnDigarPlan, ProfileOnDigarPlan,
                    SitesPlan, sites_batch, PileupOnSitesPlan, ClassifyPlan, classify_batch, ClassifyOnPileupPlan)
 
 __all__ = ["LcdGpuError", "lib", "lib_path", "build_library", "init", "shutdown", "launch_count", "reserve_sms", "split_pool", "stream", "aux_stream", "set_thread_stream",
@@ -18,5 +18,5 @@ __all__ = ["LcdGpuError", "lib", "lib_path", "build_library", "init", "shutdown"
            "HEUR_NONE", "HEUR_ADAPTIVE", "HEUR_ZDROP",
            "PoaParams", "poa_params", "PoaPlan", "poa_batch", "pack_poa",
            "MODE_NW", "MODE_SHW", "MODE_HW", "EdlibPlan", "edlib_batch", "xgaps",
-           "PhasePlan", "phase_batch", "PileupPlan", "pileup_batch", "profile_batch", "DigarPlan", "digar_batch", "digar_md_batch", "PileupOnDigarPlan", "ProfileOnDigarPlan",
+           "PhasePlan", "phase_batch", "PileupPlan", "pileup_batch", "profile_batch", "DigarPlan", "digar_batch", "digar_md_batch", "digar_tags_batch", "PileupOnDigarPlan", "ProfileOnDigarPlan",
            "SitesPlan", "sites_batch", "PileupOnSitesPlan", "ClassifyPlan", "classify_batch", "ClassifyOnPileupPlan"]

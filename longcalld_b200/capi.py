@@ -424,6 +424,35 @@ def digar_md_batch(chunks, tags):
     return _digar_finish(outs, results)
 
 
+class ReadTags(C.Structure):
+    _fields_ = [("kind", C.c_void_p), ("off", C.c_void_p), ("text", C.c_void_p), ("ref_seq", C.c_void_p), ("ref_beg", C.c_int64), ("ref_end", C.c_int64)]
+
+
+TAG_EQX, TAG_MD, TAG_CS, TAG_REFSEQ = -1, 0, 1, 2
+
+
+def digar_tags_batch(chunks, tags):
+    """lcd_digar_tags_batch: every read names the variant of the reference's pass it takes (TAG_EQX / TAG_MD / TAG_CS / TAG_REFSEQ).
+    tags[i] = dict(kind int8 [n_reads], off int64 [n_reads] or None, text uint8 bytes or None, ref_seq uint8 ASCII or None, ref_beg, ref_end)."""
+    ins, keep = _digar_inputs(chunks)
+    sizes = digar_capacity(ins, len(chunks))
+    sizes = [(d + int(np.asarray(c["l_qseq"][:c["n_reads"]]).sum()), a + int(np.asarray(c["l_qseq"][:c["n_reads"]]).sum()), r + int(np.asarray(c["l_qseq"][:c["n_reads"]]).sum()))
+             for (d, a, r), c in zip(sizes, chunks)]                      # an M op expands into up to its length in records
+    outs, results = _digar_outputs(chunks, sizes)
+    tkeep, arr = [], []
+    for t in tags:
+        k = np.ascontiguousarray(t["kind"], np.int8)
+        o = np.ascontiguousarray(t["off"], np.int64) if t.get("off") is not None else None
+        x = np.ascontiguousarray(t["text"], np.uint8) if t.get("text") is not None else None
+        r = np.ascontiguousarray(t["ref_seq"], np.uint8) if t.get("ref_seq") is not None else None
+        tkeep.append((k, o, x, r))
+        arr.append(ReadTags(k.ctypes.data, o.ctypes.data if o is not None else None, x.ctypes.data if x is not None else None, r.ctypes.data if r is not None else None,
+                            int(t.get("ref_beg", 0)), int(t.get("ref_end", -1))))
+    tarr = (ReadTags * max(len(chunks), 1))(*arr)
+    _check(lib().lcd_digar_tags_batch(C.c_int(len(chunks)), ins, tarr, outs), "lcd_digar_tags_batch")
+    return _digar_finish(outs, results)
+
+
 class DigarPlan(_Plan):
     """Inputs (CIGAR words, packed SEQ, QUAL of every chunk) resident in HBM; run() = count + scan + fill + histogram."""
     def __init__(self, chunks):

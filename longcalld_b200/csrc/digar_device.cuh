@@ -25,7 +25,10 @@
 namespace lcd {
 namespace digar {
 
-enum { CMATCH = 0, CINS = 1, CDEL = 2, CREF_SKIP = 3, CSOFT = 4, CHARD = 5, CPAD = 6, CEQUAL = 7, CDIFF = 8 };
+enum { CMATCH = 0, CINS = 1, CDEL = 2, CREF_SKIP = 3, CSOFT = 4, CHARD = 5, CPAD = 6, CEQUAL = 7, CDIFF = 8,
+       // pseudo-ops the tag front end (md_device.cuh) emits for the cs-tag and the no-tag variants of the reference's pass
+       CSKIP = 9,               // bases outside the chunk's reference window: position and query index advance, no record (src/bam_utils.c:1209-1215)
+       CCS_SOFT = 10, CCS_HARD = 11 };   // a clip of a cs-tagged read: a long one counts as a candidate wherever it lies (src/bam_utils.c:876-889, 953-966)
 enum { ST_BAD_OP = 1, ST_OVERFLOW = 2 };
 
 struct __align__(8) Chunk {
@@ -41,6 +44,7 @@ struct KernelArgs {
     const int32_t *read_chunk; const uint8_t *read_active;      // active = listed in ordered_read_ids and not skipped by the loader
     const long long *read_pos0; const uint8_t *read_is_rev, *is_palindrome;
     const int32_t *n_cigar; const long long *cigar_off; const uint32_t *cigar;
+    const long long *rlen;                                       // nullptr, or the reference length of every read's own CIGAR (tag front end: the op stream may differ)
     const int32_t *l_qseq; const long long *seq_off; const uint8_t *bseq; const long long *qual_off; const uint8_t *qual;
     // sizes (count pass) and their exclusive scans
     long long *cnt;                                              // [3][n_reads_total + 1]: records, alt bases, interval capacity
@@ -71,7 +75,7 @@ __device__ void count_read(const KernelArgs &a, long long g) {
             if (op == CDIFF) { nd += len; na += len; n_x += len; }
             else if (op == CINS) { nd++; na += len; n_gap++; }
             else if (op == CDEL) { nd++; n_gap++; }
-            else if (op == CEQUAL || op == CSOFT || op == CHARD) nd++;
+            else if (op == CEQUAL || op == CSOFT || op == CHARD || op == CCS_SOFT || op == CCS_HARD) nd++;
         }
         // a dense window holds an indel or more than max_s X bases of its own; plus the two clip intervals
         ncap = n_gap + n_x / (max_s > 0 ? max_s + 1 : 1) + 2;
@@ -142,7 +146,8 @@ __device__ void fill_read(const KernelArgs &a, long long g) {
     const uint32_t *cg = a.cigar + a.cigar_off[g]; const int nc = a.n_cigar[g];
     const uint8_t *bseq = a.bseq + a.seq_off[g], *qual = a.qual + a.qual_off[g];
     long long pos = a.read_pos0[g] + 1, rlen = 0, qi = 0;
-    for (int k = 0; k < nc; ++k) { const int op = cg[k] & 15; if (op == CMATCH || op == CDEL || op == CREF_SKIP || op == CEQUAL || op == CDIFF) rlen += cg[k] >> 4; }
+    if (a.rlen) rlen = a.rlen[g];
+    else for (int k = 0; k < nc; ++k) { const int op = cg[k] & 15; if (op == CMATCH || op == CDEL || op == CREF_SKIP || op == CEQUAL || op == CDIFF) rlen += cg[k] >> 4; }
     const long long beg = pos, end = a.read_pos0[g] + (rlen ? rlen : 1);              // bam_endpos
     a.read_beg[g] = beg; a.read_end[g] = end;
     long long d = a.first[g], at = a.first[a.stride + g];
@@ -190,7 +195,19 @@ __device__ void fill_read(const KernelArgs &a, long long g) {
                 else if (k != 0 && !right_pal) { if (pos < ch.whole_ref_len && !add_reg(r, pos - 1 - ch.flank_win, pos, 0)) { err = ST_OVERFLOW; break; } ++n_cand; }
             }
             if (op == CSOFT) qi += len;
+        } else if (op == CCS_SOFT || op == CCS_HARD) {                            // cs-tag variant: first / last CIGAR op, src/bam_utils.c:876-889, 953-966
+            const int cop = op == CCS_SOFT ? CSOFT : CHARD;
+            const bool pal = (k == 0 && left_pal) || (k != 0 && right_pal);
+            LCD_PUT(pos, pal ? CHARD : cop, len, 0);
+            ++d;
+            if (len > ch.end_clip_reg && !pal) {
+                if (k == 0) { if (pos > 10 && !add_reg(r, pos - 1, pos + ch.flank_win, 0)) { err = ST_OVERFLOW; break; } }
+                else if (pos < ch.whole_ref_len - 10 && !add_reg(r, pos - 1 - ch.flank_win, pos, 0)) { err = ST_OVERFLOW; break; }
+                ++n_cand;
+            }
+            if (cop == CSOFT) qi += len;
         } else if (op == CREF_SKIP) pos += len;
+        else if (op == CSKIP) { pos += len; qi += len; }
         else if (op == CMATCH) err = ST_BAD_OP;                                   // 'M' is not expected in an =/X CIGAR (:766-768)
     }
 #undef LCD_PUT

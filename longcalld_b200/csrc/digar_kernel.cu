@@ -143,17 +143,19 @@ struct DigarPlan : Plan {
     long long tot_reads = 0, tot_cigar = 0, tot_seq = 0, tot_qual = 0, stride = 1;
     long long tot_digar = -1, tot_alt = 0, tot_ncap = 0;
     DevBuf<Chunk> d_chunks; DevBuf<int32_t> d_read_chunk, d_ncig, d_lq; DevBuf<uint8_t> d_active, d_rev, d_pal, d_bseq, d_qual; DevBuf<uint32_t> d_cigar;
-    DevBuf<long long> d_pos0, d_coff, d_soff, d_qoff, d_cnt, d_first;
+    DevBuf<long long> d_pos0, d_coff, d_soff, d_qoff, d_cnt, d_first, d_rlen;
     DevBuf<uint8_t> d_skip, d_dlow, d_dalt; DevBuf<long long> d_beg, d_end, d_dpos, d_daoff, d_nbeg, d_nend; DevBuf<int8_t> d_dtype;
     DevBuf<int32_t> d_dlen, d_dqi, d_nnreg, d_nlabel, d_status, d_ndig; DevBuf<unsigned long long> d_qc;
     std::vector<long long> h_first; std::vector<int32_t> h_nnreg; bool have_index = false;
 
-    int build(int n_, const lcd_digar_input_t *in, const lcd_md_tags_t *tags = nullptr) {
+    // tags: MD strings only (lcd_digar_md_*); rtags: the general form, a variant per read (lcd_digar_tags_*)
+    int build(int n_, const lcd_digar_input_t *in, const lcd_md_tags_t *tags = nullptr, const lcd_read_tags_t *rtags = nullptr) {
         n = n_;
         Context &c = ctx();
         if (n == 0) return 0;
         std::vector<int32_t> read_chunk, ncig, lq; std::vector<uint8_t> rev, pal; std::vector<long long> pos0, coff, soff, qoff;
         std::vector<long long> cig_base(n), seq_base(n), qual_base(n), cig_n(n), seq_n(n), qual_n(n), md_base(n, 0), md_n(n, 0), md_off; long long tot_md = 0;
+        std::vector<int8_t> kinds; std::vector<long long> ref_off(n, 0), ref_beg(n, 0), ref_end(n, -1), ref_n(n, 0); long long tot_ref = 0;
         chunks.resize(n); read_off.resize(n + 1); reg_beg.resize(n); reg_end.resize(n);
         for (int i = 0; i < n; ++i) {
             const lcd_digar_input_t &x = in[i];
@@ -175,14 +177,26 @@ struct DigarPlan : Plan {
                 nq = std::max<long long>(nq, x.qual_off[r] + x.l_qseq[r]);
             }
             cig_base[i] = tot_cigar; seq_base[i] = tot_seq; qual_base[i] = tot_qual; cig_n[i] = nc; seq_n[i] = ns; qual_n[i] = nq;
-            if (tags) {               // MD tags: NUL-terminated strings in tags[i].md at md_off[r] (< 0: the read's CIGAR is =/X already)
-                long long top = 0;
+            if (tags || rtags) {      // tags: NUL-terminated strings at text + off[r] (< 0: none)
+                long long top = 0; bool need_ref = false;
+                const int64_t *t_off = tags ? tags[i].md_off : rtags[i].off; const char *t_text = tags ? tags[i].md : rtags[i].text;
                 for (int r = 0; r < x.n_reads; ++r) {
-                    const bool act = listed[r] && !x.is_skipped[r]; const long long o = act ? tags[i].md_off[r] : -1;
+                    const bool act = listed[r] && !x.is_skipped[r];
+                    int kind = !act ? md::KIND_EQX : tags ? (t_off[r] < 0 ? md::KIND_EQX : md::KIND_MD) : rtags[i].kind[r];
+                    if (kind < md::KIND_EQX || kind > md::KIND_REFSEQ) { set_error("lcd_digar: chunk %d read %d has an unknown tag kind %d", i, r, kind); return -1; }
+                    const bool has_text = kind == md::KIND_MD || kind == md::KIND_CS;
+                    if (has_text && (!t_off || !t_text || t_off[r] < 0)) { set_error("lcd_digar: chunk %d read %d is tagged but has no tag text", i, r); return -1; }
+                    const long long o = has_text ? t_off[r] : -1;
                     md_off.push_back(o < 0 ? -1 : tot_md + o);
-                    if (o >= 0) top = std::max<long long>(top, o + (long long)strlen(tags[i].md + o) + 1);
+                    if (o >= 0) top = std::max<long long>(top, o + (long long)strlen(t_text + o) + 1);
+                    kinds.push_back((int8_t)kind);
+                    if (kind == md::KIND_REFSEQ) need_ref = true;
                 }
                 md_base[i] = tot_md; md_n[i] = top; tot_md += top;
+                if (need_ref) {
+                    if (!rtags[i].ref_seq || rtags[i].ref_end < rtags[i].ref_beg) { set_error("lcd_digar: chunk %d has untagged plain-M reads but no reference window", i); return -1; }
+                    ref_off[i] = tot_ref; ref_beg[i] = rtags[i].ref_beg; ref_end[i] = rtags[i].ref_end; ref_n[i] = rtags[i].ref_end - rtags[i].ref_beg + 1; tot_ref += (ref_n[i] + 15) & ~15ll;
+                }
             }
             append(ordered, x.ordered_read_ids, x.n_reads);
             append(pos0, x.read_pos0, x.n_reads); append(rev, x.read_is_rev, x.n_reads); append(pal, x.is_palindrome, x.n_reads);
@@ -193,7 +207,7 @@ struct DigarPlan : Plan {
         read_off[n] = tot_reads; stride = tot_reads + 1;
         auto pad = [](auto &v) { v.push_back(0); };
         pad(read_chunk); pad(h_active); pad(pos0); pad(rev); pad(pal); pad(ncig); pad(lq); pad(coff); pad(soff); pad(qoff);
-        if (tags) md_off.push_back(-1);
+        if (tags || rtags) { md_off.push_back(-1); kinds.push_back((int8_t)md::KIND_EQX); }
         cudaStream_t s = cur_stream();
         if (d_chunks.upload(chunks.data(), n, s) || d_read_chunk.upload(read_chunk.data(), read_chunk.size(), s) || d_active.upload(h_active.data(), h_active.size(), s) ||
             d_pos0.upload(pos0.data(), pos0.size(), s) || d_rev.upload(rev.data(), rev.size(), s) || d_pal.upload(pal.data(), pal.size(), s) ||
@@ -210,23 +224,36 @@ struct DigarPlan : Plan {
         if (d_cnt.alloc(3 * stride) || d_first.alloc(3 * stride) || d_skip.alloc(stride) || d_beg.alloc(stride) || d_end.alloc(stride) || d_nnreg.alloc(stride) || d_ndig.alloc(stride) ||
             d_qc.alloc(256 * (size_t)n) || d_status.alloc(1)) return -1;
         LCD_CUDA_OK(cudaStreamSynchronize(s));
-        if (tags && tot_reads && convert_md(s, md_off, tags, md_base, md_n, tot_md)) return -1;
+        if ((tags || rtags) && tot_reads) {
+            std::vector<const char *> text(n), ref(n, nullptr);
+            for (int i = 0; i < n; ++i) { text[i] = tags ? tags[i].md : rtags[i].text; if (rtags && ref_n[i]) ref[i] = rtags[i].ref_seq; }
+            if (convert_md(s, md_off, text, md_base, md_n, tot_md, rtags ? &kinds : nullptr, ref, ref_off, ref_beg, ref_end, ref_n, tot_ref)) return -1;
+        }
         return 0;
     }
 
     // MD-tagged reads: d_cigar / d_coff / d_ncig so far hold the reads' own CIGARs; replace them by the =/X CIGARs of the reference's MD walk
-    int convert_md(cudaStream_t s, const std::vector<long long> &md_off, const lcd_md_tags_t *tags, const std::vector<long long> &md_base,
-                   const std::vector<long long> &md_n, long long tot_md) {
+    // (the same for cs-tagged and untagged plain-M reads: kinds says which walk a read takes)
+    int convert_md(cudaStream_t s, const std::vector<long long> &md_off, const std::vector<const char *> &text, const std::vector<long long> &md_base,
+                   const std::vector<long long> &md_n, long long tot_md, const std::vector<int8_t> *kinds, const std::vector<const char *> &ref,
+                   const std::vector<long long> &ref_off, const std::vector<long long> &ref_beg, const std::vector<long long> &ref_end,
+                   const std::vector<long long> &ref_n, long long tot_ref) {
         Context &c = ctx();
         DevBuf<long long> d_mdoff, d_cnt1, d_first1; DevBuf<char> d_md; DevBuf<uint32_t> d_cig2; DevBuf<long long> d_coff2; DevBuf<int32_t> d_ncig2, d_st;
+        DevBuf<int8_t> d_kind; DevBuf<long long> d_roff, d_rbeg, d_rend; DevBuf<char> d_ref;
+        if (kinds && (d_kind.upload(kinds->data(), kinds->size(), s) || d_roff.upload(ref_off.data(), ref_off.size(), s) || d_rbeg.upload(ref_beg.data(), ref_beg.size(), s) ||
+                      d_rend.upload(ref_end.data(), ref_end.size(), s) || d_ref.alloc(tot_ref + 16))) return -1;
+        if (kinds) for (int i = 0; i < n; ++i) if (ref_n[i]) LCD_CUDA_OK(cudaMemcpyAsync(d_ref.p + ref_off[i], ref[i], (size_t)ref_n[i], cudaMemcpyHostToDevice, s));
         if (d_mdoff.upload(md_off.data(), md_off.size(), s) || d_md.alloc(tot_md + 16) || d_cnt1.alloc(stride) || d_first1.alloc(stride) || d_coff2.alloc(stride) ||
             d_ncig2.alloc(stride) || d_st.alloc(1)) return -1;
         LCD_CUDA_OK(cudaMemsetAsync(d_md.p + tot_md, 0, 16, d_md.st));          // NUL slack behind the last tag: a truncated tag ends the walk, it is never read past
-        for (int i = 0; i < n; ++i) if (md_n[i]) LCD_CUDA_OK(cudaMemcpyAsync(d_md.p + md_base[i], tags[i].md, (size_t)md_n[i], cudaMemcpyHostToDevice, s));
+        for (int i = 0; i < n; ++i) if (md_n[i]) LCD_CUDA_OK(cudaMemcpyAsync(d_md.p + md_base[i], text[i], (size_t)md_n[i], cudaMemcpyHostToDevice, s));
         LCD_CUDA_OK(cudaMemsetAsync(d_st.p, 0, sizeof(int32_t), s));
         md::KernelArgs a; memset(&a, 0, sizeof(a));
         a.n_reads_total = tot_reads; a.read_active = d_active.p; a.n_cigar0 = d_ncig.p; a.cigar_off0 = d_coff.p; a.cigar0 = d_cigar.p; a.md_off = d_mdoff.p; a.md = d_md.p;
         a.cnt = d_cnt1.p; a.first = d_first1.p; a.n_cigar = d_ncig2.p; a.cigar_off = d_coff2.p; a.status = d_st.p;
+        if (kinds) { a.kind = d_kind.p; a.read_chunk = d_read_chunk.p; a.ref_off = d_roff.p; a.ref_beg = d_rbeg.p; a.ref_end = d_rend.p; a.ref = d_ref.p; }
+        a.read_pos0 = d_pos0.p; a.l_qseq = d_lq.p; a.seq_off = d_soff.p; a.bseq = d_bseq.p;
         const int grid = (int)std::min<long long>((tot_reads + THREADS - 1) / THREADS, (long long)c.sm_count * 16);
         md_count_kernel<<<grid, THREADS, 0, s>>>(a);
         digar_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(d_cnt1.p, d_first1.p, tot_reads, stride);
@@ -239,8 +266,11 @@ struct DigarPlan : Plan {
         LCD_CUDA_OK(cudaStreamSynchronize(s));
         if (st == md::MD_MISMATCH) { set_error("lcd_digar: a read's MD tag and CIGAR do not match (the reference stops as well: src/bam_utils.c:1083)"); return -2; }
         if (st == md::MD_EQX_OP) { set_error("lcd_digar: a read with an MD tag has =/X CIGAR ops (the reference stops as well: src/bam_utils.c:1139); pass md_off < 0 for such reads"); return -2; }
-        if (d_cig2.alloc(total + 4)) return -1;
-        a.cigar = d_cig2.p;
+        if (st == md::CS_BAD) { set_error("lcd_digar: a read's cs tag is malformed (the reference stops as well: src/bam_utils.c:949)"); return -2; }
+        if (st == md::CS_SEQ_MISMATCH) { set_error("lcd_digar: a read's cs tag spells bases that differ from its SEQ (the reference takes the alt bases from the tag; such reads are not handled on the GPU)"); return -2; }
+        if (st) { set_error("lcd_digar: tag front end failed with status %d", st); return -2; }
+        if (d_cig2.alloc(total + 4) || d_rlen.alloc(stride)) return -1;
+        a.cigar = d_cig2.p; a.rlen = d_rlen.p;
         md_fill_kernel<<<grid, THREADS, 0, s>>>(a);
         LCD_CUDA_OK(cudaGetLastError());
         c.launches++;
@@ -255,7 +285,7 @@ struct DigarPlan : Plan {
     void args(KernelArgs &a) {
         memset(&a, 0, sizeof(a));
         a.chunks = d_chunks.p; a.n_reads_total = tot_reads; a.read_chunk = d_read_chunk.p; a.read_active = d_active.p;
-        a.read_pos0 = d_pos0.p; a.read_is_rev = d_rev.p; a.is_palindrome = d_pal.p; a.n_cigar = d_ncig.p; a.cigar_off = d_coff.p; a.cigar = d_cigar.p;
+        a.read_pos0 = d_pos0.p; a.read_is_rev = d_rev.p; a.is_palindrome = d_pal.p; a.n_cigar = d_ncig.p; a.cigar_off = d_coff.p; a.cigar = d_cigar.p; a.rlen = d_rlen.p;
         a.l_qseq = d_lq.p; a.seq_off = d_soff.p; a.bseq = d_bseq.p; a.qual_off = d_qoff.p; a.qual = d_qual.p;
         a.cnt = d_cnt.p; a.first = d_first.p; a.stride = stride;
         a.skip = d_skip.p; a.read_beg = d_beg.p; a.read_end = d_end.p; a.n_digar = d_ndig.p;
@@ -467,6 +497,24 @@ lcd_plan_t *lcd_digar_md_plan_create(int n_chunks, const lcd_digar_input_t *in, 
 
 int lcd_digar_md_batch(int n_chunks, const lcd_digar_input_t *in, const lcd_md_tags_t *tags, lcd_digar_output_t *out) {
     lcd_plan_t *plan = lcd_digar_md_plan_create(n_chunks, in, tags);
+    if (!plan) return -1;
+    int rc = lcd_plan_run(plan, nullptr);
+    if (!rc) rc = lcd_digar_plan_fetch(plan, nullptr, out);
+    lcd_plan_destroy(plan);
+    return rc;
+}
+
+lcd_plan_t *lcd_digar_tags_plan_create(int n_chunks, const lcd_digar_input_t *in, const lcd_read_tags_t *tags) {
+    if (ensure_ready()) return nullptr;
+    if (n_chunks < 0 || (n_chunks > 0 && (!in || !tags))) { set_error("lcd_digar_tags_plan_create: invalid arguments"); return nullptr; }
+    for (int i = 0; i < n_chunks; ++i) if (in[i].n_reads > 0 && !tags[i].kind) { set_error("lcd_digar_tags_plan_create: chunk %d has no kind array", i); return nullptr; }
+    digar::DigarPlan *p = new digar::DigarPlan();
+    if (p->build(n_chunks, in, nullptr, tags)) { delete p; return nullptr; }
+    return reinterpret_cast<lcd_plan_t *>(p);
+}
+
+int lcd_digar_tags_batch(int n_chunks, const lcd_digar_input_t *in, const lcd_read_tags_t *tags, lcd_digar_output_t *out) {
+    lcd_plan_t *plan = lcd_digar_tags_plan_create(n_chunks, in, tags);
     if (!plan) return -1;
     int rc = lcd_plan_run(plan, nullptr);
     if (!rc) rc = lcd_digar_plan_fetch(plan, nullptr, out);

@@ -144,22 +144,17 @@ void collect_digars_from_bam(bam_chunk_t *chunk, const struct call_var_pl_t *pl)
     FORWARD_UNLESS_PILEUP_ON_GPU(void, "collect_digars_from_bam", (bam_chunk_t *, const struct call_var_pl_t *), (chunk, pl))
     const call_var_opt_t *opt = pl->opt;
     const int nr = chunk->n_reads;
-    /* the reference picks per read: =/X CIGAR, else cs tag, else MD tag, else the reference sequence (src/collect_var.c:1072-1080); on the
-       GPU: =/X CIGARs and MD tags.  A chunk with a read that would take the cs / reference-sequence path is forwarded whole. */
-    int all_eqx = 1, n_md = 0;
-    for (int i = 0; i < nr && all_eqx >= 0; ++i) {
-        const int r = chunk->ordered_read_ids[i];
+    /* the reference picks per read: =/X CIGAR, else cs tag, else MD tag, else the reference sequence (src/collect_var.c:1072-1080); the
+       library's tag front end takes the same four variants (lcd_digar_tags_batch) */
+    int n_tagged = 0;
+    int8_t *kind = (int8_t*)calloc(nr + 1, 1);
+    for (int r = 0; r < nr; ++r) {
+        kind[r] = LCD_TAG_EQX;
         if (chunk->is_skipped[r] || has_equal_X_in_bam_cigar(chunk->reads[r])) continue;
-        if (!has_cs_in_bam(chunk->reads[r]) && has_MD_in_bam(chunk->reads[r])) { all_eqx = 0; n_md++; }
-        else all_eqx = -1;
+        kind[r] = has_cs_in_bam(chunk->reads[r]) ? LCD_TAG_CS : has_MD_in_bam(chunk->reads[r]) ? LCD_TAG_MD : LCD_TAG_REFSEQ;
+        n_tagged++;
     }
-    if (all_eqx < 0) {           /* cs-tagged / untagged plain-M reads: the reference's own paths */
-        static void (*orig)(bam_chunk_t *, const struct call_var_pl_t *) = NULL;
-        if (!orig) orig = (void (*)(bam_chunk_t *, const struct call_var_pl_t *))dlsym(RTLD_NEXT, "collect_digars_from_bam");
-        COUNT(9);
-        orig(chunk, pl);
-        return;
-    }
+    const int n_md = n_tagged;
     chunk->chunk_noisy_regs = cr_init();
     size_t n_cig = 0, n_seq = 0, n_q = 0;
     for (int r = 0; r < nr; ++r) { const bam1_t *b = chunk->reads[r]; n_cig += b->core.n_cigar; n_seq += ((size_t)b->core.l_qseq + 1) / 2; n_q += b->core.l_qseq; }
@@ -194,20 +189,36 @@ void collect_digars_from_bam(bam_chunk_t *chunk, const struct call_var_pl_t *pl)
     A(qual_counts, int64_t, 256);
 #undef A
     o.digar_cap = dcap; o.alt_cap = acap; o.nreg_cap = ncap; o.cnreg_cap = ncap;
-    if (n_md == 0) { if (lcd_digar_batch(1, &in, &o)) die("lcd_digar_batch"); }
-    else {                       /* MD-tagged reads: the tags go along, the library walks them on the device */
-        int64_t *md_off = (int64_t*)calloc(nr + 1, sizeof(int64_t)); size_t md_len = 1;
+    if (n_tagged == 0) { if (lcd_digar_batch(1, &in, &o)) die("lcd_digar_batch"); }
+    else {                       /* tagged / untagged plain-M reads: tags and the reference window go along, the library walks them on the device */
+        int64_t *t_off = (int64_t*)calloc(nr + 1, sizeof(int64_t)); size_t t_len = 1;
         for (int r = 0; r < nr; ++r) {
-            md_off[r] = -1;
-            if (chunk->is_skipped[r] || has_equal_X_in_bam_cigar(chunk->reads[r])) continue;
-            md_off[r] = (int64_t)md_len; md_len += strlen(bam_aux2Z(bam_aux_get(chunk->reads[r], "MD"))) + 1;
+            t_off[r] = -1;
+            if (kind[r] != LCD_TAG_CS && kind[r] != LCD_TAG_MD) continue;
+            t_off[r] = (int64_t)t_len; t_len += strlen(bam_aux2Z(bam_aux_get(chunk->reads[r], kind[r] == LCD_TAG_CS ? "cs" : "MD"))) + 1;
         }
-        char *md = (char*)calloc(md_len + 1, 1);
-        for (int r = 0; r < nr; ++r) if (md_off[r] >= 0) strcpy(md + md_off[r], bam_aux2Z(bam_aux_get(chunk->reads[r], "MD")));
-        lcd_md_tags_t tags = { md_off, md };
-        if (lcd_digar_md_batch(1, &in, &tags, &o)) die("lcd_digar_md_batch");
-        free(md_off); free(md);
+        char *text = (char*)calloc(t_len + 1, 1);
+        for (int r = 0; r < nr; ++r) if (t_off[r] >= 0) strcpy(text + t_off[r], bam_aux2Z(bam_aux_get(chunk->reads[r], kind[r] == LCD_TAG_CS ? "cs" : "MD")));
+        lcd_read_tags_t tags = { kind, t_off, text, chunk->ref_seq, chunk->ref_beg, chunk->ref_end };
+        const int rc = lcd_digar_tags_batch(1, &in, &tags, &o);
+        free(t_off); free(text);
+        if (rc && strstr(lcd_gpu_last_error(), "differ from its SEQ")) {
+            /* a cs tag that spells other bases than the read's SEQ: the reference takes its alt bases from the tag -- its own path for this chunk */
+            static void (*orig)(bam_chunk_t *, const struct call_var_pl_t *) = NULL;
+            if (!orig) orig = (void (*)(bam_chunk_t *, const struct call_var_pl_t *))dlsym(RTLD_NEXT, "collect_digars_from_bam");
+            free(pos0); free(coff); free(soff); free(qoff); free(rev); free(pal); free(bseq); free(qual); free(ncig); free(lq); free(cig); free(kind);
+            free(o.skip); free(o.read_beg); free(o.read_end); free(o.digar_first); free(o.n_digar); free(o.digar_pos); free(o.digar_type); free(o.digar_len); free(o.digar_qi);
+            free(o.digar_low_qual); free(o.digar_alt_off); free(o.digar_alt); free(o.nreg_first); free(o.n_nreg); free(o.nreg_beg); free(o.nreg_end); free(o.nreg_label);
+            free(o.cnreg_beg); free(o.cnreg_end); free(o.cnreg_label); free(o.qual_counts);
+            cr_destroy(chunk->chunk_noisy_regs);
+            memset(chunk->is_ont_palindrome, 0, nr);
+            COUNT(9);
+            orig(chunk, pl);
+            return;
+        }
+        if (rc) die("lcd_digar_tags_batch");
     }
+    free(kind);
     COUNT(8);
     for (int i = 0; i < nr; ++i) {
         const int r = chunk->ordered_read_ids[i];

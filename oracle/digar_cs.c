@@ -57,7 +57,12 @@ void lcd_oracle_cr_order(int n, const int32_t *start, const int32_t *label, int3
 
 static int nt4(char c) { switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; } }
 
-int lcd_oracle_collect_digar_cs(const lcd_digar_input_t *in, const int64_t *cs_off, const char *cs_all, lcd_digar_output_t *out) {
+/* mode 1: the cs-tag variant; mode 2: the no-tag variant, collect_digar_from_ref_seq (src/bam_utils.c:1176-1290) -- every base of an M / = / X op
+ * against the chunk's reference window ref_seq = positions ref_beg .. ref_end; a base outside the window is passed over without a record and
+ * without closing the running match (:1209-1215), whose record is placed by counting back from where it ends (:1219, :1236); clips as in the
+ * =/X variant (any op, :1264-1282). */
+static int collect_tagged(int mode, const lcd_digar_input_t *in, const int64_t *cs_off, const char *cs_all, const char *ref_seq, int64_t ref_beg, int64_t ref_end,
+                          lcd_digar_output_t *out) {
     int64_t dtop = 0, atop = 0, rtop = 0;
     out->n_cnreg = 0;
     memset(out->qual_counts, 0, sizeof(int64_t) * 256);
@@ -81,9 +86,56 @@ int lcd_oracle_collect_digar_cs(const lcd_digar_input_t *in, const int64_t *cs_o
         int n_cand = 0, rc = 0;
 #define PUSH_DIGAR(p_, t_, l_, q_, low_) do { if (dtop >= out->digar_cap) { rc = -3; goto done; } out->digar_pos[dtop] = (p_); out->digar_type[dtop] = (int8_t)(t_); \
             out->digar_len[dtop] = (l_); out->digar_qi[dtop] = (q_); out->digar_low_qual[dtop] = (uint8_t)(low_); out->digar_alt_off[dtop] = atop; dtop++; } while (0)
-        const char *cs = cs_all + cs_off[r];
-        if (nc <= 0) { rc = -2; goto done; }
-        {   /* left-end clipping: the first CIGAR op only (:876-889) */
+        const char *cs = mode == 1 ? cs_all + cs_off[r] : "";
+        if (mode == 2) {
+            const uint8_t *bs = in->bseq + in->seq_off[r];
+            for (int k = 0; k < nc; ++k) {
+                const int op = cigar[k] & 15, len = (int)(cigar[k] >> 4);
+                if (op == CMATCH || op == CDIFF || op == CEQUAL) {
+                    int eq_len = 0;
+                    for (int j = 0; j < len; ++j) {
+                        if (pos < ref_beg || pos > ref_end) { pos++; qi++; continue; }
+                        const int ref_base = nt4(ref_seq[pos - ref_beg]);
+                        const int c = (bs[qi >> 1] >> ((~qi & 1) << 2)) & 15;
+                        const int read_base = c == 1 ? 0 : c == 2 ? 1 : c == 4 ? 2 : c == 8 ? 3 : 4;
+                        if (ref_base != read_base) {
+                            if (eq_len > 0) { PUSH_DIGAR(pos - eq_len, CEQUAL, eq_len, qi - eq_len, 0); eq_len = 0; }
+                            const int low = !(qual[qi] >= in->min_bq);
+                            if (!low && push_win(&q, pos, 1, 1, in->noisy_reg_slide_win, in->noisy_reg_max_xgaps, &g)) { rc = -4; goto done; }
+                            PUSH_DIGAR(pos, CDIFF, 1, qi, low);
+                            if (atop >= out->alt_cap) { rc = -3; goto done; }
+                            out->digar_alt[atop++] = (uint8_t)read_base;
+                            n_cand++;
+                        } else eq_len++;
+                        pos++; qi++;
+                    }
+                    if (eq_len > 0) PUSH_DIGAR(pos - eq_len, CEQUAL, eq_len, qi - eq_len, 0);
+                } else if (op == CDEL) {
+                    const int ok = (qi == 0 || qual[qi - 1] >= in->min_bq) && qual[qi] >= in->min_bq;
+                    if (ok && push_win(&q, pos, len, len, in->noisy_reg_slide_win, in->noisy_reg_max_xgaps, &g)) { rc = -4; goto done; }
+                    PUSH_DIGAR(pos, CDEL, len, qi, !ok);
+                    n_cand++; pos += len;
+                } else if (op == CINS) {
+                    int low = 1;
+                    for (int j = 0; j < len; ++j) if (qual[qi + j] >= in->min_bq) { low = 0; break; }
+                    if (!low && push_win(&q, pos, 0, len, in->noisy_reg_slide_win, in->noisy_reg_max_xgaps, &g)) { rc = -4; goto done; }
+                    PUSH_DIGAR(pos, CINS, len, qi, low);
+                    if (atop + len > out->alt_cap) { rc = -3; goto done; }
+                    for (int j = 0; j < len; ++j) { const int c = (bs[(qi + j) >> 1] >> ((~(qi + j) & 1) << 2)) & 15; out->digar_alt[atop++] = (uint8_t)(c == 1 ? 0 : c == 2 ? 1 : c == 4 ? 2 : c == 8 ? 3 : 4); }
+                    n_cand++; qi += len;
+                } else if (op == CSOFT || op == CHARD) {
+                    const int pal = (k == 0 && left_pal) || (k != 0 && right_pal);
+                    PUSH_DIGAR(pos, pal ? CHARD : op, len, qi, 0);
+                    if (((k == 0 && pos > 10) || (k != 0 && pos < in->whole_ref_len - 10)) && len > in->end_clip_reg) {
+                        if (k == 0 && !left_pal) { if (pos > 1 && add_reg(&g, pos - 1, pos + in->end_clip_reg_flank_win, 0)) { rc = -4; goto done; } n_cand++; }
+                        else if (k != 0 && !right_pal) { if (pos < in->whole_ref_len && add_reg(&g, pos - 1 - in->end_clip_reg_flank_win, pos, 0)) { rc = -4; goto done; } n_cand++; }
+                    }
+                    if (op == CSOFT) qi += len;
+                } else if (op == CREF_SKIP) pos += len;
+            }
+        }
+        if (mode == 1 && nc <= 0) { rc = -2; goto done; }
+        if (mode == 1) {   /* left-end clipping: the first CIGAR op only (:876-889) */
             const int op = cigar[0] & 15, len = (int)(cigar[0] >> 4);
             if (op == CSOFT || op == CHARD) {
                 PUSH_DIGAR(pos, left_pal ? CHARD : op, len, qi, 0);
@@ -127,7 +179,7 @@ int lcd_oracle_collect_digar_cs(const lcd_digar_input_t *in, const int64_t *cs_o
                 while (isalpha((unsigned char)*cs) || isdigit((unsigned char)*cs)) cs++;
             } else { rc = -2; goto done; }
         }
-        {   /* right-end clipping: the last CIGAR op only (:953-966) */
+        if (mode == 1) {   /* right-end clipping: the last CIGAR op only (:953-966) */
             const int op = cigar[nc - 1] & 15, len = (int)(cigar[nc - 1] >> 4);
             if (op == CSOFT || op == CHARD) {
                 PUSH_DIGAR(pos, right_pal ? CHARD : op, len, qi, 0);
@@ -173,4 +225,11 @@ done:
     }
     out->n_digar_total = dtop; out->n_alt_total = atop; out->n_nreg_total = rtop;
     return 0;
+}
+
+int lcd_oracle_collect_digar_cs(const lcd_digar_input_t *in, const int64_t *cs_off, const char *cs_all, lcd_digar_output_t *out) {
+    return collect_tagged(1, in, cs_off, cs_all, NULL, 0, -1, out);
+}
+int lcd_oracle_collect_digar_refseq(const lcd_digar_input_t *in, const char *ref_seq, int64_t ref_beg, int64_t ref_end, lcd_digar_output_t *out) {
+    return collect_tagged(2, in, NULL, NULL, ref_seq, ref_beg, ref_end, out);
 }

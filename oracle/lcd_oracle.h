@@ -174,6 +174,7 @@ int lcd_oracle_collect_digar_eqx(const lcd_digar_input_t *in, lcd_digar_output_t
 /* (CIGAR with M, MD tag) -> the equivalent =/X CIGAR, as collect_digar_from_MD_tag walks them (src/bam_utils.c:1037-1094); oracle/md.c */
 /* the cs-tag variant (src/bam_utils.c:844-1001): read r's tag is the NUL-terminated string at cs + cs_off[r]; oracle/digar_cs.c */
 int lcd_oracle_collect_digar_cs(const lcd_digar_input_t *in, const int64_t *cs_off, const char *cs, lcd_digar_output_t *out);
+int lcd_oracle_collect_digar_refseq(const lcd_digar_input_t *in, const char *ref_seq, int64_t ref_beg, int64_t ref_end, lcd_digar_output_t *out);
 int64_t lcd_oracle_md_to_eqx(int n_cigar, const uint32_t *cigar, const char *md, uint32_t *out, int64_t cap);
 
 /* ---- pileup scan, step 1.2: sorted unique candidate sites (src/collect_var.c:1209-1254) ---------------------------- */

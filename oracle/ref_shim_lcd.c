@@ -399,6 +399,19 @@ int ref_collect_digar_md(const lcd_digar_input_t *in, const int64_t *md_off, con
     return ref_digar_finish(job, in, out);
 }
 
+/* collect_digar_from_ref_seq (src/bam_utils.c:1176-1290) on the same synthetic chunk: plain-M reads without tags against the reference window */
+int ref_collect_digar_refseq(const lcd_digar_input_t *in, const char *ref_seq, int64_t ref_beg, int64_t ref_end, lcd_digar_output_t *out) {
+    ref_digar_job_t *job = (ref_digar_job_t*)ref_digar_prepare(in);
+    if (!job) return -9;
+    job->chunk.ref_seq = (char*)ref_seq; job->chunk.ref_beg = ref_beg; job->chunk.ref_end = ref_end;
+    for (int i = 0; i < in->n_reads; ++i) {
+        const int r = in->ordered_read_ids[i];
+        if (in->is_skipped[r]) continue;
+        job->ret[r] = collect_digar_from_ref_seq(&job->chunk, r, &job->opt, job->chunk.digars + r) < 0;
+    }
+    return ref_digar_finish(job, in, out);
+}
+
 /* collect_digar_from_cs_tag (src/bam_utils.c:844-1001) on the same synthetic chunk: every read gets a cs tag (cs + cs_off[r], NUL terminated) */
 int ref_collect_digar_cs(const lcd_digar_input_t *in, const int64_t *cs_off, const char *cs, lcd_digar_output_t *out) {
     ref_digar_job_t *job = (ref_digar_job_t*)ref_digar_prepare(in);

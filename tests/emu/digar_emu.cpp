@@ -8,6 +8,7 @@
 using namespace lcd::digar;
 extern "C" void lcd_oracle_cr_order(int n, const int32_t *start, const int32_t *label, int32_t *order_out);   // cgranges order (> 64 intervals)
 
+static const long long *g_rlen = nullptr;       // set by emu_collect_digar_tags: the reads' own reference lengths
 extern "C" int emu_collect_digar_eqx(const lcd_digar_input_t *in, lcd_digar_output_t *out) {
     const long long nr = in->n_reads, stride = nr + 1;
     Chunk c; memset(&c, 0, sizeof(c));
@@ -23,7 +24,7 @@ extern "C" int emu_collect_digar_eqx(const lcd_digar_input_t *in, lcd_digar_outp
     KernelArgs a; memset(&a, 0, sizeof(a));
     a.chunks = &c; a.n_reads_total = nr; a.read_chunk = read_chunk.data(); a.read_active = active.data();
     a.read_pos0 = (const long long *)in->read_pos0; a.read_is_rev = in->read_is_rev; a.is_palindrome = in->is_palindrome;
-    a.n_cigar = in->n_cigar; a.cigar_off = (const long long *)in->cigar_off; a.cigar = in->cigar;
+    a.n_cigar = in->n_cigar; a.cigar_off = (const long long *)in->cigar_off; a.cigar = in->cigar; a.rlen = g_rlen;
     a.l_qseq = in->l_qseq; a.seq_off = (const long long *)in->seq_off; a.bseq = in->bseq; a.qual_off = (const long long *)in->qual_off; a.qual = qual;
     std::vector<int32_t> ndig(nr + 1, 0); a.n_digar = ndig.data();
     a.cnt = cnt.data(); a.first = first.data(); a.stride = stride; a.qual_counts = qc.data(); a.status = &status;
@@ -68,5 +69,36 @@ extern "C" int emu_collect_digar_eqx(const lcd_digar_input_t *in, lcd_digar_outp
     }
     out->n_digar_total = nd; out->n_alt_total = na; out->n_nreg_total = top;
     free(qual);
+    return rc;
+}
+
+// The tag front end (md_device.cuh: count, scan, fill, thread per read) followed by the pass above: what lcd_digar_tags_batch runs.
+// kind / off / text as in lcd_read_tags_t; returns -20 - status when the front end rejects a read.
+#include "../../longcalld_b200/csrc/md_device.cuh"
+extern "C" int emu_collect_digar_tags(const lcd_digar_input_t *in, const int8_t *kind, const int64_t *off, const char *text, const char *ref, int64_t ref_beg, int64_t ref_end,
+                                      lcd_digar_output_t *out) {
+    namespace M = lcd::md;
+    const long long nr = in->n_reads;
+    std::vector<uint8_t> active(nr + 1, 0);
+    for (int i = 0; i < nr; ++i) { const int r = in->ordered_read_ids[i]; if (!in->is_skipped[r]) active[r] = 1; }
+    std::vector<long long> cnt(nr + 2, 0), first(nr + 2, 0), coff(nr + 1, 0), toff(nr + 1, -1); std::vector<int32_t> ncig(nr + 1, 0), read_chunk(nr + 1, 0); int32_t status = 0;
+    for (long long r = 0; r < nr; ++r) toff[r] = (kind[r] == M::KIND_MD || kind[r] == M::KIND_CS) ? off[r] : -1;
+    long long roff = 0, rb = ref_beg, re = ref_end;
+    M::KernelArgs a; memset(&a, 0, sizeof(a));
+    a.n_reads_total = nr; a.read_active = active.data(); a.n_cigar0 = in->n_cigar; a.cigar_off0 = (const long long *)in->cigar_off; a.cigar0 = in->cigar;
+    a.md_off = toff.data(); a.md = text; a.kind = kind; a.read_chunk = read_chunk.data(); a.ref_off = &roff; a.ref_beg = &rb; a.ref_end = &re; a.ref = ref;
+    a.read_pos0 = (const long long *)in->read_pos0; a.l_qseq = in->l_qseq; a.seq_off = (const long long *)in->seq_off; a.bseq = in->bseq;
+    a.cnt = cnt.data(); a.first = first.data(); a.n_cigar = ncig.data(); a.cigar_off = coff.data(); a.status = &status;
+    for (long long g = 0; g < nr; ++g) M::count_read(a, g);
+    if (status) return -20 - status;
+    long long run = 0; for (long long g = 0; g <= nr; ++g) { first[g] = run; run += g < nr ? cnt[g] : 0; }
+    std::vector<uint32_t> cig(run + 4, 0); a.cigar = cig.data();
+    std::vector<long long> rlen(nr + 1, 0); a.rlen = rlen.data();
+    for (long long g = 0; g < nr; ++g) M::fill_read(a, g);
+    lcd_digar_input_t x = *in;
+    x.cigar = cig.data(); x.cigar_off = (const int64_t *)coff.data(); x.n_cigar = ncig.data();
+    g_rlen = rlen.data();
+    const int rc = emu_collect_digar_eqx(&x, out);
+    g_rlen = nullptr;
     return rc;
 }

@@ -70,6 +70,26 @@ int lcd_digar_md_batch(int n, const lcd_digar_input_t *in, const lcd_md_tags_t *
     }
     return 0;
 }
+int lcd_oracle_collect_digar_cs(const lcd_digar_input_t *in, const int64_t *cs_off, const char *cs, lcd_digar_output_t *out);
+int lcd_oracle_collect_digar_refseq(const lcd_digar_input_t *in, const char *ref_seq, int64_t ref_beg, int64_t ref_end, lcd_digar_output_t *out);
+int lcd_digar_tags_batch(int n, const lcd_digar_input_t *in, const lcd_read_tags_t *tags, lcd_digar_output_t *out) {
+    /* the double answers chunks whose tagged reads are all of one variant (what the bundled data holds); =/X and MD reads may mix */
+    for (int i = 0; i < n; ++i) {
+        int n_cs = 0, n_ref = 0, n_other = 0;
+        for (int k = 0; k < in[i].n_reads; ++k) { const int r = in[i].ordered_read_ids[k]; if (in[i].is_skipped[r]) continue; if (tags[i].kind[r] == LCD_TAG_CS) n_cs++; else if (tags[i].kind[r] == LCD_TAG_REFSEQ) n_ref++; else n_other++; }
+        if (n_cs && !n_ref && !n_other) { __atomic_fetch_add(&n_batches, 1, __ATOMIC_RELAXED); if (lcd_oracle_collect_digar_cs(in + i, tags[i].off, tags[i].text, out + i)) return -1; }
+        else if (n_ref && !n_cs && !n_other) { __atomic_fetch_add(&n_batches, 1, __ATOMIC_RELAXED); if (lcd_oracle_collect_digar_refseq(in + i, tags[i].ref_seq, tags[i].ref_beg, tags[i].ref_end, out + i)) return -1; }
+        else if (!n_cs && !n_ref) {
+            int64_t *mo = (int64_t*)malloc(sizeof(int64_t) * (in[i].n_reads + 1));
+            for (int r = 0; r < in[i].n_reads; ++r) mo[r] = tags[i].kind[r] == LCD_TAG_MD ? tags[i].off[r] : -1;
+            lcd_md_tags_t t = { mo, tags[i].text };
+            const int rc = lcd_digar_md_batch(1, in + i, &t, out + i);
+            free(mo);
+            if (rc) return -1;
+        } else return -1;
+    }
+    return 0;
+}
 int lcd_sites_batch(int n, const lcd_pileup_input_t *in, const lcd_sites_params_t *par, lcd_sites_output_t *out) {
     __atomic_fetch_add(&n_batches, 1, __ATOMIC_RELAXED);
     for (int i = 0; i < n; ++i) { lcd_pileup_input_t x = in[i]; x.min_sv_len = par[i].min_sv_len; if (lcd_oracle_collect_sites(&x, par[i].reg_beg, par[i].reg_end, out + i)) return -1; }

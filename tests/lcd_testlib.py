@@ -325,11 +325,12 @@ def digar_input(d):
     return inp, keep
 
 
-def collect_digar(lib, fn, d, mid_args=(), cap_like=None):
+def collect_digar(lib, fn, d, mid_args=(), cap_like=None, slack=0):
     """Run an implementation of the =/X difference-list pass -> dict with per-read records (in read-id order, layout independent).
     mid_args: extra ctypes arguments between the input and the output struct (the MD-tag shim takes the tags there)."""
     inp, keep = digar_input(d)
     nr = d["n_reads"]; dc, ac, rc_ = digar_capacity(cap_like if cap_like is not None else d)        # (cap_like: a chunk whose CIGARs size the outputs)
+    dc += slack; ac += slack; rc_ += slack
     size = {"r": nr + 1, "d": dc, "a": ac}
     buf = {k: np.full(size[w], 77, t) for k, t, w in DIGAR_OUT_FIELDS}
     nf, nn = np.zeros(nr + 1, np.int64), np.zeros(nr + 1, np.int32)

@@ -53,3 +53,23 @@ def test_serial_regions_give_the_same_vcf(dropin_cpu):
     """LCD_DROPIN_SERIAL=1 runs the regions one after the other (every engine call a batch of one): same records."""
     md5, line = run(dropin_cpu, "hifi", 2, {"LCD_DROPIN_SERIAL": "1"})
     assert md5 == GOLDEN["hifi"], line
+
+
+@pytest.mark.parametrize("style", ["m", "md", "cs"])
+def test_every_cigar_flavour_through_the_binding(dropin_cpu, style, tmp_path):
+    """Plain-M reads without tags / with MD tags / with cs tags (tools/synth_bam.c): the binding hands every read's variant to lcd_digar_tags_batch
+    (the double answers with the oracle's restatements of the reference's three other passes); same VCF as the unmodified reference, no chunk forwarded."""
+    synth = os.path.join(T.ROOT, "tools", "_build", "synth_bam")
+    if not os.path.exists(synth):
+        pytest.skip("tools/_build/synth_bam was not built")
+    prefix = str(tmp_path / f"s_{style}")
+    subprocess.check_call([synth, prefix, "0.6", "hifi", "11", "30", "1", "0", style], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    body = lambda out: hashlib.md5(b"".join(l + b"\n" for l in out.split(b"\n") if l and not l.startswith(b"#"))).hexdigest()
+    cmd = ["call", "--hifi", prefix + ".fa", prefix + ".bam", "-t", "4"]
+    want = subprocess.run([os.path.join(REF_DIR, "longcallD_ref")] + cmd, capture_output=True, timeout=900)
+    got = subprocess.run([os.path.join(REF_DIR, "longcallD_so")] + cmd, capture_output=True, timeout=900, env=dict(os.environ, LD_PRELOAD=dropin_cpu, LCD_DROPIN_VERBOSE="1"))
+    assert want.returncode == 0 and got.returncode == 0, got.stderr.decode()[-2000:]
+    line = [l for l in got.stderr.decode().splitlines() if "[lcd_dropin] GPU calls" in l][-1]
+    m = re.search(r"digar (\d+) \(forwarded: (\d+)\)", line)
+    assert int(m.group(1)) > 0 and int(m.group(2)) == 0, line
+    assert body(got.stdout) == body(want.stdout) and want.stdout.count(b"\n") > 300, line

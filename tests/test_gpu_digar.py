@@ -137,3 +137,33 @@ def test_gpu_md_tagged_reads(gpu, oracle):
     e2 = dict(e, is_skipped=np.zeros_like(e["is_skipped"]))
     with pytest.raises(gpu.LcdGpuError, match="MD tag and CIGAR do not match"):
         gpu.digar_md_batch([e2], [(md_off, bad)])
+
+
+def test_gpu_cs_tagged_and_untagged_reads(gpu, oracle):
+    """The two other variants of the reference's driver (src/collect_var.c:1072-1080) through lcd_digar_tags_batch: plain-M reads with a cs tag
+    (collect_digar_from_cs_tag) and without any tag (collect_digar_from_ref_seq, bases against the chunk's reference window, reads hanging over
+    its ends included), one batch with both kinds of chunks, against the oracle restatements that tests/test_oracle_digar_cs.py and
+    tests/test_oracle_digar_refseq.py pin to the unmodified reference.  A cs tag whose letters differ from SEQ is refused."""
+    from test_oracle_digar_cs import to_cs
+    from test_oracle_digar_refseq import to_refseq, refseq_args
+    import ctypes as C
+    from longcalld_b200.capi import TAG_CS, TAG_REFSEQ
+    rng = np.random.default_rng(113)
+    cases = list(digar_cases(115, 80))
+    chunks, tags, want = [], [], []
+    for n, d in enumerate(cases):
+        if n % 2 == 0:
+            e, off, cs = to_cs(d, rng)
+            chunks.append(e); tags.append(dict(kind=np.full(e["n_reads"] + 1, TAG_CS, np.int8), off=off, text=cs))
+            want.append(T.collect_digar(oracle, "lcd_oracle_collect_digar_cs", e, mid_args=(off.ctypes.data_as(C.c_void_p), cs.ctypes.data_as(C.c_void_p)), cap_like=d, slack=64))
+        else:
+            e, ref, rb, re_ = to_refseq(d, rng, trim=n % 3 != 0)
+            chunks.append(e); tags.append(dict(kind=np.full(e["n_reads"] + 1, TAG_REFSEQ, np.int8), ref_seq=ref, ref_beg=rb, ref_end=re_))
+            want.append(T.collect_digar(oracle, "lcd_oracle_collect_digar_refseq", e, mid_args=refseq_args(ref, rb, re_), cap_like=d, slack=2000))
+    res = gpu.digar_tags_batch(chunks, tags)
+    for i, (e, o, w) in enumerate(zip(chunks, res, want)):
+        same(view(e, o), w, i)
+    e, off, cs = to_cs(cases[0], rng)
+    bad = cs.copy(); i = [k for k in range(len(bad) - 2) if bad[k] == ord("*")][0]; bad[i + 2] = ord("a") if bad[i + 2] != ord("a") else ord("c")
+    with pytest.raises(gpu.LcdGpuError, match="differ from its SEQ"):
+        gpu.digar_tags_batch([dict(e, is_skipped=np.zeros_like(e["is_skipped"]))], [dict(kind=np.full(e["n_reads"] + 1, TAG_CS, np.int8), off=off, text=bad)])

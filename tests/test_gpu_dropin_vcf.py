@@ -53,3 +53,26 @@ def test_vcf_identical_with_gpu_dropin(tech):
     assert fwd_poa == FORWARDED_POA[tech], calls[-1]
     print(calls[-1])
     assert md5 == GOLDEN[tech], (md5, calls[-1])
+
+
+@pytest.mark.parametrize("style", ["m", "md", "cs"])
+def test_vcf_identical_for_every_cigar_flavour(style, tmp_path):
+    """The reference picks one of four difference-list variants per read (src/collect_var.c:1072-1080).  A synthetic 1 Mb HiFi BAM whose reads carry
+    plain-M CIGARs without tags / with MD tags / with cs tags (tools/synth_bam.c) goes through the unmodified reference and through the GPU drop-in
+    (K1's tag front end on the device): same VCF body, no chunk forwarded to the reference's own pass."""
+    synth = os.path.join(T.ROOT, "tools", "_build", "synth_bam")
+    exe, ref_exe = os.path.join(REF_DIR, "longcallD_so"), os.path.join(REF_DIR, "longcallD_ref")
+    if not all(os.path.exists(p) for p in (synth, exe, ref_exe, DROPIN)):
+        pytest.skip("tools/_build/synth_bam, oracle/_ref or the drop-in were not built in this checkout")
+    prefix = str(tmp_path / f"s_{style}")
+    subprocess.check_call([synth, prefix, "1", "hifi", "11", "30", "1", "0", style], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    body = lambda out: hashlib.md5(b"".join(l + b"\n" for l in out.split(b"\n") if l and not l.startswith(b"#"))).hexdigest()
+    want = subprocess.run([ref_exe, "call", "--hifi", prefix + ".fa", prefix + ".bam", "-t", "4"], capture_output=True, timeout=900)
+    assert want.returncode == 0
+    got = subprocess.run([exe, "call", "--hifi", prefix + ".fa", prefix + ".bam", "-t", "4"], capture_output=True, timeout=900,
+                         env=dict(os.environ, LD_PRELOAD=DROPIN, LCD_DROPIN_VERBOSE="1", LCD_DROPIN_STAGES="all"))
+    assert got.returncode == 0, got.stderr.decode()[-2000:]
+    line = [l for l in got.stderr.decode().splitlines() if "[lcd_dropin] GPU calls" in l][-1]
+    m = __import__("re").search(r"digar (\d+) \(forwarded: (\d+)\)", line)
+    assert int(m.group(1)) > 0 and int(m.group(2)) == 0, line
+    assert body(got.stdout) == body(want.stdout) and want.stdout.count(b"\n") > 500, line

@@ -1,8 +1,10 @@
 /* tools/synth_bam.c -- MEASUREMENT INFRASTRUCTURE: synthetic long-read BAM + FASTA of the shape BASELINE.json names
  * (SURVEY.md section 8d), so that `longcallD call` itself -- the unmodified reference and the GPU build -- can be timed on the same input.
  *
- *   synth_bam <out_prefix> <ref_mb> <hifi|ont> [seed=11] [coverage=30] [n_contigs=1] [mosaic=0]
- *     -> <out_prefix>.fa (+ .fai), <out_prefix>.bam (+ .bai): coordinate-sorted, MAPQ 60, true alignments with =/X CIGARs + NM
+ *   synth_bam <out_prefix> <ref_mb> <hifi|ont> [seed=11] [coverage=30] [n_contigs=1] [mosaic=0] [style=eqx|m|md|cs]
+ *     -> <out_prefix>.fa (+ .fai), <out_prefix>.bam (+ .bai): coordinate-sorted, MAPQ 60, true alignments + NM; style picks which of the
+ *        reference's four difference-list variants the reads take (src/collect_var.c:1072-1080): =/X CIGARs (default), plain-M CIGARs
+ *        without tags (bases are compared with the reference), plain-M + MD tag, plain-M + cs tag (short form)
  *
  * reference : uniform ACGT; a homopolymer (6-30 bp) every ~0.8 kb; an STR / VNTR (unit 2-60 bp x 3-40 copies) every ~6 kb
  * diploid   : SNPs 1 / 1 000 bp (2/3 het), small indels 1 / 3 000 bp (70 % as copy-number changes of the planted repeats), SV insertions /
@@ -40,10 +42,12 @@ static char *rand_seq(int n) { char *s = (char*)malloc(n + 1); for (int i = 0; i
 typedef struct { int64_t pos; int unit, copies; } rep_t;
 
 int main(int argc, char **argv) {
-    if (argc < 4) { fprintf(stderr, "usage: synth_bam <out_prefix> <ref_mb> <hifi|ont> [seed] [coverage] [n_contigs] [mosaic]\n"); return 1; }
+    if (argc < 4) { fprintf(stderr, "usage: synth_bam <out_prefix> <ref_mb> <hifi|ont> [seed] [coverage] [n_contigs] [mosaic] [eqx|m|md|cs]\n"); return 1; }
     const char *prefix = argv[1]; const double ref_mb = atof(argv[2]); const int ont = strcmp(argv[3], "ont") == 0;
     const uint64_t seed = argc > 4 ? strtoull(argv[4], 0, 10) : 11; const double cov = argc > 5 ? atof(argv[5]) : 30.0;
     const int n_ctg = argc > 6 ? atoi(argv[6]) : 1, mosaic = argc > 7 ? atoi(argv[7]) : 0;
+    const int style = argc > 8 ? (strcmp(argv[8], "m") == 0 ? 1 : strcmp(argv[8], "md") == 0 ? 2 : strcmp(argv[8], "cs") == 0 ? 3 : 0) : 0;
+    kstring_t md = { 0, 0, NULL }, cs = { 0, 0, NULL }; uint32_t *mcig = NULL; size_t n_mcig = 0, m_mcig = 0;
     rs ^= seed * 0x9E3779B97F4A7C15ull; for (int i = 0; i < 8; ++i) rnd();
     const int64_t L = (int64_t)(ref_mb * 1e6 / n_ctg);
     char fn[4096];
@@ -150,8 +154,33 @@ int main(int argc, char **argv) {
             if (n_cig == 0 || seq.l == 0) continue;
             { const int op = cig[n_cig - 1] & 15; if (op == BAM_CDEL) n_cig--; }                  /* an alignment does not end in a deletion */
             char name[64]; snprintf(name, sizeof(name), "r%d_%llu", ctg + 1, (unsigned long long)n_reads);
-            if (bam_set1(b, strlen(name), name, (rnd() & 1) ? BAM_FREVERSE : 0, ctg, s, 60, n_cig, cig, -1, -1, 0, seq.l, seq.s, qual.s, 16) < 0) return 1;
+            const uint32_t *wcig = cig; size_t n_wcig = n_cig;
+            if (style) {                   /* the same alignment as a plain-M CIGAR, with its MD and (short-form) cs strings */
+                md.l = cs.l = 0; n_mcig = 0;
+                int64_t rp = s; size_t qi = 0; long md_run = 0, cs_run = 0; uint32_t m = 0;
+#define MPUSH(op, ln) do { if (n_mcig == m_mcig) { m_mcig = m_mcig ? 2 * m_mcig : 1024; mcig = (uint32_t*)realloc(mcig, m_mcig * 4); } mcig[n_mcig++] = ((uint32_t)(ln) << 4) | (op); } while (0)
+#define MFLUSH() do { if (m) { MPUSH(BAM_CMATCH, m); m = 0; } } while (0)
+#define CSFLUSH() do { if (cs_run) { ksprintf(&cs, ":%ld", cs_run); cs_run = 0; } } while (0)
+                for (size_t k = 0; k < n_cig; ++k) {
+                    const int op = cig[k] & 15; const uint32_t ln = cig[k] >> 4;
+                    if (op == BAM_CEQUAL) { m += ln; md_run += ln; cs_run += ln; rp += ln; qi += ln; }
+                    else if (op == BAM_CDIFF) {
+                        for (uint32_t j = 0; j < ln; ++j) { ksprintf(&md, "%ld%c", md_run, ref[rp]); md_run = 0; CSFLUSH(); ksprintf(&cs, "*%c%c", ref[rp] | 0x20, seq.s[qi] | 0x20); ++rp; ++qi; }
+                        m += ln;
+                    } else if (op == BAM_CINS) { MFLUSH(); MPUSH(BAM_CINS, ln); CSFLUSH(); kputc('+', &cs); for (uint32_t j = 0; j < ln; ++j) kputc(seq.s[qi + j] | 0x20, &cs); qi += ln; }
+                    else if (op == BAM_CDEL) {
+                        MFLUSH(); MPUSH(BAM_CDEL, ln); ksprintf(&md, "%ld^", md_run); md_run = 0; CSFLUSH(); kputc('-', &cs);
+                        for (uint32_t j = 0; j < ln; ++j) { kputc(ref[rp + j], &md); kputc(ref[rp + j] | 0x20, &cs); }
+                        rp += ln;
+                    } else { MFLUSH(); MPUSH(op, ln); if (op == BAM_CSOFT_CLIP) qi += ln; }
+                }
+                MFLUSH(); CSFLUSH(); ksprintf(&md, "%ld", md_run);
+                wcig = mcig; n_wcig = n_mcig;
+            }
+            if (bam_set1(b, strlen(name), name, (rnd() & 1) ? BAM_FREVERSE : 0, ctg, s, 60, n_wcig, wcig, -1, -1, 0, seq.l, seq.s, qual.s, 16 + (style == 2 ? md.l + 8 : 0) + (style == 3 ? cs.l + 8 : 0)) < 0) return 1;
             bam_aux_update_int(b, "NM", nm);
+            if (style == 2 && bam_aux_append(b, "MD", 'Z', (int)md.l + 1, (const uint8_t*)md.s) < 0) return 1;
+            if (style == 3 && bam_aux_append(b, "cs", 'Z', (int)cs.l + 1, (const uint8_t*)cs.s) < 0) return 1;
             if (sam_write1(out, hdr, b) < 0) return 1;
             n_reads++; n_bases += seq.l;
         }
