@@ -406,7 +406,7 @@ typedef struct {
 } lcd_poa_params_t;
 
 enum { LCD_POA_OK = 0, LCD_POA_NEEDS_INT32 = -1, LCD_POA_BAND = -2, LCD_POA_BACKTRACK = -3,
-       LCD_POA_NO_BASE = -4, LCD_POA_OOM = -5, LCD_POA_MSA_CAP = -6 };
+       LCD_POA_NO_BASE = -4, LCD_POA_OOM = -5, LCD_POA_MSA_CAP = -6, LCD_POA_BAD_ANCHORS = -7, LCD_POA_SUB_UNSUPPORTED = -8 };
 typedef struct {
     int32_t status;                /* LCD_POA_* */
     int32_t cons_len;              /* abc->cons_len[0] */
@@ -432,6 +432,26 @@ lcd_plan_t *lcd_poa_plan_create(int n, const uint8_t *seqs, size_t seqs_len,
 int  lcd_poa_plan_fetch(lcd_plan_t *plan, void *stream, uint8_t *cons, const int64_t *cons_off,
                         uint8_t *msa, const int64_t *msa_off, const int64_t *msa_cap,
                         lcd_poa_result_t *results);
+
+/* Partially covering reads (abpoa_partial_aln_msa_cons, src/align.c:790-812): read r > 0 of a problem is aligned against the SUB-GRAPH
+ * abpoa_subgraph_nodes (abPOA/src/abpoa_graph.c:666) finds between two nodes of the first read -- sub_beg[r] = ref_beg + 1 and
+ * sub_end[r] = ref_end + 1, with ref_beg / ref_end the 1-based positions in the first read that collect_partial_aln_beg_end
+ * (src/align.c:709) returns, and the read passed here already cut to [read_beg, read_end] -- or against the whole graph (both 0), or is
+ * left out of the graph (sub_beg[r] < 0: its MSA row stays empty).  sub_beg / sub_end are indexed like read_off / read_len; both NULL is
+ * lcd_poa_batch.  The device keeps abPOA's BFS node index for such problems (the sub-graph and the nodes a read spans are index ranges). */
+int lcd_poa_sub_batch(int n, const uint8_t *seqs, size_t seqs_len,
+                      const int32_t *first_read, const int32_t *n_reads,
+                      const int64_t *read_off, const int32_t *read_len, int n_total_reads,
+                      const int32_t *sub_beg, const int32_t *sub_end,
+                      const lcd_poa_params_t *params,
+                      uint8_t *cons, const int64_t *cons_off,
+                      uint8_t *msa, const int64_t *msa_off, const int64_t *msa_cap,
+                      lcd_poa_result_t *results);
+lcd_plan_t *lcd_poa_sub_plan_create(int n, const uint8_t *seqs, size_t seqs_len,
+                                    const int32_t *first_read, const int32_t *n_reads,
+                                    const int64_t *read_off, const int32_t *read_len, int n_total_reads,
+                                    const int32_t *sub_beg, const int32_t *sub_end,
+                                    const lcd_poa_params_t *params);
 
 #ifdef __cplusplus
 }

@@ -921,12 +921,15 @@ class PoaPlan(_Plan):
         return res, cons, cons_off, msa, msa_off
 
 
-def poa_batch(problems, params, want_msa=True):
-    """Drop-in batch call over HOST buffers (lcd_poa_batch).  -> [(status, consensus bytes, msa (n+1, msa_len))]"""
+def poa_batch(problems, params, want_msa=True, sub=None):
+    """Drop-in batch call over HOST buffers (lcd_poa_batch; lcd_poa_sub_batch when sub = [(sub_beg, sub_end) per problem] names the reads that
+    cover their region only partially).  -> [(status, consensus bytes, msa (n+1, msa_len))]"""
     n = len(problems)
     if n == 0:
         return []
     seqs, first, n_reads, read_off, read_len = pack_poa(problems)
+    sb = np.ascontiguousarray(np.concatenate([np.asarray(b, np.int32) for b, _ in sub])) if sub is not None else None
+    se = np.ascontiguousarray(np.concatenate([np.asarray(e, np.int32) for _, e in sub])) if sub is not None else None
     par = _poa_params_array(params, n)
     sum_len = np.add.reduceat(read_len.astype(np.int64), first)
     max_len = np.maximum.reduceat(read_len, first).astype(np.int64)
@@ -938,12 +941,15 @@ def poa_batch(problems, params, want_msa=True):
     cons = np.zeros(max(int(cons_off[-1]), 1), dtype=np.uint8)
     msa = np.zeros(max(int(msa_off[-1]), 1), dtype=np.uint8) if want_msa else None
     res = np.zeros(n, dtype=POA_RESULT_DTYPE)
-    rc = lib().lcd_poa_batch(C.c_int(n), _ptr(seqs, C.c_uint8), C.c_size_t(seqs.size), _ptr(first, C.c_int32),
-                             _ptr(n_reads, C.c_int32), _ptr(read_off, C.c_int64), _ptr(read_len, C.c_int32),
-                             C.c_int(len(read_len)), par.ctypes.data_as(C.c_void_p),
-                             _ptr(cons, C.c_uint8), _ptr(cons_off, C.c_int64),
-                             _ptr(msa, C.c_uint8) if want_msa else None, _ptr(msa_off, C.c_int64) if want_msa else None,
-                             _ptr(msa_cap, C.c_int64) if want_msa else None, res.ctypes.data_as(C.c_void_p))
+    tail = (par.ctypes.data_as(C.c_void_p), _ptr(cons, C.c_uint8), _ptr(cons_off, C.c_int64),
+            _ptr(msa, C.c_uint8) if want_msa else None, _ptr(msa_off, C.c_int64) if want_msa else None,
+            _ptr(msa_cap, C.c_int64) if want_msa else None, res.ctypes.data_as(C.c_void_p))
+    head = (C.c_int(n), _ptr(seqs, C.c_uint8), C.c_size_t(seqs.size), _ptr(first, C.c_int32), _ptr(n_reads, C.c_int32), _ptr(read_off, C.c_int64),
+            _ptr(read_len, C.c_int32), C.c_int(len(read_len)))
+    if sub is None:
+        rc = lib().lcd_poa_batch(*head, *tail)
+    else:
+        rc = lib().lcd_poa_sub_batch(*head, _ptr(sb, C.c_int32), _ptr(se, C.c_int32), *tail)
     _check(rc, "lcd_poa_batch")
     out = []
     for i in range(n):

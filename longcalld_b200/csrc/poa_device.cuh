@@ -38,7 +38,8 @@ constexpr int LOGN = 5;
 constexpr int POA_SMEM_HALFS = 2 * 3 * 8 * 32;   // per-warp shared memory (int16): two row buffers x 3 planes x NVC vectors
 constexpr int GARBAGE = 0x5555;        // what a read of a never-written DP cell returns (never decisive)
 
-enum { ST_OK = 0, ST_INT32 = -1, ST_BAND = -2, ST_BACKTRACK = -3, ST_NOBASE = -4, ST_OOM = -5 };
+enum { ST_OK = 0, ST_INT32 = -1, ST_BAND = -2, ST_BACKTRACK = -3, ST_NOBASE = -4, ST_OOM = -5,
+       ST_SUBGRAPH = -7, ST_SUB_UNSUPPORTED = -8 };      // bad anchors of a partially covering read / sub-graph alignment asked of a kernel variant without it
 
 struct __align__(16) Problem {
     uint64_t seq_base;        // byte offset of the first read in the packed sequence buffer
@@ -86,6 +87,9 @@ struct KernelArgs {
     int32_t *arena;               // per-group arenas
     uint64_t arena_words;         // int32 words per group
     int32_t worst_case;           // 1: ignore Problem.node_cap / edge_cap, size for the worst case
+    // partially covering reads (nullptr: none): read r is aligned against the sub-graph between the nodes sub_beg[r] and sub_end[r] of the
+    // first read (abpoa_subgraph_nodes; both 0: the whole graph), or left out (sub_beg[r] < 0).  Indexed like read_off / read_len.
+    const int32_t *sub_beg, *sub_end;
 };
 
 // per-group workspace carved from the arena for one problem
@@ -256,6 +260,10 @@ template <class L> struct Poa {
     // back from HBM/L2 (~250 cycles) is the critical path of the whole DP.  nullptr = disabled.
     int16_t *row_cache = nullptr;
     static constexpr int NVC = 8;
+    // the (sub-)graph the current read is aligned against: first / last node, rows of the order taken, and the in-edge lists as the alignment
+    // sees them (a sub-graph alignment sees only predecessors inside the sub-graph: prepare_sub)
+    int beg_id = 0, end_id = 1, n_rows = 0; bool sub = false;
+    const int4 *ai_pool = nullptr; const int *ai_off = nullptr, *ai_n = nullptr;
     // scratch of a multi-warp group (shared memory): F carries of the row's vectors + row-max partials
     int *gs = nullptr;
     static constexpr int MAXV = 512, GS_INTS = 2 * MAXV + 4 + 3 * 32;
@@ -454,8 +462,8 @@ template <class L> struct Poa {
         for (int q = lane; q < qlen; q += 32) path[q] = -1;
         int best = inf_min, bi = 0, bj = 0;
         {
-            const int4 *ie = w.in_pool + w.in_off[1];
-            for (int k = 0; k < w.in_n[1]; ++k) {
+            const int4 *ie = ai_pool + ai_off[end_id];
+            for (int k = 0; k < ai_n[end_id]; ++k) {
                 const int r = ie[k].x;
                 const Row rr = unpack(w.rinfo[r]);
                 const int e = qlen > rr.end ? rr.end : qlen;
@@ -467,7 +475,7 @@ template <class L> struct Poa {
         enum { M_OP = 1, E1_OP = 2, E2_OP = 4, E_OP = 6, F1_OP = 8, F2_OP = 16, F_OP = 24, ALL_OP = 31 };
         int id = bi, j = bj, cur_op = ALL_OP, rc = 0;
         Row cur = unpack(w.rinfo[id]);
-        while (id != 0 && j > 0) {
+        while (id != beg_id && j > 0) {
             if (cur_op == ALL_OP) {
                 const int pos = w.pos[id];
                 int ok = 0, nl = -1, pl = -1;
@@ -495,8 +503,8 @@ template <class L> struct Poa {
             }
             const int nb = w.base[id], qb = query[j - 1];
             const int s = (nb > 3 || qb > 3) ? 0 : (nb == qb ? par.match : -par.mismatch);
-            const int4 *ie = w.in_pool + w.in_off[id];
-            const int nin = w.in_n[id];
+            const int4 *ie = ai_pool + ai_off[id];
+            const int nin = ai_n[id];
             const int hj = cell(cur, 0, j);
             int hit = 0;
             for (int pass = 0; pass < 2 && !hit; ++pass) {
@@ -615,7 +623,7 @@ template <class L> struct Poa {
         if (seq_l <= 0) return;
         int *tgt = path + ((seq_l + 3) & ~3), *heads = w.s1;
         if (lane == 0) { w.tmp[8] = w.in_top; w.tmp[9] = w.out_top; w.tmp[1] = 0; }
-        int n_new = 0, n_heads = 0, last_exist = 0, prev_t = 0, prev_node = 0;   // carries across 32-base chunks
+        int n_new = 0, n_heads = 0, last_exist = beg_id, prev_t = beg_id, prev_node = beg_id;   // carries across 32-base chunks
         for (int base = 0; base < seq_l; base += 32) {
             const int q = base + lane;
             const bool in = q < seq_l;
@@ -674,7 +682,7 @@ template <class L> struct Poa {
                 int at;
                 if (node >= 0) { at = node; add_aligned(node, h); }
                 else {
-                    const int last = q > 0 ? tgt[q - 1] : 0;
+                    const int last = q > 0 ? tgt[q - 1] : beg_id;
                     at = last;
                     for (;;) {                                               // end of the aligned column of `last`
                         const int nx = w.next[at];
@@ -692,9 +700,9 @@ template <class L> struct Poa {
         __syncwarp();
         // 3. edges
         for (int q = lane; q <= seq_l; q += 32) {
-            const int from = q == 0 ? 0 : tgt[q - 1], to = q == seq_l ? 1 : tgt[q];
+            const int from = q == 0 ? beg_id : tgt[q - 1], to = q == seq_l ? end_id : tgt[q];
             const int check = (q > 0 && from >= n0) ? 0 : 1;
-            const int add = (first_read || q == seq_l) ? 1 : ((from != 0 || inc) ? 1 : 0);
+            const int add = (first_read || q == seq_l) ? 1 : ((from != beg_id || inc) ? 1 : 0);
             add_edge_par(from, to, check, add, read_id);
         }
         __syncwarp();
@@ -707,9 +715,104 @@ template <class L> struct Poa {
     // per-node exchange sort of the edge lists, out-weight sums, edge path scores (abpoa_get_incre_path_score
     // :429-437), n_span; then the flattened topological order and the heaviest-path remain values
     // (abpoa_BFS_set_node_remain :268-309) by pointer jumping over the list / heaviest-successor links.
-    __device__ void after_add(int first_read) {
+    // abpoa_BFS_set_node_index (abpoa_graph.c:221-266), single lane: Kahn's order with a FIFO queue, a node entering only together with the
+    // nodes aligned to it, over the out-edge lists as they stand BEFORE this round's edge sort.  Needed only by problems with partially
+    // covering reads: the sub-graph of such a read and the nodes it spans are defined by ranges of this index.  The queue is the
+    // index -> node table (w.maxr), w.maxl the node -> index table; both live until the next call.
+    __device__ void bfs_index() {
+        const int n = w.n_nodes;
+        int *deg = w.msa_rank, *q = w.maxr, *idx = w.maxl;
+        for (int i = 0; i < n; ++i) { deg[i] = w.in_n[i]; idx[i] = -1; }
+        int qh = 0, qt = 0;
+        q[qt++] = 0;
+        while (qh < qt) {
+            const int cur = q[qh]; idx[cur] = qh; ++qh;
+            if (cur == 1) break;
+            for (int i = 0; i < w.out_n[cur]; ++i) {
+                const int out = out_entry(cur, i)[0];
+                if (--deg[out] == 0) {
+                    bool ok = true;
+                    for (int j = 0; j < w.aln_n[out]; ++j) if (deg[w.aln_pool[w.aln_off[out] + j]] != 0) { ok = false; break; }
+                    if (!ok) continue;
+                    q[qt++] = out;
+                    for (int j = 0; j < w.aln_n[out]; ++j) q[qt++] = w.aln_pool[w.aln_off[out] + j];
+                }
+            }
+        }
+    }
+
+    // The sub-graph a partially covering read is aligned against (abpoa_subgraph_nodes, abpoa_graph.c:595-680, on the BFS index of the last
+    // bfs_index()) and the alignment's view of it; single lane.  inc_beg / inc_end: the two anchor nodes (bases of the first read).
+    //   * exc_beg / exc_end: the nodes at the outermost index reached by in-edges on the left / out-edges on the right of the anchors' range
+    //   * rows: the nodes of that index range that can be reached from exc_beg (index_map, abpoa_align_simd.c:1259-1269), kept in the
+    //     order of the topological list (w.order / w.meta / w.pos are compacted in place; after_add rebuilds them after the read)
+    //   * in-edges: only predecessors inside the sub-graph, compacted; the k-th one carries the path score of the node's k-th in-edge
+    //     OVERALL, as the reference computes it (abpoa_get_incre_path_score is called with the index into the restricted list)
+    // Results in w.tmp[2..5]: exc_beg, exc_end, rows, cells of the DP arena taken by the compacted lists (its top end).
+    __device__ int prepare_sub(int inc_beg, int inc_end) {
+        const int n = w.n_nodes;
+        const int *idx = w.maxl, *at = w.maxr;
+        if (inc_beg < 2 || inc_end < 2 || inc_beg >= n || inc_end >= n || idx[inc_beg] < 0 || idx[inc_end] < 0 || idx[inc_beg] > idx[inc_end]) return ST_SUBGRAPH;
+        auto full_up = [&](int up, int down, int b, int e) {
+            const int mn = up < b ? up : b, mx = down > e ? down : e;
+            for (int i = up + 1; i <= down; ++i) {
+                const int id = at[i]; const int4 *ie = w.in_pool + w.in_off[id];
+                for (int j = 0; j < w.in_n[id]; ++j) { const int x = idx[ie[j].x]; if (x < mn || x > mx) return false; }
+            }
+            return true;
+        };
+        int exc_b, exc_e;
+        {
+            int b = idx[inc_beg], e = idx[inc_end];
+            for (;;) {
+                int mn = b;
+                for (int i = b; i <= e; ++i) { const int id = at[i]; const int4 *ie = w.in_pool + w.in_off[id]; for (int j = 0; j < w.in_n[id]; ++j) { const int x = idx[ie[j].x]; if (x < mn) mn = x; } }
+                if (full_up(mn, b, b, e)) { exc_b = mn; break; }
+                e = b; b = mn;
+            }
+            b = idx[inc_beg]; e = idx[inc_end];
+            for (;;) {
+                int mx = e;
+                for (int i = b; i <= e; ++i) { const int id = at[i]; for (int j = 0; j < w.out_n[id]; ++j) { const int x = idx[out_entry(id, j)[0]]; if (x > mx) mx = x; } }
+                if (full_up(e, mx, b, e)) { exc_e = mx; break; }
+                b = e; e = mx;
+            }
+        }
+        if (exc_b < 0 || exc_e >= n) return ST_SUBGRAPH;
+        int *in_sub = w.msa_rank;
+        for (int i = 0; i < n; ++i) in_sub[i] = 0;
+        in_sub[at[exc_b]] = 1; in_sub[at[exc_e]] = 1;
+        for (int i = exc_b; i < exc_e - 1; ++i) {
+            const int id = at[i];
+            if (!in_sub[id]) continue;
+            for (int j = 0; j < w.out_n[id]; ++j) in_sub[out_entry(id, j)[0]] = 1;
+        }
+        // rows, restricted in-edge lists (from the top of the DP arena downwards), first in-edge / position tables
+        int *so = w.s2, *sn = w.s3;
+        int4 *pool = reinterpret_cast<int4 *>(w.dp + ((size_t)w.dp_capacity & ~(size_t)7)) - w.in_top - 8;
+        int top = 0, k = 0;
+        for (int oi = 0; oi < n; ++oi) {
+            const int id = w.order[oi];
+            if (!in_sub[id] || idx[id] < exc_b || idx[id] > exc_e) continue;
+            const int4 *ie = w.in_pool + w.in_off[id];
+            int nf = 0;
+            if (idx[id] != exc_b)
+                for (int j = 0; j < w.in_n[id]; ++j) { const int p = ie[j].x; if (in_sub[p] && idx[p] >= exc_b && idx[p] <= exc_e) { pool[top + nf] = make_int4(p, ie[j].y, ie[nf].z, 0); ++nf; } }
+            so[id] = top; sn[id] = nf; top += nf;
+            const int f = nf ? pool[so[id]].x : -1, ps0 = nf ? pool[so[id]].z : 0;
+            w.fp_id[id] = f; w.fp_ps[id] = ps0; w.pos[id] = k; w.order[k] = id;
+            w.meta[k] = make_int4(id, f, w.base[id] | ((nf < 255 ? nf : 255) << 8) | ((ps0 & 0xff) << 16), w.remain[id]);
+            ++k;
+        }
+        w.tmp[2] = at[exc_b]; w.tmp[3] = at[exc_e]; w.tmp[4] = k; w.tmp[5] = (w.in_top + 8) * 8 + 8;
+        return ST_OK;
+    }
+
+    __device__ void after_add(int first_read, bool do_bfs = false, bool partial = false) {
         const int n = w.n_nodes, lane = L::tid();
         const int inc = par.sub_aln ? 0 : 1;
+        if (do_bfs) { if (lane == 0) bfs_index(); L::sync(); }
+        const int ib = partial ? w.maxl[beg_id] : 0, ie_ = partial ? w.maxl[end_id] : 0;
         int *jn_a = w.s1, *jn_b = w.s2, *dn_a = w.s3, *dn_b = w.s4;       // list links / distance to list end
         int *jh_a = w.s5, *jh_b = w.s6, *dh_a = w.remain, *dh_b = w.s7;   // heaviest-successor links / hops to SINK
         for (int i = lane; i < n; i += L::NT) {
@@ -724,7 +827,8 @@ template <class L> struct Poa {
             }
             for (int j = 0; j < nout; ++j) ws += out_entry(i, j)[1];
             w.wsum[i] = ws;
-            if (first_read || inc || i >= 2) w.n_span[i] += 1;
+            // abpoa_update_node_n_span_reads :559-571: the nodes whose index lies between the alignment's first and last node
+            if (partial ? ((w.maxl[i] > ib && w.maxl[i] < ie_) || (inc && (i == beg_id || i == end_id))) : (first_read || inc || i >= 2)) w.n_span[i] += 1;
             const int nx = w.next[i];
             jn_a[i] = nx < 0 ? i : nx; dn_a[i] = nx < 0 ? 0 : 1;
             // heaviest out edge = first entry after the descending exchange sort
@@ -1075,7 +1179,7 @@ template <class L> struct Poa {
     }
     // Computes rows oi, oi + 1, ... while they are chain rows that fit C columns per lane; returns the first position not taken.
     // first_sn: first vector of row oi's band (the register window starts there).
-    template <int C> __device__ int chain_segment(int oi, const int first_sn, const int n, const int qlen, const int dp_sn, const int wband, const bool banded,
+    template <int C> __device__ int chain_segment(int oi, const int first_sn, const int n, const int n_tot, const int qlen, const int dp_sn, const int wband, const bool banded,
                                                   const int rem_end, ChainState &st, int &err) {
         constexpr int P = C / 2;
         const int lane = threadIdx.x & 31;
@@ -1107,9 +1211,9 @@ template <class L> struct Poa {
         int n_done = 0, narrow = 0;
         for (;;) {
             const int id = mt.x, nb = mt.z & 0xff, ps = (int)(int8_t)((mt.z >> 16) & 0xff);
-            if (id == 1 || ((mt.z >> 8) & 0xff) != 1 || mt.y != last_id) break;
+            if (id == end_id || ((mt.z >> 8) & 0xff) != 1 || mt.y != last_id) break;
             int beg, end, beg_sn;
-            chain_band(lr, mt.w, rem_end, qlen, n, wband, banded, beg, end, beg_sn);
+            chain_band(lr, mt.w, rem_end, qlen, n_tot, wband, banded, beg, end, beg_sn);
             const int end_sn = end >> 5, nvd = end_sn - beg_sn + 1, nv = nvd + 1;
             const int dl = (beg_sn - c0sn) * (32 / C);
             // a band reaching ONE vector past the predecessor's last one (every ~32nd row of a diagonal) is taken too: that
@@ -1294,7 +1398,7 @@ template <class L> struct Poa {
     // one sequence against the whole graph: simd_abpoa_cg_align_sequence_to_graph_core (:1200-1228)
     // returns number of cigar entries (reverse order) or <0
     __device__ int align(const uint8_t *query, int qlen) {
-        const int n = w.n_nodes;
+        const int n = n_rows, n_tot = w.n_nodes;       // rows of the (sub-)graph; node count of the whole graph (reset value of max_pos_left)
         const int dp_sn = (qlen + 1 + PN - 1) / PN;
         const int wband = par.wb < 0 ? qlen : par.wb + (int)(par.wf * qlen);
         const int o1 = par.gap_open1, e1 = par.gap_ext1, o2 = par.gap_open2, e2 = par.gap_ext2;
@@ -1315,19 +1419,19 @@ template <class L> struct Poa {
         }
 #endif
         uint32_t dp_top = 0;
-        int last_id = 0, cache_buf = 0; bool last_cached = false; Row last_row;
-        const int rem_end = banded ? w.remain[1] : 0;
+        int last_id = beg_id, cache_buf = 0; bool last_cached = false; Row last_row;
+        const int rem_end = banded ? w.remain[end_id] : 0;
         // ---- first row (SRC) :627-688 ; max_pos_left/right of SRC are 0, i.e. left_max_i = right_max_i = -1 + ...
         {
             int end0 = qlen;
             if (banded) {
-                const int r = qlen - (w.remain[0] - rem_end - 1);
+                const int r = qlen - (w.remain[beg_id] - rem_end - 1);
                 end0 = (0 > r ? 0 : r) + wband; if (end0 > qlen) end0 = qlen;
             }
             const int nv = (end0 >> 5) + 2;
             if ((uint64_t)nv * PN * 5 > w.dp_capacity) return ST_OOM;
             // successors of SRC start from max_pos_left = max_pos_right = 1: encode as left_max_i = right_max_i = 0
-            if (L::tid() == 0) w.rinfo[0] = pack(0, 0, end0, 0, 0);
+            if (L::tid() == 0) w.rinfo[beg_id] = pack(0, 0, end0, 0, 0);
             dp_top = (uint32_t)nv * PN * 5;
             int16_t *h = w.dp, *pe1 = h + (size_t)nv * PN, *pe2 = pe1 + (size_t)nv * PN, *pf1 = pe2 + (size_t)nv * PN, *pf2 = pf1 + (size_t)nv * PN;
             const int esn = ((end0 >> 5) + 1 < dp_sn - 1) ? (end0 >> 5) + 1 : dp_sn - 1;
@@ -1365,9 +1469,9 @@ template <class L> struct Poa {
                 // last vector) are computed by chain_segment: previous row in registers, int16x2 cells, no memory on the
                 // critical path.  It returns the position of the first row it did not take.
                 const int4 mt = w.meta[oi];
-                if (mt.x != 1 && ((mt.z >> 8) & 0xff) == 1 && mt.y == last_id) {
+                if (mt.x != end_id && ((mt.z >> 8) & 0xff) == 1 && mt.y == last_id) {
                     int beg, end, beg_sn;
-                    chain_band(last_row, mt.w, rem_end, qlen, n, wband, banded, beg, end, beg_sn);
+                    chain_band(last_row, mt.w, rem_end, qlen, n_tot, wband, banded, beg, end, beg_sn);
                     const int end_sn = end >> 5, nvd = end_sn - beg_sn + 1;
 #ifdef LCD_SIMT_EMU
                     if (L::tid() == 0 && getenv("SIMT_WHY")) { if (!(end_sn <= (last_row.end >> 5) + 1)) fprintf(stderr, "why: end_sn %d pend_sn %d beg_sn %d pbeg_sn %d qlen %d nin-prev? left1 %d right1 %d prev beg %d end %d\n", end_sn, last_row.end >> 5, beg_sn, last_row.beg >> 5, qlen, last_row.left1, last_row.right1, last_row.beg, last_row.end); else if (!(beg_sn <= (last_row.end >> 5))) fprintf(stderr, "why: beg_sn\n"); else if (nvd > 8) fprintf(stderr, "why: nvd %d\n", nvd); }
@@ -1376,9 +1480,9 @@ template <class L> struct Poa {
                         ChainState st; st.last_id = last_id; st.last_row = last_row; st.last_cached = last_cached; st.cache_buf = cache_buf; st.dp_top = dp_top;
                         int err = 0, noi;
                         LCD_T0();
-                        if (nvd <= 2) noi = chain_segment<2>(oi, beg_sn, n, qlen, dp_sn, wband, banded, rem_end, st, err);
-                        else if (nvd <= 4) noi = chain_segment<4>(oi, beg_sn, n, qlen, dp_sn, wband, banded, rem_end, st, err);
-                        else noi = chain_segment<8>(oi, beg_sn, n, qlen, dp_sn, wband, banded, rem_end, st, err);
+                        if (nvd <= 2) noi = chain_segment<2>(oi, beg_sn, n, n_tot, qlen, dp_sn, wband, banded, rem_end, st, err);
+                        else if (nvd <= 4) noi = chain_segment<4>(oi, beg_sn, n, n_tot, qlen, dp_sn, wband, banded, rem_end, st, err);
+                        else noi = chain_segment<8>(oi, beg_sn, n, n_tot, qlen, dp_sn, wband, banded, rem_end, st, err);
                         LCD_T1(t_seg);
                         if (err) return err;
                         if (noi > oi) {
@@ -1394,15 +1498,15 @@ template <class L> struct Poa {
             }
 #endif
             const int id = w.order[oi++];
-            if (id == 1) continue;
+            if (id == end_id) continue;
 #ifdef LCD_POA_TIMING
             const long long tg0_ = clock64(); n_gen++;
 #endif
 #ifdef LCD_SIMT_EMU
-            if (L::tid() == 0) { simt_stat[1]++; if (w.in_n[id] == 1 && w.in_pool[w.in_off[id]].x == last_id) simt_stat[2]++; }
+            if (L::tid() == 0) { simt_stat[1]++; if (ai_n[id] == 1 && ai_pool[ai_off[id]].x == last_id) simt_stat[2]++; }
 #endif
-            const int nin = w.in_n[id], nb = w.base[id], rem = banded ? w.remain[id] : 0;
-            const int4 *ie = w.in_pool + w.in_off[id];
+            const int nin = ai_n[id], nb = w.base[id], rem = banded ? w.remain[id] : 0;
+            const int4 *ie = ai_pool + ai_off[id];
             const int4 ie0 = nin > 0 ? ie[0] : make_int4(0, 0, 0, 0);
             // predecessor descriptors: the first MAXP in registers, any further ones re-read per vector
             constexpr int MAXP = 4;
@@ -1416,7 +1520,7 @@ template <class L> struct Poa {
             else {
                 // max_pos_left/right pulled from the predecessors' row maxima (simd_abpoa_ada_max_i :1121-1130
                 // pushes left_max_i+1 / right_max_i+1 to every successor; reset values are node_n and 0)
-                int maxl = n, maxr = 0, min_pre_beg = INT32_MAX, min_pre_beg_sn = INT32_MAX; max_pre_end_sn = -1;
+                int maxl = n_tot, maxr = 0, min_pre_beg = INT32_MAX, min_pre_beg_sn = INT32_MAX; max_pre_end_sn = -1;
                 for (int k = 0; k < nin; ++k) {
                     Row r;
                     if (k < MAXP) {
@@ -1625,8 +1729,8 @@ template <class L> struct Poa {
         const int e1 = par.gap_ext1, e2 = par.gap_ext2;
         int best = inf_min, bi = 0, bj = 0;
         {
-            const int4 *ie = w.in_pool + w.in_off[1];
-            for (int k = 0; k < w.in_n[1]; ++k) {
+            const int4 *ie = ai_pool + ai_off[end_id];
+            for (int k = 0; k < ai_n[end_id]; ++k) {
                 const int r = ie[k].x;
                 const Row rr = unpack(w.rinfo[r]);
                 const int e = qlen > rr.end ? rr.end : qlen;
@@ -1638,11 +1742,11 @@ template <class L> struct Poa {
         int n = 0, id = bi, j = bj, cur_op = ALL_OP, rc = 0;
         if (bj < qlen) cig_push(n, 1, qlen - bj, -1);
         Row cur = unpack(w.rinfo[id]);
-        while (id != 0 && j > 0) {
+        while (id != beg_id && j > 0) {
             const int nb = w.base[id], qb = query[j - 1];
             const int s = (nb > 3 || qb > 3) ? 0 : (nb == qb ? par.match : -par.mismatch);
-            const int4 *ie = w.in_pool + w.in_off[id];
-            const int nin = w.in_n[id];
+            const int4 *ie = ai_pool + ai_off[id];
+            const int nin = ai_n[id];
             const int hj = cell(cur, 0, j);
             int hit = 0;
             for (int pass = 0; pass < 2 && !hit; ++pass) {
@@ -1821,16 +1925,38 @@ template <class L> struct Poa {
             else w.n_nodes = 2;
             L::sync();
             const uint8_t *seqs = a.seqs + pb.seq_base;
+            const int32_t *sbp = a.sub_beg ? a.sub_beg + pb.read_first : nullptr, *sep = a.sub_end ? a.sub_end + pb.read_first : nullptr;
+            bool any_sub = false;                  // a problem with partially covering reads keeps the reference's BFS node index up to date
+            if (sbp) for (int r = 1; r < pb.n_reads; ++r) if (sbp[r] > 0) any_sub = true;
             for (int r = 0; r < pb.n_reads && status == ST_OK; ++r) {
+                if (r > 0 && sbp && sbp[r] < 0) continue;        // left out of the graph (src/align.c:800)
                 const uint8_t *q = seqs + a.read_off[pb.read_first + r];
                 const int ql = a.read_len[pb.read_first + r];
                 int n_cig = 0;
                 const int first_read = (w.n_nodes == 2);
+                beg_id = 0; end_id = 1; n_rows = w.n_nodes; sub = false;
+                ai_pool = w.in_pool; ai_off = w.in_off; ai_n = w.in_n;
+                const uint32_t dp_cap0 = w.dp_capacity;
+                if (!first_read && r > 0 && sbp && sbp[r] > 0) {
+#ifdef LCD_EMU
+                    status = ST_SUB_UNSUPPORTED; break;      // (the sub-graph alignment lives in the warp policy)
+#else
+                    if (!L::STRIP) { status = ST_SUB_UNSUPPORTED; break; }
+#endif
+                    if (L::tid() == 0) w.tmp[6] = prepare_sub(sbp[r], sep[r]);
+                    L::sync();
+                    if (w.tmp[6] != ST_OK) { status = w.tmp[6]; break; }
+                    beg_id = w.tmp[2]; end_id = w.tmp[3]; n_rows = w.tmp[4]; sub = true;
+                    if ((uint32_t)w.tmp[5] + 1024 > w.dp_capacity) { status = ST_OOM; break; }
+                    ai_pool = reinterpret_cast<const int4 *>(w.dp + ((size_t)w.dp_capacity & ~(size_t)7)) - w.in_top - 8; ai_off = w.s2; ai_n = w.s3;
+                    w.dp_capacity -= (uint32_t)w.tmp[5];
+                }
                 if (!first_read) {
-                    const int gn = w.n_nodes, len = ql > gn ? ql : gn;
+                    const int gn = sub ? w.maxl[end_id] - w.maxl[beg_id] + 1 : w.n_nodes, len = ql > gn ? ql : gn;
                     const int ms = (ql * par.match > len * par.gap_ext1 + par.gap_open1) ? ql * par.match : len * par.gap_ext1 + par.gap_open1;
                     if (!(ms <= INT16_MAX - par.mismatch - oe1 - oe2)) { status = ST_INT32; break; }
                     { LCD_T0(); n_cig = align(q, ql); LCD_T1(t_dp); }
+                    w.dp_capacity = dp_cap0;
                     if (n_cig < 0) { status = n_cig; break; }
                 }
                 bool fused = false;
@@ -1852,7 +1978,7 @@ template <class L> struct Poa {
                 // pool cursors are only used by lane 0; n_nodes and oom are shared through tmp[]
                 L::sync();
                 if (w.oom) { status = ST_OOM; break; }
-                if (w.n_nodes > 2) { LCD_T0(); after_add(first_read); LCD_T1(t_after); }
+                if (w.n_nodes > 2) { LCD_T0(); after_add(first_read, any_sub, sub); LCD_T1(t_after); }
             }
             if (status == ST_OK && w.n_nodes > 2) {
                 LCD_T0();

@@ -98,7 +98,8 @@ struct PoaPlan : Plan {
     DevBuf<uint8_t> d_seqs, d_cons, d_msa;
     DevBuf<Problem> d_problems;
     DevBuf<int64_t> d_read_off;
-    DevBuf<int32_t> d_read_len, d_order;
+    DevBuf<int32_t> d_read_len, d_order, d_sub_beg, d_sub_end;
+    std::vector<uint8_t> has_sub;          // per problem: a read is aligned against a sub-graph (partially covering reads)
     DevBuf<DevResult> d_results;
     DevBuf<uint32_t> d_queue;
     DevBuf<unsigned long long> d_msa_used, d_pack_off;
@@ -123,8 +124,10 @@ struct PoaPlan : Plan {
     }
 
     int build(int n_, const uint8_t *seqs, size_t seqs_len, const int32_t *first_read, const int32_t *n_reads,
-              const int64_t *read_off, const int32_t *read_len, int n_total_reads, const lcd_poa_params_t *params) {
+              const int64_t *read_off, const int32_t *read_len, int n_total_reads, const lcd_poa_params_t *params,
+              const int32_t *sub_beg = nullptr, const int32_t *sub_end = nullptr) {
         n = n_;
+        has_sub.assign(n, 0);
         Context &c = ctx();
         problems.resize(n); cons_dev_off.resize(n); need_small.resize(n); need_full.resize(n);
         std::vector<double> work(n);
@@ -138,7 +141,16 @@ struct PoaPlan : Plan {
             memset(&p, 0, sizeof(p));
             p.seq_base = 0; p.read_first = first_read[i]; p.n_reads = n_reads[i]; p.par = params[i];
             int mn = INT32_MAX;
-            for (int r = 0; r < n_reads[i]; ++r) { const int l = read_len[first_read[i] + r]; p.sum_len += l; p.max_len = std::max(p.max_len, l); mn = std::min(mn, l); }
+            for (int r = 0; r < n_reads[i]; ++r) {
+                const int l = read_len[first_read[i] + r]; p.sum_len += l; p.max_len = std::max(p.max_len, l);
+                const bool part = sub_beg && r > 0 && sub_beg[first_read[i] + r] != 0;
+                if (!part) mn = std::min(mn, l);                    // (a partially covering read is shorter by design: it does not widen the band estimate)
+                if (sub_beg && r > 0 && sub_beg[first_read[i] + r] > 0) {
+                    has_sub[i] = 1;
+                    if (!sub_end || sub_end[first_read[i] + r] < sub_beg[first_read[i] + r] || !params[i].sub_aln || params[i].wb < 0) { set_error("lcd_poa: problem %d read %d has invalid sub-graph anchors (they need sub_aln = 1, a band, and beg <= end)", i, r); return -1; }
+                }
+            }
+            if (mn == INT32_MAX) mn = p.max_len;
             p.cons_off = (int32_t)cons_total; cons_dev_off[i] = (int64_t)cons_total;
             cons_total += ((size_t)p.sum_len + 15) & ~(size_t)15;
             if (cons_total > 0x7fffffffull) { set_error("lcd_poa: batch too large (consensus buffer > 2 GiB); split it"); return -1; }
@@ -166,6 +178,7 @@ struct PoaPlan : Plan {
         if (d_problems.upload(problems.data(), n, s)) return -1;
         if (d_read_off.upload(read_off, n_total_reads, s)) return -1;
         if (d_read_len.upload(read_len, n_total_reads, s)) return -1;
+        if (sub_beg && (d_sub_beg.upload(sub_beg, n_total_reads, s) || d_sub_end.upload(sub_end, n_total_reads, s))) return -1;
         if (d_order.alloc(std::max(n, 1))) return -1;
         if (d_cons.alloc(cons_bytes + 16)) return -1;
         if (d_msa.alloc(msa_pool_bytes)) return -1;
@@ -207,6 +220,7 @@ struct PoaPlan : Plan {
         ka.problems = d_problems.p; ka.order = d_idx; ka.n = (int)idx.size(); ka.queue = d_q;
         ka.seqs = d_seqs.p; ka.read_off = d_read_off.p; ka.read_len = d_read_len.p;
         ka.cons = d_cons.p; ka.msa = d_msa.p; ka.msa_cap = msa_pool_bytes; ka.msa_used = d_msa_used.p;
+        ka.sub_beg = d_sub_beg.p; ka.sub_end = d_sub_end.p;
         ka.results = d_results.p; ka.arena = c.pool + win->off + pool_lo; ka.arena_words = words; ka.worst_case = worst_case ? 1 : 0;
         static int carve_set = -2;          // shared-memory carve-out of the SMs the persistent grid sits on (see lcd_gpu_reserve_sms)
         if (carve_set == -2) {
@@ -301,7 +315,9 @@ struct PoaPlan : Plan {
         if (!rescue.empty()) {
             rescue_words = std::min<uint64_t>((rescue_words + 63) & ~63ull, (win->words / WARPS_PER_CTA) & ~63ull);
             LCD_CUDA_OK(cudaStreamWaitEvent(s, win->done, 0));
-            if (launch(s, rescue, d_order.p, d_queue.p, rescue_words, c.sm_count * 4, 2, true, 0, win->words, nullptr)) return -1;
+            bool sub_rescue = false;           // sub-graph alignment lives in the warp kernel only
+            for (int32_t i : rescue) if (has_sub[i]) sub_rescue = true;
+            if (launch(s, rescue, d_order.p, d_queue.p, rescue_words, sub_rescue ? c.dp_sms() * WARPS_PER_CTA * POA_MIN_CTAS : c.sm_count * 4, sub_rescue ? 1 : 2, true, 0, win->words, nullptr)) return -1;
             LCD_CUDA_OK(cudaEventRecord(win->done, s));
             LCD_CUDA_OK(cudaStreamSynchronize(s));
         }
@@ -393,17 +409,24 @@ using namespace lcd;
 
 extern "C" {
 
+lcd_plan_t *lcd_poa_sub_plan_create(int n, const uint8_t *seqs, size_t seqs_len,
+                                    const int32_t *first_read, const int32_t *n_reads,
+                                    const int64_t *read_off, const int32_t *read_len, int n_total_reads,
+                                    const int32_t *sub_beg, const int32_t *sub_end,
+                                    const lcd_poa_params_t *params) {
+    if (ensure_ready()) return nullptr;
+    if (n < 0 || (n > 0 && (!seqs || !first_read || !n_reads || !read_off || !read_len || !params)) || ((sub_beg == nullptr) != (sub_end == nullptr))) {
+        set_error("lcd_poa_plan_create: invalid arguments"); return nullptr;
+    }
+    poa::PoaPlan *p = new poa::PoaPlan();
+    if (p->build(n, seqs, seqs_len, first_read, n_reads, read_off, read_len, n_total_reads, params, sub_beg, sub_end)) { delete p; return nullptr; }
+    return reinterpret_cast<lcd_plan_t *>(p);
+}
 lcd_plan_t *lcd_poa_plan_create(int n, const uint8_t *seqs, size_t seqs_len,
                                 const int32_t *first_read, const int32_t *n_reads,
                                 const int64_t *read_off, const int32_t *read_len, int n_total_reads,
                                 const lcd_poa_params_t *params) {
-    if (ensure_ready()) return nullptr;
-    if (n < 0 || (n > 0 && (!seqs || !first_read || !n_reads || !read_off || !read_len || !params))) {
-        set_error("lcd_poa_plan_create: invalid arguments"); return nullptr;
-    }
-    poa::PoaPlan *p = new poa::PoaPlan();
-    if (p->build(n, seqs, seqs_len, first_read, n_reads, read_off, read_len, n_total_reads, params)) { delete p; return nullptr; }
-    return reinterpret_cast<lcd_plan_t *>(p);
+    return lcd_poa_sub_plan_create(n, seqs, seqs_len, first_read, n_reads, read_off, read_len, n_total_reads, nullptr, nullptr, params);
 }
 
 int lcd_poa_plan_fetch(lcd_plan_t *plan, void *stream, uint8_t *cons, const int64_t *cons_off,
@@ -411,6 +434,22 @@ int lcd_poa_plan_fetch(lcd_plan_t *plan, void *stream, uint8_t *cons, const int6
     poa::PoaPlan *p = dynamic_cast<poa::PoaPlan *>(reinterpret_cast<Plan *>(plan));
     if (!p || !results) { set_error("lcd_poa_plan_fetch: not a POA plan / null results"); return -1; }
     return p->fetch(pick_stream(stream), cons, cons_off, msa, msa_off, msa_cap, results);
+}
+
+int lcd_poa_sub_batch(int n, const uint8_t *seqs, size_t seqs_len,
+                      const int32_t *first_read, const int32_t *n_reads,
+                      const int64_t *read_off, const int32_t *read_len, int n_total_reads,
+                      const int32_t *sub_beg, const int32_t *sub_end,
+                      const lcd_poa_params_t *params,
+                      uint8_t *cons, const int64_t *cons_off,
+                      uint8_t *msa, const int64_t *msa_off, const int64_t *msa_cap,
+                      lcd_poa_result_t *results) {
+    lcd_plan_t *plan = lcd_poa_sub_plan_create(n, seqs, seqs_len, first_read, n_reads, read_off, read_len, n_total_reads, sub_beg, sub_end, params);
+    if (!plan) return -1;
+    int rc = lcd_plan_run(plan, nullptr);
+    if (!rc) rc = lcd_poa_plan_fetch(plan, nullptr, cons, cons_off, msa, msa_off, msa_cap, results);
+    lcd_plan_destroy(plan);
+    return rc;
 }
 
 int lcd_poa_batch(int n, const uint8_t *seqs, size_t seqs_len,

@@ -66,6 +66,8 @@ typedef struct {
 int lcd_oracle_poa(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len,
                    const lcd_poa_params_t *p, uint8_t *cons, int32_t *cons_len,
                    uint8_t *msa, int32_t *msa_len, int32_t msa_cap);
+int lcd_oracle_poa_sub(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len, const int32_t *sub_beg, const int32_t *sub_end,
+                       const lcd_poa_params_t *p, uint8_t *cons, int32_t *cons_len, uint8_t *msa, int32_t *msa_len, int32_t msa_cap);
 
 /* ---- read -> haplotype assignment and phasing (src/assign_hap.c:16-547) ----------------------------- */
 typedef struct {

@@ -548,9 +548,59 @@ static int node_col(const pgraph_t *g, int id) {     /* 1-based MSA column of a 
     return rank;
 }
 
+/* is_full_upstream_subgraph / abpoa_upstream_index / abpoa_downstream_index / abpoa_subgraph_nodes, abpoa_graph.c:595-680: the sub-graph a
+ * partially covering read is aligned against -- the nodes whose BFS index lies between the outermost predecessors / successors of the
+ * index range of the two anchor nodes (bases of the first read), closed under in-edges on the left and out-edges on the right */
+static int full_upstream(const pgraph_t *g, int up_index, int down_index, int beg_index, int end_index) {
+    const int min_index = MIN2(up_index, beg_index), max_index = MAX2(down_index, end_index);
+    for (int i = up_index + 1; i <= down_index; ++i) {
+        const pnode_t *nd = &g->node[g->idx2id[i]];
+        for (int j = 0; j < nd->in_n; ++j) { const int x = g->id2idx[nd->in_id[j]]; if (x < min_index || x > max_index) return 0; }
+    }
+    return 1;
+}
+static int upstream_index(const pgraph_t *g, int beg_index, int end_index) {
+    for (;;) {
+        int min_index = beg_index;
+        for (int i = beg_index; i <= end_index; ++i) {
+            const pnode_t *nd = &g->node[g->idx2id[i]];
+            for (int j = 0; j < nd->in_n; ++j) min_index = MIN2(min_index, g->id2idx[nd->in_id[j]]);
+        }
+        if (full_upstream(g, min_index, beg_index, beg_index, end_index)) return min_index;
+        end_index = beg_index; beg_index = min_index;
+    }
+}
+static int downstream_index(const pgraph_t *g, int beg_index, int end_index) {
+    for (;;) {
+        int max_index = end_index;
+        for (int i = beg_index; i <= end_index; ++i) {
+            const pnode_t *nd = &g->node[g->idx2id[i]];
+            for (int j = 0; j < nd->out_n; ++j) max_index = MAX2(max_index, g->id2idx[nd->out_id[j]]);
+        }
+        if (full_upstream(g, end_index, max_index, beg_index, end_index)) return max_index;       /* (the reference tests the upstream property here too: :653) */
+        beg_index = end_index; end_index = max_index;
+    }
+}
+static void subgraph_nodes(const pgraph_t *g, int inc_beg_id, int inc_end_id, int *exc_beg, int *exc_end) {
+    const int b = g->id2idx[inc_beg_id], e = g->id2idx[inc_end_id];
+    *exc_beg = g->idx2id[upstream_index(g, b, e)]; *exc_end = g->idx2id[downstream_index(g, b, e)];
+}
+
+static int poa_run(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len, const int32_t *sub_beg, const int32_t *sub_end,
+                   const lcd_poa_params_t *p, uint8_t *cons, int32_t *cons_len, uint8_t *msa, int32_t *msa_len, int32_t msa_cap);
 int lcd_oracle_poa(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len,
                    const lcd_poa_params_t *p, uint8_t *cons, int32_t *cons_len,
                    uint8_t *msa, int32_t *msa_len, int32_t msa_cap) {
+    return poa_run(n_seq, seqs, seq_off, seq_len, NULL, NULL, p, cons, cons_len, msa, msa_len, msa_cap);
+}
+/* abpoa_partial_aln_msa_cons with partially covering reads (src/align.c:790-812): read r > 0 is aligned against the sub-graph between the nodes
+ * sub_beg[r] and sub_end[r] (abpoa_subgraph_nodes; both 0: the whole graph) or left out altogether (sub_beg[r] < 0: :800 `continue`) */
+int lcd_oracle_poa_sub(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len, const int32_t *sub_beg, const int32_t *sub_end,
+                       const lcd_poa_params_t *p, uint8_t *cons, int32_t *cons_len, uint8_t *msa, int32_t *msa_len, int32_t msa_cap) {
+    return poa_run(n_seq, seqs, seq_off, seq_len, sub_beg, sub_end, p, cons, cons_len, msa, msa_len, msa_cap);
+}
+static int poa_run(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len, const int32_t *sub_beg, const int32_t *sub_end,
+                   const lcd_poa_params_t *p, uint8_t *cons, int32_t *cons_len, uint8_t *msa, int32_t *msa_len, int32_t msa_cap) {
     ppar_t par; par.wb = p->wb; par.wf = p->wf; par.match = p->match; par.mismatch = p->mismatch;
     par.o1 = p->gap_open1; par.e1 = p->gap_ext1; par.o2 = p->gap_open2; par.e2 = p->gap_ext2;
     par.inc_both_ends = p->sub_aln ? 0 : 1; par.sub_aln = p->sub_aln;
@@ -562,8 +612,14 @@ int lcd_oracle_poa(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const
     for (int r = 0; r < n_seq && rc == 0; ++r) {
         const uint8_t *q = seqs + seq_off[r]; const int ql = seq_len[r];
         gcigar_t cig; memset(&cig, 0, sizeof(cig));
-        if (g.n > 2) rc = poa_align(&g, &par, 0, 1, q, ql, &cig);      /* abpoa_align_sequence_to_subgraph: -1 when node_n <= 2 */
-        if (rc == 0) poa_add_alignment(&g, &par, 0, 1, q, ql, &cig, r);
+        int exc_beg = 0, exc_end = 1;
+        if (r > 0 && sub_beg && sub_beg[r] < 0) continue;
+        if (r > 0 && sub_beg && sub_beg[r] > 0 && g.n > 2) {
+            if (sub_beg[r] >= g.n || sub_end[r] >= g.n || sub_end[r] < 2 || sub_beg[r] < 2) { rc = -6; break; }
+            subgraph_nodes(&g, sub_beg[r], sub_end[r], &exc_beg, &exc_end);
+        }
+        if (g.n > 2) rc = poa_align(&g, &par, exc_beg, exc_end, q, ql, &cig);      /* abpoa_align_sequence_to_subgraph: -1 when node_n <= 2 */
+        if (rc == 0) poa_add_alignment(&g, &par, exc_beg, exc_end, q, ql, &cig, r);
         free(cig.a);
     }
     if (rc == 0 && g.n > 2) {

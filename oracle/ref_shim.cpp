@@ -154,6 +154,44 @@ int ref_poa(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_
 }
 
 
+// abpoa_partial_aln_msa_cons (src/align.c:790-812) with partially covering reads: read i > 0 goes against the sub-graph abpoa_subgraph_nodes
+// finds between the nodes sub_beg[i] and sub_end[i] (both 0: the whole graph), or is left out (sub_beg[i] < 0).  The unmodified abPOA does the work.
+int ref_poa_sub(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len, const int32_t *sub_beg, const int32_t *sub_end,
+                const lcd_poa_params_t *p, uint8_t *cons, int32_t *cons_len, uint8_t *msa, int32_t *msa_len, int32_t msa_cap) {
+    abpoa_t *ab = abpoa_init();
+    abpoa_para_t *abpt = abpoa_init_para();
+    abpt->cons_algrm = ABPOA_MF; abpt->sub_aln = 1; abpt->inc_path_score = 1;
+    abpt->out_cons = 1; abpt->out_msa = 1;
+    abpt->max_n_cons = p->max_n_cons; abpt->min_freq = 0.20;
+    abpt->match = p->match; abpt->mismatch = p->mismatch;
+    abpt->gap_open1 = p->gap_open1; abpt->gap_ext1 = p->gap_ext1; abpt->gap_open2 = p->gap_open2; abpt->gap_ext2 = p->gap_ext2;
+    abpt->wb = p->wb; abpt->wf = p->wf;
+    *cons_len = 0; *msa_len = 0;
+    abpoa_post_set_para(abpt);
+    ab->abs->n_seq = n_seq;
+    for (int i = 0; i < n_seq; ++i) {
+        abpoa_res_t res; res.graph_cigar = 0; res.n_cigar = 0;
+        int exc_beg = 0, exc_end = 1;
+        if (i != 0 && sub_beg[i] < 0) continue;
+        if (i != 0 && sub_beg[i] > 0) abpoa_subgraph_nodes(ab, abpt, sub_beg[i], sub_end[i], &exc_beg, &exc_end);
+        uint8_t *q = (uint8_t*)seqs + seq_off[i];
+        abpoa_align_sequence_to_subgraph(ab, abpt, exc_beg, exc_end, q, seq_len[i], &res);
+        abpoa_add_subgraph_alignment(ab, abpt, exc_beg, exc_end, q, NULL, seq_len[i], NULL, res, i, n_seq, 0);
+        if (res.n_cigar) free(res.graph_cigar);
+    }
+    abpoa_output(ab, abpt, NULL);
+    abpoa_cons_t *abc = ab->abc;
+    int rc = 0;
+    if (abc->n_cons > 0) { *cons_len = abc->cons_len[0]; memcpy(cons, abc->cons_base[0], abc->cons_len[0]); }
+    if (msa) {
+        if ((int64_t)(abc->n_seq + abc->n_cons) * abc->msa_len > msa_cap || abc->n_cons != 1) rc = -5;
+        else { *msa_len = abc->msa_len; for (int i = 0; i < abc->n_seq + 1; ++i) memcpy(msa + (size_t)i * abc->msa_len, abc->msa_base[i], abc->msa_len); }
+    }
+    abpoa_free_para(abpt); abpoa_free(ab);
+    return rc;
+}
+
+
 // Batch driver for bench.py's cpu_baseline / --impl reference legs (one problem per worker thread, like kt_for).
 int ref_poa_batch(int n, const uint8_t *seqs, const int32_t *first_read, const int32_t *n_reads,
                   const int64_t *read_off, const int32_t *read_len, const lcd_poa_params_t *params,

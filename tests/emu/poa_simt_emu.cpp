@@ -9,6 +9,18 @@ using namespace lcd::poa;
 static int mode = 0;     /* bit1: tight workspace budgets */
 extern "C" void emu_poa_mode(int m) { mode = m; }
 extern "C" long emu_poa_stat(int i) { return simt_stat[i]; }
+static const int32_t *g_sub_beg = nullptr, *g_sub_end = nullptr;
+extern "C" int emu_poa(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len,
+                       const lcd_poa_params_t *p, uint8_t *cons, int32_t *cons_len,
+                       uint8_t *msa, int32_t *msa_len, int32_t msa_cap);
+// partially covering reads: same signature as the oracle's lcd_oracle_poa_sub
+extern "C" int emu_poa_sub(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len, const int32_t *sub_beg, const int32_t *sub_end,
+                           const lcd_poa_params_t *p, uint8_t *cons, int32_t *cons_len, uint8_t *msa, int32_t *msa_len, int32_t msa_cap) {
+    g_sub_beg = sub_beg; g_sub_end = sub_end;
+    const int rc = emu_poa(n_seq, seqs, seq_off, seq_len, p, cons, cons_len, msa, msa_len, msa_cap);
+    g_sub_beg = g_sub_end = nullptr;
+    return rc;
+}
 extern "C" int emu_poa(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len,
                        const lcd_poa_params_t *p, uint8_t *cons, int32_t *cons_len,
                        uint8_t *msa, int32_t *msa_len, int32_t msa_cap) {
@@ -24,7 +36,7 @@ extern "C" int emu_poa(int n_seq, const uint8_t *seqs, const int64_t *seq_off, c
     KernelArgs a; memset(&a, 0, sizeof(a));
     a.problems = &pb; a.order = &order; a.n = 1; a.queue = &queue; a.seqs = seqs; a.read_off = seq_off; a.read_len = seq_len;
     a.cons = cons; a.msa = msa_pool.data(); a.msa_cap = (unsigned long long)msa_cap; a.msa_used = &msa_used;
-    a.results = &dr; a.arena = arena; a.arena_words = words;
+    a.results = &dr; a.arena = arena; a.arena_words = words; a.sub_beg = g_sub_beg; a.sub_end = g_sub_end;
     pb.node_cap = pb.sum_len + 34; pb.edge_cap = 3 * (pb.sum_len + n_seq) + 64;
     if (mode & 2) { pb.node_cap = 2 * pb.max_len + 64; pb.edge_cap = 3 * pb.node_cap; }
     static __attribute__((aligned(16))) int16_t cache[POA_SMEM_HALFS];

@@ -186,6 +186,49 @@ def poa(lib, fn, seqs, par):
     return rc, cons[:cl.value].tobytes(), msa[:(n + 1) * ml.value].reshape(n + 1, ml.value).copy()
 
 
+def poa_sub(lib, fn, seqs, sub_beg, sub_end, par):
+    """The sub-graph form (partially covering reads): sub_beg / sub_end per read as lcd_poa_sub_batch takes them."""
+    n = len(seqs)
+    lens = np.array([len(s) for s in seqs], dtype=np.int32)
+    off = np.zeros(n, dtype=np.int64)
+    if n > 1:
+        off[1:] = np.cumsum(lens[:-1])
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.uint8) for s in seqs] + [np.zeros(1, np.uint8)]))
+    tot = int(lens.sum())
+    cons = np.zeros(tot + 8, dtype=np.uint8)
+    cap = (n + 1) * (tot + 8)
+    msa = np.zeros(cap, dtype=np.uint8)
+    cl, ml = C.c_int32(0), C.c_int32(0)
+    sb, se = np.ascontiguousarray(sub_beg, np.int32), np.ascontiguousarray(sub_end, np.int32)
+    rc = getattr(lib, fn)(C.c_int(n), flat.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p),
+                          sb.ctypes.data_as(C.c_void_p), se.ctypes.data_as(C.c_void_p), C.byref(par), cons.ctypes.data_as(C.c_void_p), C.byref(cl),
+                          msa.ctypes.data_as(C.c_void_p), C.byref(ml), C.c_int32(min(cap, 2**31 - 1)))
+    return rc, cons[:cl.value].tobytes(), msa[:(n + 1) * ml.value].reshape(n + 1, ml.value).copy()
+
+
+def partial_cover_problems(mbp, tech, seed, rng, max_len=1500):
+    """(reads, sub_beg, sub_end) per (region, haplotype): some reads of every problem are cut to a prefix / suffix / inner piece of the region and
+    anchored on the nodes of the first read they were cut at (what collect_partial_aln_beg_end + abpoa_subgraph_nodes's caller computes,
+    src/align.c:795-803: beg_id = ref_beg + 1, end_id = ref_end + 1 with 1-based positions in the first read), some are left out (sub_beg < 0)."""
+    from longcalld_b200 import synth
+    for r in synth.make_regions(mbp, tech, seed=seed):
+        for hap in (1, 2):
+            seqs = [np.asarray(s, np.uint8) for s, h in zip(r.reads, r.read_hap) if h == hap and len(s) > 0]
+            if len(seqs) < 3 or len(seqs[0]) < 40 or max(len(s) for s in seqs) > max_len:
+                continue
+            L0 = len(seqs[0]); out, sb, se = [seqs[0]], [0], [0]
+            for s in seqs[1:]:
+                u = rng.random()
+                if u < 0.45 or len(s) < 30: out.append(s); sb.append(0); se.append(0); continue
+                if u < 0.5: out.append(s); sb.append(-1); se.append(-1); continue
+                a = int(rng.integers(0, len(s) // 2)) if u > 0.7 else 0                 # cut on the left
+                b = int(rng.integers(len(s) // 2 + 8, len(s))) if u < 0.9 else len(s)    # cut on the right
+                rb = min(max(1, int(a * L0 / len(s)) + 1 + int(rng.integers(-3, 4))), L0 - 1)     # 1-based positions in the first read
+                re_ = min(max(rb + 1, int(b * L0 / len(s)) + int(rng.integers(-3, 4))), L0)
+                out.append(s[a:b]); sb.append(rb + 1); se.append(re_ + 1)
+            yield out, np.array(sb, np.int32), np.array(se, np.int32)
+
+
 # ----------------------------------------------------------------------------- phasing (K4) helpers
 class PhaseInput(C.Structure):
     _fields_ = [("n_reads", C.c_int32), ("n_vars", C.c_int32), ("target_var_cate", C.c_int32), ("is_ont", C.c_int32),

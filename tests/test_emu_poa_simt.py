@@ -41,3 +41,20 @@ def test_simt_poa_vs_oracle(emu, oracle, tech, mbp, seed):
     # the packed chain segments must be what computed (almost) all rows, in all three strip widths
     seg, gen = emu.emu_poa_stat(0), emu.emu_poa_stat(1)
     assert seg > 3 * gen and all(emu.emu_poa_stat(i) > 0 for i in (3, 4, 6)), (seg, gen)
+
+
+@pytest.mark.parametrize("tech,mbp,seed", [("hifi", 0.5, 61), ("ont", 0.1, 62)])
+def test_simt_poa_partial_cover_vs_oracle(emu, oracle, tech, mbp, seed):
+    """Partially covering reads: the device-side BFS node index, abpoa_subgraph_nodes, the sub-graph view of the alignment (rows, restricted
+    in-edge lists with the reference's path-score indexing), fusion between two inner nodes and the span update -- against the oracle that
+    tests/test_oracle_poa_sub.py pins to the unmodified abPOA."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    par = T.poa_params(1, 10)
+    n = n_sub = 0
+    for seqs, sb, se in T.partial_cover_problems(mbp, tech, seed, rng, max_len=900):
+        a = T.poa_sub(oracle, "lcd_oracle_poa_sub", seqs, sb, se, par)
+        b = T.poa_sub(emu, "emu_poa_sub", seqs, sb, se, par)
+        assert a[0] == b[0] == 0 and a[1] == b[1] and a[2].shape == b[2].shape and (a[2] == b[2]).all(), (n, sb.tolist(), se.tolist())
+        n += 1; n_sub += int((sb > 0).sum())
+    assert n > 40 and n_sub > 150, (n, n_sub)

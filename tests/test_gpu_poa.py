@@ -90,3 +90,29 @@ def test_gpu_poa_full_size_properties(gpu):
             row = msa[r]
             assert row[row != 5].tobytes() == np.asarray(s, np.uint8).tobytes()
         assert msa[len(seqs)][msa[len(seqs)] != 5].tobytes() == cons
+
+
+@pytest.mark.parametrize("tech,mbp,seed", [("hifi", 1.5, 71), ("ont", 0.3, 72)])
+def test_gpu_poa_partial_cover_reads(gpu, oracle, tech, mbp, seed):
+    """Reads that cover their region only partly (abpoa_partial_aln_msa_cons, src/align.c:790-812): lcd_poa_sub_batch aligns them against the
+    sub-graph abpoa_subgraph_nodes finds between their anchor nodes, leaves out the ones marked so, and mixes such problems with plain ones in one
+    launch; consensus and every MSA cell against the oracle that tests/test_oracle_poa_sub.py pins to the unmodified abPOA."""
+    rng = np.random.default_rng(seed)
+    cases = list(T.partial_cover_problems(mbp, tech, seed, rng, max_len=3000))
+    plain = _problems(tech, mbp / 8, seed + 1, max_len=1500)
+    problems = [c[0] for c in cases] + plain
+    sub = [(c[1], c[2]) for c in cases] + [(np.zeros(len(p), np.int32), np.zeros(len(p), np.int32)) for p in plain]
+    got = gpu.poa_batch(problems, gpu.poa_params(1, 10), sub=sub)
+    par = T.poa_params(1, 10)
+    bad = []
+    for i, (seqs, (sb, se)) in enumerate(zip(problems, sub)):
+        rc, cons, msa = T.poa_sub(oracle, "lcd_oracle_poa_sub", seqs, sb, se, par)
+        g = got[i]
+        if not (g[0] == rc == 0 and g[1] == cons and g[2].shape == msa.shape and (g[2] == msa).all()):
+            bad.append(i)
+    assert not bad and len(cases) > 300 and sum(int((c[1] > 0).sum()) for c in cases) > 1000, (len(bad), bad[:10], len(cases))
+    # anchors outside the first read are refused, loudly
+    seqs, sb, se = cases[0]
+    sb = sb.copy(); se = se.copy(); k = int(np.argmax(sb > 0)); sb[k] = 10 ** 6; se[k] = 10 ** 6 + 5
+    with pytest.raises(gpu.LcdGpuError):
+        gpu.poa_batch([seqs], gpu.poa_params(1, 10), sub=[(sb, se)])
