@@ -1978,7 +1978,12 @@ template <class L> struct Poa {
                 // pool cursors are only used by lane 0; n_nodes and oom are shared through tmp[]
                 L::sync();
                 if (w.oom) { status = ST_OOM; break; }
-                if (w.n_nodes > 2) { LCD_T0(); after_add(first_read, any_sub, sub); LCD_T1(t_after); }
+                if (w.n_nodes > 2) {
+                    // the BFS index is needed when this read went against a sub-graph (the nodes it spans) or the next read that joins the graph will
+                    bool bfs = sub;
+                    if (any_sub && !bfs) for (int r2 = r + 1; r2 < pb.n_reads; ++r2) if (sbp[r2] >= 0) { bfs = sbp[r2] > 0; break; }
+                    LCD_T0(); after_add(first_read, bfs, sub); LCD_T1(t_after);
+                }
             }
             if (status == ST_OK && w.n_nodes > 2) {
                 LCD_T0();

@@ -32,22 +32,6 @@ poa_kernel(const KernelArgs a) {
     }
 }
 
-// one THREAD per problem (ThreadLanes): for the thousands of ~100-node problems, where the serial graph
-// phases dominate and run 32 problems per warp instead of one
-constexpr int THREADS_PER_CTA = 64;
-__global__ void __launch_bounds__(THREADS_PER_CTA)
-poa_thread_kernel(const KernelArgs a) {
-    const int tid = blockIdx.x * THREADS_PER_CTA + threadIdx.x;
-    int32_t *arena = a.arena + (size_t)tid * a.arena_words;
-    Poa<ThreadLanes> poa;
-    for (;;) {
-        const uint32_t item = atomicAdd(a.queue, 1u);
-        if (item >= (uint32_t)a.n) break;
-        const int pi = a.order[item];
-        poa.run(a, a.problems[pi], a.results + pi, arena);
-    }
-}
-
 // one CTA of CTA_WARPS warps per problem (kilobase regions): the vectors of every DP row are dealt to the warps
 constexpr int CTA_WARPS = 4;
 __global__ void __launch_bounds__(32 * CTA_WARPS)
@@ -195,14 +179,14 @@ struct PoaPlan : Plan {
     }
 
     // one launch over `idx` with per-group arenas of `words`
-    // kind: 0 = poa_thread_kernel (one problem per thread), 1 = poa_kernel (one per warp), 2 = poa_cta_kernel (one per CTA).
+    // kind: 1 = poa_kernel (one problem per warp), 2 = poa_cta_kernel (one per CTA: unbanded problems, rescue launches).
     // The launch uses pool words [pool_lo, pool_hi) for its arenas and reports how many it took in *used.
     int launch(cudaStream_t s, const std::vector<int32_t> &idx, int32_t *d_idx, uint32_t *d_q, uint64_t words, int max_groups,
                int kind, bool worst_case, uint64_t pool_lo, uint64_t pool_hi, uint64_t *used) {
         Context &c = ctx();
         if (used) *used = 0;
         if (idx.empty()) return 0;
-        const int per_cta = kind == 0 ? THREADS_PER_CTA : kind == 1 ? WARPS_PER_CTA : 1;
+        const int per_cta = kind == 1 ? WARPS_PER_CTA : 1;
         const uint64_t avail = pool_hi > pool_lo ? pool_hi - pool_lo : 0;
         const uint64_t fit = avail / words;
         if (fit == 0) { set_error("lcd_poa: a problem needs %zu MiB of workspace but the pool has %zu MiB", (size_t)(words * 4 >> 20), (size_t)(win->words * 4 >> 20)); return -1; }
@@ -228,8 +212,7 @@ struct PoaPlan : Plan {
             carve_set = cv ? atoi(cv) : POA_CARVEOUT_PCT;
             if (carve_set >= 0) LCD_CUDA_OK(cudaFuncSetAttribute(poa_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve_set));
         }
-        if (kind == 0) poa_thread_kernel<<<grid, THREADS_PER_CTA, 0, s>>>(ka);
-        else if (kind == 1) poa_kernel<<<grid, 32 * WARPS_PER_CTA, 0, s>>>(ka);
+        if (kind == 1) poa_kernel<<<grid, 32 * WARPS_PER_CTA, 0, s>>>(ka);
         else poa_cta_kernel<<<grid, 32 * CTA_WARPS, 0, s>>>(ka);
         LCD_CUDA_OK(cudaGetLastError());
         c.launches++;
@@ -243,37 +226,28 @@ struct PoaPlan : Plan {
         if (n == 0) return 0;
         if (pending && finish_locked(s)) return -1;
         LCD_CUDA_OK(cudaMemsetAsync(d_msa_used.p, 0, sizeof(unsigned long long), s));
-        // class T: small problems, one per THREAD; class W: medium, one per warp; class C: kilobase regions, one per
-        // CTA; rescue: problems that outgrew their first-attempt budget, re-run with the worst-case budget.
-        // The three classes run concurrently (two side streams) in disjoint parts of the pool.
-        const uint64_t thread_words = (uint64_t)(512u << 10) / 4;     // <= 512 KiB per thread arena
+        // class W (1): one problem per warp -- every banded problem; class C (2): one per CTA -- rows wider than the warp kernel's on-chip row
+        // cache (unbanded POA of reads over 224 bp); rescue: problems that outgrew their first-attempt budget, re-run with the worst-case
+        // budget.  The two classes run concurrently (side streams) in disjoint parts of the plan's pool window.
         for (int k = 0; k < 3; ++k) cls[k].clear();         // (member: the launch's index upload reads them after run() has returned)
         uint64_t cw[3] = {0, 0, 0};
-        const char *tml = getenv("LCD_POA_THREAD_MAXLEN");      // tuning knob: longest read of a thread-per-problem POA
-        const int thread_max_len = tml ? atoi(tml) : 0;          // default: every banded problem on the warp kernel (measured fastest)
-        const char *force = getenv("LCD_POA_FORCE_KIND");      // debug / profiling: 0 thread, 1 warp, 2 CTA for every problem
-        const char *ctop = getenv("LCD_POA_CTA_TOP");          // tuning knob: the K largest problems (the tail of the launch) go to the CTA kernel
-        int cta_top = ctop ? atoi(ctop) : 0;
         for (int32_t i : order_all) {
-            // kilobase problems run on the warp kernel as well: its strip rows, 32-wide backtrack and parallel fusion beat
-            // the CTA kernel's two-phase rows (kept for rows wider than the warp kernel's on-chip row cache: unbanded POA)
-            int k = (need_small[i] <= thread_words && problems[i].max_len <= thread_max_len) ? 0 : ((problems[i].par.wb >= 0 || problems[i].max_len <= 224) ? 1 : 2);
-            if (force && force[0] >= '0' && force[0] <= '2' && !(force[0] == '0' && need_small[i] > thread_words)) k = force[0] - '0';
-            if (cta_top > 0) { k = 2; --cta_top; }
+            // kilobase problems run on the warp kernel as well: its strip rows, 32-wide backtrack and parallel fusion beat the CTA kernel's
+            // two-phase rows (measured: profiles/README.md, r1 v5)
+            const int k = (problems[i].par.wb >= 0 || problems[i].max_len <= 224 || has_sub[i]) ? 1 : 2;
             cls[k].push_back(i); cw[k] = std::max(cw[k], need_small[i]);
         }
-        for (int k = 0; k < 3; ++k) cw[k] = (cw[k] + 63) & ~63ull;
-        const int max_groups[3] = { c.sm_count * 256, c.dp_sms() * WARPS_PER_CTA * POA_MIN_CTAS, c.sm_count * 4 };
-        // pool split: threads get what they need (at most half), CTAs and warps share the rest in proportion to demand
-        uint64_t want[3];
-        const int per_cta[3] = { THREADS_PER_CTA, WARPS_PER_CTA, 1 };
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 1; k < 3; ++k) cw[k] = (cw[k] + 63) & ~63ull;
+        const int max_groups[3] = { 0, c.dp_sms() * WARPS_PER_CTA * POA_MIN_CTAS, c.sm_count * 4 };
+        // pool split: CTAs and warps share the window in proportion to demand
+        uint64_t want[3] = {0, 0, 0};
+        const int per_cta[3] = { 1, WARPS_PER_CTA, 1 };
+        for (int k = 1; k < 3; ++k) {
             const uint64_t g = std::min<uint64_t>(cls[k].size(), (uint64_t)max_groups[k]);
             want[k] = (g + per_cta[k] - 1) / per_cta[k] * per_cta[k] * cw[k];       // launches round up to whole CTAs
         }
-        uint64_t lo[4]; lo[0] = 0;
-        lo[1] = std::min<uint64_t>(want[0], win->words / 2);
-        const uint64_t rest_pool = win->words - lo[1];
+        uint64_t lo[4]; lo[0] = 0; lo[1] = 0;
+        const uint64_t rest_pool = win->words;
         const uint64_t w12 = want[1] + want[2];
         lo[2] = lo[1] + (w12 <= rest_pool ? want[1] : (uint64_t)((double)rest_pool * ((double)want[1] / (double)w12)));
         lo[3] = win->words;
@@ -287,7 +261,6 @@ struct PoaPlan : Plan {
             if (launch(ss, cls[k], d_order.p + off, d_queue.p + k, cw[k], max_groups[k], k, false, lo[k], lo[k + 1], nullptr)) return -1;
             LCD_CUDA_OK(cudaEventRecord(ev_join[k - 1], ss));
         }
-        if (!cls[0].empty() && launch(s, cls[0], d_order.p, d_queue.p, cw[0], max_groups[0], 0, false, lo[0], lo[1], nullptr)) return -1;
         for (int k = 1; k <= 2; ++k) if (!cls[k].empty()) LCD_CUDA_OK(cudaStreamWaitEvent(s, ev_join[k - 1], 0));
         pending = true;
         return 0;

@@ -56,12 +56,12 @@ static void trace(const char *what, long a, long b) {
     trace_t e = { t, (unsigned long)pthread_self(), what, a, b }; trace_buf[trace_n++] = e;
     pthread_mutex_unlock(&t_mu);
 }
-static unsigned long n_calls[11];
+static unsigned long n_calls[12];
 #define COUNT(i) __atomic_fetch_add(&n_calls[i], 1, __ATOMIC_RELAXED)      /* the reference's worker threads call in concurrently */
 __attribute__((destructor)) static void report(void) {
     if (trace_on > 0 && trace_n) { FILE *f = fopen(getenv("LCD_DROPIN_TRACE"), "w"); if (f) { for (size_t i = 0; i < trace_n; ++i) fprintf(f, "%.6f\t%lx\t%s\t%ld\t%ld\n", trace_buf[i].t - trace_buf[0].t, trace_buf[i].tid, trace_buf[i].what, trace_buf[i].a, trace_buf[i].b); fclose(f); } }
-    if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: digar %lu (forwarded: %lu), sites %lu, pileup %lu, profile %lu, phase %lu, edlib %lu, wfa %lu, poa %lu (forwarded to abPOA: %lu) in %lu engine batches (library time: poa %.2f s, wfa %.2f s, edlib %.2f s; threads blocked %.2f s in total; forwarded abPOA %.2f s); kernel launches %llu\n",
-                                              n_calls[8], n_calls[9], n_calls[10], n_calls[0], n_calls[1], n_calls[2], n_calls[3], n_calls[4], n_calls[5], n_calls[6], n_calls[7], t_batch[0], t_batch[1], t_batch[2], t_blocked, t_fwd_poa, (unsigned long long)lcd_gpu_launch_count());
+    if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: digar %lu (forwarded: %lu), sites %lu, pileup %lu, profile %lu, phase %lu, edlib %lu, wfa %lu, poa %lu (with partially covering reads: %lu; forwarded to abPOA: %lu) in %lu engine batches (library time: poa %.2f s, wfa %.2f s, edlib %.2f s; threads blocked %.2f s in total; forwarded abPOA %.2f s); kernel launches %llu\n",
+                                              n_calls[8], n_calls[9], n_calls[10], n_calls[0], n_calls[1], n_calls[2], n_calls[3], n_calls[4], n_calls[5], n_calls[11], n_calls[6], n_calls[7], t_batch[0], t_batch[1], t_batch[2], t_blocked, t_fwd_poa, (unsigned long long)lcd_gpu_launch_count());
 }
 
 /* LCD_DROPIN_STAGES=engines keeps the pileup scan and the phasing (K1 - K4) on the reference's own host code and sends only the DP engines
@@ -441,6 +441,7 @@ typedef struct req_t {
     /* inputs (owned by the caller, alive until done) */
     const uint8_t *seqs; size_t seqs_len;                 /* POA: the reads back to back; WFA: pattern then text; edlib: query then target */
     int n_reads; const int64_t *read_off; const int32_t *read_len; lcd_poa_params_t ppar; int want_msa; int max_len;
+    const int32_t *sub_beg, *sub_end;                     /* POA: partially covering reads (NULL: none), see lcd_poa_sub_batch */
     int plen, tlen; lcd_wfa_params_t wpar;
     int qlen, mode, want_path;
     /* outputs (buffers owned by the caller) */
@@ -488,17 +489,19 @@ static void run_batch(int kind, req_t **r, int n) {
         uint8_t *seqs = (uint8_t*)malloc(tot + 1), *cons = (uint8_t*)malloc(cons_tot + 1), *msa = (uint8_t*)malloc(msa_tot + 1);
         int32_t *first = (int32_t*)malloc(sizeof(int32_t) * n), *nr = (int32_t*)malloc(sizeof(int32_t) * n), *len = (int32_t*)malloc(sizeof(int32_t) * (n_rd + 1));
         int64_t *off = (int64_t*)malloc(sizeof(int64_t) * (n_rd + 1)), *coff = (int64_t*)malloc(sizeof(int64_t) * n), *moff = (int64_t*)malloc(sizeof(int64_t) * n), *mcap = (int64_t*)malloc(sizeof(int64_t) * n);
+        int32_t *sb = (int32_t*)calloc(n_rd + 1, sizeof(int32_t)), *se = (int32_t*)calloc(n_rd + 1, sizeof(int32_t)); int any_sub = 0;
         lcd_poa_params_t *par = (lcd_poa_params_t*)malloc(sizeof(lcd_poa_params_t) * n);
         lcd_poa_result_t *res = (lcd_poa_result_t*)calloc(n, sizeof(lcd_poa_result_t));
         size_t o = 0, rd = 0, co = 0, mo = 0;
         for (int i = 0; i < n; ++i) {
             memcpy(seqs + o, r[i]->seqs, r[i]->seqs_len);
             first[i] = (int32_t)rd; nr[i] = r[i]->n_reads; par[i] = r[i]->ppar; coff[i] = (int64_t)co; moff[i] = (int64_t)mo; mcap[i] = r[i]->want_msa ? r[i]->msa_cap : 0;
-            for (int k = 0; k < r[i]->n_reads; ++k, ++rd) { off[rd] = (int64_t)o + r[i]->read_off[k]; len[rd] = r[i]->read_len[k]; }
+            for (int k = 0; k < r[i]->n_reads; ++k, ++rd) { off[rd] = (int64_t)o + r[i]->read_off[k]; len[rd] = r[i]->read_len[k]; if (r[i]->sub_beg) { sb[rd] = r[i]->sub_beg[k]; se[rd] = r[i]->sub_end[k]; any_sub = 1; } }
             o += r[i]->seqs_len; co += r[i]->seqs_len + 16; mo += (size_t)mcap[i];
         }
         trace("lib_begin", kind, n);
-        const int rc = lcd_poa_batch(n, seqs, tot, first, nr, off, len, (int)n_rd, par, cons, coff, msa, moff, mcap, res);
+        const int rc = any_sub ? lcd_poa_sub_batch(n, seqs, tot, first, nr, off, len, (int)n_rd, sb, se, par, cons, coff, msa, moff, mcap, res)
+                               : lcd_poa_batch(n, seqs, tot, first, nr, off, len, (int)n_rd, par, cons, coff, msa, moff, mcap, res);
         trace("lib_end", kind, n);
         if (rc == -1) die("lcd_poa_batch");                /* -2: some problems were refused on the device (their status says why) */
         for (int i = 0; i < n; ++i) {
@@ -508,7 +511,7 @@ static void run_batch(int kind, req_t **r, int n) {
                 if (r[i]->want_msa) memcpy(r[i]->msa, msa + moff[i], (size_t)(r[i]->n_reads + 1) * res[i].msa_len);
             }
         }
-        free(seqs); free(cons); free(msa); free(first); free(nr); free(len); free(off); free(coff); free(moff); free(mcap); free(par); free(res);
+        free(seqs); free(cons); free(msa); free(first); free(nr); free(len); free(off); free(coff); free(moff); free(mcap); free(par); free(res); free(sb); free(se);
         __atomic_fetch_add(&n_calls[5], (unsigned long)n, __ATOMIC_RELAXED); COUNT(7);
     } else if (kind == RQ_WFA) {
         size_t tot = 0, ops_tot = 0;
@@ -621,7 +624,7 @@ static void combine(req_t **r, int n) {
 
 /* ---- coroutines: one per pending noisy region of the chunk a worker thread is on */
 enum { CO_READY, CO_PARKED, CO_TURN, CO_DONE };
-typedef struct co_t { ucontext_t ctx; void *stack; int state, idx, reg_i, ret; req_t *req; bam_chunk_t *chunk; const call_var_opt_t *opt; } co_t;
+typedef struct co_t { ucontext_t ctx; void *stack; int state, idx, reg_i, ret; req_t **reqs; int n_reqs; bam_chunk_t *chunk; const call_var_opt_t *opt; } co_t;
 typedef struct { ucontext_t main; co_t *cos; int n, next_turn; } sched_t;
 static __thread sched_t *tl_sched = NULL;
 static __thread co_t *tl_co = NULL;
@@ -636,11 +639,13 @@ static void co_entry(void) {
 }
 
 /* an engine call: parked when made from a region's coroutine, a batch of one (merged with other threads' requests) otherwise */
-static void gpu_call(req_t *r) {
-    r->done = 0;
-    if (tl_co) { tl_co->req = r; tl_co->state = CO_PARKED; swapcontext(&tl_co->ctx, &tl_sched->main); }
-    else { req_t *one = r; combine(&one, 1); }
+static void gpu_call_many(req_t **rs, int n) {             /* independent requests of one region: they travel in the same batch */
+    if (n <= 0) return;
+    for (int i = 0; i < n; ++i) rs[i]->done = 0;
+    if (tl_co) { tl_co->reqs = rs; tl_co->n_reqs = n; tl_co->state = CO_PARKED; swapcontext(&tl_co->ctx, &tl_sched->main); }
+    else combine(rs, n);
 }
+static void gpu_call(req_t *r) { req_t *one = r; gpu_call_many(&one, 1); }
 
 /* all pending regions of one pass side by side; ret[k] = collect_noisy_vars1's return value for regs[k] */
 static void run_regions(bam_chunk_t *chunk, const call_var_opt_t *opt, int n, const int *regs, int *ret) {
@@ -654,7 +659,7 @@ static void run_regions(bam_chunk_t *chunk, const call_var_opt_t *opt, int n, co
         getcontext(&c->ctx); c->ctx.uc_stack.ss_sp = c->stack; c->ctx.uc_stack.ss_size = CO_STACK; c->ctx.uc_link = NULL;
         makecontext(&c->ctx, co_entry, 0);
     }
-    req_t **parked = (req_t**)malloc(sizeof(req_t*) * n);
+    req_t **parked = NULL; int parked_cap = 0;
     tl_sched = &sc;
     for (;;) {
         int ran = 0;
@@ -666,7 +671,10 @@ static void run_regions(bam_chunk_t *chunk, const call_var_opt_t *opt, int n, co
             }
         }
         int np = 0;
-        for (int i = 0; i < n; ++i) if (sc.cos[i].state == CO_PARKED) parked[np++] = sc.cos[i].req;
+        for (int i = 0; i < n; ++i) if (sc.cos[i].state == CO_PARKED) {
+            if (np + sc.cos[i].n_reqs > parked_cap) { parked_cap = 2 * (np + sc.cos[i].n_reqs) + 64; parked = (req_t**)realloc(parked, sizeof(req_t*) * parked_cap); }
+            for (int k = 0; k < sc.cos[i].n_reqs; ++k) parked[np++] = sc.cos[i].reqs[k];
+        }
         if (np) {
             combine(parked, np);
             for (int i = 0; i < n; ++i) if (sc.cos[i].state == CO_PARKED) sc.cos[i].state = CO_READY;
@@ -792,6 +800,7 @@ int classify_cand_vars(bam_chunk_t *chunk, int n_var_sites, const call_var_opt_t
 int *sort_noisy_regs(bam_chunk_t *chunk);                                                                                   /* :2745 */
 void collect_somatic_var(bam_chunk_t *chunk, const call_var_opt_t *opt);                                                    /* :2857 */
 
+void collect_aln_beg_end(uint32_t *cigar_buf, int cigar_len, int ext_direction, int ref_len, int *ref_beg, int *ref_end, int read_len, int *read_beg, int *read_end);   /* src/align.c:633 */
 void collect_var_main(const call_var_pl_t *pl, bam_chunk_t *chunk) {
     call_var_opt_t *opt = pl->opt;
     new_thread_stream();
@@ -834,15 +843,27 @@ void collect_var_main(const call_var_pl_t *pl, bam_chunk_t *chunk) {
 }
 
 /* ------------------------------------------------------------------------------------------ K7 */
-static int edlib1(uint8_t *target, int tlen, uint8_t *query, int qlen, int mode, int want_path, uint8_t **aln, lcd_edlib_result_t *res) {
+static void edlib_req_init(req_t *r, uint8_t *target, int tlen, uint8_t *query, int qlen, int mode, int want_path) {
     uint8_t *seqs = (uint8_t*)malloc((size_t)qlen + tlen + 1);
     memcpy(seqs, query, qlen); memcpy(seqs + qlen, target, tlen);
-    *aln = (uint8_t*)malloc((size_t)qlen + tlen + 2);
-    req_t r; memset(&r, 0, sizeof(r));
-    r.kind = RQ_EDLIB; r.seqs = seqs; r.seqs_len = (size_t)qlen + tlen; r.qlen = qlen; r.tlen = tlen; r.mode = mode; r.want_path = want_path; r.aln = *aln;
+    memset(r, 0, sizeof(*r));
+    r->kind = RQ_EDLIB; r->seqs = seqs; r->seqs_len = (size_t)qlen + tlen; r->qlen = qlen; r->tlen = tlen; r->mode = mode; r->want_path = want_path;
+    r->aln = (uint8_t*)malloc((size_t)qlen + tlen + 2);
+}
+static int edlib_req_xgaps(req_t *r) {                    /* edlibAlignmentToXGAPS, src/align.c:189-208; releases the request's buffers */
+    int n_gaps = 0, n_mis = 0;
+    for (int i = 0; i < r->eres.aln_len; ++i) {
+        if (r->aln[i] == 3) n_mis++;
+        else if ((r->aln[i] == 1 || r->aln[i] == 2) && (i == 0 || r->aln[i - 1] != r->aln[i])) n_gaps++;
+    }
+    free((void*)r->seqs); free(r->aln);
+    return n_mis + n_gaps;
+}
+static int edlib1(uint8_t *target, int tlen, uint8_t *query, int qlen, int mode, int want_path, uint8_t **aln, lcd_edlib_result_t *res) {
+    req_t r; edlib_req_init(&r, target, tlen, query, qlen, mode, want_path);
     gpu_call(&r);
-    *res = r.eres;
-    free(seqs);
+    *res = r.eres; *aln = r.aln;
+    free((void*)r.seqs);
     return 0;
 }
 int edlib_edit_distance(uint8_t *target, int tlen, uint8_t *query, int qlen) {                 /* src/align.c:210 */
@@ -873,8 +894,8 @@ int edlib_end2end_aln(uint8_t *target, int tlen, uint8_t *query, int qlen, int *
 int edlib_infix_aln(uint8_t *target, int tlen, uint8_t *query, int qlen, int *n_eq, int *n_xid) { return edlib_path_counts(target, tlen, query, qlen, LCD_EDLIB_MODE_HW, n_eq, n_xid); }     /* src/align.c:256 */
 
 /* ------------------------------------------------------------------------------------------ K6 */
-int wfa_end2end_aln(uint8_t *pattern, int plen, uint8_t *text, int tlen, int gap_aln, int b, int q, int e, int q2, int e2, int heuristic, int affine_gap,
-                    uint32_t **cigar_buf, int *cigar_length, uint8_t **pattern_alg, uint8_t **text_alg, int *alg_length) {      /* src/align.c:374-460 */
+typedef struct { req_t r; uint8_t *seqs, *p, *t; char *ops; int plen, tlen, left; } wfa_job_t;
+static void wfa_job_init(wfa_job_t *jb, uint8_t *pattern, int plen, uint8_t *text, int tlen, int gap_aln, int b, int q, int e, int q2, int e2, int heuristic, int affine_gap) {
     lcd_wfa_params_t par; memset(&par, 0, sizeof(par));
     par.mismatch = b; par.gap_open1 = q; par.gap_ext1 = e; par.gap_open2 = q2; par.gap_ext2 = e2;
     par.affine2p = affine_gap == LONGCALLD_WFA_AFFINE_2P;
@@ -892,10 +913,13 @@ int wfa_end2end_aln(uint8_t *pattern, int plen, uint8_t *text, int tlen, int gap
         for (int i = 0; i < tlen; ++i) t[i] = text[tlen - i - 1];
     } else { memcpy(p, pattern, plen); memcpy(t, text, tlen); }
     char *ops = (char*)malloc(2 * ((size_t)plen + tlen) + 16);
-    req_t r; memset(&r, 0, sizeof(r));
-    r.kind = RQ_WFA; r.seqs = seqs; r.seqs_len = (size_t)plen + tlen; r.plen = plen; r.tlen = tlen; r.wpar = par; r.ops = ops;
-    gpu_call(&r);
-    const lcd_wfa_result_t res = r.wres;
+    memset(&jb->r, 0, sizeof(jb->r));
+    jb->r.kind = RQ_WFA; jb->r.seqs = seqs; jb->r.seqs_len = (size_t)plen + tlen; jb->r.plen = plen; jb->r.tlen = tlen; jb->r.wpar = par; jb->r.ops = ops;
+    jb->seqs = seqs; jb->p = p; jb->t = t; jb->ops = ops; jb->plen = plen; jb->tlen = tlen; jb->left = left;
+}
+static void wfa_job_finish(wfa_job_t *jb, uint32_t **cigar_buf, int *cigar_length, uint8_t **pattern_alg, uint8_t **text_alg, int *alg_length) {
+    const lcd_wfa_result_t res = jb->r.wres;
+    uint8_t *seqs = jb->seqs, *p = jb->p, *t = jb->t; char *ops = jb->ops; const int plen = jb->plen, tlen = jb->tlen, left = jb->left;
     const int n = res.n_ops;
     if (cigar_buf != NULL && cigar_length != NULL) {         /* cigar_get_CIGAR(cigar, true, ...) (WFA2-lib/alignment/cigar.c:181-240), reversed for left alignment */
         uint32_t *tmp = (uint32_t*)malloc(((size_t)n + 1) * sizeof(uint32_t)); int m = 0;
@@ -926,6 +950,12 @@ int wfa_end2end_aln(uint8_t *pattern, int plen, uint8_t *text, int tlen, int gap
         *pattern_alg = pa; *text_alg = ta; *alg_length = k;
     }
     free(ops); free(seqs);
+}
+int wfa_end2end_aln(uint8_t *pattern, int plen, uint8_t *text, int tlen, int gap_aln, int b, int q, int e, int q2, int e2, int heuristic, int affine_gap,
+                    uint32_t **cigar_buf, int *cigar_length, uint8_t **pattern_alg, uint8_t **text_alg, int *alg_length) {      /* src/align.c:374-460 */
+    wfa_job_t jb; wfa_job_init(&jb, pattern, plen, text, tlen, gap_aln, b, q, e, q2, e2, heuristic, affine_gap);
+    gpu_call(&jb.r);
+    wfa_job_finish(&jb, cigar_buf, cigar_length, pattern_alg, text_alg, alg_length);
     return 0;
 }
 
@@ -936,41 +966,111 @@ int abpoa_partial_aln_msa_cons(const call_var_opt_t *opt, abpoa_t *ab, int sampl
     typedef int (*fn_t)(const call_var_opt_t *, abpoa_t *, int, int, int *, uint8_t **, uint8_t **, int *, int *, char **, int, int *, uint8_t **, int *, int **, int *, uint8_t **);
     static fn_t orig = NULL;
     if (!orig) orig = (fn_t)dlsym(RTLD_NEXT, "abpoa_partial_aln_msa_cons");
-    /* the GPU kernel covers the case every read is aligned end to end against the whole graph: collect_partial_aln_beg_end
-     * (:709-745) returns the full range for reads that cover the region (or reach a side with a gap) when reads are not sampled */
-    int ok = ab == NULL && !sampling_reads && max_n_cons == 1 && n_reads >= 1 && cons_lens && cons_seqs && LONGCALLD_NOISY_IS_BOTH_COVER(read_full_cover[0]);
-    size_t tot = 0;
-    for (int i = 0; ok && i < n_reads; ++i) {
-        const int c = read_full_cover[i];
-        if (!(LONGCALLD_NOISY_IS_BOTH_COVER(c) || (LONGCALLD_NOISY_IS_LEFT_COVER(c) && LONGCALLD_NOISY_IS_RIGHT_GAP(c)) ||
-              (LONGCALLD_NOISY_IS_RIGHT_COVER(c) && LONGCALLD_NOISY_IS_LEFT_GAP(c))) || read_lens[i] <= 0) ok = 0;
-        tot += read_lens[i] > 0 ? read_lens[i] : 0;
-    }
+    /* Per read i > 0 the reference decides (collect_partial_aln_beg_end, :709-745) whether the read goes against the whole graph, against the
+     * sub-graph between two bases of the first read (it covers the region only on one side: an extension alignment to the first read finds where
+     * it ends, cal_wfa_partial_aln_beg_end :672-707), or is left out (sampled regions: more than 10 % mismatches + gap openings to the first read;
+     * one-sided reads: the same test on the overlapping end).  Here the same decisions are taken for all reads of the region at once: one batch
+     * of edlib problems (K7), one batch of WFA extension alignments (K6), then ONE POA problem with the reads' anchors (K5, lcd_poa_sub_batch). */
+    int ok = ab == NULL && max_n_cons == 1 && n_reads >= 1 && cons_lens && cons_seqs && LONGCALLD_NOISY_IS_BOTH_COVER(read_full_cover[0]) && read_lens[0] > 0;
+    for (int i = 0; ok && i < n_reads; ++i) if (read_lens[i] <= 0) ok = 0;
     if (ok) {
-        uint8_t *seqs = (uint8_t*)malloc(tot + 1), *cons = (uint8_t*)malloc(tot + 17);
-        int64_t *off = (int64_t*)malloc(sizeof(int64_t) * n_reads); int32_t *len = (int32_t*)malloc(sizeof(int32_t) * n_reads);
-        size_t o = 0; int max_len = 0;
-        for (int i = 0; i < n_reads; ++i) { off[i] = (int64_t)o; len[i] = read_lens[i]; memcpy(seqs + o, read_seqs[i], read_lens[i]); o += read_lens[i]; if (len[i] > max_len) max_len = len[i]; }
-        const lcd_poa_params_t par = { opt->match, opt->mismatch, opt->gap_open1, opt->gap_ext1, opt->gap_open2, opt->gap_ext2, 10, 0.01f, 1, 1 };   /* abpoa_init_para defaults wb / wf */
-        const int64_t msa_cap = (int64_t)(n_reads + 1) * (2 * (int64_t)max_len + 64);
-        uint8_t *msa = (msa_seq_lens && msa_seqs) ? (uint8_t*)malloc((size_t)msa_cap) : NULL;
-        req_t r; memset(&r, 0, sizeof(r));
-        r.kind = RQ_POA; r.seqs = seqs; r.seqs_len = tot; r.n_reads = n_reads; r.read_off = off; r.read_len = len; r.ppar = par; r.want_msa = msa != NULL; r.max_len = max_len;
-        r.cons = cons; r.msa = msa; r.msa_cap = msa_cap;
-        gpu_call(&r);
-        const lcd_poa_result_t res = r.pres;
-        if (res.status == LCD_POA_OK && res.cons_len > 0) {
-            cons_lens[0] = res.cons_len; cons_seqs[0] = (uint8_t*)malloc(res.cons_len); memcpy(cons_seqs[0], cons, res.cons_len);
-            if (clu_n_seqs != NULL && clu_read_ids != NULL) { *clu_n_seqs = n_reads; *clu_read_ids = (int*)malloc(n_reads * sizeof(int)); for (int i = 0; i < n_reads; ++i) (*clu_read_ids)[i] = read_ids[i]; }
-            if (msa) {
-                *msa_seq_lens = res.msa_len;
-                for (int i = 0; i < n_reads + 1; ++i) { msa_seqs[i] = (uint8_t*)malloc(res.msa_len); memcpy(msa_seqs[i], msa + (size_t)i * res.msa_len, res.msa_len); }
-            }
-            free(seqs); free(cons); free(off); free(len); free(msa);
-            return 1;
+        enum { RD_FULL = 0, RD_FULL_SAMPLED, RD_L2R, RD_R2L, RD_SKIP };
+        const int tlen0 = read_lens[0];
+        int *cls = (int*)calloc(n_reads, sizeof(int)), *sub_beg = (int*)calloc(n_reads, sizeof(int)), *sub_end = (int*)calloc(n_reads, sizeof(int));
+        int *cut_beg = (int*)calloc(n_reads, sizeof(int)), *cut_end = (int*)calloc(n_reads, sizeof(int));
+        typedef struct { uint8_t *target, *query; int tlen, qlen, gap_aln; } ext_t;            /* the (trimmed) pair of cal_wfa_partial_aln_beg_end */
+        ext_t *ext = (ext_t*)calloc(n_reads, sizeof(ext_t));
+        req_t *er = (req_t*)calloc(n_reads, sizeof(req_t)); req_t **list = (req_t**)malloc(sizeof(req_t*) * n_reads); int nl = 0, any_sub = 0;
+        for (int i = 1; i < n_reads; ++i) {
+            const int c = read_full_cover[i], qlen0 = read_lens[i];
+            if (LONGCALLD_NOISY_IS_BOTH_COVER(c) || (LONGCALLD_NOISY_IS_LEFT_COVER(c) && LONGCALLD_NOISY_IS_RIGHT_GAP(c)) || (LONGCALLD_NOISY_IS_RIGHT_COVER(c) && LONGCALLD_NOISY_IS_LEFT_GAP(c))) {
+                cls[i] = sampling_reads ? RD_FULL_SAMPLED : RD_FULL;
+                if (sampling_reads) { edlib_req_init(er + i, read_seqs[0], tlen0, read_seqs[i], qlen0, LCD_EDLIB_MODE_NW, 1); list[nl++] = er + i; }
+            } else if (LONGCALLD_NOISY_IS_LEFT_COVER(c) || LONGCALLD_NOISY_IS_RIGHT_COVER(c)) {
+                const int l2r = LONGCALLD_NOISY_IS_LEFT_COVER(c) != 0;
+                const double ratio = opt->partial_aln_ratio;
+                ext_t *x = ext + i; x->target = read_seqs[0]; x->query = read_seqs[i]; x->tlen = tlen0; x->qlen = qlen0;
+                if (l2r) { if (tlen0 > qlen0 * ratio) x->tlen = (int)(qlen0 * ratio); else if (qlen0 > tlen0 * ratio) x->qlen = (int)(tlen0 * ratio); }
+                else {
+                    if (tlen0 > qlen0 * ratio) { x->target = read_seqs[0] + tlen0 - (int)(qlen0 * ratio); x->tlen = (int)(qlen0 * ratio); }
+                    else if (qlen0 > tlen0 * ratio) { x->query = read_seqs[i] + qlen0 - (int)(tlen0 * ratio); x->qlen = (int)(tlen0 * ratio); }
+                }
+                x->gap_aln = opt->gap_aln;
+                if (l2r) x->gap_aln = (opt->gap_aln == LONGCALLD_GAP_RIGHT_ALN) ? LONGCALLD_GAP_LEFT_ALN : LONGCALLD_GAP_RIGHT_ALN;
+                cls[i] = l2r ? RD_L2R : RD_R2L;
+                const int mn = x->tlen < x->qlen ? x->tlen : x->qlen;
+                if (l2r) edlib_req_init(er + i, x->target, mn, x->query, mn, LCD_EDLIB_MODE_NW, 1);
+                else edlib_req_init(er + i, x->target + x->tlen - mn, mn, x->query + x->qlen - mn, mn, LCD_EDLIB_MODE_NW, 1);
+                list[nl++] = er + i;
+            } else cls[i] = RD_FULL;                       /* covers neither end: the reference keeps the full ranges (:711, ret = 1) */
         }
-        /* outside the kernel's envelope (e.g. LCD_POA_NEEDS_INT32, MSA wider than the estimate): let abPOA handle this region */
-        free(seqs); free(cons); free(off); free(len); free(msa);
+        gpu_call_many(list, nl);                            /* K7: every read's filter in one batch */
+        wfa_job_t *wj = (wfa_job_t*)calloc(n_reads, sizeof(wfa_job_t)); nl = 0;
+        for (int i = 1; i < n_reads; ++i) {
+            if (cls[i] == RD_FULL_SAMPLED) {
+                const int mn = tlen0 < read_lens[i] ? tlen0 : read_lens[i];
+                if (edlib_req_xgaps(er + i) > mn * 0.10) cls[i] = RD_SKIP;
+            } else if (cls[i] == RD_L2R || cls[i] == RD_R2L) {
+                ext_t *x = ext + i; const int mn = x->tlen < x->qlen ? x->tlen : x->qlen;
+                if (edlib_req_xgaps(er + i) > mn * 0.10) { cls[i] = RD_SKIP; continue; }
+                wfa_job_init(wj + i, x->target, x->tlen, x->query, x->qlen, x->gap_aln, opt->mismatch, opt->gap_open1, opt->gap_ext1, opt->gap_open2, opt->gap_ext2,
+                             LONGCALLD_WFA_NO_HEURISTIC, LONGCALLD_WFA_AFFINE_2P);
+                list[nl++] = &wj[i].r;
+            }
+        }
+        gpu_call_many(list, nl);                            /* K6: every one-sided read's extension alignment in one batch */
+        size_t tot = 0;
+        for (int i = 0; i < n_reads; ++i) {
+            if (cls[i] == RD_L2R || cls[i] == RD_R2L) {
+                uint32_t *cg = NULL; int ncg = 0;
+                wfa_job_finish(wj + i, &cg, &ncg, NULL, NULL, NULL);
+                if (ncg == 0) cls[i] = RD_SKIP;
+                else {
+                    int rb, re, qb, qe;
+                    collect_aln_beg_end(cg, ncg, cls[i] == RD_L2R ? LONGCALLD_EXT_ALN_LEFT_TO_RIGHT : LONGCALLD_EXT_ALN_RIGHT_TO_LEFT, tlen0, &rb, &re, read_lens[i], &qb, &qe);
+                    sub_beg[i] = rb + 1; sub_end[i] = re + 1; cut_beg[i] = qb - 1; cut_end[i] = read_lens[i] - qe; any_sub = 1;
+                    if (rb == 1 && re == tlen0) { sub_beg[i] = 0; sub_end[i] = 0; }            /* the whole first read: abpoa_subgraph_nodes yields the whole graph */
+                }
+                if (cg) free(cg);
+            }
+            if (cls[i] == RD_SKIP) { sub_beg[i] = sub_end[i] = -1; any_sub = 1; }
+            if (read_lens[i] - cut_beg[i] - cut_end[i] <= 0 && cls[i] != RD_SKIP) ok = 0;      /* (an empty piece: the reference's abPOA handles it its own way) */
+            tot += (size_t)read_lens[i];
+        }
+        free(wj); free(er); free(list); free(ext);
+        if (ok) {
+            uint8_t *seqs = (uint8_t*)malloc(tot + 1), *cons = (uint8_t*)malloc(tot + 17);
+            int64_t *off = (int64_t*)malloc(sizeof(int64_t) * n_reads); int32_t *len = (int32_t*)malloc(sizeof(int32_t) * n_reads);
+            size_t o = 0; int max_len = 0;
+            for (int i = 0; i < n_reads; ++i) {
+                const int l = cls[i] == RD_SKIP ? read_lens[i] : read_lens[i] - cut_beg[i] - cut_end[i];
+                off[i] = (int64_t)o; len[i] = l; memcpy(seqs + o, read_seqs[i] + (cls[i] == RD_SKIP ? 0 : cut_beg[i]), l); o += l; if (l > max_len) max_len = l;
+            }
+            const lcd_poa_params_t par = { opt->match, opt->mismatch, opt->gap_open1, opt->gap_ext1, opt->gap_open2, opt->gap_ext2, 10, 0.01f, 1, 1 };   /* abpoa_init_para defaults wb / wf */
+            const int64_t msa_cap = (int64_t)(n_reads + 1) * (2 * (int64_t)max_len + 64);
+            uint8_t *msa = (msa_seq_lens && msa_seqs) ? (uint8_t*)malloc((size_t)msa_cap) : NULL;
+            req_t r; memset(&r, 0, sizeof(r));
+            r.kind = RQ_POA; r.seqs = seqs; r.seqs_len = o; r.n_reads = n_reads; r.read_off = off; r.read_len = len; r.ppar = par; r.want_msa = msa != NULL; r.max_len = max_len;
+            r.cons = cons; r.msa = msa; r.msa_cap = msa_cap;
+            if (any_sub) { r.sub_beg = sub_beg; r.sub_end = sub_end; }
+            gpu_call(&r);
+            const lcd_poa_result_t res = r.pres;
+            if (res.status == LCD_POA_OK && res.cons_len > 0) {
+                cons_lens[0] = res.cons_len; cons_seqs[0] = (uint8_t*)malloc(res.cons_len); memcpy(cons_seqs[0], cons, res.cons_len);
+                if (clu_n_seqs != NULL && clu_read_ids != NULL) { *clu_n_seqs = n_reads; *clu_read_ids = (int*)malloc(n_reads * sizeof(int)); for (int i = 0; i < n_reads; ++i) (*clu_read_ids)[i] = read_ids[i]; }
+                if (msa) {
+                    *msa_seq_lens = res.msa_len;
+                    for (int i = 0; i < n_reads + 1; ++i) { msa_seqs[i] = (uint8_t*)malloc(res.msa_len); memcpy(msa_seqs[i], msa + (size_t)i * res.msa_len, res.msa_len); }
+                }
+                free(seqs); free(cons); free(off); free(len); free(msa);
+                free(cls); free(sub_beg); free(sub_end); free(cut_beg); free(cut_end);
+                if (any_sub) COUNT(11);
+                return 1;
+            }
+            /* outside the kernel's envelope (e.g. LCD_POA_NEEDS_INT32, MSA wider than the estimate): let abPOA handle this region */
+            free(seqs); free(cons); free(off); free(len); free(msa);
+        }
+        free(cls); free(sub_beg); free(sub_end); free(cut_beg); free(cut_end);
     }
     COUNT(6);
     const double t0_ = now_s();

@@ -15,7 +15,8 @@ REF_DIR = os.path.join(T.ROOT, "oracle", "_ref")
 DROPIN = os.path.join(T.ROOT, "longcalld_b200", "dropin", "liblcd_dropin.so")
 GOLDEN = {"hifi": "dcbd4523c01ab37cce5dd88d5e56b564", "ont": "71f0e1aa2ee7667ad2a1f31e2eace81d",
           "mosaic": "ea77d40096193eb9ad4497c297c21fd7"}
-FORWARDED_POA = {"hifi": 23, "ont": 34, "mosaic": 23}          # mosaic: HiFi with -s -T <TE consensus> (BASELINE configs[4] on the bundled data)
+FORWARDED_POA = {"hifi": 0, "ont": 0, "mosaic": 0}             # mosaic: HiFi with -s -T <TE consensus> (BASELINE configs[4] on the bundled data)
+PARTIAL_POA = {"hifi": 23, "ont": 34, "mosaic": 23}            # POA problems with partially covering / sampled reads: sub-graph alignment on the GPU
 
 
 def _run(tech, preload, threads=4):
@@ -47,10 +48,11 @@ def test_vcf_identical_with_gpu_dropin(tech):
     fwd = int(__import__("re").search(r"digar \d+ \(forwarded: (\d+)\)", calls[-1]).group(1))
     assert fwd == 0, calls[-1]                      # (the bundled ONT BAM carries plain-M CIGARs + MD tags: K1's MD front end)
     assert all(counts[k] > 0 for k in need), calls[-1]                                             # the kernels really ran on the GPU
-    # POA calls outside the kernel's envelope go to the reference's abPOA: exactly the known partial-cover / sampled / de-novo regions of
-    # the bundled data -- a kernel that starts refusing problems (a silent CPU fallback) fails here, not in the md5
+    # no POA call of abpoa_partial_aln_msa_cons goes to the reference's abPOA any more: a kernel that starts refusing problems (a silent
+    # CPU fallback) fails here, not in the md5; the problems with partially covering / sampled reads are counted
     fwd_poa = int(__import__("re").search(r"forwarded to abPOA: (\d+)", calls[-1]).group(1))
-    assert fwd_poa == FORWARDED_POA[tech], calls[-1]
+    part_poa = int(__import__("re").search(r"with partially covering reads: (\d+)", calls[-1]).group(1))
+    assert fwd_poa == FORWARDED_POA[tech] and part_poa == PARTIAL_POA[tech], calls[-1]
     print(calls[-1])
     assert md5 == GOLDEN[tech], (md5, calls[-1])
 
