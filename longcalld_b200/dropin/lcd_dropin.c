@@ -556,20 +556,21 @@ static void run_batch(int kind, req_t **r, int n) {
     t_add(&t_batch[kind], now_s() - t0_);
 }
 
-/* Group-commit combiner over ALL worker threads (kt_for) and all three engines.  A thread that has parked requests adds them to the
- * queue; the first one there becomes the leader.  Only ONE batch is in flight at a time: while the batch before is on the GPU the leader
- * waits and the queue keeps growing (every thread that reaches an engine call meanwhile joins), so the batch size follows the GPU's
- * round-trip time -- the slower a round, the wider the next one.  Before it goes the leader also gives the worker threads that are inside
- * collect_var_main but not blocked here yet a bounded moment to arrive.  The three engines of one batch run side by side (K5 in the lower
- * window of the workspace pool, K6 / K7 in the upper one: lcd_gpu_split_pool).  With more worker threads than cores (-t 64 on 16 cores:
- * the threads mostly wait for the GPU) the batches are tens of chunks wide. */
-static struct { pthread_mutex_t mu; pthread_cond_t cv; req_t **pend; int n, cap, leader, busy, n_active, n_blocked; } cq = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, 0, 0, 0, 0, 0 };
-static int linger_us(void) { static int v = -1; if (v < 0) { const char *e = getenv("LCD_DROPIN_LINGER_US"); v = e ? atoi(e) : 2000; } return v; }
-static void worker_enter(void) { pthread_mutex_lock(&cq.mu); cq.n_active++; pthread_mutex_unlock(&cq.mu); }
-static void worker_leave(void) { pthread_mutex_lock(&cq.mu); cq.n_active--; pthread_cond_broadcast(&cq.cv); pthread_mutex_unlock(&cq.mu); }
+/* Group-commit combiner over ALL worker threads (kt_for) and all three engines.  Whoever has parked requests adds them to the queue; up to
+ * max_inflight RUNNER threads take whatever the queue holds and make one library call per engine (the three engines of a batch side by
+ * side: K5 in a window of the lower part of the workspace pool, K6 / K7 in a window of the upper part -- lcd_gpu_pool_windows).  While every
+ * runner is on the GPU the queue keeps growing, so the batch size follows the GPU's round-trip time: the slower a round, the wider the
+ * next one.  A waiting worker does not sleep if it can help it: kt_for (below) keeps several CHUNKS in flight per worker thread and
+ * switches to another one. */
+typedef struct { int n; cand_var_t *vars; int *cate; read_var_profile_t *p; int *map; } pend_merge_t;
+typedef struct { pend_merge_t *v; int n, cap, on; } merge_tl_t;
+static __thread merge_tl_t tl_merge;                       /* a13: the pass's queued merge_var_profile calls (further down) */
+static struct { pthread_mutex_t mu; pthread_cond_t cv_work, cv_done; req_t **pend; int n, cap; unsigned long done_gen; } cq =
+    { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, 0, 0 };
+static int linger_us(void) { static int v = -1; if (v < 0) { const char *e = getenv("LCD_DROPIN_LINGER_US"); v = e ? atoi(e) : 300; } return v; }
 
 typedef struct { int kind, n, slot; req_t **r; } kind_job_t;
-static struct { int used; void *st[RQ_KINDS]; } slots[MAX_INFLIGHT];          /* a batch in flight: one stream per engine */
+static struct { void *st[RQ_KINDS]; } slots[MAX_INFLIGHT];          /* a batch in flight: one stream per engine */
 static void run_kind(kind_job_t *j) {
     void *mine = tl_stream;
     if (!slots[j->slot].st[j->kind]) { slots[j->slot].st[j->kind] = lcd_gpu_new_stream(); if (!slots[j->slot].st[j->kind]) die("lcd_gpu_new_stream"); }
@@ -579,26 +580,17 @@ static void run_kind(kind_job_t *j) {
 }
 static void *kind_thread(void *a) { pthread_once(&init_once, dropin_init); run_kind((kind_job_t*)a); return NULL; }
 
-static void combine(req_t **r, int n) {
-    if (n == 0) return;
-    const double t0_ = now_s();
-    trace("wait_begin", n, 0);
-    pthread_mutex_lock(&cq.mu);
-    if (cq.n + n > cq.cap) { cq.cap = 2 * (cq.n + n); cq.pend = (req_t**)realloc(cq.pend, sizeof(req_t*) * cq.cap); }
-    memcpy(cq.pend + cq.n, r, sizeof(req_t*) * n); cq.n += n;
-    cq.n_blocked++;
-    pthread_cond_broadcast(&cq.cv);                            /* a lingering leader re-checks whether everybody has arrived */
-    if (!cq.leader) {
-        cq.leader = 1;
-        while (cq.busy >= max_inflight) pthread_cond_wait(&cq.cv, &cq.mu);     /* group commit: every batch slot is on the GPU */
-        struct timespec until; clock_gettime(CLOCK_REALTIME, &until);
-        until.tv_nsec += (long)linger_us() * 1000; until.tv_sec += until.tv_nsec / 1000000000; until.tv_nsec %= 1000000000;
-        while (cq.n_blocked < cq.n_active) if (pthread_cond_timedwait(&cq.cv, &cq.mu, &until) != 0) break;
+static void *runner_main(void *a) {
+    const int slot = (int)(long)a;
+    pthread_once(&init_once, dropin_init);
+    for (;;) {
+        pthread_mutex_lock(&cq.mu);
+        while (cq.n == 0) pthread_cond_wait(&cq.cv_work, &cq.mu);
+        if (linger_us() > 0) { pthread_mutex_unlock(&cq.mu); usleep(linger_us()); pthread_mutex_lock(&cq.mu); }       /* a burst arrives over a few hundred microseconds */
         req_t **take = cq.pend; const int nt = cq.n;
-        int slot = 0; while (slots[slot].used) ++slot;
-        slots[slot].used = 1;
-        cq.pend = NULL; cq.n = cq.cap = 0; cq.leader = 0; cq.busy++;        /* the next batch collects while this one runs */
+        cq.pend = NULL; cq.n = cq.cap = 0;
         pthread_mutex_unlock(&cq.mu);
+        if (nt == 0) continue;                              /* another runner took the burst */
         req_t **byk = (req_t**)malloc(sizeof(req_t*) * nt);
         kind_job_t job[RQ_KINDS]; pthread_t th[RQ_KINDS]; int started[RQ_KINDS], m = 0, n_kinds = 0;
         for (int k = 0; k < RQ_KINDS; ++k) { job[k].kind = k; job[k].slot = slot; job[k].r = byk + m; job[k].n = 0; for (int i = 0; i < nt; ++i) if (take[i]->kind == k) { byk[m++] = take[i]; job[k].n++; } if (job[k].n) n_kinds++; }
@@ -607,17 +599,49 @@ static void combine(req_t **r, int n) {
         for (int k = 1; k < RQ_KINDS; ++k) { if (started[k]) pthread_join(th[k], NULL); else if (job[k].n) run_kind(&job[k]); }
         free(byk); free(take);
         pthread_mutex_lock(&cq.mu);
-        cq.busy--; slots[slot].used = 0;
-        pthread_cond_broadcast(&cq.cv);
+        cq.done_gen++;
+        pthread_cond_broadcast(&cq.cv_done);
+        pthread_mutex_unlock(&cq.mu);
     }
-    for (;;) {
-        int all = 1;
-        for (int i = 0; i < n; ++i) if (!__atomic_load_n(&r[i]->done, __ATOMIC_ACQUIRE)) { all = 0; break; }
-        if (all) break;
-        pthread_cond_wait(&cq.cv, &cq.mu);
+    return NULL;
+}
+static pthread_once_t runners_once = PTHREAD_ONCE_INIT;
+static void start_runners(void) {
+    pthread_once(&init_once, dropin_init);
+    for (long k = 0; k < max_inflight; ++k) { pthread_t t; if (pthread_create(&t, NULL, runner_main, (void*)k) != 0) die("pthread_create"); pthread_detach(t); }
+}
+
+/* ---- chunks in flight: kt_for (src/kthread.c:48) with several chunks per worker thread.
+ * The reference gives every worker thread one chunk at a time (call_var_main.c:773); its thread would sleep through every engine batch.
+ * This kt_for runs each call of the worker function on a stack of its own (ucontext) and keeps up to LCD_DROPIN_CHUNKS_PER_THREAD of them
+ * going per thread: a chunk that waits for its requests yields, and the thread loads / scans / post-processes another chunk meanwhile.
+ * A thread's chunks share its tid (the reference's per-thread BAM handle): they only ever switch inside combine(), never inside the loader. */
+enum { CK_FREE = 0, CK_READY, CK_WAITING, CK_DONE };
+struct sched_t; struct co_t;
+typedef struct chunk_co_t { ucontext_t ctx; void *stack; int state; long i; req_t **wait; int n_wait; struct sched_t *sv_sched; struct co_t *sv_co; merge_tl_t sv_merge; } chunk_co_t;
+typedef struct { ucontext_t main; chunk_co_t *cur; void (*func)(void*, long, int); void *data; int tid; long n; long *next; } kworker_t;
+static __thread kworker_t *tl_kw = NULL;
+#define CHUNK_STACK ((size_t)8 << 20)
+static int chunks_per_thread(void) { static int v = -1; if (v < 0) { const char *e = getenv("LCD_DROPIN_CHUNKS_PER_THREAD"); v = e ? atoi(e) : 3; if (v < 1) v = 1; if (v > 16) v = 16; } return v; }
+static int all_done(req_t **r, int n) { for (int i = 0; i < n; ++i) if (!__atomic_load_n(&r[i]->done, __ATOMIC_ACQUIRE)) return 0; return 1; }
+
+static void combine(req_t **r, int n) {
+    if (n == 0) return;
+    const double t0_ = now_s();
+    trace("wait_begin", n, 0);
+    pthread_once(&runners_once, start_runners);
+    pthread_mutex_lock(&cq.mu);
+    if (cq.n + n > cq.cap) { cq.cap = 2 * (cq.n + n); cq.pend = (req_t**)realloc(cq.pend, sizeof(req_t*) * cq.cap); }
+    memcpy(cq.pend + cq.n, r, sizeof(req_t*) * n); cq.n += n;
+    pthread_cond_signal(&cq.cv_work);
+    if (tl_kw && tl_kw->cur) {                              /* a chunk of kt_for: let the thread work on another chunk meanwhile */
+        pthread_mutex_unlock(&cq.mu);
+        chunk_co_t *c = tl_kw->cur; c->wait = r; c->n_wait = n;
+        while (!all_done(r, n)) { c->state = CK_WAITING; swapcontext(&c->ctx, &tl_kw->main); }
+    } else {
+        while (!all_done(r, n)) pthread_cond_wait(&cq.cv_done, &cq.mu);
+        pthread_mutex_unlock(&cq.mu);
     }
-    cq.n_blocked--;
-    pthread_mutex_unlock(&cq.mu);
     trace("wait_end", n, 0);
     t_add(&t_blocked, now_s() - t0_);
 }
@@ -625,7 +649,7 @@ static void combine(req_t **r, int n) {
 /* ---- coroutines: one per pending noisy region of the chunk a worker thread is on */
 enum { CO_READY, CO_PARKED, CO_TURN, CO_DONE };
 typedef struct co_t { ucontext_t ctx; void *stack; int state, idx, reg_i, ret; req_t **reqs; int n_reqs; bam_chunk_t *chunk; const call_var_opt_t *opt; } co_t;
-typedef struct { ucontext_t main; co_t *cos; int n, next_turn; } sched_t;
+typedef struct sched_t { ucontext_t main; co_t *cos; int n, next_turn; } sched_t;
 static __thread sched_t *tl_sched = NULL;
 static __thread co_t *tl_co = NULL;
 #define CO_STACK ((size_t)1 << 20)
@@ -647,10 +671,57 @@ static void gpu_call_many(req_t **rs, int n) {             /* independent reques
 }
 static void gpu_call(req_t *r) { req_t *one = r; gpu_call_many(&one, 1); }
 
+/* coroutine stacks come from a free list of the OS thread: the chunks a thread keeps in flight (kt_for) run their regions at the same time */
+static __thread void **free_stacks = NULL; static __thread int n_free_stacks = 0, cap_free_stacks = 0;
+static void *co_stack_get(void) { return n_free_stacks > 0 ? free_stacks[--n_free_stacks] : malloc(CO_STACK); }
+static void co_stack_put(void *st) {
+    if (n_free_stacks == cap_free_stacks) { cap_free_stacks = 2 * cap_free_stacks + 64; free_stacks = (void**)realloc(free_stacks, sizeof(void*) * cap_free_stacks); }
+    free_stacks[n_free_stacks++] = st;
+}
+
+/* fork / join inside a region: independent pieces of one region's work (the two haplotypes' POA, then their two WFA alignments) run on child
+ * stacks until each has parked its engine requests; the region then parks with the union, so the pieces cost one round trip, not one each. */
+typedef struct { void (*fn)(void *); void *arg; } task_t;
+static __thread task_t *tl_tasks = NULL;
+static void task_entry(void) {
+    co_t *c = tl_co;
+    tl_tasks[c->idx].fn(tl_tasks[c->idx].arg);
+    c->state = CO_DONE;
+    swapcontext(&c->ctx, &tl_sched->main);
+}
+static void fork_join(task_t *tasks, int n) {
+    if (!tl_co || n == 1) { for (int i = 0; i < n; ++i) tasks[i].fn(tasks[i].arg); return; }       /* not inside a region coroutine: one after the other */
+    sched_t *outer_sched = tl_sched; co_t *outer_co = tl_co; task_t *outer_tasks = tl_tasks;
+    sched_t sc; memset(&sc, 0, sizeof(sc));
+    sc.cos = (co_t*)calloc(n, sizeof(co_t)); sc.n = n;
+    for (int i = 0; i < n; ++i) {
+        co_t *c = sc.cos + i;
+        c->stack = co_stack_get(); c->state = CO_READY; c->idx = i;
+        getcontext(&c->ctx); c->ctx.uc_stack.ss_sp = c->stack; c->ctx.uc_stack.ss_size = CO_STACK; c->ctx.uc_link = NULL;
+        makecontext(&c->ctx, task_entry, 0);
+    }
+    req_t **parked = NULL; int cap = 0;
+    for (;;) {
+        for (int i = 0; i < n; ++i) if (sc.cos[i].state == CO_READY) { tl_sched = &sc; tl_tasks = tasks; tl_co = sc.cos + i; swapcontext(&sc.main, &sc.cos[i].ctx); }
+        int np = 0;
+        for (int i = 0; i < n; ++i) if (sc.cos[i].state == CO_PARKED) {
+            if (np + sc.cos[i].n_reqs > cap) { cap = 2 * (np + sc.cos[i].n_reqs) + 16; parked = (req_t**)realloc(parked, sizeof(req_t*) * cap); }
+            for (int k = 0; k < sc.cos[i].n_reqs; ++k) parked[np++] = sc.cos[i].reqs[k];
+        }
+        if (np == 0) break;
+        tl_sched = outer_sched; tl_co = outer_co; tl_tasks = outer_tasks;
+        gpu_call_many(parked, np);                          /* the region parks with all the pieces' requests */
+        for (int i = 0; i < n; ++i) if (sc.cos[i].state == CO_PARKED) sc.cos[i].state = CO_READY;
+    }
+    tl_sched = outer_sched; tl_co = outer_co; tl_tasks = outer_tasks;
+    for (int i = 0; i < n; ++i) co_stack_put(sc.cos[i].stack);
+    free(parked); free(sc.cos);
+}
+
 /* all pending regions of one pass side by side; ret[k] = collect_noisy_vars1's return value for regs[k] */
 static void run_regions(bam_chunk_t *chunk, const call_var_opt_t *opt, int n, const int *regs, int *ret) {
-    static __thread void **stack_pool = NULL; static __thread int n_stacks = 0;
-    if (n > n_stacks) { stack_pool = (void**)realloc(stack_pool, sizeof(void*) * n); for (int i = n_stacks; i < n; ++i) stack_pool[i] = malloc(CO_STACK); n_stacks = n; }
+    void **stack_pool = (void**)malloc(sizeof(void*) * n);
+    for (int i = 0; i < n; ++i) stack_pool[i] = co_stack_get();
     sched_t sc; memset(&sc, 0, sizeof(sc));
     sc.cos = (co_t*)calloc(n, sizeof(co_t)); sc.n = n; sc.next_turn = 0;
     for (int i = 0; i < n; ++i) {
@@ -685,7 +756,73 @@ static void run_regions(bam_chunk_t *chunk, const call_var_opt_t *opt, int n, co
     }
     tl_sched = NULL;
     for (int i = 0; i < n; ++i) ret[i] = sc.cos[i].ret;
+    for (int i = 0; i < n; ++i) co_stack_put(stack_pool[i]);
+    free(stack_pool);
     free(parked); free(sc.cos);
+}
+
+/* kt_for with several chunks in flight per worker thread (see above) */
+static void chunk_entry(void) {
+    kworker_t *kw = tl_kw; chunk_co_t *c = kw->cur;
+    kw->func(kw->data, c->i, kw->tid);
+    c->state = CK_DONE;
+    swapcontext(&c->ctx, &kw->main);
+}
+static void *kworker_main(void *a) {
+    kworker_t *kw = (kworker_t*)a;
+    tl_kw = kw;
+    const int K = chunks_per_thread();
+    chunk_co_t *sl = (chunk_co_t*)calloc(K, sizeof(chunk_co_t));
+    int exhausted = 0;
+    for (;;) {
+        pthread_mutex_lock(&cq.mu); const unsigned long gen = cq.done_gen; pthread_mutex_unlock(&cq.mu);
+        int progressed = 0, n_live = 0;
+        for (int k = 0; k < K; ++k) {
+            chunk_co_t *c = sl + k;
+            if (c->state == CK_WAITING && all_done(c->wait, c->n_wait)) c->state = CK_READY;
+            if (c->state == CK_FREE && !exhausted) {
+                const long i = __atomic_fetch_add(kw->next, 1, __ATOMIC_RELAXED);
+                if (i >= kw->n) exhausted = 1;
+                else {
+                    if (!c->stack) c->stack = malloc(CHUNK_STACK);
+                    getcontext(&c->ctx); c->ctx.uc_stack.ss_sp = c->stack; c->ctx.uc_stack.ss_size = CHUNK_STACK; c->ctx.uc_link = NULL;
+                    makecontext(&c->ctx, chunk_entry, 0);
+                    c->i = i; c->state = CK_READY; c->sv_sched = NULL; c->sv_co = NULL; memset(&c->sv_merge, 0, sizeof(c->sv_merge));
+                }
+            }
+            if (c->state == CK_READY) {
+                tl_sched = c->sv_sched; tl_co = c->sv_co; tl_merge = c->sv_merge;          /* the chunk's thread-local state travels with it */
+                kw->cur = c; swapcontext(&kw->main, &c->ctx); kw->cur = NULL;
+                c->sv_sched = tl_sched; c->sv_co = tl_co; c->sv_merge = tl_merge;
+                tl_sched = NULL; tl_co = NULL; memset(&tl_merge, 0, sizeof(tl_merge));
+                progressed = 1;
+                if (c->state == CK_DONE) { free(c->sv_merge.v); c->state = CK_FREE; }
+            }
+            if (c->state != CK_FREE) n_live++;
+        }
+        if (n_live == 0 && exhausted) break;
+        if (!progressed) {                                   /* every chunk of this thread waits for the GPU */
+            pthread_mutex_lock(&cq.mu);
+            if (cq.done_gen == gen) pthread_cond_wait(&cq.cv_done, &cq.mu);
+            pthread_mutex_unlock(&cq.mu);
+        }
+    }
+    for (int k = 0; k < K; ++k) free(sl[k].stack);
+    free(sl);
+    tl_kw = NULL;
+    return NULL;
+}
+void kt_for(int n_threads, void (*func)(void*, long, int), void *data, long n) {                      /* src/kthread.c:48-66 */
+    if (n_threads < 1) n_threads = 1;
+    long next = 0;
+    kworker_t *kw = (kworker_t*)calloc(n_threads, sizeof(kworker_t)); pthread_t *th = (pthread_t*)calloc(n_threads, sizeof(pthread_t));
+    for (int t = 0; t < n_threads; ++t) { kw[t].func = func; kw[t].data = data; kw[t].tid = t; kw[t].n = n; kw[t].next = &next; }
+    if (n_threads == 1) kworker_main(&kw[0]);
+    else {
+        for (int t = 0; t < n_threads; ++t) if (pthread_create(&th[t], NULL, kworker_main, &kw[t]) != 0) die("pthread_create");
+        for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+    }
+    free(kw); free(th);
 }
 
 /* make_vars_from_msa_cons_aln (src/collect_var.c:2279) starts the part of a region that edits the chunk's variant list: regions take it
@@ -710,8 +847,6 @@ int make_vars_from_msa_cons_aln(const call_var_opt_t *opt, bam_chunk_t *chunk, i
 int exact_comp_cand_var(const call_var_opt_t *opt, cand_var_t *var1, cand_var_t *var2);     /* src/collect_var.c:1255 */
 void free_cand_vars1(cand_var_t *cand_vars);                                                /* :54 */
 void free_read_var_profile(read_var_profile_t *p, int n_reads);                             /* src/bam_utils.c:46 */
-typedef struct { int n; cand_var_t *vars; int *cate; read_var_profile_t *p; int *map; } pend_merge_t;
-static __thread struct { pend_merge_t *v; int n, cap, on; } tl_merge;
 
 int merge_var_profile(const call_var_opt_t *opt, bam_chunk_t *chunk, int n_new_vars, cand_var_t *new_vars, int *new_var_cate, read_var_profile_t *new_p) {
     if (!tl_merge.on) {
@@ -824,7 +959,6 @@ void collect_var_main(const call_var_pl_t *pl, bam_chunk_t *chunk) {
         /* -s / --refine-aln rewrite the reads' difference lists region by region (update_digars_from_aln_str, src/align.c:1796): one at a time */
         const int one_by_one = opt->out_somatic || (opt->refine_bam && opt->out_aln_fp != NULL) || getenv("LCD_DROPIN_SERIAL") != NULL;
         trace("regions_begin", (long)chunk->reg_beg, n_regs);
-        worker_enter();                                       /* from here on this thread's engine calls are batched with the other threads' */
         for (;;) {
             int new_region_is_done = 0, new_var = 0, np = 0;
             for (int i = 0; i < n_regs; ++i) if (!is_done[sorted[i]]) pend[np++] = sorted[i];
@@ -834,7 +968,6 @@ void collect_var_main(const call_var_pl_t *pl, bam_chunk_t *chunk) {
             if (new_var) assign_hap_based_on_germline_het_vars_kmeans(opt, chunk, LONGCALLD_CAND_GERMLINE_VAR_CATE);
             if (new_region_is_done == 0) break;
         }
-        worker_leave();
         trace("regions_end", (long)chunk->reg_beg, n_regs);
         free(sorted); free(is_done); free(pend); free(ret);
     }
@@ -1078,4 +1211,85 @@ int abpoa_partial_aln_msa_cons(const call_var_opt_t *opt, abpoa_t *ab, int sampl
                 clu_n_seqs, clu_read_ids, msa_seq_lens, msa_seqs);
     t_add(&t_fwd_poa, now_s() - t0_);
     return rc_;
+}
+
+/* ------------------------------------------------------------------------------------------ a8: the two haplotypes of a region side by side
+ * wfa_collect_noisy_aln_str_with_ps_hap (src/align.c:1286-1375): the same steps -- the reads of each haplotype of the phase set, one POA per
+ * haplotype, ref-vs-consensus alignment strings, consensus-vs-read strings from the MSA rows -- with the two POA problems issued together and
+ * then the two WFA problems issued together (fork_join), so a region costs two engine round trips here instead of four. */
+int is_homopolymer(uint8_t *seq, int seq_len, int flank_len, int *hp_start, int *hp_end, int *hp_len);                                  /* src/align.c:1000 */
+int make_cons_read_aln_str(const call_var_opt_t *opt, uint8_t *cons_str, uint8_t *read_str, int msa_len, int full_cover, aln_str_t *cons_read_aln_str);   /* :1029 */
+int make_ref_read_aln_str(const call_var_opt_t *opt, aln_str_t *ref_cons_aln_str, aln_str_t *cons_read_aln_str, aln_str_t *ref_read_aln_str);          /* :1056 */
+int wfa_collect_aln_str(const call_var_opt_t *opt, uint8_t *target, int tlen, uint8_t *query, int qlen, int full_cover, int heuristic, int affine_gap, aln_str_t *aln_str);   /* :565 */
+typedef struct {
+    const call_var_opt_t *opt; int sampling_reads, n; int *ids; uint8_t **seqs, **quals; int *lens, *covers; char **names;
+    int *cons_len; uint8_t **cons_seq; int *clu_n; int **clu_ids; int *msa_len; uint8_t **msa; int ret;
+} hap_poa_t;
+static void hap_poa_task(void *a) {
+    hap_poa_t *h = (hap_poa_t*)a;
+    h->ret = abpoa_partial_aln_msa_cons(h->opt, NULL, h->sampling_reads, h->n, h->ids, h->seqs, h->quals, h->lens, h->covers, h->names, 1, h->cons_len, h->cons_seq, h->clu_n, h->clu_ids, h->msa_len, h->msa);
+}
+typedef struct { const call_var_opt_t *opt; uint8_t *ref; int ref_len; uint8_t *cons; int cons_len; aln_str_t *out; } hap_wfa_t;
+static void hap_wfa_task(void *a) {
+    hap_wfa_t *h = (hap_wfa_t*)a;
+    wfa_collect_aln_str(h->opt, h->ref, h->ref_len, h->cons, h->cons_len, LONGCALLD_NOISY_BOTH_COVER, LONGCALLD_WFA_NO_HEURISTIC, LONGCALLD_WFA_AFFINE_2P, h->out);
+}
+int wfa_collect_noisy_aln_str_with_ps_hap(const call_var_opt_t *opt, int sampling_reads, int n_reads, int *noisy_read_ids, int *lens, uint8_t **seqs, uint8_t *strands, uint8_t **quals, char **names,
+                                          int *haps, hts_pos_t *phase_sets, int *fully_covers, hts_pos_t ps, int min_hap_full_reads, int min_hap_all_reads, uint8_t *ref_seq, int ref_seq_len,
+                                          int *clu_n_seqs, int **clu_read_ids, aln_str_t **aln_strs, int collect_ref_read_aln_str) {
+    (void)strands; (void)min_hap_full_reads; (void)min_hap_all_reads;
+    const int total = n_reads + 2;
+    int n_cons = 0;
+    int cons_lens[2] = {0, 0}; uint8_t *cons_seqs[2] = {NULL, NULL}; int msa_seq_lens[2] = {0, 0}; uint8_t **msa_seqs[2];
+    int *h_ids[2], *h_lens[2], *h_cov[2]; uint8_t **h_seqs[2], **h_quals[2]; char **h_names[2];
+    for (int i = 0; i < 2; ++i) {
+        msa_seqs[i] = (uint8_t**)calloc(n_reads + 1, sizeof(uint8_t*));
+        h_ids[i] = (int*)malloc(total * sizeof(int)); h_lens[i] = (int*)malloc(total * sizeof(int)); h_cov[i] = (int*)calloc(total, sizeof(int));
+        h_seqs[i] = (uint8_t**)malloc(total * sizeof(uint8_t*)); h_quals[i] = (uint8_t**)malloc(total * sizeof(uint8_t*)); h_names[i] = (char**)malloc(total * sizeof(char*));
+    }
+    int hp_s, hp_e, hp_l, use_non_full = 1;
+    if (is_homopolymer(ref_seq, ref_seq_len, opt->noisy_reg_flank_len, &hp_s, &hp_e, &hp_l)) use_non_full = 0;
+    /* the reads of each haplotype (:1312-1326).  The reference gives up at the first haplotype whose first read is as long as max_noisy_reg_len
+     * (:1327-1330; for a haplotype without reads it looks at the slot the haplotype before left, which has passed the test) and skips a
+     * haplotype without reads (:1332); one consensus alone counts as none (:1338). */
+    hap_poa_t hp[2]; task_t tasks[2]; int n_tasks = 0;
+    for (int hap = 1; hap <= 2; ++hap) {
+        const int x = hap - 1; int m = 0;
+        for (int i = 0; i < n_reads; ++i) {
+            if (lens[i] <= 0 || phase_sets[i] != ps || haps[i] != hap) continue;
+            if (use_non_full == 0 && LONGCALLD_NOISY_IS_BOTH_COVER(fully_covers[i]) == 0) continue;
+            h_ids[x][m] = noisy_read_ids[i]; h_lens[x][m] = lens[i]; h_seqs[x][m] = seqs[i]; h_quals[x][m] = quals[i]; h_cov[x][m] = fully_covers[i]; h_names[x][m] = names[i]; ++m;
+        }
+
+        if (m > 0 && h_lens[x][0] >= opt->max_noisy_reg_len) break;
+        if (m == 0) continue;
+        hap_poa_t h = { opt, sampling_reads, m, h_ids[x], h_seqs[x], h_quals[x], h_lens[x], h_cov[x], h_names[x], cons_lens + x, cons_seqs + x, clu_n_seqs + x, clu_read_ids + x, msa_seq_lens + x, msa_seqs[x], 0 };
+        hp[n_tasks] = h; tasks[n_tasks].fn = hap_poa_task; tasks[n_tasks].arg = &hp[n_tasks]; ++n_tasks;
+    }
+    fork_join(tasks, n_tasks);                               /* K5 (and the filters / extension alignments of partially covering reads) of both haplotypes */
+    for (int k = 0; k < n_tasks; ++k) n_cons += hp[k].ret;
+    if (n_cons != 2) n_cons = 0;
+    else {
+        hap_wfa_t hw[2];
+        for (int x = 0; x < 2; ++x) { hap_wfa_t h = { opt, ref_seq, ref_seq_len, cons_seqs[x], cons_lens[x], LONGCALLD_REF_CONS_ALN_STR(aln_strs[x]) }; hw[x] = h; tasks[x].fn = hap_wfa_task; tasks[x].arg = &hw[x]; }
+        fork_join(tasks, 2);                                 /* K6: ref vs consensus, both haplotypes */
+        for (int hap = 1; hap <= 2; ++hap) {
+            aln_str_t *clu_aln_str = aln_strs[hap - 1];
+            int m = 0;
+            for (int i = 0; i < n_reads; ++i) {
+                if (lens[i] <= 0 || phase_sets[i] != ps || haps[i] != hap) continue;
+                if (use_non_full == 0 && LONGCALLD_NOISY_IS_BOTH_COVER(fully_covers[i]) == 0) continue;
+                make_cons_read_aln_str(opt, msa_seqs[hap - 1][clu_n_seqs[hap - 1]], msa_seqs[hap - 1][m], msa_seq_lens[hap - 1], fully_covers[i], LONGCALLD_CONS_READ_ALN_STR(clu_aln_str, m));
+                if (collect_ref_read_aln_str)
+                    make_ref_read_aln_str(opt, LONGCALLD_REF_CONS_ALN_STR(clu_aln_str), LONGCALLD_CONS_READ_ALN_STR(clu_aln_str, m), LONGCALLD_REF_READ_ALN_STR(clu_aln_str, m));
+                ++m;
+            }
+        }
+    }
+    for (int i = 0; i < 2; ++i) {
+        free(cons_seqs[i]);
+        for (int j = 0; j < n_reads + 1; ++j) free(msa_seqs[i][j]);
+        free(msa_seqs[i]); free(h_ids[i]); free(h_lens[i]); free(h_cov[i]); free(h_seqs[i]); free(h_quals[i]); free(h_names[i]);
+    }
+    return n_cons;
 }

@@ -1,13 +1,8 @@
-# whole-program probe: reference vs GPU drop-in at several worker-thread counts on one synthetic BAM (scratch tool)
-mkdir -p /tmp/wp && cd /tmp/wp && [ -f s50.bam.bai ] || /root/repo/tools/_build/synth_bam s50 ${MB:-50} hifi 11 >/dev/null 2>&1
-R=/root/repo
-P=$R/tools/_build/libref_prof.so
-D=$R/longcalld_b200/dropin/liblcd_dropin.so
-export LCD_DROPIN_VERBOSE=1
-$R/oracle/_ref/longcallD_ref call --hifi -t 16 s50.fa s50.bam 2>ref.err | grep -v '^#' | md5sum; grep Real ref.err
-for t in ${THREADS:-16 32 64 100}; do
-  for st in ${STAGES:-all engines}; do
-    echo "== -t $t stages $st"
-    LCD_DROPIN_STAGES=$st LD_PRELOAD="$D" $R/oracle/_ref/longcallD_so call --hifi -t $t s50.fa s50.bam 2>gpu.err | grep -v '^#' | md5sum; grep "Real\|dropin" gpu.err
-  done
+mkdir -p /tmp/wp && cd /tmp/wp && [ -f s50.bam.bai ] || /root/repo/tools/_build/synth_bam s50 50 hifi 11 >/dev/null 2>&1
+R=/root/repo; D=$R/longcalld_b200/dropin/liblcd_dropin.so
+$R/oracle/_ref/longcallD_ref call --hifi -t 16 s50.fa s50.bam 2>ref.err >/dev/null; grep -o "Real time: [0-9.]*" ref.err
+for cfg in "3 2 48 300" "3 2 48 300" "5 2 80 300" "5 3 80 300" "4 2 64 300" "3 2 48 0" "3 2 48 1000" "3 3 48 1000" "2 2 48 300"; do
+  set -- $cfg
+  printf "inflight %s cpt %s pool %s linger %s: " $1 $2 $3 $4
+  LCD_DROPIN_INFLIGHT=$1 LCD_DROPIN_CHUNKS_PER_THREAD=$2 LCD_DROPIN_POOL_GB=$3 LCD_DROPIN_LINGER_US=$4 LCD_DROPIN_STAGES=engines LD_PRELOAD="$D" $R/oracle/_ref/longcallD_so call --hifi -t 16 s50.fa s50.bam 2>gpu.err >/dev/null; grep -o "Real time: [0-9.]*" gpu.err
 done
