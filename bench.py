@@ -38,7 +38,7 @@ EDLIB_BYTES_PER_BLOCKCOL = 28    # Peq word in + (P, M, score) s
 PHASE_BYTES_PER_PAIR = 24        # allele + variant state in, counts out, per (read, variant) pair and pass
 
 
-NCU_CAPTURES = ("r1_poa_full_v5.raw.csv", "r1_poa_full_v3.raw.csv")       # newest first
+NCU_CAPTURES = ("r2_poa_full_v2.raw.csv", "r1_poa_full_v5.raw.csv", "r1_poa_full_v3.raw.csv")       # newest first
 
 
 def ncu_capture():
@@ -50,7 +50,7 @@ def ncu_capture():
 
 def ncu_traffic(kernel="poa_kernel"):
     """DRAM bytes (read + write) of one launch of the dominant kernel from the committed `ncu --set full` capture of this
-    same command (profiles/r1_poa_full_v*.raw.csv); None when the file is missing."""
+    same workload (profiles/r2_poa_full_v*.raw.csv: tools/poa_prof.py 50 = the step's POA batch); None when the file is missing."""
     try:
         import csv
         rows = list(csv.reader(open(os.path.join(ROOT, "profiles", ncu_capture()))))
@@ -521,7 +521,8 @@ def run_b200(args, rank, world):
     aux_h = lcd.aux_stream()
     lcd.reserve_sms(args.reserve_sms)              # room for the pileup / phasing kernels next to the persistent DP grids
     aux = torch.cuda.ExternalStream(aux_h, device=local)
-    wl = Workload(args.mbp, args.tech, args.seed + rank)            # weak scaling: one shard per GPU
+    shard_seed = args.seed + (rank if args.distinct_shards else 0)
+    wl = Workload(args.mbp, args.tech, shard_seed)            # weak scaling: one shard per GPU (the same synthetic shard on every rank unless --distinct-shards: the step's length is its longest POA problem, so shards drawn with different seeds measure the draw, not the scaling)
     _pin = torch.from_numpy(wl.seqs).pin_memory(); wl.seqs = _pin.numpy()      # the loader's read buffer: page-locked, as the K1 inputs are
     L = lcd.lib()
     n = wl.n_poa
@@ -671,7 +672,7 @@ def run_b200(args, rank, world):
 
     from longcalld_b200 import synth as _synth
     gpu_sites = lambda bare, outs, regs: [_synth.site_list_from_sites(o, st) for o, st in zip(outs, lcd.sites_batch(bare, regs))]
-    ps = PileupStage(args.mbp, args.tech, args.seed + rank, lcd.digar_batch, gpu_sites, lcd.pileup_batch, pin=True)
+    ps = PileupStage(args.mbp, args.tech, shard_seed, lcd.digar_batch, gpu_sites, lcd.pileup_batch, pin=True)
     min_sv = [50] * ps.n_chunks
     pile_res = {}
 
@@ -815,8 +816,11 @@ def run_b200(args, rank, world):
     d2h = int(pile_d2h + sum(a.nbytes for r in ph_res for a in r.values()) + eres.nbytes + int(eres["aln_len"].sum()) + pres["cons_len"].sum() + 32 * n + wres.nbytes + 2 * (pl.astype(np.int64) + tl + 4).sum())
 
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    per_rank = [t.clone() for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank, t)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    per_rank_ms = [[round(float(x[0]) / args.steps, 3), round(float(x[1]) / args.steps, 3)] for x in per_rank]       # [device, e2e] ms per step of every rank
     dev_ms_max, e2e_ms_max = t.tolist()
     total_mbp = args.mbp * world
     value = total_mbp * args.steps / (dev_ms_max / 1e3)
@@ -862,12 +866,13 @@ def run_b200(args, rank, world):
                 "dtype": "int16/int32", "data": "synthetic", "config": workload_config(args, wl, ps),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "e2e_pileup_ms": pile_res.get("t"), "e2e_phase_ms": pile_res.get("t_phase"),
+                "ms_per_step_per_rank": per_rank_ms, "shards": ("seeded by rank" if args.distinct_shards else "the same synthetic shard on every rank"),
                 "gpu_launches": int(launches), "clocks": clocks,
                 "gather": (None if world == 1 else {"what": "per-chunk POA/WFA result records to rank 0 (NCCL gather, inside e2e)",
                                                     "bytes_per_step": int(gathered["bytes"])}),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": ncu_traffic() if dominant_is_poa else None,
-                             "traffic_source": f"profiles/{ncu_capture()} (ncu --set full of this command, one poa_kernel launch)",
+                             "traffic_source": f"profiles/{ncu_capture()} (ncu --set full of one poa_kernel launch over this step's POA batch: tools/poa_prof.py 50)",
                              "kernel": "poa_kernel" if dominant_is_poa else "wfa_kernel<32>+wfa_kernel<256>",
                              "algorithmic": (f"{poa_cells} banded POA cells x {POA_BYTES_PER_CELL} B" if dominant_is_poa
                                              else f"{wfa_cells} wavefront cells x {WFA_BYTES_PER_CELL} B"),
@@ -906,6 +911,7 @@ def main():
     ap.add_argument("--tech", default="hifi", choices=["hifi", "ont"])
     ap.add_argument("--seed", type=int, default=11)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--distinct-shards", action="store_true", help="seed every rank's shard differently (default: the same synthetic shard on every rank)")
     ap.add_argument("--no-whole-program", action="store_true", help="skip the BAM -> VCF run of `longcallD call` (reference binary vs GPU drop-in)")
     ap.add_argument("--no-pipeline", dest="pipeline", action="store_false", help="K6 / K7 after K5 on one stream instead of overlapping the next batch's K5")
     ap.add_argument("--reserve-sms", type=int, default=12, help="SMs whose CTA slots the persistent DP grids leave to the concurrently running pileup / phasing kernels")

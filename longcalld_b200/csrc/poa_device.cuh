@@ -1943,8 +1943,8 @@ template <class L> struct Poa {
 #else
                     if (!L::STRIP) { status = ST_SUB_UNSUPPORTED; break; }
 #endif
-                    if (L::tid() == 0) w.tmp[6] = prepare_sub(sbp[r], sep[r]);
-                    L::sync();
+                    { LCD_T0(); if (L::tid() == 0) w.tmp[6] = prepare_sub(sbp[r], sep[r]);
+                    L::sync(); LCD_T1(t_pro); }
                     if (w.tmp[6] != ST_OK) { status = w.tmp[6]; break; }
                     beg_id = w.tmp[2]; end_id = w.tmp[3]; n_rows = w.tmp[4]; sub = true;
                     if ((uint32_t)w.tmp[5] + 1024 > w.dp_capacity) { status = ST_OOM; break; }

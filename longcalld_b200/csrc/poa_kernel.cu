@@ -334,20 +334,23 @@ struct PoaPlan : Plan {
         return 0;
     }
 
+#ifdef LCD_POA_TIMING
+    void timing_report() {      // debug builds: phase cycles of the 12 slowest problems and the batch totals
+        std::vector<int> idx(n); for (int i = 0; i < n; ++i) idx[i] = i;
+        auto tot = [&](int i) { const DevResult &r = h_results[i]; return r.t_dp + r.t_bt + r.t_add + r.t_after + r.t_fin + r.t_pro; };
+        std::sort(idx.begin(), idx.end(), [&](int x, int y) { return tot(x) > tot(y); });
+        unsigned long long T[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < n; ++i) { const DevResult &r = h_results[i]; T[0] += r.t_dp; T[1] += r.t_bt; T[2] += r.t_add; T[3] += r.t_after; T[4] += r.t_fin; T[5] += r.t_seg; T[6] += r.t_gen; T[7] += r.n_seg; T[8] += r.n_gen; T[9] += r.t_pro; }
+        fprintf(stderr, "[poa timing] batch Mcycles: dp %.1f (segments %.1f for %.2f Mrows, general %.1f for %.2f Mrows) bt %.1f add %.1f after %.1f (incl. BFS index) fin %.1f sub-graph set-up %.1f\n", T[0] / 1e6, T[5] / 1e6, T[7] / 1e6, T[6] / 1e6, T[8] / 1e6, T[1] / 1e6, T[2] / 1e6, T[3] / 1e6, T[4] / 1e6, T[9] / 1e6);
+        for (int k = 0; k < std::min(n, 12); ++k) { const int i = idx[k]; const DevResult &r = h_results[i];
+            fprintf(stderr, "[poa timing] #%d reads %d max_len %d nodes %d cells %u : dp %.1f (seg %.1f / %llu rows, gen %.1f / %llu rows) bt %.1f add %.1f after %.1f fin %.1f sub %.1f Mcycles\n", i, problems[i].n_reads,
+                    problems[i].max_len, r.n_nodes, r.cells_lo, r.t_dp / 1e6, r.t_seg / 1e6, r.n_seg, r.t_gen / 1e6, r.n_gen, r.t_bt / 1e6, r.t_add / 1e6, r.t_after / 1e6, r.t_fin / 1e6, r.t_pro / 1e6); }
+    }
+#endif
     int work_units(cudaStream_t s, uint64_t *units) override {
         if (download(s, false, false)) return -1;
 #ifdef LCD_POA_TIMING
-        {   // debug: phase cycles of the 12 slowest problems and the batch totals
-            std::vector<int> idx(n); for (int i = 0; i < n; ++i) idx[i] = i;
-            auto tot = [&](int i) { const DevResult &r = h_results[i]; return r.t_dp + r.t_bt + r.t_add + r.t_after + r.t_fin; };
-            std::sort(idx.begin(), idx.end(), [&](int x, int y) { return tot(x) > tot(y); });
-            unsigned long long T[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            for (int i = 0; i < n; ++i) { const DevResult &r = h_results[i]; T[0] += r.t_dp; T[1] += r.t_bt; T[2] += r.t_add; T[3] += r.t_after; T[4] += r.t_fin; T[5] += r.t_seg; T[6] += r.t_gen; T[7] += r.n_seg; T[8] += r.n_gen; }
-            fprintf(stderr, "[poa timing] batch Mcycles: dp %.1f (segments %.1f for %.2f Mrows, general %.1f for %.2f Mrows) bt %.1f add %.1f after %.1f fin %.1f\n", T[0] / 1e6, T[5] / 1e6, T[7] / 1e6, T[6] / 1e6, T[8] / 1e6, T[1] / 1e6, T[2] / 1e6, T[3] / 1e6, T[4] / 1e6);
-            for (int k = 0; k < std::min(n, 12); ++k) { const int i = idx[k]; const DevResult &r = h_results[i];
-                fprintf(stderr, "[poa timing] #%d reads %d max_len %d nodes %d cells %u : dp %.1f (seg %.1f / %llu rows, gen %.1f / %llu rows) bt %.1f add %.1f after %.1f fin %.1f Mcycles\n", i, problems[i].n_reads,
-                        problems[i].max_len, r.n_nodes, r.cells_lo, r.t_dp / 1e6, r.t_seg / 1e6, r.n_seg, r.t_gen / 1e6, r.n_gen, r.t_bt / 1e6, r.t_add / 1e6, r.t_after / 1e6, r.t_fin / 1e6); }
-        }
+        timing_report();
 #endif
         uint64_t t = 0;
         for (int i = 0; i < n; ++i) t += ((uint64_t)h_results[i].cells_hi << 32) | h_results[i].cells_lo;
@@ -358,6 +361,9 @@ struct PoaPlan : Plan {
     int fetch(cudaStream_t s, uint8_t *cons, const int64_t *cons_off, uint8_t *msa, const int64_t *msa_off, const int64_t *msa_cap,
               lcd_poa_result_t *results) {
         if (download(s, cons && cons_off, msa && msa_off && msa_cap)) return -1;
+#ifdef LCD_POA_TIMING
+        if (getenv("LCD_POA_TIMING_PRINT")) timing_report();
+#endif
         int bad = 0, first_bad = 0;
         for (int i = 0; i < n; ++i) {
             const DevResult &r = h_results[i];

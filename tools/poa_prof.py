@@ -10,7 +10,7 @@ from longcalld_b200.capi import pack_poa
 
 mbp = float(sys.argv[1]); lo = int(sys.argv[2]) if len(sys.argv) > 2 else 0; hi = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 30
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-lcd.init(0, 0)
+lcd.init(0, int(float(os.environ.get("POOL_GB", "0")) * (1 << 30)))
 problems = []
 for r in synth.make_regions(mbp, "hifi", seed=11, with_reads=True):
     for hap in (1, 2):
