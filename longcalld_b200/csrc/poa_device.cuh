@@ -715,103 +715,169 @@ template <class L> struct Poa {
     // per-node exchange sort of the edge lists, out-weight sums, edge path scores (abpoa_get_incre_path_score
     // :429-437), n_span; then the flattened topological order and the heaviest-path remain values
     // (abpoa_BFS_set_node_remain :268-309) by pointer jumping over the list / heaviest-successor links.
-    // abpoa_BFS_set_node_index (abpoa_graph.c:221-266), single lane: Kahn's order with a FIFO queue, a node entering only together with the
-    // nodes aligned to it, over the out-edge lists as they stand BEFORE this round's edge sort.  Needed only by problems with partially
-    // covering reads: the sub-graph of such a read and the nodes it spans are defined by ranges of this index.  The queue is the
-    // index -> node table (w.maxr), w.maxl the node -> index table; both live until the next call.
+#ifndef LCD_EMU
+    // abpoa_BFS_set_node_index (abpoa_graph.c:221-266): Kahn's order with a FIFO queue, a node entering only together with the nodes aligned
+    // to it, over the out-edge lists as they stand BEFORE this round's edge sort.  Needed only by problems with partially covering reads: the
+    // sub-graph of such a read and the nodes it spans are defined by ranges of this index.  The queue is the index -> node table (w.maxr),
+    // w.maxl the node -> index table; both live until the next call.  The order is inherently sequential (on a chain the queue holds one node),
+    // so one lane walks it -- but on records the whole warp prepared: {first out-edge target, out-degree, in-degree, aligned nodes} per node
+    // in one 16-byte load (w.rinfo is free between two alignments).  A node with one out-edge into a node with one in-edge and no aligned
+    // nodes -- a link of a chain, ~97 % of a region's graph -- then costs ONE dependent load (the successor's record) instead of five.
     __device__ void bfs_index() {
-        const int n = w.n_nodes;
+        const int n = w.n_nodes, lane = threadIdx.x & 31;
         int *deg = w.msa_rank, *q = w.maxr, *idx = w.maxl;
-        for (int i = 0; i < n; ++i) { deg[i] = w.in_n[i]; idx[i] = -1; }
-        int qh = 0, qt = 0;
-        q[qt++] = 0;
-        while (qh < qt) {
-            const int cur = q[qh]; idx[cur] = qh; ++qh;
-            if (cur == 1) break;
-            for (int i = 0; i < w.out_n[cur]; ++i) {
-                const int out = out_entry(cur, i)[0];
-                if (--deg[out] == 0) {
-                    bool ok = true;
-                    for (int j = 0; j < w.aln_n[out]; ++j) if (deg[w.aln_pool[w.aln_off[out] + j]] != 0) { ok = false; break; }
-                    if (!ok) continue;
-                    q[qt++] = out;
-                    for (int j = 0; j < w.aln_n[out]; ++j) q[qt++] = w.aln_pool[w.aln_off[out] + j];
+        int4 *rec = w.rinfo;
+        for (int i = lane; i < n; i += 32) {
+            const int on = w.out_n[i], in = w.in_n[i];
+            rec[i] = make_int4(on > 0 ? out_entry(i, 0)[0] : -1, on, in, w.aln_n[i]);
+            deg[i] = in; idx[i] = -1;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int qh = 0, qt = 0;
+            q[qt++] = 0;
+            int known = 0; int4 rc = rec[0];                   // the node at the queue's head and its record, when they are in registers already
+            while (qh < qt) {
+                const int cur = known >= 0 ? known : q[qh];
+                if (known < 0) rc = rec[cur];
+                known = -1;
+                idx[cur] = qh; ++qh;
+                if (cur == 1) break;
+                if (rc.y == 1) {
+                    const int out = rc.x; const int4 ro = rec[out];
+                    if (ro.z == 1 && ro.w == 0) {                  // ready at once; nobody looks at its in-degree counter again
+                        q[qt] = out;
+                        if (qh == qt) { known = out; rc = ro; }
+                        ++qt;
+                        continue;
+                    }
+                }
+                for (int i = 0; i < rc.y; ++i) {
+                    const int out = i == 0 ? rc.x : out_entry(cur, i)[0];
+                    if (--deg[out] == 0) {
+                        bool ok = true;
+                        for (int j = 0; j < w.aln_n[out]; ++j) if (deg[w.aln_pool[w.aln_off[out] + j]] != 0) { ok = false; break; }
+                        if (!ok) continue;
+                        q[qt++] = out;
+                        for (int j = 0; j < w.aln_n[out]; ++j) q[qt++] = w.aln_pool[w.aln_off[out] + j];
+                    }
                 }
             }
         }
+        __syncwarp();
     }
 
     // The sub-graph a partially covering read is aligned against (abpoa_subgraph_nodes, abpoa_graph.c:595-680, on the BFS index of the last
-    // bfs_index()) and the alignment's view of it; single lane.  inc_beg / inc_end: the two anchor nodes (bases of the first read).
+    // bfs_index()) and the alignment's view of it; the whole warp.  inc_beg / inc_end: the two anchor nodes (bases of the first read).
     //   * exc_beg / exc_end: the nodes at the outermost index reached by in-edges on the left / out-edges on the right of the anchors' range
-    //   * rows: the nodes of that index range that can be reached from exc_beg (index_map, abpoa_align_simd.c:1259-1269), kept in the
-    //     order of the topological list (w.order / w.meta / w.pos are compacted in place; after_add rebuilds them after the read)
+    //     (the reference's closure loops, 32 indices of the range per step, min / max / any by warp reductions)
+    //   * rows: the nodes of that index range that can be reached from exc_beg (index_map, abpoa_align_simd.c:1259-1269: a forward propagation
+    //     in index order -- 32 indices per step, the dependencies inside a step resolved by OR-reductions of the lanes' target masks), kept in
+    //     the order of the topological list (w.order / w.meta / w.pos are compacted in place; after_add rebuilds them after the read)
     //   * in-edges: only predecessors inside the sub-graph, compacted; the k-th one carries the path score of the node's k-th in-edge
     //     OVERALL, as the reference computes it (abpoa_get_incre_path_score is called with the index into the restricted list)
-    // Results in w.tmp[2..5]: exc_beg, exc_end, rows, cells of the DP arena taken by the compacted lists (its top end).
+    // Results: beg_id, end_id, n_rows set (uniformly); returns the cells of the DP arena taken by the compacted lists (its top end), < 0: error.
     __device__ int prepare_sub(int inc_beg, int inc_end) {
-        const int n = w.n_nodes;
+        const int n = w.n_nodes, lane = threadIdx.x & 31;
         const int *idx = w.maxl, *at = w.maxr;
         if (inc_beg < 2 || inc_end < 2 || inc_beg >= n || inc_end >= n || idx[inc_beg] < 0 || idx[inc_end] < 0 || idx[inc_beg] > idx[inc_end]) return ST_SUBGRAPH;
-        auto full_up = [&](int up, int down, int b, int e) {
+        // every in-edge of the nodes at indices (up, down] comes from an index inside [min(up, b), max(down, e)]   (is_full_upstream_subgraph :595-606)
+        auto full_up = [&](int up, int down, int b, int e) -> bool {
             const int mn = up < b ? up : b, mx = down > e ? down : e;
-            for (int i = up + 1; i <= down; ++i) {
+            bool bad = false;
+            for (int i = up + 1 + lane; i <= down; i += 32) {
                 const int id = at[i]; const int4 *ie = w.in_pool + w.in_off[id];
-                for (int j = 0; j < w.in_n[id]; ++j) { const int x = idx[ie[j].x]; if (x < mn || x > mx) return false; }
+                for (int j = 0; j < w.in_n[id]; ++j) { const int x = idx[ie[j].x]; if (x < mn || x > mx) bad = true; }
             }
-            return true;
+            return !__any_sync(0xffffffffu, bad);
         };
         int exc_b, exc_e;
         {
             int b = idx[inc_beg], e = idx[inc_end];
-            for (;;) {
+            for (;;) {                                                   // abpoa_upstream_index :608-628
                 int mn = b;
-                for (int i = b; i <= e; ++i) { const int id = at[i]; const int4 *ie = w.in_pool + w.in_off[id]; for (int j = 0; j < w.in_n[id]; ++j) { const int x = idx[ie[j].x]; if (x < mn) mn = x; } }
+                for (int i = b + lane; i <= e; i += 32) { const int id = at[i]; const int4 *ie = w.in_pool + w.in_off[id]; for (int j = 0; j < w.in_n[id]; ++j) { const int x = idx[ie[j].x]; if (x < mn) mn = x; } }
+                mn = __reduce_min_sync(0xffffffffu, mn);
                 if (full_up(mn, b, b, e)) { exc_b = mn; break; }
                 e = b; b = mn;
             }
             b = idx[inc_beg]; e = idx[inc_end];
-            for (;;) {
+            for (;;) {                                                   // abpoa_downstream_index :642-662
                 int mx = e;
-                for (int i = b; i <= e; ++i) { const int id = at[i]; for (int j = 0; j < w.out_n[id]; ++j) { const int x = idx[out_entry(id, j)[0]]; if (x > mx) mx = x; } }
+                for (int i = b + lane; i <= e; i += 32) { const int id = at[i]; for (int j = 0; j < w.out_n[id]; ++j) { const int x = idx[out_entry(id, j)[0]]; if (x > mx) mx = x; } }
+                mx = __reduce_max_sync(0xffffffffu, mx);
                 if (full_up(e, mx, b, e)) { exc_e = mx; break; }
                 b = e; e = mx;
             }
         }
         if (exc_b < 0 || exc_e >= n) return ST_SUBGRAPH;
         int *in_sub = w.msa_rank;
-        for (int i = 0; i < n; ++i) in_sub[i] = 0;
-        in_sub[at[exc_b]] = 1; in_sub[at[exc_e]] = 1;
-        for (int i = exc_b; i < exc_e - 1; ++i) {
-            const int id = at[i];
-            if (!in_sub[id]) continue;
-            for (int j = 0; j < w.out_n[id]; ++j) in_sub[out_entry(id, j)[0]] = 1;
+        for (int i = lane; i < n; i += 32) in_sub[i] = 0;
+        __syncwarp();
+        if (lane == 0) { in_sub[at[exc_b]] = 1; in_sub[at[exc_e]] = 1; }
+        __syncwarp();
+        for (int c0 = exc_b; c0 < exc_e - 1; c0 += 32) {
+            const int i = c0 + lane; const bool act = i < exc_e - 1;
+            const int id = act ? at[i] : 0;
+            bool mark = act && in_sub[id] != 0;
+            unsigned tmask = 0;                                          // out-edge targets whose index lies in this step
+            const int on = act ? w.out_n[id] : 0;
+            for (int j = 0; j < on; ++j) { const int ti = idx[out_entry(id, j)[0]]; if (ti >= c0 && ti < c0 + 32) tmask |= 1u << (ti - c0); }
+            for (;;) {
+                const unsigned agg = __reduce_or_sync(0xffffffffu, mark ? tmask : 0u);
+                const bool nm = mark || (act && ((agg >> lane) & 1u));
+                const bool changed = nm != mark;
+                mark = nm;
+                if (!__any_sync(0xffffffffu, changed)) break;
+            }
+            if (mark) { in_sub[id] = 1; for (int j = 0; j < on; ++j) in_sub[out_entry(id, j)[0]] = 1; }
+            __syncwarp();
         }
         // rows, restricted in-edge lists (from the top of the DP arena downwards), first in-edge / position tables
         int *so = w.s2, *sn = w.s3;
         int4 *pool = reinterpret_cast<int4 *>(w.dp + ((size_t)w.dp_capacity & ~(size_t)7)) - w.in_top - 8;
         int top = 0, k = 0;
-        for (int oi = 0; oi < n; ++oi) {
-            const int id = w.order[oi];
-            if (!in_sub[id] || idx[id] < exc_b || idx[id] > exc_e) continue;
+        for (int o0 = 0; o0 < n; o0 += 32) {
+            const int oi = o0 + lane;
+            const int id = oi < n ? w.order[oi] : 0;
+            const bool sel = oi < n && in_sub[id] && idx[id] >= exc_b && idx[id] <= exc_e;
             const int4 *ie = w.in_pool + w.in_off[id];
             int nf = 0;
-            if (idx[id] != exc_b)
-                for (int j = 0; j < w.in_n[id]; ++j) { const int p = ie[j].x; if (in_sub[p] && idx[p] >= exc_b && idx[p] <= exc_e) { pool[top + nf] = make_int4(p, ie[j].y, ie[nf].z, 0); ++nf; } }
-            so[id] = top; sn[id] = nf; top += nf;
-            const int f = nf ? pool[so[id]].x : -1, ps0 = nf ? pool[so[id]].z : 0;
-            w.fp_id[id] = f; w.fp_ps[id] = ps0; w.pos[id] = k; w.order[k] = id;
-            w.meta[k] = make_int4(id, f, w.base[id] | ((nf < 255 ? nf : 255) << 8) | ((ps0 & 0xff) << 16), w.remain[id]);
-            ++k;
+            if (sel && idx[id] != exc_b)
+                for (int j = 0; j < w.in_n[id]; ++j) { const int p = ie[j].x; if (in_sub[p] && idx[p] >= exc_b && idx[p] <= exc_e) ++nf; }
+            const unsigned ms = __ballot_sync(0xffffffffu, sel);
+            int pre = nf;                                                // exclusive prefix of nf over the lanes
+            for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, pre, d); if (lane >= d) pre += y; }
+            const int tot = __shfl_sync(0xffffffffu, pre, 31);
+            pre -= nf;
+            __syncwarp();                                                // every lane has read order[] of this step before it is overwritten
+            if (sel) {
+                const int my_k = k + __popc(ms & ((1u << lane) - 1)), my_top = top + pre;
+                int f = 0;
+                if (idx[id] != exc_b)
+                    for (int j = 0; j < w.in_n[id]; ++j) { const int p = ie[j].x; if (in_sub[p] && idx[p] >= exc_b && idx[p] <= exc_e) { pool[my_top + f] = make_int4(p, ie[j].y, ie[f].z, 0); ++f; } }
+                so[id] = my_top; sn[id] = nf;
+                const int fp = nf ? pool[my_top].x : -1, ps0 = nf ? pool[my_top].z : 0;
+                w.fp_id[id] = fp; w.fp_ps[id] = ps0; w.pos[id] = my_k; w.order[my_k] = id;
+                w.meta[my_k] = make_int4(id, fp, w.base[id] | ((nf < 255 ? nf : 255) << 8) | ((ps0 & 0xff) << 16), w.remain[id]);
+            }
+            k += __popc(ms); top += tot;
+            __syncwarp();
         }
-        w.tmp[2] = at[exc_b]; w.tmp[3] = at[exc_e]; w.tmp[4] = k; w.tmp[5] = (w.in_top + 8) * 8 + 8;
-        return ST_OK;
+        beg_id = at[exc_b]; end_id = at[exc_e]; n_rows = k;
+        return (w.in_top + 8) * 8 + 8;
     }
+#else
+    __device__ void bfs_index() {}
+    __device__ int prepare_sub(int, int) { return ST_SUB_UNSUPPORTED; }
+#endif
 
     __device__ void after_add(int first_read, bool do_bfs = false, bool partial = false) {
         const int n = w.n_nodes, lane = L::tid();
         const int inc = par.sub_aln ? 0 : 1;
-        if (do_bfs) { if (lane == 0) bfs_index(); L::sync(); }
+#ifndef LCD_EMU
+        if (do_bfs) { if constexpr (L::STRIP) bfs_index(); L::sync(); }
+#endif
         const int ib = partial ? w.maxl[beg_id] : 0, ie_ = partial ? w.maxl[end_id] : 0;
         int *jn_a = w.s1, *jn_b = w.s2, *dn_a = w.s3, *dn_b = w.s4;       // list links / distance to list end
         int *jh_a = w.s5, *jh_b = w.s6, *dh_a = w.remain, *dh_b = w.s7;   // heaviest-successor links / hops to SINK
@@ -1943,13 +2009,13 @@ template <class L> struct Poa {
 #else
                     if (!L::STRIP) { status = ST_SUB_UNSUPPORTED; break; }
 #endif
-                    { LCD_T0(); if (L::tid() == 0) w.tmp[6] = prepare_sub(sbp[r], sep[r]);
-                    L::sync(); LCD_T1(t_pro); }
-                    if (w.tmp[6] != ST_OK) { status = w.tmp[6]; break; }
-                    beg_id = w.tmp[2]; end_id = w.tmp[3]; n_rows = w.tmp[4]; sub = true;
-                    if ((uint32_t)w.tmp[5] + 1024 > w.dp_capacity) { status = ST_OOM; break; }
+                    int taken;
+                    { LCD_T0(); taken = prepare_sub(sbp[r], sep[r]); L::sync(); LCD_T1(t_pro); }
+                    if (taken < 0) { status = taken; break; }
+                    sub = true;
+                    if ((uint32_t)taken + 1024 > w.dp_capacity) { status = ST_OOM; break; }
                     ai_pool = reinterpret_cast<const int4 *>(w.dp + ((size_t)w.dp_capacity & ~(size_t)7)) - w.in_top - 8; ai_off = w.s2; ai_n = w.s3;
-                    w.dp_capacity -= (uint32_t)w.tmp[5];
+                    w.dp_capacity -= (uint32_t)taken;
                 }
                 if (!first_read) {
                     const int gn = sub ? w.maxl[end_id] - w.maxl[beg_id] + 1 : w.n_nodes, len = ql > gn ? ql : gn;
