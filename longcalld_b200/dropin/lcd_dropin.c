@@ -622,7 +622,7 @@ typedef struct chunk_co_t { ucontext_t ctx; void *stack; int state; long i; req_
 typedef struct { ucontext_t main; chunk_co_t *cur; void (*func)(void*, long, int); void *data; int tid; long n; long *next; } kworker_t;
 static __thread kworker_t *tl_kw = NULL;
 #define CHUNK_STACK ((size_t)8 << 20)
-static int chunks_per_thread(void) { static int v = -1; if (v < 0) { const char *e = getenv("LCD_DROPIN_CHUNKS_PER_THREAD"); v = e ? atoi(e) : 3; if (v < 1) v = 1; if (v > 16) v = 16; } return v; }
+static int chunks_per_thread(void) { static int v = -1; if (v < 0) { const char *e = getenv("LCD_DROPIN_CHUNKS_PER_THREAD"); v = e ? atoi(e) : 2; if (v < 1) v = 1; if (v > 16) v = 16; } return v; }
 static int all_done(req_t **r, int n) { for (int i = 0; i < n; ++i) if (!__atomic_load_n(&r[i]->done, __ATOMIC_ACQUIRE)) return 0; return 1; }
 
 static void combine(req_t **r, int n) {
