@@ -264,6 +264,11 @@ template <class L> struct Poa {
     // sees them (a sub-graph alignment sees only predecessors inside the sub-graph: prepare_sub)
     int beg_id = 0, end_id = 1, n_rows = 0; bool sub = false;
     const int4 *ai_pool = nullptr; const int *ai_off = nullptr, *ai_n = nullptr;
+    // Row descriptors of the order (w.meta, 16 B per row) reach the row loop through a two-half ring in shared memory that ONE lane keeps
+    // filled with 1-D TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier per half): the next 32 rows' descriptors
+    // land while the current 32 are computed, so the row loop never waits for a global load of its own.  nullptr: disabled (emulator, CTA kernel).
+    int4 *ring = nullptr; unsigned long long *ring_bar = nullptr;
+    int ring_block = -1, ring_issued = -1, ring_n = 0; unsigned ring_fill[2] = {0, 0}, ring_seen[2] = {0, 0};
     // scratch of a multi-warp group (shared memory): F carries of the row's vectors + row-max partials
     int *gs = nullptr;
     static constexpr int MAXV = 512, GS_INTS = 2 * MAXV + 4 + 3 * 32;
@@ -1217,6 +1222,56 @@ template <class L> struct Poa {
     //     score, remain) one 16-byte load fetched a row ahead.
     // Results (all five planes of every row, the row descriptor) go to the same HBM layout the general path and the
     // backtrack read.  Cell values are those of chain_row / strip_core (same formulas; see the notes there).
+#if !defined(LCD_EMU) && !defined(LCD_SIMT_EMU)
+    __device__ __forceinline__ void ring_issue(int k) {          // one lane: block k (rows 32k .. 32k+31) into half k & 1
+        const int h = k & 1, rows = ring_n - 32 * k < 32 ? ring_n - 32 * k : 32;
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(ring_bar + h), dst = (unsigned)__cvta_generic_to_shared(ring + 32 * h), bytes = 16u * (unsigned)rows;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(w.meta + 32 * k), "r"(bytes), "r"(bar) : "memory");
+    }
+    __device__ __forceinline__ void ring_wait(int h) {           // all lanes: the oldest outstanding fill of half h
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(ring_bar + h), parity = ring_seen[h] & 1u;
+        unsigned ok = 0; int spins = 0;
+        do {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            if (!ok && ++spins > (1 << 24)) __trap();            // a copy that never lands must not hang the GPU
+        } while (!ok);
+        ring_seen[h]++;
+    }
+    __device__ __forceinline__ void ring_start(int n) {           // at the start of an alignment: the order's descriptors were just (re)written
+        if (!ring) return;
+        ring_n = n; ring_block = -1;
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");     // the warp's generic-proxy stores to w.meta before the async-proxy reads
+            ring_issue(0); if (n > 32) ring_issue(1);
+        }
+        ring_fill[0]++; if (n > 32) ring_fill[1]++;
+        ring_issued = n > 32 ? 1 : 0;
+    }
+    __device__ __forceinline__ int4 ring_get(int oi) {            // all lanes, rows are asked for in increasing order
+        if (!ring) return w.meta[oi];
+        const int k = oi >> 5;
+        if (k != ring_block) {
+            ring_wait(k & 1);
+            ring_block = k;
+            if (k + 1 > ring_issued && 32 * (k + 1) < ring_n) {   // the other half held block k - 1: consumed
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0) ring_issue(k + 1);
+                ring_fill[(k + 1) & 1]++; ring_issued = k + 1;
+            }
+        }
+        return ring[32 * (k & 1) + (oi & 31)];
+    }
+    __device__ __forceinline__ void ring_drain() {                // fills issued but never read (the alignment ended early)
+        if (!ring) return;
+        for (int h = 0; h < 2; ++h) while (ring_seen[h] < ring_fill[h]) ring_wait(h);
+    }
+#else
+    __device__ __forceinline__ void ring_start(int) {}
+    __device__ __forceinline__ int4 ring_get(int oi) { return w.meta[oi]; }
+    __device__ __forceinline__ void ring_drain() {}
+#endif
     struct ChainState { int last_id; Row last_row; bool last_cached; int cache_buf; uint32_t dp_top; };
     __device__ static __forceinline__ uint32_t pk2(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
     __device__ static __forceinline__ uint32_t dup2(int x) { return ((uint32_t)x & 0xffffu) * 0x10001u; }
@@ -1273,7 +1328,7 @@ template <class L> struct Poa {
         }
         Row lr = st.last_row; int last_id = st.last_id;
         uint32_t dp_top = st.dp_top;
-        int4 mt = w.meta[oi];
+        int4 mt = ring_get(oi);
         int n_done = 0, narrow = 0;
         for (;;) {
             const int id = mt.x, nb = mt.z & 0xff, ps = (int)(int8_t)((mt.z >> 16) & 0xff);
@@ -1291,7 +1346,7 @@ template <class L> struct Poa {
             if (dp_top + need > w.dp_capacity) { err = ST_OOM; return oi; }
             const uint32_t off = dp_top; dp_top += need;
             cells += (unsigned long long)(end - beg + 1);
-            if (oi + 1 < n) mt = w.meta[oi + 1];
+            if (oi + 1 < n) mt = ring_get(oi + 1);
             // the band's first vector moved right: shift the previous row across the lanes
             uint32_t lh = lh_next;                       // H of the previous row at column c0 - 1 (high half)
             lh_next = INF2;
@@ -1534,7 +1589,7 @@ template <class L> struct Poa {
                 // Runs of chain rows (one in-edge, from the row computed just before, band not reaching past the predecessor's
                 // last vector) are computed by chain_segment: previous row in registers, int16x2 cells, no memory on the
                 // critical path.  It returns the position of the first row it did not take.
-                const int4 mt = w.meta[oi];
+                const int4 mt = ring_get(oi);
                 if (mt.x != end_id && ((mt.z >> 8) & 0xff) == 1 && mt.y == last_id) {
                     int beg, end, beg_sn;
                     chain_band(last_row, mt.w, rem_end, qlen, n_tot, wband, banded, beg, end, beg_sn);
@@ -2021,7 +2076,7 @@ template <class L> struct Poa {
                     const int gn = sub ? w.maxl[end_id] - w.maxl[beg_id] + 1 : w.n_nodes, len = ql > gn ? ql : gn;
                     const int ms = (ql * par.match > len * par.gap_ext1 + par.gap_open1) ? ql * par.match : len * par.gap_ext1 + par.gap_open1;
                     if (!(ms <= INT16_MAX - par.mismatch - oe1 - oe2)) { status = ST_INT32; break; }
-                    { LCD_T0(); n_cig = align(q, ql); LCD_T1(t_dp); }
+                    { LCD_T0(); ring_start(n_rows); n_cig = align(q, ql); ring_drain(); LCD_T1(t_dp); }
                     w.dp_capacity = dp_cap0;
                     if (n_cig < 0) { status = n_cig; break; }
                 }

@@ -20,8 +20,18 @@ poa_kernel(const KernelArgs a) {
     const int group_id = blockIdx.x * WARPS_PER_CTA + gi;
     int32_t *arena = a.arena + (size_t)group_id * a.arena_words;
     __shared__ __align__(16) int16_t row_cache[WARPS_PER_CTA][2 * 3 * Poa<WarpLanes>::NVC * PN];
+    __shared__ __align__(128) int4 meta_ring[WARPS_PER_CTA][64];             // two halves of 32 row descriptors per warp, filled by TMA bulk copies
+    __shared__ __align__(8) unsigned long long meta_bar[WARPS_PER_CTA][2];
     Poa<WarpLanes> poa;
     poa.row_cache = row_cache[gi];
+#ifndef POA_NO_TMA_RING
+    if (lane == 0) {
+        for (int h = 0; h < 2; ++h) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(&meta_bar[gi][h])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    poa.ring = meta_ring[gi]; poa.ring_bar = meta_bar[gi];
+#endif
     for (;;) {
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(a.queue, 1u);
