@@ -632,7 +632,7 @@ static int poa_run(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const
         for (int i = 0; i < ml; ++i) {
             int max_c = 0, total = 0, max_base = 5;
             for (int j = 0; j < 4; ++j) { const int c = cnt[i * 5 + j]; if (c > max_c) { max_c = c; max_base = j; } total += c; }
-            if (max_base == 5) { rc = -4; break; }       /* the reference would read out of bounds */
+            if (max_base == 5) { if (par.sub_aln) { rc = -4; break; } continue; }       /* sub_aln: the reference would read out of bounds; else 0 >= n_seq - 0 fails: no base */
             const int gap_c = (par.sub_aln ? g.node[nid[i * 5 + max_base]].n_span : n_seq) - total;
             if (max_c >= gap_c) { cons_ids[cl] = nid[i * 5 + max_base]; cons[cl] = (uint8_t)max_base; cl++; }
         }
@@ -654,5 +654,34 @@ static int poa_run(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const
         free(cnt); free(nid); free(cons_ids);
     }
     g_free(&g);
+    return rc;
+}
+
+/* abpoa_aln_msa_cons with max_n_cons = 2 (src/align.c:872-953; wb = -1, sub_aln = 0): the progressive POA of all reads, abPOA's read
+ * clustering on the row-column MSA (poa_cluster.c) and one most-frequent consensus per cluster.  cons: the consensus sequences back to
+ * back; msa: (n_seq + n_cons) rows.  min_freq = opt->min_af (abpt->min_freq, a double: min_w = MAX(2, ceil(n_seq * min_freq))). */
+int lcd_oracle_poa_cluster(const uint8_t *msa, int n_seq, int ml, int min_w, uint8_t *read_clu);
+void lcd_oracle_poa_cluster_cons(uint8_t *msa, int n_seq, int ml, int n_clu, const uint8_t *read_clu, uint8_t *cons, int32_t *cons_len);
+int lcd_oracle_poa_ncons(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len, const lcd_poa_params_t *p, double min_freq,
+                         uint8_t *cons, int32_t *cons_len, int32_t *n_cons, uint8_t *read_clu, uint8_t *msa, int32_t *msa_len, int32_t msa_cap) {
+    if (p->sub_aln) return -7;
+    int64_t tot = 0; for (int r = 0; r < n_seq; ++r) tot += seq_len[r];
+    const int64_t cap1 = (int64_t)(n_seq + 1) * (tot + 8);
+    uint8_t *m1 = (uint8_t*)malloc((size_t)cap1), *c1 = (uint8_t*)malloc((size_t)tot + 8);
+    int32_t cl1 = 0, ml = 0;
+    cons_len[0] = cons_len[1] = 0; *n_cons = 0; *msa_len = 0;
+    int rc = poa_run(n_seq, seqs, seq_off, seq_len, NULL, NULL, p, c1, &cl1, m1, &ml, (int32_t)(cap1 > INT32_MAX ? INT32_MAX : cap1));
+    if (rc == 0 && ml > 0) {
+        int n_clu = 1;
+        memset(read_clu, 0, (size_t)n_seq);
+        if (p->max_n_cons > 1) { const int cw = (int)ceil(n_seq * min_freq); n_clu = lcd_oracle_poa_cluster(m1, n_seq, ml, cw > 2 ? cw : 2, read_clu); }
+        if ((int64_t)(n_seq + n_clu) * ml > msa_cap) rc = -5;
+        else {
+            memcpy(msa, m1, (size_t)n_seq * ml);
+            lcd_oracle_poa_cluster_cons(msa, n_seq, ml, n_clu, read_clu, cons, cons_len);
+            *n_cons = n_clu; *msa_len = ml;
+        }
+    }
+    free(m1); free(c1);
     return rc;
 }

@@ -427,3 +427,38 @@ int ref_collect_digar_cs(const lcd_digar_input_t *in, const int64_t *cs_off, con
     }
     return ref_digar_finish(job, in, out);
 }
+
+/* abpoa_aln_msa_cons (src/align.c:872-953) itself: the de-novo POA of a region's fully covering reads with max_n_cons consensus sequences.
+ * cons: the consensus sequences back to back; read_clu: cluster of each read; msa: (n_seq + n_cons) rows (reads in input order, then the consensus rows). */
+int abpoa_aln_msa_cons(const call_var_opt_t *opt, int n_reads, int *read_ids, uint8_t **read_seqs, int *read_lens, int max_n_cons, int *cons_lens, uint8_t **cons_seqs,
+                       int *clu_n_seqs, int **clu_read_ids, int *msa_seq_len, uint8_t ***msa_seq);      /* (no prototype in the headers) */
+int ref_poa_ncons(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len, const lcd_poa_params_t *p, double min_freq,
+                  uint8_t *cons, int32_t *cons_len, int32_t *n_cons, uint8_t *read_clu, uint8_t *msa, int32_t *msa_len, int32_t msa_cap) {
+    call_var_opt_t opt; memset(&opt, 0, sizeof(opt));
+    opt.min_af = min_freq; opt.match = p->match; opt.mismatch = p->mismatch;
+    opt.gap_open1 = p->gap_open1; opt.gap_ext1 = p->gap_ext1; opt.gap_open2 = p->gap_open2; opt.gap_ext2 = p->gap_ext2;
+    int *ids = (int*)malloc(sizeof(int) * (n_seq + 1)), *lens = (int*)malloc(sizeof(int) * (n_seq + 1));
+    uint8_t **ptr = (uint8_t**)malloc(sizeof(uint8_t*) * (n_seq + 1));
+    for (int i = 0; i < n_seq; ++i) { ids[i] = i; lens[i] = seq_len[i]; ptr[i] = (uint8_t*)seqs + seq_off[i]; }
+    int cl[2] = {0, 0}, clu_n[2] = {0, 0}, ml[2] = {0, 0}; uint8_t *cs[2] = {NULL, NULL}; int *clu_ids[2] = {NULL, NULL};
+    uint8_t ***ms = (uint8_t***)malloc(2 * sizeof(uint8_t**));
+    for (int i = 0; i < 2; ++i) ms[i] = (uint8_t**)calloc(n_seq + 1, sizeof(uint8_t*));
+    const int nc = abpoa_aln_msa_cons(&opt, n_seq, ids, ptr, lens, p->max_n_cons, cl, cs, clu_n, clu_ids, ml, ms);
+    int rc = 0, at = 0;
+    *n_cons = nc; cons_len[0] = cons_len[1] = 0; *msa_len = nc > 0 ? ml[0] : 0;
+    memset(read_clu, 0, n_seq);
+    if ((int64_t)(n_seq + nc) * (nc > 0 ? ml[0] : 0) > msa_cap) rc = -5;
+    for (int c = 0; c < nc; ++c) {
+        cons_len[c] = cl[c]; memcpy(cons + at, cs[c], cl[c]); at += cl[c];
+        const int cn = nc == 2 ? clu_n[c] : n_seq;
+        for (int j = 0; j < cn; ++j) {
+            const int r = nc == 2 ? clu_ids[c][j] : clu_ids[0][j];
+            read_clu[r] = (uint8_t)c;
+            if (rc == 0) memcpy(msa + (size_t)r * ml[0], ms[c][j], ml[0]);
+        }
+        if (rc == 0) memcpy(msa + (size_t)(n_seq + c) * ml[0], ms[c][cn], ml[0]);
+    }
+    for (int c = 0; c < 2; ++c) { for (int j = 0; j < n_seq + 1; ++j) free(ms[c][j]); free(ms[c]); free(cs[c]); free(clu_ids[c]); }
+    free(ms); free(ids); free(lens); free(ptr);
+    return rc;
+}

@@ -186,6 +186,40 @@ def poa(lib, fn, seqs, par):
     return rc, cons[:cl.value].tobytes(), msa[:(n + 1) * ml.value].reshape(n + 1, ml.value).copy()
 
 
+def poa_ncons(lib, fn, seqs, par, min_freq=0.20):
+    """abpoa_aln_msa_cons with max_n_cons consensus sequences -> (rc, [consensus bytes], read clusters, msa as (n_seq + n_cons, msa_len))"""
+    n = len(seqs)
+    lens = np.array([len(s) for s in seqs], dtype=np.int32)
+    off = np.zeros(n, dtype=np.int64)
+    if n > 1:
+        off[1:] = np.cumsum(lens[:-1])
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.uint8) for s in seqs] + [np.zeros(1, np.uint8)]))
+    tot = int(lens.sum())
+    cons = np.zeros(tot + 8, dtype=np.uint8)
+    cap = (n + 2) * (tot + 8)
+    msa = np.zeros(cap, dtype=np.uint8)
+    clu = np.zeros(n + 1, dtype=np.uint8)
+    cl = (C.c_int32 * 2)(0, 0)
+    nc, ml = C.c_int32(0), C.c_int32(0)
+    rc = getattr(lib, fn)(C.c_int(n), flat.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p), C.byref(par),
+                          C.c_double(min_freq), cons.ctypes.data_as(C.c_void_p), cl, C.byref(nc), clu.ctypes.data_as(C.c_void_p),
+                          msa.ctypes.data_as(C.c_void_p), C.byref(ml), C.c_int32(min(cap, 2**31 - 1)))
+    cs, at = [], 0
+    for c in range(nc.value):
+        cs.append(cons[at:at + cl[c]].tobytes()); at += cl[c]
+    return rc, cs, clu[:n].copy(), msa[:(n + nc.value) * ml.value].reshape(n + nc.value, ml.value).copy()
+
+
+def denovo_problems(mbp, tech, seed, max_len=600, max_reads=40):
+    """Read sets as wfa_collect_noisy_aln_str_no_ps_hap hands them to abpoa_aln_msa_cons (src/align.c:1180): all fully covering reads of a region,
+    both haplotypes mixed in input order."""
+    from longcalld_b200 import synth
+    for r in synth.make_regions(mbp, tech, seed=seed, with_reads=True):
+        seqs = [s for s in r.reads if len(s)]
+        if 2 <= len(seqs) <= max_reads and max(len(s) for s in seqs) <= max_len:
+            yield seqs
+
+
 def poa_sub(lib, fn, seqs, sub_beg, sub_end, par):
     """The sub-graph form (partially covering reads): sub_beg / sub_end per read as lcd_poa_sub_batch takes them."""
     n = len(seqs)
