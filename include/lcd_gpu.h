@@ -402,7 +402,7 @@ typedef struct {
     int32_t match, mismatch, gap_open1, gap_ext1, gap_open2, gap_ext2;  /* 2,6,6,2,24,1: src/align.h:21-26 */
     int32_t wb; float wf;          /* adaptive band (abpoa.h:17-18: 10, 0.01); wb = -1: unbanded */
     int32_t sub_aln;               /* 1: phased set-up (inc_both_ends = 0, span-read consensus rule); 0: abpoa_msa */
-    int32_t max_n_cons;            /* 1 (the 2-consensus de-novo clustering is not on the GPU yet: rejected) */
+    int32_t max_n_cons;            /* 1; 2 (de-novo read clustering, sub_aln = 0) through lcd_poa_ncons_* only */
 } lcd_poa_params_t;
 
 enum { LCD_POA_OK = 0, LCD_POA_NEEDS_INT32 = -1, LCD_POA_BAND = -2, LCD_POA_BACKTRACK = -3,
@@ -452,6 +452,28 @@ lcd_plan_t *lcd_poa_sub_plan_create(int n, const uint8_t *seqs, size_t seqs_len,
                                     const int64_t *read_off, const int32_t *read_len, int n_total_reads,
                                     const int32_t *sub_beg, const int32_t *sub_end,
                                     const lcd_poa_params_t *params);
+
+/* Two consensus sequences (abpoa_aln_msa_cons with max_n_cons = 2, src/align.c:872-953, called by wfa_collect_noisy_aln_str_no_ps_hap :1180 for a
+ * region without a usable phase set): after the progressive POA of all reads the device runs abPOA's read clustering on the row-column MSA
+ * (abpoa_multip_read_clu_kmedoids, abPOA/src/abpoa_output.c:1135-1180: candidate het columns, merged read partitions, k-medoids) and, when it
+ * finds two clusters, one most-frequent consensus per cluster (abpoa_most_frequent :549-586).  min_freq[i] = abpt->min_freq = opt->min_af (a
+ * double, as the reference keeps it: min_w = MAX(2, ceil(n_reads * min_freq))).  Per problem: n_cons (abc->n_cons: 1 or 2), cons_len2 (length
+ * of the second consensus, stored right after the first at cons[cons_off[i] + results[i].cons_len]); per read (indexed like read_off):
+ * read_cluster (abc->clu_read_ids as a 0 / 1 label).  The MSA has n_reads + n_cons rows (msa_cap[i] must allow n_reads + 2).  Problems
+ * with max_n_cons = 1 may share the batch. */
+int lcd_poa_ncons_batch(int n, const uint8_t *seqs, size_t seqs_len,
+                        const int32_t *first_read, const int32_t *n_reads,
+                        const int64_t *read_off, const int32_t *read_len, int n_total_reads,
+                        const lcd_poa_params_t *params, const double *min_freq,
+                        uint8_t *cons, const int64_t *cons_off,
+                        uint8_t *msa, const int64_t *msa_off, const int64_t *msa_cap,
+                        lcd_poa_result_t *results, int32_t *n_cons, int32_t *cons_len2, uint8_t *read_cluster);
+lcd_plan_t *lcd_poa_ncons_plan_create(int n, const uint8_t *seqs, size_t seqs_len,
+                                      const int32_t *first_read, const int32_t *n_reads,
+                                      const int64_t *read_off, const int32_t *read_len, int n_total_reads,
+                                      const lcd_poa_params_t *params, const double *min_freq);
+/* after lcd_poa_plan_fetch; any of the three outputs may be NULL */
+int lcd_poa_plan_fetch_clusters(lcd_plan_t *plan, void *stream, int32_t *n_cons, int32_t *cons_len2, uint8_t *read_cluster);
 
 #ifdef __cplusplus
 }

@@ -961,3 +961,39 @@ def poa_batch(problems, params, want_msa=True, sub=None):
             m = msa[msa_off[i]:msa_off[i] + rows * int(r["msa_len"])].reshape(rows, int(r["msa_len"])).copy()
         out.append((int(r["status"]), c, m))
     return out
+
+
+def poa_ncons_batch(problems, params, min_freq=0.20):
+    """De-novo POA with up to two consensus sequences (lcd_poa_ncons_batch: abpoa_aln_msa_cons, max_n_cons = 2) over HOST buffers.
+    -> [(status, [consensus bytes per cluster], read clusters (uint8 per read), msa (n_reads + n_cons, msa_len))]"""
+    n = len(problems)
+    if n == 0:
+        return []
+    seqs, first, n_reads, read_off, read_len = pack_poa(problems)
+    par = _poa_params_array(params, n)
+    mf = np.ascontiguousarray(np.broadcast_to(np.asarray(min_freq, dtype=np.float64), (n,)))
+    sum_len = np.add.reduceat(read_len.astype(np.int64), first)
+    max_len = np.maximum.reduceat(read_len, first).astype(np.int64)
+    cons_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(sum_len, out=cons_off[1:])
+    msa_cap = (n_reads.astype(np.int64) + 2) * (2 * max_len + 64)
+    msa_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(msa_cap, out=msa_off[1:])
+    cons = np.zeros(max(int(cons_off[-1]), 1), dtype=np.uint8)
+    msa = np.zeros(max(int(msa_off[-1]), 1), dtype=np.uint8)
+    res = np.zeros(n, dtype=POA_RESULT_DTYPE)
+    n_cons, len2, clu = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(max(len(read_len), 1), np.uint8)
+    rc = lib().lcd_poa_ncons_batch(C.c_int(n), _ptr(seqs, C.c_uint8), C.c_size_t(seqs.size), _ptr(first, C.c_int32), _ptr(n_reads, C.c_int32),
+                                   _ptr(read_off, C.c_int64), _ptr(read_len, C.c_int32), C.c_int(len(read_len)), par.ctypes.data_as(C.c_void_p),
+                                   _ptr(mf, C.c_double), _ptr(cons, C.c_uint8), _ptr(cons_off, C.c_int64), _ptr(msa, C.c_uint8), _ptr(msa_off, C.c_int64),
+                                   _ptr(msa_cap, C.c_int64), res.ctypes.data_as(C.c_void_p), _ptr(n_cons, C.c_int32), _ptr(len2, C.c_int32), _ptr(clu, C.c_uint8))
+    _check(rc, "lcd_poa_ncons_batch")
+    out = []
+    for i in range(n):
+        r = res[i]
+        l1, l2, nc = int(r["cons_len"]), int(len2[i]), int(n_cons[i])
+        cs = [cons[cons_off[i]:cons_off[i] + l1].tobytes()] + ([cons[cons_off[i] + l1:cons_off[i] + l1 + l2].tobytes()] if nc == 2 else [])
+        rows = int(n_reads[i]) + nc
+        m = msa[msa_off[i]:msa_off[i] + rows * int(r["msa_len"])].reshape(rows, int(r["msa_len"])).copy()
+        out.append((int(r["status"]), cs, clu[first[i]:first[i] + n_reads[i]].copy(), m))
+    return out

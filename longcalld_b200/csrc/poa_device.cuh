@@ -49,7 +49,7 @@ struct __align__(16) Problem {
     int32_t cons_off;         // byte offset in the consensus buffer (capacity sum_len)
     int32_t node_cap;         // workspace budget of the first attempt (host estimate); a problem that outgrows
     int32_t edge_cap;         // it ends with ST_OOM and is re-run with worst-case budgets (KernelArgs.worst_case)
-    int32_t pad;
+    int32_t min_w;            // max_n_cons = 2: MAX(2, ceil(n_reads * min_freq)) (abpoa_output.c:1141), computed on the host in double
     lcd_poa_params_t par;
 };
 
@@ -60,6 +60,7 @@ struct __align__(16) DevResult {
     int32_t n_nodes;
     uint64_t msa_off;         // byte offset in the MSA output pool
     uint32_t cells_lo, cells_hi;
+    int32_t n_cons, cons_len2; // max_n_cons = 2: number of read clusters (1 or 2) and the length of the second consensus (stored right after the first)
 #ifdef LCD_POA_TIMING
     unsigned long long t_dp, t_bt, t_add, t_after, t_fin, t_seg, t_gen, n_seg, n_gen, t_pro;   // SM clock cycles per phase (debug builds); rows by chain segments / the general path
 #endif
@@ -90,6 +91,7 @@ struct KernelArgs {
     // partially covering reads (nullptr: none): read r is aligned against the sub-graph between the nodes sub_beg[r] and sub_end[r] of the
     // first read (abpoa_subgraph_nodes; both 0: the whole graph), or left out (sub_beg[r] < 0).  Indexed like read_off / read_len.
     const int32_t *sub_beg, *sub_end;
+    uint8_t *read_clu;            // max_n_cons = 2: cluster (0 / 1) of every read, indexed like read_off / read_len
 };
 
 // per-group workspace carved from the arena for one problem
@@ -1935,8 +1937,164 @@ template <class L> struct Poa {
         return w.tmp[0];
     }
 
+    // ---- de-novo read clustering for max_n_cons = 2 (abpoa_multip_read_clu_kmedoids, abPOA/src/abpoa_output.c:676-1180) --------------
+    // Works on the row-column MSA the warp / CTA has just written (a node's out-edge read sets restricted to a cluster, :345-352, are counts
+    // over the MSA rows of the cluster's reads).  Candidate het columns (:676-720) are found by the lanes, one column each; a candidate is
+    // kept as its column and a 6-nibble map base -> allele index in order of first appearance, so that a read's allele at a candidate is one
+    // MSA byte and a shift; candidates with identical read partitions (allele_clu_exist :647-674) are found through a 64-bit fingerprint and
+    // verified read by read.  Priorities (:772-791: a stable sort) are ranks counted by the lanes, the distance matrix (:802-862) is dealt
+    // pair by pair; the k-medoids rounds (:865-1121; two clusters: two dozen reads) run on one lane.  Scratch: the DP arena, free by now.
+    __device__ static __forceinline__ int cl_alle(const uint8_t *msa, int ml, int col, unsigned map, int r) {
+        return (int)((map >> (4 * msa[(size_t)r * ml + col])) & 15u) - 1;
+    }
+    // returns the number of clusters (1 or 2) or ST_OOM; with two clusters the consensus rows n_seq, n_seq + 1 of the MSA, the two consensus
+    // sequences (back to back in cons) and read_clu are (re)written
+    __device__ int cluster(uint8_t *msa, int n_seq, int ml, int min_w, uint8_t *cons, uint8_t *read_clu, int *cons_len0, int *cons_len1) {
+        const int lane = L::tid();
+        int *S = reinterpret_cast<int *>(w.dp);
+        const uint64_t need = 10ull * (uint64_t)ml + (uint64_t)n_seq * n_seq + 2ull * n_seq + 64;
+        if (need * 2 > w.dp_capacity) return ST_OOM;
+        int *c_map = S, *c_info = S + ml, *c_hlo = S + 2 * (size_t)ml, *c_hhi = S + 3 * (size_t)ml, *list = S + 4 * (size_t)ml, *rep = S + 5 * (size_t)ml;
+        int *h_k = S + 6 * (size_t)ml, *h_cnt = S + 7 * (size_t)ml, *h_vt = S + 8 * (size_t)ml, *prio = S + 9 * (size_t)ml;
+        int *dis = S + 10 * (size_t)ml, *clu = dis + (size_t)n_seq * n_seq;
+        const int min_het = min_w / 2 > 2 ? min_w / 2 : 2, min_hom = n_seq - min_het;
+        for (int r = lane; r < n_seq; r += L::NT) read_clu[r] = 0;
+        for (int i = lane; i < ml; i += L::NT) {
+            int depth[6] = {0, 0, 0, 0, 0, 0}, first[6] = {0, 0, 0, 0, 0, 0};
+            for (int r = 0; r < n_seq; ++r) { const int b = msa[(size_t)r * ml + i]; if (++depth[b] == 1) first[b] = r; }
+            int al[6], nu = 0, vt = 0, tot = 0;
+            for (int j = 0; j < 6; ++j) if (depth[j] >= min_het && depth[j] <= min_hom) { al[nu++] = j; tot += depth[j]; if (j == 5) vt = 1; }
+            if (nu < 2) { c_info[i] = 0; continue; }
+            for (int j = 0; j < nu - 1; ++j) for (int k = j + 1; k < nu; ++k) if (first[al[j]] > first[al[k]]) { const int t = al[j]; al[j] = al[k]; al[k] = t; }
+            unsigned map = 0;
+            for (int j = 0; j < nu; ++j) map |= (unsigned)(j + 1) << (4 * al[j]);
+            unsigned long long h = 1469598103934665603ull;
+            for (int r = 0; r < n_seq; ++r) h = (h ^ ((map >> (4 * msa[(size_t)r * ml + i])) & 15u)) * 1099511628211ull;
+            c_map[i] = (int)map; c_info[i] = 1 | (vt << 1) | (nu << 4) | (tot << 8); c_hlo[i] = (int)(unsigned)h; c_hhi[i] = (int)(unsigned)(h >> 32);
+        }
+        L::sync();
+        if (lane == 0) { int nc = 0; for (int i = 0; i < ml; ++i) if (c_info[i]) list[nc++] = i; w.tmp[0] = nc; }
+        L::sync();
+        const int nc = w.tmp[0];
+        if (nc == 0) return 1;
+        for (int k = lane; k < nc; k += L::NT) {
+            const int ck = list[k]; int rp = k;
+            for (int j = 0; j < k; ++j) {
+                const int cj = list[j];
+                if (c_hlo[cj] != c_hlo[ck] || c_hhi[cj] != c_hhi[ck] || ((c_info[cj] ^ c_info[ck]) & 0xf0)) continue;
+                bool eq = true;
+                for (int r = 0; r < n_seq && eq; ++r) if (cl_alle(msa, ml, cj, (unsigned)c_map[cj], r) != cl_alle(msa, ml, ck, (unsigned)c_map[ck], r)) eq = false;
+                if (eq) { rp = j; break; }
+            }
+            rep[k] = rp;
+        }
+        L::sync();
+        if (lane == 0) {             // the merged candidates in column order: count, X-if-any-X (:722-727)
+            int nh = 0;
+            for (int k = 0; k < nc; ++k) {
+                const int ck = list[k], vt = (c_info[ck] >> 1) & 1, r0 = rep[k];
+                if (r0 == k) { h_k[nh] = ck; h_cnt[nh] = 1; h_vt[nh] = vt; rep[k] = nh++; }
+                else { const int e = rep[r0]; h_cnt[e]++; if (!vt) h_vt[e] = 0; }
+            }
+            w.tmp[0] = nh;
+        }
+        L::sync();
+        const int nh = w.tmp[0];
+        for (int e = lane; e < nh; e += L::NT) {
+            const int ce = h_cnt[e], de = c_info[h_k[e]] >> 8, ve = h_vt[e]; int rank = 0;
+            for (int f = 0; f < nh; ++f) {
+                if (f == e) continue;
+                const int cf = h_cnt[f], df = c_info[h_k[f]] >> 8, vf = h_vt[f];
+                if (cf > ce || (cf == ce && (df > de || (df == de && (vf < ve || (vf == ve && f < e)))))) ++rank;
+            }
+            prio[rank] = e;
+        }
+        for (int p = lane; p < n_seq * n_seq; p += L::NT) {
+            const int i = p / n_seq, j = p - i * n_seq;
+            if (i == j) dis[p] = 0;
+            if (i >= j) continue;
+            int d = 0;
+            for (int e = 0; e < nh; ++e) {
+                const int col = h_k[e]; const unsigned map = (unsigned)c_map[col];
+                const int a = cl_alle(msa, ml, col, map, i), b = cl_alle(msa, ml, col, map, j);
+                if (a >= 0 && b >= 0 && a != b) d += (h_vt[e] == 0 ? 2 : 1) * h_cnt[e];
+            }
+            dis[i * n_seq + j] = d; dis[j * n_seq + i] = d;
+        }
+        L::sync();
+        if (lane == 0) {
+            int n_clu = 1, med0 = -1, med1 = -1, have = 0;
+            for (int t = 0; t < nh && !have; ++t) {             // abpoa_collect_2medoids on the candidates in priority order (:865-890,996-1003)
+                const int e = prio[t], col = h_k[e], nu = (c_info[col] >> 4) & 15; const unsigned map = (unsigned)c_map[col];
+                int max_dis = 0;
+                for (int a = 0; a < nu - 1; ++a) for (int b = a + 1; b < nu; ++b)
+                    for (int r1 = 0; r1 < n_seq; ++r1) {
+                        if (cl_alle(msa, ml, col, map, r1) != a) continue;
+                        for (int r2 = 0; r2 < n_seq; ++r2) {
+                            if (cl_alle(msa, ml, col, map, r2) != b) continue;
+                            if (dis[r1 * n_seq + r2] > max_dis) { max_dis = dis[r1 * n_seq + r2]; med0 = r1; med1 = r2; }
+                        }
+                    }
+                if (max_dis > 0) have = 1;
+            }
+            int ncs0 = 0, ncs1 = 0;
+            if (have) {
+                for (int iter = 0; iter < 10; ++iter) {          // abpoa_update_kmedoids (:1030-1093)
+                    ncs0 = ncs1 = 0;
+                    for (int i = 0; i < n_seq; ++i) {
+                        const int d0 = dis[i * n_seq + med0], d1 = dis[i * n_seq + med1];
+                        const int c = d1 < d0 ? 1 : d1 == d0 ? (ncs0 < ncs1 ? 0 : 1) : 0;
+                        if (c) clu[n_seq + ncs1++] = i; else clu[ncs0++] = i;
+                    }
+                    int nm[2] = {-1, -1};
+                    for (int c = 0; c < 2; ++c) {
+                        const int *cr = clu + c * n_seq, cn = c ? ncs1 : ncs0; int best = INT32_MAX;
+                        for (int j = 0; j < cn; ++j) {
+                            int sum = 0;
+                            for (int k = 0; k < cn; ++k) if (k != j) sum += dis[cr[j] * n_seq + cr[k]];
+                            if (sum < best) { best = sum; nm[c] = cr[j]; }
+                        }
+                    }
+                    if (nm[0] > nm[1]) { const int t = nm[0]; nm[0] = nm[1]; nm[1] = t; }
+                    int changed = 0;
+                    if (nm[0] != -1 && nm[1] != -1) changed = (nm[0] != med0 || nm[1] != med1) ? 1 : 0;
+                    med0 = nm[0]; med1 = nm[1];
+                    if (!changed) break;
+                }
+                if (ncs0 >= min_w && ncs1 >= min_w) { n_clu = 2; for (int j = 0; j < ncs1; ++j) read_clu[clu[n_seq + j]] = 1; }
+            }
+            w.tmp[0] = n_clu; w.tmp[1] = ncs0; w.tmp[2] = ncs1;
+        }
+        L::sync();
+        const int n_clu = w.tmp[0];
+        if (n_clu != 2) return 1;
+        const int csz[2] = { w.tmp[1], w.tmp[2] };
+        for (int i = lane; i < ml; i += L::NT) {                  // abpoa_set_major_voting_cons per cluster, sub_aln = 0 (:393-424)
+            int cnt[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+            for (int r = 0; r < n_seq; ++r) { const int b = msa[(size_t)r * ml + i]; if (b < 4) cnt[read_clu[r]][b]++; }
+            for (int c = 0; c < 2; ++c) {
+                int max_c = 0, total = 0, max_base = 5;
+                for (int j = 0; j < 4; ++j) { if (cnt[c][j] > max_c) { max_c = cnt[c][j]; max_base = j; } total += cnt[c][j]; }
+                msa[(size_t)(n_seq + c) * ml + i] = (uint8_t)(max_c >= csz[c] - total ? max_base : 5);
+            }
+        }
+        L::sync();
+        if (lane == 0) {
+            int at = 0;
+            for (int c = 0; c < 2; ++c) {
+                const uint8_t *row = msa + (size_t)(n_seq + c) * ml; const int a0 = at;
+                for (int i = 0; i < ml; ++i) if (row[i] != 5) cons[at++] = row[i];
+                w.tmp[1 + c] = at - a0;
+            }
+        }
+        L::sync();
+        *cons_len0 = w.tmp[1]; *cons_len1 = w.tmp[2];
+        return 2;
+    }
+
     // ---- output: MSA ranks (abpoa_DFS_set_msa_rank :359-410), most-frequent consensus, RC-MSA ----------
-    __device__ int finish(int n_seq, uint8_t *cons, int *cons_len_out, const KernelArgs &a, unsigned long long *msa_off_out, int *msa_len_out) {
+    __device__ int finish(int n_seq, uint8_t *cons, int *cons_len_out, const KernelArgs &a, unsigned long long *msa_off_out, int *msa_len_out,
+                          int min_w, uint8_t *read_clu, int *n_cons_out, int *cons_len2_out) {
         const int n = w.n_nodes, lane = L::tid();
         int *deg = w.tmp, *st = w.order;          // order[] is free now; DFS stack needs <= n entries... see below
         if (lane == 0) {
@@ -1985,7 +2143,7 @@ template <class L> struct Poa {
         for (int i = lane; i < ml; i += L::NT) {
             int max_c = 0, total = 0, max_base = 5;
             for (int j = 0; j < 4; ++j) { const int c = cnt[i * 5 + j]; if (c > max_c) { max_c = c; max_base = j; } total += c; }
-            if (max_base == 5) { bad = 1; emit[i] = -1; continue; }
+            if (max_base == 5) { if (par.sub_aln) bad = 1; emit[i] = -1; continue; }      // sub_aln: the reference would read out of bounds; else 0 >= n_seq fails: no base
             const int gap_c = (par.sub_aln ? w.n_span[nid[i * 5 + max_base]] : n_seq) - total;
             emit[i] = max_c >= gap_c ? nid[i * 5 + max_base] : -1;
         }
@@ -1996,7 +2154,7 @@ template <class L> struct Poa {
             for (int i = 0; i < ml; ++i) if (emit[i] >= 0) { cons_ids[cl] = emit[i]; cons[cl] = (uint8_t)w.base[emit[i]]; cl++; }
             w.tmp[0] = cl;
             // MSA output slot
-            const unsigned long long bytes = ((unsigned long long)(n_seq + 1) * ml + 15) & ~15ull;
+            const unsigned long long bytes = ((unsigned long long)(n_seq + (par.max_n_cons == 2 ? 2 : 1)) * ml + 15) & ~15ull;
             const unsigned long long off = atomicAdd(a.msa_used, bytes);
             w.tmp[1] = (off + bytes <= a.msa_cap) ? 1 : 0;
             w.tmp[2] = (int)(off & 0xffffffffu); w.tmp[3] = (int)(off >> 32);
@@ -2024,6 +2182,12 @@ template <class L> struct Poa {
         }
         for (int i = lane; i < cl; i += L::NT) msa[(size_t)n_seq * ml + col[cons_ids[i]]] = cons[i];
         L::sync();
+        *n_cons_out = 1; *cons_len2_out = 0;
+        if (par.max_n_cons == 2) {
+            const int nc = cluster(msa, n_seq, ml, min_w, cons, read_clu, cons_len_out, cons_len2_out);
+            if (nc < 0) return nc;
+            *n_cons_out = nc;
+        }
         return ST_OK;
     }
 
@@ -2031,7 +2195,7 @@ template <class L> struct Poa {
     __device__ void run(const KernelArgs &a, const Problem &pb, DevResult *res, int32_t *arena) {
         par = pb.par; n_reads = pb.n_reads; cells = 0; t_dp = t_bt = t_add = t_after = t_fin = t_seg = t_gen = n_seg = n_gen = t_pro = 0;
         oe1 = par.gap_open1 + par.gap_ext1; oe2 = par.gap_open2 + par.gap_ext2;
-        int status = ST_OK, cons_len = 0, msa_len = 0; unsigned long long msa_off = 0;
+        int status = ST_OK, cons_len = 0, msa_len = 0, n_cons = 0, cons_len2 = 0; unsigned long long msa_off = 0;
         {
             const int m1 = INT16_MIN + par.mismatch, m2 = INT16_MIN + oe1, m3 = INT16_MIN + oe2;
             int m = m1 > m2 ? m1 : m2; if (m3 > m) m = m3;
@@ -2039,7 +2203,7 @@ template <class L> struct Poa {
         }
         L::sync();
         const int ncap = a.worst_case ? pb.sum_len + 34 : pb.node_cap, ecap = a.worst_case ? 3 * (pb.sum_len + pb.n_reads) + 64 : pb.edge_cap;
-        if (!carve(arena, a.arena_words, ncap, ecap, pb.max_len, pb.n_reads) || par.max_n_cons != 1) status = ST_OOM;
+        if (!carve(arena, a.arena_words, ncap, ecap, pb.max_len, pb.n_reads) || (par.max_n_cons != 1 && !(par.max_n_cons == 2 && !par.sub_aln && a.read_clu))) status = ST_OOM;
         else {
             w.in_top = w.out_top = w.aln_top = 0; w.n_nodes = 0; w.oom = 0;
             if (L::tid() == 0) { add_node(0); add_node(0); w.next[0] = 1; w.next[1] = -1; }
@@ -2076,7 +2240,11 @@ template <class L> struct Poa {
                     const int gn = sub ? w.maxl[end_id] - w.maxl[beg_id] + 1 : w.n_nodes, len = ql > gn ? ql : gn;
                     const int ms = (ql * par.match > len * par.gap_ext1 + par.gap_open1) ? ql * par.match : len * par.gap_ext1 + par.gap_open1;
                     if (!(ms <= INT16_MAX - par.mismatch - oe1 - oe2)) { status = ST_INT32; break; }
+#ifndef LCD_EMU
                     { LCD_T0(); ring_start(n_rows); n_cig = align(q, ql); ring_drain(); LCD_T1(t_dp); }
+#else
+                    n_cig = align(q, ql);
+#endif
                     w.dp_capacity = dp_cap0;
                     if (n_cig < 0) { status = n_cig; break; }
                 }
@@ -2108,7 +2276,7 @@ template <class L> struct Poa {
             }
             if (status == ST_OK && w.n_nodes > 2) {
                 LCD_T0();
-                status = finish(pb.n_reads, a.cons + pb.cons_off, &cons_len, a, &msa_off, &msa_len);
+                status = finish(pb.n_reads, a.cons + pb.cons_off, &cons_len, a, &msa_off, &msa_len, pb.min_w, a.read_clu ? a.read_clu + pb.read_first : nullptr, &n_cons, &cons_len2);
                 LCD_T1(t_fin);
             }
         }
@@ -2116,6 +2284,7 @@ template <class L> struct Poa {
             DevResult r;
             r.status = status; r.cons_len = cons_len; r.msa_len = msa_len; r.n_nodes = w.n_nodes; r.msa_off = msa_off;
             r.cells_lo = (uint32_t)cells; r.cells_hi = (uint32_t)(cells >> 32);
+            r.n_cons = n_cons; r.cons_len2 = cons_len2;
 #ifdef LCD_POA_TIMING
             r.t_dp = t_dp - t_bt; r.t_bt = t_bt; r.t_add = t_add; r.t_after = t_after; r.t_fin = t_fin; r.t_seg = t_seg; r.t_gen = t_gen; r.n_seg = n_seg; r.n_gen = n_gen; r.t_pro = t_pro;
 #endif

@@ -73,7 +73,7 @@ poa_gather_cons_kernel(const uint8_t *cons, const Problem *problems, const DevRe
         if (results[i].status != ST_OK) continue;
         const uint8_t *src = cons + problems[i].cons_off;
         uint8_t *dst = packed + dst_off[i];
-        for (int k = lane; k < results[i].cons_len; k += 32) dst[k] = src[k];
+        for (int k = lane; k < results[i].cons_len + results[i].cons_len2; k += 32) dst[k] = src[k];
     }
 }
 
@@ -89,7 +89,9 @@ static uint64_t arena_need_words(uint64_t N, uint64_t E, int max_len, int n_read
 }
 
 struct PoaPlan : Plan {
-    DevBuf<uint8_t> d_seqs, d_cons, d_msa;
+    DevBuf<uint8_t> d_seqs, d_cons, d_msa, d_read_clu;
+    bool any_ncons = false;                // a problem asks for two consensus sequences (de-novo clustering)
+    int n_total_reads_ = 0;
     DevBuf<Problem> d_problems;
     DevBuf<int64_t> d_read_off;
     DevBuf<int32_t> d_read_len, d_order, d_sub_beg, d_sub_end;
@@ -119,8 +121,8 @@ struct PoaPlan : Plan {
 
     int build(int n_, const uint8_t *seqs, size_t seqs_len, const int32_t *first_read, const int32_t *n_reads,
               const int64_t *read_off, const int32_t *read_len, int n_total_reads, const lcd_poa_params_t *params,
-              const int32_t *sub_beg = nullptr, const int32_t *sub_end = nullptr) {
-        n = n_;
+              const int32_t *sub_beg = nullptr, const int32_t *sub_end = nullptr, const double *min_freq = nullptr) {
+        n = n_; n_total_reads_ = n_total_reads;
         has_sub.assign(n, 0);
         Context &c = ctx();
         problems.resize(n); cons_dev_off.resize(n); need_small.resize(n); need_full.resize(n);
@@ -130,9 +132,16 @@ struct PoaPlan : Plan {
         size_t cons_total = 0; double msa_est = 0;
         for (int i = 0; i < n; ++i) {
             if (n_reads[i] < 1 || first_read[i] < 0 || first_read[i] + n_reads[i] > n_total_reads) { set_error("lcd_poa: problem %d has an invalid read range", i); return -1; }
-            if (params[i].max_n_cons != 1) { set_error("lcd_poa: problem %d asks for max_n_cons=%d; only the single-consensus path is implemented on the GPU", i, params[i].max_n_cons); return -1; }
+            if (params[i].max_n_cons != 1 && !(params[i].max_n_cons == 2 && min_freq && !params[i].sub_aln)) {
+                set_error("lcd_poa: problem %d asks for max_n_cons=%d; two consensus sequences come from lcd_poa_ncons_* (sub_aln = 0), more are not implemented", i, params[i].max_n_cons); return -1;
+            }
             Problem &p = problems[i];
             memset(&p, 0, sizeof(p));
+            if (params[i].max_n_cons == 2) {           // abpoa_output.c:1141, in double as the reference computes it
+                any_ncons = true;
+                const int cw = (int)ceil((double)n_reads[i] * min_freq[i]);
+                p.min_w = cw > 2 ? cw : 2;
+            }
             p.seq_base = 0; p.read_first = first_read[i]; p.n_reads = n_reads[i]; p.par = params[i];
             int mn = INT32_MAX;
             for (int r = 0; r < n_reads[i]; ++r) {
@@ -160,7 +169,7 @@ struct PoaPlan : Plan {
             need_full[i] = arena_need_words((uint64_t)p.sum_len + 34, 3ull * (p.sum_len + p.n_reads) + 64, p.max_len, p.n_reads,
                                             (uint64_t)((double)(p.sum_len + 34) * (dp_sn + 1) * 160));
             work[i] = (double)p.n_reads * rows * nv;
-            msa_est += (double)(p.n_reads + 1) * (1.5 * p.max_len + 64);
+            msa_est += (double)(p.n_reads + params[i].max_n_cons) * (1.5 * p.max_len + 64);
         }
         cons_bytes = cons_total;
         msa_pool_bytes = ((size_t)(msa_est * 1.5) + 4096 + 15) & ~(size_t)15;
@@ -184,6 +193,7 @@ struct PoaPlan : Plan {
         }
         LCD_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         if (d_msa_used.alloc(1)) return -1;
+        if (any_ncons) { if (d_read_clu.alloc(std::max(n_total_reads, 1))) return -1; LCD_CUDA_OK(cudaMemsetAsync(d_read_clu.p, 0, std::max(n_total_reads, 1), s)); }
         LCD_CUDA_OK(cudaStreamSynchronize(s));
         return 0;
     }
@@ -214,7 +224,7 @@ struct PoaPlan : Plan {
         ka.problems = d_problems.p; ka.order = d_idx; ka.n = (int)idx.size(); ka.queue = d_q;
         ka.seqs = d_seqs.p; ka.read_off = d_read_off.p; ka.read_len = d_read_len.p;
         ka.cons = d_cons.p; ka.msa = d_msa.p; ka.msa_cap = msa_pool_bytes; ka.msa_used = d_msa_used.p;
-        ka.sub_beg = d_sub_beg.p; ka.sub_end = d_sub_end.p;
+        ka.sub_beg = d_sub_beg.p; ka.sub_end = d_sub_end.p; ka.read_clu = any_ncons ? d_read_clu.p : nullptr;
         ka.results = d_results.p; ka.arena = c.pool + win->off + pool_lo; ka.arena_words = words; ka.worst_case = worst_case ? 1 : 0;
         static int carve_set = -2;          // shared-memory carve-out of the SMs the persistent grid sits on (see lcd_gpu_reserve_sms)
         if (carve_set == -2) {
@@ -321,7 +331,7 @@ struct PoaPlan : Plan {
         if (want_cons) {
             pack_off.resize(n + 1);
             unsigned long long tot = 0;
-            for (int i = 0; i < n; ++i) { pack_off[i] = tot; if (h_results[i].status == ST_OK) tot += (unsigned long long)h_results[i].cons_len; }
+            for (int i = 0; i < n; ++i) { pack_off[i] = tot; if (h_results[i].status == ST_OK) tot += (unsigned long long)h_results[i].cons_len + (unsigned long long)h_results[i].cons_len2; }
             pack_off[n] = tot;
             h_cons.resize(tot + 16);
             if (tot) {
@@ -379,14 +389,25 @@ struct PoaPlan : Plan {
             const DevResult &r = h_results[i];
             results[i].status = r.status; results[i].cons_len = r.cons_len; results[i].msa_len = r.msa_len; results[i].n_nodes = r.n_nodes;
             if (r.status != ST_OK) { if (!bad) first_bad = r.status; ++bad; continue; }
-            if (cons && cons_off) memcpy(cons + cons_off[i], h_cons.data() + pack_off[i], r.cons_len);
+            if (cons && cons_off) memcpy(cons + cons_off[i], h_cons.data() + pack_off[i], (size_t)r.cons_len + r.cons_len2);
             if (msa && msa_off && msa_cap) {
-                const int64_t bytes = (int64_t)(problems[i].n_reads + 1) * r.msa_len;
+                const int64_t bytes = (int64_t)(problems[i].n_reads + (r.n_cons == 2 ? 2 : 1)) * r.msa_len;
                 if (bytes > msa_cap[i]) { results[i].status = LCD_POA_MSA_CAP; if (!bad) first_bad = LCD_POA_MSA_CAP; ++bad; continue; }
                 memcpy(msa + msa_off[i], h_msa.data() + r.msa_off, bytes);
             }
         }
         if (bad) { set_error("lcd_poa: %d of %d problems failed on the device (first status %d; see LCD_POA_* in lcd_gpu.h)", bad, n, first_bad); return -2; }
+        return 0;
+    }
+
+    // after fetch(): the clusters of the problems that asked for two consensus sequences
+    int fetch_clusters(cudaStream_t s, int32_t *n_cons, int32_t *cons_len2, uint8_t *read_cluster) {
+        if ((int)h_results.size() != n) { set_error("lcd_poa_plan_fetch_clusters: call lcd_poa_plan_fetch first"); return -1; }
+        for (int i = 0; i < n; ++i) { if (n_cons) n_cons[i] = h_results[i].status == ST_OK ? h_results[i].n_cons : 0; if (cons_len2) cons_len2[i] = h_results[i].status == ST_OK ? h_results[i].cons_len2 : 0; }
+        if (read_cluster && n_total_reads_ > 0) {
+            if (any_ncons) { LCD_DRAIN(s); LCD_CUDA_OK(cudaMemcpyAsync(read_cluster, d_read_clu.p, n_total_reads_, cudaMemcpyDeviceToHost, s)); LCD_CUDA_OK(cudaStreamSynchronize(s)); }
+            else memset(read_cluster, 0, n_total_reads_);
+        }
         return 0;
     }
 };
@@ -411,6 +432,37 @@ lcd_plan_t *lcd_poa_sub_plan_create(int n, const uint8_t *seqs, size_t seqs_len,
     if (p->build(n, seqs, seqs_len, first_read, n_reads, read_off, read_len, n_total_reads, params, sub_beg, sub_end)) { delete p; return nullptr; }
     return reinterpret_cast<lcd_plan_t *>(p);
 }
+lcd_plan_t *lcd_poa_ncons_plan_create(int n, const uint8_t *seqs, size_t seqs_len,
+                                      const int32_t *first_read, const int32_t *n_reads,
+                                      const int64_t *read_off, const int32_t *read_len, int n_total_reads,
+                                      const lcd_poa_params_t *params, const double *min_freq) {
+    if (ensure_ready()) return nullptr;
+    if (n < 0 || (n > 0 && (!seqs || !first_read || !n_reads || !read_off || !read_len || !params || !min_freq))) { set_error("lcd_poa_ncons_plan_create: invalid arguments"); return nullptr; }
+    poa::PoaPlan *p = new poa::PoaPlan();
+    if (p->build(n, seqs, seqs_len, first_read, n_reads, read_off, read_len, n_total_reads, params, nullptr, nullptr, min_freq)) { delete p; return nullptr; }
+    return reinterpret_cast<lcd_plan_t *>(p);
+}
+int lcd_poa_plan_fetch_clusters(lcd_plan_t *plan, void *stream, int32_t *n_cons, int32_t *cons_len2, uint8_t *read_cluster) {
+    poa::PoaPlan *p = dynamic_cast<poa::PoaPlan *>(reinterpret_cast<Plan *>(plan));
+    if (!p) { set_error("lcd_poa_plan_fetch_clusters: not a POA plan"); return -1; }
+    return p->fetch_clusters(pick_stream(stream), n_cons, cons_len2, read_cluster);
+}
+int lcd_poa_ncons_batch(int n, const uint8_t *seqs, size_t seqs_len,
+                        const int32_t *first_read, const int32_t *n_reads,
+                        const int64_t *read_off, const int32_t *read_len, int n_total_reads,
+                        const lcd_poa_params_t *params, const double *min_freq,
+                        uint8_t *cons, const int64_t *cons_off,
+                        uint8_t *msa, const int64_t *msa_off, const int64_t *msa_cap,
+                        lcd_poa_result_t *results, int32_t *n_cons, int32_t *cons_len2, uint8_t *read_cluster) {
+    lcd_plan_t *plan = lcd_poa_ncons_plan_create(n, seqs, seqs_len, first_read, n_reads, read_off, read_len, n_total_reads, params, min_freq);
+    if (!plan) return -1;
+    int rc = lcd_plan_run(plan, nullptr);
+    if (!rc) rc = lcd_poa_plan_fetch(plan, nullptr, cons, cons_off, msa, msa_off, msa_cap, results);
+    if (!rc || rc == -2) { const int rc2 = lcd_poa_plan_fetch_clusters(plan, nullptr, n_cons, cons_len2, read_cluster); if (!rc) rc = rc2; }
+    lcd_plan_destroy(plan);
+    return rc;
+}
+
 lcd_plan_t *lcd_poa_plan_create(int n, const uint8_t *seqs, size_t seqs_len,
                                 const int32_t *first_read, const int32_t *n_reads,
                                 const int64_t *read_off, const int32_t *read_len, int n_total_reads,

@@ -56,12 +56,12 @@ static void trace(const char *what, long a, long b) {
     trace_t e = { t, (unsigned long)pthread_self(), what, a, b }; trace_buf[trace_n++] = e;
     pthread_mutex_unlock(&t_mu);
 }
-static unsigned long n_calls[12];
+static unsigned long n_calls[14];      /* [12]: de-novo POA problems with two consensus sequences on the GPU, [13]: abpoa_aln_msa_cons calls forwarded */
 #define COUNT(i) __atomic_fetch_add(&n_calls[i], 1, __ATOMIC_RELAXED)      /* the reference's worker threads call in concurrently */
 __attribute__((destructor)) static void report(void) {
     if (trace_on > 0 && trace_n) { FILE *f = fopen(getenv("LCD_DROPIN_TRACE"), "w"); if (f) { for (size_t i = 0; i < trace_n; ++i) fprintf(f, "%.6f\t%lx\t%s\t%ld\t%ld\n", trace_buf[i].t - trace_buf[0].t, trace_buf[i].tid, trace_buf[i].what, trace_buf[i].a, trace_buf[i].b); fclose(f); } }
-    if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: digar %lu (forwarded: %lu), sites %lu, pileup %lu, profile %lu, phase %lu, edlib %lu, wfa %lu, poa %lu (with partially covering reads: %lu; forwarded to abPOA: %lu) in %lu engine batches (library time: poa %.2f s, wfa %.2f s, edlib %.2f s; threads blocked %.2f s in total; forwarded abPOA %.2f s); kernel launches %llu\n",
-                                              n_calls[8], n_calls[9], n_calls[10], n_calls[0], n_calls[1], n_calls[2], n_calls[3], n_calls[4], n_calls[5], n_calls[11], n_calls[6], n_calls[7], t_batch[0], t_batch[1], t_batch[2], t_blocked, t_fwd_poa, (unsigned long long)lcd_gpu_launch_count());
+    if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: digar %lu (forwarded: %lu), sites %lu, pileup %lu, profile %lu, phase %lu, edlib %lu, wfa %lu, poa %lu (with partially covering reads: %lu; de-novo with max_n_cons = 2: %lu; forwarded to abPOA: %lu + %lu) in %lu engine batches (library time: poa %.2f s, wfa %.2f s, edlib %.2f s; threads blocked %.2f s in total; forwarded abPOA %.2f s); kernel launches %llu\n",
+                                              n_calls[8], n_calls[9], n_calls[10], n_calls[0], n_calls[1], n_calls[2], n_calls[3], n_calls[4], n_calls[5], n_calls[11], n_calls[12], n_calls[6], n_calls[13], n_calls[7], t_batch[0], t_batch[1], t_batch[2], t_blocked, t_fwd_poa, (unsigned long long)lcd_gpu_launch_count());
 }
 
 /* LCD_DROPIN_STAGES=engines keeps the pileup scan and the phasing (K1 - K4) on the reference's own host code and sends only the DP engines
@@ -442,6 +442,7 @@ typedef struct req_t {
     const uint8_t *seqs; size_t seqs_len;                 /* POA: the reads back to back; WFA: pattern then text; edlib: query then target */
     int n_reads; const int64_t *read_off; const int32_t *read_len; lcd_poa_params_t ppar; int want_msa; int max_len;
     const int32_t *sub_beg, *sub_end;                     /* POA: partially covering reads (NULL: none), see lcd_poa_sub_batch */
+    double min_freq; uint8_t *read_clu; int32_t n_cons, cons_len2;   /* POA with ppar.max_n_cons = 2 (de-novo clustering), see lcd_poa_ncons_batch */
     int plen, tlen; lcd_wfa_params_t wpar;
     int qlen, mode, want_path;
     /* outputs (buffers owned by the caller) */
@@ -484,6 +485,16 @@ static void run_batch(int kind, req_t **r, int n) {
     trace("batch_begin", kind, n);
     new_thread_stream();
     if (kind == RQ_POA) {
+        int n2 = 0;
+        for (int i = 0; i < n; ++i) n2 += r[i]->ppar.max_n_cons == 2;
+        if (n2 > 0 && n2 < n) {                              /* de-novo problems (two consensus sequences) go in a library call of their own */
+            req_t **a = (req_t**)malloc(sizeof(req_t*) * n); int na = 0, nb = 0;
+            for (int i = 0; i < n; ++i) if (r[i]->ppar.max_n_cons == 2) a[na++] = r[i];
+            for (int i = 0; i < n; ++i) if (r[i]->ppar.max_n_cons != 2) a[na + nb++] = r[i];
+            run_batch(kind, a, na); run_batch(kind, a + na, nb);
+            free(a);
+            return;
+        }
         size_t tot = 0, n_rd = 0, cons_tot = 0, msa_tot = 0;
         for (int i = 0; i < n; ++i) { tot += r[i]->seqs_len; n_rd += r[i]->n_reads; cons_tot += r[i]->seqs_len + 16; msa_tot += r[i]->want_msa ? (size_t)r[i]->msa_cap : 0; }
         uint8_t *seqs = (uint8_t*)malloc(tot + 1), *cons = (uint8_t*)malloc(cons_tot + 1), *msa = (uint8_t*)malloc(msa_tot + 1);
@@ -500,17 +511,23 @@ static void run_batch(int kind, req_t **r, int n) {
             o += r[i]->seqs_len; co += r[i]->seqs_len + 16; mo += (size_t)mcap[i];
         }
         trace("lib_begin", kind, n);
-        const int rc = any_sub ? lcd_poa_sub_batch(n, seqs, tot, first, nr, off, len, (int)n_rd, sb, se, par, cons, coff, msa, moff, mcap, res)
+        double *mf = NULL; int32_t *ncs = NULL, *cl2 = NULL; uint8_t *rclu = NULL;
+        if (n2) { mf = (double*)malloc(sizeof(double) * n); ncs = (int32_t*)calloc(n, sizeof(int32_t)); cl2 = (int32_t*)calloc(n, sizeof(int32_t)); rclu = (uint8_t*)calloc(n_rd + 1, 1); for (int i = 0; i < n; ++i) mf[i] = r[i]->min_freq; }
+        const int rc = n2 ? lcd_poa_ncons_batch(n, seqs, tot, first, nr, off, len, (int)n_rd, par, mf, cons, coff, msa, moff, mcap, res, ncs, cl2, rclu)
+                     : any_sub ? lcd_poa_sub_batch(n, seqs, tot, first, nr, off, len, (int)n_rd, sb, se, par, cons, coff, msa, moff, mcap, res)
                                : lcd_poa_batch(n, seqs, tot, first, nr, off, len, (int)n_rd, par, cons, coff, msa, moff, mcap, res);
         trace("lib_end", kind, n);
         if (rc == -1) die("lcd_poa_batch");                /* -2: some problems were refused on the device (their status says why) */
         for (int i = 0; i < n; ++i) {
             r[i]->pres = res[i]; r[i]->rc = rc;
             if (res[i].status == LCD_POA_OK) {
-                memcpy(r[i]->cons, cons + coff[i], res[i].cons_len);
-                if (r[i]->want_msa) memcpy(r[i]->msa, msa + moff[i], (size_t)(r[i]->n_reads + 1) * res[i].msa_len);
+                const int nc = n2 ? ncs[i] : 1, l2 = n2 ? cl2[i] : 0;
+                memcpy(r[i]->cons, cons + coff[i], (size_t)res[i].cons_len + l2);
+                if (r[i]->want_msa) memcpy(r[i]->msa, msa + moff[i], (size_t)(r[i]->n_reads + nc) * res[i].msa_len);
+                if (n2) { r[i]->n_cons = nc; r[i]->cons_len2 = l2; memcpy(r[i]->read_clu, rclu + first[i], r[i]->n_reads); }
             }
         }
+        free(mf); free(ncs); free(cl2); free(rclu);
         free(seqs); free(cons); free(msa); free(first); free(nr); free(len); free(off); free(coff); free(moff); free(mcap); free(par); free(res); free(sb); free(se);
         __atomic_fetch_add(&n_calls[5], (unsigned long)n, __ATOMIC_RELAXED); COUNT(7);
     } else if (kind == RQ_WFA) {
@@ -1209,6 +1226,69 @@ int abpoa_partial_aln_msa_cons(const call_var_opt_t *opt, abpoa_t *ab, int sampl
     const double t0_ = now_s();
     const int rc_ = orig(opt, ab, sampling_reads, n_reads, read_ids, read_seqs, read_quals, read_lens, read_full_cover, names, max_n_cons, cons_lens, cons_seqs,
                 clu_n_seqs, clu_read_ids, msa_seq_lens, msa_seqs);
+    t_add(&t_fwd_poa, now_s() - t0_);
+    return rc_;
+}
+
+/* abpoa_aln_msa_cons (src/align.c:872-953): the de-novo POA of a region without a usable phase set -- all fully covering reads, unbanded, up to
+ * two consensus sequences from abPOA's read clustering -- as ONE problem of lcd_poa_ncons_batch (the clustering runs on the device). */
+int abpoa_aln_msa_cons(const call_var_opt_t *opt, int n_reads, int *read_ids, uint8_t **read_seqs, int *read_lens, int max_n_cons, int *cons_lens, uint8_t **cons_seqs,
+                       int *clu_n_seqs, int **clu_read_ids, int *msa_seq_len, uint8_t ***msa_seq) {
+    typedef int (*fn_t)(const call_var_opt_t *, int, int *, uint8_t **, int *, int, int *, uint8_t **, int *, int **, int *, uint8_t ***);
+    static fn_t orig = NULL;
+    if (!orig) orig = (fn_t)dlsym(RTLD_NEXT, "abpoa_aln_msa_cons");
+    int ok = n_reads >= 1 && (max_n_cons == 1 || max_n_cons == 2) && cons_lens && cons_seqs && clu_n_seqs && clu_read_ids;
+    size_t tot = 0; int max_len = 0;
+    for (int i = 0; ok && i < n_reads; ++i) { if (read_lens[i] <= 0) ok = 0; else { tot += (size_t)read_lens[i]; if (read_lens[i] > max_len) max_len = read_lens[i]; } }
+    if (ok) {
+        uint8_t *seqs = (uint8_t*)malloc(tot + 1), *cons = (uint8_t*)malloc(tot + 17), *rclu = (uint8_t*)calloc(n_reads + 1, 1);
+        int64_t *off = (int64_t*)malloc(sizeof(int64_t) * n_reads); int32_t *len = (int32_t*)malloc(sizeof(int32_t) * n_reads);
+        size_t o = 0;
+        for (int i = 0; i < n_reads; ++i) { off[i] = (int64_t)o; len[i] = read_lens[i]; memcpy(seqs + o, read_seqs[i], read_lens[i]); o += read_lens[i]; }
+        const lcd_poa_params_t par = { opt->match, opt->mismatch, opt->gap_open1, opt->gap_ext1, opt->gap_open2, opt->gap_ext2, -1, 0.01f, 0, max_n_cons };
+        const int want_msa = msa_seq != NULL && msa_seq_len != NULL;
+        const int64_t msa_cap = (int64_t)(n_reads + 2) * (2 * (int64_t)max_len + 64);
+        uint8_t *msa = want_msa ? (uint8_t*)malloc((size_t)msa_cap) : NULL;
+        req_t r; memset(&r, 0, sizeof(r));
+        r.kind = RQ_POA; r.seqs = seqs; r.seqs_len = o; r.n_reads = n_reads; r.read_off = off; r.read_len = len; r.ppar = par; r.want_msa = want_msa; r.max_len = max_len;
+        r.cons = cons; r.msa = msa; r.msa_cap = msa_cap; r.min_freq = opt->min_af; r.read_clu = rclu; r.n_cons = 1;
+        gpu_call(&r);
+        const lcd_poa_result_t res = r.pres;
+        int done = 0;
+        if (res.status == LCD_POA_OK && res.cons_len > 0 && (max_n_cons == 1 || r.n_cons >= 1)) {
+            const int nc = max_n_cons == 2 ? r.n_cons : 1;
+            const int cl[2] = { res.cons_len, r.cons_len2 };
+            int at = 0;
+            for (int c = 0; c < nc; ++c) { cons_lens[c] = cl[c]; cons_seqs[c] = (uint8_t*)malloc(cl[c] > 0 ? cl[c] : 1); memcpy(cons_seqs[c], cons + at, cl[c]); at += cl[c]; }
+            int cn[2] = { n_reads, 0 };
+            if (nc == 2) {
+                cn[0] = cn[1] = 0;
+                for (int c = 0; c < 2; ++c) clu_read_ids[c] = (int*)malloc((n_reads + 1) * sizeof(int));
+                for (int i = 0; i < n_reads; ++i) { const int c = rclu[i] ? 1 : 0; clu_read_ids[c][cn[c]++] = read_ids[i]; }
+                clu_n_seqs[0] = cn[0]; clu_n_seqs[1] = cn[1];
+            } else {
+                *clu_n_seqs = n_reads; *clu_read_ids = (int*)malloc((n_reads + 1) * sizeof(int));
+                for (int i = 0; i < n_reads; ++i) (*clu_read_ids)[i] = read_ids[i];
+            }
+            if (want_msa) {
+                const size_t ml = (size_t)res.msa_len;
+                for (int c = 0; c < nc; ++c) {
+                    msa_seq_len[c] = res.msa_len;
+                    int j = 0;
+                    for (int i = 0; i < n_reads; ++i) if (nc == 1 || (rclu[i] ? 1 : 0) == c) { msa_seq[c][j] = (uint8_t*)malloc(ml > 0 ? ml : 1); memcpy(msa_seq[c][j], msa + (size_t)i * ml, ml); ++j; }
+                    msa_seq[c][cn[c]] = (uint8_t*)malloc(ml > 0 ? ml : 1); memcpy(msa_seq[c][cn[c]], msa + (size_t)(n_reads + c) * ml, ml);
+                }
+            }
+            if (nc == 2) COUNT(12);
+            done = nc;
+        }
+        free(seqs); free(cons); free(rclu); free(off); free(len); free(msa);
+        if (done) return done;
+        /* outside the kernel's envelope (e.g. LCD_POA_NEEDS_INT32): let abPOA handle this region */
+    }
+    COUNT(13);
+    const double t0_ = now_s();
+    const int rc_ = orig(opt, n_reads, read_ids, read_seqs, read_lens, max_n_cons, cons_lens, cons_seqs, clu_n_seqs, clu_read_ids, msa_seq_len, msa_seq);
     t_add(&t_fwd_poa, now_s() - t0_);
     return rc_;
 }

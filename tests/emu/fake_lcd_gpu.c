@@ -174,3 +174,26 @@ int lcd_poa_batch(int n, const uint8_t *seqs, size_t seqs_len, const int32_t *fi
     }
     return bad ? -2 : 0;
 }
+
+int lcd_oracle_poa_ncons(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len, const lcd_poa_params_t *p, double min_freq,
+                         uint8_t *cons, int32_t *cons_len, int32_t *n_cons, uint8_t *read_clu, uint8_t *msa, int32_t *msa_len, int32_t msa_cap);
+int lcd_poa_ncons_batch(int n, const uint8_t *seqs, size_t seqs_len, const int32_t *first, const int32_t *nr, const int64_t *off, const int32_t *len, int n_total,
+                        const lcd_poa_params_t *par, const double *min_freq, uint8_t *cons, const int64_t *coff, uint8_t *msa, const int64_t *moff, const int64_t *mcap,
+                        lcd_poa_result_t *res, int32_t *n_cons, int32_t *cons_len2, uint8_t *read_cluster) {
+    (void)seqs_len; (void)n_total; __atomic_fetch_add(&n_batches, 1, __ATOMIC_RELAXED);
+    int bad = 0;
+    for (int i = 0; i < n; ++i) {
+        int32_t cl[2] = {0, 0}, ml = 0, nc = 0;
+        const int want = msa && moff && mcap && mcap[i] > 0;
+        int64_t cap = 0; for (int k = 0; k < nr[i]; ++k) cap += 2 * (int64_t)len[first[i] + k] + 64;
+        cap *= nr[i] + 2;
+        uint8_t *tmp = (uint8_t*)malloc((size_t)cap + 16);
+        const int rc = lcd_oracle_poa_ncons(nr[i], seqs, off + first[i], len + first[i], par + i, min_freq[i], cons + coff[i], cl, &nc, read_cluster + first[i], tmp, &ml,
+                                            (int32_t)(cap > 0x7fffffff ? 0x7fffffff : cap));
+        res[i].status = rc; res[i].cons_len = cl[0]; res[i].msa_len = ml; res[i].n_nodes = 0; n_cons[i] = nc; cons_len2[i] = cl[1];
+        if (rc == 0 && want) { if ((int64_t)(nr[i] + nc) * ml > mcap[i]) res[i].status = LCD_POA_MSA_CAP; else memcpy(msa + moff[i], tmp, (size_t)(nr[i] + nc) * ml); }
+        if (res[i].status) ++bad;
+        free(tmp);
+    }
+    return bad ? -2 : 0;
+}

@@ -40,6 +40,7 @@ using namespace lcd::poa;
 
 static int mode = 0;     /* bit0: thread-per-problem lane policy (packed int16x2); bit1: tight workspace budgets; bit2: on-chip previous-row cache; bit3: two-phase rows (the CTA-per-problem code path) */
 extern "C" void emu_poa_mode(int m) { mode = m; }
+static uint8_t *g_read_clu = nullptr; static int g_min_w = 0; static DevResult g_last;      /* the 2-consensus form (emu_poa_ncons) */
 extern "C" int emu_poa(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len,
                        const lcd_poa_params_t *p, uint8_t *cons, int32_t *cons_len,
                        uint8_t *msa, int32_t *msa_len, int32_t msa_cap) {
@@ -55,13 +56,27 @@ extern "C" int emu_poa(int n_seq, const uint8_t *seqs, const int64_t *seq_off, c
     KernelArgs a; memset(&a, 0, sizeof(a));
     a.problems = &pb; a.order = &order; a.n = 1; a.queue = &queue; a.seqs = seqs; a.read_off = seq_off; a.read_len = seq_len;
     a.cons = cons; a.msa = msa_pool.data(); a.msa_cap = (unsigned long long)msa_cap; a.msa_used = &msa_used;
-    a.results = &dr; a.arena = arena; a.arena_words = words;
+    a.results = &dr; a.arena = arena; a.arena_words = words; a.read_clu = g_read_clu; pb.min_w = g_min_w;
     pb.node_cap = pb.sum_len + 34; pb.edge_cap = 3 * (pb.sum_len + n_seq) + 64;
     if (mode & 2) { pb.node_cap = 2 * pb.max_len + 64; pb.edge_cap = 3 * pb.node_cap; }   /* tight first-attempt budgets */
     if (mode & 1) { Poa<ThreadLanes> poa; poa.run(a, pb, &dr, arena); }
     else if (mode & 8) { Poa<HostLanes2> poa; static int gsbuf[Poa<HostLanes2>::GS_INTS]; poa.gs = gsbuf; poa.run(a, pb, &dr, arena); }
     else { Poa<HostLanes> poa; static int16_t cache[2 * 3 * 8 * 32]; poa.row_cache = (mode & 4) ? cache : nullptr; poa.run(a, pb, &dr, arena); }
     *cons_len = dr.cons_len; *msa_len = 0;
-    if (dr.status == ST_OK && msa) { *msa_len = dr.msa_len; memcpy(msa, msa_pool.data() + dr.msa_off, (size_t)(n_seq + 1) * dr.msa_len); }
+    if (dr.status == ST_OK && msa) { *msa_len = dr.msa_len; memcpy(msa, msa_pool.data() + dr.msa_off, (size_t)(n_seq + (dr.n_cons == 2 ? 2 : 1)) * dr.msa_len); }
+    g_last = dr;
     return dr.status;
+}
+
+// abpoa_aln_msa_cons with max_n_cons consensus sequences: same signature as the oracle's lcd_oracle_poa_ncons
+#include <math.h>
+extern "C" int emu_poa_ncons(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len, const lcd_poa_params_t *p, double min_freq,
+                             uint8_t *cons, int32_t *cons_len, int32_t *n_cons, uint8_t *read_clu, uint8_t *msa, int32_t *msa_len, int32_t msa_cap) {
+    const int cw = (int)ceil(n_seq * min_freq);
+    g_read_clu = read_clu; g_min_w = cw > 2 ? cw : 2;
+    memset(read_clu, 0, n_seq);
+    const int rc = emu_poa(n_seq, seqs, seq_off, seq_len, p, cons, cons_len, msa, msa_len, msa_cap);
+    g_read_clu = nullptr; g_min_w = 0;
+    *n_cons = rc == 0 ? g_last.n_cons : 0; cons_len[1] = rc == 0 ? g_last.cons_len2 : 0;
+    return rc;
 }

@@ -45,6 +45,10 @@ def test_vcf_identical_through_the_batched_driver(dropin_cpu, tech, threads):
     c = {k: int(v) for k, v in re.findall(r"(edlib|wfa|poa) (\d+)", line.split("(library time")[0])}
     batches = int(re.search(r"in (\d+) engine batches", line).group(1))
     assert c["poa"] > 100 and c["wfa"] > 100
+    fwd = re.search(r"forwarded to abPOA: (\d+) \+ (\d+)", line)
+    assert fwd and int(fwd.group(1)) == 0 and int(fwd.group(2)) == 0, line          # partial-cover and de-novo (two-consensus) POA included
+    if tech == "ont":
+        assert int(re.search(r"max_n_cons = 2: (\d+)", line).group(1)) > 0, line
     if tech != "mosaic":                 # -s rewrites the difference lists region by region: one region at a time there
         assert batches * 4 < c["poa"] + c["wfa"] + c["edlib"], line
 

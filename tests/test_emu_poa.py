@@ -51,3 +51,19 @@ def test_emu_poa_vs_fixtures(emu):
         rc, cons, msa = T.poa(emu, "emu_poa", seqs, T.poa_params(c["sub_aln"], c["wb"]))
         assert rc == 0 and "".join(map(str, cons)) == c["cons"], i
         assert list(msa.shape) == c["msa_shape"] and hashlib.sha1(msa.tobytes()).hexdigest() == c["msa_sha1"], i
+
+
+@pytest.mark.parametrize("mode", [0, 8])
+def test_emu_poa_two_consensus_vs_oracle(emu, oracle, mode):
+    """max_n_cons = 2 (de-novo clustering on the MSA + one consensus per cluster): the device code on the host against the oracle"""
+    emu.emu_poa_mode(mode)
+    par = T.poa_params(0, -1); par.max_n_cons = 2
+    n = two = 0
+    for tech, mbp, seed in (("hifi", 0.2, 43), ("ont", 0.08, 44)):
+        for seqs in T.denovo_problems(mbp, tech, seed, max_len=400):
+            for mf in (0.2, 0.34):
+                a = T.poa_ncons(oracle, "lcd_oracle_poa_ncons", seqs, par, mf)
+                b = T.poa_ncons(emu, "emu_poa_ncons", seqs, par, mf)
+                assert a[0] == b[0] == 0 and a[1] == b[1] and np.array_equal(a[2], b[2]) and a[3].shape == b[3].shape and (a[3] == b[3]).all(), (n, mf)
+            n += 1; two += len(a[1]) == 2
+    assert n >= 40 and two >= 10

@@ -58,3 +58,19 @@ def test_simt_poa_partial_cover_vs_oracle(emu, oracle, tech, mbp, seed):
         assert a[0] == b[0] == 0 and a[1] == b[1] and a[2].shape == b[2].shape and (a[2] == b[2]).all(), (n, sb.tolist(), se.tolist())
         n += 1; n_sub += int((sb > 0).sum())
     assert n > 40 and n_sub > 150, (n, n_sub)
+
+
+def test_simt_poa_two_consensus_vs_oracle(emu, oracle):
+    """max_n_cons = 2 under the one-warp SIMT emulator (lanes dealt over columns / candidates / read pairs)"""
+    import numpy as np
+    emu.emu_poa_mode(0)
+    par = T.poa_params(0, -1); par.max_n_cons = 2
+    n = two = 0
+    for seqs in T.denovo_problems(0.5, "hifi", 45, max_len=260, max_reads=24):
+        a = T.poa_ncons(oracle, "lcd_oracle_poa_ncons", seqs, par)
+        b = T.poa_ncons(emu, "emu_poa_ncons", seqs, par)
+        assert a[0] == b[0] == 0 and a[1] == b[1] and np.array_equal(a[2], b[2]) and a[3].shape == b[3].shape and (a[3] == b[3]).all(), n
+        n += 1; two += len(a[1]) == 2
+        if n >= 20:
+            break
+    assert n >= 10 and two >= 3

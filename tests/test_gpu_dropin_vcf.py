@@ -50,9 +50,13 @@ def test_vcf_identical_with_gpu_dropin(tech):
     assert all(counts[k] > 0 for k in need), calls[-1]                                             # the kernels really ran on the GPU
     # no POA call of abpoa_partial_aln_msa_cons goes to the reference's abPOA any more: a kernel that starts refusing problems (a silent
     # CPU fallback) fails here, not in the md5; the problems with partially covering / sampled reads are counted
-    fwd_poa = int(__import__("re").search(r"forwarded to abPOA: (\d+)", calls[-1]).group(1))
+    m_fwd = __import__("re").search(r"forwarded to abPOA: (\d+) \+ (\d+)", calls[-1])
+    fwd_poa, fwd_denovo = int(m_fwd.group(1)), int(m_fwd.group(2))
     part_poa = int(__import__("re").search(r"with partially covering reads: (\d+)", calls[-1]).group(1))
+    two_cons = int(__import__("re").search(r"max_n_cons = 2: (\d+)", calls[-1]).group(1))
     assert fwd_poa == FORWARDED_POA[tech] and part_poa == PARTIAL_POA[tech], calls[-1]
+    # the de-novo POA of regions without a usable phase set (abpoa_aln_msa_cons, two consensus sequences from the read clustering) runs on the GPU too
+    assert fwd_denovo == 0 and (two_cons > 0 if tech == "ont" else True), calls[-1]
     print(calls[-1])
     assert md5 == GOLDEN[tech], (md5, calls[-1])
 

@@ -116,3 +116,39 @@ def test_gpu_poa_partial_cover_reads(gpu, oracle, tech, mbp, seed):
     sb = sb.copy(); se = se.copy(); k = int(np.argmax(sb > 0)); sb[k] = 10 ** 6; se[k] = 10 ** 6 + 5
     with pytest.raises(gpu.LcdGpuError):
         gpu.poa_batch([seqs], gpu.poa_params(1, 10), sub=[(sb, se)])
+
+
+def test_gpu_poa_two_consensus_vs_oracle(gpu, oracle):
+    """lcd_poa_ncons_batch (abpoa_aln_msa_cons, max_n_cons = 2): number of clusters, both consensus sequences, every read's cluster and the
+    (n_reads + n_cons)-row MSA, bit-exact; warp kernel (reads <= 224 bp) and CTA kernel (longer reads, unbanded) in one batch; problems
+    with max_n_cons = 1 in the same batch; another min_freq."""
+    problems = list(T.denovo_problems(0.5, "hifi", 51, max_len=700)) + list(T.denovo_problems(0.12, "ont", 52, max_len=500))
+    assert len(problems) >= 80 and any(max(len(s) for s in p) > 224 for p in problems) and any(max(len(s) for s in p) <= 224 for p in problems)
+    par2 = list(gpu.poa_params(0, -1)); par2[9] = 2
+    par = T.poa_params(0, -1); par.max_n_cons = 2
+    two = 0
+    for mf in (0.20, 0.34):
+        got = gpu.poa_ncons_batch(problems, tuple(par2), mf)
+        bad = []
+        for i, seqs in enumerate(problems):
+            a = T.poa_ncons(oracle, "lcd_oracle_poa_ncons", seqs, par, mf)
+            g = got[i]
+            if not (g[0] == a[0] == 0 and g[1] == a[1] and np.array_equal(g[2], a[2]) and g[3].shape == a[3].shape and (g[3] == a[3]).all()):
+                bad.append(i)
+            two += len(a[1]) == 2
+        assert not bad, (mf, len(bad), bad[:10])
+    assert two >= 30
+    # mixed batch: every other problem asks for one consensus only
+    pars = [tuple(par2) if i % 2 else gpu.poa_params(0, -1) for i in range(len(problems))]
+    got = gpu.poa_ncons_batch(problems, pars, 0.20)
+    p1 = T.poa_params(0, -1)
+    for i, seqs in enumerate(problems[:60]):
+        if i % 2:
+            a = T.poa_ncons(oracle, "lcd_oracle_poa_ncons", seqs, par, 0.20)
+            assert got[i][1] == a[1] and np.array_equal(got[i][2], a[2]) and (got[i][3] == a[3]).all(), i
+        else:
+            rc, cons, msa = T.poa(oracle, "lcd_oracle_poa", seqs, p1)
+            assert got[i][0] == rc == 0 and got[i][1] == [cons] and (got[i][3] == msa).all() and not got[i][2].any(), i
+    # lcd_poa_batch keeps refusing max_n_cons = 2 (it cannot return the clusters)
+    with pytest.raises(gpu.LcdGpuError):
+        gpu.poa_batch(problems[:2], tuple(par2))
