@@ -69,6 +69,32 @@ int lcd_oracle_poa(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const
 int lcd_oracle_poa_sub(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const int32_t *seq_len, const int32_t *sub_beg, const int32_t *sub_end,
                        const lcd_poa_params_t *p, uint8_t *cons, int32_t *cons_len, uint8_t *msa, int32_t *msa_len, int32_t msa_cap);
 
+/* ---- pileup scan, step 2 (rest): the chunk's noisy-region set and the sites that stay clean-region candidates ---------------------
+ * pre_process_noisy_regs (src/collect_var.c:557-643) then classify_cand_vars after its first loop (:925-1033, out_somatic = 0) with
+ * cr_extend_noisy_regs_with_low_comp (:538-553), cr_add_var_cr (:754-778), var_noisy_reads_ratio (:657-751), post_process_noisy_regs +
+ * collect_noisy_reg_start_end (:482-535,646-655) and the reference's own cr_merge / cr_merge2 / cr_is_contained (src/cgranges.c:225-335,512-530).
+ * Interval lists are cgranges (st, en, label) triples as cr_add takes them. */
+typedef struct {
+    int64_t reg_beg, reg_end;          /* chunk->reg_beg / reg_end */
+    int32_t min_alt_dp, noisy_reg_flank_len, is_ont, pad;       /* call_var_opt_t (noisy_reg_merge_dis / min_sv_len reach cr_merge but are unused there) */
+    double min_af;
+    int32_t n_sites;                   /* candidate sites in collect_all_cand_var_sites' order, with classify_var_cate's category (K2b) */
+    int32_t n_reads;
+    const int64_t *site_pos; const int32_t *site_type, *site_ref_len, *var_cate;
+    int64_t n_cnreg; const int64_t *cnreg_beg, *cnreg_end; const int32_t *cnreg_label;       /* chunk->chunk_noisy_regs as K1 leaves it (cr_add order) */
+    int64_t n_low; const int64_t *low_beg, *low_end;                                          /* chunk->low_comp_cr (sdust; may be empty) */
+    const uint8_t *is_skipped;         /* chunk->is_skipped after K1 */
+    const int64_t *read_beg, *read_end;                                                        /* digar_t.beg / end */
+    const int64_t *digar_first; const int32_t *n_digar; const int64_t *digar_pos; const int8_t *digar_type; const int32_t *digar_len;
+    const int64_t *nreg_first; const int32_t *n_nreg; const int64_t *nreg_beg, *nreg_end;     /* digar_t.noisy_regs */
+} lcd_noisyreg_input_t;
+typedef struct {
+    int32_t *var_cate;                 /* [n_sites] the working var_i_to_cate after classify_cand_vars */
+    uint8_t *keep;                     /* [n_sites] 1: the site stays in chunk->cand_vars (chunk->var_i_to_cate gets var_cate of the kept sites, in order) */
+    int64_t *reg_beg, *reg_end; int32_t *reg_label; int64_t reg_cap, n_regs;                   /* chunk->chunk_noisy_regs at the end (cr_index order) */
+} lcd_noisyreg_output_t;
+int lcd_oracle_noisy_regs(const lcd_noisyreg_input_t *in, lcd_noisyreg_output_t *out);
+
 /* ---- read -> haplotype assignment and phasing (src/assign_hap.c:16-547) ----------------------------- */
 typedef struct {
     int32_t n_reads, n_vars;

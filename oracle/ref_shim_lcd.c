@@ -462,3 +462,64 @@ int ref_poa_ncons(int n_seq, const uint8_t *seqs, const int64_t *seq_off, const 
     free(ms); free(ids); free(lens); free(ptr);
     return rc;
 }
+
+/* pre_process_noisy_regs (src/collect_var.c:557) + classify_cand_vars (:902) themselves, on a chunk assembled from the flat arrays: the candidate
+ * sites with their counters (the reference runs its own classify_var_cate on them), the reads' difference lists and noisy intervals as K1 leaves
+ * them, chunk_noisy_regs in cr_add order, the low-complexity intervals.  Out: the compacted chunk->cand_vars (kept_pos / type / ref_len / cate,
+ * *n_kept) and chunk->chunk_noisy_regs. */
+void pre_process_noisy_regs(bam_chunk_t *chunk, call_var_opt_t *opt);
+int classify_cand_vars(bam_chunk_t *chunk, int n_var_sites, const call_var_opt_t *opt);
+int ref_noisy_regs(const lcd_classify_input_t *ci, const lcd_noisyreg_input_t *in, int64_t *kept_pos, int32_t *kept_type, int32_t *kept_ref_len, int32_t *kept_cate, int32_t *n_kept,
+                   lcd_noisyreg_output_t *out) {
+    call_var_opt_t opt; memset(&opt, 0, sizeof(opt));
+    opt.noisy_reg_max_xgaps = ci->max_xgaps; opt.is_ont = ci->is_ont; opt.min_dp = ci->min_dp; opt.min_alt_dp = ci->min_alt_dp; opt.min_af = ci->min_af; opt.max_af = ci->max_af;
+    opt.noisy_reg_merge_dis = LONGCALLD_NOISY_REG_MERGE_DIS; opt.min_sv_len = LONGCALLD_MIN_SV_LEN; opt.noisy_reg_flank_len = in->noisy_reg_flank_len; opt.out_somatic = 0;
+    if (ci->is_ont) { opt.strand_bias_pval = LONGCALLD_STRAND_BIAS_PVAL_ONT; initialize_lgamma_cache(&opt); }
+    const int n = ci->n_sites, nr = in->n_reads;
+    bam_chunk_t chunk; memset(&chunk, 0, sizeof(chunk));
+    chunk.tname = (char*)"cr"; chunk.reg_beg = in->reg_beg; chunk.reg_end = in->reg_end;
+    chunk.ref_seq = (char*)ci->ref_seq; chunk.ref_beg = ci->ref_beg; chunk.ref_end = ci->ref_end;
+    chunk.n_reads = chunk.m_reads = nr;
+    chunk.ordered_read_ids = (int*)malloc(sizeof(int) * (nr + 1)); chunk.is_skipped = (uint8_t*)malloc(nr + 1);
+    chunk.digars = (digar_t*)calloc(nr + 1, sizeof(digar_t));
+    for (int r = 0; r < nr; ++r) {
+        chunk.ordered_read_ids[r] = r; chunk.is_skipped[r] = in->is_skipped[r];
+        digar_t *d = chunk.digars + r;
+        d->beg = in->read_beg[r]; d->end = in->read_end[r]; d->n_digar = d->m_digar = in->n_digar[r];
+        d->digars = (digar1_t*)calloc(in->n_digar[r] + 1, sizeof(digar1_t));
+        for (int j = 0; j < in->n_digar[r]; ++j) { const int64_t q = in->digar_first[r] + j; d->digars[j].pos = in->digar_pos[q]; d->digars[j].type = in->digar_type[q]; d->digars[j].len = in->digar_len[q]; }
+        d->noisy_regs = cr_init();
+        for (int x = 0; x < in->n_nreg[r]; ++x) { const int64_t q = in->nreg_first[r] + x; cr_add(d->noisy_regs, "cr", (int32_t)in->nreg_beg[q], (int32_t)in->nreg_end[q], 1); }
+        cr_index(d->noisy_regs);
+    }
+    chunk.chunk_noisy_regs = cr_init();
+    for (int64_t i = 0; i < in->n_cnreg; ++i) cr_add(chunk.chunk_noisy_regs, "cr", (int32_t)in->cnreg_beg[i], (int32_t)in->cnreg_end[i], in->cnreg_label[i]);
+    if (in->n_low > 0) {
+        chunk.low_comp_cr = cr_init();
+        for (int64_t i = 0; i < in->n_low; ++i) cr_add(chunk.low_comp_cr, "cr", (int32_t)in->low_beg[i], (int32_t)in->low_end[i], 0);
+        cr_index(chunk.low_comp_cr);
+    }
+    chunk.n_cand_vars = n;
+    chunk.cand_vars = (cand_var_t*)calloc(n + 1, sizeof(cand_var_t));
+    for (int i = 0; i < n; ++i) {
+        const int32_t *c = ci->site_counts + 8 * (int64_t)i;
+        cand_var_t *v = chunk.cand_vars + i;
+        v->pos = ci->site_pos[i]; v->var_type = ci->site_type[i]; v->total_cov = c[0]; v->low_qual_cov = c[1]; v->n_uniq_alles = 2;
+        v->alle_covs = (int*)malloc(2 * sizeof(int)); v->alle_covs[0] = c[2]; v->alle_covs[1] = c[3];
+        v->strand_to_alle_covs = (int**)malloc(2 * sizeof(int*));
+        for (int s = 0; s < 2; ++s) { v->strand_to_alle_covs[s] = (int*)malloc(2 * sizeof(int)); v->strand_to_alle_covs[s][0] = c[4 + 2 * s]; v->strand_to_alle_covs[s][1] = c[5 + 2 * s]; }
+        v->ref_len = ci->site_ref_len[i]; v->alt_len = ci->site_alt_len[i];
+        if (v->var_type == BAM_CDIFF || v->var_type == BAM_CINS) { v->alt_seq = (uint8_t*)malloc(v->alt_len > 0 ? v->alt_len : 1); memcpy(v->alt_seq, ci->site_alt + ci->site_alt_off[i], v->alt_len); }
+    }
+    pre_process_noisy_regs(&chunk, &opt);
+    int nk = 0;
+    if (n > 0) nk = classify_cand_vars(&chunk, n, &opt);
+    *n_kept = nk;
+    for (int i = 0; i < nk; ++i) { kept_pos[i] = chunk.cand_vars[i].pos; kept_type[i] = chunk.cand_vars[i].var_type; kept_ref_len[i] = chunk.cand_vars[i].ref_len; kept_cate[i] = chunk.var_i_to_cate[i]; }
+    int rc = 0;
+    out->n_regs = chunk.chunk_noisy_regs ? chunk.chunk_noisy_regs->n_r : 0;
+    if (out->n_regs > out->reg_cap) rc = -5;
+    else for (int64_t k = 0; k < out->n_regs; ++k) { out->reg_beg[k] = cr_start(chunk.chunk_noisy_regs, k); out->reg_end[k] = cr_end(chunk.chunk_noisy_regs, k); out->reg_label[k] = cr_label(chunk.chunk_noisy_regs, k); }
+    /* (test infrastructure: the chunk's allocations are left to the process) */
+    return rc;
+}

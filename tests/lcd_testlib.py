@@ -402,9 +402,8 @@ def digar_input(d):
     return inp, keep
 
 
-def collect_digar(lib, fn, d, mid_args=(), cap_like=None, slack=0):
-    """Run an implementation of the =/X difference-list pass -> dict with per-read records (in read-id order, layout independent).
-    mid_args: extra ctypes arguments between the input and the output struct (the MD-tag shim takes the tags there)."""
+def collect_digar_raw(lib, fn, d, mid_args=(), cap_like=None, slack=0):
+    """Run an implementation of the difference-list pass -> its flat output arrays (the layout lcd_digar_output_t / the GPU plan's fetch() use)."""
     inp, keep = digar_input(d)
     nr = d["n_reads"]; dc, ac, rc_ = digar_capacity(cap_like if cap_like is not None else d)        # (cap_like: a chunk whose CIGARs size the outputs)
     dc += slack; ac += slack; rc_ += slack
@@ -418,6 +417,18 @@ def collect_digar(lib, fn, d, mid_args=(), cap_like=None, slack=0):
                       nl.ctypes.data, rc_, cb.ctypes.data, ce.ctypes.data, cl.ctypes.data, rc_, 0, qc.ctypes.data, 0, 0, 0)
     rc = getattr(lib, fn)(C.byref(inp), *mid_args, C.byref(out))
     assert rc == 0, rc
+    o = dict(buf)
+    o.update(nreg_first=nf, n_nreg=nn, nreg_beg=nb, nreg_end=ne, nreg_label=nl, cnreg_beg=cb, cnreg_end=ce, cnreg_label=cl, n_cnreg=int(out.n_cnreg), qual_counts=qc,
+             n_digar_total=int(out.n_digar_total), n_alt_total=int(out.n_alt_total), n_nreg_total=int(out.n_nreg_total))
+    return o
+
+
+def collect_digar(lib, fn, d, mid_args=(), cap_like=None, slack=0):
+    """Run an implementation of the =/X difference-list pass -> dict with per-read records (in read-id order, layout independent).
+    mid_args: extra ctypes arguments between the input and the output struct (the MD-tag shim takes the tags there)."""
+    o = collect_digar_raw(lib, fn, d, mid_args, cap_like, slack)
+    nr = d["n_reads"]; buf = o
+    nf, nn, nb, ne, nl, cb, ce, cl = (o[k] for k in ("nreg_first", "n_nreg", "nreg_beg", "nreg_end", "nreg_label", "cnreg_beg", "cnreg_end", "cnreg_label"))
     reads = {}
     for i in range(nr):
         r = int(d["ordered_read_ids"][i])
@@ -430,8 +441,8 @@ def collect_digar(lib, fn, d, mid_args=(), cap_like=None, slack=0):
             ev.append((int(buf["digar_pos"][k]), t, ln, int(buf["digar_qi"][k]), int(buf["digar_low_qual"][k]), alt))
         iv = [(int(nb[k]), int(ne[k]), int(nl[k])) for k in range(int(nf[r]), int(nf[r]) + int(nn[r]))]
         reads[r] = (int(buf["skip"][r]), int(buf["read_beg"][r]), int(buf["read_end"][r]), ev, iv)
-    chunk_iv = [(int(cb[k]), int(ce[k]), int(cl[k])) for k in range(out.n_cnreg)]
-    return dict(reads=reads, chunk_noisy=chunk_iv, qual_counts=qc.tolist(), totals=(out.n_digar_total, out.n_alt_total, out.n_nreg_total))
+    chunk_iv = [(int(cb[k]), int(ce[k]), int(cl[k])) for k in range(o["n_cnreg"])]
+    return dict(reads=reads, chunk_noisy=chunk_iv, qual_counts=o["qual_counts"].tolist(), totals=(o["n_digar_total"], o["n_alt_total"], o["n_nreg_total"]))
 
 
 def digar_digest(res):
@@ -462,7 +473,7 @@ class SitesOutput(C.Structure):
                 ("cap", C.c_int64), ("n_sites", C.c_int64)]
 
 
-def collect_sites(lib, fn, d, reg_beg, reg_end, src_is_offset=False):
+def collect_sites(lib, fn, d, reg_beg, reg_end, src_is_offset=False, raw=False):
     """Run an implementation of collect_all_cand_var_sites over a chunk in lcd_pileup_input_t layout (sites unused)
     -> [(pos, type, ref_len, alt_len, alt bytes)] in output order."""
     keep = {k: np.ascontiguousarray(d[k], dtype=t) for k, t in PILEUP_IN_FIELDS}
@@ -473,6 +484,8 @@ def collect_sites(lib, fn, d, reg_beg, reg_end, src_is_offset=False):
     getattr(lib, fn).argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     rc = getattr(lib, fn)(C.byref(inp), reg_beg, reg_end, C.byref(out))
     assert rc == 0, rc
+    if raw:
+        return dict(n_sites=int(out.n_sites), site_pos=pos, site_type=typ, site_ref_len=rl, site_alt_len=al, site_src=src)
     return sites_view(d, pos, typ, rl, al, src, out.n_sites, src_is_offset)
 
 
@@ -536,3 +549,93 @@ def classify_case_from_json(j):
     for k, t in CLASSIFY_FIELDS: d[k] = np.array(j[k], dtype=t)
     d["site_counts"] = d["site_counts"].reshape(-1, 8)
     return d
+
+
+# ----------------------------------------------------------------------------- noisy-region set (a5, second half) helpers
+NOISYREG_FIELDS = (("site_pos", np.int64), ("site_type", np.int32), ("site_ref_len", np.int32), ("var_cate", np.int32))
+NOISYREG_READ_FIELDS = (("is_skipped", np.uint8), ("read_beg", np.int64), ("read_end", np.int64), ("digar_first", np.int64), ("n_digar", np.int32),
+                        ("digar_pos", np.int64), ("digar_type", np.int8), ("digar_len", np.int32), ("nreg_first", np.int64), ("n_nreg", np.int32),
+                        ("nreg_beg", np.int64), ("nreg_end", np.int64))
+
+
+class NoisyRegInput(C.Structure):
+    _fields_ = [("reg_beg", C.c_int64), ("reg_end", C.c_int64), ("min_alt_dp", C.c_int32), ("noisy_reg_flank_len", C.c_int32), ("is_ont", C.c_int32), ("pad", C.c_int32),
+                ("min_af", C.c_double), ("n_sites", C.c_int32), ("n_reads", C.c_int32)] + [(k, C.c_void_p) for k, _ in NOISYREG_FIELDS] + \
+               [("n_cnreg", C.c_int64), ("cnreg_beg", C.c_void_p), ("cnreg_end", C.c_void_p), ("cnreg_label", C.c_void_p),
+                ("n_low", C.c_int64), ("low_beg", C.c_void_p), ("low_end", C.c_void_p)] + [(k, C.c_void_p) for k, _ in NOISYREG_READ_FIELDS]
+
+
+class NoisyRegOutput(C.Structure):
+    _fields_ = [("var_cate", C.c_void_p), ("keep", C.c_void_p), ("reg_beg", C.c_void_p), ("reg_end", C.c_void_p), ("reg_label", C.c_void_p), ("reg_cap", C.c_int64), ("n_regs", C.c_int64)]
+
+
+def noisyreg_input(d):
+    keep = {k: np.ascontiguousarray(d[k], dtype=t) for k, t in NOISYREG_FIELDS + NOISYREG_READ_FIELDS}
+    for k, t in (("cnreg_beg", np.int64), ("cnreg_end", np.int64), ("cnreg_label", np.int32), ("low_beg", np.int64), ("low_end", np.int64)):
+        keep[k] = np.ascontiguousarray(np.append(np.asarray(d[k]), 0), dtype=t)
+    inp = NoisyRegInput(d["reg_beg"], d["reg_end"], d["min_alt_dp"], d["noisy_reg_flank_len"], d["is_ont"], 0, d["min_af"], d["n_sites"], d["n_reads"],
+                        *[keep[k].ctypes.data for k, _ in NOISYREG_FIELDS], d["n_cnreg"], keep["cnreg_beg"].ctypes.data, keep["cnreg_end"].ctypes.data,
+                        keep["cnreg_label"].ctypes.data, d["n_low"], keep["low_beg"].ctypes.data, keep["low_end"].ctypes.data,
+                        *[keep[k].ctypes.data for k, _ in NOISYREG_READ_FIELDS])
+    return inp, keep
+
+
+def noisyreg_cap(d):
+    return int(d["n_cnreg"]) + int(d["n_sites"]) + 8
+
+
+def noisy_regs(lib, fn, d):
+    """-> (kept sites [(pos, type, ref_len, cate)], regions [(st, en, label)], working categories)"""
+    inp, keep = noisyreg_input(d)
+    n, cap = d["n_sites"], noisyreg_cap(d)
+    cate, kp = np.full(n + 1, -7, np.int32), np.zeros(n + 1, np.uint8)
+    rb, re_, rl = np.zeros(cap, np.int64), np.zeros(cap, np.int64), np.zeros(cap, np.int32)
+    out = NoisyRegOutput(cate.ctypes.data, kp.ctypes.data, rb.ctypes.data, re_.ctypes.data, rl.ctypes.data, cap, 0)
+    rc = getattr(lib, fn)(C.byref(inp), C.byref(out))
+    assert rc == 0, rc
+    kept = [(int(d["site_pos"][i]), int(d["site_type"][i]), int(d["site_ref_len"][i]), int(cate[i])) for i in np.nonzero(kp[:n])[0]]
+    return kept, [(int(rb[k]), int(re_[k]), int(rl[k])) for k in range(out.n_regs)], cate[:n].copy()
+
+
+def ref_noisy_regs(ref, ci, d):
+    """The unmodified pre_process_noisy_regs + classify_cand_vars through the shim -> (kept sites, regions)"""
+    cinp, ckeep = classify_input(ci)
+    inp, keep = noisyreg_input(d)
+    n, cap = d["n_sites"], noisyreg_cap(d)
+    kpos, ktyp, krl, kc = np.zeros(n + 1, np.int64), np.zeros(n + 1, np.int32), np.zeros(n + 1, np.int32), np.zeros(n + 1, np.int32)
+    nk = C.c_int32(0)
+    rb, re_, rl = np.zeros(cap, np.int64), np.zeros(cap, np.int64), np.zeros(cap, np.int32)
+    out = NoisyRegOutput(None, None, rb.ctypes.data, re_.ctypes.data, rl.ctypes.data, cap, 0)
+    rc = ref.ref_noisy_regs(C.byref(cinp), C.byref(inp), kpos.ctypes.data_as(C.c_void_p), ktyp.ctypes.data_as(C.c_void_p), krl.ctypes.data_as(C.c_void_p),
+                            kc.ctypes.data_as(C.c_void_p), C.byref(nk), C.byref(out))
+    assert rc == 0, rc
+    return [(int(kpos[i]), int(ktyp[i]), int(krl[i]), int(kc[i])) for i in range(nk.value)], [(int(rb[k]), int(re_[k]), int(rl[k])) for k in range(out.n_regs)]
+
+
+def noisyreg_case(orc, d, seed, is_ont=0, low_every=400, min_sv_len=50):
+    """The inputs of the noisy-region set for the chunk `d` (a K1 input): K1 -> K1b -> K2 -> K2b run by the oracle, plus synthetic low-complexity
+    intervals (sdust's output in the reference: here random short intervals, a third of them planted on candidate sites and noisy intervals).
+    -> (noisy-region input dict, classify input dict)"""
+    from longcalld_b200 import synth
+    rng = np.random.default_rng(seed)
+    o = collect_digar_raw(orc, "lcd_oracle_collect_digar_eqx", d)
+    raw = collect_sites(orc, "lcd_oracle_collect_sites", synth.pileup_input_from_digar(d, o, synth.empty_site_list(min_sv_len)), int(d["reg_beg"]), int(d["reg_end"]), raw=True)
+    st = synth.site_list_from_sites(o, raw, min_sv_len)
+    pin = synth.pileup_input_from_digar(d, o, st)
+    counts = pileup(orc, "lcd_oracle_collect_cand_vars", pin)
+    ci = synth.classify_input_from_sites(d, st, counts, seed, is_ont=is_ont)
+    cate = classify(orc, "lcd_oracle_classify_sites", ci)
+    n = st["n_sites"]
+    span = int(d["reg_end"]) - int(d["reg_beg"])
+    k = max(1, span // low_every)
+    lb = rng.integers(int(d["reg_beg"]) - 200, int(d["reg_end"]) + 200, k)
+    if n: lb[::3] = np.asarray(st["site_pos"][:n])[rng.integers(0, n, len(lb[::3]))] - rng.integers(0, 6, len(lb[::3]))
+    if o["n_cnreg"]: lb[1::5] = o["cnreg_beg"][:o["n_cnreg"]][rng.integers(0, o["n_cnreg"], len(lb[1::5]))] - rng.integers(-3, 12, len(lb[1::5]))
+    lb = np.sort(lb); le = lb + rng.integers(4, 40, k)
+    nr = d["n_reads"]
+    case = dict(reg_beg=int(d["reg_beg"]), reg_end=int(d["reg_end"]), min_alt_dp=2, noisy_reg_flank_len=10, is_ont=int(is_ont), min_af=0.20, n_sites=n, n_reads=nr,
+                site_pos=st["site_pos"], site_type=st["site_type"], site_ref_len=st["site_ref_len"], var_cate=np.append(cate, 0),
+                n_cnreg=o["n_cnreg"], cnreg_beg=o["cnreg_beg"][:o["n_cnreg"]], cnreg_end=o["cnreg_end"][:o["n_cnreg"]], cnreg_label=o["cnreg_label"][:o["n_cnreg"]],
+                n_low=k, low_beg=lb, low_end=le, is_skipped=np.maximum(np.asarray(d["is_skipped"][:nr]), o["skip"][:nr]),
+                **{f: o[f] for f in ("read_beg", "read_end", "digar_first", "n_digar", "digar_pos", "digar_type", "digar_len", "nreg_first", "n_nreg", "nreg_beg", "nreg_end")})
+    return case, ci
