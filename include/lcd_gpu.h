@@ -286,6 +286,40 @@ typedef struct {
 } lcd_classify_params_t;
 lcd_plan_t *lcd_classify_plan_create_on_pileup(lcd_plan_t *pileup_plan, int n_chunks, const lcd_classify_params_t *params);
 
+/* ---------------------------------------------------------------- K2c: pileup scan, the noisy-region set (second half)
+ * Replaces void pre_process_noisy_regs(bam_chunk_t *chunk, call_var_opt_t *opt) (src/collect_var.c:557-643) followed by
+ * int classify_cand_vars(bam_chunk_t *chunk, int n_var_sites, const call_var_opt_t *opt) (:902-1033) after its classify_var_cate loop (K2b),
+ * for out_somatic = 0: the reads' noisy intervals are widened by the low-complexity intervals they touch (:538-553), merged with the
+ * reference's own cr_merge (src/cgranges.c:225-301: an interval absorbs later ones within min(label, label') of its growing end), kept when
+ * at least min_alt_dp reads and min_af of the reads spanning them are noisy there; sites inside a region are dropped, repeat-region sites and
+ * sites overlapping another site (when enough of their reads carry differences there: var_noisy_reads_ratio :718) open regions of their own
+ * (cr_add_var_cr :754, cr_merge2), every region is widened by noisy_reg_flank_len past the candidate sites next to it (:482-535) and merged
+ * again; what is left of the sites is chunk->cand_vars.  Interval lists are cgranges (st, en, label) triples as cr_add takes them.
+ * Inputs: the candidate sites in collect_all_cand_var_sites' order (ascending anchors: exact_comp_var_site) with K2b's categories, K1's per-read outputs
+ * (spans, records, noisy intervals; is_skipped = the loader's flag OR K1's skip), chunk->chunk_noisy_regs in cr_add order (K1's cnreg_*), and
+ * chunk->low_comp_cr with ascending starts (cr_index order; sdust on the host).  All pointers are HOST memory. */
+typedef struct {
+    int64_t reg_beg, reg_end;          /* chunk->reg_beg / reg_end */
+    int32_t min_alt_dp, noisy_reg_flank_len, is_ont, pad;       /* call_var_opt_t (noisy_reg_merge_dis / min_sv_len reach cr_merge but are unused there) */
+    double min_af;
+    int32_t n_sites, n_reads;
+    const int64_t *site_pos; const int32_t *site_type, *site_ref_len, *var_cate;
+    int64_t n_cnreg; const int64_t *cnreg_beg, *cnreg_end; const int32_t *cnreg_label;
+    int64_t n_low; const int64_t *low_beg, *low_end;
+    const uint8_t *is_skipped;
+    const int64_t *read_beg, *read_end;
+    const int64_t *digar_first; const int32_t *n_digar; const int64_t *digar_pos; const int8_t *digar_type; const int32_t *digar_len;
+    const int64_t *nreg_first; const int32_t *n_nreg; const int64_t *nreg_beg, *nreg_end;
+} lcd_noisyreg_input_t;
+typedef struct {
+    int32_t *var_cate;                 /* [n_sites] the working var_i_to_cate after classify_cand_vars */
+    uint8_t *keep;                     /* [n_sites] 1: the site stays in chunk->cand_vars (chunk->var_i_to_cate = var_cate of the kept sites, in order) */
+    int64_t *reg_beg, *reg_end; int32_t *reg_label; int64_t reg_cap, n_regs;      /* chunk->chunk_noisy_regs at the end (cr_index order); n_cnreg + n_sites entries always suffice */
+} lcd_noisyreg_output_t;
+int lcd_noisyreg_batch(int n_chunks, const lcd_noisyreg_input_t *in, lcd_noisyreg_output_t *out);
+lcd_plan_t *lcd_noisyreg_plan_create(int n_chunks, const lcd_noisyreg_input_t *in);
+int  lcd_noisyreg_plan_fetch(lcd_plan_t *plan, void *stream, lcd_noisyreg_output_t *out);
+
 /* ---------------------------------------------------------------- K3: pileup scan, read x variant profile
  * Replaces read_var_profile_t *collect_read_var_profile(const call_var_opt_t *opt, bam_chunk_t *chunk)
  * (src/collect_var.c:1389-1431: update_read_vs_all_var_profile_from_digar, src/bam_utils.c:446-552, for every kept read;

@@ -840,6 +840,73 @@ class PhasePlan(_Plan):
         return self.results
 
 
+# ----------------------------------------------------------------------------- K2c: the noisy-region set (a5, second half)
+_NOISYREG_SITE = (("site_pos", np.int64), ("site_type", np.int32), ("site_ref_len", np.int32), ("var_cate", np.int32))
+_NOISYREG_READ = (("is_skipped", np.uint8), ("read_beg", np.int64), ("read_end", np.int64), ("digar_first", np.int64), ("n_digar", np.int32),
+                  ("digar_pos", np.int64), ("digar_type", np.int8), ("digar_len", np.int32), ("nreg_first", np.int64), ("n_nreg", np.int32),
+                  ("nreg_beg", np.int64), ("nreg_end", np.int64))
+_NOISYREG_IV = (("cnreg_beg", np.int64), ("cnreg_end", np.int64), ("cnreg_label", np.int32), ("low_beg", np.int64), ("low_end", np.int64))
+
+
+class NoisyRegInput(C.Structure):
+    _fields_ = [("reg_beg", C.c_int64), ("reg_end", C.c_int64), ("min_alt_dp", C.c_int32), ("noisy_reg_flank_len", C.c_int32), ("is_ont", C.c_int32), ("pad", C.c_int32),
+                ("min_af", C.c_double), ("n_sites", C.c_int32), ("n_reads", C.c_int32)] + [(k, C.c_void_p) for k, _ in _NOISYREG_SITE] + \
+               [("n_cnreg", C.c_int64), ("cnreg_beg", C.c_void_p), ("cnreg_end", C.c_void_p), ("cnreg_label", C.c_void_p),
+                ("n_low", C.c_int64), ("low_beg", C.c_void_p), ("low_end", C.c_void_p)] + [(k, C.c_void_p) for k, _ in _NOISYREG_READ]
+
+
+class NoisyRegOutput(C.Structure):
+    _fields_ = [("var_cate", C.c_void_p), ("keep", C.c_void_p), ("reg_beg", C.c_void_p), ("reg_end", C.c_void_p), ("reg_label", C.c_void_p), ("reg_cap", C.c_int64), ("n_regs", C.c_int64)]
+
+
+def _noisyreg_structs(chunks):
+    n = len(chunks)
+    ins, outs, keep, res = (NoisyRegInput * max(n, 1))(), (NoisyRegOutput * max(n, 1))(), [], []
+    for i, d in enumerate(chunks):
+        a = {k: np.ascontiguousarray(d[k], dtype=t) for k, t in _NOISYREG_SITE + _NOISYREG_READ}
+        for k, t in _NOISYREG_IV:
+            a[k] = np.ascontiguousarray(np.append(np.asarray(d[k]), 0), dtype=t)
+        keep.append(a)
+        ins[i] = NoisyRegInput(d["reg_beg"], d["reg_end"], d["min_alt_dp"], d["noisy_reg_flank_len"], d.get("is_ont", 0), 0, d["min_af"], d["n_sites"], d["n_reads"],
+                               *[a[k].ctypes.data for k, _ in _NOISYREG_SITE], d["n_cnreg"], a["cnreg_beg"].ctypes.data, a["cnreg_end"].ctypes.data, a["cnreg_label"].ctypes.data,
+                               d["n_low"], a["low_beg"].ctypes.data, a["low_end"].ctypes.data, *[a[k].ctypes.data for k, _ in _NOISYREG_READ])
+        cap = int(d["n_cnreg"]) + int(d["n_sites"]) + 8
+        r = dict(var_cate=np.full(d["n_sites"] + 1, -7, np.int32), keep=np.zeros(d["n_sites"] + 1, np.uint8), reg_beg=np.zeros(cap, np.int64), reg_end=np.zeros(cap, np.int64),
+                 reg_label=np.zeros(cap, np.int32))
+        res.append(r)
+        outs[i] = NoisyRegOutput(r["var_cate"].ctypes.data, r["keep"].ctypes.data, r["reg_beg"].ctypes.data, r["reg_end"].ctypes.data, r["reg_label"].ctypes.data, cap, 0)
+    return ins, outs, keep, res
+
+
+def _noisyreg_results(chunks, outs, res):
+    out = []
+    for i, (d, r) in enumerate(zip(chunks, res)):
+        k = int(outs[i].n_regs); ns = d["n_sites"]
+        out.append(dict(var_cate=r["var_cate"][:ns], keep=r["keep"][:ns], n_regs=k, reg_beg=r["reg_beg"][:k], reg_end=r["reg_end"][:k], reg_label=r["reg_label"][:k]))
+    return out
+
+
+def noisyreg_batch(chunks):
+    """Drop-in batch call over HOST buffers (lcd_noisyreg_batch): per chunk the noisy-region set and the candidate sites that stay clean-region
+    candidates (pre_process_noisy_regs + classify_cand_vars after classify_var_cate).  dict keys: lcd_noisyreg_input_t's fields.
+    -> [dict(var_cate, keep, n_regs, reg_beg, reg_end, reg_label)]"""
+    ins, outs, keep, res = _noisyreg_structs(chunks)
+    _check(lib().lcd_noisyreg_batch(C.c_int(len(chunks)), ins, outs), "lcd_noisyreg_batch")
+    return _noisyreg_results(chunks, outs, res)
+
+
+class NoisyRegPlan(_Plan):
+    def __init__(self, chunks):
+        self.chunks = chunks
+        self.ins, self.outs, self.keep, self.res = _noisyreg_structs(chunks)
+        lib().lcd_noisyreg_plan_create.restype = C.c_void_p
+        super().__init__(lib().lcd_noisyreg_plan_create(C.c_int(len(chunks)), self.ins), len(chunks))
+
+    def fetch(self, stream=None):
+        _check(lib().lcd_noisyreg_plan_fetch(self.h, C.c_void_p(stream or 0), self.outs), "lcd_noisyreg_plan_fetch")
+        return _noisyreg_results(self.chunks, self.outs, self.res)
+
+
 # ----------------------------------------------------------------------------- K5: POA
 class PoaParams(C.Structure):
     _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open1", C.c_int32), ("gap_ext1", C.c_int32),

@@ -6,7 +6,7 @@ import pytest
 import lcd_testlib as T
 
 
-def _cases(oracle):
+def noisyreg_cases(oracle):
     from longcalld_b200 import synth
     rng = np.random.default_rng(81)
     for i in range(14):          # chunks with many dense clusters / clips (noisy intervals), tight sites
@@ -20,7 +20,7 @@ def _cases(oracle):
 def test_oracle_noisy_regs_vs_live_reference(oracle, ref):
     n = n_regs = n_kept = n_sites = 0
     cates = set()
-    for case, ci in _cases(oracle):
+    for case, ci in noisyreg_cases(oracle):
         kept, regs, cate = T.noisy_regs(oracle, "lcd_oracle_noisy_regs", case)
         rkept, rregs = T.ref_noisy_regs(ref, ci, case)
         assert regs == rregs, (n, regs[:5], rregs[:5])
