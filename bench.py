@@ -173,7 +173,7 @@ class PileupStage:
     derived once at set-up from K2's counters (synth.classify_sites) and that step is not timed in either arm."""
     N_TEMPLATE = 10
 
-    def __init__(self, mbp, tech, seed, digar_fn, sites_fn, pileup_fn, pin=False):
+    def __init__(self, mbp, tech, seed, digar_fn, sites_fn, pileup_fn, classify_fn, pin=False):
         from longcalld_b200 import synth
         self.n_chunks = max(1, int(round(mbp / 0.5)))
         nt = min(self.N_TEMPLATE, self.n_chunks)
@@ -190,11 +190,13 @@ class PileupStage:
         piles = [synth.pileup_input_from_digar(d, o, s) for d, o, s in zip(self.template, outs, raw)]
         counts = pileup_fn(piles)
         self.cls = [synth.classify_input_from_sites(d, s, c, seed + 977 * i, is_ont=int(tech == "ont")) for i, (d, s, c) in enumerate(zip(self.template, raw, counts))]      # K2b's input
+        cates = classify_fn(self.cls)
+        nreg = [synth.noisyreg_input_from(d, o, s, ct, seed + 311 * i, is_ont=int(tech == "ont")) for i, (d, o, s, ct) in enumerate(zip(self.template, outs, raw, cates))]      # K2c's input
         var = [synth.classify_sites(s, c) for s, c in zip(raw, counts)]
         profs = [synth.pileup_input_from_digar(d, o, s) for d, o, s in zip(self.template, outs, var)]
         tile = lambda xs: [xs[i % nt] for i in range(self.n_chunks)]
         self.chunks, self.raw_sites, self.var_sites, self.piles, self.profs = tile(self.template), tile(raw), tile(var), tile(piles), tile(profs)
-        self.bare, self.regs, self.cls = tile(bare), tile(self.regs), tile(self.cls)
+        self.bare, self.regs, self.cls, self.nreg = tile(bare), tile(self.regs), tile(self.cls), tile(nreg)
         self.n_reads = [d["n_reads"] for d in self.chunks]
         self.read_bases = int(sum(int(d["l_qseq"].sum()) for d in self.chunks))
         self.cigar_ops = int(sum(int(d["n_cigar"].sum()) for d in self.chunks))
@@ -208,6 +210,12 @@ class PileupStage:
         self.k2_bytes = int(32 * self.records + 24 * self.n_raw_sites)
         self.k2b_bytes = int((32 + 24 + 4) * self.n_raw_sites)              # K2b: the site's counters and record in, its category out (+ ~36 reference bases for small indels)
         self.k3_bytes = int(32 * self.records + 24 * self.n_vars)
+        # K2c: a site record + category in, category + keep flag out; per read its span and noisy intervals; the interval lists (12 B each); records only where asked
+        self.n_low = int(sum(x["n_low"] for x in self.nreg)); self.n_cnreg = int(sum(x["n_cnreg"] for x in self.nreg))
+        self.k2c_bytes = int((20 + 5) * self.n_raw_sites + 24 * sum(self.n_reads) + 16 * self.n_low + 20 * self.n_cnreg)
+        self.k2c_h2d = int(sum(sum(np.asarray(x[k]).nbytes for k in ("site_pos", "site_type", "site_ref_len", "var_cate", "cnreg_beg", "cnreg_end", "cnreg_label", "low_beg", "low_end",
+                                                                     "is_skipped", "read_beg", "read_end", "digar_first", "n_digar", "nreg_first", "n_nreg", "nreg_beg", "nreg_end")) +
+                                   13 * int(np.asarray(x["digar_pos"]).size) for x in self.nreg))
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -310,6 +318,14 @@ def parity_check(ref, pile_ref, wl, ps, gpu):
             raise AssertionError(f"parity: coverage counters of chunk {c} differ from the reference's")
         if not np.array_equal(pile_ref["cate"][c][:rs["n_sites"]], gpu["cate"][c][:rs["n_sites"]]):
             raise AssertionError(f"parity: site categories of chunk {c} differ from the reference's")
+        # K2c: the compacted cand_vars (position, type, ref_len, category of the kept sites, in order) and chunk_noisy_regs
+        gn, rn, rk = gpu["nreg"][c], pile_ref["nreg_regs"][c], pile_ref["nreg_kept"][c]
+        x = ps.nreg[c]; kidx = np.nonzero(gn["keep"])[0]
+        if not (np.array_equal(np.asarray(x["site_pos"])[kidx], rk[0]) and np.array_equal(np.asarray(x["site_type"])[kidx], rk[1]) and np.array_equal(np.asarray(x["site_ref_len"])[kidx], rk[2])
+                and np.array_equal(gn["var_cate"][kidx], rk[3])):
+            raise AssertionError(f"parity: the candidate sites kept after classify_cand_vars of chunk {c} differ from the reference's")
+        if gn["n_regs"] != rn["n_regs"] or any(not np.array_equal(gn[key], rn[key]) for key in ("reg_beg", "reg_end", "reg_label")):
+            raise AssertionError(f"parity: noisy regions of chunk {c} differ from the reference's")
         rp, gp = pile_ref["prof"][c], gpu["prof"][c]
         nr = ps.n_reads[c]
         if not (np.array_equal(rp[0][:nr], gp["prof_start"][:nr]) and np.array_equal(rp[1][:nr], gp["prof_end"][:nr])):
@@ -348,11 +364,18 @@ def ref_pileup_fns(lib, n_threads):
         ins, outs, keep, results = capi._pileup_structs(piles)
         if lib.ref_pileup_batch(C.c_int(len(piles)), ins, outs, C.c_int(n_threads)): raise RuntimeError("ref_pileup_batch failed")
         return [r[:d["n_sites"]] for r, d in zip(results, piles)]
-    return digar, sites, pileup
+
+    def classify(cls):
+        cins, _, ckeep, cres = capi._classify_structs(cls)
+        cptr = (C.c_void_p * max(len(cls), 1))(*[r.ctypes.data for r in cres])
+        if lib.ref_classify_batch(C.c_int(len(cls)), cins, cptr, C.c_int(n_threads)): raise RuntimeError("ref_classify_batch failed")
+        return [r[:d["n_sites"]] for r, d in zip(cres, cls)]
+    return digar, sites, pileup, classify
 
 
 def reference_pileup_step(lib, ps, k, n_threads, out=None):
-    """K1 + K1b + K2 + K2b + K3 of the reference on the first k chunks of the batch; returns seconds (total, K1, K2, K3, K1b, K2b)."""
+    """K1 + K1b + K2 + K2b + K2c + K3 of the reference on the first k chunks of the batch; returns seconds (total, K1, K2, K3, K1b, K2b, K2c).
+    (K2c = pre_process_noisy_regs + classify_cand_vars, which runs the reference's classify_var_cate loop again inside: K2b's 3 ms count twice.)"""
     from longcalld_b200 import capi
     chunks, piles, profs = ps.chunks[:k], ps.piles[:k], ps.profs[:k]
     ins, keep = capi._digar_inputs(chunks)
@@ -382,13 +405,21 @@ def reference_pileup_step(lib, ps, k, n_threads, out=None):
     rc |= lib.ref_pileup_batch(C.c_int(k), pins, pouts, C.c_int(n_threads))
     t2 = time.perf_counter()
     rc |= lib.ref_classify_batch(C.c_int(k), cins, cptr, C.c_int(n_threads))
+    t2b0 = time.perf_counter()
+    nins, nouts, nkeep, nres = capi._noisyreg_structs(ps.nreg[:k])
+    kp = [[np.zeros(x["n_sites"] + 1, t) for t in (np.int64, np.int32, np.int32, np.int32)] for x in ps.nreg[:k]]
+    kptr = [(C.c_void_p * k)(*[kp[i][j].ctypes.data for i in range(k)]) for j in range(4)]
+    nkept = np.zeros(k + 1, np.int32)
+    t2c0 = time.perf_counter()
+    rc |= lib.ref_noisyreg_batch(C.c_int(k), cins, nins, kptr[0], kptr[1], kptr[2], kptr[3], _vp(nkept), nouts, C.c_int(n_threads))
     t2b = time.perf_counter()
     rc |= lib.ref_profile_batch(C.c_int(k), fins, exs, fouts, C.c_int(n_threads))
     t3 = time.perf_counter()
     if rc: raise RuntimeError("reference K1-K3 failed")
     if out is not None:
-        out.update(k=k, digar=capi._digar_finish(outs, results), sites=capi._sites_finish(souts, sres), counts=[r for r in pres], cate=cres, prof=fres)
-    return core.value + score.value + (t3 - t1), core.value, t2 - t1, t3 - t2b, score.value, t2b - t2
+        out.update(k=k, digar=capi._digar_finish(outs, results), sites=capi._sites_finish(souts, sres), counts=[r for r in pres], cate=cres, prof=fres,
+                   nreg_kept=[[a[:int(nkept[i])].copy() for a in kp[i]] for i in range(k)], nreg_regs=capi._noisyreg_results(ps.nreg[:k], nouts, nres))
+    return core.value + score.value + (t3 - t1) - (t2c0 - t2b0), core.value, t2 - t1, t3 - t2b, score.value, t2b0 - t2, t2b - t2c0
 
 
 def region_sample(wl, frac, seed=1):
@@ -464,7 +495,8 @@ def run_reference(args, rank):
                              "poa_s": sum(x[1] for x in t) / args.steps, "wfa_s": sum(x[2] for x in t) / args.steps,
                              "phase_s": sum(x[3] for x in t) / args.steps, "edlib_s": sum(x[4] for x in t) / args.steps,
                              "digar_s": pile_scale * sum(x[1] for x in tp) / args.steps, "pileup_s": pile_scale * sum(x[2] for x in tp) / args.steps,
-                             "profile_s": pile_scale * sum(x[3] for x in tp) / args.steps, "sites_s": pile_scale * sum(x[4] for x in tp) / args.steps, "classify_s": pile_scale * sum(x[5] for x in tp) / args.steps},
+                             "profile_s": pile_scale * sum(x[3] for x in tp) / args.steps, "sites_s": pile_scale * sum(x[4] for x in tp) / args.steps, "classify_s": pile_scale * sum(x[5] for x in tp) / args.steps,
+                             "noisyreg_s": pile_scale * sum(x[6] for x in tp) / args.steps},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "whole_program": None if args.no_whole_program else whole_program(args, with_gpu=False)}
     print(json.dumps(line))
@@ -477,15 +509,14 @@ def workload_config(args, wl, ps=None):
                        "K1b candidate-site list: sorted distinct X/I/D records incl. the large-insertion merge, on K1's lists in HBM (collect_var.c:1209)",
                        "K2 per-site coverage of the candidate sites, on K1's lists and K1b's sites in HBM (collect_var.c:238)",
                        "K2b category of every candidate site: depth / allele-fraction thresholds, homopolymer and repeat context of small indels (collect_var.c:413)",
+                       "K2c noisy-region set + the sites that stay clean-region candidates: low-complexity extension, label-window merges, read votes, site-overlap / noisy-read-ratio rules, flank sweep (collect_var.c:557,902)",
                        "K3 read x variant profile of the classified variants, on K1's lists in HBM (collect_var.c:1389)",
                        "K4 read->haplotype assignment + phasing per 500 kb chunk, clean then germline mask (assign_hap.c:473)",
                        "K7 edlib NW path read-vs-first-read sampling filter (align.c:722)",
                        "K5 abPOA consensus+MSA per (region, haplotype) (align.c:762)",
                        "K6 WFA gap-affine-2p ref-vs-consensus (align.c:565)"],
-            "stages_not_yet_on_gpu": ["2-consensus de-novo clustering (abpoa_aln_msa_cons; 0 calls on the synthetic BAM, 12 of 702 POA calls on the bundled ONT data)",
-                                      "noisy-region set of the classification (a5, second half): the variants K3 runs on are prepared at set-up, untimed in both arms",
-                                      "noisy-region orchestration (a8: the reference's host code, run as coroutines by the drop-in), vars from MSA (a13: merge_var_profile restructured in the drop-in, the rest host code), somatic chain (a14)"],
-            "not_in_this_step": "regions with partially covering / sampled reads (sub-graph POA, lcd_poa_sub_batch) and cs / MD / untagged plain-M reads (K1's tag front end) run on the GPU in the tests and in whole_program; the synthetic step holds full-cover regions and =/X CIGARs",
+            "stages_not_yet_on_gpu": ["noisy-region orchestration (a8: the reference's host code, run as coroutines by the drop-in), vars from MSA (a13: merge_var_profile restructured in the drop-in, the rest host code), somatic chain (a14)"],
+            "not_in_this_step": "regions with partially covering / sampled reads (sub-graph POA, lcd_poa_sub_batch), de-novo regions with two consensus sequences (lcd_poa_ncons_batch) and cs / MD / untagged plain-M reads (K1's tag front end) run on the GPU in the tests and in whole_program; the synthetic step holds full-cover regions and =/X CIGARs",
             "pileup": (None if ps is None else {"chunks": ps.n_chunks, "distinct_chunks": min(ps.N_TEMPLATE, ps.n_chunks), "reads": int(sum(ps.n_reads)),
                                                  "read_bases": ps.read_bases, "cigar_ops": ps.cigar_ops, "records": ps.records,
                                                  "candidate_sites": ps.n_raw_sites, "classified_variants": ps.n_vars}),
@@ -672,7 +703,7 @@ def run_b200(args, rank, world):
 
     from longcalld_b200 import synth as _synth
     gpu_sites = lambda bare, outs, regs: [_synth.site_list_from_sites(o, st) for o, st in zip(outs, lcd.sites_batch(bare, regs))]
-    ps = PileupStage(args.mbp, args.tech, shard_seed, lcd.digar_batch, gpu_sites, lcd.pileup_batch, pin=True)
+    ps = PileupStage(args.mbp, args.tech, shard_seed, lcd.digar_batch, gpu_sites, lcd.pileup_batch, lcd.classify_batch, pin=True)
     min_sv = [50] * ps.n_chunks
     pile_res = {}
 
@@ -684,10 +715,11 @@ def run_b200(args, rank, world):
         k1b = lcd.SitesPlan(None, ps.regs, min_sv_len=min_sv, digar_plan=dp); k1b.run(); pile_res["sites"] = k1b.fetch()
         k2 = lcd.PileupOnSitesPlan(dp, k1b); t.append(time.perf_counter()); k2.run(); pile_res["counts"] = k2.fetch(); t.append(time.perf_counter())
         k2b = lcd.ClassifyOnPileupPlan(k2, ps.cls, k2.n_sites); k2b.run(); pile_res["cate"] = k2b.fetch(); k2b.destroy()      # K2b on K2's sites and counters in HBM (the reference windows come from the host)
+        pile_res["nreg"] = lcd.noisyreg_batch(ps.nreg)                                                                      # K2c through its host-buffer call (sites + categories, read spans / records / noisy intervals, low-complexity intervals up; categories, keep flags, regions back)
         k3 = lcd.ProfileOnDigarPlan(dp, ps.var_sites, ps.n_reads); t.append(time.perf_counter()); k3.run(); pile_res["prof"] = k3.fetch(); t.append(time.perf_counter())
         for x in (k3, k2, k1b, dp): x.destroy()
         t.append(time.perf_counter())
-        # ms (second host thread, overlapped with the POA launch): K1 plan incl. H2D, K1 run, K1b plan+run+fetch and K2 plan, K2 run+fetch, K2b batch and K3 plan, K3 run+fetch, destroy
+        # ms (second host thread, overlapped with the POA launch): K1 plan incl. H2D, K1 run, K1b plan+run+fetch and K2 plan, K2 run+fetch, K2b + K2c batches and K3 plan, K3 run+fetch, destroy
         pile_res["t"] = [round(1e3 * t_plan, 2)] + [round(1e3 * (b - a), 2) for a, b in zip(t, t[1:])]
 
     def pileup_stage_thread():
@@ -720,6 +752,7 @@ def run_b200(args, rank, world):
     k2_plan = lcd.PileupOnSitesPlan(digar_plan, sites_plan)
     k3_plan = lcd.ProfileOnDigarPlan(digar_plan, ps.var_sites, ps.n_reads)
     k2b_plan = lcd.ClassifyOnPileupPlan(k2_plan, ps.cls, k2_plan.n_sites)
+    k2c_plan = lcd.NoisyRegPlan(ps.nreg)
     poa_plan = lcd.PoaPlan(wl.seqs, wl.first, wl.n_reads, wl.read_off, wl.read_len, lcd.poa_params())
     wfa_plan = lcd.WfaPlan(wseqs, po, pl, to, tl, lcd.wfa_params())
     phase_plan = lcd.PhasePlan(wl.phase)
@@ -738,7 +771,7 @@ def run_b200(args, rank, world):
         overlap=True (what `value` is): the pool-free stages (K1 -> K1b -> K2 -> K3, K4) on the auxiliary stream, K5 on the library
         stream and, under the pipeline, K6 -> K7 -- which then stand for the batch before, whose consensus is resident -- on a third
         stream with their own window of the workspace pool; the library stream waits for the other two before ev[10]."""
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(14)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(15)]
         with torch.cuda.stream(stream):
             flush.zero_()
             ev[9].record(stream)
@@ -753,6 +786,7 @@ def run_b200(args, rank, world):
             ev[8].record(sa); sites_plan.run(sa_h)
             ev[6].record(sa); k2_plan.run(sa_h)
             ev[13].record(sa); k2b_plan.run(sa_h)
+            ev[14].record(sa); k2c_plan.run(sa_h)
             ev[7].record(sa); k3_plan.run(sa_h)
             ev[2].record(sa); phase_plan.run(sa_h)
             ev[3].record(sa)
@@ -791,7 +825,7 @@ def run_b200(args, rank, world):
     wfa_ms = sum(e[1].elapsed_time(e[4]) for e in seq)
     phase_ms = sum(e[2].elapsed_time(e[3]) for e in seq)
     edlib_ms = sum(e[4].elapsed_time(e[11]) for e in seq)
-    k1_ms = sum(e[5].elapsed_time(e[8]) for e in seq); k1b_ms = sum(e[8].elapsed_time(e[6]) for e in seq); k2_ms = sum(e[6].elapsed_time(e[13]) for e in seq); k2b_ms = sum(e[13].elapsed_time(e[7]) for e in seq); k3_ms = sum(e[7].elapsed_time(e[2]) for e in seq)
+    k1_ms = sum(e[5].elapsed_time(e[8]) for e in seq); k1b_ms = sum(e[8].elapsed_time(e[6]) for e in seq); k2_ms = sum(e[6].elapsed_time(e[13]) for e in seq); k2b_ms = sum(e[13].elapsed_time(e[14]) for e in seq); k2c_ms = sum(e[14].elapsed_time(e[7]) for e in seq); k3_ms = sum(e[7].elapsed_time(e[2]) for e in seq)
     seq_ms = sum(e[9].elapsed_time(e[10]) for e in seq)
     dev_ms = sum(e[9].elapsed_time(e[10]) for e in evs)            # whole step: all streams, fork at ev[9], join at ev[10]
     poa_ovl_ms = sum(e[0].elapsed_time(e[12]) for e in evs)
@@ -811,7 +845,8 @@ def run_b200(args, rank, world):
     e2e_s = time.perf_counter() - t0
     phase_bytes = sum(a.nbytes for k in ph_keep for a in k.values())
     pile_d2h = int(sum(sum(a.nbytes for a in st.values() if hasattr(a, "nbytes")) for st in pile_res["sites"]) + sum(c.nbytes for c in pile_res["counts"]) + sum(sum(a.nbytes for a in o.values()) for o in pile_res["prof"]))
-    cls_h2d = int(sum(d["ref_seq"].nbytes for d in ps.cls)); pile_d2h += int(sum(c.nbytes for c in pile_res["cate"]))
+    cls_h2d = int(sum(d["ref_seq"].nbytes for d in ps.cls)) + ps.k2c_h2d; pile_d2h += int(sum(c.nbytes for c in pile_res["cate"]))
+    pile_d2h += int(sum(g["var_cate"].nbytes + g["keep"].nbytes + 20 * g["n_regs"] for g in pile_res["nreg"]))
     h2d = int(ps.h2d + cls_h2d + phase_bytes + eseqs.size + 24 * ne + wl.seqs.size + 12 * len(wl.read_len) + 64 * n + (pl.astype(np.int64) + tl + 56).sum() + 96 * n)
     d2h = int(pile_d2h + sum(a.nbytes for r in ph_res for a in r.values()) + eres.nbytes + int(eres["aln_len"].sum()) + pres["cons_len"].sum() + 32 * n + wres.nbytes + 2 * (pl.astype(np.int64) + tl + 4).sum())
 
@@ -845,12 +880,12 @@ def run_b200(args, rank, world):
             ops_g, off_g, b_g = stage_err["ops"]
             parity = parity_check(ref_out, pile_out, wl, ps, dict(cons=bufs[b_g][R:], cons_len=press[b_g]["cons_len"], wfa_res=wress[b_g], wfa_ops=ops_g, wfa_off=off_g,
                                                                   phase=ph_res, edlib_res=eres, edlib_aln=ealn, edlib_off=eoff,
-                                                                  sites=pile_res["sites"], counts=pile_res["counts"], cate=pile_res["cate"], prof=pile_res["prof"], digar=pile_res["digar"]))
+                                                                  sites=pile_res["sites"], counts=pile_res["counts"], cate=pile_res["cate"], prof=pile_res["prof"], digar=pile_res["digar"], nreg=pile_res["nreg"]))
             cpu_baseline = {"value": mbp_sample / (dt + pile_scale * dtp[0]), "unit": UNIT, "cores": nt, "kind": "reference",
                             "sample": f"{len(regs)} of {wl.n_regions} regions ({mbp_sample:.3f} Mb): the unmodified reference's own functions via oracle/_ref; "
                                       f"K1-K3 on {k_chunks} of {ps.n_chunks} chunks, time scaled by {pile_scale:.4f}",
                             "poa_s": dt_poa, "wfa_s": dt_wfa, "phase_s": dt_phase, "edlib_s": dt_edlib,
-                            "digar_s": pile_scale * dtp[1], "pileup_s": pile_scale * dtp[2], "profile_s": pile_scale * dtp[3], "sites_s": pile_scale * dtp[4], "classify_s": pile_scale * dtp[5]}
+                            "digar_s": pile_scale * dtp[1], "pileup_s": pile_scale * dtp[2], "profile_s": pile_scale * dtp[3], "sites_s": pile_scale * dtp[4], "classify_s": pile_scale * dtp[5], "noisyreg_s": pile_scale * dtp[6]}
     wp_line = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_whole_program:
         torch.cuda.synchronize()
@@ -891,6 +926,9 @@ def run_b200(args, rank, world):
                                             "pileup_kernel": {"ms": k2_ms / args.steps, "records": ps.records, "sites": ps.n_raw_sites,
                                                               "GBps": ps.k2_bytes / (k2_ms / args.steps / 1e3) / 1e9},
                                             "classify_kernel": {"ms": k2b_ms / args.steps, "sites": ps.n_raw_sites, "GBps": ps.k2b_bytes / (k2b_ms / args.steps / 1e3) / 1e9},
+                                            "noisyreg_kernel": {"ms": k2c_ms / args.steps, "sites": ps.n_raw_sites, "noisy_intervals": ps.n_cnreg, "low_complexity_intervals": ps.n_low,
+                                                                "GBps": ps.k2c_bytes / (k2c_ms / args.steps / 1e3) / 1e9,
+                                                                "note": "one CTA per chunk; interval merges and the flank sweep run on one thread of it (order-dependent in the reference): latency-bound by design"},
                                             "profile_kernel": {"ms": k3_ms / args.steps, "records": ps.records, "variants": ps.n_vars,
                                                                "GBps": ps.k3_bytes / (k3_ms / args.steps / 1e3) / 1e9},
                                             "edlib_kernel": {"ms": edlib_ms / args.steps, "block_columns": edlib_units,

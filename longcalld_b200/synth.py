@@ -569,3 +569,22 @@ def classify_input_from_sites(d, sites, counts, seed, flank=64, max_xgaps=5, is_
                 ref_seq=np.frombuffer(b"ACGT", np.uint8)[ref].copy(), site_pos=sites["site_pos"], site_type=sites["site_type"], site_ref_len=sites["site_ref_len"],
                 site_alt_len=sites["site_alt_len"], site_alt_off=sites["site_alt_off"], site_alt=sites["site_alt"],
                 site_counts=np.ascontiguousarray(np.vstack([counts[:n], np.zeros((1, 8), np.int32)]), dtype=np.int32))
+
+
+def noisyreg_input_from(d, o, sites, cate, seed, low_every=250, is_ont=0):
+    """lcd_noisyreg_input_t of a chunk: K1's host-side output `o`, the candidate sites `sites` (K1b) with K2b's categories `cate`, and
+    low-complexity intervals at sdust-like density (one 8 - 40 bp interval per ~250 bp; the bench's reads are CIGARs without a reference of
+    their own, so the intervals are drawn, a third of them on candidate sites / noisy intervals as homopolymer runs are in real data)."""
+    rng = np.random.default_rng(seed)
+    n = int(sites["n_sites"]); nr = int(d["n_reads"]); ncn = int(o["n_cnreg"])
+    span = int(d["reg_end"]) - int(d["reg_beg"])
+    k = max(1, span // low_every)
+    lb = rng.integers(int(d["reg_beg"]) - 200, int(d["reg_end"]) + 200, k)
+    if n: lb[::3] = np.asarray(sites["site_pos"][:n])[rng.integers(0, n, len(lb[::3]))] - rng.integers(0, 6, len(lb[::3]))
+    if ncn: lb[1::7] = np.asarray(o["cnreg_beg"][:ncn])[rng.integers(0, ncn, len(lb[1::7]))] - rng.integers(-3, 12, len(lb[1::7]))
+    lb = np.sort(lb).astype(np.int64); le = lb + rng.integers(8, 40, k)
+    return dict(reg_beg=int(d["reg_beg"]), reg_end=int(d["reg_end"]), min_alt_dp=2, noisy_reg_flank_len=10, is_ont=int(is_ont), min_af=0.20, n_sites=n, n_reads=nr,
+                site_pos=sites["site_pos"], site_type=sites["site_type"], site_ref_len=sites["site_ref_len"], var_cate=np.append(np.asarray(cate[:n], np.int32), 0).astype(np.int32),
+                n_cnreg=ncn, cnreg_beg=np.asarray(o["cnreg_beg"][:ncn], np.int64), cnreg_end=np.asarray(o["cnreg_end"][:ncn], np.int64), cnreg_label=np.asarray(o["cnreg_label"][:ncn], np.int32),
+                n_low=k, low_beg=lb, low_end=le, is_skipped=np.maximum(np.asarray(d["is_skipped"][:nr]), np.asarray(o["skip"][:nr])),
+                **{f: o[f] for f in ("read_beg", "read_end", "digar_first", "n_digar", "digar_pos", "digar_type", "digar_len", "nreg_first", "n_nreg", "nreg_beg", "nreg_end")})

@@ -295,6 +295,13 @@ int ref_classify_sites(const lcd_classify_input_t *in, int32_t *var_cate);
 int ref_classify_batch(int n, const lcd_classify_input_t *in, int32_t **var_cate, int n_threads) {
     return run_chunks(n, n_threads, [&](int i) { return ref_classify_sites(&in[i], var_cate[i]); });
 }
+// pre_process_noisy_regs + classify_cand_vars of many chunks (the reference runs its own classify_var_cate loop inside)
+int ref_noisy_regs(const lcd_classify_input_t *ci, const lcd_noisyreg_input_t *in, int64_t *kept_pos, int32_t *kept_type, int32_t *kept_ref_len, int32_t *kept_cate, int32_t *n_kept,
+                   lcd_noisyreg_output_t *out);
+int ref_noisyreg_batch(int n, const lcd_classify_input_t *ci, const lcd_noisyreg_input_t *in, int64_t **kept_pos, int32_t **kept_type, int32_t **kept_ref_len, int32_t **kept_cate,
+                       int32_t *n_kept, lcd_noisyreg_output_t *out, int n_threads) {
+    return run_chunks(n, n_threads, [&](int i) { return ref_noisy_regs(&ci[i], &in[i], kept_pos[i], kept_type[i], kept_ref_len[i], kept_cate[i], &n_kept[i], &out[i]); });
+}
 int ref_profile_batch(int n, const lcd_pileup_input_t *in, const lcd_profile_extra_t *ex, lcd_profile_output_t *out, int n_threads) {
     return run_chunks(n, n_threads, [&](int i) { return ref_read_var_profile(&in[i], &ex[i], &out[i]); });
 }

@@ -520,6 +520,19 @@ int ref_noisy_regs(const lcd_classify_input_t *ci, const lcd_noisyreg_input_t *i
     out->n_regs = chunk.chunk_noisy_regs ? chunk.chunk_noisy_regs->n_r : 0;
     if (out->n_regs > out->reg_cap) rc = -5;
     else for (int64_t k = 0; k < out->n_regs; ++k) { out->reg_beg[k] = cr_start(chunk.chunk_noisy_regs, k); out->reg_end[k] = cr_end(chunk.chunk_noisy_regs, k); out->reg_label[k] = cr_label(chunk.chunk_noisy_regs, k); }
-    /* (test infrastructure: the chunk's allocations are left to the process) */
+    for (int i = 0; i < nk; ++i) {          /* the kept entries (classify_cand_vars freed the dropped ones itself) */
+        cand_var_t *v = chunk.cand_vars + i;
+        free(v->alle_covs); for (int s = 0; s < 2; ++s) free(v->strand_to_alle_covs[s]); free(v->strand_to_alle_covs); free(v->alt_seq);
+    }
+    if (n > 0) free(chunk.var_i_to_cate);
+    else for (int i = 0; i < n; ++i) { cand_var_t *v = chunk.cand_vars + i; free(v->alle_covs); free(v->alt_seq); }
+    free(chunk.cand_vars);
+    for (int r = 0; r < nr; ++r) { free(chunk.digars[r].digars); cr_destroy(chunk.digars[r].noisy_regs); }
+    free(chunk.digars); free(chunk.ordered_read_ids); free(chunk.is_skipped);
+    if (chunk.chunk_noisy_regs) cr_destroy(chunk.chunk_noisy_regs);
+    if (chunk.low_comp_cr) cr_destroy(chunk.low_comp_cr);
+    if (chunk.var_noisy_read_cov_cr) cr_destroy(chunk.var_noisy_read_cov_cr);
+    if (chunk.var_noisy_read_err_cr) cr_destroy(chunk.var_noisy_read_err_cr);
+    free(chunk.var_noisy_read_marks);
     return rc;
 }

@@ -24,6 +24,6 @@ def test_reference_arm_line():
     assert j["value"] > 0 and j["e2e"]["value"] == j["value"] and j["e2e"]["h2d_bytes_per_step"] == 0
     cb = j["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1
-    for k in ("poa_s", "wfa_s", "phase_s", "edlib_s", "digar_s", "sites_s", "pileup_s", "classify_s", "profile_s"):
+    for k in ("poa_s", "wfa_s", "phase_s", "edlib_s", "digar_s", "sites_s", "pileup_s", "classify_s", "noisyreg_s", "profile_s"):
         assert cb[k] > 0, k
-    assert len(j["config"]["stages"]) == 9 and j["config"]["pileup"]["candidate_sites"] > 0
+    assert len(j["config"]["stages"]) == 10 and j["config"]["pileup"]["candidate_sites"] > 0
