@@ -56,12 +56,12 @@ static void trace(const char *what, long a, long b) {
     trace_t e = { t, (unsigned long)pthread_self(), what, a, b }; trace_buf[trace_n++] = e;
     pthread_mutex_unlock(&t_mu);
 }
-static unsigned long n_calls[14];      /* [12]: de-novo POA problems with two consensus sequences on the GPU, [13]: abpoa_aln_msa_cons calls forwarded */
+static unsigned long n_calls[16];      /* [12]: de-novo POA problems with two consensus sequences on the GPU, [13]: abpoa_aln_msa_cons calls forwarded, [14] / [15]: chunks whose noisy-region set (K2b + K2c) ran on the GPU / was forwarded */
 #define COUNT(i) __atomic_fetch_add(&n_calls[i], 1, __ATOMIC_RELAXED)      /* the reference's worker threads call in concurrently */
 __attribute__((destructor)) static void report(void) {
     if (trace_on > 0 && trace_n) { FILE *f = fopen(getenv("LCD_DROPIN_TRACE"), "w"); if (f) { for (size_t i = 0; i < trace_n; ++i) fprintf(f, "%.6f\t%lx\t%s\t%ld\t%ld\n", trace_buf[i].t - trace_buf[0].t, trace_buf[i].tid, trace_buf[i].what, trace_buf[i].a, trace_buf[i].b); fclose(f); } }
-    if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: digar %lu (forwarded: %lu), sites %lu, pileup %lu, profile %lu, phase %lu, edlib %lu, wfa %lu, poa %lu (with partially covering reads: %lu; de-novo with max_n_cons = 2: %lu; forwarded to abPOA: %lu + %lu) in %lu engine batches (library time: poa %.2f s, wfa %.2f s, edlib %.2f s; threads blocked %.2f s in total; forwarded abPOA %.2f s); kernel launches %llu\n",
-                                              n_calls[8], n_calls[9], n_calls[10], n_calls[0], n_calls[1], n_calls[2], n_calls[3], n_calls[4], n_calls[5], n_calls[11], n_calls[12], n_calls[6], n_calls[13], n_calls[7], t_batch[0], t_batch[1], t_batch[2], t_blocked, t_fwd_poa, (unsigned long long)lcd_gpu_launch_count());
+    if (getenv("LCD_DROPIN_VERBOSE")) fprintf(stderr, "[lcd_dropin] GPU calls: digar %lu (forwarded: %lu), sites %lu, pileup %lu, noisy-region set %lu (forwarded: %lu), profile %lu, phase %lu, edlib %lu, wfa %lu, poa %lu (with partially covering reads: %lu; de-novo with max_n_cons = 2: %lu; forwarded to abPOA: %lu + %lu) in %lu engine batches (library time: poa %.2f s, wfa %.2f s, edlib %.2f s; threads blocked %.2f s in total; forwarded abPOA %.2f s); kernel launches %llu\n",
+                                              n_calls[8], n_calls[9], n_calls[10], n_calls[0], n_calls[14], n_calls[15], n_calls[1], n_calls[2], n_calls[3], n_calls[4], n_calls[5], n_calls[11], n_calls[12], n_calls[6], n_calls[13], n_calls[7], t_batch[0], t_batch[1], t_batch[2], t_blocked, t_fwd_poa, (unsigned long long)lcd_gpu_launch_count());
 }
 
 /* LCD_DROPIN_STAGES=engines keeps the pileup scan and the phasing (K1 - K4) on the reference's own host code and sends only the DP engines
@@ -952,6 +952,138 @@ int classify_cand_vars(bam_chunk_t *chunk, int n_var_sites, const call_var_opt_t
 int *sort_noisy_regs(bam_chunk_t *chunk);                                                                                   /* :2745 */
 void collect_somatic_var(bam_chunk_t *chunk, const call_var_opt_t *opt);                                                    /* :2857 */
 
+
+/* ------------------------------------------------------------------------------------------ K2b + K2c
+ * pre_process_noisy_regs (src/collect_var.c:557) + classify_cand_vars (:902) of a chunk on the GPU (out_somatic = 0): the candidate sites with their
+ * counters go through lcd_classify_batch (the category loop), then sites + categories, the reads' spans / records / noisy intervals, the chunk's noisy
+ * list and the low-complexity intervals through lcd_noisyreg_batch; chunk->chunk_noisy_regs, the compacted chunk->cand_vars and chunk->var_i_to_cate
+ * are rebuilt from the answer exactly as classify_cand_vars leaves them (copy_var :436, the frees of :1028-1034).  Returns 0 when the chunk was
+ * handed to the reference's own functions instead (a site too close to the reference window's ends for K2b). */
+void copy_var(cand_var_t *to_var, cand_var_t *from_var);                                                                      /* src/collect_var.c:436 */
+static int classify_on_gpu(bam_chunk_t *chunk, int n_var_sites, call_var_opt_t *opt) {
+    const int n = n_var_sites, nr = chunk->n_reads;
+    cand_var_t *cv = chunk->cand_vars;
+    int rc_ok = 1;
+    /* K2b */
+    int32_t *cate = (int32_t*)calloc((size_t)n + 1, sizeof(int32_t));
+    int64_t *spos = (int64_t*)calloc((size_t)n + 1, sizeof(int64_t)), *saoff = (int64_t*)calloc((size_t)n + 1, sizeof(int64_t));
+    int32_t *stype = (int32_t*)calloc((size_t)n + 1, sizeof(int32_t)), *sref = (int32_t*)calloc((size_t)n + 1, sizeof(int32_t)), *salt = (int32_t*)calloc((size_t)n + 1, sizeof(int32_t));
+    int32_t *counts = (int32_t*)calloc(8 * (size_t)n + 8, sizeof(int32_t));
+    size_t na = 0;
+    for (int i = 0; i < n; ++i) na += (size_t)cv[i].alt_len;
+    uint8_t *alt = (uint8_t*)calloc(na + 1, 1); na = 0;
+    for (int i = 0; i < n; ++i) {
+        spos[i] = cv[i].pos; stype[i] = cv[i].var_type; sref[i] = cv[i].ref_len; salt[i] = cv[i].alt_len; saoff[i] = (int64_t)na;
+        if ((cv[i].var_type == BAM_CDIFF || cv[i].var_type == BAM_CINS) && cv[i].alt_seq) { memcpy(alt + na, cv[i].alt_seq, cv[i].alt_len); na += cv[i].alt_len; }
+        int32_t *o = counts + 8 * (size_t)i;
+        o[0] = cv[i].total_cov; o[1] = cv[i].low_qual_cov; o[2] = cv[i].alle_covs[0]; o[3] = cv[i].alle_covs[1];
+        for (int st = 0; st < 2; ++st) for (int a = 0; a < 2; ++a) o[4 + 2 * st + a] = cv[i].strand_to_alle_covs[st][a];
+    }
+    if (n > 0) {
+        lcd_classify_input_t ci; memset(&ci, 0, sizeof(ci));
+        ci.n_sites = n; ci.min_dp = opt->min_dp; ci.min_alt_dp = opt->min_alt_dp; ci.max_xgaps = opt->noisy_reg_max_xgaps; ci.is_ont = opt->is_ont; ci.min_af = opt->min_af; ci.max_af = opt->max_af;
+        ci.ref_beg = chunk->ref_beg; ci.ref_end = chunk->ref_end; ci.ref_seq = chunk->ref_seq;
+        ci.site_pos = spos; ci.site_type = stype; ci.site_ref_len = sref; ci.site_alt_len = salt; ci.site_alt_off = saoff; ci.site_alt = alt; ci.site_counts = counts;
+        lcd_classify_output_t co = { cate };
+        if (lcd_classify_batch(1, &ci, &co)) rc_ok = 0;           /* (a small indel within the margin of the window's ends: the reference reads it unchecked) */
+    }
+    if (rc_ok) {
+        /* K2c inputs */
+        size_t nd = 0, nn = 0;
+        for (int r = 0; r < nr; ++r) if (!chunk->is_skipped[r]) { nd += chunk->digars[r].n_digar; nn += chunk->digars[r].noisy_regs ? chunk->digars[r].noisy_regs->n_r : 0; }
+        int64_t *rb = (int64_t*)calloc((size_t)nr + 1, 8), *re = (int64_t*)calloc((size_t)nr + 1, 8), *df = (int64_t*)calloc((size_t)nr + 1, 8), *nf = (int64_t*)calloc((size_t)nr + 1, 8);
+        int32_t *ndg = (int32_t*)calloc((size_t)nr + 1, 4), *nng = (int32_t*)calloc((size_t)nr + 1, 4);
+        int64_t *dpos = (int64_t*)calloc(nd + 1, 8), *nb = (int64_t*)calloc(nn + 1, 8), *ne = (int64_t*)calloc(nn + 1, 8);
+        int8_t *dtype = (int8_t*)calloc(nd + 1, 1); int32_t *dlen = (int32_t*)calloc(nd + 1, 4);
+        size_t d = 0, q = 0;
+        for (int r = 0; r < nr; ++r) {
+            df[r] = (int64_t)d; nf[r] = (int64_t)q;
+            if (chunk->is_skipped[r]) continue;
+            const digar_t *g = chunk->digars + r;
+            rb[r] = g->beg; re[r] = g->end; ndg[r] = g->n_digar;
+            for (int k = 0; k < g->n_digar; ++k, ++d) { dpos[d] = g->digars[k].pos; dtype[d] = (int8_t)g->digars[k].type; dlen[d] = g->digars[k].len; }
+            if (g->noisy_regs) { nng[r] = (int32_t)g->noisy_regs->n_r; for (int64_t k = 0; k < g->noisy_regs->n_r; ++k, ++q) { nb[q] = cr_start(g->noisy_regs, k); ne[q] = cr_end(g->noisy_regs, k); } }
+        }
+        cgranges_t *cn = chunk->chunk_noisy_regs, *lc = chunk->low_comp_cr;
+        const int64_t ncn = cn ? cn->n_r : 0, nl = lc ? lc->n_r : 0;
+        if (ncn > 0) cr_index(cn);                  /* (as pre_process_noisy_regs does first: before cr_index the entries hold (contig, start) / end, not start / end) */
+        int64_t *cb = (int64_t*)calloc((size_t)ncn + 1, 8), *ce = (int64_t*)calloc((size_t)ncn + 1, 8), *lb = (int64_t*)calloc((size_t)nl + 1, 8), *le = (int64_t*)calloc((size_t)nl + 1, 8);
+        int32_t *cl = (int32_t*)calloc((size_t)ncn + 1, 4);
+        for (int64_t k = 0; k < ncn; ++k) { cb[k] = cr_start(cn, k); ce[k] = cr_end(cn, k); cl[k] = cr_label(cn, k); }
+        for (int64_t k = 0; k < nl; ++k) { lb[k] = cr_start(lc, k); le[k] = cr_end(lc, k); }          /* cr_index'ed by the loader: ascending starts */
+        lcd_noisyreg_input_t in; memset(&in, 0, sizeof(in));
+        in.reg_beg = chunk->reg_beg; in.reg_end = chunk->reg_end; in.min_alt_dp = opt->min_alt_dp; in.noisy_reg_flank_len = opt->noisy_reg_flank_len; in.is_ont = opt->is_ont; in.min_af = opt->min_af;
+        in.n_sites = n; in.n_reads = nr; in.site_pos = spos; in.site_type = stype; in.site_ref_len = sref; in.var_cate = cate;
+        in.n_cnreg = ncn; in.cnreg_beg = cb; in.cnreg_end = ce; in.cnreg_label = cl; in.n_low = nl; in.low_beg = lb; in.low_end = le;
+        in.is_skipped = chunk->is_skipped; in.read_beg = rb; in.read_end = re; in.digar_first = df; in.n_digar = ndg; in.digar_pos = dpos; in.digar_type = dtype; in.digar_len = dlen;
+        in.nreg_first = nf; in.n_nreg = nng; in.nreg_beg = nb; in.nreg_end = ne;
+        const int64_t cap = ncn + n + 8;
+        lcd_noisyreg_output_t out; memset(&out, 0, sizeof(out));
+        out.var_cate = (int32_t*)calloc((size_t)n + 1, 4); out.keep = (uint8_t*)calloc((size_t)n + 1, 1);
+        out.reg_beg = (int64_t*)calloc((size_t)cap, 8); out.reg_end = (int64_t*)calloc((size_t)cap, 8); out.reg_label = (int32_t*)calloc((size_t)cap, 4); out.reg_cap = cap;
+        if (lcd_noisyreg_batch(1, &in, &out)) die("lcd_noisyreg_batch");
+        if (getenv("LCD_DROPIN_CHECK_K2C")) {          /* self-check: the reference's own functions on the same chunk, compared with the library's answer (which is then dropped) */
+            if (ncn > 0) { cgranges_t *raw = cr_init(); for (int64_t k = 0; k < ncn; ++k) cr_add(raw, "cr", (int32_t)cb[k], (int32_t)ce[k], cl[k]); cr_destroy(cn); cn = NULL; chunk->chunk_noisy_regs = raw; }
+            pre_process_noisy_regs(chunk, opt);
+            {   /* stage 1 alone: the library with no sites returns the list after pre_process_noisy_regs */
+                lcd_noisyreg_input_t in0 = in; in0.n_sites = 0;
+                lcd_noisyreg_output_t o0 = out; o0.reg_beg = (int64_t*)calloc((size_t)cap, 8); o0.reg_end = (int64_t*)calloc((size_t)cap, 8); o0.reg_label = (int32_t*)calloc((size_t)cap, 4);
+                if (lcd_noisyreg_batch(1, &in0, &o0)) die("lcd_noisyreg_batch");
+                const int64_t n1 = chunk->chunk_noisy_regs ? chunk->chunk_noisy_regs->n_r : 0;
+                int b1 = n1 != o0.n_regs; int64_t first = -1;
+                for (int64_t k = 0; k < n1 && k < o0.n_regs; ++k) if (cr_start(chunk->chunk_noisy_regs, k) != o0.reg_beg[k] || cr_end(chunk->chunk_noisy_regs, k) != o0.reg_end[k] || cr_label(chunk->chunk_noisy_regs, k) != o0.reg_label[k]) { b1 = 1; if (first < 0) first = k; }
+                fprintf(stderr, "[k2c check] after pre_process_noisy_regs: %ld regions (reference %ld): %s", (long)o0.n_regs, (long)n1, b1 ? "DIFFERENT" : "identical");
+                if (first >= 0) fprintf(stderr, " first at %ld: (%ld, %ld, %d) vs reference (%d, %d, %d)", (long)first, (long)o0.reg_beg[first], (long)o0.reg_end[first], o0.reg_label[first], cr_start(chunk->chunk_noisy_regs, first), cr_end(chunk->chunk_noisy_regs, first), cr_label(chunk->chunk_noisy_regs, first));
+                fprintf(stderr, "\n");
+                free(o0.reg_beg); free(o0.reg_end); free(o0.reg_label);
+            }
+            const int nk_ref = n > 0 ? classify_cand_vars(chunk, n, opt) : 0;
+            int bad = 0, w = 0;
+            for (int i = 0; i < n; ++i) if (out.keep[i]) {
+                if (w >= nk_ref || cv[w].pos != spos[i] || cv[w].var_type != stype[i] || cv[w].ref_len != sref[i] || chunk->var_i_to_cate[w] != out.var_cate[i]) { if (!bad) fprintf(stderr, "[k2c check] kept site %d differs (pos %ld)\n", w, (long)spos[i]); bad = 1; }
+                ++w;
+            }
+            if (w != nk_ref) bad = 1;
+            const int64_t nr_ref = chunk->chunk_noisy_regs ? chunk->chunk_noisy_regs->n_r : 0;
+            if (nr_ref != out.n_regs) bad = 1;
+            else for (int64_t k = 0; k < nr_ref; ++k) if (cr_start(chunk->chunk_noisy_regs, k) != out.reg_beg[k] || cr_end(chunk->chunk_noisy_regs, k) != out.reg_end[k] || cr_label(chunk->chunk_noisy_regs, k) != out.reg_label[k]) bad = 1;
+            fprintf(stderr, "[k2c check] chunk %ld: %d sites, kept %d (reference %d), regions %ld (reference %ld): %s\n", (long)chunk->reg_beg, n, w, nk_ref, (long)out.n_regs, (long)nr_ref, bad ? "DIFFERENT" : "identical");
+            free(out.var_cate); free(out.keep); free(out.reg_beg); free(out.reg_end); free(out.reg_label);
+            free(rb); free(re); free(df); free(nf); free(ndg); free(nng); free(dpos); free(nb); free(ne); free(dtype); free(dlen); free(cb); free(ce); free(lb); free(le); free(cl);
+            free(cate); free(spos); free(saoff); free(stype); free(sref); free(salt); free(counts); free(alt);
+            return 1;
+        }
+        /* chunk->chunk_noisy_regs */
+        cgranges_t *R = cr_init();
+        for (int64_t k = 0; k < out.n_regs; ++k) cr_add(R, "cr", (int32_t)out.reg_beg[k], (int32_t)out.reg_end[k], out.reg_label[k]);
+        cr_index(R);
+        if (cn) cr_destroy(cn);
+        chunk->chunk_noisy_regs = R;
+        /* the compacted cand_vars (src/collect_var.c:1012-1034) */
+        if (n > 0) {
+            chunk->var_i_to_cate = (int*)malloc((size_t)n * sizeof(int));
+            int w = 0;
+            for (int i = 0; i < n; ++i) {
+                if (!out.keep[i]) continue;
+                if (i != w) copy_var(cv + w, cv + i);
+                chunk->var_i_to_cate[w++] = out.var_cate[i];
+            }
+            for (int i = w; i < n; ++i) {
+                free(cv[i].alle_covs);
+                for (int j = 0; j < cv[i].n_uniq_alles; ++j) free(cv[i].strand_to_alle_covs[j]);
+                free(cv[i].strand_to_alle_covs);
+                if (cv[i].alt_seq != NULL) free(cv[i].alt_seq);
+                if (cv[i].tsd_len > 0) free(cv[i].tsd_seq);
+            }
+            chunk->n_cand_vars = w;
+        }
+        free(out.var_cate); free(out.keep); free(out.reg_beg); free(out.reg_end); free(out.reg_label);
+        free(rb); free(re); free(df); free(nf); free(ndg); free(nng); free(dpos); free(nb); free(ne); free(dtype); free(dlen); free(cb); free(ce); free(lb); free(le); free(cl);
+    }
+    free(cate); free(spos); free(saoff); free(stype); free(sref); free(salt); free(counts); free(alt);
+    return rc_ok;
+}
+
 void collect_aln_beg_end(uint32_t *cigar_buf, int cigar_len, int ext_direction, int ref_len, int *ref_beg, int *ref_end, int read_len, int *read_beg, int *read_end);   /* src/align.c:633 */
 void collect_var_main(const call_var_pl_t *pl, bam_chunk_t *chunk) {
     call_var_opt_t *opt = pl->opt;
@@ -962,8 +1094,12 @@ void collect_var_main(const call_var_pl_t *pl, bam_chunk_t *chunk) {
     const int n_var_sites = collect_all_cand_var_sites(opt, chunk, &var_sites);                                              /* 1.2 */
     if (n_var_sites > 0) collect_cand_vars(opt, chunk, n_var_sites, var_sites);                                              /* 1.3 */
     free(var_sites);
-    pre_process_noisy_regs(chunk, opt);                                                                                      /* 2.1 */
-    if (n_var_sites > 0) classify_cand_vars(chunk, n_var_sites, opt);                                                        /* 2.2 - 2.4 */
+    if (pileup_on_gpu() && !opt->out_somatic && classify_on_gpu(chunk, n_var_sites, opt)) COUNT(14);                          /* 2.1 - 2.4 on the GPU (K2b + K2c) */
+    else {
+        if (pileup_on_gpu() && !opt->out_somatic) COUNT(15);
+        pre_process_noisy_regs(chunk, opt);                                                                                  /* 2.1 */
+        if (n_var_sites > 0) classify_cand_vars(chunk, n_var_sites, opt);                                                    /* 2.2 - 2.4 */
+    }
     if (chunk->n_cand_vars == 0 && (chunk->chunk_noisy_regs == NULL || chunk->chunk_noisy_regs->n_r == 0)) return;
     if (chunk->n_cand_vars > 0) {
         chunk->read_var_profile = collect_read_var_profile(opt, chunk);                                                      /* 3.1 */

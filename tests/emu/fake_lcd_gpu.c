@@ -197,3 +197,16 @@ int lcd_poa_ncons_batch(int n, const uint8_t *seqs, size_t seqs_len, const int32
     }
     return bad ? -2 : 0;
 }
+
+int lcd_oracle_classify_sites(const lcd_classify_input_t *in, int32_t *var_cate);
+int lcd_classify_batch(int n, const lcd_classify_input_t *in, lcd_classify_output_t *out) {
+    __atomic_fetch_add(&n_batches, 1, __ATOMIC_RELAXED);
+    for (int i = 0; i < n; ++i) if (lcd_oracle_classify_sites(&in[i], out[i].var_cate)) return -1;
+    return 0;
+}
+int lcd_oracle_noisy_regs(const lcd_noisyreg_input_t *in, lcd_noisyreg_output_t *out);
+int lcd_noisyreg_batch(int n, const lcd_noisyreg_input_t *in, lcd_noisyreg_output_t *out) {
+    __atomic_fetch_add(&n_batches, 1, __ATOMIC_RELAXED);
+    for (int i = 0; i < n; ++i) if (lcd_oracle_noisy_regs(&in[i], &out[i])) return -1;
+    return 0;
+}

@@ -49,6 +49,8 @@ def test_vcf_identical_through_the_batched_driver(dropin_cpu, tech, threads):
     assert fwd and int(fwd.group(1)) == 0 and int(fwd.group(2)) == 0, line          # partial-cover and de-novo (two-consensus) POA included
     if tech == "ont":
         assert int(re.search(r"max_n_cons = 2: (\d+)", line).group(1)) > 0, line
+    nrs = re.search(r"noisy-region set (\d+) \(forwarded: (\d+)\)", line)
+    assert (int(nrs.group(1)) > 0 and int(nrs.group(2)) == 0) if tech != "mosaic" else int(nrs.group(1)) == 0, line      # -s keeps the reference's own classification
     if tech != "mosaic":                 # -s rewrites the difference lists region by region: one region at a time there
         assert batches * 4 < c["poa"] + c["wfa"] + c["edlib"], line
 
@@ -77,3 +79,17 @@ def test_every_cigar_flavour_through_the_binding(dropin_cpu, style, tmp_path):
     m = re.search(r"digar (\d+) \(forwarded: (\d+)\)", line)
     assert int(m.group(1)) > 0 and int(m.group(2)) == 0, line
     assert body(got.stdout) == body(want.stdout) and want.stdout.count(b"\n") > 300, line
+
+
+@pytest.mark.parametrize("tech", ["hifi", "ont"])
+def test_noisy_region_set_self_check_on_the_bundled_data(dropin_cpu, tech):
+    """LCD_DROPIN_CHECK_K2C=1: per chunk the binding asks the library (here the oracle-backed double) for the noisy-region set, then runs the unmodified
+    pre_process_noisy_regs + classify_cand_vars on the same chunk and compares both stages -- the restatement pinned on real reads."""
+    md5, line = run(dropin_cpu, tech, 2, {"LCD_DROPIN_CHECK_K2C": "1"})
+    assert md5 == GOLDEN[tech]
+    data = os.path.join(REF_DIR, "test_data")
+    r = subprocess.run([os.path.join(REF_DIR, "longcallD_so"), "call", "--" + tech, os.path.join(data, "chr11_2M.fa"), os.path.join(data, f"HG002_chr11_{tech}_test.bam"), "-t", "2"],
+                       env=dict(os.environ, LD_PRELOAD=dropin_cpu, LCD_DROPIN_CHECK_K2C="1"), capture_output=True, timeout=900)
+    checks = [l for l in r.stderr.decode().splitlines() if l.startswith("[k2c check]")]
+    big = [l for l in checks if re.search(r"chunk \d+: (\d+) sites", l) and int(re.search(r"chunk \d+: (\d+) sites", l).group(1)) > 1000]
+    assert big and all("identical" in l and "DIFFERENT" not in l for l in checks), [l for l in checks if "DIFFERENT" in l][:3]

@@ -57,6 +57,9 @@ def test_vcf_identical_with_gpu_dropin(tech):
     assert fwd_poa == FORWARDED_POA[tech] and part_poa == PARTIAL_POA[tech], calls[-1]
     # the de-novo POA of regions without a usable phase set (abpoa_aln_msa_cons, two consensus sequences from the read clustering) runs on the GPU too
     assert fwd_denovo == 0 and (two_cons > 0 if tech == "ont" else True), calls[-1]
+    # the noisy-region set of every chunk (K2b + K2c) ran on the GPU; -s (mosaic) keeps the reference's own classification (somatic candidates: a14)
+    nrs = __import__("re").search(r"noisy-region set (\d+) \(forwarded: (\d+)\)", calls[-1])
+    assert (int(nrs.group(1)) > 0 and int(nrs.group(2)) == 0) if tech != "mosaic" else int(nrs.group(1)) == 0, calls[-1]
     print(calls[-1])
     assert md5 == GOLDEN[tech], (md5, calls[-1])
 
