@@ -213,9 +213,7 @@ class PileupStage:
         # K2c: a site record + category in, category + keep flag out; per read its span and noisy intervals; the interval lists (12 B each); records only where asked
         self.n_low = int(sum(x["n_low"] for x in self.nreg)); self.n_cnreg = int(sum(x["n_cnreg"] for x in self.nreg))
         self.k2c_bytes = int((20 + 5) * self.n_raw_sites + 24 * sum(self.n_reads) + 16 * self.n_low + 20 * self.n_cnreg)
-        self.k2c_h2d = int(sum(sum(np.asarray(x[k]).nbytes for k in ("site_pos", "site_type", "site_ref_len", "var_cate", "cnreg_beg", "cnreg_end", "cnreg_label", "low_beg", "low_end",
-                                                                     "is_skipped", "read_beg", "read_end", "digar_first", "n_digar", "nreg_first", "n_nreg", "nreg_beg", "nreg_end")) +
-                                   13 * int(np.asarray(x["digar_pos"]).size) for x in self.nreg))
+        self.k2c_h2d = int(sum(np.asarray(x["low_beg"]).nbytes + np.asarray(x["low_end"]).nbytes + 40 for x in self.nreg))      # K2c in place: options + low-complexity intervals
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -714,8 +712,8 @@ def run_b200(args, rank, world):
         if pile_res.get("want_digar"): pile_res["digar"] = dp.fetch()
         k1b = lcd.SitesPlan(None, ps.regs, min_sv_len=min_sv, digar_plan=dp); k1b.run(); pile_res["sites"] = k1b.fetch()
         k2 = lcd.PileupOnSitesPlan(dp, k1b); t.append(time.perf_counter()); k2.run(); pile_res["counts"] = k2.fetch(); t.append(time.perf_counter())
-        k2b = lcd.ClassifyOnPileupPlan(k2, ps.cls, k2.n_sites); k2b.run(); pile_res["cate"] = k2b.fetch(); k2b.destroy()      # K2b on K2's sites and counters in HBM (the reference windows come from the host)
-        pile_res["nreg"] = lcd.noisyreg_batch(ps.nreg)                                                                      # K2c through its host-buffer call (sites + categories, read spans / records / noisy intervals, low-complexity intervals up; categories, keep flags, regions back)
+        k2b = lcd.ClassifyOnPileupPlan(k2, ps.cls, k2.n_sites); k2b.run(); pile_res["cate"] = k2b.fetch()      # K2b on K2's sites and counters in HBM (the reference windows come from the host)
+        k2c = lcd.NoisyRegOnClassifyPlan(dp, k2b, ps.nreg, k2.n_sites, [s_[2] for s_ in dp.sizes()]); k2c.run(); pile_res["nreg"] = k2c.fetch(); k2c.destroy(); k2b.destroy()      # K2c on K1's lists and K2b's categories in HBM (options + low-complexity intervals come from the host)
         k3 = lcd.ProfileOnDigarPlan(dp, ps.var_sites, ps.n_reads); t.append(time.perf_counter()); k3.run(); pile_res["prof"] = k3.fetch(); t.append(time.perf_counter())
         for x in (k3, k2, k1b, dp): x.destroy()
         t.append(time.perf_counter())
@@ -752,7 +750,7 @@ def run_b200(args, rank, world):
     k2_plan = lcd.PileupOnSitesPlan(digar_plan, sites_plan)
     k3_plan = lcd.ProfileOnDigarPlan(digar_plan, ps.var_sites, ps.n_reads)
     k2b_plan = lcd.ClassifyOnPileupPlan(k2_plan, ps.cls, k2_plan.n_sites)
-    k2c_plan = lcd.NoisyRegPlan(ps.nreg)
+    k2c_plan = lcd.NoisyRegOnClassifyPlan(digar_plan, k2b_plan, ps.nreg, k2_plan.n_sites, [s_[2] for s_ in digar_plan.sizes()])
     poa_plan = lcd.PoaPlan(wl.seqs, wl.first, wl.n_reads, wl.read_off, wl.read_len, lcd.poa_params())
     wfa_plan = lcd.WfaPlan(wseqs, po, pl, to, tl, lcd.wfa_params())
     phase_plan = lcd.PhasePlan(wl.phase)

@@ -319,6 +319,17 @@ typedef struct {
 int lcd_noisyreg_batch(int n_chunks, const lcd_noisyreg_input_t *in, lcd_noisyreg_output_t *out);
 lcd_plan_t *lcd_noisyreg_plan_create(int n_chunks, const lcd_noisyreg_input_t *in);
 int  lcd_noisyreg_plan_fetch(lcd_plan_t *plan, void *stream, lcd_noisyreg_output_t *out);
+/* K1 -> ... -> K2b -> K2c in place: the reads' spans, records and noisy intervals are read where a digar plan (run) left them in HBM -- the chunk's
+ * own noisy list is gathered from them on the device (the intervals of kept reads that touch the region, src/bam_utils.c:819-832) -- and the sites
+ * with their categories where a classify plan holds them (lcd_classify_plan_create_on_pileup; it must have run, on the same stream or one this
+ * plan's stream waits for, before this plan runs).  Only the options and the low-complexity intervals come from the host.  The region is the
+ * digar plan's.  Fetch as above (reg_cap: the chunk's reads' noisy intervals + n_sites entries always suffice). */
+typedef struct {
+    int32_t min_alt_dp, noisy_reg_flank_len, is_ont, pad;
+    double min_af;
+    int64_t n_low; const int64_t *low_beg, *low_end;
+} lcd_noisyreg_params_t;
+lcd_plan_t *lcd_noisyreg_plan_create_on_classify(lcd_plan_t *digar_plan, lcd_plan_t *classify_plan, int n_chunks, const lcd_noisyreg_params_t *params);
 
 /* ---------------------------------------------------------------- K3: pileup scan, read x variant profile
  * Replaces read_var_profile_t *collect_read_var_profile(const call_var_opt_t *opt, bam_chunk_t *chunk)

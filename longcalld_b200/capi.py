@@ -907,6 +907,35 @@ class NoisyRegPlan(_Plan):
         return _noisyreg_results(self.chunks, self.outs, self.res)
 
 
+class NoisyRegParams(C.Structure):
+    _fields_ = [("min_alt_dp", C.c_int32), ("noisy_reg_flank_len", C.c_int32), ("is_ont", C.c_int32), ("pad", C.c_int32), ("min_af", C.c_double),
+                ("n_low", C.c_int64), ("low_beg", C.c_void_p), ("low_end", C.c_void_p)]
+
+
+class NoisyRegOnClassifyPlan(_Plan):
+    """K2c on what a DigarPlan (run) and a ClassifyOnPileupPlan hold in HBM; params: per chunk a dict(min_alt_dp, noisy_reg_flank_len, is_ont, min_af,
+    n_low, low_beg, low_end); n_sites: the classify plan's site counts; n_nreg: the digar plan's noisy intervals per chunk (DigarPlan.sizes())."""
+    def __init__(self, digar_plan, classify_plan, params, n_sites, n_nreg):
+        self.digar_plan, self.classify_plan, self.n_sites = digar_plan, classify_plan, list(n_sites)
+        n = len(params)
+        self.keep = [(np.ascontiguousarray(np.append(np.asarray(d["low_beg"]), 0), np.int64), np.ascontiguousarray(np.append(np.asarray(d["low_end"]), 0), np.int64)) for d in params]
+        self.par = (NoisyRegParams * max(n, 1))(*[NoisyRegParams(d["min_alt_dp"], d["noisy_reg_flank_len"], d.get("is_ont", 0), 0, d["min_af"], d["n_low"], a.ctypes.data, b.ctypes.data)
+                                                  for d, (a, b) in zip(params, self.keep)])
+        lib().lcd_noisyreg_plan_create_on_classify.restype = C.c_void_p
+        super().__init__(lib().lcd_noisyreg_plan_create_on_classify(digar_plan.h, classify_plan.h, C.c_int(n), self.par), n)
+        self.res, outs = [], []
+        for k, m in zip(self.n_sites, n_nreg):
+            cap = int(k) + int(m) + 8
+            r = dict(var_cate=np.full(k + 1, -7, np.int32), keep=np.zeros(k + 1, np.uint8), reg_beg=np.zeros(cap, np.int64), reg_end=np.zeros(cap, np.int64), reg_label=np.zeros(cap, np.int32))
+            self.res.append(r)
+            outs.append(NoisyRegOutput(r["var_cate"].ctypes.data, r["keep"].ctypes.data, r["reg_beg"].ctypes.data, r["reg_end"].ctypes.data, r["reg_label"].ctypes.data, cap, 0))
+        self.outs = (NoisyRegOutput * max(n, 1))(*outs)
+
+    def fetch(self, stream=None):
+        _check(lib().lcd_noisyreg_plan_fetch(self.h, C.c_void_p(stream or 0), self.outs), "lcd_noisyreg_plan_fetch")
+        return _noisyreg_results([dict(n_sites=k) for k in self.n_sites], self.outs, self.res)
+
+
 # ----------------------------------------------------------------------------- K5: POA
 class PoaParams(C.Structure):
     _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open1", C.c_int32), ("gap_ext1", C.c_int32),

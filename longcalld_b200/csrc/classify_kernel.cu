@@ -156,6 +156,15 @@ struct ClassifyPlan : Plan {
 };
 
 } // namespace classify
+
+int classify_plan_view(Plan *plan, ClassifyView *v) {
+    classify::ClassifyPlan *p = dynamic_cast<classify::ClassifyPlan *>(plan);
+    if (!p) { set_error("not a classify (K2b) plan"); return -1; }
+    v->n_chunks = p->n; v->site_off = p->site_off;
+    if ((int)v->site_off.size() != p->n + 1) v->site_off.assign(p->n + 1, 0);
+    v->spos = p->p_spos; v->stype = p->p_stype; v->sref = p->p_sref; v->cate = p->d_cate.p;
+    return 0;
+}
 } // namespace lcd
 
 using namespace lcd;

@@ -352,7 +352,7 @@ struct DigarPlan : Plan {
         v->read_off = read_off; v->alt_base.assign(n, 0); v->min_bq.assign(n, 0); v->h_active = h_active;
         for (int i = 0; i < n; ++i) { v->alt_base[i] = tot_reads ? h_first[stride + read_off[i]] : 0; v->min_bq[i] = chunks[i].min_bq; }
         v->h_beg.assign(stride, 0); v->h_end.assign(stride, 0);
-        if (tot_reads) {
+        if (tot_reads && v->want_host_spans) {
             LCD_CUDA_OK(cudaMemcpyAsync(v->h_beg.data(), d_beg.p, sizeof(long long) * tot_reads, cudaMemcpyDeviceToHost, s));
             LCD_CUDA_OK(cudaMemcpyAsync(v->h_end.data(), d_end.p, sizeof(long long) * tot_reads, cudaMemcpyDeviceToHost, s));
             LCD_CUDA_OK(cudaStreamSynchronize(s));
@@ -360,7 +360,9 @@ struct DigarPlan : Plan {
         v->active = d_active.p; v->dropped = d_skip.p; v->rev = d_rev.p; v->qual = d_qual.p; v->dlow = d_dlow.p; v->dalt = d_dalt.p;
         v->beg = d_beg.p; v->end = d_end.p; v->dfirst = d_first.p; v->qoff = d_qoff.p; v->dpos = d_dpos.p; v->daoff = d_daoff.p;
         v->nfirst = d_first.p + 2 * stride; v->nbeg = d_nbeg.p; v->nend = d_nend.p;
-        v->ndig = d_ndig.p; v->dlen = d_dlen.p; v->dqi = d_dqi.p; v->nnreg = d_nnreg.p; v->dtype = d_dtype.p;
+        v->ndig = d_ndig.p; v->dlen = d_dlen.p; v->dqi = d_dqi.p; v->nnreg = d_nnreg.p; v->dtype = d_dtype.p; v->nlabel = d_nlabel.p;
+        v->nreg_total.assign(n, 0); v->reg_beg.assign(n, 0); v->reg_end.assign(n, 0);
+        for (int i = 0; i < n; ++i) { long long t = 0; for (long long g = read_off[i]; g < read_off[i + 1]; ++g) t += h_nnreg[g]; v->nreg_total[i] = t; v->reg_beg[i] = reg_beg[i]; v->reg_end[i] = reg_end[i]; }
         return 0;
     }
 

@@ -118,7 +118,10 @@ struct DigarView {
     std::vector<long long> read_off, alt_base, h_beg, h_end; std::vector<int32_t> min_bq; std::vector<uint8_t> h_active;
     const uint8_t *active = nullptr, *dropped = nullptr, *rev = nullptr, *qual = nullptr, *dlow = nullptr, *dalt = nullptr;
     const long long *beg = nullptr, *end = nullptr, *dfirst = nullptr, *qoff = nullptr, *dpos = nullptr, *daoff = nullptr, *nfirst = nullptr, *nbeg = nullptr, *nend = nullptr;
-    const int32_t *ndig = nullptr, *dlen = nullptr, *dqi = nullptr, *nnreg = nullptr; const int8_t *dtype = nullptr;
+    const int32_t *ndig = nullptr, *dlen = nullptr, *dqi = nullptr, *nnreg = nullptr, *nlabel = nullptr; const int8_t *dtype = nullptr;
+    bool want_host_spans = true;              // h_beg / h_end (a D2H copy of every read's span): consumers that work on the device only switch it off
+    std::vector<long long> nreg_total;        // per chunk: noisy intervals of its reads
+    std::vector<long long> reg_beg, reg_end;  // per chunk: the region
 };
 int digar_plan_view(Plan *plan, cudaStream_t s, DigarView *v);      // digar_kernel.cu
 
@@ -142,6 +145,14 @@ struct PileupView {
     const long long *spos = nullptr, *saoff = nullptr; const int32_t *stype = nullptr, *sref = nullptr, *salt = nullptr, *counts = nullptr; const uint8_t *site_alt = nullptr;
 };
 int pileup_plan_view(Plan *plan, PileupView *v);      // pileup_kernel.cu
+
+// K2b's sites and categories as K2c consumes them in place (device pointers into a classify plan; valid while it -- and the plans it was
+// created on -- live; the categories are there once the plan has run on the stream K2c runs on, or an earlier one it waits for).
+struct ClassifyView {
+    int n_chunks = 0; std::vector<long long> site_off;
+    const long long *spos = nullptr; const int32_t *stype = nullptr, *sref = nullptr, *cate = nullptr;
+};
+int classify_plan_view(Plan *plan, ClassifyView *v);  // classify_kernel.cu
 
 inline cudaStream_t pick_stream(void *s) { bind_thread(); return s ? (cudaStream_t)s : cur_stream(); }
 

@@ -40,15 +40,18 @@ struct Chunk {
     const long long *site_pos; const int *site_type, *site_ref_len, *var_cate_in;
     const long long *cn_beg, *cn_end; const int *cn_label;
     const long long *low_beg, *low_end;                                             // ascending starts
-    const unsigned char *is_skipped; const long long *read_beg, *read_end, *digar_first; const int *n_digar;
+    const unsigned char *is_skipped, *active;                                       // a read counts when !is_skipped[r] (K1's skip) and, where given, active[r] (not skipped by the loader)
+    const long long *read_beg, *read_end, *digar_first; const int *n_digar;
     const long long *digar_pos; const signed char *digar_type; const int *digar_len;
     const long long *nreg_first; const int *n_nreg; const long long *nreg_beg, *nreg_end;
+    const int *nreg_label; int cn_from_reads;                                      // 1: chunk_noisy_regs is gathered from the reads' intervals that touch the region (src/bam_utils.c:819-832), as K1 left them in HBM
     // outputs
-    int *var_cate; unsigned char *keep; long long *out_beg, *out_end; int *out_label; long long reg_cap; long long *n_regs; int *status;
+    int *var_cate; unsigned char *keep; long long *out_regs; long long reg_cap; long long *n_regs; int *status;     // out_regs: n_regs starts, n_regs ends (int64), n_regs labels (int32), back to back
     // scratch
     Ivs A, B; int *low_pmax, *vp_pmax, *tot, *noi, *ctr;                             // ctr[0]: list length, ctr[1]: appended intervals
 };
 
+__device__ __forceinline__ bool skipped(const Chunk &c, int r) { return c.is_skipped[r] || (c.active && !c.active[r]); }
 __device__ __forceinline__ unsigned long long key_of(int st, int en) { return ((unsigned long long)(long long)st << 32) | (unsigned long long)(long long)en; }
 
 // cr_index: B <- A sorted by key (ties: input order)
@@ -104,9 +107,12 @@ __device__ __forceinline__ float noisy_reads_ratio(const Chunk &c, long long var
     const int qs = (int)(var_start - 1), qe = (int)var_end;
     int total = 0, noisy = 0;
     for (int r = 0; r < c.n_reads; ++r) {
-        if (c.is_skipped[r] || c.n_digar[r] <= 0 || c.read_beg[r] > c.read_end[r]) continue;
-        if ((int)(c.read_beg[r] - 1) < qe && qs < (int)c.read_end[r]) ++total;
-        // (a read is noisy here whether or not its span counts: an insertion after its last base lies past read_end)
+        if (skipped(c, r) || c.n_digar[r] <= 0 || c.read_beg[r] > c.read_end[r]) continue;
+        const int rb = (int)(c.read_beg[r] - 1), re = (int)c.read_end[r];
+        if (rb < qe && qs < re) ++total;
+        // (a read is noisy here whether or not its span counts: an insertion after its last base lies one past read_end; K1's records lie in
+        // [read_beg, read_end + 1], so a read whose widened span misses the query has no record on it)
+        if (!(rb - 1 < qe && qs < re + 2)) continue;
         // the read's records are in reference order: the last one starting before qe, then back while they still reach past qs
         const long long f = c.digar_first[r]; int lo = 0, hi = c.n_digar[r];
         while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)(c.digar_pos[f + mid] - 1) < qe) lo = mid + 1; else hi = mid; }
@@ -144,10 +150,26 @@ template <class SyncF> __device__ void run_chunk(Chunk c, int tid, int nt, SyncF
     Ivs A = c.A, B = c.B;
     const int n = c.n_sites;
     // running maximum of the low-complexity ends (for the walk-back overlap queries)
-    if (tid == 0) { int m = INT32_MIN; for (int j = 0; j < c.n_low; ++j) { const int e = (int)c.low_end[j]; if (e > m) m = e; c.low_pmax[j] = m; } c.ctr[0] = 0; c.ctr[1] = 0; *c.status = ST_OK; }
-    for (int i = tid; i < c.n_cnreg; i += nt) { A.st[i] = (int)c.cn_beg[i]; A.en[i] = (int)c.cn_end[i]; A.label[i] = c.cn_label[i]; }
-    SYNC();
+    if (tid == 0) { int m = INT32_MIN; for (int j = 0; j < c.n_low; ++j) { const int e = (int)c.low_end[j]; if (e > m) m = e; c.low_pmax[j] = m; } c.ctr[0] = 0; c.ctr[1] = 0; c.ctr[2] = 0; *c.status = ST_OK; }
     int nR = c.n_cnreg;
+    if (c.cn_from_reads) {
+        SYNC();
+        for (int r = tid; r < c.n_reads; r += nt) {
+            if (skipped(c, r)) continue;
+            for (int x = 0; x < c.n_nreg[r]; ++x) {
+                const long long q = c.nreg_first[r] + x, b = c.nreg_beg[q], e = c.nreg_end[q];
+                if (b + 1 > c.reg_end || e < c.reg_beg) continue;
+                const int at = atomicAdd(&c.ctr[2], 1);
+                if (at < c.cap) { A.st[at] = (int)b; A.en[at] = (int)e; A.label[at] = c.nreg_label[q]; }
+            }
+        }
+        SYNC();
+        nR = c.ctr[2];
+        if (nR > c.cap) { if (tid == 0) { *c.status = ST_REG_CAP; *c.n_regs = 0; } return; }
+    } else {
+        for (int i = tid; i < c.n_cnreg; i += nt) { A.st[i] = (int)c.cn_beg[i]; A.en[i] = (int)c.cn_end[i]; A.label[i] = c.cn_label[i]; }
+        SYNC();
+    }
     // ---- pre_process_noisy_regs
     if (nR > 0) {
         rank_sort(A, B, nR, tid, nt);                                               // cr_index
@@ -173,7 +195,7 @@ template <class SyncF> __device__ void run_chunk(Chunk c, int tid, int nt, SyncF
         SYNC();
         // every kept read votes in the regions its span overlaps: noisy when one of its own noisy intervals overlaps the region
         for (int r = tid; r < c.n_reads; r += nt) {
-            if (c.is_skipped[r]) continue;
+            if (skipped(c, r)) continue;
             const int qs = (int)(c.read_beg[r] - 1), qe = (int)c.read_end[r];
             const int ub = starts_below(A.st, nR, qe);
             for (int k = ub - 1; k >= 0 && qs < A.en[k]; --k) {                      // disjoint + sorted: ends ascend too
@@ -197,7 +219,7 @@ template <class SyncF> __device__ void run_chunk(Chunk c, int tid, int nt, SyncF
     }
     if (n == 0) {            // classify_cand_vars is not called for a chunk without candidate sites (src/collect_var.c:2923)
         if (tid == 0) { *c.n_regs = nR; if (nR > c.reg_cap) *c.status = ST_REG_CAP; }
-        if (nR <= c.reg_cap) for (int k = tid; k < nR; k += nt) { c.out_beg[k] = A.st[k]; c.out_end[k] = A.en[k]; c.out_label[k] = A.label[k]; }
+        if (nR <= c.reg_cap) for (int k = tid; k < nR; k += nt) { c.out_regs[k] = A.st[k]; c.out_regs[nR + k] = A.en[k]; reinterpret_cast<int *>(c.out_regs + 2 * (size_t)nR)[k] = A.label[k]; }
         return;
     }
     // ---- classify_cand_vars after classify_var_cate.  var_pos_cr: the sites that are not LOW_COV (ONT: nor strand-biased), with a running
@@ -306,7 +328,7 @@ template <class SyncF> __device__ void run_chunk(Chunk c, int tid, int nt, SyncF
         c.keep[i] = 1;
     }
     if (tid == 0) { *c.n_regs = nR; if (nR > c.reg_cap) *c.status = ST_REG_CAP; }
-    if (nR <= c.reg_cap) for (int k = tid; k < nR; k += nt) { c.out_beg[k] = A.st[k]; c.out_end[k] = A.en[k]; c.out_label[k] = A.label[k]; }
+    if (nR <= c.reg_cap) for (int k = tid; k < nR; k += nt) { c.out_regs[k] = A.st[k]; c.out_regs[nR + k] = A.en[k]; reinterpret_cast<int *>(c.out_regs + 2 * (size_t)nR)[k] = A.label[k]; }
 }
 
 } // namespace noisyreg

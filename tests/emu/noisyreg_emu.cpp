@@ -20,9 +20,9 @@ extern "C" int emu_noisy_regs(const lcd_noisyreg_input_t *in, lcd_noisyreg_outpu
     c.n_digar = in->n_digar; c.digar_pos = (const long long *)in->digar_pos; c.digar_type = (const signed char *)in->digar_type; c.digar_len = in->digar_len;
     c.nreg_first = (const long long *)in->nreg_first; c.n_nreg = in->n_nreg; c.nreg_beg = (const long long *)in->nreg_beg; c.nreg_end = (const long long *)in->nreg_end;
     std::vector<int> sc(6 * cap + 4 * cap + (size_t)in->n_low + in->n_sites + 64, 0x55555555);      // poisoned scratch
-    std::vector<long long> ob(cap), oe(cap); std::vector<int> ol(cap);
+    std::vector<long long> ob(3 * cap + 2);
     long long nregs = 0; int status = 0;
-    c.var_cate = out->var_cate; c.keep = out->keep; c.out_beg = ob.data(); c.out_end = oe.data(); c.out_label = ol.data(); c.reg_cap = (long long)cap; c.n_regs = &nregs; c.status = &status;
+    c.var_cate = out->var_cate; c.keep = out->keep; c.out_regs = ob.data(); c.reg_cap = (long long)cap; c.n_regs = &nregs; c.status = &status;
     int *p = sc.data();
     c.A.st = p; c.A.en = p + cap; c.A.label = p + 2 * cap; c.B.st = p + 3 * cap; c.B.en = p + 4 * cap; c.B.label = p + 5 * cap; p += 6 * cap;
     c.tot = p; c.noi = p + cap; p += 2 * cap; c.low_pmax = p; p += in->n_low + 1; c.vp_pmax = p; p += in->n_sites + 1; c.ctr = p;
@@ -30,6 +30,6 @@ extern "C" int emu_noisy_regs(const lcd_noisyreg_input_t *in, lcd_noisyreg_outpu
     if (status) return status;
     out->n_regs = nregs;
     if (nregs > out->reg_cap) return -5;
-    for (long long k = 0; k < nregs; ++k) { out->reg_beg[k] = ob[k]; out->reg_end[k] = oe[k]; out->reg_label[k] = ol[k]; }
+    for (long long k = 0; k < nregs; ++k) { out->reg_beg[k] = ob[k]; out->reg_end[k] = ob[nregs + k]; out->reg_label[k] = reinterpret_cast<const int *>(ob.data() + 2 * nregs)[k]; }
     return 0;
 }

@@ -60,3 +60,31 @@ def test_gpu_noisy_regs_rejections(gpu, oracle):
         bad = dict(case, low_beg=np.asarray(case["low_beg"])[::-1].copy())
         with pytest.raises(gpu.LcdGpuError, match="ascend by start"):
             gpu.noisyreg_batch([bad])
+
+
+def test_gpu_chain_in_place(gpu, oracle):
+    """K1 -> K1b -> K2 -> K2b -> K2c with everything left in HBM (only the reference windows, the options and the low-complexity intervals are uploaded):
+    K2c's answer against the oracle run on the fetched K1 / K1b / K2b results; the plan is re-runnable."""
+    from longcalld_b200 import synth
+    rng = np.random.default_rng(88)
+    cases = [synth.make_digar_chunk(rng, n_reads=200, read_len=(4000, 12000), err_every=300, ref_len=80000) for _ in range(2)] + synth.digar_chunks_30x(2, seed=89, chunk_len=60000, read_mean=8000)
+    regs = [(int(d["reg_beg"]), int(d["reg_end"])) for d in cases]
+    k1 = gpu.DigarPlan(cases); k1.run(); k1.sync()
+    k1b = gpu.SitesPlan(None, regs, min_sv_len=[50] * len(cases), digar_plan=k1); k1b.run(); k1b.sync()
+    k2 = gpu.PileupOnSitesPlan(k1, k1b); k2.run(); k2.sync()
+    recs, sites, counts = k1.fetch(), k1b.fetch(), k2.fetch()
+    lists = [synth.site_list_from_sites(o, st) for o, st in zip(recs, sites)]
+    cls = [synth.classify_input_from_sites(d, sl, c, 2000 + i) for i, (d, sl, c) in enumerate(zip(cases, lists, counts))]
+    k2b = gpu.ClassifyOnPileupPlan(k2, cls, [c["n_sites"] for c in cls]); k2b.run(); k2b.sync()
+    cates = k2b.fetch()
+    inputs = [synth.noisyreg_input_from(d, o, sl, ct, 3000 + i) for i, (d, o, sl, ct) in enumerate(zip(cases, recs, lists, cates))]
+    k2c = gpu.NoisyRegOnClassifyPlan(k1, k2b, inputs, [c["n_sites"] for c in cls], [s[2] for s in k1.sizes()])
+    for _ in range(2):
+        k2c.run(); k2c.sync()
+    got = k2c.fetch()
+    for g, x in zip(got, inputs):
+        assert _same(g, T.noisy_regs(oracle, "lcd_oracle_noisy_regs", x))
+    assert sum(g["n_regs"] for g in got) > 20 and sum(int(g["keep"].sum()) for g in got) > 100
+    # the host-buffer form on the same inputs gives the same answer
+    for g, h in zip(got, gpu.noisyreg_batch(inputs)):
+        assert np.array_equal(g["var_cate"], h["var_cate"]) and np.array_equal(g["keep"], h["keep"]) and np.array_equal(g["reg_beg"], h["reg_beg"]) and np.array_equal(g["reg_end"], h["reg_end"])
