@@ -38,7 +38,7 @@ EDLIB_BYTES_PER_BLOCKCOL = 28    # Peq word in + (P, M, score) s
 PHASE_BYTES_PER_PAIR = 24        # allele + variant state in, counts out, per (read, variant) pair and pass
 
 
-NCU_CAPTURES = ("r2_poa_full_v2.raw.csv", "r1_poa_full_v5.raw.csv", "r1_poa_full_v3.raw.csv")       # newest first
+NCU_CAPTURES = ("r2_poa_full_v4.raw.csv", "r2_poa_full_v2.raw.csv", "r1_poa_full_v5.raw.csv", "r1_poa_full_v3.raw.csv")       # newest first
 
 
 def ncu_capture():
@@ -522,7 +522,7 @@ def workload_config(args, wl, ps=None):
             "n_poa": wl.n_poa, "n_poa_reads": wl.n_poa_reads, "n_wfa": wl.n_poa,
             "l2": "flushed between timed steps (256 MiB write)", "seed": args.seed,
             "pipeline": ("K6 / K7 of batch k - 1 overlap K5 of batch k: own stream and window of the workspace pool (all batches are the same synthetic batch; the e2e run drains the last batch inside the timed region)" if getattr(args, "pipeline", False) else "none"),
-            "streams": f"K5 (-> K6 -> K7 without the pipeline) on the library stream, K1 -> K1b -> K2 -> K3 -> K4 on the auxiliary stream (CTA slots of {getattr(args, 'reserve_sms', 0)} SMs left free by the persistent DP grids); the step is timed fork to join"}
+            "streams": f"K5 (-> K6 -> K7 without the pipeline) on the library stream, K1 -> K1b -> K2 -> K2b -> K2c -> K3 -> K4 on the auxiliary stream (CTA slots of {getattr(args, 'reserve_sms', 0)} SMs left free by the persistent DP grids); the step is timed fork to join"}
 
 
 # ------------------------------------------------------------------------------------------ B200 arm
