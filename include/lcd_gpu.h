@@ -65,7 +65,7 @@ int lcd_gpu_pool_windows(int n_poa, int n_aln, size_t lower_bytes);
  * Replaces wavefront_aligner_new + wavefront_align + reading wf_aligner->cigar, as called by
  * wfa_end2end_aln (src/align.c:374-460) and is_diff_between_ref_hap_aln (src/assign_hap.c:972).
  * The left-alignment reversal and the aligned-string construction (src/align.c:410-452,277-329)
- * are host glue: see longcalld_b200/host. */
+ * are host glue: see wfa_job_init / wfa_job_finish in longcalld_b200/dropin/lcd_dropin.c. */
 enum { LCD_WFA_HEUR_NONE = 0, LCD_WFA_HEUR_ADAPTIVE = 1, LCD_WFA_HEUR_ZDROP = 2 };
 enum { LCD_WFA_STATUS_COMPLETED = 0, LCD_WFA_STATUS_PARTIAL = 1, LCD_WFA_STATUS_ERROR = -1,
        LCD_WFA_STATUS_OOM = -2 };
