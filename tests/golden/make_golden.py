@@ -9,6 +9,8 @@
   classify_lcd.json.gz per-site categories of the UNMODIFIED reference (classify_var_cate) on seeded sites / reference windows.
   pileup_lcd.json.gz  outputs of the UNMODIFIED reference per-site coverage pass (collect_cand_vars) on seeded chunks.
   phase_lcd.json.gz   outputs of the UNMODIFIED reference read->haplotype assignment / phasing on seeded chunks.
+  poa_ncons_lcd.json.gz outputs of the UNMODIFIED abpoa_aln_msa_cons (two consensus sequences by read clustering) on seeded de-novo regions.
+  noisyreg_lcd.json.gz  kept sites + chunk_noisy_regs of the UNMODIFIED pre_process_noisy_regs + classify_cand_vars on seeded chunks.
   edlib_lcd.json.gz   outputs of the UNMODIFIED reference edlib (NW / HW, path) on seeded inputs.
   wfa_lcd.json.gz     outputs of the UNMODIFIED reference WFA2-lib (oracle/_ref/libref_shim.so)
                       at longcallD's own parameter points (src/align.h:21-26, src/align.c:398-406)
@@ -227,9 +229,41 @@ def classify_lcd():
     return {"cases": cases}
 
 
+def poa_ncons_lcd():
+    """Outputs of the UNMODIFIED abpoa_aln_msa_cons (src/align.c:872-953: wb = -1, max_n_cons = 2, min_freq = 0.20, via oracle/_ref/libref_shim.so) on the
+    mixed-haplotype reads of seeded noisy regions: number of clusters, the consensus sequences, every read's cluster, sha1 of the MSA."""
+    import hashlib
+    par = T.poa_params(0, -1); par.max_n_cons = 2
+    ref = T.ref_lib()
+    cases = []
+    for tech, mbp, seed in (("hifi", 0.25, 23), ("ont", 0.06, 24)):
+        for seqs in T.denovo_problems(mbp, tech, seed, max_len=500):
+            rc, cons, clu, msa = T.poa_ncons(ref, "ref_poa_ncons", seqs, par, 0.20)
+            assert rc == 0
+            cases.append({"seqs": ["".join(map(str, np.asarray(s).tolist())) for s in seqs], "cons": ["".join(map(str, c)) for c in cons], "clu": "".join(map(str, clu.tolist())),
+                          "msa_shape": list(msa.shape), "msa_sha1": hashlib.sha1(msa.tobytes()).hexdigest()})
+    return {"cases": cases}
+
+
+def noisyreg_lcd():
+    """Outputs of the UNMODIFIED pre_process_noisy_regs + classify_cand_vars (src/collect_var.c:557,902, via oracle/_ref/libref_shim.so) on seeded chunks:
+    the kept sites with their categories and chunk_noisy_regs.  The inputs are K1 / K1b / K2 / K2b results of the same chunks (the oracle's, pinned separately)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from longcalld_b200 import synth
+    orc, ref = T.oracle_lib(), T.ref_lib()
+    rng = np.random.default_rng(20261101)
+    cases = []
+    for it in range(8):
+        d = synth.make_digar_chunk(rng, n_reads=int(rng.integers(40, 90)), read_len=(1500, 5000), err_every=int(rng.choice([150, 400])), ref_len=12000, tech="ont" if it % 4 == 3 else "hifi")
+        case, ci = T.noisyreg_case(orc, d, 700 + it, is_ont=int(it % 4 == 3), low_every=int(rng.choice([150, 400])))
+        kept, regs = T.ref_noisy_regs(ref, ci, case)
+        cases.append({"in": T.noisyreg_case_to_json(case), "kept": kept, "regs": regs})
+    return {"cases": cases}
+
+
 def main():
     only = sys.argv[1:]
-    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd), ("poa_lcd", poa_lcd), ("edlib_lcd", edlib_lcd), ("phase_lcd", phase_lcd), ("pileup_lcd", pileup_lcd), ("digar_lcd", digar_lcd), ("sites_lcd", sites_lcd), ("classify_lcd", classify_lcd)):
+    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd), ("poa_lcd", poa_lcd), ("edlib_lcd", edlib_lcd), ("phase_lcd", phase_lcd), ("pileup_lcd", pileup_lcd), ("digar_lcd", digar_lcd), ("sites_lcd", sites_lcd), ("classify_lcd", classify_lcd), ("poa_ncons_lcd", poa_ncons_lcd), ("noisyreg_lcd", noisyreg_lcd)):
         if only and name not in only:
             continue
         path = os.path.join(HERE, name + ".json.gz")

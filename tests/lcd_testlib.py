@@ -639,3 +639,27 @@ def noisyreg_case(orc, d, seed, is_ont=0, low_every=400, min_sv_len=50):
                 n_low=k, low_beg=lb, low_end=le, is_skipped=np.maximum(np.asarray(d["is_skipped"][:nr]), o["skip"][:nr]),
                 **{f: o[f] for f in ("read_beg", "read_end", "digar_first", "n_digar", "digar_pos", "digar_type", "digar_len", "nreg_first", "n_nreg", "nreg_beg", "nreg_end")})
     return case, ci
+
+
+NOISYREG_SCALARS = ("reg_beg", "reg_end", "min_alt_dp", "noisy_reg_flank_len", "is_ont", "min_af", "n_sites", "n_reads", "n_cnreg", "n_low")
+NOISYREG_ARRAYS = dict(list(NOISYREG_FIELDS + NOISYREG_READ_FIELDS) + [("cnreg_beg", np.int64), ("cnreg_end", np.int64), ("cnreg_label", np.int32), ("low_beg", np.int64), ("low_end", np.int64)])
+
+
+def noisyreg_case_to_json(d):
+    """Only what the stage reads: records other than X / I / D keep their place (the per-read lists are position-sorted walks)."""
+    out = {k: (float(d[k]) if k == "min_af" else int(d[k])) for k in NOISYREG_SCALARS}
+    nr = d["n_reads"]
+    nd = int(max([int(d["digar_first"][r]) + int(d["n_digar"][r]) for r in range(nr)] + [0])); nn = int(max([int(d["nreg_first"][r]) + int(d["n_nreg"][r]) for r in range(nr)] + [0]))
+    size = dict(site_pos=d["n_sites"], site_type=d["n_sites"], site_ref_len=d["n_sites"], var_cate=d["n_sites"], is_skipped=nr, read_beg=nr, read_end=nr, digar_first=nr, n_digar=nr,
+                digar_pos=nd, digar_type=nd, digar_len=nd, nreg_first=nr, n_nreg=nr, nreg_beg=nn, nreg_end=nn, cnreg_beg=d["n_cnreg"], cnreg_end=d["n_cnreg"], cnreg_label=d["n_cnreg"],
+                low_beg=d["n_low"], low_end=d["n_low"])
+    for k, n in size.items():
+        out[k] = np.asarray(d[k])[:n].astype(np.int64).tolist()
+    return out
+
+
+def noisyreg_case_from_json(j):
+    d = {k: j[k] for k in NOISYREG_SCALARS}
+    for k, t in NOISYREG_ARRAYS.items():
+        d[k] = np.array(j[k] + [0], dtype=t)
+    return d

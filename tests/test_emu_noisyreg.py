@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import lcd_testlib as T
-from test_oracle_noisyreg import noisyreg_cases
+from test_oracle_noisyreg import noisyreg_cases, noisyreg_fixture_cases
 
 EMU_DIR = os.path.join(T.ROOT, "tests", "emu")
 
@@ -73,3 +73,9 @@ def test_emu_vs_oracle_fabricated(emu, oracle):
         assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2]), n
         adds += len(a[1])
     assert adds > 300
+
+
+def test_emu_vs_fixtures(emu):
+    for n, (case, kept, regs) in enumerate(noisyreg_fixture_cases()):
+        got = T.noisy_regs(emu, "emu_noisy_regs", case)
+        assert got[0] == kept and got[1] == regs, n

@@ -67,3 +67,11 @@ def test_emu_poa_two_consensus_vs_oracle(emu, oracle, mode):
                 assert a[0] == b[0] == 0 and a[1] == b[1] and np.array_equal(a[2], b[2]) and a[3].shape == b[3].shape and (a[3] == b[3]).all(), (n, mf)
             n += 1; two += len(a[1]) == 2
     assert n >= 40 and two >= 10
+
+
+def test_emu_poa_two_consensus_vs_fixtures(emu):
+    from test_oracle_poa_ncons import ncons_fixture_cases, same_as_fixture
+    emu.emu_poa_mode(0)
+    par = T.poa_params(0, -1); par.max_n_cons = 2
+    for i, want in enumerate(list(ncons_fixture_cases())[::3]):
+        assert same_as_fixture(T.poa_ncons(emu, "emu_poa_ncons", want[0], par), want), i

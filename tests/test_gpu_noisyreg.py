@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import lcd_testlib as T
-from test_oracle_noisyreg import noisyreg_cases
+from test_oracle_noisyreg import noisyreg_cases, noisyreg_fixture_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -88,3 +88,12 @@ def test_gpu_chain_in_place(gpu, oracle):
     # the host-buffer form on the same inputs gives the same answer
     for g, h in zip(got, gpu.noisyreg_batch(inputs)):
         assert np.array_equal(g["var_cate"], h["var_cate"]) and np.array_equal(g["keep"], h["keep"]) and np.array_equal(g["reg_beg"], h["reg_beg"]) and np.array_equal(g["reg_end"], h["reg_end"])
+
+
+def test_gpu_noisy_regs_vs_reference_fixtures(gpu):
+    """committed outputs of the unmodified reference functions: no oracle, no /root/reference in this comparison"""
+    cases = list(noisyreg_fixture_cases())
+    for g, (case, kept, regs) in zip(gpu.noisyreg_batch([c for c, _, _ in cases]), cases):
+        idx = np.nonzero(g["keep"])[0]
+        got_kept = [(int(case["site_pos"][i]), int(case["site_type"][i]), int(case["site_ref_len"][i]), int(g["var_cate"][i])) for i in idx]
+        assert got_kept == kept and list(zip(g["reg_beg"].tolist(), g["reg_end"].tolist(), g["reg_label"].tolist())) == regs

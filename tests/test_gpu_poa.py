@@ -152,3 +152,13 @@ def test_gpu_poa_two_consensus_vs_oracle(gpu, oracle):
     # lcd_poa_batch keeps refusing max_n_cons = 2 (it cannot return the clusters)
     with pytest.raises(gpu.LcdGpuError):
         gpu.poa_batch(problems[:2], tuple(par2))
+
+
+def test_gpu_poa_two_consensus_vs_reference_fixtures(gpu):
+    """committed outputs of the unmodified abpoa_aln_msa_cons: no oracle, no /root/reference in this comparison"""
+    from test_oracle_poa_ncons import ncons_fixture_cases, same_as_fixture
+    cases = list(ncons_fixture_cases())
+    par2 = list(gpu.poa_params(0, -1)); par2[9] = 2
+    got = gpu.poa_ncons_batch([c[0] for c in cases], tuple(par2), 0.20)
+    bad = [i for i, (g, c) in enumerate(zip(got, cases)) if not same_as_fixture(g, c)]
+    assert not bad and len(cases) >= 40, bad[:10]

@@ -45,3 +45,18 @@ def test_oracle_noisy_regs_edge_cases(oracle, ref):
         kept, regs, _ = T.noisy_regs(oracle, "lcd_oracle_noisy_regs", c)
         rkept, rregs = T.ref_noisy_regs(ref, k, c)
         assert regs == rregs and kept == rkept
+
+
+def noisyreg_fixture_cases():
+    for c in T.load_golden("noisyreg_lcd")["cases"]:
+        yield T.noisyreg_case_from_json(c["in"]), [tuple(k) for k in c["kept"]], [tuple(r) for r in c["regs"]]
+
+
+def test_oracle_noisy_regs_vs_reference_fixtures(oracle):
+    """committed outputs of the unmodified pre_process_noisy_regs + classify_cand_vars (tests/golden/make_golden.py noisyreg_lcd)"""
+    n = 0
+    for case, kept, regs in noisyreg_fixture_cases():
+        got = T.noisy_regs(oracle, "lcd_oracle_noisy_regs", case)
+        assert got[0] == kept and got[1] == regs, n
+        n += 1
+    assert n == 8

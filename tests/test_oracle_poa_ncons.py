@@ -47,3 +47,25 @@ def test_oracle_ncons_other_min_freq_and_one_cluster(oracle, ref):
         a = T.poa_ncons(oracle, "lcd_oracle_poa_ncons", seqs, _par())
         b = T.poa_ncons(ref, "ref_poa_ncons", seqs, _par())
         assert _same(a, b)
+
+
+def ncons_fixture_cases():
+    import hashlib
+    for c in T.load_golden("poa_ncons_lcd")["cases"]:
+        seqs = [np.array([int(x) for x in s], dtype=np.uint8) for s in c["seqs"]]
+        yield seqs, [bytes(int(x) for x in s) for s in c["cons"]], np.array([int(x) for x in c["clu"]], np.uint8), c["msa_shape"], c["msa_sha1"]
+
+
+def same_as_fixture(got, want):
+    import hashlib
+    _, cons, clu, shape, sha = want
+    return got[0] == 0 and got[1] == cons and np.array_equal(got[2], clu) and list(got[3].shape) == shape and hashlib.sha1(got[3].tobytes()).hexdigest() == sha
+
+
+def test_oracle_ncons_vs_reference_fixtures(oracle):
+    """committed outputs of the unmodified abpoa_aln_msa_cons (tests/golden/make_golden.py poa_ncons_lcd): runs where /root/reference does not exist"""
+    n = two = 0
+    for want in ncons_fixture_cases():
+        assert same_as_fixture(T.poa_ncons(oracle, "lcd_oracle_poa_ncons", want[0], _par()), want), n
+        n += 1; two += len(want[1]) == 2
+    assert n >= 40 and two >= 10
