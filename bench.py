@@ -615,12 +615,16 @@ def run_b200(args, rank, world):
         return nxt
 
     def wfa_stage(b, own_stream=False):
-        """consensus in host memory (slot b) -> lcd_wfa_batch -> host CIGAR ops; then K7 through its host-buffer batch call"""
+        """K7 through its host-buffer batch call, then consensus in host memory (slot b) -> lcd_wfa_batch -> host CIGAR ops"""
         try:
             tw = [time.perf_counter()]
-            if own_stream:
-                lcd.set_thread_stream(dp_h)
-                pile_gpu_done.wait()            # K6's persistent grid would keep the reserved CTA slots to itself: it follows the short kernels
+            if own_stream: lcd.set_thread_stream(dp_h)
+            # K7 first: it depends on nothing the other threads produce, and its one-thread-per-problem grid is light enough to run beside the short kernels
+            if L.lcd_edlib_batch(C.c_int(ne), _vp(eseqs), C.c_size_t(eseqs.size), _vp(eqo), _vp(eql), _vp(eto), _vp(etl), _vp(emode), _vp(ewant),
+                                 _vp(ealn), _vp(eoff), _vp(eres)):
+                raise RuntimeError(L.lcd_gpu_last_error().decode())
+            tw.append(time.perf_counter())
+            if own_stream: pile_gpu_done.wait()            # K6's persistent grid would keep the reserved CTA slots to itself: it follows the short kernels
             tw.append(time.perf_counter())
             tl = np.ascontiguousarray(press[b]["cons_len"])
             cap = 2 * (ref_len.astype(np.int64) + tl) + 8
@@ -629,10 +633,6 @@ def run_b200(args, rank, world):
             rc = L.lcd_wfa_batch(C.c_int(n), _vp(bufs[b]), C.c_size_t(bufs[b].size), _vp(ref_off), _vp(ref_len), _vp(txt_off), _vp(tl),
                                  _vp(wpar), ops.ctypes.data_as(C.c_char_p), _vp(off), _vp(wress[b]))
             if rc:
-                raise RuntimeError(L.lcd_gpu_last_error().decode())
-            tw.append(time.perf_counter())
-            if L.lcd_edlib_batch(C.c_int(ne), _vp(eseqs), C.c_size_t(eseqs.size), _vp(eqo), _vp(eql), _vp(eto), _vp(etl), _vp(emode), _vp(ewant),
-                                 _vp(ealn), _vp(eoff), _vp(eres)):
                 raise RuntimeError(L.lcd_gpu_last_error().decode())
             tw.append(time.perf_counter())
             stage_err["tl"] = tl; stage_err["t_wfa"] = [round(1e3 * (y - x), 1) for x, y in zip(tw, tw[1:])]
@@ -663,7 +663,7 @@ def run_b200(args, rank, world):
             pile_thread.join(); ph_thread.join()
             if os.environ.get("LCD_BENCH_VERBOSE"):
                 print(f"[e2e step {k}] {1e3 * (time.perf_counter() - t_it):.1f} ms; main: [launch + next plan, fetch] {stage_err.get('t_poa')}; "
-                      f"K6/K7 thread [wait, wfa batch, edlib batch] {stage_err.get('t_wfa')}; pileup thread {pile_res.get('t')}; K4 batch {pile_res.get('t_phase')}", file=sys.stderr)
+                      f"K7/K6 thread [edlib batch, wait, wfa batch] {stage_err.get('t_wfa')}; pileup thread {pile_res.get('t')}; K4 batch {pile_res.get('t_phase')}", file=sys.stderr)
             for d in (pile_res, stage_err):
                 if "error" in d: raise d.pop("error")
             if world > 1 and (prev is not None or not args.pipeline):

@@ -16,7 +16,10 @@ constexpr int NCOMP = 5;            // M, I1, D1, I2, D2
 enum { C_M = 0, C_I1 = 1, C_D1 = 2, C_I2 = 3, C_D2 = 4 };
 constexpr int STATUS_ESCALATED = -100;   // internal: handed over to the CTA kernel
 constexpr int WARP_GROUPS_PER_CTA = 8;
-constexpr int CTA_GROUP_THREADS = 256;
+#ifndef LCD_WFA_CTA_THREADS
+#define LCD_WFA_CTA_THREADS 256
+#endif
+constexpr int CTA_GROUP_THREADS = LCD_WFA_CTA_THREADS;
 constexpr int WARP_SEQ_SMEM = 2560;   // bytes of staged pattern+text per warp group
 constexpr int CTA_SEQ_SMEM = 96 * 1024;
 constexpr uint32_t OVERFLOW_CHUNK_UNITS = (8u << 20) / 16;   // 8 MiB overflow chunks (16-byte units)

@@ -193,7 +193,7 @@ struct WfaPlan : Plan {
         const int occ_small = 4;                                   // CTAs per SM of the warp kernel
         int grid_small = n_small ? std::min((n_small + WARP_GROUPS_PER_CTA - 1) / WARP_GROUPS_PER_CTA, c.dp_sms() * occ_small) : 0;
         // CTA groups serve the pre-classified large problems and, afterwards, whatever the warp kernel escalates
-        int grid_large = (n_large || n_small) ? c.dp_sms() * 2 : 0;
+        int grid_large = (n_large || n_small) ? c.dp_sms() * (CTA_GROUP_THREADS > 256 ? 1 : 2) : 0;
         const int cap_large = std::max(this->cap_large, n_small ? cap_small : 0);
         const size_t groups_small = (size_t)grid_small * WARP_GROUPS_PER_CTA, groups_large = grid_large;
         const size_t pool_units = win->words / 4;
