@@ -522,7 +522,7 @@ def workload_config(args, wl, ps=None):
             "n_poa": wl.n_poa, "n_poa_reads": wl.n_poa_reads, "n_wfa": wl.n_poa,
             "l2": "flushed between timed steps (256 MiB write)", "seed": args.seed,
             "pipeline": ("K6 / K7 of batch k - 1 overlap K5 of batch k: own stream and window of the workspace pool (all batches are the same synthetic batch; the e2e run drains the last batch inside the timed region)" if getattr(args, "pipeline", False) else "none"),
-            "streams": f"K5 (-> K6 -> K7 without the pipeline) on the library stream, K1 -> K1b -> K2 -> K2b -> K2c -> K3 -> K4 on the auxiliary stream (CTA slots of {getattr(args, 'reserve_sms', 0)} SMs left free by the persistent DP grids); the step is timed fork to join"}
+            "streams": f"K5 (-> K7 -> K6 without the pipeline) on the library stream, K1 -> K1b -> K2 -> K2b -> K2c -> K3 -> K4 on the auxiliary stream (CTA slots of {getattr(args, 'reserve_sms', 0)} SMs left free by the persistent DP grids); the step is timed fork to join"}
 
 
 # ------------------------------------------------------------------------------------------ B200 arm
@@ -767,7 +767,7 @@ def run_b200(args, rank, world):
         """One pass over the batch, inputs resident, bracketed by ev[9] .. ev[10] on the library stream.
         overlap=False: every stage on the library stream, one after the other -- the per-kernel times of the roofline come from here.
         overlap=True (what `value` is): the pool-free stages (K1 -> K1b -> K2 -> K3, K4) on the auxiliary stream, K5 on the library
-        stream and, under the pipeline, K6 -> K7 -- which then stand for the batch before, whose consensus is resident -- on a third
+        stream and, under the pipeline, K7 -> K6 -- which then stand for the batch before, whose consensus is resident -- on a third
         stream with their own window of the workspace pool; the library stream waits for the other two before ev[10]."""
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(15)]
         with torch.cuda.stream(stream):
@@ -777,7 +777,7 @@ def run_b200(args, rank, world):
         sd, sd_h = (dp_stream, dp_h) if (overlap and args.pipeline) else (stream, None)
 
         def dp_tail():
-            ev[1].record(sd); wfa_plan.run(sd_h); ev[4].record(sd); edlib_plan.run(sd_h); ev[11].record(sd)
+            ev[1].record(sd); edlib_plan.run(sd_h); ev[4].record(sd); wfa_plan.run(sd_h); ev[11].record(sd)      # K7 (light, independent) first: the stream's tail is K6 alone
 
         def pile_chain():
             ev[5].record(sa); digar_plan.run(sa_h)
@@ -820,9 +820,9 @@ def run_b200(args, rank, world):
     clocks = sampler.stop()
     launches = lcd.launch_count() - launches0
     poa_ms = sum(e[0].elapsed_time(e[12]) for e in seq)
-    wfa_ms = sum(e[1].elapsed_time(e[4]) for e in seq)
+    wfa_ms = sum(e[4].elapsed_time(e[11]) for e in seq)
     phase_ms = sum(e[2].elapsed_time(e[3]) for e in seq)
-    edlib_ms = sum(e[4].elapsed_time(e[11]) for e in seq)
+    edlib_ms = sum(e[1].elapsed_time(e[4]) for e in seq)
     k1_ms = sum(e[5].elapsed_time(e[8]) for e in seq); k1b_ms = sum(e[8].elapsed_time(e[6]) for e in seq); k2_ms = sum(e[6].elapsed_time(e[13]) for e in seq); k2b_ms = sum(e[13].elapsed_time(e[14]) for e in seq); k2c_ms = sum(e[14].elapsed_time(e[7]) for e in seq); k3_ms = sum(e[7].elapsed_time(e[2]) for e in seq)
     seq_ms = sum(e[9].elapsed_time(e[10]) for e in seq)
     dev_ms = sum(e[9].elapsed_time(e[10]) for e in evs)            # whole step: all streams, fork at ev[9], join at ev[10]
