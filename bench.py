@@ -173,7 +173,7 @@ class PileupStage:
     derived once at set-up from K2's counters (synth.classify_sites) and that step is not timed in either arm."""
     N_TEMPLATE = 10
 
-    def __init__(self, mbp, tech, seed, digar_fn, sites_fn, pileup_fn, classify_fn, pin=False):
+    def __init__(self, mbp, tech, seed, digar_fn, sites_fn, pileup_fn, classify_fn, noisyreg_fn, pin=False):
         from longcalld_b200 import synth
         self.n_chunks = max(1, int(round(mbp / 0.5)))
         nt = min(self.N_TEMPLATE, self.n_chunks)
@@ -192,7 +192,8 @@ class PileupStage:
         self.cls = [synth.classify_input_from_sites(d, s, c, seed + 977 * i, is_ont=int(tech == "ont")) for i, (d, s, c) in enumerate(zip(self.template, raw, counts))]      # K2b's input
         cates = classify_fn(self.cls)
         nreg = [synth.noisyreg_input_from(d, o, s, ct, seed + 311 * i, is_ont=int(tech == "ont")) for i, (d, o, s, ct) in enumerate(zip(self.template, outs, raw, cates))]      # K2c's input
-        var = [synth.classify_sites(s, c) for s, c in zip(raw, counts)]
+        kept = noisyreg_fn(nreg, self.cls)                                   # K2c: the sites that stay, with their categories
+        var = [synth.kept_site_list(s, k["keep"], k["var_cate"]) for s, k in zip(raw, kept)]       # chunk->cand_vars after classify_cand_vars: K3's input
         profs = [synth.pileup_input_from_digar(d, o, s) for d, o, s in zip(self.template, outs, var)]
         tile = lambda xs: [xs[i % nt] for i in range(self.n_chunks)]
         self.chunks, self.raw_sites, self.var_sites, self.piles, self.profs = tile(self.template), tile(raw), tile(var), tile(piles), tile(profs)
@@ -368,7 +369,17 @@ def ref_pileup_fns(lib, n_threads):
         cptr = (C.c_void_p * max(len(cls), 1))(*[r.ctypes.data for r in cres])
         if lib.ref_classify_batch(C.c_int(len(cls)), cins, cptr, C.c_int(n_threads)): raise RuntimeError("ref_classify_batch failed")
         return [r[:d["n_sites"]] for r, d in zip(cres, cls)]
-    return digar, sites, pileup, classify
+
+    def noisyreg(nreg, cls):
+        k = len(nreg)
+        cins, _, ckeep, _ = capi._classify_structs(cls)
+        nins, nouts, nkeep, nres = capi._noisyreg_structs(nreg)
+        kp = [[np.zeros(x["n_sites"] + 1, t) for t in (np.int64, np.int32, np.int32, np.int32)] for x in nreg]
+        kptr = [(C.c_void_p * max(k, 1))(*[kp[i][j].ctypes.data for i in range(k)]) for j in range(4)]
+        nkept = np.zeros(k + 1, np.int32)
+        if lib.ref_noisyreg_batch(C.c_int(k), cins, nins, kptr[0], kptr[1], kptr[2], kptr[3], _vp(nkept), nouts, C.c_int(n_threads)): raise RuntimeError("ref_noisyreg_batch failed")
+        return capi._noisyreg_results(nreg, nouts, nres)
+    return digar, sites, pileup, classify, noisyreg
 
 
 def reference_pileup_step(lib, ps, k, n_threads, out=None):
@@ -701,7 +712,7 @@ def run_b200(args, rank, world):
 
     from longcalld_b200 import synth as _synth
     gpu_sites = lambda bare, outs, regs: [_synth.site_list_from_sites(o, st) for o, st in zip(outs, lcd.sites_batch(bare, regs))]
-    ps = PileupStage(args.mbp, args.tech, shard_seed, lcd.digar_batch, gpu_sites, lcd.pileup_batch, lcd.classify_batch, pin=True)
+    ps = PileupStage(args.mbp, args.tech, shard_seed, lcd.digar_batch, gpu_sites, lcd.pileup_batch, lcd.classify_batch, lambda nreg, cls: lcd.noisyreg_batch(nreg), pin=True)
     min_sv = [50] * ps.n_chunks
     pile_res = {}
 

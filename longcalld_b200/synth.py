@@ -588,3 +588,17 @@ def noisyreg_input_from(d, o, sites, cate, seed, low_every=250, is_ont=0):
                 n_cnreg=ncn, cnreg_beg=np.asarray(o["cnreg_beg"][:ncn], np.int64), cnreg_end=np.asarray(o["cnreg_end"][:ncn], np.int64), cnreg_label=np.asarray(o["cnreg_label"][:ncn], np.int32),
                 n_low=k, low_beg=lb, low_end=le, is_skipped=np.maximum(np.asarray(d["is_skipped"][:nr]), np.asarray(o["skip"][:nr])),
                 **{f: o[f] for f in ("read_beg", "read_end", "digar_first", "n_digar", "digar_pos", "digar_type", "digar_len", "nreg_first", "n_nreg", "nreg_beg", "nreg_end")})
+
+
+def kept_site_list(sites, keep, cate):
+    """The compacted candidate list classify_cand_vars leaves (chunk->cand_vars + var_i_to_cate): the sites K2c kept, with its categories."""
+    n = int(sites["n_sites"])
+    idx = np.nonzero(np.asarray(keep[:n]))[0]
+    alt_len = np.asarray(sites["site_alt_len"])[idx]; off = np.asarray(sites["site_alt_off"])[idx]; t = np.asarray(sites["site_type"])[idx]
+    al = np.where(t == 2, 0, alt_len).astype(np.int64)
+    new_off = np.zeros(len(idx) + 1, np.int64); np.cumsum(al, out=new_off[1:])
+    src = np.repeat(off - new_off[:-1], al) + np.arange(int(new_off[-1]), dtype=np.int64)
+    pad = lambda a, dt: np.concatenate([np.asarray(a), np.zeros(1, dt)]).astype(dt)
+    return dict(n_sites=len(idx), min_sv_len=sites["min_sv_len"], site_pos=pad(np.asarray(sites["site_pos"])[idx], np.int64), site_type=pad(t, np.int32),
+                site_ref_len=pad(np.asarray(sites["site_ref_len"])[idx], np.int32), site_alt_len=pad(alt_len, np.int32), site_alt_off=new_off.copy(),
+                site_alt=pad(np.asarray(sites["site_alt"], np.uint8)[src], np.uint8), var_cate=pad(np.asarray(cate[:n])[idx], np.int32))

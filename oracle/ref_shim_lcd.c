@@ -509,6 +509,7 @@ int ref_noisy_regs(const lcd_classify_input_t *ci, const lcd_noisyreg_input_t *i
         v->strand_to_alle_covs = (int**)malloc(2 * sizeof(int*));
         for (int s = 0; s < 2; ++s) { v->strand_to_alle_covs[s] = (int*)malloc(2 * sizeof(int)); v->strand_to_alle_covs[s][0] = c[4 + 2 * s]; v->strand_to_alle_covs[s][1] = c[5 + 2 * s]; }
         v->ref_len = ci->site_ref_len[i]; v->alt_len = ci->site_alt_len[i];
+        v->te_seq_i = i;          /* the site's index rides along (copy_var copies the field; nothing reads it when tsd_len == 0): tells which sites were kept */
         if (v->var_type == BAM_CDIFF || v->var_type == BAM_CINS) { v->alt_seq = (uint8_t*)malloc(v->alt_len > 0 ? v->alt_len : 1); memcpy(v->alt_seq, ci->site_alt + ci->site_alt_off[i], v->alt_len); }
     }
     pre_process_noisy_regs(&chunk, &opt);
@@ -516,6 +517,10 @@ int ref_noisy_regs(const lcd_classify_input_t *ci, const lcd_noisyreg_input_t *i
     if (n > 0) nk = classify_cand_vars(&chunk, n, &opt);
     *n_kept = nk;
     for (int i = 0; i < nk; ++i) { kept_pos[i] = chunk.cand_vars[i].pos; kept_type[i] = chunk.cand_vars[i].var_type; kept_ref_len[i] = chunk.cand_vars[i].ref_len; kept_cate[i] = chunk.var_i_to_cate[i]; }
+    if (out->keep && out->var_cate) {          /* the same as a mask over the input sites */
+        for (int i = 0; i < n; ++i) { out->keep[i] = 0; out->var_cate[i] = -1; }
+        for (int i = 0; i < nk; ++i) { const int k = chunk.cand_vars[i].te_seq_i; out->keep[k] = 1; out->var_cate[k] = chunk.var_i_to_cate[i]; }
+    }
     int rc = 0;
     out->n_regs = chunk.chunk_noisy_regs ? chunk.chunk_noisy_regs->n_r : 0;
     if (out->n_regs > out->reg_cap) rc = -5;
