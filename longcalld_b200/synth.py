@@ -476,26 +476,6 @@ def empty_site_list(min_sv_len=50):
                 site_alt_len=np.zeros(1, np.int32), site_alt_off=np.zeros(1, np.int64), site_alt=np.zeros(1, np.uint8))
 
 
-def classify_sites(sites, counts, min_alt=2, min_af=0.20, max_af=0.80):
-    """Workload preparation (stand-in for the reference's step 2, classify_cand_vars src/collect_var.c:902, allele-fraction rule
-    only): keeps sites with >= min_alt alternative observations and labels them clean het SNP / het indel / hom by allele
-    fraction (src/call_var_main.h:22-23); everything else is dropped, as the reference compacts cand_vars."""
-    n = sites["n_sites"]; c = counts[:n]
-    tot, alt = c[:, 0].astype(np.float64), c[:, 3]
-    af = np.where(tot > 0, alt / np.maximum(tot, 1), 0.0)
-    keep = np.nonzero((alt >= min_alt) & (af >= min_af))[0]
-    t = sites["site_type"][keep]
-    cate = np.where(af[keep] > max_af, CATE["CLEAN_HOM_VAR"], np.where(t == 8, CATE["CLEAN_HET_SNP"], CATE["CLEAN_HET_INDEL"])).astype(np.int32)
-    alt_len = sites["site_alt_len"][keep]; off = sites["site_alt_off"][keep]
-    new_alt, new_off = [], []
-    for o_, l_ in zip(off.tolist(), alt_len.tolist()):
-        new_off.append(len(new_alt)); new_alt.extend(sites["site_alt"][o_:o_ + l_].tolist())
-    pad = lambda a, dt: np.concatenate([a, np.zeros(1, dt)]).astype(dt)
-    return dict(n_sites=len(keep), min_sv_len=sites["min_sv_len"], site_pos=pad(sites["site_pos"][keep], np.int64), site_type=pad(t, np.int32),
-                site_ref_len=pad(sites["site_ref_len"][keep], np.int32), site_alt_len=pad(alt_len, np.int32),
-                site_alt_off=np.array(new_off + [0], np.int64), site_alt=np.array(new_alt + [0], np.uint8), var_cate=pad(cate, np.int32))
-
-
 def pileup_input_from_digar(d, o, sites):
     """lcd_pileup_input_t (+ lcd_profile_extra_t when `sites` carries var_cate) for a chunk from K1's host-side output."""
     nr = d["n_reads"]
