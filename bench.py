@@ -560,6 +560,7 @@ def run_b200(args, rank, world):
     stream = torch.cuda.ExternalStream(lcd.stream(), device=local)
     aux_h = lcd.aux_stream()
     lcd.reserve_sms(args.reserve_sms)              # room for the pileup / phasing kernels next to the persistent DP grids
+    lcd.reserve_plan_memory(12 << 30)              # the e2e pass creates plans from four host threads while the POA grid is resident: no pool growth under it
     aux = torch.cuda.ExternalStream(aux_h, device=local)
     shard_seed = args.seed + (rank if args.distinct_shards else 0)
     wl = Workload(args.mbp, args.tech, shard_seed)            # weak scaling: one shard per GPU (the same synthetic shard on every rank unless --distinct-shards: the step's length is its longest POA problem, so shards drawn with different seeds measure the draw, not the scaling)

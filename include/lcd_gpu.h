@@ -60,6 +60,11 @@ int lcd_gpu_split_pool(size_t lower_bytes);
  * so up to n batches of one engine -- created and run by different host threads on different streams -- are on the GPU together: a
  * batch whose launch has shrunk to its last long problems no longer keeps the next one waiting.  lcd_gpu_split_pool(b) is (1, 1, b). */
 int lcd_gpu_pool_windows(int n_poa, int n_aln, size_t lower_bytes);
+/* Plan buffers come from the device's stream-ordered memory pool (kept between calls).  A host that creates plans from several threads while persistent DP
+ * grids are resident should map a reserve once (after lcd_gpu_init): a block freed on one stream is not reused on another before that stream synchronises, and
+ * a pool that has to grow under a resident grid stalls the allocating threads until the grid retires.  Costs its mapping time once (~0.1 s per GiB): a short-lived
+ * process (one `longcallD call` on a small input) is better off without. */
+int lcd_gpu_reserve_plan_memory(size_t bytes);
 
 /* ---------------------------------------------------------------- K6: WFA gap-affine(-2p)
  * Replaces wavefront_aligner_new + wavefront_align + reading wf_aligner->cigar, as called by

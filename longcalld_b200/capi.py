@@ -107,6 +107,12 @@ def set_thread_stream(s):
     lib().lcd_gpu_set_thread_stream(C.c_void_p(s or 0))
 
 
+def reserve_plan_memory(n_bytes):
+    """lcd_gpu_reserve_plan_memory: map a reserve for the plans' stream-ordered allocations once (hosts that create plans from several threads)"""
+    lib().lcd_gpu_reserve_plan_memory.argtypes = [C.c_size_t]
+    _check(lib().lcd_gpu_reserve_plan_memory(C.c_size_t(n_bytes)), "lcd_gpu_reserve_plan_memory")
+
+
 def split_pool(lower_bytes):
     """POA plans carve from the lower `lower_bytes` of the workspace pool, WFA / edlib plans from the rest (lcd_gpu_split_pool)."""
     lib().lcd_gpu_split_pool.argtypes = [C.c_size_t]

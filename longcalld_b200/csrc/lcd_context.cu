@@ -65,6 +65,24 @@ using namespace lcd;
 extern "C" {
 
 int lcd_gpu_abi_version(void) { return LCD_GPU_ABI_VERSION; }
+
+// Grows the device's stream-ordered memory pool (what every plan's buffers come from) by `bytes` once: a block freed on one stream is not handed to another stream
+// before that stream has synchronised, so host threads that create plans side by side now and then find no reusable block and make the pool grow -- and growing it
+// while a persistent grid is resident stalled every allocating thread until the grid retired (measured: one e2e step in ~15 of bench.py at 450 ms instead of 320 ms,
+// all four host threads blocked for the length of the POA launch).  With a reserve mapped beforehand the pool hands out cached memory instead.
+int lcd_gpu_reserve_plan_memory(size_t bytes) {
+    if (ensure_ready()) return -1;
+    Context &c = ctx();
+    size_t free_b = 0, total_b = 0;
+    LCD_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+    if (bytes > free_b / 2) bytes = free_b / 2;
+    if (bytes < ((size_t)1 << 20)) return 0;
+    void *p = nullptr;
+    LCD_CUDA_OK(cudaMallocAsync(&p, bytes, c.stream));
+    LCD_CUDA_OK(cudaFreeAsync(p, c.stream));
+    LCD_CUDA_OK(cudaStreamSynchronize(c.stream));
+    return 0;
+}
 const char *lcd_gpu_last_error(void) {
     if (g_err[0]) return g_err;
     std::lock_guard<std::mutex> lk(g_err_mu);                 // another thread's last message, copied into this thread's buffer
@@ -155,21 +173,6 @@ int lcd_gpu_init(int device, size_t pool_bytes) {
     LCD_CUDA_OK(cudaMalloc((void**)&c.pool, pool_bytes));
     c.pool_words = pool_bytes / 4;
     if (c.set_windows(1, 0, 0)) return -1;
-    {   // Grow the stream-ordered pool once, up front: a block freed on one stream is not handed to another stream before that stream has synchronised, so
-        // host threads that create plans side by side now and then find no reusable block and make the pool grow -- and growing it while a persistent
-        // grid is resident stalled every allocating thread until the grid retired (measured: one e2e step in ~15 of bench.py at 450 ms instead of 320 ms,
-        // all four host threads blocked for the length of the POA launch).  With a reserve mapped at start the pool hands out cached memory instead.
-        size_t free_b = 0, total_b = 0;
-        LCD_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
-        const char *e = getenv("LCD_GPU_PLAN_POOL_GB");
-        size_t reserve = (size_t)((e ? atof(e) : 12.0) * (double)(1ull << 30));
-        if (reserve > free_b / 4) reserve = free_b / 4;
-        if (reserve >= ((size_t)64 << 20)) {
-            void *p = nullptr;
-            if (cudaMallocAsync(&p, reserve, c.stream) == cudaSuccess) { cudaFreeAsync(p, c.stream); cudaStreamSynchronize(c.stream); }
-            else cudaGetLastError();
-        }
-    }
     c.ready = true;
     return 0;
 }
