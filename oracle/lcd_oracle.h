@@ -95,6 +95,9 @@ typedef struct {
 } lcd_noisyreg_output_t;
 int lcd_oracle_noisy_regs(const lcd_noisyreg_input_t *in, lcd_noisyreg_output_t *out);
 
+/* ---- symmetric DUST over a reference window (src/sdust.c as the loader calls it, src/bam_utils.c:1574-1583) -> chunk->low_comp_cr ---- */
+int lcd_oracle_sdust(const uint8_t *seq, int l_seq, int T, int W, int64_t *beg, int64_t *end, int64_t cap);
+
 /* ---- read -> haplotype assignment and phasing (src/assign_hap.c:16-547) ----------------------------- */
 typedef struct {
     int32_t n_reads, n_vars;

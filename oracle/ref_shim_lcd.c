@@ -541,3 +541,14 @@ int ref_noisy_regs(const lcd_classify_input_t *ci, const lcd_noisyreg_input_t *i
     free(chunk.var_noisy_read_marks);
     return rc;
 }
+
+/* sdust() itself (src/sdust.c:184) on a sequence: the 0-based half-open intervals it returns */
+#include "sdust.h"
+int ref_sdust(const uint8_t *seq, int l_seq, int T, int W, int64_t *beg, int64_t *end, int64_t cap) {
+    int n = 0;
+    uint64_t *r = sdust(0, seq, l_seq, T, W, &n);
+    if (n > cap) { free(r); return -1; }
+    for (int i = 0; i < n; ++i) { beg[i] = (int64_t)(r[i] >> 32); end[i] = (int64_t)(uint32_t)r[i]; }
+    free(r);
+    return n;
+}

@@ -663,3 +663,31 @@ def noisyreg_case_from_json(j):
     for k, t in NOISYREG_ARRAYS.items():
         d[k] = np.array(j[k] + [0], dtype=t)
     return d
+
+
+# ----------------------------------------------------------------------------- sdust helpers
+def sdust(lib, fn, seq, T=5, W=20):
+    """-> [(beg, end)] 0-based half-open low-complexity intervals of an ASCII sequence"""
+    s = np.ascontiguousarray(np.frombuffer(bytes(seq), np.uint8) if not isinstance(seq, np.ndarray) else seq, dtype=np.uint8)
+    cap = len(s) // 2 + 16
+    b, e = np.zeros(cap, np.int64), np.zeros(cap, np.int64)
+    f = getattr(lib, fn); f.restype = C.c_int
+    n = f(s.ctypes.data_as(C.c_void_p), C.c_int(len(s)), C.c_int(T), C.c_int(W), b.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p), C.c_int64(cap))
+    assert n >= 0, n
+    return list(zip(b[:n].tolist(), e[:n].tolist()))
+
+
+def sdust_sequence(rng, n, lc_every=120, n_frac=0.002):
+    """ASCII reference-like sequence with planted homopolymers / short tandem repeats / low-entropy stretches, a few N runs and lower-case bases"""
+    s = rng.integers(0, 4, n).astype(np.uint8)
+    p = int(rng.integers(0, lc_every))
+    while p < n - 80:
+        kind = int(rng.integers(0, 4))
+        if kind == 0: L = int(rng.integers(4, 40)); s[p:p + L] = rng.integers(0, 4)
+        elif kind == 1: u = int(rng.integers(2, 7)); c = int(rng.integers(3, 15)); s[p:p + u * c] = np.tile(rng.integers(0, 4, u).astype(np.uint8), c)[:max(0, min(u * c, n - p))]
+        elif kind == 2: L = int(rng.integers(10, 60)); s[p:p + L] = rng.choice(np.array([0, 3], np.uint8), L)      # AT-rich
+        p += int(rng.integers(5, 2 * lc_every))
+    a = np.frombuffer(b"ACGT", np.uint8)[s].copy()
+    for q in rng.integers(0, n, max(1, int(n * n_frac))): a[q:q + int(rng.integers(1, 30))] = ord("N")
+    low = rng.random(n) < 0.05; a[low & (a != ord("N"))] |= 0x20
+    return a
