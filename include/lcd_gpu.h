@@ -291,6 +291,17 @@ typedef struct {
 } lcd_classify_params_t;
 lcd_plan_t *lcd_classify_plan_create_on_pileup(lcd_plan_t *pileup_plan, int n_chunks, const lcd_classify_params_t *params);
 
+/* ---------------------------------------------------------------- K0: low-complexity intervals of the reference
+ * Replaces uint64_t *sdust(void *km, const uint8_t *seq, int l_seq, int T, int W, int *n) (src/sdust.c:184, symmetric DUST) as the chunk loader calls it to
+ * fill chunk->low_comp_cr (src/bam_utils.c:1574-1583: seq = the chunk's region of the reference, T = LONGCALLD_SDUST_T = 5, W = LONGCALLD_SDUST_W = 20,
+ * every interval added as (reg_beg + start - 1, reg_beg + end - 1): pass base = reg_beg - 1).  Output: the intervals in ascending order, base added to
+ * the 0-based half-open (start, end) pairs sdust() returns; l_seq / 4 + 16 entries always suffice.  W up to 24 is supported. */
+typedef struct { const char *seq; int32_t l_seq; int32_t T, W; int32_t pad; int64_t base; } lcd_sdust_input_t;
+typedef struct { int64_t *beg, *end; int64_t cap, n; } lcd_sdust_output_t;
+int lcd_sdust_batch(int n_chunks, const lcd_sdust_input_t *in, lcd_sdust_output_t *out);
+lcd_plan_t *lcd_sdust_plan_create(int n_chunks, const lcd_sdust_input_t *in);
+int  lcd_sdust_plan_fetch(lcd_plan_t *plan, void *stream, lcd_sdust_output_t *out);
+
 /* ---------------------------------------------------------------- K2c: pileup scan, the noisy-region set (second half)
  * Replaces void pre_process_noisy_regs(bam_chunk_t *chunk, call_var_opt_t *opt) (src/collect_var.c:557-643) followed by
  * int classify_cand_vars(bam_chunk_t *chunk, int n_var_sites, const call_var_opt_t *opt) (:902-1033) after its classify_var_cate loop (K2b),

@@ -11,7 +11,7 @@ from .capi import (LcdGpuError, lib, lib_path, build_library, init, shutdown, la
                    PoaParams, poa_params, PoaPlan, poa_batch, poa_ncons_batch, pack_poa,
                    MODE_NW, MODE_SHW, MODE_HW, EdlibPlan, edlib_batch, xgaps,
                    PhasePlan, phase_batch, PileupPlan, pileup_batch, profile_batch, DigarPlan, digar_batch, digar_md_batch, digar_tags_batch, PileupOnDigarPlan, ProfileOnDigarPlan,
-                   SitesPlan, sites_batch, PileupOnSitesPlan, ClassifyPlan, classify_batch, ClassifyOnPileupPlan, NoisyRegPlan, NoisyRegOnClassifyPlan, noisyreg_batch)
+                   SitesPlan, sites_batch, PileupOnSitesPlan, ClassifyPlan, classify_batch, ClassifyOnPileupPlan, NoisyRegPlan, NoisyRegOnClassifyPlan, noisyreg_batch, SdustPlan, sdust_batch)
 
 __all__ = ["LcdGpuError", "lib", "lib_path", "build_library", "init", "shutdown", "launch_count", "reserve_sms", "reserve_plan_memory", "split_pool", "stream", "aux_stream", "set_thread_stream",
            "WfaParams", "WfaResult", "wfa_params", "WfaPlan", "wfa_batch",
@@ -19,4 +19,4 @@ __all__ = ["LcdGpuError", "lib", "lib_path", "build_library", "init", "shutdown"
            "PoaParams", "poa_params", "PoaPlan", "poa_batch", "poa_ncons_batch", "pack_poa",
            "MODE_NW", "MODE_SHW", "MODE_HW", "EdlibPlan", "edlib_batch", "xgaps",
            "PhasePlan", "phase_batch", "PileupPlan", "pileup_batch", "profile_batch", "DigarPlan", "digar_batch", "digar_md_batch", "digar_tags_batch", "PileupOnDigarPlan", "ProfileOnDigarPlan",
-           "SitesPlan", "sites_batch", "PileupOnSitesPlan", "ClassifyPlan", "classify_batch", "ClassifyOnPileupPlan", "NoisyRegPlan", "NoisyRegOnClassifyPlan", "noisyreg_batch"]
+           "SitesPlan", "sites_batch", "PileupOnSitesPlan", "ClassifyPlan", "classify_batch", "ClassifyOnPileupPlan", "NoisyRegPlan", "NoisyRegOnClassifyPlan", "noisyreg_batch", "SdustPlan", "sdust_batch"]

@@ -942,6 +942,45 @@ class NoisyRegOnClassifyPlan(_Plan):
         return _noisyreg_results([dict(n_sites=k) for k in self.n_sites], self.outs, self.res)
 
 
+# ----------------------------------------------------------------------------- K0: low-complexity intervals (symmetric DUST)
+class SdustInput(C.Structure):
+    _fields_ = [("seq", C.c_void_p), ("l_seq", C.c_int32), ("T", C.c_int32), ("W", C.c_int32), ("pad", C.c_int32), ("base", C.c_int64)]
+
+
+class SdustOutput(C.Structure):
+    _fields_ = [("beg", C.c_void_p), ("end", C.c_void_p), ("cap", C.c_int64), ("n", C.c_int64)]
+
+
+def _sdust_structs(seqs, T, W, base):
+    n = len(seqs)
+    keep = [np.ascontiguousarray(np.frombuffer(bytes(s), np.uint8) if not isinstance(s, np.ndarray) else s, dtype=np.uint8) for s in seqs]
+    keep = [np.append(k, np.uint8(0)) for k in keep]
+    bases = np.broadcast_to(np.asarray(base, np.int64), (n,))
+    ins = (SdustInput * max(n, 1))(*[SdustInput(k.ctypes.data, len(k) - 1, T, W, 0, int(b)) for k, b in zip(keep, bases)])
+    res = [(np.zeros((len(k) - 1) // 4 + 16, np.int64), np.zeros((len(k) - 1) // 4 + 16, np.int64)) for k in keep]
+    outs = (SdustOutput * max(n, 1))(*[SdustOutput(b.ctypes.data, e.ctypes.data, len(b), 0) for b, e in res])
+    return ins, outs, keep, res
+
+
+def sdust_batch(seqs, T=5, W=20, base=0):
+    """Drop-in batch call over HOST buffers (lcd_sdust_batch): per ASCII sequence the low-complexity intervals sdust() returns, `base` added
+    -> [[(beg, end), ...]]"""
+    ins, outs, keep, res = _sdust_structs(seqs, T, W, base)
+    _check(lib().lcd_sdust_batch(C.c_int(len(seqs)), ins, outs), "lcd_sdust_batch")
+    return [list(zip(b[:outs[i].n].tolist(), e[:outs[i].n].tolist())) for i, (b, e) in enumerate(res)]
+
+
+class SdustPlan(_Plan):
+    def __init__(self, seqs, T=5, W=20, base=0):
+        self.ins, self.outs, self.keep, self.res = _sdust_structs(seqs, T, W, base)
+        lib().lcd_sdust_plan_create.restype = C.c_void_p
+        super().__init__(lib().lcd_sdust_plan_create(C.c_int(len(seqs)), self.ins), len(seqs))
+
+    def fetch(self, stream=None):
+        _check(lib().lcd_sdust_plan_fetch(self.h, C.c_void_p(stream or 0), self.outs), "lcd_sdust_plan_fetch")
+        return [list(zip(b[:self.outs[i].n].tolist(), e[:self.outs[i].n].tolist())) for i, (b, e) in enumerate(self.res)]
+
+
 # ----------------------------------------------------------------------------- K5: POA
 class PoaParams(C.Structure):
     _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open1", C.c_int32), ("gap_ext1", C.c_int32),

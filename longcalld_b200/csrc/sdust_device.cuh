@@ -1,0 +1,235 @@
+// sdust_device.cuh -- K0: the low-complexity intervals of a chunk's reference window (chunk->low_comp_cr), one CTA per chunk.
+//
+// What it replaces: sdust(0, seq, l_seq, T, W, &n) (src/sdust.c:184, H. Li's symmetric DUST) as the chunk loader calls it over the chunk's region of the
+// reference (src/bam_utils.c:1574-1583: T = 5, W = 20), whose intervals K2c (noisyreg_device.cuh) extends the noisy regions and the sites' spans with.
+//
+// The reference is one sequential pass whose state is (a) the window: the last <= W - 2 words (triplets), with their counts, the number of equal pairs rw, and
+// the longest suffix L whose words all occur at most 2T / 10 times (with its own counts and pair number rv), and (b) the list P of "perfect intervals" of the
+// window, which are written out (merged with the previous output interval when they touch it) once the window has moved past their start.  (a) is a function
+// of the last <= W - 2 words alone -- words, not bases: the reference does NOT clear the window at an N, only its run length, so the window reaches back over
+// N runs --; (b) is empty whenever no interval has been inserted for W + 20 positions (an interval's start lies at most 17 past the window's start, which
+// passes it at most W + 17 positions after its insertion; an N flushes the list).  So:
+//   1. every position decides by itself, from the last <= W - 2 words, whether the reference would look for perfect intervals there (rw * 10 > L * T);
+//   2. the positions where it would, with less than W + 20 quiet positions between them, form independent SEGMENTS; one thread replays the reference's
+//      pass over one segment, starting from the reconstructed window and an empty P, once to count its output intervals and once to write them
+//      (the segments' outputs cannot touch each other: the next segment's first interval starts past anything this one can end with).
+#pragma once
+#include <stdint.h>
+
+namespace lcd {
+namespace sdust {
+
+constexpr int WLEN = 3, WTOT = 64, WMSK = 63, MAXW = 32;      // MAXW: capacity of the window ring (W - 2 <= MAXW: W <= MAX_W)
+constexpr int MAX_W = 24;                                      // the reference runs W = 20 (src/call_var_main.h:83); the per-thread state is sized for windows up to this
+constexpr int MAXP = 768;                                      // perfect intervals alive at once (~300 seen at W = 20, ~400 at W = 24; overflow is reported, not ignored)
+enum { ST_OK = 0, ST_CAP = -5, ST_PLIST = -6 };
+
+struct Chunk {
+    const char *seq; int n;              // the region of the reference (ASCII) and its length
+    int T, W;
+    long long base;                      // added to the 0-based interval starts / ends on output (the loader adds reg_beg - 1)
+    // outputs
+    long long *out_beg, *out_end; long long cap; long long *n_out; int *status;
+    // scratch
+    int *prevvalid;                      // [n] last position <= i at which a word (three A/C/G/T bases in a row) ends
+    unsigned char *trig;                 // [n] the reference calls find_perfect at this position
+    int *seg_start, *seg_cnt, *seg_off;  // [seg_cap] segments: first position, number of output intervals, offset of the first one
+    int seg_cap; int *ctr;               // ctr[0]: number of segments
+};
+
+__device__ __forceinline__ int nt4(unsigned char c) {
+    if (c < 4) return c;
+    switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; }
+}
+__device__ __forceinline__ int word_at(const Chunk &c, int i) { return (nt4((unsigned char)c.seq[i - 2]) << 4 | nt4((unsigned char)c.seq[i - 1]) << 2 | nt4((unsigned char)c.seq[i])) & WMSK; }
+__device__ __forceinline__ bool valid_at(const Chunk &c, int i) { return i >= 2 && c.prevvalid[i] == i; }
+// run length of A/C/G/T bases ending at i, as far as it matters (capped at lim)
+__device__ __forceinline__ int run_len(const Chunk &c, int i, int lim) { int l = 0; while (l < lim && i - l >= 0 && nt4((unsigned char)c.seq[i - l]) < 4) ++l; return l; }
+
+// the window after position i's word has been pushed: its words, oldest first; returns their number
+__device__ __forceinline__ int window_at(const Chunk &c, int i, int *w) {
+    const int maxn = c.W - WLEN + 1;
+    int tmp[MAXW], k = 0;
+    for (int j = i; j >= 2 && k < maxn;) {
+        if (c.prevvalid[j] != j) { j = c.prevvalid[j]; if (j < 2) break; continue; }
+        tmp[k++] = word_at(c, j); --j;
+    }
+    for (int x = 0; x < k; ++x) w[x] = tmp[k - 1 - x];
+    return k;
+}
+// (rw, L, rv) of a window: pairs of equal words, the longest suffix whose words all occur at most 2T / 10 times, pairs within it
+__device__ __forceinline__ void window_stats(const int *w, int cnt, int T, int &rw, int &L, int &rv) {
+    rw = 0;
+    for (int a = 0; a < cnt; ++a) for (int b = a + 1; b < cnt; ++b) rw += w[a] == w[b];
+    L = 0; rv = 0;
+    for (int s = cnt - 1; s >= 0; --s) {
+        int occ = 0;
+        for (int b = s + 1; b < cnt; ++b) occ += w[b] == w[s];
+        if ((occ + 1) * 10 > (T << 1)) break;
+        rv += occ; ++L;
+    }
+}
+
+// One segment: the reference's pass from position a, starting with the window as it is before a's word is pushed and an empty list of perfect intervals,
+// until W + 20 positions in a row have not looked for perfect intervals (or the sequence ends).  out == nullptr: count only.  Returns the number of output
+// intervals, or a negative status.
+__device__ inline int replay(const Chunk &c, int a, long long *out_beg, long long *out_end) {
+    const int T = c.T, W = c.W, maxn = W - WLEN + 1, QUIET = W + 20;
+    int ring[MAXW], front = 0, cnt = 0;
+    int cv[WTOT], cw[WTOT];
+    for (int x = 0; x < WTOT; ++x) { cv[x] = 0; cw[x] = 0; }
+    int rv = 0, rw = 0, L = 0;
+    {   // the window before a: the words that end at the last valid positions before a
+        int w0[MAXW];
+        cnt = a >= 1 ? window_at(c, a - 1, w0) : 0;
+        for (int x = 0; x < cnt; ++x) { ring[x] = w0[x]; cw[w0[x]]++; }
+        int rw0, L0, rv0; window_stats(w0, cnt, T, rw0, L0, rv0);
+        rw = rw0; L = L0; rv = rv0;
+        for (int x = cnt - L; x < cnt; ++x) cv[w0[x]]++;
+    }
+    int l = a >= 1 ? run_len(c, a - 1, W + 2) : 0;               // (only min(l, W) and l >= WLEN matter below)
+    struct Perf { int start, finish, r, l; } P[MAXP]; int np = 0;
+    int n_res = 0; long long last_beg = 0, last_end = 0; bool have_last = false;
+    int quiet = 0;
+    auto save = [&](int start) {                                 // save_masked_regions (src/sdust.c:87-103)
+        if (np == 0 || P[np - 1].start >= start) return;
+        const Perf p = P[np - 1];
+        bool saved = false;
+        if (have_last && p.start <= last_end) { saved = true; if (p.finish > last_end) { last_end = p.finish; if (out_end) out_end[n_res - 1] = c.base + last_end; } }
+        if (!saved) { last_beg = p.start; last_end = p.finish; have_last = true; if (out_beg) { out_beg[n_res] = c.base + last_beg; out_end[n_res] = c.base + last_end; } ++n_res; }
+        int i = np - 1; while (i >= 0 && P[i].start < start) --i;
+        np = i + 1;
+    };
+    for (int i = a; i <= c.n; ++i) {
+        const int b = i < c.n ? nt4((unsigned char)c.seq[i]) : 4;
+        if (b < 4) {
+            if (l < W + 2) ++l;
+            if (l >= WLEN) {
+                const int t = word_at(c, i);
+                const int start = (l - W > 0 ? l - W : 0) + (i + 1 - l);       // l is exact while l <= W; beyond, i + 1 - W either way
+                const int start_ = l > W ? i + 1 - W : start;
+                save(start_);
+                if (cnt >= maxn) {                                // shift_window (src/sdust.c:66-85)
+                    const int s = ring[front]; front = (front + 1) % MAXW; --cnt;
+                    rw -= --cw[s];
+                    if (L > cnt) { --L; rv -= --cv[s]; }
+                }
+                ring[(front + cnt) % MAXW] = t; ++cnt;
+                ++L;
+                rw += cw[t]++;
+                rv += cv[t]++;
+                if (cv[t] * 10 > (T << 1)) {
+                    int s;
+                    do { s = ring[(front + cnt - L) % MAXW]; rv -= --cv[s]; --L; } while (s != t);
+                }
+                if (rw * 10 > L * T) {                            // find_perfect (src/sdust.c:105-131)
+                    quiet = 0;
+                    int cc[WTOT];
+                    for (int x = 0; x < WTOT; ++x) cc[x] = cv[x];
+                    int r = rv, max_r = 0, max_l = 0;
+                    for (int k = cnt - L - 1; k >= 0; --k) {
+                        const int tt = ring[(front + k) % MAXW];
+                        r += cc[tt]++;
+                        const int new_r = r, new_l = cnt - k - 1;
+                        if (new_r * 10 > T * new_l) {
+                            int j;
+                            for (j = 0; j < np && P[j].start >= k + start_; ++j)
+                                if (max_r == 0 || P[j].r * max_l > max_r * P[j].l) { max_r = P[j].r; max_l = P[j].l; }
+                            if (max_r == 0 || new_r * max_l >= max_r * new_l) {
+                                max_r = new_r; max_l = new_l;
+                                if (np >= MAXP) return ST_PLIST;
+                                for (int x = np; x > j; --x) P[x] = P[x - 1];
+                                ++np;
+                                P[j].start = k + start_; P[j].finish = cnt + (WLEN - 1) + start_; P[j].r = new_r; P[j].l = new_l;
+                            }
+                        }
+                    }
+                } else ++quiet;
+            } else ++quiet;
+        } else {
+            int start = (l - W + 1 > 0 ? l - W + 1 : 0) + (i + 1 - l);
+            if (l > W) start = i + 2 - W;
+            while (np) { save(start); ++start; }
+            l = 0; ++quiet;
+        }
+        if (quiet >= QUIET) { if (np) return ST_PLIST; break; }      // (the bound the segmentation rests on: checked, not assumed)
+    }
+    return n_res;
+}
+
+// steps 1 and 2: the chunk's segments (first positions, in position order) in seg_start[0 .. ctr[0])
+template <class SyncF> __device__ void find_segments(Chunk c, int tid, int nt, SyncF SYNC) {
+    const int n = c.n;
+    if (tid == 0) { c.ctr[0] = 0; *c.status = ST_OK; *c.n_out = 0; }
+    // ---- prevvalid: every thread a contiguous block; a block's carry-in is the last valid position before it
+    const int B = (n + nt - 1) / nt, lo = tid * B, hi = lo + B < n ? lo + B : n;
+    int *carry = c.seg_cnt;                                      // (free until the segments are known; needs nt <= seg_cap)
+    {
+        int last = -1, l = lo > 0 ? run_len(c, lo - 1, 2) : 0;
+        for (int i = lo; i < hi; ++i) { if (nt4((unsigned char)c.seq[i]) < 4) { if (l < WLEN) ++l; } else l = 0; if (l >= WLEN) last = i; }
+        carry[tid] = last;
+    }
+    SYNC();
+    if (tid == 0) { int m = -1; for (int t = 0; t < nt; ++t) { const int v = carry[t]; carry[t] = m; if (v > m) m = v; } }
+    SYNC();
+    {
+        int last = carry[tid], l = lo > 0 ? run_len(c, lo - 1, 2) : 0;
+        for (int i = lo; i < hi; ++i) { if (nt4((unsigned char)c.seq[i]) < 4) { if (l < WLEN) ++l; } else l = 0; if (l >= WLEN) last = i; c.prevvalid[i] = last; }
+    }
+    SYNC();
+    // ---- 1. where the reference looks for perfect intervals
+    for (int i = tid; i < n; i += nt) {
+        unsigned char tr = 0;
+        if (valid_at(c, i)) {
+            int w[MAXW], rw, L, rv;
+            const int cnt = window_at(c, i, w);
+            window_stats(w, cnt, c.T, rw, L, rv);
+            tr = rw * 10 > L * c.T;
+        }
+        c.trig[i] = tr;
+    }
+    SYNC();
+    // ---- 2. segments: a position that looks, after W + 20 that did not
+    const int QUIET = c.W + 20;
+    for (int i = tid; i < n; i += nt) {
+        if (!c.trig[i]) continue;
+        bool first = true;
+        for (int j = i - 1; j >= 0 && j > i - 1 - QUIET && first; --j) if (c.trig[j]) first = false;
+        if (first) { const int at = atomicAdd(&c.ctr[0], 1); if (at < c.seg_cap) c.seg_start[at] = i; }
+    }
+    SYNC();
+    const int ns = c.ctr[0];
+    if (ns > c.seg_cap) { if (tid == 0) *c.status = ST_CAP; return; }
+    // position order (the appends raced): rank sort through seg_off
+    for (int s = tid; s < ns; s += nt) { int r = 0; for (int t = 0; t < ns; ++t) r += c.seg_start[t] < c.seg_start[s]; c.seg_off[r] = c.seg_start[s]; }
+    SYNC();
+    for (int s = tid; s < ns; s += nt) c.seg_start[s] = c.seg_off[s];
+    SYNC();
+}
+
+// after the count pass: offsets of the segments' outputs, their total, the status (one thread per chunk)
+__device__ inline void finish_counts(const Chunk &c) {
+    if (*c.status != ST_OK) return;
+    const int ns = c.ctr[0];
+    long long tot = 0; int bad = 0;
+    for (int s = 0; s < ns; ++s) { if (c.seg_cnt[s] < 0) { bad = c.seg_cnt[s]; break; } c.seg_off[s] = (int)tot; tot += c.seg_cnt[s]; }
+    if (bad) *c.status = bad; else if (tot > c.cap) *c.status = ST_CAP;
+    *c.n_out = tot;
+}
+
+// the whole chunk on one group of threads (host emulation; the GPU runs the segments of all chunks side by side: sdust_kernel.cu)
+template <class SyncF> __device__ void run_chunk(Chunk c, int tid, int nt, SyncF SYNC) {
+    find_segments(c, tid, nt, SYNC);
+    SYNC();
+    if (*c.status != ST_OK) return;
+    const int ns = c.ctr[0];
+    for (int s = tid; s < ns; s += nt) c.seg_cnt[s] = replay(c, c.seg_start[s], nullptr, nullptr);
+    SYNC();
+    if (tid == 0) finish_counts(c);
+    SYNC();
+    if (*c.status != ST_OK) return;
+    for (int s = tid; s < ns; s += nt) replay(c, c.seg_start[s], c.out_beg + c.seg_off[s], c.out_end + c.seg_off[s]);
+}
+
+} // namespace sdust
+} // namespace lcd

@@ -1,0 +1,34 @@
+"""CPU: the product's K0 device logic (longcalld_b200/csrc/sdust_device.cuh: per-position window statistics, independent segments replayed by one thread each)
+compiled for the host with a one-thread CTA (tests/emu) against the oracle."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import lcd_testlib as T
+
+EMU_DIR = os.path.join(T.ROOT, "tests", "emu")
+
+
+@pytest.fixture(scope="module", params=["libsdust_emu.so", "libsdust_simt_emu.so"])
+def emu(request):
+    """one thread per chunk / 32 cooperating fibers per chunk (tests/emu/simt_emu.h)"""
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR, request.param])
+    return C.CDLL(os.path.join(EMU_DIR, request.param))
+
+
+def test_emu_sdust_vs_oracle(emu, oracle):
+    rng = np.random.default_rng(92)
+    n_iv = 0
+    for it in range(80):
+        n = int(rng.choice([1, 2, 3, 19, 20, 21, 45, 200, 3000, 40000]))
+        seq = T.sdust_sequence(rng, n, lc_every=int(rng.choice([30, 120, 400])), n_frac=float(rng.choice([0.0, 0.002, 0.05])))
+        for Tt, W in ((5, 20), (8, 16), (4, 24)):
+            a, b = T.sdust(emu, "emu_sdust", seq, Tt, W), T.sdust(oracle, "lcd_oracle_sdust", seq, Tt, W)
+            assert a == b, (it, n, Tt, W, a[:3], b[:3])
+            n_iv += len(b)
+    assert n_iv > 5000
+    for seq in (b"", b"A", b"AC", b"ACG", b"N" * 50, b"A" * 300, b"AC" * 200, b"ACGT" * 100 + b"N" + b"T" * 40, b"acgtnACGTN" * 30, b"ANCNGN" * 50 + b"A" * 30, b"AAAN" * 60):
+        assert T.sdust(emu, "emu_sdust", seq) == T.sdust(oracle, "lcd_oracle_sdust", seq), seq[:20]
