@@ -11,7 +11,7 @@
 // passes it at most W + 17 positions after its insertion; an N flushes the list).  So:
 //   1. every position decides by itself, from the last <= W - 2 words, whether the reference would look for perfect intervals there (rw * 10 > L * T);
 //   2. the positions where it would, with less than W + 20 quiet positions between them, form independent SEGMENTS; one thread replays the reference's
-//      pass over one segment, starting from the reconstructed window and an empty P, once to count its output intervals and once to write them
+//      pass over one segment, starting from the reconstructed window and an empty P, into a staging range of its own; the intervals are then packed
 //      (the segments' outputs cannot touch each other: the next segment's first interval starts past anything this one can end with).
 #pragma once
 #include <stdint.h>
@@ -35,6 +35,7 @@ struct Chunk {
     unsigned char *trig;                 // [n] the reference calls find_perfect at this position
     int *seg_start, *seg_cnt, *seg_off;  // [seg_cap] segments: first position, number of output intervals, offset of the first one
     int seg_cap; int *ctr;               // ctr[0]: number of segments
+    long long *stage_beg, *stage_end; long long stage_cap;      // the segments' intervals before they are packed: segment s writes from stage_at(c, s) on
 };
 
 __device__ __forceinline__ int nt4(unsigned char c) {
@@ -43,6 +44,9 @@ __device__ __forceinline__ int nt4(unsigned char c) {
 }
 __device__ __forceinline__ int word_at(const Chunk &c, int i) { return (nt4((unsigned char)c.seq[i - 2]) << 4 | nt4((unsigned char)c.seq[i - 1]) << 2 | nt4((unsigned char)c.seq[i])) & WMSK; }
 __device__ __forceinline__ bool valid_at(const Chunk &c, int i) { return i >= 2 && c.prevvalid[i] == i; }
+// Where segment s stages its intervals.  They are disjoint, do not touch and hold a word each, so their starts are >= 4 apart, and they lie between W before
+// the segment's first position and the next segment's: at most (seg_start[s + 1] - seg_start[s] + W) / 4 + 1 of them, which the spacing below leaves room for.
+__device__ __forceinline__ long long stage_at(const Chunk &c, int s) { return (long long)(c.seg_start[s] / 4) + (long long)s * (c.W / 4 + 3); }
 // run length of A/C/G/T bases ending at i, as far as it matters (capped at lim)
 __device__ __forceinline__ int run_len(const Chunk &c, int i, int lim) { int l = 0; while (l < lim && i - l >= 0 && nt4((unsigned char)c.seq[i - l]) < 4) ++l; return l; }
 
@@ -73,30 +77,35 @@ __device__ __forceinline__ void window_stats(const int *w, int cnt, int T, int &
 // One segment: the reference's pass from position a, starting with the window as it is before a's word is pushed and an empty list of perfect intervals,
 // until W + 20 positions in a row have not looked for perfect intervals (or the sequence ends).  out == nullptr: count only.  Returns the number of output
 // intervals, or a negative status.
-__device__ inline int replay(const Chunk &c, int a, long long *out_beg, long long *out_end) {
+//
+// The state a step touches all the time -- the window's words and the two count tables -- is 160 bytes of bytes (a count is at most W - 2), which the kernel
+// keeps in shared memory: as int arrays in the thread's stack frame it was 1.2 TB/s of DRAM traffic (ncu: L1 / L2 hit rates of 30 % / 26 %) with every SM
+// full of threads, each on its own path.
+struct Hot { unsigned char ring[MAXW], cw[WTOT], cv[WTOT], pad[4]; };       // (164 bytes = 41 words: neighbouring threads' copies start in different banks)
+__device__ inline int replay(const Chunk &c, int a, long long *out_beg, long long *out_end, long long lim, Hot &hot) {
     const int T = c.T, W = c.W, maxn = W - WLEN + 1, QUIET = W + 20;
-    int ring[MAXW], front = 0, cnt = 0;
-    int cv[WTOT], cw[WTOT];
+    unsigned char *ring = hot.ring, *cv = hot.cv, *cw = hot.cw;
+    int front = 0, cnt = 0;
     for (int x = 0; x < WTOT; ++x) { cv[x] = 0; cw[x] = 0; }
     int rv = 0, rw = 0, L = 0;
     {   // the window before a: the words that end at the last valid positions before a
         int w0[MAXW];
         cnt = a >= 1 ? window_at(c, a - 1, w0) : 0;
-        for (int x = 0; x < cnt; ++x) { ring[x] = w0[x]; cw[w0[x]]++; }
+        for (int x = 0; x < cnt; ++x) { ring[x] = (unsigned char)w0[x]; cw[w0[x]]++; }
         int rw0, L0, rv0; window_stats(w0, cnt, T, rw0, L0, rv0);
         rw = rw0; L = L0; rv = rv0;
         for (int x = cnt - L; x < cnt; ++x) cv[w0[x]]++;
     }
     int l = a >= 1 ? run_len(c, a - 1, W + 2) : 0;               // (only min(l, W) and l >= WLEN matter below)
-    struct Perf { int start, finish, r, l; } P[MAXP]; int np = 0;
-    int n_res = 0; long long last_beg = 0, last_end = 0; bool have_last = false;
+    struct Perf { int start, finish; short r, l; } P[MAXP]; int np = 0;      // (r <= (W - 2)(W - 3) / 2, l <= W - 2)
+    long long n_res = 0; long long last_beg = 0, last_end = 0; bool have_last = false, over = false;
     int quiet = 0;
     auto save = [&](int start) {                                 // save_masked_regions (src/sdust.c:87-103)
         if (np == 0 || P[np - 1].start >= start) return;
         const Perf p = P[np - 1];
         bool saved = false;
-        if (have_last && p.start <= last_end) { saved = true; if (p.finish > last_end) { last_end = p.finish; if (out_end) out_end[n_res - 1] = c.base + last_end; } }
-        if (!saved) { last_beg = p.start; last_end = p.finish; have_last = true; if (out_beg) { out_beg[n_res] = c.base + last_beg; out_end[n_res] = c.base + last_end; } ++n_res; }
+        if (have_last && p.start <= last_end) { saved = true; if (p.finish > last_end) { last_end = p.finish; if (!over) out_end[n_res - 1] = c.base + last_end; } }
+        if (!saved) { last_beg = p.start; last_end = p.finish; have_last = true; if (n_res < lim) { out_beg[n_res] = c.base + last_beg; out_end[n_res] = c.base + last_end; } else over = true; ++n_res; }
         int i = np - 1; while (i >= 0 && P[i].start < start) --i;
         np = i + 1;
     };
@@ -124,12 +133,11 @@ __device__ inline int replay(const Chunk &c, int a, long long *out_beg, long lon
                 }
                 if (rw * 10 > L * T) {                            // find_perfect (src/sdust.c:105-131)
                     quiet = 0;
-                    int cc[WTOT];
-                    for (int x = 0; x < WTOT; ++x) cc[x] = cv[x];
+                    // (the reference counts on in a copy of cv; here cv itself, and the loop after this one takes the words out again)
                     int r = rv, max_r = 0, max_l = 0;
                     for (int k = cnt - L - 1; k >= 0; --k) {
                         const int tt = ring[(front + k) % MAXW];
-                        r += cc[tt]++;
+                        r += cv[tt]++;
                         const int new_r = r, new_l = cnt - k - 1;
                         if (new_r * 10 > T * new_l) {
                             int j;
@@ -140,10 +148,11 @@ __device__ inline int replay(const Chunk &c, int a, long long *out_beg, long lon
                                 if (np >= MAXP) return ST_PLIST;
                                 for (int x = np; x > j; --x) P[x] = P[x - 1];
                                 ++np;
-                                P[j].start = k + start_; P[j].finish = cnt + (WLEN - 1) + start_; P[j].r = new_r; P[j].l = new_l;
+                                P[j].start = k + start_; P[j].finish = cnt + (WLEN - 1) + start_; P[j].r = (short)new_r; P[j].l = (short)new_l;
                             }
                         }
                     }
+                    for (int k = cnt - L - 1; k >= 0; --k) cv[ring[(front + k) % MAXW]]--;
                 } else ++quiet;
             } else ++quiet;
         } else {
@@ -154,7 +163,7 @@ __device__ inline int replay(const Chunk &c, int a, long long *out_beg, long lon
         }
         if (quiet >= QUIET) { if (np) return ST_PLIST; break; }      // (the bound the segmentation rests on: checked, not assumed)
     }
-    return n_res;
+    return over ? ST_CAP : (int)n_res;
 }
 
 // steps 1 and 2: the chunk's segments (first positions, in position order) in seg_start[0 .. ctr[0])
@@ -218,17 +227,28 @@ __device__ inline void finish_counts(const Chunk &c) {
 }
 
 // the whole chunk on one group of threads (host emulation; the GPU runs the segments of all chunks side by side: sdust_kernel.cu)
+// a segment's replay into its staging range; pack_segment moves the intervals to their place in the chunk's output
+__device__ inline void stage_segment(const Chunk &c, int s, Hot &hot) {
+    const long long at = stage_at(c, s), lim = (s + 1 < c.ctr[0] ? stage_at(c, s + 1) : c.stage_cap) - at;
+    c.seg_cnt[s] = replay(c, c.seg_start[s], c.stage_beg + at, c.stage_end + at, lim, hot);
+}
+__device__ inline void pack_segment(const Chunk &c, int s) {
+    const long long at = stage_at(c, s); const int o = c.seg_off[s];
+    for (int x = 0; x < c.seg_cnt[s]; ++x) { c.out_beg[o + x] = c.stage_beg[at + x]; c.out_end[o + x] = c.stage_end[at + x]; }
+}
+
+// the whole chunk on one group of threads (host emulation; the GPU runs the segments of all chunks side by side: sdust_kernel.cu)
 template <class SyncF> __device__ void run_chunk(Chunk c, int tid, int nt, SyncF SYNC) {
     find_segments(c, tid, nt, SYNC);
     SYNC();
     if (*c.status != ST_OK) return;
     const int ns = c.ctr[0];
-    for (int s = tid; s < ns; s += nt) c.seg_cnt[s] = replay(c, c.seg_start[s], nullptr, nullptr);
+    { Hot hot; for (int s = tid; s < ns; s += nt) stage_segment(c, s, hot); }
     SYNC();
     if (tid == 0) finish_counts(c);
     SYNC();
     if (*c.status != ST_OK) return;
-    for (int s = tid; s < ns; s += nt) replay(c, c.seg_start[s], c.out_beg + c.seg_off[s], c.out_end + c.seg_off[s]);
+    for (int s = tid; s < ns; s += nt) pack_segment(c, s);
 }
 
 } // namespace sdust

@@ -16,15 +16,15 @@ sdust_segments_kernel(const Chunk *chunks, int n) {
     for (int i = blockIdx.x; i < n; i += gridDim.x) { find_segments(chunks[i], (int)threadIdx.x, THREADS, CtaSync()); __syncthreads(); }
 }
 
-// pass 0 counts a segment's intervals, pass 1 writes them at the segment's offset
+// pass 0 replays a segment into its staging range, pass 1 packs the staged intervals at the segment's offset
 __global__ void __launch_bounds__(RTHREADS)
 sdust_replay_kernel(const Chunk *chunks, int pass) {
-    const Chunk &c = chunks[blockIdx.y];
+    __shared__ Hot hot[RTHREADS];
+    const Chunk c = chunks[blockIdx.y];
     if (*c.status != ST_OK) return;
     const int s = (int)(blockIdx.x * RTHREADS + threadIdx.x);
     if (s >= c.ctr[0]) return;
-    if (pass == 0) c.seg_cnt[s] = replay(c, c.seg_start[s], nullptr, nullptr);
-    else replay(c, c.seg_start[s], c.out_beg + c.seg_off[s], c.out_end + c.seg_off[s]);
+    if (pass == 0) stage_segment(c, s, hot[threadIdx.x]); else pack_segment(c, s);
 }
 
 __global__ void sdust_offsets_kernel(const Chunk *chunks, int n) {
@@ -58,7 +58,8 @@ struct SdustPlan : Plan {
             const size_t L = (size_t)in[i].l_seq, cap = L / 4 + 16, seg_cap = L / (size_t)(in[i].W + 20) + THREADS + 16;
             caps[i] = (long long)cap;
             beg_off[i] = take(work, cap * 8); end_off[i] = take(work, cap * 8);
-            for (size_t b : { (L + 1) * 4, L + 1, seg_cap * 4, seg_cap * 4, seg_cap * 4, (size_t)16 }) wk[i].push_back(take(work, b));
+            const size_t stage_cap = L / 4 + seg_cap * (size_t)(in[i].W / 4 + 3) + 16;
+            for (size_t b : { (L + 1) * 4, L + 1, seg_cap * 4, seg_cap * 4, seg_cap * 4, (size_t)16, stage_cap * 8, stage_cap * 8 }) wk[i].push_back(take(work, b));
             tot_bases += (long long)L;
         }
         std::vector<uint8_t> h(seq_bytes + 16, 0);
@@ -74,6 +75,7 @@ struct SdustPlan : Plan {
             c.prevvalid = (int *)(w + wk[i][0]); c.trig = w + wk[i][1]; c.seg_start = (int *)(w + wk[i][2]); c.seg_cnt = (int *)(w + wk[i][3]); c.seg_off = (int *)(w + wk[i][4]);
             c.seg_cap = (int)((size_t)in[i].l_seq / (size_t)(in[i].W + 20) + THREADS + 16); c.ctr = (int *)(w + wk[i][5]);
             max_seg_cap = std::max(max_seg_cap, c.seg_cap);
+            c.stage_beg = (long long *)(w + wk[i][6]); c.stage_end = (long long *)(w + wk[i][7]); c.stage_cap = (long long)((size_t)in[i].l_seq / 4 + (size_t)c.seg_cap * (size_t)(in[i].W / 4 + 3) + 16);
         }
         if (d_chunks.upload(chunks.data(), n, s)) return -1;
         LCD_CUDA_OK(cudaStreamSynchronize(s));      // host staging vector goes out of scope

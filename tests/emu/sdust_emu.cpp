@@ -17,6 +17,8 @@ extern "C" int emu_sdust(const uint8_t *seq, int l_seq, int T, int W, int64_t *b
     c.seq = (const char *)seq; c.n = l_seq; c.T = T; c.W = W; c.base = 0;
     c.out_beg = ob.data(); c.out_end = oe.data(); c.cap = cap; c.n_out = &n_out; c.status = &status;
     c.prevvalid = pv.data(); c.trig = tr.data(); c.seg_start = ss.data(); c.seg_cnt = sc.data(); c.seg_off = so.data(); c.seg_cap = seg_cap; c.ctr = ctr.data();
+    std::vector<long long> sb((size_t)l_seq / 4 + (size_t)seg_cap * (W / 4 + 3) + 16, 0x5555555555555555LL), se(sb.size(), 0x5555555555555555LL);
+    c.stage_beg = sb.data(); c.stage_end = se.data(); c.stage_cap = (long long)sb.size();
     run_chunk(c, 0, 1, NoSync());
     if (status) return status;
     for (long long k = 0; k < n_out; ++k) { beg[k] = ob[k]; end[k] = oe[k]; }
