@@ -99,7 +99,7 @@ __device__ inline int replay(const Chunk &c, int a, long long *out_beg, long lon
     int l = a >= 1 ? run_len(c, a - 1, W + 2) : 0;               // (only min(l, W) and l >= WLEN matter below)
     struct Perf { int start, finish; short r, l; } P[MAXP]; int np = 0;      // (r <= (W - 2)(W - 3) / 2, l <= W - 2)
     long long n_res = 0; long long last_beg = 0, last_end = 0; bool have_last = false, over = false;
-    int quiet = 0;
+    int quiet = 0, err = 0;
     auto save = [&](int start) {                                 // save_masked_regions (src/sdust.c:87-103)
         if (np == 0 || P[np - 1].start >= start) return;
         const Perf p = P[np - 1];
@@ -145,10 +145,12 @@ __device__ inline int replay(const Chunk &c, int a, long long *out_beg, long lon
                                 if (max_r == 0 || P[j].r * max_l > max_r * P[j].l) { max_r = P[j].r; max_l = P[j].l; }
                             if (max_r == 0 || new_r * max_l >= max_r * new_l) {
                                 max_r = new_r; max_l = new_l;
-                                if (np >= MAXP) return ST_PLIST;
-                                for (int x = np; x > j; --x) P[x] = P[x - 1];
-                                ++np;
-                                P[j].start = k + start_; P[j].finish = cnt + (WLEN - 1) + start_; P[j].r = (short)new_r; P[j].l = (short)new_l;
+                                if (np >= MAXP) err = ST_PLIST;               // (reported at the end; no early exit: the threads of a warp stay in step)
+                                else {
+                                    for (int x = np; x > j; --x) P[x] = P[x - 1];
+                                    ++np;
+                                    P[j].start = k + start_; P[j].finish = cnt + (WLEN - 1) + start_; P[j].r = (short)new_r; P[j].l = (short)new_l;
+                                }
                             }
                         }
                     }
@@ -161,16 +163,15 @@ __device__ inline int replay(const Chunk &c, int a, long long *out_beg, long lon
             while (np) { save(start); ++start; }
             l = 0; ++quiet;
         }
-        if (quiet >= QUIET) { if (np) return ST_PLIST; break; }      // (the bound the segmentation rests on: checked, not assumed)
+        if (quiet >= QUIET) { if (np) err = ST_PLIST; break; }      // (the bound the segmentation rests on: checked, not assumed)
     }
-    return over ? ST_CAP : (int)n_res;
+    return err ? err : over ? ST_CAP : (int)n_res;
 }
 
-// steps 1 and 2: the chunk's segments (first positions, in position order) in seg_start[0 .. ctr[0])
-template <class SyncF> __device__ void find_segments(Chunk c, int tid, int nt, SyncF SYNC) {
+// prevvalid[]: every thread a contiguous block; a block's carry-in is the last valid position before it
+template <class SyncF> __device__ void scan_valid(const Chunk &c, int tid, int nt, SyncF SYNC) {
     const int n = c.n;
     if (tid == 0) { c.ctr[0] = 0; *c.status = ST_OK; *c.n_out = 0; }
-    // ---- prevvalid: every thread a contiguous block; a block's carry-in is the last valid position before it
     const int B = (n + nt - 1) / nt, lo = tid * B, hi = lo + B < n ? lo + B : n;
     int *carry = c.seg_cnt;                                      // (free until the segments are known; needs nt <= seg_cap)
     {
@@ -186,20 +187,21 @@ template <class SyncF> __device__ void find_segments(Chunk c, int tid, int nt, S
         for (int i = lo; i < hi; ++i) { if (nt4((unsigned char)c.seq[i]) < 4) { if (l < WLEN) ++l; } else l = 0; if (l >= WLEN) last = i; c.prevvalid[i] = last; }
     }
     SYNC();
-    // ---- 1. where the reference looks for perfect intervals
-    for (int i = tid; i < n; i += nt) {
-        unsigned char tr = 0;
-        if (valid_at(c, i)) {
-            int w[MAXW], rw, L, rv;
-            const int cnt = window_at(c, i, w);
-            window_stats(w, cnt, c.T, rw, L, rv);
-            tr = rw * 10 > L * c.T;
-        }
-        c.trig[i] = tr;
+}
+// 1. does the reference look for perfect intervals at position i?
+__device__ __forceinline__ void decide_at(const Chunk &c, int i) {
+    unsigned char tr = 0;
+    if (valid_at(c, i)) {
+        int w[MAXW], rw, L, rv;
+        const int cnt = window_at(c, i, w);
+        window_stats(w, cnt, c.T, rw, L, rv);
+        tr = rw * 10 > L * c.T;
     }
-    SYNC();
-    // ---- 2. segments: a position that looks, after W + 20 that did not
-    const int QUIET = c.W + 20;
+    c.trig[i] = tr;
+}
+// 2. segments: a position that looks, after W + 20 that did not; their first positions in position order in seg_start[0 .. ctr[0])
+template <class SyncF> __device__ void collect_segments(const Chunk &c, int tid, int nt, SyncF SYNC) {
+    const int n = c.n, QUIET = c.W + 20;
     for (int i = tid; i < n; i += nt) {
         if (!c.trig[i]) continue;
         bool first = true;
@@ -214,6 +216,12 @@ template <class SyncF> __device__ void find_segments(Chunk c, int tid, int nt, S
     SYNC();
     for (int s = tid; s < ns; s += nt) c.seg_start[s] = c.seg_off[s];
     SYNC();
+}
+template <class SyncF> __device__ void find_segments(const Chunk &c, int tid, int nt, SyncF SYNC) {
+    scan_valid(c, tid, nt, SYNC);
+    for (int i = tid; i < c.n; i += nt) decide_at(c, i);
+    SYNC();
+    collect_segments(c, tid, nt, SYNC);
 }
 
 // after the count pass: offsets of the segments' outputs, their total, the status (one thread per chunk)

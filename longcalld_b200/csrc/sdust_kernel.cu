@@ -11,9 +11,19 @@ constexpr int THREADS = 1024;       // a chunk's segment search: one CTA
 constexpr int RTHREADS = 128;       // the replays: one thread per segment, the segments of all chunks side by side
 struct CtaSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
 
+// step 0 (prevvalid) and step 2 (the segments) of a chunk on one CTA; step 1 in between is a thread per position over all chunks
 __global__ void __launch_bounds__(THREADS)
-sdust_segments_kernel(const Chunk *chunks, int n) {
-    for (int i = blockIdx.x; i < n; i += gridDim.x) { find_segments(chunks[i], (int)threadIdx.x, THREADS, CtaSync()); __syncthreads(); }
+sdust_segments_kernel(const Chunk *chunks, int n, int step) {
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const Chunk c = chunks[i];
+        if (step == 0) scan_valid(c, (int)threadIdx.x, THREADS, CtaSync()); else collect_segments(c, (int)threadIdx.x, THREADS, CtaSync());
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256)
+sdust_decide_kernel(const Chunk *chunks) {
+    const Chunk c = chunks[blockIdx.y];
+    for (int i = (int)(blockIdx.x * 256 + threadIdx.x); i < c.n; i += (int)(gridDim.x * 256)) decide_at(c, i);
 }
 
 // pass 0 replays a segment into its staging range, pass 1 packs the staged intervals at the segment's offset
@@ -36,7 +46,7 @@ struct SdustPlan : Plan {
     bool uses_pool() const override { return false; }
     std::vector<Chunk> chunks; std::vector<size_t> hdr_off, beg_off, end_off; std::vector<long long> caps;
     DevBuf<uint8_t> d_seq, d_work; DevBuf<Chunk> d_chunks;
-    long long tot_bases = 0; int max_seg_cap = 0;
+    long long tot_bases = 0; int max_seg_cap = 0, max_len = 0;
 
     int build(int n_, const lcd_sdust_input_t *in) {
         n = n_;
@@ -74,7 +84,7 @@ struct SdustPlan : Plan {
             c.n_out = (long long *)(w + hdr_off[i]); c.status = (int *)(w + hdr_off[i] + 8);
             c.prevvalid = (int *)(w + wk[i][0]); c.trig = w + wk[i][1]; c.seg_start = (int *)(w + wk[i][2]); c.seg_cnt = (int *)(w + wk[i][3]); c.seg_off = (int *)(w + wk[i][4]);
             c.seg_cap = (int)((size_t)in[i].l_seq / (size_t)(in[i].W + 20) + THREADS + 16); c.ctr = (int *)(w + wk[i][5]);
-            max_seg_cap = std::max(max_seg_cap, c.seg_cap);
+            max_seg_cap = std::max(max_seg_cap, c.seg_cap); max_len = std::max(max_len, c.n);
             c.stage_beg = (long long *)(w + wk[i][6]); c.stage_end = (long long *)(w + wk[i][7]); c.stage_cap = (long long)((size_t)in[i].l_seq / 4 + (size_t)c.seg_cap * (size_t)(in[i].W / 4 + 3) + 16);
         }
         if (d_chunks.upload(chunks.data(), n, s)) return -1;
@@ -86,12 +96,15 @@ struct SdustPlan : Plan {
         Context &c = ctx();
         if (n == 0) return 0;
         const dim3 rgrid((unsigned)((max_seg_cap + RTHREADS - 1) / RTHREADS), (unsigned)n);
-        sdust_segments_kernel<<<std::min(n, c.sm_count * 2), THREADS, 0, s>>>(d_chunks.p, n);
+        const dim3 dgrid((unsigned)std::max(1, std::min((max_len + 255) / 256, 64)), (unsigned)n);
+        sdust_segments_kernel<<<std::min(n, c.sm_count * 2), THREADS, 0, s>>>(d_chunks.p, n, 0);
+        sdust_decide_kernel<<<dgrid, 256, 0, s>>>(d_chunks.p);
+        sdust_segments_kernel<<<std::min(n, c.sm_count * 2), THREADS, 0, s>>>(d_chunks.p, n, 1);
         sdust_replay_kernel<<<rgrid, RTHREADS, 0, s>>>(d_chunks.p, 0);
         sdust_offsets_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_chunks.p, n);
         sdust_replay_kernel<<<rgrid, RTHREADS, 0, s>>>(d_chunks.p, 1);
         LCD_CUDA_OK(cudaGetLastError());
-        c.launches += 4;
+        c.launches += 6;
         return 0;
     }
     int work_units(cudaStream_t, uint64_t *units) override { *units = (uint64_t)tot_bases; return 0; }      // reference bases scanned
