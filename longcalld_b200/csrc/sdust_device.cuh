@@ -34,7 +34,7 @@ struct Chunk {
     int *prevvalid;                      // [n] last position <= i at which a word (three A/C/G/T bases in a row) ends
     unsigned char *trig;                 // [n] the reference calls find_perfect at this position
     int *seg_start, *seg_cnt, *seg_off;  // [seg_cap] segments: first position, number of output intervals, offset of the first one
-    int seg_cap; int *ctr;               // ctr[0]: number of segments
+    int seg_cap; int *ctr;               // ctr[0]: number of segments, ctr[1]: the next one to replay
     long long *stage_beg, *stage_end; long long stage_cap;      // the segments' intervals before they are packed: segment s writes from stage_at(c, s) on
 };
 
@@ -74,42 +74,49 @@ __device__ __forceinline__ void window_stats(const int *w, int cnt, int T, int &
     }
 }
 
-// One segment: the reference's pass from position a, starting with the window as it is before a's word is pushed and an empty list of perfect intervals,
-// until W + 20 positions in a row have not looked for perfect intervals (or the sequence ends).  out == nullptr: count only.  Returns the number of output
-// intervals, or a negative status.
+// One segment: the reference's pass from its first position, starting with the window as it is before that position's word is pushed and an empty list of
+// perfect intervals, until W + 20 positions in a row have not looked for perfect intervals (or the sequence ends); its intervals go to its staging range,
+// their number (or a negative status) to seg_cnt[].
 //
 // The state a step touches all the time -- the window's words and the two count tables -- is 160 bytes of bytes (a count is at most W - 2), which the kernel
 // keeps in shared memory: as int arrays in the thread's stack frame it was 1.2 TB/s of DRAM traffic (ncu: L1 / L2 hit rates of 30 % / 26 %) with every SM
 // full of threads, each on its own path.
 struct Hot { unsigned char ring[MAXW], cw[WTOT], cv[WTOT], pad[4]; };       // (164 bytes = 41 words: neighbouring threads' copies start in different banks)
-__device__ inline int replay(const Chunk &c, int a, long long *out_beg, long long *out_end, long long lim, Hot &hot) {
-    const int T = c.T, W = c.W, maxn = W - WLEN + 1, QUIET = W + 20;
+// fetch() hands the thread its next segment (or -1): the GPU's threads take them from a counter of the chunk, so that a thread whose segment was short goes
+// on with another one, and the loop is one body per position -- a new segment is set up inside it -- so that the threads of a warp meet again at every position.
+template <class Fetch> __device__ inline void replay_segments(const Chunk &c, Hot &hot, Fetch fetch) {
+    const int T = c.T, W = c.W, maxn = W - WLEN + 1, QUIET = W + 20, ns = c.ctr[0];
     unsigned char *ring = hot.ring, *cv = hot.cv, *cw = hot.cw;
-    int front = 0, cnt = 0;
-    for (int x = 0; x < WTOT; ++x) { cv[x] = 0; cw[x] = 0; }
-    int rv = 0, rw = 0, L = 0;
-    {   // the window before a: the words that end at the last valid positions before a
-        int w0[MAXW];
-        cnt = a >= 1 ? window_at(c, a - 1, w0) : 0;
-        for (int x = 0; x < cnt; ++x) { ring[x] = (unsigned char)w0[x]; cw[w0[x]]++; }
-        int rw0, L0, rv0; window_stats(w0, cnt, T, rw0, L0, rv0);
-        rw = rw0; L = L0; rv = rv0;
-        for (int x = cnt - L; x < cnt; ++x) cv[w0[x]]++;
-    }
-    int l = a >= 1 ? run_len(c, a - 1, W + 2) : 0;               // (only min(l, W) and l >= WLEN matter below)
     struct Perf { int start, finish; short r, l; } P[MAXP]; int np = 0;      // (r <= (W - 2)(W - 3) / 2, l <= W - 2)
-    long long n_res = 0; long long last_beg = 0, last_end = 0; bool have_last = false, over = false;
-    int quiet = 0, err = 0;
+    int front = 0, cnt = 0, rv = 0, rw = 0, L = 0, l = 0, quiet = 0, err = 0, i = 0;
+    long long n_res = 0, last_beg = 0, last_end = 0, lim = 0; bool have_last = false, over = false;
+    long long *out_beg = nullptr, *out_end = nullptr;
     auto save = [&](int start) {                                 // save_masked_regions (src/sdust.c:87-103)
         if (np == 0 || P[np - 1].start >= start) return;
         const Perf p = P[np - 1];
         bool saved = false;
         if (have_last && p.start <= last_end) { saved = true; if (p.finish > last_end) { last_end = p.finish; if (!over) out_end[n_res - 1] = c.base + last_end; } }
         if (!saved) { last_beg = p.start; last_end = p.finish; have_last = true; if (n_res < lim) { out_beg[n_res] = c.base + last_beg; out_end[n_res] = c.base + last_end; } else over = true; ++n_res; }
-        int i = np - 1; while (i >= 0 && P[i].start < start) --i;
-        np = i + 1;
+        int x = np - 1; while (x >= 0 && P[x].start < start) --x;
+        np = x + 1;
     };
-    for (int i = a; i <= c.n; ++i) {
+    int s = fetch();
+    bool fresh = true;
+    while (s >= 0) {
+        if (fresh) {       // the window before the segment's first position: the words that end at the last valid positions before it; no perfect intervals
+            fresh = false;
+            const int a = c.seg_start[s];
+            const long long at = stage_at(c, s);
+            out_beg = c.stage_beg + at; out_end = c.stage_end + at; lim = (s + 1 < ns ? stage_at(c, s + 1) : c.stage_cap) - at;
+            for (int x = 0; x < WTOT; ++x) { cv[x] = 0; cw[x] = 0; }
+            int w0[MAXW];
+            front = 0; cnt = a >= 1 ? window_at(c, a - 1, w0) : 0;
+            for (int x = 0; x < cnt; ++x) { ring[x] = (unsigned char)w0[x]; cw[w0[x]]++; }
+            window_stats(w0, cnt, T, rw, L, rv);
+            for (int x = cnt - L; x < cnt; ++x) cv[w0[x]]++;
+            l = a >= 1 ? run_len(c, a - 1, W + 2) : 0;           // (only min(l, W) and l >= WLEN matter below)
+            np = 0; n_res = 0; have_last = false; over = false; quiet = 0; err = 0; i = a;
+        }
         const int b = i < c.n ? nt4((unsigned char)c.seq[i]) : 4;
         if (b < 4) {
             if (l < W + 2) ++l;
@@ -119,37 +126,40 @@ __device__ inline int replay(const Chunk &c, int a, long long *out_beg, long lon
                 const int start_ = l > W ? i + 1 - W : start;
                 save(start_);
                 if (cnt >= maxn) {                                // shift_window (src/sdust.c:66-85)
-                    const int s = ring[front]; front = (front + 1) % MAXW; --cnt;
-                    rw -= --cw[s];
-                    if (L > cnt) { --L; rv -= --cv[s]; }
+                    const int o = ring[front]; front = (front + 1) % MAXW; --cnt;
+                    rw -= --cw[o];
+                    if (L > cnt) { --L; rv -= --cv[o]; }
                 }
                 ring[(front + cnt) % MAXW] = t; ++cnt;
                 ++L;
                 rw += cw[t]++;
                 rv += cv[t]++;
                 if (cv[t] * 10 > (T << 1)) {
-                    int s;
-                    do { s = ring[(front + cnt - L) % MAXW]; rv -= --cv[s]; --L; } while (s != t);
+                    int o;
+                    do { o = ring[(front + cnt - L) % MAXW]; rv -= --cv[o]; --L; } while (o != t);
                 }
                 if (rw * 10 > L * T) {                            // find_perfect (src/sdust.c:105-131)
                     quiet = 0;
                     // (the reference counts on in a copy of cv; here cv itself, and the loop after this one takes the words out again)
-                    int r = rv, max_r = 0, max_l = 0;
+                    // The reference scans P from its head for every k: the intervals that start at or after k + start_, a prefix that only grows as k
+                    // falls, for the best r / l among them -- a running maximum (an interval is inserted only when it is at least as good), so the scan
+                    // goes on from where the previous k's stopped: O(np + W) per position instead of O(np * W), the same answers.
+                    int r = rv, max_r = 0, max_l = 0, j = 0;
                     for (int k = cnt - L - 1; k >= 0; --k) {
                         const int tt = ring[(front + k) % MAXW];
                         r += cv[tt]++;
                         const int new_r = r, new_l = cnt - k - 1;
                         if (new_r * 10 > T * new_l) {
-                            int j;
-                            for (j = 0; j < np && P[j].start >= k + start_; ++j)
+                            for (; j < np && P[j].start >= k + start_; ++j)
                                 if (max_r == 0 || P[j].r * max_l > max_r * P[j].l) { max_r = P[j].r; max_l = P[j].l; }
                             if (max_r == 0 || new_r * max_l >= max_r * new_l) {
                                 max_r = new_r; max_l = new_l;
-                                if (np >= MAXP) err = ST_PLIST;               // (reported at the end; no early exit: the threads of a warp stay in step)
+                                if (np >= MAXP) err = ST_PLIST;               // (reported with the segment's count; no early exit)
                                 else {
                                     for (int x = np; x > j; --x) P[x] = P[x - 1];
                                     ++np;
                                     P[j].start = k + start_; P[j].finish = cnt + (WLEN - 1) + start_; P[j].r = (short)new_r; P[j].l = (short)new_l;
+                                    ++j;                                        // (the new one is the maximum itself)
                                 }
                             }
                         }
@@ -163,15 +173,19 @@ __device__ inline int replay(const Chunk &c, int a, long long *out_beg, long lon
             while (np) { save(start); ++start; }
             l = 0; ++quiet;
         }
-        if (quiet >= QUIET) { if (np) err = ST_PLIST; break; }      // (the bound the segmentation rests on: checked, not assumed)
+        ++i;
+        if (quiet >= QUIET || i > c.n) {                          // the segment is over
+            if (quiet >= QUIET && np) err = ST_PLIST;             // (the bound the segmentation rests on: checked, not assumed)
+            c.seg_cnt[s] = err ? err : over ? ST_CAP : (int)n_res;
+            s = fetch(); fresh = true;
+        }
     }
-    return err ? err : over ? ST_CAP : (int)n_res;
 }
 
 // prevvalid[]: every thread a contiguous block; a block's carry-in is the last valid position before it
 template <class SyncF> __device__ void scan_valid(const Chunk &c, int tid, int nt, SyncF SYNC) {
     const int n = c.n;
-    if (tid == 0) { c.ctr[0] = 0; *c.status = ST_OK; *c.n_out = 0; }
+    if (tid == 0) { c.ctr[0] = 0; c.ctr[1] = 0; *c.status = ST_OK; *c.n_out = 0; }
     const int B = (n + nt - 1) / nt, lo = tid * B, hi = lo + B < n ? lo + B : n;
     int *carry = c.seg_cnt;                                      // (free until the segments are known; needs nt <= seg_cap)
     {
@@ -188,16 +202,43 @@ template <class SyncF> __device__ void scan_valid(const Chunk &c, int tid, int n
     }
     SYNC();
 }
-// 1. does the reference look for perfect intervals at position i?
-__device__ __forceinline__ void decide_at(const Chunk &c, int i) {
-    unsigned char tr = 0;
-    if (valid_at(c, i)) {
-        int w[MAXW], rw, L, rv;
-        const int cnt = window_at(c, i, w);
-        window_stats(w, cnt, c.T, rw, L, rv);
-        tr = rw * 10 > L * c.T;
+// 1. does the reference look for perfect intervals at position i?  For a run of positions [i0, i1): the window before i0 reconstructed once (O(W^2)), then
+// the reference's own window update per position (a position by itself cost ~3 500 instructions: 8 ms of a 28 ms chain for 50 Mb).
+constexpr int DECIDE_RUN = 64;
+__device__ inline void decide_run(const Chunk &c, Hot &hot, int i0, int i1) {
+    const int T = c.T, W = c.W, maxn = W - WLEN + 1;
+    unsigned char *ring = hot.ring, *cv = hot.cv, *cw = hot.cw;
+    for (int x = 0; x < WTOT; ++x) { cv[x] = 0; cw[x] = 0; }
+    int w0[MAXW], rw, L, rv, front = 0;
+    int cnt = i0 >= 1 ? window_at(c, i0 - 1, w0) : 0;
+    for (int x = 0; x < cnt; ++x) { ring[x] = (unsigned char)w0[x]; cw[w0[x]]++; }
+    window_stats(w0, cnt, T, rw, L, rv);
+    for (int x = cnt - L; x < cnt; ++x) cv[w0[x]]++;
+    int l = i0 >= 1 ? run_len(c, i0 - 1, WLEN) : 0;               // (only l >= WLEN matters here)
+    for (int i = i0; i < i1; ++i) {
+        unsigned char tr = 0;
+        if (nt4((unsigned char)c.seq[i]) < 4) {
+            if (l < WLEN) ++l;
+            if (l >= WLEN) {
+                const int t = word_at(c, i);
+                if (cnt >= maxn) {                                // shift_window (src/sdust.c:66-85)
+                    const int o = ring[front]; front = (front + 1) % MAXW; --cnt;
+                    rw -= --cw[o];
+                    if (L > cnt) { --L; rv -= --cv[o]; }
+                }
+                ring[(front + cnt) % MAXW] = t; ++cnt;
+                ++L;
+                rw += cw[t]++;
+                rv += cv[t]++;
+                if (cv[t] * 10 > (T << 1)) {
+                    int o;
+                    do { o = ring[(front + cnt - L) % MAXW]; rv -= --cv[o]; --L; } while (o != t);
+                }
+                tr = rw * 10 > L * T;
+            }
+        } else l = 0;
+        c.trig[i] = tr;
     }
-    c.trig[i] = tr;
 }
 // 2. segments: a position that looks, after W + 20 that did not; their first positions in position order in seg_start[0 .. ctr[0])
 template <class SyncF> __device__ void collect_segments(const Chunk &c, int tid, int nt, SyncF SYNC) {
@@ -219,7 +260,7 @@ template <class SyncF> __device__ void collect_segments(const Chunk &c, int tid,
 }
 template <class SyncF> __device__ void find_segments(const Chunk &c, int tid, int nt, SyncF SYNC) {
     scan_valid(c, tid, nt, SYNC);
-    for (int i = tid; i < c.n; i += nt) decide_at(c, i);
+    { Hot hot; for (int i0 = tid * DECIDE_RUN; i0 < c.n; i0 += nt * DECIDE_RUN) decide_run(c, hot, i0, i0 + DECIDE_RUN < c.n ? i0 + DECIDE_RUN : c.n); }
     SYNC();
     collect_segments(c, tid, nt, SYNC);
 }
@@ -235,11 +276,7 @@ __device__ inline void finish_counts(const Chunk &c) {
 }
 
 // the whole chunk on one group of threads (host emulation; the GPU runs the segments of all chunks side by side: sdust_kernel.cu)
-// a segment's replay into its staging range; pack_segment moves the intervals to their place in the chunk's output
-__device__ inline void stage_segment(const Chunk &c, int s, Hot &hot) {
-    const long long at = stage_at(c, s), lim = (s + 1 < c.ctr[0] ? stage_at(c, s + 1) : c.stage_cap) - at;
-    c.seg_cnt[s] = replay(c, c.seg_start[s], c.stage_beg + at, c.stage_end + at, lim, hot);
-}
+// pack_segment moves a segment's staged intervals to their place in the chunk's output
 __device__ inline void pack_segment(const Chunk &c, int s) {
     const long long at = stage_at(c, s); const int o = c.seg_off[s];
     for (int x = 0; x < c.seg_cnt[s]; ++x) { c.out_beg[o + x] = c.stage_beg[at + x]; c.out_end[o + x] = c.stage_end[at + x]; }
@@ -251,7 +288,7 @@ template <class SyncF> __device__ void run_chunk(Chunk c, int tid, int nt, SyncF
     SYNC();
     if (*c.status != ST_OK) return;
     const int ns = c.ctr[0];
-    { Hot hot; for (int s = tid; s < ns; s += nt) stage_segment(c, s, hot); }
+    { Hot hot; int nxt = tid; replay_segments(c, hot, [&]() { const int s = nxt; nxt += nt; return s < ns ? s : -1; }); }
     SYNC();
     if (tid == 0) finish_counts(c);
     SYNC();

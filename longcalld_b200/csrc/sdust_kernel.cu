@@ -11,7 +11,7 @@ constexpr int THREADS = 1024;       // a chunk's segment search: one CTA
 constexpr int RTHREADS = 128;       // the replays: one thread per segment, the segments of all chunks side by side
 struct CtaSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
 
-// step 0 (prevvalid) and step 2 (the segments) of a chunk on one CTA; step 1 in between is a thread per position over all chunks
+// step 0 (prevvalid) and step 2 (the segments) of a chunk on one CTA; step 1 in between is a thread per run of DECIDE_RUN positions over all chunks
 __global__ void __launch_bounds__(THREADS)
 sdust_segments_kernel(const Chunk *chunks, int n, int step) {
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
@@ -20,21 +20,29 @@ sdust_segments_kernel(const Chunk *chunks, int n, int step) {
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(RTHREADS)
 sdust_decide_kernel(const Chunk *chunks) {
+    __shared__ Hot hot[RTHREADS];
     const Chunk c = chunks[blockIdx.y];
-    for (int i = (int)(blockIdx.x * 256 + threadIdx.x); i < c.n; i += (int)(gridDim.x * 256)) decide_at(c, i);
+    const int i0 = (int)(blockIdx.x * RTHREADS + threadIdx.x) * DECIDE_RUN;
+    if (i0 < c.n) decide_run(c, hot[threadIdx.x], i0, i0 + DECIDE_RUN < c.n ? i0 + DECIDE_RUN : c.n);
 }
 
-// pass 0 replays a segment into its staging range, pass 1 packs the staged intervals at the segment's offset
+// the chunk's segments, taken from the chunk's counter by the threads of blockIdx.y's CTAs
 __global__ void __launch_bounds__(RTHREADS)
-sdust_replay_kernel(const Chunk *chunks, int pass) {
+sdust_replay_kernel(const Chunk *chunks) {
     __shared__ Hot hot[RTHREADS];
     const Chunk c = chunks[blockIdx.y];
     if (*c.status != ST_OK) return;
+    const int ns = c.ctr[0];
+    replay_segments(c, hot[threadIdx.x], [&]() { const int s = atomicAdd(&c.ctr[1], 1); return s < ns ? s : -1; });
+}
+__global__ void __launch_bounds__(RTHREADS)
+sdust_pack_kernel(const Chunk *chunks) {
+    const Chunk c = chunks[blockIdx.y];
+    if (*c.status != ST_OK) return;
     const int s = (int)(blockIdx.x * RTHREADS + threadIdx.x);
-    if (s >= c.ctr[0]) return;
-    if (pass == 0) stage_segment(c, s, hot[threadIdx.x]); else pack_segment(c, s);
+    if (s < c.ctr[0]) pack_segment(c, s);
 }
 
 __global__ void sdust_offsets_kernel(const Chunk *chunks, int n) {
@@ -96,13 +104,15 @@ struct SdustPlan : Plan {
         Context &c = ctx();
         if (n == 0) return 0;
         const dim3 rgrid((unsigned)((max_seg_cap + RTHREADS - 1) / RTHREADS), (unsigned)n);
-        const dim3 dgrid((unsigned)std::max(1, std::min((max_len + 255) / 256, 64)), (unsigned)n);
+        const dim3 dgrid((unsigned)std::max(1, (max_len + RTHREADS * DECIDE_RUN - 1) / (RTHREADS * DECIDE_RUN)), (unsigned)n);
         sdust_segments_kernel<<<std::min(n, c.sm_count * 2), THREADS, 0, s>>>(d_chunks.p, n, 0);
-        sdust_decide_kernel<<<dgrid, 256, 0, s>>>(d_chunks.p);
+        sdust_decide_kernel<<<dgrid, RTHREADS, 0, s>>>(d_chunks.p);
         sdust_segments_kernel<<<std::min(n, c.sm_count * 2), THREADS, 0, s>>>(d_chunks.p, n, 1);
-        sdust_replay_kernel<<<rgrid, RTHREADS, 0, s>>>(d_chunks.p, 0);
+        static const int spt = getenv("LCD_SDUST_SPT") ? std::max(1, atoi(getenv("LCD_SDUST_SPT"))) : 4;      // segment slots per replay thread
+        const dim3 pgrid((unsigned)((max_seg_cap / spt + RTHREADS - 1) / RTHREADS), (unsigned)n);
+        sdust_replay_kernel<<<pgrid, RTHREADS, 0, s>>>(d_chunks.p);
         sdust_offsets_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_chunks.p, n);
-        sdust_replay_kernel<<<rgrid, RTHREADS, 0, s>>>(d_chunks.p, 1);
+        sdust_pack_kernel<<<rgrid, RTHREADS, 0, s>>>(d_chunks.p);
         LCD_CUDA_OK(cudaGetLastError());
         c.launches += 6;
         return 0;

@@ -32,3 +32,25 @@ def test_emu_sdust_vs_oracle(emu, oracle):
     assert n_iv > 5000
     for seq in (b"", b"A", b"AC", b"ACG", b"N" * 50, b"A" * 300, b"AC" * 200, b"ACGT" * 100 + b"N" + b"T" * 40, b"acgtnACGTN" * 30, b"ANCNGN" * 50 + b"A" * 30, b"AAAN" * 60):
         assert T.sdust(emu, "emu_sdust", seq) == T.sdust(oracle, "lcd_oracle_sdust", seq), seq[:20]
+
+
+def test_emu_sdust_long_repeats(emu, oracle):
+    """long tandem repeats / homopolymers with mutations sprinkled in: hundreds of perfect intervals alive at once (the incremental scan of that list)"""
+    rng = np.random.default_rng(93)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    n_iv = 0
+    for it in range(40):
+        parts = []
+        for _ in range(int(rng.integers(1, 6))):
+            u = int(rng.integers(1, 9)); reps = int(rng.integers(20, 400))
+            unit = rng.integers(0, 4, u)
+            s = np.tile(unit, reps)
+            hit = rng.random(len(s)) < float(rng.choice([0.0, 0.01, 0.05, 0.15])); s[hit] = rng.integers(0, 4, int(hit.sum()))
+            parts.append(acgt[s])
+            parts.append(acgt[rng.integers(0, 4, int(rng.integers(0, 80)))])
+        seq = np.concatenate(parts)
+        for Tt, W in ((5, 20), (8, 16), (4, 24)):
+            a, b = T.sdust(emu, "emu_sdust", seq, Tt, W), T.sdust(oracle, "lcd_oracle_sdust", seq, Tt, W)
+            assert a == b, (it, len(seq), Tt, W, a[:3], b[:3])
+            n_iv += len(b)
+    assert n_iv > 100
