@@ -87,7 +87,8 @@ struct Hot { unsigned char ring[MAXW], cw[WTOT], cv[WTOT], pad[4]; };       // (
 template <class Fetch> __device__ inline void replay_segments(const Chunk &c, Hot &hot, Fetch fetch) {
     const int T = c.T, W = c.W, maxn = W - WLEN + 1, QUIET = W + 20, ns = c.ctr[0];
     unsigned char *ring = hot.ring, *cv = hot.cv, *cw = hot.cw;
-    struct Perf { int start, finish; short r, l; } P[MAXP]; int np = 0;      // (r <= (W - 2)(W - 3) / 2, l <= W - 2)
+    // a perfect interval in 8 bytes, so that the list's shifts move one word pair per entry: finish - start <= W, r <= (W - 2)(W - 3) / 2, l <= W - 2
+    struct __align__(8) Perf { int start; unsigned m; __device__ int finish() const { return start + (int)(m >> 24); } __device__ int r() const { return (int)(m & 0xffff); } __device__ int l() const { return (int)(m >> 16 & 0xff); } } P[MAXP]; int np = 0;
     int front = 0, cnt = 0, rv = 0, rw = 0, L = 0, l = 0, quiet = 0, err = 0, i = 0;
     long long n_res = 0, last_beg = 0, last_end = 0, lim = 0; bool have_last = false, over = false;
     long long *out_beg = nullptr, *out_end = nullptr;
@@ -95,8 +96,8 @@ template <class Fetch> __device__ inline void replay_segments(const Chunk &c, Ho
         if (np == 0 || P[np - 1].start >= start) return;
         const Perf p = P[np - 1];
         bool saved = false;
-        if (have_last && p.start <= last_end) { saved = true; if (p.finish > last_end) { last_end = p.finish; if (!over) out_end[n_res - 1] = c.base + last_end; } }
-        if (!saved) { last_beg = p.start; last_end = p.finish; have_last = true; if (n_res < lim) { out_beg[n_res] = c.base + last_beg; out_end[n_res] = c.base + last_end; } else over = true; ++n_res; }
+        if (have_last && p.start <= last_end) { saved = true; if (p.finish() > last_end) { last_end = p.finish(); if (!over) out_end[n_res - 1] = c.base + last_end; } }
+        if (!saved) { last_beg = p.start; last_end = p.finish(); have_last = true; if (n_res < lim) { out_beg[n_res] = c.base + last_beg; out_end[n_res] = c.base + last_end; } else over = true; ++n_res; }
         int x = np - 1; while (x >= 0 && P[x].start < start) --x;
         np = x + 1;
     };
@@ -151,14 +152,14 @@ template <class Fetch> __device__ inline void replay_segments(const Chunk &c, Ho
                         const int new_r = r, new_l = cnt - k - 1;
                         if (new_r * 10 > T * new_l) {
                             for (; j < np && P[j].start >= k + start_; ++j)
-                                if (max_r == 0 || P[j].r * max_l > max_r * P[j].l) { max_r = P[j].r; max_l = P[j].l; }
+                                { const int pr = P[j].r(), pl = P[j].l(); if (max_r == 0 || pr * max_l > max_r * pl) { max_r = pr; max_l = pl; } }
                             if (max_r == 0 || new_r * max_l >= max_r * new_l) {
                                 max_r = new_r; max_l = new_l;
                                 if (np >= MAXP) err = ST_PLIST;               // (reported with the segment's count; no early exit)
                                 else {
                                     for (int x = np; x > j; --x) P[x] = P[x - 1];
                                     ++np;
-                                    P[j].start = k + start_; P[j].finish = cnt + (WLEN - 1) + start_; P[j].r = (short)new_r; P[j].l = (short)new_l;
+                                    P[j].start = k + start_; P[j].m = (unsigned)(cnt + (WLEN - 1) - k) << 24 | (unsigned)new_l << 16 | (unsigned)new_r;
                                     ++j;                                        // (the new one is the maximum itself)
                                 }
                             }
