@@ -896,6 +896,10 @@ def run_b200(args, rank, world):
                                       f"K1-K3 on {k_chunks} of {ps.n_chunks} chunks, time scaled by {pile_scale:.4f}",
                             "poa_s": dt_poa, "wfa_s": dt_wfa, "phase_s": dt_phase, "edlib_s": dt_edlib,
                             "digar_s": pile_scale * dtp[1], "pileup_s": pile_scale * dtp[2], "profile_s": pile_scale * dtp[3], "sites_s": pile_scale * dtp[4], "classify_s": pile_scale * dtp[5], "noisyreg_s": pile_scale * dtp[6]}
+    widening = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.cuda.synchronize()
+        widening = {"sdust_kernels": sdust_widening(args, ps, ref_shim())}
     wp_line = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_whole_program:
         torch.cuda.synchronize()
@@ -943,10 +947,47 @@ def run_b200(args, rank, world):
                                                                "GBps": ps.k3_bytes / (k3_ms / args.steps / 1e3) / 1e9},
                                             "edlib_kernel": {"ms": edlib_ms / args.steps, "block_columns": edlib_units,
                                                              "GBps": edlib_units * EDLIB_BYTES_PER_BLOCKCOL / (edlib_ms / args.steps / 1e3) / 1e9}}},
-                "cpu_baseline": cpu_baseline, "parity_checked": parity, "whole_program": wp_line}
+                "cpu_baseline": cpu_baseline, "parity_checked": parity, "whole_program": wp_line, "widening": widening}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def sdust_widening(args, ps, lib):
+    """K0, outside the timed step: the low-complexity intervals of the chunks' reference windows (sdust, T = 5, W = 20) -- one window of the
+    chunk's length per chunk, ten distinct ones tiled like the chunks themselves -- timed with CUDA events on the library's stream, and compared interval
+    for interval with the unmodified reference's sdust() (oracle/_ref) on the distinct windows."""
+    import torch
+    import longcalld_b200 as lcd
+    from longcalld_b200 import synth
+    n_chunks = ps.n_chunks; L = int(round(args.mbp * 1e6 / n_chunks))
+    rng = np.random.default_rng(args.seed + 4242)
+    tmpl = [synth.sdust_window(rng, L) for _ in range(min(10, n_chunks))]
+    plan = lcd.SdustPlan([tmpl[i % len(tmpl)] for i in range(n_chunks)], 5, 20)
+    st = torch.cuda.ExternalStream(lcd.stream())
+    ms = []
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st); plan.run(); e1.record(st); plan.sync()
+        ms.append(e0.elapsed_time(e1))
+    out = plan.fetch()
+    res = {"ms": float(np.median(ms[1:])), "windows": n_chunks, "window_bases": L, "intervals": int(sum(len(x) for x in out)), "launches_per_run": 6,
+           "Mbp_per_s": n_chunks * L / 1e6 / (float(np.median(ms[1:])) / 1e3), "in_timed_step": False, "parity_checked": None, "reference_s_per_window": None}
+    if lib is not None and hasattr(lib, "ref_sdust"):
+        lib.ref_sdust.restype = C.c_int
+        dt = 0.0
+        for k, seq in enumerate(tmpl):
+            cap = len(seq) // 2 + 16
+            b, e = np.zeros(cap, np.int64), np.zeros(cap, np.int64)
+            t0 = time.perf_counter()
+            n = lib.ref_sdust(_vp(seq), C.c_int(len(seq)), C.c_int(5), C.c_int(20), _vp(b), _vp(e), C.c_int64(cap))
+            dt += time.perf_counter() - t0
+            got = np.asarray(out[k], np.int64).reshape(-1, 2)
+            if n != len(got) or not (np.array_equal(got[:, 0], b[:n]) and np.array_equal(got[:, 1], e[:n])):
+                raise SystemExit(f"K0: window {k} differs from the reference's sdust() ({n} vs {len(got)} intervals)")
+        res["parity_checked"] = f"{len(tmpl)} distinct windows ({sum(len(x) for x in out[:len(tmpl)])} intervals) identical to the reference's sdust()"
+        res["reference_s_per_window"] = dt / len(tmpl)
+    return res
 
 
 def main():

@@ -22,6 +22,26 @@ def _low_complexity(rng, n):
     return np.resize(unit, n)
 
 
+def sdust_window(rng, n, lc_every=2000, n_frac=0.0005):
+    """ASCII reference window of n bases for K0: random sequence with homopolymers, short tandem repeats and AT-rich stretches planted every ~lc_every
+    bases, a few N runs and soft-masked (lower-case) bases.  (At the reference's T = 5 random sequence alone gives an interval every ~65 bases.)"""
+    s = rng.integers(0, 4, n).astype(np.uint8)
+    p = int(rng.integers(0, lc_every))
+    while p < n - 80:
+        kind = int(rng.integers(0, 3))
+        if kind == 0: s[p:p + int(rng.integers(4, 40))] = rng.integers(0, 4)
+        elif kind == 1:
+            u, c = int(rng.integers(2, 7)), int(rng.integers(3, 15))
+            s[p:p + u * c] = np.tile(rng.integers(0, 4, u).astype(np.uint8), c)
+        else:
+            L = int(rng.integers(10, 60)); s[p:p + L] = rng.choice(np.array([0, 3], np.uint8), L)
+        p += int(rng.integers(5, 2 * lc_every))
+    a = np.frombuffer(b"ACGT", np.uint8)[s].copy()
+    for q in rng.integers(0, n, max(1, int(n * n_frac))): a[q:q + int(rng.integers(1, 30))] = ord("N")
+    low = rng.random(n) < 0.05; a[low & (a != ord("N"))] |= 0x20
+    return a
+
+
 def _region_ref(rng, L):
     ref = rng.integers(0, 4, L).astype(np.uint8)
     if rng.random() < 0.6 and L >= 24:             # most noisy regions sit on a repeat tract
