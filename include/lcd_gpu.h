@@ -346,6 +346,10 @@ typedef struct {
     int64_t n_low; const int64_t *low_beg, *low_end;
 } lcd_noisyreg_params_t;
 lcd_plan_t *lcd_noisyreg_plan_create_on_classify(lcd_plan_t *digar_plan, lcd_plan_t *classify_plan, int n_chunks, const lcd_noisyreg_params_t *params);
+/* The same with the low-complexity intervals read where a K0 plan (lcd_sdust_plan_create, one window per chunk, `base` chosen so that its intervals are in
+ * the chunk's coordinates: what src/bam_utils.c:1574-1583 adds to chunk->low_comp_cr) leaves them -- their number too is read on the device, so the K0 plan
+ * only has to have run before this one in stream order.  params[i].n_low must be 0.  A chunk whose K0 window failed fails here as well (fetch reports it). */
+lcd_plan_t *lcd_noisyreg_plan_create_on_sdust(lcd_plan_t *digar_plan, lcd_plan_t *classify_plan, lcd_plan_t *sdust_plan, int n_chunks, const lcd_noisyreg_params_t *params);
 
 /* ---------------------------------------------------------------- K3: pileup scan, read x variant profile
  * Replaces read_var_profile_t *collect_read_var_profile(const call_var_opt_t *opt, bam_chunk_t *chunk)

@@ -921,14 +921,21 @@ class NoisyRegParams(C.Structure):
 class NoisyRegOnClassifyPlan(_Plan):
     """K2c on what a DigarPlan (run) and a ClassifyOnPileupPlan hold in HBM; params: per chunk a dict(min_alt_dp, noisy_reg_flank_len, is_ont, min_af,
     n_low, low_beg, low_end); n_sites: the classify plan's site counts; n_nreg: the digar plan's noisy intervals per chunk (DigarPlan.sizes())."""
-    def __init__(self, digar_plan, classify_plan, params, n_sites, n_nreg):
-        self.digar_plan, self.classify_plan, self.n_sites = digar_plan, classify_plan, list(n_sites)
+    def __init__(self, digar_plan, classify_plan, params, n_sites, n_nreg, sdust_plan=None):
+        """sdust_plan: a SdustPlan (one window per chunk, intervals in the chunk's coordinates) whose intervals K2c reads in HBM instead of params' low_beg / low_end
+        (lcd_noisyreg_plan_create_on_sdust)"""
+        self.digar_plan, self.classify_plan, self.sdust_plan, self.n_sites = digar_plan, classify_plan, sdust_plan, list(n_sites)
         n = len(params)
+        if sdust_plan is not None: params = [dict(d, n_low=0, low_beg=np.zeros(0, np.int64), low_end=np.zeros(0, np.int64)) for d in params]
         self.keep = [(np.ascontiguousarray(np.append(np.asarray(d["low_beg"]), 0), np.int64), np.ascontiguousarray(np.append(np.asarray(d["low_end"]), 0), np.int64)) for d in params]
         self.par = (NoisyRegParams * max(n, 1))(*[NoisyRegParams(d["min_alt_dp"], d["noisy_reg_flank_len"], d.get("is_ont", 0), 0, d["min_af"], d["n_low"], a.ctypes.data, b.ctypes.data)
                                                   for d, (a, b) in zip(params, self.keep)])
-        lib().lcd_noisyreg_plan_create_on_classify.restype = C.c_void_p
-        super().__init__(lib().lcd_noisyreg_plan_create_on_classify(digar_plan.h, classify_plan.h, C.c_int(n), self.par), n)
+        if sdust_plan is None:
+            lib().lcd_noisyreg_plan_create_on_classify.restype = C.c_void_p
+            super().__init__(lib().lcd_noisyreg_plan_create_on_classify(digar_plan.h, classify_plan.h, C.c_int(n), self.par), n)
+        else:
+            lib().lcd_noisyreg_plan_create_on_sdust.restype = C.c_void_p
+            super().__init__(lib().lcd_noisyreg_plan_create_on_sdust(digar_plan.h, classify_plan.h, sdust_plan.h, C.c_int(n), self.par), n)
         self.res, outs = [], []
         for k, m in zip(self.n_sites, n_nreg):
             cap = int(k) + int(m) + 8

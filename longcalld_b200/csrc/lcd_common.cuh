@@ -156,7 +156,7 @@ int classify_plan_view(Plan *plan, ClassifyView *v);  // classify_kernel.cu
 
 // K0's intervals as K2c consumes them in place (per chunk: device arrays of starts / ends in ascending order and the device word that holds their number).
 struct SdustView {
-    int n_chunks = 0; std::vector<const long long *> beg, end, n_out; std::vector<long long> cap;
+    int n_chunks = 0; std::vector<const long long *> beg, end, n_out; std::vector<const int *> status; std::vector<long long> cap;
 };
 int sdust_plan_view(Plan *plan, SdustView *v);        // sdust_kernel.cu
 

@@ -29,7 +29,7 @@ namespace noisyreg {
 enum { CINS = 1, CDEL = 2, CDIFF = 8 };
 enum { NON_VAR = 0x800, LOW_COV_VAR = 0x001, STRAND_BIAS_VAR = 0x002, LOW_AF_VAR = 0x400, REP_HET_VAR = 0x010 };
 constexpr int NOT_CAND = NON_VAR | LOW_COV_VAR | STRAND_BIAS_VAR;
-enum { ST_OK = 0, ST_REG_CAP = -5 };
+enum { ST_OK = 0, ST_REG_CAP = -5, ST_LOW = -7 };      // ST_LOW: the sdust plan the chunk reads its low-complexity intervals from failed for it
 
 struct Ivs { int *st, *en, *label; };
 
@@ -40,6 +40,7 @@ struct Chunk {
     const long long *site_pos; const int *site_type, *site_ref_len, *var_cate_in;
     const long long *cn_beg, *cn_end; const int *cn_label;
     const long long *low_beg, *low_end;                                             // ascending starts
+    const long long *n_low_dev; const int *low_status;                              // chained to K0 (sdust_device.cuh): the number of intervals and K0's status, read on the device
     const unsigned char *is_skipped, *active;                                       // a read counts when !is_skipped[r] (K1's skip) and, where given, active[r] (not skipped by the loader)
     const long long *read_beg, *read_end, *digar_first; const int *n_digar;
     const long long *digar_pos; const signed char *digar_type; const int *digar_len;
@@ -147,6 +148,10 @@ __device__ __forceinline__ void add_var_cr(const Chunk &c, int i, bool check_rat
 
 // The whole chunk.  tid / nt: this thread and the number of threads working on the chunk; SYNC: barrier between phases.
 template <class SyncF> __device__ void run_chunk(Chunk c, int tid, int nt, SyncF SYNC) {
+    if (c.n_low_dev) {
+        if (*c.low_status != 0) { if (tid == 0) { *c.status = ST_LOW; *c.n_regs = 0; } return; }
+        c.n_low = (int)*c.n_low_dev;
+    }
     Ivs A = c.A, B = c.B;
     const int n = c.n_sites;
     // running maximum of the low-complexity ends (for the walk-back overlap queries)

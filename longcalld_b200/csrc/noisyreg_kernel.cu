@@ -125,9 +125,11 @@ struct NoisyRegPlan : Plan {
 
     // K2c on what K1 and K2b left in HBM: the reads' spans, records and noisy intervals (the chunk's own list is gathered from them on the device),
     // the sites and their categories; only the options and the low-complexity intervals are uploaded.
-    int build_on(Plan *digar, Plan *classify, int n_, const lcd_noisyreg_params_t *par) {
+    // sdust != nullptr: the low-complexity intervals are read where a K0 plan leaves them (their number too: nothing of them passes through the host)
+    int build_on(Plan *digar, Plan *classify, int n_, const lcd_noisyreg_params_t *par, Plan *sdust = nullptr) {
         n = n_;
-        DigarView dv; ClassifyView cv;
+        DigarView dv; ClassifyView cv; SdustView sv;
+        if (sdust) { if (sdust_plan_view(sdust, &sv)) return -1; if (sv.n_chunks != n_) { set_error("lcd_noisyreg: %d parameter sets for an sdust plan of %d chunks", n_, sv.n_chunks); return -1; } }
         dv.want_host_spans = false;
         if (digar_plan_view(digar, cur_stream(), &dv) || classify_plan_view(classify, &cv)) return -1;
         if (dv.n_chunks != n || cv.n_chunks != n) { set_error("lcd_noisyreg: %d parameter sets for a digar plan of %d and a classify plan of %d chunks", n, dv.n_chunks, cv.n_chunks); return -1; }
@@ -141,8 +143,9 @@ struct NoisyRegPlan : Plan {
             const lcd_noisyreg_params_t &x = par[i];
             if (x.n_low < 0 || (x.n_low > 0 && (!x.low_beg || !x.low_end)) || x.noisy_reg_flank_len < 0) { set_error("lcd_noisyreg: chunk %d has invalid options", i); return -1; }
             for (long long k = 1; k < x.n_low; ++k) if (x.low_beg[k] < x.low_beg[k - 1]) { set_error("lcd_noisyreg: chunk %d: low-complexity intervals must ascend by start (interval %lld)", i, k); return -1; }
-            const size_t nl = (size_t)x.n_low, ns = (size_t)(cv.site_off[i + 1] - cv.site_off[i]);
-            in_off[i].push_back(take(in_bytes, nl * 8)); in_off[i].push_back(take(in_bytes, nl * 8));
+            if (sdust && x.n_low) { set_error("lcd_noisyreg: chunk %d passes low-complexity intervals of its own to a plan chained to an sdust plan", i); return -1; }
+            const size_t nl = sdust ? (size_t)sv.cap[i] : (size_t)x.n_low, ns = (size_t)(cv.site_off[i + 1] - cv.site_off[i]);      // (chained: scratch for as many as K0 can write)
+            in_off[i].push_back(take(in_bytes, (size_t)x.n_low * 8)); in_off[i].push_back(take(in_bytes, (size_t)x.n_low * 8));
             const size_t cap = (size_t)dv.nreg_total[i] + ns + 8;
             n_sites[i] = (int)ns; reg_cap[i] = (int)cap; tot_sites += (long long)ns;
             v_ns.push_back(ns); v_cap.push_back(cap); v_nl.push_back(nl);
@@ -160,6 +163,7 @@ struct NoisyRegPlan : Plan {
             c.n_sites = n_sites[i]; c.n_reads = (int)(dv.read_off[i + 1] - r0); c.n_cnreg = 0; c.n_low = (int)x.n_low; c.cap = reg_cap[i]; c.cn_from_reads = 1;
             c.site_pos = cv.spos + s0; c.site_type = cv.stype + s0; c.site_ref_len = cv.sref + s0; c.var_cate_in = cv.cate + s0;
             c.low_beg = (const long long *)(d_in.p + in_off[i][0]); c.low_end = (const long long *)(d_in.p + in_off[i][1]);
+            if (sdust) { c.low_beg = sv.beg[i]; c.low_end = sv.end[i]; c.n_low_dev = sv.n_out[i]; c.low_status = sv.status[i]; }
             c.is_skipped = dv.dropped + r0; c.active = dv.active + r0; c.read_beg = dv.beg + r0; c.read_end = dv.end + r0; c.digar_first = dv.dfirst + r0; c.n_digar = dv.ndig + r0;
             c.digar_pos = dv.dpos; c.digar_type = (const signed char *)dv.dtype; c.digar_len = dv.dlen;
             c.nreg_first = dv.nfirst + r0; c.n_nreg = dv.nnreg + r0; c.nreg_beg = dv.nbeg; c.nreg_end = dv.nend; c.nreg_label = dv.nlabel;
@@ -191,7 +195,7 @@ struct NoisyRegPlan : Plan {
         std::vector<std::vector<uint8_t>> regs(n);
         for (int i = 0; i < n; ++i) {
             long long nreg; int st; memcpy(&nreg, hdr.data() + 16 * (size_t)i, 8); memcpy(&st, hdr.data() + 16 * (size_t)i + 8, 4);
-            if (st != ST_OK) { set_error("lcd_noisyreg: chunk %d failed on the device (status %d: interval list capacity)", i, st); return -2; }
+            if (st != ST_OK) { set_error("lcd_noisyreg: chunk %d failed on the device (status %d: %s)", i, st, st == ST_LOW ? "the sdust plan it reads its low-complexity intervals from failed for this chunk" : "interval list capacity"); return -2; }
             out[i].n_regs = nreg;
             if (nreg > out[i].reg_cap) { set_error("lcd_noisyreg: chunk %d has %lld noisy regions, the caller's arrays hold %lld", i, nreg, (long long)out[i].reg_cap); return -3; }
             if (n_sites[i]) {
@@ -229,6 +233,13 @@ lcd_plan_t *lcd_noisyreg_plan_create_on_classify(lcd_plan_t *digar_plan, lcd_pla
     if (!digar_plan || !classify_plan || n_chunks < 0 || (n_chunks > 0 && !params)) { set_error("lcd_noisyreg_plan_create_on_classify: invalid arguments"); return nullptr; }
     noisyreg::NoisyRegPlan *p = new noisyreg::NoisyRegPlan();
     if (p->build_on(reinterpret_cast<Plan *>(digar_plan), reinterpret_cast<Plan *>(classify_plan), n_chunks, params)) { delete p; return nullptr; }
+    return reinterpret_cast<lcd_plan_t *>(p);
+}
+lcd_plan_t *lcd_noisyreg_plan_create_on_sdust(lcd_plan_t *digar_plan, lcd_plan_t *classify_plan, lcd_plan_t *sdust_plan, int n_chunks, const lcd_noisyreg_params_t *params) {
+    if (ensure_ready()) return nullptr;
+    if (!digar_plan || !classify_plan || !sdust_plan || n_chunks < 0 || (n_chunks > 0 && !params)) { set_error("lcd_noisyreg_plan_create_on_sdust: invalid arguments"); return nullptr; }
+    noisyreg::NoisyRegPlan *p = new noisyreg::NoisyRegPlan();
+    if (p->build_on(reinterpret_cast<Plan *>(digar_plan), reinterpret_cast<Plan *>(classify_plan), n_chunks, params, reinterpret_cast<Plan *>(sdust_plan))) { delete p; return nullptr; }
     return reinterpret_cast<lcd_plan_t *>(p);
 }
 int lcd_noisyreg_plan_fetch(lcd_plan_t *plan, void *stream, lcd_noisyreg_output_t *out) {

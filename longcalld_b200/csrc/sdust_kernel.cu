@@ -145,8 +145,8 @@ struct SdustPlan : Plan {
 int sdust_plan_view(Plan *plan, SdustView *v) {
     sdust::SdustPlan *p = dynamic_cast<sdust::SdustPlan *>(plan);
     if (!p) { set_error("not an sdust (K0) plan"); return -1; }
-    v->n_chunks = p->n; v->beg.resize(p->n); v->end.resize(p->n); v->n_out.resize(p->n); v->cap = p->caps;
-    for (int i = 0; i < p->n; ++i) { v->beg[i] = p->chunks[i].out_beg; v->end[i] = p->chunks[i].out_end; v->n_out[i] = p->chunks[i].n_out; }
+    v->n_chunks = p->n; v->beg.resize(p->n); v->end.resize(p->n); v->n_out.resize(p->n); v->status.resize(p->n); v->cap = p->caps;
+    for (int i = 0; i < p->n; ++i) { v->beg[i] = p->chunks[i].out_beg; v->end[i] = p->chunks[i].out_end; v->n_out[i] = p->chunks[i].n_out; v->status[i] = p->chunks[i].status; }
     return 0;
 }
 } // namespace lcd

@@ -89,6 +89,23 @@ def test_gpu_chain_in_place(gpu, oracle):
     for g, h in zip(got, gpu.noisyreg_batch(inputs)):
         assert np.array_equal(g["var_cate"], h["var_cate"]) and np.array_equal(g["keep"], h["keep"]) and np.array_equal(g["reg_beg"], h["reg_beg"]) and np.array_equal(g["reg_end"], h["reg_end"])
 
+    # K0 -> K2c: the low-complexity intervals read where an sdust plan leaves them (their number too), against the oracle on K0's fetched intervals
+    wins = [synth.sdust_window(rng, b - a + 2000, lc_every=400) for a, b in regs]
+    k0 = gpu.SdustPlan(wins, 5, 20, base=[a - 1000 for a, _ in regs]); k0.run()
+    k2c0 = gpu.NoisyRegOnClassifyPlan(k1, k2b, inputs, [c["n_sites"] for c in cls], [s[2] for s in k1.sizes()], sdust_plan=k0)
+    for _ in range(2):
+        k2c0.run(); k2c0.sync()
+    low = k0.fetch()
+    assert min(len(x) for x in low) > 200
+    for g, x, iv in zip(k2c0.fetch(), inputs, low):
+        x0 = dict(x, n_low=len(iv), low_beg=np.asarray([p[0] for p in iv], np.int64), low_end=np.asarray([p[1] for p in iv], np.int64))
+        assert _same(g, T.noisy_regs(oracle, "lcd_oracle_noisy_regs", x0))
+    # intervals from the host AND an sdust plan: rejected
+    import ctypes as C
+    from longcalld_b200 import capi
+    capi.lib().lcd_noisyreg_plan_create_on_sdust.restype = C.c_void_p
+    assert not capi.lib().lcd_noisyreg_plan_create_on_sdust(k1.h, k2b.h, k0.h, C.c_int(len(inputs)), k2c.par)
+    assert b"of its own" in capi.lib().lcd_gpu_last_error()
 
 def test_gpu_noisy_regs_vs_reference_fixtures(gpu):
     """committed outputs of the unmodified reference functions: no oracle, no /root/reference in this comparison"""
