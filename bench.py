@@ -987,6 +987,16 @@ def sdust_widening(args, ps, lib):
                 raise SystemExit(f"K0: window {k} differs from the reference's sdust() ({n} vs {len(got)} intervals)")
         res["parity_checked"] = f"{len(tmpl)} distinct windows ({sum(len(x) for x in out[:len(tmpl)])} intervals) identical to the reference's sdust()"
         res["reference_s_per_window"] = dt / len(tmpl)
+        # the same batch on all host cores: the distinct windows, a thread each, as often as the batch tiles them
+        from concurrent.futures import ThreadPoolExecutor
+        nt = os.cpu_count() or 1; reps = [tmpl[i % len(tmpl)] for i in range(min(n_chunks, 2 * nt))]
+
+        def one(seq):
+            cap = len(seq) // 2 + 16; b, e = np.zeros(cap, np.int64), np.zeros(cap, np.int64)
+            return lib.ref_sdust(_vp(seq), C.c_int(len(seq)), C.c_int(5), C.c_int(20), _vp(b), _vp(e), C.c_int64(cap))
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(nt) as ex: list(ex.map(one, reps))
+        res["reference_all_cores"] = {"cores": nt, "windows": len(reps), "s": time.perf_counter() - t0, "Mbp_per_s": len(reps) * L / 1e6 / (time.perf_counter() - t0)}
     return res
 
 
