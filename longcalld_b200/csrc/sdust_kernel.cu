@@ -45,9 +45,26 @@ sdust_pack_kernel(const Chunk *chunks) {
     if (s < c.ctr[0]) pack_segment(c, s);
 }
 
-__global__ void sdust_offsets_kernel(const Chunk *chunks, int n) {
-    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (i < n) finish_counts(chunks[i]);
+// finish_counts() by one warp per chunk: the segments' counts scanned 32 at a time
+__global__ void __launch_bounds__(128)
+sdust_offsets_kernel(const Chunk *chunks, int n) {
+    const int i = (int)(blockIdx.x * 4 + threadIdx.x / 32), lane = (int)(threadIdx.x & 31);
+    if (i >= n) return;
+    const Chunk c = chunks[i];
+    if (*c.status != ST_OK) return;
+    const int ns = c.ctr[0];
+    long long tot = 0; int bad = 0;
+    for (int b0 = 0; b0 < ns; b0 += 32) {
+        const int s = b0 + lane, v = s < ns ? c.seg_cnt[s] : 0;
+        const unsigned neg = __ballot_sync(0xffffffffu, v < 0);
+        if (neg) { bad = __shfl_sync(0xffffffffu, v, __ffs(neg) - 1); break; }      // (the first failed segment's status, as the one-thread version reports it)
+        int x = v;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (s < ns) c.seg_off[s] = (int)(tot + x - v);
+        tot += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane == 0) { if (bad) *c.status = bad; else if (tot > c.cap) *c.status = ST_CAP; *c.n_out = tot; }
 }
 
 struct SdustPlan : Plan {
@@ -111,7 +128,7 @@ struct SdustPlan : Plan {
         static const int spt = getenv("LCD_SDUST_SPT") ? std::max(1, atoi(getenv("LCD_SDUST_SPT"))) : 4;      // segment slots per replay thread
         const dim3 pgrid((unsigned)((max_seg_cap / spt + RTHREADS - 1) / RTHREADS), (unsigned)n);
         sdust_replay_kernel<<<pgrid, RTHREADS, 0, s>>>(d_chunks.p);
-        sdust_offsets_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_chunks.p, n);
+        sdust_offsets_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_chunks.p, n);
         sdust_pack_kernel<<<rgrid, RTHREADS, 0, s>>>(d_chunks.p);
         LCD_CUDA_OK(cudaGetLastError());
         c.launches += 6;
