@@ -145,7 +145,11 @@ template <class Fetch> __device__ inline void replay_segments(const Chunk &c, Ho
                     // The reference scans P from its head for every k: the intervals that start at or after k + start_, a prefix that only grows as k
                     // falls, for the best r / l among them -- a running maximum (an interval is inserted only when it is at least as good), so the scan
                     // goes on from where the previous k's stopped: O(np + W) per position instead of O(np * W), the same answers.
-                    int r = rv, max_r = 0, max_l = 0, j = 0;
+                    // The intervals found at this position (at most W - 2, by falling start) are kept aside with the place each belongs at and merged into P
+                    // in one pass from its tail afterwards -- the scan never needs them (each is the running maximum itself when it is found) --: one
+                    // move per entry behind the first place instead of one per entry and interval.
+                    int r = rv, max_r = 0, max_l = 0, j = 0, m = 0;
+                    Perf ins[MAXW]; int ins_at[MAXW];
                     for (int k = cnt - L - 1; k >= 0; --k) {
                         const int tt = ring[(front + k) % MAXW];
                         r += cv[tt]++;
@@ -155,15 +159,19 @@ template <class Fetch> __device__ inline void replay_segments(const Chunk &c, Ho
                                 { const int pr = P[j].r(), pl = P[j].l(); if (max_r == 0 || pr * max_l > max_r * pl) { max_r = pr; max_l = pl; } }
                             if (max_r == 0 || new_r * max_l >= max_r * new_l) {
                                 max_r = new_r; max_l = new_l;
-                                if (np >= MAXP) err = ST_PLIST;               // (reported with the segment's count; no early exit)
-                                else {
-                                    for (int x = np; x > j; --x) P[x] = P[x - 1];
-                                    ++np;
-                                    P[j].start = k + start_; P[j].m = (unsigned)(cnt + (WLEN - 1) - k) << 24 | (unsigned)new_l << 16 | (unsigned)new_r;
-                                    ++j;                                        // (the new one is the maximum itself)
-                                }
+                                ins[m].start = k + start_; ins[m].m = (unsigned)(cnt + (WLEN - 1) - k) << 24 | (unsigned)new_l << 16 | (unsigned)new_r;
+                                ins_at[m++] = j;
                             }
                         }
+                    }
+                    if (np + m > MAXP) err = ST_PLIST;                      // (reported with the segment's count; no early exit)
+                    else if (m) {
+                        int i = np - 1, w = np + m - 1;
+                        for (int t = m - 1; t >= 0; --t) {
+                            for (; i >= ins_at[t]; --i) P[w--] = P[i];
+                            P[w--] = ins[t];
+                        }
+                        np += m;
                     }
                     for (int k = cnt - L - 1; k >= 0; --k) cv[ring[(front + k) % MAXW]]--;
                 } else ++quiet;
