@@ -8,7 +8,9 @@
 using namespace lcd::noisyreg;
 struct NoSync { void operator()() const {} };
 
-extern "C" int emu_noisy_regs(const lcd_noisyreg_input_t *in, lcd_noisyreg_output_t *out) {
+// chained: 0 = the interval count in the chunk struct; 1 = read through n_low_dev as when K2c is chained to a K0 plan (the struct's own count poisoned);
+// 2 = the same with K0 reporting a failure for the chunk
+static int emu_run(const lcd_noisyreg_input_t *in, lcd_noisyreg_output_t *out, int chained) {
     Chunk c; memset(&c, 0, sizeof(c));
     const size_t cap = (size_t)in->n_cnreg + in->n_sites + 8;
     c.reg_beg = in->reg_beg; c.reg_end = in->reg_end; c.min_af = in->min_af; c.min_alt_dp = in->min_alt_dp; c.flank = in->noisy_reg_flank_len; c.is_ont = in->is_ont;
@@ -26,6 +28,8 @@ extern "C" int emu_noisy_regs(const lcd_noisyreg_input_t *in, lcd_noisyreg_outpu
     int *p = sc.data();
     c.A.st = p; c.A.en = p + cap; c.A.label = p + 2 * cap; c.B.st = p + 3 * cap; c.B.en = p + 4 * cap; c.B.label = p + 5 * cap; p += 6 * cap;
     c.tot = p; c.noi = p + cap; p += 2 * cap; c.low_pmax = p; p += in->n_low + 1; c.vp_pmax = p; p += in->n_sites + 1; c.ctr = p;
+    const long long n_low_dev = in->n_low; const int low_status = chained == 2 ? -5 : 0;
+    if (chained) { c.n_low = -12345; c.n_low_dev = &n_low_dev; c.low_status = &low_status; }
     run_chunk(c, 0, 1, NoSync());
     if (status) return status;
     out->n_regs = nregs;
@@ -33,3 +37,6 @@ extern "C" int emu_noisy_regs(const lcd_noisyreg_input_t *in, lcd_noisyreg_outpu
     for (long long k = 0; k < nregs; ++k) { out->reg_beg[k] = ob[k]; out->reg_end[k] = ob[nregs + k]; out->reg_label[k] = reinterpret_cast<const int *>(ob.data() + 2 * nregs)[k]; }
     return 0;
 }
+extern "C" int emu_noisy_regs(const lcd_noisyreg_input_t *in, lcd_noisyreg_output_t *out) { return emu_run(in, out, 0); }
+extern "C" int emu_noisy_regs_chained(const lcd_noisyreg_input_t *in, lcd_noisyreg_output_t *out) { return emu_run(in, out, 1); }
+extern "C" int emu_noisy_regs_k0_failed(const lcd_noisyreg_input_t *in, lcd_noisyreg_output_t *out) { return emu_run(in, out, 2); }

@@ -79,3 +79,16 @@ def test_emu_vs_fixtures(emu):
     for n, (case, kept, regs) in enumerate(noisyreg_fixture_cases()):
         got = T.noisy_regs(emu, "emu_noisy_regs", case)
         assert got[0] == kept and got[1] == regs, n
+
+
+def test_emu_chained_to_sdust(emu, oracle):
+    """K2c chained to a K0 plan (lcd_noisyreg_plan_create_on_sdust): the number of low-complexity intervals and K0's status are read through pointers on the
+    device; the answers are those of the plain form, and a window K0 failed on fails the chunk (status -7) instead of being read"""
+    rng = np.random.default_rng(87)
+    for n in range(120):
+        case = fabricated_case(rng, n_sites=int(rng.integers(2, 220)), span=int(rng.choice([60, 300, 900])))
+        a = T.noisy_regs(oracle, "lcd_oracle_noisy_regs", case)
+        b = T.noisy_regs(emu, "emu_noisy_regs_chained", case)
+        assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2]), n
+    with pytest.raises(AssertionError, match="-7"):
+        T.noisy_regs(emu, "emu_noisy_regs_k0_failed", case)
