@@ -54,3 +54,14 @@ def test_emu_sdust_long_repeats(emu, oracle):
             assert a == b, (it, len(seq), Tt, W, a[:3], b[:3])
             n_iv += len(b)
     assert n_iv > 100
+
+
+def test_emu_sdust_every_byte(emu, oracle):
+    """every byte value as a 'base' (the reference's table: A / C / G / T in either case and the codes 0 .. 3 are bases, the rest breaks a word)"""
+    rng = np.random.default_rng(94)
+    for it in range(30):
+        n = int(rng.integers(50, 4000))
+        seq = np.frombuffer(b"ACGTacgt\x00\x01\x02\x03", np.uint8)[rng.integers(0, 12, n)].copy()
+        hit = rng.random(n) < float(rng.choice([0.0, 0.02, 0.2])); seq[hit] = rng.integers(0, 256, int(hit.sum()))
+        if it % 3 == 0: seq[n // 3:n // 3 + 40] = seq[n // 3]            # a run, so that there is something to find
+        assert T.sdust(emu, "emu_sdust", seq) == T.sdust(oracle, "lcd_oracle_sdust", seq), it

@@ -21,3 +21,14 @@ def test_oracle_sdust_vs_live_reference(oracle, ref):
 def test_oracle_sdust_edge_cases(oracle, ref):
     for seq in (b"", b"A", b"AC", b"ACG", b"N" * 50, b"A" * 300, b"AC" * 200, b"ACGT" * 100 + b"N" + b"T" * 40, b"acgtnACGTN" * 30, bytes([0, 1, 2, 3] * 40)):
         assert T.sdust(oracle, "lcd_oracle_sdust", seq) == T.sdust(ref, "ref_sdust", seq), seq[:20]
+
+
+def test_oracle_sdust_every_byte(oracle, ref):
+    """every byte value as a 'base': the reference's table makes A / C / G / T in either case and the codes 0 .. 3 bases, the rest breaks a word"""
+    rng = np.random.default_rng(94)
+    for it in range(60):
+        n = int(rng.integers(50, 4000))
+        seq = np.frombuffer(b"ACGTacgt\x00\x01\x02\x03", np.uint8)[rng.integers(0, 12, n)].copy()
+        hit = rng.random(n) < float(rng.choice([0.0, 0.02, 0.2])); seq[hit] = rng.integers(0, 256, int(hit.sum()))
+        if it % 3 == 0: seq[n // 3:n // 3 + 40] = seq[n // 3]
+        assert T.sdust(oracle, "lcd_oracle_sdust", seq) == T.sdust(ref, "ref_sdust", seq), it
