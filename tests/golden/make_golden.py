@@ -11,6 +11,7 @@
   phase_lcd.json.gz   outputs of the UNMODIFIED reference read->haplotype assignment / phasing on seeded chunks.
   poa_ncons_lcd.json.gz outputs of the UNMODIFIED abpoa_aln_msa_cons (two consensus sequences by read clustering) on seeded de-novo regions.
   noisyreg_lcd.json.gz  kept sites + chunk_noisy_regs of the UNMODIFIED pre_process_noisy_regs + classify_cand_vars on seeded chunks.
+  sdust_lcd.json.gz   low-complexity intervals of the UNMODIFIED sdust() (src/sdust.c:184) on seeded reference windows (T = 5, W = 20 and two more settings).
   edlib_lcd.json.gz   outputs of the UNMODIFIED reference edlib (NW / HW, path) on seeded inputs.
   wfa_lcd.json.gz     outputs of the UNMODIFIED reference WFA2-lib (oracle/_ref/libref_shim.so)
                       at longcallD's own parameter points (src/align.h:21-26, src/align.c:398-406)
@@ -261,9 +262,31 @@ def noisyreg_lcd():
     return {"cases": cases}
 
 
+def sdust_lcd():
+    """Outputs of the UNMODIFIED sdust() (src/sdust.c:184, via oracle/_ref/libref_shim.so) on seeded reference-like windows: random sequence with planted
+    homopolymers / tandem repeats / AT-rich stretches, N runs, lower case, long repeats, the codes 0 .. 3 and stray bytes."""
+    import base64
+    ref = T.ref_lib()
+    rng = np.random.default_rng(20261102)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    seqs = [T.sdust_sequence(rng, int(n), lc_every=int(e), n_frac=float(f)) for n, e, f in ((20000, 400, 0.002), (6000, 60, 0.0), (3000, 120, 0.05), (45, 30, 0.0), (21, 30, 0.0))]
+    for _ in range(3):      # long tandem repeats with mutations: many perfect intervals alive at once
+        u, reps = int(rng.integers(1, 8)), int(rng.integers(100, 400))
+        s = np.tile(rng.integers(0, 4, u), reps); hit = rng.random(len(s)) < 0.03; s[hit] = rng.integers(0, 4, int(hit.sum()))
+        seqs.append(np.concatenate([acgt[rng.integers(0, 4, 50)], acgt[s], acgt[rng.integers(0, 4, 50)]]))
+    s = np.frombuffer(b"ACGTacgt\x00\x01\x02\x03", np.uint8)[rng.integers(0, 12, 2500)].copy(); hit = rng.random(len(s)) < 0.03; s[hit] = rng.integers(0, 256, int(hit.sum())); s[800:860] = s[800]
+    seqs.append(s)
+    cases = []
+    for q in seqs:
+        q = np.ascontiguousarray(q, np.uint8)
+        for Tt, W in ((5, 20), (8, 16), (4, 24)):
+            cases.append({"seq": base64.b64encode(q.tobytes()).decode(), "T": Tt, "W": W, "iv": [list(x) for x in T.sdust(ref, "ref_sdust", q, Tt, W)]})
+    return {"cases": cases}
+
+
 def main():
     only = sys.argv[1:]
-    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd), ("poa_lcd", poa_lcd), ("edlib_lcd", edlib_lcd), ("phase_lcd", phase_lcd), ("pileup_lcd", pileup_lcd), ("digar_lcd", digar_lcd), ("sites_lcd", sites_lcd), ("classify_lcd", classify_lcd), ("poa_ncons_lcd", poa_ncons_lcd), ("noisyreg_lcd", noisyreg_lcd)):
+    for name, fn in (("wfa_utest", wfa_utest), ("wfa_lcd", wfa_lcd), ("poa_lcd", poa_lcd), ("edlib_lcd", edlib_lcd), ("phase_lcd", phase_lcd), ("pileup_lcd", pileup_lcd), ("digar_lcd", digar_lcd), ("sites_lcd", sites_lcd), ("classify_lcd", classify_lcd), ("poa_ncons_lcd", poa_ncons_lcd), ("noisyreg_lcd", noisyreg_lcd), ("sdust_lcd", sdust_lcd)):
         if only and name not in only:
             continue
         path = os.path.join(HERE, name + ".json.gz")

@@ -677,6 +677,14 @@ def sdust(lib, fn, seq, T=5, W=20):
     return list(zip(b[:n].tolist(), e[:n].tolist()))
 
 
+def sdust_fixture_cases():
+    """tests/golden/sdust_lcd.json.gz: (sequence, T, W, intervals of the UNMODIFIED sdust()) -- generated by tests/golden/make_golden.py"""
+    import base64, gzip, json
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "sdust_lcd.json.gz")) as f:
+        d = json.load(f)
+    return [(np.frombuffer(base64.b64decode(c["seq"]), np.uint8).copy(), int(c["T"]), int(c["W"]), [tuple(x) for x in c["iv"]]) for c in d["cases"]]
+
+
 def sdust_sequence(rng, n, lc_every=120, n_frac=0.002):
     """ASCII reference-like sequence with planted homopolymers / short tandem repeats / low-entropy stretches, a few N runs and lower-case bases"""
     s = rng.integers(0, 4, n).astype(np.uint8)

@@ -65,3 +65,9 @@ def test_emu_sdust_every_byte(emu, oracle):
         hit = rng.random(n) < float(rng.choice([0.0, 0.02, 0.2])); seq[hit] = rng.integers(0, 256, int(hit.sum()))
         if it % 3 == 0: seq[n // 3:n // 3 + 40] = seq[n // 3]            # a run, so that there is something to find
         assert T.sdust(emu, "emu_sdust", seq) == T.sdust(oracle, "lcd_oracle_sdust", seq), it
+
+
+def test_emu_sdust_vs_fixtures(emu):
+    """the device logic against the committed outputs of the unmodified sdust()"""
+    for k, (seq, Tt, W, iv) in enumerate(T.sdust_fixture_cases()):
+        assert T.sdust(emu, "emu_sdust", seq, Tt, W) == iv, k

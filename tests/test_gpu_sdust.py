@@ -34,3 +34,12 @@ def test_gpu_sdust_chunk_shaped(gpu, oracle):
     for g, s, b in zip(plan.fetch(), seqs, (999999, 1499999, 7)):
         want = [(x + b, y + b) for x, y in T.sdust(oracle, "lcd_oracle_sdust", s)]
         assert g == want and len(g) > 2000
+
+
+def test_gpu_sdust_vs_reference_fixtures(gpu):
+    """the committed outputs of the unmodified sdust() (tests/golden/sdust_lcd.json.gz), one batch per (T, W)"""
+    cases = T.sdust_fixture_cases()
+    for Tt, W in sorted({(c[1], c[2]) for c in cases}):
+        sub = [c for c in cases if (c[1], c[2]) == (Tt, W)]
+        got = gpu.sdust_batch([c[0] for c in sub], Tt, W)
+        assert [list(map(tuple, g)) for g in got] == [c[3] for c in sub], (Tt, W)

@@ -32,3 +32,11 @@ def test_oracle_sdust_every_byte(oracle, ref):
         hit = rng.random(n) < float(rng.choice([0.0, 0.02, 0.2])); seq[hit] = rng.integers(0, 256, int(hit.sum()))
         if it % 3 == 0: seq[n // 3:n // 3 + 40] = seq[n // 3]
         assert T.sdust(oracle, "lcd_oracle_sdust", seq) == T.sdust(ref, "ref_sdust", seq), it
+
+
+def test_oracle_sdust_vs_fixtures(oracle):
+    """the committed outputs of the unmodified sdust() (tests/golden/sdust_lcd.json.gz): what pins the oracle where /root/reference is absent"""
+    cases = T.sdust_fixture_cases()
+    assert len(cases) >= 27 and sum(len(c[3]) for c in cases) > 1500
+    for k, (seq, Tt, W, iv) in enumerate(cases):
+        assert T.sdust(oracle, "lcd_oracle_sdust", seq, Tt, W) == iv, k
