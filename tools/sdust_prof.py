@@ -1,4 +1,6 @@
-"""K0 timing: 100 windows of 500 kb, (a) low-complexity stretches planted every ~2 kb (a genome-like density) and (b) every ~150 b (stress: long segments)"""
+"""K0 timing: 100 windows of 500 kb, (a) low-complexity stretches planted every ~2 kb (a genome-like density) and (b) every ~150 b (stress: long segments).
+Measurement tooling, not product: the sequences come from the test library and the oracle is the checker of the first window (and is timed beside it);
+SDUST_QUICK=1 runs (a) only; LCD_SDUST_SPT sets the segment slots per replay thread."""
 import sys, time
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 import numpy as np, torch
