@@ -1,4 +1,4 @@
-// sdust_device.cuh -- K0: the low-complexity intervals of a chunk's reference window (chunk->low_comp_cr), one CTA per chunk.
+// sdust_device.cuh -- K0: the low-complexity intervals of a chunk's reference window (chunk->low_comp_cr): per-position decisions, independent segments, one replay thread each.
 //
 // What it replaces: sdust(0, seq, l_seq, T, W, &n) (src/sdust.c:184, H. Li's symmetric DUST) as the chunk loader calls it over the chunk's region of the
 // reference (src/bam_utils.c:1574-1583: T = 5, W = 20), whose intervals K2c (noisyreg_device.cuh) extends the noisy regions and the sites' spans with.

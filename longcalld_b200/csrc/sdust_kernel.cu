@@ -1,4 +1,4 @@
-// sdust_kernel.cu -- K0 launcher and host plan: the low-complexity intervals (symmetric DUST) of the reference windows of many chunks, one CTA per chunk.
+// sdust_kernel.cu -- K0 launcher and host plan: the low-complexity intervals (symmetric DUST) of the reference windows of many chunks: six launches over all of them.
 // Device logic and design notes: sdust_device.cuh.
 #include "lcd_common.cuh"
 #include "sdust_device.cuh"
